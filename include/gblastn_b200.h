@@ -1,0 +1,249 @@
+/* gblastn_b200.h — C ABI of the B200-native blastn preliminary-search hot path.
+ *
+ * Drop-in boundary.  Plain C: POD structs, pointers and sizes only.
+ * Every entry point names the reference interface it replaces; paths are relative to the
+ * reference tree (core/ = c++/src/algo/blast/core, inc-core/ = c++/include/algo/blast/core,
+ * gpu/ = c++/src/algo/blast/gpu_blast, inc-gpu/ = c++/include/algo/blast/gpu_blast).
+ *
+ * Layering, mirroring where the reference draws its own lines:
+ *
+ *   bn_init / bn_release            <->  Blast_gpu_Init / Blast_gpu_Release
+ *                                        (inc-gpu/gpu_blastn.h:50-51, app/blast/blastn_app.cpp:462,491)
+ *   bn_db_load / bn_db_free         <->  the per-GPU subject cache G-BLASTN fills on first sight
+ *                                        of an oid (gpu/gpu_blastn_MB_and_smallNa.cu:1462-1468);
+ *                                        input is what BlastSeqSrcGetSequence hands the engine
+ *                                        (core/blast_engine.c:1203; packed ncbi2na, inc-core/blast_def.h:242)
+ *   bn_query_load / bn_query_free   <->  GpuLookUpSetUp / gpu_InitQueryMemory
+ *                                        (gpu/gpu_blastn_na_ungapped_v3.cpp:595-696): the arrays of
+ *                                        LookupTableWrap (inc-core/blast_nalookup.h:60,236), the query
+ *                                        BLAST_SequenceBlk, BlastQueryInfo contexts, and the derived
+ *                                        BlastInitialWordParameters / BlastExtensionParameters /
+ *                                        BlastHitSavingParameters values (inc-core/blast_parameters.h)
+ *   bn_prelim_search                <->  BLAST_PreliminarySearchEngine's subject loop
+ *                                        (core/blast_engine.c:1187-1330): per subject chunk
+ *                                        BlastNaWordFinder (core/na_ungapped.c:1559) +
+ *                                        BLAST_GetGappedScore (core/blast_gapalign.c:3233) +
+ *                                        the post-processing of s_BlastSearchEngineOneContext
+ *                                        (core/blast_engine.c:503-540) and E-values (:788-806)
+ *   bn_word_finder                  <->  BlastWordFinderType  (inc-core/blast_engine.h:227-238)
+ *   bn_get_gapped_score             <->  BlastGetGappedScoreType (inc-core/blast_engine.h:212-224)
+ *   bn_scan_subject                 <->  TNaScanSubjectFunction (inc-core/blast_nascan.h:43-47), whole-
+ *                                        subject form (max_hits batching is invisible to results)
+ *   bn_setup_*                      <->  host-side set-up the reference does before the path:
+ *                                        BLAST_MainSetUp / LookupTableWrapInit / BLAST_GapAlignSetUp /
+ *                                        BlastInitialWordParametersNew (see each function)
+ *
+ * Error convention (core/blast_engine.c:1237-1243): 0 = success, non-zero aborts; no exceptions,
+ * no exit().  bn_last_error() returns a thread-local message.  There is NO CPU fallback: when no
+ * CUDA device is usable every compute entry point returns BN_ERR_NO_DEVICE.
+ */
+#ifndef GBLASTN_B200_H
+#define GBLASTN_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BN_OK               0
+#define BN_ERR_INVALID      1
+#define BN_ERR_MEMORY       2   /* BLASTERR_MEMORY analogue */
+#define BN_ERR_NO_DEVICE    3
+#define BN_ERR_CUDA         4
+#define BN_ERR_UNSUPPORTED  5
+#define BN_ERR_OVERFLOW     6
+
+#define BN_LUT_MB        0      /* eMBLookupTable      (inc-core/blast_options.h:164) */
+#define BN_LUT_SMALL_NA  1      /* eSmallNaLookupTable */
+
+#define BN_DIAG_ARRAY    0      /* eDiagArray (inc-core/blast_parameters.h) */
+#define BN_DIAG_HASH     1      /* eDiagHash  */
+
+#define BN_GAP_DP        0      /* eDynProgScoreOnly  -> s_BlastDynProgNtGappedAlignment */
+#define BN_GAP_GREEDY    1      /* eGreedyScoreOnly   -> BLAST_GreedyGappedAlignment    */
+
+#define BN_MAX_DBSEQ_LEN        200000000  /* MAX_DBSEQ_LEN, inc-core/blast_gapalign.h:54-55 (G-BLASTN value) */
+#define BN_DBSEQ_CHUNK_OVERLAP  100        /* DBSEQ_CHUNK_OVERLAP, inc-core/blast_hits.h:169 */
+
+/* One query context = one strand of one query (BlastContextInfo, inc-core/blast_query_info.h:46-58)
+ * plus the per-context cutoffs the reference keeps in BlastUngappedCutoffs /
+ * BlastGappedCutoffs (inc-core/blast_parameters.h) and the gapped Karlin block. */
+typedef struct BnContext {
+    int32_t query_offset;       /* offset in the concatenated query */
+    int32_t query_length;
+    int32_t query_index;
+    int32_t frame;              /* +1 / -1 */
+    int32_t is_valid;
+    int32_t length_adjustment;
+    int64_t eff_searchsp;
+    int32_t x_dropoff;          /* ungapped X (raw, positive)              */
+    int32_t cutoff_score;       /* ungapped cutoff (gap trigger)           */
+    int32_t reduced_cutoff;     /* reduced_nucl_cutoff_score               */
+    int32_t gapped_cutoff;      /* hit_params->cutoffs[ctx].cutoff_score   */
+    double  gap_lambda;         /* sbp->kbp_gap[ctx]->Lambda               */
+    double  gap_logK;           /* sbp->kbp_gap[ctx]->logK                 */
+} BnContext;
+
+/* Everything the path needs from one query batch.  All pointers are HOST pointers owned by
+ * the caller; bn_query_load copies what it needs to the device(s). */
+typedef struct BnQueryBatch {
+    /* query BLAST_SequenceBlk: sequence_start (leading sentinel) .. trailing sentinel */
+    const uint8_t *query_start;      /* concat_len + 2 bytes, blastna, sentinel 15 */
+    int32_t        concat_len;       /* query->length */
+    int32_t        num_contexts;
+    const BnContext *contexts;
+    int32_t        num_queries;
+
+    /* lookup table arrays (layout is the reference's: SURVEY.md A.3) */
+    int32_t        lut_type;         /* BN_LUT_*            */
+    int32_t        word_length;      /* full word size       */
+    int32_t        lut_word_length;
+    int32_t        scan_step;
+    int64_t        hashsize;         /* MB: 4^lut; SmallNa: backbone_size */
+    const int32_t *hashtable;        /* MB */
+    const int32_t *next_pos;         /* MB, concat_len + 1 */
+    const uint32_t *pv_array;        /* MB, optional (NULL => not used; the device builds its own) */
+    int32_t        pv_array_bts;
+    const int16_t *backbone;         /* SmallNa final_backbone */
+    const int16_t *overflow;         /* SmallNa */
+    int64_t        overflow_len;
+    const int32_t *masked_locations; /* pairs [left,right]; NULL when lut->masked_locations == NULL */
+    int32_t        n_masked_locations;
+
+    /* BlastInitialWordParameters / options */
+    int32_t        container_type;   /* BN_DIAG_*           */
+    int32_t        window_size;      /* two-hit window (0 = one-hit) */
+    int32_t        scan_range;
+    int32_t        nucl_score_table[256];
+    int32_t        matrix[256];      /* 16 x 16, row-major  */
+
+    /* BlastScoringParameters / BlastExtensionParameters / BlastHitSavingOptions */
+    int32_t        gap_algo;         /* BN_GAP_*            */
+    int32_t        reward, penalty, gap_open, gap_extend;
+    int32_t        gap_x_dropoff;    /* raw */
+    int32_t        min_diag_separation;
+    int32_t        round_down;       /* sbp->round_down (odd-score rounding) */
+    int32_t        hsp_num_max;      /* 0 => unlimited */
+    int32_t        hitlist_size;     /* for the low_score rule */
+    double         evalue_cutoff;    /* hit_options->expect_value */
+    double         low_score_perc;   /* 0 disables the rule */
+} BnQueryBatch;
+
+/* BlastOffsetPair (inc-core/blast_def.h:141) tagged with its subject. */
+typedef struct BnOffsetPair { uint32_t q_off, s_off; } BnOffsetPair;
+
+/* BlastInitHSP + BlastUngappedData (inc-core/blast_extend.h:141-163). */
+typedef struct BnInitHit {
+    int32_t oid, chunk_off;
+    int32_t q_off, s_off;                    /* seed (word start) */
+    int32_t q_start, s_start, length, score; /* ungapped_data    */
+} BnInitHit;
+
+/* BlastHSP after the preliminary stage (inc-core/blast_hits.h:107). */
+typedef struct BnHSP {
+    int32_t oid, context;
+    int32_t q_off, q_end, s_off, s_end;
+    int32_t score;
+    int32_t q_gapped_start, s_gapped_start;
+    int32_t chunk_off;          /* subject chunk the HSP came from (diagnostic) */
+    double  evalue;
+} BnHSP;
+
+/* BlastUngappedStats / BlastGappedStats (inc-core/blast_diagnostics.h) + timing. */
+typedef struct BnStats {
+    int64_t lookup_hits, init_extends, good_init_extends, gap_extensions, good_extensions;
+    int64_t subject_bases_scanned;
+    double  ms_scan, ms_extend, ms_gapped, ms_host, ms_total;   /* CUDA-event / host timers */
+    int64_t kernel_launches;
+} BnStats;
+
+typedef struct BnResults {
+    BnHSP    *hsps;      int64_t n_hsps;       /* per subject, oid ascending, list order */
+    BnInitHit *init;     int64_t n_init;       /* only when BN_TAP_INIT */
+    BnHSP    *gapped;    int64_t n_gapped;     /* only when BN_TAP_GAPPED: per-chunk lists before post-processing */
+    BnStats   stats;
+} BnResults;
+
+#define BN_TAP_INIT    2
+#define BN_TAP_GAPPED  4
+
+/* ---- lifecycle --------------------------------------------------------------------------- */
+int  bn_init(int n_gpu, const int *device_ids);     /* n_gpu <= 0: all visible devices */
+void bn_release(void);
+int  bn_device_count(void);
+const char *bn_last_error(void);
+const char *bn_version(void);
+
+/* ---- database residency: one volume per handle, bound to one device ------------------------
+ * packed: ncbi2na bytes; sequence i = bytes [seq_byte_off[i], ...), seq_len[i] bases.
+ * >= 16 readable bytes must follow the last sequence. */
+int  bn_db_load(int device, const uint8_t *packed, int64_t packed_bytes,
+                const int64_t *seq_byte_off, const int32_t *seq_len, int32_t n_seq,
+                int *vol_handle);
+int  bn_db_free(int vol_handle);
+
+/* ---- query batch: replicated to every device in use ------------------------------------------ */
+int  bn_query_load(const BnQueryBatch *batch, int *query_handle);
+int  bn_query_free(int query_handle);
+
+/* ---- the path ------------------------------------------------------------------------------- */
+/* Whole preliminary stage for oids [oid_begin, oid_end) of a resident volume. */
+int  bn_prelim_search(int vol_handle, int query_handle, int32_t oid_begin, int32_t oid_end,
+                      int taps, BnResults *out);
+/* HOST-buffer convenience used by the reference-facing plugin path and bench e2e:
+ * H2D of the volume + search + D2H inside one call. */
+int  bn_prelim_search_host(int device, const BnQueryBatch *batch,
+                           const uint8_t *packed, int64_t packed_bytes,
+                           const int64_t *seq_byte_off, const int32_t *seq_len, int32_t n_seq,
+                           int taps, BnResults *out);
+void bn_results_free(BnResults *r);
+
+/* Stage-level entry points (parity taps; same semantics as the reference callbacks). */
+int  bn_scan_subject(int vol_handle, int query_handle, int32_t oid, int32_t chunk_off,
+                     int32_t chunk_len, BnOffsetPair **pairs, int64_t *n_pairs);
+int  bn_word_finder(int vol_handle, int query_handle, int32_t oid_begin, int32_t oid_end,
+                    BnInitHit **init, int64_t *n_init);
+void bn_free(void *p);
+
+/* Kernel-only timing hook for bench.py / ncu: runs the scan(+mini-extension) kernel `iters`
+ * times over the resident volume and returns the average device time per launch. */
+int  bn_bench_scan(int vol_handle, int query_handle, int iters, double *ms_per_launch,
+                   int64_t *bases_per_launch, int64_t *hits);
+
+/* ---- host-side set-up mirror (what the reference computes before the path) ------------------- */
+typedef struct BnSetupOptions {
+    int32_t task;               /* 0 megablast, 1 blastn */
+    int32_t word_size;          /* 0 => 28 / 11 */
+    int32_t reward, penalty;    /* 0 => 1/-2 or 2/-3 */
+    int32_t gap_open, gap_extend; /* -1 => 0/0 or 5/2 */
+    int32_t greedy;             /* -1 => task default */
+    int32_t window_size, scan_range;
+    int32_t min_diag_separation; /* -1 => 6 / 50 */
+    int32_t hitlist_size;       /* 0 => 500 */
+    int32_t mask_at_hash;
+    double  xdrop_ungap, xdrop_gap, xdrop_gap_final, evalue, low_score_perc;
+    int64_t db_length;          /* total bases of the database (all volumes) */
+    int32_t db_num_seqs;
+    int32_t avg_subject_length; /* BlastSeqSrcGetAvgSeqLen */
+} BnSetupOptions;
+
+typedef struct BnSetup BnSetup;   /* opaque; owns the arrays a BnQueryBatch points to */
+
+/* queries: blastna bytes concatenated; masks: optional plus-strand inclusive intervals. */
+int  bn_setup_create(const BnSetupOptions *opt, int32_t n_queries, const uint8_t *qseq,
+                     const int32_t *qlens, const int32_t *qmask_n, const int32_t *qmask_iv,
+                     BnSetup **out);
+const BnQueryBatch *bn_setup_batch(const BnSetup *s);
+/* Karlin-Altschul blocks computed by the set-up: 4 doubles (Lambda, K, logK, H) per context. */
+const double *bn_setup_kbp_std(const BnSetup *s);
+const double *bn_setup_kbp_gap(const BnSetup *s);
+int32_t bn_setup_gap_x_dropoff_final(const BnSetup *s);
+int32_t bn_setup_longest_chain(const BnSetup *s);
+void bn_setup_free(BnSetup *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GBLASTN_B200_H */
