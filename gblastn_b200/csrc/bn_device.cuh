@@ -1,0 +1,143 @@
+// bn_device.cuh — device-side views shared by the kernels of the blastn hot path.
+//
+// Memory layout in HBM:
+//   volume   : packed ncbi2na bytes of every sequence back to back (+>=16 pad bytes), resident for
+//              the lifetime of the volume handle; per-sequence byte offset / length tables.
+//   chunks   : per (volume, query-batch) table of subject chunks (the reference's
+//              s_GetNextSubjectChunk split, core/blast_engine.c:220-301) with the prefix sum of
+//              scan positions, so one launch covers a whole volume (SURVEY.md §7 hard part 6).
+//   query    : blastna bytes with sentinels, context table, lookup-table arrays exactly as the
+//              reference lays them out, replicated per device.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace bn {
+
+struct DevContext {
+    int32_t query_offset, query_length, query_index, frame;
+    int32_t x_dropoff, cutoff_score, reduced_cutoff, gapped_cutoff;
+};
+
+struct DevChunk {
+    int64_t byte_off;      // byte offset of the chunk's first base in the volume
+    int64_t pos_prefix;    // number of scan positions in all earlier chunks
+    int32_t len;           // bases in this chunk (subject->length for the word finder)
+    int32_t oid;
+    int32_t chunk_off;     // base offset of the chunk inside its sequence
+    int32_t npos;          // scan positions in this chunk
+    int32_t diag_offset;   // BLAST_DiagHash/BLAST_DiagTable ::offset while this chunk is scanned
+    int32_t diag_epoch;    // number of container resets (core/blast_extend.c:170-182) before this chunk
+};
+
+struct DevQuery {
+    const uint8_t *query;        // query->sequence (byte before it is the leading sentinel)
+    int32_t concat_len;
+    const DevContext *ctx;
+    int32_t num_contexts;
+    int32_t lut_type, word_length, lut_word_length, scan_step;
+    uint32_t hash_mask;
+    const int32_t *hashtable, *next_pos;   // MB
+    const uint32_t *presence;              // MB: exact 1 bit / cell bitmap built at load time
+    const int16_t *backbone, *overflow;    // SmallNa
+    int32_t has_locations;                 // lut->masked_locations != NULL
+    int32_t container_type, window_size, scan_range;
+    const int32_t *score_table;            // 256
+    const int32_t *matrix;                 // 16 x 16
+    int32_t gap_algo, reward, penalty, gap_open, gap_extend, gap_x_dropoff;
+};
+
+// A word hit that survived the mini-extension (input of the diagonal stage).
+struct SeedHit {
+    uint32_t chunk;      // index into the chunk table
+    uint32_t scan_pos;   // subject offset of the lookup word inside the chunk
+    uint32_t q_off;      // query offset after the left shift (q_offset - ext_left)
+    uint32_t s_off;      // subject offset after the left shift
+};
+
+struct DevInitHit {      // == BnInitHit + ordering info
+    int32_t chunk, q_off, s_off, q_start, s_start, length, score;
+    uint32_t order;      // rank of the seed in global emission order (tie-break of the stable sort)
+};
+
+struct DevGapResult {
+    int32_t q_start, q_stop, s_start, s_stop, score, q_seed, s_seed, status;  // status 1 = scratch overflow
+};
+
+// NCBI2NA_UNPACK_BASE (inc-core/blast_util.h:52-55)
+__device__ __forceinline__ int sbase(const uint8_t *s, int32_t pos)
+{
+    return (__ldg(s + (pos >> 2)) >> (6 - 2 * (pos & 3))) & 3;
+}
+
+// 32-bit big-endian window starting at byte `b` of a byte stream (unaligned).
+__device__ __forceinline__ uint32_t be32(const uint8_t *p)
+{
+    return ((uint32_t)__ldg(p) << 24) | ((uint32_t)__ldg(p + 1) << 16) |
+           ((uint32_t)__ldg(p + 2) << 8) | (uint32_t)__ldg(p + 3);
+}
+
+// BSearchContextInfo (core/blast_query_info.c:220-236)
+__device__ __forceinline__ int32_t ctx_search(const DevQuery &q, int32_t n)
+{
+    int32_t lo = 0, hi = q.num_contexts;
+    while (lo < hi - 1) {
+        int32_t m = (lo + hi) / 2;
+        if (__ldg(&q.ctx[m].query_offset) > n) hi = m; else lo = m;
+    }
+    return lo;
+}
+
+// ---- launchers implemented in the .cu files ----------------------------------------------------
+struct ScanLaunch {
+    const uint8_t *packed;
+    const DevChunk *chunks;
+    int32_t n_chunks;
+    int64_t total_pos;
+    SeedHit *hits;            // capacity entries
+    uint64_t *keys;           // sort key per hit
+    unsigned long long *counters;   // [0] = #survivors, [1] = #lookup hits
+    int64_t capacity;
+    const int32_t *block_chunk;   // first chunk of every BLOCK_POS-sized slice of positions
+    int32_t raw_pairs;            // 1: emit every lookup hit (q_off, scan_pos) without mini-extension (scan tap)
+};
+cudaError_t launch_scan(const DevQuery &q, const ScanLaunch &s, cudaStream_t st);
+int scan_positions_per_block();
+
+struct ExtendLaunch {
+    const uint8_t *packed;
+    const DevChunk *chunks;
+    const SeedHit *hits;          // sorted by (group, emission order)
+    const uint32_t *order;        // emission rank of hits[i]
+    int32_t *cells;               // hash: 4 ints per cell, one region per group (same offsets as hits)
+    DevInitHit *init;
+    unsigned long long *counters; // [2] = #init hits, [3] = #extended
+    int64_t init_capacity;
+};
+cudaError_t launch_extend_groups(const DevQuery &q, const ExtendLaunch &e, const uint64_t *group_key,
+                                 int64_t n_hits, cudaStream_t st);
+cudaError_t launch_group_keys(const DevQuery &q, const SeedHit *hits, const uint32_t *perm, int64_t n,
+                              int32_t diag_array_length, uint64_t *keys, cudaStream_t st);
+cudaError_t launch_gather_hits(const SeedHit *in, const uint32_t *perm, int64_t n, SeedHit *out,
+                               cudaStream_t st);
+cudaError_t launch_iota(uint32_t *p, int64_t n, cudaStream_t st);
+
+struct GappedLaunch {
+    const uint8_t *packed;
+    const DevChunk *chunks;
+    const DevInitHit *init;
+    const unsigned long long *n_init;   // device counter
+    int64_t max_init;
+    DevGapResult *out;
+    int32_t *scratch;             // per-thread scratch
+    int64_t scratch_ints_per_thread;
+    int32_t tier_d;               // greedy: max distance this tier can hold; dp: ring capacity
+    const int32_t *todo;          // optional list of init indices (tier 2); nullptr = all
+    int32_t n_todo;
+    int32_t grid_blocks;          // 0 = default persistent grid
+};
+cudaError_t launch_gapped(const DevQuery &q, const GappedLaunch &g, cudaStream_t st);
+int gapped_threads();
+int gapped_threads_per_block();
+
+}  // namespace bn

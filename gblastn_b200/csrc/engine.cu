@@ -1,0 +1,857 @@
+// engine.cu — host orchestration of the blastn hot path and the C ABI of include/gblastn_b200.h.
+//
+// One search = per (resident volume, query batch):
+//   chunk table -> scan kernel -> radix sorts (emission order, then diagonal group) -> diagonal /
+//   ungapped kernel -> speculative gapped kernel -> D2H -> host replay (hostpost.cpp).
+// Everything runs on one CUDA stream per device; the only host<->device round trips are the
+// survivor / init-hit counters (needed to size the sorts) and the final D2H of init-HSPs.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cub/cub.cuh>
+
+#include "bn_device.cuh"
+#include "hostpost.h"
+
+namespace bn {
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define CU_TRY(expr)                                                                         \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return fail(e__ == cudaErrorMemoryAllocation ? BN_ERR_MEMORY : BN_ERR_CUDA,      \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));                \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 64;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Workspace {
+    DevBuf<SeedHit> hits_a, hits_b;
+    DevBuf<uint64_t> keys_a, keys_b, gkeys_a, gkeys_b;
+    DevBuf<uint32_t> perm_a, perm_b, order_a, order_b;
+    DevBuf<int4> cells;
+    DevBuf<DevInitHit> init;
+    DevBuf<DevGapResult> gap_out;
+    DevBuf<int32_t> scratch, todo;
+    DevBuf<unsigned long long> counters;
+    DevBuf<uint8_t> cub_temp;
+    unsigned long long *h_counters = nullptr;   // pinned
+    void release()
+    {
+        hits_a.release(); hits_b.release(); keys_a.release(); keys_b.release(); gkeys_a.release();
+        gkeys_b.release(); perm_a.release(); perm_b.release(); order_a.release(); order_b.release();
+        cells.release(); init.release(); gap_out.release(); scratch.release(); todo.release();
+        counters.release(); cub_temp.release();
+        if (h_counters) cudaFreeHost(h_counters);
+        h_counters = nullptr;
+    }
+};
+
+struct Device {
+    int id = -1;
+    cudaStream_t stream = nullptr;
+    Workspace ws;
+    std::mutex mu;       // one search at a time per device
+};
+
+struct ChunkTable {
+    std::vector<DevChunk> host;
+    std::vector<HostChunk> hchunks;
+    DevBuf<DevChunk> dev;
+    DevBuf<int32_t> block_chunk;
+    int64_t total_pos = 0;
+    int64_t total_bases = 0;
+    int64_t n_blocks = 0;
+};
+
+struct Volume {
+    int device = 0;
+    uint8_t *d_packed = nullptr;
+    int64_t bytes = 0;
+    std::vector<int64_t> byte_off;
+    std::vector<int32_t> seq_len;
+    std::map<std::string, std::shared_ptr<ChunkTable>> tables;
+};
+
+struct QueryDev {
+    uint8_t *query = nullptr;
+    DevContext *ctx = nullptr;
+    int32_t *hashtable = nullptr, *next_pos = nullptr;
+    uint32_t *presence = nullptr;
+    int16_t *backbone = nullptr, *overflow = nullptr;
+    int32_t *score_table = nullptr, *matrix = nullptr;
+    DevQuery view{};
+    bool ready = false;
+};
+
+struct Query {
+    BnQueryBatch batch{};                 // host copy; pointers re-targeted at the vectors below
+    std::vector<uint8_t> query;
+    std::vector<BnContext> ctx;
+    std::vector<int32_t> hashtable, next_pos;
+    std::vector<uint32_t> presence;
+    std::vector<int16_t> backbone, overflow;
+    std::vector<int32_t> masked;
+    std::vector<QueryDev> dev;            // per device
+    int32_t diag_array_length = 1;
+    int32_t max_query_length = 0;
+};
+
+static std::mutex g_mu;
+static std::vector<std::unique_ptr<Device>> g_devices;
+static std::vector<std::unique_ptr<Volume>> g_volumes;
+static std::vector<std::unique_ptr<Query>> g_queries;
+static bool g_inited = false;
+
+static int ensure_init()
+{
+    if (g_inited) return BN_OK;
+    return bn_init(0, nullptr);
+}
+
+static Device *device_at(int d)
+{
+    if (d < 0 || d >= (int)g_devices.size()) return nullptr;
+    return g_devices[d].get();
+}
+
+// ------------------------------------------------------------------------------------------------
+static void free_query_dev(QueryDev &q)
+{
+    cudaFree(q.query); cudaFree(q.ctx); cudaFree(q.hashtable); cudaFree(q.next_pos);
+    cudaFree(q.presence); cudaFree(q.backbone); cudaFree(q.overflow); cudaFree(q.score_table);
+    cudaFree(q.matrix);
+    q = QueryDev{};
+}
+
+template <typename T>
+static cudaError_t upload(T **dst, const T *src, size_t n, cudaStream_t st)
+{
+    *dst = nullptr;
+    if (n == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(dst, n * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, st);
+}
+
+static int query_to_device(Query &Q, int d)
+{
+    Device *dev = device_at(d);
+    QueryDev &qd = Q.dev[d];
+    if (qd.ready) return BN_OK;
+    CU_TRY(cudaSetDevice(dev->id));
+    const BnQueryBatch &b = Q.batch;
+    std::vector<DevContext> dctx((size_t)b.num_contexts);
+    for (int i = 0; i < b.num_contexts; i++) {
+        const BnContext &c = Q.ctx[i];
+        dctx[i] = DevContext{c.query_offset, c.query_length, c.query_index, c.frame,
+                             c.x_dropoff, c.cutoff_score, c.reduced_cutoff, c.gapped_cutoff};
+    }
+    CU_TRY(upload(&qd.query, Q.query.data(), Q.query.size(), dev->stream));
+    CU_TRY(upload(&qd.ctx, dctx.data(), dctx.size(), dev->stream));
+    if (b.lut_type == BN_LUT_MB) {
+        CU_TRY(upload(&qd.hashtable, Q.hashtable.data(), Q.hashtable.size(), dev->stream));
+        CU_TRY(upload(&qd.next_pos, Q.next_pos.data(), Q.next_pos.size(), dev->stream));
+        CU_TRY(upload(&qd.presence, Q.presence.data(), Q.presence.size(), dev->stream));
+    } else {
+        CU_TRY(upload(&qd.backbone, Q.backbone.data(), Q.backbone.size(), dev->stream));
+        CU_TRY(upload(&qd.overflow, Q.overflow.data(), Q.overflow.size(), dev->stream));
+    }
+    CU_TRY(upload(&qd.score_table, b.nucl_score_table, (size_t)256, dev->stream));
+    CU_TRY(upload(&qd.matrix, b.matrix, (size_t)256, dev->stream));
+    CU_TRY(cudaStreamSynchronize(dev->stream));
+
+    DevQuery &v = qd.view;
+    v.query = qd.query + 1;
+    v.concat_len = b.concat_len;
+    v.ctx = qd.ctx; v.num_contexts = b.num_contexts;
+    v.lut_type = b.lut_type; v.word_length = b.word_length; v.lut_word_length = b.lut_word_length;
+    v.scan_step = b.scan_step; v.hash_mask = (uint32_t)(b.hashsize - 1);
+    v.hashtable = qd.hashtable; v.next_pos = qd.next_pos; v.presence = qd.presence;
+    v.backbone = qd.backbone; v.overflow = qd.overflow;
+    v.has_locations = b.masked_locations != nullptr;
+    v.container_type = b.container_type; v.window_size = b.window_size; v.scan_range = b.scan_range;
+    v.score_table = qd.score_table; v.matrix = qd.matrix;
+    v.gap_algo = b.gap_algo; v.reward = b.reward; v.penalty = b.penalty;
+    v.gap_open = b.gap_open; v.gap_extend = b.gap_extend; v.gap_x_dropoff = b.gap_x_dropoff;
+    qd.ready = true;
+    return BN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Chunk table: the reference's subject split (s_GetNextSubjectChunk core/blast_engine.c:220-301,
+// unmasked subjects) + scan-position prefix sums + the evolution of the diagonal container's
+// `offset` (Blast_ExtendWordExit core/blast_extend.c:164-186).
+// ------------------------------------------------------------------------------------------------
+static int build_chunk_table(Volume &V, const Query &Q, int32_t oid_begin, int32_t oid_end,
+                             cudaStream_t st, std::shared_ptr<ChunkTable> *out)
+{
+    const BnQueryBatch &b = Q.batch;
+    char key[128];
+    snprintf(key, sizeof key, "%d/%d/%d/%d/%d", b.lut_word_length, b.scan_step, b.window_size,
+             oid_begin, oid_end);
+    auto it = V.tables.find(key);
+    if (it != V.tables.end()) { *out = it->second; return BN_OK; }
+
+    auto T = std::make_shared<ChunkTable>();
+    const int32_t lut = b.lut_word_length, step = b.scan_step, window = b.window_size;
+    int32_t diag_offset = window, epoch = 0;
+    int64_t prefix = 0;
+    for (int32_t oid = oid_begin; oid < oid_end; oid++) {
+        const int32_t full = V.seq_len[oid];
+        int32_t next = 0;
+        while (next < full) {
+            const int32_t offset = next - next % 4;
+            DevChunk c{};
+            c.byte_off = V.byte_off[oid] + offset / 4;
+            c.oid = oid; c.chunk_off = offset;
+            if ((int64_t)offset + BN_MAX_DBSEQ_LEN < (int64_t)full) {
+                c.len = BN_MAX_DBSEQ_LEN;
+                next = offset + BN_MAX_DBSEQ_LEN - BN_DBSEQ_CHUNK_OVERLAP;
+            } else { c.len = full - offset; next = full; }
+            c.npos = c.len >= lut ? (c.len - lut) / step + 1 : 0;
+            c.pos_prefix = prefix;
+            c.diag_offset = diag_offset; c.diag_epoch = epoch;
+            prefix += c.npos;
+            T->total_bases += c.len;
+            T->host.push_back(c);
+            T->hchunks.push_back(HostChunk{oid, offset, c.len});
+            if (diag_offset >= INT32_MAX / 4) { diag_offset = window; ++epoch; }
+            else diag_offset += c.len + window;
+        }
+    }
+    T->total_pos = prefix;
+    const int ppb = scan_positions_per_block();
+    T->n_blocks = (prefix + ppb - 1) / ppb;
+    std::vector<int32_t> bc((size_t)T->n_blocks + 1, 0);
+    {
+        size_t c = 0;
+        const size_t n = T->host.size();
+        for (int64_t blk = 0; blk < T->n_blocks; blk++) {
+            const int64_t g = blk * ppb;
+            while (c + 1 < n && T->host[c + 1].pos_prefix <= g) ++c;
+            bc[(size_t)blk] = (int32_t)c;
+        }
+        bc[(size_t)T->n_blocks] = n ? (int32_t)n - 1 : 0;
+    }
+    if (!T->host.empty()) {
+        CU_TRY(T->dev.reserve(T->host.size()));
+        CU_TRY(cudaMemcpyAsync(T->dev.p, T->host.data(), T->host.size() * sizeof(DevChunk),
+                               cudaMemcpyHostToDevice, st));
+        CU_TRY(T->block_chunk.reserve(bc.size()));
+        CU_TRY(cudaMemcpyAsync(T->block_chunk.p, bc.data(), bc.size() * sizeof(int32_t),
+                               cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaStreamSynchronize(st));
+    }
+    V.tables[key] = T;
+    *out = T;
+    return BN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct Timer {
+    cudaEvent_t a, b;
+    cudaStream_t st;
+    explicit Timer(cudaStream_t s) : st(s) { cudaEventCreate(&a); cudaEventCreate(&b); }
+    ~Timer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+    void start() { cudaEventRecord(a, st); }
+    void stop() { cudaEventRecord(b, st); }
+    double ms() { float f = 0; cudaEventSynchronize(b); cudaEventElapsedTime(&f, a, b); return f; }
+};
+
+static double now_ms()
+{
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+static int sort_pairs_u64(Workspace &ws, const uint64_t *kin, uint64_t *kout, const uint32_t *vin,
+                          uint32_t *vout, int64_t n, int end_bit, cudaStream_t st)
+{
+    size_t bytes = 0;
+    CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)n, 0, end_bit, st));
+    CU_TRY(ws.cub_temp.reserve(bytes));
+    CU_TRY(cub::DeviceRadixSort::SortPairs(ws.cub_temp.p, bytes, kin, kout, vin, vout, (int)n, 0, end_bit, st));
+    return BN_OK;
+}
+
+static int bits_for(uint64_t v) { int b = 1; while (b < 64 && (v >> b)) ++b; return b; }
+
+struct StageCounts { int64_t n_hits = 0, lookup_hits = 0, n_init = 0, n_extended = 0; };
+
+// scan + sorts + diagonal/ungapped kernel.  Leaves init hits in ws.init (unsorted) on the device.
+static int run_word_finder(Device &D, Volume &V, Query &Q, ChunkTable &T, bool raw_pairs,
+                           StageCounts &cnt, BnStats *stats)
+{
+    Workspace &ws = D.ws;
+    cudaStream_t st = D.stream;
+    const DevQuery &dq = Q.dev[V.device].view;
+    CU_TRY(ws.counters.reserve(8));
+    if (!ws.h_counters) CU_TRY(cudaMallocHost(&ws.h_counters, 8 * sizeof(unsigned long long)));
+
+    Timer t_scan(st), t_ext(st);
+    int64_t cap = std::max<int64_t>((int64_t)ws.hits_a.cap, std::max<int64_t>(1 << 16, T.total_pos / 16));
+    for (int attempt = 0;; attempt++) {
+        CU_TRY(ws.hits_a.reserve((size_t)cap));
+        CU_TRY(ws.keys_a.reserve((size_t)cap));
+        cap = (int64_t)std::min(ws.hits_a.cap, ws.keys_a.cap);
+        CU_TRY(cudaMemsetAsync(ws.counters.p, 0, 8 * sizeof(unsigned long long), st));
+        ScanLaunch s{};
+        s.packed = V.d_packed; s.chunks = T.dev.p; s.n_chunks = (int32_t)T.host.size();
+        s.total_pos = T.total_pos; s.hits = ws.hits_a.p; s.keys = ws.keys_a.p;
+        s.counters = ws.counters.p; s.capacity = cap; s.block_chunk = T.block_chunk.p;
+        s.raw_pairs = raw_pairs ? 1 : 0;
+        t_scan.start();
+        CU_TRY(launch_scan(dq, s, st));
+        t_scan.stop();
+        if (stats) stats->kernel_launches += 1;
+        CU_TRY(cudaMemcpyAsync(ws.h_counters, ws.counters.p, 8 * sizeof(unsigned long long),
+                               cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        cnt.n_hits = (int64_t)ws.h_counters[0];
+        cnt.lookup_hits = (int64_t)ws.h_counters[1];
+        if (cnt.n_hits <= cap) break;
+        if (attempt > 2) return fail(BN_ERR_OVERFLOW, "seed-hit buffer overflow");
+        cap = cnt.n_hits + cnt.n_hits / 16 + 1024;
+    }
+    if (stats) stats->ms_scan += t_scan.ms();
+    if (cnt.n_hits >= (int64_t)INT32_MAX) return fail(BN_ERR_OVERFLOW, "more than 2^31 seed hits in one search");
+    const int64_t n = cnt.n_hits;
+    if (n == 0) return BN_OK;
+
+    // 1) emission order: sort by (global scan position, chain rank)
+    t_ext.start();
+    CU_TRY(ws.keys_b.reserve((size_t)n)); CU_TRY(ws.perm_a.reserve((size_t)n)); CU_TRY(ws.perm_b.reserve((size_t)n));
+    CU_TRY(ws.hits_b.reserve((size_t)n));
+    CU_TRY(launch_iota(ws.perm_a.p, n, st));
+    const int key_bits = std::min(64, 24 + bits_for((uint64_t)std::max<int64_t>(T.total_pos, 1)));
+    int rc = sort_pairs_u64(ws, ws.keys_a.p, ws.keys_b.p, ws.perm_a.p, ws.perm_b.p, n, key_bits, st);
+    if (rc) return rc;
+    CU_TRY(launch_gather_hits(ws.hits_a.p, ws.perm_b.p, n, ws.hits_b.p, st));   // hits_b: emission order
+    if (stats) stats->kernel_launches += 4;
+    if (raw_pairs) { t_ext.stop(); if (stats) stats->ms_extend += t_ext.ms(); return BN_OK; }
+
+    // 2) group by diagonal bucket / cell, stable, so each group stays in emission order
+    CU_TRY(ws.gkeys_a.reserve((size_t)n)); CU_TRY(ws.gkeys_b.reserve((size_t)n));
+    CU_TRY(ws.order_a.reserve((size_t)n)); CU_TRY(ws.order_b.reserve((size_t)n));
+    CU_TRY(launch_iota(ws.order_a.p, n, st));
+    CU_TRY(launch_group_keys(dq, ws.hits_b.p, ws.order_a.p, n, Q.diag_array_length, ws.gkeys_a.p, st));
+    const int gbits = Q.batch.container_type == BN_DIAG_HASH ? 9 : 32 + bits_for((uint64_t)std::max<size_t>(T.host.size(), 1));
+    rc = sort_pairs_u64(ws, ws.gkeys_a.p, ws.gkeys_b.p, ws.order_a.p, ws.order_b.p, n, std::min(64, gbits), st);
+    if (rc) return rc;
+    CU_TRY(launch_gather_hits(ws.hits_b.p, ws.order_b.p, n, ws.hits_a.p, st));  // hits_a: grouped
+    CU_TRY(ws.cells.reserve((size_t)n + 2));
+    if (stats) stats->kernel_launches += 5;
+
+    // 3) replay groups
+    int64_t init_cap = std::max<int64_t>((int64_t)ws.init.cap, std::max<int64_t>(4096, n / 4));
+    for (int attempt = 0;; attempt++) {
+        CU_TRY(ws.init.reserve((size_t)init_cap));
+        init_cap = (int64_t)ws.init.cap;
+        CU_TRY(cudaMemsetAsync(ws.counters.p + 2, 0, 2 * sizeof(unsigned long long), st));
+        ExtendLaunch e{};
+        e.packed = V.d_packed; e.chunks = T.dev.p; e.hits = ws.hits_a.p; e.order = ws.order_b.p;
+        e.cells = reinterpret_cast<int32_t *>(ws.cells.p); e.init = ws.init.p;
+        e.counters = ws.counters.p; e.init_capacity = init_cap;
+        CU_TRY(launch_extend_groups(dq, e, ws.gkeys_b.p, n, st));
+        if (stats) stats->kernel_launches += 1;
+        CU_TRY(cudaMemcpyAsync(ws.h_counters, ws.counters.p, 8 * sizeof(unsigned long long),
+                               cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        cnt.n_init = (int64_t)ws.h_counters[2];
+        cnt.n_extended = (int64_t)ws.h_counters[3];
+        if (cnt.n_init <= init_cap) break;
+        if (attempt > 2) return fail(BN_ERR_OVERFLOW, "init-hit buffer overflow");
+        init_cap = cnt.n_init + cnt.n_init / 16 + 1024;
+    }
+    t_ext.stop();
+    if (stats) stats->ms_extend += t_ext.ms();
+    return BN_OK;
+}
+
+static int32_t greedy_xdrop_offset(const BnQueryBatch &b)
+{
+    int32_t match = b.reward, mismatch = -b.penalty, xd = b.gap_x_dropoff;
+    if (match % 2 == 1) { match *= 2; mismatch *= 2; xd *= 2; }
+    return (xd + match / 2) / (match + mismatch) + 1;
+}
+
+static int run_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t n_init,
+                      std::vector<DevInitHit> &h_init, std::vector<DevGapResult> &h_gap, BnStats *stats)
+{
+    Workspace &ws = D.ws;
+    cudaStream_t st = D.stream;
+    const DevQuery &dq = Q.dev[V.device].view;
+    const BnQueryBatch &b = Q.batch;
+    h_init.resize((size_t)n_init); h_gap.resize((size_t)n_init);
+    if (n_init == 0) return BN_OK;
+    Timer t(st);
+    t.start();
+    CU_TRY(ws.gap_out.reserve((size_t)n_init));
+    const bool greedy = b.gap_algo == BN_GAP_GREEDY;
+    const int32_t xo = greedy_xdrop_offset(b);
+    int32_t tier = greedy ? 256 : 1024;
+    int64_t per_thread = greedy ? (2 * (2 * (int64_t)tier + 6) + tier + 1 + xo + 8) : 2 * (int64_t)tier;
+    const int64_t threads = std::min<int64_t>(gapped_threads(), ((n_init + 63) / 64) * 64);
+    CU_TRY(ws.scratch.reserve((size_t)(per_thread * threads)));
+    GappedLaunch g{};
+    g.packed = V.d_packed; g.chunks = T.dev.p; g.init = ws.init.p; g.n_init = ws.counters.p + 2;
+    g.max_init = n_init; g.out = ws.gap_out.p; g.scratch = ws.scratch.p;
+    g.scratch_ints_per_thread = per_thread; g.tier_d = tier; g.todo = nullptr; g.n_todo = 0;
+    g.grid_blocks = (int32_t)(threads / gapped_threads_per_block());
+    CU_TRY(launch_gapped(dq, g, st));
+    if (stats) stats->kernel_launches += 1;
+    CU_TRY(cudaMemcpyAsync(h_init.data(), ws.init.p, (size_t)n_init * sizeof(DevInitHit), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(h_gap.data(), ws.gap_out.p, (size_t)n_init * sizeof(DevGapResult), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+
+    // tier 2: worst-case scratch for the few extensions that outgrew tier 1
+    std::vector<int32_t> todo;
+    for (int64_t i = 0; i < n_init; i++) if (h_gap[(size_t)i].status == 1) todo.push_back((int32_t)i);
+    if (!todo.empty()) {
+        int32_t max_len = 0;
+        for (const auto &c : T.host) max_len = std::max(max_len, c.len);
+        if (greedy) {
+            tier = std::min(10000, max_len / 2 + 1);
+            per_thread = 2 * (2 * (int64_t)tier + 6) + tier + 1 + xo + 8;
+        } else {
+            tier = Q.max_query_length + 8;
+            per_thread = 2 * (int64_t)tier;
+        }
+        const int tpb = gapped_threads_per_block();
+        int64_t blocks = std::min<int64_t>(((int64_t)todo.size() + tpb - 1) / tpb, 64);
+        CU_TRY(ws.scratch.reserve((size_t)(per_thread * blocks * tpb)));
+        CU_TRY(ws.todo.reserve(todo.size()));
+        CU_TRY(cudaMemcpyAsync(ws.todo.p, todo.data(), todo.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        g.scratch = ws.scratch.p; g.scratch_ints_per_thread = per_thread; g.tier_d = tier;
+        g.todo = ws.todo.p; g.n_todo = (int32_t)todo.size(); g.grid_blocks = (int32_t)blocks;
+        CU_TRY(launch_gapped(dq, g, st));
+        if (stats) stats->kernel_launches += 1;
+        CU_TRY(cudaMemcpyAsync(h_gap.data(), ws.gap_out.p, (size_t)n_init * sizeof(DevGapResult), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        for (int32_t i : todo)
+            if (h_gap[(size_t)i].status != 0) return fail(BN_ERR_OVERFLOW, "gapped extension scratch overflow in tier 2");
+    }
+    t.stop();
+    if (stats) stats->ms_gapped += t.ms();
+    return BN_OK;
+}
+
+template <typename T>
+static T *to_malloc(const std::vector<T> &v)
+{
+    if (v.empty()) return nullptr;
+    T *p = (T *)malloc(v.size() * sizeof(T));
+    if (p) memcpy(p, v.data(), v.size() * sizeof(T));
+    return p;
+}
+
+static int prelim_search_locked(Device &D, Volume &V, Query &Q, int32_t oid_begin, int32_t oid_end,
+                                int taps, BnResults *out)
+{
+    memset(out, 0, sizeof *out);
+    const double t0 = now_ms();
+    CU_TRY(cudaSetDevice(D.id));
+    int rc = query_to_device(Q, V.device);
+    if (rc) return rc;
+    std::shared_ptr<ChunkTable> T;
+    rc = build_chunk_table(V, Q, oid_begin, oid_end, D.stream, &T);
+    if (rc) return rc;
+    BnStats &stats = out->stats;
+    stats.subject_bases_scanned = T->total_bases;
+
+    StageCounts cnt;
+    rc = run_word_finder(D, V, Q, *T, false, cnt, &stats);
+    if (rc) return rc;
+    std::vector<DevInitHit> h_init;
+    std::vector<DevGapResult> h_gap;
+    rc = run_gapped(D, V, Q, *T, cnt.n_init, h_init, h_gap, &stats);
+    if (rc) return rc;
+    stats.lookup_hits = cnt.lookup_hits;
+    stats.init_extends = cnt.n_extended;
+    stats.good_init_extends = cnt.n_init;
+
+    // ---- host replay -------------------------------------------------------------------------
+    const double th0 = now_ms();
+    const BnQueryBatch &b = Q.batch;
+    std::vector<HostInit> inits((size_t)cnt.n_init);
+    for (size_t i = 0; i < inits.size(); i++) {
+        const DevInitHit &h = h_init[i];
+        const DevGapResult &g = h_gap[i];
+        inits[i] = HostInit{h.chunk, h.q_off, h.s_off, h.q_start, h.s_start, h.length, h.score, h.order,
+                            g.q_start, g.q_stop, g.s_start, g.s_stop, g.score, g.q_seed, g.s_seed};
+    }
+    sort_init_hits(inits);
+
+    std::vector<BnHSP> final_hsps, gapped_tap, comb, fresh;
+    std::vector<BnInitHit> init_tap;
+    LowScoreTracker tracker(b);
+    int32_t cur_oid = -1;
+    auto finish_oid = [&]() {
+        if (cur_oid < 0) return;
+        evalues_and_reap(b, comb);
+        if (!comb.empty()) {
+            stats.good_extensions += (int64_t)comb.size();
+            final_hsps.insert(final_hsps.end(), comb.begin(), comb.end());
+            tracker.subject_done(b, comb);
+        }
+        comb.clear();
+    };
+    size_t i = 0;
+    while (i < inits.size()) {
+        size_t j = i;
+        while (j < inits.size() && inits[j].chunk == inits[i].chunk) ++j;
+        const HostChunk &ch = T->hchunks[(size_t)inits[i].chunk];
+        if (ch.oid != cur_oid) { finish_oid(); cur_oid = ch.oid; }
+        if (taps & BN_TAP_INIT)
+            for (size_t k = i; k < j; k++)
+                init_tap.push_back(BnInitHit{ch.oid, ch.chunk_off, inits[k].q_off, inits[k].s_off,
+                                             inits[k].q_start, inits[k].s_start, inits[k].length,
+                                             inits[k].score});
+        fresh.clear();
+        replay_gapped(b, ch, &inits[i], j - i, tracker.low_score(), fresh, stats);
+        if (taps & BN_TAP_GAPPED) gapped_tap.insert(gapped_tap.end(), fresh.begin(), fresh.end());
+        finish_chunk_list(b, fresh);
+        for (auto &h : fresh) { h.s_off += ch.chunk_off; h.s_end += ch.chunk_off; h.s_gapped_start += ch.chunk_off; }
+        merge_chunk_lists(comb, fresh, ch.chunk_off, ch.chunk_off == 0 ? 0 : BN_DBSEQ_CHUNK_OVERLAP);
+        i = j;
+    }
+    finish_oid();
+    stats.ms_host = now_ms() - th0;
+
+    out->n_hsps = (int64_t)final_hsps.size(); out->hsps = to_malloc(final_hsps);
+    out->n_init = (int64_t)init_tap.size();   out->init = to_malloc(init_tap);
+    out->n_gapped = (int64_t)gapped_tap.size(); out->gapped = to_malloc(gapped_tap);
+    stats.ms_total = now_ms() - t0;
+    return BN_OK;
+}
+
+}  // namespace bn
+
+using namespace bn;
+
+// ================================================================================================
+//                                             C ABI
+// ================================================================================================
+extern "C" {
+
+const char *bn_last_error(void) { return g_err.c_str(); }
+const char *bn_version(void) { return "gblastn_b200 0.1.0 (sm_100a)"; }
+
+int bn_init(int n_gpu, const int *device_ids)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_inited) return BN_OK;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(BN_ERR_NO_DEVICE, std::string("no usable CUDA device: ") +
+                                          (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    std::vector<int> ids;
+    if (n_gpu <= 0 || !device_ids) { for (int i = 0; i < (n_gpu > 0 ? std::min(n_gpu, count) : count); i++) ids.push_back(i); }
+    else for (int i = 0; i < n_gpu; i++) ids.push_back(device_ids[i]);
+    for (int id : ids) {
+        if (id < 0 || id >= count) return fail(BN_ERR_INVALID, "device id out of range");
+        auto d = std::make_unique<Device>();
+        d->id = id;
+        CU_TRY(cudaSetDevice(id));
+        CU_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+        g_devices.push_back(std::move(d));
+    }
+    g_inited = true;
+    return BN_OK;
+}
+
+void bn_release(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto &q : g_queries) if (q) for (size_t d = 0; d < q->dev.size(); d++) {
+        if (q->dev[d].ready) { cudaSetDevice(g_devices[d]->id); free_query_dev(q->dev[d]); }
+    }
+    g_queries.clear();
+    for (auto &v : g_volumes) if (v) {
+        cudaSetDevice(g_devices[v->device]->id);
+        cudaFree(v->d_packed);
+        for (auto &kv : v->tables) { kv.second->dev.release(); kv.second->block_chunk.release(); }
+    }
+    g_volumes.clear();
+    for (auto &d : g_devices) {
+        cudaSetDevice(d->id);
+        d->ws.release();
+        if (d->stream) cudaStreamDestroy(d->stream);
+    }
+    g_devices.clear();
+    g_inited = false;
+}
+
+int bn_device_count(void)
+{
+    if (ensure_init() != BN_OK) return 0;
+    return (int)g_devices.size();
+}
+
+int bn_db_load(int device, const uint8_t *packed, int64_t packed_bytes, const int64_t *seq_byte_off,
+               const int32_t *seq_len, int32_t n_seq, int *vol_handle)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!packed || !seq_byte_off || !seq_len || n_seq < 0 || !vol_handle) return fail(BN_ERR_INVALID, "bn_db_load: bad argument");
+    Device *D = device_at(device);
+    if (!D) return fail(BN_ERR_INVALID, "bn_db_load: bad device");
+    for (int32_t i = 0; i < n_seq; i++) {
+        const int64_t end = seq_byte_off[i] + (seq_len[i] + 3) / 4;
+        if (seq_byte_off[i] < 0 || seq_len[i] < 0 || end + 16 > packed_bytes)
+            return fail(BN_ERR_INVALID, "bn_db_load: sequence outside the packed buffer (16 pad bytes required)");
+    }
+    auto V = std::make_unique<Volume>();
+    V->device = device; V->bytes = packed_bytes;
+    V->byte_off.assign(seq_byte_off, seq_byte_off + n_seq);
+    V->seq_len.assign(seq_len, seq_len + n_seq);
+    CU_TRY(cudaSetDevice(D->id));
+    CU_TRY(cudaMalloc(&V->d_packed, (size_t)packed_bytes + 64));
+    CU_TRY(cudaMemcpyAsync(V->d_packed, packed, (size_t)packed_bytes, cudaMemcpyHostToDevice, D->stream));
+    CU_TRY(cudaMemsetAsync(V->d_packed + packed_bytes, 0, 64, D->stream));
+    CU_TRY(cudaStreamSynchronize(D->stream));
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_volumes.push_back(std::move(V));
+    *vol_handle = (int)g_volumes.size() - 1;
+    return BN_OK;
+}
+
+int bn_db_free(int h)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (h < 0 || h >= (int)g_volumes.size() || !g_volumes[h]) return fail(BN_ERR_INVALID, "bn_db_free: bad handle");
+    Volume &V = *g_volumes[h];
+    cudaSetDevice(g_devices[V.device]->id);
+    cudaFree(V.d_packed);
+    for (auto &kv : V.tables) { kv.second->dev.release(); kv.second->block_chunk.release(); }
+    g_volumes[h].reset();
+    return BN_OK;
+}
+
+int bn_query_load(const BnQueryBatch *b, int *query_handle)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!b || !query_handle || !b->query_start || !b->contexts || b->num_contexts <= 0)
+        return fail(BN_ERR_INVALID, "bn_query_load: bad argument");
+    if (b->window_size > 0) return fail(BN_ERR_UNSUPPORTED, "two-hit mode (window_size > 0) is not implemented on the GPU path yet");
+    if (b->gap_algo == BN_GAP_GREEDY && (b->gap_open != 0 || b->gap_extend != 0))
+        return fail(BN_ERR_UNSUPPORTED, "affine greedy extension is not implemented");
+    if (b->lut_type != BN_LUT_MB && b->lut_type != BN_LUT_SMALL_NA)
+        return fail(BN_ERR_UNSUPPORTED, "only eMBLookupTable and eSmallNaLookupTable are supported");
+    auto Q = std::make_unique<Query>();
+    Q->batch = *b;
+    Q->query.assign(b->query_start, b->query_start + b->concat_len + 2);
+    Q->ctx.assign(b->contexts, b->contexts + b->num_contexts);
+    for (const auto &c : Q->ctx) Q->max_query_length = std::max(Q->max_query_length, c.query_length);
+    if (b->lut_type == BN_LUT_MB) {
+        if (!b->hashtable || !b->next_pos) return fail(BN_ERR_INVALID, "bn_query_load: MB table arrays missing");
+        Q->hashtable.assign(b->hashtable, b->hashtable + b->hashsize);
+        Q->next_pos.assign(b->next_pos, b->next_pos + b->concat_len + 1);
+        // exact presence bitmap (replaces the reference's compressed pv_array: same answers,
+        // PV_TEST is only a filter in front of hashtable[index] != 0)
+        Q->presence.assign((size_t)((b->hashsize + 31) / 32), 0u);
+        for (int64_t i = 0; i < b->hashsize; i++)
+            if (Q->hashtable[(size_t)i]) Q->presence[(size_t)(i >> 5)] |= 1u << (i & 31);
+    } else {
+        if (!b->backbone) return fail(BN_ERR_INVALID, "bn_query_load: small table arrays missing");
+        Q->backbone.assign(b->backbone, b->backbone + b->hashsize);
+        if (b->overflow && b->overflow_len > 0) Q->overflow.assign(b->overflow, b->overflow + b->overflow_len);
+        else Q->overflow.assign(2, (int16_t)-1);
+    }
+    if (b->masked_locations && b->n_masked_locations > 0)
+        Q->masked.assign(b->masked_locations, b->masked_locations + 2 * (size_t)b->n_masked_locations);
+    // re-target the host copy
+    Q->batch.query_start = Q->query.data();
+    Q->batch.contexts = Q->ctx.data();
+    Q->batch.hashtable = Q->hashtable.data(); Q->batch.next_pos = Q->next_pos.data();
+    Q->batch.pv_array = nullptr;
+    Q->batch.backbone = Q->backbone.data(); Q->batch.overflow = Q->overflow.data();
+    Q->batch.masked_locations = b->masked_locations ? (Q->masked.empty() ? (const int32_t *)Q->query.data() : Q->masked.data()) : nullptr;
+    int32_t n = 1;
+    while (n < b->concat_len + b->window_size) n <<= 1;   // s_BlastDiagTableNew core/blast_extend.c:46-72
+    Q->diag_array_length = n;
+    Q->dev.resize(g_devices.size());
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_queries.push_back(std::move(Q));
+    *query_handle = (int)g_queries.size() - 1;
+    return BN_OK;
+}
+
+int bn_query_free(int h)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (h < 0 || h >= (int)g_queries.size() || !g_queries[h]) return fail(BN_ERR_INVALID, "bn_query_free: bad handle");
+    Query &Q = *g_queries[h];
+    for (size_t d = 0; d < Q.dev.size(); d++)
+        if (Q.dev[d].ready) { cudaSetDevice(g_devices[d]->id); free_query_dev(Q.dev[d]); }
+    g_queries[h].reset();
+    return BN_OK;
+}
+
+static int get_handles(int vol_handle, int query_handle, Volume **V, Query **Q, Device **D)
+{
+    if (vol_handle < 0 || vol_handle >= (int)g_volumes.size() || !g_volumes[vol_handle])
+        return fail(BN_ERR_INVALID, "bad volume handle");
+    if (query_handle < 0 || query_handle >= (int)g_queries.size() || !g_queries[query_handle])
+        return fail(BN_ERR_INVALID, "bad query handle");
+    *V = g_volumes[vol_handle].get();
+    *Q = g_queries[query_handle].get();
+    *D = device_at((*V)->device);
+    return BN_OK;
+}
+
+int bn_prelim_search(int vol_handle, int query_handle, int32_t oid_begin, int32_t oid_end, int taps,
+                     BnResults *out)
+{
+    Volume *V; Query *Q; Device *D;
+    if (!out) return fail(BN_ERR_INVALID, "bn_prelim_search: out is NULL");
+    int rc = get_handles(vol_handle, query_handle, &V, &Q, &D);
+    if (rc) return rc;
+    const int32_t n = (int32_t)V->seq_len.size();
+    if (oid_begin < 0) oid_begin = 0;
+    if (oid_end < 0 || oid_end > n) oid_end = n;
+    std::lock_guard<std::mutex> lk(D->mu);
+    return prelim_search_locked(*D, *V, *Q, oid_begin, oid_end, taps, out);
+}
+
+int bn_prelim_search_host(int device, const BnQueryBatch *batch, const uint8_t *packed,
+                          int64_t packed_bytes, const int64_t *seq_byte_off, const int32_t *seq_len,
+                          int32_t n_seq, int taps, BnResults *out)
+{
+    int vh = -1, qh = -1;
+    int rc = bn_db_load(device, packed, packed_bytes, seq_byte_off, seq_len, n_seq, &vh);
+    if (rc) return rc;
+    rc = bn_query_load(batch, &qh);
+    if (rc == BN_OK) rc = bn_prelim_search(vh, qh, 0, n_seq, taps, out);
+    if (qh >= 0) bn_query_free(qh);
+    bn_db_free(vh);
+    return rc;
+}
+
+void bn_results_free(BnResults *r)
+{
+    if (!r) return;
+    free(r->hsps); free(r->init); free(r->gapped);
+    memset(r, 0, sizeof *r);
+}
+
+void bn_free(void *p) { free(p); }
+
+int bn_scan_subject(int vol_handle, int query_handle, int32_t oid, int32_t chunk_off, int32_t chunk_len,
+                    BnOffsetPair **pairs, int64_t *n_pairs)
+{
+    (void)chunk_off; (void)chunk_len;
+    Volume *V; Query *Q; Device *D;
+    if (!pairs || !n_pairs) return fail(BN_ERR_INVALID, "bn_scan_subject: NULL output");
+    int rc = get_handles(vol_handle, query_handle, &V, &Q, &D);
+    if (rc) return rc;
+    if (oid < 0 || oid >= (int32_t)V->seq_len.size()) return fail(BN_ERR_INVALID, "bn_scan_subject: bad oid");
+    std::lock_guard<std::mutex> lk(D->mu);
+    CU_TRY(cudaSetDevice(D->id));
+    rc = query_to_device(*Q, V->device);
+    if (rc) return rc;
+    std::shared_ptr<ChunkTable> T;
+    rc = build_chunk_table(*V, *Q, oid, oid + 1, D->stream, &T);
+    if (rc) return rc;
+    StageCounts cnt;
+    rc = run_word_finder(*D, *V, *Q, *T, true, cnt, nullptr);
+    if (rc) return rc;
+    std::vector<SeedHit> h((size_t)cnt.n_hits);
+    if (cnt.n_hits) {
+        CU_TRY(cudaMemcpyAsync(h.data(), D->ws.hits_b.p, h.size() * sizeof(SeedHit), cudaMemcpyDeviceToHost, D->stream));
+        CU_TRY(cudaStreamSynchronize(D->stream));
+    }
+    BnOffsetPair *o = (BnOffsetPair *)malloc(std::max<size_t>(h.size(), 1) * sizeof(BnOffsetPair));
+    if (!o) return fail(BN_ERR_MEMORY, "bn_scan_subject: out of memory");
+    for (size_t i = 0; i < h.size(); i++) {
+        // chunk-relative subject offsets, like the reference's per-chunk scansub calls
+        o[i].q_off = h[i].q_off; o[i].s_off = h[i].s_off;
+    }
+    *pairs = o; *n_pairs = (int64_t)h.size();
+    return BN_OK;
+}
+
+int bn_word_finder(int vol_handle, int query_handle, int32_t oid_begin, int32_t oid_end,
+                   BnInitHit **init, int64_t *n_init)
+{
+    BnResults r;
+    if (!init || !n_init) return fail(BN_ERR_INVALID, "bn_word_finder: NULL output");
+    int rc = bn_prelim_search(vol_handle, query_handle, oid_begin, oid_end, BN_TAP_INIT, &r);
+    if (rc) return rc;
+    *init = r.init; *n_init = r.n_init;
+    r.init = nullptr;
+    bn_results_free(&r);
+    return BN_OK;
+}
+
+int bn_bench_scan(int vol_handle, int query_handle, int iters, double *ms_per_launch,
+                  int64_t *bases_per_launch, int64_t *hits)
+{
+    Volume *V; Query *Q; Device *D;
+    int rc = get_handles(vol_handle, query_handle, &V, &Q, &D);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(D->mu);
+    CU_TRY(cudaSetDevice(D->id));
+    rc = query_to_device(*Q, V->device);
+    if (rc) return rc;
+    std::shared_ptr<ChunkTable> T;
+    rc = build_chunk_table(*V, *Q, 0, (int32_t)V->seq_len.size(), D->stream, &T);
+    if (rc) return rc;
+    Workspace &ws = D->ws;
+    cudaStream_t st = D->stream;
+    CU_TRY(ws.counters.reserve(8));
+    int64_t cap = std::max<int64_t>((int64_t)ws.hits_a.cap, std::max<int64_t>(1 << 16, T->total_pos / 16));
+    CU_TRY(ws.hits_a.reserve((size_t)cap)); CU_TRY(ws.keys_a.reserve((size_t)cap));
+    cap = (int64_t)std::min(ws.hits_a.cap, ws.keys_a.cap);
+    ScanLaunch s{};
+    s.packed = V->d_packed; s.chunks = T->dev.p; s.n_chunks = (int32_t)T->host.size();
+    s.total_pos = T->total_pos; s.hits = ws.hits_a.p; s.keys = ws.keys_a.p;
+    s.counters = ws.counters.p; s.capacity = cap; s.block_chunk = T->block_chunk.p; s.raw_pairs = 0;
+    const DevQuery &dq = Q->dev[V->device].view;
+    Timer t(st);
+    double total = 0;
+    unsigned long long h_c[2] = {0, 0};
+    for (int i = 0; i < iters; i++) {
+        CU_TRY(cudaMemsetAsync(ws.counters.p, 0, 8 * sizeof(unsigned long long), st));
+        t.start();
+        CU_TRY(launch_scan(dq, s, st));
+        t.stop();
+        total += t.ms();
+    }
+    CU_TRY(cudaMemcpyAsync(h_c, ws.counters.p, sizeof h_c, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    if (ms_per_launch) *ms_per_launch = iters > 0 ? total / iters : 0;
+    if (bases_per_launch) *bases_per_launch = T->total_bases;
+    if (hits) *hits = (int64_t)h_c[0];
+    return BN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,318 @@
+// gapped_kernel.cu — stage 3: score-only gapped extension of every ungapped HSP.
+//
+// Replaces (semantics, not code):
+//   greedy (megablast)  BLAST_GreedyGappedAlignment core/blast_gapalign.c:2620-2751
+//                       BLAST_AffineGreedyAlign dispatch core/greedy_align.c:801-815
+//                       BLAST_GreedyAlign :385-681, s_FindFirstMismatch :318-381
+//   DP (blastn)         s_BlastDynProgNtGappedAlignment core/blast_gapalign.c:2763-2825
+//                       s_BlastAlignPackedNucl :2843-3056
+//   start points        BLAST_GetGappedScore :3466-3497 (middle of the ungapped HSP for greedy,
+//                       seed + 3 for DP)
+//
+// Parallel formulation: an extension's result depends only on (query context,
+// subject, start point, parameters), never on earlier extensions, so ALL init-HSPs are extended
+// speculatively, one per thread, and the host afterwards replays the reference's sequential
+// interval-tree containment filter over the sorted list, discarding results whose init-HSP the
+// reference would have skipped.  Each thread keeps the exact serial recurrence (row-major
+// best_score pruning for the DP, per-distance diagonal bounds for greedy), so scores, end points
+// and seed estimates are bit-identical.
+//
+// Scratch is tiered: tier 1 gives every thread a small window (greedy: distances <= tier_d,
+// DP: a ring of tier_d cells); an extension that outgrows it reports status 1 and is redone
+// in tier 2 with worst-case scratch (greedy max_dist 10000 rows, DP ring >= query length).
+#include "bn_device.cuh"
+
+namespace bn {
+
+constexpr int GAP_THREADS = 64;
+constexpr int GAP_BLOCKS = 592;          // 4 x 148 SMs
+int gapped_threads() { return GAP_THREADS * GAP_BLOCKS; }
+int gapped_threads_per_block() { return GAP_THREADS; }
+
+constexpr int32_t GREEDY_MAX_COST = 10000;
+constexpr int32_t GREEDY_INVALID = -2;
+constexpr int32_t MININT = INT32_MIN / 2;
+
+// seq1 = query bytes, seq2 = packed subject (s_FindFirstMismatch, compressed branch)
+__device__ __forceinline__ int32_t first_mismatch(const uint8_t *seq1, const uint8_t *seq2,
+                                                  int32_t len1, int32_t len2, int32_t i1, int32_t i2,
+                                                  bool reverse, int rem)
+{
+    const int32_t start = i1;
+    if (reverse) {
+        while (i1 < len1 && i2 < len2 &&
+               (int)__ldg(seq1 + (len1 - 1 - i1)) == sbase(seq2, len2 - 1 - i2)) { ++i1; ++i2; }
+    } else {
+        while (i1 < len1 && i2 < len2 &&
+               (int)__ldg(seq1 + i1) == sbase(seq2, i2 + rem)) { ++i1; ++i2; }
+    }
+    return i1 - start;
+}
+
+struct GreedySeed { int32_t start_q, start_s, match_length; };
+
+// BLAST_GreedyAlign, score only.  rows: 2 x (2*D + 6) ints; max_score: D + 1 + xdrop_offset ints.
+// Diagonal k of the reference is stored at index k - diag_origin + D + 2.
+__device__ int32_t greedy_align(const uint8_t *seq1, int32_t len1, const uint8_t *seq2, int32_t len2,
+                                bool reverse, int32_t xdrop_threshold, int32_t match_cost,
+                                int32_t mismatch_cost, int32_t &seq1_len, int32_t &seq2_len,
+                                int32_t *row0, int32_t *row1, int32_t *max_score_mem, int32_t D,
+                                int rem, GreedySeed &seed, bool &overflow)
+{
+    int32_t best_dist = 0;
+    const int32_t max_dist = min(GREEDY_MAX_COST, len2 / 2 + 1);
+    const int32_t origin = D + 2;                 // re-biased diag_origin
+    const int32_t xdrop_offset = (xdrop_threshold + match_cost / 2) / (match_cost + mismatch_cost) + 1;
+
+    int32_t index = first_mismatch(seq1, seq2, len1, len2, 0, 0, reverse, rem);
+    seq1_len = index; seq2_len = index;
+    int32_t seq1_index = index, seq2_index;
+    seed.start_q = 0; seed.start_s = 0;
+    int32_t longest_match_run = index;
+    seed.match_length = index;
+    if (index == len1 || index == len2) return 0;
+
+    int32_t *max_score = max_score_mem + xdrop_offset;
+    for (int32_t i = 0; i < xdrop_offset; i++) max_score_mem[i] = 0;
+    row0[origin] = seq1_index;
+    max_score[0] = seq1_index * match_cost;
+    int32_t diag_lower = origin - 1, diag_upper = origin + 1;
+    bool end1_reached = false, end2_reached = false;
+
+    for (int32_t d = 1; d <= max_dist; d++) {
+        if (d > D) { overflow = true; return best_dist; }
+        int32_t curr_extent = 0, curr_seq2_index = 0, curr_diag = 0;
+        const int32_t tmp_lower = diag_lower, tmp_upper = diag_upper;
+        int32_t *prev = ((d - 1) & 1) ? row1 : row0;
+        int32_t *cur = (d & 1) ? row1 : row0;
+        prev[diag_lower - 1] = GREEDY_INVALID;
+        prev[diag_lower] = GREEDY_INVALID;
+        prev[diag_upper] = GREEDY_INVALID;
+        prev[diag_upper + 1] = GREEDY_INVALID;
+
+        int32_t xdrop_score = max_score[d - xdrop_offset] + (match_cost + mismatch_cost) * d - xdrop_threshold;
+        // (Int4)ceil((double)x / (match_cost/2)); match_cost/2 >= 1, exact integer ceiling
+        {
+            const int32_t h = match_cost / 2;
+            int32_t qd = xdrop_score / h, r = xdrop_score % h;
+            if (r > 0) ++qd;
+            xdrop_score = qd;
+        }
+        for (int32_t k = tmp_lower; k <= tmp_upper; k++) {
+            seq2_index = max(prev[k + 1], prev[k]) + 1;
+            seq2_index = max(seq2_index, prev[k - 1]);
+            seq1_index = seq2_index + k - origin;
+            if (seq2_index < 0 || seq1_index + seq2_index < xdrop_score) {
+                if (k == diag_lower) diag_lower++;
+                else cur[k] = GREEDY_INVALID;
+                continue;
+            }
+            diag_upper = k;
+            index = first_mismatch(seq1, seq2, len1, len2, seq1_index, seq2_index, reverse, rem);
+            if (index > longest_match_run) {
+                seed.start_q = seq1_index; seed.start_s = seq2_index;
+                seed.match_length = longest_match_run = index;
+            }
+            seq1_index += index; seq2_index += index;
+            cur[k] = seq2_index;
+            if (seq1_index + seq2_index > curr_extent) {
+                curr_extent = seq1_index + seq2_index;
+                curr_seq2_index = seq2_index;
+                curr_diag = k;
+            }
+            if (seq2_index == len2) { diag_lower = k + 1; end2_reached = true; }
+            if (seq1_index == len1) { diag_upper = k - 1; end1_reached = true; }
+        }
+        const int32_t curr_score = curr_extent * (match_cost / 2) - d * (match_cost + mismatch_cost);
+        if (curr_score > max_score[d - 1]) {
+            max_score[d] = curr_score;
+            best_dist = d;
+            seq2_len = curr_seq2_index;
+            seq1_len = curr_seq2_index + curr_diag - origin;
+        } else max_score[d] = max_score[d - 1];
+        if (diag_lower > diag_upper) break;
+        if (!end2_reached) diag_lower--;
+        if (!end1_reached) diag_upper++;
+    }
+    return best_dist;
+}
+
+__device__ void greedy_gapped(const DevQuery &q, const uint8_t *query, int32_t qlen, const uint8_t *S,
+                              int32_t slen, int32_t q_off, int32_t s_off, int32_t *scratch, int32_t D,
+                              DevGapResult &g)
+{
+    int32_t match = q.reward, mismatch = -q.penalty, xd = q.gap_x_dropoff;
+    if (match % 2 == 1) { match *= 2; mismatch *= 2; xd *= 2; }
+    int32_t *row0 = scratch, *row1 = scratch + (2 * D + 6), *ms = scratch + 2 * (2 * D + 6);
+    int32_t q_ext_r, s_ext_r, q_ext_l, s_ext_l;
+    GreedySeed fwd, rev;
+    bool overflow = false;
+    int32_t score = greedy_align(query + q_off, qlen - q_off, S + s_off / 4, slen - s_off, false, xd,
+                                 match, mismatch, q_ext_r, s_ext_r, row0, row1, ms, D, s_off % 4, fwd,
+                                 overflow);
+    if (!overflow)
+        score += greedy_align(query, q_off, S, s_off, true, xd, match, mismatch, q_ext_l, s_ext_l,
+                              row0, row1, ms, D, 0, rev, overflow);
+    if (overflow) { g.status = 1; return; }
+    score = (q_ext_r + s_ext_r + q_ext_l + s_ext_l) * q.reward / 2 - score * (q.reward - q.penalty);
+
+    const int32_t q_box_l = q_off - q_ext_l, s_box_l = s_off - s_ext_l;
+    const int32_t q_box_r = q_off + q_ext_r, s_box_r = s_off + s_ext_r;
+    int32_t q_seed_l = q_off - rev.start_q, s_seed_l = s_off - rev.start_s;
+    int32_t q_seed_r = q_off + fwd.start_q, s_seed_r = s_off + fwd.start_s;
+    int32_t vl = 0, vr = 0;
+    if (q_seed_r < q_box_r && s_seed_r < s_box_r) {
+        vr = min(q_box_r - q_seed_r, s_box_r - s_seed_r);
+        vr = min(vr, fwd.match_length) / 2;
+    } else { q_seed_r = q_off; s_seed_r = s_off; }
+    if (q_seed_l > q_box_l && s_seed_l > s_box_l) {
+        vl = min(q_seed_l - q_box_l, s_seed_l - s_box_l);
+        vl = min(vl, rev.match_length) / 2;
+    } else { q_seed_l = q_off; s_seed_l = s_off; }
+    if (vr > vl) { g.q_seed = q_seed_r + vr; g.s_seed = s_seed_r + vr; }
+    else { g.q_seed = q_seed_l - vl; g.s_seed = s_seed_l - vl; }
+    g.q_start = q_box_l; g.s_start = s_box_l; g.q_stop = q_box_r; g.s_stop = s_box_r;
+    g.score = score;
+    g.status = 0;
+}
+
+// s_BlastAlignPackedNucl with the score_array kept in a ring of C cells: only indices in
+// [first_b_index, b_size] are live, so index i lives at slot i % C as long as the live span <= C.
+__device__ int32_t dp_packed(const uint8_t *B, const uint8_t *A, int32_t N, int32_t M,
+                             int32_t &b_offset, int32_t &a_offset, const int32_t *matrix,
+                             int32_t gap_open, int32_t gap_extend, int32_t x_dropoff, bool reverse,
+                             int2 *ring, int32_t C, bool &overflow)
+{
+    const int32_t gap_open_extend = gap_open + gap_extend;
+    a_offset = 0; b_offset = 0;
+    if (x_dropoff < gap_open_extend) x_dropoff = gap_open_extend;
+    if (N <= 0 || M <= 0) return 0;
+
+    int32_t score = -gap_open_extend;
+    ring[0] = make_int2(0, -gap_open_extend);
+    int32_t i;
+    for (i = 1; i <= N; i++) {
+        if (score < -x_dropoff) break;
+        if (i >= C) { overflow = true; return 0; }
+        ring[i % C] = make_int2(score, score - gap_open_extend);
+        score -= gap_extend;
+    }
+    int32_t b_size = i, best_score = 0, first_b_index = 0;
+    const int32_t b_inc = reverse ? -1 : 1;
+
+    for (int32_t a_index = 1; a_index <= M; a_index++) {
+        int a_bp;
+        if (reverse) a_bp = (__ldg(A + (M - a_index) / 4) >> (2 * ((a_index - 1) % 4))) & 3;
+        else a_bp = (__ldg(A + 1 + (a_index - 1) / 4) >> (2 * (3 - (a_index - 1) % 4))) & 3;
+        const int32_t *mrow = matrix + 16 * a_bp;
+        const uint8_t *b_ptr = reverse ? (B + N - first_b_index) : (B + first_b_index);
+        score = MININT;
+        int32_t score_gap_row = MININT, last_b_index = first_b_index;
+
+        for (int32_t b_index = first_b_index; b_index < b_size; b_index++) {
+            b_ptr += b_inc;
+            int2 cell = ring[b_index % C];
+            int32_t score_gap_col = cell.y;
+            const int32_t next_score = cell.x + __ldg(mrow + (int)__ldg(b_ptr));
+            if (score < score_gap_col) score = score_gap_col;
+            if (score < score_gap_row) score = score_gap_row;
+            if (best_score - score > x_dropoff) {
+                if (b_index == first_b_index) first_b_index++;
+                else { cell.x = MININT; ring[b_index % C] = cell; }
+            } else {
+                last_b_index = b_index;
+                if (score > best_score) { best_score = score; a_offset = a_index; b_offset = b_index; }
+                score_gap_row -= gap_extend;
+                score_gap_col -= gap_extend;
+                cell.y = max(score - gap_open_extend, score_gap_col);
+                score_gap_row = max(score - gap_open_extend, score_gap_row);
+                cell.x = score;
+                ring[b_index % C] = cell;
+            }
+            score = next_score;
+        }
+        if (first_b_index == b_size) break;
+        if (last_b_index < b_size - 1) b_size = last_b_index + 1;
+        else {
+            while (score_gap_row >= (best_score - x_dropoff) && b_size <= N) {
+                if (b_size - first_b_index + 2 >= C) { overflow = true; return 0; }
+                ring[b_size % C] = make_int2(score_gap_row, score_gap_row - gap_open_extend);
+                score_gap_row -= gap_extend;
+                b_size++;
+            }
+        }
+        if (b_size <= N) {
+            if (b_size - first_b_index + 2 >= C) { overflow = true; return 0; }
+            ring[b_size % C] = make_int2(MININT, MININT);
+            b_size++;
+        }
+    }
+    return best_score;
+}
+
+__device__ void dp_gapped(const DevQuery &q, const uint8_t *query, int32_t qlen, const uint8_t *S,
+                          int32_t slen, int32_t q_off, int32_t s_off, int32_t *scratch, int32_t C,
+                          DevGapResult &g)
+{
+    const int32_t adj = 4 - (s_off % 4);
+    int32_t q_length = q_off + adj, s_length = s_off + adj;
+    if (q_length > qlen || s_length > slen) { q_length -= 4; s_length -= 4; }
+    int2 *ring = reinterpret_cast<int2 *>(scratch);
+    bool overflow = false;
+    int32_t pq, ps, right = 0;
+    const int32_t left = dp_packed(query, S, q_length, s_length, pq, ps, q.matrix, q.gap_open,
+                                   q.gap_extend, q.gap_x_dropoff, true, ring, C, overflow);
+    if (overflow) { g.status = 1; return; }
+    g.q_start = q_length - pq; g.s_start = s_length - ps;
+    if (q_length < qlen && s_length < slen) {
+        int32_t qs, ss;
+        right = dp_packed(query + q_length - 1, S + (s_length + 3) / 4 - 1, qlen - q_length,
+                          slen - s_length, qs, ss, q.matrix, q.gap_open, q.gap_extend,
+                          q.gap_x_dropoff, false, ring, C, overflow);
+        if (overflow) { g.status = 1; return; }
+        g.q_stop = qs + q_length; g.s_stop = ss + s_length;
+    } else { g.q_stop = q_length; g.s_stop = s_length; }
+    g.score = left + right;
+    g.q_seed = q_off; g.s_seed = s_off;
+    g.status = 0;
+}
+
+__global__ void __launch_bounds__(GAP_THREADS)
+gapped_kernel(const DevQuery q, const GappedLaunch L)
+{
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    int64_t n = L.todo ? (int64_t)L.n_todo : (int64_t)min((unsigned long long)L.max_init, *L.n_init);
+    int32_t *scratch = L.scratch + tid * L.scratch_ints_per_thread;
+
+    for (int64_t w = tid; w < n; w += nthreads) {
+        const int64_t i = L.todo ? (int64_t)L.todo[w] : w;
+        const DevInitHit h = L.init[i];
+        const DevChunk ch = L.chunks[h.chunk];
+        const uint8_t *S = L.packed + ch.byte_off;
+        const int32_t context = ctx_search(q, h.q_off);
+        const DevContext c = q.ctx[context];
+        const uint8_t *query = q.query + c.query_offset;
+        DevGapResult g;
+        g.q_start = g.q_stop = g.s_start = g.s_stop = g.score = g.q_seed = g.s_seed = 0;
+        g.status = 0;
+        if (q.gap_algo == 1) {
+            const int32_t q_off = (h.q_start - c.query_offset) + h.length / 2;
+            const int32_t s_off = h.s_start + h.length / 2;
+            greedy_gapped(q, query, c.query_length, S, ch.len, q_off, s_off, scratch, L.tier_d, g);
+        } else {
+            int32_t q_off = h.q_off - c.query_offset, s_off = h.s_off;
+            if (h.s_start + h.length >= s_off + 8) { s_off += 3; q_off += 3; }
+            dp_gapped(q, query, c.query_length, S, ch.len, q_off, s_off, scratch, L.tier_d, g);
+        }
+        L.out[i] = g;
+    }
+}
+
+cudaError_t launch_gapped(const DevQuery &q, const GappedLaunch &g, cudaStream_t st)
+{
+    gapped_kernel<<<g.grid_blocks > 0 ? g.grid_blocks : GAP_BLOCKS, GAP_THREADS, 0, st>>>(q, g);
+    return cudaGetLastError();
+}
+
+}  // namespace bn

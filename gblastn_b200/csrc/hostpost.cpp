@@ -1,0 +1,549 @@
+// hostpost.cpp — see hostpost.h.  Host-side, sequential, touches only the handful of HSPs per
+// subject that survive the GPU stages.
+#include "hostpost.h"
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdlib>
+
+namespace bn {
+
+// ------------------------------------------------------------------------------------------------
+// Interval tree (core/blast_itree.c).  Node fields keep the reference's meaning: internal nodes
+// cover [leftend, rightend]; a leaf (item >= 0) stores the query-strand offset in leftptr and uses
+// midptr as the "next" link of a midpoint list.
+// ------------------------------------------------------------------------------------------------
+IntervalTree::IntervalTree(int32_t q_min, int32_t q_max, int32_t s_min, int32_t s_max)
+    : s_min_(s_min), s_max_(s_max)
+{
+    nodes_.reserve(128);
+    new_root(q_min, q_max);
+}
+
+int32_t IntervalTree::new_root(int32_t lo, int32_t hi)
+{
+    nodes_.push_back(Node{lo, hi, 0, 0, 0, -1});
+    return (int32_t)nodes_.size() - 1;
+}
+
+int32_t IntervalTree::new_child(int32_t parent, bool left)
+{
+    const Node p = nodes_[parent];
+    const int32_t mid = (p.leftend + p.rightend) / 2;
+    Node n{0, 0, 0, 0, 0, -1};
+    if (left) { n.leftend = p.leftend; n.rightend = mid; }
+    else { n.leftend = mid + 1; n.rightend = p.rightend; }
+    nodes_.push_back(n);
+    return (int32_t)nodes_.size() - 1;
+}
+
+int32_t IntervalTree::new_leaf(int32_t item, int32_t q_strand_start)
+{
+    nodes_.push_back(Node{0, 0, q_strand_start, 0, 0, item});
+    return (int32_t)nodes_.size() - 1;
+}
+
+// s_HSPIsContained (core/blast_itree.c:815-853)
+static bool item_contained(const IntervalTree::Item &in, const IntervalTree::Item &t, int32_t tree_q_start,
+                           int32_t mds)
+{
+    if (in.q_strand_start != tree_q_start) return false;
+    if (in.score <= t.score &&
+        t.q_off <= in.q_off && t.q_end >= in.q_off && t.s_off <= in.s_off && t.s_end >= in.s_off &&
+        t.q_off <= in.q_end && t.q_end >= in.q_end && t.s_off <= in.s_end && t.s_end >= in.s_end) {
+        if (mds == 0) return true;
+        if (std::abs((t.q_off - t.s_off) - (in.q_off - in.s_off)) < mds ||
+            std::abs((t.q_end - t.s_end) - (in.q_end - in.s_end)) < mds)
+            return true;
+    }
+    return false;
+}
+
+// s_MidpointTreeContainsHSP (core/blast_itree.c:871-932)
+bool IntervalTree::mid_contains(int32_t root, const Item &in, int32_t mds) const
+{
+    const Node *node = &nodes_[root];
+    const int32_t region_start = in.s_off, region_end = in.s_end;
+    while (node->item < 0) {
+        for (int32_t t = node->midptr; t != 0; t = nodes_[t].midptr) {
+            const Node &ln = nodes_[t];
+            if (item_contained(in, items_[ln.item], ln.leftptr, mds)) return true;
+        }
+        int32_t next = 0;
+        const int32_t middle = (node->leftend + node->rightend) / 2;
+        if (region_end < middle) next = node->leftptr;
+        else if (region_start > middle) next = node->rightptr;
+        if (next == 0) return false;
+        node = &nodes_[next];
+    }
+    return item_contained(in, items_[node->item], node->leftptr, mds);
+}
+
+// BlastIntervalTreeContainsHSP (core/blast_itree.c:936-1000)
+bool IntervalTree::contains(const Item &in, int32_t mds) const
+{
+    const Node *node = &nodes_[0];
+    const int32_t region_start = in.q_strand_start + in.q_off;
+    const int32_t region_end = in.q_strand_start + in.q_end;
+    while (node->item < 0) {
+        if (node->midptr > 0 && mid_contains(node->midptr, in, mds)) return true;
+        int32_t next = 0;
+        const int32_t middle = (node->leftend + node->rightend) / 2;
+        if (region_end < middle) next = node->leftptr;
+        else if (region_start > middle) next = node->rightptr;
+        if (next == 0) return false;
+        node = &nodes_[next];
+    }
+    return item_contained(in, items_[node->item], node->leftptr, mds);
+}
+
+// s_HSPsHaveCommonEndpoint (core/blast_itree.c:251-306): 0 = no match, 1 = tree item wins, 2 = new
+static int common_endpoint(const IntervalTree::Item &in, const IntervalTree::Item &t, int32_t tree_q_start,
+                           bool right)
+{
+    if (in.q_strand_start != tree_q_start) return 0;
+    const bool match = right ? (in.q_end == t.q_end && in.s_end == t.s_end)
+                             : (in.q_off == t.q_off && in.s_off == t.s_off);
+    if (!match) return 0;
+    if (in.score > t.score) return 2;
+    if (in.score < t.score) return 1;
+    const int32_t iq = in.q_end - in.q_off, tq = t.q_end - t.q_off;
+    if (iq > tq) return 1;
+    if (iq < tq) return 2;
+    const int32_t is = in.s_end - in.s_off, ts = t.s_end - t.s_off;
+    if (is > ts) return 1;
+    if (is < ts) return 2;
+    return 1;
+}
+
+// s_MidpointTreeHasHSPEndpoint (core/blast_itree.c:324-420)
+bool IntervalTree::mid_has_endpoint(int32_t root, const Item &in, bool right)
+{
+    int32_t root_i = root;
+    const int32_t target = right ? in.s_end : in.s_off;
+    for (;;) {
+        // walk the midpoint list; the reference advances its "previous" pointer onto a node it
+        // has just unlinked, so of two adjacent losers only the first leaves the list
+        int32_t list_i = root_i;
+        int32_t tmp = nodes_[root_i].midptr;
+        while (tmp != 0) {
+            const int32_t next_i = tmp;
+            const int r = common_endpoint(in, items_[nodes_[next_i].item], nodes_[next_i].leftptr, right);
+            tmp = nodes_[next_i].midptr;
+            if (r == 1) return true;
+            if (r == 2) nodes_[list_i].midptr = tmp;
+            list_i = next_i;
+        }
+        int32_t next = 0;
+        const int32_t midpt = (nodes_[root_i].leftend + nodes_[root_i].rightend) / 2;
+        if (target < midpt) next = nodes_[root_i].leftptr;
+        else if (target > midpt) next = nodes_[root_i].rightptr;
+        if (next == 0) return false;
+        if (nodes_[next].item >= 0) {
+            const int r = common_endpoint(in, items_[nodes_[next].item], nodes_[next].leftptr, right);
+            if (r == 1) return true;
+            if (r == 2) {
+                if (target < midpt) nodes_[root_i].leftptr = 0;
+                else if (target > midpt) nodes_[root_i].rightptr = 0;
+                return false;
+            }
+            break;
+        }
+        root_i = next;
+    }
+    return false;
+}
+
+// s_IntervalTreeHasHSPEndpoint (core/blast_itree.c:438-510)
+bool IntervalTree::has_endpoint(const Item &in, bool right)
+{
+    int32_t root_i = 0;
+    const int32_t target = in.q_strand_start + (right ? in.q_end : in.q_off);
+    for (;;) {
+        const int32_t mid_tree = nodes_[root_i].midptr;
+        if (mid_tree != 0 && mid_has_endpoint(mid_tree, in, right)) return true;
+        int32_t next = 0;
+        const int32_t midpt = (nodes_[root_i].leftend + nodes_[root_i].rightend) / 2;
+        if (target < midpt) next = nodes_[root_i].leftptr;
+        else if (target > midpt) next = nodes_[root_i].rightptr;
+        if (next == 0) return false;
+        if (nodes_[next].item >= 0) {
+            const int r = common_endpoint(in, items_[nodes_[next].item], nodes_[next].leftptr, right);
+            if (r == 1) return true;
+            if (r == 2) {
+                if (target < midpt) nodes_[root_i].leftptr = 0;
+                else if (target > midpt) nodes_[root_i].rightptr = 0;
+                return false;
+            }
+            break;
+        }
+        root_i = next;
+    }
+    return false;
+}
+
+// BlastIntervalTreeAddHSP, index_method == eQueryAndSubject (core/blast_itree.c:514-800)
+void IntervalTree::add(const Item &in)
+{
+    if (has_endpoint(in, false)) return;
+    if (has_endpoint(in, true)) return;
+
+    items_.push_back(in);
+    const int32_t item = (int32_t)items_.size() - 1;
+    int32_t region_start = in.q_strand_start + in.q_off;
+    int32_t region_end = in.q_strand_start + in.q_end;
+    bool by_subject = false;
+    int32_t root = 0;
+    const int32_t leaf = new_leaf(item, in.q_strand_start);
+
+    for (;;) {
+        int32_t middle = (nodes_[root].leftend + nodes_[root].rightend) / 2;
+        int32_t old;
+        bool left_half;
+        if (region_end < middle) {
+            if (nodes_[root].leftptr == 0) { nodes_[root].leftptr = leaf; return; }
+            old = nodes_[root].leftptr;
+            if (nodes_[old].item < 0) { root = old; continue; }
+            left_half = true;
+        } else if (region_start > middle) {
+            if (nodes_[root].rightptr == 0) { nodes_[root].rightptr = leaf; return; }
+            old = nodes_[root].rightptr;
+            if (nodes_[old].item < 0) { root = old; continue; }
+            left_half = false;
+        } else {
+            if (by_subject) {
+                nodes_[leaf].midptr = nodes_[root].midptr;
+                nodes_[root].midptr = leaf;
+                return;
+            }
+            by_subject = true;
+            if (nodes_[root].midptr == 0) {
+                const int32_t m = new_root(s_min_, s_max_);
+                nodes_[root].midptr = m;
+            }
+            root = nodes_[root].midptr;
+            region_start = in.s_off;
+            region_end = in.s_end;
+            continue;
+        }
+        // two leaves want the same slot: interpose an internal node and re-hang the old leaf
+        const int32_t mid_index = new_child(root, left_half);
+        const Item &old_item = items_[nodes_[old].item];
+        if (left_half) nodes_[root].leftptr = mid_index; else nodes_[root].rightptr = mid_index;
+        int32_t old_start, old_end;
+        if (by_subject) { old_start = old_item.s_off; old_end = old_item.s_end; }
+        else { old_start = nodes_[old].leftptr + old_item.q_off; old_end = nodes_[old].leftptr + old_item.q_end; }
+        root = mid_index;
+        middle = (nodes_[root].leftend + nodes_[root].rightend) / 2;
+        if (old_end < middle) nodes_[mid_index].leftptr = old;
+        else if (old_start > middle) nodes_[mid_index].rightptr = old;
+        else if (by_subject) nodes_[mid_index].midptr = old;
+        else {
+            const int32_t m2 = new_root(s_min_, s_max_);
+            nodes_[mid_index].midptr = m2;
+            const int32_t middle2 = (nodes_[m2].leftend + nodes_[m2].rightend) / 2;
+            if (old_item.s_end < middle2) nodes_[m2].leftptr = old;
+            else if (old_item.s_off > middle2) nodes_[m2].rightptr = old;
+            else nodes_[m2].midptr = old;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+static int32_t ctx_search(const BnQueryBatch &b, int32_t n)
+{
+    int32_t lo = 0, hi = b.num_contexts;
+    while (lo < hi - 1) {
+        const int32_t m = (lo + hi) / 2;
+        if (b.contexts[m].query_offset > n) hi = m; else lo = m;
+    }
+    return lo;
+}
+
+// s_GetQueryStrandOffset (core/blast_itree.c:219-234)
+static int32_t strand_offset(const BnQueryBatch &b, int32_t context)
+{
+    int32_t c = context;
+    while (c) {
+        const int f = b.contexts[c].frame, pf = b.contexts[c - 1].frame;
+        const int sf = (f > 0) - (f < 0), spf = (pf > 0) - (pf < 0);
+        if (f == 0 || sf != spf) break;
+        c--;
+    }
+    return b.contexts[c].query_offset;
+}
+
+void sort_init_hits(std::vector<HostInit> &v)
+{
+    std::sort(v.begin(), v.end(), [](const HostInit &a, const HostInit &c) {
+        if (a.chunk != c.chunk) return a.chunk < c.chunk;
+        if (a.score != c.score) return a.score > c.score;
+        if (a.s_start != c.s_start) return a.s_start < c.s_start;
+        if (a.length != c.length) return a.length > c.length;
+        if (a.q_start != c.q_start) return a.q_start < c.q_start;
+        return a.order < c.order;      // glibc qsort is a stable merge sort: ties keep emission order
+    });
+}
+
+void replay_gapped(const BnQueryBatch &b, const HostChunk &ch, const HostInit *init, size_t n,
+                   const int32_t *low_score, std::vector<BnHSP> &out, BnStats &stats)
+{
+    if (n == 0) return;
+    IntervalTree tree(0, b.concat_len + 1, 0, ch.len + 1);
+    std::vector<uint8_t> found_high;
+    if (low_score) {
+        found_high.assign((size_t)b.num_queries, 0);
+        for (size_t i = 0; i < n; i++) {
+            const int32_t qi = b.contexts[ctx_search(b, init[i].q_off)].query_index;
+            if (init[i].score > low_score[qi]) found_high[qi] = 1;
+        }
+    }
+    for (size_t i = 0; i < n; i++) {
+        const HostInit &h = init[i];
+        const int32_t context = ctx_search(b, h.q_off);
+        const BnContext &c = b.contexts[context];
+        if (low_score && !found_high[c.query_index]) continue;
+        IntervalTree::Item t;
+        t.q_strand_start = strand_offset(b, context);
+        t.q_off = h.q_start - c.query_offset;
+        t.q_end = t.q_off + h.length;
+        t.s_off = h.s_start;
+        t.s_end = h.s_start + h.length;
+        t.score = h.score;
+        if (tree.contains(t, b.min_diag_separation)) continue;
+        ++stats.gap_extensions;
+        if (h.g_score >= c.gapped_cutoff) {
+            BnHSP o;
+            o.oid = ch.oid; o.context = context; o.chunk_off = ch.chunk_off;
+            o.q_off = h.g_q_start; o.q_end = h.g_q_stop; o.s_off = h.g_s_start; o.s_end = h.g_s_stop;
+            o.score = h.g_score; o.q_gapped_start = h.g_q_seed; o.s_gapped_start = h.g_s_seed;
+            o.evalue = 0.0;
+            out.push_back(o);
+            IntervalTree::Item nt{t.q_strand_start, o.q_off, o.q_end, o.s_off, o.s_end, o.score};
+            tree.add(nt);
+        }
+    }
+}
+
+void finish_chunk_list(const BnQueryBatch &b, std::vector<BnHSP> &list)
+{
+    // Blast_HSPListPurgeHSPsWithCommonEndpoints(purge = TRUE), core/blast_hits.c:2224-2300
+    std::stable_sort(list.begin(), list.end(), [](const BnHSP &x, const BnHSP &y) {
+        if (x.context != y.context) return x.context < y.context;
+        if (x.q_off != y.q_off) return x.q_off < y.q_off;
+        if (x.s_off != y.s_off) return x.s_off < y.s_off;
+        if (x.score != y.score) return x.score > y.score;
+        if (x.q_end != y.q_end) return x.q_end > y.q_end;
+        if (x.s_end != y.s_end) return x.s_end > y.s_end;
+        return false;
+    });
+    size_t o = 0;
+    for (size_t i = 0; i < list.size(); i++) {
+        if (o > 0 && list[o - 1].context == list[i].context && list[o - 1].q_off == list[i].q_off &&
+            list[o - 1].s_off == list[i].s_off) continue;
+        list[o++] = list[i];
+    }
+    list.resize(o);
+    std::stable_sort(list.begin(), list.end(), [](const BnHSP &x, const BnHSP &y) {
+        if (x.context != y.context) return x.context < y.context;
+        if (x.q_end != y.q_end) return x.q_end < y.q_end;
+        if (x.s_end != y.s_end) return x.s_end < y.s_end;
+        if (x.score != y.score) return x.score > y.score;
+        if (x.q_off != y.q_off) return x.q_off > y.q_off;
+        if (x.s_off != y.s_off) return x.s_off > y.s_off;
+        return false;
+    });
+    o = 0;
+    for (size_t i = 0; i < list.size(); i++) {
+        if (o > 0 && list[o - 1].context == list[i].context && list[o - 1].q_end == list[i].q_end &&
+            list[o - 1].s_end == list[i].s_end) continue;
+        list[o++] = list[i];
+    }
+    list.resize(o);
+    // Blast_HSPListAdjustOddBlastnScores, core/blast_hits.c:2734-2749
+    if (b.round_down)
+        for (auto &h : list) h.score &= ~1;
+    // Blast_HSPListSortByScore (ScoreCompareHSPs, core/blast_hits.c:1182-1210)
+    std::stable_sort(list.begin(), list.end(), [](const BnHSP &x, const BnHSP &y) {
+        if (x.score != y.score) return x.score > y.score;
+        if (x.s_off != y.s_off) return x.s_off < y.s_off;
+        if (x.s_end != y.s_end) return x.s_end > y.s_end;
+        if (x.q_off != y.q_off) return x.q_off < y.q_off;
+        if (x.q_end != y.q_end) return x.q_end > y.q_end;
+        return false;
+    });
+}
+
+static bool score_less(const BnHSP &x, const BnHSP &y)
+{
+    if (x.score != y.score) return x.score > y.score;
+    if (x.s_off != y.s_off) return x.s_off < y.s_off;
+    if (x.s_end != y.s_end) return x.s_end > y.s_end;
+    if (x.q_off != y.q_off) return x.q_off < y.q_off;
+    if (x.q_end != y.q_end) return x.q_end > y.q_end;
+    return false;
+}
+
+void merge_chunk_lists(std::vector<BnHSP> &comb, std::vector<BnHSP> &fresh, int32_t split_offset,
+                       int32_t overlap)
+{
+    if (fresh.empty()) return;
+    if (comb.empty()) { comb.swap(fresh); return; }
+    size_t n1 = 0, n2 = 0;
+    for (size_t i = 0; i < comb.size(); i++)
+        if (comb[i].s_end > split_offset) { std::swap(comb[n1], comb[i]); ++n1; }
+    for (size_t i = 0; i < fresh.size(); i++)
+        if (fresh[i].s_off < split_offset + overlap) { std::swap(fresh[n2], fresh[i]); ++n2; }
+    if (n1 > 0 && n2 > 0) {
+        std::vector<uint8_t> dead(fresh.size(), 0);
+        for (size_t i = 0; i < n1; i++) {
+            BnHSP &h1 = comb[i];
+            for (size_t j = 0; j < n2; j++) {
+                BnHSP &h2 = fresh[j];
+                if (dead[j] || h1.context != h2.context) continue;
+                // OVERLAP_DIAG_CLOSE 10; s_BlastMergeTwoHSPs core/blast_hits.c:1337-1375
+                if (std::abs((h1.q_end - h1.s_end) - (h2.q_off - h2.s_off)) >= 10) continue;
+                const bool c1 = h1.q_off <= h2.q_off && h1.q_end >= h2.q_off &&
+                                h1.s_off <= h2.s_off && h1.s_end >= h2.s_off;
+                const bool c2 = h1.q_off <= h2.q_end && h1.q_end >= h2.q_end &&
+                                h1.s_off <= h2.s_end && h1.s_end >= h2.s_end;
+                if (!(c1 || c2)) continue;
+                h1.q_off = std::min(h1.q_off, h2.q_off); h1.s_off = std::min(h1.s_off, h2.s_off);
+                h1.q_end = std::max(h1.q_end, h2.q_end); h1.s_end = std::max(h1.s_end, h2.s_end);
+                if (h2.score > h1.score) {
+                    h1.q_gapped_start = h2.q_gapped_start;
+                    h1.s_gapped_start = h2.s_gapped_start;
+                    h1.score = h2.score;
+                }
+                dead[j] = 1;
+            }
+        }
+        size_t o = 0;
+        for (size_t j = 0; j < fresh.size(); j++) if (!dead[j]) fresh[o++] = fresh[j];
+        fresh.resize(o);
+    }
+    comb.insert(comb.end(), fresh.begin(), fresh.end());
+    fresh.clear();
+    std::stable_sort(comb.begin(), comb.end(), score_less);
+}
+
+void evalues_and_reap(const BnQueryBatch &b, std::vector<BnHSP> &list)
+{
+    size_t o = 0;
+    for (size_t i = 0; i < list.size(); i++) {
+        BnHSP h = list[i];
+        const BnContext &c = b.contexts[h.context];
+        // BLAST_KarlinStoE_simple, core/blast_stat.c:4111-4125
+        h.evalue = (double)c.eff_searchsp * std::exp((double)(-c.gap_lambda * h.score) + c.gap_logK);
+        if (h.evalue > b.evalue_cutoff) continue;
+        list[o++] = h;
+    }
+    list.resize(o);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Hit-list model for the low_score feedback.
+// ------------------------------------------------------------------------------------------------
+namespace {
+typedef HitListKey ListKey;
+
+int fuzzy_cmp(double e1, double e2)     // s_FuzzyEvalueComp, FUZZY_EVALUE_COMPARE_FACTOR 1e-6
+{
+    if (e1 < (1 - 1e-6) * e2) return -1;
+    if (e1 > (1 + 1e-6) * e2) return 1;
+    return 0;
+}
+int list_cmp(const ListKey &a, const ListKey &c)   // s_EvalueCompareHSPLists
+{
+    int r = fuzzy_cmp(a.best_evalue, c.best_evalue);
+    if (r) return r;
+    if (a.best_score > c.best_score) return -1;
+    if (a.best_score < c.best_score) return 1;
+    return (c.oid > a.oid) ? 1 : (c.oid < a.oid ? -1 : 0);
+}
+// s_Heapify / s_CreateHeap (core/blast_hits.c:1470-1521): worst list at the root
+void sift(std::vector<ListKey> &h, size_t base, size_t lim, size_t last)
+{
+    size_t left = 2 * base + 1;
+    while (base <= lim) {
+        size_t large;
+        if (left == last) large = left;
+        else large = list_cmp(h[left], h[left + 1]) >= 0 ? left : left + 1;
+        if (list_cmp(h[base], h[large]) < 0) {
+            std::swap(h[base], h[large]);
+            base = large;
+            left = 2 * base + 1;
+        } else break;
+    }
+}
+void make_heap(std::vector<ListKey> &h)
+{
+    const size_t n = h.size();
+    if (n < 2) return;
+    const size_t lim = (n - 2) / 2, last = n - 1;
+    for (size_t i = n / 2; i > 0; i--) sift(h, i - 1, lim, last);
+}
+}  // namespace
+
+LowScoreTracker::LowScoreTracker(const BnQueryBatch &b)
+{
+    enabled_ = b.low_score_perc > 0.00001;
+    perc_ = b.low_score_perc;
+    // BlastHSPCollectorParamsNew, core/hspfilter_collector.c:335-342 (gapped search)
+    int32_t hs = b.hitlist_size > 0 ? b.hitlist_size : 500;
+    hs = std::min(2 * hs, hs + 50);
+    hitlist_size_ = std::max(hs, 10);
+    low_.assign((size_t)std::max(b.num_queries, 1), 0);
+    states_.resize((size_t)std::max(b.num_queries, 1));
+}
+
+void LowScoreTracker::subject_done(const BnQueryBatch &b, const std::vector<BnHSP> &list)
+{
+    if (!enabled_ || list.empty()) return;
+    // the collector splits the subject's list per query (core/hspfilter_collector.c:104-150);
+    // `list` is sorted by score, so the first HSP of a query is its hsp_array[0]
+    std::vector<int32_t> touched;
+    std::vector<ListKey> keys;
+    std::vector<int32_t> slot((size_t)b.num_queries, -1);
+    for (const BnHSP &h : list) {
+        const int32_t qi = b.contexts[h.context].query_index;
+        if (slot[qi] < 0) {
+            slot[qi] = (int32_t)keys.size();
+            keys.push_back(ListKey{h.evalue, h.score, h.oid});
+            touched.push_back(qi);
+        } else {
+            ListKey &k = keys[slot[qi]];
+            k.best_evalue = std::min(k.best_evalue, h.evalue);
+        }
+    }
+    std::sort(touched.begin(), touched.end());
+    for (int32_t qi : touched) {
+        HitListState &S = states_[qi];
+        const ListKey &k = keys[slot[qi]];
+        if ((int32_t)S.lists.size() < hitlist_size_) {
+            S.lists.push_back(k);
+            S.worst_evalue = std::max(k.best_evalue, S.worst_evalue);
+            S.low_score = std::min(k.best_score, S.low_score);
+        } else {
+            const int order = fuzzy_cmp(k.best_evalue, S.worst_evalue);
+            if (!(order > 0 || (order == 0 && k.best_score < S.low_score))) {
+                if (!S.heapified) { make_heap(S.lists); S.heapified = true; }
+                S.lists[0] = k;
+                if (S.lists.size() >= 2) sift(S.lists, 0, S.lists.size() / 2 - 1, S.lists.size() - 1);
+                S.worst_evalue = S.lists[0].best_evalue;
+                S.low_score = S.lists[0].best_score;
+            }
+        }
+    }
+    // core/blast_engine.c:1313-1320
+    for (size_t qi = 0; qi < states_.size(); qi++) {
+        const HitListState &S = states_[qi];
+        if (S.heapified) {
+            const double v = perc_ * (double)S.low_score;
+            if ((double)low_[qi] < v) low_[qi] = (int32_t)v;
+        }
+    }
+}
+
+}  // namespace bn

@@ -1,0 +1,90 @@
+// hostpost.h — host-side sequential replay that follows the GPU stages.
+//
+// The GPU extends every init-HSP speculatively; this code replays the reference's serial
+// decisions over those precomputed results so the surviving HSP lists are identical:
+//   containment filter   BLAST_GetGappedScore loop        core/blast_gapalign.c:3351-3547
+//   interval tree        BlastIntervalTreeAddHSP/ContainsHSP core/blast_itree.c:545-1000
+//   list post-processing s_BlastSearchEngineOneContext     core/blast_engine.c:503-540
+//   E-values / reap      s_BlastSearchEngineCore           core/blast_engine.c:788-806
+#pragma once
+#include <cstdint>
+#include <vector>
+#include "../../include/gblastn_b200.h"
+
+namespace bn {
+
+struct HostInit {          // one init-HSP with its speculative gapped result
+    int32_t chunk;         // chunk table index
+    int32_t q_off, s_off, q_start, s_start, length, score;
+    uint32_t order;
+    // gapped result
+    int32_t g_q_start, g_q_stop, g_s_start, g_s_stop, g_score, g_q_seed, g_s_seed;
+};
+
+struct HostChunk { int32_t oid, chunk_off, len; };
+
+// Interval tree over (query range, subject range) of saved HSPs; faithful to the reference's
+// node layout and traversal, including its common-endpoint pruning on insertion.
+class IntervalTree {
+public:
+    IntervalTree(int32_t q_min, int32_t q_max, int32_t s_min, int32_t s_max);
+    struct Item { int32_t q_strand_start, q_off, q_end, s_off, s_end, score; };
+    bool contains(const Item &in, int32_t min_diag_separation) const;
+    void add(const Item &in);
+private:
+    struct Node { int32_t leftend, rightend, leftptr, midptr, rightptr, item; };
+    std::vector<Node> nodes_;
+    std::vector<Item> items_;
+    int32_t s_min_, s_max_;
+    int32_t new_root(int32_t lo, int32_t hi);
+    int32_t new_child(int32_t parent, bool left);
+    int32_t new_leaf(int32_t item, int32_t q_strand_start);
+    bool mid_contains(int32_t root, const Item &in, int32_t mds) const;
+    bool has_endpoint(const Item &in, bool right);
+    bool mid_has_endpoint(int32_t root, const Item &in, bool right);
+};
+
+struct PostParams {
+    const BnQueryBatch *batch;      // host copy (contexts, cutoffs, Karlin blocks, options)
+};
+
+// Sort key of Blast_InitHitListSortByScore (core/blast_extend.c:274-296) + emission order.
+void sort_init_hits(std::vector<HostInit> &v);
+
+// Replays BLAST_GetGappedScore for one chunk; appends saved HSPs (chunk-relative subject coords).
+void replay_gapped(const BnQueryBatch &b, const HostChunk &ch, const HostInit *init, size_t n,
+                   const int32_t *low_score, std::vector<BnHSP> &out, BnStats &stats);
+
+// purge common endpoints + odd-score rounding + sort (core/blast_engine.c:507-513)
+void finish_chunk_list(const BnQueryBatch &b, std::vector<BnHSP> &list);
+
+// Blast_HSPListsMerge for a split subject (core/blast_hits.c:2545-2716)
+void merge_chunk_lists(std::vector<BnHSP> &combined, std::vector<BnHSP> &fresh, int32_t split_offset,
+                       int32_t overlap);
+
+// E-values + reap (core/blast_engine.c:788-806)
+void evalues_and_reap(const BnQueryBatch &b, std::vector<BnHSP> &list);
+
+// The hit-list bookkeeping behind hit_params->low_score (core/blast_engine.c:1313-1320,
+// Blast_HitListUpdate core/blast_hits.c:2924-2981): one instance per search.
+struct HitListKey { double best_evalue; int32_t best_score; int32_t oid; };
+struct HitListState {
+    std::vector<HitListKey> lists;
+    bool heapified = false;
+    double worst_evalue = 0.0;
+    int32_t low_score = INT32_MAX;
+};
+class LowScoreTracker {
+public:
+    explicit LowScoreTracker(const BnQueryBatch &b);
+    const int32_t *low_score() const { return enabled_ ? low_.data() : nullptr; }
+    void subject_done(const BnQueryBatch &b, const std::vector<BnHSP> &list);
+private:
+    bool enabled_;
+    int32_t hitlist_size_;
+    double perc_;
+    std::vector<int32_t> low_;
+    std::vector<HitListState> states_;
+};
+
+}  // namespace bn

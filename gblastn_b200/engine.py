@@ -1,0 +1,161 @@
+"""Python binding of libgblastn_b200.so (the C ABI of include/gblastn_b200.h).
+
+The library is the product: this module only marshals numpy arrays into the POD structs.
+There is no fallback — if the shared library is missing, or no CUDA device is usable, calls
+raise (the product path must fail loudly, never route through the oracle).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgblastn_b200.so")
+
+EXPORTS = [
+    "bn_init", "bn_release", "bn_device_count", "bn_last_error", "bn_version",
+    "bn_db_load", "bn_db_free", "bn_query_load", "bn_query_free",
+    "bn_prelim_search", "bn_prelim_search_host", "bn_results_free",
+    "bn_scan_subject", "bn_word_finder", "bn_free", "bn_bench_scan",
+    "bn_setup_create", "bn_setup_batch", "bn_setup_kbp_std", "bn_setup_kbp_gap",
+    "bn_setup_gap_x_dropoff_final", "bn_setup_longest_chain", "bn_setup_free",
+]
+
+
+class BnError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"gblastn_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BnError(-1, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.bn_last_error.restype = C.c_char_p
+        _lib.bn_version.restype = C.c_char_p
+        _lib.bn_setup_batch.restype = C.POINTER(abi.BnQueryBatch)
+        _lib.bn_setup_kbp_std.restype = C.POINTER(C.c_double)
+        _lib.bn_setup_kbp_gap.restype = C.POINTER(C.c_double)
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise BnError(rc, lib().bn_last_error().decode())
+
+
+def init(n_gpu=0, device_ids=None):
+    ids = None
+    if device_ids is not None:
+        ids = (C.c_int * len(device_ids))(*device_ids)
+        n_gpu = len(device_ids)
+    _check(lib().bn_init(C.c_int(n_gpu), ids))
+
+
+def release():
+    lib().bn_release()
+
+
+def device_count() -> int:
+    return int(lib().bn_device_count())
+
+
+class Volume:
+    """A database volume resident in one GPU's HBM."""
+
+    def __init__(self, vol, device=0):
+        self.packed = np.ascontiguousarray(vol.packed, dtype=np.uint8)
+        self.byte_off = np.ascontiguousarray(vol.byte_off, dtype=np.int64)
+        self.seq_len = np.ascontiguousarray(vol.seq_len, dtype=np.int32)
+        h = C.c_int(-1)
+        _check(lib().bn_db_load(C.c_int(device), self.packed.ctypes.data_as(C.c_void_p),
+                                C.c_int64(self.packed.shape[0]),
+                                self.byte_off.ctypes.data_as(C.c_void_p),
+                                self.seq_len.ctypes.data_as(C.c_void_p),
+                                C.c_int32(self.seq_len.shape[0]), C.byref(h)))
+        self.handle = h.value
+        self.device = device
+
+    def free(self):
+        if self.handle >= 0:
+            lib().bn_db_free(C.c_int(self.handle))
+            self.handle = -1
+
+
+class Query:
+    """A query batch (lookup table + parameters) loaded for every device in use."""
+
+    def __init__(self, holder):
+        self.holder = holder       # keeps the numpy arrays alive
+        batch = holder.batch if hasattr(holder, "batch") else holder
+        h = C.c_int(-1)
+        _check(lib().bn_query_load(C.byref(batch), C.byref(h)))
+        self.handle = h.value
+
+    def free(self):
+        if self.handle >= 0:
+            lib().bn_query_free(C.c_int(self.handle))
+            self.handle = -1
+
+
+def _results(res: abi.BnResults) -> dict:
+    try:
+        return {
+            "hsps": abi.struct_array(res.hsps, res.n_hsps, abi.HSP_DTYPE),
+            "init": abi.struct_array(res.init, res.n_init, abi.INIT_DTYPE),
+            "gapped": abi.struct_array(res.gapped, res.n_gapped, abi.HSP_DTYPE),
+            "stats": {k: getattr(res.stats, k) for k, _ in abi.BnStats._fields_},
+        }
+    finally:
+        lib().bn_results_free(C.byref(res))
+
+
+def prelim_search(volume: Volume, query: Query, oid_begin=0, oid_end=-1, taps=0) -> dict:
+    res = abi.BnResults()
+    _check(lib().bn_prelim_search(C.c_int(volume.handle), C.c_int(query.handle),
+                                  C.c_int32(oid_begin), C.c_int32(oid_end), C.c_int(taps),
+                                  C.byref(res)))
+    return _results(res)
+
+
+def prelim_search_host(holder, vol, device=0, taps=0) -> dict:
+    """Reference-facing path: host buffers in, H2D + search + D2H inside the call."""
+    batch = holder.batch if hasattr(holder, "batch") else holder
+    packed = np.ascontiguousarray(vol.packed, dtype=np.uint8)
+    boff = np.ascontiguousarray(vol.byte_off, dtype=np.int64)
+    slen = np.ascontiguousarray(vol.seq_len, dtype=np.int32)
+    res = abi.BnResults()
+    _check(lib().bn_prelim_search_host(C.c_int(device), C.byref(batch),
+                                       packed.ctypes.data_as(C.c_void_p), C.c_int64(packed.shape[0]),
+                                       boff.ctypes.data_as(C.c_void_p), slen.ctypes.data_as(C.c_void_p),
+                                       C.c_int32(slen.shape[0]), C.c_int(taps), C.byref(res)))
+    return _results(res)
+
+
+def scan_subject(volume: Volume, query: Query, oid: int) -> np.ndarray:
+    p = C.POINTER(abi.BnOffsetPair)()
+    n = C.c_int64(0)
+    _check(lib().bn_scan_subject(C.c_int(volume.handle), C.c_int(query.handle), C.c_int32(oid),
+                                 C.c_int32(0), C.c_int32(0), C.byref(p), C.byref(n)))
+    try:
+        return abi.struct_array(p, n.value, abi.PAIR_DTYPE)
+    finally:
+        lib().bn_free(p)
+
+
+def bench_scan(volume: Volume, query: Query, iters: int):
+    ms = C.c_double(0)
+    bases = C.c_int64(0)
+    hits = C.c_int64(0)
+    _check(lib().bn_bench_scan(C.c_int(volume.handle), C.c_int(query.handle), C.c_int(iters),
+                               C.byref(ms), C.byref(bases), C.byref(hits)))
+    return ms.value, bases.value, hits.value

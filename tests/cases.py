@@ -1,0 +1,64 @@
+"""Seeded parity cases shared by the oracle tests (CPU) and the GPU parity tests.
+
+Each case = (task, reference-config overrides, volume spec, query spec).  Sizes are chosen so the
+reference engine and the C port finish in well under a second; the table types, strides, diagonal
+containers and gapped aligners they exercise are listed per case.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from gblastn_b200 import synth
+
+CASES = {
+    # name: dict(task, cfg, seq_lens, vol_seed, nq, qlen, q_seed, sub, indel, planted)
+    # C1 of BASELINE.json: megablast 1 x 10 kb vs 1 Mb -> MB lut 11 / stride 18, hash, greedy
+    "c1_megablast_10kb_vs_1mb": dict(task="megablast", cfg={}, seq_lens=[1_000_000], vol_seed=1,
+                                     nq=1, qlen=10_000, q_seed=11, sub=0.02, indel=0.0, planted=1.0),
+    # many short queries, indels, ragged subject lengths incl. shorter-than-word sequences
+    "mb_lut11_hash_indels": dict(task="megablast", cfg={}, seq_lens=[300_000, 50_000, 777, 120_001, 13, 27, 28, 29],
+                                 vol_seed=2, nq=40, qlen=500, q_seed=12, sub=0.03, indel=0.004, planted=0.8),
+    # small total query -> eSmallNaLookupTable lut 8 / stride 21, diag ARRAY container
+    "mb_smallna_diagarray": dict(task="megablast", cfg={}, seq_lens=[300_000, 50_000, 777, 120_001],
+                                 vol_seed=2, nq=3, qlen=700, q_seed=13, sub=0.05, indel=0.01, planted=1.0),
+    # blastn ws 11 -> MB lut 11 / stride 1 (no mini-extension), hash, packed DP, odd-score rounding
+    "blastn_mb11_dp": dict(task="blastn", cfg={}, seq_lens=[300_000, 50_000, 777, 120_001, 13],
+                           vol_seed=2, nq=30, qlen=800, q_seed=14, sub=0.08, indel=0.01, planted=0.8),
+    # blastn, tiny query -> small table lut 8 / stride 4 (AlignedOneByte), diag array, DP
+    "blastn_smallna_dp": dict(task="blastn", cfg={}, seq_lens=[300_000, 50_000, 777, 120_001],
+                              vol_seed=2, nq=4, qlen=600, q_seed=15, sub=0.08, indel=0.01, planted=1.0),
+    # word size 16 megablast: MB lut 11 / stride 6; word size 12 blastn-like
+    "mb_ws16": dict(task="megablast", cfg={"word_size": 16}, seq_lens=[200_000, 90_000], vol_seed=5,
+                    nq=25, qlen=600, q_seed=16, sub=0.06, indel=0.005, planted=0.8),
+    # word size 27 + large query batch -> lut 12 / stride 16 (byte-aligned scan + ExtendAligned)
+    "mb_ws27_lut12_aligned": dict(task="megablast", cfg={"word_size": 27}, seq_lens=[400_000, 100_000], vol_seed=6,
+                                  nq=160, qlen=1000, q_seed=17, sub=0.02, indel=0.002, planted=0.5),
+    # default megablast with > 300 k table entries -> lut 12 / stride 17 (config C2's table shape)
+    "mb_lut12_stride17": dict(task="megablast", cfg={}, seq_lens=[500_000, 250_000], vol_seed=7,
+                              nq=170, qlen=1000, q_seed=18, sub=0.02, indel=0.002, planted=0.5),
+    # word size 11 megablast scoring with DP turned on / blastn with greedy
+    "blastn_ws11_greedy": dict(task="blastn", cfg={"greedy": 1, "gap_open": 0, "gap_extend": 0},
+                               seq_lens=[150_000, 60_000], vol_seed=8, nq=20, qlen=700, q_seed=19,
+                               sub=0.05, indel=0.005, planted=0.8),
+    # small word sizes on the array container: word_length < 11 exact-extension branch
+    "blastn_ws7_array": dict(task="blastn", cfg={"word_size": 7}, seq_lens=[20_000, 5_000], vol_seed=9,
+                             nq=2, qlen=300, q_seed=20, sub=0.10, indel=0.01, planted=1.0),
+    # queries with ambiguity codes (N) : words containing them are not indexed
+    "mb_with_N": dict(task="megablast", cfg={}, seq_lens=[200_000, 100_000], vol_seed=10,
+                      nq=30, qlen=600, q_seed=21, sub=0.02, indel=0.002, planted=0.9, n_frac=0.004),
+    # empty result: random queries only
+    "mb_no_hits": dict(task="megablast", cfg={}, seq_lens=[100_000], vol_seed=11,
+                       nq=5, qlen=400, q_seed=22, sub=0.0, indel=0.0, planted=0.0),
+}
+
+FAST = ["c1_megablast_10kb_vs_1mb", "mb_lut11_hash_indels", "mb_smallna_diagarray", "blastn_mb11_dp",
+        "blastn_smallna_dp", "mb_ws16", "blastn_ws11_greedy", "blastn_ws7_array", "mb_with_N", "mb_no_hits"]
+ALL = list(CASES.keys())
+
+
+def make_case(name):
+    c = CASES[name]
+    vol = synth.random_volume(c["seq_lens"], seed=c["vol_seed"])
+    qs = synth.planted_queries(vol, c["nq"], c["qlen"], seed=c["q_seed"], planted_frac=c["planted"],
+                               sub_rate=c["sub"], indel_rate=c["indel"], n_frac=c.get("n_frac", 0.0))
+    return c["task"], dict(c["cfg"]), vol, qs

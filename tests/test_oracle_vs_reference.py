@@ -1,0 +1,57 @@
+"""The C port (oracle/port) against the reference engine itself (oracle/_ref), tap by tap.
+
+This is what pins the oracle: scan pairs, init-HSPs, per-chunk gapped lists and the final
+per-subject lists with E-value bit patterns must all be identical.
+Skipped where the reference sources are not available (oracle/_ref is built from /root/reference).
+"""
+import numpy as np
+import pytest
+
+from tests import cases
+
+
+def _both(name, built):
+    from oracle import refdriver as R, portdriver as P
+    if not R.available():
+        pytest.skip("oracle/_ref/libblastref.so not built (needs /root/reference)")
+    task, cfgkw, vol, qs = cases.make_case(name)
+    cfg = R.default_config(task, taps=R.TAP_SCAN | R.TAP_INIT | R.TAP_GAPPED | R.TAP_LUT, **cfgkw)
+    r = R.search(qs, vol, cfg)
+    assert r["status"] == 0
+    h = P.batch_from_reference(r, task=task, cfg=cfg)
+    p = P.search(h, vol, taps=P.TAP_SCAN | P.TAP_INIT | P.TAP_GAPPED)
+    assert p["status"] == 0
+    return r, p
+
+
+@pytest.mark.parametrize("name", cases.ALL)
+def test_port_matches_reference(name, built):
+    from oracle import portdriver as P
+    r, p = _both(name, built)
+    scan = np.stack([p["scan_oid"], p["scan_chunk"], p["scan"]["q_off"].astype(np.int32),
+                     p["scan"]["s_off"].astype(np.int32)], axis=1) if p["scan"].size else np.zeros((0, 4), np.int32)
+    assert np.array_equal(r["scan"], scan), "scan tap differs"
+    assert np.array_equal(r["init"], P.init_table(p["init"])), "init-HSP tap differs"
+    assert np.array_equal(r["gapped"], P.gapped_table(p["gapped"])), "gapped tap differs"
+    assert np.array_equal(r["final"], P.final_table(p["hsps"])), "final lists / E-value bits differ"
+    st = p["stats"]
+    assert (st["lookup_hits"], st["init_extends"], st["good_init_extends"], st["gap_extensions"],
+            st["good_extensions"]) == (r["lookup_hits"], r["init_extends"], r["good_init_extends"],
+                                       r["gap_extensions"], r["good_extensions"])
+
+
+def test_cases_exercise_every_table_shape(built):
+    """The case list must keep covering MB lut 11/12, small table, both containers, both aligners."""
+    from oracle import refdriver as R
+    if not R.available():
+        pytest.skip("reference not built")
+    seen = set()
+    for name in cases.ALL:
+        task, cfgkw, vol, qs = cases.make_case(name)
+        r = R.search(qs, vol, R.default_config(task, **cfgkw))
+        seen.add((r["lut_type"], r["lut_word_length"], r["scan_step"] % 4 == 0, r["container_type"]))
+    assert any(s[0] == 0 and s[1] == 11 for s in seen)
+    assert any(s[0] == 0 and s[1] == 12 for s in seen)
+    assert any(s[0] == 1 for s in seen)
+    assert {s[3] for s in seen} == {0, 1}
+    assert any(s[2] for s in seen) and any(not s[2] for s in seen)
