@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py — Gbases/s of subject scanned by the blastn preliminary-search hot path.
+
+Workload at N=1: BASELINE.json configs[1] — megablast, 1 000 x 1 kb synthetic queries (80 % planted,
+2 % substitutions, half reverse-complemented) vs a 250 Mb synthetic DB (one chr1-sized sequence,
+split at MAX_DBSEQ_LEN like the reference does).  At N>1 every rank owns one volume of the same
+shape (volume sharding, weak scaling, no collective on the data path).
+
+A "step" = one pass of the whole preliminary stage (scan -> mini-extension -> diagonal/ungapped ->
+gapped score-only -> host replay -> E-values) of one query batch over one resident volume.
+  value : subject bases scanned / second, volume + query tables already resident in HBM
+  e2e   : same, through the host-buffer entry point (H2D of the packed volume and the query
+          tables from pinned memory, search, D2H of results inside the timed region)
+  roofline : scan kernel alone, algorithmic bytes = 0.25 B per subject base
+  cpu_baseline : the reference engine (oracle/_ref, compiled from the reference's own sources)
+          on this box's host cores, same inputs
+
+`--impl reference` times the reference's own CPU implementation of the path instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from gblastn_b200 import synth  # noqa: E402
+
+METRIC = "Gbases/s subject scanned (megablast) at 1/2/4/8 B200; HSPs bit-exact vs blastn"
+UNIT = "Gbases/s"
+N_QUERIES, QUERY_LEN, DB_BASES = 1000, 1000, 250_000_000
+WORKLOAD = "megablast: 1000x1kb synthetic queries vs 250Mb synthetic DB (BASELINE configs[1])"
+
+
+def make_workload(rank: int):
+    vol = synth.random_volume([DB_BASES], seed=2 + 1000 * rank)
+    qs = synth.planted_queries(vol, N_QUERIES, QUERY_LEN, seed=22 + 1000 * rank, planted_frac=0.8,
+                               sub_rate=0.02, rc_frac=0.5)
+    return vol, qs
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+def scan_traffic():
+    """dram bytes per scan launch from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "scan_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.index = index
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip().splitlines()
+                if out:
+                    f = [x.strip() for x in out[0].split(",")]
+                    self.samples.append(float(f[0]))
+                    self.max_mhz = float(f[1])
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                        "sw_power_cap"), f[2:6]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path (oracle/_ref) on the host cores."""
+    if rank != 0:
+        return
+    from oracle import refdriver as R
+    if not R.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libblastref.so was not built"}))
+        return
+    vol, qs = make_workload(0)
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, vol.n_seqs))
+    cfg = R.default_config("megablast", num_threads=threads)
+    times = []
+    for i in range(args.warmup + args.steps):
+        r = R.search(qs, vol, cfg)
+        assert r["status"] == 0
+        if i >= args.warmup:
+            times.append(r["seconds_prelim"])
+    total = float(sum(times))
+    value = DB_BASES * len(times) / total / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic", "config": {"workload": WORKLOAD},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
+                         "sample": f"full workload per step; reference parallelises over subject "
+                                   f"sequences only, the DB has {vol.n_seqs} -> {threads} thread(s) of {cores} cores"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gblastn_b200", choices=["gblastn_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from gblastn_b200 import engine, setup, abi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    vol, qs = make_workload(rank)
+    # packed volume in pinned host memory (source of the e2e H2D copies)
+    pinned = torch.empty(vol.packed.shape[0], dtype=torch.uint8).pin_memory()
+    pinned.numpy()[:] = vol.packed
+    vol.packed = pinned.numpy()
+
+    engine.init(0, [local_rank])
+    s = setup.Setup(qs, task="megablast", db_length=vol.total_bases, db_num_seqs=vol.n_seqs)
+    V = engine.Volume(vol, device=0)
+    Q = engine.Query(s.batch)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def l2_flush():
+        flush.fill_(1)
+        torch.cuda.synchronize()
+
+    # ---- resident-input throughput -----------------------------------------------------------------
+    for _ in range(args.warmup):
+        g = engine.prelim_search(V, Q)
+    launches = 0
+    step_ms = []
+    stage = {"ms_scan": 0.0, "ms_extend": 0.0, "ms_gapped": 0.0, "ms_host": 0.0}
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        for _ in range(args.steps):
+            l2_flush()
+            barrier()
+            t0 = time.perf_counter()
+            g = engine.prelim_search(V, Q)
+            torch.cuda.synchronize()
+            step_ms.append(1e3 * (time.perf_counter() - t0))
+            launches += g["stats"]["kernel_launches"]
+            for k in stage:
+                stage[k] += g["stats"][k]
+        # ---- end to end through the host-buffer entry point --------------------------------------
+        e2e_ms = []
+        for i in range(3 + args.steps):
+            l2_flush()
+            barrier()
+            t0 = time.perf_counter()
+            ge = engine.prelim_search_host(s.batch, vol, device=0)
+            torch.cuda.synchronize()
+            if i >= 3:
+                e2e_ms.append(1e3 * (time.perf_counter() - t0))
+        # ---- scan kernel alone (roofline) -----------------------------------------------------------
+        engine.bench_scan(V, Q, 3)
+        scan_ms, scan_bases, survivors = engine.bench_scan(V, Q, max(args.steps, 10))
+    total_ms = float(sum(step_ms))
+    total_e2e_ms = float(sum(e2e_ms))
+    t = torch.tensor([total_ms, total_e2e_ms, scan_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, total_e2e_ms, scan_ms_max = [float(x) for x in t.tolist()]
+    bases_per_step = int(g["stats"]["subject_bases_scanned"])
+    value = world * bases_per_step * args.steps / (total_ms * 1e-3) / 1e9
+    e2e_value = world * bases_per_step * len(e2e_ms) / (total_e2e_ms * 1e-3) / 1e9
+
+    b = s.batch
+    h2d = int(vol.packed.shape[0] + 4 * b.hashsize + 4 * (b.concat_len + 1) + b.hashsize // 8 +
+              (b.concat_len + 2) + 32 * b.num_contexts + 2048)
+    d2h = int(ge["hsps"].size * abi.HSP_DTYPE.itemsize + g["stats"]["good_init_extends"] * (32 + 32) + 64)
+
+    peak, peak_kind = peak_hbm()
+    achieved = scan_bases * 0.25 / (scan_ms * 1e-3) / 1e9      # GB/s of algorithmic bytes
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "volumes": world, "l2": "flushed between timed steps (256 MiB write)",
+                   "lut": f"MB lut {b.lut_word_length} / stride {b.scan_step}", "hsps_per_step": int(g["hsps"].size)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": scan_traffic(), "kernel": "bn::scan_kernel",
+                     "peak_kind": peak_kind, "ms_per_launch": scan_ms,
+                     "algorithmic_bytes_per_launch": scan_bases * 0.25},
+        "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
+        "clocks": clk.summary(),
+    }
+
+    # ---- CPU baseline (reference engine on the host cores), rank 0 at N=1 only --------------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import refdriver as R, portdriver as P
+            if R.available():
+                cores = os.cpu_count() or 1
+                threads = max(1, min(cores, vol.n_seqs))
+                cfg = R.default_config("megablast", num_threads=threads)
+                secs, reps = 0.0, 0
+                t_begin = time.perf_counter()
+                while reps < 3 or (time.perf_counter() - t_begin < 10.0 and reps < 40):
+                    r = R.search(qs, vol, cfg)
+                    secs += r["seconds_prelim"]
+                    reps += 1
+                line["cpu_baseline"] = {
+                    "value": DB_BASES * reps / secs / 1e9, "unit": UNIT, "cores": threads, "kind": "reference",
+                    "sample": f"{reps} repeats of the full workload (prelim stage only); the reference "
+                              f"parallelises over subject sequences, DB has {vol.n_seqs} -> {threads} thread"}
+                line["parity_vs_reference"] = bool(np.array_equal(P.final_table(g["hsps"]), r["final"]))
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                                        "sample": "oracle/_ref/libblastref.so not present on this box"}
+        except Exception as e:  # the baseline must never take the bench down
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                                    "sample": f"failed: {e}"}
+    if rank == 0:
+        print(json.dumps(line))
+    Q.free()
+    V.free()
+    s.free()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
