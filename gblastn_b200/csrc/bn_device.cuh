@@ -42,6 +42,7 @@ struct DevQuery {
     const int16_t *backbone, *overflow;    // SmallNa
     int32_t has_locations;                 // lut->masked_locations != NULL
     int32_t container_type, window_size, scan_range;
+    const uint2 *qpk;                      // 2-bit packed query windows: .x bases, .y ambiguity (see qwin)
     const int32_t *score_table;            // 256
     const int32_t *matrix;                 // 16 x 16
     int32_t gap_algo, reward, penalty, gap_open, gap_extend, gap_x_dropoff;
@@ -75,6 +76,71 @@ __device__ __forceinline__ uint32_t be32(const uint8_t *p)
 {
     return ((uint32_t)__ldg(p) << 24) | ((uint32_t)__ldg(p + 1) << 16) |
            ((uint32_t)__ldg(p + 2) << 8) | (uint32_t)__ldg(p + 3);
+}
+
+// ---- 16-base windows -------------------------------------------------------------------------
+// Both sequences are compared 16 bases at a time.  A window is a 32-bit word with base j of the
+// window in bits 31-2j..30-2j (the subject's own ncbi2na bit order, inc-core/blast_util.h:52-55).
+//
+// Query: qpk[i] covers concatenated-query positions 16*(i-1) .. 16*(i-1)+15 (one leading pad word
+// so that the sentinel at -1 and reverse windows are addressable); .x = 2-bit bases, .y = 01 in the
+// base's bit pair when the blastna code is >= 4 (ambiguity / sentinel) or the position lies outside
+// the buffer.  Built on the host at bn_query_load from the bytes the reference uses.
+__device__ __forceinline__ void qwin(const DevQuery &q, int32_t pos, uint32_t &bases, uint32_t &amb)
+{
+    const int32_t a = pos + 16;
+    const uint2 w0 = __ldg(&q.qpk[a >> 4]);
+    const uint2 w1 = __ldg(&q.qpk[(a >> 4) + 1]);
+    const uint32_t sh = (uint32_t)(a & 15) * 2;
+    bases = __funnelshift_l(w1.x, w0.x, sh);
+    amb = __funnelshift_l(w1.y, w0.y, sh);
+}
+
+// Subject: `packed` is the volume base (4-byte aligned, >= 64 readable bytes in front of it),
+// abs_base = 4 * byte offset of the chunk + position inside the chunk (may be negative).
+__device__ __forceinline__ uint32_t swin(const uint8_t *packed, int64_t abs_base)
+{
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(packed) + (abs_base >> 4);
+    const uint32_t a = __byte_perm(__ldg(w), 0, 0x0123);
+    const uint32_t b = __byte_perm(__ldg(w + 1), 0, 0x0123);
+    return __funnelshift_l(b, a, (uint32_t)(abs_base & 15) * 2);
+}
+
+// one bit (the low bit of each pair) per mismatching base of two windows
+__device__ __forceinline__ uint32_t mismatch_bits(uint32_t qb, uint32_t qamb, uint32_t sb)
+{
+    const uint32_t x = qb ^ sb;
+    return ((x | (x >> 1)) & 0x55555555u) | qamb;
+}
+
+// number of equal bases query[qpos + t] == subject[spos + t], t = 0 .. n-1, before the first mismatch
+__device__ __forceinline__ int32_t match_run_fwd(const DevQuery &q, const uint8_t *packed, int32_t qpos,
+                                                 int64_t spos, int32_t n)
+{
+    int32_t cnt = 0;
+    while (cnt < n) {
+        uint32_t qb, qa;
+        qwin(q, qpos + cnt, qb, qa);
+        const uint32_t m = mismatch_bits(qb, qa, swin(packed, spos + cnt));
+        if (m) return min(cnt + (__clz(m) >> 1), n);
+        cnt += 16;
+    }
+    return n;
+}
+
+// number of equal bases query[qend - 1 - t] == subject[send - 1 - t], t = 0 .. n-1
+__device__ __forceinline__ int32_t match_run_rev(const DevQuery &q, const uint8_t *packed, int32_t qend,
+                                                 int64_t send, int32_t n)
+{
+    int32_t cnt = 0;
+    while (cnt < n) {
+        uint32_t qb, qa;
+        qwin(q, qend - cnt - 16, qb, qa);
+        const uint32_t m = mismatch_bits(qb, qa, swin(packed, send - cnt - 16));
+        if (m) return min(cnt + ((__ffs(m) - 1) >> 1), n);
+        cnt += 16;
+    }
+    return n;
 }
 
 // BSearchContextInfo (core/blast_query_info.c:220-236)
@@ -111,11 +177,11 @@ struct ExtendLaunch {
     const uint32_t *order;        // emission rank of hits[i]
     int32_t *cells;               // hash: 4 ints per cell, one region per group (same offsets as hits)
     DevInitHit *init;
-    unsigned long long *counters; // [2] = #init hits, [3] = #extended
+    unsigned long long *counters; // [2] = #init hits, [3] = #extended, [4] = #groups
     int64_t init_capacity;
 };
 cudaError_t launch_extend_groups(const DevQuery &q, const ExtendLaunch &e, const uint64_t *group_key,
-                                 int64_t n_hits, cudaStream_t st);
+                                 uint32_t *heads, int64_t n_hits, cudaStream_t st);
 cudaError_t launch_group_keys(const DevQuery &q, const SeedHit *hits, const uint32_t *perm, int64_t n,
                               int32_t diag_array_length, uint64_t *keys, cudaStream_t st);
 cudaError_t launch_gather_hits(const SeedHit *in, const uint32_t *perm, int64_t n, SeedHit *out,

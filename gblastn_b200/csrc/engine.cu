@@ -53,7 +53,7 @@ struct DevBuf {
 struct Workspace {
     DevBuf<SeedHit> hits_a, hits_b;
     DevBuf<uint64_t> keys_a, keys_b, gkeys_a, gkeys_b;
-    DevBuf<uint32_t> perm_a, perm_b, order_a, order_b;
+    DevBuf<uint32_t> perm_a, perm_b, order_a, order_b, heads;
     DevBuf<int4> cells;
     DevBuf<DevInitHit> init;
     DevBuf<DevGapResult> gap_out;
@@ -65,7 +65,7 @@ struct Workspace {
     {
         hits_a.release(); hits_b.release(); keys_a.release(); keys_b.release(); gkeys_a.release();
         gkeys_b.release(); perm_a.release(); perm_b.release(); order_a.release(); order_b.release();
-        cells.release(); init.release(); gap_out.release(); scratch.release(); todo.release();
+        cells.release(); heads.release(); init.release(); gap_out.release(); scratch.release(); todo.release();
         counters.release(); cub_temp.release();
         if (h_counters) cudaFreeHost(h_counters);
         h_counters = nullptr;
@@ -91,7 +91,8 @@ struct ChunkTable {
 
 struct Volume {
     int device = 0;
-    uint8_t *d_packed = nullptr;
+    uint8_t *d_raw = nullptr;      // allocation
+    uint8_t *d_packed = nullptr;   // d_raw + 64
     int64_t bytes = 0;
     std::vector<int64_t> byte_off;
     std::vector<int32_t> seq_len;
@@ -105,6 +106,7 @@ struct QueryDev {
     uint32_t *presence = nullptr;
     int16_t *backbone = nullptr, *overflow = nullptr;
     int32_t *score_table = nullptr, *matrix = nullptr;
+    uint2 *qpk = nullptr;
     DevQuery view{};
     bool ready = false;
 };
@@ -117,6 +119,7 @@ struct Query {
     std::vector<uint32_t> presence;
     std::vector<int16_t> backbone, overflow;
     std::vector<int32_t> masked;
+    std::vector<uint2> qpk;               // 16-base query windows (bn_device.cuh: qwin)
     std::vector<QueryDev> dev;            // per device
     int32_t diag_array_length = 1;
     int32_t max_query_length = 0;
@@ -145,7 +148,7 @@ static void free_query_dev(QueryDev &q)
 {
     cudaFree(q.query); cudaFree(q.ctx); cudaFree(q.hashtable); cudaFree(q.next_pos);
     cudaFree(q.presence); cudaFree(q.backbone); cudaFree(q.overflow); cudaFree(q.score_table);
-    cudaFree(q.matrix);
+    cudaFree(q.matrix); cudaFree(q.qpk);
     q = QueryDev{};
 }
 
@@ -184,6 +187,7 @@ static int query_to_device(Query &Q, int d)
     }
     CU_TRY(upload(&qd.score_table, b.nucl_score_table, (size_t)256, dev->stream));
     CU_TRY(upload(&qd.matrix, b.matrix, (size_t)256, dev->stream));
+    CU_TRY(upload(&qd.qpk, Q.qpk.data(), Q.qpk.size(), dev->stream));
     CU_TRY(cudaStreamSynchronize(dev->stream));
 
     DevQuery &v = qd.view;
@@ -196,7 +200,7 @@ static int query_to_device(Query &Q, int d)
     v.backbone = qd.backbone; v.overflow = qd.overflow;
     v.has_locations = b.masked_locations != nullptr;
     v.container_type = b.container_type; v.window_size = b.window_size; v.scan_range = b.scan_range;
-    v.score_table = qd.score_table; v.matrix = qd.matrix;
+    v.score_table = qd.score_table; v.matrix = qd.matrix; v.qpk = qd.qpk;
     v.gap_algo = b.gap_algo; v.reward = b.reward; v.penalty = b.penalty;
     v.gap_open = b.gap_open; v.gap_extend = b.gap_extend; v.gap_x_dropoff = b.gap_x_dropoff;
     qd.ready = true;
@@ -366,6 +370,7 @@ static int run_word_finder(Device &D, Volume &V, Query &Q, ChunkTable &T, bool r
     if (rc) return rc;
     CU_TRY(launch_gather_hits(ws.hits_b.p, ws.order_b.p, n, ws.hits_a.p, st));  // hits_a: grouped
     CU_TRY(ws.cells.reserve((size_t)n + 2));
+    CU_TRY(ws.heads.reserve((size_t)n + 1));
     if (stats) stats->kernel_launches += 5;
 
     // 3) replay groups
@@ -373,13 +378,13 @@ static int run_word_finder(Device &D, Volume &V, Query &Q, ChunkTable &T, bool r
     for (int attempt = 0;; attempt++) {
         CU_TRY(ws.init.reserve((size_t)init_cap));
         init_cap = (int64_t)ws.init.cap;
-        CU_TRY(cudaMemsetAsync(ws.counters.p + 2, 0, 2 * sizeof(unsigned long long), st));
+        CU_TRY(cudaMemsetAsync(ws.counters.p + 2, 0, 3 * sizeof(unsigned long long), st));
         ExtendLaunch e{};
         e.packed = V.d_packed; e.chunks = T.dev.p; e.hits = ws.hits_a.p; e.order = ws.order_b.p;
         e.cells = reinterpret_cast<int32_t *>(ws.cells.p); e.init = ws.init.p;
         e.counters = ws.counters.p; e.init_capacity = init_cap;
-        CU_TRY(launch_extend_groups(dq, e, ws.gkeys_b.p, n, st));
-        if (stats) stats->kernel_launches += 1;
+        CU_TRY(launch_extend_groups(dq, e, ws.gkeys_b.p, ws.heads.p, n, st));
+        if (stats) stats->kernel_launches += 2;
         CU_TRY(cudaMemcpyAsync(ws.h_counters, ws.counters.p, 8 * sizeof(unsigned long long),
                                cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
@@ -596,7 +601,7 @@ void bn_release(void)
     g_queries.clear();
     for (auto &v : g_volumes) if (v) {
         cudaSetDevice(g_devices[v->device]->id);
-        cudaFree(v->d_packed);
+        cudaFree(v->d_raw);
         for (auto &kv : v->tables) { kv.second->dev.release(); kv.second->block_chunk.release(); }
     }
     g_volumes.clear();
@@ -633,9 +638,12 @@ int bn_db_load(int device, const uint8_t *packed, int64_t packed_bytes, const in
     V->byte_off.assign(seq_byte_off, seq_byte_off + n_seq);
     V->seq_len.assign(seq_len, seq_len + n_seq);
     CU_TRY(cudaSetDevice(D->id));
-    CU_TRY(cudaMalloc(&V->d_packed, (size_t)packed_bytes + 64));
+    // 64 readable bytes in front (reverse 16-base windows may start before the first base) and behind
+    CU_TRY(cudaMalloc(&V->d_raw, (size_t)packed_bytes + 192));
+    V->d_packed = V->d_raw + 64;
+    CU_TRY(cudaMemsetAsync(V->d_raw, 0, 64, D->stream));
     CU_TRY(cudaMemcpyAsync(V->d_packed, packed, (size_t)packed_bytes, cudaMemcpyHostToDevice, D->stream));
-    CU_TRY(cudaMemsetAsync(V->d_packed + packed_bytes, 0, 64, D->stream));
+    CU_TRY(cudaMemsetAsync(V->d_packed + packed_bytes, 0, 128, D->stream));
     CU_TRY(cudaStreamSynchronize(D->stream));
     std::lock_guard<std::mutex> lk(g_mu);
     g_volumes.push_back(std::move(V));
@@ -649,7 +657,7 @@ int bn_db_free(int h)
     if (h < 0 || h >= (int)g_volumes.size() || !g_volumes[h]) return fail(BN_ERR_INVALID, "bn_db_free: bad handle");
     Volume &V = *g_volumes[h];
     cudaSetDevice(g_devices[V.device]->id);
-    cudaFree(V.d_packed);
+    cudaFree(V.d_raw);
     for (auto &kv : V.tables) { kv.second->dev.release(); kv.second->block_chunk.release(); }
     g_volumes[h].reset();
     return BN_OK;
@@ -685,6 +693,20 @@ int bn_query_load(const BnQueryBatch *b, int *query_handle)
         Q->backbone.assign(b->backbone, b->backbone + b->hashsize);
         if (b->overflow && b->overflow_len > 0) Q->overflow.assign(b->overflow, b->overflow + b->overflow_len);
         else Q->overflow.assign(2, (int16_t)-1);
+    }
+    {   // 16-base windows of the query: 2-bit bases + ambiguity flags, one leading pad word
+        const size_t nw = (size_t)((b->concat_len + 2 + 16) >> 4) + 3;
+        Q->qpk.assign(nw, make_uint2(0u, 0u));
+        for (size_t i = 0; i < nw; i++) {
+            uint32_t bases = 0, amb = 0;
+            for (int j = 0; j < 16; j++) {
+                const int64_t pos = 16 * ((int64_t)i - 1) + j;
+                const uint8_t code = (pos >= -1 && pos <= b->concat_len) ? Q->query[(size_t)(pos + 1)] : 15;
+                bases |= (uint32_t)(code & 3) << (30 - 2 * j);
+                amb |= (uint32_t)(code >= 4 ? 1u : 0u) << (30 - 2 * j);
+            }
+            Q->qpk[i] = make_uint2(bases, amb);
+        }
     }
     if (b->masked_locations && b->n_masked_locations > 0)
         Q->masked.assign(b->masked_locations, b->masked_locations + 2 * (size_t)b->n_masked_locations);

@@ -15,90 +15,220 @@
 //                 a chain's content depend on the order of all insertions into that bucket
 //                                                                  -> independent per bucket
 // so hits are grouped by cell / bucket, kept in the reference's emission order inside a group, and
-// one thread replays its group's hits serially, doing the ungapped extension inline (its result
-// feeds the next hit's test).  The hash chains are bit-faithful: same prepend-at-head, same
-// overwrite-first-stale-cell rule, same carry-over from earlier subjects (BLAST_DiagHash::offset
-// grows, core/blast_extend.c:164-186) and the same reset when offset passes INT4_MAX/4.
+// ONE WARP replays a group serially.  The warp runs the control flow uniformly (all lanes hold the
+// same values); the ungapped extension — the expensive, data-dependent part — is spread over the
+// 32 lanes: the serial recurrence
+//        sum += s_k;  if (sum > 0) { score += sum; sum = 0; best = k; }  if (sum < X) break;
+// is the same as "T_k = prefix sum, M_k = running (strict) maximum of T, stop at the first k with
+// T_k - M_k < X, report M and the first position where it was reached", which is computed per
+// block of 32 lanes x (4 four-base steps | 16 bases) with two warp scans.  Sequences are compared
+// as 16-base windows (bn_device.cuh); windows touching an ambiguous / sentinel query base take the
+// byte-exact slow path so garbage-in semantics of the reference are preserved.
+// The hash chains are bit-faithful: prepend at head, overwrite the first stale cell, carry-over
+// across subjects through `offset`, reset when offset passes INT4_MAX/4 (chunk table epochs).
 #include "bn_device.cuh"
 
 namespace bn {
 
+constexpr int EXT_WARPS_PER_BLOCK = 4;
+constexpr int EXT_BLOCKS = 148 * 4;
+constexpr unsigned FULL = 0xffffffffu;
+
 struct Ungapped { int32_t q_start, s_start, length, score; };
 
-// s_NuclUngappedExtendExact
-__device__ void ungapped_exact(const DevQuery &q, const uint8_t *S, int32_t slen, int32_t q_off,
-                               int32_t s_off, int32_t X, Ungapped &u)
+// ---- warp scans ---------------------------------------------------------------------------------
+__device__ __forceinline__ long long warp_excl_sum(long long v, int lane, long long &total)
 {
-    const uint8_t *query = q.query;
-    int32_t sum = 0, score = 0;
-    int32_t qp = q_off, q_beg = q_off, q_end = q_off;
-    const int32_t q_avail = q.concat_len - q_off, s_avail = slen - s_off;
-    const int32_t s_lo = (q_off < s_off) ? s_off - q_off : 0;
-    int32_t sp = s_off;
-    while (sp > s_lo) {
-        --sp; --qp;
-        sum += __ldg(&q.matrix[16 * (int)__ldg(query + qp) + sbase(S, sp)]);
-        if (sum > 0) { q_beg = qp; score += sum; sum = 0; }
-        else if (sum < X) break;
+    long long x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        long long y = __shfl_up_sync(FULL, x, o);
+        if (lane >= o) x += y;
     }
-    u.q_start = q_beg;
-    u.s_start = s_off - (q_off - q_beg);
-    const int32_t s_hi = (q_avail < s_avail) ? s_off + q_avail : slen;
-    qp = q_off; sp = s_off; sum = 0;
-    while (sp < s_hi) {
-        sum += __ldg(&q.matrix[16 * (int)__ldg(query + qp) + sbase(S, sp)]);
-        ++qp; ++sp;
-        if (sum > 0) { q_end = qp; score += sum; sum = 0; }
-        else if (sum < X) break;
+    total = __shfl_sync(FULL, x, 31);
+    return x - v;
+}
+__device__ __forceinline__ long long warp_excl_max(long long v, int lane, long long identity)
+{
+    long long x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        long long y = __shfl_up_sync(FULL, x, o);
+        if (lane >= o) x = max(x, y);
     }
-    u.length = q_end - q_beg;
-    u.score = score;
+    long long e = __shfl_up_sync(FULL, x, 1);
+    return lane == 0 ? identity : e;
 }
 
-__device__ __forceinline__ uint32_t qbyte(const uint8_t *query, int32_t p)
+// State of one direction of an X-drop walk, uniform across the warp.
+struct Walk {
+    long long T;       // running total
+    long long M;       // running strict maximum (starts at 0: "no improvement yet")
+    int32_t best;      // index of the step that set M, -1 if none
+    bool stopped;
+};
+
+// Consume one block of per-lane step values.  v[0..cnt) are this lane's consecutive steps, the
+// lane's first step has global index k0.  NV = steps per lane.  Returns with W updated; W.stopped
+// set when the X-drop test fired inside the block.
+template <int NV>
+__device__ __forceinline__ void walk_block(Walk &W, const int32_t (&v)[NV], int cnt, int32_t k0, int32_t X,
+                                           int lane)
 {
-    // (q[0] << 6) | (q[1] << 4) | (q[2] << 2) | q[3], truncated to 8 bits like the reference's Uint1
+    long long S = 0, P = LLONG_MIN;
+#pragma unroll
+    for (int j = 0; j < NV; j++)
+        if (j < cnt) { S += v[j]; P = max(P, S); }
+    long long total;
+    const long long off = warp_excl_sum(S, lane, total);
+    const long long Tstart = W.T + off;
+    const long long cand = (cnt > 0) ? Tstart + P : LLONG_MIN;
+    const long long Mstart = max(W.M, warp_excl_max(cand, lane, LLONG_MIN));
+    // second pass with the true running values
+    long long T = Tstart, M = Mstart;
+    int32_t arg = -1;
+    int brk = -1;
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+        if (j < cnt && brk < 0) {
+            T += v[j];
+            if (T > M) { M = T; arg = k0 + j; }
+            if (T - M < (long long)X) brk = j;
+        }
+    }
+    const unsigned bmask = __ballot_sync(FULL, brk >= 0);
+    const int last_lane = bmask ? (__ffs(bmask) - 1) : 31;
+    const unsigned raised = __ballot_sync(FULL, arg >= 0) & (last_lane == 31 ? FULL : ((2u << last_lane) - 1));
+    if (raised) {
+        const int src = 31 - __clz(raised);
+        W.best = __shfl_sync(FULL, arg, src);
+    }
+    W.M = __shfl_sync(FULL, M, last_lane);
+    W.T = __shfl_sync(FULL, T, last_lane);   // only meaningful when not stopped
+    W.stopped = bmask != 0;
+}
+
+// ---- approximate extension: 4 bases per step (s_NuclUngappedExtend) ------------------------------
+// raw 4-base byte of the query exactly as the reference builds it (values >= 4 overlap bit fields)
+__device__ __forceinline__ uint32_t qbyte_raw(const uint8_t *query, int32_t p)
+{
     return (((uint32_t)__ldg(query + p) << 6) | ((uint32_t)__ldg(query + p + 1) << 4) |
             ((uint32_t)__ldg(query + p + 2) << 2) | (uint32_t)__ldg(query + p + 3)) & 0xFFu;
 }
 
-// s_NuclUngappedExtend
-__device__ void ungapped_extend(const DevQuery &q, const uint8_t *S, int32_t slen, int32_t q_off,
-                                int32_t s_match_end, int32_t s_off, int32_t X, int32_t reduced_cutoff,
-                                Ungapped &u)
+// Right: steps k = 0.. cover query [q_ext + 4k, q_ext + 4k + 4), subject bytes from s_ext (4-aligned).
+// Left : steps k = 0.. cover query [q_ext - 4k - 4, q_ext - 4k).
+template <bool RIGHT>
+__device__ void approx_walk(const DevQuery &q, const uint8_t *packed, int64_t chunk_base,
+                            const int32_t *s_tab, int32_t q_ext, int32_t s_ext, int32_t nsteps, int32_t X,
+                            int lane, Walk &W)
 {
-    const uint8_t *query = q.query;
-    int32_t len = (4 - (s_off % 4)) % 4;
-    const int32_t q_ext = q_off + len, s_ext = s_off + len;
-    int32_t qp = q_ext, sb = s_ext / 4;
-    int32_t sum = 0, score = 0, new_q = q_ext;
-
-    len = min(q_ext, s_ext) / 4;
-    for (int32_t i = 0; i < len; --sb, qp -= 4, ++i) {
-        sum += __ldg(&q.score_table[qbyte(query, qp - 4) ^ (uint32_t)__ldg(S + sb - 1)]);
-        if (sum > 0) { new_q = qp - 4; score += sum; sum = 0; }
-        if (sum < X) break;
+    W.T = 0; W.M = 0; W.best = -1; W.stopped = false;
+    for (int32_t base = 0; base < nsteps && !W.stopped; base += 128) {
+        const int32_t k0 = base + 4 * lane;
+        const int cnt = max(0, min(4, nsteps - k0));
+        int32_t v[4] = {0, 0, 0, 0};
+        if (cnt > 0) {
+            const int32_t qpos = RIGHT ? q_ext + 4 * k0 : q_ext - 4 * k0 - 16;
+            const int64_t spos = chunk_base + (RIGHT ? (int64_t)s_ext + 4 * k0 : (int64_t)s_ext - 4 * k0 - 16);
+            uint32_t qb, qa;
+            qwin(q, qpos, qb, qa);
+            const uint32_t sb = swin(packed, spos);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (j >= cnt) break;
+                // step j of this lane = byte j of the window (right) or byte 3-j (left)
+                const int byte = RIGHT ? j : 3 - j;
+                const uint32_t sh = 24 - 8 * byte;
+                uint32_t qq = (qb >> sh) & 0xFFu;
+                if ((qa >> sh) & 0xFFu) qq = qbyte_raw(q.query, qpos + 4 * byte);
+                v[j] = s_tab[qq ^ ((sb >> sh) & 0xFFu)];
+            }
+        }
+        walk_block<4>(W, v, cnt, k0, X, lane);
     }
+}
+
+// ---- exact extension: 1 base per step (s_NuclUngappedExtendExact) ---------------------------------
+template <bool RIGHT>
+__device__ void exact_walk(const DevQuery &q, const uint8_t *packed, int64_t chunk_base, int32_t q_off,
+                           int32_t s_off, int32_t nsteps, int32_t X, int lane, Walk &W)
+{
+    W.T = 0; W.M = 0; W.best = -1; W.stopped = false;
+    const int32_t reward = q.reward, penalty = q.penalty;
+    for (int32_t base = 0; base < nsteps && !W.stopped; base += 512) {
+        const int32_t k0 = base + 16 * lane;
+        const int cnt = max(0, min(16, nsteps - k0));
+        int32_t v[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] = 0;
+        if (cnt > 0) {
+            const int32_t qpos = RIGHT ? q_off + k0 : q_off - k0 - 16;
+            const int64_t spos = chunk_base + (RIGHT ? (int64_t)s_off + k0 : (int64_t)s_off - k0 - 16);
+            uint32_t qb, qa;
+            qwin(q, qpos, qb, qa);
+            const uint32_t sb = swin(packed, spos);
+            const uint32_t mm = mismatch_bits(qb, 0u, sb);
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                if (j >= cnt) break;
+                const int b = RIGHT ? j : 15 - j;          // base index inside the window
+                const uint32_t sh = 30 - 2 * b;
+                int32_t val = ((mm >> sh) & 1u) ? penalty : reward;
+                if ((qa >> sh) & 1u)                        // ambiguity code or sentinel: matrix row
+                    val = __ldg(&q.matrix[16 * (int)__ldg(q.query + qpos + b) + (int)((sb >> sh) & 3u)]);
+                v[j] = val;
+            }
+        }
+        walk_block<16>(W, v, cnt, k0, X, lane);
+    }
+}
+
+__device__ void ungapped_exact(const DevQuery &q, const uint8_t *packed, int64_t chunk_base, int32_t slen,
+                               int32_t q_off, int32_t s_off, int32_t X, int lane, Ungapped &u)
+{
+    Walk W;
+    // left: while subject position > max(0, s_off - q_off); the sentinel row (INT4_MIN/2) stops it
+    const int32_t nleft = (q_off < s_off) ? q_off : s_off;
+    exact_walk<false>(q, packed, chunk_base, q_off, s_off, nleft, X, lane, W);
+    int32_t score = (int32_t)W.M;
+    const int32_t q_beg = W.best >= 0 ? q_off - 1 - W.best : q_off;
+    u.q_start = q_beg;
+    u.s_start = s_off - (q_off - q_beg);
+    const int32_t q_avail = q.concat_len - q_off, s_avail = slen - s_off;
+    const int32_t nright = (q_avail < s_avail) ? q_avail : s_avail;
+    exact_walk<true>(q, packed, chunk_base, q_off, s_off, nright, X, lane, W);
+    score += (int32_t)W.M;
+    const int32_t q_end = W.best >= 0 ? q_off + W.best + 1 : q_off;
+    u.length = q_end - q_beg;
+    u.score = score;
+}
+
+__device__ void ungapped_extend(const DevQuery &q, const uint8_t *packed, int64_t chunk_base, int32_t slen,
+                                const int32_t *s_tab, int32_t q_off, int32_t s_match_end, int32_t s_off,
+                                int32_t X, int32_t reduced_cutoff, int lane, Ungapped &u)
+{
+    const int32_t shift = (4 - (s_off % 4)) % 4;
+    const int32_t q_ext = q_off + shift, s_ext = s_off + shift;
+    Walk W;
+    approx_walk<false>(q, packed, chunk_base, s_tab, q_ext, s_ext, min(q_ext, s_ext) / 4, X, lane, W);
+    int32_t score = (int32_t)W.M;
+    int32_t new_q = W.best >= 0 ? q_ext - 4 * (W.best + 1) : q_ext;
     u.q_start = new_q;
     u.s_start = s_ext - (q_ext - new_q);
-
-    qp = q_ext; sb = s_ext / 4;
-    len = min(q.concat_len - q_ext, slen - s_ext) / 4;
-    sum = 0; new_q = qp;
-    for (int32_t i = 0; i < len; ++sb, qp += 4, ++i) {
-        sum += __ldg(&q.score_table[qbyte(query, qp) ^ (uint32_t)__ldg(S + sb)]);
-        if (sum > 0) { new_q = qp + 3; score += sum; sum = 0; }
-        if (sum < X) break;
-    }
+    approx_walk<true>(q, packed, chunk_base, s_tab, q_ext, s_ext,
+                      min(q.concat_len - q_ext, slen - s_ext) / 4, X, lane, W);
+    score += (int32_t)W.M;
+    new_q = W.best >= 0 ? q_ext + 4 * W.best + 3 : q_ext;
     if (score >= reduced_cutoff) {
-        ungapped_exact(q, S, slen, q_off, s_off, X, u);
+        ungapped_exact(q, packed, chunk_base, slen, q_off, s_off, X, lane, u);
     } else {
         u.score = score;
         u.length = max(s_match_end - u.s_start, new_q - u.q_start + 1);
     }
 }
 
-// s_MBLookup / s_SmallNaLookup
+// ---- lookup probes (warp-uniform) ----------------------------------------------------------------
 __device__ bool lut_contains(const DevQuery &q, uint32_t index, int32_t q_pos)
 {
     if (q.lut_type == 0) {
@@ -122,7 +252,6 @@ __device__ bool lut_contains(const DevQuery &q, uint32_t index, int32_t q_pos)
     return false;
 }
 
-// s_IsSeedMasked
 __device__ __forceinline__ bool seed_masked(const DevQuery &q, const uint8_t *S, int32_t s_off,
                                             int32_t lut, int32_t q_pos)
 {
@@ -159,18 +288,18 @@ __device__ int type_of_word(const DevQuery &q, const uint8_t *S, int32_t &q_off,
 }
 
 // ---- bucket chain (BLAST_DiagHash restricted to one bucket) -------------------------------------
-// cell = int4 {diag, level, (hit_len << 1) | hit_saved, next}; index 0 = null.
+// cell = int4 {diag, level, (hit_len << 1) | hit_saved, next}; index 0 = null.  All lanes execute
+// the walk on identical values; lane 0 stores.
 struct Chain {
-    int4 *cells;        // cells[1..]: storage region of this group
-    int32_t head;       // backbone[bucket]
-    int32_t used;       // cells allocated so far in this region
+    int4 *cells;
+    int32_t head, used;
 };
 
 __device__ __forceinline__ bool chain_get(const Chain &c, int32_t diag, int32_t &level)
 {
     int32_t i = c.head;
     while (i) {
-        int4 v = c.cells[i];
+        const int4 v = c.cells[i];
         if (v.x == diag) { level = v.y; return true; }
         i = v.w;
     }
@@ -178,19 +307,21 @@ __device__ __forceinline__ bool chain_get(const Chain &c, int32_t diag, int32_t 
 }
 
 __device__ __forceinline__ void chain_put(Chain &c, int32_t diag, int32_t level, int32_t len,
-                                          int32_t saved, int32_t s_off_pos, int32_t window)
+                                          int32_t saved, int32_t s_off_pos, int32_t window, int lane)
 {
     int32_t i = c.head;
     while (i) {
-        int4 v = c.cells[i];
+        const int4 v = c.cells[i];
         if (v.x == diag || s_off_pos - v.y > window) {
-            c.cells[i] = make_int4(diag, level, (len << 1) | saved, v.w);
+            if (lane == 0) c.cells[i] = make_int4(diag, level, (len << 1) | saved, v.w);
+            __syncwarp();
             return;
         }
         i = v.w;
     }
     const int32_t n = ++c.used;
-    c.cells[n] = make_int4(diag, level, (len << 1) | saved, c.head);
+    if (lane == 0) c.cells[n] = make_int4(diag, level, (len << 1) | saved, c.head);
+    __syncwarp();
     c.head = n;
 }
 
@@ -199,14 +330,29 @@ __device__ __forceinline__ uint32_t diag_bucket(int32_t diag)
     return ((uint32_t)diag * 0x9E370001u) % 512u;
 }
 
-// One thread per sorted hit; only the first hit of every group does work and replays the group.
-__global__ void __launch_bounds__(128)
-extend_kernel(const DevQuery q, const ExtendLaunch e, const uint64_t *group_key, int64_t n_hits)
+// heads[i] = index of the first hit of group i (any order)
+__global__ void group_heads_kernel(const uint64_t *group_key, int64_t n, uint32_t *heads,
+                                   unsigned long long *counters)
 {
-    const int64_t j0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j0 >= n_hits) return;
-    const uint64_t gk = group_key[j0];
-    if (j0 > 0 && group_key[j0 - 1] == gk) return;        // not a group head
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    if (j > 0 && group_key[j - 1] == group_key[j]) return;
+    const unsigned long long slot = atomicAdd(&counters[4], 1ull);
+    heads[slot] = (uint32_t)j;
+}
+
+__global__ void __launch_bounds__(EXT_WARPS_PER_BLOCK * 32)
+extend_kernel(const DevQuery q, const ExtendLaunch e, const uint64_t *group_key, const uint32_t *heads,
+              int64_t n_hits)
+{
+    __shared__ int32_t s_tab[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = q.score_table[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * EXT_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * EXT_WARPS_PER_BLOCK;
+    const int64_t n_groups = (int64_t)e.counters[4];
 
     const bool is_hash = q.container_type == 1;
     const int32_t word = q.word_length, lut = q.lut_word_length;
@@ -215,77 +361,86 @@ extend_kernel(const DevQuery q, const ExtendLaunch e, const uint64_t *group_key,
     // window_size == 0  =>  Delta = MIN(scan_range, -word_length); staleness window = Delta + 1
     const int32_t stale_window = min(q.scan_range, -word) + 1;
 
-    Chain chain;
-    chain.cells = reinterpret_cast<int4 *>(e.cells) + j0;   // region [j0+1 .. j0+group_size]
-    chain.head = 0; chain.used = 0;
-    int32_t last_hit_cell = 0;      // eDiagArray: the cell's last_hit
-    uint32_t cur_chunk = 0xFFFFFFFFu;
-    int32_t cur_epoch = -1;
-    DevChunk ch;
-    const uint8_t *S = nullptr;
-    unsigned long long n_extended = 0;
+    for (int64_t g = warp0; g < n_groups; g += nwarps) {
+        const int64_t j0 = (int64_t)heads[g];
+        const uint64_t gk = group_key[j0];
+        Chain chain;
+        chain.cells = reinterpret_cast<int4 *>(e.cells) + j0;   // region [j0+1 .. j0+group_size]
+        chain.head = 0; chain.used = 0;
+        int32_t last_hit_cell = 0;      // eDiagArray: the cell's last_hit
+        uint32_t cur_chunk = 0xFFFFFFFFu;
+        int32_t cur_epoch = -1;
+        DevChunk ch{};
+        const uint8_t *S = nullptr;
+        int64_t chunk_base = 0;
+        unsigned long long n_extended = 0;
 
-    for (int64_t j = j0; j < n_hits && group_key[j] == gk; ++j) {
-        const SeedHit h = e.hits[j];
-        if (h.chunk != cur_chunk) {
-            cur_chunk = h.chunk;
-            ch = e.chunks[cur_chunk];
-            S = e.packed + ch.byte_off;
-            if (is_hash) {
-                // Blast_ExtendWordExit resets happen between chunks; replay every reset that
-                // occurred since the previous chunk this bucket saw (any one empties the chain).
-                if (cur_epoch >= 0 && ch.diag_epoch != cur_epoch) {
-                    chain.head = 0; chain.used = 0;
-                    chain.cells = reinterpret_cast<int4 *>(e.cells) + j;
+        for (int64_t j = j0; j < n_hits; ++j) {
+            if (j > j0 && group_key[j] != gk) break;
+            const SeedHit h = e.hits[j];
+            if (h.chunk != cur_chunk) {
+                cur_chunk = h.chunk;
+                ch = e.chunks[cur_chunk];
+                S = e.packed + ch.byte_off;
+                chunk_base = ch.byte_off * 4;
+                if (is_hash) {
+                    // Blast_ExtendWordExit may have reset the container between chunks
+                    if (cur_epoch >= 0 && ch.diag_epoch != cur_epoch) {
+                        chain.head = 0; chain.used = 0;
+                        chain.cells = reinterpret_cast<int4 *>(e.cells) + j;
+                    }
+                    cur_epoch = ch.diag_epoch;
                 }
-                cur_epoch = ch.diag_epoch;
             }
-        }
-        int32_t q_off = (int32_t)h.q_off, s_off = (int32_t)h.s_off;
-        const int32_t s_range = ch.len;
-        int32_t s_end = s_off + word;
-        const int32_t s_off_pos = s_off + ch.diag_offset;
-        int32_t s_end_pos = s_end + ch.diag_offset;
-        const int32_t diag = s_off - q_off;
-        int32_t last_hit = 0;
-        if (is_hash) { if (!chain_get(chain, diag, last_hit)) last_hit = 0; }
-        else last_hit = last_hit_cell;
-        if (s_off_pos < last_hit) continue;
+            int32_t q_off = (int32_t)h.q_off, s_off = (int32_t)h.s_off;
+            const int32_t s_range = ch.len;
+            int32_t s_end = s_off + word;
+            const int32_t s_off_pos = s_off + ch.diag_offset;
+            int32_t s_end_pos = s_end + ch.diag_offset;
+            const int32_t diag = s_off - q_off;
+            int32_t last_hit = 0;
+            if (is_hash) { if (!chain_get(chain, diag, last_hit)) last_hit = 0; }
+            else last_hit = last_hit_cell;
+            if (s_off_pos < last_hit) continue;
 
-        int32_t extended = 0;
-        if (!type_of_word(q, S, q_off, s_off, has_loc, (uint32_t)s_range, word, direct ? word : lut, extended))
-            continue;
-        s_end += extended; s_end_pos += extended;
+            int32_t extended = 0;
+            if (!type_of_word(q, S, q_off, s_off, has_loc, (uint32_t)s_range, word, direct ? word : lut, extended))
+                continue;
+            s_end += extended; s_end_pos += extended;
 
-        const int32_t context = ctx_search(q, q_off);
-        const DevContext c = q.ctx[context];
-        Ungapped u;
-        if (!is_hash && word < 11)
-            ungapped_exact(q, S, ch.len, q_off, s_off, -c.x_dropoff, u);
-        else
-            ungapped_extend(q, S, ch.len, q_off, s_end, s_off, -c.x_dropoff, c.reduced_cutoff, u);
+            const int32_t context = ctx_search(q, q_off);
+            const DevContext c = q.ctx[context];
+            Ungapped u;
+            if (!is_hash && word < 11)
+                ungapped_exact(q, e.packed, chunk_base, ch.len, q_off, s_off, -c.x_dropoff, lane, u);
+            else
+                ungapped_extend(q, e.packed, chunk_base, ch.len, s_tab, q_off, s_end, s_off, -c.x_dropoff,
+                                c.reduced_cutoff, lane, u);
 
-        int32_t hit_ready = 0;
-        if (u.score >= c.cutoff_score) {
-            hit_ready = 1;
-            unsigned long long slot = atomicAdd(&e.counters[2], 1ull);
-            if ((int64_t)slot < e.init_capacity) {
-                DevInitHit o;
-                o.chunk = (int32_t)cur_chunk; o.q_off = q_off; o.s_off = s_off;
-                o.q_start = u.q_start; o.s_start = u.s_start; o.length = u.length; o.score = u.score;
-                o.order = e.order[j];
-                e.init[slot] = o;
+            int32_t hit_ready = 0;
+            if (u.score >= c.cutoff_score) {
+                hit_ready = 1;
+                if (lane == 0) {
+                    const unsigned long long slot = atomicAdd(&e.counters[2], 1ull);
+                    if ((int64_t)slot < e.init_capacity) {
+                        DevInitHit o;
+                        o.chunk = (int32_t)cur_chunk; o.q_off = q_off; o.s_off = s_off;
+                        o.q_start = u.q_start; o.s_start = u.s_start; o.length = u.length; o.score = u.score;
+                        o.order = e.order[j];
+                        e.init[slot] = o;
+                    }
+                }
+                s_end_pos = u.length + u.s_start + ch.diag_offset;
+                ++n_extended;
             }
-            s_end_pos = u.length + u.s_start + ch.diag_offset;
-            ++n_extended;
+            if (is_hash)
+                chain_put(chain, diag, s_end_pos, hit_ready ? 0 : s_end_pos - s_off_pos, hit_ready,
+                          s_off_pos, stale_window, lane);
+            else
+                last_hit_cell = s_end_pos;
         }
-        if (is_hash)
-            chain_put(chain, diag, s_end_pos, hit_ready ? 0 : s_end_pos - s_off_pos, hit_ready,
-                      s_off_pos, stale_window);
-        else
-            last_hit_cell = s_end_pos;
+        if (lane == 0 && n_extended) atomicAdd(&e.counters[3], n_extended);
     }
-    if (n_extended) atomicAdd(&e.counters[3], n_extended);
 }
 
 // group key of every sorted hit: hash -> bucket id; array -> (chunk, real diagonal)
@@ -338,10 +493,15 @@ cudaError_t launch_iota(uint32_t *p, int64_t n, cudaStream_t st)
 }
 
 cudaError_t launch_extend_groups(const DevQuery &q, const ExtendLaunch &e, const uint64_t *group_key,
-                                 int64_t n_hits, cudaStream_t st)
+                                 uint32_t *heads, int64_t n_hits, cudaStream_t st)
 {
     if (n_hits <= 0) return cudaSuccess;
-    extend_kernel<<<(unsigned)((n_hits + 127) / 128), 128, 0, st>>>(q, e, group_key, n_hits);
+    group_heads_kernel<<<(unsigned)((n_hits + 255) / 256), 256, 0, st>>>(group_key, n_hits, heads, e.counters);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    const int64_t want = (n_hits + EXT_WARPS_PER_BLOCK - 1) / EXT_WARPS_PER_BLOCK;
+    const unsigned blocks = (unsigned)(want < EXT_BLOCKS ? (want < 1 ? 1 : want) : EXT_BLOCKS);
+    extend_kernel<<<blocks, EXT_WARPS_PER_BLOCK * 32, 0, st>>>(q, e, group_key, heads, n_hits);
     return cudaGetLastError();
 }
 

@@ -33,38 +33,41 @@ constexpr int32_t GREEDY_MAX_COST = 10000;
 constexpr int32_t GREEDY_INVALID = -2;
 constexpr int32_t MININT = INT32_MIN / 2;
 
-// seq1 = query bytes, seq2 = packed subject (s_FindFirstMismatch, compressed branch)
-__device__ __forceinline__ int32_t first_mismatch(const uint8_t *seq1, const uint8_t *seq2,
-                                                  int32_t len1, int32_t len2, int32_t i1, int32_t i2,
-                                                  bool reverse, int rem)
+// s_FindFirstMismatch (compressed seq2 branch) on 16-base windows.  seq1 = query (absolute
+// concatenated position qbase + i), seq2 = subject (absolute volume base sbase + i).
+struct SeqPair {
+    const DevQuery *q;
+    const uint8_t *packed;
+    int32_t qbase;      // forward: position of seq1[0]; reverse: position of seq1[0] as well
+    int64_t sbase;      // absolute base index of seq2[0]
+    int32_t len1, len2;
+    bool reverse;
+};
+__device__ __forceinline__ int32_t first_mismatch(const SeqPair &p, int32_t i1, int32_t i2)
 {
-    const int32_t start = i1;
-    if (reverse) {
-        while (i1 < len1 && i2 < len2 &&
-               (int)__ldg(seq1 + (len1 - 1 - i1)) == sbase(seq2, len2 - 1 - i2)) { ++i1; ++i2; }
-    } else {
-        while (i1 < len1 && i2 < len2 &&
-               (int)__ldg(seq1 + i1) == sbase(seq2, i2 + rem)) { ++i1; ++i2; }
-    }
-    return i1 - start;
+    const int32_t n = min(p.len1 - i1, p.len2 - i2);
+    if (n <= 0) return 0;
+    if (p.reverse)
+        return match_run_rev(*p.q, p.packed, p.qbase + p.len1 - i1, p.sbase + p.len2 - i2, n);
+    return match_run_fwd(*p.q, p.packed, p.qbase + i1, p.sbase + i2, n);
 }
 
 struct GreedySeed { int32_t start_q, start_s, match_length; };
 
 // BLAST_GreedyAlign, score only.  rows: 2 x (2*D + 6) ints; max_score: D + 1 + xdrop_offset ints.
 // Diagonal k of the reference is stored at index k - diag_origin + D + 2.
-__device__ int32_t greedy_align(const uint8_t *seq1, int32_t len1, const uint8_t *seq2, int32_t len2,
-                                bool reverse, int32_t xdrop_threshold, int32_t match_cost,
+__device__ int32_t greedy_align(const SeqPair &sp, int32_t xdrop_threshold, int32_t match_cost,
                                 int32_t mismatch_cost, int32_t &seq1_len, int32_t &seq2_len,
                                 int32_t *row0, int32_t *row1, int32_t *max_score_mem, int32_t D,
-                                int rem, GreedySeed &seed, bool &overflow)
+                                GreedySeed &seed, bool &overflow)
 {
+    const int32_t len1 = sp.len1, len2 = sp.len2;
     int32_t best_dist = 0;
     const int32_t max_dist = min(GREEDY_MAX_COST, len2 / 2 + 1);
     const int32_t origin = D + 2;                 // re-biased diag_origin
     const int32_t xdrop_offset = (xdrop_threshold + match_cost / 2) / (match_cost + mismatch_cost) + 1;
 
-    int32_t index = first_mismatch(seq1, seq2, len1, len2, 0, 0, reverse, rem);
+    int32_t index = first_mismatch(sp, 0, 0);
     seq1_len = index; seq2_len = index;
     int32_t seq1_index = index, seq2_index;
     seed.start_q = 0; seed.start_s = 0;
@@ -108,7 +111,7 @@ __device__ int32_t greedy_align(const uint8_t *seq1, int32_t len1, const uint8_t
                 continue;
             }
             diag_upper = k;
-            index = first_mismatch(seq1, seq2, len1, len2, seq1_index, seq2_index, reverse, rem);
+            index = first_mismatch(sp, seq1_index, seq2_index);
             if (index > longest_match_run) {
                 seed.start_q = seq1_index; seed.start_s = seq2_index;
                 seed.match_length = longest_match_run = index;
@@ -137,9 +140,9 @@ __device__ int32_t greedy_align(const uint8_t *seq1, int32_t len1, const uint8_t
     return best_dist;
 }
 
-__device__ void greedy_gapped(const DevQuery &q, const uint8_t *query, int32_t qlen, const uint8_t *S,
-                              int32_t slen, int32_t q_off, int32_t s_off, int32_t *scratch, int32_t D,
-                              DevGapResult &g)
+__device__ void greedy_gapped(const DevQuery &q, const uint8_t *packed, int32_t ctx_off, int32_t qlen,
+                              int64_t chunk_base, int32_t slen, int32_t q_off, int32_t s_off,
+                              int32_t *scratch, int32_t D, DevGapResult &g)
 {
     int32_t match = q.reward, mismatch = -q.penalty, xd = q.gap_x_dropoff;
     if (match % 2 == 1) { match *= 2; mismatch *= 2; xd *= 2; }
@@ -147,12 +150,15 @@ __device__ void greedy_gapped(const DevQuery &q, const uint8_t *query, int32_t q
     int32_t q_ext_r, s_ext_r, q_ext_l, s_ext_l;
     GreedySeed fwd, rev;
     bool overflow = false;
-    int32_t score = greedy_align(query + q_off, qlen - q_off, S + s_off / 4, slen - s_off, false, xd,
-                                 match, mismatch, q_ext_r, s_ext_r, row0, row1, ms, D, s_off % 4, fwd,
-                                 overflow);
-    if (!overflow)
-        score += greedy_align(query, q_off, S, s_off, true, xd, match, mismatch, q_ext_l, s_ext_l,
-                              row0, row1, ms, D, 0, rev, overflow);
+    SeqPair sp;
+    sp.q = &q; sp.packed = packed;
+    sp.qbase = ctx_off + q_off; sp.sbase = chunk_base + s_off;
+    sp.len1 = qlen - q_off; sp.len2 = slen - s_off; sp.reverse = false;
+    int32_t score = greedy_align(sp, xd, match, mismatch, q_ext_r, s_ext_r, row0, row1, ms, D, fwd, overflow);
+    if (!overflow) {
+        sp.qbase = ctx_off; sp.sbase = chunk_base; sp.len1 = q_off; sp.len2 = s_off; sp.reverse = true;
+        score += greedy_align(sp, xd, match, mismatch, q_ext_l, s_ext_l, row0, row1, ms, D, rev, overflow);
+    }
     if (overflow) { g.status = 1; return; }
     score = (q_ext_r + s_ext_r + q_ext_l + s_ext_l) * q.reward / 2 - score * (q.reward - q.penalty);
 
@@ -299,7 +305,7 @@ gapped_kernel(const DevQuery q, const GappedLaunch L)
         if (q.gap_algo == 1) {
             const int32_t q_off = (h.q_start - c.query_offset) + h.length / 2;
             const int32_t s_off = h.s_start + h.length / 2;
-            greedy_gapped(q, query, c.query_length, S, ch.len, q_off, s_off, scratch, L.tier_d, g);
+            greedy_gapped(q, L.packed, c.query_offset, c.query_length, ch.byte_off * 4, ch.len, q_off, s_off, scratch, L.tier_d, g);
         } else {
             int32_t q_off = h.q_off - c.query_offset, s_off = h.s_off;
             if (h.s_start + h.length >= s_off + 8) { s_off += 3; q_off += 3; }
