@@ -112,14 +112,8 @@ struct QueryDev {
 };
 
 struct Query {
-    BnQueryBatch batch{};                 // host copy; pointers re-targeted at the vectors below
-    std::vector<uint8_t> query;
-    std::vector<BnContext> ctx;
-    std::vector<int32_t> hashtable, next_pos;
-    std::vector<uint32_t> presence;
-    std::vector<int16_t> backbone, overflow;
-    std::vector<int32_t> masked;
-    std::vector<uint2> qpk;               // 16-base query windows (bn_device.cuh: qwin)
+    BnQueryBatch batch{};                 // host copy of the scalars; array pointers are NULL except contexts
+    std::vector<BnContext> ctx;           // the host replay needs contexts, cutoffs and Karlin blocks only
     std::vector<QueryDev> dev;            // per device
     int32_t diag_array_length = 1;
     int32_t max_query_length = 0;
@@ -144,30 +138,44 @@ static Device *device_at(int d)
 }
 
 // ------------------------------------------------------------------------------------------------
-static void free_query_dev(QueryDev &q)
+// Device arrays of a query batch come from the stream-ordered pool (release threshold = never), so
+// loading a new batch re-uses the previous batch's memory without touching the OS allocator.
+static void free_query_dev(QueryDev &q, cudaStream_t st)
 {
-    cudaFree(q.query); cudaFree(q.ctx); cudaFree(q.hashtable); cudaFree(q.next_pos);
-    cudaFree(q.presence); cudaFree(q.backbone); cudaFree(q.overflow); cudaFree(q.score_table);
-    cudaFree(q.matrix); cudaFree(q.qpk);
+    void *ptrs[] = {q.query, q.ctx, q.hashtable, q.next_pos, q.presence, q.backbone, q.overflow,
+                    q.score_table, q.matrix, q.qpk};
+    for (void *p : ptrs) if (p) cudaFreeAsync(p, st);
     q = QueryDev{};
+}
+
+template <typename T>
+static cudaError_t dev_alloc(T **dst, size_t n, cudaStream_t st)
+{
+    *dst = nullptr;
+    if (n == 0) return cudaSuccess;
+    return cudaMallocAsync((void **)dst, n * sizeof(T), st);
 }
 
 template <typename T>
 static cudaError_t upload(T **dst, const T *src, size_t n, cudaStream_t st)
 {
-    *dst = nullptr;
-    if (n == 0) return cudaSuccess;
-    cudaError_t e = cudaMalloc(dst, n * sizeof(T));
-    if (e != cudaSuccess) return e;
+    cudaError_t e = dev_alloc(dst, n, st);
+    if (e != cudaSuccess || n == 0) return e;
     return cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, st);
 }
 
-static int query_to_device(Query &Q, int d)
+cudaError_t launch_build_presence(const int32_t *hashtable, int64_t hashsize, uint32_t *presence, cudaStream_t st);
+cudaError_t launch_build_qpk(const uint8_t *query_start, int32_t concat_len, uint2 *qpk, int64_t nwords, cudaStream_t st);
+
+// Uploads one query batch to device d straight from the caller's arrays (no host staging copy);
+// the presence bitmap and the 16-base query windows are derived on the device.
+static int query_to_device(Query &Q, const BnQueryBatch &src, int d)
 {
     Device *dev = device_at(d);
     QueryDev &qd = Q.dev[d];
     if (qd.ready) return BN_OK;
     CU_TRY(cudaSetDevice(dev->id));
+    cudaStream_t st = dev->stream;
     const BnQueryBatch &b = Q.batch;
     std::vector<DevContext> dctx((size_t)b.num_contexts);
     for (int i = 0; i < b.num_contexts; i++) {
@@ -175,20 +183,27 @@ static int query_to_device(Query &Q, int d)
         dctx[i] = DevContext{c.query_offset, c.query_length, c.query_index, c.frame,
                              c.x_dropoff, c.cutoff_score, c.reduced_cutoff, c.gapped_cutoff};
     }
-    CU_TRY(upload(&qd.query, Q.query.data(), Q.query.size(), dev->stream));
-    CU_TRY(upload(&qd.ctx, dctx.data(), dctx.size(), dev->stream));
+    CU_TRY(upload(&qd.query, src.query_start, (size_t)b.concat_len + 2, st));
+    CU_TRY(upload(&qd.ctx, dctx.data(), dctx.size(), st));
     if (b.lut_type == BN_LUT_MB) {
-        CU_TRY(upload(&qd.hashtable, Q.hashtable.data(), Q.hashtable.size(), dev->stream));
-        CU_TRY(upload(&qd.next_pos, Q.next_pos.data(), Q.next_pos.size(), dev->stream));
-        CU_TRY(upload(&qd.presence, Q.presence.data(), Q.presence.size(), dev->stream));
+        CU_TRY(upload(&qd.hashtable, src.hashtable, (size_t)b.hashsize, st));
+        CU_TRY(upload(&qd.next_pos, src.next_pos, (size_t)b.concat_len + 1, st));
+        // exact presence bitmap (replaces the reference's compressed pv_array: same answers,
+        // PV_TEST is only a filter in front of hashtable[index] != 0)
+        CU_TRY(dev_alloc(&qd.presence, (size_t)((b.hashsize + 31) / 32), st));
+        CU_TRY(launch_build_presence(qd.hashtable, b.hashsize, qd.presence, st));
     } else {
-        CU_TRY(upload(&qd.backbone, Q.backbone.data(), Q.backbone.size(), dev->stream));
-        CU_TRY(upload(&qd.overflow, Q.overflow.data(), Q.overflow.size(), dev->stream));
+        static const int16_t kEmptyOverflow[2] = {-1, -1};
+        CU_TRY(upload(&qd.backbone, src.backbone, (size_t)b.hashsize, st));
+        if (src.overflow && b.overflow_len > 0) CU_TRY(upload(&qd.overflow, src.overflow, (size_t)b.overflow_len, st));
+        else CU_TRY(upload(&qd.overflow, kEmptyOverflow, (size_t)2, st));
     }
-    CU_TRY(upload(&qd.score_table, b.nucl_score_table, (size_t)256, dev->stream));
-    CU_TRY(upload(&qd.matrix, b.matrix, (size_t)256, dev->stream));
-    CU_TRY(upload(&qd.qpk, Q.qpk.data(), Q.qpk.size(), dev->stream));
-    CU_TRY(cudaStreamSynchronize(dev->stream));
+    CU_TRY(upload(&qd.score_table, b.nucl_score_table, (size_t)256, st));
+    CU_TRY(upload(&qd.matrix, b.matrix, (size_t)256, st));
+    const int64_t nw = (int64_t)((b.concat_len + 2 + 16) >> 4) + 3;
+    CU_TRY(dev_alloc(&qd.qpk, (size_t)nw, st));
+    CU_TRY(launch_build_qpk(qd.query, b.concat_len, qd.qpk, nw, st));
+    CU_TRY(cudaStreamSynchronize(st));     // caller's arrays may go away after bn_query_load returns
 
     DevQuery &v = qd.view;
     v.query = qd.query + 1;
@@ -198,7 +213,7 @@ static int query_to_device(Query &Q, int d)
     v.scan_step = b.scan_step; v.hash_mask = (uint32_t)(b.hashsize - 1);
     v.hashtable = qd.hashtable; v.next_pos = qd.next_pos; v.presence = qd.presence;
     v.backbone = qd.backbone; v.overflow = qd.overflow;
-    v.has_locations = b.masked_locations != nullptr;
+    v.has_locations = Q.batch.masked_locations != nullptr;
     v.container_type = b.container_type; v.window_size = b.window_size; v.scan_range = b.scan_range;
     v.score_table = qd.score_table; v.matrix = qd.matrix; v.qpk = qd.qpk;
     v.gap_algo = b.gap_algo; v.reward = b.reward; v.penalty = b.penalty;
@@ -482,8 +497,8 @@ static int prelim_search_locked(Device &D, Volume &V, Query &Q, int32_t oid_begi
     memset(out, 0, sizeof *out);
     const double t0 = now_ms();
     CU_TRY(cudaSetDevice(D.id));
-    int rc = query_to_device(Q, V.device);
-    if (rc) return rc;
+    if (!Q.dev[V.device].ready) return fail(BN_ERR_INVALID, "query batch is not loaded on the volume's device");
+    int rc;
     std::shared_ptr<ChunkTable> T;
     rc = build_chunk_table(V, Q, oid_begin, oid_end, D.stream, &T);
     if (rc) return rc;
@@ -586,6 +601,13 @@ int bn_init(int n_gpu, const int *device_ids)
         d->id = id;
         CU_TRY(cudaSetDevice(id));
         CU_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+        {   // keep freed blocks in the stream-ordered pool (volumes / query tables are re-loaded often)
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, id) == cudaSuccess) {
+                uint64_t keep = UINT64_MAX;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+        }
         g_devices.push_back(std::move(d));
     }
     g_inited = true;
@@ -596,12 +618,12 @@ void bn_release(void)
 {
     std::lock_guard<std::mutex> lk(g_mu);
     for (auto &q : g_queries) if (q) for (size_t d = 0; d < q->dev.size(); d++) {
-        if (q->dev[d].ready) { cudaSetDevice(g_devices[d]->id); free_query_dev(q->dev[d]); }
+        if (q->dev[d].ready) { cudaSetDevice(g_devices[d]->id); free_query_dev(q->dev[d], g_devices[d]->stream); }
     }
     g_queries.clear();
     for (auto &v : g_volumes) if (v) {
         cudaSetDevice(g_devices[v->device]->id);
-        cudaFree(v->d_raw);
+        cudaFreeAsync(v->d_raw, g_devices[v->device]->stream);
         for (auto &kv : v->tables) { kv.second->dev.release(); kv.second->block_chunk.release(); }
     }
     g_volumes.clear();
@@ -639,7 +661,7 @@ int bn_db_load(int device, const uint8_t *packed, int64_t packed_bytes, const in
     V->seq_len.assign(seq_len, seq_len + n_seq);
     CU_TRY(cudaSetDevice(D->id));
     // 64 readable bytes in front (reverse 16-base windows may start before the first base) and behind
-    CU_TRY(cudaMalloc(&V->d_raw, (size_t)packed_bytes + 192));
+    CU_TRY(cudaMallocAsync((void **)&V->d_raw, (size_t)packed_bytes + 192, D->stream));
     V->d_packed = V->d_raw + 64;
     CU_TRY(cudaMemsetAsync(V->d_raw, 0, 64, D->stream));
     CU_TRY(cudaMemcpyAsync(V->d_packed, packed, (size_t)packed_bytes, cudaMemcpyHostToDevice, D->stream));
@@ -657,7 +679,7 @@ int bn_db_free(int h)
     if (h < 0 || h >= (int)g_volumes.size() || !g_volumes[h]) return fail(BN_ERR_INVALID, "bn_db_free: bad handle");
     Volume &V = *g_volumes[h];
     cudaSetDevice(g_devices[V.device]->id);
-    cudaFree(V.d_raw);
+    cudaFreeAsync(V.d_raw, g_devices[V.device]->stream);
     for (auto &kv : V.tables) { kv.second->dev.release(); kv.second->block_chunk.release(); }
     g_volumes[h].reset();
     return BN_OK;
@@ -674,53 +696,29 @@ int bn_query_load(const BnQueryBatch *b, int *query_handle)
         return fail(BN_ERR_UNSUPPORTED, "affine greedy extension is not implemented");
     if (b->lut_type != BN_LUT_MB && b->lut_type != BN_LUT_SMALL_NA)
         return fail(BN_ERR_UNSUPPORTED, "only eMBLookupTable and eSmallNaLookupTable are supported");
+    if (b->lut_type == BN_LUT_MB && (!b->hashtable || !b->next_pos)) return fail(BN_ERR_INVALID, "bn_query_load: MB table arrays missing");
+    if (b->lut_type == BN_LUT_SMALL_NA && !b->backbone) return fail(BN_ERR_INVALID, "bn_query_load: small table arrays missing");
     auto Q = std::make_unique<Query>();
     Q->batch = *b;
-    Q->query.assign(b->query_start, b->query_start + b->concat_len + 2);
     Q->ctx.assign(b->contexts, b->contexts + b->num_contexts);
     for (const auto &c : Q->ctx) Q->max_query_length = std::max(Q->max_query_length, c.query_length);
-    if (b->lut_type == BN_LUT_MB) {
-        if (!b->hashtable || !b->next_pos) return fail(BN_ERR_INVALID, "bn_query_load: MB table arrays missing");
-        Q->hashtable.assign(b->hashtable, b->hashtable + b->hashsize);
-        Q->next_pos.assign(b->next_pos, b->next_pos + b->concat_len + 1);
-        // exact presence bitmap (replaces the reference's compressed pv_array: same answers,
-        // PV_TEST is only a filter in front of hashtable[index] != 0)
-        Q->presence.assign((size_t)((b->hashsize + 31) / 32), 0u);
-        for (int64_t i = 0; i < b->hashsize; i++)
-            if (Q->hashtable[(size_t)i]) Q->presence[(size_t)(i >> 5)] |= 1u << (i & 31);
-    } else {
-        if (!b->backbone) return fail(BN_ERR_INVALID, "bn_query_load: small table arrays missing");
-        Q->backbone.assign(b->backbone, b->backbone + b->hashsize);
-        if (b->overflow && b->overflow_len > 0) Q->overflow.assign(b->overflow, b->overflow + b->overflow_len);
-        else Q->overflow.assign(2, (int16_t)-1);
-    }
-    {   // 16-base windows of the query: 2-bit bases + ambiguity flags, one leading pad word
-        const size_t nw = (size_t)((b->concat_len + 2 + 16) >> 4) + 3;
-        Q->qpk.assign(nw, make_uint2(0u, 0u));
-        for (size_t i = 0; i < nw; i++) {
-            uint32_t bases = 0, amb = 0;
-            for (int j = 0; j < 16; j++) {
-                const int64_t pos = 16 * ((int64_t)i - 1) + j;
-                const uint8_t code = (pos >= -1 && pos <= b->concat_len) ? Q->query[(size_t)(pos + 1)] : 15;
-                bases |= (uint32_t)(code & 3) << (30 - 2 * j);
-                amb |= (uint32_t)(code >= 4 ? 1u : 0u) << (30 - 2 * j);
-            }
-            Q->qpk[i] = make_uint2(bases, amb);
-        }
-    }
-    if (b->masked_locations && b->n_masked_locations > 0)
-        Q->masked.assign(b->masked_locations, b->masked_locations + 2 * (size_t)b->n_masked_locations);
-    // re-target the host copy
-    Q->batch.query_start = Q->query.data();
-    Q->batch.contexts = Q->ctx.data();
-    Q->batch.hashtable = Q->hashtable.data(); Q->batch.next_pos = Q->next_pos.data();
-    Q->batch.pv_array = nullptr;
-    Q->batch.backbone = Q->backbone.data(); Q->batch.overflow = Q->overflow.data();
-    Q->batch.masked_locations = b->masked_locations ? (Q->masked.empty() ? (const int32_t *)Q->query.data() : Q->masked.data()) : nullptr;
+    // keep only scalars + contexts on the host; remember whether masked_locations was non-NULL
+    Q->batch.query_start = nullptr; Q->batch.contexts = Q->ctx.data();
+    Q->batch.hashtable = nullptr; Q->batch.next_pos = nullptr; Q->batch.pv_array = nullptr;
+    Q->batch.backbone = nullptr; Q->batch.overflow = nullptr;
+    Q->batch.masked_locations = b->masked_locations ? reinterpret_cast<const int32_t *>(Q->ctx.data()) : nullptr;
     int32_t n = 1;
     while (n < b->concat_len + b->window_size) n <<= 1;   // s_BlastDiagTableNew core/blast_extend.c:46-72
     Q->diag_array_length = n;
     Q->dev.resize(g_devices.size());
+    for (size_t d = 0; d < g_devices.size(); d++) {
+        rc = query_to_device(*Q, *b, (int)d);
+        if (rc) {
+            for (size_t k = 0; k < g_devices.size(); k++)
+                if (Q->dev[k].ready) { cudaSetDevice(g_devices[k]->id); free_query_dev(Q->dev[k], g_devices[k]->stream); }
+            return rc;
+        }
+    }
     std::lock_guard<std::mutex> lk(g_mu);
     g_queries.push_back(std::move(Q));
     *query_handle = (int)g_queries.size() - 1;
@@ -733,7 +731,7 @@ int bn_query_free(int h)
     if (h < 0 || h >= (int)g_queries.size() || !g_queries[h]) return fail(BN_ERR_INVALID, "bn_query_free: bad handle");
     Query &Q = *g_queries[h];
     for (size_t d = 0; d < Q.dev.size(); d++)
-        if (Q.dev[d].ready) { cudaSetDevice(g_devices[d]->id); free_query_dev(Q.dev[d]); }
+        if (Q.dev[d].ready) { cudaSetDevice(g_devices[d]->id); free_query_dev(Q.dev[d], g_devices[d]->stream); }
     g_queries[h].reset();
     return BN_OK;
 }
@@ -798,8 +796,7 @@ int bn_scan_subject(int vol_handle, int query_handle, int32_t oid, int32_t chunk
     if (oid < 0 || oid >= (int32_t)V->seq_len.size()) return fail(BN_ERR_INVALID, "bn_scan_subject: bad oid");
     std::lock_guard<std::mutex> lk(D->mu);
     CU_TRY(cudaSetDevice(D->id));
-    rc = query_to_device(*Q, V->device);
-    if (rc) return rc;
+    if (!Q->dev[V->device].ready) return fail(BN_ERR_INVALID, "query batch is not loaded on the volume's device");
     std::shared_ptr<ChunkTable> T;
     rc = build_chunk_table(*V, *Q, oid, oid + 1, D->stream, &T);
     if (rc) return rc;
@@ -842,8 +839,7 @@ int bn_bench_scan(int vol_handle, int query_handle, int iters, double *ms_per_la
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(D->mu);
     CU_TRY(cudaSetDevice(D->id));
-    rc = query_to_device(*Q, V->device);
-    if (rc) return rc;
+    if (!Q->dev[V->device].ready) return fail(BN_ERR_INVALID, "query batch is not loaded on the volume's device");
     std::shared_ptr<ChunkTable> T;
     rc = build_chunk_table(*V, *Q, 0, (int32_t)V->seq_len.size(), D->stream, &T);
     if (rc) return rc;

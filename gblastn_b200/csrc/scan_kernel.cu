@@ -225,6 +225,54 @@ scan_kernel(const DevQuery q, const ScanLaunch s)
     if ((threadIdx.x & 31) == 0 && my_lookup_hits) atomicAdd(&s.counters[1], my_lookup_hits);
 }
 
+// ---- query-load helpers: derived device arrays -----------------------------------------------------
+// presence[w] bit b  <=>  hashtable[32 w + b] != 0.  One warp per 1024 cells: coalesced loads + ballot.
+__global__ void build_presence_kernel(const int32_t *hashtable, int64_t hashsize, uint32_t *presence)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t cell0 = warp * 1024;
+    if (cell0 >= hashsize) return;
+    uint32_t mine = 0;
+#pragma unroll 4
+    for (int i = 0; i < 32; i++) {
+        const int64_t c = cell0 + 32 * i + lane;
+        const uint32_t bits = __ballot_sync(0xffffffffu, c < hashsize && hashtable[c] != 0);
+        if (lane == i) mine = bits;
+    }
+    const int64_t w = (cell0 >> 5) + lane;
+    if (w < (hashsize + 31) / 32) presence[w] = mine;
+}
+
+// qpk[i]: 16-base window of concatenated-query positions 16 (i-1) .. 16 (i-1) + 15 (bn_device.cuh: qwin)
+__global__ void build_qpk_kernel(const uint8_t *query_start, int32_t concat_len, uint2 *qpk, int64_t nwords)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nwords) return;
+    uint32_t bases = 0, amb = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const int64_t pos = 16 * (i - 1) + j;
+        const uint32_t code = (pos >= -1 && pos <= concat_len) ? query_start[pos + 1] : 15u;
+        bases |= (code & 3u) << (30 - 2 * j);
+        amb |= (code >= 4u ? 1u : 0u) << (30 - 2 * j);
+    }
+    qpk[i] = make_uint2(bases, amb);
+}
+
+cudaError_t launch_build_presence(const int32_t *hashtable, int64_t hashsize, uint32_t *presence, cudaStream_t st)
+{
+    const int64_t warps = (hashsize + 1023) / 1024;
+    const int64_t blocks = (warps * 32 + 255) / 256;
+    build_presence_kernel<<<(unsigned)blocks, 256, 0, st>>>(hashtable, hashsize, presence);
+    return cudaGetLastError();
+}
+cudaError_t launch_build_qpk(const uint8_t *query_start, int32_t concat_len, uint2 *qpk, int64_t nwords, cudaStream_t st)
+{
+    build_qpk_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, st>>>(query_start, concat_len, qpk, nwords);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_scan(const DevQuery &q, const ScanLaunch &s, cudaStream_t st)
 {
     if (s.total_pos <= 0) return cudaSuccess;

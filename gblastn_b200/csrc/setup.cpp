@@ -29,9 +29,49 @@
 #include <string>
 #include <vector>
 
+#include <cuda_runtime_api.h>
+
 #include "../../include/gblastn_b200.h"
 
 namespace {
+
+// Zero-filled host array; page-locked when a CUDA driver is present so bn_query_load's H2D copies
+// run at full PCIe speed, plain calloc otherwise (CPU-only set-up tests).
+template <typename T>
+struct HostArray {
+    T *p = nullptr;
+    size_t n = 0;
+    bool pinned = false;
+    HostArray() = default;
+    HostArray(const HostArray &) = delete;
+    HostArray &operator=(const HostArray &) = delete;
+    ~HostArray() { release(); }
+    void release()
+    {
+        if (p) { if (pinned) cudaFreeHost(p); else free(p); }
+        p = nullptr; n = 0; pinned = false;
+    }
+    void assign_zero(size_t count)
+    {
+        release();
+        if (count == 0) return;
+        void *q = nullptr;
+        if (count * sizeof(T) >= (1u << 20) && cudaHostAlloc(&q, count * sizeof(T), cudaHostAllocDefault) == cudaSuccess) {
+            pinned = true;
+            memset(q, 0, count * sizeof(T));
+        } else {
+            (void)cudaGetLastError();
+            q = calloc(count, sizeof(T));
+        }
+        p = (T *)q; n = count;
+    }
+    T &operator[](size_t i) { return p[i]; }
+    const T &operator[](size_t i) const { return p[i]; }
+    T *data() { return p; }
+    const T *data() const { return p; }
+    bool empty() const { return n == 0; }
+    size_t size() const { return n; }
+};
 
 const double kLn2 = 0.69314718055994530941723212145818;
 
@@ -368,9 +408,10 @@ int32_t e_to_s(double E, const KBlk &k, int64_t searchsp)
 // ================================================================================================
 struct BnSetup {
     BnQueryBatch batch{};
-    std::vector<uint8_t> query;
+    HostArray<uint8_t> query;
     std::vector<BnContext> ctx;
-    std::vector<int32_t> hashtable, next_pos, masked;
+    HostArray<int32_t> hashtable, next_pos;
+    std::vector<int32_t> masked;
     std::vector<uint32_t> pv;
     std::vector<int16_t> backbone, overflow;
     std::vector<double> kbp_std, kbp_gap;
@@ -512,7 +553,7 @@ int bn_setup_create(const BnSetupOptions *opt, int32_t nq, const uint8_t *qseq, 
     int64_t total = 1;
     for (int32_t i = 0; i < nq; i++) { if (qlens[i] <= 0) return bail(BN_ERR_INVALID); total += 2 * ((int64_t)qlens[i] + 1); }
     if (total > INT32_MAX - 16) return bail(BN_ERR_OVERFLOW);
-    S->query.resize((size_t)total);
+    S->query.assign_zero((size_t)total);
     S->ctx.resize((size_t)2 * nq);
     {
         size_t pos = 0;
@@ -683,8 +724,8 @@ int bn_setup_create(const BnSetupOptions *opt, int32_t nq, const uint8_t *qseq, 
     if (lut_type == 0) {
         b.lut_type = BN_LUT_MB;
         b.hashsize = (int64_t)1 << (2 * lut_width);
-        S->hashtable.assign((size_t)b.hashsize, 0);
-        S->next_pos.assign((size_t)concat_len + 1, 0);
+        S->hashtable.assign_zero((size_t)b.hashsize);
+        S->next_pos.assign_zero((size_t)concat_len + 1);
         const int64_t kTargetPVSize = 131072;
         int64_t pv_size = b.hashsize <= 8 * kTargetPVSize ? (b.hashsize >> 5) : kTargetPVSize / 4;
         if (entries <= 15000 || entries >= 800000) pv_size /= 2;
