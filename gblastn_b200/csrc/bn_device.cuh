@@ -203,6 +203,8 @@ struct GappedLaunch {
     int32_t grid_blocks;          // 0 = default persistent grid
 };
 cudaError_t launch_gapped(const DevQuery &q, const GappedLaunch &g, cudaStream_t st);
+cudaError_t launch_greedy_warp(const DevQuery &q, const GappedLaunch &g, int warps_per_block, int blocks,
+                               bool use_smem, cudaStream_t st);
 int gapped_threads();
 int gapped_threads_per_block();
 

@@ -435,16 +435,25 @@ static int run_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t n_i
     CU_TRY(ws.gap_out.reserve((size_t)n_init));
     const bool greedy = b.gap_algo == BN_GAP_GREEDY;
     const int32_t xo = greedy_xdrop_offset(b);
-    int32_t tier = greedy ? 256 : 1024;
+    const int wpb = 4;                                   // greedy: warps per block
+    int32_t tier = greedy ? 254 : 1024;
     int64_t per_thread = greedy ? (2 * (2 * (int64_t)tier + 6) + tier + 1 + xo + 8) : 2 * (int64_t)tier;
-    const int64_t threads = std::min<int64_t>(gapped_threads(), ((n_init + 63) / 64) * 64);
-    CU_TRY(ws.scratch.reserve((size_t)(per_thread * threads)));
     GappedLaunch g{};
     g.packed = V.d_packed; g.chunks = T.dev.p; g.init = ws.init.p; g.n_init = ws.counters.p + 2;
-    g.max_init = n_init; g.out = ws.gap_out.p; g.scratch = ws.scratch.p;
+    g.max_init = n_init; g.out = ws.gap_out.p;
     g.scratch_ints_per_thread = per_thread; g.tier_d = tier; g.todo = nullptr; g.n_todo = 0;
-    g.grid_blocks = (int32_t)(threads / gapped_threads_per_block());
-    CU_TRY(launch_gapped(dq, g, st));
+    if (greedy) {
+        // one warp per init-HSP, rows in shared memory
+        const int blocks = (int)std::min<int64_t>((n_init + wpb - 1) / wpb, 148 * 8);
+        g.scratch = nullptr;
+        CU_TRY(launch_greedy_warp(dq, g, wpb, blocks, true, st));
+    } else {
+        const int64_t threads = std::min<int64_t>(gapped_threads(), ((n_init + 63) / 64) * 64);
+        CU_TRY(ws.scratch.reserve((size_t)(per_thread * threads)));
+        g.scratch = ws.scratch.p;
+        g.grid_blocks = (int32_t)(threads / gapped_threads_per_block());
+        CU_TRY(launch_gapped(dq, g, st));
+    }
     if (stats) stats->kernel_launches += 1;
     CU_TRY(cudaMemcpyAsync(h_init.data(), ws.init.p, (size_t)n_init * sizeof(DevInitHit), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaMemcpyAsync(h_gap.data(), ws.gap_out.p, (size_t)n_init * sizeof(DevGapResult), cudaMemcpyDeviceToHost, st));
@@ -463,14 +472,15 @@ static int run_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t n_i
             tier = Q.max_query_length + 8;
             per_thread = 2 * (int64_t)tier;
         }
-        const int tpb = gapped_threads_per_block();
+        const int tpb = greedy ? wpb : gapped_threads_per_block();      // workers (warps | threads) per block
         int64_t blocks = std::min<int64_t>(((int64_t)todo.size() + tpb - 1) / tpb, 64);
         CU_TRY(ws.scratch.reserve((size_t)(per_thread * blocks * tpb)));
         CU_TRY(ws.todo.reserve(todo.size()));
         CU_TRY(cudaMemcpyAsync(ws.todo.p, todo.data(), todo.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         g.scratch = ws.scratch.p; g.scratch_ints_per_thread = per_thread; g.tier_d = tier;
         g.todo = ws.todo.p; g.n_todo = (int32_t)todo.size(); g.grid_blocks = (int32_t)blocks;
-        CU_TRY(launch_gapped(dq, g, st));
+        if (greedy) CU_TRY(launch_greedy_warp(dq, g, wpb, (int)blocks, false, st));
+        else CU_TRY(launch_gapped(dq, g, st));
         if (stats) stats->kernel_launches += 1;
         CU_TRY(cudaMemcpyAsync(h_gap.data(), ws.gap_out.p, (size_t)n_init * sizeof(DevGapResult), cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));

@@ -182,6 +182,246 @@ __device__ void greedy_gapped(const DevQuery &q, const uint8_t *packed, int32_t 
     g.status = 0;
 }
 
+// ================================================================================================
+// Warp-parallel greedy: one warp per extension, one lane per diagonal of the current distance.
+// Within a distance d the reference visits diagonals k in ascending order; each diagonal's new
+// offset depends only on row d-1, so all lanes compute theirs at once (each walks its own run of
+// matches on 16-base windows) and the ORDER-DEPENDENT bookkeeping — diag_lower++ while the lowest
+// diagonals fail, diag_upper = last success, the end-of-sequence clamps, "first maximum wins" for
+// the extent and for the longest match run — is then replayed from ballots in ascending k.
+// ================================================================================================
+constexpr unsigned FULLW = 0xffffffffu;
+
+// exact-match run measured by the whole warp (used for the long initial run of each direction)
+__device__ int32_t first_mismatch_warp(const SeqPair &p, int32_t i1, int32_t i2, int lane)
+{
+    const int32_t n = min(p.len1 - i1, p.len2 - i2);
+    if (n <= 0) return 0;
+    for (int32_t base = 0; base < n; base += 512) {
+        const int32_t off = base + 16 * lane;
+        int32_t c = 16;
+        if (off < n) {
+            uint32_t qb, qa, m;
+            if (p.reverse) {
+                qwin(*p.q, p.qbase + p.len1 - i1 - off - 16, qb, qa);
+                m = mismatch_bits(qb, qa, swin(p.packed, p.sbase + p.len2 - i2 - off - 16));
+                if (m) c = (__ffs(m) - 1) >> 1;
+            } else {
+                qwin(*p.q, p.qbase + i1 + off, qb, qa);
+                m = mismatch_bits(qb, qa, swin(p.packed, p.sbase + i2 + off));
+                if (m) c = __clz(m) >> 1;
+            }
+        }
+        const unsigned stop = __ballot_sync(FULLW, off < n && c < 16);
+        if (stop) {
+            const int src = __ffs(stop) - 1;
+            const int32_t cc = __shfl_sync(FULLW, c, src);
+            return min(base + 16 * src + cc, n);
+        }
+    }
+    return n;
+}
+
+__device__ int32_t greedy_align_warp(const SeqPair &sp, int32_t xdrop_threshold, int32_t match_cost,
+                                     int32_t mismatch_cost, int32_t &seq1_len, int32_t &seq2_len,
+                                     int32_t *row0, int32_t *row1, int32_t *max_score_mem, int32_t D,
+                                     GreedySeed &seed, bool &overflow, int lane)
+{
+    const int32_t len1 = sp.len1, len2 = sp.len2;
+    int32_t best_dist = 0;
+    const int32_t max_dist = min(GREEDY_MAX_COST, len2 / 2 + 1);
+    const int32_t origin = D + 2;
+    const int32_t xdrop_offset = (xdrop_threshold + match_cost / 2) / (match_cost + mismatch_cost) + 1;
+
+    int32_t index = first_mismatch_warp(sp, 0, 0, lane);
+    seq1_len = index; seq2_len = index;
+    seed.start_q = 0; seed.start_s = 0;
+    int32_t longest_match_run = index;
+    seed.match_length = index;
+    if (index == len1 || index == len2) return 0;
+
+    int32_t *max_score = max_score_mem + xdrop_offset;
+    for (int32_t i = lane; i < xdrop_offset; i += 32) max_score_mem[i] = 0;
+    if (lane == 0) { row0[origin] = index; max_score[0] = index * match_cost; }
+    __syncwarp();
+    int32_t diag_lower = origin - 1, diag_upper = origin + 1;
+    bool end1_reached = false, end2_reached = false;
+
+    for (int32_t d = 1; d <= max_dist; d++) {
+        if (d > D) { overflow = true; return best_dist; }
+        int32_t curr_extent = 0, curr_seq2_index = 0, curr_diag = 0;
+        const int32_t tmp_lower = diag_lower, tmp_upper = diag_upper;
+        int32_t *prev = ((d - 1) & 1) ? row1 : row0;
+        int32_t *cur = (d & 1) ? row1 : row0;
+        if (lane == 0) {
+            prev[diag_lower - 1] = GREEDY_INVALID;
+            prev[diag_lower] = GREEDY_INVALID;
+            prev[diag_upper] = GREEDY_INVALID;
+            prev[diag_upper + 1] = GREEDY_INVALID;
+        }
+        __syncwarp();
+        int32_t xdrop_score = max_score[d - xdrop_offset] + (match_cost + mismatch_cost) * d - xdrop_threshold;
+        {
+            const int32_t h = match_cost / 2;
+            int32_t qd = xdrop_score / h;
+            if (xdrop_score % h > 0) ++qd;
+            xdrop_score = qd;
+        }
+        for (int32_t kb = tmp_lower; kb <= tmp_upper; kb += 32) {
+            const int32_t k = kb + lane;
+            const bool active = k <= tmp_upper;
+            bool ok = false;
+            int32_t seq1_index = 0, seq2_index = 0, run = 0;
+            if (active) {
+                seq2_index = max(prev[k + 1], prev[k]) + 1;
+                seq2_index = max(seq2_index, prev[k - 1]);
+                seq1_index = seq2_index + k - origin;
+                ok = !(seq2_index < 0 || seq1_index + seq2_index < xdrop_score);
+                if (ok) {
+                    run = first_mismatch(sp, seq1_index, seq2_index);
+                    seq1_index += run; seq2_index += run;
+                }
+            }
+            const unsigned act = __ballot_sync(FULLW, active);
+            const unsigned succ = __ballot_sync(FULLW, ok);
+            const unsigned e2 = __ballot_sync(FULLW, ok && seq2_index == len2);
+            const unsigned e1 = __ballot_sync(FULLW, ok && seq1_index == len1);
+            // ordered replay of the bookkeeping
+            unsigned inv = 0;
+            for (unsigned rem = act; rem; rem &= rem - 1) {
+                const int b = __ffs(rem) - 1;
+                const unsigned bit = 1u << b;
+                const int32_t kk = kb + b;
+                if (!(succ & bit)) {
+                    if (kk == diag_lower) diag_lower++;
+                    else inv |= bit;
+                } else {
+                    diag_upper = kk;
+                    if (e2 & bit) { diag_lower = kk + 1; end2_reached = true; }
+                    if (e1 & bit) { diag_upper = kk - 1; end1_reached = true; }
+                }
+            }
+            if (ok) cur[k] = seq2_index;
+            else if (inv & (1u << lane)) cur[k] = GREEDY_INVALID;
+            if (succ) {
+                // longest run of matches: first diagonal (ascending k) holding the strict maximum
+                int32_t best_run = ok ? run : -1;
+                for (int o = 16; o > 0; o >>= 1) best_run = max(best_run, __shfl_xor_sync(FULLW, best_run, o));
+                if (best_run > longest_match_run) {
+                    const int src = __ffs(__ballot_sync(FULLW, ok && run == best_run)) - 1;
+                    seed.start_q = __shfl_sync(FULLW, seq1_index - run, src);
+                    seed.start_s = __shfl_sync(FULLW, seq2_index - run, src);
+                    seed.match_length = longest_match_run = best_run;
+                }
+                // extent: first diagonal with the strict maximum of seq1 + seq2
+                int32_t ext = ok ? seq1_index + seq2_index : -1;
+                int32_t best_ext = ext;
+                for (int o = 16; o > 0; o >>= 1) best_ext = max(best_ext, __shfl_xor_sync(FULLW, best_ext, o));
+                if (best_ext > curr_extent) {
+                    const int src = __ffs(__ballot_sync(FULLW, ok && ext == best_ext)) - 1;
+                    curr_extent = best_ext;
+                    curr_seq2_index = __shfl_sync(FULLW, seq2_index, src);
+                    curr_diag = kb + src;
+                }
+            }
+        }
+        const int32_t curr_score = curr_extent * (match_cost / 2) - d * (match_cost + mismatch_cost);
+        const int32_t prev_best = max_score[d - 1];
+        __syncwarp();
+        if (curr_score > prev_best) {
+            if (lane == 0) max_score[d] = curr_score;
+            best_dist = d;
+            seq2_len = curr_seq2_index;
+            seq1_len = curr_seq2_index + curr_diag - origin;
+        } else if (lane == 0) max_score[d] = prev_best;
+        __syncwarp();
+        if (diag_lower > diag_upper) break;
+        if (!end2_reached) diag_lower--;
+        if (!end1_reached) diag_upper++;
+    }
+    return best_dist;
+}
+
+// one warp per init-HSP; rows live in shared memory (tier 1) or in global scratch (tier 2)
+__global__ void __launch_bounds__(128)
+greedy_kernel(const DevQuery q, const GappedLaunch L, int use_smem)
+{
+    extern __shared__ int32_t smem_rows[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t n = L.todo ? (int64_t)L.n_todo : (int64_t)min((unsigned long long)L.max_init, *L.n_init);
+    const int32_t D = L.tier_d;
+    int32_t *scratch = use_smem ? smem_rows + (size_t)wib * L.scratch_ints_per_thread
+                                : L.scratch + warp * L.scratch_ints_per_thread;
+    int32_t *row0 = scratch, *row1 = scratch + (2 * D + 6), *ms = scratch + 2 * (2 * D + 6);
+    int32_t match = q.reward, mismatch = -q.penalty, xd = q.gap_x_dropoff;
+    if (match % 2 == 1) { match *= 2; mismatch *= 2; xd *= 2; }
+
+    for (int64_t w = warp; w < n; w += nwarps) {
+        const int64_t i = L.todo ? (int64_t)L.todo[w] : w;
+        const DevInitHit h = L.init[i];
+        const DevChunk ch = L.chunks[h.chunk];
+        const int32_t context = ctx_search(q, h.q_off);
+        const DevContext c = q.ctx[context];
+        const int32_t q_off = (h.q_start - c.query_offset) + h.length / 2;
+        const int32_t s_off = h.s_start + h.length / 2;
+        const int64_t chunk_base = ch.byte_off * 4;
+        DevGapResult g;
+        g.q_start = g.q_stop = g.s_start = g.s_stop = g.score = g.q_seed = g.s_seed = 0;
+        g.status = 0;
+        int32_t q_ext_r = 0, s_ext_r = 0, q_ext_l = 0, s_ext_l = 0;
+        GreedySeed fwd{0, 0, 0}, rev{0, 0, 0};
+        bool overflow = false;
+        SeqPair sp;
+        sp.q = &q; sp.packed = L.packed;
+        sp.qbase = c.query_offset + q_off; sp.sbase = chunk_base + s_off;
+        sp.len1 = c.query_length - q_off; sp.len2 = ch.len - s_off; sp.reverse = false;
+        int32_t dist = greedy_align_warp(sp, xd, match, mismatch, q_ext_r, s_ext_r, row0, row1, ms, D, fwd, overflow, lane);
+        __syncwarp();
+        if (!overflow) {
+            sp.qbase = c.query_offset; sp.sbase = chunk_base; sp.len1 = q_off; sp.len2 = s_off; sp.reverse = true;
+            dist += greedy_align_warp(sp, xd, match, mismatch, q_ext_l, s_ext_l, row0, row1, ms, D, rev, overflow, lane);
+            __syncwarp();
+        }
+        if (overflow) g.status = 1;
+        else {
+            const int32_t score = (q_ext_r + s_ext_r + q_ext_l + s_ext_l) * q.reward / 2 - dist * (q.reward - q.penalty);
+            const int32_t q_box_l = q_off - q_ext_l, s_box_l = s_off - s_ext_l;
+            const int32_t q_box_r = q_off + q_ext_r, s_box_r = s_off + s_ext_r;
+            int32_t q_seed_l = q_off - rev.start_q, s_seed_l = s_off - rev.start_s;
+            int32_t q_seed_r = q_off + fwd.start_q, s_seed_r = s_off + fwd.start_s;
+            int32_t vl = 0, vr = 0;
+            if (q_seed_r < q_box_r && s_seed_r < s_box_r) {
+                vr = min(q_box_r - q_seed_r, s_box_r - s_seed_r);
+                vr = min(vr, fwd.match_length) / 2;
+            } else { q_seed_r = q_off; s_seed_r = s_off; }
+            if (q_seed_l > q_box_l && s_seed_l > s_box_l) {
+                vl = min(q_seed_l - q_box_l, s_seed_l - s_box_l);
+                vl = min(vl, rev.match_length) / 2;
+            } else { q_seed_l = q_off; s_seed_l = s_off; }
+            if (vr > vl) { g.q_seed = q_seed_r + vr; g.s_seed = s_seed_r + vr; }
+            else { g.q_seed = q_seed_l - vl; g.s_seed = s_seed_l - vl; }
+            g.q_start = q_box_l; g.s_start = s_box_l; g.q_stop = q_box_r; g.s_stop = s_box_r;
+            g.score = score;
+        }
+        if (lane == 0) L.out[i] = g;
+    }
+}
+
+cudaError_t launch_greedy_warp(const DevQuery &q, const GappedLaunch &g, int warps_per_block, int blocks,
+                               bool use_smem, cudaStream_t st)
+{
+    const size_t smem = use_smem ? (size_t)warps_per_block * (size_t)g.scratch_ints_per_thread * sizeof(int32_t) : 0;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    greedy_kernel<<<blocks, warps_per_block * 32, smem, st>>>(q, g, use_smem ? 1 : 0);
+    return cudaGetLastError();
+}
+
 // s_BlastAlignPackedNucl with the score_array kept in a ring of C cells: only indices in
 // [first_b_index, b_size] are live, so index i lives at slot i % C as long as the live span <= C.
 __device__ int32_t dp_packed(const uint8_t *B, const uint8_t *A, int32_t N, int32_t M,

@@ -46,6 +46,9 @@ CASES = {
     # queries with ambiguity codes (N) : words containing them are not indexed
     "mb_with_N": dict(task="megablast", cfg={}, seq_lens=[200_000, 100_000], vol_seed=10,
                       nq=30, qlen=600, q_seed=21, sub=0.02, indel=0.002, planted=0.9, n_frac=0.004),
+    # long, divergent queries: greedy distance > 254 -> exercises the tier-2 (global scratch) path on the GPU
+    "mb_long_divergent_tier2": dict(task="megablast", cfg={}, seq_lens=[600_000, 200_000], vol_seed=12,
+                                    nq=3, qlen=30_000, q_seed=23, sub=0.03, indel=0.002, planted=1.0),
     # empty result: random queries only
     "mb_no_hits": dict(task="megablast", cfg={}, seq_lens=[100_000], vol_seed=11,
                        nq=5, qlen=400, q_seed=22, sub=0.0, indel=0.0, planted=0.0),
