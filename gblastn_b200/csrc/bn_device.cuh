@@ -39,6 +39,8 @@ struct DevQuery {
     uint32_t hash_mask;
     const int32_t *hashtable, *next_pos;   // MB
     const uint32_t *presence;              // MB: exact 1 bit / cell bitmap built at load time
+    const uint2 *prk;                      // MB compact table: {presence word, rank of its first occupied cell}
+    const int32_t *dense;                  // MB compact table: hashtable values of occupied cells, in cell order
     const int16_t *backbone, *overflow;    // SmallNa
     int32_t has_locations;                 // lut->masked_locations != NULL
     int32_t container_type, window_size, scan_range;
@@ -166,6 +168,8 @@ struct ScanLaunch {
     int64_t capacity;
     const int32_t *block_chunk;   // first chunk of every BLOCK_POS-sized slice of positions
     int32_t raw_pairs;            // 1: emit every lookup hit (q_off, scan_pos) without mini-extension (scan tap)
+    int32_t gbits;                // bits of the global position in the sort key
+    int32_t diag_array_length;    // eDiagArray: cells (power of two)
 };
 cudaError_t launch_scan(const DevQuery &q, const ScanLaunch &s, cudaStream_t st);
 int scan_positions_per_block();
@@ -173,20 +177,14 @@ int scan_positions_per_block();
 struct ExtendLaunch {
     const uint8_t *packed;
     const DevChunk *chunks;
-    const SeedHit *hits;          // sorted by (group, emission order)
-    const uint32_t *order;        // emission rank of hits[i]
+    const SeedHit *hits;          // sorted by (group, global scan position)
     int32_t *cells;               // hash: 4 ints per cell, one region per group (same offsets as hits)
     DevInitHit *init;
     unsigned long long *counters; // [2] = #init hits, [3] = #extended, [4] = #groups
     int64_t init_capacity;
 };
-cudaError_t launch_extend_groups(const DevQuery &q, const ExtendLaunch &e, const uint64_t *group_key,
-                                 uint32_t *heads, int64_t n_hits, cudaStream_t st);
-cudaError_t launch_group_keys(const DevQuery &q, const SeedHit *hits, const uint32_t *perm, int64_t n,
-                              int32_t diag_array_length, uint64_t *keys, cudaStream_t st);
-cudaError_t launch_gather_hits(const SeedHit *in, const uint32_t *perm, int64_t n, SeedHit *out,
-                               cudaStream_t st);
-cudaError_t launch_iota(uint32_t *p, int64_t n, cudaStream_t st);
+cudaError_t launch_extend_groups(const DevQuery &q, const ExtendLaunch &e, const uint64_t *keys,
+                                 uint32_t *heads, int64_t n_hits, int gbits, cudaStream_t st);
 
 struct GappedLaunch {
     const uint8_t *packed;

@@ -52,8 +52,8 @@ struct DevBuf {
 
 struct Workspace {
     DevBuf<SeedHit> hits_a, hits_b;
-    DevBuf<uint64_t> keys_a, keys_b, gkeys_a, gkeys_b;
-    DevBuf<uint32_t> perm_a, perm_b, order_a, order_b, heads;
+    DevBuf<uint64_t> keys_a, keys_b;
+    DevBuf<uint32_t> heads;
     DevBuf<int4> cells;
     DevBuf<DevInitHit> init;
     DevBuf<DevGapResult> gap_out;
@@ -63,8 +63,7 @@ struct Workspace {
     unsigned long long *h_counters = nullptr;   // pinned
     void release()
     {
-        hits_a.release(); hits_b.release(); keys_a.release(); keys_b.release(); gkeys_a.release();
-        gkeys_b.release(); perm_a.release(); perm_b.release(); order_a.release(); order_b.release();
+        hits_a.release(); hits_b.release(); keys_a.release(); keys_b.release();
         cells.release(); heads.release(); init.release(); gap_out.release(); scratch.release(); todo.release();
         counters.release(); cub_temp.release();
         if (h_counters) cudaFreeHost(h_counters);
@@ -107,6 +106,8 @@ struct QueryDev {
     int16_t *backbone = nullptr, *overflow = nullptr;
     int32_t *score_table = nullptr, *matrix = nullptr;
     uint2 *qpk = nullptr;
+    uint2 *prk = nullptr;
+    int32_t *dense = nullptr;
     DevQuery view{};
     bool ready = false;
 };
@@ -143,7 +144,7 @@ static Device *device_at(int d)
 static void free_query_dev(QueryDev &q, cudaStream_t st)
 {
     void *ptrs[] = {q.query, q.ctx, q.hashtable, q.next_pos, q.presence, q.backbone, q.overflow,
-                    q.score_table, q.matrix, q.qpk};
+                    q.score_table, q.matrix, q.qpk, q.prk, q.dense};
     for (void *p : ptrs) if (p) cudaFreeAsync(p, st);
     q = QueryDev{};
 }
@@ -166,6 +167,9 @@ static cudaError_t upload(T **dst, const T *src, size_t n, cudaStream_t st)
 
 cudaError_t launch_build_presence(const int32_t *hashtable, int64_t hashsize, uint32_t *presence, cudaStream_t st);
 cudaError_t launch_build_qpk(const uint8_t *query_start, int32_t concat_len, uint2 *qpk, int64_t nwords, cudaStream_t st);
+cudaError_t launch_popc(const uint32_t *presence, int64_t nwords, uint32_t *counts, cudaStream_t st);
+cudaError_t launch_build_compact(const int32_t *hashtable, const uint32_t *presence, const uint32_t *prefix,
+                                 int64_t nwords, uint2 *prk, int32_t *dense, cudaStream_t st);
 
 // Uploads one query batch to device d straight from the caller's arrays (no host staging copy);
 // the presence bitmap and the 16-base query windows are derived on the device.
@@ -192,6 +196,23 @@ static int query_to_device(Query &Q, const BnQueryBatch &src, int d)
         // PV_TEST is only a filter in front of hashtable[index] != 0)
         CU_TRY(dev_alloc(&qd.presence, (size_t)((b.hashsize + 31) / 32), st));
         CU_TRY(launch_build_presence(qd.hashtable, b.hashsize, qd.presence, st));
+        // compact table for the scan kernel: {presence word, rank} + dense values (L2-resident)
+        {
+            const int64_t nwords = (b.hashsize + 31) / 32;
+            uint32_t *counts = nullptr, *prefix = nullptr;
+            CU_TRY(dev_alloc(&counts, (size_t)nwords, st));
+            CU_TRY(dev_alloc(&prefix, (size_t)nwords, st));
+            CU_TRY(dev_alloc(&qd.prk, (size_t)nwords, st));
+            CU_TRY(dev_alloc(&qd.dense, (size_t)b.concat_len + 2, st));
+            CU_TRY(launch_popc(qd.presence, nwords, counts, st));
+            size_t tmp_bytes = 0;
+            CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, prefix, (int)nwords, st));
+            CU_TRY(dev->ws.cub_temp.reserve(tmp_bytes));
+            CU_TRY(cub::DeviceScan::ExclusiveSum(dev->ws.cub_temp.p, tmp_bytes, counts, prefix, (int)nwords, st));
+            CU_TRY(launch_build_compact(qd.hashtable, qd.presence, prefix, nwords, qd.prk, qd.dense, st));
+            CU_TRY(cudaFreeAsync(counts, st));
+            CU_TRY(cudaFreeAsync(prefix, st));
+        }
     } else {
         static const int16_t kEmptyOverflow[2] = {-1, -1};
         CU_TRY(upload(&qd.backbone, src.backbone, (size_t)b.hashsize, st));
@@ -216,6 +237,7 @@ static int query_to_device(Query &Q, const BnQueryBatch &src, int d)
     v.has_locations = Q.batch.masked_locations != nullptr;
     v.container_type = b.container_type; v.window_size = b.window_size; v.scan_range = b.scan_range;
     v.score_table = qd.score_table; v.matrix = qd.matrix; v.qpk = qd.qpk;
+    v.prk = (b.word_length <= 200) ? qd.prk : nullptr; v.dense = qd.dense;
     v.gap_algo = b.gap_algo; v.reward = b.reward; v.penalty = b.penalty;
     v.gap_open = b.gap_open; v.gap_extend = b.gap_extend; v.gap_x_dropoff = b.gap_x_dropoff;
     qd.ready = true;
@@ -309,21 +331,12 @@ static double now_ms()
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
-static int sort_pairs_u64(Workspace &ws, const uint64_t *kin, uint64_t *kout, const uint32_t *vin,
-                          uint32_t *vout, int64_t n, int end_bit, cudaStream_t st)
-{
-    size_t bytes = 0;
-    CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)n, 0, end_bit, st));
-    CU_TRY(ws.cub_temp.reserve(bytes));
-    CU_TRY(cub::DeviceRadixSort::SortPairs(ws.cub_temp.p, bytes, kin, kout, vin, vout, (int)n, 0, end_bit, st));
-    return BN_OK;
-}
-
 static int bits_for(uint64_t v) { int b = 1; while (b < 64 && (v >> b)) ++b; return b; }
 
 struct StageCounts { int64_t n_hits = 0, lookup_hits = 0, n_init = 0, n_extended = 0; };
 
-// scan + sorts + diagonal/ungapped kernel.  Leaves init hits in ws.init (unsorted) on the device.
+// scan -> one stable radix sort on (diagonal group, global position) -> diagonal/ungapped kernel.
+// Leaves the sorted seed hits in ws.hits_b and the init hits (unsorted) in ws.init.
 static int run_word_finder(Device &D, Volume &V, Query &Q, ChunkTable &T, bool raw_pairs,
                            StageCounts &cnt, BnStats *stats)
 {
@@ -332,6 +345,9 @@ static int run_word_finder(Device &D, Volume &V, Query &Q, ChunkTable &T, bool r
     const DevQuery &dq = Q.dev[V.device].view;
     CU_TRY(ws.counters.reserve(8));
     if (!ws.h_counters) CU_TRY(cudaMallocHost(&ws.h_counters, 8 * sizeof(unsigned long long)));
+    if (T.total_pos >= (int64_t)1 << 32) return fail(BN_ERR_OVERFLOW, "more than 2^32 scan positions in one search");
+    const int gbits = bits_for((uint64_t)std::max<int64_t>(T.total_pos, 1));
+    const int grp_bits = raw_pairs ? 0 : (Q.batch.container_type == BN_DIAG_HASH ? 9 : bits_for((uint64_t)Q.diag_array_length));
 
     Timer t_scan(st), t_ext(st);
     int64_t cap = std::max<int64_t>((int64_t)ws.hits_a.cap, std::max<int64_t>(1 << 16, T.total_pos / 16));
@@ -344,7 +360,7 @@ static int run_word_finder(Device &D, Volume &V, Query &Q, ChunkTable &T, bool r
         s.packed = V.d_packed; s.chunks = T.dev.p; s.n_chunks = (int32_t)T.host.size();
         s.total_pos = T.total_pos; s.hits = ws.hits_a.p; s.keys = ws.keys_a.p;
         s.counters = ws.counters.p; s.capacity = cap; s.block_chunk = T.block_chunk.p;
-        s.raw_pairs = raw_pairs ? 1 : 0;
+        s.raw_pairs = raw_pairs ? 1 : 0; s.gbits = gbits; s.diag_array_length = Q.diag_array_length;
         t_scan.start();
         CU_TRY(launch_scan(dq, s, st));
         t_scan.stop();
@@ -363,42 +379,33 @@ static int run_word_finder(Device &D, Volume &V, Query &Q, ChunkTable &T, bool r
     const int64_t n = cnt.n_hits;
     if (n == 0) return BN_OK;
 
-    // 1) emission order: sort by (global scan position, chain rank)
     t_ext.start();
-    CU_TRY(ws.keys_b.reserve((size_t)n)); CU_TRY(ws.perm_a.reserve((size_t)n)); CU_TRY(ws.perm_b.reserve((size_t)n));
+    CU_TRY(ws.keys_b.reserve((size_t)n));
     CU_TRY(ws.hits_b.reserve((size_t)n));
-    CU_TRY(launch_iota(ws.perm_a.p, n, st));
-    const int key_bits = std::min(64, 24 + bits_for((uint64_t)std::max<int64_t>(T.total_pos, 1)));
-    int rc = sort_pairs_u64(ws, ws.keys_a.p, ws.keys_b.p, ws.perm_a.p, ws.perm_b.p, n, key_bits, st);
-    if (rc) return rc;
-    CU_TRY(launch_gather_hits(ws.hits_a.p, ws.perm_b.p, n, ws.hits_b.p, st));   // hits_b: emission order
-    if (stats) stats->kernel_launches += 4;
+    {
+        size_t bytes = 0;
+        const int end_bit = std::min(64, gbits + grp_bits);
+        CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, ws.keys_a.p, ws.keys_b.p, ws.hits_a.p, ws.hits_b.p,
+                                               (int)n, 0, end_bit, st));
+        CU_TRY(ws.cub_temp.reserve(bytes));
+        CU_TRY(cub::DeviceRadixSort::SortPairs(ws.cub_temp.p, bytes, ws.keys_a.p, ws.keys_b.p, ws.hits_a.p,
+                                               ws.hits_b.p, (int)n, 0, end_bit, st));
+        if (stats) stats->kernel_launches += 2 + (end_bit + 7) / 8;
+    }
     if (raw_pairs) { t_ext.stop(); if (stats) stats->ms_extend += t_ext.ms(); return BN_OK; }
 
-    // 2) group by diagonal bucket / cell, stable, so each group stays in emission order
-    CU_TRY(ws.gkeys_a.reserve((size_t)n)); CU_TRY(ws.gkeys_b.reserve((size_t)n));
-    CU_TRY(ws.order_a.reserve((size_t)n)); CU_TRY(ws.order_b.reserve((size_t)n));
-    CU_TRY(launch_iota(ws.order_a.p, n, st));
-    CU_TRY(launch_group_keys(dq, ws.hits_b.p, ws.order_a.p, n, Q.diag_array_length, ws.gkeys_a.p, st));
-    const int gbits = Q.batch.container_type == BN_DIAG_HASH ? 9 : 32 + bits_for((uint64_t)std::max<size_t>(T.host.size(), 1));
-    rc = sort_pairs_u64(ws, ws.gkeys_a.p, ws.gkeys_b.p, ws.order_a.p, ws.order_b.p, n, std::min(64, gbits), st);
-    if (rc) return rc;
-    CU_TRY(launch_gather_hits(ws.hits_b.p, ws.order_b.p, n, ws.hits_a.p, st));  // hits_a: grouped
     CU_TRY(ws.cells.reserve((size_t)n + 2));
     CU_TRY(ws.heads.reserve((size_t)n + 1));
-    if (stats) stats->kernel_launches += 5;
-
-    // 3) replay groups
     int64_t init_cap = std::max<int64_t>((int64_t)ws.init.cap, std::max<int64_t>(4096, n / 4));
     for (int attempt = 0;; attempt++) {
         CU_TRY(ws.init.reserve((size_t)init_cap));
         init_cap = (int64_t)ws.init.cap;
         CU_TRY(cudaMemsetAsync(ws.counters.p + 2, 0, 3 * sizeof(unsigned long long), st));
         ExtendLaunch e{};
-        e.packed = V.d_packed; e.chunks = T.dev.p; e.hits = ws.hits_a.p; e.order = ws.order_b.p;
+        e.packed = V.d_packed; e.chunks = T.dev.p; e.hits = ws.hits_b.p;
         e.cells = reinterpret_cast<int32_t *>(ws.cells.p); e.init = ws.init.p;
         e.counters = ws.counters.p; e.init_capacity = init_cap;
-        CU_TRY(launch_extend_groups(dq, e, ws.gkeys_b.p, ws.heads.p, n, st));
+        CU_TRY(launch_extend_groups(dq, e, ws.keys_b.p, ws.heads.p, n, gbits, st));
         if (stats) stats->kernel_launches += 2;
         CU_TRY(cudaMemcpyAsync(ws.h_counters, ws.counters.p, 8 * sizeof(unsigned long long),
                                cudaMemcpyDeviceToHost, st));
@@ -863,6 +870,7 @@ int bn_bench_scan(int vol_handle, int query_handle, int iters, double *ms_per_la
     s.packed = V->d_packed; s.chunks = T->dev.p; s.n_chunks = (int32_t)T->host.size();
     s.total_pos = T->total_pos; s.hits = ws.hits_a.p; s.keys = ws.keys_a.p;
     s.counters = ws.counters.p; s.capacity = cap; s.block_chunk = T->block_chunk.p; s.raw_pairs = 0;
+    s.gbits = bits_for((uint64_t)std::max<int64_t>(T->total_pos, 1)); s.diag_array_length = Q->diag_array_length;
     const DevQuery &dq = Q->dev[V->device].view;
     Timer t(st);
     double total = 0;

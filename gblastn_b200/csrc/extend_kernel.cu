@@ -330,20 +330,30 @@ __device__ __forceinline__ uint32_t diag_bucket(int32_t diag)
     return ((uint32_t)diag * 0x9E370001u) % 512u;
 }
 
+// Sorted key = (group << gbits) | global scan position.  Two consecutive hits belong to the same
+// replay group when their group fields match and, for the diagonal ARRAY (whose cells are
+// independent per subject chunk), they come from the same chunk.
+__device__ __forceinline__ bool same_group(const uint64_t *keys, const SeedHit *hits, int64_t a, int64_t b,
+                                           int gbits, bool is_hash)
+{
+    if ((keys[a] >> gbits) != (keys[b] >> gbits)) return false;
+    return is_hash || hits[a].chunk == hits[b].chunk;
+}
+
 // heads[i] = index of the first hit of group i (any order)
-__global__ void group_heads_kernel(const uint64_t *group_key, int64_t n, uint32_t *heads,
-                                   unsigned long long *counters)
+__global__ void group_heads_kernel(const uint64_t *keys, const SeedHit *hits, int64_t n, int gbits,
+                                   int is_hash, uint32_t *heads, unsigned long long *counters)
 {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    if (j > 0 && group_key[j - 1] == group_key[j]) return;
+    if (j > 0 && same_group(keys, hits, j - 1, j, gbits, is_hash != 0)) return;
     const unsigned long long slot = atomicAdd(&counters[4], 1ull);
     heads[slot] = (uint32_t)j;
 }
 
 __global__ void __launch_bounds__(EXT_WARPS_PER_BLOCK * 32)
-extend_kernel(const DevQuery q, const ExtendLaunch e, const uint64_t *group_key, const uint32_t *heads,
-              int64_t n_hits)
+extend_kernel(const DevQuery q, const ExtendLaunch e, const uint64_t *keys, const uint32_t *heads,
+              int64_t n_hits, int gbits)
 {
     __shared__ int32_t s_tab[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = q.score_table[i];
@@ -363,7 +373,6 @@ extend_kernel(const DevQuery q, const ExtendLaunch e, const uint64_t *group_key,
 
     for (int64_t g = warp0; g < n_groups; g += nwarps) {
         const int64_t j0 = (int64_t)heads[g];
-        const uint64_t gk = group_key[j0];
         Chain chain;
         chain.cells = reinterpret_cast<int4 *>(e.cells) + j0;   // region [j0+1 .. j0+group_size]
         chain.head = 0; chain.used = 0;
@@ -376,7 +385,7 @@ extend_kernel(const DevQuery q, const ExtendLaunch e, const uint64_t *group_key,
         unsigned long long n_extended = 0;
 
         for (int64_t j = j0; j < n_hits; ++j) {
-            if (j > j0 && group_key[j] != gk) break;
+            if (j > j0 && !same_group(keys, e.hits, j - 1, j, gbits, is_hash)) break;
             const SeedHit h = e.hits[j];
             if (h.chunk != cur_chunk) {
                 cur_chunk = h.chunk;
@@ -426,7 +435,7 @@ extend_kernel(const DevQuery q, const ExtendLaunch e, const uint64_t *group_key,
                         DevInitHit o;
                         o.chunk = (int32_t)cur_chunk; o.q_off = q_off; o.s_off = s_off;
                         o.q_start = u.q_start; o.s_start = u.s_start; o.length = u.length; o.score = u.score;
-                        o.order = e.order[j];
+                        o.order = (uint32_t)(keys[j] & ((1ull << gbits) - 1ull));
                         e.init[slot] = o;
                     }
                 }
@@ -443,65 +452,17 @@ extend_kernel(const DevQuery q, const ExtendLaunch e, const uint64_t *group_key,
     }
 }
 
-// group key of every sorted hit: hash -> bucket id; array -> (chunk, real diagonal)
-__global__ void group_key_kernel(const DevQuery q, const SeedHit *hits, const uint32_t *perm,
-                                 int64_t n, int32_t diag_array_length, uint64_t *keys)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const SeedHit h = hits[perm[i]];
-    if (q.container_type == 1) {
-        keys[i] = diag_bucket((int32_t)h.s_off - (int32_t)h.q_off);
-    } else {
-        uint32_t real = (uint32_t)((int32_t)h.s_off + diag_array_length - (int32_t)h.q_off) &
-                        (uint32_t)(diag_array_length - 1);
-        keys[i] = ((uint64_t)h.chunk << 32) | real;
-    }
-}
-
-__global__ void gather_hits_kernel(const SeedHit *in, const uint32_t *perm, int64_t n, SeedHit *out)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = in[perm[i]];
-}
-
-__global__ void iota_kernel(uint32_t *p, int64_t n)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = (uint32_t)i;
-}
-
-cudaError_t launch_group_keys(const DevQuery &q, const SeedHit *hits, const uint32_t *perm, int64_t n,
-                              int32_t diag_array_length, uint64_t *keys, cudaStream_t st)
-{
-    if (n <= 0) return cudaSuccess;
-    group_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q, hits, perm, n, diag_array_length, keys);
-    return cudaGetLastError();
-}
-cudaError_t launch_gather_hits(const SeedHit *in, const uint32_t *perm, int64_t n, SeedHit *out,
-                               cudaStream_t st)
-{
-    if (n <= 0) return cudaSuccess;
-    gather_hits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, perm, n, out);
-    return cudaGetLastError();
-}
-cudaError_t launch_iota(uint32_t *p, int64_t n, cudaStream_t st)
-{
-    if (n <= 0) return cudaSuccess;
-    iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_extend_groups(const DevQuery &q, const ExtendLaunch &e, const uint64_t *group_key,
-                                 uint32_t *heads, int64_t n_hits, cudaStream_t st)
+cudaError_t launch_extend_groups(const DevQuery &q, const ExtendLaunch &e, const uint64_t *keys,
+                                 uint32_t *heads, int64_t n_hits, int gbits, cudaStream_t st)
 {
     if (n_hits <= 0) return cudaSuccess;
-    group_heads_kernel<<<(unsigned)((n_hits + 255) / 256), 256, 0, st>>>(group_key, n_hits, heads, e.counters);
+    group_heads_kernel<<<(unsigned)((n_hits + 255) / 256), 256, 0, st>>>(keys, e.hits, n_hits, gbits,
+                                                                         q.container_type == 1, heads, e.counters);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;
     const int64_t want = (n_hits + EXT_WARPS_PER_BLOCK - 1) / EXT_WARPS_PER_BLOCK;
     const unsigned blocks = (unsigned)(want < EXT_BLOCKS ? (want < 1 ? 1 : want) : EXT_BLOCKS);
-    extend_kernel<<<blocks, EXT_WARPS_PER_BLOCK * 32, 0, st>>>(q, e, group_key, heads, n_hits);
+    extend_kernel<<<blocks, EXT_WARPS_PER_BLOCK * 32, 0, st>>>(q, e, keys, heads, n_hits, gbits);
     return cudaGetLastError();
 }
 

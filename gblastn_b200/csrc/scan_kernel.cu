@@ -12,11 +12,24 @@
 //                 :1347-1427, s_BlastSmallNaExtend :1450-1555
 //
 // One launch covers every chunk of a resident volume.  A block owns POS_PER_BLOCK consecutive scan
-// positions of the volume-wide position space (prefix sums in the chunk table); each thread forms its
-// lookup words from two aligned 32-bit loads + a funnel shift, probes an exact presence bitmap
-// (L2-resident, 1 bit per table cell), walks the chain and runs the mini-extension in registers.
-// Survivors (a tiny fraction of lookup hits) are appended with warp-aggregated atomics together
-// with a 64-bit key = (global position, chain rank) that restores the reference's emission order.
+// positions of the volume-wide position space (prefix sums in the chunk table).
+//
+//   phase 0  the block's slice of the packed subject (a few KB, contiguous in the volume) is staged
+//            into shared memory with coalesced 128-bit loads
+//   phase A  every thread forms the lookup words of its positions from the tile and probes the
+//            compact table word {presence bits, rank} (one 8-byte L2 access per position); positions
+//            whose cell is occupied are pushed to a shared-memory candidate queue
+//   phase B  candidates are processed DENSELY (one per thread, no idle lanes): first query offset
+//            from dense[rank], chain walk through next_pos, mini-extension on 16-base windows
+//            (subject from the tile, query from the packed query), survivors appended with
+//            warp-aggregated atomics
+//
+// A survivor carries the 64-bit key (group << gbits | global position): group = diagonal-hash bucket
+// or diagonal-array cell.  One stable radix sort on that key both groups the hits for the diagonal
+// stage and restores the reference's emission order inside a group (a position is handled by one
+// thread, which emits its chain in chain order).
+// The generic kernel (direct global loads, full hashtable) is kept for small tables and for blocks
+// whose byte span does not fit the tile.
 #include "bn_device.cuh"
 
 namespace bn {
@@ -24,6 +37,8 @@ namespace bn {
 constexpr int SCAN_THREADS = 256;
 constexpr int POS_PER_THREAD = 4;
 constexpr int POS_PER_BLOCK = SCAN_THREADS * POS_PER_THREAD;
+constexpr int TILE_BYTES = 20 * 1024;      // staged subject slice (incl. 64-byte margins)
+constexpr int TILE_MARGIN = 64;
 
 int scan_positions_per_block() { return POS_PER_BLOCK; }
 
@@ -35,8 +50,15 @@ __device__ __forceinline__ uint32_t load_window(const uint8_t *packed, int64_t b
     return __funnelshift_l(b, a, (uint32_t)(byte & 3) * 8);
 }
 
-__device__ __forceinline__ void emit_hit(const ScanLaunch &s, uint32_t chunk, uint32_t p, int64_t g,
-                                         uint32_t rank, int32_t q_off, int32_t s_off)
+__device__ __forceinline__ uint32_t diag_group(const DevQuery &q, const ScanLaunch &s, int32_t q_off, int32_t s_off)
+{
+    if (s.raw_pairs) return 0;
+    if (q.container_type == 1) return ((uint32_t)(s_off - q_off) * 0x9E370001u) % 512u;       // hash bucket
+    return (uint32_t)(s_off + s.diag_array_length - q_off) & (uint32_t)(s.diag_array_length - 1);  // array cell
+}
+
+__device__ __forceinline__ void emit_hit(const DevQuery &q, const ScanLaunch &s, uint32_t chunk, uint32_t p,
+                                         int64_t g, int32_t q_off, int32_t s_off)
 {
     // warp-aggregated append
     unsigned mask = __activemask();
@@ -50,7 +72,7 @@ __device__ __forceinline__ void emit_hit(const ScanLaunch &s, uint32_t chunk, ui
         SeedHit h;
         h.chunk = chunk; h.scan_pos = p; h.q_off = (uint32_t)q_off; h.s_off = (uint32_t)s_off;
         s.hits[slot] = h;
-        s.keys[slot] = ((uint64_t)g << 24) | (uint64_t)(rank & 0xFFFFFFu);
+        s.keys[slot] = ((uint64_t)diag_group(q, s, q_off, s_off) << s.gbits) | (uint64_t)g;
     }
 }
 
@@ -193,29 +215,25 @@ scan_kernel(const DevQuery q, const ScanLaunch s)
         if (q.lut_type == 0) {
             if (!((__ldg(&q.presence[idx >> 5]) >> (idx & 31)) & 1u)) continue;
             int32_t qp = __ldg(&q.hashtable[idx]);
-            uint32_t rank = 0;
             while (qp) {
                 ++my_lookup_hits;
                 int32_t qo, so;
-                if (s.raw_pairs) emit_hit(s, (uint32_t)lo, (uint32_t)p, g, rank, qp - 1, p);
+                if (s.raw_pairs) emit_hit(q, s, (uint32_t)lo, (uint32_t)p, g, qp - 1, p);
                 else if (mini_extend_mb(q, S, ch.len, qp - 1, p, qo, so))
-                    emit_hit(s, (uint32_t)lo, (uint32_t)p, g, rank, qo, so);
-                ++rank;
+                    emit_hit(q, s, (uint32_t)lo, (uint32_t)p, g, qo, so);
                 qp = __ldg(&q.next_pos[qp]);
             }
         } else {
             int32_t v = __ldg(&q.backbone[idx]);
             if (v == -1) continue;
-            uint32_t rank = 0;
             int32_t src = 0;
             if (v < 0) { src = -v; v = __ldg(&q.overflow[src++]); }
             do {
                 ++my_lookup_hits;
                 int32_t qo, so;
-                if (s.raw_pairs) emit_hit(s, (uint32_t)lo, (uint32_t)p, g, rank, v, p);
+                if (s.raw_pairs) emit_hit(q, s, (uint32_t)lo, (uint32_t)p, g, v, p);
                 else if (mini_extend_small(q, S, ch.len, v, p, qo, so))
-                    emit_hit(s, (uint32_t)lo, (uint32_t)p, g, rank, qo, so);
-                ++rank;
+                    emit_hit(q, s, (uint32_t)lo, (uint32_t)p, g, qo, so);
                 v = src ? (int32_t)__ldg(&q.overflow[src++]) : -1;
             } while (v >= 0);
         }
@@ -223,6 +241,146 @@ scan_kernel(const DevQuery q, const ScanLaunch s)
     // one atomic per warp for the lookup-hit statistic (BlastUngappedStats.lookup_hits)
     for (int o = 16; o > 0; o >>= 1) my_lookup_hits += __shfl_down_sync(0xffffffffu, my_lookup_hits, o);
     if ((threadIdx.x & 31) == 0 && my_lookup_hits) atomicAdd(&s.counters[1], my_lookup_hits);
+}
+
+// ---- staged kernel (megablast tables) ------------------------------------------------------------
+struct Candidate { uint32_t chunk; int32_t p; uint32_t idx; uint32_t gl; };   // gl = position index inside the block
+
+// 16-base window of the staged tile starting at tile-relative base position tb (>= 0)
+__device__ __forceinline__ uint32_t tile_win(const uint32_t *tile, int32_t tb)
+{
+    const uint32_t a = __byte_perm(tile[tb >> 4], 0, 0x0123);
+    const uint32_t b = __byte_perm(tile[(tb >> 4) + 1], 0, 0x0123);
+    return __funnelshift_l(b, a, (uint32_t)(tb & 15) * 2);
+}
+
+// s_BlastNaExtend on 16-base windows; tbase = tile-relative base index of the chunk's base 0
+__device__ __forceinline__ bool mini_extend_tile(const DevQuery &q, const uint32_t *tile, int64_t tbase,
+                                                 int32_t s_range, int32_t q_offset, int32_t s_offset,
+                                                 int32_t &q_out, int32_t &s_out)
+{
+    const int32_t lut = q.lut_word_length, ext_to = q.word_length - lut;
+    int32_t ext_left = 0;
+    if (ext_to > 0) {
+        const int32_t lim = min(ext_to, s_offset);
+        while (ext_left < lim) {
+            uint32_t qb, qa;
+            qwin(q, q_offset - ext_left - 16, qb, qa);
+            const uint32_t m = mismatch_bits(qb, qa, tile_win(tile, (int32_t)(tbase + s_offset - ext_left - 16)));
+            if (m) { ext_left = min(ext_left + ((__ffs(m) - 1) >> 1), lim); break; }
+            ext_left = min(ext_left + 16, lim);
+        }
+        if (ext_left < ext_to) {
+            const int32_t need = ext_to - ext_left;
+            const int32_t sp = s_offset + lut;
+            if ((uint32_t)(sp + need) > (uint32_t)s_range) return false;
+            int32_t ext_right = 0;
+            while (ext_right < need) {
+                uint32_t qb, qa;
+                qwin(q, q_offset + lut + ext_right, qb, qa);
+                const uint32_t m = mismatch_bits(qb, qa, tile_win(tile, (int32_t)(tbase + sp + ext_right)));
+                if (m) { ext_right = min(ext_right + (__clz(m) >> 1), need); break; }
+                ext_right = min(ext_right + 16, need);
+            }
+            if (ext_right < need) return false;
+        }
+    }
+    q_out = q_offset - ext_left;
+    s_out = s_offset - ext_left;
+    return true;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_kernel_staged(const DevQuery q, const ScanLaunch s)
+{
+    __shared__ __align__(16) uint32_t tile[TILE_BYTES / 4];
+    __shared__ Candidate cand[POS_PER_BLOCK];
+    __shared__ int32_t sh_c_lo, sh_c_hi, sh_ncand;
+    __shared__ int64_t sh_tile_lo, sh_tile_hi;
+
+    const int tid = threadIdx.x;
+    const int64_t block_pos0 = (int64_t)blockIdx.x * POS_PER_BLOCK;
+    const int32_t lut = q.lut_word_length, step = q.scan_step;
+    if (tid == 0) {
+        const int32_t c_lo = s.block_chunk[blockIdx.x];
+        int32_t lo = c_lo, hi = s.block_chunk[blockIdx.x + 1];
+        const int64_t g_last = min(block_pos0 + POS_PER_BLOCK, s.total_pos) - 1;
+        while (lo < hi) {                       // chunk of the block's last position
+            const int32_t m = (lo + hi + 1) >> 1;
+            if (s.chunks[m].pos_prefix <= g_last) lo = m; else hi = m - 1;
+        }
+        const DevChunk a = s.chunks[c_lo], b = s.chunks[lo];
+        const int64_t first_byte = a.byte_off + (((block_pos0 - a.pos_prefix) * step) >> 2);
+        const int64_t last_byte = b.byte_off + ((((g_last - b.pos_prefix) * step) + q.word_length + 32) >> 2);
+        sh_c_lo = c_lo; sh_c_hi = lo;
+        sh_tile_lo = (first_byte - TILE_MARGIN) & ~int64_t(15);
+        sh_tile_hi = last_byte + TILE_MARGIN;
+        sh_ncand = 0;
+    }
+    __syncthreads();
+    const int32_t c_lo = sh_c_lo, c_hi = sh_c_hi;
+    const int64_t tile_lo = sh_tile_lo;
+    const int32_t tile_bytes = (int32_t)(sh_tile_hi - tile_lo);
+    const bool staged = tile_bytes <= TILE_BYTES - 16;
+    if (staged) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(s.packed + tile_lo);
+        uint4 *dst = reinterpret_cast<uint4 *>(tile);
+        for (int i = tid; i < (tile_bytes + 15) / 16; i += SCAN_THREADS) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+
+    // ---- phase A: lookup words + presence probe ------------------------------------------------
+#pragma unroll 1
+    for (int it = 0; it < POS_PER_THREAD; it++) {
+        const uint32_t gl = (uint32_t)(it * SCAN_THREADS + tid);
+        const int64_t g = block_pos0 + gl;
+        if (g >= s.total_pos) break;
+        int32_t lo = c_lo, hi = c_hi;
+        while (lo < hi) {
+            const int32_t m = (lo + hi + 1) >> 1;
+            if (__ldg(&s.chunks[m].pos_prefix) <= g) lo = m; else hi = m - 1;
+        }
+        const int64_t prefix = __ldg(&s.chunks[lo].pos_prefix);
+        const int64_t byte_off = __ldg(&s.chunks[lo].byte_off);
+        const int32_t p = (int32_t)(g - prefix) * step;
+        uint32_t window;
+        if (staged) window = tile_win(tile, (int32_t)((byte_off - tile_lo) * 4 + p));
+        else window = load_window(s.packed, byte_off + (p >> 2)) << (2 * (p & 3));
+        const uint32_t idx = window >> (2 * (16 - lut));
+        const uint2 w = __ldg(&q.prk[idx >> 5]);
+        if ((w.x >> (idx & 31)) & 1u) {
+            const int slot = atomicAdd(&sh_ncand, 1);
+            cand[slot] = Candidate{(uint32_t)lo, p, idx, gl};
+        }
+    }
+    __syncthreads();
+
+    // ---- phase B: dense candidate processing ------------------------------------------------------
+    const int ncand = sh_ncand;
+    unsigned long long my_lookup_hits = 0;
+    for (int ci = tid; ci < ncand; ci += SCAN_THREADS) {
+        const Candidate c = cand[ci];
+        const uint2 w = __ldg(&q.prk[c.idx >> 5]);
+        const uint32_t rank = w.y + __popc(w.x & ((1u << (c.idx & 31)) - 1u));
+        int32_t qp = __ldg(&q.dense[rank]);
+        const int64_t byte_off = __ldg(&s.chunks[c.chunk].byte_off);
+        const int32_t len = __ldg(&s.chunks[c.chunk].len);
+        const int64_t g = block_pos0 + c.gl;
+        while (qp) {
+            ++my_lookup_hits;
+            int32_t qo, so;
+            if (s.raw_pairs) emit_hit(q, s, c.chunk, (uint32_t)c.p, g, qp - 1, c.p);
+            else {
+                bool ok;
+                if (staged) ok = mini_extend_tile(q, tile, (byte_off - tile_lo) * 4, len, qp - 1, c.p, qo, so);
+                else ok = mini_extend_mb(q, s.packed + byte_off, len, qp - 1, c.p, qo, so);
+                if (ok) emit_hit(q, s, c.chunk, (uint32_t)c.p, g, qo, so);
+            }
+            qp = __ldg(&q.next_pos[qp]);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) my_lookup_hits += __shfl_down_sync(0xffffffffu, my_lookup_hits, o);
+    if ((tid & 31) == 0 && my_lookup_hits) atomicAdd(&s.counters[1], my_lookup_hits);
 }
 
 // ---- query-load helpers: derived device arrays -----------------------------------------------------
@@ -260,6 +418,39 @@ __global__ void build_qpk_kernel(const uint8_t *query_start, int32_t concat_len,
     qpk[i] = make_uint2(bases, amb);
 }
 
+// prk[w] = {presence word, number of occupied cells before word w}; dense[rank] = hashtable value of
+// the rank-th occupied cell.  `prefix` = exclusive scan of popcounts (done by the caller with cub).
+__global__ void popc_kernel(const uint32_t *presence, int64_t nwords, uint32_t *counts)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nwords) counts[i] = __popc(presence[i]);
+}
+__global__ void build_compact_kernel(const int32_t *hashtable, const uint32_t *presence, const uint32_t *prefix,
+                                     int64_t nwords, uint2 *prk, int32_t *dense)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nwords) return;
+    uint32_t bits = presence[i];
+    uint32_t r = prefix[i];
+    prk[i] = make_uint2(bits, r);
+    while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        dense[r++] = hashtable[i * 32 + b];
+    }
+}
+cudaError_t launch_popc(const uint32_t *presence, int64_t nwords, uint32_t *counts, cudaStream_t st)
+{
+    popc_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, st>>>(presence, nwords, counts);
+    return cudaGetLastError();
+}
+cudaError_t launch_build_compact(const int32_t *hashtable, const uint32_t *presence, const uint32_t *prefix,
+                                 int64_t nwords, uint2 *prk, int32_t *dense, cudaStream_t st)
+{
+    build_compact_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, st>>>(hashtable, presence, prefix, nwords, prk, dense);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_build_presence(const int32_t *hashtable, int64_t hashsize, uint32_t *presence, cudaStream_t st)
 {
     const int64_t warps = (hashsize + 1023) / 1024;
@@ -277,7 +468,10 @@ cudaError_t launch_scan(const DevQuery &q, const ScanLaunch &s, cudaStream_t st)
 {
     if (s.total_pos <= 0) return cudaSuccess;
     int64_t blocks = (s.total_pos + POS_PER_BLOCK - 1) / POS_PER_BLOCK;
-    scan_kernel<<<(unsigned)blocks, SCAN_THREADS, 0, st>>>(q, s);
+    if (q.lut_type == 0 && q.prk != nullptr)
+        scan_kernel_staged<<<(unsigned)blocks, SCAN_THREADS, 0, st>>>(q, s);
+    else
+        scan_kernel<<<(unsigned)blocks, SCAN_THREADS, 0, st>>>(q, s);
     return cudaGetLastError();
 }
 
