@@ -41,6 +41,7 @@ struct DevQuery {
     const uint32_t *presence;              // MB: exact 1 bit / cell bitmap built at load time
     const uint2 *prk;                      // MB compact table: {presence word, rank of its first occupied cell}
     const int32_t *dense;                  // MB compact table: hashtable values of occupied cells, in cell order
+    const uint4 *qinfo;                    // MB: per query position {next_pos, 16 bases left, 16 right, ambiguity}
     const int16_t *backbone, *overflow;    // SmallNa
     int32_t has_locations;                 // lut->masked_locations != NULL
     int32_t container_type, window_size, scan_range;
@@ -170,9 +171,13 @@ struct ScanLaunch {
     int32_t raw_pairs;            // 1: emit every lookup hit (q_off, scan_pos) without mini-extension (scan tap)
     int32_t gbits;                // bits of the global position in the sort key
     int32_t diag_array_length;    // eDiagArray: cells (power of two)
+    int32_t tile_cap;             // staged kernel: bytes of shared memory for the subject slice
 };
 cudaError_t launch_scan(const DevQuery &q, const ScanLaunch &s, cudaStream_t st);
 int scan_positions_per_block();
+int scan_tile_cap(int scan_step, int word_length);
+cudaError_t launch_build_qinfo(const DevQuery &q, const int32_t *next_pos, int32_t concat_len, uint4 *qinfo,
+                               cudaStream_t st);
 
 struct ExtendLaunch {
     const uint8_t *packed;

@@ -108,6 +108,7 @@ struct QueryDev {
     uint2 *qpk = nullptr;
     uint2 *prk = nullptr;
     int32_t *dense = nullptr;
+    uint4 *qinfo = nullptr;
     DevQuery view{};
     bool ready = false;
 };
@@ -144,7 +145,7 @@ static Device *device_at(int d)
 static void free_query_dev(QueryDev &q, cudaStream_t st)
 {
     void *ptrs[] = {q.query, q.ctx, q.hashtable, q.next_pos, q.presence, q.backbone, q.overflow,
-                    q.score_table, q.matrix, q.qpk, q.prk, q.dense};
+                    q.score_table, q.matrix, q.qpk, q.prk, q.dense, q.qinfo};
     for (void *p : ptrs) if (p) cudaFreeAsync(p, st);
     q = QueryDev{};
 }
@@ -224,8 +225,6 @@ static int query_to_device(Query &Q, const BnQueryBatch &src, int d)
     const int64_t nw = (int64_t)((b.concat_len + 2 + 16) >> 4) + 3;
     CU_TRY(dev_alloc(&qd.qpk, (size_t)nw, st));
     CU_TRY(launch_build_qpk(qd.query, b.concat_len, qd.qpk, nw, st));
-    CU_TRY(cudaStreamSynchronize(st));     // caller's arrays may go away after bn_query_load returns
-
     DevQuery &v = qd.view;
     v.query = qd.query + 1;
     v.concat_len = b.concat_len;
@@ -240,6 +239,12 @@ static int query_to_device(Query &Q, const BnQueryBatch &src, int d)
     v.prk = (b.word_length <= 200) ? qd.prk : nullptr; v.dense = qd.dense;
     v.gap_algo = b.gap_algo; v.reward = b.reward; v.penalty = b.penalty;
     v.gap_open = b.gap_open; v.gap_extend = b.gap_extend; v.gap_x_dropoff = b.gap_x_dropoff;
+    if (b.lut_type == BN_LUT_MB) {
+        CU_TRY(dev_alloc(&qd.qinfo, (size_t)b.concat_len + 2, st));
+        CU_TRY(launch_build_qinfo(v, qd.next_pos, b.concat_len, qd.qinfo, st));
+        v.qinfo = qd.qinfo;
+    }
+    CU_TRY(cudaStreamSynchronize(st));     // caller's arrays may go away after bn_query_load returns
     qd.ready = true;
     return BN_OK;
 }
@@ -361,6 +366,7 @@ static int run_word_finder(Device &D, Volume &V, Query &Q, ChunkTable &T, bool r
         s.total_pos = T.total_pos; s.hits = ws.hits_a.p; s.keys = ws.keys_a.p;
         s.counters = ws.counters.p; s.capacity = cap; s.block_chunk = T.block_chunk.p;
         s.raw_pairs = raw_pairs ? 1 : 0; s.gbits = gbits; s.diag_array_length = Q.diag_array_length;
+        s.tile_cap = scan_tile_cap(Q.batch.scan_step, Q.batch.word_length);
         t_scan.start();
         CU_TRY(launch_scan(dq, s, st));
         t_scan.stop();
@@ -871,6 +877,7 @@ int bn_bench_scan(int vol_handle, int query_handle, int iters, double *ms_per_la
     s.total_pos = T->total_pos; s.hits = ws.hits_a.p; s.keys = ws.keys_a.p;
     s.counters = ws.counters.p; s.capacity = cap; s.block_chunk = T->block_chunk.p; s.raw_pairs = 0;
     s.gbits = bits_for((uint64_t)std::max<int64_t>(T->total_pos, 1)); s.diag_array_length = Q->diag_array_length;
+    s.tile_cap = scan_tile_cap(Q->batch.scan_step, Q->batch.word_length);
     const DevQuery &dq = Q->dev[V->device].view;
     Timer t(st);
     double total = 0;

@@ -42,6 +42,15 @@ constexpr int TILE_MARGIN = 64;
 
 int scan_positions_per_block() { return POS_PER_BLOCK; }
 
+// bytes of shared memory for the staged subject slice of one block (multiple of 16, <= TILE_BYTES)
+int scan_tile_cap(int scan_step, int word_length)
+{
+    long need = (long)POS_PER_BLOCK * scan_step / 4 + word_length / 4 + 2 * TILE_MARGIN + 64;
+    need = (need + 15) & ~15L;
+    if (need < 1024) need = 1024;
+    return (int)(need > TILE_BYTES ? TILE_BYTES : need);
+}
+
 __device__ __forceinline__ uint32_t load_window(const uint8_t *packed, int64_t byte)
 {
     const uint32_t *w = reinterpret_cast<const uint32_t *>(packed + (byte & ~int64_t(3)));
@@ -244,7 +253,8 @@ scan_kernel(const DevQuery q, const ScanLaunch s)
 }
 
 // ---- staged kernel (megablast tables) ------------------------------------------------------------
-struct Candidate { uint32_t chunk; int32_t p; uint32_t idx; uint32_t gl; };   // gl = position index inside the block
+// candidate = occupied table cell met at a scan position: rank into dense[] + (chunk delta << 10 | position in block)
+struct Candidate { uint32_t rank; uint32_t where; };
 
 // 16-base window of the staged tile starting at tile-relative base position tb (>= 0)
 __device__ __forceinline__ uint32_t tile_win(const uint32_t *tile, int32_t tb)
@@ -254,35 +264,48 @@ __device__ __forceinline__ uint32_t tile_win(const uint32_t *tile, int32_t tb)
     return __funnelshift_l(b, a, (uint32_t)(tb & 15) * 2);
 }
 
-// s_BlastNaExtend on 16-base windows; tbase = tile-relative base index of the chunk's base 0
+// s_BlastNaExtend on 16-base windows.  The query's 16 bases on either side of the lookup word come
+// with the chain element (qinfo), so the common case needs no further query access; tbase =
+// tile-relative base index of the chunk's base 0.
 __device__ __forceinline__ bool mini_extend_tile(const DevQuery &q, const uint32_t *tile, int64_t tbase,
                                                  int32_t s_range, int32_t q_offset, int32_t s_offset,
-                                                 int32_t &q_out, int32_t &s_out)
+                                                 const uint4 qi, int32_t &q_out, int32_t &s_out)
 {
     const int32_t lut = q.lut_word_length, ext_to = q.word_length - lut;
     int32_t ext_left = 0;
     if (ext_to > 0) {
         const int32_t lim = min(ext_to, s_offset);
-        while (ext_left < lim) {
-            uint32_t qb, qa;
-            qwin(q, q_offset - ext_left - 16, qb, qa);
-            const uint32_t m = mismatch_bits(qb, qa, tile_win(tile, (int32_t)(tbase + s_offset - ext_left - 16)));
-            if (m) { ext_left = min(ext_left + ((__ffs(m) - 1) >> 1), lim); break; }
-            ext_left = min(ext_left + 16, lim);
+        if (lim > 0) {
+            const uint32_t m = mismatch_bits(qi.y, qi.w & 0x55555555u, tile_win(tile, (int32_t)(tbase + s_offset - 16)));
+            ext_left = m ? ((__ffs(m) - 1) >> 1) : 16;
+            if (ext_left >= lim) ext_left = lim;
+            else if (!m) {                       // all 16 matched and more are wanted: continue on windows
+                while (ext_left < lim) {
+                    uint32_t qb, qa;
+                    qwin(q, q_offset - ext_left - 16, qb, qa);
+                    const uint32_t mm = mismatch_bits(qb, qa, tile_win(tile, (int32_t)(tbase + s_offset - ext_left - 16)));
+                    if (mm) { ext_left = min(ext_left + ((__ffs(mm) - 1) >> 1), lim); break; }
+                    ext_left = min(ext_left + 16, lim);
+                }
+            }
         }
         if (ext_left < ext_to) {
             const int32_t need = ext_to - ext_left;
             const int32_t sp = s_offset + lut;
             if ((uint32_t)(sp + need) > (uint32_t)s_range) return false;
-            int32_t ext_right = 0;
-            while (ext_right < need) {
-                uint32_t qb, qa;
-                qwin(q, q_offset + lut + ext_right, qb, qa);
-                const uint32_t m = mismatch_bits(qb, qa, tile_win(tile, (int32_t)(tbase + sp + ext_right)));
-                if (m) { ext_right = min(ext_right + (__clz(m) >> 1), need); break; }
-                ext_right = min(ext_right + 16, need);
+            const uint32_t m = mismatch_bits(qi.z, (qi.w >> 1) & 0x55555555u, tile_win(tile, (int32_t)(tbase + sp)));
+            int32_t ext_right = m ? (__clz(m) >> 1) : 16;
+            if (ext_right < need) {
+                if (m) return false;
+                while (ext_right < need) {       // need > 16
+                    uint32_t qb, qa;
+                    qwin(q, q_offset + lut + ext_right, qb, qa);
+                    const uint32_t mm = mismatch_bits(qb, qa, tile_win(tile, (int32_t)(tbase + sp + ext_right)));
+                    if (mm) { ext_right = min(ext_right + (__clz(mm) >> 1), need); break; }
+                    ext_right = min(ext_right + 16, need);
+                }
+                if (ext_right < need) return false;
             }
-            if (ext_right < need) return false;
         }
     }
     q_out = q_offset - ext_left;
@@ -293,8 +316,9 @@ __device__ __forceinline__ bool mini_extend_tile(const DevQuery &q, const uint32
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_kernel_staged(const DevQuery q, const ScanLaunch s)
 {
-    __shared__ __align__(16) uint32_t tile[TILE_BYTES / 4];
-    __shared__ Candidate cand[POS_PER_BLOCK];
+    extern __shared__ __align__(16) uint32_t smem_dyn[];
+    uint32_t *tile = smem_dyn;                                              // s.tile_cap bytes
+    Candidate *cand = reinterpret_cast<Candidate *>(smem_dyn + s.tile_cap / 4);   // POS_PER_BLOCK entries
     __shared__ int32_t sh_c_lo, sh_c_hi, sh_ncand;
     __shared__ int64_t sh_tile_lo, sh_tile_hi;
 
@@ -320,8 +344,9 @@ scan_kernel_staged(const DevQuery q, const ScanLaunch s)
     __syncthreads();
     const int32_t c_lo = sh_c_lo, c_hi = sh_c_hi;
     const int64_t tile_lo = sh_tile_lo;
-    const int32_t tile_bytes = (int32_t)(sh_tile_hi - tile_lo);
-    const bool staged = tile_bytes <= TILE_BYTES - 16;
+    const int32_t tile_bytes = (int32_t)min(sh_tile_hi - tile_lo, (int64_t)INT32_MAX);
+    // a block spanning > 2^22 chunks or more bytes than the tile holds takes the direct-load path
+    const bool staged = tile_bytes <= s.tile_cap - 16 && (c_hi - c_lo) < (1 << 22);
     if (staged) {
         const uint4 *src = reinterpret_cast<const uint4 *>(s.packed + tile_lo);
         uint4 *dst = reinterpret_cast<uint4 *>(tile);
@@ -329,28 +354,40 @@ scan_kernel_staged(const DevQuery q, const ScanLaunch s)
     }
     __syncthreads();
 
-    // ---- phase A: lookup words + presence probe ------------------------------------------------
-#pragma unroll 1
+    // ---- phase A: lookup words, then all presence probes of the thread in flight together -----------
+    uint32_t idxs[POS_PER_THREAD], wheres[POS_PER_THREAD];
+    uint2 words[POS_PER_THREAD];
+#pragma unroll
     for (int it = 0; it < POS_PER_THREAD; it++) {
         const uint32_t gl = (uint32_t)(it * SCAN_THREADS + tid);
         const int64_t g = block_pos0 + gl;
-        if (g >= s.total_pos) break;
-        int32_t lo = c_lo, hi = c_hi;
-        while (lo < hi) {
-            const int32_t m = (lo + hi + 1) >> 1;
-            if (__ldg(&s.chunks[m].pos_prefix) <= g) lo = m; else hi = m - 1;
+        idxs[it] = 0xFFFFFFFFu;
+        wheres[it] = 0;
+        if (g < s.total_pos) {
+            int32_t lo = c_lo, hi = c_hi;
+            while (lo < hi) {
+                const int32_t m = (lo + hi + 1) >> 1;
+                if (__ldg(&s.chunks[m].pos_prefix) <= g) lo = m; else hi = m - 1;
+            }
+            const int64_t prefix = __ldg(&s.chunks[lo].pos_prefix);
+            const int64_t byte_off = __ldg(&s.chunks[lo].byte_off);
+            const int32_t p = (int32_t)(g - prefix) * step;
+            uint32_t window;
+            if (staged) window = tile_win(tile, (int32_t)((byte_off - tile_lo) * 4 + p));
+            else window = load_window(s.packed, byte_off + (p >> 2)) << (2 * (p & 3));
+            idxs[it] = window >> (2 * (16 - lut));
+            wheres[it] = ((uint32_t)(lo - c_lo) << 10) | gl;
         }
-        const int64_t prefix = __ldg(&s.chunks[lo].pos_prefix);
-        const int64_t byte_off = __ldg(&s.chunks[lo].byte_off);
-        const int32_t p = (int32_t)(g - prefix) * step;
-        uint32_t window;
-        if (staged) window = tile_win(tile, (int32_t)((byte_off - tile_lo) * 4 + p));
-        else window = load_window(s.packed, byte_off + (p >> 2)) << (2 * (p & 3));
-        const uint32_t idx = window >> (2 * (16 - lut));
-        const uint2 w = __ldg(&q.prk[idx >> 5]);
-        if ((w.x >> (idx & 31)) & 1u) {
+    }
+#pragma unroll
+    for (int it = 0; it < POS_PER_THREAD; it++)
+        words[it] = (idxs[it] != 0xFFFFFFFFu) ? __ldg(&q.prk[idxs[it] >> 5]) : make_uint2(0u, 0u);
+#pragma unroll
+    for (int it = 0; it < POS_PER_THREAD; it++) {
+        const uint32_t bit = idxs[it] & 31;
+        if (idxs[it] != 0xFFFFFFFFu && ((words[it].x >> bit) & 1u)) {
             const int slot = atomicAdd(&sh_ncand, 1);
-            cand[slot] = Candidate{(uint32_t)lo, p, idx, gl};
+            cand[slot] = Candidate{words[it].y + (uint32_t)__popc(words[it].x & ((1u << bit) - 1u)), wheres[it]};
         }
     }
     __syncthreads();
@@ -360,27 +397,49 @@ scan_kernel_staged(const DevQuery q, const ScanLaunch s)
     unsigned long long my_lookup_hits = 0;
     for (int ci = tid; ci < ncand; ci += SCAN_THREADS) {
         const Candidate c = cand[ci];
-        const uint2 w = __ldg(&q.prk[c.idx >> 5]);
-        const uint32_t rank = w.y + __popc(w.x & ((1u << (c.idx & 31)) - 1u));
-        int32_t qp = __ldg(&q.dense[rank]);
-        const int64_t byte_off = __ldg(&s.chunks[c.chunk].byte_off);
-        const int32_t len = __ldg(&s.chunks[c.chunk].len);
-        const int64_t g = block_pos0 + c.gl;
+        int32_t qp = __ldg(&q.dense[c.rank]);
+        const uint32_t chunk = (uint32_t)c_lo + (c.where >> 10);
+        const int64_t g = block_pos0 + (c.where & 1023u);
+        const int64_t byte_off = __ldg(&s.chunks[chunk].byte_off);
+        const int32_t len = __ldg(&s.chunks[chunk].len);
+        const int32_t p = (int32_t)(g - __ldg(&s.chunks[chunk].pos_prefix)) * step;
         while (qp) {
             ++my_lookup_hits;
+            const uint4 qi = __ldg(&q.qinfo[qp]);         // {next, left 16 bases, right 16 bases, ambiguity}
             int32_t qo, so;
-            if (s.raw_pairs) emit_hit(q, s, c.chunk, (uint32_t)c.p, g, qp - 1, c.p);
+            if (s.raw_pairs) emit_hit(q, s, chunk, (uint32_t)p, g, qp - 1, p);
             else {
                 bool ok;
-                if (staged) ok = mini_extend_tile(q, tile, (byte_off - tile_lo) * 4, len, qp - 1, c.p, qo, so);
-                else ok = mini_extend_mb(q, s.packed + byte_off, len, qp - 1, c.p, qo, so);
-                if (ok) emit_hit(q, s, c.chunk, (uint32_t)c.p, g, qo, so);
+                if (staged) ok = mini_extend_tile(q, tile, (byte_off - tile_lo) * 4, len, qp - 1, p, qi, qo, so);
+                else ok = mini_extend_mb(q, s.packed + byte_off, len, qp - 1, p, qo, so);
+                if (ok) emit_hit(q, s, chunk, (uint32_t)p, g, qo, so);
             }
-            qp = __ldg(&q.next_pos[qp]);
+            qp = (int32_t)qi.x;
         }
     }
     for (int o = 16; o > 0; o >>= 1) my_lookup_hits += __shfl_down_sync(0xffffffffu, my_lookup_hits, o);
     if ((tid & 31) == 0 && my_lookup_hits) atomicAdd(&s.counters[1], my_lookup_hits);
+}
+
+// qinfo[qp] for every 1-based query position qp: {next_pos[qp], 16 bases left of the lookup word that
+// starts at qp-1, 16 bases right of it, ambiguity flags (left in the even bits, right in the odd bits)}
+__global__ void build_qinfo_kernel(const DevQuery q, const int32_t *next_pos, int32_t concat_len, uint4 *qinfo)
+{
+    const int64_t qp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (qp > concat_len) return;
+    uint32_t lb = 0, la = 0x55555555u, rb = 0, ra = 0x55555555u;
+    if (qp >= 1) {
+        qwin(q, (int32_t)qp - 1 - 16, lb, la);
+        qwin(q, (int32_t)qp - 1 + q.lut_word_length, rb, ra);
+    }
+    qinfo[qp] = make_uint4((uint32_t)next_pos[qp], lb, rb, (la & 0x55555555u) | ((ra & 0x55555555u) << 1));
+}
+cudaError_t launch_build_qinfo(const DevQuery &q, const int32_t *next_pos, int32_t concat_len, uint4 *qinfo,
+                               cudaStream_t st)
+{
+    const int64_t n = (int64_t)concat_len + 1;
+    build_qinfo_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q, next_pos, concat_len, qinfo);
+    return cudaGetLastError();
 }
 
 // ---- query-load helpers: derived device arrays -----------------------------------------------------
@@ -468,8 +527,10 @@ cudaError_t launch_scan(const DevQuery &q, const ScanLaunch &s, cudaStream_t st)
 {
     if (s.total_pos <= 0) return cudaSuccess;
     int64_t blocks = (s.total_pos + POS_PER_BLOCK - 1) / POS_PER_BLOCK;
-    if (q.lut_type == 0 && q.prk != nullptr)
-        scan_kernel_staged<<<(unsigned)blocks, SCAN_THREADS, 0, st>>>(q, s);
+    if (q.lut_type == 0 && q.prk != nullptr) {
+        const size_t smem = (size_t)s.tile_cap + sizeof(Candidate) * POS_PER_BLOCK;
+        scan_kernel_staged<<<(unsigned)blocks, SCAN_THREADS, smem, st>>>(q, s);
+    }
     else
         scan_kernel<<<(unsigned)blocks, SCAN_THREADS, 0, st>>>(q, s);
     return cudaGetLastError();
