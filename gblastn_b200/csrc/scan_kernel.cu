@@ -35,10 +35,11 @@
 namespace bn {
 
 constexpr int SCAN_THREADS = 256;
-constexpr int POS_PER_THREAD = 4;
+constexpr int POS_PER_THREAD = 8;
 constexpr int POS_PER_BLOCK = SCAN_THREADS * POS_PER_THREAD;
 constexpr int TILE_BYTES = 20 * 1024;      // staged subject slice (incl. 64-byte margins)
 constexpr int TILE_MARGIN = 64;
+static_assert(POS_PER_BLOCK <= 4096, "candidate packing holds 12 bits of in-block position");
 
 int scan_positions_per_block() { return POS_PER_BLOCK; }
 
@@ -253,7 +254,7 @@ scan_kernel(const DevQuery q, const ScanLaunch s)
 }
 
 // ---- staged kernel (megablast tables) ------------------------------------------------------------
-// candidate = occupied table cell met at a scan position: rank into dense[] + (chunk delta << 10 | position in block)
+// candidate = occupied table cell met at a scan position: rank into dense[] + (chunk delta << 12 | position in block)
 struct Candidate { uint32_t rank; uint32_t where; };
 
 // 16-base window of the staged tile starting at tile-relative base position tb (>= 0)
@@ -346,7 +347,7 @@ scan_kernel_staged(const DevQuery q, const ScanLaunch s)
     const int64_t tile_lo = sh_tile_lo;
     const int32_t tile_bytes = (int32_t)min(sh_tile_hi - tile_lo, (int64_t)INT32_MAX);
     // a block spanning > 2^22 chunks or more bytes than the tile holds takes the direct-load path
-    const bool staged = tile_bytes <= s.tile_cap - 16 && (c_hi - c_lo) < (1 << 22);
+    const bool staged = tile_bytes <= s.tile_cap - 16 && (c_hi - c_lo) < (1 << 20);
     if (staged) {
         const uint4 *src = reinterpret_cast<const uint4 *>(s.packed + tile_lo);
         uint4 *dst = reinterpret_cast<uint4 *>(tile);
@@ -376,7 +377,7 @@ scan_kernel_staged(const DevQuery q, const ScanLaunch s)
             if (staged) window = tile_win(tile, (int32_t)((byte_off - tile_lo) * 4 + p));
             else window = load_window(s.packed, byte_off + (p >> 2)) << (2 * (p & 3));
             idxs[it] = window >> (2 * (16 - lut));
-            wheres[it] = ((uint32_t)(lo - c_lo) << 10) | gl;
+            wheres[it] = ((uint32_t)(lo - c_lo) << 12) | gl;
         }
     }
 #pragma unroll
@@ -398,8 +399,8 @@ scan_kernel_staged(const DevQuery q, const ScanLaunch s)
     for (int ci = tid; ci < ncand; ci += SCAN_THREADS) {
         const Candidate c = cand[ci];
         int32_t qp = __ldg(&q.dense[c.rank]);
-        const uint32_t chunk = (uint32_t)c_lo + (c.where >> 10);
-        const int64_t g = block_pos0 + (c.where & 1023u);
+        const uint32_t chunk = (uint32_t)c_lo + (c.where >> 12);
+        const int64_t g = block_pos0 + (c.where & 4095u);
         const int64_t byte_off = __ldg(&s.chunks[chunk].byte_off);
         const int32_t len = __ldg(&s.chunks[chunk].len);
         const int32_t p = (int32_t)(g - __ldg(&s.chunks[chunk].pos_prefix)) * step;
