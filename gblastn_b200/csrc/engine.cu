@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -541,6 +542,8 @@ static int prelim_search_locked(Device &D, Volume &V, Query &Q, int32_t oid_begi
 
     // ---- host replay -------------------------------------------------------------------------
     const double th0 = now_ms();
+    static const bool trace = getenv("BN_TRACE") != nullptr;
+    double t_sort = 0, t_replay = 0, t_finish = 0, t_merge = 0, t_eval = 0, t_track = 0;
     const BnQueryBatch &b = Q.batch;
     std::vector<HostInit> inits((size_t)cnt.n_init);
     for (size_t i = 0; i < inits.size(); i++) {
@@ -550,6 +553,7 @@ static int prelim_search_locked(Device &D, Volume &V, Query &Q, int32_t oid_begi
                             g.q_start, g.q_stop, g.s_start, g.s_stop, g.score, g.q_seed, g.s_seed};
     }
     sort_init_hits(inits);
+    t_sort = now_ms() - th0;
 
     std::vector<BnHSP> final_hsps, gapped_tap, comb, fresh;
     std::vector<BnInitHit> init_tap;
@@ -557,12 +561,15 @@ static int prelim_search_locked(Device &D, Volume &V, Query &Q, int32_t oid_begi
     int32_t cur_oid = -1;
     auto finish_oid = [&]() {
         if (cur_oid < 0) return;
+        double ta = now_ms();
         evalues_and_reap(b, comb);
+        t_eval += now_ms() - ta; ta = now_ms();
         if (!comb.empty()) {
             stats.good_extensions += (int64_t)comb.size();
             final_hsps.insert(final_hsps.end(), comb.begin(), comb.end());
             tracker.subject_done(b, comb);
         }
+        t_track += now_ms() - ta;
         comb.clear();
     };
     size_t i = 0;
@@ -577,15 +584,22 @@ static int prelim_search_locked(Device &D, Volume &V, Query &Q, int32_t oid_begi
                                              inits[k].q_start, inits[k].s_start, inits[k].length,
                                              inits[k].score});
         fresh.clear();
+        double ta = now_ms();
         replay_gapped(b, ch, &inits[i], j - i, tracker.low_score(), fresh, stats);
+        t_replay += now_ms() - ta; ta = now_ms();
         if (taps & BN_TAP_GAPPED) gapped_tap.insert(gapped_tap.end(), fresh.begin(), fresh.end());
         finish_chunk_list(b, fresh);
+        t_finish += now_ms() - ta; ta = now_ms();
         for (auto &h : fresh) { h.s_off += ch.chunk_off; h.s_end += ch.chunk_off; h.s_gapped_start += ch.chunk_off; }
         merge_chunk_lists(comb, fresh, ch.chunk_off, ch.chunk_off == 0 ? 0 : BN_DBSEQ_CHUNK_OVERLAP);
+        t_merge += now_ms() - ta;
         i = j;
     }
     finish_oid();
     stats.ms_host = now_ms() - th0;
+    if (trace)
+        fprintf(stderr, "[bn] host %.3f ms: sort %.3f replay %.3f finish %.3f merge %.3f eval %.3f track %.3f (n_init %lld)\n",
+                stats.ms_host, t_sort, t_replay, t_finish, t_merge, t_eval, t_track, (long long)cnt.n_init);
 
     out->n_hsps = (int64_t)final_hsps.size(); out->hsps = to_malloc(final_hsps);
     out->n_init = (int64_t)init_tap.size();   out->init = to_malloc(init_tap);

@@ -228,6 +228,24 @@ __device__ void ungapped_extend(const DevQuery &q, const uint8_t *packed, int64_
     }
 }
 
+// BSearchContextInfo (core/blast_query_info.c:220-236) with 32 pivots per round: the largest
+// context index whose query_offset <= n.  Warp-uniform result.
+__device__ __forceinline__ int32_t ctx_search_warp(const DevQuery &q, int32_t n, int lane)
+{
+    int32_t lo = 0, hi = q.num_contexts;
+    while (hi - lo > 1) {
+        const int32_t step = (hi - lo + 31) >> 5;
+        const int32_t piv = lo + lane * step;
+        const bool ok = piv < hi && __ldg(&q.ctx[piv].query_offset) <= n;
+        const unsigned m = __ballot_sync(FULL, ok) | 1u;      // pivot 0 (= lo) always qualifies
+        const int top = 31 - __clz(m);
+        const int32_t nlo = lo + top * step;
+        hi = min(hi, nlo + step);
+        lo = nlo;
+    }
+    return lo;
+}
+
 // ---- lookup probes (warp-uniform) ----------------------------------------------------------------
 __device__ bool lut_contains(const DevQuery &q, uint32_t index, int32_t q_pos)
 {
@@ -262,12 +280,12 @@ __device__ __forceinline__ bool seed_masked(const DevQuery &q, const uint8_t *S,
 // s_TypeOfWord with check_double == FALSE (window_size == 0)
 __device__ int type_of_word(const DevQuery &q, const uint8_t *S, int32_t &q_off, int32_t &s_off,
                             bool has_locations, uint32_t s_range, int32_t word_length, int32_t lut,
-                            int32_t &extended)
+                            int32_t &extended, int lane)
 {
     extended = 0;
     if (word_length == lut) return 1;
     int32_t q_end = q_off + word_length, s_end = s_off + word_length;
-    const int32_t context = ctx_search(q, q_end);
+    const int32_t context = ctx_search_warp(q, q_end, lane);
     const int32_t q_range = __ldg(&q.ctx[context].query_offset) + __ldg(&q.ctx[context].query_length);
     if (has_locations) {
         if (seed_masked(q, S, s_end - lut, lut, q_end - lut)) return 0;
@@ -384,69 +402,96 @@ extend_kernel(const DevQuery q, const ExtendLaunch e, const uint64_t *keys, cons
         int64_t chunk_base = 0;
         unsigned long long n_extended = 0;
 
-        for (int64_t j = j0; j < n_hits; ++j) {
-            if (j > j0 && !same_group(keys, e.hits, j - 1, j, gbits, is_hash)) break;
-            const SeedHit h = e.hits[j];
-            if (h.chunk != cur_chunk) {
-                cur_chunk = h.chunk;
-                ch = e.chunks[cur_chunk];
-                S = e.packed + ch.byte_off;
-                chunk_base = ch.byte_off * 4;
+        // most-recently-stored diagonal of this bucket: a get() right after put(d) returns what was
+        // stored (no other put intervened), so runs of seeds on one diagonal skip the chain walk
+        int32_t cache_diag = 0, cache_level = 0;
+        bool cache_ok = false;
+        bool group_done = false;
+        for (int64_t base = j0; base < n_hits && !group_done; base += 32) {
+            // prefetch up to 32 hits of the group, one per lane
+            const int64_t jm = base + lane;
+            SeedHit mine{0, 0, 0, 0};
+            uint64_t mykey = 0;
+            bool in_group = false;
+            if (jm < n_hits) {
+                mine = e.hits[jm];
+                mykey = keys[jm];
+                in_group = (jm == j0) || same_group(keys, e.hits, jm - 1, jm, gbits, is_hash);
+            }
+            const unsigned brk = __ballot_sync(FULL, !in_group);
+            const int cnt = brk ? (__ffs(brk) - 1) : 32;
+            if (cnt < 32) group_done = true;
+            for (int t = 0; t < cnt; t++) {
+                const int64_t j = base + t;
+                SeedHit h;
+                h.chunk = __shfl_sync(FULL, mine.chunk, t);
+                h.q_off = __shfl_sync(FULL, mine.q_off, t);
+                h.s_off = __shfl_sync(FULL, mine.s_off, t);
+                if (h.chunk != cur_chunk) {
+                    cur_chunk = h.chunk;
+                    ch = e.chunks[cur_chunk];
+                    S = e.packed + ch.byte_off;
+                    chunk_base = ch.byte_off * 4;
+                    if (is_hash) {
+                        // Blast_ExtendWordExit may have reset the container between chunks
+                        if (cur_epoch >= 0 && ch.diag_epoch != cur_epoch) {
+                            chain.head = 0; chain.used = 0;
+                            chain.cells = reinterpret_cast<int4 *>(e.cells) + j;
+                            cache_ok = false;
+                        }
+                        cur_epoch = ch.diag_epoch;
+                    }
+                }
+                int32_t q_off = (int32_t)h.q_off, s_off = (int32_t)h.s_off;
+                const int32_t s_range = ch.len;
+                int32_t s_end = s_off + word;
+                const int32_t s_off_pos = s_off + ch.diag_offset;
+                int32_t s_end_pos = s_end + ch.diag_offset;
+                const int32_t diag = s_off - q_off;
+                int32_t last_hit = 0;
                 if (is_hash) {
-                    // Blast_ExtendWordExit may have reset the container between chunks
-                    if (cur_epoch >= 0 && ch.diag_epoch != cur_epoch) {
-                        chain.head = 0; chain.used = 0;
-                        chain.cells = reinterpret_cast<int4 *>(e.cells) + j;
+                    if (cache_ok && cache_diag == diag) last_hit = cache_level;
+                    else if (!chain_get(chain, diag, last_hit)) last_hit = 0;
+                } else last_hit = last_hit_cell;
+                if (s_off_pos < last_hit) continue;
+
+                int32_t extended = 0;
+                if (!type_of_word(q, S, q_off, s_off, has_loc, (uint32_t)s_range, word, direct ? word : lut, extended, lane))
+                    continue;
+                s_end += extended; s_end_pos += extended;
+
+                const int32_t context = ctx_search_warp(q, q_off, lane);
+                const DevContext c = q.ctx[context];
+                Ungapped u;
+                if (!is_hash && word < 11)
+                    ungapped_exact(q, e.packed, chunk_base, ch.len, q_off, s_off, -c.x_dropoff, lane, u);
+                else
+                    ungapped_extend(q, e.packed, chunk_base, ch.len, s_tab, q_off, s_end, s_off, -c.x_dropoff,
+                                    c.reduced_cutoff, lane, u);
+
+                int32_t hit_ready = 0;
+                if (u.score >= c.cutoff_score) {
+                    hit_ready = 1;
+                    const uint64_t kj = __shfl_sync(FULL, mykey, t);
+                    if (lane == 0) {
+                        const unsigned long long slot = atomicAdd(&e.counters[2], 1ull);
+                        if ((int64_t)slot < e.init_capacity) {
+                            DevInitHit o;
+                            o.chunk = (int32_t)cur_chunk; o.q_off = q_off; o.s_off = s_off;
+                            o.q_start = u.q_start; o.s_start = u.s_start; o.length = u.length; o.score = u.score;
+                            o.order = (uint32_t)(kj & ((1ull << gbits) - 1ull));
+                            e.init[slot] = o;
+                        }
                     }
-                    cur_epoch = ch.diag_epoch;
+                    s_end_pos = u.length + u.s_start + ch.diag_offset;
+                    ++n_extended;
                 }
+                if (is_hash) {
+                    chain_put(chain, diag, s_end_pos, hit_ready ? 0 : s_end_pos - s_off_pos, hit_ready,
+                              s_off_pos, stale_window, lane);
+                    cache_diag = diag; cache_level = s_end_pos; cache_ok = true;
+                } else last_hit_cell = s_end_pos;
             }
-            int32_t q_off = (int32_t)h.q_off, s_off = (int32_t)h.s_off;
-            const int32_t s_range = ch.len;
-            int32_t s_end = s_off + word;
-            const int32_t s_off_pos = s_off + ch.diag_offset;
-            int32_t s_end_pos = s_end + ch.diag_offset;
-            const int32_t diag = s_off - q_off;
-            int32_t last_hit = 0;
-            if (is_hash) { if (!chain_get(chain, diag, last_hit)) last_hit = 0; }
-            else last_hit = last_hit_cell;
-            if (s_off_pos < last_hit) continue;
-
-            int32_t extended = 0;
-            if (!type_of_word(q, S, q_off, s_off, has_loc, (uint32_t)s_range, word, direct ? word : lut, extended))
-                continue;
-            s_end += extended; s_end_pos += extended;
-
-            const int32_t context = ctx_search(q, q_off);
-            const DevContext c = q.ctx[context];
-            Ungapped u;
-            if (!is_hash && word < 11)
-                ungapped_exact(q, e.packed, chunk_base, ch.len, q_off, s_off, -c.x_dropoff, lane, u);
-            else
-                ungapped_extend(q, e.packed, chunk_base, ch.len, s_tab, q_off, s_end, s_off, -c.x_dropoff,
-                                c.reduced_cutoff, lane, u);
-
-            int32_t hit_ready = 0;
-            if (u.score >= c.cutoff_score) {
-                hit_ready = 1;
-                if (lane == 0) {
-                    const unsigned long long slot = atomicAdd(&e.counters[2], 1ull);
-                    if ((int64_t)slot < e.init_capacity) {
-                        DevInitHit o;
-                        o.chunk = (int32_t)cur_chunk; o.q_off = q_off; o.s_off = s_off;
-                        o.q_start = u.q_start; o.s_start = u.s_start; o.length = u.length; o.score = u.score;
-                        o.order = (uint32_t)(keys[j] & ((1ull << gbits) - 1ull));
-                        e.init[slot] = o;
-                    }
-                }
-                s_end_pos = u.length + u.s_start + ch.diag_offset;
-                ++n_extended;
-            }
-            if (is_hash)
-                chain_put(chain, diag, s_end_pos, hit_ready ? 0 : s_end_pos - s_off_pos, hit_ready,
-                          s_off_pos, stale_window, lane);
-            else
-                last_hit_cell = s_end_pos;
         }
         if (lane == 0 && n_extended) atomicAdd(&e.counters[3], n_extended);
     }

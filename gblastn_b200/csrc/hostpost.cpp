@@ -14,10 +14,11 @@ namespace bn {
 // cover [leftend, rightend]; a leaf (item >= 0) stores the query-strand offset in leftptr and uses
 // midptr as the "next" link of a midpoint list.
 // ------------------------------------------------------------------------------------------------
-IntervalTree::IntervalTree(int32_t q_min, int32_t q_max, int32_t s_min, int32_t s_max)
+IntervalTree::IntervalTree(int32_t q_min, int32_t q_max, int32_t s_min, int32_t s_max, size_t expected_items)
     : s_min_(s_min), s_max_(s_max)
 {
-    nodes_.reserve(128);
+    nodes_.reserve(128 + 4 * expected_items);
+    items_.reserve(expected_items);
     new_root(q_min, q_max);
 }
 
@@ -184,10 +185,12 @@ bool IntervalTree::has_endpoint(const Item &in, bool right)
 }
 
 // BlastIntervalTreeAddHSP, index_method == eQueryAndSubject (core/blast_itree.c:514-800)
-void IntervalTree::add(const Item &in)
+void IntervalTree::add(const Item &in, bool check_endpoints)
 {
-    if (has_endpoint(in, false)) return;
-    if (has_endpoint(in, true)) return;
+    if (check_endpoints) {
+        if (has_endpoint(in, false)) return;
+        if (has_endpoint(in, true)) return;
+    }
 
     items_.push_back(in);
     const int32_t item = (int32_t)items_.size() - 1;
@@ -290,18 +293,26 @@ void replay_gapped(const BnQueryBatch &b, const HostChunk &ch, const HostInit *i
                    const int32_t *low_score, std::vector<BnHSP> &out, BnStats &stats)
 {
     if (n == 0) return;
-    IntervalTree tree(0, b.concat_len + 1, 0, ch.len + 1);
+    IntervalTree tree(0, b.concat_len + 1, 0, ch.len + 1, n);
+    // contexts of every init-HSP (BSearchContextInfo on the seed's query offset)
+    std::vector<int32_t> ctx_of(n);
+    for (size_t i = 0; i < n; i++) ctx_of[i] = ctx_search(b, init[i].q_off);
     std::vector<uint8_t> found_high;
     if (low_score) {
         found_high.assign((size_t)b.num_queries, 0);
         for (size_t i = 0; i < n; i++) {
-            const int32_t qi = b.contexts[ctx_search(b, init[i].q_off)].query_index;
+            const int32_t qi = b.contexts[ctx_of[i]].query_index;
             if (init[i].score > low_score[qi]) found_high[qi] = 1;
         }
     }
+    // Containment and common-endpoint tests can only succeed against an HSP of the same query
+    // strand (s_HSPIsContained / s_HSPsHaveCommonEndpoint compare the strand offsets first), so they
+    // are skipped - not approximated - while the tree holds nothing for that strand yet.  Insertion
+    // itself always runs: it shapes the tree that later tests walk.
+    std::vector<int32_t> strand_items((size_t)b.num_contexts, 0);
     for (size_t i = 0; i < n; i++) {
         const HostInit &h = init[i];
-        const int32_t context = ctx_search(b, h.q_off);
+        const int32_t context = ctx_of[i];
         const BnContext &c = b.contexts[context];
         if (low_score && !found_high[c.query_index]) continue;
         IntervalTree::Item t;
@@ -311,7 +322,8 @@ void replay_gapped(const BnQueryBatch &b, const HostChunk &ch, const HostInit *i
         t.s_off = h.s_start;
         t.s_end = h.s_start + h.length;
         t.score = h.score;
-        if (tree.contains(t, b.min_diag_separation)) continue;
+        const bool strand_seen = strand_items[context] != 0;
+        if (strand_seen && tree.contains(t, b.min_diag_separation)) continue;
         ++stats.gap_extensions;
         if (h.g_score >= c.gapped_cutoff) {
             BnHSP o;
@@ -321,13 +333,58 @@ void replay_gapped(const BnQueryBatch &b, const HostChunk &ch, const HostInit *i
             o.evalue = 0.0;
             out.push_back(o);
             IntervalTree::Item nt{t.q_strand_start, o.q_off, o.q_end, o.s_off, o.s_end, o.score};
-            tree.add(nt);
+            tree.add(nt, strand_seen);
+            ++strand_items[context];
         }
     }
 }
 
+// true when two HSPs of the list share (context, query start, subject start) or (context, query
+// end, subject end) - the only situation in which the purge pass changes anything
+static bool has_common_endpoints(const std::vector<BnHSP> &list)
+{
+    const size_t n = list.size();
+    if (n < 2) return false;
+    size_t cap = 64;
+    while (cap < 4 * n) cap <<= 1;
+    std::vector<uint64_t> tab(2 * cap, ~0ull);
+    auto probe = [&](uint64_t *t, uint64_t a, uint64_t c) -> bool {
+        // 96-bit key folded into a 64-bit value + verified on collision by storing both halves
+        uint64_t h = (a * 0x9E3779B97F4A7C15ull) ^ (c * 0xC2B2AE3D27D4EB4Full);
+        size_t i = (size_t)(h >> 20) & (cap - 1);
+        for (;;) {
+            if (t[i] == ~0ull) { t[i] = h; return false; }
+            if (t[i] == h) return true;      // equal 64-bit hash: treat as a potential collision
+            i = (i + 1) & (cap - 1);
+        }
+    };
+    for (const BnHSP &h : list) {
+        const uint64_t c = (uint64_t)(uint32_t)h.context;
+        if (probe(tab.data(), ((uint64_t)(uint32_t)h.q_off << 32) | (uint32_t)h.s_off, c)) return true;
+        if (probe(tab.data() + cap, ((uint64_t)(uint32_t)h.q_end << 32) | (uint32_t)h.s_end, c)) return true;
+    }
+    return false;
+}
+
 void finish_chunk_list(const BnQueryBatch &b, std::vector<BnHSP> &list)
 {
+    if (!has_common_endpoints(list)) {
+        // Nothing to purge.  The reference still sorts by query offset, then by query end, then
+        // (after the odd-score rounding) by score with a stable sort; two HSPs that tie on the score
+        // comparator can only differ in context, and the query-end order puts the lower context
+        // first, so a single sort with context as the last key gives the identical list.
+        if (b.round_down)
+            for (auto &h : list) h.score &= ~1;
+        std::sort(list.begin(), list.end(), [](const BnHSP &x, const BnHSP &y) {
+            if (x.score != y.score) return x.score > y.score;
+            if (x.s_off != y.s_off) return x.s_off < y.s_off;
+            if (x.s_end != y.s_end) return x.s_end > y.s_end;
+            if (x.q_off != y.q_off) return x.q_off < y.q_off;
+            if (x.q_end != y.q_end) return x.q_end > y.q_end;
+            return x.context < y.context;
+        });
+        return;
+    }
     // Blast_HSPListPurgeHSPsWithCommonEndpoints(purge = TRUE), core/blast_hits.c:2224-2300
     std::stable_sort(list.begin(), list.end(), [](const BnHSP &x, const BnHSP &y) {
         if (x.context != y.context) return x.context < y.context;
@@ -503,24 +560,24 @@ void LowScoreTracker::subject_done(const BnQueryBatch &b, const std::vector<BnHS
     if (!enabled_ || list.empty()) return;
     // the collector splits the subject's list per query (core/hspfilter_collector.c:104-150);
     // `list` is sorted by score, so the first HSP of a query is its hsp_array[0]
-    std::vector<int32_t> touched;
-    std::vector<ListKey> keys;
-    std::vector<int32_t> slot((size_t)b.num_queries, -1);
+    touched_.clear();
+    keys_.clear();
+    if (slot_.size() != (size_t)b.num_queries) slot_.assign((size_t)b.num_queries, -1);
     for (const BnHSP &h : list) {
         const int32_t qi = b.contexts[h.context].query_index;
-        if (slot[qi] < 0) {
-            slot[qi] = (int32_t)keys.size();
-            keys.push_back(ListKey{h.evalue, h.score, h.oid});
-            touched.push_back(qi);
+        if (slot_[qi] < 0) {
+            slot_[qi] = (int32_t)keys_.size();
+            keys_.push_back(HitListKey{h.evalue, h.score, h.oid});
+            touched_.push_back(qi);
         } else {
-            ListKey &k = keys[slot[qi]];
+            HitListKey &k = keys_[slot_[qi]];
             k.best_evalue = std::min(k.best_evalue, h.evalue);
         }
     }
-    std::sort(touched.begin(), touched.end());
-    for (int32_t qi : touched) {
+    std::sort(touched_.begin(), touched_.end());
+    for (int32_t qi : touched_) {
         HitListState &S = states_[qi];
-        const ListKey &k = keys[slot[qi]];
+        const HitListKey &k = keys_[slot_[qi]];
         if ((int32_t)S.lists.size() < hitlist_size_) {
             S.lists.push_back(k);
             S.worst_evalue = std::max(k.best_evalue, S.worst_evalue);
@@ -535,14 +592,12 @@ void LowScoreTracker::subject_done(const BnQueryBatch &b, const std::vector<BnHS
                 S.low_score = S.lists[0].best_score;
             }
         }
-    }
-    // core/blast_engine.c:1313-1320
-    for (size_t qi = 0; qi < states_.size(); qi++) {
-        const HitListState &S = states_[qi];
+        // core/blast_engine.c:1313-1320 (only a query whose hit list changed can change its bound)
         if (S.heapified) {
             const double v = perc_ * (double)S.low_score;
             if ((double)low_[qi] < v) low_[qi] = (int32_t)v;
         }
+        slot_[qi] = -1;
     }
 }
 

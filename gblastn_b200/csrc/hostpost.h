@@ -27,10 +27,12 @@ struct HostChunk { int32_t oid, chunk_off, len; };
 // node layout and traversal, including its common-endpoint pruning on insertion.
 class IntervalTree {
 public:
-    IntervalTree(int32_t q_min, int32_t q_max, int32_t s_min, int32_t s_max);
+    IntervalTree(int32_t q_min, int32_t q_max, int32_t s_min, int32_t s_max, size_t expected_items = 0);
     struct Item { int32_t q_strand_start, q_off, q_end, s_off, s_end, score; };
     bool contains(const Item &in, int32_t min_diag_separation) const;
-    void add(const Item &in);
+    // check_endpoints = false skips the common-endpoint search; only valid when the tree holds no item
+    // of in's query strand (the search could not match anything)
+    void add(const Item &in, bool check_endpoints = true);
 private:
     struct Node { int32_t leftend, rightend, leftptr, midptr, rightptr, item; };
     std::vector<Node> nodes_;
@@ -85,6 +87,8 @@ private:
     double perc_;
     std::vector<int32_t> low_;
     std::vector<HitListState> states_;
+    std::vector<int32_t> slot_, touched_;      // scratch of subject_done
+    std::vector<HitListKey> keys_;
 };
 
 }  // namespace bn
