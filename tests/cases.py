@@ -49,6 +49,12 @@ CASES = {
     # long, divergent queries: greedy distance > 254 -> exercises the tier-2 (global scratch) path on the GPU
     "mb_long_divergent_tier2": dict(task="megablast", cfg={}, seq_lens=[600_000, 200_000], vol_seed=12,
                                     nq=3, qlen=30_000, q_seed=23, sub=0.03, indel=0.002, planted=1.0),
+    # nt-like volume: thousands of short sequences (log-normal lengths, many shorter than a word),
+    # one launch must cover them all and hits must not leak across sequence boundaries
+    "mb_ntlike_many_subjects": dict(task="megablast", cfg={}, seq_lens="lognormal:4000:7:1500:1.0", vol_seed=13,
+                                    nq=60, qlen=400, q_seed=24, sub=0.02, indel=0.002, planted=0.9),
+    "blastn_ntlike_many_subjects": dict(task="blastn", cfg={}, seq_lens="lognormal:1500:8:1200:0.9", vol_seed=14,
+                                        nq=12, qlen=500, q_seed=25, sub=0.06, indel=0.008, planted=0.9),
     # empty result: random queries only
     "mb_no_hits": dict(task="megablast", cfg={}, seq_lens=[100_000], vol_seed=11,
                        nq=5, qlen=400, q_seed=22, sub=0.0, indel=0.0, planted=0.0),
@@ -59,9 +65,20 @@ FAST = ["c1_megablast_10kb_vs_1mb", "mb_lut11_hash_indels", "mb_smallna_diagarra
 ALL = list(CASES.keys())
 
 
+def _seq_lens(spec, seed):
+    if not isinstance(spec, str):
+        return spec
+    _, n, seed2, median, sigma = spec.split(":")
+    rng = np.random.default_rng(int(seed2) * 7919 + seed)
+    lens = np.exp(rng.normal(np.log(float(median)), float(sigma), size=int(n))).astype(np.int64)
+    lens = np.clip(lens, 1, 400_000)
+    lens[::97] = rng.integers(1, 30, size=lens[::97].shape[0])      # sprinkle sequences shorter than a word
+    return lens
+
+
 def make_case(name):
     c = CASES[name]
-    vol = synth.random_volume(c["seq_lens"], seed=c["vol_seed"])
+    vol = synth.random_volume(_seq_lens(c["seq_lens"], c["vol_seed"]), seed=c["vol_seed"])
     qs = synth.planted_queries(vol, c["nq"], c["qlen"], seed=c["q_seed"], planted_frac=c["planted"],
                                sub_rate=c["sub"], indel_rate=c["indel"], n_frac=c.get("n_frac", 0.0))
     return c["task"], dict(c["cfg"]), vol, qs
