@@ -44,7 +44,11 @@ def test_gpu_matches_reference_and_port(name):
         assert st["gap_extensions"] == r["gap_extensions"]
         assert st["good_extensions"] == r["good_extensions"]
         # scan tap, per subject
-        for oid in range(len(vol.seq_len)):
+        oids = list(range(len(vol.seq_len)))
+        if len(oids) > 12:      # many-subject volumes: the 6 longest + 6 seeded picks
+            longest = np.argsort(vol.seq_len)[-6:].tolist()
+            oids = sorted(set(longest + np.random.default_rng(1).choice(len(vol.seq_len), 6, replace=False).tolist()))
+        for oid in oids:
             if vol.seq_len[oid] > 200_000_000:
                 continue
             pairs = E.scan_subject(V, Q, oid)
