@@ -40,7 +40,8 @@ struct DevQuery {
     const int32_t *hashtable, *next_pos;   // MB
     const uint32_t *presence;              // MB: exact 1 bit / cell bitmap built at load time
     const uint2 *prk;                      // MB compact table: {presence word, rank of its first occupied cell}
-    const int32_t *dense;                  // MB compact table: hashtable values of occupied cells, in cell order
+    const uint4 *cinfo;                    // MB compact table: per occupied cell (in cell order) the qinfo of its
+                                           // first chain element, .x = {qp, bit 31: chain continues}
     const uint4 *qinfo;                    // MB: per query position {next_pos, 16 bases left, 16 right, ambiguity}
     const int16_t *backbone, *overflow;    // SmallNa
     int32_t has_locations;                 // lut->masked_locations != NULL
@@ -179,13 +180,23 @@ int scan_tile_cap(int scan_step, int word_length);
 cudaError_t launch_build_qinfo(const DevQuery &q, const int32_t *next_pos, int32_t concat_len, uint4 *qinfo,
                                cudaStream_t st);
 
+// Outcome of s_TypeOfWord + ungapped extension of one word hit (extend_kernel.cu), 32 bytes.
+struct SpecResult {
+    int32_t status;          // SPEC_* (0 = not computed)
+    int32_t q_off, s_off;    // after s_TypeOfWord's shift
+    int32_t extended;
+    int32_t q_start, s_start, length, score;
+};
+
 struct ExtendLaunch {
     const uint8_t *packed;
     const DevChunk *chunks;
     const SeedHit *hits;          // sorted by (group, global scan position)
     int32_t *cells;               // hash: 4 ints per cell, one region per group (same offsets as hits)
     DevInitHit *init;
-    unsigned long long *counters; // [2] = #init hits, [3] = #extended, [4] = #groups
+    SpecResult *spec;             // per hit: outcome of the speculative extension
+    uint32_t *leaders;            // indices of the hits extended speculatively
+    unsigned long long *counters; // [2] = #init hits, [3] = #extended, [4] = #groups, [5] = #leaders
     int64_t init_capacity;
 };
 cudaError_t launch_extend_groups(const DevQuery &q, const ExtendLaunch &e, const uint64_t *keys,

@@ -54,7 +54,8 @@ struct DevBuf {
 struct Workspace {
     DevBuf<SeedHit> hits_a, hits_b;
     DevBuf<uint64_t> keys_a, keys_b;
-    DevBuf<uint32_t> heads;
+    DevBuf<uint32_t> heads, leaders;
+    DevBuf<SpecResult> spec;
     DevBuf<int4> cells;
     DevBuf<DevInitHit> init;
     DevBuf<DevGapResult> gap_out;
@@ -65,7 +66,7 @@ struct Workspace {
     void release()
     {
         hits_a.release(); hits_b.release(); keys_a.release(); keys_b.release();
-        cells.release(); heads.release(); init.release(); gap_out.release(); scratch.release(); todo.release();
+        cells.release(); heads.release(); leaders.release(); spec.release(); init.release(); gap_out.release(); scratch.release(); todo.release();
         counters.release(); cub_temp.release();
         if (h_counters) cudaFreeHost(h_counters);
         h_counters = nullptr;
@@ -108,7 +109,7 @@ struct QueryDev {
     int32_t *score_table = nullptr, *matrix = nullptr;
     uint2 *qpk = nullptr;
     uint2 *prk = nullptr;
-    int32_t *dense = nullptr;
+    uint4 *cinfo = nullptr;
     uint4 *qinfo = nullptr;
     DevQuery view{};
     bool ready = false;
@@ -146,7 +147,7 @@ static Device *device_at(int d)
 static void free_query_dev(QueryDev &q, cudaStream_t st)
 {
     void *ptrs[] = {q.query, q.ctx, q.hashtable, q.next_pos, q.presence, q.backbone, q.overflow,
-                    q.score_table, q.matrix, q.qpk, q.prk, q.dense, q.qinfo};
+                    q.score_table, q.matrix, q.qpk, q.prk, q.cinfo, q.qinfo};
     for (void *p : ptrs) if (p) cudaFreeAsync(p, st);
     q = QueryDev{};
 }
@@ -171,7 +172,7 @@ cudaError_t launch_build_presence(const int32_t *hashtable, int64_t hashsize, ui
 cudaError_t launch_build_qpk(const uint8_t *query_start, int32_t concat_len, uint2 *qpk, int64_t nwords, cudaStream_t st);
 cudaError_t launch_popc(const uint32_t *presence, int64_t nwords, uint32_t *counts, cudaStream_t st);
 cudaError_t launch_build_compact(const int32_t *hashtable, const uint32_t *presence, const uint32_t *prefix,
-                                 int64_t nwords, uint2 *prk, int32_t *dense, cudaStream_t st);
+                                 int64_t nwords, uint2 *prk, const uint4 *qinfo, uint4 *cinfo, cudaStream_t st);
 
 // Uploads one query batch to device d straight from the caller's arrays (no host staging copy);
 // the presence bitmap and the 16-base query windows are derived on the device.
@@ -198,23 +199,6 @@ static int query_to_device(Query &Q, const BnQueryBatch &src, int d)
         // PV_TEST is only a filter in front of hashtable[index] != 0)
         CU_TRY(dev_alloc(&qd.presence, (size_t)((b.hashsize + 31) / 32), st));
         CU_TRY(launch_build_presence(qd.hashtable, b.hashsize, qd.presence, st));
-        // compact table for the scan kernel: {presence word, rank} + dense values (L2-resident)
-        {
-            const int64_t nwords = (b.hashsize + 31) / 32;
-            uint32_t *counts = nullptr, *prefix = nullptr;
-            CU_TRY(dev_alloc(&counts, (size_t)nwords, st));
-            CU_TRY(dev_alloc(&prefix, (size_t)nwords, st));
-            CU_TRY(dev_alloc(&qd.prk, (size_t)nwords, st));
-            CU_TRY(dev_alloc(&qd.dense, (size_t)b.concat_len + 2, st));
-            CU_TRY(launch_popc(qd.presence, nwords, counts, st));
-            size_t tmp_bytes = 0;
-            CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, prefix, (int)nwords, st));
-            CU_TRY(dev->ws.cub_temp.reserve(tmp_bytes));
-            CU_TRY(cub::DeviceScan::ExclusiveSum(dev->ws.cub_temp.p, tmp_bytes, counts, prefix, (int)nwords, st));
-            CU_TRY(launch_build_compact(qd.hashtable, qd.presence, prefix, nwords, qd.prk, qd.dense, st));
-            CU_TRY(cudaFreeAsync(counts, st));
-            CU_TRY(cudaFreeAsync(prefix, st));
-        }
     } else {
         static const int16_t kEmptyOverflow[2] = {-1, -1};
         CU_TRY(upload(&qd.backbone, src.backbone, (size_t)b.hashsize, st));
@@ -237,13 +221,30 @@ static int query_to_device(Query &Q, const BnQueryBatch &src, int d)
     v.has_locations = Q.batch.masked_locations != nullptr;
     v.container_type = b.container_type; v.window_size = b.window_size; v.scan_range = b.scan_range;
     v.score_table = qd.score_table; v.matrix = qd.matrix; v.qpk = qd.qpk;
-    v.prk = (b.word_length <= 200) ? qd.prk : nullptr; v.dense = qd.dense;
     v.gap_algo = b.gap_algo; v.reward = b.reward; v.penalty = b.penalty;
     v.gap_open = b.gap_open; v.gap_extend = b.gap_extend; v.gap_x_dropoff = b.gap_x_dropoff;
     if (b.lut_type == BN_LUT_MB) {
         CU_TRY(dev_alloc(&qd.qinfo, (size_t)b.concat_len + 2, st));
         CU_TRY(launch_build_qinfo(v, qd.next_pos, b.concat_len, qd.qinfo, st));
         v.qinfo = qd.qinfo;
+        // compact table for the scan kernel: {presence word, rank} per 32 cells (4^lut / 4 bytes,
+        // L2-resident) + the first chain element of every occupied cell in cell order
+        const int64_t nwords = (b.hashsize + 31) / 32;
+        uint32_t *counts = nullptr, *prefix = nullptr;
+        CU_TRY(dev_alloc(&counts, (size_t)nwords, st));
+        CU_TRY(dev_alloc(&prefix, (size_t)nwords, st));
+        CU_TRY(dev_alloc(&qd.prk, (size_t)nwords, st));
+        CU_TRY(dev_alloc(&qd.cinfo, (size_t)b.concat_len + 2, st));
+        CU_TRY(launch_popc(qd.presence, nwords, counts, st));
+        size_t tmp_bytes = 0;
+        CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, prefix, (int)nwords, st));
+        CU_TRY(dev->ws.cub_temp.reserve(tmp_bytes));
+        CU_TRY(cub::DeviceScan::ExclusiveSum(dev->ws.cub_temp.p, tmp_bytes, counts, prefix, (int)nwords, st));
+        CU_TRY(launch_build_compact(qd.hashtable, qd.presence, prefix, nwords, qd.prk, qd.qinfo, qd.cinfo, st));
+        CU_TRY(cudaFreeAsync(counts, st));
+        CU_TRY(cudaFreeAsync(prefix, st));
+        v.prk = (b.word_length <= 200) ? qd.prk : nullptr;
+        v.cinfo = qd.cinfo;
     }
     CU_TRY(cudaStreamSynchronize(st));     // caller's arrays may go away after bn_query_load returns
     qd.ready = true;
@@ -403,17 +404,20 @@ static int run_word_finder(Device &D, Volume &V, Query &Q, ChunkTable &T, bool r
 
     CU_TRY(ws.cells.reserve((size_t)n + 2));
     CU_TRY(ws.heads.reserve((size_t)n + 1));
+    CU_TRY(ws.leaders.reserve((size_t)n + 1));
+    CU_TRY(ws.spec.reserve((size_t)n + 1));
     int64_t init_cap = std::max<int64_t>((int64_t)ws.init.cap, std::max<int64_t>(4096, n / 4));
     for (int attempt = 0;; attempt++) {
         CU_TRY(ws.init.reserve((size_t)init_cap));
         init_cap = (int64_t)ws.init.cap;
-        CU_TRY(cudaMemsetAsync(ws.counters.p + 2, 0, 3 * sizeof(unsigned long long), st));
+        CU_TRY(cudaMemsetAsync(ws.counters.p + 2, 0, 4 * sizeof(unsigned long long), st));
         ExtendLaunch e{};
         e.packed = V.d_packed; e.chunks = T.dev.p; e.hits = ws.hits_b.p;
         e.cells = reinterpret_cast<int32_t *>(ws.cells.p); e.init = ws.init.p;
         e.counters = ws.counters.p; e.init_capacity = init_cap;
+        e.spec = ws.spec.p; e.leaders = ws.leaders.p;
         CU_TRY(launch_extend_groups(dq, e, ws.keys_b.p, ws.heads.p, n, gbits, st));
-        if (stats) stats->kernel_launches += 2;
+        if (stats) stats->kernel_launches += 3;
         CU_TRY(cudaMemcpyAsync(ws.h_counters, ws.counters.p, 8 * sizeof(unsigned long long),
                                cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
@@ -728,7 +732,9 @@ int bn_query_load(const BnQueryBatch *b, int *query_handle)
     if (rc) return rc;
     if (!b || !query_handle || !b->query_start || !b->contexts || b->num_contexts <= 0)
         return fail(BN_ERR_INVALID, "bn_query_load: bad argument");
-    if (b->window_size > 0) return fail(BN_ERR_UNSUPPORTED, "two-hit mode (window_size > 0) is not implemented on the GPU path yet");
+    if (b->window_size > 0 && std::min(b->scan_range, b->window_size - b->word_length) > 0)
+        return fail(BN_ERR_UNSUPPORTED, "two-hit mode with an off-diagonal search (scan_range > 0) is not implemented: "
+                                        "neighbouring diagonals live in other replay groups");
     if (b->gap_algo == BN_GAP_GREEDY && (b->gap_open != 0 || b->gap_extend != 0))
         return fail(BN_ERR_UNSUPPORTED, "affine greedy extension is not implemented");
     if (b->lut_type != BN_LUT_MB && b->lut_type != BN_LUT_SMALL_NA)

@@ -32,6 +32,7 @@ namespace bn {
 
 constexpr int EXT_WARPS_PER_BLOCK = 4;
 constexpr int EXT_BLOCKS = 148 * 4;
+constexpr int SPEC_BLOCKS = 148 * 12;     // speculative pass: 48 warps per SM
 constexpr unsigned FULL = 0xffffffffu;
 
 struct Ungapped { int32_t q_start, s_start, length, score; };
@@ -277,13 +278,15 @@ __device__ __forceinline__ bool seed_masked(const DevQuery &q, const uint8_t *S,
     return !lut_contains(q, w >> (2 * (16 - s_off % 4 - lut)), q_pos);
 }
 
-// s_TypeOfWord with check_double == FALSE (window_size == 0)
+// s_TypeOfWord (core/na_ungapped.c:489-588): 0 = not a word, 1 = single word, 2 = double word
 __device__ int type_of_word(const DevQuery &q, const uint8_t *S, int32_t &q_off, int32_t &s_off,
                             bool has_locations, uint32_t s_range, int32_t word_length, int32_t lut,
-                            int32_t &extended, int lane)
+                            bool check_double, int32_t &extended, int lane)
 {
     extended = 0;
     if (word_length == lut) return 1;
+    // one-hit mode without masked locations: q_end - q_off stays word_length, ext_to is 0, nothing runs
+    if (!has_locations && !check_double) return 1;
     int32_t q_end = q_off + word_length, s_end = s_off + word_length;
     const int32_t context = ctx_search_warp(q, q_end, lane);
     const int32_t q_range = __ldg(&q.ctx[context].query_offset) + __ldg(&q.ctx[context].query_length);
@@ -292,9 +295,9 @@ __device__ int type_of_word(const DevQuery &q, const uint8_t *S, int32_t &q_off,
         for (;; ++s_off, ++q_off)
             if (!seed_masked(q, S, s_off, lut, q_off)) break;
     }
-    const int32_t ext_to = word_length - (q_end - q_off);
+    int32_t ext_to = word_length - (q_end - q_off);
     const uint32_t a = (uint32_t)(q_range - q_end), c = s_range - (uint32_t)s_end;
-    const int32_t ext_max = (int32_t)(a > c ? c : a);   // unsigned MIN, as in the reference (:534)
+    int32_t ext_max = (int32_t)(a > c ? c : a);   // unsigned MIN, as in the reference (:534)
     if (ext_to || has_locations) {
         if (ext_to > ext_max) return 0;
         q_end += ext_to; s_end += ext_to;
@@ -302,7 +305,84 @@ __device__ int type_of_word(const DevQuery &q, const uint8_t *S, int32_t &q_off,
             if (seed_masked(q, S, s_pos, lut, q_pos)) return 0;
         extended = ext_to;
     }
-    return 1;
+    if (!check_double) return 1;
+    // right extension to a double word: seed by seed, then base by base (:557-585)
+    ext_to += word_length;
+    ext_max = min(ext_max, ext_to);
+    int32_t s_pos = s_end, q_pos = q_end;
+    for (; (uint32_t)extended + (uint32_t)lut <= (uint32_t)ext_max; s_pos += lut, q_pos += lut, extended += lut)
+        if (seed_masked(q, S, s_pos, lut, q_pos)) break;
+    s_pos -= lut - 1; q_pos -= lut - 1;
+    while (extended < ext_max) {
+        if (seed_masked(q, S, s_pos, lut, q_pos)) return 1;
+        ++extended; ++s_pos; ++q_pos;
+    }
+    return ext_max == ext_to ? 2 : 1;
+}
+
+// ---- one word hit: s_TypeOfWord + ungapped extension + cutoff test -----------------------------------
+// The outcome depends only on (q_off, s_off, chunk), never on the diagonal container, so it can be
+// computed for many hits at once (speculative pass) or inline by the replay warp.  Warp-uniform.
+constexpr int32_t SPEC_NONE = 0;       // not computed speculatively
+constexpr int32_t SPEC_MASKED = 2;     // s_TypeOfWord returned 0
+constexpr int32_t SPEC_LOW = 3;        // extended, score below the cutoff
+constexpr int32_t SPEC_READY = 4;      // extended, score >= cutoff_score
+constexpr int32_t SPEC_SINGLE = 5;     // two-hit mode: single word, no neighbour yet -> recorded, not extended
+
+struct CtxCache { int32_t lo, hi, x_dropoff, cutoff_score, reduced_cutoff; };   // context covering [lo, hi)
+
+__device__ __forceinline__ void ctx_lookup(const DevQuery &q, int32_t q_off, int lane, CtxCache &cc)
+{
+    if (q_off >= cc.lo && q_off < cc.hi) return;
+    const int32_t context = ctx_search_warp(q, q_off, lane);
+    const DevContext c = q.ctx[context];
+    cc.lo = c.query_offset;
+    cc.hi = (context + 1 < q.num_contexts) ? __ldg(&q.ctx[context + 1].query_offset) : INT32_MAX;
+    cc.x_dropoff = c.x_dropoff; cc.cutoff_score = c.cutoff_score; cc.reduced_cutoff = c.reduced_cutoff;
+}
+
+// touch the cache lines both X-drop walks are about to read (subject +-2 kb, query windows +-2 kb)
+__device__ __forceinline__ void prefetch_around(const DevQuery &q, const uint8_t *packed, const DevChunk &ch,
+                                                int32_t q_off, int32_t s_off, int lane)
+{
+    if (lane < 8) {
+        int64_t b = ch.byte_off + (s_off >> 2) + (int64_t)(lane - 4) * 128;
+        b = max(b, ch.byte_off); b = min(b, ch.byte_off + (ch.len >> 2));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(packed + b));
+    } else if (lane < 24) {
+        int32_t i = ((q_off + 16) >> 4) + (lane - 16) * 16;
+        i = max(i, 0); i = min(i, (q.concat_len + 18) >> 4);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q.qpk + i));
+    }
+}
+
+__device__ void extend_one(const DevQuery &q, const uint8_t *packed, const DevChunk &ch, const int32_t *s_tab,
+                           bool is_hash, bool has_loc, int32_t word, int32_t lut, bool direct, bool check_double,
+                           int32_t q_off, int32_t s_off, int lane, CtxCache &cc, SpecResult &r)
+{
+    int32_t extended = 0;
+    const int32_t s_end0 = s_off + word;      // the reference fixes s_end before s_TypeOfWord may shift s_off
+    const int word_type = type_of_word(q, packed + ch.byte_off, q_off, s_off, has_loc, (uint32_t)ch.len, word,
+                                       direct ? word : lut, check_double, extended, lane);
+    if (!word_type) {
+        r.status = SPEC_MASKED;
+        return;
+    }
+    r.q_off = q_off; r.s_off = s_off; r.extended = extended;
+    if (check_double && word_type == 1) {     // off-diagonal search needs scan_range > 0 (rejected at load)
+        r.status = SPEC_SINGLE;
+        return;
+    }
+    ctx_lookup(q, q_off, lane, cc);
+    Ungapped u;
+    const int64_t chunk_base = ch.byte_off * 4;
+    if (!is_hash && word < 11)
+        ungapped_exact(q, packed, chunk_base, ch.len, q_off, s_off, -cc.x_dropoff, lane, u);
+    else
+        ungapped_extend(q, packed, chunk_base, ch.len, s_tab, q_off, s_end0 + extended, s_off, -cc.x_dropoff,
+                        cc.reduced_cutoff, lane, u);
+    r.status = (u.score >= cc.cutoff_score) ? SPEC_READY : SPEC_LOW;
+    r.q_start = u.q_start; r.s_start = u.s_start; r.length = u.length; r.score = u.score;
 }
 
 // ---- bucket chain (BLAST_DiagHash restricted to one bucket) -------------------------------------
@@ -313,12 +393,12 @@ struct Chain {
     int32_t head, used;
 };
 
-__device__ __forceinline__ bool chain_get(const Chain &c, int32_t diag, int32_t &level)
+__device__ __forceinline__ bool chain_get(const Chain &c, int32_t diag, int32_t &level, int32_t &saved)
 {
     int32_t i = c.head;
     while (i) {
         const int4 v = c.cells[i];
-        if (v.x == diag) { level = v.y; return true; }
+        if (v.x == diag) { level = v.y; saved = v.z & 1; return true; }
         i = v.w;
     }
     return false;
@@ -358,15 +438,63 @@ __device__ __forceinline__ bool same_group(const uint64_t *keys, const SeedHit *
     return is_hash || hits[a].chunk == hits[b].chunk;
 }
 
-// heads[i] = index of the first hit of group i (any order)
+// heads[i] = index of the first hit of group i (any order); leaders[] = hits that open a run of
+// consecutive hits on one diagonal of one chunk (the hits the replay is most likely to extend)
 __global__ void group_heads_kernel(const uint64_t *keys, const SeedHit *hits, int64_t n, int gbits,
-                                   int is_hash, uint32_t *heads, unsigned long long *counters)
+                                   int is_hash, int spec_enabled, uint32_t *heads, uint32_t *leaders,
+                                   SpecResult *spec, unsigned long long *counters)
 {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    if (j > 0 && same_group(keys, hits, j - 1, j, gbits, is_hash != 0)) return;
-    const unsigned long long slot = atomicAdd(&counters[4], 1ull);
-    heads[slot] = (uint32_t)j;
+    bool head = true, leader = spec_enabled != 0;
+    if (j > 0) {
+        const SeedHit a = hits[j - 1], b = hits[j];
+        const bool same_grp = (keys[j - 1] >> gbits) == (keys[j] >> gbits) && (is_hash || a.chunk == b.chunk);
+        head = !same_grp;
+        leader = spec_enabled && (head || a.chunk != b.chunk || (a.s_off - a.q_off) != (b.s_off - b.q_off));
+    }
+    spec[j].status = SPEC_NONE;
+    if (head) heads[atomicAdd(&counters[4], 1ull)] = (uint32_t)j;
+    if (leader) {
+        // warp-aggregated append
+        const unsigned m = __activemask();
+        const int lane = threadIdx.x & 31, ldr = __ffs(m) - 1;
+        unsigned long long base = 0;
+        if (lane == ldr) base = atomicAdd(&counters[5], (unsigned long long)__popc(m));
+        base = __shfl_sync(m, base, ldr);
+        leaders[base + __popc(m & ((1u << lane) - 1))] = (uint32_t)j;
+    }
+}
+
+// Speculative pass: one warp per leader runs s_TypeOfWord + the ungapped extension and parks the
+// outcome next to the hit; the replay consumes it if (and only if) the diagonal test lets the hit
+// through, exactly where the reference would have extended.
+__global__ void __launch_bounds__(EXT_WARPS_PER_BLOCK * 32)
+extend_leaders_kernel(const DevQuery q, const ExtendLaunch e)
+{
+    __shared__ int32_t s_tab[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = q.score_table[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * EXT_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * EXT_WARPS_PER_BLOCK;
+    const int64_t n = (int64_t)e.counters[5];
+    const bool is_hash = q.container_type == 1;
+    const int32_t word = q.word_length, lut = q.lut_word_length;
+    const bool direct = (word == lut);
+    const bool has_loc = q.has_locations && !direct;
+    CtxCache cc{0, -1, 0, 0, 0};
+    for (int64_t w = warp0; w < n; w += nwarps) {
+        const uint32_t j = e.leaders[w];
+        const SeedHit h = e.hits[j];
+        const DevChunk ch = e.chunks[h.chunk];
+        prefetch_around(q, e.packed, ch, (int32_t)h.q_off, (int32_t)h.s_off, lane);
+        SpecResult r;
+        r.status = SPEC_NONE; r.q_off = r.s_off = r.extended = r.q_start = r.s_start = r.length = r.score = 0;
+        extend_one(q, e.packed, ch, s_tab, is_hash, has_loc, word, lut, direct, false, (int32_t)h.q_off,
+                   (int32_t)h.s_off, lane, cc, r);
+        if (lane == 0) e.spec[j] = r;
+    }
 }
 
 __global__ void __launch_bounds__(EXT_WARPS_PER_BLOCK * 32)
@@ -386,36 +514,41 @@ extend_kernel(const DevQuery q, const ExtendLaunch e, const uint64_t *keys, cons
     const int32_t word = q.word_length, lut = q.lut_word_length;
     const bool direct = (word == lut);
     const bool has_loc = q.has_locations && !direct;
-    // window_size == 0  =>  Delta = MIN(scan_range, -word_length); staleness window = Delta + 1
-    const int32_t stale_window = min(q.scan_range, -word) + 1;
+    // one-hit mode: Delta = MIN(scan_range, -word_length); two-hit mode with scan_range == 0: Delta <= 0,
+    // clamped to 0 on the single-word path only (core/na_ungapped.c:833)
+    const int32_t window = q.window_size;
+    const bool two_hits = window > 0;
+    const int32_t Delta = min(q.scan_range, window - word);
 
     for (int64_t g = warp0; g < n_groups; g += nwarps) {
         const int64_t j0 = (int64_t)heads[g];
         Chain chain;
         chain.cells = reinterpret_cast<int4 *>(e.cells) + j0;   // region [j0+1 .. j0+group_size]
         chain.head = 0; chain.used = 0;
-        int32_t last_hit_cell = 0;      // eDiagArray: the cell's last_hit
+        int32_t last_hit_cell = 0, flag_cell = 0;      // eDiagArray: the cell's last_hit / flag
         uint32_t cur_chunk = 0xFFFFFFFFu;
         int32_t cur_epoch = -1;
         DevChunk ch{};
-        const uint8_t *S = nullptr;
-        int64_t chunk_base = 0;
         unsigned long long n_extended = 0;
+        CtxCache cc{0, -1, 0, 0, 0};
 
         // most-recently-stored diagonal of this bucket: a get() right after put(d) returns what was
         // stored (no other put intervened), so runs of seeds on one diagonal skip the chain walk
-        int32_t cache_diag = 0, cache_level = 0;
+        int32_t cache_diag = 0, cache_level = 0, cache_saved = 0;
         bool cache_ok = false;
         bool group_done = false;
         for (int64_t base = j0; base < n_hits && !group_done; base += 32) {
             // prefetch up to 32 hits of the group, one per lane
             const int64_t jm = base + lane;
             SeedHit mine{0, 0, 0, 0};
+            SpecResult myspec;
+            myspec.status = SPEC_NONE;
             uint64_t mykey = 0;
             bool in_group = false;
             if (jm < n_hits) {
                 mine = e.hits[jm];
                 mykey = keys[jm];
+                myspec = e.spec[jm];
                 in_group = (jm == j0) || same_group(keys, e.hits, jm - 1, jm, gbits, is_hash);
             }
             const unsigned brk = __ballot_sync(FULL, !in_group);
@@ -430,8 +563,6 @@ extend_kernel(const DevQuery q, const ExtendLaunch e, const uint64_t *keys, cons
                 if (h.chunk != cur_chunk) {
                     cur_chunk = h.chunk;
                     ch = e.chunks[cur_chunk];
-                    S = e.packed + ch.byte_off;
-                    chunk_base = ch.byte_off * 4;
                     if (is_hash) {
                         // Blast_ExtendWordExit may have reset the container between chunks
                         if (cur_epoch >= 0 && ch.diag_epoch != cur_epoch) {
@@ -443,34 +574,38 @@ extend_kernel(const DevQuery q, const ExtendLaunch e, const uint64_t *keys, cons
                     }
                 }
                 int32_t q_off = (int32_t)h.q_off, s_off = (int32_t)h.s_off;
-                const int32_t s_range = ch.len;
                 int32_t s_end = s_off + word;
                 const int32_t s_off_pos = s_off + ch.diag_offset;
                 int32_t s_end_pos = s_end + ch.diag_offset;
                 const int32_t diag = s_off - q_off;
-                int32_t last_hit = 0;
+                int32_t last_hit = 0, hit_saved = 0;
                 if (is_hash) {
-                    if (cache_ok && cache_diag == diag) last_hit = cache_level;
-                    else if (!chain_get(chain, diag, last_hit)) last_hit = 0;
-                } else last_hit = last_hit_cell;
+                    if (cache_ok && cache_diag == diag) { last_hit = cache_level; hit_saved = cache_saved; }
+                    else if (!chain_get(chain, diag, last_hit, hit_saved)) { last_hit = 0; hit_saved = 0; }
+                } else { last_hit = last_hit_cell; hit_saved = flag_cell; }
                 if (s_off_pos < last_hit) continue;
+                // two-hit mode: a hit far from the previous one on its diagonal is only recorded unless it
+                // is a double word by itself
+                const bool check_double = two_hits && (hit_saved || s_end_pos > last_hit + window);
 
-                int32_t extended = 0;
-                if (!type_of_word(q, S, q_off, s_off, has_loc, (uint32_t)s_range, word, direct ? word : lut, extended, lane))
-                    continue;
-                s_end += extended; s_end_pos += extended;
-
-                const int32_t context = ctx_search_warp(q, q_off, lane);
-                const DevContext c = q.ctx[context];
-                Ungapped u;
-                if (!is_hash && word < 11)
-                    ungapped_exact(q, e.packed, chunk_base, ch.len, q_off, s_off, -c.x_dropoff, lane, u);
-                else
-                    ungapped_extend(q, e.packed, chunk_base, ch.len, s_tab, q_off, s_end, s_off, -c.x_dropoff,
-                                    c.reduced_cutoff, lane, u);
+                SpecResult r;
+                r.status = __shfl_sync(FULL, myspec.status, t);
+                if (r.status != SPEC_NONE && !check_double) {
+                    if (r.status == SPEC_MASKED) continue;
+                    r.q_off = __shfl_sync(FULL, myspec.q_off, t); r.s_off = __shfl_sync(FULL, myspec.s_off, t);
+                    r.extended = __shfl_sync(FULL, myspec.extended, t);
+                    r.q_start = __shfl_sync(FULL, myspec.q_start, t); r.s_start = __shfl_sync(FULL, myspec.s_start, t);
+                    r.length = __shfl_sync(FULL, myspec.length, t); r.score = __shfl_sync(FULL, myspec.score, t);
+                } else {
+                    extend_one(q, e.packed, ch, s_tab, is_hash, has_loc, word, lut, direct, check_double, q_off, s_off,
+                               lane, cc, r);
+                    if (r.status == SPEC_MASKED) continue;
+                }
+                q_off = r.q_off; s_off = r.s_off;
+                s_end += r.extended; s_end_pos += r.extended;
 
                 int32_t hit_ready = 0;
-                if (u.score >= c.cutoff_score) {
+                if (r.status == SPEC_READY) {
                     hit_ready = 1;
                     const uint64_t kj = __shfl_sync(FULL, mykey, t);
                     if (lane == 0) {
@@ -478,19 +613,20 @@ extend_kernel(const DevQuery q, const ExtendLaunch e, const uint64_t *keys, cons
                         if ((int64_t)slot < e.init_capacity) {
                             DevInitHit o;
                             o.chunk = (int32_t)cur_chunk; o.q_off = q_off; o.s_off = s_off;
-                            o.q_start = u.q_start; o.s_start = u.s_start; o.length = u.length; o.score = u.score;
+                            o.q_start = r.q_start; o.s_start = r.s_start; o.length = r.length; o.score = r.score;
                             o.order = (uint32_t)(kj & ((1ull << gbits) - 1ull));
                             e.init[slot] = o;
                         }
                     }
-                    s_end_pos = u.length + u.s_start + ch.diag_offset;
+                    s_end_pos = r.length + r.s_start + ch.diag_offset;
                     ++n_extended;
                 }
                 if (is_hash) {
+                    const int32_t d_eff = (r.status == SPEC_SINGLE) ? max(Delta, 0) : Delta;
                     chain_put(chain, diag, s_end_pos, hit_ready ? 0 : s_end_pos - s_off_pos, hit_ready,
-                              s_off_pos, stale_window, lane);
-                    cache_diag = diag; cache_level = s_end_pos; cache_ok = true;
-                } else last_hit_cell = s_end_pos;
+                              s_off_pos, window + d_eff + 1, lane);
+                    cache_diag = diag; cache_level = s_end_pos; cache_saved = hit_ready; cache_ok = true;
+                } else { last_hit_cell = s_end_pos; flag_cell = hit_ready; }
             }
         }
         if (lane == 0 && n_extended) atomicAdd(&e.counters[3], n_extended);
@@ -501,11 +637,21 @@ cudaError_t launch_extend_groups(const DevQuery &q, const ExtendLaunch &e, const
                                  uint32_t *heads, int64_t n_hits, int gbits, cudaStream_t st)
 {
     if (n_hits <= 0) return cudaSuccess;
+    // two-hit mode: which s_TypeOfWord variant runs depends on the diagonal state, so nothing is
+    // extended ahead of the replay there
+    const int spec_enabled = q.window_size > 0 ? 0 : 1;
     group_heads_kernel<<<(unsigned)((n_hits + 255) / 256), 256, 0, st>>>(keys, e.hits, n_hits, gbits,
-                                                                         q.container_type == 1, heads, e.counters);
+                                                                         q.container_type == 1, spec_enabled, heads,
+                                                                         e.leaders, e.spec, e.counters);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;
     const int64_t want = (n_hits + EXT_WARPS_PER_BLOCK - 1) / EXT_WARPS_PER_BLOCK;
+    const unsigned spec_blocks = (unsigned)(want < SPEC_BLOCKS ? (want < 1 ? 1 : want) : SPEC_BLOCKS);
+    if (spec_enabled) {
+        extend_leaders_kernel<<<spec_blocks, EXT_WARPS_PER_BLOCK * 32, 0, st>>>(q, e);
+        err = cudaGetLastError();
+        if (err != cudaSuccess) return err;
+    }
     const unsigned blocks = (unsigned)(want < EXT_BLOCKS ? (want < 1 ? 1 : want) : EXT_BLOCKS);
     extend_kernel<<<blocks, EXT_WARPS_PER_BLOCK * 32, 0, st>>>(q, e, keys, heads, n_hits, gbits);
     return cudaGetLastError();

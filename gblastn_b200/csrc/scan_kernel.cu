@@ -15,14 +15,17 @@
 // positions of the volume-wide position space (prefix sums in the chunk table).
 //
 //   phase 0  the block's slice of the packed subject (a few KB, contiguous in the volume) is staged
-//            into shared memory with coalesced 128-bit loads
-//   phase A  every thread forms the lookup words of its positions from the tile and probes the
-//            compact table word {presence bits, rank} (one 8-byte L2 access per position); positions
-//            whose cell is occupied are pushed to a shared-memory candidate queue
-//   phase B  candidates are processed DENSELY (one per thread, no idle lanes): first query offset
-//            from dense[rank], chain walk through next_pos, mini-extension on 16-base windows
-//            (subject from the tile, query from the packed query), survivors appended with
-//            warp-aggregated atomics
+//            into shared memory by ONE TMA bulk copy (cp.async.bulk + mbarrier); meanwhile the block
+//            builds a shared-memory table of the chunks it spans, so position -> (chunk, offset) is a
+//            32-bit cursor walk instead of a 64-bit binary search in global memory
+//   phase A  every thread forms the lookup words of its 8 positions from the tile and probes the
+//            compact table word {presence bits, rank} (one 8-byte L2 access per position, all 8 in
+//            flight together); occupied cells are pushed to a shared-memory candidate queue with one
+//            reservation per warp
+//   phase B  candidates are processed DENSELY (one per thread, no idle lanes): cinfo[rank] holds the
+//            first chain element together with the query's 16 bases on either side of the word, so
+//            the common case is one 16-byte load + two tile windows; chains continue through
+//            next_pos / qinfo; survivors are appended with warp-aggregated atomics
 //
 // A survivor carries the 64-bit key (group << gbits | global position): group = diagonal-hash bucket
 // or diagonal-array cell.  One stable radix sort on that key both groups the hits for the diagonal
@@ -39,7 +42,7 @@ constexpr int POS_PER_THREAD = 8;
 constexpr int POS_PER_BLOCK = SCAN_THREADS * POS_PER_THREAD;
 constexpr int TILE_BYTES = 20 * 1024;      // staged subject slice (incl. 64-byte margins)
 constexpr int TILE_MARGIN = 64;
-static_assert(POS_PER_BLOCK <= 4096, "candidate packing holds 12 bits of in-block position");
+static_assert(POS_PER_BLOCK <= 2048, "candidate packing holds 11 bits of in-block position");
 
 int scan_positions_per_block() { return POS_PER_BLOCK; }
 
@@ -254,9 +257,7 @@ scan_kernel(const DevQuery q, const ScanLaunch s)
 }
 
 // ---- staged kernel (megablast tables) ------------------------------------------------------------
-// candidate = occupied table cell met at a scan position: rank into dense[] + (chunk delta << 12 | position in block)
-struct Candidate { uint32_t rank; uint32_t where; };
-
+// candidate = occupied table cell met at a scan position: {rank of the cell, chunk delta << 11 | position in block}
 // 16-base window of the staged tile starting at tile-relative base position tb (>= 0)
 __device__ __forceinline__ uint32_t tile_win(const uint32_t *tile, int32_t tb)
 {
@@ -268,7 +269,7 @@ __device__ __forceinline__ uint32_t tile_win(const uint32_t *tile, int32_t tb)
 // s_BlastNaExtend on 16-base windows.  The query's 16 bases on either side of the lookup word come
 // with the chain element (qinfo), so the common case needs no further query access; tbase =
 // tile-relative base index of the chunk's base 0.
-__device__ __forceinline__ bool mini_extend_tile(const DevQuery &q, const uint32_t *tile, int64_t tbase,
+__device__ __forceinline__ bool mini_extend_tile(const DevQuery &q, const uint32_t *tile, int32_t tbase,
                                                  int32_t s_range, int32_t q_offset, int32_t s_offset,
                                                  const uint4 qi, int32_t &q_out, int32_t &s_out)
 {
@@ -277,14 +278,14 @@ __device__ __forceinline__ bool mini_extend_tile(const DevQuery &q, const uint32
     if (ext_to > 0) {
         const int32_t lim = min(ext_to, s_offset);
         if (lim > 0) {
-            const uint32_t m = mismatch_bits(qi.y, qi.w & 0x55555555u, tile_win(tile, (int32_t)(tbase + s_offset - 16)));
+            const uint32_t m = mismatch_bits(qi.y, qi.w & 0x55555555u, tile_win(tile, tbase + s_offset - 16));
             ext_left = m ? ((__ffs(m) - 1) >> 1) : 16;
             if (ext_left >= lim) ext_left = lim;
             else if (!m) {                       // all 16 matched and more are wanted: continue on windows
                 while (ext_left < lim) {
                     uint32_t qb, qa;
                     qwin(q, q_offset - ext_left - 16, qb, qa);
-                    const uint32_t mm = mismatch_bits(qb, qa, tile_win(tile, (int32_t)(tbase + s_offset - ext_left - 16)));
+                    const uint32_t mm = mismatch_bits(qb, qa, tile_win(tile, tbase + s_offset - ext_left - 16));
                     if (mm) { ext_left = min(ext_left + ((__ffs(mm) - 1) >> 1), lim); break; }
                     ext_left = min(ext_left + 16, lim);
                 }
@@ -294,14 +295,14 @@ __device__ __forceinline__ bool mini_extend_tile(const DevQuery &q, const uint32
             const int32_t need = ext_to - ext_left;
             const int32_t sp = s_offset + lut;
             if ((uint32_t)(sp + need) > (uint32_t)s_range) return false;
-            const uint32_t m = mismatch_bits(qi.z, (qi.w >> 1) & 0x55555555u, tile_win(tile, (int32_t)(tbase + sp)));
+            const uint32_t m = mismatch_bits(qi.z, (qi.w >> 1) & 0x55555555u, tile_win(tile, tbase + sp));
             int32_t ext_right = m ? (__clz(m) >> 1) : 16;
             if (ext_right < need) {
                 if (m) return false;
                 while (ext_right < need) {       // need > 16
                     uint32_t qb, qa;
                     qwin(q, q_offset + lut + ext_right, qb, qa);
-                    const uint32_t mm = mismatch_bits(qb, qa, tile_win(tile, (int32_t)(tbase + sp + ext_right)));
+                    const uint32_t mm = mismatch_bits(qb, qa, tile_win(tile, tbase + sp + ext_right));
                     if (mm) { ext_right = min(ext_right + (__clz(mm) >> 1), need); break; }
                     ext_right = min(ext_right + 16, need);
                 }
@@ -314,22 +315,90 @@ __device__ __forceinline__ bool mini_extend_tile(const DevQuery &q, const uint32
     return true;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS)
-scan_kernel_staged(const DevQuery q, const ScanLaunch s)
+// ---- TMA (bulk async copy) + mbarrier helpers ------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
 {
-    extern __shared__ __align__(16) uint32_t smem_dyn[];
-    uint32_t *tile = smem_dyn;                                              // s.tile_cap bytes
-    Candidate *cand = reinterpret_cast<Candidate *>(smem_dyn + s.tile_cap / 4);   // POS_PER_BLOCK entries
-    __shared__ int32_t sh_c_lo, sh_c_hi, sh_ncand;
-    __shared__ int64_t sh_tile_lo, sh_tile_hi;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy executed by the TMA unit (SASS UBLKCP); src/dst 16-byte aligned, bytes % 16 == 0
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 
-    const int tid = threadIdx.x;
+constexpr int MAXC = 256;          // chunks one staged block may span (more: direct-load path)
+
+// Direct-load path for the rare block whose byte span does not fit the tile (runs of sequences
+// shorter than a word) : same semantics, per-position global loads.
+__device__ __noinline__ void scan_block_direct(const DevQuery &q, const ScanLaunch &s, int64_t block_pos0,
+                                               int32_t c_lo, int32_t c_hi, unsigned long long &my_lookup_hits)
+{
+    const int32_t lut = q.lut_word_length, step = q.scan_step;
+    for (int it = 0; it < POS_PER_THREAD; it++) {
+        const int64_t g = block_pos0 + (int64_t)it * SCAN_THREADS + threadIdx.x;
+        if (g >= s.total_pos) break;
+        int32_t lo = c_lo, hi = c_hi;
+        while (lo < hi) {
+            const int32_t m = (lo + hi + 1) >> 1;
+            if (__ldg(&s.chunks[m].pos_prefix) <= g) lo = m; else hi = m - 1;
+        }
+        const DevChunk ch = s.chunks[lo];
+        const int32_t p = (int32_t)(g - ch.pos_prefix) * step;
+        const uint32_t window = load_window(s.packed, ch.byte_off + (p >> 2));
+        const uint32_t idx = (window >> (2 * (16 - ((p & 3) + lut)))) & q.hash_mask;
+        if (!((__ldg(&q.presence[idx >> 5]) >> (idx & 31)) & 1u)) continue;
+        int32_t qp = __ldg(&q.hashtable[idx]);
+        while (qp) {
+            ++my_lookup_hits;
+            int32_t qo, so;
+            if (s.raw_pairs) emit_hit(q, s, (uint32_t)lo, (uint32_t)p, g, qp - 1, p);
+            else if (mini_extend_mb(q, s.packed + ch.byte_off, ch.len, qp - 1, p, qo, so))
+                emit_hit(q, s, (uint32_t)lo, (uint32_t)p, g, qo, so);
+            qp = __ldg(&q.next_pos[qp]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS, 6)
+scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ ScanLaunch s)
+{
+    extern __shared__ __align__(128) uint32_t smem_dyn[];
+    uint32_t *tile = smem_dyn;                                               // s.tile_cap bytes
+    uint2 *cand = reinterpret_cast<uint2 *>(smem_dyn + s.tile_cap / 4);      // POS_PER_BLOCK entries {rank, where}
+    // block-local chunk table: first position (block-relative, may be negative for the first chunk),
+    // tile-relative base index of the chunk's base 0, chunk length
+    __shared__ int32_t ct_start[MAXC + 1], ct_tbase[MAXC], ct_len[MAXC];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ int32_t sh_c_lo, sh_c_hi, sh_staged;
+    __shared__ int64_t sh_tile_lo;
+
+    const int tid = threadIdx.x, lane = tid & 31;
     const int64_t block_pos0 = (int64_t)blockIdx.x * POS_PER_BLOCK;
+    const int32_t npos = (int32_t)min((int64_t)POS_PER_BLOCK, s.total_pos - block_pos0);
     const int32_t lut = q.lut_word_length, step = q.scan_step;
     if (tid == 0) {
         const int32_t c_lo = s.block_chunk[blockIdx.x];
         int32_t lo = c_lo, hi = s.block_chunk[blockIdx.x + 1];
-        const int64_t g_last = min(block_pos0 + POS_PER_BLOCK, s.total_pos) - 1;
+        const int64_t g_last = block_pos0 + npos - 1;
         while (lo < hi) {                       // chunk of the block's last position
             const int32_t m = (lo + hi + 1) >> 1;
             if (s.chunks[m].pos_prefix <= g_last) lo = m; else hi = m - 1;
@@ -337,89 +406,130 @@ scan_kernel_staged(const DevQuery q, const ScanLaunch s)
         const DevChunk a = s.chunks[c_lo], b = s.chunks[lo];
         const int64_t first_byte = a.byte_off + (((block_pos0 - a.pos_prefix) * step) >> 2);
         const int64_t last_byte = b.byte_off + ((((g_last - b.pos_prefix) * step) + q.word_length + 32) >> 2);
+        const int64_t tile_lo = (first_byte - TILE_MARGIN) & ~int64_t(15);
+        const int64_t bytes = (last_byte + TILE_MARGIN - tile_lo + 15) & ~int64_t(15);
+        const bool staged = bytes <= (int64_t)s.tile_cap && (lo - c_lo) < MAXC;
         sh_c_lo = c_lo; sh_c_hi = lo;
-        sh_tile_lo = (first_byte - TILE_MARGIN) & ~int64_t(15);
-        sh_tile_hi = last_byte + TILE_MARGIN;
-        sh_ncand = 0;
-    }
-    __syncthreads();
-    const int32_t c_lo = sh_c_lo, c_hi = sh_c_hi;
-    const int64_t tile_lo = sh_tile_lo;
-    const int32_t tile_bytes = (int32_t)min(sh_tile_hi - tile_lo, (int64_t)INT32_MAX);
-    // a block spanning > 2^22 chunks or more bytes than the tile holds takes the direct-load path
-    const bool staged = tile_bytes <= s.tile_cap - 16 && (c_hi - c_lo) < (1 << 20);
-    if (staged) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(s.packed + tile_lo);
-        uint4 *dst = reinterpret_cast<uint4 *>(tile);
-        for (int i = tid; i < (tile_bytes + 15) / 16; i += SCAN_THREADS) dst[i] = __ldg(src + i);
-    }
-    __syncthreads();
-
-    // ---- phase A: lookup words, then all presence probes of the thread in flight together -----------
-    uint32_t idxs[POS_PER_THREAD], wheres[POS_PER_THREAD];
-    uint2 words[POS_PER_THREAD];
-#pragma unroll
-    for (int it = 0; it < POS_PER_THREAD; it++) {
-        const uint32_t gl = (uint32_t)(it * SCAN_THREADS + tid);
-        const int64_t g = block_pos0 + gl;
-        idxs[it] = 0xFFFFFFFFu;
-        wheres[it] = 0;
-        if (g < s.total_pos) {
-            int32_t lo = c_lo, hi = c_hi;
-            while (lo < hi) {
-                const int32_t m = (lo + hi + 1) >> 1;
-                if (__ldg(&s.chunks[m].pos_prefix) <= g) lo = m; else hi = m - 1;
-            }
-            const int64_t prefix = __ldg(&s.chunks[lo].pos_prefix);
-            const int64_t byte_off = __ldg(&s.chunks[lo].byte_off);
-            const int32_t p = (int32_t)(g - prefix) * step;
-            uint32_t window;
-            if (staged) window = tile_win(tile, (int32_t)((byte_off - tile_lo) * 4 + p));
-            else window = load_window(s.packed, byte_off + (p >> 2)) << (2 * (p & 3));
-            idxs[it] = window >> (2 * (16 - lut));
-            wheres[it] = ((uint32_t)(lo - c_lo) << 12) | gl;
-        }
-    }
-#pragma unroll
-    for (int it = 0; it < POS_PER_THREAD; it++)
-        words[it] = (idxs[it] != 0xFFFFFFFFu) ? __ldg(&q.prk[idxs[it] >> 5]) : make_uint2(0u, 0u);
-#pragma unroll
-    for (int it = 0; it < POS_PER_THREAD; it++) {
-        const uint32_t bit = idxs[it] & 31;
-        if (idxs[it] != 0xFFFFFFFFu && ((words[it].x >> bit) & 1u)) {
-            const int slot = atomicAdd(&sh_ncand, 1);
-            cand[slot] = Candidate{words[it].y + (uint32_t)__popc(words[it].x & ((1u << bit) - 1u)), wheres[it]};
+        sh_tile_lo = tile_lo;
+        sh_staged = staged ? 1 : 0;
+        if (staged) {                           // the block's slice of the packed subject: one TMA bulk copy
+            mbar_init(&bar, 1);
+            mbar_expect_tx(&bar, (uint32_t)bytes);
+            tma_bulk_g2s(tile, s.packed + tile_lo, (uint32_t)bytes, &bar);
         }
     }
     __syncthreads();
-
-    // ---- phase B: dense candidate processing ------------------------------------------------------
-    const int ncand = sh_ncand;
+    const int32_t c_lo = sh_c_lo;
+    const int32_t nch = sh_c_hi - c_lo + 1;
     unsigned long long my_lookup_hits = 0;
-    for (int ci = tid; ci < ncand; ci += SCAN_THREADS) {
-        const Candidate c = cand[ci];
-        int32_t qp = __ldg(&q.dense[c.rank]);
-        const uint32_t chunk = (uint32_t)c_lo + (c.where >> 12);
-        const int64_t g = block_pos0 + (c.where & 4095u);
-        const int64_t byte_off = __ldg(&s.chunks[chunk].byte_off);
-        const int32_t len = __ldg(&s.chunks[chunk].len);
-        const int32_t p = (int32_t)(g - __ldg(&s.chunks[chunk].pos_prefix)) * step;
-        while (qp) {
-            ++my_lookup_hits;
-            const uint4 qi = __ldg(&q.qinfo[qp]);         // {next, left 16 bases, right 16 bases, ambiguity}
-            int32_t qo, so;
-            if (s.raw_pairs) emit_hit(q, s, chunk, (uint32_t)p, g, qp - 1, p);
-            else {
-                bool ok;
-                if (staged) ok = mini_extend_tile(q, tile, (byte_off - tile_lo) * 4, len, qp - 1, p, qi, qo, so);
-                else ok = mini_extend_mb(q, s.packed + byte_off, len, qp - 1, p, qo, so);
-                if (ok) emit_hit(q, s, chunk, (uint32_t)p, g, qo, so);
+    if (!sh_staged) {
+        scan_block_direct(q, s, block_pos0, c_lo, sh_c_hi, my_lookup_hits);
+    } else {
+        const int64_t tile_lo = sh_tile_lo;
+        for (int i = tid; i < nch; i += SCAN_THREADS) {
+            const DevChunk c = s.chunks[c_lo + i];
+            ct_start[i] = (int32_t)(c.pos_prefix - block_pos0);
+            ct_tbase[i] = (int32_t)((c.byte_off - tile_lo) * 4);
+            ct_len[i] = c.len;
+        }
+        if (tid == 0) ct_start[nch] = INT32_MAX;
+        __syncthreads();
+        mbar_wait(&bar, 0);
+
+        // From here on every warp works alone on its 256 positions (block-relative position of lane l,
+        // round it: it * 256 + warp * 32 + l): no block barrier between the probe and the candidate phase.
+        // ---- phase A: lookup words from the tile, all 8 presence probes of the thread in flight ------
+        uint2 words[POS_PER_THREAD];
+        uint32_t bitpack[POS_PER_THREAD / 4], cpack[POS_PER_THREAD / 4];
+        const uint32_t shr = 32u - 2u * (uint32_t)lut;
+        if (nch == 1) {
+            // the whole block lies in one chunk: tile offsets are an arithmetic progression
+            const int32_t tb0 = ct_tbase[0] - ct_start[0] * step;
+#pragma unroll
+            for (int it = 0; it < POS_PER_THREAD; it++) {
+                const int32_t gl = min(it * SCAN_THREADS + tid, npos - 1);
+                const int32_t tb = tb0 + gl * step;
+                const uint32_t w0 = tile[tb >> 4], w1 = tile[(tb >> 4) + 1];
+                // 4 consecutive stream bytes from byte (tb >> 2) on, most significant first
+                const uint32_t W = __byte_perm(w0, w1, 0x0123u + 0x1111u * ((uint32_t)(tb >> 2) & 3u));
+                const uint32_t idx = (W << (2u * ((uint32_t)tb & 3u))) >> shr;
+                words[it] = __ldg(&q.prk[idx >> 5]);
+                if ((it & 3) == 0) bitpack[it >> 2] = 0;
+                bitpack[it >> 2] |= (idx & 31u) << (8 * (it & 3));
             }
-            qp = (int32_t)qi.x;
+            cpack[0] = cpack[1] = 0;
+        } else {
+            {   // chunk of each of the thread's positions: monotone cursor over the block's chunk table
+                int32_t c = 0, cnext = ct_start[1];
+#pragma unroll
+                for (int it = 0; it < POS_PER_THREAD; it++) {
+                    const int32_t gl = min(it * SCAN_THREADS + tid, npos - 1);
+                    while (gl >= cnext) { ++c; cnext = ct_start[c + 1]; }
+                    if ((it & 3) == 0) cpack[it >> 2] = 0;
+                    cpack[it >> 2] |= (uint32_t)c << (8 * (it & 3));
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < POS_PER_THREAD; it++) {
+                const int32_t gl = min(it * SCAN_THREADS + tid, npos - 1);
+                const uint32_t c = (cpack[it >> 2] >> (8 * (it & 3))) & 255u;
+                const int32_t tb = ct_tbase[c] + (gl - ct_start[c]) * step;
+                const uint32_t w0 = tile[tb >> 4], w1 = tile[(tb >> 4) + 1];
+                const uint32_t W = __byte_perm(w0, w1, 0x0123u + 0x1111u * ((uint32_t)(tb >> 2) & 3u));
+                const uint32_t idx = (W << (2u * ((uint32_t)tb & 3u))) >> shr;
+                words[it] = __ldg(&q.prk[idx >> 5]);
+                if ((it & 3) == 0) bitpack[it >> 2] = 0;
+                bitpack[it >> 2] |= (idx & 31u) << (8 * (it & 3));
+            }
+        }
+        // ---- warp-local compaction of the occupied cells (ballots, no atomics) ----------------------
+        uint2 *wcand = cand + (tid >> 5) * (32 * POS_PER_THREAD);
+        int ncand = 0;
+        {
+            const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+            for (int it = 0; it < POS_PER_THREAD; it++) {
+                const uint32_t bit = (bitpack[it >> 2] >> (8 * (it & 3))) & 31u;
+                const bool hit = (it * SCAN_THREADS + tid < npos) && ((words[it].x >> bit) & 1u);
+                const uint32_t m = __ballot_sync(0xffffffffu, hit);
+                if (hit) {
+                    const uint32_t c = (cpack[it >> 2] >> (8 * (it & 3))) & 255u;
+                    wcand[ncand + __popc(m & lt)] =
+                        make_uint2(words[it].y + (uint32_t)__popc(words[it].x & ((1u << bit) - 1u)),
+                                   (c << 11) | (uint32_t)(it * SCAN_THREADS + tid));
+                }
+                ncand += __popc(m);
+            }
+        }
+        __syncwarp();
+
+        // ---- phase B: the warp's candidates, one per lane ----------------------------------------------
+        for (int ci = lane; ci < ncand; ci += 32) {
+            const uint2 cd = wcand[ci];
+            const int32_t gl = (int32_t)(cd.y & 2047u), k = (int32_t)(cd.y >> 11);
+            uint4 qi = __ldg(&q.cinfo[cd.x]);      // first chain element: {qp | more << 31, left 16, right 16, ambiguity}
+            const int32_t p = (gl - ct_start[k]) * step;
+            const int32_t tbase = ct_tbase[k], len = ct_len[k];
+            const uint32_t chunk = (uint32_t)(c_lo + k);
+            const int64_t g = block_pos0 + gl;
+            int32_t qp = (int32_t)(qi.x & 0x7fffffffu);
+            bool more = (qi.x >> 31) != 0;
+            for (;;) {
+                ++my_lookup_hits;
+                int32_t qo, so;
+                if (s.raw_pairs) emit_hit(q, s, chunk, (uint32_t)p, g, qp - 1, p);
+                else if (mini_extend_tile(q, tile, tbase, len, qp - 1, p, qi, qo, so))
+                    emit_hit(q, s, chunk, (uint32_t)p, g, qo, so);
+                if (!more) break;
+                qp = __ldg(&q.next_pos[qp]);
+                qi = __ldg(&q.qinfo[qp]);           // {next, left 16 bases, right 16 bases, ambiguity}
+                more = qi.x != 0;
+            }
         }
     }
+    // one atomic per warp for the lookup-hit statistic (BlastUngappedStats.lookup_hits)
     for (int o = 16; o > 0; o >>= 1) my_lookup_hits += __shfl_down_sync(0xffffffffu, my_lookup_hits, o);
-    if ((tid & 31) == 0 && my_lookup_hits) atomicAdd(&s.counters[1], my_lookup_hits);
+    if (lane == 0 && my_lookup_hits) atomicAdd(&s.counters[1], my_lookup_hits);
 }
 
 // qinfo[qp] for every 1-based query position qp: {next_pos[qp], 16 bases left of the lookup word that
@@ -485,8 +595,9 @@ __global__ void popc_kernel(const uint32_t *presence, int64_t nwords, uint32_t *
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nwords) counts[i] = __popc(presence[i]);
 }
+// cinfo[rank] = qinfo of the cell's first chain element with .x = {first qp, bit 31 = chain continues}
 __global__ void build_compact_kernel(const int32_t *hashtable, const uint32_t *presence, const uint32_t *prefix,
-                                     int64_t nwords, uint2 *prk, int32_t *dense)
+                                     int64_t nwords, uint2 *prk, const uint4 *qinfo, uint4 *cinfo)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nwords) return;
@@ -496,7 +607,10 @@ __global__ void build_compact_kernel(const int32_t *hashtable, const uint32_t *p
     while (bits) {
         const int b = __ffs(bits) - 1;
         bits &= bits - 1;
-        dense[r++] = hashtable[i * 32 + b];
+        const uint32_t qp = (uint32_t)hashtable[i * 32 + b];
+        uint4 v = qinfo[qp];
+        v.x = qp | (v.x ? 0x80000000u : 0u);
+        cinfo[r++] = v;
     }
 }
 cudaError_t launch_popc(const uint32_t *presence, int64_t nwords, uint32_t *counts, cudaStream_t st)
@@ -505,9 +619,9 @@ cudaError_t launch_popc(const uint32_t *presence, int64_t nwords, uint32_t *coun
     return cudaGetLastError();
 }
 cudaError_t launch_build_compact(const int32_t *hashtable, const uint32_t *presence, const uint32_t *prefix,
-                                 int64_t nwords, uint2 *prk, int32_t *dense, cudaStream_t st)
+                                 int64_t nwords, uint2 *prk, const uint4 *qinfo, uint4 *cinfo, cudaStream_t st)
 {
-    build_compact_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, st>>>(hashtable, presence, prefix, nwords, prk, dense);
+    build_compact_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, st>>>(hashtable, presence, prefix, nwords, prk, qinfo, cinfo);
     return cudaGetLastError();
 }
 
@@ -528,8 +642,8 @@ cudaError_t launch_scan(const DevQuery &q, const ScanLaunch &s, cudaStream_t st)
 {
     if (s.total_pos <= 0) return cudaSuccess;
     int64_t blocks = (s.total_pos + POS_PER_BLOCK - 1) / POS_PER_BLOCK;
-    if (q.lut_type == 0 && q.prk != nullptr) {
-        const size_t smem = (size_t)s.tile_cap + sizeof(Candidate) * POS_PER_BLOCK;
+    if (q.lut_type == 0 && q.prk != nullptr && q.lut_word_length <= 13) {
+        const size_t smem = (size_t)s.tile_cap + sizeof(uint2) * POS_PER_BLOCK;
         scan_kernel_staged<<<(unsigned)blocks, SCAN_THREADS, smem, st>>>(q, s);
     }
     else

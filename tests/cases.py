@@ -55,6 +55,16 @@ CASES = {
                                     nq=60, qlen=400, q_seed=24, sub=0.02, indel=0.002, planted=0.9),
     "blastn_ntlike_many_subjects": dict(task="blastn", cfg={}, seq_lens="lognormal:1500:8:1200:0.9", vol_seed=14,
                                         nq=12, qlen=500, q_seed=25, sub=0.06, indel=0.008, planted=0.9),
+    # two-hit mode (window_size > 0): s_TypeOfWord's double-word test, hit_len / hit_saved bookkeeping
+    "mb_two_hit_w40_hash": dict(task="megablast", cfg={"word_size": 16, "window_size": 40}, seq_lens=[200_000, 90_000],
+                                vol_seed=15, nq=25, qlen=600, q_seed=26, sub=0.06, indel=0.005, planted=0.8),
+    "blastn_two_hit_w40_direct": dict(task="blastn", cfg={"window_size": 40}, seq_lens=[150_000, 60_000, 900],
+                                      vol_seed=16, nq=20, qlen=700, q_seed=27, sub=0.08, indel=0.01, planted=0.8),
+    "mb_two_hit_smallna_array": dict(task="megablast", cfg={"word_size": 20, "window_size": 50},
+                                     seq_lens=[300_000, 50_000, 777], vol_seed=17, nq=3, qlen=700, q_seed=28,
+                                     sub=0.05, indel=0.01, planted=1.0),
+    "blastn_two_hit_array_ws7": dict(task="blastn", cfg={"word_size": 7, "window_size": 30}, seq_lens=[20_000, 5_000],
+                                     vol_seed=18, nq=2, qlen=300, q_seed=29, sub=0.10, indel=0.01, planted=1.0),
     # empty result: random queries only
     "mb_no_hits": dict(task="megablast", cfg={}, seq_lens=[100_000], vol_seed=11,
                        nq=5, qlen=400, q_seed=22, sub=0.0, indel=0.0, planted=0.0),
