@@ -51,6 +51,25 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// grow-only pinned host buffer (target of the D2H result copies: pageable targets go through a
+// driver staging copy)
+template <typename T>
+struct PinnedBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 1024;
+        cudaError_t e = cudaMallocHost((void **)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
 struct Workspace {
     DevBuf<SeedHit> hits_a, hits_b;
     DevBuf<uint64_t> keys_a, keys_b;
@@ -63,8 +82,13 @@ struct Workspace {
     DevBuf<unsigned long long> counters;
     DevBuf<uint8_t> cub_temp;
     unsigned long long *h_counters = nullptr;   // pinned
+    PinnedBuf<DevInitHit> h_init;
+    PinnedBuf<DevGapResult> h_gap;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // stage timers, created once
     void release()
     {
+        h_init.release(); h_gap.release();
+        for (auto &e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
         hits_a.release(); hits_b.release(); keys_a.release(); keys_b.release();
         cells.release(); heads.release(); leaders.release(); spec.release(); init.release(); gap_out.release(); scratch.release(); todo.release();
         counters.release(); cub_temp.release();
@@ -325,8 +349,15 @@ static int build_chunk_table(Volume &V, const Query &Q, int32_t oid_begin, int32
 struct Timer {
     cudaEvent_t a, b;
     cudaStream_t st;
-    explicit Timer(cudaStream_t s) : st(s) { cudaEventCreate(&a); cudaEventCreate(&b); }
-    ~Timer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+    bool own;
+    explicit Timer(cudaStream_t s) : st(s), own(true) { cudaEventCreate(&a); cudaEventCreate(&b); }
+    // borrows a pair of long-lived events (slot 0..2) of the workspace
+    Timer(cudaStream_t s, Workspace &ws, int slot) : st(s), own(false)
+    {
+        for (int k = 2 * slot; k < 2 * slot + 2; k++) if (!ws.ev[k]) cudaEventCreate(&ws.ev[k]);
+        a = ws.ev[2 * slot]; b = ws.ev[2 * slot + 1];
+    }
+    ~Timer() { if (own) { cudaEventDestroy(a); cudaEventDestroy(b); } }
     void start() { cudaEventRecord(a, st); }
     void stop() { cudaEventRecord(b, st); }
     double ms() { float f = 0; cudaEventSynchronize(b); cudaEventElapsedTime(&f, a, b); return f; }
@@ -356,7 +387,7 @@ static int run_word_finder(Device &D, Volume &V, Query &Q, ChunkTable &T, bool r
     const int gbits = bits_for((uint64_t)std::max<int64_t>(T.total_pos, 1));
     const int grp_bits = raw_pairs ? 0 : (Q.batch.container_type == BN_DIAG_HASH ? 9 : bits_for((uint64_t)Q.diag_array_length));
 
-    Timer t_scan(st), t_ext(st);
+    Timer t_scan(st, ws, 0), t_ext(st, ws, 1);
     int64_t cap = std::max<int64_t>((int64_t)ws.hits_a.cap, std::max<int64_t>(1 << 16, T.total_pos / 16));
     for (int attempt = 0;; attempt++) {
         CU_TRY(ws.hits_a.reserve((size_t)cap));
@@ -440,15 +471,16 @@ static int32_t greedy_xdrop_offset(const BnQueryBatch &b)
 }
 
 static int run_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t n_init,
-                      std::vector<DevInitHit> &h_init, std::vector<DevGapResult> &h_gap, BnStats *stats)
+                      DevInitHit *&h_init, DevGapResult *&h_gap, BnStats *stats)
 {
     Workspace &ws = D.ws;
     cudaStream_t st = D.stream;
     const DevQuery &dq = Q.dev[V.device].view;
     const BnQueryBatch &b = Q.batch;
-    h_init.resize((size_t)n_init); h_gap.resize((size_t)n_init);
+    CU_TRY(ws.h_init.reserve((size_t)n_init + 1)); CU_TRY(ws.h_gap.reserve((size_t)n_init + 1));
+    h_init = ws.h_init.p; h_gap = ws.h_gap.p;
     if (n_init == 0) return BN_OK;
-    Timer t(st);
+    Timer t(st, ws, 2);
     t.start();
     CU_TRY(ws.gap_out.reserve((size_t)n_init));
     const bool greedy = b.gap_algo == BN_GAP_GREEDY;
@@ -461,8 +493,8 @@ static int run_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t n_i
     g.max_init = n_init; g.out = ws.gap_out.p;
     g.scratch_ints_per_thread = per_thread; g.tier_d = tier; g.todo = nullptr; g.n_todo = 0;
     if (greedy) {
-        // one warp per init-HSP, rows in shared memory
-        const int blocks = (int)std::min<int64_t>((n_init + wpb - 1) / wpb, 148 * 8);
+        // two warps per init-HSP (one per direction), rows in shared memory
+        const int blocks = (int)std::min<int64_t>((n_init + 1) / 2, 148 * 8);
         g.scratch = nullptr;
         CU_TRY(launch_greedy_warp(dq, g, wpb, blocks, true, st));
     } else {
@@ -473,8 +505,8 @@ static int run_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t n_i
         CU_TRY(launch_gapped(dq, g, st));
     }
     if (stats) stats->kernel_launches += 1;
-    CU_TRY(cudaMemcpyAsync(h_init.data(), ws.init.p, (size_t)n_init * sizeof(DevInitHit), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(h_gap.data(), ws.gap_out.p, (size_t)n_init * sizeof(DevGapResult), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(h_init, ws.init.p, (size_t)n_init * sizeof(DevInitHit), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(h_gap, ws.gap_out.p, (size_t)n_init * sizeof(DevGapResult), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
 
     // tier 2: worst-case scratch for the few extensions that outgrew tier 1
@@ -491,7 +523,8 @@ static int run_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t n_i
             per_thread = 2 * (int64_t)tier;
         }
         const int tpb = greedy ? wpb : gapped_threads_per_block();      // workers (warps | threads) per block
-        int64_t blocks = std::min<int64_t>(((int64_t)todo.size() + tpb - 1) / tpb, 64);
+        const int hpb = greedy ? wpb / 2 : tpb;                         // init-HSPs in flight per block
+        int64_t blocks = std::min<int64_t>(((int64_t)todo.size() + hpb - 1) / hpb, 64);
         CU_TRY(ws.scratch.reserve((size_t)(per_thread * blocks * tpb)));
         CU_TRY(ws.todo.reserve(todo.size()));
         CU_TRY(cudaMemcpyAsync(ws.todo.p, todo.data(), todo.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -500,7 +533,7 @@ static int run_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t n_i
         if (greedy) CU_TRY(launch_greedy_warp(dq, g, wpb, (int)blocks, false, st));
         else CU_TRY(launch_gapped(dq, g, st));
         if (stats) stats->kernel_launches += 1;
-        CU_TRY(cudaMemcpyAsync(h_gap.data(), ws.gap_out.p, (size_t)n_init * sizeof(DevGapResult), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(h_gap, ws.gap_out.p, (size_t)n_init * sizeof(DevGapResult), cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
         for (int32_t i : todo)
             if (h_gap[(size_t)i].status != 0) return fail(BN_ERR_OVERFLOW, "gapped extension scratch overflow in tier 2");
@@ -536,8 +569,8 @@ static int prelim_search_locked(Device &D, Volume &V, Query &Q, int32_t oid_begi
     StageCounts cnt;
     rc = run_word_finder(D, V, Q, *T, false, cnt, &stats);
     if (rc) return rc;
-    std::vector<DevInitHit> h_init;
-    std::vector<DevGapResult> h_gap;
+    DevInitHit *h_init = nullptr;
+    DevGapResult *h_gap = nullptr;
     rc = run_gapped(D, V, Q, *T, cnt.n_init, h_init, h_gap, &stats);
     if (rc) return rc;
     stats.lookup_hits = cnt.lookup_hits;

@@ -288,17 +288,39 @@ __device__ int32_t greedy_align_warp(const SeqPair &sp, int32_t xdrop_threshold,
             const unsigned e1 = __ballot_sync(FULLW, ok && seq1_index == len1);
             // ordered replay of the bookkeeping
             unsigned inv = 0;
-            for (unsigned rem = act; rem; rem &= rem - 1) {
-                const int b = __ffs(rem) - 1;
-                const unsigned bit = 1u << b;
-                const int32_t kk = kb + b;
-                if (!(succ & bit)) {
-                    if (kk == diag_lower) diag_lower++;
-                    else inv |= bit;
-                } else {
-                    diag_upper = kk;
-                    if (e2 & bit) { diag_lower = kk + 1; end2_reached = true; }
-                    if (e1 & bit) { diag_upper = kk - 1; end1_reached = true; }
+            if (e2 == 0) {
+                // no diagonal reached the end of seq2 in this round: diag_lower only moves over the
+                // leading run of failures (and only if it still sits on the round's first diagonal),
+                // every later failure is marked invalid, diag_upper follows the last success
+                const unsigned fail = act & ~succ;
+                unsigned lead = 0;
+                if (diag_lower == kb) {
+                    lead = (unsigned)__ffs(~fail) - 1u;          // fail has no bits above act, so ~fail != 0 ... unless act is full
+                    if (fail == 0xffffffffu) lead = 32;
+                    diag_lower += (int32_t)lead;
+                }
+                inv = lead >= 32 ? 0u : (fail & ~((1u << lead) - 1u));
+                if (succ) {
+                    const int top = 31 - __clz(succ);
+                    diag_upper = kb + top;
+                    if (e1) {
+                        end1_reached = true;
+                        if ((e1 >> top) & 1u) diag_upper = kb + top - 1;
+                    }
+                }
+            } else {
+                for (unsigned rem = act; rem; rem &= rem - 1) {
+                    const int b = __ffs(rem) - 1;
+                    const unsigned bit = 1u << b;
+                    const int32_t kk = kb + b;
+                    if (!(succ & bit)) {
+                        if (kk == diag_lower) diag_lower++;
+                        else inv |= bit;
+                    } else {
+                        diag_upper = kk;
+                        if (e2 & bit) { diag_lower = kk + 1; end2_reached = true; }
+                        if (e1 & bit) { diag_upper = kk - 1; end1_reached = true; }
+                    }
                 }
             }
             if (ok) cur[k] = seq2_index;
@@ -342,15 +364,20 @@ __device__ int32_t greedy_align_warp(const SeqPair &sp, int32_t xdrop_threshold,
     return best_dist;
 }
 
-// one warp per init-HSP; rows live in shared memory (tier 1) or in global scratch (tier 2)
+// TWO warps per init-HSP — the forward (right) and the reverse (left) extension are independent, so
+// they run side by side and meet at a named barrier; rows live in shared memory (tier 1) or in global
+// scratch (tier 2).  Block = 4 warps = 2 init-HSPs in flight.
 __global__ void __launch_bounds__(128)
 greedy_kernel(const DevQuery q, const GappedLaunch L, int use_smem)
 {
     extern __shared__ int32_t smem_rows[];
+    __shared__ int32_t xch[2][8];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
+    const int pair = wib >> 1, dir = wib & 1;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
-    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t pair0 = (int64_t)blockIdx.x * 2 + pair;
+    const int64_t npairs = (int64_t)gridDim.x * 2;
     const int64_t n = L.todo ? (int64_t)L.n_todo : (int64_t)min((unsigned long long)L.max_init, *L.n_init);
     const int32_t D = L.tier_d;
     int32_t *scratch = use_smem ? smem_rows + (size_t)wib * L.scratch_ints_per_thread
@@ -359,7 +386,7 @@ greedy_kernel(const DevQuery q, const GappedLaunch L, int use_smem)
     int32_t match = q.reward, mismatch = -q.penalty, xd = q.gap_x_dropoff;
     if (match % 2 == 1) { match *= 2; mismatch *= 2; xd *= 2; }
 
-    for (int64_t w = warp; w < n; w += nwarps) {
+    for (int64_t w = pair0; w < n; w += npairs) {
         const int64_t i = L.todo ? (int64_t)L.todo[w] : w;
         const DevInitHit h = L.init[i];
         const DevChunk ch = L.chunks[h.chunk];
@@ -368,45 +395,58 @@ greedy_kernel(const DevQuery q, const GappedLaunch L, int use_smem)
         const int32_t q_off = (h.q_start - c.query_offset) + h.length / 2;
         const int32_t s_off = h.s_start + h.length / 2;
         const int64_t chunk_base = ch.byte_off * 4;
-        DevGapResult g;
-        g.q_start = g.q_stop = g.s_start = g.s_stop = g.score = g.q_seed = g.s_seed = 0;
-        g.status = 0;
-        int32_t q_ext_r = 0, s_ext_r = 0, q_ext_l = 0, s_ext_l = 0;
-        GreedySeed fwd{0, 0, 0}, rev{0, 0, 0};
+        int32_t q_ext = 0, s_ext = 0;
+        GreedySeed seed{0, 0, 0};
         bool overflow = false;
         SeqPair sp;
         sp.q = &q; sp.packed = L.packed;
-        sp.qbase = c.query_offset + q_off; sp.sbase = chunk_base + s_off;
-        sp.len1 = c.query_length - q_off; sp.len2 = ch.len - s_off; sp.reverse = false;
-        int32_t dist = greedy_align_warp(sp, xd, match, mismatch, q_ext_r, s_ext_r, row0, row1, ms, D, fwd, overflow, lane);
-        __syncwarp();
-        if (!overflow) {
+        if (dir == 0) {
+            sp.qbase = c.query_offset + q_off; sp.sbase = chunk_base + s_off;
+            sp.len1 = c.query_length - q_off; sp.len2 = ch.len - s_off; sp.reverse = false;
+        } else {
             sp.qbase = c.query_offset; sp.sbase = chunk_base; sp.len1 = q_off; sp.len2 = s_off; sp.reverse = true;
-            dist += greedy_align_warp(sp, xd, match, mismatch, q_ext_l, s_ext_l, row0, row1, ms, D, rev, overflow, lane);
-            __syncwarp();
         }
-        if (overflow) g.status = 1;
-        else {
-            const int32_t score = (q_ext_r + s_ext_r + q_ext_l + s_ext_l) * q.reward / 2 - dist * (q.reward - q.penalty);
-            const int32_t q_box_l = q_off - q_ext_l, s_box_l = s_off - s_ext_l;
-            const int32_t q_box_r = q_off + q_ext_r, s_box_r = s_off + s_ext_r;
-            int32_t q_seed_l = q_off - rev.start_q, s_seed_l = s_off - rev.start_s;
-            int32_t q_seed_r = q_off + fwd.start_q, s_seed_r = s_off + fwd.start_s;
-            int32_t vl = 0, vr = 0;
-            if (q_seed_r < q_box_r && s_seed_r < s_box_r) {
-                vr = min(q_box_r - q_seed_r, s_box_r - s_seed_r);
-                vr = min(vr, fwd.match_length) / 2;
-            } else { q_seed_r = q_off; s_seed_r = s_off; }
-            if (q_seed_l > q_box_l && s_seed_l > s_box_l) {
-                vl = min(q_seed_l - q_box_l, s_seed_l - s_box_l);
-                vl = min(vl, rev.match_length) / 2;
-            } else { q_seed_l = q_off; s_seed_l = s_off; }
-            if (vr > vl) { g.q_seed = q_seed_r + vr; g.s_seed = s_seed_r + vr; }
-            else { g.q_seed = q_seed_l - vl; g.s_seed = s_seed_l - vl; }
-            g.q_start = q_box_l; g.s_start = s_box_l; g.q_stop = q_box_r; g.s_stop = s_box_r;
-            g.score = score;
+        const int32_t dist_mine = greedy_align_warp(sp, xd, match, mismatch, q_ext, s_ext, row0, row1, ms, D, seed, overflow, lane);
+        __syncwarp();
+        if (dir == 1 && lane == 0) {
+            xch[pair][0] = dist_mine; xch[pair][1] = q_ext; xch[pair][2] = s_ext;
+            xch[pair][3] = seed.start_q; xch[pair][4] = seed.start_s; xch[pair][5] = seed.match_length;
+            xch[pair][6] = overflow ? 1 : 0;
         }
-        if (lane == 0) L.out[i] = g;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
+        if (dir == 0) {
+            DevGapResult g;
+            g.q_start = g.q_stop = g.s_start = g.s_stop = g.score = g.q_seed = g.s_seed = 0;
+            g.status = 0;
+            const int32_t q_ext_r = q_ext, s_ext_r = s_ext;
+            const GreedySeed fwd = seed;
+            const int32_t dist = dist_mine + xch[pair][0];
+            const int32_t q_ext_l = xch[pair][1], s_ext_l = xch[pair][2];
+            const GreedySeed rev{xch[pair][3], xch[pair][4], xch[pair][5]};
+            if (overflow || xch[pair][6]) g.status = 1;
+            else {
+                const int32_t score = (q_ext_r + s_ext_r + q_ext_l + s_ext_l) * q.reward / 2 - dist * (q.reward - q.penalty);
+                const int32_t q_box_l = q_off - q_ext_l, s_box_l = s_off - s_ext_l;
+                const int32_t q_box_r = q_off + q_ext_r, s_box_r = s_off + s_ext_r;
+                int32_t q_seed_l = q_off - rev.start_q, s_seed_l = s_off - rev.start_s;
+                int32_t q_seed_r = q_off + fwd.start_q, s_seed_r = s_off + fwd.start_s;
+                int32_t vl = 0, vr = 0;
+                if (q_seed_r < q_box_r && s_seed_r < s_box_r) {
+                    vr = min(q_box_r - q_seed_r, s_box_r - s_seed_r);
+                    vr = min(vr, fwd.match_length) / 2;
+                } else { q_seed_r = q_off; s_seed_r = s_off; }
+                if (q_seed_l > q_box_l && s_seed_l > s_box_l) {
+                    vl = min(q_seed_l - q_box_l, s_seed_l - s_box_l);
+                    vl = min(vl, rev.match_length) / 2;
+                } else { q_seed_l = q_off; s_seed_l = s_off; }
+                if (vr > vl) { g.q_seed = q_seed_r + vr; g.s_seed = s_seed_r + vr; }
+                else { g.q_seed = q_seed_l - vl; g.s_seed = s_seed_l - vl; }
+                g.q_start = q_box_l; g.s_start = s_box_l; g.q_stop = q_box_r; g.s_stop = s_box_r;
+                g.score = score;
+            }
+            if (lane == 0) L.out[i] = g;
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");     // xch is reused by the next init-HSP
     }
 }
 

@@ -578,18 +578,30 @@ void LowScoreTracker::subject_done(const BnQueryBatch &b, const std::vector<BnHS
     for (int32_t qi : touched_) {
         HitListState &S = states_[qi];
         const HitListKey &k = keys_[slot_[qi]];
-        if ((int32_t)S.lists.size() < hitlist_size_) {
-            S.lists.push_back(k);
+        if (S.count < hitlist_size_) {
+            arena_.push_back(ArenaNode{k, S.head});
+            S.head = (int32_t)arena_.size() - 1;
+            ++S.count;
             S.worst_evalue = std::max(k.best_evalue, S.worst_evalue);
             S.low_score = std::min(k.best_score, S.low_score);
         } else {
             const int order = fuzzy_cmp(k.best_evalue, S.worst_evalue);
             if (!(order > 0 || (order == 0 && k.best_score < S.low_score))) {
-                if (!S.heapified) { make_heap(S.lists); S.heapified = true; }
-                S.lists[0] = k;
-                if (S.lists.size() >= 2) sift(S.lists, 0, S.lists.size() / 2 - 1, S.lists.size() - 1);
-                S.worst_evalue = S.lists[0].best_evalue;
-                S.low_score = S.lists[0].best_score;
+                if (!S.heapified) {
+                    // copy the chain out in insertion order, then s_CreateHeap
+                    full_.emplace_back((size_t)S.count);
+                    S.full = (int32_t)full_.size() - 1;
+                    std::vector<HitListKey> &L = full_.back();
+                    int32_t at = S.head;
+                    for (int32_t i = S.count - 1; i >= 0 && at >= 0; i--) { L[(size_t)i] = arena_[(size_t)at].key; at = arena_[(size_t)at].prev; }
+                    make_heap(L);
+                    S.heapified = true;
+                }
+                std::vector<HitListKey> &L = full_[(size_t)S.full];
+                L[0] = k;
+                if (L.size() >= 2) sift(L, 0, L.size() / 2 - 1, L.size() - 1);
+                S.worst_evalue = L[0].best_evalue;
+                S.low_score = L[0].best_score;
             }
         }
         // core/blast_engine.c:1313-1320 (only a query whose hit list changed can change its bound)

@@ -70,8 +70,13 @@ void evalues_and_reap(const BnQueryBatch &b, std::vector<BnHSP> &list);
 // The hit-list bookkeeping behind hit_params->low_score (core/blast_engine.c:1313-1320,
 // Blast_HitListUpdate core/blast_hits.c:2924-2981): one instance per search.
 struct HitListKey { double best_evalue; int32_t best_score; int32_t oid; };
+// A query's hit list while it is still filling up is a chain through one shared arena (no per-query
+// allocation: most queries of a batch never fill their list); it is copied out into `full` only when
+// the first replacement needs the heap.
 struct HitListState {
-    std::vector<HitListKey> lists;
+    int32_t count = 0;
+    int32_t head = -1;              // newest arena node
+    int32_t full = -1;              // index into LowScoreTracker::full_ once heapified
     bool heapified = false;
     double worst_evalue = 0.0;
     int32_t low_score = INT32_MAX;
@@ -89,6 +94,9 @@ private:
     std::vector<HitListState> states_;
     std::vector<int32_t> slot_, touched_;      // scratch of subject_done
     std::vector<HitListKey> keys_;
+    struct ArenaNode { HitListKey key; int32_t prev; };
+    std::vector<ArenaNode> arena_;
+    std::vector<std::vector<HitListKey>> full_;
 };
 
 }  // namespace bn

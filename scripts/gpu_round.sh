@@ -13,6 +13,7 @@ cat gpurun_out/tests_$TAG.log
 BN_TRACE=1 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_err_$TAG.log
 cat gpurun_out/bench_$TAG.json
 tail -3 gpurun_out/bench_err_$TAG.log
+if [ "$3" = "noncu" ]; then exit 0; fi
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/b_ncu_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:scan_kernel -s 4 -c 2 -o gpurun_out/prof_scan_$TAG -f \
