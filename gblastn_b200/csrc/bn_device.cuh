@@ -37,11 +37,10 @@ struct DevQuery {
     int32_t num_contexts;
     int32_t lut_type, word_length, lut_word_length, scan_step;
     uint32_t hash_mask;
-    const int32_t *hashtable, *next_pos;   // MB
-    const uint32_t *presence;              // MB: exact 1 bit / cell bitmap built at load time
+    const int32_t *next_pos;               // MB chain links (the 4^lut hashtable itself is not kept: mb_cell)
     const uint2 *prk;                      // MB compact table: {presence word, rank of its first occupied cell}
-    const uint4 *cinfo;                    // MB compact table: per occupied cell (in cell order) the qinfo of its
-                                           // first chain element, .x = {qp, bit 31: chain continues}
+    const uint4 *cinfo;                    // MB compact table: per occupied cell (in cell order) TWO entries = the qinfo
+                                           // of its first and second chain element, .x = {qp, bit 31: chain continues}
     const uint4 *qinfo;                    // MB: per query position {next_pos, 16 bases left, 16 right, ambiguity}
     const int16_t *backbone, *overflow;    // SmallNa
     int32_t has_locations;                 // lut->masked_locations != NULL
@@ -158,7 +157,28 @@ __device__ __forceinline__ int32_t ctx_search(const DevQuery &q, int32_t n)
     return lo;
 }
 
+// hashtable[idx] of BlastMBLookupTable (inc-core/blast_nalookup.h:236) recovered from the compact
+// table: 0 when the cell is empty, else the 1-based query position that heads the cell's chain.
+__device__ __forceinline__ int32_t mb_cell(const DevQuery &q, uint32_t idx)
+{
+    const uint2 w = __ldg(&q.prk[idx >> 5]);
+    const uint32_t bit = idx & 31u;
+    if (!((w.x >> bit) & 1u)) return 0;
+    return (int32_t)(__ldg(&q.cinfo[2 * (size_t)(w.y + (uint32_t)__popc(w.x & ((1u << bit) - 1u)))].x) & 0x7fffffffu);
+}
+
 // ---- launchers implemented in the .cu files ----------------------------------------------------
+// Per scan block (scan_positions_per_block() consecutive positions): the slice of the volume it stages
+// and the chunks it spans; built on the host with the chunk table.  32 bytes = one sector.
+struct ScanBlockDesc {
+    int64_t tile_lo;      // first byte of the staged slice (16-byte aligned, may reach into the front pad)
+    int32_t bytes;        // slice size (multiple of 16)
+    int32_t c_lo, c_hi;   // first / last chunk with a position in the block
+    int32_t staged;       // 0: slice does not fit the tile (or too many chunks) -> direct-load path
+    int32_t pad0, pad1;
+};
+static_assert(sizeof(ScanBlockDesc) == 32, "one sector");
+
 struct ScanLaunch {
     const uint8_t *packed;
     const DevChunk *chunks;
@@ -168,7 +188,8 @@ struct ScanLaunch {
     uint64_t *keys;           // sort key per hit
     unsigned long long *counters;   // [0] = #survivors, [1] = #lookup hits
     int64_t capacity;
-    const int32_t *block_chunk;   // first chunk of every BLOCK_POS-sized slice of positions
+    const int32_t *block_chunk;   // first chunk of every BLOCK_POS-sized slice of positions (generic kernel)
+    const ScanBlockDesc *block_desc;  // staged kernel
     int32_t raw_pairs;            // 1: emit every lookup hit (q_off, scan_pos) without mini-extension (scan tap)
     int32_t gbits;                // bits of the global position in the sort key
     int32_t diag_array_length;    // eDiagArray: cells (power of two)
@@ -177,6 +198,8 @@ struct ScanLaunch {
 cudaError_t launch_scan(const DevQuery &q, const ScanLaunch &s, cudaStream_t st);
 int scan_positions_per_block();
 int scan_tile_cap(int scan_step, int word_length);
+int scan_max_block_chunks();
+int scan_tile_margin();
 cudaError_t launch_build_qinfo(const DevQuery &q, const int32_t *next_pos, int32_t concat_len, uint4 *qinfo,
                                cudaStream_t st);
 

@@ -109,6 +109,7 @@ struct ChunkTable {
     std::vector<HostChunk> hchunks;
     DevBuf<DevChunk> dev;
     DevBuf<int32_t> block_chunk;
+    DevBuf<ScanBlockDesc> block_desc;
     int64_t total_pos = 0;
     int64_t total_bases = 0;
     int64_t n_blocks = 0;
@@ -127,8 +128,7 @@ struct Volume {
 struct QueryDev {
     uint8_t *query = nullptr;
     DevContext *ctx = nullptr;
-    int32_t *hashtable = nullptr, *next_pos = nullptr;
-    uint32_t *presence = nullptr;
+    int32_t *next_pos = nullptr;
     int16_t *backbone = nullptr, *overflow = nullptr;
     int32_t *score_table = nullptr, *matrix = nullptr;
     uint2 *qpk = nullptr;
@@ -170,7 +170,7 @@ static Device *device_at(int d)
 // loading a new batch re-uses the previous batch's memory without touching the OS allocator.
 static void free_query_dev(QueryDev &q, cudaStream_t st)
 {
-    void *ptrs[] = {q.query, q.ctx, q.hashtable, q.next_pos, q.presence, q.backbone, q.overflow,
+    void *ptrs[] = {q.query, q.ctx, q.next_pos, q.backbone, q.overflow,
                     q.score_table, q.matrix, q.qpk, q.prk, q.cinfo, q.qinfo};
     for (void *p : ptrs) if (p) cudaFreeAsync(p, st);
     q = QueryDev{};
@@ -197,6 +197,13 @@ cudaError_t launch_build_qpk(const uint8_t *query_start, int32_t concat_len, uin
 cudaError_t launch_popc(const uint32_t *presence, int64_t nwords, uint32_t *counts, cudaStream_t st);
 cudaError_t launch_build_compact(const int32_t *hashtable, const uint32_t *presence, const uint32_t *prefix,
                                  int64_t nwords, uint2 *prk, const uint4 *qinfo, uint4 *cinfo, cudaStream_t st);
+cudaError_t launch_build_prk_cinfo(const uint32_t *presence, const uint32_t *prefix, int64_t nwords, uint2 *prk,
+                                   const int32_t *first_qp, int64_t n_ranks, const uint4 *qinfo, uint4 *cinfo,
+                                   cudaStream_t st);
+cudaError_t launch_rebuild_hashtable(const DevQuery &q, int64_t hashsize, int32_t *out, cudaStream_t st);
+cudaError_t build_mb_lookup_device(const uint8_t *d_query, int32_t concat_len, int32_t word_length, int32_t lut,
+                                   const int32_t *h_segs, int32_t n_segs, int32_t *d_next_pos, uint32_t *d_presence,
+                                   int32_t *d_first_qp, int64_t *n_launches, cudaStream_t st);
 
 // Uploads one query batch to device d straight from the caller's arrays (no host staging copy);
 // the presence bitmap and the 16-base query windows are derived on the device.
@@ -216,13 +223,28 @@ static int query_to_device(Query &Q, const BnQueryBatch &src, int d)
     }
     CU_TRY(upload(&qd.query, src.query_start, (size_t)b.concat_len + 2, st));
     CU_TRY(upload(&qd.ctx, dctx.data(), dctx.size(), st));
+    // temporaries of the table derivation (freed stream-ordered at the end)
+    int32_t *t_hashtable = nullptr, *t_first_qp = nullptr;
+    uint32_t *t_presence = nullptr, *t_counts = nullptr, *t_prefix = nullptr;
+    const bool device_fill = b.lut_type == BN_LUT_MB && !src.hashtable;
     if (b.lut_type == BN_LUT_MB) {
-        CU_TRY(upload(&qd.hashtable, src.hashtable, (size_t)b.hashsize, st));
-        CU_TRY(upload(&qd.next_pos, src.next_pos, (size_t)b.concat_len + 1, st));
         // exact presence bitmap (replaces the reference's compressed pv_array: same answers,
         // PV_TEST is only a filter in front of hashtable[index] != 0)
-        CU_TRY(dev_alloc(&qd.presence, (size_t)((b.hashsize + 31) / 32), st));
-        CU_TRY(launch_build_presence(qd.hashtable, b.hashsize, qd.presence, st));
+        CU_TRY(dev_alloc(&t_presence, (size_t)((b.hashsize + 31) / 32), st));
+        CU_TRY(dev_alloc(&qd.next_pos, (size_t)b.concat_len + 1, st));
+        if (device_fill) {
+            // s_FillContigMBTable on the device: only the query bytes and the segment list cross PCIe
+            CU_TRY(dev_alloc(&t_first_qp, (size_t)b.concat_len + 1, st));
+            CU_TRY(cudaMemsetAsync(t_first_qp, 0, ((size_t)b.concat_len + 1) * sizeof(int32_t), st));
+            CU_TRY(build_mb_lookup_device(qd.query + 1, b.concat_len, b.word_length, b.lut_word_length,
+                                          src.lookup_segments, src.n_lookup_segments, qd.next_pos, t_presence,
+                                          t_first_qp, nullptr, st));
+        } else {
+            CU_TRY(dev_alloc(&t_hashtable, (size_t)b.hashsize, st));
+            CU_TRY(cudaMemcpyAsync(t_hashtable, src.hashtable, (size_t)b.hashsize * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+            CU_TRY(cudaMemcpyAsync(qd.next_pos, src.next_pos, ((size_t)b.concat_len + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+            CU_TRY(launch_build_presence(t_hashtable, b.hashsize, t_presence, st));
+        }
     } else {
         static const int16_t kEmptyOverflow[2] = {-1, -1};
         CU_TRY(upload(&qd.backbone, src.backbone, (size_t)b.hashsize, st));
@@ -240,7 +262,7 @@ static int query_to_device(Query &Q, const BnQueryBatch &src, int d)
     v.ctx = qd.ctx; v.num_contexts = b.num_contexts;
     v.lut_type = b.lut_type; v.word_length = b.word_length; v.lut_word_length = b.lut_word_length;
     v.scan_step = b.scan_step; v.hash_mask = (uint32_t)(b.hashsize - 1);
-    v.hashtable = qd.hashtable; v.next_pos = qd.next_pos; v.presence = qd.presence;
+    v.next_pos = qd.next_pos;
     v.backbone = qd.backbone; v.overflow = qd.overflow;
     v.has_locations = Q.batch.masked_locations != nullptr;
     v.container_type = b.container_type; v.window_size = b.window_size; v.scan_range = b.scan_range;
@@ -251,24 +273,30 @@ static int query_to_device(Query &Q, const BnQueryBatch &src, int d)
         CU_TRY(dev_alloc(&qd.qinfo, (size_t)b.concat_len + 2, st));
         CU_TRY(launch_build_qinfo(v, qd.next_pos, b.concat_len, qd.qinfo, st));
         v.qinfo = qd.qinfo;
-        // compact table for the scan kernel: {presence word, rank} per 32 cells (4^lut / 4 bytes,
-        // L2-resident) + the first chain element of every occupied cell in cell order
+        // compact table: {presence word, rank} per 32 cells (4^lut / 4 bytes, L2-resident) + the first
+        // chain element of every occupied cell in cell order.  It stands in for hashtable[] everywhere
+        // on the device (mb_cell), so the 4^lut-entry table is not kept in HBM.
         const int64_t nwords = (b.hashsize + 31) / 32;
-        uint32_t *counts = nullptr, *prefix = nullptr;
-        CU_TRY(dev_alloc(&counts, (size_t)nwords, st));
-        CU_TRY(dev_alloc(&prefix, (size_t)nwords, st));
+        CU_TRY(dev_alloc(&t_counts, (size_t)nwords, st));
+        CU_TRY(dev_alloc(&t_prefix, (size_t)nwords, st));
         CU_TRY(dev_alloc(&qd.prk, (size_t)nwords, st));
-        CU_TRY(dev_alloc(&qd.cinfo, (size_t)b.concat_len + 2, st));
-        CU_TRY(launch_popc(qd.presence, nwords, counts, st));
+        CU_TRY(dev_alloc(&qd.cinfo, 2 * ((size_t)b.concat_len + 2), st));
+        CU_TRY(launch_popc(t_presence, nwords, t_counts, st));
         size_t tmp_bytes = 0;
-        CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, prefix, (int)nwords, st));
+        CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, t_counts, t_prefix, (int)nwords, st));
         CU_TRY(dev->ws.cub_temp.reserve(tmp_bytes));
-        CU_TRY(cub::DeviceScan::ExclusiveSum(dev->ws.cub_temp.p, tmp_bytes, counts, prefix, (int)nwords, st));
-        CU_TRY(launch_build_compact(qd.hashtable, qd.presence, prefix, nwords, qd.prk, qd.qinfo, qd.cinfo, st));
-        CU_TRY(cudaFreeAsync(counts, st));
-        CU_TRY(cudaFreeAsync(prefix, st));
-        v.prk = (b.word_length <= 200) ? qd.prk : nullptr;
+        CU_TRY(cub::DeviceScan::ExclusiveSum(dev->ws.cub_temp.p, tmp_bytes, t_counts, t_prefix, (int)nwords, st));
+        if (device_fill)
+            CU_TRY(launch_build_prk_cinfo(t_presence, t_prefix, nwords, qd.prk, t_first_qp, (int64_t)b.concat_len + 1,
+                                          qd.qinfo, qd.cinfo, st));
+        else
+            CU_TRY(launch_build_compact(t_hashtable, t_presence, t_prefix, nwords, qd.prk, qd.qinfo, qd.cinfo, st));
+        v.prk = qd.prk;
         v.cinfo = qd.cinfo;
+    }
+    {
+        void *tmp[] = {t_hashtable, t_first_qp, t_presence, t_counts, t_prefix};
+        for (void *p : tmp) if (p) CU_TRY(cudaFreeAsync(p, st));
     }
     CU_TRY(cudaStreamSynchronize(st));     // caller's arrays may go away after bn_query_load returns
     qd.ready = true;
@@ -331,12 +359,39 @@ static int build_chunk_table(Volume &V, const Query &Q, int32_t oid_begin, int32
         }
         bc[(size_t)T->n_blocks] = n ? (int32_t)n - 1 : 0;
     }
+    // staged scan kernel: the slice of the volume every block copies into shared memory
+    std::vector<ScanBlockDesc> bd((size_t)T->n_blocks);
+    {
+        const int32_t tile_cap = scan_tile_cap(step, b.word_length), margin = scan_tile_margin();
+        const int32_t maxc = scan_max_block_chunks();
+        size_t c = 0;
+        const size_t n = T->host.size();
+        for (int64_t blk = 0; blk < T->n_blocks; blk++) {
+            const int64_t g0 = blk * ppb, g_last = std::min<int64_t>(g0 + ppb, prefix) - 1;
+            const int32_t c_lo = bc[(size_t)blk];
+            c = std::max<size_t>(c, (size_t)c_lo);
+            while (c + 1 < n && T->host[c + 1].pos_prefix <= g_last) ++c;
+            const DevChunk &a = T->host[(size_t)c_lo], &z = T->host[c];
+            const int64_t first_byte = a.byte_off + (((g0 - a.pos_prefix) * step) >> 2);
+            const int64_t last_byte = z.byte_off + ((((g_last - z.pos_prefix) * step) + b.word_length + 32) >> 2);
+            ScanBlockDesc d{};
+            d.tile_lo = (first_byte - margin) & ~int64_t(15);
+            const int64_t bytes = (last_byte + margin - d.tile_lo + 15) & ~int64_t(15);
+            d.c_lo = c_lo; d.c_hi = (int32_t)c;
+            d.staged = (bytes <= (int64_t)tile_cap && (d.c_hi - d.c_lo) < maxc) ? 1 : 0;
+            d.bytes = d.staged ? (int32_t)bytes : 0;
+            bd[(size_t)blk] = d;
+        }
+    }
     if (!T->host.empty()) {
         CU_TRY(T->dev.reserve(T->host.size()));
         CU_TRY(cudaMemcpyAsync(T->dev.p, T->host.data(), T->host.size() * sizeof(DevChunk),
                                cudaMemcpyHostToDevice, st));
         CU_TRY(T->block_chunk.reserve(bc.size()));
         CU_TRY(cudaMemcpyAsync(T->block_chunk.p, bc.data(), bc.size() * sizeof(int32_t),
+                               cudaMemcpyHostToDevice, st));
+        CU_TRY(T->block_desc.reserve(bd.size() + 1));
+        CU_TRY(cudaMemcpyAsync(T->block_desc.p, bd.data(), bd.size() * sizeof(ScanBlockDesc),
                                cudaMemcpyHostToDevice, st));
         CU_TRY(cudaStreamSynchronize(st));
     }
@@ -397,7 +452,7 @@ static int run_word_finder(Device &D, Volume &V, Query &Q, ChunkTable &T, bool r
         ScanLaunch s{};
         s.packed = V.d_packed; s.chunks = T.dev.p; s.n_chunks = (int32_t)T.host.size();
         s.total_pos = T.total_pos; s.hits = ws.hits_a.p; s.keys = ws.keys_a.p;
-        s.counters = ws.counters.p; s.capacity = cap; s.block_chunk = T.block_chunk.p;
+        s.counters = ws.counters.p; s.capacity = cap; s.block_chunk = T.block_chunk.p; s.block_desc = T.block_desc.p;
         s.raw_pairs = raw_pairs ? 1 : 0; s.gbits = gbits; s.diag_array_length = Q.diag_array_length;
         s.tile_cap = scan_tile_cap(Q.batch.scan_step, Q.batch.word_length);
         t_scan.start();
@@ -698,7 +753,7 @@ void bn_release(void)
     for (auto &v : g_volumes) if (v) {
         cudaSetDevice(g_devices[v->device]->id);
         cudaFreeAsync(v->d_raw, g_devices[v->device]->stream);
-        for (auto &kv : v->tables) { kv.second->dev.release(); kv.second->block_chunk.release(); }
+        for (auto &kv : v->tables) { kv.second->dev.release(); kv.second->block_chunk.release(); kv.second->block_desc.release(); }
     }
     g_volumes.clear();
     for (auto &d : g_devices) {
@@ -754,7 +809,7 @@ int bn_db_free(int h)
     Volume &V = *g_volumes[h];
     cudaSetDevice(g_devices[V.device]->id);
     cudaFreeAsync(V.d_raw, g_devices[V.device]->stream);
-    for (auto &kv : V.tables) { kv.second->dev.release(); kv.second->block_chunk.release(); }
+    for (auto &kv : V.tables) { kv.second->dev.release(); kv.second->block_chunk.release(); kv.second->block_desc.release(); }
     g_volumes[h].reset();
     return BN_OK;
 }
@@ -772,7 +827,13 @@ int bn_query_load(const BnQueryBatch *b, int *query_handle)
         return fail(BN_ERR_UNSUPPORTED, "affine greedy extension is not implemented");
     if (b->lut_type != BN_LUT_MB && b->lut_type != BN_LUT_SMALL_NA)
         return fail(BN_ERR_UNSUPPORTED, "only eMBLookupTable and eSmallNaLookupTable are supported");
-    if (b->lut_type == BN_LUT_MB && (!b->hashtable || !b->next_pos)) return fail(BN_ERR_INVALID, "bn_query_load: MB table arrays missing");
+    if (b->lut_type == BN_LUT_MB && (!b->hashtable != !b->next_pos)) return fail(BN_ERR_INVALID, "bn_query_load: hashtable and next_pos must come together");
+    if (b->lut_type == BN_LUT_MB && !b->hashtable && (!b->lookup_segments || b->n_lookup_segments <= 0))
+        return fail(BN_ERR_INVALID, "bn_query_load: MB batch carries neither the table arrays nor lookup_segments");
+    if (b->lut_type == BN_LUT_MB && !b->hashtable)
+        for (int32_t i = 0; i + 1 < b->n_lookup_segments; i++)
+            if (b->lookup_segments[2 * i + 1] >= b->lookup_segments[2 * i + 2])
+                return fail(BN_ERR_INVALID, "bn_query_load: lookup_segments must be ascending and disjoint");
     if (b->lut_type == BN_LUT_SMALL_NA && !b->backbone) return fail(BN_ERR_INVALID, "bn_query_load: small table arrays missing");
     auto Q = std::make_unique<Query>();
     Q->batch = *b;
@@ -782,6 +843,7 @@ int bn_query_load(const BnQueryBatch *b, int *query_handle)
     Q->batch.query_start = nullptr; Q->batch.contexts = Q->ctx.data();
     Q->batch.hashtable = nullptr; Q->batch.next_pos = nullptr; Q->batch.pv_array = nullptr;
     Q->batch.backbone = nullptr; Q->batch.overflow = nullptr;
+    Q->batch.lookup_segments = nullptr; Q->batch.n_lookup_segments = 0;
     Q->batch.masked_locations = b->masked_locations ? reinterpret_cast<const int32_t *>(Q->ctx.data()) : nullptr;
     int32_t n = 1;
     while (n < b->concat_len + b->window_size) n <<= 1;   // s_BlastDiagTableNew core/blast_extend.c:46-72
@@ -907,6 +969,28 @@ int bn_word_finder(int vol_handle, int query_handle, int32_t oid_begin, int32_t 
     return BN_OK;
 }
 
+int bn_query_download_lookup(int query_handle, int device, int32_t *hashtable, int32_t *next_pos)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (query_handle < 0 || query_handle >= (int)g_queries.size() || !g_queries[query_handle])
+        return fail(BN_ERR_INVALID, "bn_query_download_lookup: bad query handle");
+    Query &Q = *g_queries[query_handle];
+    Device *D = device_at(device);
+    if (!D || !Q.dev[device].ready || Q.batch.lut_type != BN_LUT_MB || !hashtable || !next_pos)
+        return fail(BN_ERR_INVALID, "bn_query_download_lookup: bad argument");
+    CU_TRY(cudaSetDevice(D->id));
+    cudaStream_t st = D->stream;
+    int32_t *tmp = nullptr;
+    CU_TRY(cudaMallocAsync((void **)&tmp, (size_t)Q.batch.hashsize * sizeof(int32_t), st));
+    CU_TRY(launch_rebuild_hashtable(Q.dev[device].view, Q.batch.hashsize, tmp, st));
+    CU_TRY(cudaMemcpyAsync(hashtable, tmp, (size_t)Q.batch.hashsize * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(next_pos, Q.dev[device].next_pos, ((size_t)Q.batch.concat_len + 1) * sizeof(int32_t),
+                           cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaFreeAsync(tmp, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return BN_OK;
+}
+
 int bn_bench_scan(int vol_handle, int query_handle, int iters, double *ms_per_launch,
                   int64_t *bases_per_launch, int64_t *hits)
 {
@@ -928,7 +1012,7 @@ int bn_bench_scan(int vol_handle, int query_handle, int iters, double *ms_per_la
     ScanLaunch s{};
     s.packed = V->d_packed; s.chunks = T->dev.p; s.n_chunks = (int32_t)T->host.size();
     s.total_pos = T->total_pos; s.hits = ws.hits_a.p; s.keys = ws.keys_a.p;
-    s.counters = ws.counters.p; s.capacity = cap; s.block_chunk = T->block_chunk.p; s.raw_pairs = 0;
+    s.counters = ws.counters.p; s.capacity = cap; s.block_chunk = T->block_chunk.p; s.block_desc = T->block_desc.p; s.raw_pairs = 0;
     s.gbits = bits_for((uint64_t)std::max<int64_t>(T->total_pos, 1)); s.diag_array_length = Q->diag_array_length;
     s.tile_cap = scan_tile_cap(Q->batch.scan_step, Q->batch.word_length);
     const DevQuery &dq = Q->dev[V->device].view;

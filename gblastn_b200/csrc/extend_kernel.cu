@@ -251,7 +251,7 @@ __device__ __forceinline__ int32_t ctx_search_warp(const DevQuery &q, int32_t n,
 __device__ bool lut_contains(const DevQuery &q, uint32_t index, int32_t q_pos)
 {
     if (q.lut_type == 0) {
-        int32_t v = __ldg(&q.hashtable[index & q.hash_mask]);
+        int32_t v = mb_cell(q, (uint32_t)index & q.hash_mask);
         ++q_pos;
         while (v) {
             if (v == q_pos) return true;

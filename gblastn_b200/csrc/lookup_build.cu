@@ -17,6 +17,8 @@
 //      the rank space of the scan kernel's compact table                     mb_link_kernel
 // The 4^lut-entry hashtable itself is never materialised on this path: the scan kernel works from
 // {presence word, rank} + the per-rank first chain element (scan_kernel.cu).
+#include <algorithm>
+
 #include <cub/cub.cuh>
 
 #include "bn_device.cuh"

@@ -226,8 +226,7 @@ scan_kernel(const DevQuery q, const ScanLaunch s)
         const uint32_t idx = (window >> (2 * (16 - ((p & 3) + lut)))) & q.hash_mask;
 
         if (q.lut_type == 0) {
-            if (!((__ldg(&q.presence[idx >> 5]) >> (idx & 31)) & 1u)) continue;
-            int32_t qp = __ldg(&q.hashtable[idx]);
+            int32_t qp = mb_cell(q, idx);
             while (qp) {
                 ++my_lookup_hits;
                 int32_t qo, so;
@@ -346,12 +345,33 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
 }
 
 constexpr int MAXC = 256;          // chunks one staged block may span (more: direct-load path)
+int scan_max_block_chunks() { return MAXC; }
+int scan_tile_margin() { return TILE_MARGIN; }
+
+// 256-bit loads (LDG.E.256): a block descriptor / a cell's first two chain elements are one 32-byte sector
+__device__ __forceinline__ ScanBlockDesc ld_block_desc(const ScanBlockDesc *p)
+{
+    uint32_t a0, a1, a2, a3, a4, a5, a6, a7;
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3), "=r"(a4), "=r"(a5), "=r"(a6), "=r"(a7) : "l"(p));
+    ScanBlockDesc d;
+    d.tile_lo = (int64_t)(((uint64_t)a1 << 32) | a0);
+    d.bytes = (int32_t)a2; d.c_lo = (int32_t)a3; d.c_hi = (int32_t)a4; d.staged = (int32_t)a5;
+    d.pad0 = d.pad1 = 0;
+    return d;
+}
+__device__ __forceinline__ void ld_cinfo_pair(const uint4 *p, uint4 &e0, uint4 &e1)
+{
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(e0.x), "=r"(e0.y), "=r"(e0.z), "=r"(e0.w), "=r"(e1.x), "=r"(e1.y), "=r"(e1.z), "=r"(e1.w) : "l"(p));
+}
 
 // Direct-load path for the rare block whose byte span does not fit the tile (runs of sequences
 // shorter than a word) : same semantics, per-position global loads.
-__device__ __noinline__ void scan_block_direct(const DevQuery &q, const ScanLaunch &s, int64_t block_pos0,
-                                               int32_t c_lo, int32_t c_hi, unsigned long long &my_lookup_hits)
+__device__ __noinline__ unsigned long long scan_block_direct(const DevQuery &q, const ScanLaunch &s, int64_t block_pos0,
+                                                             int32_t c_lo, int32_t c_hi)
 {
+    unsigned long long my_lookup_hits = 0;
     const int32_t lut = q.lut_word_length, step = q.scan_step;
     for (int it = 0; it < POS_PER_THREAD; it++) {
         const int64_t g = block_pos0 + (int64_t)it * SCAN_THREADS + threadIdx.x;
@@ -365,8 +385,7 @@ __device__ __noinline__ void scan_block_direct(const DevQuery &q, const ScanLaun
         const int32_t p = (int32_t)(g - ch.pos_prefix) * step;
         const uint32_t window = load_window(s.packed, ch.byte_off + (p >> 2));
         const uint32_t idx = (window >> (2 * (16 - ((p & 3) + lut)))) & q.hash_mask;
-        if (!((__ldg(&q.presence[idx >> 5]) >> (idx & 31)) & 1u)) continue;
-        int32_t qp = __ldg(&q.hashtable[idx]);
+        int32_t qp = mb_cell(q, idx);
         while (qp) {
             ++my_lookup_hits;
             int32_t qo, so;
@@ -376,6 +395,7 @@ __device__ __noinline__ void scan_block_direct(const DevQuery &q, const ScanLaun
             qp = __ldg(&q.next_pos[qp]);
         }
     }
+    return my_lookup_hits;
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS, 6)
@@ -388,44 +408,25 @@ scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ S
     // tile-relative base index of the chunk's base 0, chunk length
     __shared__ int32_t ct_start[MAXC + 1], ct_tbase[MAXC], ct_len[MAXC];
     __shared__ __align__(8) unsigned long long bar;
-    __shared__ int32_t sh_c_lo, sh_c_hi, sh_staged;
-    __shared__ int64_t sh_tile_lo;
-
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t block_pos0 = (int64_t)blockIdx.x * POS_PER_BLOCK;
     const int32_t npos = (int32_t)min((int64_t)POS_PER_BLOCK, s.total_pos - block_pos0);
     const int32_t lut = q.lut_word_length, step = q.scan_step;
-    if (tid == 0) {
-        const int32_t c_lo = s.block_chunk[blockIdx.x];
-        int32_t lo = c_lo, hi = s.block_chunk[blockIdx.x + 1];
-        const int64_t g_last = block_pos0 + npos - 1;
-        while (lo < hi) {                       // chunk of the block's last position
-            const int32_t m = (lo + hi + 1) >> 1;
-            if (s.chunks[m].pos_prefix <= g_last) lo = m; else hi = m - 1;
-        }
-        const DevChunk a = s.chunks[c_lo], b = s.chunks[lo];
-        const int64_t first_byte = a.byte_off + (((block_pos0 - a.pos_prefix) * step) >> 2);
-        const int64_t last_byte = b.byte_off + ((((g_last - b.pos_prefix) * step) + q.word_length + 32) >> 2);
-        const int64_t tile_lo = (first_byte - TILE_MARGIN) & ~int64_t(15);
-        const int64_t bytes = (last_byte + TILE_MARGIN - tile_lo + 15) & ~int64_t(15);
-        const bool staged = bytes <= (int64_t)s.tile_cap && (lo - c_lo) < MAXC;
-        sh_c_lo = c_lo; sh_c_hi = lo;
-        sh_tile_lo = tile_lo;
-        sh_staged = staged ? 1 : 0;
-        if (staged) {                           // the block's slice of the packed subject: one TMA bulk copy
-            mbar_init(&bar, 1);
-            mbar_expect_tx(&bar, (uint32_t)bytes);
-            tma_bulk_g2s(tile, s.packed + tile_lo, (uint32_t)bytes, &bar);
-        }
+    // the block's slice of the volume was worked out once per (volume, table shape) on the host:
+    // one uniform 32-byte load instead of a binary search + two chunk loads in front of the TMA issue
+    const ScanBlockDesc bd = ld_block_desc(s.block_desc + blockIdx.x);
+    if (tid == 0 && bd.staged) {                // the block's slice of the packed subject: one TMA bulk copy
+        mbar_init(&bar, 1);
+        mbar_expect_tx(&bar, (uint32_t)bd.bytes);
+        tma_bulk_g2s(tile, s.packed + bd.tile_lo, (uint32_t)bd.bytes, &bar);
     }
-    __syncthreads();
-    const int32_t c_lo = sh_c_lo;
-    const int32_t nch = sh_c_hi - c_lo + 1;
-    unsigned long long my_lookup_hits = 0;
-    if (!sh_staged) {
-        scan_block_direct(q, s, block_pos0, c_lo, sh_c_hi, my_lookup_hits);
+    const int32_t c_lo = bd.c_lo;
+    const int32_t nch = bd.c_hi - c_lo + 1;
+    uint32_t my_lookup_hits = 0;
+    if (!bd.staged) {
+        my_lookup_hits = (uint32_t)scan_block_direct(q, s, block_pos0, c_lo, bd.c_hi);
     } else {
-        const int64_t tile_lo = sh_tile_lo;
+        const int64_t tile_lo = bd.tile_lo;
         for (int i = tid; i < nch; i += SCAN_THREADS) {
             const DevChunk c = s.chunks[c_lo + i];
             ct_start[i] = (int32_t)(c.pos_prefix - block_pos0);
@@ -507,13 +508,15 @@ scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ S
         for (int ci = lane; ci < ncand; ci += 32) {
             const uint2 cd = wcand[ci];
             const int32_t gl = (int32_t)(cd.y & 2047u), k = (int32_t)(cd.y >> 11);
-            uint4 qi = __ldg(&q.cinfo[cd.x]);      // first chain element: {qp | more << 31, left 16, right 16, ambiguity}
+            // first two chain elements of the cell in ONE 32-byte sector: {qp | more << 31, left 16, right 16, ambiguity} x 2
+            uint4 qi, qi1;
+            ld_cinfo_pair(q.cinfo + 2 * (size_t)cd.x, qi, qi1);
             const int32_t p = (gl - ct_start[k]) * step;
             const int32_t tbase = ct_tbase[k], len = ct_len[k];
             const uint32_t chunk = (uint32_t)(c_lo + k);
             const int64_t g = block_pos0 + gl;
             int32_t qp = (int32_t)(qi.x & 0x7fffffffu);
-            bool more = (qi.x >> 31) != 0;
+            bool more = (qi.x >> 31) != 0, second = true;
             for (;;) {
                 ++my_lookup_hits;
                 int32_t qo, so;
@@ -521,15 +524,22 @@ scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ S
                 else if (mini_extend_tile(q, tile, tbase, len, qp - 1, p, qi, qo, so))
                     emit_hit(q, s, chunk, (uint32_t)p, g, qo, so);
                 if (!more) break;
-                qp = __ldg(&q.next_pos[qp]);
-                qi = __ldg(&q.qinfo[qp]);           // {next, left 16 bases, right 16 bases, ambiguity}
-                more = qi.x != 0;
+                if (second) {                       // second element came with the first
+                    second = false;
+                    qi = qi1;
+                    qp = (int32_t)(qi.x & 0x7fffffffu);
+                    more = (qi.x >> 31) != 0;
+                } else {                            // third and later (rare): pointer chase
+                    qp = __ldg(&q.next_pos[qp]);
+                    qi = __ldg(&q.qinfo[qp]);       // {next, left 16 bases, right 16 bases, ambiguity}
+                    more = qi.x != 0;
+                }
             }
         }
     }
-    // one atomic per warp for the lookup-hit statistic (BlastUngappedStats.lookup_hits)
-    for (int o = 16; o > 0; o >>= 1) my_lookup_hits += __shfl_down_sync(0xffffffffu, my_lookup_hits, o);
-    if (lane == 0 && my_lookup_hits) atomicAdd(&s.counters[1], my_lookup_hits);
+    // one atomic per warp for the lookup-hit statistic (BlastUngappedStats.lookup_hits); REDUX.SUM
+    const uint32_t warp_hits = __reduce_add_sync(0xffffffffu, my_lookup_hits);
+    if (lane == 0 && warp_hits) atomicAdd(&s.counters[1], (unsigned long long)warp_hits);
 }
 
 // qinfo[qp] for every 1-based query position qp: {next_pos[qp], 16 bases left of the lookup word that
@@ -595,7 +605,20 @@ __global__ void popc_kernel(const uint32_t *presence, int64_t nwords, uint32_t *
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nwords) counts[i] = __popc(presence[i]);
 }
-// cinfo[rank] = qinfo of the cell's first chain element with .x = {first qp, bit 31 = chain continues}
+// cinfo[2 rank], cinfo[2 rank + 1] = qinfo of the cell's first / second chain element with
+// .x = {qp, bit 31 = chain continues}; the second entry is zero for single-element cells
+__device__ __forceinline__ void store_cinfo_pair(uint4 *cinfo, uint32_t rank, uint32_t qp, const uint4 *qinfo)
+{
+    uint4 v = qinfo[qp], w = make_uint4(0, 0, 0, 0);
+    const uint32_t nxt = v.x;
+    v.x = qp | (nxt ? 0x80000000u : 0u);
+    if (nxt) {
+        w = qinfo[nxt];
+        w.x = nxt | (w.x ? 0x80000000u : 0u);
+    }
+    cinfo[2 * (size_t)rank] = v;
+    cinfo[2 * (size_t)rank + 1] = w;
+}
 __global__ void build_compact_kernel(const int32_t *hashtable, const uint32_t *presence, const uint32_t *prefix,
                                      int64_t nwords, uint2 *prk, const uint4 *qinfo, uint4 *cinfo)
 {
@@ -607,12 +630,43 @@ __global__ void build_compact_kernel(const int32_t *hashtable, const uint32_t *p
     while (bits) {
         const int b = __ffs(bits) - 1;
         bits &= bits - 1;
-        const uint32_t qp = (uint32_t)hashtable[i * 32 + b];
-        uint4 v = qinfo[qp];
-        v.x = qp | (v.x ? 0x80000000u : 0u);
-        cinfo[r++] = v;
+        store_cinfo_pair(cinfo, r++, (uint32_t)hashtable[i * 32 + b], qinfo);
     }
 }
+// device-built tables: prk from the presence bitmap, cinfo[rank] from the per-rank chain heads
+__global__ void build_prk_kernel(const uint32_t *presence, const uint32_t *prefix, int64_t nwords, uint2 *prk)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nwords) prk[i] = make_uint2(presence[i], prefix[i]);
+}
+__global__ void build_cinfo_ranks_kernel(const int32_t *first_qp, int64_t n, const uint4 *qinfo, uint4 *cinfo)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const uint32_t qp = (uint32_t)first_qp[r];
+    if (qp) store_cinfo_pair(cinfo, (uint32_t)r, qp, qinfo);
+}
+cudaError_t launch_build_prk_cinfo(const uint32_t *presence, const uint32_t *prefix, int64_t nwords, uint2 *prk,
+                                   const int32_t *first_qp, int64_t n_ranks, const uint4 *qinfo, uint4 *cinfo,
+                                   cudaStream_t st)
+{
+    build_prk_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, st>>>(presence, prefix, nwords, prk);
+    if (n_ranks > 0)
+        build_cinfo_ranks_kernel<<<(unsigned)((n_ranks + 255) / 256), 256, 0, st>>>(first_qp, n_ranks, qinfo, cinfo);
+    return cudaGetLastError();
+}
+// parity tap: hashtable[] reconstructed from the compact table
+__global__ void rebuild_hashtable_kernel(const DevQuery q, int64_t hashsize, int32_t *out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < hashsize) out[i] = mb_cell(q, (uint32_t)i);
+}
+cudaError_t launch_rebuild_hashtable(const DevQuery &q, int64_t hashsize, int32_t *out, cudaStream_t st)
+{
+    rebuild_hashtable_kernel<<<(unsigned)((hashsize + 255) / 256), 256, 0, st>>>(q, hashsize, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_popc(const uint32_t *presence, int64_t nwords, uint32_t *counts, cudaStream_t st)
 {
     popc_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, st>>>(presence, nwords, counts);

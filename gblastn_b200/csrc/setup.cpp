@@ -411,7 +411,7 @@ struct BnSetup {
     HostArray<uint8_t> query;
     std::vector<BnContext> ctx;
     HostArray<int32_t> hashtable, next_pos;
-    std::vector<int32_t> masked;
+    std::vector<int32_t> masked, segments;
     std::vector<uint32_t> pv;
     std::vector<int16_t> backbone, overflow;
     std::vector<double> kbp_std, kbp_gap;
@@ -724,8 +724,11 @@ int bn_setup_create(const BnSetupOptions *opt, int32_t nq, const uint8_t *qseq, 
     if (lut_type == 0) {
         b.lut_type = BN_LUT_MB;
         b.hashsize = (int64_t)1 << (2 * lut_width);
-        S->hashtable.assign_zero((size_t)b.hashsize);
-        S->next_pos.assign_zero((size_t)concat_len + 1);
+        const bool device_fill = opt->device_lookup != 0;
+        if (!device_fill) {
+            S->hashtable.assign_zero((size_t)b.hashsize);
+            S->next_pos.assign_zero((size_t)concat_len + 1);
+        }
         const int64_t kTargetPVSize = 131072;
         int64_t pv_size = b.hashsize <= 8 * kTargetPVSize ? (b.hashsize >> 5) : kTargetPVSize / 4;
         if (entries <= 15000 || entries >= 800000) pv_size /= 2;
@@ -734,6 +737,7 @@ int bn_setup_create(const BnSetupOptions *opt, int32_t nq, const uint8_t *qseq, 
         std::vector<uint32_t> helper((size_t)(b.hashsize / 2048), 0u);
         const int32_t mask = (int32_t)(b.hashsize - 1);
         for (const Range &loc : segs) {
+            if (device_fill) break;                 // bn_query_load fills the table on the device
             int32_t from = loc.left;
             const int32_t to = loc.right - lut_width;
             if (word_size > loc.right - loc.left + 1) continue;
@@ -758,6 +762,7 @@ int bn_setup_create(const BnSetupOptions *opt, int32_t nq, const uint8_t *qseq, 
         uint32_t longest = 2;
         for (uint32_t h : helper) longest = std::max(longest, h);
         S->longest_chain = (int32_t)longest;
+        if (device_fill) S->pv.clear();
     } else {
         b.lut_type = BN_LUT_SMALL_NA;
         b.hashsize = (int64_t)1 << (2 * lut_width);
@@ -816,6 +821,9 @@ int bn_setup_create(const BnSetupOptions *opt, int32_t nq, const uint8_t *qseq, 
     b.overflow = S->overflow.empty() ? nullptr : S->overflow.data();
     b.masked_locations = S->masked.empty() ? nullptr : S->masked.data();
     b.n_masked_locations = (int32_t)(S->masked.size() / 2);
+    for (const Range &r : segs) { S->segments.push_back(r.left); S->segments.push_back(r.right); }
+    b.lookup_segments = S->segments.empty() ? nullptr : S->segments.data();
+    b.n_lookup_segments = (int32_t)(S->segments.size() / 2);
     b.container_type = concat_len > 8000 ? BN_DIAG_HASH : BN_DIAG_ARRAY;   // kQueryLenForHashTable
     b.window_size = opt->window_size; b.scan_range = opt->scan_range;
     b.gap_algo = greedy ? BN_GAP_GREEDY : BN_GAP_DP;

@@ -19,7 +19,7 @@ EXPORTS = [
     "bn_init", "bn_release", "bn_device_count", "bn_last_error", "bn_version",
     "bn_db_load", "bn_db_free", "bn_query_load", "bn_query_free",
     "bn_prelim_search", "bn_prelim_search_host", "bn_results_free",
-    "bn_scan_subject", "bn_word_finder", "bn_free", "bn_bench_scan",
+    "bn_scan_subject", "bn_word_finder", "bn_free", "bn_bench_scan", "bn_query_download_lookup",
     "bn_setup_create", "bn_setup_batch", "bn_setup_kbp_std", "bn_setup_kbp_gap",
     "bn_setup_gap_x_dropoff_final", "bn_setup_longest_chain", "bn_setup_free",
 ]
@@ -150,6 +150,16 @@ def scan_subject(volume: Volume, query: Query, oid: int) -> np.ndarray:
         return abi.struct_array(p, n.value, abi.PAIR_DTYPE)
     finally:
         lib().bn_free(p)
+
+
+def download_lookup(query: Query, device=0):
+    """Parity tap: (hashtable, next_pos) of an MB batch as resident on `device`."""
+    batch = query.holder.batch if hasattr(query.holder, "batch") else query.holder
+    ht = np.zeros(int(batch.hashsize), dtype=np.int32)
+    nx = np.zeros(int(batch.concat_len) + 1, dtype=np.int32)
+    _check(lib().bn_query_download_lookup(C.c_int(query.handle), C.c_int(device),
+                                          ht.ctypes.data_as(C.c_void_p), nx.ctypes.data_as(C.c_void_p)))
+    return ht, nx
 
 
 def bench_scan(volume: Volume, query: Query, iters: int):

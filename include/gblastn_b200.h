@@ -102,7 +102,7 @@ typedef struct BnQueryBatch {
     int32_t        lut_word_length;
     int32_t        scan_step;
     int64_t        hashsize;         /* MB: 4^lut; SmallNa: backbone_size */
-    const int32_t *hashtable;        /* MB */
+    const int32_t *hashtable;        /* MB; NULL (with next_pos NULL) => built on the device from lookup_segments */
     const int32_t *next_pos;         /* MB, concat_len + 1 */
     const uint32_t *pv_array;        /* MB, optional (NULL => not used; the device builds its own) */
     int32_t        pv_array_bts;
@@ -129,6 +129,14 @@ typedef struct BnQueryBatch {
     int32_t        hitlist_size;     /* for the low_score rule */
     double         evalue_cutoff;    /* hit_options->expect_value */
     double         low_score_perc;   /* 0 disables the rule */
+
+    /* lookup_segments of LookupTableWrapInit (core/lookup_wrap.c:49-122): unmasked [left, right]
+     * intervals of the concatenated query, ascending.  When an MB batch arrives WITHOUT
+     * hashtable/next_pos, bn_query_load runs the fill of s_FillContigMBTable
+     * (core/blast_nalookup.c:832-937) on the device from these (same table, bit for bit) and the
+     * 4^lut-entry table never crosses PCIe. */
+    const int32_t *lookup_segments;
+    int32_t        n_lookup_segments;
 } BnQueryBatch;
 
 /* BlastOffsetPair (inc-core/blast_def.h:141) tagged with its subject. */
@@ -207,6 +215,10 @@ int  bn_word_finder(int vol_handle, int query_handle, int32_t oid_begin, int32_t
                     BnInitHit **init, int64_t *n_init);
 void bn_free(void *p);
 
+/* Parity tap for the device-side table fill: reconstructs hashtable[hashsize] and
+ * next_pos[concat_len + 1] of an MB batch from the arrays resident on `device`. */
+int  bn_query_download_lookup(int query_handle, int device, int32_t *hashtable, int32_t *next_pos);
+
 /* Kernel-only timing hook for bench.py / ncu: runs the scan(+mini-extension) kernel `iters`
  * times over the resident volume and returns the average device time per launch. */
 int  bn_bench_scan(int vol_handle, int query_handle, int iters, double *ms_per_launch,
@@ -227,6 +239,8 @@ typedef struct BnSetupOptions {
     int64_t db_length;          /* total bases of the database (all volumes) */
     int32_t db_num_seqs;
     int32_t avg_subject_length; /* BlastSeqSrcGetAvgSeqLen */
+    int32_t device_lookup;      /* 1: leave the megablast table fill to bn_query_load (device); the batch
+                                   then carries lookup_segments and NULL hashtable/next_pos */
 } BnSetupOptions;
 
 typedef struct BnSetup BnSetup;   /* opaque; owns the arrays a BnQueryBatch points to */

@@ -124,6 +124,34 @@ def test_gpu_with_product_setup(name):
         Q.free(); V.free(); s.free()
 
 
+@pytest.mark.parametrize("name", ["c1_megablast_10kb_vs_1mb", "mb_lut11_hash_indels", "mb_lut12_stride17",
+                                  "mb_with_N", "blastn_mb11_dp", "mb_ws16", "mb_ntlike_many_subjects"])
+def test_gpu_device_lookup_fill(name):
+    """s_FillContigMBTable on the device (bn_query_load without hashtable/next_pos): the table is the
+    reference's bit for bit, with and without query masks, and the search results do not change."""
+    from gblastn_b200 import engine as E, setup as S
+    from oracle import refdriver as R, portdriver as P
+    if not R.available():
+        pytest.skip("reference library not present")
+    task, cfgkw, vol, qs = cases.make_case(name)
+    for masks in (None, _masks_for(qs, 5)):
+        cfg = R.default_config(task, taps=R.TAP_LUT, **cfgkw)
+        r = R.search(qs, vol, cfg, masks=masks)
+        assert r["status"] == 0
+        s = S.Setup(qs, task=task, db_length=vol.total_bases, db_num_seqs=vol.n_seqs, masks=masks,
+                    device_lookup=1, **cfgkw)
+        assert s.hashtable is None and s.batch.n_lookup_segments > 0
+        V, Q = E.Volume(vol), E.Query(s.batch)
+        try:
+            ht, nx = E.download_lookup(Q)
+            assert np.array_equal(ht, r["hashtable"]), "device-built hashtable differs from the reference"
+            assert np.array_equal(nx, r["next_pos"]), "device-built next_pos differs from the reference"
+            g = E.prelim_search(V, Q)
+            assert np.array_equal(P.final_table(g["hsps"]), r["final"])
+        finally:
+            Q.free(); V.free(); s.free()
+
+
 def test_gpu_full_size_properties():
     """BASELINE configs[1] at full size (1000 x 1 kb vs 250 Mb): size-independent properties.
     * determinism / idempotence: two searches of the same resident inputs give identical bytes
