@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -100,6 +101,8 @@ struct Workspace {
 struct Device {
     int id = -1;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // volume uploads of the host-buffer entry point (overlap with the table build)
+    cudaEvent_t alloc_ev = nullptr;
     Workspace ws;
     std::mutex mu;       // one search at a time per device
 };
@@ -117,6 +120,7 @@ struct ChunkTable {
 
 struct Volume {
     int device = 0;
+    cudaEvent_t ready = nullptr;   // set while an asynchronous upload may still be in flight
     uint8_t *d_raw = nullptr;      // allocation
     uint8_t *d_packed = nullptr;   // d_raw + 64
     int64_t bytes = 0;
@@ -202,12 +206,15 @@ cudaError_t launch_build_prk_cinfo(const uint32_t *presence, const uint32_t *pre
                                    cudaStream_t st);
 cudaError_t launch_rebuild_hashtable(const DevQuery &q, int64_t hashsize, int32_t *out, cudaStream_t st);
 cudaError_t build_mb_lookup_device(const uint8_t *d_query, int32_t concat_len, int32_t word_length, int32_t lut,
-                                   const int32_t *h_segs, int32_t n_segs, int32_t *d_next_pos, uint32_t *d_presence,
+                                   const int32_t *d_segs, int32_t n_segs, int32_t *d_next_pos, uint32_t *d_presence,
                                    int32_t *d_first_qp, int64_t *n_launches, cudaStream_t st);
 
 // Uploads one query batch to device d straight from the caller's arrays (no host staging copy);
 // the presence bitmap and the 16-base query windows are derived on the device.
-static int query_to_device(Query &Q, const BnQueryBatch &src, int d)
+// `after_h2d` (optional) runs once every host->device copy of the batch has been queued and before the
+// derivation kernels are: the host-buffer entry point starts the volume upload there, so the small
+// query copies are not stuck behind it in the copy engine and the table build overlaps the upload.
+static int query_to_device(Query &Q, const BnQueryBatch &src, int d, const std::function<int()> *after_h2d = nullptr)
 {
     Device *dev = device_at(d);
     QueryDev &qd = Q.dev[d];
@@ -221,29 +228,22 @@ static int query_to_device(Query &Q, const BnQueryBatch &src, int d)
         dctx[i] = DevContext{c.query_offset, c.query_length, c.query_index, c.frame,
                              c.x_dropoff, c.cutoff_score, c.reduced_cutoff, c.gapped_cutoff};
     }
+    // ---- host -> device copies first ------------------------------------------------------------------
     CU_TRY(upload(&qd.query, src.query_start, (size_t)b.concat_len + 2, st));
     CU_TRY(upload(&qd.ctx, dctx.data(), dctx.size(), st));
+    CU_TRY(upload(&qd.score_table, b.nucl_score_table, (size_t)256, st));
+    CU_TRY(upload(&qd.matrix, b.matrix, (size_t)256, st));
     // temporaries of the table derivation (freed stream-ordered at the end)
-    int32_t *t_hashtable = nullptr, *t_first_qp = nullptr;
+    int32_t *t_hashtable = nullptr, *t_first_qp = nullptr, *t_segs = nullptr;
     uint32_t *t_presence = nullptr, *t_counts = nullptr, *t_prefix = nullptr;
     const bool device_fill = b.lut_type == BN_LUT_MB && !src.hashtable;
     if (b.lut_type == BN_LUT_MB) {
-        // exact presence bitmap (replaces the reference's compressed pv_array: same answers,
-        // PV_TEST is only a filter in front of hashtable[index] != 0)
-        CU_TRY(dev_alloc(&t_presence, (size_t)((b.hashsize + 31) / 32), st));
         CU_TRY(dev_alloc(&qd.next_pos, (size_t)b.concat_len + 1, st));
         if (device_fill) {
-            // s_FillContigMBTable on the device: only the query bytes and the segment list cross PCIe
-            CU_TRY(dev_alloc(&t_first_qp, (size_t)b.concat_len + 1, st));
-            CU_TRY(cudaMemsetAsync(t_first_qp, 0, ((size_t)b.concat_len + 1) * sizeof(int32_t), st));
-            CU_TRY(build_mb_lookup_device(qd.query + 1, b.concat_len, b.word_length, b.lut_word_length,
-                                          src.lookup_segments, src.n_lookup_segments, qd.next_pos, t_presence,
-                                          t_first_qp, nullptr, st));
+            CU_TRY(upload(&t_segs, src.lookup_segments, 2 * (size_t)src.n_lookup_segments, st));
         } else {
-            CU_TRY(dev_alloc(&t_hashtable, (size_t)b.hashsize, st));
-            CU_TRY(cudaMemcpyAsync(t_hashtable, src.hashtable, (size_t)b.hashsize * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+            CU_TRY(upload(&t_hashtable, src.hashtable, (size_t)b.hashsize, st));
             CU_TRY(cudaMemcpyAsync(qd.next_pos, src.next_pos, ((size_t)b.concat_len + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-            CU_TRY(launch_build_presence(t_hashtable, b.hashsize, t_presence, st));
         }
     } else {
         static const int16_t kEmptyOverflow[2] = {-1, -1};
@@ -251,8 +251,24 @@ static int query_to_device(Query &Q, const BnQueryBatch &src, int d)
         if (src.overflow && b.overflow_len > 0) CU_TRY(upload(&qd.overflow, src.overflow, (size_t)b.overflow_len, st));
         else CU_TRY(upload(&qd.overflow, kEmptyOverflow, (size_t)2, st));
     }
-    CU_TRY(upload(&qd.score_table, b.nucl_score_table, (size_t)256, st));
-    CU_TRY(upload(&qd.matrix, b.matrix, (size_t)256, st));
+    if (after_h2d) { const int rc = (*after_h2d)(); if (rc) return rc; }
+
+    // ---- derived arrays (device only) --------------------------------------------------------------------
+    if (b.lut_type == BN_LUT_MB) {
+        // exact presence bitmap (replaces the reference's compressed pv_array: same answers,
+        // PV_TEST is only a filter in front of hashtable[index] != 0)
+        CU_TRY(dev_alloc(&t_presence, (size_t)((b.hashsize + 31) / 32), st));
+        if (device_fill) {
+            // s_FillContigMBTable on the device: only the query bytes and the segment list cross PCIe
+            CU_TRY(dev_alloc(&t_first_qp, (size_t)b.concat_len + 1, st));
+            CU_TRY(cudaMemsetAsync(t_first_qp, 0, ((size_t)b.concat_len + 1) * sizeof(int32_t), st));
+            CU_TRY(build_mb_lookup_device(qd.query + 1, b.concat_len, b.word_length, b.lut_word_length,
+                                          t_segs, src.n_lookup_segments, qd.next_pos, t_presence,
+                                          t_first_qp, nullptr, st));
+        } else {
+            CU_TRY(launch_build_presence(t_hashtable, b.hashsize, t_presence, st));
+        }
+    }
     const int64_t nw = (int64_t)((b.concat_len + 2 + 16) >> 4) + 3;
     CU_TRY(dev_alloc(&qd.qpk, (size_t)nw, st));
     CU_TRY(launch_build_qpk(qd.query, b.concat_len, qd.qpk, nw, st));
@@ -295,7 +311,7 @@ static int query_to_device(Query &Q, const BnQueryBatch &src, int d)
         v.cinfo = qd.cinfo;
     }
     {
-        void *tmp[] = {t_hashtable, t_first_qp, t_presence, t_counts, t_prefix};
+        void *tmp[] = {t_hashtable, t_first_qp, t_segs, t_presence, t_counts, t_prefix};
         for (void *p : tmp) if (p) CU_TRY(cudaFreeAsync(p, st));
     }
     CU_TRY(cudaStreamSynchronize(st));     // caller's arrays may go away after bn_query_load returns
@@ -620,14 +636,18 @@ static int prelim_search_locked(Device &D, Volume &V, Query &Q, int32_t oid_begi
     if (rc) return rc;
     BnStats &stats = out->stats;
     stats.subject_bases_scanned = T->total_bases;
+    if (V.ready) CU_TRY(cudaStreamWaitEvent(D.stream, V.ready, 0));
 
     StageCounts cnt;
+    const double tw0 = now_ms();
     rc = run_word_finder(D, V, Q, *T, false, cnt, &stats);
     if (rc) return rc;
+    const double tw1 = now_ms();
     DevInitHit *h_init = nullptr;
     DevGapResult *h_gap = nullptr;
     rc = run_gapped(D, V, Q, *T, cnt.n_init, h_init, h_gap, &stats);
     if (rc) return rc;
+    const double tw2 = now_ms();
     stats.lookup_hits = cnt.lookup_hits;
     stats.init_extends = cnt.n_extended;
     stats.good_init_extends = cnt.n_init;
@@ -690,8 +710,9 @@ static int prelim_search_locked(Device &D, Volume &V, Query &Q, int32_t oid_begi
     finish_oid();
     stats.ms_host = now_ms() - th0;
     if (trace)
-        fprintf(stderr, "[bn] host %.3f ms: sort %.3f replay %.3f finish %.3f merge %.3f eval %.3f track %.3f (n_init %lld)\n",
-                stats.ms_host, t_sort, t_replay, t_finish, t_merge, t_eval, t_track, (long long)cnt.n_init);
+        fprintf(stderr, "[bn] wall: table %.3f word-finder %.3f gapped %.3f | host %.3f ms: sort %.3f replay %.3f finish %.3f merge %.3f eval %.3f track %.3f (n_hits %lld n_init %lld)\n",
+                tw0 - t0, tw1 - tw0, tw2 - tw1, stats.ms_host, t_sort, t_replay, t_finish, t_merge, t_eval, t_track,
+                (long long)cnt.n_hits, (long long)cnt.n_init);
 
     out->n_hsps = (int64_t)final_hsps.size(); out->hsps = to_malloc(final_hsps);
     out->n_init = (int64_t)init_tap.size();   out->init = to_malloc(init_tap);
@@ -730,6 +751,8 @@ int bn_init(int n_gpu, const int *device_ids)
         d->id = id;
         CU_TRY(cudaSetDevice(id));
         CU_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+        CU_TRY(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+        CU_TRY(cudaEventCreateWithFlags(&d->alloc_ev, cudaEventDisableTiming));
         {   // keep freed blocks in the stream-ordered pool (volumes / query tables are re-loaded often)
             cudaMemPool_t pool;
             if (cudaDeviceGetDefaultMemPool(&pool, id) == cudaSuccess) {
@@ -752,6 +775,7 @@ void bn_release(void)
     g_queries.clear();
     for (auto &v : g_volumes) if (v) {
         cudaSetDevice(g_devices[v->device]->id);
+        if (v->ready) { cudaEventSynchronize(v->ready); cudaEventDestroy(v->ready); }
         cudaFreeAsync(v->d_raw, g_devices[v->device]->stream);
         for (auto &kv : v->tables) { kv.second->dev.release(); kv.second->block_chunk.release(); kv.second->block_desc.release(); }
     }
@@ -759,6 +783,8 @@ void bn_release(void)
     for (auto &d : g_devices) {
         cudaSetDevice(d->id);
         d->ws.release();
+        if (d->alloc_ev) cudaEventDestroy(d->alloc_ev);
+        if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
         if (d->stream) cudaStreamDestroy(d->stream);
     }
     g_devices.clear();
@@ -771,8 +797,10 @@ int bn_device_count(void)
     return (int)g_devices.size();
 }
 
-int bn_db_load(int device, const uint8_t *packed, int64_t packed_bytes, const int64_t *seq_byte_off,
-               const int32_t *seq_len, int32_t n_seq, int *vol_handle)
+// async: the upload runs on the device's copy stream and the call returns at once; searches on the
+// volume wait for it on the device (Volume::ready)
+static int db_load_impl(int device, const uint8_t *packed, int64_t packed_bytes, const int64_t *seq_byte_off,
+                        const int32_t *seq_len, int32_t n_seq, bool async, int *vol_handle)
 {
     int rc = ensure_init();
     if (rc) return rc;
@@ -792,14 +820,28 @@ int bn_db_load(int device, const uint8_t *packed, int64_t packed_bytes, const in
     // 64 readable bytes in front (reverse 16-base windows may start before the first base) and behind
     CU_TRY(cudaMallocAsync((void **)&V->d_raw, (size_t)packed_bytes + 192, D->stream));
     V->d_packed = V->d_raw + 64;
-    CU_TRY(cudaMemsetAsync(V->d_raw, 0, 64, D->stream));
-    CU_TRY(cudaMemcpyAsync(V->d_packed, packed, (size_t)packed_bytes, cudaMemcpyHostToDevice, D->stream));
-    CU_TRY(cudaMemsetAsync(V->d_packed + packed_bytes, 0, 128, D->stream));
-    CU_TRY(cudaStreamSynchronize(D->stream));
+    cudaStream_t cs = async ? D->copy_stream : D->stream;
+    if (async) {
+        CU_TRY(cudaEventRecord(D->alloc_ev, D->stream));
+        CU_TRY(cudaStreamWaitEvent(cs, D->alloc_ev, 0));
+    }
+    CU_TRY(cudaMemsetAsync(V->d_raw, 0, 64, cs));
+    CU_TRY(cudaMemcpyAsync(V->d_packed, packed, (size_t)packed_bytes, cudaMemcpyHostToDevice, cs));
+    CU_TRY(cudaMemsetAsync(V->d_packed + packed_bytes, 0, 128, cs));
+    if (async) {
+        CU_TRY(cudaEventCreateWithFlags(&V->ready, cudaEventDisableTiming));
+        CU_TRY(cudaEventRecord(V->ready, cs));
+    } else CU_TRY(cudaStreamSynchronize(cs));
     std::lock_guard<std::mutex> lk(g_mu);
     g_volumes.push_back(std::move(V));
     *vol_handle = (int)g_volumes.size() - 1;
     return BN_OK;
+}
+
+int bn_db_load(int device, const uint8_t *packed, int64_t packed_bytes, const int64_t *seq_byte_off,
+               const int32_t *seq_len, int32_t n_seq, int *vol_handle)
+{
+    return db_load_impl(device, packed, packed_bytes, seq_byte_off, seq_len, n_seq, false, vol_handle);
 }
 
 int bn_db_free(int h)
@@ -808,13 +850,15 @@ int bn_db_free(int h)
     if (h < 0 || h >= (int)g_volumes.size() || !g_volumes[h]) return fail(BN_ERR_INVALID, "bn_db_free: bad handle");
     Volume &V = *g_volumes[h];
     cudaSetDevice(g_devices[V.device]->id);
+    if (V.ready) { cudaStreamWaitEvent(g_devices[V.device]->stream, V.ready, 0); cudaEventDestroy(V.ready); V.ready = nullptr; }
     cudaFreeAsync(V.d_raw, g_devices[V.device]->stream);
     for (auto &kv : V.tables) { kv.second->dev.release(); kv.second->block_chunk.release(); kv.second->block_desc.release(); }
     g_volumes[h].reset();
     return BN_OK;
 }
 
-int bn_query_load(const BnQueryBatch *b, int *query_handle)
+static int query_load_impl(const BnQueryBatch *b, int *query_handle, int hook_device,
+                           const std::function<int()> *after_h2d)
 {
     int rc = ensure_init();
     if (rc) return rc;
@@ -850,7 +894,7 @@ int bn_query_load(const BnQueryBatch *b, int *query_handle)
     Q->diag_array_length = n;
     Q->dev.resize(g_devices.size());
     for (size_t d = 0; d < g_devices.size(); d++) {
-        rc = query_to_device(*Q, *b, (int)d);
+        rc = query_to_device(*Q, *b, (int)d, (int)d == hook_device ? after_h2d : nullptr);
         if (rc) {
             for (size_t k = 0; k < g_devices.size(); k++)
                 if (Q->dev[k].ready) { cudaSetDevice(g_devices[k]->id); free_query_dev(Q->dev[k], g_devices[k]->stream); }
@@ -861,6 +905,11 @@ int bn_query_load(const BnQueryBatch *b, int *query_handle)
     g_queries.push_back(std::move(Q));
     *query_handle = (int)g_queries.size() - 1;
     return BN_OK;
+}
+
+int bn_query_load(const BnQueryBatch *b, int *query_handle)
+{
+    return query_load_impl(b, query_handle, -1, nullptr);
 }
 
 int bn_query_free(int h)
@@ -905,12 +954,32 @@ int bn_prelim_search_host(int device, const BnQueryBatch *batch, const uint8_t *
                           int32_t n_seq, int taps, BnResults *out)
 {
     int vh = -1, qh = -1;
-    int rc = bn_db_load(device, packed, packed_bytes, seq_byte_off, seq_len, n_seq, &vh);
+    static const bool trace = getenv("BN_TRACE") != nullptr;
+    const double t0 = now_ms();
+    // the volume streams to the device on the copy stream while the query tables are built on the main
+    // one; its copy is queued right behind the (small) query copies
+    int rc = ensure_init();
     if (rc) return rc;
-    rc = bn_query_load(batch, &qh);
+    double t1 = t0;
+    int rc_load = BN_OK;
+    const std::function<int()> start_volume = [&]() {
+        rc_load = db_load_impl(device, packed, packed_bytes, seq_byte_off, seq_len, n_seq, true, &vh);
+        t1 = now_ms();
+        return rc_load;
+    };
+    rc = query_load_impl(batch, &qh, device, &start_volume);
+    if (vh < 0) {       // the hook did not run or failed
+        if (qh >= 0) bn_query_free(qh);
+        return rc ? rc : fail(BN_ERR_INVALID, "bn_prelim_search_host: bad device");
+    }
+    const double t2 = now_ms();
     if (rc == BN_OK) rc = bn_prelim_search(vh, qh, 0, n_seq, taps, out);
+    const double t3 = now_ms();
     if (qh >= 0) bn_query_free(qh);
     bn_db_free(vh);
+    if (trace)
+        fprintf(stderr, "[bn] host-buffer call %.3f ms: query copies + volume enqueue %.3f table build %.3f search %.3f free %.3f\n",
+                now_ms() - t0, t1 - t0, t2 - t1, t3 - t2, now_ms() - t3);
     return rc;
 }
 
@@ -938,6 +1007,7 @@ int bn_scan_subject(int vol_handle, int query_handle, int32_t oid, int32_t chunk
     std::shared_ptr<ChunkTable> T;
     rc = build_chunk_table(*V, *Q, oid, oid + 1, D->stream, &T);
     if (rc) return rc;
+    if (V->ready) CU_TRY(cudaStreamWaitEvent(D->stream, V->ready, 0));
     StageCounts cnt;
     rc = run_word_finder(*D, *V, *Q, *T, true, cnt, nullptr);
     if (rc) return rc;
@@ -1003,6 +1073,7 @@ int bn_bench_scan(int vol_handle, int query_handle, int iters, double *ms_per_la
     std::shared_ptr<ChunkTable> T;
     rc = build_chunk_table(*V, *Q, 0, (int32_t)V->seq_len.size(), D->stream, &T);
     if (rc) return rc;
+    if (V->ready) CU_TRY(cudaStreamWaitEvent(D->stream, V->ready, 0));
     Workspace &ws = D->ws;
     cudaStream_t st = D->stream;
     CU_TRY(ws.counters.reserve(8));

@@ -84,13 +84,12 @@ __global__ void mb_link_kernel(const uint32_t *keys, const uint32_t *vals, const
 struct LookupBuildTemp {
     uint8_t *segmark;
     uint32_t *keys_a, *keys_b, *vals_a, *vals_b, *flags;
-    int32_t *segs;
 };
 
 // Builds next_pos (concat_len + 1 ints, zero-filled here), the presence bitmap (zero-filled here) and
 // first_qp[rank].  All temporaries come from the stream-ordered pool.
 cudaError_t build_mb_lookup_device(const uint8_t *d_query /* base 0 */, int32_t concat_len, int32_t word_length,
-                                   int32_t lut, const int32_t *h_segs, int32_t n_segs, int32_t *d_next_pos,
+                                   int32_t lut, const int32_t *d_segs, int32_t n_segs, int32_t *d_next_pos,
                                    uint32_t *d_presence, int32_t *d_first_qp, int64_t *n_launches, cudaStream_t st)
 {
     if (concat_len <= 0) return cudaSuccess;
@@ -106,13 +105,11 @@ cudaError_t build_mb_lookup_device(const uint8_t *d_query /* base 0 */, int32_t 
     LB_TRY(cudaMallocAsync((void **)&t.vals_a, (size_t)n * 4, st));
     LB_TRY(cudaMallocAsync((void **)&t.vals_b, (size_t)n * 4, st));
     LB_TRY(cudaMallocAsync((void **)&t.flags, (size_t)n * 4, st));
-    LB_TRY(cudaMallocAsync((void **)&t.segs, (size_t)std::max(n_segs, 1) * 8, st));
     LB_TRY(cudaMemsetAsync(t.segmark, 0, (size_t)n, st));
     LB_TRY(cudaMemsetAsync(d_next_pos, 0, ((size_t)concat_len + 1) * 4, st));
     LB_TRY(cudaMemsetAsync(d_presence, 0, (size_t)((hashsize + 31) / 32) * 4, st));
     if (n_segs > 0) {
-        LB_TRY(cudaMemcpyAsync(t.segs, h_segs, (size_t)n_segs * 8, cudaMemcpyHostToDevice, st));
-        mark_segments_kernel<<<n_segs, 128, 0, st>>>(t.segs, n_segs, word_length, concat_len, t.segmark);
+        mark_segments_kernel<<<n_segs, 128, 0, st>>>(d_segs, n_segs, word_length, concat_len, t.segmark);
         LB_TRY(cudaGetLastError());
     }
     {
@@ -136,7 +133,7 @@ cudaError_t build_mb_lookup_device(const uint8_t *d_query /* base 0 */, int32_t 
 #undef LB_TRY
 done:
     {
-        void *ptrs[] = {t.segmark, t.keys_a, t.keys_b, t.vals_a, t.vals_b, t.flags, t.segs, cub_tmp};
+        void *ptrs[] = {t.segmark, t.keys_a, t.keys_b, t.vals_a, t.vals_b, t.flags, cub_tmp};
         for (void *p : ptrs) if (p) cudaFreeAsync(p, st);
     }
     return e;
