@@ -194,6 +194,7 @@ struct ScanLaunch {
     int32_t gbits;                // bits of the global position in the sort key
     int32_t diag_array_length;    // eDiagArray: cells (power of two)
     int32_t tile_cap;             // staged kernel: bytes of shared memory for the subject slice
+    uint32_t *bucket_count;       // optional: survivors per diagonal-hash bucket (group_sort.cu)
 };
 cudaError_t launch_scan(const DevQuery &q, const ScanLaunch &s, cudaStream_t st);
 int scan_positions_per_block();
@@ -219,11 +220,33 @@ struct ExtendLaunch {
     DevInitHit *init;
     SpecResult *spec;             // per hit: outcome of the speculative extension
     uint32_t *leaders;            // indices of the hits extended speculatively
-    unsigned long long *counters; // [2] = #init hits, [3] = #extended, [4] = #groups, [5] = #leaders
+    unsigned long long *counters; // [2] = #init hits, [3] = #extended, [4] = #groups, [5] = #leaders, [6] = fast path refused
     int64_t init_capacity;
+    int32_t n_from_device;        // 1: the number of hits is counters[0] (no host round trip), kernels idle if counters[6]
 };
 cudaError_t launch_extend_groups(const DevQuery &q, const ExtendLaunch &e, const uint64_t *keys,
                                  uint32_t *heads, int64_t n_hits, int gbits, cudaStream_t st);
+cudaError_t launch_extend_grouped(const DevQuery &q, const ExtendLaunch &e, const uint64_t *keys,
+                                  const uint32_t *heads, int gbits, cudaStream_t st);
+
+// Device-side grouping of the seed hits by diagonal-hash bucket (group_sort.cu).
+struct BucketLaunch {
+    const SeedHit *hits_in;       // scan output, emission order by slot
+    const uint64_t *keys_in;      // (bucket << gbits) | global scan position
+    uint32_t *bucket_count;       // 512, filled by the scan kernel
+    uint32_t *bucket_start;       // 513
+    uint32_t *cursor;             // 512
+    uint64_t *keys_tmp;           // n_limit
+    SeedHit *hits_out;            // grouped + ordered hits
+    uint64_t *keys_out;           // same key format as keys_in, ordered
+    uint32_t *heads, *leaders;
+    SpecResult *spec;
+    unsigned long long *counters; // [0] = #hits (in), [4] = #groups, [5] = #leaders, [6] = fast path refused (out)
+    int64_t n_limit;              // most hits the fast path takes (buffer sizes, <= 2^24)
+    int32_t gbits, spec_enabled;
+};
+cudaError_t launch_bucket_group(const BucketLaunch &L, cudaStream_t st);
+int group_sort_buckets();
 
 struct GappedLaunch {
     const uint8_t *packed;

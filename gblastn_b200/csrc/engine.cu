@@ -74,7 +74,8 @@ struct PinnedBuf {
 struct Workspace {
     DevBuf<SeedHit> hits_a, hits_b;
     DevBuf<uint64_t> keys_a, keys_b;
-    DevBuf<uint32_t> heads, leaders;
+    DevBuf<uint32_t> heads, leaders, buckets;
+    DevBuf<uint64_t> keys_tmp;
     DevBuf<SpecResult> spec;
     DevBuf<int4> cells;
     DevBuf<DevInitHit> init;
@@ -91,7 +92,7 @@ struct Workspace {
         h_init.release(); h_gap.release();
         for (auto &e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
         hits_a.release(); hits_b.release(); keys_a.release(); keys_b.release();
-        cells.release(); heads.release(); leaders.release(); spec.release(); init.release(); gap_out.release(); scratch.release(); todo.release();
+        cells.release(); heads.release(); leaders.release(); buckets.release(); keys_tmp.release(); spec.release(); init.release(); gap_out.release(); scratch.release(); todo.release();
         counters.release(); cub_temp.release();
         if (h_counters) cudaFreeHost(h_counters);
         h_counters = nullptr;
@@ -149,6 +150,7 @@ struct Query {
     std::vector<QueryDev> dev;            // per device
     int32_t diag_array_length = 1;
     int32_t max_query_length = 0;
+    bool fast_path_refused = false;       // the device-grouped word finder did not apply to this batch last time
 };
 
 static std::mutex g_mu;
@@ -541,8 +543,44 @@ static int32_t greedy_xdrop_offset(const BnQueryBatch &b)
     return (xd + match / 2) / (match + mismatch) + 1;
 }
 
-static int run_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t n_init,
-                      DevInitHit *&h_init, DevGapResult *&h_gap, BnStats *stats)
+// Tier-1 gapped launch over the init hits in ws.init; their number is read on the device
+// (counters[2], capped at max_init), so the call needs no host knowledge of it.
+static int enqueue_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t max_init, BnStats *stats)
+{
+    Workspace &ws = D.ws;
+    cudaStream_t st = D.stream;
+    const DevQuery &dq = Q.dev[V.device].view;
+    const BnQueryBatch &b = Q.batch;
+    CU_TRY(ws.gap_out.reserve((size_t)max_init));
+    const bool greedy = b.gap_algo == BN_GAP_GREEDY;
+    const int32_t xo = greedy_xdrop_offset(b);
+    const int wpb = 4;                                   // greedy: warps per block
+    const int32_t tier = greedy ? 254 : 1024;
+    const int64_t per_thread = greedy ? (2 * (2 * (int64_t)tier + 6) + tier + 1 + xo + 8) : 2 * (int64_t)tier;
+    GappedLaunch g{};
+    g.packed = V.d_packed; g.chunks = T.dev.p; g.init = ws.init.p; g.n_init = ws.counters.p + 2;
+    g.max_init = max_init; g.out = ws.gap_out.p;
+    g.scratch_ints_per_thread = per_thread; g.tier_d = tier; g.todo = nullptr; g.n_todo = 0;
+    if (greedy) {
+        // two warps per init-HSP (one per direction), rows in shared memory
+        const int blocks = (int)std::min<int64_t>((max_init + 1) / 2, 148 * 8);
+        g.scratch = nullptr;
+        CU_TRY(launch_greedy_warp(dq, g, wpb, blocks, true, st));
+    } else {
+        const int64_t threads = std::min<int64_t>(gapped_threads(), ((max_init + 63) / 64) * 64);
+        CU_TRY(ws.scratch.reserve((size_t)(per_thread * threads)));
+        g.scratch = ws.scratch.p;
+        g.grid_blocks = (int32_t)(threads / gapped_threads_per_block());
+        CU_TRY(launch_gapped(dq, g, st));
+    }
+    if (stats) stats->kernel_launches += 1;
+    return BN_OK;
+}
+
+// D2H of the init hits and tier-1 results, then tier 2 (worst-case scratch) for the few extensions
+// that outgrew tier 1.
+static int finish_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t n_init,
+                         DevInitHit *&h_init, DevGapResult *&h_gap, BnStats *stats)
 {
     Workspace &ws = D.ws;
     cudaStream_t st = D.stream;
@@ -551,41 +589,20 @@ static int run_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t n_i
     CU_TRY(ws.h_init.reserve((size_t)n_init + 1)); CU_TRY(ws.h_gap.reserve((size_t)n_init + 1));
     h_init = ws.h_init.p; h_gap = ws.h_gap.p;
     if (n_init == 0) return BN_OK;
-    Timer t(st, ws, 2);
-    t.start();
-    CU_TRY(ws.gap_out.reserve((size_t)n_init));
     const bool greedy = b.gap_algo == BN_GAP_GREEDY;
     const int32_t xo = greedy_xdrop_offset(b);
-    const int wpb = 4;                                   // greedy: warps per block
-    int32_t tier = greedy ? 254 : 1024;
-    int64_t per_thread = greedy ? (2 * (2 * (int64_t)tier + 6) + tier + 1 + xo + 8) : 2 * (int64_t)tier;
-    GappedLaunch g{};
-    g.packed = V.d_packed; g.chunks = T.dev.p; g.init = ws.init.p; g.n_init = ws.counters.p + 2;
-    g.max_init = n_init; g.out = ws.gap_out.p;
-    g.scratch_ints_per_thread = per_thread; g.tier_d = tier; g.todo = nullptr; g.n_todo = 0;
-    if (greedy) {
-        // two warps per init-HSP (one per direction), rows in shared memory
-        const int blocks = (int)std::min<int64_t>((n_init + 1) / 2, 148 * 8);
-        g.scratch = nullptr;
-        CU_TRY(launch_greedy_warp(dq, g, wpb, blocks, true, st));
-    } else {
-        const int64_t threads = std::min<int64_t>(gapped_threads(), ((n_init + 63) / 64) * 64);
-        CU_TRY(ws.scratch.reserve((size_t)(per_thread * threads)));
-        g.scratch = ws.scratch.p;
-        g.grid_blocks = (int32_t)(threads / gapped_threads_per_block());
-        CU_TRY(launch_gapped(dq, g, st));
-    }
-    if (stats) stats->kernel_launches += 1;
+    const int wpb = 4;
     CU_TRY(cudaMemcpyAsync(h_init, ws.init.p, (size_t)n_init * sizeof(DevInitHit), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaMemcpyAsync(h_gap, ws.gap_out.p, (size_t)n_init * sizeof(DevGapResult), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
 
-    // tier 2: worst-case scratch for the few extensions that outgrew tier 1
     std::vector<int32_t> todo;
     for (int64_t i = 0; i < n_init; i++) if (h_gap[(size_t)i].status == 1) todo.push_back((int32_t)i);
     if (!todo.empty()) {
         int32_t max_len = 0;
         for (const auto &c : T.host) max_len = std::max(max_len, c.len);
+        int32_t tier;
+        int64_t per_thread;
         if (greedy) {
             tier = std::min(10000, max_len / 2 + 1);
             per_thread = 2 * (2 * (int64_t)tier + 6) + tier + 1 + xo + 8;
@@ -599,6 +616,9 @@ static int run_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t n_i
         CU_TRY(ws.scratch.reserve((size_t)(per_thread * blocks * tpb)));
         CU_TRY(ws.todo.reserve(todo.size()));
         CU_TRY(cudaMemcpyAsync(ws.todo.p, todo.data(), todo.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        GappedLaunch g{};
+        g.packed = V.d_packed; g.chunks = T.dev.p; g.init = ws.init.p; g.n_init = ws.counters.p + 2;
+        g.max_init = n_init; g.out = ws.gap_out.p;
         g.scratch = ws.scratch.p; g.scratch_ints_per_thread = per_thread; g.tier_d = tier;
         g.todo = ws.todo.p; g.n_todo = (int32_t)todo.size(); g.grid_blocks = (int32_t)blocks;
         if (greedy) CU_TRY(launch_greedy_warp(dq, g, wpb, (int)blocks, false, st));
@@ -609,8 +629,112 @@ static int run_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t n_i
         for (int32_t i : todo)
             if (h_gap[(size_t)i].status != 0) return fail(BN_ERR_OVERFLOW, "gapped extension scratch overflow in tier 2");
     }
+    return BN_OK;
+}
+
+static int run_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t n_init,
+                      DevInitHit *&h_init, DevGapResult *&h_gap, BnStats *stats)
+{
+    Workspace &ws = D.ws;
+    if (n_init == 0) {
+        CU_TRY(ws.h_init.reserve(1)); CU_TRY(ws.h_gap.reserve(1));
+        h_init = ws.h_init.p; h_gap = ws.h_gap.p;
+        return BN_OK;
+    }
+    Timer t(D.stream, ws, 2);
+    t.start();
+    int rc = enqueue_gapped(D, V, Q, T, n_init, stats);
+    if (rc) return rc;
+    rc = finish_gapped(D, V, Q, T, n_init, h_init, h_gap, stats);
+    if (rc) return rc;
     t.stop();
     if (stats) stats->ms_gapped += t.ms();
+    return BN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast path (diagonal HASH container): scan -> device-side bucket grouping -> speculative ungapped
+// pass -> bucket replay -> tier-1 gapped extension, all queued back to back; the host learns the
+// counts at ONE synchronisation after the gapped kernel.  *redo is set (and nothing else is to be
+// trusted) when the device refused the fast path or a buffer was too small: the caller then runs the
+// general path.
+// ------------------------------------------------------------------------------------------------
+static int run_fused(Device &D, Volume &V, Query &Q, ChunkTable &T, StageCounts &cnt, BnStats &stats,
+                     DevInitHit *&h_init, DevGapResult *&h_gap, bool *redo)
+{
+    *redo = false;
+    Workspace &ws = D.ws;
+    cudaStream_t st = D.stream;
+    const DevQuery &dq = Q.dev[V.device].view;
+    CU_TRY(ws.counters.reserve(8));
+    if (!ws.h_counters) CU_TRY(cudaMallocHost(&ws.h_counters, 8 * sizeof(unsigned long long)));
+    if (T.total_pos >= (int64_t)1 << 32) return fail(BN_ERR_OVERFLOW, "more than 2^32 scan positions in one search");
+    const int gbits = bits_for((uint64_t)std::max<int64_t>(T.total_pos, 1));
+    const int nb = group_sort_buckets();
+
+    int64_t cap = std::max<int64_t>((int64_t)ws.hits_a.cap, std::max<int64_t>(1 << 16, T.total_pos / 16));
+    CU_TRY(ws.hits_a.reserve((size_t)cap)); CU_TRY(ws.keys_a.reserve((size_t)cap));
+    cap = (int64_t)std::min(ws.hits_a.cap, ws.keys_a.cap);
+    const int64_t n_limit = std::min<int64_t>(cap, (int64_t)1 << 18);
+    CU_TRY(ws.hits_b.reserve((size_t)n_limit)); CU_TRY(ws.keys_b.reserve((size_t)n_limit));
+    CU_TRY(ws.keys_tmp.reserve((size_t)n_limit));
+    CU_TRY(ws.cells.reserve((size_t)n_limit + 2));
+    CU_TRY(ws.heads.reserve((size_t)nb + 1));
+    CU_TRY(ws.leaders.reserve((size_t)n_limit + 1));
+    CU_TRY(ws.spec.reserve((size_t)n_limit + 1));
+    CU_TRY(ws.buckets.reserve((size_t)3 * nb + 8));
+    CU_TRY(ws.init.reserve((size_t)std::max<int64_t>(4096, n_limit / 4)));
+    const int64_t init_cap = (int64_t)ws.init.cap;
+
+    Timer t_scan(st, ws, 0), t_ext(st, ws, 1), t_gap(st, ws, 2);
+    CU_TRY(cudaMemsetAsync(ws.counters.p, 0, 8 * sizeof(unsigned long long), st));
+    CU_TRY(cudaMemsetAsync(ws.buckets.p, 0, (size_t)nb * sizeof(uint32_t), st));
+    ScanLaunch s{};
+    s.packed = V.d_packed; s.chunks = T.dev.p; s.n_chunks = (int32_t)T.host.size();
+    s.total_pos = T.total_pos; s.hits = ws.hits_a.p; s.keys = ws.keys_a.p;
+    s.counters = ws.counters.p; s.capacity = cap; s.block_chunk = T.block_chunk.p; s.block_desc = T.block_desc.p;
+    s.raw_pairs = 0; s.gbits = gbits; s.diag_array_length = Q.diag_array_length;
+    s.tile_cap = scan_tile_cap(Q.batch.scan_step, Q.batch.word_length);
+    s.bucket_count = ws.buckets.p;
+    t_scan.start();
+    CU_TRY(launch_scan(dq, s, st));
+    t_scan.stop();
+
+    t_ext.start();
+    BucketLaunch L{};
+    L.hits_in = ws.hits_a.p; L.keys_in = ws.keys_a.p;
+    L.bucket_count = ws.buckets.p; L.bucket_start = ws.buckets.p + nb; L.cursor = ws.buckets.p + 2 * nb + 1;
+    L.keys_tmp = ws.keys_tmp.p; L.hits_out = ws.hits_b.p; L.keys_out = ws.keys_b.p;
+    L.heads = ws.heads.p; L.leaders = ws.leaders.p; L.spec = ws.spec.p; L.counters = ws.counters.p;
+    L.n_limit = n_limit; L.gbits = gbits; L.spec_enabled = Q.batch.window_size > 0 ? 0 : 1;
+    CU_TRY(launch_bucket_group(L, st));
+    ExtendLaunch e{};
+    e.packed = V.d_packed; e.chunks = T.dev.p; e.hits = ws.hits_b.p;
+    e.cells = reinterpret_cast<int32_t *>(ws.cells.p); e.init = ws.init.p;
+    e.counters = ws.counters.p; e.init_capacity = init_cap;
+    e.spec = ws.spec.p; e.leaders = ws.leaders.p; e.n_from_device = 1;
+    CU_TRY(launch_extend_grouped(dq, e, ws.keys_b.p, ws.heads.p, gbits, st));
+    t_ext.stop();
+
+    t_gap.start();
+    int rc = enqueue_gapped(D, V, Q, T, init_cap, nullptr);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(ws.h_counters, ws.counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    cnt.n_hits = (int64_t)ws.h_counters[0];
+    cnt.lookup_hits = (int64_t)ws.h_counters[1];
+    cnt.n_init = (int64_t)ws.h_counters[2];
+    cnt.n_extended = (int64_t)ws.h_counters[3];
+    if (cnt.n_hits > cap) {                    // scan output overflowed: grow for the general path's retry
+        CU_TRY(ws.hits_a.reserve((size_t)(cnt.n_hits + cnt.n_hits / 16 + 1024)));
+        CU_TRY(ws.keys_a.reserve((size_t)(cnt.n_hits + cnt.n_hits / 16 + 1024)));
+    }
+    if (cnt.n_hits > cap || ws.h_counters[6] || cnt.n_init > init_cap) { *redo = true; return BN_OK; }
+    rc = finish_gapped(D, V, Q, T, cnt.n_init, h_init, h_gap, &stats);
+    if (rc) return rc;
+    t_gap.stop();
+    stats.kernel_launches += 1 + 3 + (L.spec_enabled ? 2 : 1) + 1;
+    stats.ms_scan += t_scan.ms(); stats.ms_extend += t_ext.ms(); stats.ms_gapped += t_gap.ms();
     return BN_OK;
 }
 
@@ -640,13 +764,24 @@ static int prelim_search_locked(Device &D, Volume &V, Query &Q, int32_t oid_begi
 
     StageCounts cnt;
     const double tw0 = now_ms();
-    rc = run_word_finder(D, V, Q, *T, false, cnt, &stats);
-    if (rc) return rc;
-    const double tw1 = now_ms();
+    double tw1 = tw0;
     DevInitHit *h_init = nullptr;
     DevGapResult *h_gap = nullptr;
-    rc = run_gapped(D, V, Q, *T, cnt.n_init, h_init, h_gap, &stats);
-    if (rc) return rc;
+    bool general = Q.batch.container_type != BN_DIAG_HASH || Q.fast_path_refused || T->total_pos <= 0;
+    if (!general) {
+        bool redo = false;
+        rc = run_fused(D, V, Q, *T, cnt, stats, h_init, h_gap, &redo);
+        if (rc) return rc;
+        if (redo) { general = true; Q.fast_path_refused = true; cnt = StageCounts{}; }
+        tw1 = now_ms();
+    }
+    if (general) {
+        rc = run_word_finder(D, V, Q, *T, false, cnt, &stats);
+        if (rc) return rc;
+        tw1 = now_ms();
+        rc = run_gapped(D, V, Q, *T, cnt.n_init, h_init, h_gap, &stats);
+        if (rc) return rc;
+    }
     const double tw2 = now_ms();
     stats.lookup_hits = cnt.lookup_hits;
     stats.init_extends = cnt.n_extended;

@@ -478,6 +478,7 @@ extend_leaders_kernel(const DevQuery q, const ExtendLaunch e)
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * EXT_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * EXT_WARPS_PER_BLOCK;
+    if (e.n_from_device && e.counters[6]) return;
     const int64_t n = (int64_t)e.counters[5];
     const bool is_hash = q.container_type == 1;
     const int32_t word = q.word_length, lut = q.lut_word_length;
@@ -501,6 +502,10 @@ __global__ void __launch_bounds__(EXT_WARPS_PER_BLOCK * 32)
 extend_kernel(const DevQuery q, const ExtendLaunch e, const uint64_t *keys, const uint32_t *heads,
               int64_t n_hits, int gbits)
 {
+    if (e.n_from_device) {
+        if (e.counters[6]) return;
+        n_hits = (int64_t)e.counters[0];
+    }
     __shared__ int32_t s_tab[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = q.score_table[i];
     __syncthreads();
@@ -631,6 +636,20 @@ extend_kernel(const DevQuery q, const ExtendLaunch e, const uint64_t *keys, cons
         }
         if (lane == 0 && n_extended) atomicAdd(&e.counters[3], n_extended);
     }
+}
+
+// Fast path: hits were grouped on the device (group_sort.cu), their number is only known there; grids
+// are sized for the buffer limit and the kernels read the count themselves.
+cudaError_t launch_extend_grouped(const DevQuery &q, const ExtendLaunch &e, const uint64_t *keys,
+                                  const uint32_t *heads, int gbits, cudaStream_t st)
+{
+    if (q.window_size <= 0) {
+        extend_leaders_kernel<<<SPEC_BLOCKS, EXT_WARPS_PER_BLOCK * 32, 0, st>>>(q, e);
+        cudaError_t err = cudaGetLastError();
+        if (err != cudaSuccess) return err;
+    }
+    extend_kernel<<<EXT_BLOCKS, EXT_WARPS_PER_BLOCK * 32, 0, st>>>(q, e, keys, heads, 0, gbits);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_extend_groups(const DevQuery &q, const ExtendLaunch &e, const uint64_t *keys,

@@ -84,8 +84,10 @@ __device__ __forceinline__ void emit_hit(const DevQuery &q, const ScanLaunch &s,
     if ((int64_t)slot < s.capacity) {
         SeedHit h;
         h.chunk = chunk; h.scan_pos = p; h.q_off = (uint32_t)q_off; h.s_off = (uint32_t)s_off;
+        const uint32_t grp = diag_group(q, s, q_off, s_off);
         s.hits[slot] = h;
-        s.keys[slot] = ((uint64_t)diag_group(q, s, q_off, s_off) << s.gbits) | (uint64_t)g;
+        s.keys[slot] = ((uint64_t)grp << s.gbits) | (uint64_t)g;
+        if (s.bucket_count) atomicAdd(&s.bucket_count[grp], 1u);
     }
 }
 
