@@ -1174,6 +1174,62 @@ int bn_word_finder(int vol_handle, int query_handle, int32_t oid_begin, int32_t 
     return BN_OK;
 }
 
+int bn_get_gapped_score(int vol_handle, int query_handle, int32_t oid, int32_t chunk_off,
+                        const BnInitHit *init, int64_t n_init, const int32_t *low_score,
+                        BnHSP **hsps, int64_t *n_hsps)
+{
+    Volume *V; Query *Q; Device *D;
+    if (!hsps || !n_hsps || n_init < 0 || (n_init > 0 && !init)) return fail(BN_ERR_INVALID, "bn_get_gapped_score: bad argument");
+    int rc = get_handles(vol_handle, query_handle, &V, &Q, &D);
+    if (rc) return rc;
+    if (oid < 0 || oid >= (int32_t)V->seq_len.size()) return fail(BN_ERR_INVALID, "bn_get_gapped_score: bad oid");
+    std::lock_guard<std::mutex> lk(D->mu);
+    CU_TRY(cudaSetDevice(D->id));
+    if (!Q->dev[V->device].ready) return fail(BN_ERR_INVALID, "query batch is not loaded on the volume's device");
+    std::shared_ptr<ChunkTable> T;
+    rc = build_chunk_table(*V, *Q, oid, oid + 1, D->stream, &T);
+    if (rc) return rc;
+    int32_t chunk = -1;
+    for (size_t c = 0; c < T->hchunks.size(); c++) if (T->hchunks[c].chunk_off == chunk_off) chunk = (int32_t)c;
+    if (chunk < 0) return fail(BN_ERR_INVALID, "bn_get_gapped_score: no subject chunk starts at chunk_off");
+    if (V->ready) CU_TRY(cudaStreamWaitEvent(D->stream, V->ready, 0));
+    *hsps = nullptr; *n_hsps = 0;
+    if (n_init == 0) return BN_OK;
+
+    Workspace &ws = D->ws;
+    cudaStream_t st = D->stream;
+    std::vector<DevInitHit> up((size_t)n_init);
+    for (int64_t i = 0; i < n_init; i++) {
+        const BnInitHit &h = init[i];
+        up[(size_t)i] = DevInitHit{chunk, h.q_off, h.s_off, h.q_start, h.s_start, h.length, h.score, (uint32_t)i};
+    }
+    CU_TRY(ws.counters.reserve(8));
+    CU_TRY(ws.init.reserve((size_t)n_init));
+    const unsigned long long n_ull = (unsigned long long)n_init;
+    CU_TRY(cudaMemsetAsync(ws.counters.p, 0, 8 * sizeof(unsigned long long), st));
+    CU_TRY(cudaMemcpyAsync(ws.counters.p + 2, &n_ull, sizeof n_ull, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(ws.init.p, up.data(), up.size() * sizeof(DevInitHit), cudaMemcpyHostToDevice, st));
+    DevInitHit *h_init = nullptr;
+    DevGapResult *h_gap = nullptr;
+    rc = run_gapped(*D, *V, *Q, *T, n_init, h_init, h_gap, nullptr);
+    if (rc) return rc;
+    std::vector<HostInit> inits((size_t)n_init);
+    for (size_t i = 0; i < inits.size(); i++) {
+        const DevInitHit &h = h_init[i];
+        const DevGapResult &g = h_gap[i];
+        inits[i] = HostInit{h.chunk, h.q_off, h.s_off, h.q_start, h.s_start, h.length, h.score, h.order,
+                            g.q_start, g.q_stop, g.s_start, g.s_stop, g.score, g.q_seed, g.s_seed};
+    }
+    sort_init_hits(inits);
+    std::vector<BnHSP> out;
+    BnStats stats{};
+    replay_gapped(Q->batch, T->hchunks[(size_t)chunk], inits.data(), inits.size(), low_score, out, stats);
+    *hsps = to_malloc(out);
+    *n_hsps = (int64_t)out.size();
+    if (!out.empty() && !*hsps) return fail(BN_ERR_MEMORY, "bn_get_gapped_score: out of memory");
+    return BN_OK;
+}
+
 int bn_query_download_lookup(int query_handle, int device, int32_t *hashtable, int32_t *next_pos)
 {
     std::lock_guard<std::mutex> lk(g_mu);

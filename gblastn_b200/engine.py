@@ -19,7 +19,7 @@ EXPORTS = [
     "bn_init", "bn_release", "bn_device_count", "bn_last_error", "bn_version",
     "bn_db_load", "bn_db_free", "bn_query_load", "bn_query_free",
     "bn_prelim_search", "bn_prelim_search_host", "bn_results_free",
-    "bn_scan_subject", "bn_word_finder", "bn_free", "bn_bench_scan", "bn_query_download_lookup",
+    "bn_scan_subject", "bn_word_finder", "bn_free", "bn_bench_scan", "bn_query_download_lookup", "bn_get_gapped_score",
     "bn_setup_create", "bn_setup_batch", "bn_setup_kbp_std", "bn_setup_kbp_gap",
     "bn_setup_gap_x_dropoff_final", "bn_setup_longest_chain", "bn_setup_free",
 ]
@@ -148,6 +148,25 @@ def scan_subject(volume: Volume, query: Query, oid: int) -> np.ndarray:
                                  C.c_int32(0), C.c_int32(0), C.byref(p), C.byref(n)))
     try:
         return abi.struct_array(p, n.value, abi.PAIR_DTYPE)
+    finally:
+        lib().bn_free(p)
+
+
+def get_gapped_score(volume: Volume, query: Query, oid: int, chunk_off: int, init: np.ndarray,
+                     low_score=None) -> np.ndarray:
+    """BlastGetGappedScoreType drop-in for one subject chunk; `init` is an INIT_DTYPE array."""
+    init = np.ascontiguousarray(init, dtype=abi.INIT_DTYPE)
+    p = C.POINTER(abi.BnHSP)()
+    n = C.c_int64(0)
+    ls = None
+    if low_score is not None:
+        ls_arr = np.ascontiguousarray(low_score, dtype=np.int32)
+        ls = ls_arr.ctypes.data_as(C.c_void_p)
+    _check(lib().bn_get_gapped_score(C.c_int(volume.handle), C.c_int(query.handle), C.c_int32(oid),
+                                     C.c_int32(chunk_off), init.ctypes.data_as(C.c_void_p),
+                                     C.c_int64(init.shape[0]), ls, C.byref(p), C.byref(n)))
+    try:
+        return abi.struct_array(p, n.value, abi.HSP_DTYPE)
     finally:
         lib().bn_free(p)
 

@@ -213,6 +213,15 @@ int  bn_scan_subject(int vol_handle, int query_handle, int32_t oid, int32_t chun
                      int32_t chunk_len, BnOffsetPair **pairs, int64_t *n_pairs);
 int  bn_word_finder(int vol_handle, int query_handle, int32_t oid_begin, int32_t oid_end,
                     BnInitHit **init, int64_t *n_init);
+/* BlastGetGappedScoreType (inc-core/blast_engine.h:212-224), i.e. BLAST_GetGappedScore
+ * (core/blast_gapalign.c:3233-3559) for ONE subject chunk: `init` is the BlastInitHitList the word
+ * finder produced for the chunk that starts at base chunk_off of sequence oid (any order; it is
+ * sorted like Blast_InitHitListSortByScore, ties keep the given order), low_score is
+ * hit_params->low_score (per query, may be NULL).  Returns the HSP list as it stands when the
+ * reference function returns (before purge / sort / E-values), subject offsets chunk-relative. */
+int  bn_get_gapped_score(int vol_handle, int query_handle, int32_t oid, int32_t chunk_off,
+                         const BnInitHit *init, int64_t n_init, const int32_t *low_score,
+                         BnHSP **hsps, int64_t *n_hsps);
 void bn_free(void *p);
 
 /* Parity tap for the device-side table fill: reconstructs hashtable[hashsize] and

@@ -60,6 +60,31 @@ def test_gpu_matches_reference_and_port(name):
         V.free()
 
 
+@pytest.mark.parametrize("name", ["mb_lut11_hash_indels", "blastn_mb11_dp", "mb_long_divergent_tier2",
+                                  "mb_smallna_diagarray"])
+def test_get_gapped_score_drop_in(name):
+    """bn_get_gapped_score == BLAST_GetGappedScore: fed the REFERENCE's init-hit list of every subject
+    chunk, it returns the reference's gapped list of that chunk."""
+    from gblastn_b200 import engine as E, abi
+    r, h, vol = _setup(name)
+    V, Q = E.Volume(vol), E.Query(h)
+    try:
+        init, gapped = r["init"], r["gapped"]
+        chunks = sorted(set(map(tuple, init[:, 0:2].tolist())))
+        assert chunks
+        for oid, chunk_off in chunks:
+            rows = init[(init[:, 0] == oid) & (init[:, 1] == chunk_off)]
+            arr = np.zeros(rows.shape[0], dtype=abi.INIT_DTYPE)
+            for k, col in enumerate(("oid", "chunk_off", "q_off", "s_off", "q_start", "s_start", "length", "score")):
+                arr[col] = rows[:, k]
+            got = E.get_gapped_score(V, Q, oid, chunk_off, arr)
+            want = gapped[(gapped[:, 0] == oid) & (gapped[:, 1] == chunk_off)]
+            from oracle import portdriver as P
+            assert np.array_equal(P.gapped_table(got), want), f"gapped list differs for oid {oid} chunk {chunk_off}"
+    finally:
+        Q.free(); V.free()
+
+
 def test_host_buffer_entry_point():
     from gblastn_b200 import engine as E
     from oracle import portdriver as P
