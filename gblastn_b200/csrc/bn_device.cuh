@@ -248,6 +248,47 @@ struct BucketLaunch {
 cudaError_t launch_bucket_group(const BucketLaunch &L, cudaStream_t st);
 int group_sort_buckets();
 
+// Derived costs of BLAST_AffineGreedyAlign (core/greedy_align.c:792-842): odd rewards double every
+// score, the three operation costs are divided by their gcd (BLAST_Gdb3 core/ncbi_math.c:427).
+struct AffineCosts {
+    int32_t match, mismatch, xdrop;           // after the doubling
+    int32_t op_cost, gap_open, gap_extend;    // after the gcd division
+    int32_t common_factor, max_penalty, xdrop_offset;
+};
+__host__ __device__ inline int32_t bn_gcd(int32_t a, int32_t b)
+{
+    if (b < 0) b = -b;
+    if (b > a) { const int32_t c = a; a = b; b = c; }
+    while (b != 0) { const int32_t c = a % b; a = b; b = c; }
+    return a;
+}
+__host__ __device__ inline AffineCosts affine_costs(int32_t reward, int32_t penalty, int32_t gap_open,
+                                                    int32_t gap_extend, int32_t xdrop)
+{
+    AffineCosts c;
+    c.match = reward; c.mismatch = -penalty; c.xdrop = xdrop;
+    int32_t go = gap_open, ge = gap_extend;
+    if (c.match % 2 == 1) { c.match *= 2; c.mismatch *= 2; c.xdrop *= 2; go *= 2; ge *= 2; }
+    c.op_cost = c.match + c.mismatch;
+    c.gap_open = go;
+    c.gap_extend = ge + c.match / 2;
+    const int32_t g = (c.gap_open == 0) ? bn_gcd(c.op_cost, c.gap_extend)
+                                        : bn_gcd(c.op_cost, bn_gcd(c.gap_open, c.gap_extend));
+    if (g > 1) { c.op_cost /= g; c.gap_open /= g; c.gap_extend /= g; }
+    c.common_factor = g;
+    const int32_t goe = c.gap_open + c.gap_extend;
+    c.max_penalty = c.op_cost > goe ? c.op_cost : goe;
+    c.xdrop_offset = (c.xdrop + c.match / 2) / g + 1;
+    return c;
+}
+// ints of per-thread scratch the affine greedy needs for diagonal half-width D
+__host__ __device__ inline int64_t affine_scratch_ints(const AffineCosts &c, int32_t D)
+{
+    const int64_t dmax = (int64_t)D * c.gap_extend;
+    return 3 * (int64_t)(c.max_penalty + 1) * (2 * (int64_t)D + 6) + 2 * (dmax + 1 + c.max_penalty) +
+           (dmax + 2 + c.xdrop_offset) + 8;
+}
+
 struct GappedLaunch {
     const uint8_t *packed;
     const DevChunk *chunks;

@@ -555,19 +555,23 @@ static int enqueue_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t
     const bool greedy = b.gap_algo == BN_GAP_GREEDY;
     const int32_t xo = greedy_xdrop_offset(b);
     const int wpb = 4;                                   // greedy: warps per block
-    const int32_t tier = greedy ? 254 : 1024;
-    const int64_t per_thread = greedy ? (2 * (2 * (int64_t)tier + 6) + tier + 1 + xo + 8) : 2 * (int64_t)tier;
+    // affine greedy (non-default gap costs with -greedy): thread-per-HSP kernel, rows for max_penalty + 1 distances
+    const bool affine = greedy && (b.gap_open != 0 || b.gap_extend != 0);
+    const AffineCosts ac = affine_costs(b.reward, b.penalty, b.gap_open, b.gap_extend, b.gap_x_dropoff);
+    const int32_t tier = affine ? 128 : (greedy ? 254 : 1024);
+    const int64_t per_thread = affine ? affine_scratch_ints(ac, tier)
+                               : (greedy ? (2 * (2 * (int64_t)tier + 6) + tier + 1 + xo + 8) : 2 * (int64_t)tier);
     GappedLaunch g{};
     g.packed = V.d_packed; g.chunks = T.dev.p; g.init = ws.init.p; g.n_init = ws.counters.p + 2;
     g.max_init = max_init; g.out = ws.gap_out.p;
     g.scratch_ints_per_thread = per_thread; g.tier_d = tier; g.todo = nullptr; g.n_todo = 0;
-    if (greedy) {
+    if (greedy && !affine) {
         // two warps per init-HSP (one per direction), rows in shared memory
         const int blocks = (int)std::min<int64_t>((max_init + 1) / 2, 148 * 8);
         g.scratch = nullptr;
         CU_TRY(launch_greedy_warp(dq, g, wpb, blocks, true, st));
     } else {
-        const int64_t threads = std::min<int64_t>(gapped_threads(), ((max_init + 63) / 64) * 64);
+        const int64_t threads = std::min<int64_t>(affine ? 4096 : gapped_threads(), ((max_init + 63) / 64) * 64);
         CU_TRY(ws.scratch.reserve((size_t)(per_thread * threads)));
         g.scratch = ws.scratch.p;
         g.grid_blocks = (int32_t)(threads / gapped_threads_per_block());
@@ -603,16 +607,23 @@ static int finish_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t 
         for (const auto &c : T.host) max_len = std::max(max_len, c.len);
         int32_t tier;
         int64_t per_thread;
-        if (greedy) {
+        const bool affine = greedy && (b.gap_open != 0 || b.gap_extend != 0);
+        if (affine) {
+            tier = std::min(10000, max_len / 2 + 1);
+            per_thread = affine_scratch_ints(affine_costs(b.reward, b.penalty, b.gap_open, b.gap_extend, b.gap_x_dropoff), tier);
+        } else if (greedy) {
             tier = std::min(10000, max_len / 2 + 1);
             per_thread = 2 * (2 * (int64_t)tier + 6) + tier + 1 + xo + 8;
         } else {
             tier = Q.max_query_length + 8;
             per_thread = 2 * (int64_t)tier;
         }
-        const int tpb = greedy ? wpb : gapped_threads_per_block();      // workers (warps | threads) per block
-        const int hpb = greedy ? wpb / 2 : tpb;                         // init-HSPs in flight per block
+        const bool warp_greedy = greedy && !affine;
+        const int tpb = warp_greedy ? wpb : gapped_threads_per_block();      // workers (warps | threads) per block
+        const int hpb = warp_greedy ? wpb / 2 : tpb;                         // init-HSPs in flight per block
         int64_t blocks = std::min<int64_t>(((int64_t)todo.size() + hpb - 1) / hpb, 64);
+        if (affine)     // worst-case affine rows are megabytes per thread: bound the scratch to ~2 GB
+            blocks = std::max<int64_t>(1, std::min<int64_t>(blocks, ((int64_t)1 << 29) / (per_thread * tpb)));
         CU_TRY(ws.scratch.reserve((size_t)(per_thread * blocks * tpb)));
         CU_TRY(ws.todo.reserve(todo.size()));
         CU_TRY(cudaMemcpyAsync(ws.todo.p, todo.data(), todo.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -621,7 +632,7 @@ static int finish_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t 
         g.max_init = n_init; g.out = ws.gap_out.p;
         g.scratch = ws.scratch.p; g.scratch_ints_per_thread = per_thread; g.tier_d = tier;
         g.todo = ws.todo.p; g.n_todo = (int32_t)todo.size(); g.grid_blocks = (int32_t)blocks;
-        if (greedy) CU_TRY(launch_greedy_warp(dq, g, wpb, (int)blocks, false, st));
+        if (warp_greedy) CU_TRY(launch_greedy_warp(dq, g, wpb, (int)blocks, false, st));
         else CU_TRY(launch_gapped(dq, g, st));
         if (stats) stats->kernel_launches += 1;
         CU_TRY(cudaMemcpyAsync(h_gap, ws.gap_out.p, (size_t)n_init * sizeof(DevGapResult), cudaMemcpyDeviceToHost, st));
@@ -1002,8 +1013,6 @@ static int query_load_impl(const BnQueryBatch *b, int *query_handle, int hook_de
     if (b->window_size > 0 && std::min(b->scan_range, b->window_size - b->word_length) > 0)
         return fail(BN_ERR_UNSUPPORTED, "two-hit mode with an off-diagonal search (scan_range > 0) is not implemented: "
                                         "neighbouring diagonals live in other replay groups");
-    if (b->gap_algo == BN_GAP_GREEDY && (b->gap_open != 0 || b->gap_extend != 0))
-        return fail(BN_ERR_UNSUPPORTED, "affine greedy extension is not implemented");
     if (b->lut_type != BN_LUT_MB && b->lut_type != BN_LUT_SMALL_NA)
         return fail(BN_ERR_UNSUPPORTED, "only eMBLookupTable and eSmallNaLookupTable are supported");
     if (b->lut_type == BN_LUT_MB && (!b->hashtable != !b->next_pos)) return fail(BN_ERR_INVALID, "bn_query_load: hashtable and next_pos must come together");

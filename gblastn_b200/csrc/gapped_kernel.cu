@@ -140,6 +140,133 @@ __device__ int32_t greedy_align(const SeqPair &sp, int32_t xdrop_threshold, int3
     return best_dist;
 }
 
+// BLAST_AffineGreedyAlign, affine body (core/greedy_align.c:817-1237), score only.  One thread, exact
+// serial recurrence.  Scratch (ints): (max_penalty + 1) rows x (2D + 6) diagonals x {insert, match,
+// delete}, diagonal bounds for D * gap_extend + 1 (+ max_penalty) distances, per-distance best scores.
+// Row of distance d = slot d % (max_penalty + 1): the reference recycles rows the same way when no
+// traceback is kept (:1165-1172).  Diagonal k of the reference is stored at k - diag_origin + D + 2; a
+// gap costs at least gap_extend, so |k - diag_origin| <= d / gap_extend + 1 <= D + 1 while d <= D * gap_extend.
+__device__ int32_t greedy_align_affine(const SeqPair &sp, const AffineCosts &ac, int32_t &seq1_len, int32_t &seq2_len,
+                                       int32_t *scratch, int32_t D, GreedySeed &seed, bool &overflow)
+{
+    const int32_t kInvalidDiag = 100000000;
+    const int32_t len1 = sp.len1, len2 = sp.len2;
+    const int32_t match_half = ac.match / 2;
+    const int32_t op_cost = ac.op_cost, gap_extend = ac.gap_extend, goe = ac.gap_open + ac.gap_extend;
+    const int32_t max_penalty = ac.max_penalty, nrows = ac.max_penalty + 1;
+    const int32_t max_dist = min(GREEDY_MAX_COST, len2 / 2 + 1);
+    const int32_t scaled_max_dist = max_dist * gap_extend;
+    const int32_t d_cap = D * gap_extend;
+    const int32_t origin = D + 2, width = 2 * D + 6;
+
+    int32_t index = first_mismatch(sp, 0, 0);
+    seq1_len = index; seq2_len = index;
+    int32_t seq1_index = index, seq2_index;
+    seed.start_q = 0; seed.start_s = 0;
+    int32_t longest_match_run = index;
+    seed.match_length = index;
+    if (index == len1 || index == len2) return index * ac.match;
+
+    int32_t *rows = scratch;                                            // [nrows][width][3]
+    int32_t *diag_lower = rows + 3 * (int64_t)nrows * width + max_penalty;
+    int32_t *diag_upper = diag_lower + d_cap + 1 + max_penalty;
+    int32_t *max_score_mem = diag_upper + d_cap + 1;
+    int32_t *max_score = max_score_mem + ac.xdrop_offset;
+#define AFF(dd, kk, f) rows[(((int64_t)((dd) % nrows)) * width + (kk)) * 3 + (f)]       // f: 0 insert, 1 match, 2 delete
+    for (int32_t i = 0; i < ac.xdrop_offset; i++) max_score_mem[i] = 0;
+    for (int32_t i = 1; i <= max_penalty; i++) { diag_lower[-i] = kInvalidDiag; diag_upper[-i] = -kInvalidDiag; }
+    AFF(0, origin, 1) = seq1_index;
+    AFF(0, origin, 0) = GREEDY_INVALID;
+    AFF(0, origin, 2) = GREEDY_INVALID;
+    max_score[0] = seq1_index * ac.match;
+    diag_lower[0] = origin; diag_upper[0] = origin;
+    int32_t curr_lower = origin - 1, curr_upper = origin + 1;
+    int32_t end1_diag = 0, end2_diag = 0, num_nonempty = 1;
+    int32_t best_dist = 0;
+    int32_t d = 1;
+
+    while (d <= scaled_max_dist) {
+        if (d > d_cap) { overflow = true; return 0; }
+        int32_t curr_extent = 0, curr_seq2_index = 0, curr_diag = 0;
+        const int32_t tmp_lower = curr_lower, tmp_upper = curr_upper;
+        int32_t xdrop_score = max_score[d - ac.xdrop_offset] + ac.common_factor * d - ac.xdrop;
+        {   // (Int4)ceil((double)x / match_half), match_half >= 1
+            int32_t qd = xdrop_score / match_half;
+            if (xdrop_score % match_half > 0) ++qd;
+            xdrop_score = qd < 0 ? 0 : qd;
+        }
+        const int32_t lo_goe = diag_lower[d - goe], up_goe = diag_upper[d - goe];
+        const int32_t lo_ge = diag_lower[d - gap_extend], up_ge = diag_upper[d - gap_extend];
+        const int32_t lo_op = diag_lower[d - op_cost], up_op = diag_upper[d - op_cost];
+        for (int32_t k = tmp_lower; k <= tmp_upper; k++) {
+            seq2_index = GREEDY_INVALID;
+            if (k + 1 <= up_goe && k + 1 >= lo_goe) seq2_index = AFF(d - goe, k + 1, 1);
+            if (k + 1 <= up_ge && k + 1 >= lo_ge) {
+                const int32_t v = AFF(d - gap_extend, k + 1, 2);
+                if (seq2_index < v) seq2_index = v;
+            }
+            const int32_t del = (seq2_index == GREEDY_INVALID) ? GREEDY_INVALID : seq2_index + 1;
+            AFF(d, k, 2) = del;
+
+            seq2_index = GREEDY_INVALID;
+            if (k - 1 <= up_goe && k - 1 >= lo_goe) seq2_index = AFF(d - goe, k - 1, 1);
+            if (k - 1 <= up_ge && k - 1 >= lo_ge) {
+                const int32_t v = AFF(d - gap_extend, k - 1, 0);
+                if (seq2_index < v) seq2_index = v;
+            }
+            AFF(d, k, 0) = seq2_index;
+
+            seq2_index = max(seq2_index, del);
+            if (k <= up_op && k >= lo_op) seq2_index = max(seq2_index, AFF(d - op_cost, k, 1) + 1);
+            seq1_index = seq2_index + k - origin;
+            if (seq2_index < 0 || seq1_index + seq2_index < xdrop_score) {
+                if (k == curr_lower) curr_lower++;
+                else AFF(d, k, 1) = GREEDY_INVALID;
+                continue;
+            }
+            curr_upper = k;
+            index = first_mismatch(sp, seq1_index, seq2_index);
+            if (index > longest_match_run) {
+                seed.start_q = seq1_index; seed.start_s = seq2_index;
+                seed.match_length = longest_match_run = index;
+            }
+            seq1_index += index; seq2_index += index;
+            AFF(d, k, 1) = seq2_index;
+            if (seq1_index + seq2_index > curr_extent) {
+                curr_extent = seq1_index + seq2_index;
+                curr_seq2_index = seq2_index;
+                curr_diag = k;
+            }
+            if (seq1_index == len1) { curr_upper = k; end1_diag = k - 1; }
+            if (seq2_index == len2) { curr_lower = k; end2_diag = k + 1; }
+        }
+        const int32_t curr_score = curr_extent * match_half - d * ac.common_factor;
+        if (curr_score > max_score[d - 1]) {
+            max_score[d] = curr_score;
+            best_dist = d;
+            seq2_len = curr_seq2_index;
+            seq1_len = curr_seq2_index + curr_diag - origin;
+        } else max_score[d] = max_score[d - 1];
+        if (curr_lower <= curr_upper) {
+            num_nonempty++;
+            diag_lower[d] = curr_lower; diag_upper[d] = curr_upper;
+        } else { diag_lower[d] = kInvalidDiag; diag_upper[d] = -kInvalidDiag; }
+        if (diag_lower[d - max_penalty] <= diag_upper[d - max_penalty]) num_nonempty--;
+        if (num_nonempty == 0) break;
+
+        d++;
+        if (d > d_cap) { if (d <= scaled_max_dist) { overflow = true; return 0; } break; }
+        curr_lower = min(diag_lower[d - goe], diag_lower[d - gap_extend]) - 1;
+        curr_lower = min(curr_lower, diag_lower[d - op_cost]);
+        if (end2_diag > 0) curr_lower = max(curr_lower, end2_diag);
+        curr_upper = max(diag_upper[d - goe], diag_upper[d - gap_extend]) + 1;
+        curr_upper = max(curr_upper, diag_upper[d - op_cost]);
+        if (end1_diag > 0) curr_upper = min(curr_upper, end1_diag);
+    }
+#undef AFF
+    return max_score[best_dist];
+}
+
 __device__ void greedy_gapped(const DevQuery &q, const uint8_t *packed, int32_t ctx_off, int32_t qlen,
                               int64_t chunk_base, int32_t slen, int32_t q_off, int32_t s_off,
                               int32_t *scratch, int32_t D, DevGapResult &g)
@@ -150,17 +277,23 @@ __device__ void greedy_gapped(const DevQuery &q, const uint8_t *packed, int32_t 
     int32_t q_ext_r, s_ext_r, q_ext_l, s_ext_l;
     GreedySeed fwd, rev;
     bool overflow = false;
+    const bool affine = q.gap_open != 0 || q.gap_extend != 0;
+    const AffineCosts ac = affine_costs(q.reward, q.penalty, q.gap_open, q.gap_extend, q.gap_x_dropoff);
     SeqPair sp;
     sp.q = &q; sp.packed = packed;
     sp.qbase = ctx_off + q_off; sp.sbase = chunk_base + s_off;
     sp.len1 = qlen - q_off; sp.len2 = slen - s_off; sp.reverse = false;
-    int32_t score = greedy_align(sp, xd, match, mismatch, q_ext_r, s_ext_r, row0, row1, ms, D, fwd, overflow);
+    int32_t score = affine ? greedy_align_affine(sp, ac, q_ext_r, s_ext_r, scratch, D, fwd, overflow)
+                           : greedy_align(sp, xd, match, mismatch, q_ext_r, s_ext_r, row0, row1, ms, D, fwd, overflow);
     if (!overflow) {
         sp.qbase = ctx_off; sp.sbase = chunk_base; sp.len1 = q_off; sp.len2 = s_off; sp.reverse = true;
-        score += greedy_align(sp, xd, match, mismatch, q_ext_l, s_ext_l, row0, row1, ms, D, rev, overflow);
+        score += affine ? greedy_align_affine(sp, ac, q_ext_l, s_ext_l, scratch, D, rev, overflow)
+                        : greedy_align(sp, xd, match, mismatch, q_ext_l, s_ext_l, row0, row1, ms, D, rev, overflow);
     }
     if (overflow) { g.status = 1; return; }
-    score = (q_ext_r + s_ext_r + q_ext_l + s_ext_l) * q.reward / 2 - score * (q.reward - q.penalty);
+    // the basic algorithm returns distances, the affine one scores in (possibly doubled) units (:2683-2690)
+    if (!affine) score = (q_ext_r + s_ext_r + q_ext_l + s_ext_l) * q.reward / 2 - score * (q.reward - q.penalty);
+    else if (q.reward % 2 == 1) score /= 2;
 
     const int32_t q_box_l = q_off - q_ext_l, s_box_l = s_off - s_ext_l;
     const int32_t q_box_r = q_off + q_ext_r, s_box_r = s_off + s_ext_r;

@@ -724,6 +724,163 @@ static int32_t greedy_align(const uint8_t *seq1, int32_t len1, const uint8_t *se
     return best_dist;
 }
 
+/* BLAST_Gcd / BLAST_Gdb3 core/ncbi_math.c:405-440 */
+static int32_t gcd_i(int32_t a, int32_t b)
+{
+    int32_t c;
+    b = abs(b);
+    if (b > a) { c = a; a = b; b = c; }
+    while (b != 0) { c = a % b; a = b; b = c; }
+    return a;
+}
+static int32_t gdb3(int32_t *a, int32_t *b, int32_t *c)
+{
+    int32_t g = (*b == 0) ? gcd_i(*a, *c) : gcd_i(*a, gcd_i(*b, *c));
+    if (g > 1) { *a /= g; *b /= g; *c /= g; }
+    return g;
+}
+
+/* BLAST_AffineGreedyAlign core/greedy_align.c:755-1237, affine body, score only (edit_block == NULL:
+ * rows of last_seq2_off are recycled every max_penalty + 1 distances, :1165-1172).  Scores arrive
+ * already doubled when the reward is odd (:792-798, done by the caller here).  Returns the SCORE
+ * (max_score[best_dist], or index * match_score on the early exit), not a distance. */
+typedef struct AffOff { int32_t insert_off, match_off, delete_off; } AffOff;
+static int32_t greedy_align_affine(const uint8_t *seq1, int32_t len1, const uint8_t *seq2, int32_t len2,
+                                   int reverse, int32_t xdrop_threshold, int32_t match_score,
+                                   int32_t mismatch_score, int32_t in_gap_open, int32_t in_gap_extend,
+                                   int32_t *seq1_len, int32_t *seq2_len, int rem, GreedySeed *seed)
+{
+    const int32_t kInvalidDiag = 100000000;
+    int32_t seq1_index, seq2_index, index, d, k, max_dist, scaled_max_dist, diag_origin;
+    int32_t best_dist = 0, best_diag = 0, longest_match_run, xdrop_offset;
+    int32_t end1_diag = 0, end2_diag = 0, curr_diag_lower, curr_diag_upper, num_nonempty_dist;
+    int32_t match_score_half = match_score / 2;
+    int32_t op_cost = match_score + mismatch_score;
+    int32_t gap_open = in_gap_open, gap_extend = in_gap_extend + match_score_half;
+    int32_t score_common_factor = gdb3(&op_cost, &gap_open, &gap_extend);
+    int32_t gap_open_extend = gap_open + gap_extend;
+    int32_t max_penalty = PMAX(op_cost, gap_open_extend);
+    int32_t width, nrows, result;
+    AffOff *store, **rows;
+    int32_t *max_score_base, *max_score, *bounds, *diag_lower, *diag_upper;
+
+    max_dist = PMIN(GREEDY_MAX_COST, len2 / 2 + 1);
+    scaled_max_dist = max_dist * gap_extend;
+    diag_origin = max_dist + 2;
+    xdrop_offset = (xdrop_threshold + match_score_half) / score_common_factor + 1;
+
+    index = first_mismatch(seq1, seq2, len1, len2, 0, 0, reverse, rem);
+    *seq1_len = index; *seq2_len = index;
+    seq1_index = index;
+    seed->start_q = 0; seed->start_s = 0;
+    seed->match_length = longest_match_run = index;
+    if (index == len1 || index == len2) return index * match_score;
+
+    width = 2 * max_dist + 6;
+    nrows = max_penalty + 1;
+    store = (AffOff *)calloc((size_t)width * (size_t)nrows, sizeof(AffOff));
+    rows = (AffOff **)malloc(((size_t)scaled_max_dist + 2) * sizeof(AffOff *));
+    max_score_base = (int32_t *)calloc((size_t)scaled_max_dist + 2 + (size_t)xdrop_offset, 4);
+    bounds = (int32_t *)calloc(2 * ((size_t)scaled_max_dist + 1 + (size_t)max_penalty), 4);
+    for (index = 0; index <= max_penalty && index <= scaled_max_dist; index++) rows[index] = store + (size_t)index * width;
+
+    max_score = max_score_base + xdrop_offset;
+    diag_lower = bounds;
+    diag_upper = bounds + scaled_max_dist + 1 + max_penalty;
+    for (index = 0; index < max_penalty; index++) { diag_lower[index] = kInvalidDiag; diag_upper[index] = -kInvalidDiag; }
+    diag_lower += max_penalty; diag_upper += max_penalty;
+
+    rows[0][diag_origin].match_off = seq1_index;
+    rows[0][diag_origin].insert_off = GREEDY_INVALID;
+    rows[0][diag_origin].delete_off = GREEDY_INVALID;
+    max_score[0] = seq1_index * match_score;
+    diag_lower[0] = diag_origin; diag_upper[0] = diag_origin;
+    curr_diag_lower = diag_origin - 1; curr_diag_upper = diag_origin + 1;
+    num_nonempty_dist = 1;
+    d = 1;
+
+    while (d <= scaled_max_dist) {
+        int32_t xdrop_score, curr_score, curr_extent = 0, curr_seq2_index = 0, curr_diag = 0;
+        const int32_t tmp_lower = curr_diag_lower, tmp_upper = curr_diag_upper;
+        AffOff *cur = rows[d];
+
+        xdrop_score = max_score[d - xdrop_offset] + score_common_factor * d - xdrop_threshold;
+        xdrop_score = (int32_t)ceil((double)xdrop_score / match_score_half);
+        if (xdrop_score < 0) xdrop_score = 0;
+
+        for (k = tmp_lower; k <= tmp_upper; k++) {
+            seq2_index = GREEDY_INVALID;
+            if (k + 1 <= diag_upper[d - gap_open_extend] && k + 1 >= diag_lower[d - gap_open_extend])
+                seq2_index = rows[d - gap_open_extend][k + 1].match_off;
+            if (k + 1 <= diag_upper[d - gap_extend] && k + 1 >= diag_lower[d - gap_extend] &&
+                seq2_index < rows[d - gap_extend][k + 1].delete_off)
+                seq2_index = rows[d - gap_extend][k + 1].delete_off;
+            cur[k].delete_off = (seq2_index == GREEDY_INVALID) ? GREEDY_INVALID : seq2_index + 1;
+
+            seq2_index = GREEDY_INVALID;
+            if (k - 1 <= diag_upper[d - gap_open_extend] && k - 1 >= diag_lower[d - gap_open_extend])
+                seq2_index = rows[d - gap_open_extend][k - 1].match_off;
+            if (k - 1 <= diag_upper[d - gap_extend] && k - 1 >= diag_lower[d - gap_extend] &&
+                seq2_index < rows[d - gap_extend][k - 1].insert_off)
+                seq2_index = rows[d - gap_extend][k - 1].insert_off;
+            cur[k].insert_off = seq2_index;
+
+            seq2_index = PMAX(cur[k].insert_off, cur[k].delete_off);
+            if (k <= diag_upper[d - op_cost] && k >= diag_lower[d - op_cost])
+                seq2_index = PMAX(seq2_index, rows[d - op_cost][k].match_off + 1);
+            seq1_index = seq2_index + k - diag_origin;
+
+            if (seq2_index < 0 || seq1_index + seq2_index < xdrop_score) {
+                if (k == curr_diag_lower) curr_diag_lower++;
+                else cur[k].match_off = GREEDY_INVALID;
+                continue;
+            }
+            curr_diag_upper = k;
+            index = first_mismatch(seq1, seq2, len1, len2, seq1_index, seq2_index, reverse, rem);
+            if (index > longest_match_run) {
+                seed->start_q = seq1_index; seed->start_s = seq2_index;
+                seed->match_length = longest_match_run = index;
+            }
+            seq1_index += index; seq2_index += index;
+            cur[k].match_off = seq2_index;
+            if (seq1_index + seq2_index > curr_extent) {
+                curr_extent = seq1_index + seq2_index;
+                curr_seq2_index = seq2_index;
+                curr_diag = k;
+            }
+            if (seq1_index == len1) { curr_diag_upper = k; end1_diag = k - 1; }
+            if (seq2_index == len2) { curr_diag_lower = k; end2_diag = k + 1; }
+        }
+
+        curr_score = curr_extent * match_score_half - d * score_common_factor;
+        if (curr_score > max_score[d - 1]) {
+            max_score[d] = curr_score;
+            best_dist = d; best_diag = curr_diag;
+            *seq2_len = curr_seq2_index;
+            *seq1_len = curr_seq2_index + best_diag - diag_origin;
+        } else max_score[d] = max_score[d - 1];
+
+        if (curr_diag_lower <= curr_diag_upper) {
+            num_nonempty_dist++;
+            diag_lower[d] = curr_diag_lower; diag_upper[d] = curr_diag_upper;
+        } else { diag_lower[d] = kInvalidDiag; diag_upper[d] = -kInvalidDiag; }
+        if (diag_lower[d - max_penalty] <= diag_upper[d - max_penalty]) num_nonempty_dist--;
+        if (num_nonempty_dist == 0) break;
+
+        d++;
+        curr_diag_lower = PMIN(diag_lower[d - gap_open_extend], diag_lower[d - gap_extend]) - 1;
+        curr_diag_lower = PMIN(curr_diag_lower, diag_lower[d - op_cost]);
+        if (end2_diag > 0) curr_diag_lower = PMAX(curr_diag_lower, end2_diag);
+        curr_diag_upper = PMAX(diag_upper[d - gap_open_extend], diag_upper[d - gap_extend]) + 1;
+        curr_diag_upper = PMAX(curr_diag_upper, diag_upper[d - op_cost]);
+        if (end1_diag > 0) curr_diag_upper = PMIN(curr_diag_upper, end1_diag);
+        if (d > max_penalty && d <= scaled_max_dist) rows[d] = rows[d - max_penalty - 1];
+    }
+    result = max_score[best_dist];
+    free(store); free(rows); free(max_score_base); free(bounds);
+    return result;
+}
+
 typedef struct GapResult {
     int32_t q_start, q_stop, s_start, s_stop, score, q_seed, s_seed;
 } GapResult;
@@ -733,18 +890,26 @@ typedef struct GapResult {
  * match/mismatch/xdrop). */
 static void greedy_gapped(const uint8_t *query, const uint8_t *subject, int32_t qlen, int32_t slen,
                           int32_t q_off, int32_t s_off, int32_t reward, int32_t penalty,
-                          int32_t X, GreedyMem *mem, GapResult *g)
+                          int32_t gap_open, int32_t gap_extend, int32_t X, GreedyMem *mem, GapResult *g)
 {
     int32_t q_ext_l, q_ext_r, s_ext_l, s_ext_r, score;
-    int32_t match = reward, mismatch = -penalty, xd = X;
+    int32_t match = reward, mismatch = -penalty, xd = X, go = gap_open, ge = gap_extend;
     GreedySeed fwd, rev;
-    if (match % 2 == 1) { match *= 2; mismatch *= 2; xd *= 2; }
+    if (match % 2 == 1) { match *= 2; mismatch *= 2; xd *= 2; go *= 2; ge *= 2; }
 
-    score = greedy_align(query + q_off, qlen - q_off, subject + s_off / 4, slen - s_off, 0, xd,
-                         match, mismatch, &q_ext_r, &s_ext_r, mem, s_off % 4, &fwd);
-    score += greedy_align(query, q_off, subject, s_off, 1, xd, match, mismatch, &q_ext_l, &s_ext_l,
-                          mem, 0, &rev);
-    score = (q_ext_r + s_ext_r + q_ext_l + s_ext_l) * reward / 2 - score * (reward - penalty);
+    if (go == 0 && ge == 0) {
+        score = greedy_align(query + q_off, qlen - q_off, subject + s_off / 4, slen - s_off, 0, xd,
+                             match, mismatch, &q_ext_r, &s_ext_r, mem, s_off % 4, &fwd);
+        score += greedy_align(query, q_off, subject, s_off, 1, xd, match, mismatch, &q_ext_l, &s_ext_l,
+                              mem, 0, &rev);
+        score = (q_ext_r + s_ext_r + q_ext_l + s_ext_l) * reward / 2 - score * (reward - penalty);
+    } else {
+        score = greedy_align_affine(query + q_off, qlen - q_off, subject + s_off / 4, slen - s_off, 0, xd,
+                                    match, mismatch, go, ge, &q_ext_r, &s_ext_r, s_off % 4, &fwd);
+        score += greedy_align_affine(query, q_off, subject, s_off, 1, xd, match, mismatch, go, ge,
+                                     &q_ext_l, &s_ext_l, 0, &rev);
+        if (reward % 2 == 1) score /= 2;
+    }
     {
         int32_t q_box_l = q_off - q_ext_l, s_box_l = s_off - s_ext_l;
         int32_t q_box_r = q_off + q_ext_r, s_box_r = s_off + s_ext_r;
@@ -980,7 +1145,7 @@ static void gapped_stage(const BnQueryBatch *b, const Subject *S, const BnInitHi
             q_off = t.q_off + init[i].length / 2;
             s_off = init[i].s_start + init[i].length / 2;
             greedy_gapped(query + qstart0, S->seq, c->query_length, S->len, q_off, s_off,
-                          b->reward, b->penalty, b->gap_x_dropoff, gm, &g);
+                          b->reward, b->penalty, b->gap_open, b->gap_extend, b->gap_x_dropoff, gm, &g);
         } else {
             if (t.s_end >= s_off + 8) { s_off += 3; q_off += 3; }
             dp_gapped(query + qstart0, S->seq, c->query_length, S->len, q_off, s_off, b->matrix,
@@ -1115,7 +1280,6 @@ int port_prelim_search(const BnQueryBatch *b, const uint8_t *packed, const int64
     int32_t *best_scores = NULL; int64_t *n_lists = NULL;   /* per query: hitlist model */
 
     memset(out, 0, sizeof *out);
-    if (b->gap_algo == BN_GAP_GREEDY && (b->gap_open != 0 || b->gap_extend != 0)) return BN_ERR_UNSUPPORTED;
     vec_init(&init, sizeof(BnInitHit)); vec_init(&gapped_tap, sizeof(BnHSP));
     vec_init(&final_, sizeof(BnHSP)); vec_init(&scanv, sizeof(BnOffsetPair));
     vec_init(&scan_oid, 4); vec_init(&scan_chunk, 4);
@@ -1217,7 +1381,7 @@ int port_greedy_align(const uint8_t *query, int32_t qlen, const uint8_t *subject
     gm.row[0] = (int32_t *)calloc((size_t)(2 * gm.max_d + 6) * 2, 4);
     gm.row[1] = gm.row[0] + 2 * gm.max_d + 6;
     gm.max_score = (int32_t *)calloc((size_t)gm.max_d + 1 + 4096, 4);
-    greedy_gapped(query, subject_packed, qlen, slen, q_off, s_off, reward, penalty, xdrop, &gm, &g);
+    greedy_gapped(query, subject_packed, qlen, slen, q_off, s_off, reward, penalty, 0, 0, xdrop, &gm, &g);
     o[0] = g.q_start; o[1] = g.q_stop; o[2] = g.s_start; o[3] = g.s_stop; o[4] = g.score;
     o[5] = g.q_seed; o[6] = g.s_seed;
     free(gm.row[0]); free(gm.max_score);

@@ -65,6 +65,19 @@ CASES = {
                                      sub=0.05, indel=0.01, planted=1.0),
     "blastn_two_hit_array_ws7": dict(task="blastn", cfg={"word_size": 7, "window_size": 30}, seq_lens=[20_000, 5_000],
                                      vol_seed=18, nq=2, qlen=300, q_seed=29, sub=0.10, indel=0.01, planted=1.0),
+    # affine greedy (BLAST_AffineGreedyAlign body): -greedy with explicit gap costs
+    "mb_affine_greedy_5_2": dict(task="megablast", cfg={"greedy": 1, "gap_open": 5, "gap_extend": 2},
+                                 seq_lens=[300_000, 50_000, 777, 120_001], vol_seed=2, nq=40, qlen=500, q_seed=12,
+                                 sub=0.03, indel=0.004, planted=0.8),
+    "blastn_affine_greedy_5_2": dict(task="blastn", cfg={"greedy": 1, "gap_open": 5, "gap_extend": 2},
+                                     seq_lens=[300_000, 50_000, 777, 120_001, 13], vol_seed=2, nq=30, qlen=800,
+                                     q_seed=14, sub=0.08, indel=0.01, planted=0.8),
+    "mb_affine_greedy_long_tier2": dict(task="megablast", cfg={"greedy": 1, "gap_open": 3, "gap_extend": 1},
+                                        seq_lens=[600_000, 200_000], vol_seed=12, nq=3, qlen=30_000, q_seed=23,
+                                        sub=0.03, indel=0.002, planted=1.0),
+    "mb_affine_greedy_0_2": dict(task="megablast", cfg={"word_size": 16, "greedy": 1, "gap_open": 0, "gap_extend": 2},
+                                 seq_lens=[200_000, 90_000], vol_seed=5, nq=25, qlen=600, q_seed=16, sub=0.06,
+                                 indel=0.005, planted=0.8),
     # empty result: random queries only
     "mb_no_hits": dict(task="megablast", cfg={}, seq_lens=[100_000], vol_seed=11,
                        nq=5, qlen=400, q_seed=22, sub=0.0, indel=0.0, planted=0.0),

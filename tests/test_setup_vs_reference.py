@@ -61,10 +61,18 @@ def _compare(r, s):
         assert c.cutoff_score == r["ctx_cutoff_score"][i]
         assert c.reduced_cutoff == r["ctx_reduced_cutoff"][i]
         assert c.gapped_cutoff == r["ctx_gapped_cutoff"][i]
-        assert c.gap_lambda == r["ctx_kbp_gap"][i, 0]
-        assert c.gap_logK == r["ctx_kbp_gap"][i, 2]
-    assert np.array_equal(s.kbp_gap(), r["ctx_kbp_gap"])
+    # The ungapped Karlin-Altschul block comes out of a Newton-Raphson iteration that the reference
+    # compiles with -ffast-math (core/Makefile.blast.lib:19): equal to 1e-12 relative, not bit for bit.
     assert np.allclose(s.kbp_std(), r["ctx_kbp_std"], rtol=1e-12, atol=0)
+    if np.array_equal(r["ctx_kbp_gap"], r["ctx_kbp_std"]):
+        # gap costs beyond the tabulated ones: Blast_KarlinBlkNuclGappedCalc copies the ungapped block
+        # (core/blast_stat.c:3868-3871), so the same tolerance applies
+        assert np.allclose(s.kbp_gap(), r["ctx_kbp_gap"], rtol=1e-12, atol=0)
+    else:
+        for i, c in enumerate(ctx):
+            assert c.gap_lambda == r["ctx_kbp_gap"][i, 0]
+            assert c.gap_logK == r["ctx_kbp_gap"][i, 2]
+        assert np.array_equal(s.kbp_gap(), r["ctx_kbp_gap"])
 
 
 @pytest.mark.parametrize("name", cases.ALL)
