@@ -76,6 +76,11 @@ class BnResults(C.Structure):
                 ("stats", BnStats)]
 
 
+class BnDbFileInfo(C.Structure):
+    _fields_ = [("n_seq", C.c_int32), ("max_len", C.c_int32), ("total_bases", C.c_int64),
+                ("nsq_bytes", C.c_int64), ("title", C.c_char * 256)]
+
+
 class BnSetupOptions(C.Structure):
     _fields_ = [("task", C.c_int32), ("word_size", C.c_int32), ("reward", C.c_int32),
                 ("penalty", C.c_int32), ("gap_open", C.c_int32), ("gap_extend", C.c_int32),

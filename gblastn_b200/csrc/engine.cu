@@ -20,6 +20,7 @@
 #include <cub/cub.cuh>
 
 #include "bn_device.cuh"
+#include "dbfile.h"
 #include "hostpost.h"
 
 namespace bn {
@@ -988,6 +989,69 @@ int bn_db_load(int device, const uint8_t *packed, int64_t packed_bytes, const in
                const int32_t *seq_len, int32_t n_seq, int *vol_handle)
 {
     return db_load_impl(device, packed, packed_bytes, seq_byte_off, seq_len, n_seq, false, vol_handle);
+}
+
+int bn_dbfile_index(const char *nin_path, const char *nsq_path, BnDbFileInfo *info, int64_t *seq_byte_off,
+                    int32_t *seq_len)
+{
+    if (!nin_path || !nsq_path || !info) return fail(BN_ERR_INVALID, "bn_dbfile_index: bad argument");
+    DbIndex idx;
+    std::string err;
+    if (!read_nin(nin_path, idx, err)) return fail(BN_ERR_INVALID, "bn_dbfile_index: " + err);
+    MappedFile nsq;
+    if (!nsq.open(nsq_path, err)) return fail(BN_ERR_INVALID, "bn_dbfile_index: " + err);
+    std::vector<int64_t> off;
+    std::vector<int32_t> len;
+    if (!sequence_table(idx, nsq.data(), nsq.size(), off, len, err)) return fail(BN_ERR_INVALID, "bn_dbfile_index: " + err);
+    memset(info, 0, sizeof *info);
+    info->n_seq = idx.n_seq; info->max_len = idx.max_len;
+    info->total_bases = (int64_t)idx.total_len; info->nsq_bytes = nsq.size();
+    strncpy(info->title, idx.title.c_str(), sizeof info->title - 1);
+    if (seq_byte_off) memcpy(seq_byte_off, off.data(), off.size() * sizeof(int64_t));
+    if (seq_len) memcpy(seq_len, len.data(), len.size() * sizeof(int32_t));
+    return BN_OK;
+}
+
+int bn_dbfile_write(const char *nin_path, const char *nsq_path, const char *title, const uint8_t *packed,
+                    const int64_t *seq_byte_off, const int32_t *seq_len, int32_t n_seq)
+{
+    if (!nin_path || !nsq_path || !packed || !seq_byte_off || !seq_len || n_seq < 0)
+        return fail(BN_ERR_INVALID, "bn_dbfile_write: bad argument");
+    std::string err;
+    if (!write_volume(nin_path, nsq_path, title, packed, seq_byte_off, seq_len, n_seq, err))
+        return fail(BN_ERR_INVALID, "bn_dbfile_write: " + err);
+    return BN_OK;
+}
+
+int bn_db_load_files(int device, const char *nin_path, const char *nsq_path, int *vol_handle)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!nin_path || !nsq_path || !vol_handle) return fail(BN_ERR_INVALID, "bn_db_load_files: bad argument");
+    Device *D = device_at(device);
+    if (!D) return fail(BN_ERR_INVALID, "bn_db_load_files: bad device");
+    DbIndex idx;
+    std::string err;
+    if (!read_nin(nin_path, idx, err)) return fail(BN_ERR_INVALID, "bn_db_load_files: " + err);
+    MappedFile nsq;
+    if (!nsq.open(nsq_path, err)) return fail(BN_ERR_INVALID, "bn_db_load_files: " + err);
+    auto V = std::make_unique<Volume>();
+    V->device = device; V->bytes = nsq.size();
+    if (!sequence_table(idx, nsq.data(), nsq.size(), V->byte_off, V->seq_len, err))
+        return fail(BN_ERR_INVALID, "bn_db_load_files: " + err);
+    CU_TRY(cudaSetDevice(D->id));
+    // the file goes to the device as it is (the bytes between sequences are ambiguity data the
+    // preliminary stage never reads); zeroed pads in front and behind as in bn_db_load
+    CU_TRY(cudaMallocAsync((void **)&V->d_raw, (size_t)nsq.size() + 192, D->stream));
+    V->d_packed = V->d_raw + 64;
+    CU_TRY(cudaMemsetAsync(V->d_raw, 0, 64, D->stream));
+    CU_TRY(cudaMemcpyAsync(V->d_packed, nsq.data(), (size_t)nsq.size(), cudaMemcpyHostToDevice, D->stream));
+    CU_TRY(cudaMemsetAsync(V->d_packed + nsq.size(), 0, 128, D->stream));
+    CU_TRY(cudaStreamSynchronize(D->stream));
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_volumes.push_back(std::move(V));
+    *vol_handle = (int)g_volumes.size() - 1;
+    return BN_OK;
 }
 
 int bn_db_free(int h)

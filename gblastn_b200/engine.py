@@ -20,6 +20,7 @@ EXPORTS = [
     "bn_db_load", "bn_db_free", "bn_query_load", "bn_query_free",
     "bn_prelim_search", "bn_prelim_search_host", "bn_results_free",
     "bn_scan_subject", "bn_word_finder", "bn_free", "bn_bench_scan", "bn_query_download_lookup", "bn_get_gapped_score",
+    "bn_dbfile_index", "bn_db_load_files", "bn_dbfile_write",
     "bn_setup_create", "bn_setup_batch", "bn_setup_kbp_std", "bn_setup_kbp_gap",
     "bn_setup_gap_x_dropoff_final", "bn_setup_longest_chain", "bn_setup_free",
 ]
@@ -89,6 +90,38 @@ class Volume:
         if self.handle >= 0:
             lib().bn_db_free(C.c_int(self.handle))
             self.handle = -1
+
+
+class FileVolume(Volume):
+    """A volume loaded from BLAST database files (.nin + .nsq) straight into HBM."""
+
+    def __init__(self, nin_path, nsq_path, device=0):
+        h = C.c_int(-1)
+        _check(lib().bn_db_load_files(C.c_int(device), str(nin_path).encode(), str(nsq_path).encode(), C.byref(h)))
+        self.handle = h.value
+        self.device = device
+
+
+def dbfile_index(nin_path, nsq_path):
+    """Host-only parse of a volume's index: (info dict, byte offsets into the .nsq, lengths)."""
+    info = abi.BnDbFileInfo()
+    _check(lib().bn_dbfile_index(str(nin_path).encode(), str(nsq_path).encode(), C.byref(info), None, None))
+    off = np.zeros(info.n_seq, dtype=np.int64)
+    ln = np.zeros(info.n_seq, dtype=np.int32)
+    _check(lib().bn_dbfile_index(str(nin_path).encode(), str(nsq_path).encode(), C.byref(info),
+                                 off.ctypes.data_as(C.c_void_p), ln.ctypes.data_as(C.c_void_p)))
+    d = {"n_seq": info.n_seq, "max_len": info.max_len, "total_bases": info.total_bases,
+         "nsq_bytes": info.nsq_bytes, "title": info.title.decode(errors="replace")}
+    return d, off, ln
+
+
+def dbfile_write(nin_path, nsq_path, vol, title="synthetic"):
+    packed = np.ascontiguousarray(vol.packed, dtype=np.uint8)
+    boff = np.ascontiguousarray(vol.byte_off, dtype=np.int64)
+    slen = np.ascontiguousarray(vol.seq_len, dtype=np.int32)
+    _check(lib().bn_dbfile_write(str(nin_path).encode(), str(nsq_path).encode(), title.encode(),
+                                 packed.ctypes.data_as(C.c_void_p), boff.ctypes.data_as(C.c_void_p),
+                                 slen.ctypes.data_as(C.c_void_p), C.c_int32(slen.shape[0])))
 
 
 class Query:

@@ -192,6 +192,23 @@ int  bn_db_load(int device, const uint8_t *packed, int64_t packed_bytes,
                 int *vol_handle);
 int  bn_db_free(int vol_handle);
 
+/* BLAST database volume files (version 4 .nin index + .nsq packed sequences, the files
+ * `makeblastdb -dbtype nucl` writes and CSeqDBVol reads: objtools/blast/seqdb_reader/seqdbfile.cpp:195-250,
+ * seqdbvol.cpp:263-285,1734-1815).  bn_dbfile_index is host-only (no device needed): it fills `info`
+ * and, when non-NULL, the per-sequence byte offsets into the .nsq and lengths (info->n_seq entries).
+ * bn_db_load_files maps the .nsq and sends it to HBM unchanged; the handle is a volume like any other.
+ * bn_dbfile_write stores an in-memory volume in the same format (no deflines, no ambiguity data). */
+typedef struct BnDbFileInfo {
+    int32_t n_seq, max_len;
+    int64_t total_bases, nsq_bytes;
+    char    title[256];
+} BnDbFileInfo;
+int  bn_dbfile_index(const char *nin_path, const char *nsq_path, BnDbFileInfo *info,
+                     int64_t *seq_byte_off, int32_t *seq_len);
+int  bn_db_load_files(int device, const char *nin_path, const char *nsq_path, int *vol_handle);
+int  bn_dbfile_write(const char *nin_path, const char *nsq_path, const char *title, const uint8_t *packed,
+                     const int64_t *seq_byte_off, const int32_t *seq_len, int32_t n_seq);
+
 /* ---- query batch: replicated to every device in use ------------------------------------------ */
 int  bn_query_load(const BnQueryBatch *batch, int *query_handle);
 int  bn_query_free(int query_handle);

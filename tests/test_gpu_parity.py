@@ -85,6 +85,58 @@ def test_get_gapped_score_drop_in(name):
         Q.free(); V.free()
 
 
+def test_file_volume_equals_memory_volume(tmp_path):
+    """bn_db_load_files: a volume written as .nin/.nsq and loaded from the files gives the same bytes
+    of results as the same volume loaded from memory (ragged lengths, many subjects)."""
+    from gblastn_b200 import engine as E, setup as S
+    task, cfgkw, vol, qs = cases.make_case("mb_ntlike_many_subjects")
+    nin, nsq = str(tmp_path / "v.nin"), str(tmp_path / "v.nsq")
+    E.dbfile_write(nin, nsq, vol)
+    s = S.Setup(qs, task=task, db_length=vol.total_bases, db_num_seqs=vol.n_seqs, device_lookup=1, **cfgkw)
+    V1, V2, Q = E.Volume(vol), E.FileVolume(nin, nsq), E.Query(s.batch)
+    try:
+        a, b = E.prelim_search(V1, Q), E.prelim_search(V2, Q)
+        assert a["hsps"].size > 0 and a["hsps"].tobytes() == b["hsps"].tobytes()
+        assert a["stats"]["lookup_hits"] == b["stats"]["lookup_hits"]
+    finally:
+        Q.free(); V1.free(); V2.free(); s.free()
+
+
+@pytest.mark.parametrize("task", ["megablast", "blastn"])
+def test_real_blast_db_volume(task):
+    """A real BLAST DB volume from the reference's test data (tests/golden/ntshort, 7 sequences with
+    ambiguity data): queries cut from its sequences, GPU search on the file-loaded volume == reference
+    engine on the same bytes."""
+    import os
+    from gblastn_b200 import engine as E, setup as S, synth
+    from oracle import refdriver as R, portdriver as P
+    if not R.available():
+        pytest.skip("reference library not present")
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    nin, nsq = os.path.join(gold, "ntshort.nin"), os.path.join(gold, "ntshort.nsq")
+    info, off, ln = E.dbfile_index(nin, nsq)
+    raw = np.fromfile(nsq, dtype=np.uint8)
+    vol = synth.Volume(packed=np.concatenate([raw, np.zeros(32, np.uint8)]), byte_off=off, seq_len=ln)
+    rng = np.random.default_rng(3)
+    qs = []
+    for i in range(info["n_seq"]):
+        b = vol.bases(i)
+        a = int(rng.integers(0, max(1, len(b) - 200)))
+        q = b[a: a + 200].copy()
+        mut = rng.random(q.size) < 0.03
+        q[mut] = (q[mut] + 1 + rng.integers(0, 3, int(mut.sum()))) % 4
+        qs.append(q if i % 2 == 0 else (3 - q[::-1]))
+    r = R.search(qs, vol, R.default_config(task))
+    assert r["status"] == 0 and r["final"].shape[0] > 0
+    s = S.Setup(qs, task=task, db_length=vol.total_bases, db_num_seqs=vol.n_seqs)
+    V, Q = E.FileVolume(nin, nsq), E.Query(s.batch)
+    try:
+        g = E.prelim_search(V, Q)
+        assert np.array_equal(P.final_table(g["hsps"]), r["final"])
+    finally:
+        Q.free(); V.free(); s.free()
+
+
 def test_host_buffer_entry_point():
     from gblastn_b200 import engine as E
     from oracle import portdriver as P
