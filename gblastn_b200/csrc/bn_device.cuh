@@ -179,18 +179,6 @@ struct ScanBlockDesc {
 };
 static_assert(sizeof(ScanBlockDesc) == 32, "one sector");
 
-// Per warp-tile (WT_POS = 256 consecutive scan positions, the unit of the pipelined scan kernel).
-struct WarpTileDesc {
-    int64_t tile_lo;      // first byte of the staged slice (16-byte aligned)
-    int32_t bytes;        // slice size (multiple of 16); 0 = not staged (tile spans several chunks or is too wide)
-    int32_t chunk;        // staged: the chunk; not staged: first chunk with a position in the tile
-    int32_t tb0;          // staged: slice-relative base index of the tile's first position; not staged: last chunk
-    int32_t p0;           // staged: chunk-relative base offset of the tile's first position
-    int32_t len;          // staged: chunk length (bases)
-    int32_t npos;         // positions in the tile (<= 256)
-};
-static_assert(sizeof(WarpTileDesc) == 32, "one sector");
-
 struct ScanLaunch {
     const uint8_t *packed;
     const DevChunk *chunks;
@@ -207,16 +195,11 @@ struct ScanLaunch {
     int32_t diag_array_length;    // eDiagArray: cells (power of two)
     int32_t tile_cap;             // staged kernel: bytes of shared memory for the subject slice
     uint32_t *bucket_count;       // optional: survivors per diagonal-hash bucket (group_sort.cu)
-    const WarpTileDesc *wt_desc;  // pipelined kernel: one descriptor per 256 positions (nullptr: not used)
-    int64_t n_wtiles;
-    int32_t wt_cap;               // pipelined kernel: bytes of one slice buffer
 };
 cudaError_t launch_scan(const DevQuery &q, const ScanLaunch &s, cudaStream_t st);
 int scan_positions_per_block();
 int scan_tile_cap(int scan_step, int word_length);
 int scan_max_block_chunks();
-int scan_wt_positions();
-int scan_wt_cap(int scan_step, int word_length);     // 0: warp-tiles of this table shape are too wide to stage
 int scan_tile_margin();
 cudaError_t launch_build_qinfo(const DevQuery &q, const int32_t *next_pos, int32_t concat_len, uint4 *qinfo,
                                cudaStream_t st);

@@ -53,6 +53,25 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// one-shot device buffer from the stream-ordered pool (no implicit device synchronisation, unlike
+// cudaMalloc): chunk tables are built per volume, and the host-buffer entry point builds one per call
+template <typename T>
+struct PoolBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaStream_t st = nullptr;
+    cudaError_t reserve(size_t n, cudaStream_t stream)
+    {
+        if (n <= cap) return cudaSuccess;
+        release();
+        st = stream;
+        cudaError_t e = cudaMallocAsync((void **)&p, n * sizeof(T), st);
+        if (e == cudaSuccess) cap = n; else p = nullptr;
+        return e;
+    }
+    void release() { if (p) cudaFreeAsync(p, st); p = nullptr; cap = 0; }
+};
+
 // grow-only pinned host buffer (target of the D2H result copies: pageable targets go through a
 // driver staging copy)
 template <typename T>
@@ -112,12 +131,11 @@ struct Device {
 struct ChunkTable {
     std::vector<DevChunk> host;
     std::vector<HostChunk> hchunks;
-    DevBuf<DevChunk> dev;
-    DevBuf<int32_t> block_chunk;
-    DevBuf<ScanBlockDesc> block_desc;
-    DevBuf<WarpTileDesc> wt_desc;     // pipelined scan kernel (empty when the table shape / volume does not suit it)
-    int64_t n_wtiles = 0;
-    int32_t wt_cap = 0;
+    std::vector<int32_t> h_block_chunk;         // sources of the asynchronous uploads: live as long as the table
+    std::vector<ScanBlockDesc> h_block_desc;
+    PoolBuf<DevChunk> dev;
+    PoolBuf<int32_t> block_chunk;
+    PoolBuf<ScanBlockDesc> block_desc;
     int64_t total_pos = 0;
     int64_t total_bases = 0;
     int64_t n_blocks = 0;
@@ -370,7 +388,8 @@ static int build_chunk_table(Volume &V, const Query &Q, int32_t oid_begin, int32
     T->total_pos = prefix;
     const int ppb = scan_positions_per_block();
     T->n_blocks = (prefix + ppb - 1) / ppb;
-    std::vector<int32_t> bc((size_t)T->n_blocks + 1, 0);
+    std::vector<int32_t> &bc = T->h_block_chunk;
+    bc.assign((size_t)T->n_blocks + 1, 0);
     {
         size_t c = 0;
         const size_t n = T->host.size();
@@ -382,7 +401,8 @@ static int build_chunk_table(Volume &V, const Query &Q, int32_t oid_begin, int32
         bc[(size_t)T->n_blocks] = n ? (int32_t)n - 1 : 0;
     }
     // staged scan kernel: the slice of the volume every block copies into shared memory
-    std::vector<ScanBlockDesc> bd((size_t)T->n_blocks);
+    std::vector<ScanBlockDesc> &bd = T->h_block_desc;
+    bd.assign((size_t)T->n_blocks, ScanBlockDesc{});
     {
         const int32_t tile_cap = scan_tile_cap(step, b.word_length), margin = scan_tile_margin();
         const int32_t maxc = scan_max_block_chunks();
@@ -405,59 +425,17 @@ static int build_chunk_table(Volume &V, const Query &Q, int32_t oid_begin, int32
             bd[(size_t)blk] = d;
         }
     }
-    // pipelined scan kernel: one descriptor per 256 positions.  Used when nearly every warp-tile lies in
-    // one chunk (long sequences); volumes of short sequences keep the block-staged kernel.
-    std::vector<WarpTileDesc> wd;
-    {
-        const int32_t cap = b.lut_type == BN_LUT_MB ? scan_wt_cap(step, b.word_length) : 0;
-        const int32_t wpos = scan_wt_positions(), margin = scan_tile_margin();
-        const int64_t n_wt = (prefix + wpos - 1) / wpos;
-        const size_t n = T->host.size();
-        if (cap > 0 && n_wt > 0 && (int64_t)n * 8 <= n_wt) {
-            wd.resize((size_t)n_wt);
-            size_t c = 0;
-            int64_t unstaged = 0;
-            for (int64_t t = 0; t < n_wt; t++) {
-                const int64_t g0 = t * wpos, g_last = std::min<int64_t>(g0 + wpos, prefix) - 1;
-                while (c + 1 < n && T->host[c + 1].pos_prefix <= g0) ++c;
-                size_t c_hi = c;
-                while (c_hi + 1 < n && T->host[c_hi + 1].pos_prefix <= g_last) ++c_hi;
-                WarpTileDesc d{};
-                d.npos = (int32_t)(g_last - g0 + 1);
-                const DevChunk &a = T->host[c];
-                const int64_t p0 = (g0 - a.pos_prefix) * step, p_last = (g_last - a.pos_prefix) * step;
-                const int64_t first_byte = a.byte_off + (p0 >> 2);
-                const int64_t last_byte = a.byte_off + ((p_last + b.word_length + 32) >> 2);
-                const int64_t tile_lo = (first_byte - margin) & ~int64_t(15);
-                const int64_t bytes = (last_byte + margin - tile_lo + 15) & ~int64_t(15);
-                if (c_hi == c && bytes <= cap) {
-                    d.tile_lo = tile_lo; d.bytes = (int32_t)bytes; d.chunk = (int32_t)c;
-                    d.tb0 = (int32_t)((a.byte_off - tile_lo) * 4 + p0); d.p0 = (int32_t)p0; d.len = a.len;
-                } else {
-                    d.tile_lo = 0; d.bytes = 0; d.chunk = (int32_t)c; d.tb0 = (int32_t)c_hi; d.p0 = 0; d.len = 0;
-                    ++unstaged;
-                }
-                wd[(size_t)t] = d;
-            }
-            if (unstaged * 20 > n_wt) wd.clear();          // > 5 % on the slow path: not this kernel's volume
-            else { T->n_wtiles = n_wt; T->wt_cap = cap; }
-        }
-    }
     if (!T->host.empty()) {
-        if (!wd.empty()) {
-            CU_TRY(T->wt_desc.reserve(wd.size() + 1));
-            CU_TRY(cudaMemcpyAsync(T->wt_desc.p, wd.data(), wd.size() * sizeof(WarpTileDesc), cudaMemcpyHostToDevice, st));
-        }
-        CU_TRY(T->dev.reserve(T->host.size()));
+        CU_TRY(T->dev.reserve(T->host.size(), st));
         CU_TRY(cudaMemcpyAsync(T->dev.p, T->host.data(), T->host.size() * sizeof(DevChunk),
                                cudaMemcpyHostToDevice, st));
-        CU_TRY(T->block_chunk.reserve(bc.size()));
+        CU_TRY(T->block_chunk.reserve(bc.size(), st));
         CU_TRY(cudaMemcpyAsync(T->block_chunk.p, bc.data(), bc.size() * sizeof(int32_t),
                                cudaMemcpyHostToDevice, st));
-        CU_TRY(T->block_desc.reserve(bd.size() + 1));
+        CU_TRY(T->block_desc.reserve(bd.size() + 1, st));
         CU_TRY(cudaMemcpyAsync(T->block_desc.p, bd.data(), bd.size() * sizeof(ScanBlockDesc),
                                cudaMemcpyHostToDevice, st));
-        CU_TRY(cudaStreamSynchronize(st));
+        // no synchronisation: the sources are members of the table and every consumer runs on `st`
     }
     V.tables[key] = T;
     *out = T;
@@ -517,7 +495,6 @@ static int run_word_finder(Device &D, Volume &V, Query &Q, ChunkTable &T, bool r
         s.packed = V.d_packed; s.chunks = T.dev.p; s.n_chunks = (int32_t)T.host.size();
         s.total_pos = T.total_pos; s.hits = ws.hits_a.p; s.keys = ws.keys_a.p;
         s.counters = ws.counters.p; s.capacity = cap; s.block_chunk = T.block_chunk.p; s.block_desc = T.block_desc.p;
-        s.wt_desc = T.n_wtiles > 0 ? T.wt_desc.p : nullptr; s.n_wtiles = T.n_wtiles; s.wt_cap = T.wt_cap;
         s.raw_pairs = raw_pairs ? 1 : 0; s.gbits = gbits; s.diag_array_length = Q.diag_array_length;
         s.tile_cap = scan_tile_cap(Q.batch.scan_step, Q.batch.word_length);
         t_scan.start();
@@ -751,7 +728,6 @@ static int run_fused(Device &D, Volume &V, Query &Q, ChunkTable &T, StageCounts 
     s.packed = V.d_packed; s.chunks = T.dev.p; s.n_chunks = (int32_t)T.host.size();
     s.total_pos = T.total_pos; s.hits = ws.hits_a.p; s.keys = ws.keys_a.p;
     s.counters = ws.counters.p; s.capacity = cap; s.block_chunk = T.block_chunk.p; s.block_desc = T.block_desc.p;
-        s.wt_desc = T.n_wtiles > 0 ? T.wt_desc.p : nullptr; s.n_wtiles = T.n_wtiles; s.wt_cap = T.wt_cap;
     s.raw_pairs = 0; s.gbits = gbits; s.diag_array_length = Q.diag_array_length;
     s.tile_cap = scan_tile_cap(Q.batch.scan_step, Q.batch.word_length);
     s.bucket_count = ws.buckets.p;
@@ -971,7 +947,7 @@ void bn_release(void)
         cudaSetDevice(g_devices[v->device]->id);
         if (v->ready) { cudaEventSynchronize(v->ready); cudaEventDestroy(v->ready); }
         cudaFreeAsync(v->d_raw, g_devices[v->device]->stream);
-        for (auto &kv : v->tables) { kv.second->dev.release(); kv.second->block_chunk.release(); kv.second->block_desc.release(); kv.second->wt_desc.release(); }
+        for (auto &kv : v->tables) { kv.second->dev.release(); kv.second->block_chunk.release(); kv.second->block_desc.release(); }
     }
     g_volumes.clear();
     for (auto &d : g_devices) {
@@ -1109,7 +1085,7 @@ int bn_db_free(int h)
     cudaSetDevice(g_devices[V.device]->id);
     if (V.ready) { cudaStreamWaitEvent(g_devices[V.device]->stream, V.ready, 0); cudaEventDestroy(V.ready); V.ready = nullptr; }
     cudaFreeAsync(V.d_raw, g_devices[V.device]->stream);
-    for (auto &kv : V.tables) { kv.second->dev.release(); kv.second->block_chunk.release(); kv.second->block_desc.release(); kv.second->wt_desc.release(); }
+    for (auto &kv : V.tables) { kv.second->dev.release(); kv.second->block_chunk.release(); kv.second->block_desc.release(); }
     g_volumes[h].reset();
     return BN_OK;
 }
@@ -1395,7 +1371,6 @@ int bn_bench_scan(int vol_handle, int query_handle, int iters, double *ms_per_la
     s.packed = V->d_packed; s.chunks = T->dev.p; s.n_chunks = (int32_t)T->host.size();
     s.total_pos = T->total_pos; s.hits = ws.hits_a.p; s.keys = ws.keys_a.p;
     s.counters = ws.counters.p; s.capacity = cap; s.block_chunk = T->block_chunk.p; s.block_desc = T->block_desc.p; s.raw_pairs = 0;
-    s.wt_desc = T->n_wtiles > 0 ? T->wt_desc.p : nullptr; s.n_wtiles = T->n_wtiles; s.wt_cap = T->wt_cap;
     s.gbits = bits_for((uint64_t)std::max<int64_t>(T->total_pos, 1)); s.diag_array_length = Q->diag_array_length;
     s.tile_cap = scan_tile_cap(Q->batch.scan_step, Q->batch.word_length);
     const DevQuery &dq = Q->dev[V->device].view;

@@ -544,208 +544,6 @@ scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ S
     if (lane == 0 && warp_hits) atomicAdd(&s.counters[1], (unsigned long long)warp_hits);
 }
 
-// ---- pipelined persistent kernel ------------------------------------------------------------------------
-// Measured on B200 (scripts/gather_probe.cu): 14.7 M random probes of an L2-resident 2-4 MB table take
-// 56 us however they are issued (LDG.32/.64, cache hints, LDGSTS, 2-8 blocks/SM; a distributed-shared-
-// memory table is 4x slower): ~0.9 sectors per cycle per SM is the machine's gather rate, and it is the
-// resource this kernel must keep busy.  The block-staged kernel above leaves it idle while a block waits
-// for its TMA slice, compacts, and walks its candidates (103 us for C2).  Here every WARP is its own
-// software pipeline over warp-tiles of 256 positions: three slice buffers fed by TMA bulk copies it
-// issues itself two tiles ahead, and the 8 probes per lane of tile i+1 are in flight while the
-// candidates of tile i are processed.  No block barrier anywhere; the grid is persistent.
-constexpr int WT_POS = 256;
-constexpr int WT_PER_LANE = WT_POS / 32;
-constexpr int WT_BUFS = 3;
-constexpr int WT_CAP_MAX = 4096;
-int scan_wt_positions() { return WT_POS; }
-int scan_wt_cap(int scan_step, int word_length)
-{
-    long need = (long)WT_POS * scan_step / 4 + word_length / 4 + 2 * TILE_MARGIN + 80;
-    need = (need + 127) & ~127L;
-    return need > WT_CAP_MAX ? 0 : (int)need;
-}
-
-__device__ __forceinline__ WarpTileDesc ld_wt_desc(const WarpTileDesc *p)
-{
-    uint32_t a0, a1, a2, a3, a4, a5, a6, a7;
-    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3), "=r"(a4), "=r"(a5), "=r"(a6), "=r"(a7) : "l"(p));
-    WarpTileDesc d;
-    d.tile_lo = (int64_t)(((uint64_t)a1 << 32) | a0);
-    d.bytes = (int32_t)a2; d.chunk = (int32_t)a3; d.tb0 = (int32_t)a4; d.p0 = (int32_t)a5; d.len = (int32_t)a6; d.npos = (int32_t)a7;
-    return d;
-}
-
-// warp-tile that was not staged (several chunks, e.g. runs of short sequences): per-position global loads
-__device__ __noinline__ uint32_t scan_wtile_direct(const DevQuery &q, const ScanLaunch &s, int64_t g0, int32_t npos,
-                                                   int32_t c_lo, int32_t c_hi, int lane)
-{
-    uint32_t my_lookup_hits = 0;
-    const int32_t lut = q.lut_word_length, step = q.scan_step;
-    for (int it = 0; it < WT_PER_LANE; it++) {
-        const int32_t gl = it * 32 + lane;
-        if (gl >= npos) break;
-        const int64_t g = g0 + gl;
-        int32_t lo = c_lo, hi = c_hi;
-        while (lo < hi) {
-            const int32_t m = (lo + hi + 1) >> 1;
-            if (__ldg(&s.chunks[m].pos_prefix) <= g) lo = m; else hi = m - 1;
-        }
-        const DevChunk ch = s.chunks[lo];
-        const int32_t p = (int32_t)(g - ch.pos_prefix) * step;
-        const uint32_t window = load_window(s.packed, ch.byte_off + (p >> 2));
-        const uint32_t idx = (window >> (2 * (16 - ((p & 3) + lut)))) & q.hash_mask;
-        int32_t qp = mb_cell(q, idx);
-        while (qp) {
-            ++my_lookup_hits;
-            int32_t qo, so;
-            if (s.raw_pairs) emit_hit(q, s, (uint32_t)lo, (uint32_t)p, g, qp - 1, p);
-            else if (mini_extend_mb(q, s.packed + ch.byte_off, ch.len, qp - 1, p, qo, so))
-                emit_hit(q, s, (uint32_t)lo, (uint32_t)p, g, qo, so);
-            qp = __ldg(&q.next_pos[qp]);
-        }
-    }
-    return my_lookup_hits;
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS, 3)
-scan_kernel_pipelined(const __grid_constant__ DevQuery q, const __grid_constant__ ScanLaunch s)
-{
-    extern __shared__ __align__(128) uint32_t smem_dyn[];
-    __shared__ __align__(8) unsigned long long bars[SCAN_THREADS / 32][WT_BUFS];
-    __shared__ int32_t wdesc[SCAN_THREADS / 32][WT_BUFS][8];       // {chunk, tb0, p0, len, npos, staged, -, -}
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int32_t cap_words = s.wt_cap >> 2;
-    uint32_t *wsm = smem_dyn + (size_t)warp * (WT_BUFS * cap_words + 2 * WT_POS);
-    uint2 *wcand = reinterpret_cast<uint2 *>(wsm + WT_BUFS * cap_words);
-    unsigned long long *bar = bars[warp];
-    const int64_t W = (int64_t)gridDim.x * (SCAN_THREADS / 32);
-    const int64_t w0 = (int64_t)blockIdx.x * (SCAN_THREADS / 32) + warp;
-    const int64_t n_tiles = s.n_wtiles;
-    const int64_t my_tiles = w0 < n_tiles ? (n_tiles - w0 + W - 1) / W : 0;
-    const int32_t lut = q.lut_word_length, step = q.scan_step;
-    const uint32_t shr = 32u - 2u * (uint32_t)lut;
-    const uint32_t lt = (1u << lane) - 1u;
-
-    if (lane == 0) {
-#pragma unroll
-        for (int b = 0; b < WT_BUFS; b++) mbar_init(&bar[b], 1);
-    }
-    __syncwarp();
-
-    // queue the slice of this warp's j-th tile into buffer j % 3
-    auto issue = [&](int64_t j) {
-        if (j >= my_tiles) return;
-        const int b = (int)(j % WT_BUFS);
-        const WarpTileDesc d = ld_wt_desc(s.wt_desc + (w0 + j * W));
-        if (lane == 0) {
-            int32_t *wd = wdesc[warp][b];
-            wd[0] = d.chunk; wd[1] = d.tb0; wd[2] = d.p0; wd[3] = d.len; wd[4] = d.npos; wd[5] = d.bytes;
-            if (d.bytes > 0) {
-                mbar_expect_tx(&bar[b], (uint32_t)d.bytes);
-                tma_bulk_g2s(wsm + b * cap_words, s.packed + d.tile_lo, (uint32_t)d.bytes, &bar[b]);
-            }
-        }
-        __syncwarp();
-    };
-
-    uint32_t ph = 0;                    // current phase parity of the three slice barriers
-    uint2 wn[WT_PER_LANE];              // probes of the tile one ahead
-    uint32_t bn[WT_PER_LANE / 4];       // their bit indices, 8 bits each
-    // phase A of tile j: lookup words from the slice, all 8 probes of the lane issued together
-    auto probe = [&](int64_t j) {
-        const int b = (int)(j % WT_BUFS);
-        const int32_t *wd = wdesc[warp][b];
-        if (wd[5] <= 0) return;                                     // not staged: handled whole in phase B
-        mbar_wait(&bar[b], (ph >> b) & 1u);
-        ph ^= 1u << b;
-        const uint32_t *tile = wsm + b * cap_words;
-        const int32_t tb0 = wd[1], npos = wd[4];
-#pragma unroll
-        for (int it = 0; it < WT_PER_LANE; it++) {
-            const int32_t gl = min(it * 32 + lane, npos - 1);
-            const int32_t tb = tb0 + gl * step;
-            const uint32_t w0_ = tile[tb >> 4], w1_ = tile[(tb >> 4) + 1];
-            const uint32_t Wd = __byte_perm(w0_, w1_, 0x0123u + 0x1111u * ((uint32_t)(tb >> 2) & 3u));
-            const uint32_t idx = (Wd << (2u * ((uint32_t)tb & 3u))) >> shr;
-            wn[it] = __ldg(&q.prk[idx >> 5]);
-            if ((it & 3) == 0) bn[it >> 2] = 0;
-            bn[it >> 2] |= (idx & 31u) << (8 * (it & 3));
-        }
-    };
-
-    uint32_t my_lookup_hits = 0;
-    issue(0); issue(1); issue(2);
-    if (my_tiles > 0) probe(0);
-    for (int64_t j = 0; j < my_tiles; j++) {
-        uint2 wc[WT_PER_LANE];
-        uint32_t bc[WT_PER_LANE / 4];
-#pragma unroll
-        for (int it = 0; it < WT_PER_LANE; it++) wc[it] = wn[it];
-#pragma unroll
-        for (int it = 0; it < WT_PER_LANE / 4; it++) bc[it] = bn[it];
-        if (j + 1 < my_tiles) probe(j + 1);                         // in flight during the candidate phase below
-
-        const int b = (int)(j % WT_BUFS);
-        const int32_t *wd = wdesc[warp][b];
-        const int32_t chunk = wd[0], tb0 = wd[1], p0 = wd[2], len = wd[3], npos = wd[4];
-        const int64_t g0 = (w0 + j * W) * WT_POS;
-        if (wd[5] <= 0) {
-            my_lookup_hits += scan_wtile_direct(q, s, g0, npos, chunk, tb0, lane);
-        } else {
-            const uint32_t *tile = wsm + b * cap_words;
-            // ---- warp-local compaction of the occupied cells (ballots, no atomics) ----------------------
-            int ncand = 0;
-#pragma unroll
-            for (int it = 0; it < WT_PER_LANE; it++) {
-                const uint32_t bit = (bc[it >> 2] >> (8 * (it & 3))) & 31u;
-                const bool hit = (it * 32 + lane < npos) && ((wc[it].x >> bit) & 1u);
-                const uint32_t m = __ballot_sync(0xffffffffu, hit);
-                if (hit)
-                    wcand[ncand + __popc(m & lt)] =
-                        make_uint2(wc[it].y + (uint32_t)__popc(wc[it].x & ((1u << bit) - 1u)), (uint32_t)(it * 32 + lane));
-                ncand += __popc(m);
-            }
-            __syncwarp();
-            // ---- the warp's candidates, one per lane ---------------------------------------------------------
-            const int32_t tbase = tb0 - p0;                         // slice-relative base index of the chunk's base 0
-            for (int ci = lane; ci < ncand; ci += 32) {
-                const uint2 cd = wcand[ci];
-                const int32_t gl = (int32_t)cd.y;
-                uint4 qi, qi1;
-                ld_cinfo_pair(q.cinfo + 2 * (size_t)cd.x, qi, qi1);
-                const int32_t p = p0 + gl * step;
-                const int64_t g = g0 + gl;
-                int32_t qp = (int32_t)(qi.x & 0x7fffffffu);
-                bool more = (qi.x >> 31) != 0, second = true;
-                for (;;) {
-                    ++my_lookup_hits;
-                    int32_t qo, so;
-                    if (s.raw_pairs) emit_hit(q, s, (uint32_t)chunk, (uint32_t)p, g, qp - 1, p);
-                    else if (mini_extend_tile(q, tile, tbase, len, qp - 1, p, qi, qo, so))
-                        emit_hit(q, s, (uint32_t)chunk, (uint32_t)p, g, qo, so);
-                    if (!more) break;
-                    if (second) {
-                        second = false;
-                        qi = qi1;
-                        qp = (int32_t)(qi.x & 0x7fffffffu);
-                        more = (qi.x >> 31) != 0;
-                    } else {
-                        qp = __ldg(&q.next_pos[qp]);
-                        qi = __ldg(&q.qinfo[qp]);
-                        more = qi.x != 0;
-                    }
-                }
-            }
-        }
-        __syncwarp();                                               // buffer b and the candidate queue are free again
-        issue(j + WT_BUFS);
-    }
-    const uint32_t warp_hits = __reduce_add_sync(0xffffffffu, my_lookup_hits);
-    if (lane == 0 && warp_hits) atomicAdd(&s.counters[1], (unsigned long long)warp_hits);
-}
-
 // qinfo[qp] for every 1-based query position qp: {next_pos[qp], 16 bases left of the lookup word that
 // starts at qp-1, 16 bases right of it, ambiguity flags (left in the even bits, right in the odd bits)}
 __global__ void build_qinfo_kernel(const DevQuery q, const int32_t *next_pos, int32_t concat_len, uint4 *qinfo)
@@ -900,20 +698,7 @@ cudaError_t launch_scan(const DevQuery &q, const ScanLaunch &s, cudaStream_t st)
 {
     if (s.total_pos <= 0) return cudaSuccess;
     int64_t blocks = (s.total_pos + POS_PER_BLOCK - 1) / POS_PER_BLOCK;
-    if (q.lut_type == 0 && q.prk != nullptr && s.wt_desc != nullptr && s.wt_cap > 0) {
-        // persistent, one software pipeline per warp
-        const size_t smem = (size_t)(SCAN_THREADS / 32) * ((size_t)WT_BUFS * s.wt_cap + sizeof(uint2) * WT_POS);
-        if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(scan_kernel_pipelined, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-        }
-        int per_sm = (int)((220 * 1024) / (smem + 1024));
-        per_sm = per_sm > 3 ? 3 : (per_sm < 1 ? 1 : per_sm);
-        const int64_t want = (s.n_wtiles + SCAN_THREADS / 32 - 1) / (SCAN_THREADS / 32);
-        const int64_t grid = want < 148 * per_sm ? want : 148 * per_sm;
-        scan_kernel_pipelined<<<(unsigned)grid, SCAN_THREADS, smem, st>>>(q, s);
-    }
-    else if (q.lut_type == 0 && q.prk != nullptr && q.lut_word_length <= 13) {
+    if (q.lut_type == 0 && q.prk != nullptr && q.lut_word_length <= 13) {
         const size_t smem = (size_t)s.tile_cap + sizeof(uint2) * POS_PER_BLOCK;
         scan_kernel_staged<<<(unsigned)blocks, SCAN_THREADS, smem, st>>>(q, s);
     }
