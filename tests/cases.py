@@ -78,6 +78,16 @@ CASES = {
     "mb_affine_greedy_0_2": dict(task="megablast", cfg={"word_size": 16, "greedy": 1, "gap_open": 0, "gap_extend": 2},
                                  seq_lens=[200_000, 90_000], vol_seed=5, nq=25, qlen=600, q_seed=16, sub=0.06,
                                  indel=0.005, planted=0.8),
+    # BASELINE configs[2..4] at reduced size (same table shapes, containers and aligners as the full configs)
+    # C3: blastn ws 11, 100 x 10 kb vs 1 Gb (10 x 100 Mb)  ->  6 x 10 kb vs 6 x 1 Mb: MB lut 11 / stride 1, DP heavy
+    "c3_scaled_blastn_10kb": dict(task="blastn", cfg={}, seq_lens=[1_000_000] * 6, vol_seed=3, nq=6, qlen=10_000,
+                                  q_seed=33, sub=0.08, indel=0.01, planted=0.8),
+    # C4: megablast 100 k x 150 bp short reads vs 3 Gb  ->  3 000 x 150 bp vs 7 x 400 kb: lut 12 / stride 17
+    "c4_scaled_short_reads": dict(task="megablast", cfg={}, seq_lens=[400_000] * 7, vol_seed=40, nq=3000, qlen=150,
+                                  q_seed=44, sub=0.02, indel=0.0, planted=0.8),
+    # C5: megablast 1 000 x 5 kb (+ masks) vs nt-like volume  ->  80 x 5 kb vs 3 000 log-normal sequences
+    "c5_scaled_ntlike_5kb": dict(task="megablast", cfg={}, seq_lens="lognormal:3000:50:2000:1.1", vol_seed=50,
+                                 nq=80, qlen=5000, q_seed=55, sub=0.02, indel=0.002, planted=0.8),
     # empty result: random queries only
     "mb_no_hits": dict(task="megablast", cfg={}, seq_lens=[100_000], vol_seed=11,
                        nq=5, qlen=400, q_seed=22, sub=0.0, indel=0.0, planted=0.0),

@@ -160,7 +160,8 @@ def _masks_for(qs, seed):
     return masks
 
 
-@pytest.mark.parametrize("name", ["mb_lut11_hash_indels", "mb_lut12_stride17", "mb_smallna_diagarray"])
+@pytest.mark.parametrize("name", ["mb_lut11_hash_indels", "mb_lut12_stride17", "mb_smallna_diagarray",
+                                  "c5_scaled_ntlike_5kb"])
 def test_gpu_with_masked_queries(name):
     """mask-at-hash query masks: lut->masked_locations != NULL switches on the lookup re-probing of
     s_TypeOfWord (core/na_ungapped.c:489-588) in the diagonal stage."""
