@@ -302,11 +302,13 @@ struct GappedLaunch {
     const int32_t *todo;          // optional list of init indices (tier 2); nullptr = all
     int32_t n_todo;
     int32_t grid_blocks;          // 0 = default persistent grid
+    int32_t dp_smem_ring;         // DP: 1 = tier-1 rings in shared memory (no global scratch), 0 = global ring of tier_d cells (power of two)
 };
 cudaError_t launch_gapped(const DevQuery &q, const GappedLaunch &g, cudaStream_t st);
 cudaError_t launch_greedy_warp(const DevQuery &q, const GappedLaunch &g, int warps_per_block, int blocks,
                                bool use_smem, cudaStream_t st);
 int gapped_threads();
 int gapped_threads_per_block();
+int gapped_dp_smem_blocks();
 
 }  // namespace bn

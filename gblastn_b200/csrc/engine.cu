@@ -594,8 +594,14 @@ static int enqueue_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t
         const int blocks = (int)std::min<int64_t>((max_init + 1) / 2, 148 * 8);
         g.scratch = nullptr;
         CU_TRY(launch_greedy_warp(dq, g, wpb, blocks, true, st));
+    } else if (!greedy) {
+        // packed DP, tier 1: one thread per init-HSP, score ring in shared memory
+        const int64_t want = (max_init + gapped_threads_per_block() - 1) / gapped_threads_per_block();
+        g.scratch = nullptr; g.dp_smem_ring = 1;
+        g.grid_blocks = (int32_t)std::max<int64_t>(1, std::min<int64_t>(gapped_dp_smem_blocks(), want));
+        CU_TRY(launch_gapped(dq, g, st));
     } else {
-        const int64_t threads = std::min<int64_t>(affine ? 4096 : gapped_threads(), ((max_init + 63) / 64) * 64);
+        const int64_t threads = std::min<int64_t>(4096, ((max_init + 63) / 64) * 64);
         CU_TRY(ws.scratch.reserve((size_t)(per_thread * threads)));
         g.scratch = ws.scratch.p;
         g.grid_blocks = (int32_t)(threads / gapped_threads_per_block());
@@ -639,7 +645,8 @@ static int finish_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t 
             tier = std::min(10000, max_len / 2 + 1);
             per_thread = 2 * (2 * (int64_t)tier + 6) + tier + 1 + xo + 8;
         } else {
-            tier = Q.max_query_length + 8;
+            tier = 256;                                                  // DP ring capacity: power of two >= longest query + 8
+            while (tier < Q.max_query_length + 8) tier <<= 1;
             per_thread = 2 * (int64_t)tier;
         }
         const bool warp_greedy = greedy && !affine;

@@ -27,6 +27,7 @@ namespace bn {
 constexpr int GAP_THREADS = 64;
 constexpr int GAP_BLOCKS = 592;          // 4 x 148 SMs
 int gapped_threads() { return GAP_THREADS * GAP_BLOCKS; }
+int gapped_dp_smem_blocks() { return 148 * 3; }     // 64 KB of rings per block: three blocks per SM
 int gapped_threads_per_block() { return GAP_THREADS; }
 
 constexpr int32_t GREEDY_MAX_COST = 10000;
@@ -595,25 +596,48 @@ cudaError_t launch_greedy_warp(const DevQuery &q, const GappedLaunch &g, int war
     return cudaGetLastError();
 }
 
-// s_BlastAlignPackedNucl with the score_array kept in a ring of C cells: only indices in
-// [first_b_index, b_size] are live, so index i lives at slot i % C as long as the live span <= C.
+// s_BlastAlignPackedNucl with the score_array kept in a ring of C cells (C a power of two): only
+// indices in [first_b_index, b_size] are live, so index i lives at slot i & (C - 1) as long as the live
+// span <= C.  Two ring homes:
+//   SmemRing   tier 1: DP_SMEM_CELLS cells per thread in shared memory, interleaved by thread
+//              (cell c of thread t at [c][t]) so a warp's 8-byte accesses never conflict, whatever
+//              cells its lanes are at.  A dependent global-memory round trip per DP cell made the
+//              longest alignment of a batch (one thread, ~4e5 cells for a 10 kb query) set the kernel time.
+//   GlobalRing tier 2: worst-case capacity in global scratch for the rare band wider than tier 1.
+constexpr int DP_SMEM_CELLS = 128;
+struct SmemRing {
+    int2 *base;                 // &ring[0][thread]
+    __device__ __forceinline__ int2 get(int32_t i) const { return base[(i & (DP_SMEM_CELLS - 1)) * GAP_THREADS]; }
+    __device__ __forceinline__ void set(int32_t i, int2 v) const { base[(i & (DP_SMEM_CELLS - 1)) * GAP_THREADS] = v; }
+    __device__ __forceinline__ int32_t capacity() const { return DP_SMEM_CELLS; }
+};
+struct GlobalRing {
+    int2 *base;
+    int32_t mask;               // capacity - 1
+    __device__ __forceinline__ int2 get(int32_t i) const { return base[i & mask]; }
+    __device__ __forceinline__ void set(int32_t i, int2 v) const { base[i & mask] = v; }
+    __device__ __forceinline__ int32_t capacity() const { return mask + 1; }
+};
+
+template <typename Ring>
 __device__ int32_t dp_packed(const uint8_t *B, const uint8_t *A, int32_t N, int32_t M,
                              int32_t &b_offset, int32_t &a_offset, const int32_t *matrix,
                              int32_t gap_open, int32_t gap_extend, int32_t x_dropoff, bool reverse,
-                             int2 *ring, int32_t C, bool &overflow)
+                             const Ring ring, bool &overflow)
 {
     const int32_t gap_open_extend = gap_open + gap_extend;
+    const int32_t C = ring.capacity();
     a_offset = 0; b_offset = 0;
     if (x_dropoff < gap_open_extend) x_dropoff = gap_open_extend;
     if (N <= 0 || M <= 0) return 0;
 
     int32_t score = -gap_open_extend;
-    ring[0] = make_int2(0, -gap_open_extend);
+    ring.set(0, make_int2(0, -gap_open_extend));
     int32_t i;
     for (i = 1; i <= N; i++) {
         if (score < -x_dropoff) break;
         if (i >= C) { overflow = true; return 0; }
-        ring[i % C] = make_int2(score, score - gap_open_extend);
+        ring.set(i, make_int2(score, score - gap_open_extend));
         score -= gap_extend;
     }
     int32_t b_size = i, best_score = 0, first_b_index = 0;
@@ -628,16 +652,21 @@ __device__ int32_t dp_packed(const uint8_t *B, const uint8_t *A, int32_t N, int3
         score = MININT;
         int32_t score_gap_row = MININT, last_b_index = first_b_index;
 
+        // the next cell and the next query byte are fetched one step ahead of their use
+        int2 cell = ring.get(first_b_index);
+        int qb = (first_b_index < b_size) ? (int)__ldg(b_ptr + b_inc) : 0;
         for (int32_t b_index = first_b_index; b_index < b_size; b_index++) {
             b_ptr += b_inc;
-            int2 cell = ring[b_index % C];
+            const bool has_next = b_index + 1 < b_size;
+            const int2 next_cell = has_next ? ring.get(b_index + 1) : cell;
+            const int next_qb = has_next ? (int)__ldg(b_ptr + b_inc) : 0;
             int32_t score_gap_col = cell.y;
-            const int32_t next_score = cell.x + __ldg(mrow + (int)__ldg(b_ptr));
+            const int32_t next_score = cell.x + mrow[qb];
             if (score < score_gap_col) score = score_gap_col;
             if (score < score_gap_row) score = score_gap_row;
             if (best_score - score > x_dropoff) {
                 if (b_index == first_b_index) first_b_index++;
-                else { cell.x = MININT; ring[b_index % C] = cell; }
+                else { cell.x = MININT; ring.set(b_index, cell); }
             } else {
                 last_b_index = b_index;
                 if (score > best_score) { best_score = score; a_offset = a_index; b_offset = b_index; }
@@ -646,48 +675,49 @@ __device__ int32_t dp_packed(const uint8_t *B, const uint8_t *A, int32_t N, int3
                 cell.y = max(score - gap_open_extend, score_gap_col);
                 score_gap_row = max(score - gap_open_extend, score_gap_row);
                 cell.x = score;
-                ring[b_index % C] = cell;
+                ring.set(b_index, cell);
             }
             score = next_score;
+            cell = next_cell;
+            qb = next_qb;
         }
         if (first_b_index == b_size) break;
         if (last_b_index < b_size - 1) b_size = last_b_index + 1;
         else {
             while (score_gap_row >= (best_score - x_dropoff) && b_size <= N) {
                 if (b_size - first_b_index + 2 >= C) { overflow = true; return 0; }
-                ring[b_size % C] = make_int2(score_gap_row, score_gap_row - gap_open_extend);
+                ring.set(b_size, make_int2(score_gap_row, score_gap_row - gap_open_extend));
                 score_gap_row -= gap_extend;
                 b_size++;
             }
         }
         if (b_size <= N) {
             if (b_size - first_b_index + 2 >= C) { overflow = true; return 0; }
-            ring[b_size % C] = make_int2(MININT, MININT);
+            ring.set(b_size, make_int2(MININT, MININT));
             b_size++;
         }
     }
     return best_score;
 }
 
-__device__ void dp_gapped(const DevQuery &q, const uint8_t *query, int32_t qlen, const uint8_t *S,
-                          int32_t slen, int32_t q_off, int32_t s_off, int32_t *scratch, int32_t C,
-                          DevGapResult &g)
+template <typename Ring>
+__device__ void dp_gapped(const DevQuery &q, const int32_t *matrix, const uint8_t *query, int32_t qlen, const uint8_t *S,
+                          int32_t slen, int32_t q_off, int32_t s_off, const Ring ring, DevGapResult &g)
 {
     const int32_t adj = 4 - (s_off % 4);
     int32_t q_length = q_off + adj, s_length = s_off + adj;
     if (q_length > qlen || s_length > slen) { q_length -= 4; s_length -= 4; }
-    int2 *ring = reinterpret_cast<int2 *>(scratch);
     bool overflow = false;
     int32_t pq, ps, right = 0;
-    const int32_t left = dp_packed(query, S, q_length, s_length, pq, ps, q.matrix, q.gap_open,
-                                   q.gap_extend, q.gap_x_dropoff, true, ring, C, overflow);
+    const int32_t left = dp_packed(query, S, q_length, s_length, pq, ps, matrix, q.gap_open,
+                                   q.gap_extend, q.gap_x_dropoff, true, ring, overflow);
     if (overflow) { g.status = 1; return; }
     g.q_start = q_length - pq; g.s_start = s_length - ps;
     if (q_length < qlen && s_length < slen) {
         int32_t qs, ss;
         right = dp_packed(query + q_length - 1, S + (s_length + 3) / 4 - 1, qlen - q_length,
-                          slen - s_length, qs, ss, q.matrix, q.gap_open, q.gap_extend,
-                          q.gap_x_dropoff, false, ring, C, overflow);
+                          slen - s_length, qs, ss, matrix, q.gap_open, q.gap_extend,
+                          q.gap_x_dropoff, false, ring, overflow);
         if (overflow) { g.status = 1; return; }
         g.q_stop = qs + q_length; g.s_stop = ss + s_length;
     } else { g.q_stop = q_length; g.s_stop = s_length; }
@@ -699,10 +729,14 @@ __device__ void dp_gapped(const DevQuery &q, const uint8_t *query, int32_t qlen,
 __global__ void __launch_bounds__(GAP_THREADS)
 gapped_kernel(const DevQuery q, const GappedLaunch L)
 {
+    extern __shared__ int2 dp_smem[];                 // tier-1 DP rings [DP_SMEM_CELLS][GAP_THREADS] (DP launches only)
+    __shared__ int32_t s_matrix[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_matrix[i] = q.matrix[i];
+    __syncthreads();
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     int64_t n = L.todo ? (int64_t)L.n_todo : (int64_t)min((unsigned long long)L.max_init, *L.n_init);
-    int32_t *scratch = L.scratch + tid * L.scratch_ints_per_thread;
+    int32_t *scratch = L.scratch ? L.scratch + tid * L.scratch_ints_per_thread : nullptr;
 
     for (int64_t w = tid; w < n; w += nthreads) {
         const int64_t i = L.todo ? (int64_t)L.todo[w] : w;
@@ -722,7 +756,11 @@ gapped_kernel(const DevQuery q, const GappedLaunch L)
         } else {
             int32_t q_off = h.q_off - c.query_offset, s_off = h.s_off;
             if (h.s_start + h.length >= s_off + 8) { s_off += 3; q_off += 3; }
-            dp_gapped(q, query, c.query_length, S, ch.len, q_off, s_off, scratch, L.tier_d, g);
+            if (L.dp_smem_ring)
+                dp_gapped(q, s_matrix, query, c.query_length, S, ch.len, q_off, s_off, SmemRing{dp_smem + threadIdx.x}, g);
+            else
+                dp_gapped(q, s_matrix, query, c.query_length, S, ch.len, q_off, s_off,
+                          GlobalRing{reinterpret_cast<int2 *>(scratch), L.tier_d - 1}, g);
         }
         L.out[i] = g;
     }
@@ -730,7 +768,12 @@ gapped_kernel(const DevQuery q, const GappedLaunch L)
 
 cudaError_t launch_gapped(const DevQuery &q, const GappedLaunch &g, cudaStream_t st)
 {
-    gapped_kernel<<<g.grid_blocks > 0 ? g.grid_blocks : GAP_BLOCKS, GAP_THREADS, 0, st>>>(q, g);
+    const size_t smem = g.dp_smem_ring ? (size_t)DP_SMEM_CELLS * GAP_THREADS * sizeof(int2) : 0;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(gapped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    gapped_kernel<<<g.grid_blocks > 0 ? g.grid_blocks : GAP_BLOCKS, GAP_THREADS, smem, st>>>(q, g);
     return cudaGetLastError();
 }
 
