@@ -65,7 +65,7 @@ struct DevInitHit {      // == BnInitHit + ordering info
 };
 
 struct DevGapResult {
-    int32_t q_start, q_stop, s_start, s_stop, score, q_seed, s_seed, status;  // status 1 = scratch overflow
+    int32_t q_start, q_stop, s_start, s_stop, score, q_seed, s_seed, status;  // status 1 = scratch overflow, 2 = long alignment (DP row budget)
 };
 
 // NCBI2NA_UNPACK_BASE (inc-core/blast_util.h:52-55)
@@ -302,6 +302,7 @@ struct GappedLaunch {
     const int32_t *todo;          // optional list of init indices (tier 2); nullptr = all
     int32_t n_todo;
     int32_t grid_blocks;          // 0 = default persistent grid
+    int32_t dp_max_rows;          // DP tier 1: rows (per direction) a single thread may walk before it reports status 2 (0 = no limit)
     int32_t dp_smem_ring;         // DP: 1 = tier-1 rings in shared memory (no global scratch), 0 = global ring of tier_d cells (power of two)
 };
 cudaError_t launch_gapped(const DevQuery &q, const GappedLaunch &g, cudaStream_t st);
@@ -310,5 +311,7 @@ cudaError_t launch_greedy_warp(const DevQuery &q, const GappedLaunch &g, int war
 int gapped_threads();
 int gapped_threads_per_block();
 int gapped_dp_smem_blocks();
+cudaError_t launch_gapped_warp(const DevQuery &q, const GappedLaunch &g, int blocks, cudaStream_t st);
+int gapped_warp_per_block();
 
 }  // namespace bn

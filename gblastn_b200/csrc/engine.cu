@@ -598,6 +598,7 @@ static int enqueue_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t
         // packed DP, tier 1: one thread per init-HSP, score ring in shared memory
         const int64_t want = (max_init + gapped_threads_per_block() - 1) / gapped_threads_per_block();
         g.scratch = nullptr; g.dp_smem_ring = 1;
+        g.dp_max_rows = 256;          // longer alignments go to the warp-parallel kernel (finish_gapped)
         g.grid_blocks = (int32_t)std::max<int64_t>(1, std::min<int64_t>(gapped_dp_smem_blocks(), want));
         CU_TRY(launch_gapped(dq, g, st));
     } else {
@@ -631,6 +632,25 @@ static int finish_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t 
     CU_TRY(cudaStreamSynchronize(st));
 
     std::vector<int32_t> todo;
+    if (!greedy) {
+        // long alignments (the thread-per-HSP kernel gave up after its row budget): one warp each
+        for (int64_t i = 0; i < n_init; i++) if (h_gap[(size_t)i].status == 2) todo.push_back((int32_t)i);
+        if (!todo.empty()) {
+            CU_TRY(ws.todo.reserve(todo.size()));
+            CU_TRY(cudaMemcpyAsync(ws.todo.p, todo.data(), todo.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+            GappedLaunch g{};
+            g.packed = V.d_packed; g.chunks = T.dev.p; g.init = ws.init.p; g.n_init = ws.counters.p + 2;
+            g.max_init = n_init; g.out = ws.gap_out.p;
+            g.todo = ws.todo.p; g.n_todo = (int32_t)todo.size();
+            const int wpb_dp = gapped_warp_per_block();
+            const int blocks = (int)std::min<int64_t>(((int64_t)todo.size() + wpb_dp - 1) / wpb_dp, 148 * 4);
+            CU_TRY(launch_gapped_warp(dq, g, blocks, st));
+            if (stats) stats->kernel_launches += 1;
+            CU_TRY(cudaMemcpyAsync(h_gap, ws.gap_out.p, (size_t)n_init * sizeof(DevGapResult), cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
+            todo.clear();
+        }
+    }
     for (int64_t i = 0; i < n_init; i++) if (h_gap[(size_t)i].status == 1) todo.push_back((int32_t)i);
     if (!todo.empty()) {
         int32_t max_len = 0;

@@ -623,7 +623,7 @@ template <typename Ring>
 __device__ int32_t dp_packed(const uint8_t *B, const uint8_t *A, int32_t N, int32_t M,
                              int32_t &b_offset, int32_t &a_offset, const int32_t *matrix,
                              int32_t gap_open, int32_t gap_extend, int32_t x_dropoff, bool reverse,
-                             const Ring ring, bool &overflow)
+                             const Ring ring, bool &overflow, int32_t max_rows, bool &too_long)
 {
     const int32_t gap_open_extend = gap_open + gap_extend;
     const int32_t C = ring.capacity();
@@ -644,6 +644,7 @@ __device__ int32_t dp_packed(const uint8_t *B, const uint8_t *A, int32_t N, int3
     const int32_t b_inc = reverse ? -1 : 1;
 
     for (int32_t a_index = 1; a_index <= M; a_index++) {
+        if (a_index > max_rows) { too_long = true; return 0; }      // a long alignment: the warp-parallel kernel takes it
         int a_bp;
         if (reverse) a_bp = (__ldg(A + (M - a_index) / 4) >> (2 * ((a_index - 1) % 4))) & 3;
         else a_bp = (__ldg(A + 1 + (a_index - 1) / 4) >> (2 * (3 - (a_index - 1) % 4))) & 3;
@@ -702,22 +703,24 @@ __device__ int32_t dp_packed(const uint8_t *B, const uint8_t *A, int32_t N, int3
 
 template <typename Ring>
 __device__ void dp_gapped(const DevQuery &q, const int32_t *matrix, const uint8_t *query, int32_t qlen, const uint8_t *S,
-                          int32_t slen, int32_t q_off, int32_t s_off, const Ring ring, DevGapResult &g)
+                          int32_t slen, int32_t q_off, int32_t s_off, const Ring ring, int32_t max_rows, DevGapResult &g)
 {
     const int32_t adj = 4 - (s_off % 4);
     int32_t q_length = q_off + adj, s_length = s_off + adj;
     if (q_length > qlen || s_length > slen) { q_length -= 4; s_length -= 4; }
-    bool overflow = false;
+    bool overflow = false, too_long = false;
     int32_t pq, ps, right = 0;
     const int32_t left = dp_packed(query, S, q_length, s_length, pq, ps, matrix, q.gap_open,
-                                   q.gap_extend, q.gap_x_dropoff, true, ring, overflow);
+                                   q.gap_extend, q.gap_x_dropoff, true, ring, overflow, max_rows, too_long);
+    if (too_long) { g.status = 2; return; }
     if (overflow) { g.status = 1; return; }
     g.q_start = q_length - pq; g.s_start = s_length - ps;
     if (q_length < qlen && s_length < slen) {
         int32_t qs, ss;
         right = dp_packed(query + q_length - 1, S + (s_length + 3) / 4 - 1, qlen - q_length,
                           slen - s_length, qs, ss, matrix, q.gap_open, q.gap_extend,
-                          q.gap_x_dropoff, false, ring, overflow);
+                          q.gap_x_dropoff, false, ring, overflow, max_rows, too_long);
+        if (too_long) { g.status = 2; return; }
         if (overflow) { g.status = 1; return; }
         g.q_stop = qs + q_length; g.s_stop = ss + s_length;
     } else { g.q_stop = q_length; g.s_stop = s_length; }
@@ -725,6 +728,214 @@ __device__ void dp_gapped(const DevQuery &q, const int32_t *matrix, const uint8_
     g.q_seed = q_off; g.s_seed = s_off;
     g.status = 0;
 }
+
+// ================================================================================================
+// Warp-parallel packed DP for LONG alignments (the thread-per-HSP kernel hands over whatever exceeds
+// its row budget): one warp per extension, one lane per band cell, exact.
+//
+// A row of s_BlastAlignPackedNucl visits the live cells b = first_b .. b_size-1 in order.  With
+//   v_b = max(best_old[b-1] + matrix[a][B_b], best_gap_old[b])            (no dependency inside the row)
+// the row is the recurrence
+//   s_b = max(v_b, r_b);  pruned_b = (best_b - s_b > X)
+//   unpruned: best_{b+1} = max(best_b, s_b),  r_{b+1} = max(s_b - goe, r_b - ge) = max(v_b - goe, r_b - ge)
+//   pruned  : best_{b+1} = best_b,            r_{b+1} = r_b           (a pruned cell neither pays nor feeds the gap)
+// For a GIVEN set of prune flags both chains are prefix maxima:  with u_b = unpruned cells before b,
+//   r_b = max(r_in, max_{unpruned j<b} (v_j - goe + ge (u_j + 1))) - ge u_b,   best_b = max(best_in, max_{unpruned j<b} s_j)
+// so a 32-cell segment costs two warp scans.  The flags are found by fixed-point iteration from the guess
+// "pruned iff best_in - v_b > X": every pass makes at least one more leading flag final (flag b depends on
+// flags < b only), the fixed point is unique and equals the serial result; in practice 1-2 passes.
+// Segments of a row run in order with (r, best, left-edge state, previous old best) carried across.
+// ================================================================================================
+constexpr int DPW_WARPS = 4;            // warps per block
+constexpr int DPW_CELLS = 512;          // ring cells per warp (power of two)
+constexpr int32_t NEGINF = INT32_MIN / 2 - (1 << 24);
+
+__device__ __forceinline__ int32_t warp_excl_prefix_max(int32_t x, int lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int32_t y = __shfl_up_sync(FULLW, x, o);
+        if (lane >= o) x = max(x, y);
+    }
+    const int32_t e = __shfl_up_sync(FULLW, x, 1);
+    return lane == 0 ? NEGINF : e;
+}
+
+__device__ int32_t dp_packed_warp(const uint8_t *B, const uint8_t *A, int32_t N, int32_t M, int32_t &b_offset,
+                                  int32_t &a_offset, const int32_t *matrix, int32_t gap_open, int32_t gap_extend,
+                                  int32_t x_dropoff, bool reverse, int2 *ring, bool &overflow, int lane)
+{
+    const int32_t goe = gap_open + gap_extend, ge = gap_extend;
+    constexpr int32_t C = DPW_CELLS, MASK = DPW_CELLS - 1;
+    a_offset = 0; b_offset = 0;
+    if (x_dropoff < goe) x_dropoff = goe;
+    if (N <= 0 || M <= 0) return 0;
+    const uint32_t lt = (1u << lane) - 1u;
+
+    // row 0: cell 0 = (0, -goe); cell i >= 1 = (-goe - (i-1) ge, that - goe) while the score is >= -X
+    int32_t b_size;
+    {
+        int32_t k = (ge == 0) ? N : (x_dropoff - goe) / ge + 1;     // number of cells i >= 1 with -goe - (i-1) ge >= -X
+        k = min(k, N);
+        if (k + 1 >= C) { overflow = true; return 0; }
+        for (int32_t i = lane; i <= k; i += 32) {
+            const int32_t sc = (i == 0) ? 0 : -goe - (i - 1) * ge;
+            ring[i & MASK] = make_int2(sc, sc - goe);
+        }
+        b_size = k + 1;
+        __syncwarp();
+    }
+    int32_t best_score = 0, first_b = 0;
+
+    for (int32_t a_index = 1; a_index <= M; a_index++) {
+        int a_bp;
+        if (reverse) a_bp = (__ldg(A + (M - a_index) / 4) >> (2 * ((a_index - 1) % 4))) & 3;
+        else a_bp = (__ldg(A + 1 + (a_index - 1) / 4) >> (2 * (3 - (a_index - 1) % 4))) & 3;
+        const int32_t *mrow = matrix + 16 * a_bp;
+        const int32_t row_first = first_b;
+        int32_t r_in = MININT, best_in = best_score, prev_old_best = MININT;
+        int32_t last_b = first_b, new_first = first_b;
+        bool lead = true;
+
+        for (int32_t seg = row_first; seg < b_size; seg += 32) {
+            const int32_t b = seg + lane;
+            const bool active = b < b_size;
+            const uint32_t amask = __ballot_sync(FULLW, active);
+            const int2 cell = active ? ring[b & MASK] : make_int2(MININT, MININT);
+            int32_t up = __shfl_up_sync(FULLW, cell.x, 1);
+            if (lane == 0) up = prev_old_best;
+            prev_old_best = __shfl_sync(FULLW, cell.x, 31);
+            int32_t v = NEGINF;
+            if (active) {
+                int32_t d = MININT;
+                if (b != row_first) d = up + mrow[(int)__ldg(reverse ? B + N - b : B + b)];
+                v = max(d, cell.y);
+            }
+            // ---- fixed point over the prune flags ------------------------------------------------------
+            uint32_t p = __ballot_sync(FULLW, active && (best_in - v > x_dropoff));
+            int32_t s = v, R = r_in;
+            for (;;) {
+                const uint32_t um = amask & ~p;
+                const bool unpruned = (um >> lane) & 1u;
+                const int32_t u = __popc(um & lt);
+                const int32_t w = unpruned ? v - goe + ge * (u + 1) : NEGINF;
+                R = max(r_in, warp_excl_prefix_max(w, lane)) - ge * u;
+                s = max(v, R);
+                const int32_t best_b = max(best_in, warp_excl_prefix_max(unpruned ? s : NEGINF, lane));
+                // flags are final from the left: keep what was decided, re-derive from the values they imply
+                const uint32_t pn = __ballot_sync(FULLW, active && (best_b - s > x_dropoff));
+                if (pn == p) break;
+                p = pn;
+            }
+            const uint32_t um = amask & ~p;
+            const bool unpruned = (um >> lane) & 1u;
+            // ---- commit the segment --------------------------------------------------------------------
+            const int nact = __popc(amask);
+            int dropped = 0;                                    // leading pruned cells leave the band
+            if (lead) {
+                dropped = um ? (__ffs(um) - 1) : nact;
+                new_first += dropped;
+                lead = (dropped == nact);
+            }
+            if (active) {
+                if (unpruned) ring[b & MASK] = make_int2(s, max(s - goe, cell.y - ge));
+                else if (lane >= dropped) ring[b & MASK] = make_int2(MININT, cell.y);
+            }
+            if (um) {
+                last_b = seg + (31 - __clz(um));
+                const int32_t m = __reduce_max_sync(FULLW, unpruned ? s : NEGINF);
+                if (m > best_in) {
+                    const uint32_t at = __ballot_sync(FULLW, unpruned && s == m);
+                    best_in = m; a_offset = a_index; b_offset = seg + (__ffs(at) - 1);
+                }
+            }
+            // gap_row leaving the segment: state after its last active cell
+            const int32_t r_next = unpruned ? max(s - goe, R - ge) : R;
+            r_in = __shfl_sync(FULLW, r_next, nact - 1);
+        }
+        __syncwarp();
+        best_score = best_in;
+        first_b = new_first;
+        if (first_b == b_size) break;
+        if (last_b < b_size - 1) b_size = last_b + 1;
+        else {
+            // while (gap_row >= best - X && b_size <= N) append (gap_row, gap_row - goe), gap_row -= ge
+            int32_t k = 0;
+            if (r_in >= best_score - x_dropoff) k = (ge == 0) ? (N - b_size + 1) : ((r_in - (best_score - x_dropoff)) / ge + 1);
+            k = max(0, min(k, N - b_size + 1));
+            if (b_size + k - first_b + 2 >= C) { overflow = true; return 0; }
+            for (int32_t i = lane; i < k; i += 32) {
+                const int32_t sc = r_in - i * ge;
+                ring[(b_size + i) & MASK] = make_int2(sc, sc - goe);
+            }
+            b_size += k;
+        }
+        if (b_size <= N) {
+            if (b_size - first_b + 2 >= C) { overflow = true; return 0; }
+            if (lane == 0) ring[b_size & MASK] = make_int2(MININT, MININT);
+            b_size++;
+        }
+        __syncwarp();
+    }
+    return best_score;
+}
+
+__global__ void __launch_bounds__(DPW_WARPS * 32)
+gapped_warp_kernel(const DevQuery q, const GappedLaunch L)
+{
+    __shared__ int2 rings[DPW_WARPS][DPW_CELLS];
+    __shared__ int32_t s_matrix[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_matrix[i] = q.matrix[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t warp0 = (int64_t)blockIdx.x * DPW_WARPS + wib, nwarps = (int64_t)gridDim.x * DPW_WARPS;
+    const int64_t n = L.todo ? (int64_t)L.n_todo : (int64_t)min((unsigned long long)L.max_init, *L.n_init);
+    int2 *ring = rings[wib];
+    for (int64_t w = warp0; w < n; w += nwarps) {
+        const int64_t i = L.todo ? (int64_t)L.todo[w] : w;
+        const DevInitHit h = L.init[i];
+        const DevChunk ch = L.chunks[h.chunk];
+        const uint8_t *S = L.packed + ch.byte_off;
+        const int32_t context = ctx_search(q, h.q_off);
+        const DevContext c = q.ctx[context];
+        const uint8_t *query = q.query + c.query_offset;
+        const int32_t qlen = c.query_length, slen = ch.len;
+        int32_t q_off = h.q_off - c.query_offset, s_off = h.s_off;
+        if (h.s_start + h.length >= s_off + 8) { s_off += 3; q_off += 3; }
+        // s_BlastDynProgNtGappedAlignment (same as dp_gapped above)
+        DevGapResult g;
+        g.q_start = g.q_stop = g.s_start = g.s_stop = g.score = g.q_seed = g.s_seed = 0;
+        g.status = 0;
+        const int32_t adj = 4 - (s_off % 4);
+        int32_t q_length = q_off + adj, s_length = s_off + adj;
+        if (q_length > qlen || s_length > slen) { q_length -= 4; s_length -= 4; }
+        bool overflow = false;
+        int32_t pq, ps, right = 0;
+        const int32_t left = dp_packed_warp(query, S, q_length, s_length, pq, ps, s_matrix, q.gap_open, q.gap_extend,
+                                            q.gap_x_dropoff, true, ring, overflow, lane);
+        if (!overflow) {
+            g.q_start = q_length - pq; g.s_start = s_length - ps;
+            if (q_length < qlen && s_length < slen) {
+                int32_t qs, ss;
+                __syncwarp();
+                right = dp_packed_warp(query + q_length - 1, S + (s_length + 3) / 4 - 1, qlen - q_length, slen - s_length,
+                                       qs, ss, s_matrix, q.gap_open, q.gap_extend, q.gap_x_dropoff, false, ring, overflow, lane);
+                g.q_stop = qs + q_length; g.s_stop = ss + s_length;
+            } else { g.q_stop = q_length; g.s_stop = s_length; }
+        }
+        if (overflow) g.status = 1;
+        else { g.score = left + right; g.q_seed = q_off; g.s_seed = s_off; }
+        if (lane == 0) L.out[i] = g;
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_gapped_warp(const DevQuery &q, const GappedLaunch &g, int blocks, cudaStream_t st)
+{
+    gapped_warp_kernel<<<blocks, DPW_WARPS * 32, 0, st>>>(q, g);
+    return cudaGetLastError();
+}
+int gapped_warp_per_block() { return DPW_WARPS; }
 
 __global__ void __launch_bounds__(GAP_THREADS)
 gapped_kernel(const DevQuery q, const GappedLaunch L)
@@ -757,10 +968,11 @@ gapped_kernel(const DevQuery q, const GappedLaunch L)
             int32_t q_off = h.q_off - c.query_offset, s_off = h.s_off;
             if (h.s_start + h.length >= s_off + 8) { s_off += 3; q_off += 3; }
             if (L.dp_smem_ring)
-                dp_gapped(q, s_matrix, query, c.query_length, S, ch.len, q_off, s_off, SmemRing{dp_smem + threadIdx.x}, g);
+                dp_gapped(q, s_matrix, query, c.query_length, S, ch.len, q_off, s_off, SmemRing{dp_smem + threadIdx.x},
+                          L.dp_max_rows > 0 ? L.dp_max_rows : INT32_MAX, g);
             else
                 dp_gapped(q, s_matrix, query, c.query_length, S, ch.len, q_off, s_off,
-                          GlobalRing{reinterpret_cast<int2 *>(scratch), L.tier_d - 1}, g);
+                          GlobalRing{reinterpret_cast<int2 *>(scratch), L.tier_d - 1}, INT32_MAX, g);
         }
         L.out[i] = g;
     }
