@@ -110,8 +110,8 @@ def batch_from_reference(r: dict, *, task: str, cfg=None, use_pv=True) -> abi.Ba
     b.gap_algo = abi.BN_GAP_GREEDY if greedy else abi.BN_GAP_DP
     b.gap_x_dropoff = int(r["gap_x_dropoff"])
     b.min_diag_separation = opt("min_diag_separation", 6, 50, none=-1)
-    # sbp->round_down: reward 2 with penalty -3/-5/-7 (core/blast_stat.c:3250,3265)
-    b.round_down = 1 if (b.reward == 2 and b.penalty in (-3, -5, -7)) else 0
+    # sbp->round_down as the reference computed it (s_GetNuclValuesArray, core/blast_stat.c:3207-3345)
+    b.round_down = int(r["round_down"])
     b.hsp_num_max = 0
     b.hitlist_size = (cfg.hitlist_size if cfg is not None and cfg.hitlist_size else 500)
     b.evalue_cutoff = (cfg.evalue if cfg is not None and cfg.evalue > 0 else 10.0)

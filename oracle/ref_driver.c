@@ -488,6 +488,7 @@ static int dump_params(const Setup *S, const BlastSeqSrc *seq_src, RefResult *re
     res->gap_x_dropoff = ext_params->gap_x_dropoff;
     res->gap_x_dropoff_final = ext_params->gap_x_dropoff_final;
     res->container_type = (word_params->container_type == eDiagHash);
+    res->round_down = S->sbp->round_down ? 1 : 0;
     memcpy(res->nucl_score_table, word_params->nucl_score_table, sizeof res->nucl_score_table);
     for (i = 0; i < 16; i++)
         for (j = 0; j < 16; j++) res->matrix[16 * i + j] = S->sbp->matrix->data[i][j];

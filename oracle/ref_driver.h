@@ -63,6 +63,7 @@ typedef struct RefResult {
     double  *ctx_kbp_gap;  /* 4 per context */
     int32_t  gap_x_dropoff, gap_x_dropoff_final;
     int32_t  container_type;   /* 0 = diag array, 1 = diag hash */
+    int32_t  round_down;       /* sbp->round_down */
     int32_t  nucl_score_table[256];
     int32_t  matrix[16 * 16];
     /* lookup table */

@@ -43,7 +43,7 @@ class RefResult(C.Structure):
         ("ctx_reduced_cutoff", C.POINTER(C.c_int32)), ("ctx_gapped_cutoff", C.POINTER(C.c_int32)),
         ("ctx_kbp_std", C.POINTER(C.c_double)), ("ctx_kbp_gap", C.POINTER(C.c_double)),
         ("gap_x_dropoff", C.c_int32), ("gap_x_dropoff_final", C.c_int32),
-        ("container_type", C.c_int32),
+        ("container_type", C.c_int32), ("round_down", C.c_int32),
         ("nucl_score_table", C.c_int32 * 256), ("matrix", C.c_int32 * 256),
         ("lut_type", C.c_int32), ("lut_word_length", C.c_int32), ("word_length", C.c_int32),
         ("scan_step", C.c_int32), ("longest_chain", C.c_int32), ("pv_array_bts", C.c_int32),
@@ -162,7 +162,7 @@ def search(queries, volume, cfg: RefConfig | None = None, *, task="megablast", m
             "ctx_kbp_std": None if n == 0 else _arr(res.ctx_kbp_std, 4 * n, np.float64).reshape(n, 4),
             "ctx_kbp_gap": None if n == 0 else _arr(res.ctx_kbp_gap, 4 * n, np.float64).reshape(n, 4),
             "gap_x_dropoff": res.gap_x_dropoff, "gap_x_dropoff_final": res.gap_x_dropoff_final,
-            "container_type": res.container_type,
+            "container_type": res.container_type, "round_down": res.round_down,
             "nucl_score_table": np.array(res.nucl_score_table, dtype=np.int32),
             "matrix": np.array(res.matrix, dtype=np.int32).reshape(16, 16),
             "lut_type": res.lut_type, "lut_word_length": res.lut_word_length,

@@ -1,0 +1,63 @@
+"""Known-answer test taken from the reference's own unit tests:
+MegablastGreedyTraceback2, c++/src/algo/blast/unit_tests/api/bl2seq_unit_test.cpp:1620-1690 —
+greedy1a.fsa vs greedy1b.fsa with megablast defaults scores 619, and 6034 with reward 10 / penalty -25 /
+gapped X-dropoff 100 (the second value needs the odd-score rounding of sbp->round_down).
+Checked for the reference engine built here, the C port, the product set-up and (on a GPU) the CUDA path."""
+import os
+
+import numpy as np
+import pytest
+
+from gblastn_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+KAT = [({}, 619), (dict(reward=10, penalty=-25, xdrop_gap=100.0, xdrop_gap_final=100.0), 6034)]
+
+
+def _fasta(path):
+    s = "".join(line.strip() for line in open(path) if not line.startswith(">"))
+    m = {"A": 0, "C": 1, "G": 2, "T": 3}
+    return np.array([m.get(c.upper(), 14) for c in s], dtype=np.uint8)
+
+
+def _inputs():
+    a, b = _fasta(os.path.join(GOLD, "greedy1a.fsa")), _fasta(os.path.join(GOLD, "greedy1b.fsa"))
+    return [a], synth.make_volume_from_bases([b])
+
+
+@pytest.mark.parametrize("kw,score", KAT)
+def test_kat_port_and_reference(kw, score):
+    from oracle import refdriver as R, portdriver as P
+    qs, vol = _inputs()
+    if R.available():
+        cfg = R.default_config("megablast", taps=R.TAP_LUT, **kw)
+        r = R.search(qs, vol, cfg)
+        assert r["status"] == 0 and r["final"].shape[0] == 1 and int(r["final"][0, 6]) == score
+        h = P.batch_from_reference(r, task="megablast", cfg=cfg)
+        p = P.search(h, vol)
+        assert np.array_equal(P.final_table(p["hsps"]), r["final"])
+    from gblastn_b200 import setup as S, abi
+    s = S.Setup(qs, task="megablast", db_length=vol.total_bases, db_num_seqs=vol.n_seqs, **kw)
+    try:
+        h2 = abi.BatchHolder()
+        h2.batch = s.batch
+        p2 = P.search(h2, vol)
+        assert p2["hsps"].size == 1 and int(p2["hsps"]["score"][0]) == score, "port + product set-up"
+    finally:
+        s.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw,score", KAT)
+def test_kat_gpu(kw, score):
+    from gblastn_b200 import engine as E, setup as S
+    qs, vol = _inputs()
+    s = S.Setup(qs, task="megablast", db_length=vol.total_bases, db_num_seqs=vol.n_seqs, **kw)
+    V, Q = E.Volume(vol), E.Query(s.batch)
+    try:
+        g = E.prelim_search(V, Q)
+        assert g["hsps"].size == 1 and int(g["hsps"]["score"][0]) == score
+        assert (int(g["hsps"]["q_off"][0]), int(g["hsps"]["q_end"][0]), int(g["hsps"]["s_off"][0]),
+                int(g["hsps"]["s_end"][0])) == (159, 874, 30, 739)
+    finally:
+        Q.free(); V.free(); s.free()
