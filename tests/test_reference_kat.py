@@ -61,3 +61,51 @@ def test_kat_gpu(kw, score):
                 int(g["hsps"]["s_end"][0])) == (159, 874, 30, 739)
     finally:
         Q.free(); V.free(); s.free()
+
+
+# ---- NucleotideBlastWordSize4 / _EOS (bl2seq_unit_test.cpp:2238-2301): invariants of the reference's test -------
+SIZE4 = [("blastn_size4a.fsa", "blastn_size4b.fsa"), ("blastn_size4c.fsa", "blastn_size4d.fsa")]
+
+
+def _well_formed(h):
+    assert h.size > 0
+    assert (h["q_off"] < h["q_end"]).all() and (h["s_off"] < h["s_end"]).all()
+    assert ((h["q_gapped_start"] >= h["q_off"]) & (h["q_gapped_start"] < h["q_end"])).all()
+    assert ((h["s_gapped_start"] >= h["s_off"]) & (h["s_gapped_start"] < h["s_end"])).all()
+    assert (h["q_end"] - h["q_off"] >= 4).all() and (h["s_end"] - h["s_off"] >= 4).all()
+
+
+@pytest.mark.parametrize("qf,sf", SIZE4)
+def test_wordsize4_port(qf, sf):
+    from oracle import refdriver as R, portdriver as P
+    from gblastn_b200 import setup as S, abi
+    qs, vol = [_fasta(os.path.join(GOLD, qf))], synth.make_volume_from_bases([_fasta(os.path.join(GOLD, sf))])
+    s = S.Setup(qs, task="blastn", db_length=vol.total_bases, db_num_seqs=vol.n_seqs, word_size=4)
+    try:
+        h = abi.BatchHolder()
+        h.batch = s.batch
+        p = P.search(h, vol)
+        _well_formed(p["hsps"])
+        if R.available():
+            r = R.search(qs, vol, R.default_config("blastn", word_size=4))
+            assert np.array_equal(P.final_table(p["hsps"]), r["final"])
+    finally:
+        s.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("qf,sf", SIZE4)
+def test_wordsize4_gpu(qf, sf):
+    from oracle import refdriver as R, portdriver as P
+    from gblastn_b200 import engine as E, setup as S
+    qs, vol = [_fasta(os.path.join(GOLD, qf))], synth.make_volume_from_bases([_fasta(os.path.join(GOLD, sf))])
+    s = S.Setup(qs, task="blastn", db_length=vol.total_bases, db_num_seqs=vol.n_seqs, word_size=4)
+    V, Q = E.Volume(vol), E.Query(s.batch)
+    try:
+        g = E.prelim_search(V, Q)
+        _well_formed(g["hsps"])
+        if R.available():
+            r = R.search(qs, vol, R.default_config("blastn", word_size=4))
+            assert np.array_equal(P.final_table(g["hsps"]), r["final"])
+    finally:
+        Q.free(); V.free(); s.free()
