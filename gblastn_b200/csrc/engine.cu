@@ -6,6 +6,7 @@
 // Everything runs on one CUDA stream per device; the only host<->device round trips are the
 // survivor / init-hit counters (needed to size the sorts) and the final D2H of init-HSPs.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -15,6 +16,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cub/cub.cuh>
@@ -854,19 +856,54 @@ static int prelim_search_locked(Device &D, Volume &V, Query &Q, int32_t oid_begi
     static const bool trace = getenv("BN_TRACE") != nullptr;
     double t_sort = 0, t_replay = 0, t_finish = 0, t_merge = 0, t_eval = 0, t_track = 0;
     const BnQueryBatch &b = Q.batch;
+    // init hits grouped by chunk (counting sort on the chunk index), each group in the reference's order
+    const size_t n_chunks = T->hchunks.size();
     std::vector<HostInit> inits((size_t)cnt.n_init);
-    for (size_t i = 0; i < inits.size(); i++) {
-        const DevInitHit &h = h_init[i];
-        const DevGapResult &g = h_gap[i];
-        inits[i] = HostInit{h.chunk, h.q_off, h.s_off, h.q_start, h.s_start, h.length, h.score, h.order,
-                            g.q_start, g.q_stop, g.s_start, g.s_stop, g.score, g.q_seed, g.s_seed};
+    std::vector<size_t> group_begin(n_chunks + 1, 0);
+    for (size_t i = 0; i < inits.size(); i++) ++group_begin[(size_t)h_init[i].chunk + 1];
+    for (size_t c = 0; c < n_chunks; c++) group_begin[c + 1] += group_begin[c];
+    {
+        std::vector<size_t> cursor(group_begin.begin(), group_begin.end() - 1);
+        for (size_t i = 0; i < inits.size(); i++) {
+            const DevInitHit &h = h_init[i];
+            const DevGapResult &g = h_gap[i];
+            inits[cursor[(size_t)h.chunk]++] = HostInit{h.chunk, h.q_off, h.s_off, h.q_start, h.s_start, h.length, h.score, h.order,
+                                                        g.q_start, g.q_stop, g.s_start, g.s_stop, g.score, g.q_seed, g.s_seed};
+        }
     }
-    sort_init_hits(inits);
-    t_sort = now_ms() - th0;
+    std::vector<size_t> groups;                       // chunks that have init hits, ascending
+    for (size_t c = 0; c < n_chunks; c++) if (group_begin[c + 1] > group_begin[c]) groups.push_back(c);
 
-    std::vector<BnHSP> final_hsps, gapped_tap, comb, fresh;
+    std::vector<BnHSP> final_hsps, gapped_tap, comb;
     std::vector<BnInitHit> init_tap;
     LowScoreTracker tracker(b);
+    struct GroupOut { std::vector<BnHSP> fresh, tap; BnStats stats{}; };
+    std::vector<GroupOut> gout(groups.size());
+    // one group: sort, containment replay, per-chunk list post-processing
+    auto do_group = [&](size_t gi) {
+        const size_t c = groups[gi], lo = group_begin[c], hi = group_begin[c + 1];
+        GroupOut &o = gout[gi];
+        sort_chunk_init_hits(inits.data() + lo, inits.data() + hi);
+        replay_gapped(b, T->hchunks[c], inits.data() + lo, hi - lo, tracker.low_score(), o.fresh, o.stats);
+        if (taps & BN_TAP_GAPPED) o.tap = o.fresh;
+        finish_chunk_list(b, o.fresh);
+    };
+    // The per-chunk work only meets other chunks through hit_params->low_score.  When no bound can move
+    // during this search (fewer subjects than a hit list holds) the chunks are independent and, for large
+    // result sets (short-read batches), are replayed by a few host threads.
+    const bool parallel = cnt.n_init >= 16384 && groups.size() >= 2 && tracker.bounds_stay_zero((int64_t)oid_end - oid_begin);
+    if (parallel) {
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const size_t n_threads = std::min<size_t>(std::min<size_t>(groups.size(), hw), 16);
+        std::atomic<size_t> next{0};
+        std::vector<std::thread> pool;
+        auto worker = [&]() { for (size_t gi; (gi = next.fetch_add(1)) < groups.size();) do_group(gi); };
+        for (size_t t = 1; t < n_threads; t++) pool.emplace_back(worker);
+        worker();
+        for (auto &th : pool) th.join();
+    }
+    t_sort = now_ms() - th0;
+
     int32_t cur_oid = -1;
     auto finish_oid = [&]() {
         if (cur_oid < 0) return;
@@ -881,28 +918,25 @@ static int prelim_search_locked(Device &D, Volume &V, Query &Q, int32_t oid_begi
         t_track += now_ms() - ta;
         comb.clear();
     };
-    size_t i = 0;
-    while (i < inits.size()) {
-        size_t j = i;
-        while (j < inits.size() && inits[j].chunk == inits[i].chunk) ++j;
-        const HostChunk &ch = T->hchunks[(size_t)inits[i].chunk];
+    for (size_t gi = 0; gi < groups.size(); gi++) {
+        const size_t c = groups[gi], lo = group_begin[c], hi = group_begin[c + 1];
+        const HostChunk &ch = T->hchunks[c];
         if (ch.oid != cur_oid) { finish_oid(); cur_oid = ch.oid; }
+        double ta = now_ms();
+        if (!parallel) do_group(gi);                  // in subject order: the bounds may move between subjects
+        GroupOut &o = gout[gi];
+        stats.gap_extensions += o.stats.gap_extensions;
+        t_replay += now_ms() - ta; ta = now_ms();
         if (taps & BN_TAP_INIT)
-            for (size_t k = i; k < j; k++)
+            for (size_t k = lo; k < hi; k++)
                 init_tap.push_back(BnInitHit{ch.oid, ch.chunk_off, inits[k].q_off, inits[k].s_off,
                                              inits[k].q_start, inits[k].s_start, inits[k].length,
                                              inits[k].score});
-        fresh.clear();
-        double ta = now_ms();
-        replay_gapped(b, ch, &inits[i], j - i, tracker.low_score(), fresh, stats);
-        t_replay += now_ms() - ta; ta = now_ms();
-        if (taps & BN_TAP_GAPPED) gapped_tap.insert(gapped_tap.end(), fresh.begin(), fresh.end());
-        finish_chunk_list(b, fresh);
-        t_finish += now_ms() - ta; ta = now_ms();
-        for (auto &h : fresh) { h.s_off += ch.chunk_off; h.s_end += ch.chunk_off; h.s_gapped_start += ch.chunk_off; }
-        merge_chunk_lists(comb, fresh, ch.chunk_off, ch.chunk_off == 0 ? 0 : BN_DBSEQ_CHUNK_OVERLAP);
+        if (taps & BN_TAP_GAPPED) gapped_tap.insert(gapped_tap.end(), o.tap.begin(), o.tap.end());
+        for (auto &h : o.fresh) { h.s_off += ch.chunk_off; h.s_end += ch.chunk_off; h.s_gapped_start += ch.chunk_off; }
+        merge_chunk_lists(comb, o.fresh, ch.chunk_off, ch.chunk_off == 0 ? 0 : BN_DBSEQ_CHUNK_OVERLAP);
+        std::vector<BnHSP>().swap(o.fresh);
         t_merge += now_ms() - ta;
-        i = j;
     }
     finish_oid();
     stats.ms_host = now_ms() - th0;

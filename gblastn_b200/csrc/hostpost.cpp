@@ -289,6 +289,17 @@ void sort_init_hits(std::vector<HostInit> &v)
     });
 }
 
+void sort_chunk_init_hits(HostInit *first, HostInit *last)
+{
+    std::sort(first, last, [](const HostInit &a, const HostInit &c) {
+        if (a.score != c.score) return a.score > c.score;
+        if (a.s_start != c.s_start) return a.s_start < c.s_start;
+        if (a.length != c.length) return a.length > c.length;
+        if (a.q_start != c.q_start) return a.q_start < c.q_start;
+        return a.order < c.order;
+    });
+}
+
 void replay_gapped(const BnQueryBatch &b, const HostChunk &ch, const HostInit *init, size_t n,
                    const int32_t *low_score, std::vector<BnHSP> &out, BnStats &stats)
 {

@@ -52,6 +52,8 @@ struct PostParams {
 
 // Sort key of Blast_InitHitListSortByScore (core/blast_extend.c:274-296) + emission order.
 void sort_init_hits(std::vector<HostInit> &v);
+// same order for the hits of ONE chunk
+void sort_chunk_init_hits(HostInit *first, HostInit *last);
 
 // Replays BLAST_GetGappedScore for one chunk; appends saved HSPs (chunk-relative subject coords).
 void replay_gapped(const BnQueryBatch &b, const HostChunk &ch, const HostInit *init, size_t n,
@@ -85,6 +87,9 @@ class LowScoreTracker {
 public:
     explicit LowScoreTracker(const BnQueryBatch &b);
     const int32_t *low_score() const { return enabled_ ? low_.data() : nullptr; }
+    // true when a search over n_subjects subjects can never raise a bound: a hit list has to be full
+    // (hitlist_size_ subjects) before a further subject can displace anything
+    bool bounds_stay_zero(int64_t n_subjects) const { return !enabled_ || n_subjects <= (int64_t)hitlist_size_; }
     void subject_done(const BnQueryBatch &b, const std::vector<BnHSP> &list);
 private:
     bool enabled_;
