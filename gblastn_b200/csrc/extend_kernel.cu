@@ -388,16 +388,23 @@ __device__ void extend_one(const DevQuery &q, const uint8_t *packed, const DevCh
 // ---- bucket chain (BLAST_DiagHash restricted to one bucket) -------------------------------------
 // cell = int4 {diag, level, (hit_len << 1) | hit_saved, next}; index 0 = null.  All lanes execute
 // the walk on identical values; lane 0 stores.
+// The first CHAIN_SMEM cells of a chain live in shared memory (stale cells are recycled in place, so a
+// bucket's chain stays far shorter than its hit count: a walk step costs a shared-memory access instead
+// of a dependent L2 round trip); cells beyond that spill to the group's region of global memory.
+constexpr int CHAIN_SMEM = 255;
 struct Chain {
-    int4 *cells;
+    int4 *cells;       // global region, index 1..
+    int4 *fast;        // shared memory, index 1..CHAIN_SMEM
     int32_t head, used;
+    __device__ __forceinline__ int4 load(int32_t i) const { return i <= CHAIN_SMEM ? fast[i] : cells[i]; }
+    __device__ __forceinline__ void store(int32_t i, int4 v) const { if (i <= CHAIN_SMEM) fast[i] = v; else cells[i] = v; }
 };
 
 __device__ __forceinline__ bool chain_get(const Chain &c, int32_t diag, int32_t &level, int32_t &saved)
 {
     int32_t i = c.head;
     while (i) {
-        const int4 v = c.cells[i];
+        const int4 v = c.load(i);
         if (v.x == diag) { level = v.y; saved = v.z & 1; return true; }
         i = v.w;
     }
@@ -409,16 +416,16 @@ __device__ __forceinline__ void chain_put(Chain &c, int32_t diag, int32_t level,
 {
     int32_t i = c.head;
     while (i) {
-        const int4 v = c.cells[i];
+        const int4 v = c.load(i);
         if (v.x == diag || s_off_pos - v.y > window) {
-            if (lane == 0) c.cells[i] = make_int4(diag, level, (len << 1) | saved, v.w);
+            if (lane == 0) c.store(i, make_int4(diag, level, (len << 1) | saved, v.w));
             __syncwarp();
             return;
         }
         i = v.w;
     }
     const int32_t n = ++c.used;
-    if (lane == 0) c.cells[n] = make_int4(diag, level, (len << 1) | saved, c.head);
+    if (lane == 0) c.store(n, make_int4(diag, level, (len << 1) | saved, c.head));
     __syncwarp();
     c.head = n;
 }
@@ -507,10 +514,16 @@ extend_kernel(const DevQuery q, const ExtendLaunch e, const uint64_t *keys, cons
         n_hits = (int64_t)e.counters[0];
     }
     __shared__ int32_t s_tab[256];
+    __shared__ int4 s_chain[EXT_WARPS_PER_BLOCK][CHAIN_SMEM + 1];
+    // the batch of 32 hits a warp replays serially: staged in shared memory so that every step reads its
+    // hit with broadcast loads whose addresses do not depend on the previous step (no shuffle chain)
+    __shared__ SeedHit s_hit[EXT_WARPS_PER_BLOCK][32];
+    __shared__ SpecResult s_spec[EXT_WARPS_PER_BLOCK][32];
+    __shared__ uint64_t s_key[EXT_WARPS_PER_BLOCK][32];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = q.score_table[i];
     __syncthreads();
 
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t warp0 = (int64_t)blockIdx.x * EXT_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * EXT_WARPS_PER_BLOCK;
     const int64_t n_groups = (int64_t)e.counters[4];
@@ -529,7 +542,9 @@ extend_kernel(const DevQuery q, const ExtendLaunch e, const uint64_t *keys, cons
         const int64_t j0 = (int64_t)heads[g];
         Chain chain;
         chain.cells = reinterpret_cast<int4 *>(e.cells) + j0;   // region [j0+1 .. j0+group_size]
+        chain.fast = s_chain[threadIdx.x >> 5];
         chain.head = 0; chain.used = 0;
+        __syncwarp();
         int32_t last_hit_cell = 0, flag_cell = 0;      // eDiagArray: the cell's last_hit / flag
         uint32_t cur_chunk = 0xFFFFFFFFu;
         int32_t cur_epoch = -1;
@@ -559,12 +574,23 @@ extend_kernel(const DevQuery q, const ExtendLaunch e, const uint64_t *keys, cons
             const unsigned brk = __ballot_sync(FULL, !in_group);
             const int cnt = brk ? (__ffs(brk) - 1) : 32;
             if (cnt < 32) group_done = true;
+            __syncwarp();
+            s_hit[wib][lane] = mine; s_spec[wib][lane] = myspec; s_key[wib][lane] = mykey;
+            __syncwarp();
             for (int t = 0; t < cnt; t++) {
+                // A run of seeds on the diagonal that was just updated, all starting before its recorded
+                // end, is what a long match produces: each of them is a plain `continue` for the reference
+                // (s_off_pos < last_hit, no state change), so the whole run is stepped over at once.
+                if (is_hash && cache_ok) {
+                    const bool covered = lane >= t && lane < cnt && mine.chunk == cur_chunk &&
+                                         (int32_t)(mine.s_off - mine.q_off) == cache_diag &&
+                                         (int32_t)mine.s_off + ch.diag_offset < cache_level;
+                    const unsigned cm = __ballot_sync(FULL, covered) >> t;
+                    const int run = (~cm) ? (__ffs(~cm) - 1) : (32 - t);
+                    if (run > 0) { t += run - 1; continue; }
+                }
                 const int64_t j = base + t;
-                SeedHit h;
-                h.chunk = __shfl_sync(FULL, mine.chunk, t);
-                h.q_off = __shfl_sync(FULL, mine.q_off, t);
-                h.s_off = __shfl_sync(FULL, mine.s_off, t);
+                const SeedHit h = s_hit[wib][t];
                 if (h.chunk != cur_chunk) {
                     cur_chunk = h.chunk;
                     ch = e.chunks[cur_chunk];
@@ -593,14 +619,9 @@ extend_kernel(const DevQuery q, const ExtendLaunch e, const uint64_t *keys, cons
                 // is a double word by itself
                 const bool check_double = two_hits && (hit_saved || s_end_pos > last_hit + window);
 
-                SpecResult r;
-                r.status = __shfl_sync(FULL, myspec.status, t);
+                SpecResult r = s_spec[wib][t];
                 if (r.status != SPEC_NONE && !check_double) {
                     if (r.status == SPEC_MASKED) continue;
-                    r.q_off = __shfl_sync(FULL, myspec.q_off, t); r.s_off = __shfl_sync(FULL, myspec.s_off, t);
-                    r.extended = __shfl_sync(FULL, myspec.extended, t);
-                    r.q_start = __shfl_sync(FULL, myspec.q_start, t); r.s_start = __shfl_sync(FULL, myspec.s_start, t);
-                    r.length = __shfl_sync(FULL, myspec.length, t); r.score = __shfl_sync(FULL, myspec.score, t);
                 } else {
                     extend_one(q, e.packed, ch, s_tab, is_hash, has_loc, word, lut, direct, check_double, q_off, s_off,
                                lane, cc, r);
@@ -612,7 +633,7 @@ extend_kernel(const DevQuery q, const ExtendLaunch e, const uint64_t *keys, cons
                 int32_t hit_ready = 0;
                 if (r.status == SPEC_READY) {
                     hit_ready = 1;
-                    const uint64_t kj = __shfl_sync(FULL, mykey, t);
+                    const uint64_t kj = s_key[wib][t];
                     if (lane == 0) {
                         const unsigned long long slot = atomicAdd(&e.counters[2], 1ull);
                         if ((int64_t)slot < e.init_capacity) {
