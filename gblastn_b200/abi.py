@@ -6,7 +6,7 @@ import numpy as np
 
 BN_OK = 0
 BN_ERR_INVALID, BN_ERR_MEMORY, BN_ERR_NO_DEVICE, BN_ERR_CUDA, BN_ERR_UNSUPPORTED, BN_ERR_OVERFLOW = 1, 2, 3, 4, 5, 6
-BN_LUT_MB, BN_LUT_SMALL_NA = 0, 1
+BN_LUT_MB, BN_LUT_SMALL_NA, BN_LUT_NA = 0, 1, 2
 BN_DIAG_ARRAY, BN_DIAG_HASH = 0, 1
 BN_GAP_DP, BN_GAP_GREEDY = 0, 1
 BN_TAP_INIT, BN_TAP_GAPPED = 2, 4
@@ -41,6 +41,7 @@ class BnQueryBatch(C.Structure):
         ("hsp_num_max", C.c_int32), ("hitlist_size", C.c_int32),
         ("evalue_cutoff", C.c_double), ("low_score_perc", C.c_double),
         ("lookup_segments", C.c_void_p), ("n_lookup_segments", C.c_int32),
+        ("na_backbone", C.c_void_p), ("na_overflow", C.c_void_p), ("na_overflow_len", C.c_int64),
     ]
 
 

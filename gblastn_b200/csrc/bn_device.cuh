@@ -43,6 +43,8 @@ struct DevQuery {
                                            // of its first and second chain element, .x = {qp, bit 31: chain continues}
     const uint4 *qinfo;                    // MB: per query position {next_pos, 16 bases left, 16 right, ambiguity}
     const int16_t *backbone, *overflow;    // SmallNa
+    const int4 *na_cells;                  // eNaLookupTable: thick backbone {num_used, entries[3] | overflow_cursor}
+    const int32_t *na_overflow;
     int32_t has_locations;                 // lut->masked_locations != NULL
     int32_t container_type, window_size, scan_range;
     const uint2 *qpk;                      // 2-bit packed query windows: .x bases, .y ambiguity (see qwin)

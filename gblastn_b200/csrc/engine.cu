@@ -159,6 +159,7 @@ struct QueryDev {
     DevContext *ctx = nullptr;
     int32_t *next_pos = nullptr;
     int16_t *backbone = nullptr, *overflow = nullptr;
+    int32_t *na_cells = nullptr, *na_overflow = nullptr;
     int32_t *score_table = nullptr, *matrix = nullptr;
     uint2 *qpk = nullptr;
     uint2 *prk = nullptr;
@@ -200,7 +201,7 @@ static Device *device_at(int d)
 // loading a new batch re-uses the previous batch's memory without touching the OS allocator.
 static void free_query_dev(QueryDev &q, cudaStream_t st)
 {
-    void *ptrs[] = {q.query, q.ctx, q.next_pos, q.backbone, q.overflow,
+    void *ptrs[] = {q.query, q.ctx, q.next_pos, q.backbone, q.overflow, q.na_cells, q.na_overflow,
                     q.score_table, q.matrix, q.qpk, q.prk, q.cinfo, q.qinfo};
     for (void *p : ptrs) if (p) cudaFreeAsync(p, st);
     q = QueryDev{};
@@ -271,6 +272,11 @@ static int query_to_device(Query &Q, const BnQueryBatch &src, int d, const std::
             CU_TRY(upload(&t_hashtable, src.hashtable, (size_t)b.hashsize, st));
             CU_TRY(cudaMemcpyAsync(qd.next_pos, src.next_pos, ((size_t)b.concat_len + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         }
+    } else if (b.lut_type == BN_LUT_NA) {
+        static const int32_t kNoOverflow[1] = {0};
+        CU_TRY(upload(&qd.na_cells, src.na_backbone, (size_t)(4 * b.hashsize), st));
+        if (src.na_overflow && src.na_overflow_len > 0) CU_TRY(upload(&qd.na_overflow, src.na_overflow, (size_t)src.na_overflow_len, st));
+        else CU_TRY(upload(&qd.na_overflow, kNoOverflow, (size_t)1, st));
     } else {
         static const int16_t kEmptyOverflow[2] = {-1, -1};
         CU_TRY(upload(&qd.backbone, src.backbone, (size_t)b.hashsize, st));
@@ -306,6 +312,7 @@ static int query_to_device(Query &Q, const BnQueryBatch &src, int d, const std::
     v.scan_step = b.scan_step; v.hash_mask = (uint32_t)(b.hashsize - 1);
     v.next_pos = qd.next_pos;
     v.backbone = qd.backbone; v.overflow = qd.overflow;
+    v.na_cells = reinterpret_cast<const int4 *>(qd.na_cells); v.na_overflow = qd.na_overflow;
     v.has_locations = Q.batch.masked_locations != nullptr;
     v.container_type = b.container_type; v.window_size = b.window_size; v.scan_range = b.scan_range;
     v.score_table = qd.score_table; v.matrix = qd.matrix; v.qpk = qd.qpk;
@@ -1161,8 +1168,9 @@ static int query_load_impl(const BnQueryBatch *b, int *query_handle, int hook_de
     if (b->window_size > 0 && std::min(b->scan_range, b->window_size - b->word_length) > 0)
         return fail(BN_ERR_UNSUPPORTED, "two-hit mode with an off-diagonal search (scan_range > 0) is not implemented: "
                                         "neighbouring diagonals live in other replay groups");
-    if (b->lut_type != BN_LUT_MB && b->lut_type != BN_LUT_SMALL_NA)
-        return fail(BN_ERR_UNSUPPORTED, "only eMBLookupTable and eSmallNaLookupTable are supported");
+    if (b->lut_type != BN_LUT_MB && b->lut_type != BN_LUT_SMALL_NA && b->lut_type != BN_LUT_NA)
+        return fail(BN_ERR_UNSUPPORTED, "unknown lookup table type");
+    if (b->lut_type == BN_LUT_NA && !b->na_backbone) return fail(BN_ERR_INVALID, "bn_query_load: standard blastn table arrays missing");
     if (b->lut_type == BN_LUT_MB && (!b->hashtable != !b->next_pos)) return fail(BN_ERR_INVALID, "bn_query_load: hashtable and next_pos must come together");
     if (b->lut_type == BN_LUT_MB && !b->hashtable && (!b->lookup_segments || b->n_lookup_segments <= 0))
         return fail(BN_ERR_INVALID, "bn_query_load: MB batch carries neither the table arrays nor lookup_segments");
@@ -1180,6 +1188,7 @@ static int query_load_impl(const BnQueryBatch *b, int *query_handle, int hook_de
     Q->batch.hashtable = nullptr; Q->batch.next_pos = nullptr; Q->batch.pv_array = nullptr;
     Q->batch.backbone = nullptr; Q->batch.overflow = nullptr;
     Q->batch.lookup_segments = nullptr; Q->batch.n_lookup_segments = 0;
+    Q->batch.na_backbone = nullptr; Q->batch.na_overflow = nullptr;
     Q->batch.masked_locations = b->masked_locations ? reinterpret_cast<const int32_t *>(Q->ctx.data()) : nullptr;
     int32_t n = 1;
     while (n < b->concat_len + b->window_size) n <<= 1;   // s_BlastDiagTableNew core/blast_extend.c:46-72

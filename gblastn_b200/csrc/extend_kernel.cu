@@ -259,6 +259,14 @@ __device__ bool lut_contains(const DevQuery &q, uint32_t index, int32_t q_pos)
         }
         return false;
     }
+    if (q.lut_type == 2) {          // s_NaLookup core/na_ungapped.c:112-138
+        const int4 cell = __ldg(&q.na_cells[index & q.hash_mask]);
+        const int32_t nh = cell.x;
+        if (nh <= 3) return (nh > 0 && cell.y == q_pos) || (nh > 1 && cell.z == q_pos) || (nh > 2 && cell.w == q_pos);
+        for (int32_t i = 0; i < nh; i++)
+            if (__ldg(&q.na_overflow[cell.y + i]) == q_pos) return true;
+        return false;
+    }
     int32_t v = __ldg(&q.backbone[index & q.hash_mask]);
     if (v == q_pos) return true;
     if (v == -1 || v >= 0) return false;

@@ -237,6 +237,18 @@ scan_kernel(const DevQuery q, const ScanLaunch s)
                     emit_hit(q, s, (uint32_t)lo, (uint32_t)p, g, qo, so);
                 qp = __ldg(&q.next_pos[qp]);
             }
+        } else if (q.lut_type == 2) {
+            // s_BlastLookupRetrieve core/blast_nascan.c:63-85; extension as for the megablast table
+            const int4 cell = __ldg(&q.na_cells[idx]);
+            const int32_t nh = cell.x;
+            for (int32_t i = 0; i < nh; i++) {
+                const int32_t v = nh <= 3 ? (i == 0 ? cell.y : (i == 1 ? cell.z : cell.w)) : __ldg(&q.na_overflow[cell.y + i]);
+                ++my_lookup_hits;
+                int32_t qo, so;
+                if (s.raw_pairs) emit_hit(q, s, (uint32_t)lo, (uint32_t)p, g, v, p);
+                else if (mini_extend_mb(q, S, ch.len, v, p, qo, so))
+                    emit_hit(q, s, (uint32_t)lo, (uint32_t)p, g, qo, so);
+            }
         } else {
             int32_t v = __ldg(&q.backbone[idx]);
             if (v == -1) continue;

@@ -414,6 +414,7 @@ struct BnSetup {
     std::vector<int32_t> masked, segments;
     std::vector<uint32_t> pv;
     std::vector<int16_t> backbone, overflow;
+    std::vector<int32_t> na_backbone, na_overflow;
     std::vector<double> kbp_std, kbp_gap;
     int32_t gap_x_dropoff_final = 0, longest_chain = 0;
     std::string error;
@@ -717,7 +718,6 @@ int bn_setup_create(const BnSetupOptions *opt, int32_t nq, const uint8_t *qseq, 
     for (const Range &r : segs) { entries += r.right - r.left; max_q_off = std::max(max_q_off, r.right); }
     int lut_width = 0;
     const int lut_type = choose_table(word_size, entries, max_q_off, lut_width);
-    if (lut_type == 2) { return bail(BN_ERR_UNSUPPORTED); }
     b.word_length = word_size; b.lut_word_length = lut_width;
     b.scan_step = word_size - lut_width + 1;
     const bool mask_at_hash = opt->mask_at_hash != 0;
@@ -764,7 +764,8 @@ int bn_setup_create(const BnSetupOptions *opt, int32_t nq, const uint8_t *qseq, 
         S->longest_chain = (int32_t)longest;
         if (device_fill) S->pv.clear();
     } else {
-        b.lut_type = BN_LUT_SMALL_NA;
+        // thin backbone of BlastLookupIndexQueryExactMatches (core/blast_lookup.c:84-138): per cell the query
+        // offsets of its words in indexing order; shared by the small and the standard blastn table
         b.hashsize = (int64_t)1 << (2 * lut_width);
         std::vector<std::vector<int32_t>> thin((size_t)b.hashsize);
         const int32_t mask = (int32_t)(b.hashsize - 1);
@@ -785,29 +786,55 @@ int bn_setup_create(const BnSetupOptions *opt, int32_t nq, const uint8_t *qseq, 
             }
             if (seq >= target) add_word(seq - lut_width, offset - lut_width);
         }
-        int64_t need = 2;
         int32_t longest = 0;
-        for (const auto &ch : thin) {
-            const int32_t n = (int32_t)ch.size();
-            if (n > 1) need += n + 1;
-            longest = std::max(longest, n);
-        }
-        if (need >= 32768) return bail(BN_ERR_UNSUPPORTED);    // reference falls back to eNaLookupTable
+        for (const auto &ch : thin) longest = std::max(longest, (int32_t)ch.size());
         S->longest_chain = longest;
-        S->backbone.assign((size_t)b.hashsize, (int16_t)-1);
-        S->overflow.assign((size_t)need, (int16_t)0);
-        int32_t cursor = 2;
-        for (int64_t i = 0; i < b.hashsize; i++) {
-            const auto &ch = thin[(size_t)i];
-            if (ch.empty()) continue;
-            if (ch.size() == 1) S->backbone[(size_t)i] = (int16_t)ch[0];
-            else {
-                S->backbone[(size_t)i] = (int16_t)-cursor;
-                for (int32_t v : ch) S->overflow[(size_t)cursor++] = (int16_t)v;
-                S->overflow[(size_t)cursor++] = (int16_t)-1;
-            }
+        // BlastSmallNaLookupTableNew fails when its 15-bit overflow array would not fit, and
+        // LookupTableWrapInit then builds the standard table instead (core/lookup_wrap.c:126-135)
+        bool standard = lut_type == 2;
+        if (!standard) {
+            int64_t need = 2;
+            for (const auto &ch : thin) if (ch.size() > 1) need += (int64_t)ch.size() + 1;
+            if (need >= 32768) standard = true;
         }
-        b.overflow_len = cursor;
+        if (standard) {
+            // s_BlastNaLookupFinalize core/blast_nalookup.c:448-538: up to 3 hits in the cell, more in overflow
+            b.lut_type = BN_LUT_NA;
+            S->na_backbone.assign((size_t)(4 * b.hashsize), 0);
+            for (int64_t i = 0; i < b.hashsize; i++) {
+                const auto &ch = thin[(size_t)i];
+                if (ch.empty()) continue;
+                int32_t *cell = &S->na_backbone[(size_t)(4 * i)];
+                cell[0] = (int32_t)ch.size();
+                if (ch.size() <= 3) for (size_t j = 0; j < ch.size(); j++) cell[1 + j] = ch[j];
+                else {
+                    cell[1] = (int32_t)S->na_overflow.size();
+                    S->na_overflow.insert(S->na_overflow.end(), ch.begin(), ch.end());
+                }
+            }
+            if (S->na_overflow.empty()) S->na_overflow.push_back(0);
+        } else {
+            b.lut_type = BN_LUT_SMALL_NA;
+            int64_t need = 2;
+            for (const auto &ch : thin) {
+                const int32_t n = (int32_t)ch.size();
+                if (n > 1) need += n + 1;
+            }
+            S->backbone.assign((size_t)b.hashsize, (int16_t)-1);
+            S->overflow.assign((size_t)need, (int16_t)0);
+            int32_t cursor = 2;
+            for (int64_t i = 0; i < b.hashsize; i++) {
+                const auto &ch = thin[(size_t)i];
+                if (ch.empty()) continue;
+                if (ch.size() == 1) S->backbone[(size_t)i] = (int16_t)ch[0];
+                else {
+                    S->backbone[(size_t)i] = (int16_t)-cursor;
+                    for (int32_t v : ch) S->overflow[(size_t)cursor++] = (int16_t)v;
+                    S->overflow[(size_t)cursor++] = (int16_t)-1;
+                }
+            }
+            b.overflow_len = cursor;
+        }
     }
     if (!segs.empty() && word_size > lut_width && mask_at_hash) invert_locations(segs, concat_len, S->masked);
 
@@ -819,6 +846,9 @@ int bn_setup_create(const BnSetupOptions *opt, int32_t nq, const uint8_t *qseq, 
     b.pv_array = S->pv.empty() ? nullptr : S->pv.data();
     b.backbone = S->backbone.empty() ? nullptr : S->backbone.data();
     b.overflow = S->overflow.empty() ? nullptr : S->overflow.data();
+    b.na_backbone = S->na_backbone.empty() ? nullptr : S->na_backbone.data();
+    b.na_overflow = S->na_overflow.empty() ? nullptr : S->na_overflow.data();
+    b.na_overflow_len = (int64_t)S->na_overflow.size();
     b.masked_locations = S->masked.empty() ? nullptr : S->masked.data();
     b.n_masked_locations = (int32_t)(S->masked.size() / 2);
     for (const Range &r : segs) { S->segments.push_back(r.left); S->segments.push_back(r.right); }

@@ -56,6 +56,14 @@ class Setup:
         return self._arr(self.batch.hashtable, self.batch.hashsize, C.c_int32, np.int32)
 
     @property
+    def na_backbone(self):
+        return self._arr(self.batch.na_backbone, 4 * self.batch.hashsize, C.c_int32, np.int32)
+
+    @property
+    def na_overflow(self):
+        return self._arr(self.batch.na_overflow, self.batch.na_overflow_len, C.c_int32, np.int32)
+
+    @property
     def next_pos(self):
         return self._arr(self.batch.next_pos, self.batch.concat_len + 1, C.c_int32, np.int32)
 

@@ -57,6 +57,7 @@ extern "C" {
 
 #define BN_LUT_MB        0      /* eMBLookupTable      (inc-core/blast_options.h:164) */
 #define BN_LUT_SMALL_NA  1      /* eSmallNaLookupTable */
+#define BN_LUT_NA        2      /* eNaLookupTable: small word sizes with a query batch beyond the 15-bit offsets of the small table */
 
 #define BN_DIAG_ARRAY    0      /* eDiagArray (inc-core/blast_parameters.h) */
 #define BN_DIAG_HASH     1      /* eDiagHash  */
@@ -137,6 +138,12 @@ typedef struct BnQueryBatch {
      * 4^lut-entry table never crosses PCIe. */
     const int32_t *lookup_segments;
     int32_t        n_lookup_segments;
+
+    /* BlastNaLookupTable (inc-core/blast_nalookup.h:111-160), lut_type BN_LUT_NA: thick_backbone as it lies
+     * in memory (hashsize cells of 4 ints: num_used, then entries[3] or overflow_cursor) and overflow. */
+    const int32_t *na_backbone;
+    const int32_t *na_overflow;
+    int64_t        na_overflow_len;
 } BnQueryBatch;
 
 /* BlastOffsetPair (inc-core/blast_def.h:141) tagged with its subject. */

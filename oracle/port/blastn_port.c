@@ -63,6 +63,14 @@ static int lut_contains(const BnQueryBatch *b, uint32_t index, int32_t q_pos)
             q = b->next_pos[q];
         }
         return 0;
+    } else if (b->lut_type == BN_LUT_NA) {
+        /* s_NaLookup core/na_ungapped.c:112-138 */
+        const int32_t *cell = b->na_backbone + 4 * (size_t)(index & (uint32_t)(b->hashsize - 1));
+        const int32_t n = cell[0];
+        const int32_t *pos = (n <= 3) ? cell + 1 : b->na_overflow + cell[1];
+        int32_t i;
+        for (i = 0; i < n; i++) if (pos[i] == q_pos) return 1;
+        return 0;
     } else {
         int32_t v = b->backbone[index & (uint32_t)(b->hashsize - 1)], src;
         if (v == q_pos) return 1;
@@ -581,6 +589,24 @@ static void word_finder(const BnQueryBatch *b, const Subject *S, DiagState *diag
                 }
                 extend_mb_hit(&w, q - 1, p, s_range);
                 q = b->next_pos[q];
+            }
+        } else if (b->lut_type == BN_LUT_NA) {
+            /* s_BlastNaScanSubject_8_4 / _Any + s_BlastLookupRetrieve core/blast_nascan.c:63-290; the
+             * extension is s_BlastNaExtend(Direct/Aligned) as for the megablast table (BlastChooseNaExtend
+             * core/na_ungapped.c:1780-1792) */
+            const int32_t *cell = b->na_backbone + 4 * (size_t)idx;
+            const int32_t n = cell[0];
+            const int32_t *pos = (n <= 3) ? cell + 1 : b->na_overflow + cell[1];
+            int32_t i;
+            for (i = 0; i < n; i++) {
+                out->stats.lookup_hits++;
+                if (taps & PORT_TAP_SCAN) {
+                    BnOffsetPair *o = (BnOffsetPair *)vec_push(scanv);
+                    o->q_off = (uint32_t)pos[i]; o->s_off = (uint32_t)p;
+                    *(int32_t *)vec_push(scan_oid) = S->oid;
+                    *(int32_t *)vec_push(scan_chunk) = S->chunk_off;
+                }
+                extend_mb_hit(&w, pos[i], p, s_range);
             }
         } else {
             int32_t v = b->backbone[idx];

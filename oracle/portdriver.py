@@ -86,7 +86,10 @@ def batch_from_reference(r: dict, *, task: str, cfg=None, use_pv=True) -> abi.Ba
         b.overflow = h.ptr(ov, np.int16)
         b.overflow_len = int(ov.shape[0])
     else:
-        raise NotImplementedError("eNaLookupTable is outside the supported path")
+        b.na_backbone = h.ptr(r["na_backbone"], np.int32)
+        ov = r["na_overflow"] if r["na_overflow"] is not None else np.zeros(1, np.int32)
+        b.na_overflow = h.ptr(ov, np.int32)
+        b.na_overflow_len = int(ov.shape[0])
     if r["n_masked_locations"] is not None and r["n_masked_locations"] >= 0:
         ml = r["masked_locations"] if r["masked_locations"] is not None else np.zeros(2, np.int32)
         b.masked_locations = h.ptr(ml, np.int32)

@@ -550,7 +550,29 @@ static int dump_params(const Setup *S, const BlastSeqSrc *seq_src, RefResult *re
             }
         }
     } else {
+        BlastNaLookupTable *l = (BlastNaLookupTable *)S->lookup_wrap->lut;
         res->lut_type = 2;
+        res->lut_word_length = l->lut_word_length; res->word_length = l->word_length;
+        res->scan_step = l->scan_step; res->longest_chain = l->longest_chain;
+        res->hashsize = l->backbone_size; res->na_overflow_len = l->overflow_size;
+        res->n_masked_locations = -1;
+        if (l->masked_locations) {
+            BlastSeqLoc *m; int32_t k = 0;
+            for (m = l->masked_locations; m; m = m->next) ++k;
+            res->n_masked_locations = k;
+            res->masked_locations = (int32_t *)malloc(8 * (size_t)(k ? k : 1));
+            for (m = l->masked_locations, k = 0; m; m = m->next, ++k) {
+                res->masked_locations[2 * k] = m->ssr->left; res->masked_locations[2 * k + 1] = m->ssr->right;
+            }
+        }
+        if (dump_lut) {
+            res->na_backbone = (int32_t *)malloc(16 * (size_t)res->hashsize);
+            memcpy(res->na_backbone, l->thick_backbone, 16 * (size_t)res->hashsize);
+            if (res->na_overflow_len > 0) {
+                res->na_overflow = (int32_t *)malloc(4 * (size_t)res->na_overflow_len);
+                memcpy(res->na_overflow, l->overflow, 4 * (size_t)res->na_overflow_len);
+            }
+        }
     }
 
     word_params = BlastInitialWordParametersFree(word_params);
@@ -707,7 +729,7 @@ void ref_free_result(RefResult *res)
     free(res->ctx_reduced_cutoff); free(res->ctx_gapped_cutoff);
     free(res->ctx_kbp_std); free(res->ctx_kbp_gap);
     free(res->hashtable); free(res->next_pos); free(res->pv_array);
-    free(res->backbone); free(res->overflow); free(res->masked_locations);
+    free(res->backbone); free(res->overflow); free(res->masked_locations); free(res->na_backbone); free(res->na_overflow);
     free(res->concat_query);
     memset(res, 0, sizeof *res);
 }

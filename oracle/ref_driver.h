@@ -81,6 +81,9 @@ typedef struct RefResult {
     int64_t  lookup_hits, init_extends, good_init_extends, gap_extensions, good_extensions;
     double   seconds_prelim;            /* wall time of the preliminary search alone */
     int32_t  status;
+    /* eNaLookupTable (lut_type 2, tap bit3): thick_backbone as 4 ints per cell {num_used, entries[3] | overflow_cursor}, overflow */
+    int32_t *na_backbone, *na_overflow;
+    int64_t  na_overflow_len;
 } RefResult;
 
 /* queries: blastna bytes (0..3 ACGT, 4..14 ambiguity) concatenated, lengths in qlens.

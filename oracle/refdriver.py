@@ -58,6 +58,8 @@ class RefResult(C.Structure):
         ("good_init_extends", C.c_int64), ("gap_extensions", C.c_int64),
         ("good_extensions", C.c_int64),
         ("seconds_prelim", C.c_double), ("status", C.c_int32),
+        ("na_backbone", C.POINTER(C.c_int32)), ("na_overflow", C.POINTER(C.c_int32)),
+        ("na_overflow_len", C.c_int64),
     ]
 
 
@@ -174,6 +176,8 @@ def search(queries, volume, cfg: RefConfig | None = None, *, task="megablast", m
             "pv_array": _arr(res.pv_array, res.pv_len, np.uint32),
             "backbone": _arr(res.backbone, res.hashsize, np.int16),
             "overflow": _arr(res.overflow, res.overflow_len, np.int16),
+            "na_backbone": _arr(res.na_backbone, 4 * res.hashsize, np.int32) if res.lut_type == 2 else None,
+            "na_overflow": _arr(res.na_overflow, res.na_overflow_len, np.int32) if res.lut_type == 2 else None,
             "n_masked_locations": res.n_masked_locations,
             "masked_locations": (_arr(res.masked_locations, 2 * max(res.n_masked_locations, 0), np.int32)
                                  if res.n_masked_locations > 0 else None),

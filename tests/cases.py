@@ -88,6 +88,12 @@ CASES = {
     # C5: megablast 1 000 x 5 kb (+ masks) vs nt-like volume  ->  80 x 5 kb vs 3 000 log-normal sequences
     "c5_scaled_ntlike_5kb": dict(task="megablast", cfg={}, seq_lens="lognormal:3000:50:2000:1.1", vol_seed=50,
                                  nq=80, qlen=5000, q_seed=55, sub=0.02, indel=0.002, planted=0.8),
+    # eNaLookupTable: word size < 9 with a query batch beyond the small table's 15-bit offsets (e.g. a batch of
+    # short-word searches); lut == word -> s_BlastNaExtendDirect, stride 1
+    "blastn_ws7_na_table": dict(task="blastn", cfg={"word_size": 7}, seq_lens=[60_000, 20_000, 900], vol_seed=21,
+                                nq=45, qlen=800, q_seed=31, sub=0.08, indel=0.01, planted=0.8),
+    "blastn_ws8_na_table_two_hit": dict(task="blastn", cfg={"word_size": 8, "window_size": 40}, seq_lens=[60_000, 20_000],
+                                        vol_seed=22, nq=60, qlen=700, q_seed=32, sub=0.08, indel=0.01, planted=0.8),
     # empty result: random queries only
     "mb_no_hits": dict(task="megablast", cfg={}, seq_lens=[100_000], vol_seed=11,
                        nq=5, qlen=400, q_seed=22, sub=0.0, indel=0.0, planted=0.0),

@@ -35,6 +35,11 @@ def _compare(r, s):
         assert np.array_equal(s.next_pos, r["next_pos"])
         assert b.pv_array_bts == r["pv_array_bts"]
         assert np.array_equal(s.pv_array, r["pv_array"])
+    elif b.lut_type == 2:
+        # eNaLookupTable: thick backbone cells {num_used, entries[3] | overflow_cursor} and overflow
+        assert np.array_equal(s.na_backbone, r["na_backbone"])
+        if r["na_overflow"] is not None and r["na_overflow"].size:
+            assert np.array_equal(s.na_overflow[: r["na_overflow"].size], r["na_overflow"])
     else:
         assert np.array_equal(s.backbone, r["backbone"])
         # overflow[0..1] are never written by the reference (malloc garbage): compare from 2
