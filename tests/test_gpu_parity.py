@@ -184,6 +184,28 @@ def test_gpu_with_masked_queries(name):
         Q.free(); V.free()
 
 
+def test_gpu_na_table_word_longer_than_lut():
+    """eNaLookupTable with word 11 > lut 8 (a long, mostly masked query: few table entries but offsets beyond
+    15 bits): s_BlastNaScanSubject_8_4 + s_BlastNaExtendAligned + s_TypeOfWord over s_NaLookup."""
+    from gblastn_b200 import engine as E, setup as S, synth, abi
+    from oracle import refdriver as R, portdriver as P
+    if not R.available():
+        pytest.skip("reference library not present")
+    vol = synth.random_volume([80_000, 30_000], seed=23)
+    qs = synth.planted_queries(vol, 1, 40_000, seed=33, planted_frac=1.0, sub_rate=0.06, indel_rate=0.005)
+    masks = [[(0, 17_000), (19_000, 36_500), (38_000, 39_999)]]
+    r = R.search(qs, vol, R.default_config("blastn", taps=R.TAP_INIT), masks=masks)
+    assert r["status"] == 0 and r["lut_type"] == 2 and (r["lut_word_length"], r["word_length"], r["scan_step"]) == (8, 11, 4)
+    s = S.Setup(qs, task="blastn", db_length=vol.total_bases, db_num_seqs=vol.n_seqs, masks=masks)
+    V, Q = E.Volume(vol), E.Query(s.batch)
+    try:
+        g = E.prelim_search(V, Q, taps=abi.BN_TAP_INIT)
+        assert np.array_equal(P.init_table(g["init"]), r["init"])
+        assert np.array_equal(P.final_table(g["hsps"]), r["final"])
+    finally:
+        Q.free(); V.free(); s.free()
+
+
 @pytest.mark.parametrize("name", ["mb_lut11_hash_indels", "blastn_mb11_dp", "mb_smallna_diagarray", "mb_lut12_stride17"])
 def test_gpu_with_product_setup(name):
     """Whole product path: our own set-up (bn_setup_*) + GPU search == reference blastn engine."""
