@@ -126,8 +126,12 @@ struct Device {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // volume uploads of the host-buffer entry point (overlap with the table build)
     cudaEvent_t alloc_ev = nullptr;
-    Workspace ws;
-    std::mutex mu;       // one search at a time per device
+    // Two workspaces: the batch pipeline (bn_prelim_search_batches) lets a host thread finish batch k-1 out of
+    // one workspace's pinned result mirrors while batch k runs in the other.  Single searches use wss[cur].
+    Workspace wss[2];
+    int cur = 0;
+    Workspace &ws() { return wss[cur]; }
+    std::mutex mu;       // one search (or one pipeline) at a time per device
 };
 
 struct ChunkTable {
@@ -333,8 +337,8 @@ static int query_to_device(Query &Q, const BnQueryBatch &src, int d, const std::
         CU_TRY(launch_popc(t_presence, nwords, t_counts, st));
         size_t tmp_bytes = 0;
         CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, t_counts, t_prefix, (int)nwords, st));
-        CU_TRY(dev->ws.cub_temp.reserve(tmp_bytes));
-        CU_TRY(cub::DeviceScan::ExclusiveSum(dev->ws.cub_temp.p, tmp_bytes, t_counts, t_prefix, (int)nwords, st));
+        CU_TRY(dev->ws().cub_temp.reserve(tmp_bytes));
+        CU_TRY(cub::DeviceScan::ExclusiveSum(dev->ws().cub_temp.p, tmp_bytes, t_counts, t_prefix, (int)nwords, st));
         if (device_fill)
             CU_TRY(launch_build_prk_cinfo(t_presence, t_prefix, nwords, qd.prk, t_first_qp, (int64_t)b.concat_len + 1,
                                           qd.qinfo, qd.cinfo, st));
@@ -484,7 +488,7 @@ struct StageCounts { int64_t n_hits = 0, lookup_hits = 0, n_init = 0, n_extended
 static int run_word_finder(Device &D, Volume &V, Query &Q, ChunkTable &T, bool raw_pairs,
                            StageCounts &cnt, BnStats *stats)
 {
-    Workspace &ws = D.ws;
+    Workspace &ws = D.ws();
     cudaStream_t st = D.stream;
     const DevQuery &dq = Q.dev[V.device].view;
     CU_TRY(ws.counters.reserve(8));
@@ -580,7 +584,7 @@ static int32_t greedy_xdrop_offset(const BnQueryBatch &b)
 // (counters[2], capped at max_init), so the call needs no host knowledge of it.
 static int enqueue_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t max_init, BnStats *stats)
 {
-    Workspace &ws = D.ws;
+    Workspace &ws = D.ws();
     cudaStream_t st = D.stream;
     const DevQuery &dq = Q.dev[V.device].view;
     const BnQueryBatch &b = Q.batch;
@@ -626,7 +630,7 @@ static int enqueue_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t
 static int finish_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t n_init,
                          DevInitHit *&h_init, DevGapResult *&h_gap, BnStats *stats)
 {
-    Workspace &ws = D.ws;
+    Workspace &ws = D.ws();
     cudaStream_t st = D.stream;
     const DevQuery &dq = Q.dev[V.device].view;
     const BnQueryBatch &b = Q.batch;
@@ -706,7 +710,7 @@ static int finish_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t 
 static int run_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t n_init,
                       DevInitHit *&h_init, DevGapResult *&h_gap, BnStats *stats)
 {
-    Workspace &ws = D.ws;
+    Workspace &ws = D.ws();
     if (n_init == 0) {
         CU_TRY(ws.h_init.reserve(1)); CU_TRY(ws.h_gap.reserve(1));
         h_init = ws.h_init.p; h_gap = ws.h_gap.p;
@@ -734,7 +738,7 @@ static int run_fused(Device &D, Volume &V, Query &Q, ChunkTable &T, StageCounts 
                      DevInitHit *&h_init, DevGapResult *&h_gap, bool *redo)
 {
     *redo = false;
-    Workspace &ws = D.ws;
+    Workspace &ws = D.ws();
     cudaStream_t st = D.stream;
     const DevQuery &dq = Q.dev[V.device].view;
     CU_TRY(ws.counters.reserve(8));
@@ -818,30 +822,39 @@ static T *to_malloc(const std::vector<T> &v)
     return p;
 }
 
-static int prelim_search_locked(Device &D, Volume &V, Query &Q, int32_t oid_begin, int32_t oid_end,
-                                int taps, BnResults *out)
+// What the GPU side of one search leaves for the host: counts and the pinned mirrors of the init-HSPs and
+// their speculative gapped results (they belong to the workspace that was current during the search).
+struct GpuOut {
+    std::shared_ptr<ChunkTable> T;
+    StageCounts cnt;
+    DevInitHit *h_init = nullptr;
+    DevGapResult *h_gap = nullptr;
+    int32_t oid_begin = 0, oid_end = 0;
+    double t0 = 0, t_table = 0, t_wf = 0, t_gap = 0;
+};
+
+static int search_gpu_phase(Device &D, Volume &V, Query &Q, int32_t oid_begin, int32_t oid_end, BnResults *out, GpuOut &G)
 {
     memset(out, 0, sizeof *out);
-    const double t0 = now_ms();
+    G.t0 = now_ms();
+    G.oid_begin = oid_begin; G.oid_end = oid_end;
     CU_TRY(cudaSetDevice(D.id));
     if (!Q.dev[V.device].ready) return fail(BN_ERR_INVALID, "query batch is not loaded on the volume's device");
     int rc;
-    std::shared_ptr<ChunkTable> T;
+    std::shared_ptr<ChunkTable> &T = G.T;
     rc = build_chunk_table(V, Q, oid_begin, oid_end, D.stream, &T);
     if (rc) return rc;
     BnStats &stats = out->stats;
     stats.subject_bases_scanned = T->total_bases;
     if (V.ready) CU_TRY(cudaStreamWaitEvent(D.stream, V.ready, 0));
 
-    StageCounts cnt;
+    StageCounts &cnt = G.cnt;
     const double tw0 = now_ms();
     double tw1 = tw0;
-    DevInitHit *h_init = nullptr;
-    DevGapResult *h_gap = nullptr;
     bool general = Q.batch.container_type != BN_DIAG_HASH || Q.fast_path_refused || T->total_pos <= 0;
     if (!general) {
         bool redo = false;
-        rc = run_fused(D, V, Q, *T, cnt, stats, h_init, h_gap, &redo);
+        rc = run_fused(D, V, Q, *T, cnt, stats, G.h_init, G.h_gap, &redo);
         if (rc) return rc;
         if (redo) { general = true; Q.fast_path_refused = true; cnt = StageCounts{}; }
         tw1 = now_ms();
@@ -850,14 +863,28 @@ static int prelim_search_locked(Device &D, Volume &V, Query &Q, int32_t oid_begi
         rc = run_word_finder(D, V, Q, *T, false, cnt, &stats);
         if (rc) return rc;
         tw1 = now_ms();
-        rc = run_gapped(D, V, Q, *T, cnt.n_init, h_init, h_gap, &stats);
+        rc = run_gapped(D, V, Q, *T, cnt.n_init, G.h_init, G.h_gap, &stats);
         if (rc) return rc;
     }
     const double tw2 = now_ms();
+    G.t_table = tw0 - G.t0; G.t_wf = tw1 - tw0; G.t_gap = tw2 - tw1;
     stats.lookup_hits = cnt.lookup_hits;
     stats.init_extends = cnt.n_extended;
     stats.good_init_extends = cnt.n_init;
+    return BN_OK;
+}
 
+// Host replay of one search (containment filter, per-chunk list post-processing, chunk merge, E-values,
+// low_score feedback).  Touches no device state: safe on a worker thread while the device runs the next batch.
+static int search_host_phase(const Query &Q, const GpuOut &G, int taps, BnResults *out)
+{
+    const std::shared_ptr<ChunkTable> &T = G.T;
+    const StageCounts &cnt = G.cnt;
+    const DevInitHit *h_init = G.h_init;
+    const DevGapResult *h_gap = G.h_gap;
+    const int32_t oid_begin = G.oid_begin, oid_end = G.oid_end;
+    const double t0 = G.t0, tw0 = G.t0 + G.t_table, tw1 = tw0 + G.t_wf, tw2 = tw1 + G.t_gap;
+    BnStats &stats = out->stats;
     // ---- host replay -------------------------------------------------------------------------
     const double th0 = now_ms();
     static const bool trace = getenv("BN_TRACE") != nullptr;
@@ -959,6 +986,15 @@ static int prelim_search_locked(Device &D, Volume &V, Query &Q, int32_t oid_begi
     return BN_OK;
 }
 
+static int prelim_search_locked(Device &D, Volume &V, Query &Q, int32_t oid_begin, int32_t oid_end,
+                                int taps, BnResults *out)
+{
+    GpuOut G;
+    int rc = search_gpu_phase(D, V, Q, oid_begin, oid_end, out, G);
+    if (rc) return rc;
+    return search_host_phase(Q, G, taps, out);
+}
+
 }  // namespace bn
 
 using namespace bn;
@@ -1020,7 +1056,7 @@ void bn_release(void)
     g_volumes.clear();
     for (auto &d : g_devices) {
         cudaSetDevice(d->id);
-        d->ws.release();
+        d->wss[0].release(); d->wss[1].release();
         if (d->alloc_ev) cudaEventDestroy(d->alloc_ev);
         if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
         if (d->stream) cudaStreamDestroy(d->stream);
@@ -1284,6 +1320,55 @@ int bn_prelim_search_host(int device, const BnQueryBatch *batch, const uint8_t *
     return rc;
 }
 
+int bn_prelim_search_batches(int vol_handle, int32_t n_batches, const BnQueryBatch *const *batches, int taps,
+                             BnResults *results)
+{
+    if (n_batches < 0 || (n_batches > 0 && (!batches || !results))) return fail(BN_ERR_INVALID, "bn_prelim_search_batches: bad argument");
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (vol_handle < 0 || vol_handle >= (int)g_volumes.size() || !g_volumes[vol_handle])
+        return fail(BN_ERR_INVALID, "bad volume handle");
+    Volume *V = g_volumes[vol_handle].get();
+    Device *D = device_at(V->device);
+    for (int32_t k = 0; k < n_batches; k++) memset(&results[k], 0, sizeof results[k]);
+    std::lock_guard<std::mutex> lk(D->mu);
+    const int32_t n_seq = (int32_t)V->seq_len.size();
+    std::vector<int> qh((size_t)n_batches, -1);
+    std::vector<GpuOut> G((size_t)n_batches);
+    std::vector<int> host_rc((size_t)n_batches, BN_OK);
+    std::vector<std::string> host_err((size_t)n_batches);
+    std::thread pending[2];
+    int first_error = BN_OK;
+    std::string first_msg;
+    const int saved_cur = D->cur;
+    for (int32_t k = 0; k < n_batches && first_error == BN_OK; k++) {
+        // tables of batch k (uploads + device-side derivation); the worker is finishing batch k-1 meanwhile
+        rc = bn_query_load(batches[k], &qh[(size_t)k]);
+        if (rc) { first_error = rc; first_msg = g_err; break; }
+        const int slot = k & 1;
+        if (pending[slot].joinable()) pending[slot].join();      // batch k-2 has left this workspace's mirrors
+        D->cur = slot;
+        Query *Q = g_queries[(size_t)qh[(size_t)k]].get();
+        rc = search_gpu_phase(*D, *V, *Q, 0, n_seq, &results[k], G[(size_t)k]);
+        if (rc) { first_error = rc; first_msg = g_err; break; }
+        pending[slot] = std::thread([&, k, Q]() {
+            host_rc[(size_t)k] = search_host_phase(*Q, G[(size_t)k], taps, &results[k]);
+            if (host_rc[(size_t)k]) host_err[(size_t)k] = g_err;      // thread-local message of the worker
+        });
+    }
+    for (auto &t : pending) if (t.joinable()) t.join();
+    D->cur = saved_cur;
+    for (int32_t k = 0; k < n_batches; k++) {
+        if (qh[(size_t)k] >= 0) bn_query_free(qh[(size_t)k]);
+        if (first_error == BN_OK && host_rc[(size_t)k]) { first_error = host_rc[(size_t)k]; first_msg = host_err[(size_t)k]; }
+    }
+    if (first_error) {
+        for (int32_t k = 0; k < n_batches; k++) bn_results_free(&results[k]);
+        return fail(first_error, first_msg);
+    }
+    return BN_OK;
+}
+
 void bn_results_free(BnResults *r)
 {
     if (!r) return;
@@ -1314,7 +1399,7 @@ int bn_scan_subject(int vol_handle, int query_handle, int32_t oid, int32_t chunk
     if (rc) return rc;
     std::vector<SeedHit> h((size_t)cnt.n_hits);
     if (cnt.n_hits) {
-        CU_TRY(cudaMemcpyAsync(h.data(), D->ws.hits_b.p, h.size() * sizeof(SeedHit), cudaMemcpyDeviceToHost, D->stream));
+        CU_TRY(cudaMemcpyAsync(h.data(), D->ws().hits_b.p, h.size() * sizeof(SeedHit), cudaMemcpyDeviceToHost, D->stream));
         CU_TRY(cudaStreamSynchronize(D->stream));
     }
     BnOffsetPair *o = (BnOffsetPair *)malloc(std::max<size_t>(h.size(), 1) * sizeof(BnOffsetPair));
@@ -1362,7 +1447,7 @@ int bn_get_gapped_score(int vol_handle, int query_handle, int32_t oid, int32_t c
     *hsps = nullptr; *n_hsps = 0;
     if (n_init == 0) return BN_OK;
 
-    Workspace &ws = D->ws;
+    Workspace &ws = D->ws();
     cudaStream_t st = D->stream;
     std::vector<DevInitHit> up((size_t)n_init);
     for (int64_t i = 0; i < n_init; i++) {
@@ -1431,7 +1516,7 @@ int bn_bench_scan(int vol_handle, int query_handle, int iters, double *ms_per_la
     rc = build_chunk_table(*V, *Q, 0, (int32_t)V->seq_len.size(), D->stream, &T);
     if (rc) return rc;
     if (V->ready) CU_TRY(cudaStreamWaitEvent(D->stream, V->ready, 0));
-    Workspace &ws = D->ws;
+    Workspace &ws = D->ws();
     cudaStream_t st = D->stream;
     CU_TRY(ws.counters.reserve(8));
     int64_t cap = std::max<int64_t>((int64_t)ws.hits_a.cap, std::max<int64_t>(1 << 16, T->total_pos / 16));

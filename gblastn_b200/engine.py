@@ -20,7 +20,7 @@ EXPORTS = [
     "bn_db_load", "bn_db_free", "bn_query_load", "bn_query_free",
     "bn_prelim_search", "bn_prelim_search_host", "bn_results_free",
     "bn_scan_subject", "bn_word_finder", "bn_free", "bn_bench_scan", "bn_query_download_lookup", "bn_get_gapped_score",
-    "bn_dbfile_index", "bn_db_load_files", "bn_dbfile_write",
+    "bn_dbfile_index", "bn_db_load_files", "bn_dbfile_write", "bn_prelim_search_batches",
     "bn_setup_create", "bn_setup_batch", "bn_setup_kbp_std", "bn_setup_kbp_gap",
     "bn_setup_gap_x_dropoff_final", "bn_setup_longest_chain", "bn_setup_free",
 ]
@@ -158,6 +158,16 @@ def prelim_search(volume: Volume, query: Query, oid_begin=0, oid_end=-1, taps=0)
                                   C.c_int32(oid_begin), C.c_int32(oid_end), C.c_int(taps),
                                   C.byref(res)))
     return _results(res)
+
+
+def prelim_search_batches(volume: Volume, holders, taps=0) -> list:
+    """Pipelined search of several query batches against one resident volume (one result dict per batch)."""
+    n = len(holders)
+    batches = [h.batch if hasattr(h, "batch") else h for h in holders]
+    ptrs = (C.POINTER(abi.BnQueryBatch) * n)(*[C.pointer(b) for b in batches])
+    res = (abi.BnResults * n)()
+    _check(lib().bn_prelim_search_batches(C.c_int(volume.handle), C.c_int32(n), ptrs, C.c_int(taps), res))
+    return [_results(res[k]) for k in range(n)]
 
 
 def prelim_search_host(holder, vol, device=0, taps=0) -> dict:

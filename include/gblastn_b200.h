@@ -230,6 +230,13 @@ int  bn_prelim_search_host(int device, const BnQueryBatch *batch,
                            const uint8_t *packed, int64_t packed_bytes,
                            const int64_t *seq_byte_off, const int32_t *seq_len, int32_t n_seq,
                            int taps, BnResults *out);
+/* A stream of query batches against one resident volume — blastn's batch loop (app/blast/blastn_app.cpp:574-640)
+ * and G-BLASTN's Prepare -> Prelim -> ... thread pipeline (gpu/work_thread.cpp:16-438) — as a two-stage pipeline:
+ * while batch k is on the GPU (table upload/fill, scan ... gapped) a host thread finishes batch k-1
+ * (containment replay, list post-processing, E-values).  results[k] receives what bn_prelim_search would
+ * return for batches[k]; every batch sees the whole volume. */
+int  bn_prelim_search_batches(int vol_handle, int32_t n_batches, const BnQueryBatch *const *batches, int taps,
+                              BnResults *results);
 void bn_results_free(BnResults *r);
 
 /* Stage-level entry points (parity taps; same semantics as the reference callbacks). */

@@ -137,6 +137,43 @@ def test_real_blast_db_volume(task):
         Q.free(); V.free(); s.free()
 
 
+def test_batch_pipeline_equals_single_searches():
+    """bn_prelim_search_batches: five different query batches (mixed table shapes, one empty result, one on
+    the general cub path) through the two-stage pipeline give byte-identical results to one search each."""
+    from gblastn_b200 import engine as E, setup as S, synth
+    vol = synth.random_volume([400_000, 150_000, 30_000, 777], seed=61)
+    specs = [dict(task="megablast", nq=120, qlen=900, seed=1, planted=0.7, sub=0.02),
+             dict(task="megablast", nq=3, qlen=600, seed=2, planted=1.0, sub=0.04),          # small table, diag array
+             dict(task="blastn", nq=8, qlen=700, seed=3, planted=0.8, sub=0.08),             # DP, many seed hits
+             dict(task="megablast", nq=5, qlen=400, seed=4, planted=0.0, sub=0.0),           # no hits
+             dict(task="megablast", nq=300, qlen=1000, seed=5, planted=0.5, sub=0.02)]       # lut 12
+    setups = []
+    for sp in specs:
+        qs = synth.planted_queries(vol, sp["nq"], sp["qlen"], seed=sp["seed"], planted_frac=sp["planted"],
+                                   sub_rate=sp["sub"], indel_rate=0.003)
+        setups.append(S.Setup(qs, task=sp["task"], db_length=vol.total_bases, db_num_seqs=vol.n_seqs,
+                              device_lookup=1 if sp["task"] == "megablast" else 0))
+    V = E.Volume(vol)
+    try:
+        singles = []
+        for st in setups:
+            Q = E.Query(st.batch)
+            singles.append(E.prelim_search(V, Q))
+            Q.free()
+        for _ in range(2):
+            piped = E.prelim_search_batches(V, [st.batch for st in setups])
+            assert len(piped) == len(singles)
+            for a, b in zip(singles, piped):
+                assert a["hsps"].tobytes() == b["hsps"].tobytes()
+                for k in ("lookup_hits", "good_init_extends", "gap_extensions", "good_extensions"):
+                    assert a["stats"][k] == b["stats"][k]
+        assert sum(x["hsps"].size for x in singles) > 0 and singles[3]["hsps"].size == 0
+    finally:
+        V.free()
+        for st in setups:
+            st.free()
+
+
 def test_host_buffer_entry_point():
     from gblastn_b200 import engine as E
     from oracle import portdriver as P
