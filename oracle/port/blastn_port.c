@@ -30,6 +30,10 @@ typedef struct Subject {
     const uint8_t *seq;   /* packed, chunk start (byte aligned) */
     int32_t len;          /* chunk length in bases */
     int32_t oid, chunk_off;
+    /* subject->seq_ranges of a masked database (unmasked [left, right) intervals, chunk-relative);
+     * masked == 0: one implicit range covering the chunk, scanned from offset 0 */
+    int32_t masked, n_ranges;
+    const int32_t *ranges;
 } Subject;
 
 /* NCBI2NA_UNPACK_BASE, inc-core/blast_util.h:52-55 */
@@ -566,11 +570,19 @@ static void word_finder(const BnQueryBatch *b, const Subject *S, DiagState *diag
 {
     WordCtx w;
     const int32_t lut = b->lut_word_length, step = b->scan_step;
-    const int32_t last = S->len - lut, s_range = S->len;
-    int32_t p;
+    int32_t p, ri;
+    const int32_t whole[2] = {0, S->len};
+    const int32_t nr = S->masked ? S->n_ranges : 1;
     w.b = b; w.S = S; w.diag = diag; w.init = init; w.n_extended = 0;
 
-    for (p = 0; p <= last; p += step) {
+    /* BlastNaWordFinder core/na_ungapped.c:1610-1645 + s_DetermineScanningOffsets core/masksubj.inl:43-59:
+     * every unmasked range is scanned from left + (word - lut) (0 for an unmasked subject) to right - lut,
+     * and its right end bounds the mini-extension and s_TypeOfWord */
+    for (ri = 0; ri < nr; ri++) {
+    const int32_t *rg = S->masked ? S->ranges + 2 * ri : whole;
+    const int32_t first = S->masked ? rg[0] + b->word_length - lut : 0;
+    const int32_t last = rg[1] - lut, s_range = rg[1];
+    for (p = first; p <= last; p += step) {
         const uint8_t *s = S->seq + p / 4;
         uint32_t word = ((uint32_t)s[0] << 24) | ((uint32_t)s[1] << 16) | ((uint32_t)s[2] << 8) | s[3];
         uint32_t idx = (word >> (2 * (16 - (p % 4 + lut)))) & (uint32_t)(b->hashsize - 1);
@@ -636,6 +648,7 @@ static void word_finder(const BnQueryBatch *b, const Subject *S, DiagState *diag
                 } while (v >= 0);
             }
         }
+    }
     }
     diag_exit(diag, S->len);
     out->stats.init_extends += w.n_extended;
@@ -1294,9 +1307,23 @@ static void merge_chunks(Vec *comb, BnHSP *nw, int64_t n_new, int32_t split_offs
 }
 
 /* ------------------------------------------------------------------ whole preliminary stage */
+int port_prelim_search_masked(const BnQueryBatch *b, const uint8_t *packed, const int64_t *seq_byte_off,
+                              const int32_t *seq_len, int32_t n_seq, int taps, int32_t smask_type,
+                              const int32_t *smask_n, const int32_t *smask_iv, PortResults *out);
+
 int port_prelim_search(const BnQueryBatch *b, const uint8_t *packed, const int64_t *seq_byte_off,
                        const int32_t *seq_len, int32_t n_seq, int taps, PortResults *out)
 {
+    return port_prelim_search_masked(b, packed, seq_byte_off, seq_len, n_seq, taps, 0, NULL, NULL, out);
+}
+
+/* smask_*: database masks (smask_type 1 soft / 2 hard): smask_n[i] masked [begin, end) intervals of subject i,
+ * flat pairs in smask_iv */
+int port_prelim_search_masked(const BnQueryBatch *b, const uint8_t *packed, const int64_t *seq_byte_off,
+                              const int32_t *seq_len, int32_t n_seq, int taps, int32_t smask_type,
+                              const int32_t *smask_n, const int32_t *smask_iv, PortResults *out)
+{
+    int64_t *smask_first = NULL;
     DiagState diag;
     Vec init, gapped_tap, final_, scanv, scan_oid, scan_chunk;
     GreedyMem gm;
@@ -1318,6 +1345,10 @@ int port_prelim_search(const BnQueryBatch *b, const uint8_t *packed, const int64
     diag_new(&diag, b);
     if (b->low_score_perc > 0.00001) low_score = (int32_t *)calloc((size_t)b->num_queries, 4);
     (void)best_scores; (void)n_lists;
+    if (smask_type && smask_n) {
+        smask_first = (int64_t *)calloc((size_t)n_seq + 1, 8);
+        for (oid = 0; oid < n_seq; oid++) smask_first[oid + 1] = smask_first[oid] + smask_n[oid];
+    }
 
     for (oid = 0; oid < n_seq; oid++) {
         /* s_BlastSearchEngineOneContext chunk loop core/blast_engine.c:459-541,
@@ -1326,17 +1357,60 @@ int port_prelim_search(const BnQueryBatch *b, const uint8_t *packed, const int64
         const int32_t full = seq_len[oid];
         int32_t next = 0;
         Vec comb;
+        /* database masks: unmasked ranges as BlastSeqBlkSetSeqRanges leaves them (core/blast_util.c:186-223) */
+        const int32_t mt = (smask_type && smask_n) ? smask_type : 0;
+        int32_t n_r = 1, hm = 0, n_hard = 1, n_soft = 1;
+        int32_t *R = NULL, *chunk_r = NULL;
+        int32_t full_range[2];
+        const int32_t *hard, *soft;
+        full_range[0] = 0; full_range[1] = full;
+        if (mt) {
+            const int32_t nm = smask_n[oid];
+            const int32_t *iv = smask_iv + 2 * smask_first[oid];
+            int32_t k;
+            n_r = nm + 1;
+            R = (int32_t *)calloc((size_t)n_r * 2, 4);
+            for (k = 0; k < nm; k++) { R[2 * k + 1] = iv[2 * k]; R[2 * k + 2] = iv[2 * k + 1]; }
+            R[0] = 0; R[2 * (n_r - 1) + 1] = full;
+            chunk_r = (int32_t *)calloc((size_t)n_r * 2, 4);
+        }
+        hard = (mt == 2) ? R : full_range; n_hard = (mt == 2) ? n_r : 1;
+        soft = (mt == 1) ? R : full_range; n_soft = (mt == 1) ? n_r : 1;
+        next = hard[0];
         vec_init(&comb, sizeof(BnHSP));
         while (next < full) {
             Subject S;
-            int32_t offset = next - next % 4;
+            const int32_t residual = next % 4;
+            int32_t offset = next - residual;
             int64_t first_init = init.n, first_hsp, n_h;
             Vec hs;
             S.seq = base + offset / 4; S.oid = oid; S.chunk_off = offset;
-            if ((int64_t)offset + BN_MAX_DBSEQ_LEN < full) {
+            if ((int64_t)offset + BN_MAX_DBSEQ_LEN < hard[2 * hm + 1]) {
                 S.len = BN_MAX_DBSEQ_LEN;
                 next = offset + BN_MAX_DBSEQ_LEN - BN_DBSEQ_CHUNK_OVERLAP;
-            } else { S.len = full - offset; next = full; }
+            } else {
+                S.len = hard[2 * hm + 1] - offset;
+                hm++;
+                next = hm < n_hard ? hard[2 * hm] : full;
+            }
+            S.masked = mt != 0; S.n_ranges = 1; S.ranges = full_range;
+            if (mt) {
+                if (offset == 0 && residual == 0 && next == full) { S.ranges = soft; S.n_ranges = n_soft; }
+                else if (mt != 1) { chunk_r[0] = residual; chunk_r[1] = S.len; S.ranges = chunk_r; S.n_ranges = 1; }
+                else {
+                    int32_t i = 0, st, cnt, k;
+                    const int32_t end = offset + S.len;
+                    while (soft[2 * i + 1] < offset) ++i;
+                    st = i;
+                    while (i < n_soft && soft[2 * i] < end) ++i;
+                    cnt = i - st;
+                    if (cnt == 0) continue;                       /* SUBJECT_SPLIT_NO_RANGE */
+                    for (k = 0; k < cnt; k++) { chunk_r[2 * k] = soft[2 * (st + k)] - offset; chunk_r[2 * k + 1] = soft[2 * (st + k) + 1] - offset; }
+                    if (chunk_r[0] < 0) chunk_r[0] = 0;
+                    if (chunk_r[2 * (cnt - 1) + 1] > S.len) chunk_r[2 * (cnt - 1) + 1] = S.len;
+                    S.ranges = chunk_r; S.n_ranges = cnt;
+                }
+            }
             out->stats.subject_bases_scanned += S.len;
 
             word_finder(b, &S, &diag, &init, first_init, out, taps, &scanv, &scan_oid, &scan_chunk);
@@ -1380,8 +1454,10 @@ int port_prelim_search(const BnQueryBatch *b, const uint8_t *packed, const int64
             if (kept) out->stats.good_extensions += kept;
         }
         free(comb.p);
+        free(R); free(chunk_r);
     }
     diag_free(&diag);
+    free(smask_first);
     free(gm.row[0]); free(gm.max_score); free(dm.best); free(dm.best_gap); free(low_score);
     out->hsps = (BnHSP *)final_.p; out->n_hsps = final_.n;
     out->init = (BnInitHit *)init.p; out->n_init = init.n;

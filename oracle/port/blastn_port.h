@@ -40,6 +40,11 @@ typedef struct PortResults {
 
 int port_prelim_search(const BnQueryBatch *b, const uint8_t *packed, const int64_t *seq_byte_off,
                        const int32_t *seq_len, int32_t n_seq, int taps, PortResults *out);
+/* same with database masks (blastn -db_soft_mask / -db_hard_mask): smask_type 1 soft / 2 hard, smask_n[i] masked
+ * [begin, end) intervals of subject i, flat pairs in smask_iv (core/blast_engine.c:136-301, core/masksubj.inl) */
+int port_prelim_search_masked(const BnQueryBatch *b, const uint8_t *packed, const int64_t *seq_byte_off,
+                              const int32_t *seq_len, int32_t n_seq, int taps, int32_t smask_type,
+                              const int32_t *smask_n, const int32_t *smask_iv, PortResults *out);
 void port_results_free(PortResults *r);
 
 /* unit-level entry points used by focused tests */

@@ -123,14 +123,24 @@ def batch_from_reference(r: dict, *, task: str, cfg=None, use_pv=True) -> abi.Ba
     return h
 
 
-def search(holder: abi.BatchHolder, volume, taps=TAP_INIT | TAP_GAPPED) -> dict:
+def search(holder: abi.BatchHolder, volume, taps=TAP_INIT | TAP_GAPPED, subject_masks=None,
+           subject_mask_type=1) -> dict:
     packed = np.ascontiguousarray(volume.packed, dtype=np.uint8)
     boff = np.ascontiguousarray(volume.byte_off, dtype=np.int64)
     slen = np.ascontiguousarray(volume.seq_len, dtype=np.int32)
     res = PortResults()
-    st = lib().port_prelim_search(C.byref(holder.batch), packed.ctypes.data_as(C.c_void_p),
-                                  boff.ctypes.data_as(C.c_void_p), slen.ctypes.data_as(C.c_void_p),
-                                  C.c_int32(slen.shape[0]), C.c_int(taps), C.byref(res))
+    if subject_masks is not None:
+        sn = np.ascontiguousarray([len(m) for m in subject_masks], dtype=np.int32)
+        flat = [x for m in subject_masks for iv in m for x in iv]
+        siv = np.ascontiguousarray(flat if flat else [0, 0], dtype=np.int32)
+        mt, sn_p, siv_p = int(subject_mask_type), sn.ctypes.data_as(C.c_void_p), siv.ctypes.data_as(C.c_void_p)
+    else:
+        mt, sn_p, siv_p = 0, None, None
+    lib().port_prelim_search_masked.restype = C.c_int
+    st = lib().port_prelim_search_masked(C.byref(holder.batch), packed.ctypes.data_as(C.c_void_p),
+                                         boff.ctypes.data_as(C.c_void_p), slen.ctypes.data_as(C.c_void_p),
+                                         C.c_int32(slen.shape[0]), C.c_int(taps), C.c_int32(mt), sn_p, siv_p,
+                                         C.byref(res))
     try:
         out = {
             "status": st,

@@ -62,6 +62,10 @@ typedef struct MemDb {
     int64_t total;
     int32_t maxlen;
     int32_t oid_begin, oid_end;   /* iteration range of this copy */
+    int32_t smask_type;           /* 0 none, 1 soft, 2 hard */
+    const int32_t *smask_n;       /* masked intervals per subject */
+    const int32_t *smask_iv;      /* flat [begin, end) pairs */
+    const int64_t *smask_first;   /* index of each subject's first interval (prefix sum) */
 } MemDb;
 
 static Int4 mdb_num_seqs(void *h, void *a) { (void)a; return ((MemDb *)h)->n; }
@@ -90,6 +94,18 @@ static Int2 mdb_get_seq(void *h, BlastSeqSrcGetSeqArg *args)
     if (args->seq) BlastSequenceBlkClean(args->seq);
     BlastSetUp_SeqBlkNew(d->packed + d->byteoff[oid], d->len[oid], &args->seq, FALSE);
     args->seq->oid = oid;
+    if (d->smask_type && d->smask_n) {      /* every sequence of a masked database carries ranges (one when it has no mask) */
+        /* what s_SeqDbGetSequence does with CSeqDB's mask list (api/seqsrc_seqdb.cpp:283-388): the unmasked
+         * ranges (0, m0.begin), (m0.end, m1.begin) ... (m_last.end, length) */
+        const int32_t n = d->smask_n[oid];
+        const int32_t *iv = d->smask_iv + 2 * d->smask_first[oid];
+        SSeqRange *r = (SSeqRange *)calloc((size_t)n + 1, sizeof(SSeqRange));
+        int32_t k;
+        for (k = 0; k < n; k++) { r[k].right = iv[2 * k]; r[k + 1].left = iv[2 * k + 1]; }
+        BlastSeqBlkSetSeqRanges(args->seq, r, (Uint4)n + 1, TRUE,
+                                d->smask_type == 2 ? eHardSubjMasking : eSoftSubjMasking);
+        free(r);
+    }
     return BLAST_SEQSRC_SUCCESS;
 }
 static void mdb_release_seq(void *h, BlastSeqSrcGetSeqArg *args) { (void)h; (void)args; }
@@ -655,6 +671,13 @@ int ref_search(const RefConfig *cfg,
     db.n = ns; db.packed = packed; db.byteoff = sbyteoff; db.len = slen;
     db.total = 0; db.maxlen = 0; db.oid_begin = 0; db.oid_end = ns;
     for (i = 0; i < ns; i++) { db.total += slen[i]; if (slen[i] > db.maxlen) db.maxlen = slen[i]; }
+    db.smask_type = cfg->smask_n ? cfg->smask_type : 0;
+    db.smask_n = cfg->smask_n; db.smask_iv = cfg->smask_iv; db.smask_first = NULL;
+    if (db.smask_type) {
+        int64_t *first = (int64_t *)calloc((size_t)ns + 1, sizeof(int64_t));
+        for (i = 0; i < ns; i++) first[i + 1] = first[i] + cfg->smask_n[i];
+        db.smask_first = first;
+    }
 
     /* the engine's callback choice mutates the table: do it once, before threads start */
     BlastChooseNucleotideScanSubject(S.lookup_wrap);

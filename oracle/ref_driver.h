@@ -36,6 +36,11 @@ typedef struct RefConfig {
     int32_t num_threads;     /* <=1 => single thread, taps allowed */
     int32_t taps;            /* bit0: scan pairs, bit1: init hits, bit2: gapped lists, bit3: lookup table dump */
     int32_t prelim_only;     /* always 1 for now (no traceback) */
+    /* database masks (blastn -db_soft_mask / -db_hard_mask): per subject smask_n[i] masked intervals,
+     * flat pairs [begin, end) in smask_iv, ascending and disjoint; smask_type 0 none, 1 soft, 2 hard */
+    int32_t smask_type;
+    const int32_t *smask_n;
+    const int32_t *smask_iv;
 } RefConfig;
 
 /* Flat growable int32 table: rows x ncol */

@@ -24,6 +24,7 @@ class RefConfig(C.Structure):
         ("evalue", C.c_double), ("low_score_perc", C.c_double),
         ("db_length", C.c_int64), ("db_num_seqs", C.c_int32), ("num_threads", C.c_int32),
         ("taps", C.c_int32), ("prelim_only", C.c_int32),
+        ("smask_type", C.c_int32), ("smask_n", C.c_void_p), ("smask_iv", C.c_void_p),
     ]
 
 
@@ -120,13 +121,28 @@ def default_config(task="megablast", **kw) -> RefConfig:
     return cfg
 
 
-def search(queries, volume, cfg: RefConfig | None = None, *, task="megablast", masks=None, **kw):
+def search(queries, volume, cfg: RefConfig | None = None, *, task="megablast", masks=None,
+           subject_masks=None, subject_mask_type=1, **kw):
     """Run the reference preliminary search. `queries`: list of uint8 blastna arrays;
     `volume`: gblastn_b200.synth.Volume (or any object with packed/byte_off/seq_len);
-    `masks`: optional list (per query) of [(left, right)] inclusive plus-strand intervals.
-    Returns a dict of numpy arrays."""
+    `masks`: optional list (per query) of [(left, right)] inclusive plus-strand intervals;
+    `subject_masks`: optional list (per subject) of [(begin, end)] half-open masked intervals (database masks,
+    soft = 1 / hard = 2).  Returns a dict of numpy arrays."""
     if cfg is None:
         cfg = default_config(task, **kw)
+    keep = []
+    if subject_masks is not None:
+        sn = np.ascontiguousarray([len(m) for m in subject_masks], dtype=np.int32)
+        sflat = [x for m in subject_masks for iv in m for x in iv]
+        siv = np.ascontiguousarray(sflat if sflat else [0, 0], dtype=np.int32)
+        keep += [sn, siv]
+        cfg.smask_type = int(subject_mask_type)
+        cfg.smask_n = sn.ctypes.data
+        cfg.smask_iv = siv.ctypes.data
+    else:
+        cfg.smask_type = 0
+        cfg.smask_n = None
+        cfg.smask_iv = None
     qcat = np.ascontiguousarray(np.concatenate(queries) if len(queries) else np.zeros(0, np.uint8),
                                 dtype=np.uint8)
     qlens = np.ascontiguousarray([len(q) for q in queries], dtype=np.int32)
