@@ -10,6 +10,7 @@ BN_LUT_MB, BN_LUT_SMALL_NA, BN_LUT_NA = 0, 1, 2
 BN_DIAG_ARRAY, BN_DIAG_HASH = 0, 1
 BN_GAP_DP, BN_GAP_GREEDY = 0, 1
 BN_TAP_INIT, BN_TAP_GAPPED = 2, 4
+BN_MASK_NONE, BN_MASK_SOFT, BN_MASK_HARD = 0, 1, 2
 
 
 class BnContext(C.Structure):

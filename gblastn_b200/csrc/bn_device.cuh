@@ -28,7 +28,16 @@ struct DevChunk {
     int32_t npos;          // scan positions in this chunk
     int32_t diag_offset;   // BLAST_DiagHash/BLAST_DiagTable ::offset while this chunk is scanned
     int32_t diag_epoch;    // number of container resets (core/blast_extend.c:170-182) before this chunk
+    // Scan unit view (database masks, core/masksubj.inl:43-59): the scan kernel walks "units" = one unmasked
+    // range of one chunk; without masks a chunk is its own unit (p_first 0, s_range len, parent = its index).
+    int32_t p_first;       // first scan position of the unit (range.left + word - lut)
+    int32_t s_range;       // right end of the unit's range: bound of the mini-extension and of s_TypeOfWord
+    int32_t parent;        // index of the chunk in the chunk table (what a seed hit records)
+    // chunk view: its unmasked ranges in the range table (n_ranges == 0: not masked)
+    int32_t range_first, n_ranges;
+    int32_t pad;
 };
+static_assert(sizeof(DevChunk) == 64, "two sectors");
 
 struct DevQuery {
     const uint8_t *query;        // query->sequence (byte before it is the leading sentinel)
@@ -217,6 +226,7 @@ struct SpecResult {
 struct ExtendLaunch {
     const uint8_t *packed;
     const DevChunk *chunks;
+    const int2 *ranges;           // unmasked [left, right) ranges of masked chunks (DevChunk::range_first)
     const SeedHit *hits;          // sorted by (group, global scan position)
     int32_t *cells;               // hash: 4 ints per cell, one region per group (same offsets as hits)
     DevInitHit *init;

@@ -135,11 +135,16 @@ struct Device {
 };
 
 struct ChunkTable {
-    std::vector<DevChunk> host;
+    std::vector<DevChunk> host;               // chunks (what seed hits, init-HSPs and the host replay refer to)
+    std::vector<DevChunk> units;              // scan units of a masked volume (empty: the chunks are the units)
+    std::vector<int2> ranges;                 // unmasked ranges of masked chunks
     std::vector<HostChunk> hchunks;
     std::vector<int32_t> h_block_chunk;         // sources of the asynchronous uploads: live as long as the table
     std::vector<ScanBlockDesc> h_block_desc;
-    PoolBuf<DevChunk> dev;
+    PoolBuf<DevChunk> dev, units_dev;
+    PoolBuf<int2> ranges_dev;
+    const DevChunk *scan_units() const { return units.empty() ? dev.p : units_dev.p; }
+    int32_t n_scan_units() const { return (int32_t)(units.empty() ? host.size() : units.size()); }
     PoolBuf<int32_t> block_chunk;
     PoolBuf<ScanBlockDesc> block_desc;
     int64_t total_pos = 0;
@@ -155,6 +160,10 @@ struct Volume {
     int64_t bytes = 0;
     std::vector<int64_t> byte_off;
     std::vector<int32_t> seq_len;
+    // database masks (bn_db_set_masks): per sequence mask_first[i]..mask_first[i+1] masked [begin, end) pairs
+    int32_t mask_type = 0, mask_version = 0;
+    std::vector<int64_t> mask_first;
+    std::vector<int32_t> mask_iv;
     std::map<std::string, std::shared_ptr<ChunkTable>> tables;
 };
 
@@ -365,32 +374,94 @@ static int build_chunk_table(Volume &V, const Query &Q, int32_t oid_begin, int32
                              cudaStream_t st, std::shared_ptr<ChunkTable> *out)
 {
     const BnQueryBatch &b = Q.batch;
-    char key[128];
-    snprintf(key, sizeof key, "%d/%d/%d/%d/%d", b.lut_word_length, b.scan_step, b.window_size,
-             oid_begin, oid_end);
+    char key[160];
+    snprintf(key, sizeof key, "%d/%d/%d/%d/%d/%d/%d", b.lut_word_length, b.scan_step, b.window_size,
+             oid_begin, oid_end, b.word_length, V.mask_version);
     auto it = V.tables.find(key);
     if (it != V.tables.end()) { *out = it->second; return BN_OK; }
 
+    // s_GetNextSubjectChunk (core/blast_engine.c:220-301): 200 Mb chunks with a 100-base overlap inside every
+    // hard range (the whole sequence without hard masks), chunk starts rounded down to a byte; soft ranges
+    // clipped to the chunk.  BlastNaWordFinder (core/na_ungapped.c:1610-1645) then scans every unmasked range
+    // of a masked subject from left + (word - lut).
     auto T = std::make_shared<ChunkTable>();
     const int32_t lut = b.lut_word_length, step = b.scan_step, window = b.window_size;
+    const int32_t ext_to = b.word_length - lut;
+    const int32_t mt = V.mask_type;
     int32_t diag_offset = window, epoch = 0;
     int64_t prefix = 0;
+    std::vector<int32_t> R;                               // unmasked ranges of the sequence, flat pairs
     for (int32_t oid = oid_begin; oid < oid_end; oid++) {
         const int32_t full = V.seq_len[oid];
-        int32_t next = 0;
+        int32_t full_range[2] = {0, full};
+        const int32_t *hard = full_range, *soft = full_range;
+        int32_t n_hard = 1, n_soft = 1;
+        if (mt) {
+            const int64_t m0 = V.mask_first[(size_t)oid], m1 = V.mask_first[(size_t)oid + 1];
+            const int32_t n_r = (int32_t)(m1 - m0) + 1;
+            R.assign((size_t)n_r * 2, 0);
+            for (int64_t k = m0; k < m1; k++) {
+                R[(size_t)(2 * (k - m0) + 1)] = V.mask_iv[(size_t)(2 * k)];
+                R[(size_t)(2 * (k - m0) + 2)] = V.mask_iv[(size_t)(2 * k + 1)];
+            }
+            R[0] = 0; R[(size_t)(2 * (n_r - 1) + 1)] = full;      // BlastSeqBlkSetSeqRanges core/blast_util.c:216-218
+            if (mt == 2) { hard = R.data(); n_hard = n_r; } else { soft = R.data(); n_soft = n_r; }
+        }
+        int32_t hm = 0;
+        int32_t next = hard[0];
         while (next < full) {
-            const int32_t offset = next - next % 4;
+            const int32_t residual = next % 4;
+            const int32_t offset = next - residual;
             DevChunk c{};
             c.byte_off = V.byte_off[oid] + offset / 4;
             c.oid = oid; c.chunk_off = offset;
-            if ((int64_t)offset + BN_MAX_DBSEQ_LEN < (int64_t)full) {
+            if ((int64_t)offset + BN_MAX_DBSEQ_LEN < (int64_t)hard[2 * hm + 1]) {
                 c.len = BN_MAX_DBSEQ_LEN;
                 next = offset + BN_MAX_DBSEQ_LEN - BN_DBSEQ_CHUNK_OVERLAP;
-            } else { c.len = full - offset; next = full; }
-            c.npos = c.len >= lut ? (c.len - lut) / step + 1 : 0;
-            c.pos_prefix = prefix;
+            } else {
+                c.len = hard[2 * hm + 1] - offset;
+                ++hm;
+                next = hm < n_hard ? hard[2 * hm] : full;
+            }
+            // the chunk's unmasked ranges (chunk-relative); unmasked volume: the chunk itself
+            std::vector<int2> cr;
+            if (mt) {
+                if (offset == 0 && residual == 0 && next == full) {
+                    for (int32_t i = 0; i < n_soft; i++) cr.push_back(make_int2(soft[2 * i], soft[2 * i + 1]));
+                } else if (mt != 1) cr.push_back(make_int2(residual, c.len));
+                else {
+                    int32_t i = 0;
+                    const int32_t end = offset + c.len;
+                    while (soft[2 * i + 1] < offset) ++i;
+                    for (; i < n_soft && soft[2 * i] < end; ++i) cr.push_back(make_int2(soft[2 * i] - offset, soft[2 * i + 1] - offset));
+                    if (cr.empty()) continue;                         // SUBJECT_SPLIT_NO_RANGE: the chunk is skipped
+                    cr.front().x = std::max(cr.front().x, 0);
+                    cr.back().y = std::min(cr.back().y, c.len);
+                }
+            }
+            const int32_t ci = (int32_t)T->host.size();
             c.diag_offset = diag_offset; c.diag_epoch = epoch;
-            prefix += c.npos;
+            c.parent = ci; c.p_first = 0; c.s_range = c.len;
+            c.pos_prefix = prefix;
+            if (!mt) {
+                c.npos = c.len >= lut ? (c.len - lut) / step + 1 : 0;
+                prefix += c.npos;
+            } else {
+                c.range_first = (int32_t)T->ranges.size(); c.n_ranges = (int32_t)cr.size();
+                int64_t total = 0;
+                for (const int2 &r : cr) {
+                    DevChunk u = c;
+                    u.p_first = r.x + ext_to; u.s_range = r.y;
+                    const int32_t last = r.y - lut;
+                    u.npos = last >= u.p_first ? (last - u.p_first) / step + 1 : 0;
+                    u.pos_prefix = prefix + total;
+                    total += u.npos;
+                    T->units.push_back(u);
+                    T->ranges.push_back(r);
+                }
+                c.npos = (int32_t)std::min<int64_t>(total, INT32_MAX);
+                prefix += total;
+            }
             T->total_bases += c.len;
             T->host.push_back(c);
             T->hchunks.push_back(HostChunk{oid, offset, c.len});
@@ -398,6 +469,7 @@ static int build_chunk_table(Volume &V, const Query &Q, int32_t oid_begin, int32
             else diag_offset += c.len + window;
         }
     }
+    const std::vector<DevChunk> &SU = T->units.empty() ? T->host : T->units;         // what the scan kernel walks
     T->total_pos = prefix;
     const int ppb = scan_positions_per_block();
     T->n_blocks = (prefix + ppb - 1) / ppb;
@@ -405,10 +477,10 @@ static int build_chunk_table(Volume &V, const Query &Q, int32_t oid_begin, int32
     bc.assign((size_t)T->n_blocks + 1, 0);
     {
         size_t c = 0;
-        const size_t n = T->host.size();
+        const size_t n = SU.size();
         for (int64_t blk = 0; blk < T->n_blocks; blk++) {
             const int64_t g = blk * ppb;
-            while (c + 1 < n && T->host[c + 1].pos_prefix <= g) ++c;
+            while (c + 1 < n && SU[c + 1].pos_prefix <= g) ++c;
             bc[(size_t)blk] = (int32_t)c;
         }
         bc[(size_t)T->n_blocks] = n ? (int32_t)n - 1 : 0;
@@ -420,15 +492,15 @@ static int build_chunk_table(Volume &V, const Query &Q, int32_t oid_begin, int32
         const int32_t tile_cap = scan_tile_cap(step, b.word_length), margin = scan_tile_margin();
         const int32_t maxc = scan_max_block_chunks();
         size_t c = 0;
-        const size_t n = T->host.size();
+        const size_t n = SU.size();
         for (int64_t blk = 0; blk < T->n_blocks; blk++) {
             const int64_t g0 = blk * ppb, g_last = std::min<int64_t>(g0 + ppb, prefix) - 1;
             const int32_t c_lo = bc[(size_t)blk];
             c = std::max<size_t>(c, (size_t)c_lo);
-            while (c + 1 < n && T->host[c + 1].pos_prefix <= g_last) ++c;
-            const DevChunk &a = T->host[(size_t)c_lo], &z = T->host[c];
-            const int64_t first_byte = a.byte_off + (((g0 - a.pos_prefix) * step) >> 2);
-            const int64_t last_byte = z.byte_off + ((((g_last - z.pos_prefix) * step) + b.word_length + 32) >> 2);
+            while (c + 1 < n && SU[c + 1].pos_prefix <= g_last) ++c;
+            const DevChunk &a = SU[(size_t)c_lo], &z = SU[c];
+            const int64_t first_byte = a.byte_off + ((a.p_first + (g0 - a.pos_prefix) * step) >> 2);
+            const int64_t last_byte = z.byte_off + (((z.p_first + (g_last - z.pos_prefix) * step) + b.word_length + 32) >> 2);
             ScanBlockDesc d{};
             d.tile_lo = (first_byte - margin) & ~int64_t(15);
             const int64_t bytes = (last_byte + margin - d.tile_lo + 15) & ~int64_t(15);
@@ -442,6 +514,14 @@ static int build_chunk_table(Volume &V, const Query &Q, int32_t oid_begin, int32
         CU_TRY(T->dev.reserve(T->host.size(), st));
         CU_TRY(cudaMemcpyAsync(T->dev.p, T->host.data(), T->host.size() * sizeof(DevChunk),
                                cudaMemcpyHostToDevice, st));
+        if (!T->units.empty()) {
+            CU_TRY(T->units_dev.reserve(T->units.size(), st));
+            CU_TRY(cudaMemcpyAsync(T->units_dev.p, T->units.data(), T->units.size() * sizeof(DevChunk),
+                                   cudaMemcpyHostToDevice, st));
+            CU_TRY(T->ranges_dev.reserve(T->ranges.size() + 1, st));
+            CU_TRY(cudaMemcpyAsync(T->ranges_dev.p, T->ranges.data(), T->ranges.size() * sizeof(int2),
+                                   cudaMemcpyHostToDevice, st));
+        }
         CU_TRY(T->block_chunk.reserve(bc.size(), st));
         CU_TRY(cudaMemcpyAsync(T->block_chunk.p, bc.data(), bc.size() * sizeof(int32_t),
                                cudaMemcpyHostToDevice, st));
@@ -505,7 +585,7 @@ static int run_word_finder(Device &D, Volume &V, Query &Q, ChunkTable &T, bool r
         cap = (int64_t)std::min(ws.hits_a.cap, ws.keys_a.cap);
         CU_TRY(cudaMemsetAsync(ws.counters.p, 0, 8 * sizeof(unsigned long long), st));
         ScanLaunch s{};
-        s.packed = V.d_packed; s.chunks = T.dev.p; s.n_chunks = (int32_t)T.host.size();
+        s.packed = V.d_packed; s.chunks = T.scan_units(); s.n_chunks = T.n_scan_units();
         s.total_pos = T.total_pos; s.hits = ws.hits_a.p; s.keys = ws.keys_a.p;
         s.counters = ws.counters.p; s.capacity = cap; s.block_chunk = T.block_chunk.p; s.block_desc = T.block_desc.p;
         s.raw_pairs = raw_pairs ? 1 : 0; s.gbits = gbits; s.diag_array_length = Q.diag_array_length;
@@ -553,7 +633,7 @@ static int run_word_finder(Device &D, Volume &V, Query &Q, ChunkTable &T, bool r
         init_cap = (int64_t)ws.init.cap;
         CU_TRY(cudaMemsetAsync(ws.counters.p + 2, 0, 4 * sizeof(unsigned long long), st));
         ExtendLaunch e{};
-        e.packed = V.d_packed; e.chunks = T.dev.p; e.hits = ws.hits_b.p;
+        e.packed = V.d_packed; e.chunks = T.dev.p; e.ranges = T.ranges_dev.p; e.hits = ws.hits_b.p;
         e.cells = reinterpret_cast<int32_t *>(ws.cells.p); e.init = ws.init.p;
         e.counters = ws.counters.p; e.init_capacity = init_cap;
         e.spec = ws.spec.p; e.leaders = ws.leaders.p;
@@ -765,7 +845,7 @@ static int run_fused(Device &D, Volume &V, Query &Q, ChunkTable &T, StageCounts 
     CU_TRY(cudaMemsetAsync(ws.counters.p, 0, 8 * sizeof(unsigned long long), st));
     CU_TRY(cudaMemsetAsync(ws.buckets.p, 0, (size_t)nb * sizeof(uint32_t), st));
     ScanLaunch s{};
-    s.packed = V.d_packed; s.chunks = T.dev.p; s.n_chunks = (int32_t)T.host.size();
+    s.packed = V.d_packed; s.chunks = T.scan_units(); s.n_chunks = T.n_scan_units();
     s.total_pos = T.total_pos; s.hits = ws.hits_a.p; s.keys = ws.keys_a.p;
     s.counters = ws.counters.p; s.capacity = cap; s.block_chunk = T.block_chunk.p; s.block_desc = T.block_desc.p;
     s.raw_pairs = 0; s.gbits = gbits; s.diag_array_length = Q.diag_array_length;
@@ -784,7 +864,7 @@ static int run_fused(Device &D, Volume &V, Query &Q, ChunkTable &T, StageCounts 
     L.n_limit = n_limit; L.gbits = gbits; L.spec_enabled = Q.batch.window_size > 0 ? 0 : 1;
     CU_TRY(launch_bucket_group(L, st));
     ExtendLaunch e{};
-    e.packed = V.d_packed; e.chunks = T.dev.p; e.hits = ws.hits_b.p;
+    e.packed = V.d_packed; e.chunks = T.dev.p; e.ranges = T.ranges_dev.p; e.hits = ws.hits_b.p;
     e.cells = reinterpret_cast<int32_t *>(ws.cells.p); e.init = ws.init.p;
     e.counters = ws.counters.p; e.init_capacity = init_cap;
     e.spec = ws.spec.p; e.leaders = ws.leaders.p; e.n_from_device = 1;
@@ -1051,7 +1131,7 @@ void bn_release(void)
         cudaSetDevice(g_devices[v->device]->id);
         if (v->ready) { cudaEventSynchronize(v->ready); cudaEventDestroy(v->ready); }
         cudaFreeAsync(v->d_raw, g_devices[v->device]->stream);
-        for (auto &kv : v->tables) { kv.second->dev.release(); kv.second->block_chunk.release(); kv.second->block_desc.release(); }
+        for (auto &kv : v->tables) { kv.second->dev.release(); kv.second->units_dev.release(); kv.second->ranges_dev.release(); kv.second->block_chunk.release(); kv.second->block_desc.release(); }
     }
     g_volumes.clear();
     for (auto &d : g_devices) {
@@ -1181,6 +1261,41 @@ int bn_db_load_files(int device, const char *nin_path, const char *nsq_path, int
     return BN_OK;
 }
 
+int bn_db_set_masks(int vol_handle, int mask_type, const int32_t *mask_n, const int32_t *mask_iv)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (vol_handle < 0 || vol_handle >= (int)g_volumes.size() || !g_volumes[vol_handle])
+        return fail(BN_ERR_INVALID, "bn_db_set_masks: bad handle");
+    Volume &V = *g_volumes[vol_handle];
+    if (mask_type != BN_MASK_NONE && mask_type != BN_MASK_SOFT && mask_type != BN_MASK_HARD)
+        return fail(BN_ERR_INVALID, "bn_db_set_masks: bad mask type");
+    const size_t n = V.seq_len.size();
+    std::vector<int64_t> first(n + 1, 0);
+    std::vector<int32_t> iv;
+    if (mask_type != BN_MASK_NONE) {
+        if (!mask_n || !mask_iv) return fail(BN_ERR_INVALID, "bn_db_set_masks: NULL mask arrays");
+        for (size_t i = 0; i < n; i++) {
+            if (mask_n[i] < 0) return fail(BN_ERR_INVALID, "bn_db_set_masks: negative interval count");
+            first[i + 1] = first[i] + mask_n[i];
+        }
+        iv.assign(mask_iv, mask_iv + 2 * first[n]);
+        for (size_t i = 0; i < n; i++) {
+            int32_t prev_end = 0;
+            for (int64_t k = first[i]; k < first[i + 1]; k++) {
+                const int32_t a = iv[(size_t)(2 * k)], e = iv[(size_t)(2 * k + 1)];
+                if (a < prev_end || e < a || e > V.seq_len[i])
+                    return fail(BN_ERR_INVALID, "bn_db_set_masks: intervals must be ascending, disjoint and inside the sequence");
+                prev_end = e;
+            }
+        }
+    }
+    V.mask_type = mask_type;
+    V.mask_first.swap(first);
+    V.mask_iv.swap(iv);
+    ++V.mask_version;                 // chunk tables are cached per mask version
+    return BN_OK;
+}
+
 int bn_db_free(int h)
 {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -1189,7 +1304,7 @@ int bn_db_free(int h)
     cudaSetDevice(g_devices[V.device]->id);
     if (V.ready) { cudaStreamWaitEvent(g_devices[V.device]->stream, V.ready, 0); cudaEventDestroy(V.ready); V.ready = nullptr; }
     cudaFreeAsync(V.d_raw, g_devices[V.device]->stream);
-    for (auto &kv : V.tables) { kv.second->dev.release(); kv.second->block_chunk.release(); kv.second->block_desc.release(); }
+    for (auto &kv : V.tables) { kv.second->dev.release(); kv.second->units_dev.release(); kv.second->ranges_dev.release(); kv.second->block_chunk.release(); kv.second->block_desc.release(); }
     g_volumes[h].reset();
     return BN_OK;
 }
@@ -1523,7 +1638,7 @@ int bn_bench_scan(int vol_handle, int query_handle, int iters, double *ms_per_la
     CU_TRY(ws.hits_a.reserve((size_t)cap)); CU_TRY(ws.keys_a.reserve((size_t)cap));
     cap = (int64_t)std::min(ws.hits_a.cap, ws.keys_a.cap);
     ScanLaunch s{};
-    s.packed = V->d_packed; s.chunks = T->dev.p; s.n_chunks = (int32_t)T->host.size();
+    s.packed = V->d_packed; s.chunks = T->scan_units(); s.n_chunks = T->n_scan_units();
     s.total_pos = T->total_pos; s.hits = ws.hits_a.p; s.keys = ws.keys_a.p;
     s.counters = ws.counters.p; s.capacity = cap; s.block_chunk = T->block_chunk.p; s.block_desc = T->block_desc.p; s.raw_pairs = 0;
     s.gbits = bits_for((uint64_t)std::max<int64_t>(T->total_pos, 1)); s.diag_array_length = Q->diag_array_length;

@@ -364,13 +364,26 @@ __device__ __forceinline__ void prefetch_around(const DevQuery &q, const uint8_t
     }
 }
 
-__device__ void extend_one(const DevQuery &q, const uint8_t *packed, const DevChunk &ch, const int32_t *s_tab,
+// s_range of the extension callbacks (core/na_ungapped.c:1634-1637): the right end of the unmasked range the
+// seed was scanned in; the chunk length when the volume carries no database masks
+__device__ __forceinline__ int32_t hit_s_range(const int2 *ranges, const DevChunk &ch, int32_t scan_pos)
+{
+    if (ch.n_ranges == 0) return ch.len;
+    int32_t lo = 0, hi = ch.n_ranges - 1;
+    while (lo < hi) {                         // last range with left <= scan_pos
+        const int32_t m = (lo + hi + 1) >> 1;
+        if (__ldg(&ranges[ch.range_first + m].x) <= scan_pos) lo = m; else hi = m - 1;
+    }
+    return __ldg(&ranges[ch.range_first + lo].y);
+}
+
+__device__ void extend_one(const DevQuery &q, const uint8_t *packed, const DevChunk &ch, int32_t s_range, const int32_t *s_tab,
                            bool is_hash, bool has_loc, int32_t word, int32_t lut, bool direct, bool check_double,
                            int32_t q_off, int32_t s_off, int lane, CtxCache &cc, SpecResult &r)
 {
     int32_t extended = 0;
     const int32_t s_end0 = s_off + word;      // the reference fixes s_end before s_TypeOfWord may shift s_off
-    const int word_type = type_of_word(q, packed + ch.byte_off, q_off, s_off, has_loc, (uint32_t)ch.len, word,
+    const int word_type = type_of_word(q, packed + ch.byte_off, q_off, s_off, has_loc, (uint32_t)s_range, word,
                                        direct ? word : lut, check_double, extended, lane);
     if (!word_type) {
         r.status = SPEC_MASKED;
@@ -507,8 +520,8 @@ extend_leaders_kernel(const DevQuery q, const ExtendLaunch e)
         prefetch_around(q, e.packed, ch, (int32_t)h.q_off, (int32_t)h.s_off, lane);
         SpecResult r;
         r.status = SPEC_NONE; r.q_off = r.s_off = r.extended = r.q_start = r.s_start = r.length = r.score = 0;
-        extend_one(q, e.packed, ch, s_tab, is_hash, has_loc, word, lut, direct, false, (int32_t)h.q_off,
-                   (int32_t)h.s_off, lane, cc, r);
+        extend_one(q, e.packed, ch, hit_s_range(e.ranges, ch, (int32_t)h.scan_pos), s_tab, is_hash, has_loc, word, lut,
+                   direct, false, (int32_t)h.q_off, (int32_t)h.s_off, lane, cc, r);
         if (lane == 0) e.spec[j] = r;
     }
 }
@@ -631,8 +644,8 @@ extend_kernel(const DevQuery q, const ExtendLaunch e, const uint64_t *keys, cons
                 if (r.status != SPEC_NONE && !check_double) {
                     if (r.status == SPEC_MASKED) continue;
                 } else {
-                    extend_one(q, e.packed, ch, s_tab, is_hash, has_loc, word, lut, direct, check_double, q_off, s_off,
-                               lane, cc, r);
+                    extend_one(q, e.packed, ch, hit_s_range(e.ranges, ch, (int32_t)h.scan_pos), s_tab, is_hash, has_loc, word,
+                               lut, direct, check_double, q_off, s_off, lane, cc, r);
                     if (r.status == SPEC_MASKED) continue;
                 }
                 q_off = r.q_off; s_off = r.s_off;

@@ -222,10 +222,11 @@ scan_kernel(const DevQuery q, const ScanLaunch s)
             if (__ldg(&s.chunks[m].pos_prefix) <= g) lo = m; else hi = m - 1;
         }
         const DevChunk ch = s.chunks[lo];
-        const int32_t p = (int32_t)(g - ch.pos_prefix) * step;
+        const int32_t p = ch.p_first + (int32_t)(g - ch.pos_prefix) * step;
         const uint8_t *S = s.packed + ch.byte_off;
         const uint32_t window = load_window(s.packed, ch.byte_off + (p >> 2));
         const uint32_t idx = (window >> (2 * (16 - ((p & 3) + lut)))) & q.hash_mask;
+        lo = ch.parent;                       // seed hits record the chunk, not the scan unit
 
         if (q.lut_type == 0) {
             int32_t qp = mb_cell(q, idx);
@@ -233,7 +234,7 @@ scan_kernel(const DevQuery q, const ScanLaunch s)
                 ++my_lookup_hits;
                 int32_t qo, so;
                 if (s.raw_pairs) emit_hit(q, s, (uint32_t)lo, (uint32_t)p, g, qp - 1, p);
-                else if (mini_extend_mb(q, S, ch.len, qp - 1, p, qo, so))
+                else if (mini_extend_mb(q, S, ch.s_range, qp - 1, p, qo, so))
                     emit_hit(q, s, (uint32_t)lo, (uint32_t)p, g, qo, so);
                 qp = __ldg(&q.next_pos[qp]);
             }
@@ -246,7 +247,7 @@ scan_kernel(const DevQuery q, const ScanLaunch s)
                 ++my_lookup_hits;
                 int32_t qo, so;
                 if (s.raw_pairs) emit_hit(q, s, (uint32_t)lo, (uint32_t)p, g, v, p);
-                else if (mini_extend_mb(q, S, ch.len, v, p, qo, so))
+                else if (mini_extend_mb(q, S, ch.s_range, v, p, qo, so))
                     emit_hit(q, s, (uint32_t)lo, (uint32_t)p, g, qo, so);
             }
         } else {
@@ -258,7 +259,7 @@ scan_kernel(const DevQuery q, const ScanLaunch s)
                 ++my_lookup_hits;
                 int32_t qo, so;
                 if (s.raw_pairs) emit_hit(q, s, (uint32_t)lo, (uint32_t)p, g, v, p);
-                else if (mini_extend_small(q, S, ch.len, v, p, qo, so))
+                else if (mini_extend_small(q, S, ch.s_range, v, p, qo, so))
                     emit_hit(q, s, (uint32_t)lo, (uint32_t)p, g, qo, so);
                 v = src ? (int32_t)__ldg(&q.overflow[src++]) : -1;
             } while (v >= 0);
@@ -396,15 +397,16 @@ __device__ __noinline__ unsigned long long scan_block_direct(const DevQuery &q, 
             if (__ldg(&s.chunks[m].pos_prefix) <= g) lo = m; else hi = m - 1;
         }
         const DevChunk ch = s.chunks[lo];
-        const int32_t p = (int32_t)(g - ch.pos_prefix) * step;
+        const int32_t p = ch.p_first + (int32_t)(g - ch.pos_prefix) * step;
         const uint32_t window = load_window(s.packed, ch.byte_off + (p >> 2));
         const uint32_t idx = (window >> (2 * (16 - ((p & 3) + lut)))) & q.hash_mask;
+        lo = ch.parent;
         int32_t qp = mb_cell(q, idx);
         while (qp) {
             ++my_lookup_hits;
             int32_t qo, so;
             if (s.raw_pairs) emit_hit(q, s, (uint32_t)lo, (uint32_t)p, g, qp - 1, p);
-            else if (mini_extend_mb(q, s.packed + ch.byte_off, ch.len, qp - 1, p, qo, so))
+            else if (mini_extend_mb(q, s.packed + ch.byte_off, ch.s_range, qp - 1, p, qo, so))
                 emit_hit(q, s, (uint32_t)lo, (uint32_t)p, g, qo, so);
             qp = __ldg(&q.next_pos[qp]);
         }
@@ -420,7 +422,7 @@ scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ S
     uint2 *cand = reinterpret_cast<uint2 *>(smem_dyn + s.tile_cap / 4);      // POS_PER_BLOCK entries {rank, where}
     // block-local chunk table: first position (block-relative, may be negative for the first chunk),
     // tile-relative base index of the chunk's base 0, chunk length
-    __shared__ int32_t ct_start[MAXC + 1], ct_tbase[MAXC], ct_len[MAXC];
+    __shared__ int32_t ct_start[MAXC + 1], ct_tbase[MAXC], ct_len[MAXC], ct_pfirst[MAXC], ct_parent[MAXC];
     __shared__ __align__(8) unsigned long long bar;
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t block_pos0 = (int64_t)blockIdx.x * POS_PER_BLOCK;
@@ -445,7 +447,9 @@ scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ S
             const DevChunk c = s.chunks[c_lo + i];
             ct_start[i] = (int32_t)(c.pos_prefix - block_pos0);
             ct_tbase[i] = (int32_t)((c.byte_off - tile_lo) * 4);
-            ct_len[i] = c.len;
+            ct_len[i] = c.s_range;              // right bound of the unit's range (the chunk length without masks)
+            ct_pfirst[i] = c.p_first;
+            ct_parent[i] = c.parent;
         }
         if (tid == 0) ct_start[nch] = INT32_MAX;
         __syncthreads();
@@ -459,7 +463,7 @@ scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ S
         const uint32_t shr = 32u - 2u * (uint32_t)lut;
         if (nch == 1) {
             // the whole block lies in one chunk: tile offsets are an arithmetic progression
-            const int32_t tb0 = ct_tbase[0] - ct_start[0] * step;
+            const int32_t tb0 = ct_tbase[0] + ct_pfirst[0] - ct_start[0] * step;
 #pragma unroll
             for (int it = 0; it < POS_PER_THREAD; it++) {
                 const int32_t gl = min(it * SCAN_THREADS + tid, npos - 1);
@@ -488,7 +492,7 @@ scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ S
             for (int it = 0; it < POS_PER_THREAD; it++) {
                 const int32_t gl = min(it * SCAN_THREADS + tid, npos - 1);
                 const uint32_t c = (cpack[it >> 2] >> (8 * (it & 3))) & 255u;
-                const int32_t tb = ct_tbase[c] + (gl - ct_start[c]) * step;
+                const int32_t tb = ct_tbase[c] + ct_pfirst[c] + (gl - ct_start[c]) * step;
                 const uint32_t w0 = tile[tb >> 4], w1 = tile[(tb >> 4) + 1];
                 const uint32_t W = __byte_perm(w0, w1, 0x0123u + 0x1111u * ((uint32_t)(tb >> 2) & 3u));
                 const uint32_t idx = (W << (2u * ((uint32_t)tb & 3u))) >> shr;
@@ -525,9 +529,9 @@ scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ S
             // first two chain elements of the cell in ONE 32-byte sector: {qp | more << 31, left 16, right 16, ambiguity} x 2
             uint4 qi, qi1;
             ld_cinfo_pair(q.cinfo + 2 * (size_t)cd.x, qi, qi1);
-            const int32_t p = (gl - ct_start[k]) * step;
+            const int32_t p = ct_pfirst[k] + (gl - ct_start[k]) * step;
             const int32_t tbase = ct_tbase[k], len = ct_len[k];
-            const uint32_t chunk = (uint32_t)(c_lo + k);
+            const uint32_t chunk = (uint32_t)ct_parent[k];
             const int64_t g = block_pos0 + gl;
             int32_t qp = (int32_t)(qi.x & 0x7fffffffu);
             bool more = (qi.x >> 31) != 0, second = true;

@@ -20,7 +20,7 @@ EXPORTS = [
     "bn_db_load", "bn_db_free", "bn_query_load", "bn_query_free",
     "bn_prelim_search", "bn_prelim_search_host", "bn_results_free",
     "bn_scan_subject", "bn_word_finder", "bn_free", "bn_bench_scan", "bn_query_download_lookup", "bn_get_gapped_score",
-    "bn_dbfile_index", "bn_db_load_files", "bn_dbfile_write", "bn_prelim_search_batches",
+    "bn_dbfile_index", "bn_db_load_files", "bn_dbfile_write", "bn_prelim_search_batches", "bn_db_set_masks",
     "bn_setup_create", "bn_setup_batch", "bn_setup_kbp_std", "bn_setup_kbp_gap",
     "bn_setup_gap_x_dropoff_final", "bn_setup_longest_chain", "bn_setup_free",
 ]
@@ -90,6 +90,18 @@ class Volume:
         if self.handle >= 0:
             lib().bn_db_free(C.c_int(self.handle))
             self.handle = -1
+
+    def set_masks(self, masks, mask_type=abi.BN_MASK_SOFT):
+        """Database masks: `masks` = per sequence a list of half-open (begin, end) masked intervals
+        (ascending, disjoint); mask_type BN_MASK_SOFT / BN_MASK_HARD; None removes them."""
+        if masks is None:
+            _check(lib().bn_db_set_masks(C.c_int(self.handle), C.c_int(abi.BN_MASK_NONE), None, None))
+            return
+        mn = np.ascontiguousarray([len(m) for m in masks], dtype=np.int32)
+        flat = [x for m in masks for iv in m for x in iv]
+        miv = np.ascontiguousarray(flat if flat else [0, 0], dtype=np.int32)
+        _check(lib().bn_db_set_masks(C.c_int(self.handle), C.c_int(mask_type), mn.ctypes.data_as(C.c_void_p),
+                                     miv.ctypes.data_as(C.c_void_p)))
 
 
 class FileVolume(Volume):

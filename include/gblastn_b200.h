@@ -13,6 +13,9 @@
  *                                        of an oid (gpu/gpu_blastn_MB_and_smallNa.cu:1462-1468);
  *                                        input is what BlastSeqSrcGetSequence hands the engine
  *                                        (core/blast_engine.c:1203; packed ncbi2na, inc-core/blast_def.h:242)
+ *   bn_db_set_masks                 <->  BlastSeqBlkSetSeqRanges (core/blast_util.c:186-223) as called by the seqsrc
+ *                                        for -db_soft_mask / -db_hard_mask
+ *   bn_db_load_files                <->  CSeqDBVol reading .nin/.nsq (objtools/blast/seqdb_reader/seqdbvol.cpp)
  *   bn_query_load / bn_query_free   <->  GpuLookUpSetUp / gpu_InitQueryMemory
  *                                        (gpu/gpu_blastn_na_ungapped_v3.cpp:595-696): the arrays of
  *                                        LookupTableWrap (inc-core/blast_nalookup.h:60,236), the query
@@ -27,6 +30,8 @@
  *                                        (core/blast_engine.c:503-540) and E-values (:788-806)
  *   bn_word_finder                  <->  BlastWordFinderType  (inc-core/blast_engine.h:227-238)
  *   bn_get_gapped_score             <->  BlastGetGappedScoreType (inc-core/blast_engine.h:212-224)
+ *   bn_prelim_search_batches        <->  blastn's query-batch loop (app/blast/blastn_app.cpp:574-640) / G-BLASTN's
+ *                                        work_thread pipeline (gpu/work_thread.cpp:16-438)
  *   bn_scan_subject                 <->  TNaScanSubjectFunction (inc-core/blast_nascan.h:43-47), whole-
  *                                        subject form (max_hits batching is invisible to results)
  *   bn_setup_*                      <->  host-side set-up the reference does before the path:
@@ -198,6 +203,15 @@ int  bn_db_load(int device, const uint8_t *packed, int64_t packed_bytes,
                 const int64_t *seq_byte_off, const int32_t *seq_len, int32_t n_seq,
                 int *vol_handle);
 int  bn_db_free(int vol_handle);
+/* Database masks (blastn -db_soft_mask / -db_hard_mask; BLAST_SequenceBlk::seq_ranges + mask_type,
+ * inc-core/blast_def.h:242; BlastSeqBlkSetSeqRanges core/blast_util.c:186-223): sequence i carries mask_n[i]
+ * masked [begin, end) intervals, ascending and disjoint, flat pairs in mask_iv.  Soft masks keep seeds out of
+ * the masked ranges (extensions may run through them); hard masks also split the subject into chunks at the
+ * masks (core/blast_engine.c:220-301).  BN_MASK_NONE removes them. */
+#define BN_MASK_NONE 0
+#define BN_MASK_SOFT 1
+#define BN_MASK_HARD 2
+int  bn_db_set_masks(int vol_handle, int mask_type, const int32_t *mask_n, const int32_t *mask_iv);
 
 /* BLAST database volume files (version 4 .nin index + .nsq packed sequences, the files
  * `makeblastdb -dbtype nucl` writes and CSeqDBVol reads: objtools/blast/seqdb_reader/seqdbfile.cpp:195-250,

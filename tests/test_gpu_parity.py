@@ -137,6 +137,55 @@ def test_real_blast_db_volume(task):
         Q.free(); V.free(); s.free()
 
 
+def _db_masks(vol, rng, k):
+    out = []
+    for L in vol.seq_len:
+        L = int(L)
+        m, pos = [], int(rng.integers(0, max(1, L // 10)))
+        if rng.random() < 0.3:
+            pos = 0
+        while pos < L and len(m) < k:
+            end = min(L, pos + int(rng.integers(5, max(6, L // 8))))
+            m.append((pos, end))
+            pos = end + int(rng.integers(1, max(2, L // 6)))
+        out.append(m)
+    return out
+
+
+@pytest.mark.parametrize("name,kw", [("mb_lut11_hash_indels", {}), ("mb_lut12_stride17", {}), ("blastn_mb11_dp", {}),
+                                     ("mb_smallna_diagarray", {}), ("mb_ntlike_many_subjects", {}),
+                                     ("blastn_ws7_na_table", {}), ("mb_two_hit_w40_hash", {})])
+@pytest.mark.parametrize("mask_type", [1, 2])
+def test_gpu_with_database_masks(name, kw, mask_type):
+    """Soft / hard database masks (BLAST_SequenceBlk::seq_ranges): chunking at hard masks, per-range scanning
+    from left + (word - lut), range-bounded mini-extension and s_TypeOfWord == reference engine."""
+    from gblastn_b200 import engine as E, abi
+    from oracle import refdriver as R, portdriver as P
+    if not R.available():
+        pytest.skip("reference library not present")
+    task, cfgkw, vol, qs = cases.make_case(name)
+    sm = _db_masks(vol, np.random.default_rng(100 * mask_type + len(name)), 5)
+    cfg = R.default_config(task, taps=R.TAP_INIT | R.TAP_GAPPED | R.TAP_LUT, **cfgkw)
+    r = R.search(qs, vol, cfg, subject_masks=sm, subject_mask_type=mask_type)
+    assert r["status"] == 0
+    h = P.batch_from_reference(r, task=task, cfg=cfg)
+    V, Q = E.Volume(vol), E.Query(h)
+    try:
+        V.set_masks(sm, mask_type)
+        g = E.prelim_search(V, Q, taps=abi.BN_TAP_INIT | abi.BN_TAP_GAPPED)
+        assert np.array_equal(P.init_table(g["init"]), r["init"]), "init-HSPs differ from reference"
+        assert np.array_equal(P.gapped_table(g["gapped"]), r["gapped"])
+        assert np.array_equal(P.final_table(g["hsps"]), r["final"])
+        assert g["stats"]["lookup_hits"] == r["lookup_hits"]
+        # masks off again: the unmasked answer comes back
+        V.set_masks(None)
+        r0 = R.search(qs, vol, R.default_config(task, **cfgkw))
+        g0 = E.prelim_search(V, Q)
+        assert np.array_equal(P.final_table(g0["hsps"]), r0["final"])
+    finally:
+        Q.free(); V.free()
+
+
 def test_batch_pipeline_equals_single_searches():
     """bn_prelim_search_batches: five different query batches (mixed table shapes, one empty result, one on
     the general cub path) through the two-stage pipeline give byte-identical results to one search each."""
