@@ -16,6 +16,6 @@ tail -3 gpurun_out/bench_err_$TAG.log
 if [ "$3" = "noncu" ]; then exit 0; fi
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/b_ncu_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:scan_kernel -s 4 -c 2 -o gpurun_out/prof_scan_$TAG -f \
+ncu --set full --clock-control none --import-source on -k regex:scan_kernel_staged -s 4 -c 2 -o gpurun_out/prof_scan_$TAG -f \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/b_ncu2_$TAG.log 2>&1
 ls -la gpurun_out | tail -8
