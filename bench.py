@@ -221,17 +221,24 @@ def main():
     for _ in range(args.warmup):
         g = engine.prelim_search(V, Q)
     launches = 0
-    step_ms = []
+    step_ms, step_ms_wall = [], []
     stage = {"ms_scan": 0.0, "ms_extend": 0.0, "ms_gapped": 0.0, "ms_host": 0.0}
+    # A step ends on the host (the replay of the precomputed extensions), so it is bracketed by two CUDA events
+    # recorded around the call: device timestamps of "call issued" and "results in host memory"; the wall clock
+    # is kept beside them as a cross-check.
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     with ClockSampler(local_rank) as clk:
         for _ in range(args.steps):
             l2_flush()
             barrier()
             t0 = time.perf_counter()
+            ev0.record()
             g = engine.prelim_search(V, Q)
-            torch.cuda.synchronize()
-            step_ms.append(1e3 * (time.perf_counter() - t0))
+            ev1.record()
+            ev1.synchronize()
+            step_ms_wall.append(1e3 * (time.perf_counter() - t0))
+            step_ms.append(ev0.elapsed_time(ev1))
             launches += g["stats"]["kernel_launches"]
             for k in stage:
                 stage[k] += g["stats"][k]
@@ -240,11 +247,12 @@ def main():
         for i in range(3 + args.steps):
             l2_flush()
             barrier()
-            t0 = time.perf_counter()
+            ev0.record()
             ge = engine.prelim_search_host(s.batch, vol, device=0)
-            torch.cuda.synchronize()
+            ev1.record()
+            ev1.synchronize()
             if i >= 3:
-                e2e_ms.append(1e3 * (time.perf_counter() - t0))
+                e2e_ms.append(ev0.elapsed_time(ev1))
         # ---- scan kernel alone (roofline) -----------------------------------------------------------
         engine.bench_scan(V, Q, 3)
         scan_ms, scan_bases, survivors = engine.bench_scan(V, Q, max(args.steps, 10))
@@ -277,6 +285,8 @@ def main():
                      "peak_kind": peak_kind, "ms_per_launch": scan_ms,
                      "algorithmic_bytes_per_launch": scan_bases * 0.25},
         "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
+        "ms_per_step_wall": float(sum(step_ms_wall)) / args.steps,
+        "timing": "CUDA events around each step (the step ends with the host replay); max over ranks",
         "clocks": clk.summary(),
     }
 
