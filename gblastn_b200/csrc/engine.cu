@@ -970,23 +970,39 @@ static int search_host_phase(const Query &Q, const GpuOut &G, int taps, BnResult
     static const bool trace = getenv("BN_TRACE") != nullptr;
     double t_sort = 0, t_replay = 0, t_finish = 0, t_merge = 0, t_eval = 0, t_track = 0;
     const BnQueryBatch &b = Q.batch;
-    // init hits grouped by chunk (counting sort on the chunk index), each group in the reference's order
+    // init hits grouped by chunk, each group in the reference's order.  groups[k] = {chunk, begin, end} into
+    // `inits`; a counting sort when the hits are many compared with the chunks, else a sort of the hits
+    // (an nt-like volume has a million chunks and a few thousand init-HSPs).
     const size_t n_chunks = T->hchunks.size();
-    std::vector<HostInit> inits((size_t)cnt.n_init);
-    std::vector<size_t> group_begin(n_chunks + 1, 0);
-    for (size_t i = 0; i < inits.size(); i++) ++group_begin[(size_t)h_init[i].chunk + 1];
-    for (size_t c = 0; c < n_chunks; c++) group_begin[c + 1] += group_begin[c];
-    {
+    const size_t n_in = (size_t)cnt.n_init;
+    std::vector<HostInit> inits(n_in);
+    struct Group { size_t chunk, lo, hi; };
+    std::vector<Group> groups;
+    auto host_init = [&](size_t i) {
+        const DevInitHit &h = h_init[i];
+        const DevGapResult &g = h_gap[i];
+        return HostInit{h.chunk, h.q_off, h.s_off, h.q_start, h.s_start, h.length, h.score, h.order,
+                        g.q_start, g.q_stop, g.s_start, g.s_stop, g.score, g.q_seed, g.s_seed};
+    };
+    if (n_in * 4 >= n_chunks) {
+        std::vector<size_t> group_begin(n_chunks + 1, 0);
+        for (size_t i = 0; i < n_in; i++) ++group_begin[(size_t)h_init[i].chunk + 1];
+        for (size_t c = 0; c < n_chunks; c++) group_begin[c + 1] += group_begin[c];
         std::vector<size_t> cursor(group_begin.begin(), group_begin.end() - 1);
-        for (size_t i = 0; i < inits.size(); i++) {
-            const DevInitHit &h = h_init[i];
-            const DevGapResult &g = h_gap[i];
-            inits[cursor[(size_t)h.chunk]++] = HostInit{h.chunk, h.q_off, h.s_off, h.q_start, h.s_start, h.length, h.score, h.order,
-                                                        g.q_start, g.q_stop, g.s_start, g.s_stop, g.score, g.q_seed, g.s_seed};
+        for (size_t i = 0; i < n_in; i++) inits[cursor[(size_t)h_init[i].chunk]++] = host_init(i);
+        for (size_t c = 0; c < n_chunks; c++)
+            if (group_begin[c + 1] > group_begin[c]) groups.push_back(Group{c, group_begin[c], group_begin[c + 1]});
+    } else {
+        std::vector<uint64_t> order(n_in);
+        for (size_t i = 0; i < n_in; i++) order[i] = ((uint64_t)(uint32_t)h_init[i].chunk << 32) | (uint64_t)i;
+        std::sort(order.begin(), order.end());
+        for (size_t k = 0; k < n_in; k++) {
+            inits[k] = host_init((size_t)(order[k] & 0xFFFFFFFFull));
+            const size_t c = (size_t)(order[k] >> 32);
+            if (groups.empty() || groups.back().chunk != c) groups.push_back(Group{c, k, k + 1});
+            else groups.back().hi = k + 1;
         }
     }
-    std::vector<size_t> groups;                       // chunks that have init hits, ascending
-    for (size_t c = 0; c < n_chunks; c++) if (group_begin[c + 1] > group_begin[c]) groups.push_back(c);
 
     std::vector<BnHSP> final_hsps, gapped_tap, comb;
     std::vector<BnInitHit> init_tap;
@@ -995,7 +1011,7 @@ static int search_host_phase(const Query &Q, const GpuOut &G, int taps, BnResult
     std::vector<GroupOut> gout(groups.size());
     // one group: sort, containment replay, per-chunk list post-processing
     auto do_group = [&](size_t gi) {
-        const size_t c = groups[gi], lo = group_begin[c], hi = group_begin[c + 1];
+        const size_t c = groups[gi].chunk, lo = groups[gi].lo, hi = groups[gi].hi;
         GroupOut &o = gout[gi];
         sort_chunk_init_hits(inits.data() + lo, inits.data() + hi);
         replay_gapped(b, T->hchunks[c], inits.data() + lo, hi - lo, tracker.low_score(), o.fresh, o.stats);
@@ -1033,7 +1049,7 @@ static int search_host_phase(const Query &Q, const GpuOut &G, int taps, BnResult
         comb.clear();
     };
     for (size_t gi = 0; gi < groups.size(); gi++) {
-        const size_t c = groups[gi], lo = group_begin[c], hi = group_begin[c + 1];
+        const size_t c = groups[gi].chunk, lo = groups[gi].lo, hi = groups[gi].hi;
         const HostChunk &ch = T->hchunks[c];
         if (ch.oid != cur_oid) { finish_oid(); cur_oid = ch.oid; }
         double ta = now_ms();
