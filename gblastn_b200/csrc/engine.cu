@@ -1021,7 +1021,8 @@ static int search_host_phase(const Query &Q, const GpuOut &G, int taps, BnResult
     // The per-chunk work only meets other chunks through hit_params->low_score.  When no bound can move
     // during this search (fewer subjects than a hit list holds) the chunks are independent and, for large
     // result sets (short-read batches), are replayed by a few host threads.
-    const bool parallel = cnt.n_init >= 16384 && groups.size() >= 2 && tracker.bounds_stay_zero((int64_t)oid_end - oid_begin);
+    const bool bounds_fixed = tracker.bounds_stay_zero((int64_t)oid_end - oid_begin);
+    const bool parallel = cnt.n_init >= 16384 && groups.size() >= 2 && bounds_fixed;
     if (parallel) {
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
         const size_t n_threads = std::min<size_t>(std::min<size_t>(groups.size(), hw), 16);
@@ -1043,7 +1044,7 @@ static int search_host_phase(const Query &Q, const GpuOut &G, int taps, BnResult
         if (!comb.empty()) {
             stats.good_extensions += (int64_t)comb.size();
             final_hsps.insert(final_hsps.end(), comb.begin(), comb.end());
-            tracker.subject_done(b, comb);
+            if (!bounds_fixed) tracker.subject_done(b, comb);      // the hit lists only matter when a bound can move
         }
         t_track += now_ms() - ta;
         comb.clear();
