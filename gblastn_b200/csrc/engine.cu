@@ -1510,6 +1510,13 @@ void bn_results_free(BnResults *r)
 
 void bn_free(void *p) { free(p); }
 
+int bn_selftest_replay(uint64_t seed, int32_t n_cases, int64_t *n_mismatch)
+{
+    if (!n_mismatch || n_cases < 0) return fail(BN_ERR_INVALID, "bn_selftest_replay: bad argument");
+    *n_mismatch = selftest_replay(seed, n_cases);
+    return BN_OK;
+}
+
 int bn_scan_subject(int vol_handle, int query_handle, int32_t oid, int32_t chunk_off, int32_t chunk_len,
                     BnOffsetPair **pairs, int64_t *n_pairs)
 {

@@ -6,6 +6,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 namespace bn {
 
@@ -17,7 +18,7 @@ namespace bn {
 IntervalTree::IntervalTree(int32_t q_min, int32_t q_max, int32_t s_min, int32_t s_max, size_t expected_items)
     : s_min_(s_min), s_max_(s_max)
 {
-    nodes_.reserve(128 + 4 * expected_items);
+    nodes_.reserve(16 + 6 * expected_items);
     items_.reserve(expected_items);
     new_root(q_min, q_max);
 }
@@ -300,7 +301,7 @@ void sort_chunk_init_hits(HostInit *first, HostInit *last)
     });
 }
 
-void replay_gapped(const BnQueryBatch &b, const HostChunk &ch, const HostInit *init, size_t n,
+void replay_gapped_single_tree(const BnQueryBatch &b, const HostChunk &ch, const HostInit *init, size_t n,
                    const int32_t *low_score, std::vector<BnHSP> &out, BnStats &stats)
 {
     if (n == 0) return;
@@ -346,6 +347,88 @@ void replay_gapped(const BnQueryBatch &b, const HostChunk &ch, const HostInit *i
             IntervalTree::Item nt{t.q_strand_start, o.q_off, o.q_end, o.s_off, o.s_end, o.score};
             tree.add(nt, strand_seen);
             ++strand_items[context];
+        }
+    }
+}
+
+// s_GetQueryStrandOffset as a context index: first context of the run of same-sign frames
+static int32_t strand_context(const BnQueryBatch &b, int32_t context)
+{
+    int32_t c = context;
+    while (c) {
+        const int f = b.contexts[c].frame, pf = b.contexts[c - 1].frame;
+        const int sf = (f > 0) - (f < 0), spf = (pf > 0) - (pf < 0);
+        if (f == 0 || sf != spf) break;
+        c--;
+    }
+    return c;
+}
+
+// BLAST_GetGappedScore's containment filter over precomputed extensions, one interval tree PER QUERY STRAND.
+//
+// The reference keeps one tree per subject chunk for all queries.  What a test or an insertion does for an
+// HSP of strand S depends only on the HSPs of S inserted before it, in their order:
+//  * items of different strands occupy disjoint ranges of the concatenated query, and the tree is a FIXED
+//    binary subdivision of [0, Qcat] (nodes are only materialised lazily): an item's home is the first node
+//    on its path whose centre it contains, so two strands never share a node's subject tree or midpoint list;
+//  * s_HSPIsContained / s_HSPsHaveCommonEndpoint compare the strand offsets first, so items of other strands
+//    met on a walk (in an ancestor's lists, or as a not-yet-displaced leaf that ends the walk) change nothing,
+//    and a leaf of another strand can only sit where no item of S lies below it;
+//  * a not-yet-displaced leaf is the deepest materialised point of its path, so the order in which the items
+//    of S are met (which is what the reference's unlink quirk in s_MidpointTreeHasHSPEndpoint depends on) is
+//    the same whether or not other strands pushed it down earlier; list order is reverse insertion order.
+// Each strand therefore gets its own tree WITH THE SAME ROOT RANGES (same node centres), created only when
+// its second HSP arrives: most strands of a batch have a single init-HSP in a chunk and need no tree at all.
+// replay_gapped_single_tree above is the one-tree formulation; bn_selftest_replay compares the two.
+void replay_gapped(const BnQueryBatch &b, const HostChunk &ch, const HostInit *init, size_t n,
+                   const int32_t *low_score, std::vector<BnHSP> &out, BnStats &stats)
+{
+    if (n == 0) return;
+    std::vector<int32_t> ctx_of(n);
+    for (size_t i = 0; i < n; i++) ctx_of[i] = ctx_search(b, init[i].q_off);
+    std::vector<uint8_t> found_high;
+    if (low_score) {
+        found_high.assign((size_t)b.num_queries, 0);
+        for (size_t i = 0; i < n; i++) {
+            const int32_t qi = b.contexts[ctx_of[i]].query_index;
+            if (init[i].score > low_score[qi]) found_high[qi] = 1;
+        }
+    }
+    // per strand: -1 nothing saved yet; -2 - k: one saved HSP, parked in first_item[k]; >= 0: index of its tree
+    std::vector<int32_t> state((size_t)b.num_contexts, -1);
+    std::vector<IntervalTree::Item> first_item;
+    std::vector<IntervalTree> trees;
+    for (size_t i = 0; i < n; i++) {
+        const HostInit &h = init[i];
+        const int32_t context = ctx_of[i];
+        const BnContext &c = b.contexts[context];
+        if (low_score && !found_high[c.query_index]) continue;
+        const int32_t sc = strand_context(b, context);
+        IntervalTree::Item t;
+        t.q_strand_start = b.contexts[sc].query_offset;
+        t.q_off = h.q_start - c.query_offset;
+        t.q_end = t.q_off + h.length;
+        t.s_off = h.s_start;
+        t.s_end = h.s_start + h.length;
+        t.score = h.score;
+        int32_t &st = state[(size_t)sc];
+        if (st <= -2) {                       // second HSP of the strand: now the tree is needed
+            trees.emplace_back(0, b.concat_len + 1, 0, ch.len + 1, 4);
+            trees.back().add(first_item[(size_t)(-2 - st)], false);
+            st = (int32_t)trees.size() - 1;
+        }
+        if (st >= 0 && trees[(size_t)st].contains(t, b.min_diag_separation)) continue;
+        ++stats.gap_extensions;
+        if (h.g_score >= c.gapped_cutoff) {
+            BnHSP o;
+            o.oid = ch.oid; o.context = context; o.chunk_off = ch.chunk_off;
+            o.q_off = h.g_q_start; o.q_end = h.g_q_stop; o.s_off = h.g_s_start; o.s_end = h.g_s_stop;
+            o.score = h.g_score; o.q_gapped_start = h.g_q_seed; o.s_gapped_start = h.g_s_seed;
+            o.evalue = 0.0;
+            out.push_back(o);
+            const IntervalTree::Item nt{t.q_strand_start, o.q_off, o.q_end, o.s_off, o.s_end, o.score};
+            if (st == -1) { first_item.push_back(nt); st = -2 - ((int32_t)first_item.size() - 1); }
+            else trees[(size_t)st].add(nt, true);
         }
     }
 }
@@ -622,6 +705,86 @@ void LowScoreTracker::subject_done(const BnQueryBatch &b, const std::vector<BnHS
         }
         slot_[qi] = -1;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Self-test of the per-strand formulation against the one-tree formulation on seeded random inputs that
+// are rich in what makes the tree interesting: several HSPs per strand, nested boxes, shared start / end
+// points, equal scores.  Returns the number of cases whose outputs differ.
+int64_t selftest_replay(uint64_t seed, int32_t n_cases)
+{
+    auto rnd = [&seed]() {                     // splitmix64
+        uint64_t z = (seed += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    };
+    auto uni = [&](int64_t lo, int64_t hi) { return lo + (int64_t)(rnd() % (uint64_t)(hi - lo + 1)); };
+    int64_t bad = 0;
+    for (int32_t cs = 0; cs < n_cases; cs++) {
+        const int nq = (int)uni(1, 6);
+        std::vector<BnContext> ctx((size_t)(2 * nq));
+        int32_t off = 0;
+        for (int c = 0; c < 2 * nq; c++) {
+            BnContext &x = ctx[(size_t)c];
+            memset(&x, 0, sizeof x);
+            x.query_length = (c % 2) ? ctx[(size_t)c - 1].query_length : (int32_t)uni(150, 2500);
+            x.query_offset = off; x.query_index = c / 2; x.frame = (c % 2) ? -1 : 1; x.is_valid = 1;
+            x.gapped_cutoff = (int32_t)uni(20, 60);
+            off += x.query_length + 1;
+        }
+        BnQueryBatch b;
+        memset(&b, 0, sizeof b);
+        b.contexts = ctx.data(); b.num_contexts = 2 * nq; b.num_queries = nq; b.concat_len = off - 1;
+        const int32_t mds_choices[3] = {0, 6, 50};
+        b.min_diag_separation = mds_choices[uni(0, 2)];
+        HostChunk ch{0, 0, (int32_t)uni(5000, 200000)};
+        // a few "true alignments" per strand; init-HSPs sit on them and their gapped boxes snap to their ends
+        struct Aln { int32_t ctx, q0, q1, s0, s1; };
+        std::vector<Aln> alns;
+        const int n_aln = (int)uni(1, 8);
+        for (int a = 0; a < n_aln; a++) {
+            Aln A;
+            A.ctx = (int32_t)uni(0, 2 * nq - 1);
+            const int32_t L = ctx[(size_t)A.ctx].query_length;
+            A.q0 = (int32_t)uni(0, L - 60); A.q1 = (int32_t)uni(A.q0 + 40, L);
+            A.s0 = (int32_t)uni(0, ch.len - (A.q1 - A.q0) - 10); A.s1 = A.s0 + (A.q1 - A.q0) + (int32_t)uni(-3, 3);
+            alns.push_back(A);
+        }
+        const int n = (int)uni(1, 160);
+        std::vector<HostInit> inits((size_t)n);
+        for (int i = 0; i < n; i++) {
+            const Aln &A = alns[(size_t)uni(0, n_aln - 1)];
+            const BnContext &c = ctx[(size_t)A.ctx];
+            HostInit h;
+            memset(&h, 0, sizeof h);
+            const int32_t len = (int32_t)uni(11, std::max<int32_t>(12, (A.q1 - A.q0) / 2));
+            const int32_t qs = (int32_t)uni(A.q0, std::max(A.q0, A.q1 - len));
+            h.chunk = 0; h.length = len; h.q_start = c.query_offset + qs;
+            h.s_start = std::max<int32_t>(0, A.s0 + (qs - A.q0) + (int32_t)uni(-2, 2));
+            h.q_off = h.q_start + (int32_t)uni(0, len - 1); h.s_off = h.s_start + (h.q_off - h.q_start);
+            h.score = (int32_t)uni(15, 120); h.order = (uint32_t)i;
+            // gapped box: usually the alignment's ends (shared endpoints), sometimes a private variation
+            const int kind = (int)uni(0, 9);
+            h.g_q_start = kind < 7 ? A.q0 : std::max(0, qs - (int32_t)uni(0, 30));
+            h.g_s_start = kind < 7 ? A.s0 : std::max(0, h.s_start - (int32_t)uni(0, 30));
+            h.g_q_stop = (kind < 6 || kind == 8) ? A.q1 : std::min(c.query_length, qs + len + (int32_t)uni(0, 30));
+            h.g_s_stop = (kind < 6 || kind == 8) ? A.s1 : std::min(ch.len, h.s_start + len + (int32_t)uni(0, 30));
+            h.g_score = (int32_t)uni(10, 200) & (kind == 9 ? ~0 : ~3);      // many equal scores
+            h.g_q_seed = h.g_q_start; h.g_s_seed = h.g_s_start;
+            inits[(size_t)i] = h;
+        }
+        sort_chunk_init_hits(inits.data(), inits.data() + inits.size());
+        std::vector<BnHSP> o1, o2;
+        BnStats s1, s2;
+        memset(&s1, 0, sizeof s1); memset(&s2, 0, sizeof s2);
+        replay_gapped_single_tree(b, ch, inits.data(), inits.size(), nullptr, o1, s1);
+        replay_gapped(b, ch, inits.data(), inits.size(), nullptr, o2, s2);
+        const bool same = o1.size() == o2.size() && s1.gap_extensions == s2.gap_extensions &&
+                          (o1.empty() || memcmp(o1.data(), o2.data(), o1.size() * sizeof(BnHSP)) == 0);
+        if (!same) ++bad;
+    }
+    return bad;
 }
 
 }  // namespace bn

@@ -59,6 +59,13 @@ void sort_chunk_init_hits(HostInit *first, HostInit *last);
 void replay_gapped(const BnQueryBatch &b, const HostChunk &ch, const HostInit *init, size_t n,
                    const int32_t *low_score, std::vector<BnHSP> &out, BnStats &stats);
 
+// the same with ONE tree for all strands, exactly as the reference lays it out (kept for bn_selftest_replay)
+void replay_gapped_single_tree(const BnQueryBatch &b, const HostChunk &ch, const HostInit *init, size_t n,
+                               const int32_t *low_score, std::vector<BnHSP> &out, BnStats &stats);
+
+// seeded comparison of the two formulations; number of differing cases
+int64_t selftest_replay(uint64_t seed, int32_t n_cases);
+
 // purge common endpoints + odd-score rounding + sort (core/blast_engine.c:507-513)
 void finish_chunk_list(const BnQueryBatch &b, std::vector<BnHSP> &list);
 

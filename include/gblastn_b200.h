@@ -269,6 +269,11 @@ int  bn_get_gapped_score(int vol_handle, int query_handle, int32_t oid, int32_t 
                          BnHSP **hsps, int64_t *n_hsps);
 void bn_free(void *p);
 
+/* Host-only self-test: the containment replay (BLAST_GetGappedScore's interval-tree filter, core/blast_itree.c)
+ * runs with one tree per query strand; this compares it with the reference's one-tree-per-subject layout on
+ * n_cases seeded random init-HSP sets and reports how many differ (0 expected).  Needs no device. */
+int  bn_selftest_replay(uint64_t seed, int32_t n_cases, int64_t *n_mismatch);
+
 /* Parity tap for the device-side table fill: reconstructs hashtable[hashsize] and
  * next_pos[concat_len + 1] of an MB batch from the arrays resident on `device`. */
 int  bn_query_download_lookup(int query_handle, int device, int32_t *hashtable, int32_t *next_pos);

@@ -46,3 +46,15 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) and f != "build.py":
                 src = open(os.path.join(dirpath, f)).read()
                 assert not bad.search(src), f"{f} uses the oracle: the product path must not depend on it"
+
+
+def test_replay_per_strand_equals_single_tree(built):
+    """The containment replay keeps one interval tree per query strand; the reference keeps one per subject
+    chunk.  Seeded random init-HSP sets (nested boxes, shared end points, equal scores, 1-12 strands):
+    identical outputs in every case.  Host-only."""
+    from gblastn_b200 import engine
+    lib = engine.lib()
+    for seed in (1, 2, 3):
+        n = C.c_int64(-1)
+        assert lib.bn_selftest_replay(C.c_uint64(seed), C.c_int32(20000), C.byref(n)) == 0
+        assert n.value == 0
