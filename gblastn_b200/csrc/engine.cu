@@ -185,6 +185,7 @@ struct QueryDev {
 struct Query {
     BnQueryBatch batch{};                 // host copy of the scalars; array pointers are NULL except contexts
     std::vector<BnContext> ctx;           // the host replay needs contexts, cutoffs and Karlin blocks only
+    std::vector<CtxLite> ctx_lite;        // compact context table of the replay
     std::vector<QueryDev> dev;            // per device
     int32_t diag_array_length = 1;
     int32_t max_query_length = 0;
@@ -1007,16 +1008,20 @@ static int search_host_phase(const Query &Q, const GpuOut &G, int taps, BnResult
     std::vector<BnHSP> final_hsps, gapped_tap, comb;
     std::vector<BnInitHit> init_tap;
     LowScoreTracker tracker(b);
-    struct GroupOut { std::vector<BnHSP> fresh, tap; BnStats stats{}; };
+    struct GroupOut { std::vector<BnHSP> fresh, tap; BnStats stats{}; double t_sort = 0, t_replay = 0, t_finish = 0; };
     std::vector<GroupOut> gout(groups.size());
     // one group: sort, containment replay, per-chunk list post-processing
     auto do_group = [&](size_t gi) {
         const size_t c = groups[gi].chunk, lo = groups[gi].lo, hi = groups[gi].hi;
         GroupOut &o = gout[gi];
+        const double ga = now_ms();
         sort_chunk_init_hits(inits.data() + lo, inits.data() + hi);
-        replay_gapped(b, T->hchunks[c], inits.data() + lo, hi - lo, tracker.low_score(), o.fresh, o.stats);
+        const double gb = now_ms();
+        replay_gapped(b, T->hchunks[c], inits.data() + lo, hi - lo, tracker.low_score(), o.fresh, o.stats, Q.ctx_lite.data());
+        const double gc = now_ms();
         if (taps & BN_TAP_GAPPED) o.tap = o.fresh;
         finish_chunk_list(b, o.fresh);
+        o.t_sort = gb - ga; o.t_replay = gc - gb; o.t_finish = now_ms() - gc;
     };
     // The per-chunk work only meets other chunks through hit_params->low_score.  When no bound can move
     // during this search (fewer subjects than a hit list holds) the chunks are independent and, for large
@@ -1072,9 +1077,14 @@ static int search_host_phase(const Query &Q, const GpuOut &G, int taps, BnResult
     finish_oid();
     stats.ms_host = now_ms() - th0;
     if (trace)
-        fprintf(stderr, "[bn] wall: table %.3f word-finder %.3f gapped %.3f | host %.3f ms: sort %.3f replay %.3f finish %.3f merge %.3f eval %.3f track %.3f (n_hits %lld n_init %lld)\n",
-                tw0 - t0, tw1 - tw0, tw2 - tw1, stats.ms_host, t_sort, t_replay, t_finish, t_merge, t_eval, t_track,
+    {
+        double gs = 0, gr = 0, gf = 0;
+        for (const auto &o : gout) { gs += o.t_sort; gr += o.t_replay; gf += o.t_finish; }
+        fprintf(stderr, "[bn] wall: table %.3f word-finder %.3f gapped %.3f | host %.3f ms: group(+parallel) %.3f [sum over chunks: sort %.3f replay %.3f finish %.3f] serial-groups %.3f merge %.3f eval %.3f track %.3f tail %.3f (n_hits %lld n_init %lld)\n",
+                tw0 - t0, tw1 - tw0, tw2 - tw1, stats.ms_host, t_sort, gs, gr, gf, t_replay, t_merge, t_eval, t_track,
+                stats.ms_host - (t_sort + t_replay + t_merge + t_eval + t_track),
                 (long long)cnt.n_hits, (long long)cnt.n_init);
+    }
 
     out->n_hsps = (int64_t)final_hsps.size(); out->hsps = to_malloc(final_hsps);
     out->n_init = (int64_t)init_tap.size();   out->init = to_malloc(init_tap);
@@ -1350,6 +1360,7 @@ static int query_load_impl(const BnQueryBatch *b, int *query_handle, int hook_de
     auto Q = std::make_unique<Query>();
     Q->batch = *b;
     Q->ctx.assign(b->contexts, b->contexts + b->num_contexts);
+
     for (const auto &c : Q->ctx) Q->max_query_length = std::max(Q->max_query_length, c.query_length);
     // keep only scalars + contexts on the host; remember whether masked_locations was non-NULL
     Q->batch.query_start = nullptr; Q->batch.contexts = Q->ctx.data();
@@ -1361,6 +1372,7 @@ static int query_load_impl(const BnQueryBatch *b, int *query_handle, int hook_de
     int32_t n = 1;
     while (n < b->concat_len + b->window_size) n <<= 1;   // s_BlastDiagTableNew core/blast_extend.c:46-72
     Q->diag_array_length = n;
+    Q->ctx_lite = make_ctx_lite(Q->batch);
     Q->dev.resize(g_devices.size());
     for (size_t d = 0; d < g_devices.size(); d++) {
         rc = query_to_device(*Q, *b, (int)d, (int)d == hook_device ? after_h2d : nullptr);
@@ -1613,7 +1625,7 @@ int bn_get_gapped_score(int vol_handle, int query_handle, int32_t oid, int32_t c
     sort_init_hits(inits);
     std::vector<BnHSP> out;
     BnStats stats{};
-    replay_gapped(Q->batch, T->hchunks[(size_t)chunk], inits.data(), inits.size(), low_score, out, stats);
+    replay_gapped(Q->batch, T->hchunks[(size_t)chunk], inits.data(), inits.size(), low_score, out, stats, Q->ctx_lite.data());
     *hsps = to_malloc(out);
     *n_hsps = (int64_t)out.size();
     if (!out.empty() && !*hsps) return fail(BN_ERR_MEMORY, "bn_get_gapped_score: out of memory");

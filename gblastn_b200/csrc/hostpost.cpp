@@ -380,17 +380,39 @@ static int32_t strand_context(const BnQueryBatch &b, int32_t context)
 // Each strand therefore gets its own tree WITH THE SAME ROOT RANGES (same node centres), created only when
 // its second HSP arrives: most strands of a batch have a single init-HSP in a chunk and need no tree at all.
 // replay_gapped_single_tree above is the one-tree formulation; bn_selftest_replay compares the two.
+std::vector<CtxLite> make_ctx_lite(const BnQueryBatch &b)
+{
+    std::vector<CtxLite> v((size_t)b.num_contexts);
+    for (int32_t c = 0; c < b.num_contexts; c++)
+        v[(size_t)c] = CtxLite{b.contexts[c].query_offset, b.contexts[c].gapped_cutoff, b.contexts[c].query_index,
+                               strand_context(b, c)};
+    return v;
+}
+
+// BSearchContextInfo (core/blast_query_info.c:220-236) over the compact table
+static int32_t ctx_search_lite(const CtxLite *L, int32_t n_ctx, int32_t n)
+{
+    int32_t lo = 0, hi = n_ctx;
+    while (lo < hi - 1) {
+        const int32_t m = (lo + hi) / 2;
+        if (L[m].query_offset > n) hi = m; else lo = m;
+    }
+    return lo;
+}
+
 void replay_gapped(const BnQueryBatch &b, const HostChunk &ch, const HostInit *init, size_t n,
-                   const int32_t *low_score, std::vector<BnHSP> &out, BnStats &stats)
+                   const int32_t *low_score, std::vector<BnHSP> &out, BnStats &stats, const CtxLite *lite)
 {
     if (n == 0) return;
+    std::vector<CtxLite> local;
+    if (!lite) { local = make_ctx_lite(b); lite = local.data(); }
     std::vector<int32_t> ctx_of(n);
-    for (size_t i = 0; i < n; i++) ctx_of[i] = ctx_search(b, init[i].q_off);
+    for (size_t i = 0; i < n; i++) ctx_of[i] = ctx_search_lite(lite, b.num_contexts, init[i].q_off);
     std::vector<uint8_t> found_high;
     if (low_score) {
         found_high.assign((size_t)b.num_queries, 0);
         for (size_t i = 0; i < n; i++) {
-            const int32_t qi = b.contexts[ctx_of[i]].query_index;
+            const int32_t qi = lite[ctx_of[i]].query_index;
             if (init[i].score > low_score[qi]) found_high[qi] = 1;
         }
     }
@@ -401,11 +423,11 @@ void replay_gapped(const BnQueryBatch &b, const HostChunk &ch, const HostInit *i
     for (size_t i = 0; i < n; i++) {
         const HostInit &h = init[i];
         const int32_t context = ctx_of[i];
-        const BnContext &c = b.contexts[context];
+        const CtxLite &c = lite[context];
         if (low_score && !found_high[c.query_index]) continue;
-        const int32_t sc = strand_context(b, context);
+        const int32_t sc = c.strand_ctx;
         IntervalTree::Item t;
-        t.q_strand_start = b.contexts[sc].query_offset;
+        t.q_strand_start = lite[sc].query_offset;
         t.q_off = h.q_start - c.query_offset;
         t.q_end = t.q_off + h.length;
         t.s_off = h.s_start;

@@ -56,8 +56,15 @@ void sort_init_hits(std::vector<HostInit> &v);
 void sort_chunk_init_hits(HostInit *first, HostInit *last);
 
 // Replays BLAST_GetGappedScore for one chunk; appends saved HSPs (chunk-relative subject coords).
+// What the replay reads of a context, 16 bytes instead of the 80-byte BnContext (a 100 k-read batch has
+// 200 k contexts; the replay touches them at random).
+struct CtxLite { int32_t query_offset, gapped_cutoff, query_index, strand_ctx; };
+std::vector<CtxLite> make_ctx_lite(const BnQueryBatch &b);
+
+// lite: optional compact context table from make_ctx_lite (built per call when NULL)
 void replay_gapped(const BnQueryBatch &b, const HostChunk &ch, const HostInit *init, size_t n,
-                   const int32_t *low_score, std::vector<BnHSP> &out, BnStats &stats);
+                   const int32_t *low_score, std::vector<BnHSP> &out, BnStats &stats,
+                   const CtxLite *lite = nullptr);
 
 // the same with ONE tree for all strands, exactly as the reference lays it out (kept for bn_selftest_replay)
 void replay_gapped_single_tree(const BnQueryBatch &b, const HostChunk &ch, const HostInit *init, size_t n,
