@@ -112,8 +112,10 @@ def struct_array(ptr, n, dtype) -> np.ndarray:
     """Copy n records behind a ctypes pointer into a numpy structured array."""
     if n <= 0 or not ptr:
         return np.zeros(0, dtype=dtype)
-    buf = C.string_at(C.cast(ptr, C.c_void_p).value, int(n) * dtype.itemsize)
-    return np.frombuffer(buf, dtype=dtype).copy()
+    nbytes = int(n) * dtype.itemsize
+    out = np.empty(int(n), dtype=dtype)
+    C.memmove(out.ctypes.data, C.cast(ptr, C.c_void_p).value, nbytes)      # one copy, straight into the array
+    return out
 
 
 class BatchHolder:

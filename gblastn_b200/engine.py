@@ -152,13 +152,16 @@ class Query:
             self.handle = -1
 
 
+_STAT_FIELDS = tuple(k for k, _ in abi.BnStats._fields_)
+
+
 def _results(res: abi.BnResults) -> dict:
     try:
         return {
             "hsps": abi.struct_array(res.hsps, res.n_hsps, abi.HSP_DTYPE),
             "init": abi.struct_array(res.init, res.n_init, abi.INIT_DTYPE),
             "gapped": abi.struct_array(res.gapped, res.n_gapped, abi.HSP_DTYPE),
-            "stats": {k: getattr(res.stats, k) for k, _ in abi.BnStats._fields_},
+            "stats": {k: getattr(res.stats, k) for k in _STAT_FIELDS},
         }
     finally:
         lib().bn_results_free(C.byref(res))

@@ -55,3 +55,39 @@ def test_cases_exercise_every_table_shape(built):
     assert any(s[0] == 1 for s in seen)
     assert {s[3] for s in seen} == {0, 1}
     assert any(s[2] for s in seen) and any(not s[2] for s in seen)
+
+
+def _db_masks(vol, rng, k):
+    out = []
+    for L in vol.seq_len:
+        L = int(L)
+        m, pos = [], int(rng.integers(0, max(1, L // 10)))
+        if rng.random() < 0.3:
+            pos = 0
+        while pos < L and len(m) < k:
+            end = min(L, pos + int(rng.integers(5, max(6, L // 8))))
+            m.append((pos, end))
+            pos = end + int(rng.integers(1, max(2, L // 6)))
+        out.append(m)
+    return out
+
+
+@pytest.mark.parametrize("name", ["mb_lut11_hash_indels", "blastn_mb11_dp", "mb_smallna_diagarray", "blastn_ws7_na_table"])
+@pytest.mark.parametrize("mask_type", [1, 2])
+def test_port_matches_reference_with_database_masks(name, mask_type, built):
+    """Soft / hard database masks (BLAST_SequenceBlk::seq_ranges, core/blast_engine.c:136-301,
+    core/masksubj.inl): init-HSPs, gapped lists, final lists and the lookup-hit count of the port == reference."""
+    from oracle import refdriver as R, portdriver as P
+    if not R.available():
+        pytest.skip("oracle/_ref/libblastref.so not built (needs /root/reference)")
+    task, cfgkw, vol, qs = cases.make_case(name)
+    sm = _db_masks(vol, np.random.default_rng(17 * mask_type + len(name)), 6)
+    cfg = R.default_config(task, taps=R.TAP_INIT | R.TAP_GAPPED | R.TAP_LUT, **cfgkw)
+    r = R.search(qs, vol, cfg, subject_masks=sm, subject_mask_type=mask_type)
+    assert r["status"] == 0
+    h = P.batch_from_reference(r, task=task, cfg=cfg)
+    p = P.search(h, vol, taps=P.TAP_INIT | P.TAP_GAPPED, subject_masks=sm, subject_mask_type=mask_type)
+    assert np.array_equal(r["init"], P.init_table(p["init"]))
+    assert np.array_equal(r["gapped"], P.gapped_table(p["gapped"]))
+    assert np.array_equal(r["final"], P.final_table(p["hsps"]))
+    assert p["stats"]["lookup_hits"] == r["lookup_hits"]
