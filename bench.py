@@ -74,12 +74,33 @@ class ClockSampler:
               "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.samples, self.reasons, self.max_mhz, self.source = [], set(), None, None
         self._stop = threading.Event()
         self.index = index
         self._t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
+        # NVML in-process (nvidia_ml_py): a query costs microseconds and spawns nothing; `nvidia-smi` every
+        # 100 ms per rank was a measurable disturbance of sub-millisecond steps.  Falls back to the CLI.
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                N.nvmlDeviceGetCurrentClocksThrottleReasons
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+            self.source = "nvml"
+            while not self._stop.is_set():
+                self.samples.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                r = int(get_reasons(h))
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                self._stop.wait(0.05)
+            return
+        except Exception:
+            self.source = "nvidia-smi"
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
@@ -95,7 +116,7 @@ class ClockSampler:
                             self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.25)
 
     def __enter__(self):
         self._t.start()
@@ -107,7 +128,29 @@ class ClockSampler:
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
-                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "source": self.source}
+
+
+def bind_near_gpu(bus_id: str):
+    """Run this rank on the cores of the NUMA node its GPU hangs off (host replay, pinned buffers and the
+    launch path then stay on one socket).  Best effort: returns the node or None."""
+    try:
+        dev = "/sys/bus/pci/devices/" + bus_id.lower()
+        if not os.path.isdir(dev) and len(bus_id.split(":")[0]) == 8:      # NVML prints an 8-digit domain
+            dev = "/sys/bus/pci/devices/" + bus_id.lower()[4:]
+        node = int(open(dev + "/numa_node").read())
+        cpus = set()
+        for part in open(dev + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node >= 0 and cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
 
 
 def _reference_worker(job):
@@ -190,6 +233,23 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = None
+    if world > 1:
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            # NVML enumerates like CUDA when CUDA_DEVICE_ORDER=PCI_BUS_ID; match by UUID to be safe
+            uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+            for i in range(N.nvmlDeviceGetCount()):
+                h = N.nvmlDeviceGetHandleByIndex(i)
+                u = N.nvmlDeviceGetUUID(h)
+                u = u.decode() if isinstance(u, bytes) else u
+                if uuid in u or u.replace("GPU-", "") == uuid:
+                    bus = N.nvmlDeviceGetPciInfo(h).busId
+                    numa = bind_near_gpu(bus.decode() if isinstance(bus, bytes) else bus)
+                    break
+        except Exception:
+            numa = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -261,6 +321,12 @@ def main():
     t = torch.tensor([total_ms, total_e2e_ms, scan_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    mine = torch.tensor([total_ms / args.steps, total_e2e_ms / max(1, len(e2e_ms)), stage["ms_scan"] / args.steps,
+                         stage["ms_extend"] / args.steps, stage["ms_gapped"] / args.steps, stage["ms_host"] / args.steps,
+                         -1.0 if numa is None else float(numa)], dtype=torch.float64, device="cuda")
+    per_rank = [mine.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank, mine)
     total_ms, total_e2e_ms, scan_ms_max = [float(x) for x in t.tolist()]
     bases_per_step = int(g["stats"]["subject_bases_scanned"])
     value = world * bases_per_step * args.steps / (total_ms * 1e-3) / 1e9
@@ -288,6 +354,8 @@ def main():
         "ms_per_step_wall": float(sum(step_ms_wall)) / args.steps,
         "timing": "CUDA events around each step (the step ends with the host replay); max over ranks",
         "clocks": clk.summary(),
+        "ranks": [dict(zip(("ms_per_step", "e2e_ms_per_step", "ms_scan", "ms_extend", "ms_gapped", "ms_host", "numa"),
+                           [round(float(x), 4) for x in r.tolist()])) for r in per_rank],
     }
 
     # ---- CPU baseline (reference engine on the host cores), rank 0 at N=1 only --------------------

@@ -206,6 +206,7 @@ struct ScanLaunch {
     int32_t diag_array_length;    // eDiagArray: cells (power of two)
     int32_t tile_cap;             // staged kernel: bytes of shared memory for the subject slice
     uint32_t *bucket_count;       // optional: survivors per diagonal-hash bucket (group_sort.cu)
+    int32_t one_group;            // 1: every survivor gets group 0 (serial replay, off-diagonal two-hit search)
 };
 cudaError_t launch_scan(const DevQuery &q, const ScanLaunch &s, cudaStream_t st);
 int scan_positions_per_block();
@@ -240,6 +241,10 @@ cudaError_t launch_extend_groups(const DevQuery &q, const ExtendLaunch &e, const
                                  uint32_t *heads, int64_t n_hits, int gbits, cudaStream_t st);
 cudaError_t launch_extend_grouped(const DevQuery &q, const ExtendLaunch &e, const uint64_t *keys,
                                   const uint32_t *heads, int gbits, cudaStream_t st);
+// two-hit mode with scan_range > 0: one warp replays ALL hits in emission order (hits sorted by global position)
+cudaError_t launch_extend_serial(const DevQuery &q, const ExtendLaunch &e, const uint64_t *keys, int64_t n_hits,
+                                 int gbits, int32_t diag_array_length, cudaStream_t st);
+int64_t extend_serial_cells(int64_t n_hits, bool is_hash, int32_t diag_array_length);
 
 // Device-side grouping of the seed hits by diagonal-hash bucket (group_sort.cu).
 struct BucketLaunch {

@@ -560,6 +560,12 @@ static double now_ms()
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
+// two-hit mode whose single-word hits search neighbouring diagonals (core/na_ungapped.c:697, :853)
+static bool serial_replay(const BnQueryBatch &b)
+{
+    return b.window_size > 0 && std::min(b.scan_range, b.window_size - b.word_length) > 0;
+}
+
 static int bits_for(uint64_t v) { int b = 1; while (b < 64 && (v >> b)) ++b; return b; }
 
 struct StageCounts { int64_t n_hits = 0, lookup_hits = 0, n_init = 0, n_extended = 0; };
@@ -576,7 +582,9 @@ static int run_word_finder(Device &D, Volume &V, Query &Q, ChunkTable &T, bool r
     if (!ws.h_counters) CU_TRY(cudaMallocHost(&ws.h_counters, 8 * sizeof(unsigned long long)));
     if (T.total_pos >= (int64_t)1 << 32) return fail(BN_ERR_OVERFLOW, "more than 2^32 scan positions in one search");
     const int gbits = bits_for((uint64_t)std::max<int64_t>(T.total_pos, 1));
-    const int grp_bits = raw_pairs ? 0 : (Q.batch.container_type == BN_DIAG_HASH ? 9 : bits_for((uint64_t)Q.diag_array_length));
+    // off-diagonal two-hit search: neighbouring diagonals live in other buckets / cells -> one serial group
+    const bool serial = !raw_pairs && serial_replay(Q.batch);
+    const int grp_bits = (raw_pairs || serial) ? 0 : (Q.batch.container_type == BN_DIAG_HASH ? 9 : bits_for((uint64_t)Q.diag_array_length));
 
     Timer t_scan(st, ws, 0), t_ext(st, ws, 1);
     int64_t cap = std::max<int64_t>((int64_t)ws.hits_a.cap, std::max<int64_t>(1 << 16, T.total_pos / 16));
@@ -590,6 +598,7 @@ static int run_word_finder(Device &D, Volume &V, Query &Q, ChunkTable &T, bool r
         s.total_pos = T.total_pos; s.hits = ws.hits_a.p; s.keys = ws.keys_a.p;
         s.counters = ws.counters.p; s.capacity = cap; s.block_chunk = T.block_chunk.p; s.block_desc = T.block_desc.p;
         s.raw_pairs = raw_pairs ? 1 : 0; s.gbits = gbits; s.diag_array_length = Q.diag_array_length;
+        s.one_group = serial ? 1 : 0;
         s.tile_cap = scan_tile_cap(Q.batch.scan_step, Q.batch.word_length);
         t_scan.start();
         CU_TRY(launch_scan(dq, s, st));
@@ -624,7 +633,7 @@ static int run_word_finder(Device &D, Volume &V, Query &Q, ChunkTable &T, bool r
     }
     if (raw_pairs) { t_ext.stop(); if (stats) stats->ms_extend += t_ext.ms(); return BN_OK; }
 
-    CU_TRY(ws.cells.reserve((size_t)n + 2));
+    CU_TRY(ws.cells.reserve((size_t)std::max<int64_t>(n + 2, serial ? extend_serial_cells(n, Q.batch.container_type == BN_DIAG_HASH, Q.diag_array_length) : 0)));
     CU_TRY(ws.heads.reserve((size_t)n + 1));
     CU_TRY(ws.leaders.reserve((size_t)n + 1));
     CU_TRY(ws.spec.reserve((size_t)n + 1));
@@ -638,8 +647,9 @@ static int run_word_finder(Device &D, Volume &V, Query &Q, ChunkTable &T, bool r
         e.cells = reinterpret_cast<int32_t *>(ws.cells.p); e.init = ws.init.p;
         e.counters = ws.counters.p; e.init_capacity = init_cap;
         e.spec = ws.spec.p; e.leaders = ws.leaders.p;
-        CU_TRY(launch_extend_groups(dq, e, ws.keys_b.p, ws.heads.p, n, gbits, st));
-        if (stats) stats->kernel_launches += 3;
+        if (serial) CU_TRY(launch_extend_serial(dq, e, ws.keys_b.p, n, gbits, Q.diag_array_length, st));
+        else CU_TRY(launch_extend_groups(dq, e, ws.keys_b.p, ws.heads.p, n, gbits, st));
+        if (stats) stats->kernel_launches += serial ? 1 : 3;
         CU_TRY(cudaMemcpyAsync(ws.h_counters, ws.counters.p, 8 * sizeof(unsigned long long),
                                cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
@@ -932,7 +942,8 @@ static int search_gpu_phase(Device &D, Volume &V, Query &Q, int32_t oid_begin, i
     StageCounts &cnt = G.cnt;
     const double tw0 = now_ms();
     double tw1 = tw0;
-    bool general = Q.batch.container_type != BN_DIAG_HASH || Q.fast_path_refused || T->total_pos <= 0;
+    bool general = Q.batch.container_type != BN_DIAG_HASH || Q.fast_path_refused || T->total_pos <= 0 ||
+                   serial_replay(Q.batch);
     if (!general) {
         bool redo = false;
         rc = run_fused(D, V, Q, *T, cnt, stats, G.h_init, G.h_gap, &redo);
@@ -1343,9 +1354,6 @@ static int query_load_impl(const BnQueryBatch *b, int *query_handle, int hook_de
     if (rc) return rc;
     if (!b || !query_handle || !b->query_start || !b->contexts || b->num_contexts <= 0)
         return fail(BN_ERR_INVALID, "bn_query_load: bad argument");
-    if (b->window_size > 0 && std::min(b->scan_range, b->window_size - b->word_length) > 0)
-        return fail(BN_ERR_UNSUPPORTED, "two-hit mode with an off-diagonal search (scan_range > 0) is not implemented: "
-                                        "neighbouring diagonals live in other replay groups");
     if (b->lut_type != BN_LUT_MB && b->lut_type != BN_LUT_SMALL_NA && b->lut_type != BN_LUT_NA)
         return fail(BN_ERR_UNSUPPORTED, "unknown lookup table type");
     if (b->lut_type == BN_LUT_NA && !b->na_backbone) return fail(BN_ERR_INVALID, "bn_query_load: standard blastn table arrays missing");

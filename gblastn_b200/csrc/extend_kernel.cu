@@ -680,6 +680,188 @@ extend_kernel(const DevQuery q, const ExtendLaunch e, const uint64_t *keys, cons
     }
 }
 
+// ---- serial replay: two-hit mode with an off-diagonal search (scan_range > 0) -----------------------
+// With Delta = MIN(scan_range, window_size - word_length) > 0 a single-word hit looks up the diagonals
+// diag +- 1 .. diag +- Delta (core/na_ungapped.c:697-726 array, :853-884 hash), which live in other
+// buckets / cells, and the stale-cell recycling of a bucket then depends on every earlier insertion of the
+// subject.  There is no independent sub-problem left, so ONE warp replays all hits in the reference's order
+// (hits sorted by global scan position) against the complete container: 512 bucket heads in shared memory
+// + one cell pool (eDiagHash), or the whole cell array {last_hit, (hit_len << 1) | flag} (eDiagArray).
+// The extension itself is still spread over the 32 lanes.  A rarely used option; exactness over speed.
+__global__ void __launch_bounds__(32)
+extend_serial_kernel(const DevQuery q, const ExtendLaunch e, const uint64_t *keys, int64_t n_hits, int gbits,
+                     int32_t diag_array_length)
+{
+    __shared__ int32_t s_tab[256];
+    __shared__ int32_t s_heads[512];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < 256; i += 32) s_tab[i] = q.score_table[i];
+    for (int i = lane; i < 512; i += 32) s_heads[i] = 0;
+    const bool is_hash = q.container_type == 1;
+    int4 *cells = reinterpret_cast<int4 *>(e.cells);          // hash: pool, index 1..
+    int2 *arr = reinterpret_cast<int2 *>(e.cells);            // array: one int2 per cell
+    const int32_t dmask = diag_array_length - 1;
+    if (!is_hash)
+        for (int32_t i = lane; i < diag_array_length; i += 32) arr[i] = make_int2(0, 0);
+    __syncwarp();
+
+    const int32_t word = q.word_length, lut = q.lut_word_length;
+    const bool direct = (word == lut);
+    const bool has_loc = q.has_locations && !direct;
+    const int32_t window = q.window_size;
+    const int32_t Delta = min(q.scan_range, window - word);      // > 0 here
+    int32_t used = 0;
+    uint32_t cur_chunk = 0xFFFFFFFFu;
+    int32_t cur_epoch = -1;
+    DevChunk ch{};
+    unsigned long long n_extended = 0;
+    CtxCache cc{0, -1, 0, 0, 0};
+
+    auto hget = [&](int32_t diag, int32_t &level, int32_t &len, int32_t &saved) -> bool {
+        int32_t i = s_heads[diag_bucket(diag)];
+        while (i) {
+            const int4 v = cells[i];
+            if (v.x == diag) { level = v.y; len = v.z >> 1; saved = v.z & 1; return true; }
+            i = v.w;
+        }
+        return false;
+    };
+
+    for (int64_t j = 0; j < n_hits; j++) {
+        const SeedHit h = e.hits[j];
+        if (h.chunk != cur_chunk) {
+            cur_chunk = h.chunk;
+            ch = e.chunks[cur_chunk];
+            if (cur_epoch >= 0 && ch.diag_epoch != cur_epoch) {      // Blast_ExtendWordExit reset (core/blast_extend.c:164-186)
+                __syncwarp();
+                if (is_hash) { for (int i = lane; i < 512; i += 32) s_heads[i] = 0; used = 0; }
+                else for (int32_t i = lane; i < diag_array_length; i += 32) arr[i] = make_int2(-window, 0);
+                __syncwarp();
+            }
+            cur_epoch = ch.diag_epoch;
+        }
+        int32_t q_off = (int32_t)h.q_off, s_off = (int32_t)h.s_off;
+        int32_t s_end = s_off + word;
+        const int32_t s_off_pos = s_off + ch.diag_offset;
+        int32_t s_end_pos = s_end + ch.diag_offset;
+        int32_t diag, real_diag = 0, last_hit = 0, hit_saved = 0, s_l = 0;
+        if (is_hash) {
+            diag = s_off - q_off;
+            if (!hget(diag, last_hit, s_l, hit_saved)) { last_hit = 0; hit_saved = 0; }
+        } else {
+            diag = s_off + diag_array_length - q_off;
+            real_diag = diag & dmask;
+            const int2 c = arr[real_diag];
+            last_hit = c.x; hit_saved = c.y & 1;
+        }
+        if (s_off_pos < last_hit) continue;
+
+        const int32_t s_range = hit_s_range(e.ranges, ch, (int32_t)h.scan_pos);
+        const uint8_t *S = e.packed + ch.byte_off;
+        int32_t extended = 0;
+        bool hit_ready = true, off_found = false;
+        if (hit_saved || s_end_pos > last_hit + window) {
+            const int wt = type_of_word(q, S, q_off, s_off, has_loc, (uint32_t)s_range, word, direct ? word : lut,
+                                        true, extended, lane);
+            if (!wt) continue;
+            s_end += extended; s_end_pos += extended;
+            if (wt == 1) {
+                // a neighbouring diagonal whose recorded (unsaved) hit ends inside the window makes the pair
+                const int32_t s_a = s_off_pos + word - window;
+                const int32_t s_b = s_end_pos - 2 * word;
+                for (int32_t delta = 1; delta <= Delta && !off_found; ++delta) {
+                    int32_t lvl = 0, len = 0, sv = 0;
+                    if (is_hash) {
+                        if (hget(diag + delta, lvl, len, sv) && len && lvl - delta >= s_a && lvl - len <= s_b) { off_found = true; break; }
+                        lvl = len = 0;
+                        if (hget(diag - delta, lvl, len, sv) && len && lvl >= s_a && lvl - len + delta <= s_b) { off_found = true; break; }
+                    } else {
+                        const int32_t orig = real_diag + diag_array_length;
+                        int2 c = arr[(orig + delta) & dmask];
+                        lvl = c.x; len = c.y >> 1;
+                        if (len && lvl - delta >= s_a && lvl - len <= s_b) { off_found = true; break; }
+                        c = arr[(orig - delta) & dmask];
+                        lvl = c.x; len = c.y >> 1;
+                        if (len && lvl >= s_a && lvl - len + delta <= s_b) { off_found = true; break; }
+                    }
+                }
+                if (!off_found) hit_ready = false;
+            }
+        } else {
+            if (!type_of_word(q, S, q_off, s_off, has_loc, (uint32_t)s_range, word, direct ? word : lut, false,
+                              extended, lane))
+                continue;
+            s_end += extended; s_end_pos += extended;
+        }
+
+        if (hit_ready) {
+            ctx_lookup(q, q_off, lane, cc);
+            Ungapped u;
+            const int64_t chunk_base = ch.byte_off * 4;
+            if (!is_hash && word < 11)
+                ungapped_exact(q, e.packed, chunk_base, ch.len, q_off, s_off, -cc.x_dropoff, lane, u);
+            else
+                ungapped_extend(q, e.packed, chunk_base, ch.len, s_tab, q_off, s_end, s_off, -cc.x_dropoff,
+                                cc.reduced_cutoff, lane, u);
+            if (off_found || u.score >= cc.cutoff_score) {
+                if (lane == 0) {
+                    const unsigned long long slot = atomicAdd(&e.counters[2], 1ull);
+                    if ((int64_t)slot < e.init_capacity) {
+                        DevInitHit o;
+                        o.chunk = (int32_t)cur_chunk; o.q_off = q_off; o.s_off = s_off;
+                        o.q_start = u.q_start; o.s_start = u.s_start; o.length = u.length; o.score = u.score;
+                        o.order = (uint32_t)(keys[j] & ((1ull << gbits) - 1ull));
+                        e.init[slot] = o;
+                    }
+                }
+                s_end_pos = u.length + u.s_start + ch.diag_offset;
+                ++n_extended;
+            } else hit_ready = false;
+        }
+        const int32_t len = hit_ready ? 0 : s_end_pos - s_off_pos;
+        __syncwarp();
+        if (is_hash) {
+            // s_BlastDiagHashInsert (core/na_ungapped.c:395-450) with the stale horizon window + Delta + 1
+            const uint32_t b = diag_bucket(diag);
+            const int32_t horizon = window + Delta + 1;
+            int32_t i = s_heads[b];
+            bool done = false;
+            while (i) {
+                const int4 v = cells[i];
+                if (v.x == diag || s_off_pos - v.y > horizon) {
+                    if (lane == 0) cells[i] = make_int4(diag, s_end_pos, (len << 1) | (hit_ready ? 1 : 0), v.w);
+                    done = true;
+                    break;
+                }
+                i = v.w;
+            }
+            if (!done) {
+                const int32_t n = ++used;
+                if (lane == 0) { cells[n] = make_int4(diag, s_end_pos, (len << 1) | (hit_ready ? 1 : 0), s_heads[b]); }
+                __syncwarp();
+                if (lane == 0) s_heads[b] = n;
+            }
+        } else if (lane == 0) {
+            arr[real_diag] = make_int2(s_end_pos, ((len & 0xFF) << 1) | (hit_ready ? 1 : 0));   // Uint1 hit_len
+        }
+        __syncwarp();
+    }
+    if (lane == 0 && n_extended) atomicAdd(&e.counters[3], n_extended);
+}
+
+int64_t extend_serial_cells(int64_t n_hits, bool is_hash, int32_t diag_array_length)
+{
+    return is_hash ? n_hits + 2 : (int64_t)diag_array_length / 2 + 2;       // int4 units
+}
+
+cudaError_t launch_extend_serial(const DevQuery &q, const ExtendLaunch &e, const uint64_t *keys, int64_t n_hits,
+                                 int gbits, int32_t diag_array_length, cudaStream_t st)
+{
+    if (n_hits <= 0) return cudaSuccess;
+    extend_serial_kernel<<<1, 32, 0, st>>>(q, e, keys, n_hits, gbits, diag_array_length);
+    return cudaGetLastError();
+}
+
 // Fast path: hits were grouped on the device (group_sort.cu), their number is only known there; grids
 // are sized for the buffer limit and the kernels read the count themselves.
 cudaError_t launch_extend_grouped(const DevQuery &q, const ExtendLaunch &e, const uint64_t *keys,

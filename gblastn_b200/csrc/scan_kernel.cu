@@ -65,7 +65,7 @@ __device__ __forceinline__ uint32_t load_window(const uint8_t *packed, int64_t b
 
 __device__ __forceinline__ uint32_t diag_group(const DevQuery &q, const ScanLaunch &s, int32_t q_off, int32_t s_off)
 {
-    if (s.raw_pairs) return 0;
+    if (s.raw_pairs || s.one_group) return 0;
     if (q.container_type == 1) return ((uint32_t)(s_off - q_off) * 0x9E370001u) % 512u;       // hash bucket
     return (uint32_t)(s_off + s.diag_array_length - q_off) & (uint32_t)(s.diag_array_length - 1);  // array cell
 }

@@ -65,6 +65,23 @@ CASES = {
                                      sub=0.05, indel=0.01, planted=1.0),
     "blastn_two_hit_array_ws7": dict(task="blastn", cfg={"word_size": 7, "window_size": 30}, seq_lens=[20_000, 5_000],
                                      vol_seed=18, nq=2, qlen=300, q_seed=29, sub=0.10, indel=0.01, planted=1.0),
+    # two-hit mode with an off-diagonal search (-off_diagonal_range, scan_range > 0): a single word pairs with an
+    # unsaved hit on a neighbouring diagonal (core/na_ungapped.c:697-726, :853-884); serial replay on the GPU
+    "mb_two_hit_offdiag_hash": dict(task="megablast", cfg={"word_size": 16, "window_size": 40, "scan_range": 4},
+                                    seq_lens=[200_000, 90_000], vol_seed=15, nq=25, qlen=600, q_seed=26, sub=0.06,
+                                    indel=0.02, planted=0.8),
+    "blastn_two_hit_offdiag_direct": dict(task="blastn", cfg={"window_size": 40, "scan_range": 6},
+                                          seq_lens=[150_000, 60_000, 900], vol_seed=16, nq=20, qlen=700, q_seed=27,
+                                          sub=0.08, indel=0.02, planted=0.8),
+    "mb_two_hit_offdiag_smallna_array": dict(task="megablast", cfg={"word_size": 20, "window_size": 50, "scan_range": 5},
+                                             seq_lens=[300_000, 50_000, 777], vol_seed=17, nq=3, qlen=700, q_seed=28,
+                                             sub=0.05, indel=0.02, planted=1.0),
+    "blastn_two_hit_offdiag_array_ws7": dict(task="blastn", cfg={"word_size": 7, "window_size": 30, "scan_range": 3},
+                                             seq_lens=[20_000, 5_000], vol_seed=18, nq=2, qlen=300, q_seed=29, sub=0.10,
+                                             indel=0.02, planted=1.0),
+    "blastn_ws8_na_table_offdiag": dict(task="blastn", cfg={"word_size": 8, "window_size": 40, "scan_range": 4},
+                                        seq_lens=[60_000, 20_000], vol_seed=22, nq=60, qlen=700, q_seed=32, sub=0.08,
+                                        indel=0.02, planted=0.8),
     # affine greedy (BLAST_AffineGreedyAlign body): -greedy with explicit gap costs
     "mb_affine_greedy_5_2": dict(task="megablast", cfg={"greedy": 1, "gap_open": 5, "gap_extend": 2},
                                  seq_lens=[300_000, 50_000, 777, 120_001], vol_seed=2, nq=40, qlen=500, q_seed=12,
