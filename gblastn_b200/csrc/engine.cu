@@ -996,7 +996,34 @@ static int search_host_phase(const Query &Q, const GpuOut &G, int taps, BnResult
         return HostInit{h.chunk, h.q_off, h.s_off, h.q_start, h.s_start, h.length, h.score, h.order,
                         g.q_start, g.q_stop, g.s_start, g.s_stop, g.score, g.q_seed, g.s_seed};
     };
-    if (n_in * 4 >= n_chunks) {
+    // Small result sets (the usual case) take ONE sort of packed integer keys {chunk, score desc, s_start,
+    // length desc, q_start, emission order} - grouping and the per-chunk Blast_InitHitListSortByScore order
+    // (core/blast_extend.c:274-296) at once - and a gather; large ones are grouped by a counting sort and
+    // sorted per chunk by the worker threads below.
+    bool presorted = false;
+    if (n_in < 16384) {
+        // the pinned result mirrors were just written by the copy engine: read them once, front to back
+        std::vector<SortKey> keys(n_in);
+        std::vector<HostInit> all(n_in);
+        for (size_t i = 0; i < n_in; i++) {
+            all[i] = host_init(i);
+            const HostInit &h = all[i];
+            keys[i] = SortKey{((uint64_t)(uint32_t)h.chunk << 32) | (uint32_t)(INT32_MAX - h.score),
+                              ((uint64_t)(uint32_t)h.s_start << 32) | (uint32_t)(INT32_MAX - h.length),
+                              ((uint64_t)(uint32_t)h.q_start << 32) | h.order, (uint32_t)i, 0u};
+        }
+        const double tr1 = now_ms();
+        sort_keys(keys);
+        const double tr2 = now_ms();
+        if (trace) fprintf(stderr, "[bn] host group: alloc+read %.3f sort %.3f ms\n", tr1 - th0, tr2 - tr1);
+        for (size_t k = 0; k < n_in; k++) {
+            inits[k] = all[(size_t)keys[k].idx];
+            const size_t c = (size_t)(keys[k].k0 >> 32);
+            if (groups.empty() || groups.back().chunk != c) groups.push_back(Group{c, k, k + 1});
+            else groups.back().hi = k + 1;
+        }
+        presorted = true;
+    } else if (n_in * 4 >= n_chunks) {
         std::vector<size_t> group_begin(n_chunks + 1, 0);
         for (size_t i = 0; i < n_in; i++) ++group_begin[(size_t)h_init[i].chunk + 1];
         for (size_t c = 0; c < n_chunks; c++) group_begin[c + 1] += group_begin[c];
@@ -1026,7 +1053,7 @@ static int search_host_phase(const Query &Q, const GpuOut &G, int taps, BnResult
         const size_t c = groups[gi].chunk, lo = groups[gi].lo, hi = groups[gi].hi;
         GroupOut &o = gout[gi];
         const double ga = now_ms();
-        sort_chunk_init_hits(inits.data() + lo, inits.data() + hi);
+        if (!presorted) sort_chunk_init_hits(inits.data() + lo, inits.data() + hi);
         const double gb = now_ms();
         replay_gapped(b, T->hchunks[c], inits.data() + lo, hi - lo, tracker.low_score(), o.fresh, o.stats, Q.ctx_lite.data());
         const double gc = now_ms();

@@ -290,6 +290,43 @@ void sort_init_hits(std::vector<HostInit> &v)
     });
 }
 
+void sort_keys(std::vector<SortKey> &v)
+{
+    const size_t n = v.size();
+    if (n < 2) return;
+    auto less = [](const SortKey &a, const SortKey &c) {
+        if (a.k0 != c.k0) return a.k0 < c.k0;
+        if (a.k1 != c.k1) return a.k1 < c.k1;
+        return a.k2 < c.k2;
+    };
+    if (n < 48) { std::sort(v.begin(), v.end(), less); return; }
+    // LSD radix sort on k0, least significant byte first, skipping the bytes that are the same in every key;
+    // runs of equal k0 (short in practice) are finished by comparison
+    uint64_t diff = 0;
+    for (size_t i = 1; i < n; i++) diff |= v[i].k0 ^ v[0].k0;
+    struct P { uint64_t k; uint32_t i, pad; };
+    std::vector<P> a(n), t(n);
+    for (size_t i = 0; i < n; i++) a[i] = P{v[i].k0, (uint32_t)i, 0u};
+    for (int byte = 0; byte < 8; byte++) {
+        const int sh = 8 * byte;
+        if (!((diff >> sh) & 0xFFull)) continue;
+        uint32_t count[257] = {0};
+        for (size_t i = 0; i < n; i++) ++count[((a[i].k >> sh) & 0xFFull) + 1];
+        for (int c = 0; c < 256; c++) count[c + 1] += count[c];
+        for (size_t i = 0; i < n; i++) t[count[(a[i].k >> sh) & 0xFFull]++] = a[i];
+        a.swap(t);
+    }
+    std::vector<SortKey> out(n);
+    for (size_t i = 0; i < n; i++) out[i] = v[a[i].i];
+    for (size_t i = 0; i < n;) {
+        size_t j = i + 1;
+        while (j < n && out[j].k0 == out[i].k0) ++j;
+        if (j - i > 1) std::sort(out.begin() + (ptrdiff_t)i, out.begin() + (ptrdiff_t)j, less);
+        i = j;
+    }
+    v.swap(out);
+}
+
 void sort_chunk_init_hits(HostInit *first, HostInit *last)
 {
     std::sort(first, last, [](const HostInit &a, const HostInit &c) {
@@ -392,12 +429,17 @@ std::vector<CtxLite> make_ctx_lite(const BnQueryBatch &b)
 // BSearchContextInfo (core/blast_query_info.c:220-236) over the compact table
 static int32_t ctx_search_lite(const CtxLite *L, int32_t n_ctx, int32_t n)
 {
-    int32_t lo = 0, hi = n_ctx;
-    while (lo < hi - 1) {
-        const int32_t m = (lo + hi) / 2;
-        if (L[m].query_offset > n) hi = m; else lo = m;
+    // same answer as the reference's loop (the last context whose offset is <= n, context 0 below the first
+    // offset), written without data-dependent branches: the probes of a replay are random, and a mispredicted
+    // branch per level cost more than the rest of the per-HSP work
+    const CtxLite *base = L;
+    int32_t len = n_ctx;
+    while (len > 1) {
+        const int32_t half = len >> 1;
+        base = (base[half].query_offset <= n) ? base + half : base;
+        len -= half;
     }
-    return lo;
+    return (int32_t)(base - L);
 }
 
 void replay_gapped(const BnQueryBatch &b, const HostChunk &ch, const HostInit *init, size_t n,
@@ -420,6 +462,8 @@ void replay_gapped(const BnQueryBatch &b, const HostChunk &ch, const HostInit *i
     std::vector<int32_t> state((size_t)b.num_contexts, -1);
     std::vector<IntervalTree::Item> first_item;
     std::vector<IntervalTree> trees;
+    first_item.reserve(n);
+    out.reserve(out.size() + n);
     for (size_t i = 0; i < n; i++) {
         const HostInit &h = init[i];
         const int32_t context = ctx_of[i];
@@ -491,14 +535,20 @@ void finish_chunk_list(const BnQueryBatch &b, std::vector<BnHSP> &list)
         // first, so a single sort with context as the last key gives the identical list.
         if (b.round_down)
             for (auto &h : list) h.score &= ~1;
-        std::sort(list.begin(), list.end(), [](const BnHSP &x, const BnHSP &y) {
-            if (x.score != y.score) return x.score > y.score;
-            if (x.s_off != y.s_off) return x.s_off < y.s_off;
-            if (x.s_end != y.s_end) return x.s_end > y.s_end;
-            if (x.q_off != y.q_off) return x.q_off < y.q_off;
-            if (x.q_end != y.q_end) return x.q_end > y.q_end;
-            return x.context < y.context;
-        });
+        // the same order through packed integer keys (scores, offsets and contexts are non-negative here):
+        // comparing three words and moving 32 bytes beats comparing six fields and moving 64
+        const size_t n = list.size();
+        std::vector<SortKey> keys(n);
+        for (size_t i = 0; i < n; i++) {
+            const BnHSP &h = list[i];
+            keys[i] = SortKey{((uint64_t)(uint32_t)(INT32_MAX - h.score) << 32) | (uint32_t)h.s_off,
+                              ((uint64_t)(uint32_t)(INT32_MAX - h.s_end) << 32) | (uint32_t)h.q_off,
+                              ((uint64_t)(uint32_t)(INT32_MAX - h.q_end) << 32) | (uint32_t)h.context, (uint32_t)i, 0u};
+        }
+        sort_keys(keys);
+        std::vector<BnHSP> sorted(n);
+        for (size_t i = 0; i < n; i++) sorted[i] = list[keys[i].idx];
+        list.swap(sorted);
         return;
     }
     // Blast_HSPListPurgeHSPsWithCommonEndpoints(purge = TRUE), core/blast_hits.c:2224-2300

@@ -50,6 +50,12 @@ struct PostParams {
     const BnQueryBatch *batch;      // host copy (contexts, cutoffs, Karlin blocks, options)
 };
 
+// Ascending sort of packed integer keys (k0, k1, k2).  The host replay's sorts are short (hundreds to a few
+// thousand elements) and random, where a comparison sort spends its time in mispredicted branches: k0 is
+// sorted by a byte-wise LSD radix sort over the bytes that vary, ties on k0 by comparison.
+struct SortKey { uint64_t k0, k1, k2; uint32_t idx, pad; };
+void sort_keys(std::vector<SortKey> &keys);
+
 // Sort key of Blast_InitHitListSortByScore (core/blast_extend.c:274-296) + emission order.
 void sort_init_hits(std::vector<HostInit> &v);
 // same order for the hits of ONE chunk
