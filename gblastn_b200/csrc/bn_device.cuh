@@ -263,6 +263,9 @@ struct BucketLaunch {
     int32_t gbits, spec_enabled;
 };
 cudaError_t launch_bucket_group(const BucketLaunch &L, cudaStream_t st);
+cudaError_t launch_mirror_results(const DevInitHit *init, const DevGapResult *gap, const unsigned long long *counters,
+                                  int64_t cap, DevInitHit *h_init, DevGapResult *h_gap, unsigned long long *h_counters,
+                                  cudaStream_t st);
 int group_sort_buckets();
 
 // Derived costs of BLAST_AffineGreedyAlign (core/greedy_align.c:792-842): odd rewards double every

@@ -719,7 +719,7 @@ static int enqueue_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t
 // D2H of the init hits and tier-1 results, then tier 2 (worst-case scratch) for the few extensions
 // that outgrew tier 1.
 static int finish_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t n_init,
-                         DevInitHit *&h_init, DevGapResult *&h_gap, BnStats *stats)
+                         DevInitHit *&h_init, DevGapResult *&h_gap, BnStats *stats, bool mirrored = false)
 {
     Workspace &ws = D.ws();
     cudaStream_t st = D.stream;
@@ -731,9 +731,11 @@ static int finish_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t 
     const bool greedy = b.gap_algo == BN_GAP_GREEDY;
     const int32_t xo = greedy_xdrop_offset(b);
     const int wpb = 4;
-    CU_TRY(cudaMemcpyAsync(h_init, ws.init.p, (size_t)n_init * sizeof(DevInitHit), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(h_gap, ws.gap_out.p, (size_t)n_init * sizeof(DevGapResult), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaStreamSynchronize(st));
+    if (!mirrored) {        // the fused pipeline has already written both arrays into the pinned mirrors
+        CU_TRY(cudaMemcpyAsync(h_init, ws.init.p, (size_t)n_init * sizeof(DevInitHit), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(h_gap, ws.gap_out.p, (size_t)n_init * sizeof(DevGapResult), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+    }
 
     std::vector<int32_t> todo;
     if (!greedy) {
@@ -883,9 +885,12 @@ static int run_fused(Device &D, Volume &V, Query &Q, ChunkTable &T, StageCounts 
     t_ext.stop();
 
     t_gap.start();
+    CU_TRY(ws.h_init.reserve((size_t)init_cap + 1)); CU_TRY(ws.h_gap.reserve((size_t)init_cap + 1));
     int rc = enqueue_gapped(D, V, Q, T, init_cap, nullptr);
     if (rc) return rc;
-    CU_TRY(cudaMemcpyAsync(ws.h_counters, ws.counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    // counters + results into the pinned mirrors by one kernel, then the only synchronisation of the step
+    CU_TRY(launch_mirror_results(ws.init.p, ws.gap_out.p, ws.counters.p, init_cap, ws.h_init.p, ws.h_gap.p,
+                                 ws.h_counters, st));
     CU_TRY(cudaStreamSynchronize(st));
     cnt.n_hits = (int64_t)ws.h_counters[0];
     cnt.lookup_hits = (int64_t)ws.h_counters[1];
@@ -896,10 +901,10 @@ static int run_fused(Device &D, Volume &V, Query &Q, ChunkTable &T, StageCounts 
         CU_TRY(ws.keys_a.reserve((size_t)(cnt.n_hits + cnt.n_hits / 16 + 1024)));
     }
     if (cnt.n_hits > cap || ws.h_counters[6] || cnt.n_init > init_cap) { *redo = true; return BN_OK; }
-    rc = finish_gapped(D, V, Q, T, cnt.n_init, h_init, h_gap, &stats);
+    rc = finish_gapped(D, V, Q, T, cnt.n_init, h_init, h_gap, &stats, true);
     if (rc) return rc;
     t_gap.stop();
-    stats.kernel_launches += 1 + 3 + (L.spec_enabled ? 2 : 1) + 1;
+    stats.kernel_launches += 1 + 3 + (L.spec_enabled ? 2 : 1) + 1 + 1;      // scan, grouping, extension, gapped, result mirror
     stats.ms_scan += t_scan.ms(); stats.ms_extend += t_ext.ms(); stats.ms_gapped += t_gap.ms();
     return BN_OK;
 }

@@ -989,4 +989,29 @@ cudaError_t launch_gapped(const DevQuery &q, const GappedLaunch &g, cudaStream_t
     return cudaGetLastError();
 }
 
+// Results of the fused pipeline straight into the pinned host mirrors: one small kernel instead of
+// "copy the counters, synchronise, copy n_init init-HSPs and n_init gapped results, synchronise" - the number of
+// results is only known on the device, and posted PCIe writes of a few tens of KB cost less than one more
+// host round trip.  Both record types are 32 bytes (two 16-byte stores).
+__global__ void mirror_results_kernel(const DevInitHit *init, const DevGapResult *gap, const unsigned long long *counters,
+                                      int64_t cap, DevInitHit *h_init, DevGapResult *h_gap, unsigned long long *h_counters)
+{
+    static_assert(sizeof(DevInitHit) == 32 && sizeof(DevGapResult) == 32, "two uint4 per record");
+    const int64_t n = min((int64_t)counters[2], cap);
+    const uint4 *si = reinterpret_cast<const uint4 *>(init), *sg = reinterpret_cast<const uint4 *>(gap);
+    uint4 *di = reinterpret_cast<uint4 *>(h_init), *dg = reinterpret_cast<uint4 *>(h_gap);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n; i += (int64_t)gridDim.x * blockDim.x) {
+        di[i] = si[i];
+        dg[i] = sg[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 8) h_counters[threadIdx.x] = counters[threadIdx.x];
+}
+cudaError_t launch_mirror_results(const DevInitHit *init, const DevGapResult *gap, const unsigned long long *counters,
+                                  int64_t cap, DevInitHit *h_init, DevGapResult *h_gap, unsigned long long *h_counters,
+                                  cudaStream_t st)
+{
+    mirror_results_kernel<<<32, 256, 0, st>>>(init, gap, counters, cap, h_init, h_gap, h_counters);
+    return cudaGetLastError();
+}
+
 }  // namespace bn
