@@ -168,6 +168,24 @@ __device__ __forceinline__ int32_t ctx_search(const DevQuery &q, int32_t n)
     return lo;
 }
 
+// BSearchContextInfo (core/blast_query_info.c:220-236) with 32 pivots per round: the largest
+// context index whose query_offset <= n.  Warp-uniform result.
+__device__ __forceinline__ int32_t ctx_search_warp(const DevQuery &q, int32_t n, int lane)
+{
+    int32_t lo = 0, hi = q.num_contexts;
+    while (hi - lo > 1) {
+        const int32_t step = (hi - lo + 31) >> 5;
+        const int32_t piv = lo + lane * step;
+        const bool ok = piv < hi && __ldg(&q.ctx[piv].query_offset) <= n;
+        const unsigned m = __ballot_sync(0xffffffffu, ok) | 1u;      // pivot 0 (= lo) always qualifies
+        const int top = 31 - __clz(m);
+        const int32_t nlo = lo + top * step;
+        hi = min(hi, nlo + step);
+        lo = nlo;
+    }
+    return lo;
+}
+
 // hashtable[idx] of BlastMBLookupTable (inc-core/blast_nalookup.h:236) recovered from the compact
 // table: 0 when the cell is empty, else the 1-based query position that heads the cell's chain.
 __device__ __forceinline__ int32_t mb_cell(const DevQuery &q, uint32_t idx)

@@ -229,24 +229,6 @@ __device__ void ungapped_extend(const DevQuery &q, const uint8_t *packed, int64_
     }
 }
 
-// BSearchContextInfo (core/blast_query_info.c:220-236) with 32 pivots per round: the largest
-// context index whose query_offset <= n.  Warp-uniform result.
-__device__ __forceinline__ int32_t ctx_search_warp(const DevQuery &q, int32_t n, int lane)
-{
-    int32_t lo = 0, hi = q.num_contexts;
-    while (hi - lo > 1) {
-        const int32_t step = (hi - lo + 31) >> 5;
-        const int32_t piv = lo + lane * step;
-        const bool ok = piv < hi && __ldg(&q.ctx[piv].query_offset) <= n;
-        const unsigned m = __ballot_sync(FULL, ok) | 1u;      // pivot 0 (= lo) always qualifies
-        const int top = 31 - __clz(m);
-        const int32_t nlo = lo + top * step;
-        hi = min(hi, nlo + step);
-        lo = nlo;
-    }
-    return lo;
-}
-
 // ---- lookup probes (warp-uniform) ----------------------------------------------------------------
 __device__ bool lut_contains(const DevQuery &q, uint32_t index, int32_t q_pos)
 {

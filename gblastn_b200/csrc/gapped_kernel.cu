@@ -461,8 +461,7 @@ __device__ int32_t greedy_align_warp(const SeqPair &sp, int32_t xdrop_threshold,
             else if (inv & (1u << lane)) cur[k] = GREEDY_INVALID;
             if (succ) {
                 // longest run of matches: first diagonal (ascending k) holding the strict maximum
-                int32_t best_run = ok ? run : -1;
-                for (int o = 16; o > 0; o >>= 1) best_run = max(best_run, __shfl_xor_sync(FULLW, best_run, o));
+                const int32_t best_run = __reduce_max_sync(FULLW, ok ? run : -1);          // REDUX.MAX
                 if (best_run > longest_match_run) {
                     const int src = __ffs(__ballot_sync(FULLW, ok && run == best_run)) - 1;
                     seed.start_q = __shfl_sync(FULLW, seq1_index - run, src);
@@ -471,8 +470,7 @@ __device__ int32_t greedy_align_warp(const SeqPair &sp, int32_t xdrop_threshold,
                 }
                 // extent: first diagonal with the strict maximum of seq1 + seq2
                 int32_t ext = ok ? seq1_index + seq2_index : -1;
-                int32_t best_ext = ext;
-                for (int o = 16; o > 0; o >>= 1) best_ext = max(best_ext, __shfl_xor_sync(FULLW, best_ext, o));
+                const int32_t best_ext = __reduce_max_sync(FULLW, ext);
                 if (best_ext > curr_extent) {
                     const int src = __ffs(__ballot_sync(FULLW, ok && ext == best_ext)) - 1;
                     curr_extent = best_ext;
@@ -524,7 +522,7 @@ greedy_kernel(const DevQuery q, const GappedLaunch L, int use_smem)
         const int64_t i = L.todo ? (int64_t)L.todo[w] : w;
         const DevInitHit h = L.init[i];
         const DevChunk ch = L.chunks[h.chunk];
-        const int32_t context = ctx_search(q, h.q_off);
+        const int32_t context = ctx_search_warp(q, h.q_off, lane);      // 32 pivots per round: 2-3 rounds, not 11-17
         const DevContext c = q.ctx[context];
         const int32_t q_off = (h.q_start - c.query_offset) + h.length / 2;
         const int32_t s_off = h.s_start + h.length / 2;
