@@ -224,6 +224,8 @@ struct ScanLaunch {
     int32_t diag_array_length;    // eDiagArray: cells (power of two)
     int32_t tile_cap;             // staged kernel: bytes of shared memory for the subject slice
     uint32_t *bucket_count;       // optional: survivors per diagonal-hash bucket (group_sort.cu)
+    uint64_t *bucket_keys;        // with bucket_count: bucket_cap keys (position << 24 | emission slot) per bucket
+    int32_t bucket_cap;
     int32_t one_group;            // 1: every survivor gets group 0 (serial replay, off-diagonal two-hit search)
 };
 cudaError_t launch_scan(const DevQuery &q, const ScanLaunch &s, cudaStream_t st);
@@ -267,13 +269,10 @@ int64_t extend_serial_cells(int64_t n_hits, bool is_hash, int32_t diag_array_len
 // Device-side grouping of the seed hits by diagonal-hash bucket (group_sort.cu).
 struct BucketLaunch {
     const SeedHit *hits_in;       // scan output, emission order by slot
-    const uint64_t *keys_in;      // (bucket << gbits) | global scan position
-    uint32_t *bucket_count;       // 512, filled by the scan kernel
-    uint32_t *bucket_start;       // 513
-    uint32_t *cursor;             // 512
-    uint64_t *keys_tmp;           // n_limit
+    const uint32_t *bucket_count; // 512, filled by the scan kernel
+    const uint64_t *keys_tmp;     // 512 regions of group_sort_bucket_cap() keys, filled by the scan kernel
     SeedHit *hits_out;            // grouped + ordered hits
-    uint64_t *keys_out;           // same key format as keys_in, ordered
+    uint64_t *keys_out;           // (bucket << gbits) | global scan position, ordered
     uint32_t *heads, *leaders;
     SpecResult *spec;
     unsigned long long *counters; // [0] = #hits (in), [4] = #groups, [5] = #leaders, [6] = fast path refused (out)
@@ -285,6 +284,7 @@ cudaError_t launch_mirror_results(const DevInitHit *init, const DevGapResult *ga
                                   int64_t cap, DevInitHit *h_init, DevGapResult *h_gap, unsigned long long *h_counters,
                                   cudaStream_t st);
 int group_sort_buckets();
+int group_sort_bucket_cap();
 
 // Derived costs of BLAST_AffineGreedyAlign (core/greedy_align.c:792-842): odd rewards double every
 // score, the three operation costs are divided by their gcd (BLAST_Gdb3 core/ncbi_math.c:427).

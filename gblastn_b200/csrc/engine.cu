@@ -845,12 +845,12 @@ static int run_fused(Device &D, Volume &V, Query &Q, ChunkTable &T, StageCounts 
     cap = (int64_t)std::min(ws.hits_a.cap, ws.keys_a.cap);
     const int64_t n_limit = std::min<int64_t>(cap, (int64_t)1 << 18);
     CU_TRY(ws.hits_b.reserve((size_t)n_limit)); CU_TRY(ws.keys_b.reserve((size_t)n_limit));
-    CU_TRY(ws.keys_tmp.reserve((size_t)n_limit));
+    CU_TRY(ws.keys_tmp.reserve((size_t)nb * (size_t)group_sort_bucket_cap()));
     CU_TRY(ws.cells.reserve((size_t)n_limit + 2));
     CU_TRY(ws.heads.reserve((size_t)nb + 1));
     CU_TRY(ws.leaders.reserve((size_t)n_limit + 1));
     CU_TRY(ws.spec.reserve((size_t)n_limit + 1));
-    CU_TRY(ws.buckets.reserve((size_t)3 * nb + 8));
+    CU_TRY(ws.buckets.reserve((size_t)nb));
     CU_TRY(ws.init.reserve((size_t)std::max<int64_t>(4096, n_limit / 4)));
     const int64_t init_cap = (int64_t)ws.init.cap;
 
@@ -863,15 +863,14 @@ static int run_fused(Device &D, Volume &V, Query &Q, ChunkTable &T, StageCounts 
     s.counters = ws.counters.p; s.capacity = cap; s.block_chunk = T.block_chunk.p; s.block_desc = T.block_desc.p;
     s.raw_pairs = 0; s.gbits = gbits; s.diag_array_length = Q.diag_array_length;
     s.tile_cap = scan_tile_cap(Q.batch.scan_step, Q.batch.word_length);
-    s.bucket_count = ws.buckets.p;
+    s.bucket_count = ws.buckets.p; s.bucket_keys = ws.keys_tmp.p; s.bucket_cap = group_sort_bucket_cap();
     t_scan.start();
     CU_TRY(launch_scan(dq, s, st));
     t_scan.stop();
 
     t_ext.start();
     BucketLaunch L{};
-    L.hits_in = ws.hits_a.p; L.keys_in = ws.keys_a.p;
-    L.bucket_count = ws.buckets.p; L.bucket_start = ws.buckets.p + nb; L.cursor = ws.buckets.p + 2 * nb + 1;
+    L.hits_in = ws.hits_a.p; L.bucket_count = ws.buckets.p;
     L.keys_tmp = ws.keys_tmp.p; L.hits_out = ws.hits_b.p; L.keys_out = ws.keys_b.p;
     L.heads = ws.heads.p; L.leaders = ws.leaders.p; L.spec = ws.spec.p; L.counters = ws.counters.p;
     L.n_limit = n_limit; L.gbits = gbits; L.spec_enabled = Q.batch.window_size > 0 ? 0 : 1;
@@ -904,7 +903,7 @@ static int run_fused(Device &D, Volume &V, Query &Q, ChunkTable &T, StageCounts 
     rc = finish_gapped(D, V, Q, T, cnt.n_init, h_init, h_gap, &stats, true);
     if (rc) return rc;
     t_gap.stop();
-    stats.kernel_launches += 1 + 3 + (L.spec_enabled ? 2 : 1) + 1 + 1;      // scan, grouping, extension, gapped, result mirror
+    stats.kernel_launches += 1 + 1 + (L.spec_enabled ? 2 : 1) + 1 + 1;      // scan, grouping, extension, gapped, result mirror
     stats.ms_scan += t_scan.ms(); stats.ms_extend += t_ext.ms(); stats.ms_gapped += t_gap.ms();
     return BN_OK;
 }

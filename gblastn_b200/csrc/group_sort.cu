@@ -6,19 +6,20 @@
 // cell's chain in chain order and the scanners walk the subject left to right).
 //
 // The general path is one cub radix sort on (bucket, global scan position), which needs the number
-// of survivors on the host (a stream synchronisation) and 7 launches.  For the usual case — at most
-// a few hundred thousand survivors, no bucket larger than BUCKET_MAX — this file does the same
-// ordering as a counting sort whose sizes never leave the device:
-//   scan kernel        counts survivors per bucket while it emits them            (scan_kernel.cu)
-//   bucket_plan        exclusive scan of the 512 counts; decides whether the fast path applies
-//   bucket_scatter     key (position << 24 | emission slot) of every survivor into its bucket's range
-//   bucket_sort        one block per bucket: bitonic sort of the keys in shared memory, gather of the
-//                      hits, group head, speculative-extension leaders (what group_heads_kernel does
+// of survivors on the host (a stream synchronisation) and 7 launches.  For the usual case - at most
+// a few hundred thousand survivors, no bucket larger than BUCKET_MAX - the same ordering comes out of
+// a counting sort whose sizes never leave the device, in ONE launch after the scan:
+//   scan kernel        its per-bucket atomic counter (needed anyway) also gives every survivor a slot in
+//                      its bucket's fixed-capacity region, where it drops the key
+//                      (position << 24 | emission slot)                                   (scan_kernel.cu)
+//   bucket_sort        one block per bucket: exclusive prefix of the 512 counts (every block sums them
+//                      itself: 2 KB of L2 reads), bitonic sort of the bucket's keys in shared memory, gather
+//                      of the hits, group head, speculative-extension leaders (what group_heads_kernel does
 //                      on the general path)
 // "emission slot" = index in the scan's output buffer.  One thread emits all hits of a scan position
 // and its atomic slot reservations are ordered in time, so (position, slot) ascending IS the
 // reference's order, and the key is unique, which makes the (unstable) bitonic network deterministic.
-// When the fast path does not apply the kernels do nothing but raise counters[6]; the host sees it
+// When the fast path does not apply the kernel does nothing but raise counters[6]; the host sees it
 // at its next synchronisation and re-runs the general path on the untouched scan output.
 #include "bn_device.cuh"
 
@@ -30,63 +31,39 @@ constexpr int SORT_THREADS = 256;
 
 int group_sort_buckets() { return NBUCKETS; }
 
-__global__ void __launch_bounds__(NBUCKETS)
-bucket_plan_kernel(const BucketLaunch L)
-{
-    __shared__ uint32_t warp_sum[NBUCKETS / 32];
-    __shared__ uint32_t warp_max[NBUCKETS / 32];
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const uint32_t c = L.bucket_count[tid];
-    uint32_t x = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= o) x += y;
-    }
-    const uint32_t m = __reduce_max_sync(0xffffffffu, c);
-    if (lane == 31) warp_sum[w] = x;
-    if (lane == 0) warp_max[w] = m;
-    __syncthreads();
-    uint32_t base = 0, mx = 0;
-    for (int i = 0; i < NBUCKETS / 32; i++) {
-        if (i < w) base += warp_sum[i];
-        mx = max(mx, warp_max[i]);
-    }
-    L.bucket_start[tid] = base + x - c;
-    if (tid == NBUCKETS - 1) L.bucket_start[NBUCKETS] = base + x;
-    L.cursor[tid] = 0;
-    if (tid == 0) {
-        const unsigned long long n = L.counters[0];
-        if (n > (unsigned long long)L.n_limit || mx > (uint32_t)BUCKET_MAX) L.counters[6] = 1ull;
-    }
-}
-
-__global__ void bucket_scatter_kernel(const BucketLaunch L)
-{
-    if (L.counters[6]) return;
-    const int64_t n = (int64_t)L.counters[0];
-    const uint64_t gmask = (1ull << L.gbits) - 1ull;
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
-        const uint64_t key = L.keys_in[j];
-        const uint32_t b = (uint32_t)(key >> L.gbits);
-        const uint32_t pos = L.bucket_start[b] + atomicAdd(&L.cursor[b], 1u);
-        L.keys_tmp[pos] = ((key & gmask) << 24) | (uint64_t)j;
-    }
-}
+int group_sort_bucket_cap() { return BUCKET_MAX; }
+static_assert(NBUCKETS == 2 * SORT_THREADS, "every thread sums two bucket counts");
 
 __global__ void __launch_bounds__(SORT_THREADS)
 bucket_sort_kernel(const BucketLaunch L)
 {
     __shared__ uint64_t sk[BUCKET_MAX];
-    if (L.counters[6]) return;
+    __shared__ uint32_t red_sum[SORT_THREADS / 32], red_max[SORT_THREADS / 32];
     const uint32_t b = blockIdx.x;
-    const uint32_t start = L.bucket_start[b];
-    const int cnt = (int)(L.bucket_start[b + 1] - start);
+    uint32_t start = 0;
+    {   // position of this bucket in the compact output = sum of the counts before it; refusal test
+        const uint32_t t = threadIdx.x;
+        const uint32_t c0 = L.bucket_count[t], c1 = L.bucket_count[t + SORT_THREADS];
+        const uint32_t before = (t < b ? c0 : 0u) + (t + SORT_THREADS < b ? c1 : 0u);
+        const uint32_t ws = __reduce_add_sync(0xffffffffu, before);
+        const uint32_t wm = __reduce_max_sync(0xffffffffu, max(c0, c1));
+        if ((t & 31) == 0) { red_sum[t >> 5] = ws; red_max[t >> 5] = wm; }
+        __syncthreads();
+        uint32_t mx = 0;
+#pragma unroll
+        for (int i = 0; i < SORT_THREADS / 32; i++) { start += red_sum[i]; mx = max(mx, red_max[i]); }
+        if (L.counters[0] > (unsigned long long)L.n_limit || mx > (uint32_t)BUCKET_MAX) {
+            if (b == 0 && t == 0) L.counters[6] = 1ull;
+            return;
+        }
+    }
+    const int cnt = (int)L.bucket_count[b];
     if (cnt == 0) return;
+    const uint64_t *mine = L.keys_tmp + (size_t)b * BUCKET_MAX;
     const int tid = threadIdx.x;
     int P = 32;
     while (P < cnt) P <<= 1;
-    for (int i = tid; i < P; i += SORT_THREADS) sk[i] = i < cnt ? L.keys_tmp[start + i] : ~0ull;
+    for (int i = tid; i < P; i += SORT_THREADS) sk[i] = i < cnt ? mine[i] : ~0ull;
     __syncthreads();
     if (cnt > 1) {
         for (int k = 2; k <= P; k <<= 1) {
@@ -133,8 +110,6 @@ bucket_sort_kernel(const BucketLaunch L)
 
 cudaError_t launch_bucket_group(const BucketLaunch &L, cudaStream_t st)
 {
-    bucket_plan_kernel<<<1, NBUCKETS, 0, st>>>(L);
-    bucket_scatter_kernel<<<148 * 2, 256, 0, st>>>(L);
     bucket_sort_kernel<<<NBUCKETS, SORT_THREADS, 0, st>>>(L);
     return cudaGetLastError();
 }

@@ -87,7 +87,11 @@ __device__ __forceinline__ void emit_hit(const DevQuery &q, const ScanLaunch &s,
         const uint32_t grp = diag_group(q, s, q_off, s_off);
         s.hits[slot] = h;
         s.keys[slot] = ((uint64_t)grp << s.gbits) | (uint64_t)g;
-        if (s.bucket_count) atomicAdd(&s.bucket_count[grp], 1u);
+        if (s.bucket_count) {       // device-side grouping: the count is also the hit's slot in its bucket's region
+            const uint32_t pos = atomicAdd(&s.bucket_count[grp], 1u);
+            if (pos < (uint32_t)s.bucket_cap)
+                s.bucket_keys[(size_t)grp * (size_t)s.bucket_cap + pos] = ((uint64_t)g << 24) | (slot & 0xFFFFFFull);
+        }
     }
 }
 
