@@ -39,6 +39,8 @@
 #include <algo/blast/core/blast_diagnostics.h>
 #include <algo/blast/core/hspfilter_collector.h>
 #include <algo/blast/core/lookup_wrap.h>
+#include <algo/blast/core/blast_traceback.h>
+#include <algo/blast/core/gapinfo.h>
 
 #include "ref_driver.h"
 
@@ -68,6 +70,20 @@ typedef struct MemDb {
     const int64_t *smask_first;   /* index of each subject's first interval (prefix sum) */
 } MemDb;
 
+/* --------------------------------------------------------------- tap state */
+typedef struct TapCtx {
+    RefResult *res;
+    int taps;
+    const MemDb *db;
+    Int4 cur_chunk_off;   /* set by the word-finder wrapper, reused by the gapped wrapper */
+    /* traceback stage */
+    const Uint1 *tb_seq;  /* blastna subject handed out last (base 0) */
+    Int4 tb_oid;
+    const Uint1 *q_base;  /* query->sequence */
+    const BlastQueryInfo *qinfo;
+} TapCtx;
+static __thread TapCtx *g_tap = NULL;
+
 static Int4 mdb_num_seqs(void *h, void *a) { (void)a; return ((MemDb *)h)->n; }
 static Int4 mdb_max_len(void *h, void *a) { (void)a; return ((MemDb *)h)->maxlen; }
 static Int4 mdb_min_len(void *h, void *a) { (void)a; (void)h; return 1; }
@@ -92,6 +108,21 @@ static Int2 mdb_get_seq(void *h, BlastSeqSrcGetSeqArg *args)
     Int4 oid = args->oid;
     if (oid < 0 || oid >= d->n) return BLAST_SEQSRC_ERROR;
     if (args->seq) BlastSequenceBlkClean(args->seq);
+    if (args->encoding == eBlastEncodingNucleotide) {
+        /* traceback stage: blastna, one base per byte, sentinel bytes on both sides
+         * (what s_SeqDbGetSequence hands out for this encoding, api/seqsrc_seqdb.cpp:283-388) */
+        const Int4 len = d->len[oid];
+        const uint8_t *pk = d->packed + d->byteoff[oid];
+        Uint1 *buf = (Uint1 *)malloc((size_t)len + 2);
+        Int4 k;
+        if (!buf) return BLAST_SEQSRC_ERROR;
+        buf[0] = buf[len + 1] = 15;
+        for (k = 0; k < len; k++) buf[k + 1] = (pk[k >> 2] >> (6 - 2 * (k & 3))) & 3;
+        BlastSetUp_SeqBlkNew(buf, len, &args->seq, TRUE);
+        args->seq->oid = oid;
+        if (g_tap) { g_tap->tb_seq = args->seq->sequence; g_tap->tb_oid = oid; }
+        return BLAST_SEQSRC_SUCCESS;
+    }
     BlastSetUp_SeqBlkNew(d->packed + d->byteoff[oid], d->len[oid], &args->seq, FALSE);
     args->seq->oid = oid;
     if (d->smask_type && d->smask_n) {      /* every sequence of a masked database carries ranges (one when it has no mask) */
@@ -155,14 +186,6 @@ static BlastSeqSrc *mdb_new(BlastSeqSrc *r, void *arg)
     return r;
 }
 
-/* --------------------------------------------------------------- tap state */
-typedef struct TapCtx {
-    RefResult *res;
-    int taps;
-    const MemDb *db;
-    Int4 cur_chunk_off;   /* set by the word-finder wrapper, reused by the gapped wrapper */
-} TapCtx;
-static __thread TapCtx *g_tap = NULL;
 
 Int2 __real_BlastNaWordFinder(BLAST_SequenceBlk *subject, BLAST_SequenceBlk *query,
                               BlastQueryInfo *query_info, LookupTableWrap *lookup_wrap,
@@ -294,6 +317,101 @@ int __wrap_BlastHSPStreamWrite(BlastHSPStream *hsp_stream, BlastHSPList **hsp_li
         }
     }
     return __real_BlastHSPStreamWrite(hsp_stream, hsp_list);
+}
+
+/* ---- traceback stage: the reference's own calls of its alignment-with-traceback routines ---------- */
+static void tap_tb_call(TapCtx *t, int kind, const Uint1 *query, const Uint1 *subject, Int4 q_start, Int4 s_start,
+                        Int4 q_len, Int4 s_len, const BlastGapAlignStruct *ga)
+{
+    int32_t *r = tab_row(&t->res->tb_calls);
+    const Int4 qoff = (Int4)(query - t->q_base);
+    Int4 ctx = -1, c, i;
+    for (c = t->qinfo->first_context; c <= t->qinfo->last_context; c++)
+        if (t->qinfo->contexts[c].is_valid && t->qinfo->contexts[c].query_offset == qoff) { ctx = c; break; }
+    r[0] = kind; r[1] = t->tb_oid; r[2] = ctx; r[3] = (int32_t)(subject - t->tb_seq);
+    r[4] = q_start; r[5] = s_start; r[6] = q_len; r[7] = s_len;
+    r[8] = ga->score; r[9] = ga->query_start; r[10] = ga->query_stop;
+    r[11] = ga->subject_start; r[12] = ga->subject_stop;
+    r[13] = (int32_t)t->res->tb_ops.rows; r[14] = 0;
+    if (ga->edit_script) {
+        r = NULL;   /* tab_row may move the table */
+        for (i = 0; i < ga->edit_script->size; i++) {
+            int32_t *o = tab_row(&t->res->tb_ops);
+            o[0] = (int32_t)ga->edit_script->op_type[i]; o[1] = ga->edit_script->num[i];
+        }
+        t->res->tb_calls.data[(t->res->tb_calls.rows - 1) * 15 + 14] = ga->edit_script->size;
+    }
+}
+
+Int2 __real_BLAST_GappedAlignmentWithTraceback(EBlastProgramType program, const Uint1 *query, const Uint1 *subject,
+                                               BlastGapAlignStruct *gap_align, const BlastScoringParameters *score_params,
+                                               Int4 q_start, Int4 s_start, Int4 query_length, Int4 subject_length,
+                                               Boolean *fence_hit);
+Int2 __wrap_BLAST_GappedAlignmentWithTraceback(EBlastProgramType program, const Uint1 *query, const Uint1 *subject,
+                                               BlastGapAlignStruct *gap_align, const BlastScoringParameters *score_params,
+                                               Int4 q_start, Int4 s_start, Int4 query_length, Int4 subject_length,
+                                               Boolean *fence_hit)
+{
+    TapCtx *t = g_tap;
+    Int2 st = __real_BLAST_GappedAlignmentWithTraceback(program, query, subject, gap_align, score_params, q_start,
+                                                        s_start, query_length, subject_length, fence_hit);
+    if (t && (t->taps & 16) && t->tb_seq)
+        tap_tb_call(t, 0, query, subject, q_start, s_start, query_length, subject_length, gap_align);
+    return st;
+}
+
+Int2 __real_BLAST_GreedyGappedAlignment(const Uint1 *query, const Uint1 *subject, Int4 query_length, Int4 subject_length,
+                                        BlastGapAlignStruct *gap_align, const BlastScoringParameters *score_params,
+                                        Int4 q_off, Int4 s_off, Boolean compressed_subject, Boolean do_traceback,
+                                        Boolean *fence_hit);
+Int2 __wrap_BLAST_GreedyGappedAlignment(const Uint1 *query, const Uint1 *subject, Int4 query_length, Int4 subject_length,
+                                        BlastGapAlignStruct *gap_align, const BlastScoringParameters *score_params,
+                                        Int4 q_off, Int4 s_off, Boolean compressed_subject, Boolean do_traceback,
+                                        Boolean *fence_hit)
+{
+    TapCtx *t = g_tap;
+    Int2 st = __real_BLAST_GreedyGappedAlignment(query, subject, query_length, subject_length, gap_align, score_params,
+                                                 q_off, s_off, compressed_subject, do_traceback, fence_hit);
+    if (t && (t->taps & 16) && do_traceback && !compressed_subject && t->tb_seq)
+        tap_tb_call(t, 1, query, subject, q_off, s_off, query_length, subject_length, gap_align);
+    return st;
+}
+
+/* final results of the traceback stage: every HSP of every hit list, in the order of BlastHSPResults */
+static void dump_tb_results(RefResult *res, const BlastHSPResults *results)
+{
+    Int4 qi, li, hi, k;
+    if (!results) return;
+    for (qi = 0; qi < results->num_queries; qi++) {
+        const BlastHitList *hl = results->hitlist_array[qi];
+        if (!hl) continue;
+        for (li = 0; li < hl->hsplist_count; li++) {
+            const BlastHSPList *l = hl->hsplist_array[li];
+            if (!l) continue;
+            for (hi = 0; hi < l->hspcnt; hi++) {
+                const BlastHSP *h = l->hsp_array[hi];
+                int32_t *r;
+                uint64_t eb, bb;
+                const int32_t off = (int32_t)res->tb_ops.rows;
+                int32_t n = 0;
+                if (h->gap_info) {
+                    n = h->gap_info->size;
+                    for (k = 0; k < n; k++) {
+                        int32_t *o = tab_row(&res->tb_ops);
+                        o[0] = (int32_t)h->gap_info->op_type[k]; o[1] = h->gap_info->num[k];
+                    }
+                }
+                r = tab_row(&res->tb_final);
+                memcpy(&eb, &h->evalue, 8); memcpy(&bb, &h->bit_score, 8);
+                r[0] = qi; r[1] = l->oid; r[2] = h->context;
+                r[3] = h->query.offset; r[4] = h->query.end; r[5] = h->subject.offset; r[6] = h->subject.end;
+                r[7] = h->score; r[8] = h->num_ident;
+                r[9] = (int32_t)(uint32_t)(eb & 0xffffffffu); r[10] = (int32_t)(uint32_t)(eb >> 32);
+                r[11] = (int32_t)(uint32_t)(bb & 0xffffffffu); r[12] = (int32_t)(uint32_t)(bb >> 32);
+                r[13] = off; r[14] = n;
+            }
+        }
+    }
 }
 
 /* ------------------------------------------------------------ query set-up */
@@ -606,6 +724,7 @@ typedef struct Worker {
     MemDb db;
     RefResult *res;     /* thread-private result for final_ rows */
     int taps;
+    int traceback;
     int status;
     BlastDiagnostics *diag;
     pthread_t th;
@@ -634,6 +753,7 @@ static void *worker_main(void *arg)
     stream = BlastHSPStreamNew(prog, S->ext_options, TRUE, S->query_info->num_queries, writer);
 
     tap.res = w->res; tap.taps = w->taps; tap.db = &w->db; tap.cur_chunk_off = 0;
+    tap.tb_seq = NULL; tap.tb_oid = -1; tap.q_base = S->query->sequence; tap.qinfo = S->query_info;
     g_tap = &tap;
     w->diag = Blast_DiagnosticsInit();
     w->status = Blast_RunPreliminarySearch(prog, S->query, S->query_info, seq_src,
@@ -641,6 +761,14 @@ static void *worker_main(void *arg)
                                            S->word_options, S->ext_options, S->hit_options,
                                            S->eff_len_options, S->psi_options, S->db_options,
                                            stream, w->diag);
+    if (w->status == 0 && w->traceback) {
+        BlastHSPResults *results = NULL;
+        w->status = Blast_RunTracebackSearch(prog, S->query, S->query_info, seq_src, S->score_options,
+                                             S->ext_options, S->hit_options, S->eff_len_options, S->db_options,
+                                             S->psi_options, S->sbp, stream, NULL, NULL, &results);
+        if (w->status == 0) dump_tb_results(w->res, results);
+        Blast_HSPResultsFree(results);
+    }
     g_tap = NULL;
     BlastHSPStreamFree(stream);
     BlastSeqSrcFree(seq_src);
@@ -664,6 +792,9 @@ int ref_search(const RefConfig *cfg,
     tab_init(&res->init, 8);
     tab_init(&res->gapped, 10);
     tab_init(&res->final_, 11);
+    tab_init(&res->tb_calls, 15);
+    tab_init(&res->tb_ops, 2);
+    tab_init(&res->tb_final, 15);
 
     st = build_setup(cfg, nq, qseq, qlens, qmask_n, qmask_iv, &S);
     if (st) { res->status = st; return st; }
@@ -700,7 +831,7 @@ int ref_search(const RefConfig *cfg,
         ws[i].S = &S; ws[i].db = db;
         ws[i].db.oid_begin = (int32_t)((int64_t)ns * i / nth);
         ws[i].db.oid_end = (int32_t)((int64_t)ns * (i + 1) / nth);
-        if (nth == 1) { ws[i].res = res; ws[i].taps = cfg->taps; }
+        if (nth == 1) { ws[i].res = res; ws[i].taps = cfg->taps; ws[i].traceback = (cfg->prelim_only == 0); }
         else {
             ws[i].res = (RefResult *)calloc(1, sizeof(RefResult));
             tab_init(&ws[i].res->final_, 11);
@@ -747,6 +878,7 @@ int ref_search(const RefConfig *cfg,
 void ref_free_result(RefResult *res)
 {
     free(res->scan.data); free(res->init.data); free(res->gapped.data); free(res->final_.data);
+    free(res->tb_calls.data); free(res->tb_ops.data); free(res->tb_final.data);
     free(res->ctx_query_offset); free(res->ctx_query_length); free(res->ctx_length_adjustment);
     free(res->ctx_eff_searchsp); free(res->ctx_x_dropoff); free(res->ctx_cutoff_score);
     free(res->ctx_reduced_cutoff); free(res->ctx_gapped_cutoff);

@@ -34,8 +34,9 @@ typedef struct RefConfig {
     int64_t db_length;       /* 0 => real */
     int32_t db_num_seqs;     /* 0 => real */
     int32_t num_threads;     /* <=1 => single thread, taps allowed */
-    int32_t taps;            /* bit0: scan pairs, bit1: init hits, bit2: gapped lists, bit3: lookup table dump */
-    int32_t prelim_only;     /* always 1 for now (no traceback) */
+    int32_t taps;            /* bit0: scan pairs, bit1: init hits, bit2: gapped lists, bit3: lookup table dump,
+                              * bit4: calls of the gapped-alignment-with-traceback routines (needs prelim_only 0) */
+    int32_t prelim_only;     /* 1: preliminary stage only; 0: Blast_RunTracebackSearch follows (single thread) */
     /* database masks (blastn -db_soft_mask / -db_hard_mask): per subject smask_n[i] masked intervals,
      * flat pairs [begin, end) in smask_iv, ascending and disjoint; smask_type 0 none, 1 soft, 2 hard */
     int32_t smask_type;
@@ -89,6 +90,14 @@ typedef struct RefResult {
     /* eNaLookupTable (lut_type 2, tap bit3): thick_backbone as 4 ints per cell {num_used, entries[3] | overflow_cursor}, overflow */
     int32_t *na_backbone, *na_overflow;
     int64_t  na_overflow_len;
+    /* traceback stage (prelim_only 0).  Edit scripts live in tb_ops as (op, num) rows, op = EGapAlignOpType
+     * (0 deletion = gap in query, 3 substitution, 6 insertion = gap in subject); esp_off / esp_n index it. */
+    RefTable tb_calls;  /* kind (0 BLAST_GappedAlignmentWithTraceback, 1 BLAST_GreedyGappedAlignment with traceback),
+                         * oid, context, s_shift (start_shift of AdjustSubjectRange), q_start, s_start, q_len, s_len,
+                         * -> score, query_start, query_stop, subject_start, subject_stop, esp_off, esp_n */
+    RefTable tb_ops;    /* op, num */
+    RefTable tb_final;  /* query_index, oid, context, q_off, q_end, s_off, s_end, score, num_ident,
+                         * evalue_lo, evalue_hi, bits_lo, bits_hi, esp_off, esp_n */
 } RefResult;
 
 /* queries: blastna bytes (0..3 ACGT, 4..14 ambiguity) concatenated, lengths in qlens.

@@ -61,6 +61,7 @@ class RefResult(C.Structure):
         ("seconds_prelim", C.c_double), ("status", C.c_int32),
         ("na_backbone", C.POINTER(C.c_int32)), ("na_overflow", C.POINTER(C.c_int32)),
         ("na_overflow_len", C.c_int64),
+        ("tb_calls", RefTable), ("tb_ops", RefTable), ("tb_final", RefTable),
     ]
 
 
@@ -80,7 +81,12 @@ def lib():
     return _lib
 
 
-TAP_SCAN, TAP_INIT, TAP_GAPPED, TAP_LUT = 1, 2, 4, 8
+TAP_SCAN, TAP_INIT, TAP_GAPPED, TAP_LUT, TAP_TRACEBACK = 1, 2, 4, 8, 16
+
+TB_CALL_COLS = ("kind", "oid", "context", "s_shift", "q_start", "s_start", "q_len", "s_len",
+                "score", "query_start", "query_stop", "subject_start", "subject_stop", "esp_off", "esp_n")
+TB_FINAL_COLS = ("query_index", "oid", "context", "q_off", "q_end", "s_off", "s_end", "score", "num_ident",
+                 "evalue_lo", "evalue_hi", "bits_lo", "bits_hi", "esp_off", "esp_n")
 
 SCAN_COLS = ("oid", "chunk_off", "q_off", "s_off")
 INIT_COLS = ("oid", "chunk_off", "q_off", "s_off", "q_start", "s_start", "length", "score")
@@ -168,6 +174,7 @@ def search(queries, volume, cfg: RefConfig | None = None, *, task="megablast", m
             "status": st,
             "scan": _tab(res.scan), "init": _tab(res.init), "gapped": _tab(res.gapped),
             "final": _tab(res.final_),
+            "tb_calls": _tab(res.tb_calls), "tb_ops": _tab(res.tb_ops), "tb_final": _tab(res.tb_final),
             "num_contexts": n,
             "ctx_query_offset": _arr(res.ctx_query_offset, n, np.int32),
             "ctx_query_length": _arr(res.ctx_query_length, n, np.int32),
