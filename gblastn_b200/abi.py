@@ -104,6 +104,12 @@ INIT_DTYPE = np.dtype([("oid", "<i4"), ("chunk_off", "<i4"), ("q_off", "<i4"), (
                        ("q_start", "<i4"), ("s_start", "<i4"), ("length", "<i4"), ("score", "<i4")])
 PAIR_DTYPE = np.dtype([("q_off", "<u4"), ("s_off", "<u4")])
 
+TB_ITEM_DTYPE = np.dtype([("oid", "<i4"), ("context", "<i4"), ("s_shift", "<i4"), ("s_length", "<i4"),
+                          ("q_start", "<i4"), ("s_start", "<i4")])
+TB_RESULT_DTYPE = np.dtype([("score", "<i4"), ("query_start", "<i4"), ("query_stop", "<i4"),
+                            ("subject_start", "<i4"), ("subject_stop", "<i4"), ("esp_n", "<i4"),
+                            ("esp_off", "<i8"), ("status", "<i4"), ("pad", "<i4")])
+EDIT_OP_DTYPE = np.dtype([("op_type", "<i4"), ("num", "<i4")])
 assert HSP_DTYPE.itemsize == C.sizeof(BnHSP)
 assert INIT_DTYPE.itemsize == C.sizeof(BnInitHit)
 

@@ -352,4 +352,36 @@ int gapped_dp_smem_blocks();
 cudaError_t launch_gapped_warp(const DevQuery &q, const GappedLaunch &g, int blocks, cudaStream_t st);
 int gapped_warp_per_block();
 
+// ---- gapped alignment with traceback (traceback_kernel.cu) -----------------------------------------
+struct DevTracebackItem {
+    int64_t byte_off;            // byte offset of the subject sequence in the volume
+    int32_t context;             // query context
+    int32_t s_shift, s_length;   // AdjustSubjectRange: subject = sequence + s_shift, s_length bases
+    int32_t q_start, s_start;    // start point (s_start relative to s_shift)
+    int32_t pad;
+};
+struct DevTracebackDir {         // one direction of one alignment
+    int32_t score, a_off, b_off; // best score and the query / subject extents of ALIGN_EX
+    int32_t n_ops;               // run-length edit operations in walk order (far end first)
+    long long ops_off;           // index of the first one in TracebackLaunch::ops
+    int32_t status;              // 0 ok, 1 band wider than the ring, 3 arena exhausted, 4 ops buffer exhausted
+    int32_t ran;                 // 0: this direction is not run (start point on the last base)
+    int32_t pad;
+};
+struct TracebackLaunch {
+    const uint8_t *packed;
+    const DevTracebackItem *items;
+    int64_t n;
+    int32_t x_dropoff;           // gap_x_dropoff_final (raw)
+    uint8_t *arena;              // script rows, row tables, temporary run lists
+    long long arena_bytes;
+    unsigned long long *arena_used;
+    int2 *ops;                   // {EGapAlignOpType, num}
+    long long ops_cap;
+    unsigned long long *ops_used;
+    DevTracebackDir *out;        // 2 n entries: left, right
+};
+cudaError_t launch_traceback_dp(const DevQuery &q, const TracebackLaunch &L, int blocks, cudaStream_t st);
+int traceback_warps_per_block();
+
 }  // namespace bn

@@ -1671,6 +1671,160 @@ int bn_get_gapped_score(int vol_handle, int query_handle, int32_t oid, int32_t c
     return BN_OK;
 }
 
+// BLAST_GappedAlignmentWithTraceback (core/blast_gapalign.c:3994-4155) for a batch of start points; the
+// alignments run on the device (traceback_kernel.cu), the two directions are joined here exactly like
+// Blast_PrelimEditBlockToGapEditScript (:2455-2517) and the leading / trailing gap pruning of :4115-4150.
+int bn_gapped_traceback(int vol_handle, int query_handle, int32_t gap_x_dropoff_final,
+                        const BnTracebackItem *items, int64_t n_items,
+                        BnTracebackResult **results, BnEditOp **ops, int64_t *n_ops)
+{
+    Volume *V; Query *Q; Device *D;
+    if (!results || !ops || !n_ops || n_items < 0 || (n_items > 0 && !items))
+        return fail(BN_ERR_INVALID, "bn_gapped_traceback: bad argument");
+    int rc = get_handles(vol_handle, query_handle, &V, &Q, &D);
+    if (rc) return rc;
+    *results = nullptr; *ops = nullptr; *n_ops = 0;
+    if (Q->batch.gap_extend <= 0)
+        return fail(BN_ERR_UNSUPPORTED, "bn_gapped_traceback: needs explicit gap costs (gap_extend > 0); "
+                                        "greedy traceback is not built yet");
+    std::lock_guard<std::mutex> lk(D->mu);
+    CU_TRY(cudaSetDevice(D->id));
+    if (!Q->dev[V->device].ready) return fail(BN_ERR_INVALID, "query batch is not loaded on the volume's device");
+    if (n_items == 0) return BN_OK;
+    if (V->ready) CU_TRY(cudaStreamWaitEvent(D->stream, V->ready, 0));
+    cudaStream_t st = D->stream;
+    const DevQuery &dq = Q->dev[V->device].view;
+
+    std::vector<DevTracebackItem> up((size_t)n_items);
+    long long rows = 0;
+    for (int64_t i = 0; i < n_items; i++) {
+        const BnTracebackItem &t = items[i];
+        if (t.oid < 0 || t.oid >= (int32_t)V->seq_len.size() || t.context < 0 || t.context >= Q->batch.num_contexts)
+            return fail(BN_ERR_INVALID, "bn_gapped_traceback: bad oid or context");
+        const int32_t qlen = Q->batch.contexts[t.context].query_length;
+        if (t.s_shift < 0 || t.s_length < 0 || (int64_t)t.s_shift + t.s_length > V->seq_len[(size_t)t.oid] ||
+            t.q_start < 0 || t.q_start >= qlen || t.s_start < 0 || t.s_start >= t.s_length)
+            return fail(BN_ERR_INVALID, "bn_gapped_traceback: start point outside the sequences");
+        up[(size_t)i] = DevTracebackItem{V->byte_off[(size_t)t.oid], t.context, t.s_shift, t.s_length, t.q_start, t.s_start, 0};
+        rows += qlen + 2;
+    }
+    // arena: row tables (12 B per query row) + script rows (band width ~ 2 (X / gap_extend) + slack) + run lists
+    const int32_t xd = std::max(gap_x_dropoff_final, Q->batch.gap_open + Q->batch.gap_extend);
+    const long long band = 2ll * (xd / Q->batch.gap_extend + 3) + 32;
+    long long arena_bytes = rows * (12 + band + 8) + 2 * n_items * (256ll << 10);
+    long long ops_cap = rows / 2 + 64 * n_items;
+
+    DevTracebackItem *d_items = nullptr;
+    DevTracebackDir *d_out = nullptr;
+    unsigned long long *d_cnt = nullptr;
+    uint8_t *d_arena = nullptr;
+    int2 *d_ops = nullptr;
+    std::vector<DevTracebackDir> dirs((size_t)(2 * n_items));
+    std::vector<int2> h_ops;
+    auto release = [&]() {
+        if (d_items) cudaFreeAsync(d_items, st);
+        if (d_out) cudaFreeAsync(d_out, st);
+        if (d_cnt) cudaFreeAsync(d_cnt, st);
+        if (d_arena) cudaFreeAsync(d_arena, st);
+        if (d_ops) cudaFreeAsync(d_ops, st);
+        d_items = nullptr; d_out = nullptr; d_cnt = nullptr; d_arena = nullptr; d_ops = nullptr;
+    };
+    struct Guard { decltype(release) &f; ~Guard() { f(); } } guard{release};
+    CU_TRY(cudaMallocAsync((void **)&d_items, up.size() * sizeof(DevTracebackItem), st));
+    CU_TRY(cudaMallocAsync((void **)&d_out, dirs.size() * sizeof(DevTracebackDir), st));
+    CU_TRY(cudaMallocAsync((void **)&d_cnt, 2 * sizeof(unsigned long long), st));
+    CU_TRY(cudaMemcpyAsync(d_items, up.data(), up.size() * sizeof(DevTracebackItem), cudaMemcpyHostToDevice, st));
+    unsigned long long used[2] = {0, 0};
+    for (int attempt = 0; attempt < 4; attempt++) {
+        if (d_arena) { cudaFreeAsync(d_arena, st); d_arena = nullptr; }
+        if (d_ops) { cudaFreeAsync(d_ops, st); d_ops = nullptr; }
+        CU_TRY(cudaMallocAsync((void **)&d_arena, (size_t)arena_bytes, st));
+        CU_TRY(cudaMallocAsync((void **)&d_ops, (size_t)ops_cap * sizeof(int2), st));
+        CU_TRY(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), st));
+        TracebackLaunch L{};
+        L.packed = V->d_packed; L.items = d_items; L.n = n_items; L.x_dropoff = gap_x_dropoff_final;
+        L.arena = d_arena; L.arena_bytes = arena_bytes; L.arena_used = d_cnt;
+        L.ops = d_ops; L.ops_cap = ops_cap; L.ops_used = d_cnt + 1; L.out = d_out;
+        const int wpb = traceback_warps_per_block();
+        const int blocks = (int)std::min<int64_t>((2 * n_items + wpb - 1) / wpb, 148 * 8);
+        CU_TRY(launch_traceback_dp(dq, L, blocks, st));
+        CU_TRY(cudaMemcpyAsync(dirs.data(), d_out, dirs.size() * sizeof(DevTracebackDir), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(used, d_cnt, sizeof used, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        bool grow_arena = false, grow_ops = false;
+        for (const DevTracebackDir &d : dirs) {
+            if (d.status == 1) return fail(BN_ERR_OVERFLOW, "bn_gapped_traceback: alignment band wider than the device ring");
+            grow_arena |= d.status == 3;
+            grow_ops |= d.status == 4;
+        }
+        if (!grow_arena && !grow_ops) break;
+        if (attempt == 3) return fail(BN_ERR_OVERFLOW, "bn_gapped_traceback: traceback scratch exhausted");
+        if (grow_arena) arena_bytes = std::max<long long>(2 * arena_bytes, (long long)used[0] + (64ll << 20));
+        if (grow_ops) ops_cap = std::max<long long>(2 * ops_cap, (long long)used[1] + 1024);
+    }
+    h_ops.resize((size_t)std::min<unsigned long long>(used[1], (unsigned long long)ops_cap));
+    if (!h_ops.empty()) {
+        CU_TRY(cudaMemcpyAsync(h_ops.data(), d_ops, h_ops.size() * sizeof(int2), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+    }
+
+    std::vector<BnTracebackResult> res((size_t)n_items);
+    std::vector<BnEditOp> out_ops;
+    out_ops.reserve(h_ops.size());
+    const int32_t gap_open = Q->batch.gap_open, gap_extend = Q->batch.gap_extend;
+    for (int64_t i = 0; i < n_items; i++) {
+        const BnTracebackItem &t = items[i];
+        const DevTracebackDir &l = dirs[(size_t)(2 * i)], &r = dirs[(size_t)(2 * i + 1)];
+        BnTracebackResult &o = res[(size_t)i];
+        int32_t score_left = l.score, score_right = 0;
+        o.query_start = t.q_start - l.a_off + 1;
+        o.subject_start = t.s_start - l.b_off + 1;
+        if (r.ran) {
+            score_right = r.score;
+            o.query_stop = t.q_start + r.a_off + 1;
+            o.subject_stop = t.s_start + r.b_off + 1;
+        } else {
+            o.query_stop = t.q_start - 1;
+            o.subject_stop = t.s_start - 1;
+        }
+        // Blast_PrelimEditBlockToGapEditScript: rev as it is, then fwd back to front, equal ops at the seam merged
+        const int2 *rev = h_ops.data() + l.ops_off, *fwd = h_ops.data() + r.ops_off;
+        const int32_t nr = l.n_ops, nf = r.ran ? r.n_ops : 0;
+        const size_t first = out_ops.size();
+        for (int32_t k = 0; k < nr; k++) out_ops.push_back(BnEditOp{rev[k].x, rev[k].y});
+        if (nf > 0) {
+            int32_t k = nf - 1;
+            if (nr > 0 && fwd[nf - 1].x == rev[nr - 1].x) { out_ops.back().num += fwd[nf - 1].y; k = nf - 2; }
+            for (; k >= 0; k--) out_ops.push_back(BnEditOp{fwd[k].x, fwd[k].y});
+        }
+        // leading / trailing gaps are cut off (core/blast_gapalign.c:4115-4150)
+        size_t size = out_ops.size() - first;
+        if (size && out_ops[first].op_type != 3) {
+            score_left += gap_open + out_ops[first].num * gap_extend;
+            if (out_ops[first].op_type == 0) o.subject_start += out_ops[first].num;
+            else o.query_start += out_ops[first].num;
+            out_ops.erase(out_ops.begin() + (long)first);
+            size--;
+        }
+        if (size && out_ops[first + size - 1].op_type != 3) {
+            score_right += gap_open + out_ops[first + size - 1].num * gap_extend;
+            if (out_ops[first + size - 1].op_type == 0) o.subject_stop -= out_ops[first + size - 1].num;
+            else o.query_stop -= out_ops[first + size - 1].num;
+            out_ops.pop_back();
+            size--;
+        }
+        o.score = score_left + score_right;
+        o.esp_off = (int64_t)first;
+        o.esp_n = (int32_t)size;
+        o.status = 0;
+    }
+    *results = to_malloc(res);
+    *ops = to_malloc(out_ops);
+    *n_ops = (int64_t)out_ops.size();
+    if (!*results || (!out_ops.empty() && !*ops)) return fail(BN_ERR_MEMORY, "bn_gapped_traceback: out of memory");
+    return BN_OK;
+}
+
 int bn_query_download_lookup(int query_handle, int device, int32_t *hashtable, int32_t *next_pos)
 {
     std::lock_guard<std::mutex> lk(g_mu);

@@ -19,7 +19,7 @@ EXPORTS = [
     "bn_init", "bn_release", "bn_device_count", "bn_last_error", "bn_version",
     "bn_db_load", "bn_db_free", "bn_query_load", "bn_query_free",
     "bn_prelim_search", "bn_prelim_search_host", "bn_results_free",
-    "bn_scan_subject", "bn_word_finder", "bn_free", "bn_bench_scan", "bn_query_download_lookup", "bn_get_gapped_score",
+    "bn_scan_subject", "bn_word_finder", "bn_free", "bn_bench_scan", "bn_query_download_lookup", "bn_get_gapped_score", "bn_gapped_traceback",
     "bn_dbfile_index", "bn_db_load_files", "bn_dbfile_write", "bn_prelim_search_batches", "bn_db_set_masks", "bn_selftest_replay",
     "bn_setup_create", "bn_setup_batch", "bn_setup_kbp_std", "bn_setup_kbp_gap",
     "bn_setup_gap_x_dropoff_final", "bn_setup_longest_chain", "bn_setup_free",
@@ -227,6 +227,22 @@ def get_gapped_score(volume: Volume, query: Query, oid: int, chunk_off: int, ini
         return abi.struct_array(p, n.value, abi.HSP_DTYPE)
     finally:
         lib().bn_free(p)
+
+
+def gapped_traceback(volume: Volume, query: Query, gap_x_dropoff_final: int, items: np.ndarray):
+    """BLAST_GappedAlignmentWithTraceback drop-in for a batch of start points (`items`: TB_ITEM_DTYPE).
+    Returns (results: TB_RESULT_DTYPE array, ops: EDIT_OP_DTYPE array)."""
+    items = np.ascontiguousarray(items, dtype=abi.TB_ITEM_DTYPE)
+    pr, po, n = C.c_void_p(), C.c_void_p(), C.c_int64(0)
+    _check(lib().bn_gapped_traceback(C.c_int(volume.handle), C.c_int(query.handle), C.c_int32(gap_x_dropoff_final),
+                                     items.ctypes.data_as(C.c_void_p), C.c_int64(items.shape[0]),
+                                     C.byref(pr), C.byref(po), C.byref(n)))
+    try:
+        return (abi.struct_array(pr, items.shape[0], abi.TB_RESULT_DTYPE),
+                abi.struct_array(po, n.value, abi.EDIT_OP_DTYPE))
+    finally:
+        lib().bn_free(pr)
+        lib().bn_free(po)
 
 
 def download_lookup(query: Query, device=0):

@@ -269,6 +269,35 @@ int  bn_get_gapped_score(int vol_handle, int query_handle, int32_t oid, int32_t 
                          BnHSP **hsps, int64_t *n_hsps);
 void bn_free(void *p);
 
+/* ---- traceback stage, first row ----------------------------------------------
+ * BLAST_GappedAlignmentWithTraceback (core/blast_gapalign.c:3994-4155; Blast_SemiGappedAlign with traceback ->
+ * ALIGN_EX :350-709) for a batch of start points, as Blast_TracebackFromHSPList makes the call for blastn with
+ * eDynProgTbck (core/blast_traceback.c:565-571): query = the context's strand of the query block, subject =
+ * sequence `oid` + s_shift with s_length bases (the window AdjustSubjectRange leaves, core/blast_traceback.c:513-520),
+ * start point (q_start, s_start) relative to those, X-drop = gap_x_dropoff_final (gap_align->gap_x_dropoff is set to
+ * it at core/blast_traceback.c:1403), costs and matrix from the query batch.  The subject is the resident packed
+ * volume (no ambiguity data: the blastna byte of a base is its 2-bit code).
+ * Results mirror BlastGapAlignStruct after the call: score, query_start/stop, subject_start/stop (relative to the
+ * window) and gap_align->edit_script as ops[esp_off .. esp_off + esp_n) with op_type = EGapAlignOpType
+ * (0 eGapAlignDel, 3 eGapAlignSub, 6 eGapAlignIns; inc-core/gapinfo.h:44-54).  Greedy traceback
+ * (BLAST_GreedyGappedAlignment with do_traceback) is not built yet: batches with gap_extend == 0 are refused
+ * with BN_ERR_UNSUPPORTED.  Free both arrays with bn_free. */
+typedef struct BnTracebackItem {
+    int32_t oid, context;
+    int32_t s_shift, s_length;
+    int32_t q_start, s_start;
+} BnTracebackItem;
+typedef struct BnTracebackResult {
+    int32_t score, query_start, query_stop, subject_start, subject_stop;
+    int32_t esp_n;
+    int64_t esp_off;
+    int32_t status, pad;
+} BnTracebackResult;
+typedef struct BnEditOp { int32_t op_type, num; } BnEditOp;
+int  bn_gapped_traceback(int vol_handle, int query_handle, int32_t gap_x_dropoff_final,
+                         const BnTracebackItem *items, int64_t n_items,
+                         BnTracebackResult **results, BnEditOp **ops, int64_t *n_ops);
+
 /* Host-only self-test: the containment replay (BLAST_GetGappedScore's interval-tree filter, core/blast_itree.c)
  * runs with one tree per query strand; this compares it with the reference's one-tree-per-subject layout on
  * n_cases seeded random init-HSP sets and reports how many differ (0 expected).  Needs no device. */

@@ -85,6 +85,50 @@ def test_get_gapped_score_drop_in(name):
         Q.free(); V.free()
 
 
+TRACEBACK_DP_CASES = ["blastn_mb11_dp", "blastn_smallna_dp", "blastn_ws7_array", "blastn_ntlike_many_subjects",
+                      "c3_scaled_blastn_10kb"]
+
+
+@pytest.mark.parametrize("name", TRACEBACK_DP_CASES)
+def test_gapped_traceback_drop_in(name):
+    """bn_gapped_traceback == BLAST_GappedAlignmentWithTraceback: fed every call the REFERENCE's own traceback
+    stage makes (Blast_TracebackFromHSPList, tapped in oracle/ref_driver.c), the device returns the same score,
+    alignment bounds and edit script, operation for operation."""
+    from gblastn_b200 import engine as E, abi
+    from oracle import refdriver as R, portdriver as P
+    task, cfgkw, vol, qs = cases.make_case(name)
+    if not R.available():
+        pytest.skip("oracle/_ref/libblastref.so did not travel to this box")
+    cfg = R.default_config(task, taps=R.TAP_LUT | R.TAP_TRACEBACK, prelim_only=0, **cfgkw)
+    r = R.search(qs, vol, cfg)
+    assert r["status"] == 0
+    calls = r["tb_calls"]
+    calls = calls[calls[:, 0] == 0]
+    assert calls.shape[0] > 0
+    h = P.batch_from_reference(r, task=task, cfg=cfg)
+    V, Q = E.Volume(vol), E.Query(h)
+    try:
+        items = np.zeros(calls.shape[0], dtype=abi.TB_ITEM_DTYPE)
+        items["oid"], items["context"], items["s_shift"] = calls[:, 1], calls[:, 2], calls[:, 3]
+        items["q_start"], items["s_start"], items["s_length"] = calls[:, 4], calls[:, 5], calls[:, 7]
+        assert np.array_equal(calls[:, 6], r["ctx_query_length"][calls[:, 2]])
+        res, ops = E.gapped_traceback(V, Q, int(r["gap_x_dropoff_final"]), items)
+        assert (res["status"] == 0).all()
+        for k, col in ((8, "score"), (9, "query_start"), (10, "query_stop"), (11, "subject_start"), (12, "subject_stop"),
+                       (14, "esp_n")):
+            bad = np.flatnonzero(res[col] != calls[:, k])
+            assert bad.size == 0, f"{col} differs for {bad.size} of {calls.shape[0]} calls, first {bad[:3]}: " \
+                                  f"{res[col][bad[:3]]} vs {calls[bad[:3], k]}"
+        ref_ops = r["tb_ops"]
+        for i in range(calls.shape[0]):
+            want = ref_ops[calls[i, 13]:calls[i, 13] + calls[i, 14]]
+            got = ops[res["esp_off"][i]:res["esp_off"][i] + res["esp_n"][i]]
+            assert np.array_equal(got["op_type"], want[:, 0]) and np.array_equal(got["num"], want[:, 1]), \
+                f"edit script differs for call {i}"
+    finally:
+        Q.free(); V.free()
+
+
 def test_file_volume_equals_memory_volume(tmp_path):
     """bn_db_load_files: a volume written as .nin/.nsq and loaded from the files gives the same bytes
     of results as the same volume loaded from memory (ragged lengths, many subjects)."""
