@@ -380,8 +380,10 @@ struct TracebackLaunch {
     long long ops_cap;
     unsigned long long *ops_used;
     DevTracebackDir *out;        // 2 n entries: left, right
+    const uint8_t *todo;         // greedy: optional per-item flags (retry of the items whose arena overflowed); nullptr = all
 };
 cudaError_t launch_traceback_dp(const DevQuery &q, const TracebackLaunch &L, int blocks, cudaStream_t st);
+cudaError_t launch_traceback_greedy(const DevQuery &q, const TracebackLaunch &L, int blocks, cudaStream_t st);
 int traceback_warps_per_block();
 
 }  // namespace bn

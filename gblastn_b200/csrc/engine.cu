@@ -1151,6 +1151,97 @@ using namespace bn;
 // ================================================================================================
 //                                             C ABI
 // ================================================================================================
+// Greedy traceback batch (BLAST_GreedyGappedAlignment with do_traceback): one thread per alignment with a private
+// arena; alignments whose rows do not fit are retried with 16x larger arenas (fewer threads).
+static int traceback_greedy_host(Device &Dv, Volume &V, Query &Q, int32_t x_dropoff, const BnTracebackItem *items, int64_t n_items,
+                                 const std::vector<DevTracebackItem> &up, BnTracebackResult **results, BnEditOp **ops, int64_t *n_ops)
+{
+    cudaStream_t st = Dv.stream;
+    const DevQuery &dq = Q.dev[V.device].view;
+    DevTracebackItem *d_items = nullptr;
+    DevTracebackDir *d_out = nullptr;
+    unsigned long long *d_cnt = nullptr;
+    uint8_t *d_arena = nullptr, *d_todo = nullptr;
+    int2 *d_ops = nullptr;
+    auto release = [&]() {
+        if (d_items) cudaFreeAsync(d_items, st);
+        if (d_out) cudaFreeAsync(d_out, st);
+        if (d_cnt) cudaFreeAsync(d_cnt, st);
+        if (d_arena) cudaFreeAsync(d_arena, st);
+        if (d_todo) cudaFreeAsync(d_todo, st);
+        if (d_ops) cudaFreeAsync(d_ops, st);
+    };
+    struct Guard { decltype(release) &f; ~Guard() { f(); } } guard{release};
+    std::vector<DevTracebackDir> pass((size_t)(2 * n_items));
+    std::vector<uint8_t> todo((size_t)n_items, 1);
+    std::vector<BnEditOp> out_ops;
+    std::vector<BnTracebackResult> res((size_t)n_items);
+    long long rows = 0;
+    for (int64_t i = 0; i < n_items; i++) rows += Q.batch.contexts[items[i].context].query_length;
+    long long ops_cap = rows / 4 + 64 * n_items;
+    CU_TRY(cudaMallocAsync((void **)&d_items, up.size() * sizeof(DevTracebackItem), st));
+    CU_TRY(cudaMallocAsync((void **)&d_out, pass.size() * sizeof(DevTracebackDir), st));
+    CU_TRY(cudaMallocAsync((void **)&d_cnt, 2 * sizeof(unsigned long long), st));
+    CU_TRY(cudaMallocAsync((void **)&d_todo, (size_t)n_items, st));
+    CU_TRY(cudaMemcpyAsync(d_items, up.data(), up.size() * sizeof(DevTracebackItem), cudaMemcpyHostToDevice, st));
+    long long per_thread = 256ll << 10;
+    int64_t left = n_items;
+    for (int attempt = 0; left > 0; attempt++) {
+        if (attempt == 8) return fail(BN_ERR_OVERFLOW, "bn_gapped_traceback: greedy traceback scratch exhausted");
+        const long long budget = 4ll << 30;
+        int64_t threads = std::min<int64_t>(std::min<int64_t>(left, 8192), std::max<long long>(budget / per_thread, 1));
+        const int blocks = (int)((threads + 31) / 32);
+        threads = (int64_t)blocks * 32;
+        const long long arena_bytes = threads * per_thread;
+        if (d_arena) { cudaFreeAsync(d_arena, st); d_arena = nullptr; }
+        if (d_ops) { cudaFreeAsync(d_ops, st); d_ops = nullptr; }
+        CU_TRY(cudaMallocAsync((void **)&d_arena, (size_t)arena_bytes, st));
+        CU_TRY(cudaMallocAsync((void **)&d_ops, (size_t)ops_cap * sizeof(int2), st));
+        CU_TRY(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), st));
+        CU_TRY(cudaMemcpyAsync(d_todo, todo.data(), todo.size(), cudaMemcpyHostToDevice, st));
+        TracebackLaunch L{};
+        L.packed = V.d_packed; L.items = d_items; L.n = n_items; L.x_dropoff = x_dropoff;
+        L.arena = d_arena; L.arena_bytes = arena_bytes; L.arena_used = d_cnt;
+        L.ops = d_ops; L.ops_cap = ops_cap; L.ops_used = d_cnt + 1; L.out = d_out; L.todo = d_todo;
+        CU_TRY(launch_traceback_greedy(dq, L, blocks, st));
+        unsigned long long used[2] = {0, 0};
+        CU_TRY(cudaMemcpyAsync(pass.data(), d_out, pass.size() * sizeof(DevTracebackDir), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(used, d_cnt, sizeof used, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        std::vector<int2> h_ops((size_t)std::min<unsigned long long>(used[1], (unsigned long long)ops_cap));
+        if (!h_ops.empty()) {
+            CU_TRY(cudaMemcpyAsync(h_ops.data(), d_ops, h_ops.size() * sizeof(int2), cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
+        }
+        bool grow_arena = false, grow_ops = false;
+        for (int64_t i = 0; i < n_items; i++) {
+            if (!todo[(size_t)i]) continue;
+            const DevTracebackDir &l = pass[(size_t)(2 * i)], &r = pass[(size_t)(2 * i + 1)];
+            if (l.status == 3) { grow_arena = true; continue; }
+            if (l.status == 4) { grow_ops = true; continue; }
+            const BnTracebackItem &t = items[i];
+            BnTracebackResult &o = res[(size_t)i];
+            o.score = l.score;
+            o.query_start = t.q_start - l.a_off; o.query_stop = t.q_start + r.a_off;
+            o.subject_start = t.s_start - l.b_off; o.subject_stop = t.s_start + r.b_off;
+            o.esp_off = (int64_t)out_ops.size(); o.esp_n = l.n_ops; o.status = 0; o.pad = 0;
+            for (int32_t k = 0; k < l.n_ops; k++) {
+                const int2 e = h_ops[(size_t)(l.ops_off + k)];
+                out_ops.push_back(BnEditOp{e.x, e.y});
+            }
+            todo[(size_t)i] = 0;
+            left--;
+        }
+        if (grow_arena) per_thread *= 16;
+        if (grow_ops) ops_cap *= 4;
+    }
+    *results = to_malloc(res);
+    *ops = to_malloc(out_ops);
+    *n_ops = (int64_t)out_ops.size();
+    if (!*results || (!out_ops.empty() && !*ops)) return fail(BN_ERR_MEMORY, "bn_gapped_traceback: out of memory");
+    return BN_OK;
+}
+
 extern "C" {
 
 const char *bn_last_error(void) { return g_err.c_str(); }
@@ -1684,9 +1775,11 @@ int bn_gapped_traceback(int vol_handle, int query_handle, int32_t gap_x_dropoff_
     int rc = get_handles(vol_handle, query_handle, &V, &Q, &D);
     if (rc) return rc;
     *results = nullptr; *ops = nullptr; *n_ops = 0;
-    if (Q->batch.gap_extend <= 0)
-        return fail(BN_ERR_UNSUPPORTED, "bn_gapped_traceback: needs explicit gap costs (gap_extend > 0); "
-                                        "greedy traceback is not built yet");
+    const bool greedy = Q->batch.gap_algo == BN_GAP_GREEDY;
+    if (greedy && (Q->batch.gap_open != 0 || Q->batch.gap_extend != 0))
+        return fail(BN_ERR_UNSUPPORTED, "bn_gapped_traceback: affine greedy traceback is not built yet");
+    if (!greedy && Q->batch.gap_extend <= 0)
+        return fail(BN_ERR_UNSUPPORTED, "bn_gapped_traceback: dynamic programming needs gap_extend > 0");
     std::lock_guard<std::mutex> lk(D->mu);
     CU_TRY(cudaSetDevice(D->id));
     if (!Q->dev[V->device].ready) return fail(BN_ERR_INVALID, "query batch is not loaded on the volume's device");
@@ -1708,6 +1801,7 @@ int bn_gapped_traceback(int vol_handle, int query_handle, int32_t gap_x_dropoff_
         up[(size_t)i] = DevTracebackItem{V->byte_off[(size_t)t.oid], t.context, t.s_shift, t.s_length, t.q_start, t.s_start, 0};
         rows += qlen + 2;
     }
+    if (greedy) return traceback_greedy_host(*D, *V, *Q, gap_x_dropoff_final, items, n_items, up, results, ops, n_ops);
     // arena: row tables (12 B per query row) + script rows (band width ~ 2 (X / gap_extend) + slack) + run lists
     const int32_t xd = std::max(gap_x_dropoff_final, Q->batch.gap_open + Q->batch.gap_extend);
     const long long band = 2ll * (xd / Q->batch.gap_extend + 3) + 32;

@@ -87,11 +87,15 @@ def test_get_gapped_score_drop_in(name):
 
 TRACEBACK_DP_CASES = ["blastn_mb11_dp", "blastn_smallna_dp", "blastn_ws7_array", "blastn_ntlike_many_subjects",
                       "c3_scaled_blastn_10kb"]
+TRACEBACK_GREEDY_CASES = ["c1_megablast_10kb_vs_1mb", "mb_lut11_hash_indels", "mb_smallna_diagarray", "mb_ws16", "mb_with_N",
+                          "blastn_ws11_greedy", "mb_ntlike_many_subjects", "mb_long_divergent_tier2", "mb_lut12_stride17",
+                          "c4_scaled_short_reads", "c5_scaled_ntlike_5kb"]
 
 
-@pytest.mark.parametrize("name", TRACEBACK_DP_CASES)
+@pytest.mark.parametrize("name", TRACEBACK_DP_CASES + TRACEBACK_GREEDY_CASES)
 def test_gapped_traceback_drop_in(name):
-    """bn_gapped_traceback == BLAST_GappedAlignmentWithTraceback: fed every call the REFERENCE's own traceback
+    """bn_gapped_traceback == BLAST_GappedAlignmentWithTraceback (dynamic programming) /
+    BLAST_GreedyGappedAlignment with traceback (megablast): fed every call the REFERENCE's own traceback
     stage makes (Blast_TracebackFromHSPList, tapped in oracle/ref_driver.c), the device returns the same score,
     alignment bounds and edit script, operation for operation."""
     from gblastn_b200 import engine as E, abi
@@ -103,8 +107,8 @@ def test_gapped_traceback_drop_in(name):
     r = R.search(qs, vol, cfg)
     assert r["status"] == 0
     calls = r["tb_calls"]
-    calls = calls[calls[:, 0] == 0]
     assert calls.shape[0] > 0
+    assert (calls[:, 0] == (1 if name in TRACEBACK_GREEDY_CASES else 0)).all()
     h = P.batch_from_reference(r, task=task, cfg=cfg)
     V, Q = E.Volume(vol), E.Query(h)
     try:
