@@ -763,9 +763,11 @@ static void *worker_main(void *arg)
                                            stream, w->diag);
     if (w->status == 0 && w->traceback) {
         BlastHSPResults *results = NULL;
+        const double tb0 = now_s();
         w->status = Blast_RunTracebackSearch(prog, S->query, S->query_info, seq_src, S->score_options,
                                              S->ext_options, S->hit_options, S->eff_len_options, S->db_options,
                                              S->psi_options, S->sbp, stream, NULL, NULL, &results);
+        w->res->seconds_traceback = now_s() - tb0;
         if (w->status == 0) dump_tb_results(w->res, results);
         Blast_HSPResultsFree(results);
     }
@@ -844,7 +846,7 @@ int ref_search(const RefConfig *cfg,
         for (i = 0; i < nth; i++) pthread_create(&ws[i].th, NULL, worker_main, &ws[i]);
         for (i = 0; i < nth; i++) pthread_join(ws[i].th, NULL);
     }
-    res->seconds_prelim = now_s() - t0;
+    res->seconds_prelim = now_s() - t0 - res->seconds_traceback;
 
     st = 0;
     for (i = 0; i < nth; i++) {

@@ -98,6 +98,7 @@ typedef struct RefResult {
     RefTable tb_ops;    /* op, num */
     RefTable tb_final;  /* query_index, oid, context, q_off, q_end, s_off, s_end, score, num_ident,
                          * evalue_lo, evalue_hi, bits_lo, bits_hi, esp_off, esp_n */
+    double   seconds_traceback; /* wall time of Blast_RunTracebackSearch */
 } RefResult;
 
 /* queries: blastna bytes (0..3 ACGT, 4..14 ambiguity) concatenated, lengths in qlens.

@@ -62,6 +62,7 @@ class RefResult(C.Structure):
         ("na_backbone", C.POINTER(C.c_int32)), ("na_overflow", C.POINTER(C.c_int32)),
         ("na_overflow_len", C.c_int64),
         ("tb_calls", RefTable), ("tb_ops", RefTable), ("tb_final", RefTable),
+        ("seconds_traceback", C.c_double),
     ]
 
 
@@ -208,6 +209,7 @@ def search(queries, volume, cfg: RefConfig | None = None, *, task="megablast", m
             "lookup_hits": res.lookup_hits, "init_extends": res.init_extends,
             "good_init_extends": res.good_init_extends, "gap_extensions": res.gap_extensions,
             "good_extensions": res.good_extensions, "seconds_prelim": res.seconds_prelim,
+            "seconds_traceback": res.seconds_traceback,
         }
     finally:
         lib().ref_free_result(C.byref(res))
