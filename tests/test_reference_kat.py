@@ -63,6 +63,53 @@ def test_kat_gpu(kw, score):
         Q.free(); V.free(); s.free()
 
 
+@pytest.mark.parametrize("kw,score", KAT)
+def test_kat_reference_traceback_stage(kw, score):
+    """The KAT is the score AFTER traceback (the unit test reads it from the Seq-align): the reference's
+    traceback stage, run by oracle/ref_driver.c over the in-memory seqsrc, must report it for its single HSP."""
+    from oracle import refdriver as R
+    if not R.available():
+        pytest.skip("oracle/_ref/libblastref.so not built")
+    qs, vol = _inputs()
+    r = R.search(qs, vol, R.default_config("megablast", taps=R.TAP_TRACEBACK, prelim_only=0, **kw))
+    assert r["status"] == 0 and r["tb_final"].shape[0] == 1 and int(r["tb_final"][0, 7]) == score
+    c = r["tb_calls"]
+    # one greedy traceback call; its raw score is rounded down to even afterwards when reward is even
+    # (Blast_HSPListAdjustOddBlastnScores in s_HSPListPostTracebackUpdate): 6035 -> 6034
+    assert c.shape[0] == 1 and int(c[0, 0]) == 1 and int(c[0, 8]) in (score, score + 1)
+    ops = r["tb_ops"][c[0, 13]:c[0, 13] + c[0, 14]]
+    # the edit script spans the alignment: substitutions + insertions = query extent, + deletions = subject extent
+    assert ops[ops[:, 0] != 0][:, 1].sum() == c[0, 10] - c[0, 9]
+    assert ops[ops[:, 0] != 6][:, 1].sum() == c[0, 12] - c[0, 11]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw,score", KAT)
+def test_kat_gpu_traceback(kw, score):
+    """bn_gapped_traceback on the KAT's traceback call: 619 / 6034 and the reference's edit script."""
+    from gblastn_b200 import engine as E, abi
+    from oracle import refdriver as R, portdriver as P
+    if not R.available():
+        pytest.skip("oracle/_ref/libblastref.so did not travel to this box")
+    qs, vol = _inputs()
+    cfg = R.default_config("megablast", taps=R.TAP_LUT | R.TAP_TRACEBACK, prelim_only=0, **kw)
+    r = R.search(qs, vol, cfg)
+    c = r["tb_calls"]
+    h = P.batch_from_reference(r, task="megablast", cfg=cfg)
+    V, Q = E.Volume(vol), E.Query(h)
+    try:
+        items = np.zeros(1, dtype=abi.TB_ITEM_DTYPE)
+        items["oid"], items["context"], items["s_shift"] = c[:, 1], c[:, 2], c[:, 3]
+        items["q_start"], items["s_start"], items["s_length"] = c[:, 4], c[:, 5], c[:, 7]
+        res, ops = E.gapped_traceback(V, Q, int(r["gap_x_dropoff_final"]), items)
+        assert int(res["score"][0]) == int(c[0, 8]) and int(c[0, 8]) in (score, score + 1)
+        assert int(r["tb_final"][0, 7]) == score
+        want = r["tb_ops"][c[0, 13]:c[0, 13] + c[0, 14]]
+        assert np.array_equal(ops["op_type"], want[:, 0]) and np.array_equal(ops["num"], want[:, 1])
+    finally:
+        Q.free(); V.free()
+
+
 # ---- NucleotideBlastWordSize4 / _EOS (bl2seq_unit_test.cpp:2238-2301): invariants of the reference's test -------
 SIZE4 = [("blastn_size4a.fsa", "blastn_size4b.fsa"), ("blastn_size4c.fsa", "blastn_size4d.fsa")]
 
