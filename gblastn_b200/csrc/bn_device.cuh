@@ -383,6 +383,12 @@ struct TracebackLaunch {
     const uint8_t *todo;         // greedy: optional per-item flags (retry of the items whose arena overflowed); nullptr = all
 };
 cudaError_t launch_traceback_dp(const DevQuery &q, const TracebackLaunch &L, int blocks, cudaStream_t st);
+struct DevTracebackHsp {         // a preliminary HSP (absolute subject coordinates) about to be traced back
+    int64_t byte_off;            // of its subject sequence
+    int32_t seq_len, context, q_off, q_end, s_off, s_end, q_gapped_start, s_gapped_start;
+};
+cudaError_t launch_traceback_start(const DevQuery &q, const uint8_t *packed, const DevTracebackHsp *hsps, int64_t n,
+                                   DevTracebackItem *items, cudaStream_t st);
 cudaError_t launch_traceback_greedy(const DevQuery &q, const TracebackLaunch &L, int blocks, cudaStream_t st);
 int traceback_warps_per_block();
 

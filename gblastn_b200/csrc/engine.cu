@@ -1765,23 +1765,17 @@ int bn_get_gapped_score(int vol_handle, int query_handle, int32_t oid, int32_t c
 // BLAST_GappedAlignmentWithTraceback (core/blast_gapalign.c:3994-4155) for a batch of start points; the
 // alignments run on the device (traceback_kernel.cu), the two directions are joined here exactly like
 // Blast_PrelimEditBlockToGapEditScript (:2455-2517) and the leading / trailing gap pruning of :4115-4150.
-int bn_gapped_traceback(int vol_handle, int query_handle, int32_t gap_x_dropoff_final,
-                        const BnTracebackItem *items, int64_t n_items,
-                        BnTracebackResult **results, BnEditOp **ops, int64_t *n_ops)
+static int traceback_core(Device *D, Volume *V, Query *Q, int32_t gap_x_dropoff_final,
+                          const BnTracebackItem *items, int64_t n_items,
+                          BnTracebackResult **results, BnEditOp **ops, int64_t *n_ops)
 {
-    Volume *V; Query *Q; Device *D;
-    if (!results || !ops || !n_ops || n_items < 0 || (n_items > 0 && !items))
-        return fail(BN_ERR_INVALID, "bn_gapped_traceback: bad argument");
-    int rc = get_handles(vol_handle, query_handle, &V, &Q, &D);
-    if (rc) return rc;
+    // the caller holds D->mu and has made the device current
     *results = nullptr; *ops = nullptr; *n_ops = 0;
     const bool greedy = Q->batch.gap_algo == BN_GAP_GREEDY;
     if (greedy && (Q->batch.gap_open != 0 || Q->batch.gap_extend != 0))
         return fail(BN_ERR_UNSUPPORTED, "bn_gapped_traceback: affine greedy traceback is not built yet");
     if (!greedy && Q->batch.gap_extend <= 0)
         return fail(BN_ERR_UNSUPPORTED, "bn_gapped_traceback: dynamic programming needs gap_extend > 0");
-    std::lock_guard<std::mutex> lk(D->mu);
-    CU_TRY(cudaSetDevice(D->id));
     if (!Q->dev[V->device].ready) return fail(BN_ERR_INVALID, "query batch is not loaded on the volume's device");
     if (n_items == 0) return BN_OK;
     if (V->ready) CU_TRY(cudaStreamWaitEvent(D->stream, V->ready, 0));
@@ -1916,6 +1910,88 @@ int bn_gapped_traceback(int vol_handle, int query_handle, int32_t gap_x_dropoff_
     *ops = to_malloc(out_ops);
     *n_ops = (int64_t)out_ops.size();
     if (!*results || (!out_ops.empty() && !*ops)) return fail(BN_ERR_MEMORY, "bn_gapped_traceback: out of memory");
+    return BN_OK;
+}
+
+int bn_gapped_traceback(int vol_handle, int query_handle, int32_t gap_x_dropoff_final,
+                        const BnTracebackItem *items, int64_t n_items,
+                        BnTracebackResult **results, BnEditOp **ops, int64_t *n_ops)
+{
+    Volume *V; Query *Q; Device *D;
+    if (!results || !ops || !n_ops || n_items < 0 || (n_items > 0 && !items))
+        return fail(BN_ERR_INVALID, "bn_gapped_traceback: bad argument");
+    int rc = get_handles(vol_handle, query_handle, &V, &Q, &D);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(D->mu);
+    CU_TRY(cudaSetDevice(D->id));
+    return traceback_core(D, V, Q, gap_x_dropoff_final, items, n_items, results, ops, n_ops);
+}
+
+// The per-HSP body of Blast_TracebackFromHSPList (core/blast_traceback.c:490-571) for a list of preliminary HSPs:
+// start point (BLAST_CheckStartForGappedAlignment :97-153, BlastGetOffsetsForGappedAlignment
+// core/blast_gapalign.c:3059-3131, BlastGetStartForGappedAlignmentNucl :3134-3182) and AdjustSubjectRange (:3608-3636)
+// on the device, then the alignment with traceback.
+int bn_traceback_hsps(int vol_handle, int query_handle, int32_t gap_x_dropoff_final,
+                      const BnHSP *hsps, int64_t n_hsps, BnTracebackItem **items_out,
+                      BnTracebackResult **results, BnEditOp **ops, int64_t *n_ops)
+{
+    Volume *V; Query *Q; Device *D;
+    if (!items_out || !results || !ops || !n_ops || n_hsps < 0 || (n_hsps > 0 && !hsps))
+        return fail(BN_ERR_INVALID, "bn_traceback_hsps: bad argument");
+    int rc = get_handles(vol_handle, query_handle, &V, &Q, &D);
+    if (rc) return rc;
+    *items_out = nullptr; *results = nullptr; *ops = nullptr; *n_ops = 0;
+    std::lock_guard<std::mutex> lk(D->mu);
+    CU_TRY(cudaSetDevice(D->id));
+    if (!Q->dev[V->device].ready) return fail(BN_ERR_INVALID, "query batch is not loaded on the volume's device");
+    if (n_hsps == 0) return BN_OK;
+    if (V->ready) CU_TRY(cudaStreamWaitEvent(D->stream, V->ready, 0));
+    cudaStream_t st = D->stream;
+    std::vector<DevTracebackHsp> up((size_t)n_hsps);
+    for (int64_t i = 0; i < n_hsps; i++) {
+        const BnHSP &h = hsps[i];
+        if (h.oid < 0 || h.oid >= (int32_t)V->seq_len.size() || h.context < 0 || h.context >= Q->batch.num_contexts)
+            return fail(BN_ERR_INVALID, "bn_traceback_hsps: bad oid or context");
+        const int32_t slen = V->seq_len[(size_t)h.oid], qlen = Q->batch.contexts[h.context].query_length;
+        if (h.q_off < 0 || h.q_end > qlen || h.q_off >= h.q_end || h.s_off < 0 || h.s_end > slen || h.s_off >= h.s_end)
+            return fail(BN_ERR_INVALID, "bn_traceback_hsps: HSP outside the sequences");
+        if (!(h.q_gapped_start == 0 && h.s_gapped_start == 0) &&
+            (h.q_gapped_start < h.q_off || h.q_gapped_start >= h.q_end || h.s_gapped_start < h.s_off || h.s_gapped_start >= h.s_end))
+            return fail(BN_ERR_INVALID, "bn_traceback_hsps: gapped start outside the HSP");
+        up[(size_t)i] = DevTracebackHsp{V->byte_off[(size_t)h.oid], slen, h.context, h.q_off, h.q_end, h.s_off, h.s_end,
+                                        h.q_gapped_start, h.s_gapped_start};
+    }
+    DevTracebackHsp *d_h = nullptr;
+    DevTracebackItem *d_it = nullptr;
+    std::vector<DevTracebackItem> its((size_t)n_hsps);
+    CU_TRY(cudaMallocAsync((void **)&d_h, up.size() * sizeof(DevTracebackHsp), st));
+    CU_TRY(cudaMallocAsync((void **)&d_it, its.size() * sizeof(DevTracebackItem), st));
+    CU_TRY(cudaMemcpyAsync(d_h, up.data(), up.size() * sizeof(DevTracebackHsp), cudaMemcpyHostToDevice, st));
+    cudaError_t e = launch_traceback_start(Q->dev[V->device].view, V->d_packed, d_h, n_hsps, d_it, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(its.data(), d_it, its.size() * sizeof(DevTracebackItem), cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(d_h, st); cudaFreeAsync(d_it, st);
+    CU_TRY(e);
+    CU_TRY(cudaStreamSynchronize(st));
+    std::vector<BnTracebackItem> all((size_t)n_hsps), found;
+    std::vector<int64_t> where;
+    for (int64_t i = 0; i < n_hsps; i++) {
+        const DevTracebackItem &t = its[(size_t)i];
+        BnTracebackItem b{hsps[i].oid, hsps[i].context, t.s_shift, t.s_length, t.q_start, t.s_start};
+        if (!t.pad) b.oid = -1;                        // no start point: the reference drops the HSP (:514-518)
+        else { found.push_back(b); where.push_back(i); }
+        all[(size_t)i] = b;
+    }
+    BnTracebackResult *r = nullptr; BnEditOp *o = nullptr; int64_t no = 0;
+    rc = traceback_core(D, V, Q, gap_x_dropoff_final, found.data(), (int64_t)found.size(), &r, &o, &no);
+    if (rc) return rc;
+    std::vector<BnTracebackResult> res((size_t)n_hsps);
+    for (auto &x : res) { memset(&x, 0, sizeof x); x.status = -1; }
+    for (size_t k = 0; k < where.size(); k++) res[(size_t)where[k]] = r[k];
+    free(r);
+    *items_out = to_malloc(all);
+    *results = to_malloc(res);
+    *ops = o; *n_ops = no;
+    if (!*items_out || !*results) return fail(BN_ERR_MEMORY, "bn_traceback_hsps: out of memory");
     return BN_OK;
 }
 

@@ -605,6 +605,111 @@ cudaError_t launch_traceback_greedy(const DevQuery &q, const TracebackLaunch &L,
     return cudaGetLastError();
 }
 
+// ================================================================================================
+// Start point of the traceback alignment, one thread per HSP: the head of Blast_TracebackFromHSPList's loop body
+// (core/blast_traceback.c:506-545): BLAST_CheckStartForGappedAlignment (:97-153), else
+// BlastGetOffsetsForGappedAlignment (core/blast_gapalign.c:3059-3131); when the stored start is good,
+// BlastGetStartForGappedAlignmentNucl (:3134-3182) moves it into the longest run of identities; then
+// AdjustSubjectRange (:3608-3636).  items[i].pad = 1 when a start point exists (0: the reference drops the HSP).
+// ================================================================================================
+__global__ void traceback_start_kernel(const DevQuery q, const uint8_t *packed, const DevTracebackHsp *hsps, int64_t n,
+                                       DevTracebackItem *items)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    constexpr int32_t HSP_MAX_WINDOW = 11, MAX_SUBJECT_OFFSET = 90000, MAX_TOTAL_GAPS = 3000;
+    const DevTracebackHsp h = hsps[i];
+    const DevContext c = q.ctx[h.context];
+    const uint8_t *Q = q.query + c.query_offset;
+    const int64_t sb = h.byte_off * 4;
+    const int32_t *M = q.matrix;
+    auto sc = [&](int32_t qi, int32_t si) -> int32_t { return __ldg(M + 16 * (int)__ldg(Q + qi) + sbase64(packed, sb + si)); };
+    int32_t qg = h.q_gapped_start, sg = h.s_gapped_start;
+    int32_t q_start = 0, s_start = 0;
+    bool found = true;
+    bool good = !(qg == 0 && sg == 0);
+    if (good) {     // BLAST_CheckStartForGappedAlignment
+        int32_t left = -HSP_MAX_WINDOW / 2;
+        left = max(left, h.q_off - qg); left = max(left, h.s_off - sg);
+        int32_t right = HSP_MAX_WINDOW / 2 + 1;
+        right = min(right, h.q_end - qg); right = min(right, h.s_end - sg);
+        int32_t score = 0;
+        for (int32_t k = left; k < right; k++) score += sc(qg + k, sg + k);
+        good = score > 0;
+    }
+    if (!good) {    // BlastGetOffsetsForGappedAlignment
+        const int32_t q_length = h.q_end - h.q_off, s_length = h.s_end - h.s_off;
+        if (q_length <= HSP_MAX_WINDOW) { q_start = h.q_off + q_length / 2; s_start = h.s_off + q_length / 2; }
+        else {
+            int32_t score = 0;
+            for (int32_t k = 0; k < HSP_MAX_WINDOW; k++) score += sc(h.q_off + k, h.s_off + k);
+            int32_t max_score = score, max_offset = h.q_off + HSP_MAX_WINDOW - 1;
+            const int32_t hsp_end = h.q_off + min(q_length, s_length);
+            for (int32_t idx = h.q_off + HSP_MAX_WINDOW; idx < hsp_end; idx++) {
+                const int32_t k = idx - h.q_off;
+                score -= sc(idx - HSP_MAX_WINDOW, h.s_off + k - HSP_MAX_WINDOW);
+                score += sc(idx, h.s_off + k);
+                if (score > max_score) { max_score = score; max_offset = idx; }
+            }
+            if (max_score > 0) { q_start = max_offset; s_start = (max_offset - h.q_off) + h.s_off; }
+            else {
+                score = 0;
+                for (int32_t k = 0; k < HSP_MAX_WINDOW; k++) score += sc(h.q_end - HSP_MAX_WINDOW + k, h.s_end - HSP_MAX_WINDOW + k);
+                if (score > 0) { q_start = h.q_end - HSP_MAX_WINDOW / 2; s_start = h.s_end - HSP_MAX_WINDOW / 2; }
+                else found = false;
+            }
+        }
+    } else {        // BlastGetStartForGappedAlignmentNucl
+        const int32_t HSP_MAX_IDENT_RUN = 20;
+        const int32_t offset = min(sg - h.s_off, qg - h.q_off);
+        const int32_t q0 = qg - offset, s0 = sg - offset;
+        const int32_t q_len = min(h.s_end - s0, h.q_end - q0);
+        int32_t max_score = 0, max_offset = q0, score = 0, index;
+        bool match = false, prev_match = false, done = false;
+        for (index = q0; index < q0 + q_len; index++) {
+            match = ((int)__ldg(Q + index) == sbase64(packed, sb + s0 + (index - q0)));
+            if (match != prev_match) {
+                prev_match = match;
+                if (match) score = 1;
+                else if (score > max_score) { max_score = score; max_offset = index - score / 2; }
+            } else if (match) {
+                ++score;
+                if (score > HSP_MAX_IDENT_RUN) {
+                    max_offset = index - HSP_MAX_IDENT_RUN / 2;
+                    qg = max_offset; sg = max_offset + s0 - q0;
+                    done = true;
+                    break;
+                }
+            }
+        }
+        if (!done) {
+            if (match && score > max_score) { max_score = score; max_offset = index - score / 2; }
+            if (max_score > 0) { qg = max_offset; sg = max_offset + s0 - q0; }
+        }
+        q_start = qg; s_start = sg;
+    }
+    // AdjustSubjectRange(&s_start, &adjusted_s_length, q_start, query_length, &start_shift)
+    int32_t shift = 0, adj_len = h.seq_len;
+    if (found && h.seq_len >= MAX_SUBJECT_OFFSET) {
+        const int32_t s_offset = s_start;
+        const int32_t max_left = q_start + MAX_TOTAL_GAPS, max_right = c.query_length - q_start + MAX_TOTAL_GAPS;
+        if (s_offset > max_left) { shift = s_offset - max_left; s_start = max_left; }
+        adj_len = min(h.seq_len, s_offset + max_right) - shift;
+    }
+    DevTracebackItem it;
+    it.byte_off = h.byte_off; it.context = h.context; it.s_shift = shift; it.s_length = adj_len;
+    it.q_start = q_start; it.s_start = s_start; it.pad = found ? 1 : 0;
+    items[i] = it;
+}
+
+cudaError_t launch_traceback_start(const DevQuery &q, const uint8_t *packed, const DevTracebackHsp *hsps, int64_t n,
+                                   DevTracebackItem *items, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    traceback_start_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(q, packed, hsps, n, items);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_traceback_dp(const DevQuery &q, const TracebackLaunch &L, int blocks, cudaStream_t st)
 {
     traceback_dp_kernel<<<blocks, TB_WARPS * 32, 0, st>>>(q, L);

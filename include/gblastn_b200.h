@@ -297,6 +297,17 @@ typedef struct BnEditOp { int32_t op_type, num; } BnEditOp;
 int  bn_gapped_traceback(int vol_handle, int query_handle, int32_t gap_x_dropoff_final,
                          const BnTracebackItem *items, int64_t n_items,
                          BnTracebackResult **results, BnEditOp **ops, int64_t *n_ops);
+/* The per-HSP body of Blast_TracebackFromHSPList's loop (core/blast_traceback.c:490-571) for a list of preliminary
+ * HSPs (what bn_prelim_search returns: absolute subject coordinates, gapped start points): on the device, the start
+ * point — BLAST_CheckStartForGappedAlignment (:97-153), else BlastGetOffsetsForGappedAlignment
+ * (core/blast_gapalign.c:3059-3131); a good stored start is moved into the longest run of identities by
+ * BlastGetStartForGappedAlignmentNucl (:3134-3182) — and AdjustSubjectRange (:3608-3636), then the alignment with
+ * traceback as in bn_gapped_traceback.  items[i] is the call the reference would make for hsps[i] (oid = -1 when no
+ * start point exists and the reference drops the HSP; results[i].status = -1 then).  Every HSP is extended: the
+ * caller replays the containment test of :449 over the results in score order.  Free the three arrays with bn_free. */
+int  bn_traceback_hsps(int vol_handle, int query_handle, int32_t gap_x_dropoff_final,
+                       const BnHSP *hsps, int64_t n_hsps, BnTracebackItem **items,
+                       BnTracebackResult **results, BnEditOp **ops, int64_t *n_ops);
 
 /* Host-only self-test: the containment replay (BLAST_GetGappedScore's interval-tree filter, core/blast_itree.c)
  * runs with one tree per query strand; this compares it with the reference's one-tree-per-subject layout on

@@ -133,6 +133,50 @@ def test_gapped_traceback_drop_in(name):
         Q.free(); V.free()
 
 
+@pytest.mark.parametrize("name", TRACEBACK_DP_CASES + TRACEBACK_GREEDY_CASES)
+def test_traceback_hsps_from_prelim_lists(name):
+    """bn_traceback_hsps: fed the reference's preliminary HSP lists (what its traceback stage reads from the HSP
+    stream), the device derives for every HSP the start point and subject window of the call
+    Blast_TracebackFromHSPList would make and aligns it.  Every call the reference really made (it skips HSPs
+    contained in better ones) must be among them with identical inputs, score, bounds and edit script."""
+    from gblastn_b200 import engine as E, abi
+    from oracle import refdriver as R, portdriver as P
+    task, cfgkw, vol, qs = cases.make_case(name)
+    if not R.available():
+        pytest.skip("oracle/_ref/libblastref.so did not travel to this box")
+    cfg = R.default_config(task, taps=R.TAP_LUT | R.TAP_TRACEBACK, prelim_only=0, **cfgkw)
+    r = R.search(qs, vol, cfg)
+    assert r["status"] == 0
+    calls, fin = r["tb_calls"], r["final"]
+    assert calls.shape[0] > 0 and fin.shape[0] >= calls.shape[0]
+    h = P.batch_from_reference(r, task=task, cfg=cfg)
+    V, Q = E.Volume(vol), E.Query(h)
+    try:
+        hsps = np.zeros(fin.shape[0], dtype=abi.HSP_DTYPE)
+        for k, col in enumerate(("oid", "context", "q_off", "q_end", "s_off", "s_end", "score", "q_gapped_start",
+                                 "s_gapped_start")):
+            hsps[col] = fin[:, k]
+        items, res, ops = E.traceback_hsps(V, Q, int(r["gap_x_dropoff_final"]), hsps)
+        index = {}
+        for i in range(items.shape[0]):
+            if items["oid"][i] >= 0:
+                key = tuple(int(items[c][i]) for c in ("oid", "context", "s_shift", "q_start", "s_start", "s_length"))
+                index.setdefault(key, i)
+        ref_ops = r["tb_ops"]
+        for j in range(calls.shape[0]):
+            c = calls[j]
+            key = (int(c[1]), int(c[2]), int(c[3]), int(c[4]), int(c[5]), int(c[7]))
+            assert key in index, f"reference call {j} {key} has no counterpart among the device's start points"
+            i = index[key]
+            got = tuple(int(res[f][i]) for f in ("score", "query_start", "query_stop", "subject_start", "subject_stop"))
+            assert got == tuple(int(x) for x in c[8:13]), f"call {j}: {got} vs {c[8:13]}"
+            want = ref_ops[c[13]:c[13] + c[14]]
+            g = ops[res["esp_off"][i]:res["esp_off"][i] + res["esp_n"][i]]
+            assert np.array_equal(g["op_type"], want[:, 0]) and np.array_equal(g["num"], want[:, 1]), f"edit script {j}"
+    finally:
+        Q.free(); V.free()
+
+
 def test_file_volume_equals_memory_volume(tmp_path):
     """bn_db_load_files: a volume written as .nin/.nsq and loaded from the files gives the same bytes
     of results as the same volume loaded from memory (ragged lengths, many subjects)."""
