@@ -877,6 +877,94 @@ int ref_search(const RefConfig *cfg,
     return st;
 }
 
+/* Direct differential oracle for the traceback-stage alignment routines: runs the reference's
+ * BLAST_GappedAlignmentWithTraceback (eDynProgTbck) or BLAST_GreedyGappedAlignment with traceback (eGreedyTbck)
+ * on arbitrary start points.  items: 6 ints per call {oid, context, s_shift, s_length, q_start, s_start};
+ * the calls are recorded in res->tb_calls / tb_ops through the same wrappers as the taps. */
+int ref_traceback_calls(const RefConfig *cfg,
+                        int32_t nq, const uint8_t *qseq, const int32_t *qlens,
+                        const int32_t *qmask_n, const int32_t *qmask_iv,
+                        int32_t ns, const uint8_t *packed, const int64_t *sbyteoff, const int32_t *slen,
+                        int32_t n_items, const int32_t *items, RefResult *res)
+{
+    const EBlastProgramType prog = eBlastTypeBlastn;
+    Setup S;
+    MemDb db;
+    BlastSeqSrcNewInfo info;
+    BlastSeqSrc *seq_src;
+    BlastScoringParameters *score_params = NULL;
+    BlastExtensionParameters *ext_params = NULL;
+    BlastHitSavingParameters *hit_params = NULL;
+    BlastEffectiveLengthsParameters *eff_len_params = NULL;
+    BlastGapAlignStruct *gap_align = NULL;
+    TapCtx tap;
+    Uint1 *buf = NULL;
+    Int4 cur_oid = -1;
+    int st, i;
+
+    memset(res, 0, sizeof *res);
+    tab_init(&res->scan, 4); tab_init(&res->init, 8); tab_init(&res->gapped, 10); tab_init(&res->final_, 11);
+    tab_init(&res->tb_calls, 15); tab_init(&res->tb_ops, 2); tab_init(&res->tb_final, 15);
+    st = build_setup(cfg, nq, qseq, qlens, qmask_n, qmask_iv, &S);
+    if (st) { res->status = st; return st; }
+    db.n = ns; db.packed = packed; db.byteoff = sbyteoff; db.len = slen;
+    db.total = 0; db.maxlen = 0; db.oid_begin = 0; db.oid_end = ns;
+    for (i = 0; i < ns; i++) { db.total += slen[i]; if (slen[i] > db.maxlen) db.maxlen = slen[i]; }
+    db.smask_type = 0; db.smask_n = NULL; db.smask_iv = NULL; db.smask_first = NULL;
+    BlastChooseNucleotideScanSubject(S.lookup_wrap);
+    BlastChooseNaExtend(S.lookup_wrap);
+    info.constructor = &mdb_new; info.ctor_argument = &db;
+    seq_src = BlastSeqSrcNew(&info);
+    st = dump_params(&S, seq_src, res, (cfg->taps & 8) != 0);
+    if (!st) {
+        st = BLAST_GapAlignSetUp(prog, seq_src, S.score_options, S.eff_len_options, S.ext_options, S.hit_options,
+                                 S.query_info, S.sbp, &score_params, &ext_params, &hit_params, &eff_len_params,
+                                 &gap_align);
+        if (st) st += 400;
+    }
+    if (!st) {
+        gap_align->gap_x_dropoff = ext_params->gap_x_dropoff_final;      /* core/blast_traceback.c:1403 */
+        tap.res = res; tap.taps = 16; tap.db = &db; tap.cur_chunk_off = 0;
+        tap.tb_seq = NULL; tap.tb_oid = -1; tap.q_base = S.query->sequence; tap.qinfo = S.query_info;
+        g_tap = &tap;
+        for (i = 0; i < n_items && !st; i++) {
+            const int32_t *it = items + 6 * i;
+            const Int4 oid = it[0], ctx = it[1], s_shift = it[2], s_len = it[3], q_start = it[4], s_start = it[5];
+            const Uint1 *query = S.query->sequence + S.query_info->contexts[ctx].query_offset;
+            const Int4 q_len = S.query_info->contexts[ctx].query_length;
+            if (oid != cur_oid) {
+                const Int4 len = slen[oid];
+                const uint8_t *pk = packed + sbyteoff[oid];
+                Int4 k;
+                free(buf);
+                buf = (Uint1 *)malloc((size_t)len + 2);
+                buf[0] = buf[len + 1] = 15;
+                for (k = 0; k < len; k++) buf[k + 1] = (pk[k >> 2] >> (6 - 2 * (k & 3))) & 3;
+                cur_oid = oid;
+            }
+            tap.tb_seq = buf + 1; tap.tb_oid = oid;
+            if (S.ext_options->eTbackExt == eGreedyTbck)
+                BLAST_GreedyGappedAlignment(query, buf + 1 + s_shift, q_len, s_len, gap_align, score_params,
+                                            q_start, s_start, FALSE, TRUE, NULL);
+            else
+                BLAST_GappedAlignmentWithTraceback(prog, query, buf + 1 + s_shift, gap_align, score_params,
+                                                   q_start, s_start, q_len, s_len, NULL);
+            gap_align->edit_script = GapEditScriptDelete(gap_align->edit_script);
+        }
+        g_tap = NULL;
+    }
+    free(buf);
+    BLAST_GapAlignStructFree(gap_align);
+    BlastScoringParametersFree(score_params);
+    BlastExtensionParametersFree(ext_params);
+    BlastHitSavingParametersFree(hit_params);
+    BlastEffectiveLengthsParametersFree(eff_len_params);
+    BlastSeqSrcFree(seq_src);
+    free_setup(&S);
+    res->status = st;
+    return st;
+}
+
 void ref_free_result(RefResult *res)
 {
     free(res->scan.data); free(res->init.data); free(res->gapped.data); free(res->final_.data);

@@ -112,6 +112,15 @@ int ref_search(const RefConfig *cfg,
                const int32_t *slen,
                RefResult *res);
 
+/* Direct calls of the reference's alignment-with-traceback routine (chosen by the configuration's traceback
+ * algorithm) on arbitrary start points; items: 6 ints per call {oid, context, s_shift, s_length, q_start, s_start}.
+ * Fills the parameter block, tb_calls and tb_ops of res. */
+int ref_traceback_calls(const RefConfig *cfg,
+                        int32_t n_queries, const uint8_t *qseq, const int32_t *qlens,
+                        const int32_t *qmask_n, const int32_t *qmask_iv,
+                        int32_t n_subjects, const uint8_t *packed, const int64_t *sbyteoff, const int32_t *slen,
+                        int32_t n_items, const int32_t *items, RefResult *res);
+
 void ref_free_result(RefResult *res);
 
 #ifdef __cplusplus

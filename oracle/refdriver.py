@@ -128,8 +128,15 @@ def default_config(task="megablast", **kw) -> RefConfig:
     return cfg
 
 
+def traceback_calls(queries, volume, items, cfg: RefConfig):
+    """The reference's alignment-with-traceback routine on arbitrary start points.  `items`: int32 array (n, 6) of
+    {oid, context, s_shift, s_length, q_start, s_start}.  Returns the same dict as search(); the calls are in
+    tb_calls / tb_ops."""
+    return search(queries, volume, cfg, tb_items=np.ascontiguousarray(items, dtype=np.int32).reshape(-1, 6))
+
+
 def search(queries, volume, cfg: RefConfig | None = None, *, task="megablast", masks=None,
-           subject_masks=None, subject_mask_type=1, **kw):
+           subject_masks=None, subject_mask_type=1, tb_items=None, **kw):
     """Run the reference preliminary search. `queries`: list of uint8 blastna arrays;
     `volume`: gblastn_b200.synth.Volume (or any object with packed/byte_off/seq_len);
     `masks`: optional list (per query) of [(left, right)] inclusive plus-strand intervals;
@@ -164,11 +171,20 @@ def search(queries, volume, cfg: RefConfig | None = None, *, task="megablast", m
     else:
         mn_p, miv_p = None, None
     res = RefResult()
-    st = lib().ref_search(C.byref(cfg), C.c_int32(len(queries)),
-                          qcat.ctypes.data_as(C.c_void_p), qlens.ctypes.data_as(C.c_void_p),
-                          mn_p, miv_p, C.c_int32(slen.shape[0]),
-                          packed.ctypes.data_as(C.c_void_p), boff.ctypes.data_as(C.c_void_p),
-                          slen.ctypes.data_as(C.c_void_p), C.byref(res))
+    if tb_items is not None:
+        lib().ref_traceback_calls.restype = C.c_int
+        st = lib().ref_traceback_calls(C.byref(cfg), C.c_int32(len(queries)),
+                                       qcat.ctypes.data_as(C.c_void_p), qlens.ctypes.data_as(C.c_void_p),
+                                       mn_p, miv_p, C.c_int32(slen.shape[0]),
+                                       packed.ctypes.data_as(C.c_void_p), boff.ctypes.data_as(C.c_void_p),
+                                       slen.ctypes.data_as(C.c_void_p), C.c_int32(tb_items.shape[0]),
+                                       tb_items.ctypes.data_as(C.c_void_p), C.byref(res))
+    else:
+        st = lib().ref_search(C.byref(cfg), C.c_int32(len(queries)),
+                              qcat.ctypes.data_as(C.c_void_p), qlens.ctypes.data_as(C.c_void_p),
+                              mn_p, miv_p, C.c_int32(slen.shape[0]),
+                              packed.ctypes.data_as(C.c_void_p), boff.ctypes.data_as(C.c_void_p),
+                              slen.ctypes.data_as(C.c_void_p), C.byref(res))
     try:
         n = res.num_contexts
         out = {

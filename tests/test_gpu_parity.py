@@ -177,6 +177,76 @@ def test_traceback_hsps_from_prelim_lists(name):
         Q.free(); V.free()
 
 
+def _random_start_items(r, vol, rng, per_hsp=3, max_hsps=60):
+    """Start points for the differential test: inside real HSPs (with a small diagonal jitter), with and
+    without a subject window, plus the corners of the sequences."""
+    fin = r["final"]
+    qlen = r["ctx_query_length"]
+    rows = []
+    pick = rng.permutation(fin.shape[0])[:max_hsps]
+    for k in pick:
+        oid, ctx, q_off, q_end, s_off = (int(x) for x in fin[k, :5])
+        slen = int(vol.seq_len[oid])
+        for _ in range(per_hsp):
+            q = int(rng.integers(q_off, q_end))
+            s = min(max(s_off + (q - q_off) + int(rng.integers(-2, 3)), 0), slen - 1)
+            if rng.random() < 0.5:
+                rows.append((oid, ctx, 0, slen, q, s))
+            else:
+                shift = max(0, s - int(rng.integers(50, 3000)))
+                length = min(slen - shift, (s - shift) + int(rng.integers(50, 3000)))
+                rows.append((oid, ctx, shift, length, q, s - shift))
+        ql = int(qlen[ctx])
+        rows.append((oid, ctx, 0, slen, 0, int(rng.integers(0, slen))))
+        rows.append((oid, ctx, 0, slen, ql - 1, int(rng.integers(0, slen))))
+        rows.append((oid, ctx, 0, slen, int(rng.integers(0, ql)), 0))
+        rows.append((oid, ctx, 0, slen, int(rng.integers(0, ql)), slen - 1))
+        rows.append((oid, ctx, 0, slen, 0, 0))
+        rows.append((oid, ctx, 0, slen, ql - 1, slen - 1))
+    return np.array(rows, dtype=np.int32)
+
+
+@pytest.mark.parametrize("name", ["blastn_mb11_dp", "c3_scaled_blastn_10kb", "blastn_ws7_array", "mb_lut11_hash_indels",
+                                  "c5_scaled_ntlike_5kb", "blastn_ws11_greedy", "mb_with_N"])
+def test_gapped_traceback_random_starts(name):
+    """Differential test on start points the search itself never produces: points anywhere inside real HSPs
+    (off the optimal diagonal, in narrow subject windows) and the corners of both sequences, against the
+    reference's BLAST_GappedAlignmentWithTraceback / BLAST_GreedyGappedAlignment called directly."""
+    from gblastn_b200 import engine as E, abi
+    from oracle import refdriver as R, portdriver as P
+    task, cfgkw, vol, qs = cases.make_case(name)
+    if not R.available():
+        pytest.skip("oracle/_ref/libblastref.so did not travel to this box")
+    cfg = R.default_config(task, taps=R.TAP_LUT, **cfgkw)
+    r = R.search(qs, vol, cfg)
+    assert r["status"] == 0 and r["final"].shape[0] > 0
+    it = _random_start_items(r, vol, np.random.default_rng(7))
+    rc = R.traceback_calls(qs, vol, it, cfg)
+    assert rc["status"] == 0
+    calls = rc["tb_calls"]
+    assert calls.shape[0] == it.shape[0]
+    h = P.batch_from_reference(r, task=task, cfg=cfg)
+    V, Q = E.Volume(vol), E.Query(h)
+    try:
+        items = np.zeros(it.shape[0], dtype=abi.TB_ITEM_DTYPE)
+        for k, col in enumerate(("oid", "context", "s_shift", "s_length", "q_start", "s_start")):
+            items[col] = it[:, k]
+        res, ops = E.gapped_traceback(V, Q, int(r["gap_x_dropoff_final"]), items)
+        for k, col in ((8, "score"), (9, "query_start"), (10, "query_stop"), (11, "subject_start"), (12, "subject_stop"),
+                       (14, "esp_n")):
+            bad = np.flatnonzero(res[col] != calls[:, k])
+            assert bad.size == 0, f"{col} differs for {bad.size} of {calls.shape[0]} calls, first {bad[:3]}: " \
+                                  f"{res[col][bad[:3]]} vs {calls[bad[:3], k]} items {it[bad[:3]]}"
+        ref_ops = rc["tb_ops"]
+        for i in range(calls.shape[0]):
+            want = ref_ops[calls[i, 13]:calls[i, 13] + calls[i, 14]]
+            got = ops[res["esp_off"][i]:res["esp_off"][i] + res["esp_n"][i]]
+            assert np.array_equal(got["op_type"], want[:, 0]) and np.array_equal(got["num"], want[:, 1]), \
+                f"edit script differs for call {i} {it[i]}"
+    finally:
+        Q.free(); V.free()
+
+
 def test_file_volume_equals_memory_volume(tmp_path):
     """bn_db_load_files: a volume written as .nin/.nsq and loaded from the files gives the same bytes
     of results as the same volume loaded from memory (ragged lengths, many subjects)."""
