@@ -110,6 +110,9 @@ TB_RESULT_DTYPE = np.dtype([("score", "<i4"), ("query_start", "<i4"), ("query_st
                             ("subject_start", "<i4"), ("subject_stop", "<i4"), ("esp_n", "<i4"),
                             ("esp_off", "<i8"), ("status", "<i4"), ("pad", "<i4")])
 EDIT_OP_DTYPE = np.dtype([("op_type", "<i4"), ("num", "<i4")])
+TB_HSP_DTYPE = np.dtype([("query_index", "<i4"), ("oid", "<i4"), ("context", "<i4"), ("q_off", "<i4"), ("q_end", "<i4"),
+                         ("s_off", "<i4"), ("s_end", "<i4"), ("score", "<i4"), ("num_ident", "<i4"), ("esp_n", "<i4"),
+                         ("esp_off", "<i8"), ("evalue", "<f8"), ("bit_score", "<f8")])
 assert HSP_DTYPE.itemsize == C.sizeof(BnHSP)
 assert INIT_DTYPE.itemsize == C.sizeof(BnInitHit)
 

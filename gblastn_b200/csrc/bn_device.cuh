@@ -389,6 +389,15 @@ struct DevTracebackHsp {         // a preliminary HSP (absolute subject coordina
 };
 cudaError_t launch_traceback_start(const DevQuery &q, const uint8_t *packed, const DevTracebackHsp *hsps, int64_t n,
                                    DevTracebackItem *items, cudaStream_t st);
+struct DevTracebackPost {        // an HSP after the list logic (absolute subject coordinates), edit script in ops[esp_off ..)
+    int64_t byte_off, esp_off;
+    int32_t seq_len, context, q_off, q_end, s_off, s_end, score, esp_n, reevaluate, pad;
+};
+struct DevTracebackPostOut {
+    int32_t deleted, q_off, q_end, s_off, s_end, score, first, last, num_ident, align_length;
+};
+cudaError_t launch_traceback_reevaluate(const DevQuery &q, const uint8_t *packed, const DevTracebackPost *items, int64_t n,
+                                        int2 *ops, DevTracebackPostOut *out, cudaStream_t st);
 cudaError_t launch_traceback_greedy(const DevQuery &q, const TracebackLaunch &L, int blocks, cudaStream_t st);
 int traceback_warps_per_block();
 

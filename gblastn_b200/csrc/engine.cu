@@ -1931,18 +1931,13 @@ int bn_gapped_traceback(int vol_handle, int query_handle, int32_t gap_x_dropoff_
 // start point (BLAST_CheckStartForGappedAlignment :97-153, BlastGetOffsetsForGappedAlignment
 // core/blast_gapalign.c:3059-3131, BlastGetStartForGappedAlignmentNucl :3134-3182) and AdjustSubjectRange (:3608-3636)
 // on the device, then the alignment with traceback.
-int bn_traceback_hsps(int vol_handle, int query_handle, int32_t gap_x_dropoff_final,
-                      const BnHSP *hsps, int64_t n_hsps, BnTracebackItem **items_out,
-                      BnTracebackResult **results, BnEditOp **ops, int64_t *n_ops)
+// start points + alignments for a list of preliminary HSPs; the caller holds D->mu and has made the device current
+static int traceback_hsps_core(Device *D, Volume *V, Query *Q, int32_t gap_x_dropoff_final, const BnHSP *hsps, int64_t n_hsps,
+                               std::vector<BnTracebackItem> &all, std::vector<BnTracebackResult> &res,
+                               BnEditOp **ops, int64_t *n_ops)
 {
-    Volume *V; Query *Q; Device *D;
-    if (!items_out || !results || !ops || !n_ops || n_hsps < 0 || (n_hsps > 0 && !hsps))
-        return fail(BN_ERR_INVALID, "bn_traceback_hsps: bad argument");
-    int rc = get_handles(vol_handle, query_handle, &V, &Q, &D);
-    if (rc) return rc;
-    *items_out = nullptr; *results = nullptr; *ops = nullptr; *n_ops = 0;
-    std::lock_guard<std::mutex> lk(D->mu);
-    CU_TRY(cudaSetDevice(D->id));
+    *ops = nullptr; *n_ops = 0;
+    all.clear(); res.clear();
     if (!Q->dev[V->device].ready) return fail(BN_ERR_INVALID, "query batch is not loaded on the volume's device");
     if (n_hsps == 0) return BN_OK;
     if (V->ready) CU_TRY(cudaStreamWaitEvent(D->stream, V->ready, 0));
@@ -1972,8 +1967,9 @@ int bn_traceback_hsps(int vol_handle, int query_handle, int32_t gap_x_dropoff_fi
     cudaFreeAsync(d_h, st); cudaFreeAsync(d_it, st);
     CU_TRY(e);
     CU_TRY(cudaStreamSynchronize(st));
-    std::vector<BnTracebackItem> all((size_t)n_hsps), found;
+    std::vector<BnTracebackItem> found;
     std::vector<int64_t> where;
+    all.resize((size_t)n_hsps);
     for (int64_t i = 0; i < n_hsps; i++) {
         const DevTracebackItem &t = its[(size_t)i];
         BnTracebackItem b{hsps[i].oid, hsps[i].context, t.s_shift, t.s_length, t.q_start, t.s_start};
@@ -1981,17 +1977,172 @@ int bn_traceback_hsps(int vol_handle, int query_handle, int32_t gap_x_dropoff_fi
         else { found.push_back(b); where.push_back(i); }
         all[(size_t)i] = b;
     }
-    BnTracebackResult *r = nullptr; BnEditOp *o = nullptr; int64_t no = 0;
-    rc = traceback_core(D, V, Q, gap_x_dropoff_final, found.data(), (int64_t)found.size(), &r, &o, &no);
+    BnTracebackResult *r = nullptr;
+    int rc = traceback_core(D, V, Q, gap_x_dropoff_final, found.data(), (int64_t)found.size(), &r, ops, n_ops);
     if (rc) return rc;
-    std::vector<BnTracebackResult> res((size_t)n_hsps);
+    res.resize((size_t)n_hsps);
     for (auto &x : res) { memset(&x, 0, sizeof x); x.status = -1; }
     for (size_t k = 0; k < where.size(); k++) res[(size_t)where[k]] = r[k];
     free(r);
+    return BN_OK;
+}
+
+int bn_traceback_hsps(int vol_handle, int query_handle, int32_t gap_x_dropoff_final,
+                      const BnHSP *hsps, int64_t n_hsps, BnTracebackItem **items_out,
+                      BnTracebackResult **results, BnEditOp **ops, int64_t *n_ops)
+{
+    Volume *V; Query *Q; Device *D;
+    if (!items_out || !results || !ops || !n_ops || n_hsps < 0 || (n_hsps > 0 && !hsps))
+        return fail(BN_ERR_INVALID, "bn_traceback_hsps: bad argument");
+    int rc = get_handles(vol_handle, query_handle, &V, &Q, &D);
+    if (rc) return rc;
+    *items_out = nullptr; *results = nullptr; *ops = nullptr; *n_ops = 0;
+    std::lock_guard<std::mutex> lk(D->mu);
+    CU_TRY(cudaSetDevice(D->id));
+    std::vector<BnTracebackItem> all;
+    std::vector<BnTracebackResult> res;
+    rc = traceback_hsps_core(D, V, Q, gap_x_dropoff_final, hsps, n_hsps, all, res, ops, n_ops);
+    if (rc) return rc;
+    if (n_hsps == 0) return BN_OK;
     *items_out = to_malloc(all);
     *results = to_malloc(res);
-    *ops = o; *n_ops = no;
     if (!*items_out || !*results) return fail(BN_ERR_MEMORY, "bn_traceback_hsps: out of memory");
+    return BN_OK;
+}
+
+// BLAST_ComputeTraceback (core/blast_traceback.c:1375-1640) for blastn / megablast database searches: every
+// preliminary HSP is aligned with traceback on the device, the list logic of Blast_TracebackFromHSPList (:336-790)
+// is replayed on the host (hostpost.cpp), the re-evaluation and identity counts run on the device again.
+int bn_traceback_search(int vol_handle, int query_handle, int32_t gap_x_dropoff_final,
+                        const BnHSP *hsps, int64_t n_hsps,
+                        BnTracebackHSP **out, int64_t *n_out, BnEditOp **ops_out, int64_t *n_ops_out)
+{
+    Volume *V; Query *Q; Device *D;
+    if (!out || !n_out || !ops_out || !n_ops_out || n_hsps < 0 || (n_hsps > 0 && !hsps))
+        return fail(BN_ERR_INVALID, "bn_traceback_search: bad argument");
+    int rc = get_handles(vol_handle, query_handle, &V, &Q, &D);
+    if (rc) return rc;
+    *out = nullptr; *n_out = 0; *ops_out = nullptr; *n_ops_out = 0;
+    std::lock_guard<std::mutex> lk(D->mu);
+    CU_TRY(cudaSetDevice(D->id));
+    const BnQueryBatch &b = Q->batch;
+    const bool greedy = b.gap_algo == BN_GAP_GREEDY;
+    std::vector<BnTracebackItem> items;
+    std::vector<BnTracebackResult> res;
+    BnEditOp *ops = nullptr; int64_t n_ops = 0;
+    rc = traceback_hsps_core(D, V, Q, gap_x_dropoff_final, hsps, n_hsps, items, res, &ops, &n_ops);
+    if (rc) return rc;
+    struct FreeOps { BnEditOp *&p; ~FreeOps() { free(p); } } free_ops{ops};
+    if (n_hsps == 0) return BN_OK;
+
+    // lists = HSPs of one (subject, query) pair in the order given (the preliminary lists are sorted by score)
+    std::vector<int64_t> order((size_t)n_hsps);
+    for (int64_t i = 0; i < n_hsps; i++) order[(size_t)i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) {
+        if (hsps[x].oid != hsps[y].oid) return hsps[x].oid < hsps[y].oid;
+        return b.contexts[hsps[x].context].query_index < b.contexts[hsps[y].context].query_index;
+    });
+    struct List { int32_t oid, query_index; std::vector<TbHsp> arr; size_t extra_start; };
+    std::vector<List> lists;
+    std::vector<TbCand> cand;
+    for (size_t k = 0; k < order.size();) {
+        const int32_t oid = hsps[order[k]].oid, qi = b.contexts[hsps[order[k]].context].query_index;
+        cand.clear();
+        size_t e = k;
+        for (; e < order.size() && hsps[order[e]].oid == oid && b.contexts[hsps[order[e]].context].query_index == qi; e++) {
+            const int64_t i = order[e];
+            TbCand c;
+            c.pre = hsps[i];
+            c.has_start = items[(size_t)i].oid >= 0;
+            c.s_shift = items[(size_t)i].s_shift; c.q_start = items[(size_t)i].q_start; c.s_start = items[(size_t)i].s_start;
+            c.res = res[(size_t)i];
+            c.ops = c.has_start ? ops + res[(size_t)i].esp_off : nullptr;
+            cand.push_back(c);
+        }
+        List L; L.oid = oid; L.query_index = qi; L.extra_start = 0;
+        traceback_list_stage1(b, V->seq_len[(size_t)oid], cand.data(), cand.size(), L.arr, L.extra_start);
+        if (!L.arr.empty()) lists.push_back(std::move(L));
+        k = e;
+    }
+    // device pass: re-evaluation (greedy: every HSP; otherwise the trimmed ones) + identities
+    std::vector<DevTracebackPost> post;
+    std::vector<int2> pops;
+    std::vector<std::pair<size_t, size_t>> who;
+    for (size_t li = 0; li < lists.size(); li++) {
+        List &L = lists[li];
+        for (size_t j = 0; j < L.arr.size(); j++) {
+            TbHsp &h = L.arr[j];
+            if (!h.alive) continue;
+            DevTracebackPost p{};
+            p.byte_off = V->byte_off[(size_t)h.oid]; p.esp_off = (int64_t)pops.size();
+            p.seq_len = V->seq_len[(size_t)h.oid]; p.context = h.context;
+            p.q_off = h.q_off; p.q_end = h.q_end; p.s_off = h.s_off; p.s_end = h.s_end; p.score = h.score;
+            p.esp_n = (int32_t)h.esp.size();
+            p.reevaluate = (greedy || j >= L.extra_start) ? 1 : 0;
+            for (const BnEditOp &o : h.esp) pops.push_back(make_int2(o.op_type, o.num));
+            post.push_back(p);
+            who.emplace_back(li, j);
+        }
+    }
+    std::vector<DevTracebackPostOut> pout(post.size());
+    if (!post.empty()) {
+        cudaStream_t st = D->stream;
+        DevTracebackPost *d_p = nullptr; int2 *d_o = nullptr; DevTracebackPostOut *d_r = nullptr;
+        CU_TRY(cudaMallocAsync((void **)&d_p, post.size() * sizeof(DevTracebackPost), st));
+        CU_TRY(cudaMallocAsync((void **)&d_o, std::max<size_t>(pops.size(), 1) * sizeof(int2), st));
+        CU_TRY(cudaMallocAsync((void **)&d_r, post.size() * sizeof(DevTracebackPostOut), st));
+        cudaError_t e = cudaMemcpyAsync(d_p, post.data(), post.size() * sizeof(DevTracebackPost), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess && !pops.empty()) e = cudaMemcpyAsync(d_o, pops.data(), pops.size() * sizeof(int2), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = launch_traceback_reevaluate(Q->dev[V->device].view, V->d_packed, d_p, (int64_t)post.size(), d_o, d_r, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(pout.data(), d_r, pout.size() * sizeof(DevTracebackPostOut), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && !pops.empty()) e = cudaMemcpyAsync(pops.data(), d_o, pops.size() * sizeof(int2), cudaMemcpyDeviceToHost, st);
+        cudaFreeAsync(d_p, st); cudaFreeAsync(d_o, st); cudaFreeAsync(d_r, st);
+        CU_TRY(e);
+        CU_TRY(cudaStreamSynchronize(st));
+    }
+    for (size_t k = 0; k < post.size(); k++) {
+        TbHsp &h = lists[who[k].first].arr[who[k].second];
+        const DevTracebackPostOut &o = pout[k];
+        if (o.deleted) { h.alive = false; continue; }
+        h.q_off = o.q_off; h.q_end = o.q_end; h.s_off = o.s_off; h.s_end = o.s_end; h.score = o.score;
+        h.num_ident = o.num_ident;
+        h.esp.clear();
+        for (int32_t x = o.first; x <= o.last; x++) {
+            const int2 e = pops[(size_t)(post[k].esp_off + x)];
+            h.esp.push_back(BnEditOp{e.x, e.y});
+        }
+    }
+    // second half of the list logic, then the per-query hit lists (Blast_HSPResultsSortByEvalue, s_BlastPruneExtraHits)
+    std::vector<size_t> keep;
+    for (size_t li = 0; li < lists.size(); li++) {
+        traceback_list_stage2(b, V->seq_len[(size_t)lists[li].oid], lists[li].arr);
+        if (!lists[li].arr.empty()) keep.push_back(li);
+    }
+    std::stable_sort(keep.begin(), keep.end(), [&](size_t x, size_t y) {
+        if (lists[x].query_index != lists[y].query_index) return lists[x].query_index < lists[y].query_index;
+        return traceback_list_before(lists[x].arr, lists[y].arr);
+    });
+    std::vector<BnTracebackHSP> result;
+    std::vector<BnEditOp> result_ops;
+    int32_t cur_q = -1, in_q = 0;
+    for (size_t li : keep) {
+        const List &L = lists[li];
+        if (L.query_index != cur_q) { cur_q = L.query_index; in_q = 0; }
+        if (b.hitlist_size > 0 && in_q >= b.hitlist_size) continue;
+        in_q++;
+        for (const TbHsp &h : L.arr) {
+            BnTracebackHSP o{};
+            o.query_index = L.query_index; o.oid = h.oid; o.context = h.context;
+            o.q_off = h.q_off; o.q_end = h.q_end; o.s_off = h.s_off; o.s_end = h.s_end;
+            o.score = h.score; o.num_ident = h.num_ident; o.esp_n = (int32_t)h.esp.size();
+            o.esp_off = (int64_t)result_ops.size(); o.evalue = h.evalue; o.bit_score = h.bit_score;
+            result_ops.insert(result_ops.end(), h.esp.begin(), h.esp.end());
+            result.push_back(o);
+        }
+    }
+    *out = to_malloc(result); *n_out = (int64_t)result.size();
+    *ops_out = to_malloc(result_ops); *n_ops_out = (int64_t)result_ops.size();
+    if ((!result.empty() && !*out) || (!result_ops.empty() && !*ops_out)) return fail(BN_ERR_MEMORY, "bn_traceback_search: out of memory");
     return BN_OK;
 }
 

@@ -860,3 +860,219 @@ int64_t selftest_replay(uint64_t seed, int32_t n_cases)
 }
 
 }  // namespace bn
+
+// ================================================================================================
+// Traceback stage: list logic (see hostpost.h)
+// ================================================================================================
+namespace bn {
+
+static bool tb_score_less(const TbHsp &x, const TbHsp &y)      // ScoreCompareHSPs; NULLs last
+{
+    if (!x.alive || !y.alive) return x.alive && !y.alive;
+    if (x.score != y.score) return x.score > y.score;
+    if (x.s_off != y.s_off) return x.s_off < y.s_off;
+    if (x.s_end != y.s_end) return x.s_end > y.s_end;
+    if (x.q_off != y.q_off) return x.q_off < y.q_off;
+    if (x.q_end != y.q_end) return x.q_end > y.q_end;
+    return false;
+}
+
+// s_CutOffGapEditScript (core/blast_hits.c:2155-2221)
+static void cut_off_edit_script(TbHsp &hsp, int32_t q_cut, int32_t s_cut, bool cut_begin)
+{
+    int32_t index, opid = 0, qid = 0, sid = 0;
+    bool found = false;
+    std::vector<BnEditOp> &esp = hsp.esp;
+    const int32_t size = (int32_t)esp.size();
+    q_cut -= hsp.q_off;
+    s_cut -= hsp.s_off;
+    for (index = 0; index < size; index++) {
+        for (opid = 0; opid < esp[(size_t)index].num;) {
+            if (esp[(size_t)index].op_type == 3) { qid++; sid++; opid++; }
+            else if (esp[(size_t)index].op_type == 0) { sid += esp[(size_t)index].num; opid += esp[(size_t)index].num; }
+            else if (esp[(size_t)index].op_type == 6) { qid += esp[(size_t)index].num; opid += esp[(size_t)index].num; }
+            else opid++;
+            if (qid >= q_cut && sid >= s_cut) found = true;
+            if (found) break;
+        }
+        if (found) break;
+    }
+    if (!found) return;
+    if (cut_begin) {
+        int32_t new_index = 0;
+        if (opid < esp[(size_t)index].num) {
+            esp[0].op_type = esp[(size_t)index].op_type;
+            esp[0].num = esp[(size_t)index].num - opid;
+            new_index++;
+        }
+        ++index;
+        for (; index < size; index++, new_index++) esp[(size_t)new_index] = esp[(size_t)index];
+        esp.resize((size_t)new_index);
+        hsp.q_off += qid;
+        hsp.s_off += sid;
+    } else {
+        if (opid < esp[(size_t)index].num) esp[(size_t)index].num = opid;
+        esp.resize((size_t)index + 1);
+        hsp.q_end = hsp.q_off + qid;
+        hsp.s_end = hsp.s_off + sid;
+    }
+}
+
+void traceback_list_stage1(const BnQueryBatch &b, int32_t subject_length, const TbCand *cand, size_t n,
+                           std::vector<TbHsp> &arr, size_t &extra_start)
+{
+    arr.clear();
+    extra_start = 0;
+    if (n == 0) return;
+    IntervalTree tree(0, b.concat_len + 1, 0, subject_length + 1, n);
+    for (size_t i = 0; i < n; i++) {
+        const TbCand &c = cand[i];
+        TbHsp h{};
+        h.alive = false; h.was_cut = false;
+        h.oid = c.pre.oid; h.context = c.pre.context;
+        IntervalTree::Item t;
+        t.q_strand_start = strand_offset(b, c.pre.context);
+        t.q_off = c.pre.q_off; t.q_end = c.pre.q_end; t.s_off = c.pre.s_off; t.s_end = c.pre.s_end; t.score = c.pre.score;
+        if (!tree.contains(t, b.min_diag_separation) && c.has_start) {
+            // Blast_HSPUpdateWithTraceback (:156-175) + Blast_HSPAdjustSubjectOffset (core/blast_hits.c:1168-1179)
+            h.alive = true;
+            h.score = c.res.score;
+            h.q_off = c.res.query_start; h.q_end = c.res.query_stop;
+            h.s_off = c.res.subject_start + c.s_shift; h.s_end = c.res.subject_stop + c.s_shift;
+            h.q_gapped_start = c.q_start; h.s_gapped_start = c.s_start + c.s_shift;
+            h.esp.assign(c.ops, c.ops + c.res.esp_n);
+            IntervalTree::Item nt{t.q_strand_start, h.q_off, h.q_end, h.s_off, h.s_end, h.score};
+            tree.add(nt, true);
+        }
+        arr.push_back(std::move(h));
+    }
+    // Blast_HSPListPurgeNullHSPs
+    {
+        size_t o = 0;
+        for (size_t i = 0; i < arr.size(); i++) if (arr[i].alive) { if (o != i) arr[o] = std::move(arr[i]); o++; }
+        arr.resize(o);
+    }
+    if (arr.empty()) return;
+    // Blast_HSPListPurgeHSPsWithCommonEndpoints(eBlastTypeBlastn, list, FALSE): works on an array of pointers
+    std::vector<int32_t> p(arr.size());
+    for (size_t i = 0; i < p.size(); i++) p[i] = (int32_t)i;
+    int32_t hsp_count = (int32_t)p.size();
+    auto by_offset = [&](int32_t a, int32_t c) {      // s_QueryOffsetCompareHSPs
+        const TbHsp &x = arr[(size_t)a], &y = arr[(size_t)c];
+        if (x.context != y.context) return x.context < y.context;
+        if (x.q_off != y.q_off) return x.q_off < y.q_off;
+        if (x.s_off != y.s_off) return x.s_off < y.s_off;
+        if (x.score != y.score) return x.score > y.score;
+        if (x.q_end != y.q_end) return x.q_end > y.q_end;
+        if (x.s_end != y.s_end) return x.s_end > y.s_end;
+        return false;
+    };
+    auto by_end = [&](int32_t a, int32_t c) {         // s_QueryEndCompareHSPs
+        const TbHsp &x = arr[(size_t)a], &y = arr[(size_t)c];
+        if (x.context != y.context) return x.context < y.context;
+        if (x.q_end != y.q_end) return x.q_end < y.q_end;
+        if (x.s_end != y.s_end) return x.s_end < y.s_end;
+        if (x.score != y.score) return x.score > y.score;
+        if (x.q_off != y.q_off) return x.q_off > y.q_off;
+        if (x.s_off != y.s_off) return x.s_off > y.s_off;
+        return false;
+    };
+    std::stable_sort(p.begin(), p.begin() + hsp_count, by_offset);
+    int32_t i = 0;
+    while (i < hsp_count) {
+        int32_t j = 1;
+        while (i + j < hsp_count && p[(size_t)i] >= 0 && p[(size_t)(i + j)] >= 0 &&
+               arr[(size_t)p[(size_t)i]].context == arr[(size_t)p[(size_t)(i + j)]].context &&
+               arr[(size_t)p[(size_t)i]].q_off == arr[(size_t)p[(size_t)(i + j)]].q_off &&
+               arr[(size_t)p[(size_t)i]].s_off == arr[(size_t)p[(size_t)(i + j)]].s_off) {
+            hsp_count--;
+            int32_t hp = p[(size_t)(i + j)];
+            TbHsp &hsp = arr[(size_t)hp];
+            const TbHsp &keep = arr[(size_t)p[(size_t)i]];
+            if (hsp.q_end > keep.q_end) { cut_off_edit_script(hsp, keep.q_end, keep.s_end, true); hsp.was_cut = true; }
+            else { hsp.alive = false; hp = -1; }
+            for (int32_t k = i + j; k < hsp_count; k++) p[(size_t)k] = p[(size_t)(k + 1)];
+            p[(size_t)hsp_count] = hp;
+        }
+        i += j;
+    }
+    std::stable_sort(p.begin(), p.begin() + hsp_count, by_end);
+    i = 0;
+    while (i < hsp_count) {
+        int32_t j = 1;
+        while (i + j < hsp_count && p[(size_t)i] >= 0 && p[(size_t)(i + j)] >= 0 &&
+               arr[(size_t)p[(size_t)i]].context == arr[(size_t)p[(size_t)(i + j)]].context &&
+               arr[(size_t)p[(size_t)i]].q_end == arr[(size_t)p[(size_t)(i + j)]].q_end &&
+               arr[(size_t)p[(size_t)i]].s_end == arr[(size_t)p[(size_t)(i + j)]].s_end) {
+            hsp_count--;
+            int32_t hp = p[(size_t)(i + j)];
+            TbHsp &hsp = arr[(size_t)hp];
+            const TbHsp &keep = arr[(size_t)p[(size_t)i]];
+            if (hsp.q_off < keep.q_off) { cut_off_edit_script(hsp, keep.q_off, keep.s_off, false); hsp.was_cut = true; }
+            else { hsp.alive = false; hp = -1; }
+            for (int32_t k = i + j; k < hsp_count; k++) p[(size_t)k] = p[(size_t)(k + 1)];
+            p[(size_t)hsp_count] = hp;
+        }
+        i += j;
+    }
+    // materialise hsp_array in its new order (NULL entries stay as dead records)
+    std::vector<TbHsp> out(p.size());
+    for (size_t k = 0; k < p.size(); k++) {
+        if (p[k] >= 0) out[k] = std::move(arr[(size_t)p[k]]);
+        else { out[k] = TbHsp{}; out[k].alive = false; }
+    }
+    arr.swap(out);
+    extra_start = (size_t)hsp_count;
+}
+
+void traceback_list_stage2(const BnQueryBatch &b, int32_t subject_length, std::vector<TbHsp> &arr)
+{
+    size_t o = 0;
+    for (size_t i = 0; i < arr.size(); i++) if (arr[i].alive) { if (o != i) arr[o] = std::move(arr[i]); o++; }
+    arr.resize(o);
+    if (arr.empty()) return;
+    std::stable_sort(arr.begin(), arr.end(), tb_score_less);
+    {   // containment among the final alignments (:741-760)
+        IntervalTree tree(0, b.concat_len + 1, 0, subject_length + 1, arr.size());
+        for (TbHsp &h : arr) {
+            IntervalTree::Item t{strand_offset(b, h.context), h.q_off, h.q_end, h.s_off, h.s_end, h.score};
+            if (tree.contains(t, b.min_diag_separation)) h.alive = false;
+            else tree.add(t, true);
+        }
+        o = 0;
+        for (size_t i = 0; i < arr.size(); i++) if (arr[i].alive) { if (o != i) arr[o] = std::move(arr[i]); o++; }
+        arr.resize(o);
+    }
+    // s_HSPListPostTracebackUpdate
+    if (b.round_down) {
+        for (TbHsp &h : arr) h.score &= ~1;
+        std::stable_sort(arr.begin(), arr.end(), tb_score_less);
+    }
+    o = 0;
+    for (size_t i = 0; i < arr.size(); i++) {
+        TbHsp &h = arr[i];
+        const BnContext &c = b.contexts[h.context];
+        h.evalue = (double)c.eff_searchsp * std::exp((double)(-c.gap_lambda * h.score) + c.gap_logK);
+        if (h.evalue > b.evalue_cutoff) continue;
+        // Blast_HSPListGetBitScores (core/blast_hits.c): (Lambda * score - logK) / ln 2
+        // the reference is built with -ffast-math (core/Makefile.blast.lib:19): the division by the constant NCBIMATH_LN2
+        // is a multiplication by its reciprocal there
+        h.bit_score = (h.score * c.gap_lambda - c.gap_logK) * (1.0 / 0.69314718055994530941723212145818);
+        if (o != i) arr[o] = std::move(arr[i]);
+        o++;
+    }
+    arr.resize(o);
+}
+
+bool traceback_list_before(const std::vector<TbHsp> &a, const std::vector<TbHsp> &c)
+{
+    double ea = a[0].evalue, ec = c[0].evalue;            // best_evalue = minimum over the list
+    for (const TbHsp &h : a) ea = std::min(ea, h.evalue);
+    for (const TbHsp &h : c) ec = std::min(ec, h.evalue);
+    const int f = fuzzy_cmp(ea, ec);
+    if (f != 0) return f < 0;
+    if (a[0].score != c[0].score) return a[0].score > c[0].score;
+    return a[0].oid > c[0].oid;                           // BLAST_CMP(h2->oid, h1->oid)
+}
+
+}  // namespace bn

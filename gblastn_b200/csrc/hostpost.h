@@ -125,3 +125,38 @@ private:
 };
 
 }  // namespace bn
+
+// ---- traceback stage: list logic around the device alignments (Blast_TracebackFromHSPList,
+// core/blast_traceback.c:336-790; the per-HSP sequence work runs on the device) ---------------------------
+namespace bn {
+
+struct TbCand {                 // one preliminary HSP with its speculative traceback alignment
+    BnHSP pre;                  // as the preliminary stage left it (absolute subject coordinates)
+    bool has_start;             // a start point exists (else the reference drops the HSP, :514-518)
+    int32_t s_shift, q_start, s_start;      // AdjustSubjectRange shift, start point (subject: window-relative)
+    BnTracebackResult res;      // alignment (subject coordinates window-relative)
+    const BnEditOp *ops;        // res.esp_n operations
+};
+
+struct TbHsp {                  // an HSP of the traceback stage
+    int32_t oid, context, q_off, q_end, s_off, s_end, score, q_gapped_start, s_gapped_start;
+    int32_t num_ident;
+    double evalue, bit_score;
+    std::vector<BnEditOp> esp;
+    bool alive;                 // false = the reference's NULL entry
+    bool was_cut;               // trimmed by the common-endpoint pass: re-evaluated afterwards
+};
+
+// Loop of :444-676 over one list (containment replay in score order, Blast_HSPUpdateWithTraceback,
+// Blast_HSPAdjustSubjectOffset, tree insertion), then Blast_HSPListPurgeHSPsWithCommonEndpoints(purge = FALSE)
+// (core/blast_hits.c:2224-2300, s_CutOffGapEditScript :2155-2221).  arr = hsp_array afterwards (dead entries
+// included, in the reference's positions); extra_start = the purge's return value.
+void traceback_list_stage1(const BnQueryBatch &b, int32_t subject_length, const TbCand *cand, size_t n,
+                           std::vector<TbHsp> &arr, size_t &extra_start);
+// :720-790 after the per-HSP re-evaluation: purge NULLs, sort by score, second containment pass,
+// s_HSPListPostTracebackUpdate (:278-335: odd-score rounding, E-values, reap, bit scores).
+void traceback_list_stage2(const BnQueryBatch &b, int32_t subject_length, std::vector<TbHsp> &arr);
+// s_EvalueCompareHSPLists order of one query's lists (Blast_HSPResultsSortByEvalue)
+bool traceback_list_before(const std::vector<TbHsp> &a, const std::vector<TbHsp> &c);
+
+}  // namespace bn

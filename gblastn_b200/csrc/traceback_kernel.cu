@@ -710,6 +710,138 @@ cudaError_t launch_traceback_start(const DevQuery &q, const uint8_t *packed, con
     return cudaGetLastError();
 }
 
+// ================================================================================================
+// Per-HSP sequence work after the list logic, one thread per HSP:
+//   Blast_HSPReevaluateWithAmbiguitiesGapped (core/blast_hits.c:350-516) + s_UpdateReevaluatedHSP (:311-348) for the
+//   HSPs the reference re-evaluates (all of them after a greedy traceback; the ones trimmed by the common-endpoint
+//   pass otherwise), then the identity count of Blast_HSPGetNumIdentities (:618-700) along the edit script.
+// The edit script lives in ops[esp_off ..) and is modified in place exactly like the reference modifies esp->num[];
+// the surviving part is ops[esp_off + first .. esp_off + last].
+// ================================================================================================
+__global__ void traceback_reevaluate_kernel(const DevQuery q, const uint8_t *packed, const DevTracebackPost *items, int64_t n,
+                                            int2 *ops, DevTracebackPostOut *out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const DevTracebackPost h = items[i];
+    const DevContext c = q.ctx[h.context];
+    const uint8_t *Q = q.query + c.query_offset;
+    const int64_t sb = h.byte_off * 4;
+    const int32_t qlen = c.query_length, slen = h.seq_len;
+    int2 *esp = ops + h.esp_off;
+    const int32_t size = h.esp_n;
+    DevTracebackPostOut o;
+    o.deleted = 0; o.q_off = h.q_off; o.q_end = h.q_end; o.s_off = h.s_off; o.s_end = h.s_end; o.score = h.score;
+    o.first = 0; o.last = size - 1; o.num_ident = 0; o.align_length = 0;
+    auto qb = [&](int32_t p) -> int { return (int)__ldg(Q + p); };
+    auto sbs = [&](int32_t p) -> int { return sbase64(packed, sb + p); };
+    if (h.reevaluate && size > 0) {
+        int32_t factor = 1, gap_open, gap_extend;
+        if (q.gap_open == 0 && q.gap_extend == 0) {
+            if (q.reward % 2 == 1) factor = 2;
+            gap_open = 0;
+            gap_extend = (q.reward - 2 * q.penalty) * factor / 2;
+        } else { gap_open = q.gap_open; gap_extend = q.gap_extend; }
+        const int32_t cutoff_score = c.gapped_cutoff;
+        int32_t query = h.q_off, subject = h.s_off;
+        int32_t score = 0, sum = 0;
+        int32_t best_q_start = query, best_q_end = query, current_q_start = query;
+        int32_t best_s_start = subject, best_s_end = subject, current_s_start = subject;
+        int32_t best_start_esp_index = 0, best_end_esp_index = 0, current_start_esp_index = 0, best_end_esp_num = -1;
+        for (int32_t index = 0; index < size; index++) {
+            for (int32_t op_index = 0; op_index < esp[index].y;) {
+                const int32_t op = esp[index].x;
+                if (op == 3) {
+                    sum += factor * __ldg(q.matrix + 16 * (qb(query) & 0x0f) + sbs(subject));
+                    query++; subject++; op_index++;
+                } else if (op == 0) {
+                    sum -= gap_open + gap_extend * esp[index].y;
+                    subject += esp[index].y; op_index += esp[index].y;
+                } else if (op == 6) {
+                    sum -= gap_open + gap_extend * esp[index].y;
+                    query += esp[index].y; op_index += esp[index].y;
+                } else op_index++;
+                if (sum < 0) {
+                    if (op_index < esp[index].y) {
+                        esp[index].y -= op_index;
+                        current_start_esp_index = index;
+                        op_index = 0;
+                    } else current_start_esp_index = index + 1;
+                    sum = 0;
+                    current_q_start = query; current_s_start = subject;
+                    if (score < cutoff_score) {
+                        best_q_start = query; best_s_start = subject;
+                        score = 0;
+                        best_start_esp_index = current_start_esp_index;
+                        best_end_esp_index = current_start_esp_index;
+                    }
+                } else if (sum > score) {
+                    score = sum;
+                    best_q_start = current_q_start; best_s_start = current_s_start;
+                    best_q_end = query; best_s_end = subject;
+                    best_start_esp_index = current_start_esp_index;
+                    best_end_esp_index = index;
+                    best_end_esp_num = op_index;
+                }
+            }
+        }
+        score /= factor;
+        if (best_start_esp_index < size && best_end_esp_index < size) {
+            int32_t qp = best_q_start, sp = best_s_start, ext = 0;
+            while (qp > 0 && sp > 0) {          // while (qp > 0 && sp > 0 && q[--qp] == s[--sp] && q[qp] < 4) ext++;
+                --qp; --sp;
+                if (!(qb(qp) == sbs(sp) && qb(qp) < 4)) break;
+                ext++;
+            }
+            best_q_start -= ext; best_s_start -= ext;
+            esp[best_start_esp_index].y += ext;
+            if (best_end_esp_index == best_start_esp_index) best_end_esp_num += ext;
+            score += ext * q.reward;
+            qp = best_q_end; sp = best_s_end; ext = 0;
+            while (qp < qlen && sp < slen && qb(qp) < 4) {   // ... && q[qp] < 4 && (q[qp++] == s[sp++])
+                const bool eq = qb(qp) == sbs(sp);
+                qp++; sp++;
+                if (!eq) break;
+                ext++;
+            }
+            best_q_end += ext; best_s_end += ext;
+            esp[best_end_esp_index].y += ext;
+            best_end_esp_num += ext;
+            score += ext * q.reward;
+        }
+        // s_UpdateReevaluatedHSP
+        o.score = score;
+        if (score >= cutoff_score) {
+            o.q_off = best_q_start; o.q_end = best_q_start + (best_q_end - best_q_start);
+            o.s_off = best_s_start; o.s_end = best_s_start + (best_s_end - best_s_start);
+            if (best_end_esp_index != size - 1 || best_start_esp_index > 0) { o.first = best_start_esp_index; o.last = best_end_esp_index; }
+            esp[o.last].y = best_end_esp_num;
+        } else o.deleted = 1;
+    }
+    if (!o.deleted) {           // Blast_HSPGetNumIdentities along the (possibly shortened) script
+        int32_t qp = o.q_off, sp = o.s_off, ident = 0, alen = 0;
+        for (int32_t index = o.first; index <= o.last; index++) {
+            const int32_t num = esp[index].y, op = esp[index].x;
+            alen += num;
+            if (op == 3) {
+                for (int32_t k = 0; k < num; k++) { if (qb(qp) == sbs(sp)) ident++; qp++; sp++; }
+            } else if (op == 0) sp += num;
+            else if (op == 6) qp += num;
+            else { sp += num; qp += num; }
+        }
+        o.num_ident = ident; o.align_length = alen;
+    }
+    out[i] = o;
+}
+
+cudaError_t launch_traceback_reevaluate(const DevQuery &q, const uint8_t *packed, const DevTracebackPost *items, int64_t n,
+                                        int2 *ops, DevTracebackPostOut *out, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    traceback_reevaluate_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(q, packed, items, n, ops, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_traceback_dp(const DevQuery &q, const TracebackLaunch &L, int blocks, cudaStream_t st)
 {
     traceback_dp_kernel<<<blocks, TB_WARPS * 32, 0, st>>>(q, L);

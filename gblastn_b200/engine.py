@@ -19,7 +19,7 @@ EXPORTS = [
     "bn_init", "bn_release", "bn_device_count", "bn_last_error", "bn_version",
     "bn_db_load", "bn_db_free", "bn_query_load", "bn_query_free",
     "bn_prelim_search", "bn_prelim_search_host", "bn_results_free",
-    "bn_scan_subject", "bn_word_finder", "bn_free", "bn_bench_scan", "bn_query_download_lookup", "bn_get_gapped_score", "bn_gapped_traceback", "bn_traceback_hsps",
+    "bn_scan_subject", "bn_word_finder", "bn_free", "bn_bench_scan", "bn_query_download_lookup", "bn_get_gapped_score", "bn_gapped_traceback", "bn_traceback_hsps", "bn_traceback_search",
     "bn_dbfile_index", "bn_db_load_files", "bn_dbfile_write", "bn_prelim_search_batches", "bn_db_set_masks", "bn_selftest_replay",
     "bn_setup_create", "bn_setup_batch", "bn_setup_kbp_std", "bn_setup_kbp_gap",
     "bn_setup_gap_x_dropoff_final", "bn_setup_longest_chain", "bn_setup_free",
@@ -261,6 +261,20 @@ def traceback_hsps(volume: Volume, query: Query, gap_x_dropoff_final: int, hsps:
         lib().bn_free(pi)
         lib().bn_free(pr)
         lib().bn_free(po)
+
+
+def traceback_search(volume: Volume, query: Query, gap_x_dropoff_final: int, hsps: np.ndarray):
+    """The traceback stage for the preliminary lists `hsps` (HSP_DTYPE).  Returns (final HSPs: TB_HSP_DTYPE, ops)."""
+    hsps = np.ascontiguousarray(hsps, dtype=abi.HSP_DTYPE)
+    po, pe, n, ne = C.c_void_p(), C.c_void_p(), C.c_int64(0), C.c_int64(0)
+    _check(lib().bn_traceback_search(C.c_int(volume.handle), C.c_int(query.handle), C.c_int32(gap_x_dropoff_final),
+                                     hsps.ctypes.data_as(C.c_void_p), C.c_int64(hsps.shape[0]),
+                                     C.byref(po), C.byref(n), C.byref(pe), C.byref(ne)))
+    try:
+        return abi.struct_array(po, n.value, abi.TB_HSP_DTYPE), abi.struct_array(pe, ne.value, abi.EDIT_OP_DTYPE)
+    finally:
+        lib().bn_free(po)
+        lib().bn_free(pe)
 
 
 def download_lookup(query: Query, device=0):

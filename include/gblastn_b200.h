@@ -308,6 +308,29 @@ int  bn_gapped_traceback(int vol_handle, int query_handle, int32_t gap_x_dropoff
 int  bn_traceback_hsps(int vol_handle, int query_handle, int32_t gap_x_dropoff_final,
                        const BnHSP *hsps, int64_t n_hsps, BnTracebackItem **items,
                        BnTracebackResult **results, BnEditOp **ops, int64_t *n_ops);
+/* The traceback stage of a blastn / megablast database search: BLAST_ComputeTraceback (core/blast_traceback.c:1375-1640)
+ * -> Blast_TracebackFromHSPList (:336-790) for every (query, subject) list -> s_HSPListPostTracebackUpdate (:278-335)
+ * -> Blast_HSPResultsSortByEvalue / s_BlastPruneExtraHits.  `hsps` = the preliminary lists as bn_prelim_search returns
+ * them (per subject, sorted by score).  All HSPs are aligned on the device at once (start point, alignment with
+ * traceback), the reference's sequential decisions — containment of an HSP in a better one's alignment, the
+ * common-endpoint pass with its edit-script trimming (Blast_HSPListPurgeHSPsWithCommonEndpoints with purge = FALSE), the
+ * second containment pass, odd-score rounding, E-values (BLAST_KarlinStoE_simple), reap, bit scores — are replayed on
+ * the host over those results, and Blast_HSPReevaluateWithAmbiguitiesGapped + the identity count run on the device
+ * in between.  Output: per query (ascending), the subject lists in s_EvalueCompareHSPLists order, at most hitlist_size
+ * of them, HSPs in list order; edit scripts in ops.  Limits: hit_options->percent_identity / min_hit_length are taken
+ * as 0 (the batch does not carry them); the identity count reads the query block the batch carries (`sequence`), which
+ * equals `sequence_nomask` unless the query was hard-masked; the per-query pruning of the preliminary hit lists
+ * (prelim_hitlist_size) is the caller's. */
+typedef struct BnTracebackHSP {
+    int32_t query_index, oid, context;
+    int32_t q_off, q_end, s_off, s_end;
+    int32_t score, num_ident, esp_n;
+    int64_t esp_off;
+    double  evalue, bit_score;
+} BnTracebackHSP;
+int  bn_traceback_search(int vol_handle, int query_handle, int32_t gap_x_dropoff_final,
+                         const BnHSP *hsps, int64_t n_hsps,
+                         BnTracebackHSP **out, int64_t *n_out, BnEditOp **ops, int64_t *n_ops);
 
 /* Host-only self-test: the containment replay (BLAST_GetGappedScore's interval-tree filter, core/blast_itree.c)
  * runs with one tree per query strand; this compares it with the reference's one-tree-per-subject layout on

@@ -177,6 +177,46 @@ def test_traceback_hsps_from_prelim_lists(name):
         Q.free(); V.free()
 
 
+@pytest.mark.parametrize("name", TRACEBACK_DP_CASES + TRACEBACK_GREEDY_CASES)
+def test_traceback_search_matches_reference(name):
+    """bn_traceback_search == the reference's whole traceback stage (Blast_RunTracebackSearch): fed the reference's
+    preliminary lists it returns the reference's final results — every HSP of every hit list in BlastHSPResults order:
+    coordinates, score, number of identities, E-value and bit-score bit patterns, edit scripts."""
+    from gblastn_b200 import engine as E, abi
+    from oracle import refdriver as R, portdriver as P
+    task, cfgkw, vol, qs = cases.make_case(name)
+    if not R.available():
+        pytest.skip("oracle/_ref/libblastref.so did not travel to this box")
+    cfg = R.default_config(task, taps=R.TAP_LUT | R.TAP_TRACEBACK, prelim_only=0, **cfgkw)
+    r = R.search(qs, vol, cfg)
+    assert r["status"] == 0
+    fin, want = r["final"], r["tb_final"]
+    assert want.shape[0] > 0
+    h = P.batch_from_reference(r, task=task, cfg=cfg)
+    V, Q = E.Volume(vol), E.Query(h)
+    try:
+        hsps = np.zeros(fin.shape[0], dtype=abi.HSP_DTYPE)
+        for k, col in enumerate(("oid", "context", "q_off", "q_end", "s_off", "s_end", "score", "q_gapped_start",
+                                 "s_gapped_start")):
+            hsps[col] = fin[:, k]
+        got, ops = E.traceback_search(V, Q, int(r["gap_x_dropoff_final"]), hsps)
+        assert got.shape[0] == want.shape[0], f"{got.shape[0]} HSPs, reference has {want.shape[0]}"
+        for k, col in enumerate(("query_index", "oid", "context", "q_off", "q_end", "s_off", "s_end", "score", "num_ident")):
+            bad = np.flatnonzero(got[col] != want[:, k])
+            assert bad.size == 0, f"{col} differs at {bad[:5]}: {got[col][bad[:5]]} vs {want[bad[:5], k]}"
+        ev = want[:, 9].astype(np.uint32).astype(np.uint64) | (want[:, 10].astype(np.uint32).astype(np.uint64) << np.uint64(32))
+        bs = want[:, 11].astype(np.uint32).astype(np.uint64) | (want[:, 12].astype(np.uint32).astype(np.uint64) << np.uint64(32))
+        assert np.array_equal(got["evalue"].view(np.uint64), ev), "E-value bit patterns differ"
+        assert np.array_equal(got["bit_score"].view(np.uint64), bs), "bit-score bit patterns differ"
+        ref_ops = r["tb_ops"]
+        for i in range(want.shape[0]):
+            w = ref_ops[want[i, 13]:want[i, 13] + want[i, 14]]
+            g = ops[got["esp_off"][i]:got["esp_off"][i] + got["esp_n"][i]]
+            assert np.array_equal(g["op_type"], w[:, 0]) and np.array_equal(g["num"], w[:, 1]), f"edit script of HSP {i}"
+    finally:
+        Q.free(); V.free()
+
+
 def _random_start_items(r, vol, rng, per_hsp=3, max_hsps=60):
     """Start points for the differential test: inside real HSPs (with a small diagonal jitter), with and
     without a subject window, plus the corners of the sequences."""
