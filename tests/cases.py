@@ -116,6 +116,15 @@ CASES = {
                        nq=5, qlen=400, q_seed=22, sub=0.0, indel=0.0, planted=0.0),
 }
 
+# Traceback-stage list logic (containment in a better HSP's final alignment, common-endpoint trimming, second
+# containment pass): queries made of several homologous segments separated by short junk / small indels, which the
+# preliminary X-drop stops at and the final X-drop (100 bits) bridges, plus queries with an internal tandem copy.
+CASES["mb_bridged_segments"] = dict(task="megablast", cfg={}, seq_lens=[300_000, 120_000, 40_000], vol_seed=61,
+                                    nq=60, qlen=900, q_seed=62, sub=0.02, indel=0.0, planted=1.0, bridged=True)
+CASES["blastn_bridged_segments"] = dict(task="blastn", cfg={}, seq_lens=[300_000, 120_000, 40_000], vol_seed=63,
+                                        nq=40, qlen=900, q_seed=64, sub=0.06, indel=0.0, planted=1.0, bridged=True)
+TRACEBACK_LIST_CASES = ["mb_bridged_segments", "blastn_bridged_segments"]
+
 FAST = ["c1_megablast_10kb_vs_1mb", "mb_lut11_hash_indels", "mb_smallna_diagarray", "blastn_mb11_dp",
         "blastn_smallna_dp", "mb_ws16", "blastn_ws11_greedy", "blastn_ws7_array", "mb_with_N", "mb_no_hits"]
 ALL = list(CASES.keys())
@@ -132,9 +141,48 @@ def _seq_lens(spec, seed):
     return lens
 
 
+def _bridged_queries(vol, nq, qlen, seed, sub_rate):
+    """Each query = 2-4 segments copied from consecutive stretches of one subject, separated by junk of 8-70 random
+    bases that replaces a subject stretch of the same length +- a small indel; some queries repeat their first
+    segment at the end (two alignments to the same subject region)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    lens = vol.seq_len.astype(np.int64)
+    ok = np.nonzero(lens >= 4 * qlen)[0]
+    for _ in range(nq):
+        oid = int(ok[rng.integers(0, ok.size)])
+        L = int(lens[oid])
+        start = int(rng.integers(0, L - 3 * qlen))
+        b0 = int(vol.byte_off[oid])
+        raw = vol.packed[b0 + start // 4: b0 + (start + 3 * qlen) // 4 + 2]
+        un = np.stack([raw >> 6, (raw >> 4) & 3, (raw >> 2) & 3, raw & 3], axis=1).reshape(-1)[start % 4:]
+        nseg = int(rng.integers(2, 5))
+        seglen = qlen // nseg - 40
+        parts, pos = [], 0
+        for k in range(nseg):
+            seg = un[pos:pos + seglen].copy()
+            m = rng.random(seglen) < sub_rate
+            seg[m] = (seg[m] + rng.integers(1, 4, size=int(m.sum()))) % 4
+            parts.append(seg.astype(np.uint8))
+            pos += seglen
+            if k + 1 < nseg:
+                junk = int(rng.integers(8, 70))
+                parts.append(rng.integers(0, 4, size=junk, dtype=np.uint8))
+                pos += junk + int(rng.integers(-12, 13))          # the subject skips a slightly different length
+        if rng.random() < 0.3:
+            parts.append(parts[0].copy())
+        q = np.concatenate(parts)[:qlen + 200]
+        if rng.random() < 0.5:
+            q = synth.revcomp(q)
+        out.append(np.ascontiguousarray(q, dtype=np.uint8))
+    return out
+
+
 def make_case(name):
     c = CASES[name]
     vol = synth.random_volume(_seq_lens(c["seq_lens"], c["vol_seed"]), seed=c["vol_seed"])
+    if c.get("bridged"):
+        return c["task"], dict(c["cfg"]), vol, _bridged_queries(vol, c["nq"], c["qlen"], c["q_seed"], c["sub"])
     qs = synth.planted_queries(vol, c["nq"], c["qlen"], seed=c["q_seed"], planted_frac=c["planted"],
                                sub_rate=c["sub"], indel_rate=c["indel"], n_frac=c.get("n_frac", 0.0))
     return c["task"], dict(c["cfg"]), vol, qs

@@ -86,10 +86,10 @@ def test_get_gapped_score_drop_in(name):
 
 
 TRACEBACK_DP_CASES = ["blastn_mb11_dp", "blastn_smallna_dp", "blastn_ws7_array", "blastn_ntlike_many_subjects",
-                      "c3_scaled_blastn_10kb"]
+                      "c3_scaled_blastn_10kb", "blastn_bridged_segments", "blastn_ws7_na_table"]
 TRACEBACK_GREEDY_CASES = ["c1_megablast_10kb_vs_1mb", "mb_lut11_hash_indels", "mb_smallna_diagarray", "mb_ws16", "mb_with_N",
                           "blastn_ws11_greedy", "mb_ntlike_many_subjects", "mb_long_divergent_tier2", "mb_lut12_stride17",
-                          "c4_scaled_short_reads", "c5_scaled_ntlike_5kb"]
+                          "c4_scaled_short_reads", "c5_scaled_ntlike_5kb", "mb_bridged_segments", "mb_two_hit_w40_hash"]
 
 
 @pytest.mark.parametrize("name", TRACEBACK_DP_CASES + TRACEBACK_GREEDY_CASES)
