@@ -217,6 +217,40 @@ def test_traceback_search_matches_reference(name):
         Q.free(); V.free()
 
 
+@pytest.mark.parametrize("name", ["mb_bridged_segments", "blastn_bridged_segments", "c4_scaled_short_reads",
+                                  "c5_scaled_ntlike_5kb", "c3_scaled_blastn_10kb", "mb_with_N"])
+def test_full_search_product_path(name):
+    """Preliminary stage + traceback stage, both on the GPU path with the product's own set-up (no reference data in
+    the loop): the final results equal the reference's Blast_RunPreliminarySearch + Blast_RunTracebackSearch."""
+    from gblastn_b200 import engine as E, setup as S
+    from oracle import refdriver as R
+    task, cfgkw, vol, qs = cases.make_case(name)
+    if not R.available():
+        pytest.skip("oracle/_ref/libblastref.so did not travel to this box")
+    r = R.search(qs, vol, R.default_config(task, taps=R.TAP_TRACEBACK, prelim_only=0, **cfgkw))
+    assert r["status"] == 0
+    want = r["tb_final"]
+    s = S.Setup(qs, task=task, db_length=vol.total_bases, db_num_seqs=vol.n_seqs, device_lookup=1, **cfgkw)
+    V, Q = E.Volume(vol), E.Query(s.batch)
+    try:
+        assert s.gap_x_dropoff_final() == r["gap_x_dropoff_final"]
+        g = E.prelim_search(V, Q)
+        got, ops = E.traceback_search(V, Q, s.gap_x_dropoff_final(), g["hsps"])
+        assert got.shape[0] == want.shape[0] and want.shape[0] > 0
+        for k, col in enumerate(("query_index", "oid", "context", "q_off", "q_end", "s_off", "s_end", "score", "num_ident")):
+            assert np.array_equal(got[col], want[:, k]), col
+        ev = want[:, 9].astype(np.uint32).astype(np.uint64) | (want[:, 10].astype(np.uint32).astype(np.uint64) << np.uint64(32))
+        bs = want[:, 11].astype(np.uint32).astype(np.uint64) | (want[:, 12].astype(np.uint32).astype(np.uint64) << np.uint64(32))
+        assert np.array_equal(got["evalue"].view(np.uint64), ev) and np.array_equal(got["bit_score"].view(np.uint64), bs)
+        ref_ops = r["tb_ops"]
+        flat = np.concatenate([ref_ops[want[i, 13]:want[i, 13] + want[i, 14]] for i in range(want.shape[0])])
+        mine = np.concatenate([np.stack([ops["op_type"][a:a + n], ops["num"][a:a + n]], axis=1)
+                               for a, n in zip(got["esp_off"], got["esp_n"])])
+        assert np.array_equal(flat, mine), "edit scripts differ"
+    finally:
+        Q.free(); V.free(); s.free()
+
+
 def _random_start_items(r, vol, rng, per_hsp=3, max_hsps=60):
     """Start points for the differential test: inside real HSPs (with a small diagonal jitter), with and
     without a subject window, plus the corners of the sequences."""
