@@ -1189,9 +1189,10 @@ static int traceback_greedy_host(Device &Dv, Volume &V, Query &Q, int32_t x_drop
     for (int attempt = 0; left > 0; attempt++) {
         if (attempt == 8) return fail(BN_ERR_OVERFLOW, "bn_gapped_traceback: greedy traceback scratch exhausted");
         const long long budget = 4ll << 30;
-        int64_t threads = std::min<int64_t>(std::min<int64_t>(left, 8192), std::max<long long>(budget / per_thread, 1));
-        const int blocks = (int)((threads + 31) / 32);
-        threads = (int64_t)blocks * 32;
+        // one WARP per alignment (traceback_greedy_warp_kernel, 4 warps per block), each with a private arena
+        int64_t threads = std::min<int64_t>(std::min<int64_t>(left, 148 * 16), std::max<long long>(budget / per_thread, 1));
+        const int blocks = (int)((threads + 3) / 4);
+        threads = (int64_t)blocks * 4;
         const long long arena_bytes = threads * per_thread;
         if (d_arena) { cudaFreeAsync(d_arena, st); d_arena = nullptr; }
         if (d_ops) { cudaFreeAsync(d_ops, st); d_ops = nullptr; }
@@ -1203,7 +1204,7 @@ static int traceback_greedy_host(Device &Dv, Volume &V, Query &Q, int32_t x_drop
         L.packed = V.d_packed; L.items = d_items; L.n = n_items; L.x_dropoff = x_dropoff;
         L.arena = d_arena; L.arena_bytes = arena_bytes; L.arena_used = d_cnt;
         L.ops = d_ops; L.ops_cap = ops_cap; L.ops_used = d_cnt + 1; L.out = d_out; L.todo = d_todo;
-        CU_TRY(launch_traceback_greedy(dq, L, blocks, st));
+        CU_TRY(launch_traceback_greedy_warp(dq, L, blocks, st));
         unsigned long long used[2] = {0, 0};
         CU_TRY(cudaMemcpyAsync(pass.data(), d_out, pass.size() * sizeof(DevTracebackDir), cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaMemcpyAsync(used, d_cnt, sizeof used, cudaMemcpyDeviceToHost, st));

@@ -493,6 +493,44 @@ __device__ int32_t greedy_align_tb(const GreedyTbSeq &sp, int32_t xdrop_threshol
     return best_dist;
 }
 
+// s_ReduceGaps (core/blast_gapalign.c:2545-2617) on {op[], num[]}; returns the new size
+__device__ int32_t reduce_gaps(const DevQuery &q, const uint8_t *packed, int32_t ctx_off, int32_t qi, int64_t si,
+                               int32_t *op, int32_t *num, int32_t size)
+{
+    const uint8_t *Qb = q.query + ctx_off;
+    auto eq = [&](int32_t a, int64_t b) -> bool { return (int)__ldg(Qb + a) == sbase64(packed, b); };
+    for (int32_t i = 0; i < size; i++) {
+        if (op[i] == 3) { qi += num[i]; si += num[i]; continue; }
+        if (i > 1 && op[i] != op[i - 2] && num[i - 2] > 0) {
+            int32_t d = num[i] + num[i - 1] + num[i - 2];
+            if (d == 3) {
+                num[i - 2] = 0; num[i - 1] = 2; num[i] = 0;
+                if (op[i] == 6) ++qi; else ++si;
+            } else if (d < 12) {
+                int32_t nm1 = 0, nm2 = 0;
+                d = min(num[i], num[i - 2]);
+                qi -= num[i - 1]; si -= num[i - 1];
+                int32_t q1 = qi; int64_t s1 = si;
+                if (op[i] == 6) si -= d; else qi -= d;
+                for (int32_t j = 0; j < num[i - 1]; ++j, ++q1, ++s1, ++qi, ++si) {
+                    if (eq(q1, s1)) nm1++;
+                    if (eq(qi, si)) nm2++;
+                }
+                for (int32_t j = 0; j < d; ++j, ++qi, ++si) if (eq(qi, si)) nm2++;
+                if (nm2 >= nm1 - d) { num[i - 2] -= d; num[i - 1] += d; num[i] -= d; }
+                else { qi = q1; si = s1; }
+            }
+        }
+        if (op[i] == 6) qi += num[i]; else si += num[i];
+    }
+    int32_t j = 0;
+    for (int32_t i = 0; i < size; i++) {
+        if (num[i] > 0) { num[j] = num[i]; op[j] = op[i]; ++j; }
+        else if (++i < size && j > 0) num[j - 1] += num[i];
+    }
+    return j;
+}
+
 }  // namespace
 
 __global__ void __launch_bounds__(32)
@@ -545,43 +583,7 @@ traceback_greedy_kernel(const DevQuery q, const TracebackLaunch L)
                     if (merge) { num[idx - 1] += fwd.num(fwd.n - 1); i = fwd.n - 2; }
                     for (; i >= 0; i--) { op[idx] = fwd.op(i); num[idx] = fwd.num(i); idx++; }
                 }
-                // s_ReduceGaps(esp, query + q_off - q_ext_l, subject + s_off - s_ext_l)
-                {
-                    const uint8_t *Qb = q.query + c.query_offset;
-                    int32_t qi = q_off - q_ext_l;
-                    int64_t si = seq_base + s_off - s_ext_l;
-                    auto eq = [&](int32_t a, int64_t b) -> bool { return (int)__ldg(Qb + a) == sbase64(L.packed, b); };
-                    for (int32_t i = 0; i < size; i++) {
-                        if (op[i] == 3) { qi += num[i]; si += num[i]; continue; }
-                        if (i > 1 && op[i] != op[i - 2] && num[i - 2] > 0) {
-                            int32_t d = num[i] + num[i - 1] + num[i - 2];
-                            if (d == 3) {
-                                num[i - 2] = 0; num[i - 1] = 2; num[i] = 0;
-                                if (op[i] == 6) ++qi; else ++si;
-                            } else if (d < 12) {
-                                int32_t nm1 = 0, nm2 = 0;
-                                d = min(num[i], num[i - 2]);
-                                qi -= num[i - 1]; si -= num[i - 1];
-                                int32_t q1 = qi; int64_t s1 = si;
-                                if (op[i] == 6) si -= d; else qi -= d;
-                                for (int32_t j = 0; j < num[i - 1]; ++j, ++q1, ++s1, ++qi, ++si) {
-                                    if (eq(q1, s1)) nm1++;
-                                    if (eq(qi, si)) nm2++;
-                                }
-                                for (int32_t j = 0; j < d; ++j, ++qi, ++si) if (eq(qi, si)) nm2++;
-                                if (nm2 >= nm1 - d) { num[i - 2] -= d; num[i - 1] += d; num[i] -= d; }
-                                else { qi = q1; si = s1; }
-                            }
-                        }
-                        if (op[i] == 6) qi += num[i]; else si += num[i];
-                    }
-                    int32_t j = 0;
-                    for (int32_t i = 0; i < size; i++) {
-                        if (num[i] > 0) { num[j] = num[i]; op[j] = op[i]; ++j; }
-                        else if (++i < size && j > 0) num[j - 1] += num[i];
-                    }
-                    size = j;
-                }
+                size = reduce_gaps(q, L.packed, c.query_offset, q_off - q_ext_l, seq_base + s_off - s_ext_l, op, num, size);
                 const unsigned long long base = atomicAdd(L.ops_used, (unsigned long long)size);
                 if ((long long)(base + size) > L.ops_cap) status = 4;
                 else {
@@ -597,6 +599,281 @@ traceback_greedy_kernel(const DevQuery q, const TracebackLaunch L)
         L.out[2 * w] = out;
         L.out[2 * w + 1] = out2;
     }
+}
+
+// ---- warp-parallel greedy with traceback -----------------------------------------------------------------------
+// One warp per alignment, one lane per diagonal of the current distance (the formulation of greedy_align_warp in
+// gapped_kernel.cu: every diagonal's new offset depends on row d-1 only; the order-dependent bookkeeping is replayed
+// from ballots in ascending k).  Rows are kept in the warp's arena; the sentinel overwrites of row d-1 are made
+// literally, so the walk reads back exactly what the reference's s_GetNextNonAffineTback reads.
+namespace {
+
+__device__ int32_t tb_first_mismatch_warp(const GreedyTbSeq &p, int32_t i1, int32_t i2, int lane)
+{
+    const int32_t n = min(p.len1 - i1, p.len2 - i2);
+    if (n <= 0) return 0;
+    for (int32_t base = 0; base < n; base += 512) {
+        const int32_t off = base + 16 * lane;
+        int32_t c = 16;
+        if (off < n) {
+            uint32_t qb, qa, m;
+            if (p.reverse) {
+                qwin(*p.q, p.qbase + p.len1 - i1 - off - 16, qb, qa);
+                m = mismatch_bits(qb, qa, swin(p.packed, p.sbase + p.len2 - i2 - off - 16));
+                if (m) c = (__ffs(m) - 1) >> 1;
+            } else {
+                qwin(*p.q, p.qbase + i1 + off, qb, qa);
+                m = mismatch_bits(qb, qa, swin(p.packed, p.sbase + i2 + off));
+                if (m) c = __clz(m) >> 1;
+            }
+        }
+        const unsigned stop = __ballot_sync(FULLW, off < n && c < 16);
+        if (stop) {
+            const int src = __ffs(stop) - 1;
+            const int32_t cc = __shfl_sync(FULLW, c, src);
+            return min(base + 16 * src + cc, n);
+        }
+    }
+    return n;
+}
+
+// A[0 .. cap): the warp's free arena (ints).  ed: lane 0's list.  Warp-uniform return value and status.
+__device__ int32_t greedy_align_tb_warp(const GreedyTbSeq &sp, int32_t xdrop_threshold, int32_t match_cost, int32_t mismatch_cost,
+                                        int32_t &seq1_len, int32_t &seq2_len, int32_t *A, int64_t cap, OpList &ed, int &status,
+                                        int lane)
+{
+    const int32_t len1 = sp.len1, len2 = sp.len2;
+    int32_t best_dist = 0, best_diag = 0;
+    const int32_t max_dist = min(GREEDY_MAX_COST, len2 / 2 + 1);
+    const int32_t origin = max_dist + 2;
+    const int32_t xdrop_offset = (xdrop_threshold + match_cost / 2) / (match_cost + mismatch_cost) + 1;
+
+    const int32_t index0 = tb_first_mismatch_warp(sp, 0, 0, lane);
+    seq1_len = index0; seq2_len = index0;
+    if (index0 == len1 || index0 == len2) { if (lane == 0) ed.add(3, index0); return 0; }
+
+    const int64_t tcap = min((int64_t)max_dist + 2, cap / 8);
+    const int64_t mcap = min((int64_t)max_dist + 1 + xdrop_offset, cap / 8);
+    if (cap < 64 || mcap <= xdrop_offset + 1) { status = 3; return 0; }
+    int32_t *rowtab = A;
+    int32_t *max_score_mem = A + tcap;
+    int64_t top = tcap + mcap;
+    int32_t *max_score = max_score_mem + xdrop_offset;
+    for (int32_t i = lane; i < xdrop_offset; i += 32) max_score_mem[i] = 0;
+    // rows 0 and 1
+    if (2 >= tcap || top + 9 + 11 > cap) { status = 3; return 0; }
+    if (lane == 0) {
+        rowtab[0] = (int32_t)(top - (origin - 4));
+        rowtab[1] = (int32_t)(top + 9 - (origin - 5));
+        (A + rowtab[0])[origin] = index0;
+        max_score[0] = index0 * match_cost;
+    }
+    top += 9 + 11;
+    __syncwarp();
+    int32_t diag_lower = origin - 1, diag_upper = origin + 1;
+    bool end1_reached = false, end2_reached = false;
+
+    for (int32_t d = 1; d <= max_dist; d++) {
+        if (d + xdrop_offset >= mcap) { status = 3; return 0; }
+        int32_t curr_extent = 0, curr_seq2_index = 0, curr_diag = 0;
+        const int32_t tmp_lower = diag_lower, tmp_upper = diag_upper;
+        int32_t *prev = A + rowtab[d - 1];
+        int32_t *cur = A + rowtab[d];
+        if (lane == 0) {
+            prev[diag_lower - 1] = GREEDY_INVALID;
+            prev[diag_lower] = GREEDY_INVALID;
+            prev[diag_upper] = GREEDY_INVALID;
+            prev[diag_upper + 1] = GREEDY_INVALID;
+        }
+        __syncwarp();
+        int32_t xdrop_score = max_score[d - xdrop_offset] + (match_cost + mismatch_cost) * d - xdrop_threshold;
+        {
+            const int32_t h = match_cost / 2;
+            int32_t qd = xdrop_score / h;
+            if (xdrop_score % h > 0) ++qd;
+            xdrop_score = qd;
+        }
+        for (int32_t kb = tmp_lower; kb <= tmp_upper; kb += 32) {
+            const int32_t k = kb + lane;
+            const bool active = k <= tmp_upper;
+            bool ok = false;
+            int32_t seq1_index = 0, seq2_index = 0;
+            if (active) {
+                seq2_index = max(prev[k + 1], prev[k]) + 1;
+                seq2_index = max(seq2_index, prev[k - 1]);
+                seq1_index = seq2_index + k - origin;
+                ok = !(seq2_index < 0 || seq1_index + seq2_index < xdrop_score);
+                if (ok) {
+                    const int32_t run = tb_first_mismatch(sp, seq1_index, seq2_index);
+                    seq1_index += run; seq2_index += run;
+                }
+            }
+            const unsigned act = __ballot_sync(FULLW, active);
+            const unsigned succ = __ballot_sync(FULLW, ok);
+            const unsigned e2 = __ballot_sync(FULLW, ok && seq2_index == len2);
+            const unsigned e1 = __ballot_sync(FULLW, ok && seq1_index == len1);
+            unsigned inv = 0;
+            for (unsigned rem = act; rem; rem &= rem - 1) {        // the bookkeeping in ascending k
+                const int b = __ffs(rem) - 1;
+                const unsigned bit = 1u << b;
+                const int32_t kk = kb + b;
+                if (!(succ & bit)) {
+                    if (kk == diag_lower) diag_lower++;
+                    else inv |= bit;
+                } else {
+                    diag_upper = kk;
+                    if (e2 & bit) { diag_lower = kk + 1; end2_reached = true; }
+                    if (e1 & bit) { diag_upper = kk - 1; end1_reached = true; }
+                }
+            }
+            if (ok) cur[k] = seq2_index;
+            else if (inv & (1u << lane)) cur[k] = GREEDY_INVALID;
+            if (succ) {     // extent: first diagonal with the strict maximum of seq1 + seq2
+                const int32_t ext = ok ? seq1_index + seq2_index : -1;
+                const int32_t best_ext = __reduce_max_sync(FULLW, ext);
+                if (best_ext > curr_extent) {
+                    const int src = __ffs(__ballot_sync(FULLW, ok && ext == best_ext)) - 1;
+                    curr_extent = best_ext;
+                    curr_seq2_index = __shfl_sync(FULLW, seq2_index, src);
+                    curr_diag = kb + src;
+                }
+            }
+        }
+        const int32_t curr_score = curr_extent * (match_cost / 2) - d * (match_cost + mismatch_cost);
+        const int32_t prev_best = max_score[d - 1];
+        __syncwarp();
+        if (curr_score > prev_best) {
+            if (lane == 0) max_score[d] = curr_score;
+            best_dist = d;
+            best_diag = curr_diag;
+            seq2_len = curr_seq2_index;
+            seq1_len = curr_seq2_index + curr_diag - origin;
+        } else if (lane == 0) max_score[d] = prev_best;
+        if (diag_lower > diag_upper) { __syncwarp(); break; }
+        if (!end2_reached) diag_lower--;
+        if (!end1_reached) diag_upper++;
+        {   // row d + 1 addressable on [diag_lower - 2, diag_upper + 4]
+            const int64_t w = (int64_t)diag_upper - diag_lower + 7;
+            if (d + 1 >= tcap || top + w > cap) { status = 3; return 0; }
+            if (lane == 0) rowtab[d + 1] = (int32_t)(top - (diag_lower - 2));
+            top += w;
+        }
+        __syncwarp();
+    }
+    // ---- traceback by lane 0 (core/greedy_align.c:687-751) ----------------------------------------------------
+    int bad = 0;
+    if (lane == 0) {
+        int32_t d = best_dist;
+        int32_t seq2_index = seq2_len;
+        if ((int64_t)(ed.top - A) - 2 * (int64_t)(ed.n + 2 * d + 2) < top) bad = 1;
+        else {
+            while (d > 0) {
+                const int32_t *pr = A + rowtab[d - 1];
+                int32_t new_diag, new_seq2_index;
+                if (pr[best_diag - 1] > max(pr[best_diag], pr[best_diag + 1])) { new_seq2_index = pr[best_diag - 1]; new_diag = best_diag - 1; }
+                else if (pr[best_diag] > pr[best_diag + 1]) { new_seq2_index = pr[best_diag]; new_diag = best_diag; }
+                else { new_seq2_index = pr[best_diag + 1]; new_diag = best_diag + 1; }
+                if (new_diag == best_diag) {
+                    if (seq2_index - new_seq2_index > 0) ed.add(3, seq2_index - new_seq2_index);
+                } else if (new_diag < best_diag) {
+                    if (seq2_index - new_seq2_index > 0) ed.add(3, seq2_index - new_seq2_index);
+                    ed.add(6, 1);
+                } else {
+                    if (seq2_index - new_seq2_index - 1 > 0) ed.add(3, seq2_index - new_seq2_index - 1);
+                    ed.add(0, 1);
+                }
+                d--;
+                best_diag = new_diag;
+                seq2_index = new_seq2_index;
+            }
+            ed.add(3, index0);
+        }
+    }
+    bad = __shfl_sync(FULLW, bad, 0);
+    if (bad) { status = 3; return 0; }
+    return best_dist;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(128)
+traceback_greedy_warp_kernel(const DevQuery q, const TracebackLaunch L)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t cap = L.arena_bytes / 4 / nw;                 // ints per warp
+    int32_t *A = reinterpret_cast<int32_t *>(L.arena) + w0 * cap;
+    int32_t match = q.reward, mismatch = -q.penalty, xd = L.x_dropoff;
+    if (match % 2 == 1) { match *= 2; mismatch *= 2; xd *= 2; }
+    for (int64_t w = w0; w < L.n; w += nw) {
+        if (L.todo && !L.todo[w]) continue;
+        const DevTracebackItem it = L.items[w];
+        const DevContext c = q.ctx[it.context];
+        const int32_t q_length = c.query_length, s_length = it.s_length;
+        const int32_t q_off = it.q_start, s_off = it.s_start;
+        const int64_t seq_base = it.byte_off * 4 + it.s_shift;
+        DevTracebackDir out, out2;
+        out.score = 0; out.a_off = 0; out.b_off = 0; out.ops_off = 0; out.n_ops = 0; out.status = 0; out.ran = 1; out.pad = 0;
+        out2 = out;
+        int status = 0;
+        int32_t q_ext_r = 0, s_ext_r = 0, q_ext_l = 0, s_ext_l = 0;
+        OpList fwd, rev;
+        fwd.top = A + cap; fwd.n = 0; fwd.last_op = 8;
+        rev = fwd;
+        GreedyTbSeq sp;
+        sp.q = &q; sp.packed = L.packed;
+        sp.qbase = c.query_offset + q_off; sp.sbase = seq_base + s_off;
+        sp.len1 = q_length - q_off; sp.len2 = s_length - s_off; sp.reverse = false;
+        __syncwarp();
+        int32_t dist = greedy_align_tb_warp(sp, xd, match, mismatch, q_ext_r, s_ext_r, A, cap, fwd, status, lane);
+        if (!status) {
+            const int32_t fn = __shfl_sync(FULLW, fwd.n, 0);
+            rev.top = fwd.top - 2 * fn; rev.n = 0; rev.last_op = 8;
+            sp.qbase = c.query_offset; sp.sbase = seq_base; sp.len1 = q_off; sp.len2 = s_off; sp.reverse = true;
+            __syncwarp();
+            dist += greedy_align_tb_warp(sp, xd, match, mismatch, q_ext_l, s_ext_l, A, (int64_t)(rev.top - A), rev, status, lane);
+        }
+        __syncwarp();
+        if (!status && lane == 0) {
+            const int32_t score = (q_ext_r + s_ext_r + q_ext_l + s_ext_l) * q.reward / 2 - dist * (q.reward - q.penalty);
+            int32_t size = fwd.n + rev.n;
+            const bool merge = fwd.n > 0 && rev.n > 0 && fwd.op(fwd.n - 1) == rev.op(rev.n - 1);
+            if (merge) size--;
+            if (2 * (int64_t)size + 2 > (int64_t)(rev.top - 2 * rev.n - A)) status = 3;
+            else {
+                int32_t *op = A, *num = A + size + 1;
+                int32_t idx = 0;
+                for (int32_t i = 0; i < rev.n; i++) { op[idx] = rev.op(i); num[idx] = rev.num(i); idx++; }
+                if (fwd.n > 0) {
+                    int32_t i = fwd.n - 1;
+                    if (merge) { num[idx - 1] += fwd.num(fwd.n - 1); i = fwd.n - 2; }
+                    for (; i >= 0; i--) { op[idx] = fwd.op(i); num[idx] = fwd.num(i); idx++; }
+                }
+                size = reduce_gaps(q, L.packed, c.query_offset, q_off - q_ext_l, seq_base + s_off - s_ext_l, op, num, size);
+                const unsigned long long base = atomicAdd(L.ops_used, (unsigned long long)size);
+                if ((long long)(base + size) > L.ops_cap) status = 4;
+                else {
+                    for (int32_t i = 0; i < size; i++) L.ops[base + i] = make_int2(op[i], num[i]);
+                    out.ops_off = (long long)base; out.n_ops = size;
+                }
+                out.score = score;
+                out.a_off = q_ext_l; out.b_off = s_ext_l;
+                out2.a_off = q_ext_r; out2.b_off = s_ext_r;
+            }
+        }
+        if (lane == 0) {
+            out.status = status; out2.status = status;
+            L.out[2 * w] = out;
+            L.out[2 * w + 1] = out2;
+        }
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_traceback_greedy_warp(const DevQuery &q, const TracebackLaunch &L, int blocks, cudaStream_t st)
+{
+    traceback_greedy_warp_kernel<<<blocks, 128, 0, st>>>(q, L);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_traceback_greedy(const DevQuery &q, const TracebackLaunch &L, int blocks, cudaStream_t st)
