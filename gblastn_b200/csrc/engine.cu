@@ -2028,6 +2028,9 @@ int bn_traceback_search(int vol_handle, int query_handle, int32_t gap_x_dropoff_
     CU_TRY(cudaSetDevice(D->id));
     const BnQueryBatch &b = Q->batch;
     const bool greedy = b.gap_algo == BN_GAP_GREEDY;
+    static const bool trace = getenv("BN_TRACE") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     std::vector<BnTracebackItem> items;
     std::vector<BnTracebackResult> res;
     BnEditOp *ops = nullptr; int64_t n_ops = 0;
@@ -2035,6 +2038,7 @@ int bn_traceback_search(int vol_handle, int query_handle, int32_t gap_x_dropoff_
     if (rc) return rc;
     struct FreeOps { BnEditOp *&p; ~FreeOps() { free(p); } } free_ops{ops};
     if (n_hsps == 0) return BN_OK;
+    const double t1 = now();
 
     // lists = HSPs of one (subject, query) pair in the order given (the preliminary lists are sorted by score)
     std::vector<int64_t> order((size_t)n_hsps);
@@ -2065,6 +2069,7 @@ int bn_traceback_search(int vol_handle, int query_handle, int32_t gap_x_dropoff_
         if (!L.arr.empty()) lists.push_back(std::move(L));
         k = e;
     }
+    const double t2 = now();
     // device pass: re-evaluation (greedy: every HSP; otherwise the trimmed ones) + identities
     std::vector<DevTracebackPost> post;
     std::vector<int2> pops;
@@ -2113,6 +2118,7 @@ int bn_traceback_search(int vol_handle, int query_handle, int32_t gap_x_dropoff_
             h.esp.push_back(BnEditOp{e.x, e.y});
         }
     }
+    const double t3 = now();
     // second half of the list logic, then the per-query hit lists (Blast_HSPResultsSortByEvalue, s_BlastPruneExtraHits)
     std::vector<size_t> keep;
     for (size_t li = 0; li < lists.size(); li++) {
@@ -2141,6 +2147,10 @@ int bn_traceback_search(int vol_handle, int query_handle, int32_t gap_x_dropoff_
             result.push_back(o);
         }
     }
+    if (trace)
+        fprintf(stderr, "[bn] traceback stage %.3f ms: start points + alignments %.3f, list stage 1 %.3f, re-evaluation %.3f, "
+                        "list stage 2 + results %.3f (%lld HSPs in, %zu out)\n", now() - t0, t1 - t0, t2 - t1, t3 - t2, now() - t3,
+                (long long)n_hsps, result.size());
     *out = to_malloc(result); *n_out = (int64_t)result.size();
     *ops_out = to_malloc(result_ops); *n_ops_out = (int64_t)result_ops.size();
     if ((!result.empty() && !*out) || (!result_ops.empty() && !*ops_out)) return fail(BN_ERR_MEMORY, "bn_traceback_search: out of memory");

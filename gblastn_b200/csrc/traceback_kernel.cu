@@ -1025,22 +1025,39 @@ __global__ void traceback_reevaluate_kernel(const DevQuery q, const uint8_t *pac
         int32_t best_q_start = query, best_q_end = query, current_q_start = query;
         int32_t best_s_start = subject, best_s_end = subject, current_s_start = subject;
         int32_t best_start_esp_index = 0, best_end_esp_index = 0, current_start_esp_index = 0, best_end_esp_num = -1;
+        // matches of unambiguous bases all score `reward`: a run of them inside a substitution block can be taken in one
+        // step (sum only grows, so the reference's per-base "sum > score" update ends on the run's last base)
+        const int32_t match_score = __ldg(q.matrix);
+        const bool uniform = __ldg(q.matrix + 17) == match_score && __ldg(q.matrix + 34) == match_score &&
+                             __ldg(q.matrix + 51) == match_score && match_score > 0;
         for (int32_t index = 0; index < size; index++) {
-            for (int32_t op_index = 0; op_index < esp[index].y;) {
-                const int32_t op = esp[index].x;
+            const int32_t op = esp[index].x;
+            int32_t num = esp[index].y;
+            for (int32_t op_index = 0; op_index < num;) {
                 if (op == 3) {
-                    sum += factor * __ldg(q.matrix + 16 * (qb(query) & 0x0f) + sbs(subject));
-                    query++; subject++; op_index++;
+                    int32_t run = 0;
+                    if (uniform && num - op_index >= 16) {
+                        uint32_t qw, qa;
+                        qwin(q, c.query_offset + query, qw, qa);
+                        const uint32_t m = mismatch_bits(qw, qa, swin(packed, sb + subject));
+                        run = m ? (__clz(m) >> 1) : 16;
+                    }
+                    if (run > 0) { sum += run * factor * match_score; query += run; subject += run; op_index += run; }
+                    else {
+                        sum += factor * __ldg(q.matrix + 16 * (qb(query) & 0x0f) + sbs(subject));
+                        query++; subject++; op_index++;
+                    }
                 } else if (op == 0) {
-                    sum -= gap_open + gap_extend * esp[index].y;
-                    subject += esp[index].y; op_index += esp[index].y;
+                    sum -= gap_open + gap_extend * num;
+                    subject += num; op_index += num;
                 } else if (op == 6) {
-                    sum -= gap_open + gap_extend * esp[index].y;
-                    query += esp[index].y; op_index += esp[index].y;
+                    sum -= gap_open + gap_extend * num;
+                    query += num; op_index += num;
                 } else op_index++;
                 if (sum < 0) {
-                    if (op_index < esp[index].y) {
-                        esp[index].y -= op_index;
+                    if (op_index < num) {
+                        num -= op_index;
+                        esp[index].y = num;
                         current_start_esp_index = index;
                         op_index = 0;
                     } else current_start_esp_index = index + 1;
@@ -1100,8 +1117,15 @@ __global__ void traceback_reevaluate_kernel(const DevQuery q, const uint8_t *pac
         for (int32_t index = o.first; index <= o.last; index++) {
             const int32_t num = esp[index].y, op = esp[index].x;
             alen += num;
-            if (op == 3) {
-                for (int32_t k = 0; k < num; k++) { if (qb(qp) == sbs(sp)) ident++; qp++; sp++; }
+            if (op == 3) {          // 16 bases per step: identical = neither different nor ambiguous
+                for (int32_t k = 0; k < num; k += 16) {
+                    const int32_t nb = min(16, num - k);
+                    uint32_t qw, qa;
+                    qwin(q, c.query_offset + qp + k, qw, qa);
+                    const uint32_t m = mismatch_bits(qw, qa, swin(packed, sb + sp + k));
+                    ident += nb - __popc(m >> (32 - 2 * nb));
+                }
+                qp += num; sp += num;
             } else if (op == 0) sp += num;
             else if (op == 6) qp += num;
             else { sp += num; qp += num; }
