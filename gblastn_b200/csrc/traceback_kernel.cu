@@ -277,35 +277,57 @@ traceback_dp_kernel(const DevQuery q, const TracebackLaunch L)
                     else {
                         int2 *runs = reinterpret_cast<int2 *>(L.arena + tmp);
                         int32_t n_runs = 0;
-                        if (lane == 0) {
+                        {
+                            // The walk is a chain of dependent loads (row table, then the script byte).  All lanes keep
+                            // the walk state; lane j prefetches the byte the walk needs after j diagonal steps from the
+                            // batch's first cell, (a0 - j, b0 - j) — an alignment mostly moves diagonally — and the steps are
+                            // fed from registers by shuffles until the path leaves that diagonal (a gap) or 32 steps are done.
                             int32_t a = a_off, b = b_off, run_op = -1, run_n = 0;
                             uint8_t script = SCRIPT_SUB;
                             const volatile uint8_t *ar = L.arena;
                             while (a > 0 || b > 0) {
-                                const uint8_t next = ar[rs.row_off[a] + (b - rs.row_first[a])];
-                                switch (script) {
-                                case SCRIPT_GAP_IN_A:
-                                    script = next & SCRIPT_OP_MASK;
-                                    if (next & SCRIPT_EXTEND_GAP_A) script = SCRIPT_GAP_IN_A;
-                                    break;
-                                case SCRIPT_GAP_IN_B:
-                                    script = next & SCRIPT_OP_MASK;
-                                    if (next & SCRIPT_EXTEND_GAP_B) script = SCRIPT_GAP_IN_B;
-                                    break;
-                                default:
-                                    script = next & SCRIPT_OP_MASK;
-                                    break;
+                                const int32_t a0 = a, b0 = b;
+                                const int32_t aj = a0 - lane, bj = b0 - lane;
+                                uint32_t pre = 0x100u;                        // bit 8 = not available
+                                if (aj >= 0 && bj >= 0) {
+                                    const long long off = rs.row_off[aj];
+                                    const int32_t first = rs.row_first[aj];
+                                    if (bj >= first && bj - first < TB_CELLS + 64 && off + (bj - first) < L.arena_bytes)
+                                        pre = ar[off + (bj - first)];
                                 }
-                                if (script == SCRIPT_GAP_IN_A) b--;
-                                else if (script == SCRIPT_GAP_IN_B) a--;
-                                else { a--; b--; }
-                                if ((int32_t)script == run_op) run_n++;
-                                else {
-                                    if (run_n) runs[n_runs++] = make_int2(run_op, run_n);
-                                    run_op = script; run_n = 1;
+                                for (;;) {
+                                    const int j = a0 - a;
+                                    if (j >= 32 || b0 - b != j) break;        // off the prefetched diagonal
+                                    uint32_t nx = __shfl_sync(FULLW, pre, j);
+                                    if (nx & 0x100u) nx = ar[rs.row_off[a] + (b - rs.row_first[a])];
+                                    const uint8_t next = (uint8_t)nx;
+                                    switch (script) {
+                                    case SCRIPT_GAP_IN_A:
+                                        script = next & SCRIPT_OP_MASK;
+                                        if (next & SCRIPT_EXTEND_GAP_A) script = SCRIPT_GAP_IN_A;
+                                        break;
+                                    case SCRIPT_GAP_IN_B:
+                                        script = next & SCRIPT_OP_MASK;
+                                        if (next & SCRIPT_EXTEND_GAP_B) script = SCRIPT_GAP_IN_B;
+                                        break;
+                                    default:
+                                        script = next & SCRIPT_OP_MASK;
+                                        break;
+                                    }
+                                    if (script == SCRIPT_GAP_IN_A) b--;
+                                    else if (script == SCRIPT_GAP_IN_B) a--;
+                                    else { a--; b--; }
+                                    if ((int32_t)script == run_op) run_n++;
+                                    else {
+                                        if (run_n && lane == 0) runs[n_runs] = make_int2(run_op, run_n);
+                                        if (run_n) n_runs++;
+                                        run_op = script; run_n = 1;
+                                    }
+                                    if (!(a > 0 || b > 0)) break;
                                 }
                             }
-                            if (run_n) runs[n_runs++] = make_int2(run_op, run_n);
+                            if (run_n && lane == 0) runs[n_runs] = make_int2(run_op, run_n);
+                            if (run_n) n_runs++;
                         }
                         n_runs = __shfl_sync(FULLW, n_runs, 0);
                         unsigned long long base = 0;
