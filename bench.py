@@ -377,6 +377,27 @@ def main():
                     "sample": f"{reps} repeats of the full workload (prelim stage only); the reference "
                               f"parallelises over subject sequences, DB has {vol.n_seqs} -> {threads} thread"}
                 line["parity_vs_reference"] = bool(np.array_equal(P.final_table(g["hsps"]), r["final"]))
+                # ---- the stage after the path, outside every timed region above: the same
+                # step's preliminary lists through bn_traceback_search, next to the reference's traceback stage
+                try:
+                    xf = s.gap_x_dropoff_final()
+                    engine.traceback_search(V, Q, xf, g["hsps"])
+                    tb_ms = []
+                    for _ in range(5):
+                        t0 = time.perf_counter()
+                        tb, tb_ops = engine.traceback_search(V, Q, xf, g["hsps"])
+                        tb_ms.append(1e3 * (time.perf_counter() - t0))
+                    rt = R.search(qs, vol, R.default_config("megablast", taps=R.TAP_TRACEBACK, prelim_only=0))
+                    w = rt["tb_final"]
+                    same = tb.shape[0] == w.shape[0] and all(
+                        np.array_equal(tb[c], w[:, k]) for k, c in enumerate(
+                            ("query_index", "oid", "context", "q_off", "q_end", "s_off", "s_end", "score", "num_ident")))
+                    line["traceback_stage"] = {
+                        "ms": float(np.median(tb_ms)), "hsps": int(tb.shape[0]), "edit_ops": int(tb_ops.shape[0]),
+                        "reference_ms_1core": 1e3 * rt["seconds_traceback"], "identical_to_reference": bool(same),
+                        "note": "not part of value / e2e; wall time of bn_traceback_search on one step's lists"}
+                except Exception as e:
+                    line["traceback_stage"] = {"ms": None, "note": f"failed: {e}"}
             else:
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
                                         "sample": "oracle/_ref/libblastref.so not present on this box"}

@@ -353,9 +353,9 @@ traceback_dp_kernel(const DevQuery q, const TracebackLaunch L)
 // Greedy alignment with traceback: BLAST_GreedyGappedAlignment with do_traceback (core/blast_gapalign.c:2620-2751)
 // -> BLAST_AffineGreedyAlign prologue (core/greedy_align.c:799-814) -> BLAST_GreedyAlign (:385-752) with an edit
 // block, then Blast_PrelimEditBlockToGapEditScript (core/blast_gapalign.c:2455-2517) and s_ReduceGaps (:2545-2617).
-// One THREAD per alignment, exact serial recurrence (first version: correctness before speed).  Unlike the
+// One WARP per alignment, one lane per diagonal (see below).  Unlike the
 // score-only kernel every row last_seq2_off[d][] is kept — including the sentinel overwrites of row d-1 the
-// reference makes before it fills row d, which the traceback reads back — in a per-thread arena that is reset for
+// reference makes before it fills row d, which the traceback reads back — in a per-warp arena that is reset for
 // every alignment.  Arena layout (ints): [row table][max_score][rows ...   ... rev list][fwd list].
 // ================================================================================================
 namespace {
@@ -391,129 +391,6 @@ struct OpList {                 // GapPrelimEditBlock: list grows DOWNWARD from 
     __device__ __forceinline__ int32_t op(int32_t i) const { return top[-2 * (i + 1)]; }
     __device__ __forceinline__ int32_t num(int32_t i) const { return top[-2 * (i + 1) + 1]; }
 };
-
-// BLAST_GreedyAlign with traceback.  A[0 .. cap): the thread's free arena.  Returns the distance; ops appended to `ed`.
-__device__ int32_t greedy_align_tb(const GreedyTbSeq &sp, int32_t xdrop_threshold, int32_t match_cost, int32_t mismatch_cost,
-                                   int32_t &seq1_len, int32_t &seq2_len, int32_t *A, int64_t cap, OpList &ed, int &status)
-{
-    const int32_t len1 = sp.len1, len2 = sp.len2;
-    int32_t best_dist = 0, best_diag = 0;
-    const int32_t max_dist = min(GREEDY_MAX_COST, len2 / 2 + 1);
-    const int32_t origin = max_dist + 2;
-    const int32_t xdrop_offset = (xdrop_threshold + match_cost / 2) / (match_cost + mismatch_cost) + 1;
-
-    int32_t index = tb_first_mismatch(sp, 0, 0);
-    seq1_len = index; seq2_len = index;
-    int32_t seq1_index = index, seq2_index;
-    if (index == len1 || index == len2) { ed.add(3, index); return 0; }
-
-    // row table (offset of row d's element 0 inside A, may be negative) and per-distance best scores
-    const int64_t tcap = min((int64_t)max_dist + 2, cap / 8);
-    const int64_t mcap = min((int64_t)max_dist + 1 + xdrop_offset, cap / 8);
-    if (cap < 64 || mcap <= xdrop_offset + 1) { status = 3; return 0; }
-    int32_t *rowtab = A;
-    int32_t *max_score_mem = A + tcap;
-    int64_t top = tcap + mcap;
-    auto alloc_row = [&](int32_t d, int32_t lo, int32_t hi) -> bool {       // row d addressable on [lo, hi]
-        const int64_t w = (int64_t)hi - lo + 1;
-        if (d >= tcap || top + w > cap) return false;
-        rowtab[d] = (int32_t)(top - lo);
-        top += w;
-        return true;
-    };
-    int32_t *max_score = max_score_mem + xdrop_offset;
-    for (int32_t i = 0; i < xdrop_offset; i++) max_score_mem[i] = 0;
-    if (!alloc_row(0, origin - 4, origin + 4) || !alloc_row(1, origin - 5, origin + 5)) { status = 3; return 0; }
-    (A + rowtab[0])[origin] = seq1_index;
-    const int32_t first_run = seq1_index;
-    max_score[0] = seq1_index * match_cost;
-    int32_t diag_lower = origin - 1, diag_upper = origin + 1;
-    bool end1_reached = false, end2_reached = false;
-
-    for (int32_t d = 1; d <= max_dist; d++) {
-        if (d + xdrop_offset >= mcap) { status = 3; return 0; }
-        int32_t curr_extent = 0, curr_seq2_index = 0, curr_diag = 0;
-        const int32_t tmp_lower = diag_lower, tmp_upper = diag_upper;
-        int32_t *prev = A + rowtab[d - 1];
-        int32_t *cur = A + rowtab[d];
-        prev[diag_lower - 1] = GREEDY_INVALID;
-        prev[diag_lower] = GREEDY_INVALID;
-        prev[diag_upper] = GREEDY_INVALID;
-        prev[diag_upper + 1] = GREEDY_INVALID;
-
-        int32_t xdrop_score = max_score[d - xdrop_offset] + (match_cost + mismatch_cost) * d - xdrop_threshold;
-        {   // (Int4)ceil((double)x / (match_cost / 2)); match_cost / 2 >= 1: exact integer ceiling
-            const int32_t h = match_cost / 2;
-            int32_t qd = xdrop_score / h;
-            if (xdrop_score % h > 0) ++qd;
-            xdrop_score = qd;
-        }
-        for (int32_t k = tmp_lower; k <= tmp_upper; k++) {
-            seq2_index = max(prev[k + 1], prev[k]) + 1;
-            seq2_index = max(seq2_index, prev[k - 1]);
-            seq1_index = seq2_index + k - origin;
-            if (seq2_index < 0 || seq1_index + seq2_index < xdrop_score) {
-                if (k == diag_lower) diag_lower++;
-                else cur[k] = GREEDY_INVALID;
-                continue;
-            }
-            diag_upper = k;
-            index = tb_first_mismatch(sp, seq1_index, seq2_index);
-            seq1_index += index; seq2_index += index;
-            cur[k] = seq2_index;
-            if (seq1_index + seq2_index > curr_extent) {
-                curr_extent = seq1_index + seq2_index;
-                curr_seq2_index = seq2_index;
-                curr_diag = k;
-            }
-            if (seq2_index == len2) { diag_lower = k + 1; end2_reached = true; }
-            if (seq1_index == len1) { diag_upper = k - 1; end1_reached = true; }
-        }
-        const int32_t curr_score = curr_extent * (match_cost / 2) - d * (match_cost + mismatch_cost);
-        if (curr_score > max_score[d - 1]) {
-            max_score[d] = curr_score;
-            best_dist = d;
-            best_diag = curr_diag;
-            seq2_len = curr_seq2_index;
-            seq1_len = curr_seq2_index + best_diag - origin;
-        } else max_score[d] = max_score[d - 1];
-        if (diag_lower > diag_upper) break;
-        if (!end2_reached) diag_lower--;
-        if (!end1_reached) diag_upper++;
-        // the reference allocates (diag_upper - diag_lower + 7) offsets starting at diag_lower - 2
-        if (!alloc_row(d + 1, diag_lower - 2, diag_upper + 4)) { status = 3; return 0; }
-    }
-
-    // ---- traceback (core/greedy_align.c:687-751) ---------------------------------------------------------
-    {
-        int32_t d = best_dist;
-        seq2_index = seq2_len;
-        // the list grows downward: make sure it cannot meet the rows
-        if ((int64_t)(ed.top - A) - 2 * (int64_t)(ed.n + 2 * d + 2) < top) { status = 3; return 0; }
-        while (d > 0) {
-            const int32_t *pr = A + rowtab[d - 1];
-            int32_t new_diag, new_seq2_index;
-            // s_GetNextNonAffineTback (:267-286)
-            if (pr[best_diag - 1] > max(pr[best_diag], pr[best_diag + 1])) { new_seq2_index = pr[best_diag - 1]; new_diag = best_diag - 1; }
-            else if (pr[best_diag] > pr[best_diag + 1]) { new_seq2_index = pr[best_diag]; new_diag = best_diag; }
-            else { new_seq2_index = pr[best_diag + 1]; new_diag = best_diag + 1; }
-            if (new_diag == best_diag) {
-                if (seq2_index - new_seq2_index > 0) ed.add(3, seq2_index - new_seq2_index);
-            } else if (new_diag < best_diag) {
-                if (seq2_index - new_seq2_index > 0) ed.add(3, seq2_index - new_seq2_index);
-                ed.add(6, 1);
-            } else {
-                if (seq2_index - new_seq2_index - 1 > 0) ed.add(3, seq2_index - new_seq2_index - 1);
-                ed.add(0, 1);
-            }
-            d--;
-            best_diag = new_diag;
-            seq2_index = new_seq2_index;
-        }
-        ed.add(3, first_run);       // last_seq2_off[0][diag_origin]
-    }
-    return best_dist;
-}
 
 // s_ReduceGaps (core/blast_gapalign.c:2545-2617) on {op[], num[]}; returns the new size
 __device__ int32_t reduce_gaps(const DevQuery &q, const uint8_t *packed, int32_t ctx_off, int32_t qi, int64_t si,
@@ -554,74 +431,6 @@ __device__ int32_t reduce_gaps(const DevQuery &q, const uint8_t *packed, int32_t
 }
 
 }  // namespace
-
-__global__ void __launch_bounds__(32)
-traceback_greedy_kernel(const DevQuery q, const TracebackLaunch L)
-{
-    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
-    const int64_t cap = L.arena_bytes / 4 / nt;                 // ints per thread
-    int32_t *A = reinterpret_cast<int32_t *>(L.arena) + t0 * cap;
-    int32_t match = q.reward, mismatch = -q.penalty, xd = L.x_dropoff;
-    if (match % 2 == 1) { match *= 2; mismatch *= 2; xd *= 2; }
-    for (int64_t w = t0; w < L.n; w += nt) {
-        if (L.todo && !L.todo[w]) continue;
-        const DevTracebackItem it = L.items[w];
-        const DevContext c = q.ctx[it.context];
-        const int32_t q_length = c.query_length, s_length = it.s_length;
-        const int32_t q_off = it.q_start, s_off = it.s_start;
-        const int64_t seq_base = it.byte_off * 4 + it.s_shift;          // volume base of the subject window
-        DevTracebackDir out, out2;
-        out.score = 0; out.a_off = 0; out.b_off = 0; out.ops_off = 0; out.n_ops = 0; out.status = 0; out.ran = 1; out.pad = 0;
-        out2 = out;
-        int status = 0;
-        int32_t q_ext_r = 0, s_ext_r = 0, q_ext_l = 0, s_ext_l = 0;
-        OpList fwd, rev;
-        fwd.top = A + cap; fwd.n = 0; fwd.last_op = 8;                  // eGapAlignInvalid
-        GreedyTbSeq sp;
-        sp.q = &q; sp.packed = L.packed;
-        // extend to the right
-        sp.qbase = c.query_offset + q_off; sp.sbase = seq_base + s_off;
-        sp.len1 = q_length - q_off; sp.len2 = s_length - s_off; sp.reverse = false;
-        int32_t dist = greedy_align_tb(sp, xd, match, mismatch, q_ext_r, s_ext_r, A, cap, fwd, status);
-        if (!status) {
-            // extend to the left
-            rev.top = fwd.top - 2 * fwd.n; rev.n = 0; rev.last_op = 8;
-            sp.qbase = c.query_offset; sp.sbase = seq_base; sp.len1 = q_off; sp.len2 = s_off; sp.reverse = true;
-            dist += greedy_align_tb(sp, xd, match, mismatch, q_ext_l, s_ext_l, A, (int64_t)(rev.top - A), rev, status);
-        }
-        if (!status) {
-            const int32_t score = (q_ext_r + s_ext_r + q_ext_l + s_ext_l) * q.reward / 2 - dist * (q.reward - q.penalty);
-            // Blast_PrelimEditBlockToGapEditScript into A[0 ..): {op, num} pairs
-            int32_t size = fwd.n + rev.n;
-            const bool merge = fwd.n > 0 && rev.n > 0 && fwd.op(fwd.n - 1) == rev.op(rev.n - 1);
-            if (merge) size--;
-            if (2 * (int64_t)size + 2 > (int64_t)(rev.top - 2 * rev.n - A)) status = 3;
-            else {
-                int32_t *op = A, *num = A + size + 1;
-                int32_t idx = 0;
-                for (int32_t i = 0; i < rev.n; i++) { op[idx] = rev.op(i); num[idx] = rev.num(i); idx++; }
-                if (fwd.n > 0) {
-                    int32_t i = fwd.n - 1;
-                    if (merge) { num[idx - 1] += fwd.num(fwd.n - 1); i = fwd.n - 2; }
-                    for (; i >= 0; i--) { op[idx] = fwd.op(i); num[idx] = fwd.num(i); idx++; }
-                }
-                size = reduce_gaps(q, L.packed, c.query_offset, q_off - q_ext_l, seq_base + s_off - s_ext_l, op, num, size);
-                const unsigned long long base = atomicAdd(L.ops_used, (unsigned long long)size);
-                if ((long long)(base + size) > L.ops_cap) status = 4;
-                else {
-                    for (int32_t i = 0; i < size; i++) L.ops[base + i] = make_int2(op[i], num[i]);
-                    out.ops_off = (long long)base; out.n_ops = size;
-                }
-                out.score = score;
-                out.a_off = q_ext_l; out.b_off = s_ext_l;       // left extents
-                out2.a_off = q_ext_r; out2.b_off = s_ext_r;     // right extents
-            }
-        }
-        out.status = status; out2.status = status;
-        L.out[2 * w] = out;
-        L.out[2 * w + 1] = out2;
-    }
-}
 
 // ---- warp-parallel greedy with traceback -----------------------------------------------------------------------
 // One warp per alignment, one lane per diagonal of the current distance (the formulation of greedy_align_warp in
@@ -898,11 +707,6 @@ cudaError_t launch_traceback_greedy_warp(const DevQuery &q, const TracebackLaunc
     return cudaGetLastError();
 }
 
-cudaError_t launch_traceback_greedy(const DevQuery &q, const TracebackLaunch &L, int blocks, cudaStream_t st)
-{
-    traceback_greedy_kernel<<<blocks, 32, 0, st>>>(q, L);
-    return cudaGetLastError();
-}
 
 // ================================================================================================
 // Start point of the traceback alignment, one thread per HSP: the head of Blast_TracebackFromHSPList's loop body
