@@ -399,6 +399,7 @@ struct DevTracebackPostOut {
 cudaError_t launch_traceback_reevaluate(const DevQuery &q, const uint8_t *packed, const DevTracebackPost *items, int64_t n,
                                         int2 *ops, DevTracebackPostOut *out, cudaStream_t st);
 cudaError_t launch_traceback_greedy_warp(const DevQuery &q, const TracebackLaunch &L, int blocks, cudaStream_t st);
+cudaError_t launch_traceback_greedy_affine(const DevQuery &q, const TracebackLaunch &L, int blocks, int threads_per_block, cudaStream_t st);
 int traceback_warps_per_block();
 
 }  // namespace bn

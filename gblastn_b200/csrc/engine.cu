@@ -1187,12 +1187,16 @@ static int traceback_greedy_host(Device &Dv, Volume &V, Query &Q, int32_t x_drop
     long long per_thread = 256ll << 10;
     int64_t left = n_items;
     for (int attempt = 0; left > 0; attempt++) {
-        if (attempt == 8) return fail(BN_ERR_OVERFLOW, "bn_gapped_traceback: greedy traceback scratch exhausted");
+        // 256 KB, 4 MB, 64 MB, 1 GB per alignment in flight; never more than the 4 GB budget in total
+        if (attempt == 4) return fail(BN_ERR_OVERFLOW, "bn_gapped_traceback: greedy traceback scratch exhausted");
         const long long budget = 4ll << 30;
         // one WARP per alignment (traceback_greedy_warp_kernel, 4 warps per block), each with a private arena
-        int64_t threads = std::min<int64_t>(std::min<int64_t>(left, 148 * 16), std::max<long long>(budget / per_thread, 1));
-        const int blocks = (int)((threads + 3) / 4);
-        threads = (int64_t)blocks * 4;
+        // affine costs (BLAST_AffineGreedyAlign's own body): one thread per alignment, 32 per block
+        const bool affine = Q.batch.gap_open != 0 || Q.batch.gap_extend != 0;
+        const int per_block = affine ? (per_thread >= (64ll << 20) ? 1 : 32) : 4;
+        int64_t threads = std::min<int64_t>(std::min<int64_t>(left, affine ? 8192 : 148 * 16), std::max<long long>(budget / per_thread, 1));
+        const int blocks = (int)((threads + per_block - 1) / per_block);
+        threads = (int64_t)blocks * per_block;
         const long long arena_bytes = threads * per_thread;
         if (d_arena) { cudaFreeAsync(d_arena, st); d_arena = nullptr; }
         if (d_ops) { cudaFreeAsync(d_ops, st); d_ops = nullptr; }
@@ -1204,7 +1208,7 @@ static int traceback_greedy_host(Device &Dv, Volume &V, Query &Q, int32_t x_drop
         L.packed = V.d_packed; L.items = d_items; L.n = n_items; L.x_dropoff = x_dropoff;
         L.arena = d_arena; L.arena_bytes = arena_bytes; L.arena_used = d_cnt;
         L.ops = d_ops; L.ops_cap = ops_cap; L.ops_used = d_cnt + 1; L.out = d_out; L.todo = d_todo;
-        CU_TRY(launch_traceback_greedy_warp(dq, L, blocks, st));
+        CU_TRY(affine ? launch_traceback_greedy_affine(dq, L, blocks, per_block, st) : launch_traceback_greedy_warp(dq, L, blocks, st));
         unsigned long long used[2] = {0, 0};
         CU_TRY(cudaMemcpyAsync(pass.data(), d_out, pass.size() * sizeof(DevTracebackDir), cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaMemcpyAsync(used, d_cnt, sizeof used, cudaMemcpyDeviceToHost, st));
@@ -1773,8 +1777,6 @@ static int traceback_core(Device *D, Volume *V, Query *Q, int32_t gap_x_dropoff_
     // the caller holds D->mu and has made the device current
     *results = nullptr; *ops = nullptr; *n_ops = 0;
     const bool greedy = Q->batch.gap_algo == BN_GAP_GREEDY;
-    if (greedy && (Q->batch.gap_open != 0 || Q->batch.gap_extend != 0))
-        return fail(BN_ERR_UNSUPPORTED, "bn_gapped_traceback: affine greedy traceback is not built yet");
     if (!greedy && Q->batch.gap_extend <= 0)
         return fail(BN_ERR_UNSUPPORTED, "bn_gapped_traceback: dynamic programming needs gap_extend > 0");
     if (!Q->dev[V->device].ready) return fail(BN_ERR_INVALID, "query batch is not loaded on the volume's device");
@@ -1800,7 +1802,7 @@ static int traceback_core(Device *D, Volume *V, Query *Q, int32_t gap_x_dropoff_
     // arena: row tables (12 B per query row) + script rows (band width ~ 2 (X / gap_extend) + slack) + run lists
     const int32_t xd = std::max(gap_x_dropoff_final, Q->batch.gap_open + Q->batch.gap_extend);
     const long long band = 2ll * (xd / Q->batch.gap_extend + 3) + 32;
-    long long arena_bytes = rows * (12 + band + 8) + 2 * n_items * (256ll << 10);
+    long long arena_bytes = 2 * rows * (12 + band + 8) + 2 * n_items * 8192ll + (16ll << 20);
     long long ops_cap = rows / 2 + 64 * n_items;
 
     DevTracebackItem *d_items = nullptr;

@@ -76,6 +76,9 @@ __device__ int32_t align_ex_warp(const TracebackLaunch &L, const uint8_t *qp, in
     const uint32_t lt = (1u << lane) - 1u;
     const int32_t num_extra = x_dropoff / ge + 3;
     uint8_t *arena = L.arena;
+    // rows are taken from the arena in chunks: about what the whole extension needs (M rows of a band of ~2 X / ge
+    // cells), between 2 KB (a short read) and ROW_CHUNK
+    const long long chunk = min(ROW_CHUNK, max(2048ll, ((long long)M + 2) * (2 * num_extra + 40)));
 
     // row 0: cell 0 = (0, -goe); cells i >= 1 = (-goe - (i-1) ge, that - goe) while the score is >= -X; script GAP_IN_A
     int32_t b_size;
@@ -84,10 +87,10 @@ __device__ int32_t align_ex_warp(const TracebackLaunch &L, const uint8_t *qp, in
         if (k + 2 >= C) { status = 1; return 0; }
         if (rs.cur + k + 2 > rs.end) {
             long long at = 0;
-            if (lane == 0) at = arena_alloc(L, ROW_CHUNK);
+            if (lane == 0) at = arena_alloc(L, chunk);
             at = __shfl_sync(FULLW, at, 0);
             if (at < 0) { status = 3; return 0; }
-            rs.cur = at; rs.end = at + ROW_CHUNK;
+            rs.cur = at; rs.end = at + chunk;
         }
         for (int32_t i = lane; i <= k; i += 32) {
             const int32_t sc = (i == 0) ? 0 : -goe - (i - 1) * ge;
@@ -109,7 +112,7 @@ __device__ int32_t align_ex_warp(const TracebackLaunch &L, const uint8_t *qp, in
             const long long need = (long long)(b_size - row_first) + num_extra + 3;
             if (rs.cur + need > rs.end) {
                 long long at = 0;
-                const long long sz = need > ROW_CHUNK ? need : ROW_CHUNK;
+                const long long sz = need > chunk ? need : chunk;
                 if (lane == 0) at = arena_alloc(L, sz);
                 at = __shfl_sync(FULLW, at, 0);
                 if (at < 0) { status = 3; return 0; }
@@ -699,6 +702,255 @@ traceback_greedy_warp_kernel(const DevQuery q, const TracebackLaunch L)
         }
         __syncwarp();
     }
+}
+
+// ---- affine greedy with traceback (BLAST_AffineGreedyAlign body with an edit block, core/greedy_align.c:817-1237;
+// s_GetNextAffineTbackFromMatch :150-182, s_GetNextAffineTbackFromIndel :201-262).  One THREAD per alignment (the
+// option is off in every blastn task default); every row {insert, match, delete} x diagonal is kept. ------------------
+namespace {
+
+__device__ int32_t greedy_align_affine_tb(const GreedyTbSeq &sp, const AffineCosts &ac, int32_t &seq1_len, int32_t &seq2_len,
+                                          int32_t *A, int64_t cap, OpList &ed, int &status)
+{
+    const int32_t kInvalidDiag = 100000000;
+    const int32_t len1 = sp.len1, len2 = sp.len2;
+    const int32_t match_half = ac.match / 2;
+    const int32_t op_cost = ac.op_cost, gap_open = ac.gap_open, gap_extend = ac.gap_extend, goe = ac.gap_open + ac.gap_extend;
+    const int32_t max_penalty = ac.max_penalty;
+    const int32_t max_dist = min(GREEDY_MAX_COST, len2 / 2 + 1);
+    const int64_t scaled_max_dist = (int64_t)max_dist * gap_extend;
+    const int32_t origin = max_dist + 2;
+
+    int32_t index = tb_first_mismatch(sp, 0, 0);
+    seq1_len = index; seq2_len = index;
+    int32_t seq1_index = index, seq2_index;
+    const int32_t first_run = index;
+    if (index == len1 || index == len2) { ed.add(3, index); return index * ac.match; }
+
+    // tables for distances 0 .. Tn-1: row table, diagonal bounds (max_penalty negative slots in front), best scores
+    const int64_t Tmin = (int64_t)max_penalty + ac.xdrop_offset + 4;       // what the shortest extension already needs
+    const int64_t Tn = min(scaled_max_dist + Tmin, cap / 16);
+    if (Tn < Tmin || cap < 256) { status = 3; return 0; }
+    int32_t *rowtab = A;
+    int32_t *diag_lower = A + Tn + max_penalty;
+    int32_t *diag_upper = diag_lower + Tn + max_penalty;
+    int32_t *max_score_mem = diag_upper + Tn;
+    int32_t *max_score = max_score_mem + ac.xdrop_offset;
+    int64_t top = 4 * Tn + 2 * max_penalty + ac.xdrop_offset + 1;
+    auto alloc_row = [&](int64_t d, int32_t lo, int32_t hi) -> bool {      // row d addressable on diagonals [lo, hi]
+        const int64_t w = hi >= lo ? 3 * ((int64_t)hi - lo + 1) : 0;
+        if (d >= Tn || top + w > cap) return false;
+        rowtab[d] = (int32_t)(top - 3 * (int64_t)lo);
+        top += w;
+        return true;
+    };
+#define AFF(dd, kk, f) A[(int64_t)rowtab[(dd)] + 3 * (int64_t)(kk) + (f)]       // f: 0 insert, 1 match, 2 delete
+    if (top >= cap) { status = 3; return 0; }
+    for (int32_t i = 0; i < ac.xdrop_offset; i++) max_score_mem[i] = 0;
+    for (int32_t i = 1; i <= max_penalty; i++) { diag_lower[-i] = kInvalidDiag; diag_upper[-i] = -kInvalidDiag; }
+    for (int32_t dd = 0; dd <= max_penalty; dd++)
+        if (!alloc_row(dd, origin - max_penalty - 3, origin + max_penalty + 3)) { status = 3; return 0; }
+    AFF(0, origin, 1) = seq1_index;
+    AFF(0, origin, 0) = GREEDY_INVALID;
+    AFF(0, origin, 2) = GREEDY_INVALID;
+    max_score[0] = seq1_index * ac.match;
+    diag_lower[0] = origin; diag_upper[0] = origin;
+    int32_t curr_lower = origin - 1, curr_upper = origin + 1;
+    int32_t end1_diag = 0, end2_diag = 0, num_nonempty = 1;
+    int32_t best_dist = 0, best_diag = 0;
+    int64_t d = 1;
+
+    while (d <= scaled_max_dist) {
+        if (d + ac.xdrop_offset + 1 >= Tn) { status = 3; return 0; }
+        int32_t curr_extent = 0, curr_seq2_index = 0, curr_diag = 0;
+        const int32_t tmp_lower = curr_lower, tmp_upper = curr_upper;
+        int32_t xdrop_score = max_score[d - ac.xdrop_offset] + ac.common_factor * (int32_t)d - ac.xdrop;
+        {
+            int32_t qd = xdrop_score / match_half;
+            if (xdrop_score % match_half > 0) ++qd;
+            xdrop_score = qd < 0 ? 0 : qd;
+        }
+        const int32_t lo_goe = diag_lower[d - goe], up_goe = diag_upper[d - goe];
+        const int32_t lo_ge = diag_lower[d - gap_extend], up_ge = diag_upper[d - gap_extend];
+        const int32_t lo_op = diag_lower[d - op_cost], up_op = diag_upper[d - op_cost];
+        for (int32_t k = tmp_lower; k <= tmp_upper; k++) {
+            seq2_index = GREEDY_INVALID;
+            if (k + 1 <= up_goe && k + 1 >= lo_goe) seq2_index = AFF(d - goe, k + 1, 1);
+            if (k + 1 <= up_ge && k + 1 >= lo_ge) {
+                const int32_t v = AFF(d - gap_extend, k + 1, 2);
+                if (seq2_index < v) seq2_index = v;
+            }
+            const int32_t del = (seq2_index == GREEDY_INVALID) ? GREEDY_INVALID : seq2_index + 1;
+            AFF(d, k, 2) = del;
+            seq2_index = GREEDY_INVALID;
+            if (k - 1 <= up_goe && k - 1 >= lo_goe) seq2_index = AFF(d - goe, k - 1, 1);
+            if (k - 1 <= up_ge && k - 1 >= lo_ge) {
+                const int32_t v = AFF(d - gap_extend, k - 1, 0);
+                if (seq2_index < v) seq2_index = v;
+            }
+            AFF(d, k, 0) = seq2_index;
+            seq2_index = max(seq2_index, del);
+            if (k <= up_op && k >= lo_op) seq2_index = max(seq2_index, AFF(d - op_cost, k, 1) + 1);
+            seq1_index = seq2_index + k - origin;
+            if (seq2_index < 0 || seq1_index + seq2_index < xdrop_score) {
+                if (k == curr_lower) curr_lower++;
+                else AFF(d, k, 1) = GREEDY_INVALID;
+                continue;
+            }
+            curr_upper = k;
+            index = tb_first_mismatch(sp, seq1_index, seq2_index);
+            seq1_index += index; seq2_index += index;
+            AFF(d, k, 1) = seq2_index;
+            if (seq1_index + seq2_index > curr_extent) {
+                curr_extent = seq1_index + seq2_index;
+                curr_seq2_index = seq2_index;
+                curr_diag = k;
+            }
+            if (seq1_index == len1) { curr_upper = k; end1_diag = k - 1; }
+            if (seq2_index == len2) { curr_lower = k; end2_diag = k + 1; }
+        }
+        const int32_t curr_score = curr_extent * match_half - (int32_t)d * ac.common_factor;
+        if (curr_score > max_score[d - 1]) {
+            max_score[d] = curr_score;
+            best_dist = (int32_t)d;
+            best_diag = curr_diag;
+            seq2_len = curr_seq2_index;
+            seq1_len = curr_seq2_index + curr_diag - origin;
+        } else max_score[d] = max_score[d - 1];
+        if (curr_lower <= curr_upper) {
+            num_nonempty++;
+            diag_lower[d] = curr_lower; diag_upper[d] = curr_upper;
+        } else { diag_lower[d] = kInvalidDiag; diag_upper[d] = -kInvalidDiag; }
+        if (diag_lower[d - max_penalty] <= diag_upper[d - max_penalty]) num_nonempty--;
+        if (num_nonempty == 0) break;
+        d++;
+        if (d >= Tn) { if (d <= scaled_max_dist) { status = 3; return 0; } break; }
+        curr_lower = min(diag_lower[d - goe], diag_lower[d - gap_extend]) - 1;
+        curr_lower = min(curr_lower, diag_lower[d - op_cost]);
+        if (end2_diag > 0) curr_lower = max(curr_lower, end2_diag);
+        curr_upper = max(diag_upper[d - goe], diag_upper[d - gap_extend]) + 1;
+        curr_upper = max(curr_upper, diag_upper[d - op_cost]);
+        if (end1_diag > 0) curr_upper = min(curr_upper, end1_diag);
+        if (d > max_penalty && !alloc_row(d, curr_lower, curr_upper)) { status = 3; return 0; }
+    }
+    // ---- traceback (:1178-1232) ---------------------------------------------------------------------------------
+    {
+        int32_t dd = best_dist;
+        seq2_index = seq2_len;
+        int32_t state = 3;
+        if ((int64_t)(ed.top - A) - 2 * (int64_t)(ed.n + 2 * (int64_t)dd + 4) < top) { status = 3; return 0; }
+        while (dd > 0) {
+            if (state == 3) {       // s_GetNextAffineTbackFromMatch
+                int32_t new_seq2_index;
+                bool took = false;
+                if (best_diag >= diag_lower[dd - op_cost] && best_diag <= diag_upper[dd - op_cost]) {
+                    new_seq2_index = AFF(dd - op_cost, best_diag, 1);
+                    if (new_seq2_index >= max(AFF(dd, best_diag, 0), AFF(dd, best_diag, 2))) {
+                        dd -= op_cost;
+                        state = 3;
+                        took = true;
+                    }
+                }
+                if (!took) {
+                    if (AFF(dd, best_diag, 0) > AFF(dd, best_diag, 2)) { new_seq2_index = AFF(dd, best_diag, 0); state = 6; }
+                    else { new_seq2_index = AFF(dd, best_diag, 2); state = 0; }
+                }
+                ed.add(3, seq2_index - new_seq2_index);
+                seq2_index = new_seq2_index;
+            } else {                // s_GetNextAffineTbackFromIndel
+                const int32_t IorD = state;
+                ed.add(IorD, 1);
+                const int32_t new_diag = (IorD == 6) ? best_diag - 1 : best_diag + 1;
+                int32_t last_d = dd - gap_extend, new_seq2_index;
+                if (new_diag >= diag_lower[last_d] && new_diag <= diag_upper[last_d])
+                    new_seq2_index = (IorD == 6) ? AFF(last_d, new_diag, 0) : AFF(last_d, new_diag, 2);
+                else new_seq2_index = GREEDY_INVALID;
+                last_d = dd - goe;
+                if (new_diag >= diag_lower[last_d] && new_diag <= diag_upper[last_d] &&
+                    new_seq2_index < AFF(last_d, new_diag, 1)) { dd -= goe; state = 3; }
+                else { dd -= gap_extend; state = IorD; }
+                if (IorD == 6) best_diag--;
+                else { best_diag++; seq2_index--; }
+            }
+        }
+        ed.add(3, first_run);       // last_seq2_off[0][diag_origin].match_off
+    }
+#undef AFF
+    (void)gap_open;
+    return max_score[best_dist];
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(32)
+traceback_greedy_affine_kernel(const DevQuery q, const TracebackLaunch L)
+{
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+    const int64_t cap = L.arena_bytes / 4 / nt;
+    int32_t *A = reinterpret_cast<int32_t *>(L.arena) + t0 * cap;
+    const AffineCosts ac = affine_costs(q.reward, q.penalty, q.gap_open, q.gap_extend, L.x_dropoff);
+    for (int64_t w = t0; w < L.n; w += nt) {
+        if (L.todo && !L.todo[w]) continue;
+        const DevTracebackItem it = L.items[w];
+        const DevContext c = q.ctx[it.context];
+        const int32_t q_length = c.query_length, s_length = it.s_length;
+        const int32_t q_off = it.q_start, s_off = it.s_start;
+        const int64_t seq_base = it.byte_off * 4 + it.s_shift;
+        DevTracebackDir out, out2;
+        out.score = 0; out.a_off = 0; out.b_off = 0; out.ops_off = 0; out.n_ops = 0; out.status = 0; out.ran = 1; out.pad = 0;
+        out2 = out;
+        int status = 0;
+        int32_t q_ext_r = 0, s_ext_r = 0, q_ext_l = 0, s_ext_l = 0;
+        OpList fwd, rev;
+        fwd.top = A + cap; fwd.n = 0; fwd.last_op = 8;
+        rev = fwd;
+        GreedyTbSeq sp;
+        sp.q = &q; sp.packed = L.packed;
+        sp.qbase = c.query_offset + q_off; sp.sbase = seq_base + s_off;
+        sp.len1 = q_length - q_off; sp.len2 = s_length - s_off; sp.reverse = false;
+        int32_t score = greedy_align_affine_tb(sp, ac, q_ext_r, s_ext_r, A, cap, fwd, status);
+        if (!status) {
+            rev.top = fwd.top - 2 * fwd.n; rev.n = 0; rev.last_op = 8;
+            sp.qbase = c.query_offset; sp.sbase = seq_base; sp.len1 = q_off; sp.len2 = s_off; sp.reverse = true;
+            score += greedy_align_affine_tb(sp, ac, q_ext_l, s_ext_l, A, (int64_t)(rev.top - A), rev, status);
+        }
+        if (!status) {
+            if (q.reward % 2 == 1) score /= 2;
+            int32_t size = fwd.n + rev.n;
+            const bool merge = fwd.n > 0 && rev.n > 0 && fwd.op(fwd.n - 1) == rev.op(rev.n - 1);
+            if (merge) size--;
+            if (2 * (int64_t)size + 2 > (int64_t)(rev.top - 2 * rev.n - A)) status = 3;
+            else {
+                int32_t *op = A, *num = A + size + 1;
+                int32_t idx = 0;
+                for (int32_t i = 0; i < rev.n; i++) { op[idx] = rev.op(i); num[idx] = rev.num(i); idx++; }
+                if (fwd.n > 0) {
+                    int32_t i = fwd.n - 1;
+                    if (merge) { num[idx - 1] += fwd.num(fwd.n - 1); i = fwd.n - 2; }
+                    for (; i >= 0; i--) { op[idx] = fwd.op(i); num[idx] = fwd.num(i); idx++; }
+                }
+                size = reduce_gaps(q, L.packed, c.query_offset, q_off - q_ext_l, seq_base + s_off - s_ext_l, op, num, size);
+                const unsigned long long base = atomicAdd(L.ops_used, (unsigned long long)size);
+                if ((long long)(base + size) > L.ops_cap) status = 4;
+                else {
+                    for (int32_t i = 0; i < size; i++) L.ops[base + i] = make_int2(op[i], num[i]);
+                    out.ops_off = (long long)base; out.n_ops = size;
+                }
+                out.score = score;
+                out.a_off = q_ext_l; out.b_off = s_ext_l;
+                out2.a_off = q_ext_r; out2.b_off = s_ext_r;
+            }
+        }
+        out.status = status; out2.status = status;
+        L.out[2 * w] = out;
+        L.out[2 * w + 1] = out2;
+    }
+}
+
+cudaError_t launch_traceback_greedy_affine(const DevQuery &q, const TracebackLaunch &L, int blocks, int threads_per_block, cudaStream_t st)
+{
+    traceback_greedy_affine_kernel<<<blocks, threads_per_block, 0, st>>>(q, L);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_traceback_greedy_warp(const DevQuery &q, const TracebackLaunch &L, int blocks, cudaStream_t st)

@@ -279,9 +279,10 @@ void bn_free(void *p);
  * volume (no ambiguity data: the blastna byte of a base is its 2-bit code).
  * Results mirror BlastGapAlignStruct after the call: score, query_start/stop, subject_start/stop (relative to the
  * window) and gap_align->edit_script as ops[esp_off .. esp_off + esp_n) with op_type = EGapAlignOpType
- * (0 eGapAlignDel, 3 eGapAlignSub, 6 eGapAlignIns; inc-core/gapinfo.h:44-54).  Greedy traceback
- * (BLAST_GreedyGappedAlignment with do_traceback) is not built yet: batches with gap_extend == 0 are refused
- * with BN_ERR_UNSUPPORTED.  Free both arrays with bn_free. */
+ * (0 eGapAlignDel, 3 eGapAlignSub, 6 eGapAlignIns; inc-core/gapinfo.h:44-54).  When the batch's gap_algo is
+ * BN_GAP_GREEDY the routine is BLAST_GreedyGappedAlignment with do_traceback (core/blast_gapalign.c:2620-2751:
+ * BLAST_GreedyAlign, or BLAST_AffineGreedyAlign's own body when gap costs are given, then s_ReduceGaps), as the
+ * reference calls it with eGreedyTbck (core/blast_traceback.c:559-563).  Free both arrays with bn_free. */
 typedef struct BnTracebackItem {
     int32_t oid, context;
     int32_t s_shift, s_length;

@@ -89,7 +89,8 @@ TRACEBACK_DP_CASES = ["blastn_mb11_dp", "blastn_smallna_dp", "blastn_ws7_array",
                       "c3_scaled_blastn_10kb", "blastn_bridged_segments", "blastn_ws7_na_table"]
 TRACEBACK_GREEDY_CASES = ["c1_megablast_10kb_vs_1mb", "mb_lut11_hash_indels", "mb_smallna_diagarray", "mb_ws16", "mb_with_N",
                           "blastn_ws11_greedy", "mb_ntlike_many_subjects", "mb_long_divergent_tier2", "mb_lut12_stride17",
-                          "c4_scaled_short_reads", "c5_scaled_ntlike_5kb", "mb_bridged_segments", "mb_two_hit_w40_hash"]
+                          "c4_scaled_short_reads", "c5_scaled_ntlike_5kb", "mb_bridged_segments", "mb_two_hit_w40_hash",
+                          "mb_affine_greedy_5_2", "blastn_affine_greedy_5_2", "mb_affine_greedy_long_tier2", "mb_affine_greedy_0_2"]
 
 
 @pytest.mark.parametrize("name", TRACEBACK_DP_CASES + TRACEBACK_GREEDY_CASES)
@@ -281,7 +282,8 @@ def _random_start_items(r, vol, rng, per_hsp=3, max_hsps=60):
 
 
 @pytest.mark.parametrize("name", ["blastn_mb11_dp", "c3_scaled_blastn_10kb", "blastn_ws7_array", "mb_lut11_hash_indels",
-                                  "c5_scaled_ntlike_5kb", "blastn_ws11_greedy", "mb_with_N"])
+                                  "c5_scaled_ntlike_5kb", "blastn_ws11_greedy", "mb_with_N", "mb_affine_greedy_5_2",
+                                  "blastn_affine_greedy_5_2", "mb_affine_greedy_0_2"])
 def test_gapped_traceback_random_starts(name):
     """Differential test on start points the search itself never produces: points anywhere inside real HSPs
     (off the optimal diagonal, in narrow subject windows) and the corners of both sequences, against the
