@@ -924,6 +924,21 @@ void traceback_list_stage1(const BnQueryBatch &b, int32_t subject_length, const 
     arr.clear();
     extra_start = 0;
     if (n == 0) return;
+    if (n == 1) {       // a list of one HSP (the usual case for short reads): nothing to be contained in, nothing to purge
+        const TbCand &c = cand[0];
+        if (!c.has_start) return;
+        TbHsp h{};
+        h.alive = true; h.was_cut = false;
+        h.oid = c.pre.oid; h.context = c.pre.context;
+        h.score = c.res.score;
+        h.q_off = c.res.query_start; h.q_end = c.res.query_stop;
+        h.s_off = c.res.subject_start + c.s_shift; h.s_end = c.res.subject_stop + c.s_shift;
+        h.q_gapped_start = c.q_start; h.s_gapped_start = c.s_start + c.s_shift;
+        h.esp.assign(c.ops, c.ops + c.res.esp_n);
+        arr.push_back(std::move(h));
+        extra_start = 1;
+        return;
+    }
     IntervalTree tree(0, b.concat_len + 1, 0, subject_length + 1, n);
     for (size_t i = 0; i < n; i++) {
         const TbCand &c = cand[i];
@@ -1032,7 +1047,7 @@ void traceback_list_stage2(const BnQueryBatch &b, int32_t subject_length, std::v
     arr.resize(o);
     if (arr.empty()) return;
     std::stable_sort(arr.begin(), arr.end(), tb_score_less);
-    {   // containment among the final alignments (:741-760)
+    if (arr.size() > 1) {   // containment among the final alignments (:741-760); a single HSP meets an empty tree
         IntervalTree tree(0, b.concat_len + 1, 0, subject_length + 1, arr.size());
         for (TbHsp &h : arr) {
             IntervalTree::Item t{strand_offset(b, h.context), h.q_off, h.q_end, h.s_off, h.s_end, h.score};

@@ -44,3 +44,11 @@ if which in ("all", "c3"):
     vol = synth.random_volume([25_000_000] * 4, seed=3)
     qs = synth.planted_queries(vol, 20, 10_000, seed=33, planted_frac=0.8, sub_rate=0.08, indel_rate=0.01)
     run("C3-shaped blastn 20x10kb vs 100Mb", "blastn", vol, qs)
+if which in ("c4",):
+    vol = synth.random_volume([50_000_000] * 4, seed=40)
+    qs = synth.planted_queries(vol, 20_000, 150, seed=44, planted_frac=0.8, sub_rate=0.02, indel_rate=0.0)
+    run("C4-shaped megablast 20000x150bp vs 200Mb", "megablast", vol, qs)
+if which in ("c5",):
+    vol = synth.random_volume(np.clip(np.exp(np.random.default_rng(5).normal(np.log(2000), 1.1, size=60_000)), 50, 400_000).astype(np.int64), seed=50)
+    qs = synth.planted_queries(vol, 500, 5000, seed=55, planted_frac=0.8, sub_rate=0.02, indel_rate=0.002)
+    run("C5-shaped megablast 500x5kb vs nt-like 60k sequences", "megablast", vol, qs)
