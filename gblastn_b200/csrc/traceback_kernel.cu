@@ -23,6 +23,7 @@ namespace {
 constexpr unsigned FULLW = 0xffffffffu;
 constexpr int TB_WARPS = 4;               // warps per block
 constexpr int TB_CELLS = 1024;            // band cells per warp kept in shared memory (power of two)
+constexpr int TBK = 4;                    // band cells per lane in a row segment
 constexpr int32_t MININT = INT32_MIN / 2;
 constexpr int32_t NEGINF = INT32_MIN / 2 - (1 << 24);
 
@@ -126,68 +127,129 @@ __device__ int32_t align_ex_warp(const TracebackLaunch &L, const uint8_t *qp, in
         bool lead = true;
         const int32_t row_end = b_size;
 
-        for (int32_t seg = row_first; seg < row_end; seg += 32) {
-            const int32_t b = seg + lane;
-            const bool active = b < row_end;
-            const uint32_t amask = __ballot_sync(FULLW, active);
-            const int2 cell = active ? ring[b & MASK] : make_int2(MININT, MININT);
-            int32_t up = __shfl_up_sync(FULLW, cell.x, 1);
-            if (lane == 0) up = prev_old_best;
-            prev_old_best = __shfl_sync(FULLW, cell.x, 31);
-            int32_t v = NEGINF, d = MININT;
-            if (active) {
-                if (b != row_first) d = up + mrow[sbase64(S, s0 + (int64_t)b * s_inc)];
-                v = max(d, cell.y);
+        // TBK consecutive cells per lane: a segment is 32 TBK cells (the usual band fits in one), the two prefix
+        // maxima run over per-lane partial results, the cells of a lane are chained in registers
+        for (int32_t seg = row_first; seg < row_end; seg += 32 * TBK) {
+            const int32_t b0 = seg + lane * TBK;
+            int2 cell[TBK];
+            bool act[TBK];
+            uint32_t amask[TBK], p[TBK];
+            int32_t v[TBK], dg[TBK];
+#pragma unroll
+            for (int j = 0; j < TBK; j++) {
+                act[j] = b0 + j < row_end;
+                cell[j] = act[j] ? ring[(b0 + j) & MASK] : make_int2(MININT, MININT);
+                amask[j] = __ballot_sync(FULLW, act[j]);
             }
-            // ---- fixed point over the prune flags (see gapped_kernel.cu) ---------------------------------
-            uint32_t p = __ballot_sync(FULLW, active && (best_in - v > x_dropoff));
-            int32_t s = v, R = r_in;
-            for (;;) {
-                const uint32_t um = amask & ~p;
-                const bool unpruned = (um >> lane) & 1u;
-                const int32_t u = __popc(um & lt);
-                const int32_t w = unpruned ? v - goe + ge * (u + 1) : NEGINF;
-                R = max(r_in, excl_prefix_max(w, lane)) - ge * u;
-                s = max(v, R);
-                const int32_t best_b = max(best_in, excl_prefix_max(unpruned ? s : NEGINF, lane));
-                const uint32_t pn = __ballot_sync(FULLW, active && (best_b - s > x_dropoff));
-                if (pn == p) break;
-                p = pn;
-            }
-            const uint32_t um = amask & ~p;
-            const bool unpruned = (um >> lane) & 1u;
-            // ---- script byte of the cell (core/blast_gapalign.c:560-612) ---------------------------------
-            if (active) {
-                // script = SUB; if (score < gap_col) GAP_IN_B; if (score < gap_row) GAP_IN_A
-                uint8_t op = (v < R) ? SCRIPT_GAP_IN_A : ((d < cell.y) ? SCRIPT_GAP_IN_B : SCRIPT_SUB);
-                if (unpruned) {
-                    if (cell.y - ge >= s - goe) op += SCRIPT_EXTEND_GAP_B;
-                    if (R - ge >= s - goe) op += SCRIPT_EXTEND_GAP_A;
+            int32_t up0 = __shfl_up_sync(FULLW, cell[TBK - 1].x, 1);
+            if (lane == 0) up0 = prev_old_best;
+            prev_old_best = __shfl_sync(FULLW, cell[TBK - 1].x, 31);
+#pragma unroll
+            for (int j = 0; j < TBK; j++) {
+                const int32_t b = b0 + j;
+                const int32_t up = j == 0 ? up0 : cell[j > 0 ? j - 1 : 0].x;
+                v[j] = NEGINF; dg[j] = MININT;
+                if (act[j]) {
+                    if (b != row_first) dg[j] = up + mrow[sbase64(S, s0 + (int64_t)b * s_inc)];
+                    v[j] = max(dg[j], cell[j].y);
                 }
-                srow[b] = op;
+                p[j] = __ballot_sync(FULLW, act[j] && (best_in - v[j] > x_dropoff));
+            }
+            // ---- fixed point over the prune flags (cell order = lane-major) -------------------------------
+            bool un[TBK];
+            int32_t R[TBK], sc[TBK];
+            for (;;) {
+                int32_t ubase = 0;
+#pragma unroll
+                for (int j = 0; j < TBK; j++) ubase += __popc(amask[j] & ~p[j] & lt);
+                int32_t u[TBK], w[TBK];
+                int32_t running = ubase, lw = NEGINF;
+#pragma unroll
+                for (int j = 0; j < TBK; j++) {
+                    un[j] = ((amask[j] & ~p[j]) >> lane) & 1u;
+                    u[j] = running;
+                    running += un[j] ? 1 : 0;
+                    w[j] = un[j] ? v[j] - goe + ge * (u[j] + 1) : NEGINF;
+                    lw = max(lw, w[j]);
+                }
+                int32_t run = max(r_in, excl_prefix_max(lw, lane));
+                int32_t ls = NEGINF;
+#pragma unroll
+                for (int j = 0; j < TBK; j++) {
+                    R[j] = run - ge * u[j];
+                    sc[j] = max(v[j], R[j]);
+                    run = max(run, w[j]);
+                    if (un[j]) ls = max(ls, sc[j]);
+                }
+                int32_t runb = max(best_in, excl_prefix_max(ls, lane));
+                bool same = true;
+#pragma unroll
+                for (int j = 0; j < TBK; j++) {
+                    const uint32_t pn = __ballot_sync(FULLW, act[j] && (runb - sc[j] > x_dropoff));
+                    if (un[j]) runb = max(runb, sc[j]);
+                    same = same && (pn == p[j]);
+                    p[j] = pn;
+                }
+                if (same) break;
+            }
+            // ---- script bytes (core/blast_gapalign.c:560-612) --------------------------------------------
+            uint32_t mine = 0;                                  // my unpruned cells, bit j
+            int32_t ls = NEGINF;
+#pragma unroll
+            for (int j = 0; j < TBK; j++) {
+                if (act[j]) {
+                    uint8_t op = (v[j] < R[j]) ? SCRIPT_GAP_IN_A : ((dg[j] < cell[j].y) ? SCRIPT_GAP_IN_B : SCRIPT_SUB);
+                    if (un[j]) {
+                        if (cell[j].y - ge >= sc[j] - goe) op += SCRIPT_EXTEND_GAP_B;
+                        if (R[j] - ge >= sc[j] - goe) op += SCRIPT_EXTEND_GAP_A;
+                    }
+                    srow[b0 + j] = op;
+                }
+                if (un[j]) { mine |= 1u << j; ls = max(ls, sc[j]); }
             }
             // ---- commit the segment ----------------------------------------------------------------------
-            const int nact = __popc(amask);
+            const int nact = min(32 * TBK, row_end - seg);
+            const uint32_t anyu = __ballot_sync(FULLW, mine != 0);
             int dropped = 0;
             if (lead) {
-                dropped = um ? (__ffs(um) - 1) : nact;
+                if (anyu) {
+                    const int l1 = __ffs(anyu) - 1;
+                    const uint32_t m1 = __shfl_sync(FULLW, mine, l1);
+                    dropped = l1 * TBK + (__ffs(m1) - 1);
+                } else dropped = nact;
                 new_first += dropped;
                 lead = (dropped == nact);
             }
-            if (active) {
-                if (unpruned) ring[b & MASK] = make_int2(s, max(s - goe, cell.y - ge));
-                else if (lane >= dropped) ring[b & MASK] = make_int2(MININT, cell.y);
-            }
-            if (um) {
-                last_b = seg + (31 - __clz(um));
-                const int32_t m = __reduce_max_sync(FULLW, unpruned ? s : NEGINF);
-                if (m > best_in) {
-                    const uint32_t at = __ballot_sync(FULLW, unpruned && s == m);
-                    best_in = m; a_offset = a_index; b_offset = seg + (__ffs(at) - 1);
+#pragma unroll
+            for (int j = 0; j < TBK; j++) {
+                if (act[j]) {
+                    if (un[j]) ring[(b0 + j) & MASK] = make_int2(sc[j], max(sc[j] - goe, cell[j].y - ge));
+                    else if (lane * TBK + j >= dropped) ring[(b0 + j) & MASK] = make_int2(MININT, cell[j].y);
                 }
             }
-            const int32_t r_next = unpruned ? max(s - goe, R - ge) : R;
-            r_in = __shfl_sync(FULLW, r_next, nact - 1);
+            if (anyu) {
+                const int l2 = 31 - __clz(anyu);
+                const uint32_t m2 = __shfl_sync(FULLW, mine, l2);
+                last_b = seg + l2 * TBK + (31 - __clz(m2));
+                const int32_t m = __reduce_max_sync(FULLW, ls);
+                if (m > best_in) {
+                    int cand = -1;
+#pragma unroll
+                    for (int j = TBK - 1; j >= 0; j--) if (un[j] && sc[j] == m) cand = j;
+                    const uint32_t at = __ballot_sync(FULLW, cand >= 0);
+                    const int l3 = __ffs(at) - 1;
+                    const int j3 = __shfl_sync(FULLW, cand, l3);
+                    best_in = m; a_offset = a_index; b_offset = seg + l3 * TBK + j3;
+                }
+            }
+            {   // gap_row leaving the segment: state after its last active cell
+                const int lr = (nact - 1) / TBK, jr = (nact - 1) % TBK;
+                int32_t rn = 0;
+#pragma unroll
+                for (int j = 0; j < TBK; j++)
+                    if (j == jr) rn = un[j] ? max(sc[j] - goe, R[j] - ge) : R[j];
+                r_in = __shfl_sync(FULLW, rn, lr);
+            }
         }
         __syncwarp();
         best_score = best_in;
