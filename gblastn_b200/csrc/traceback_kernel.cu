@@ -66,7 +66,7 @@ constexpr long long ROW_CHUNK = 128 << 10;
 // status: 0 ok, 1 band wider than the shared-memory ring, 3 arena exhausted.
 __device__ int32_t align_ex_warp(const TracebackLaunch &L, const uint8_t *qp, int q_inc, const uint8_t *S, int64_t s0, int s_inc,
                                  int32_t M, int32_t N, const int32_t *matrix, int32_t gap_open, int32_t gap_extend,
-                                 int32_t x_dropoff, int2 *ring, RowStore &rs, int32_t &a_offset, int32_t &b_offset,
+                                 int32_t x_dropoff, int2 *ring, uint8_t *pf, RowStore &rs, int32_t &a_offset, int32_t &b_offset,
                                  int &status, int lane)
 {
     const int32_t goe = gap_open + gap_extend, ge = gap_extend;
@@ -99,6 +99,7 @@ __device__ int32_t align_ex_warp(const TracebackLaunch &L, const uint8_t *qp, in
             arena[rs.cur + i] = SCRIPT_GAP_IN_A;
         }
         if (lane == 0) { rs.row_off[0] = rs.cur; rs.row_first[0] = 0; }
+        for (int32_t i = lane; i < C; i += 32) pf[i] = 0;      // first guess of the prune flags: the previous row's
         rs.cur += k + 2;
         b_size = k + 1;
         __syncwarp();
@@ -153,7 +154,9 @@ __device__ int32_t align_ex_warp(const TracebackLaunch &L, const uint8_t *qp, in
                     if (b != row_first) dg[j] = up + mrow[sbase64(S, s0 + (int64_t)b * s_inc)];
                     v[j] = max(dg[j], cell[j].y);
                 }
-                p[j] = __ballot_sync(FULLW, act[j] && (best_in - v[j] > x_dropoff));
+                // first guess: what became of the cell's diagonal predecessor in the previous row (the band follows
+                // the diagonal); any guess converges to the same flags, a good one in one or two passes
+                p[j] = __ballot_sync(FULLW, act[j] && pf[(b - 1) & MASK] != 0);
             }
             // ---- fixed point over the prune flags (cell order = lane-major) -------------------------------
             bool un[TBK];
@@ -195,6 +198,7 @@ __device__ int32_t align_ex_warp(const TracebackLaunch &L, const uint8_t *qp, in
             // ---- script bytes (core/blast_gapalign.c:560-612) --------------------------------------------
             uint32_t mine = 0;                                  // my unpruned cells, bit j
             int32_t ls = NEGINF;
+            uint8_t pfn[TBK];
 #pragma unroll
             for (int j = 0; j < TBK; j++) {
                 if (act[j]) {
@@ -206,7 +210,12 @@ __device__ int32_t align_ex_warp(const TracebackLaunch &L, const uint8_t *qp, in
                     srow[b0 + j] = op;
                 }
                 if (un[j]) { mine |= 1u << j; ls = max(ls, sc[j]); }
+                pfn[j] = un[j] ? 0 : 1;
             }
+            // the guesses of this segment were all read before the first ballot; the next segment of this row reads
+            // pf[seg + 32 TBK - 1 ...], the flag of THIS row's last cell here instead of the previous row's: still a guess
+#pragma unroll
+            for (int j = 0; j < TBK; j++) if (act[j]) pf[(b0 + j) & MASK] = pfn[j];
             // ---- commit the segment ----------------------------------------------------------------------
             const int nact = min(32 * TBK, row_end - seg);
             const uint32_t anyu = __ballot_sync(FULLW, mine != 0);
@@ -286,6 +295,7 @@ __global__ void __launch_bounds__(TB_WARPS * 32)
 traceback_dp_kernel(const DevQuery q, const TracebackLaunch L)
 {
     __shared__ int2 rings[TB_WARPS][TB_CELLS];
+    __shared__ uint8_t s_pf[TB_WARPS][TB_CELLS];
     __shared__ int32_t s_matrix[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_matrix[i] = q.matrix[i];
     __syncthreads();
@@ -328,7 +338,7 @@ traceback_dp_kernel(const DevQuery q, const TracebackLaunch L)
                 rs.row_first = reinterpret_cast<int32_t *>(L.arena + tab + (long long)(M + 1) * 8);
                 int32_t a_off, b_off;
                 out.score = align_ex_warp(L, qp, q_inc, S, s0, s_inc, M, N, s_matrix, q.gap_open, q.gap_extend,
-                                          L.x_dropoff, ring, rs, a_off, b_off, status, lane);
+                                          L.x_dropoff, ring, s_pf[wib], rs, a_off, b_off, status, lane);
                 out.a_off = a_off; out.b_off = b_off;
                 __syncwarp();
                 __threadfence_block();
