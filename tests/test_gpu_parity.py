@@ -252,6 +252,37 @@ def test_full_search_product_path(name):
         Q.free(); V.free(); s.free()
 
 
+@pytest.mark.parametrize("name", cases.TRACEBACK_LIST_CASES)
+def test_full_search_against_golden_fixture(name):
+    """The same product path against the committed fixture tests/golden/traceback_<case>.npz (the reference's final
+    results, written by tests/golden/make_traceback_golden.py): needs neither /root/reference nor oracle/_ref."""
+    import os
+    from gblastn_b200 import engine as E, setup as S
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"traceback_{name}.npz"))
+    want, ref_ops = gold["tb_final"], gold["tb_ops"]
+    task, cfgkw, vol, qs = cases.make_case(name)
+    s = S.Setup(qs, task=task, db_length=vol.total_bases, db_num_seqs=vol.n_seqs, device_lookup=1, **cfgkw)
+    V, Q = E.Volume(vol), E.Query(s.batch)
+    try:
+        assert s.gap_x_dropoff_final() == int(gold["gap_x_dropoff_final"])
+        g = E.prelim_search(V, Q)
+        from oracle import portdriver as P
+        assert np.array_equal(P.final_table(g["hsps"]), gold["prelim_final"])
+        got, ops = E.traceback_search(V, Q, s.gap_x_dropoff_final(), g["hsps"])
+        assert got.shape[0] == want.shape[0]
+        for k, col in enumerate(("query_index", "oid", "context", "q_off", "q_end", "s_off", "s_end", "score", "num_ident")):
+            assert np.array_equal(got[col], want[:, k]), col
+        ev = want[:, 9].astype(np.uint32).astype(np.uint64) | (want[:, 10].astype(np.uint32).astype(np.uint64) << np.uint64(32))
+        bs = want[:, 11].astype(np.uint32).astype(np.uint64) | (want[:, 12].astype(np.uint32).astype(np.uint64) << np.uint64(32))
+        assert np.array_equal(got["evalue"].view(np.uint64), ev) and np.array_equal(got["bit_score"].view(np.uint64), bs)
+        flat = np.concatenate([ref_ops[want[i, 13]:want[i, 13] + want[i, 14]] for i in range(want.shape[0])])
+        mine = np.concatenate([np.stack([ops["op_type"][a:a + n], ops["num"][a:a + n]], axis=1)
+                               for a, n in zip(got["esp_off"], got["esp_n"])])
+        assert np.array_equal(flat, mine), "edit scripts differ"
+    finally:
+        Q.free(); V.free(); s.free()
+
+
 def _random_start_items(r, vol, rng, per_hsp=3, max_hsps=60):
     """Start points for the differential test: inside real HSPs (with a small diagonal jitter), with and
     without a subject window, plus the corners of the sequences."""

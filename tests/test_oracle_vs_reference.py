@@ -91,3 +91,22 @@ def test_port_matches_reference_with_database_masks(name, mask_type, built):
     assert np.array_equal(r["gapped"], P.gapped_table(p["gapped"]))
     assert np.array_equal(r["final"], P.final_table(p["hsps"]))
     assert p["stats"]["lookup_hits"] == r["lookup_hits"]
+
+
+@pytest.mark.parametrize("name", ["mb_bridged_segments", "blastn_bridged_segments"])
+def test_traceback_golden_fixture_is_current(name):
+    """tests/golden/traceback_<case>.npz equals what the reference built here produces today."""
+    import os
+    from tests import cases
+    from oracle import refdriver as R
+    if not R.available():
+        pytest.skip("oracle/_ref/libblastref.so not built")
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"traceback_{name}.npz"))
+    task, cfgkw, vol, qs = cases.make_case(name)
+    r = R.search(qs, vol, R.default_config(task, taps=R.TAP_TRACEBACK, prelim_only=0, **cfgkw))
+    assert r["status"] == 0
+    assert np.array_equal(r["tb_final"], gold["tb_final"]) and np.array_equal(r["tb_ops"], gold["tb_ops"])
+    assert np.array_equal(r["final"], gold["prelim_final"])
+    # the adversarial cases must keep exercising the list logic: fewer alignments than preliminary HSPs, fewer results still
+    assert r["tb_calls"].shape[0] < r["final"].shape[0]
+    assert r["tb_final"].shape[0] <= r["tb_calls"].shape[0]
