@@ -619,17 +619,39 @@ __device__ int32_t greedy_align_tb_warp(const GreedyTbSeq &sp, int32_t xdrop_thr
             const unsigned e2 = __ballot_sync(FULLW, ok && seq2_index == len2);
             const unsigned e1 = __ballot_sync(FULLW, ok && seq1_index == len1);
             unsigned inv = 0;
-            for (unsigned rem = act; rem; rem &= rem - 1) {        // the bookkeeping in ascending k
-                const int b = __ffs(rem) - 1;
-                const unsigned bit = 1u << b;
-                const int32_t kk = kb + b;
-                if (!(succ & bit)) {
-                    if (kk == diag_lower) diag_lower++;
-                    else inv |= bit;
-                } else {
-                    diag_upper = kk;
-                    if (e2 & bit) { diag_lower = kk + 1; end2_reached = true; }
-                    if (e1 & bit) { diag_upper = kk - 1; end1_reached = true; }
+            if (e2 == 0) {
+                // no diagonal reached the end of seq2 in this round (the usual case): diag_lower only moves over the
+                // leading run of failures (and only if it still sits on the round's first diagonal), every later
+                // failure is marked invalid, diag_upper follows the last success (same closed form as greedy_kernel)
+                const unsigned fail = act & ~succ;
+                unsigned lead = 0;
+                if (diag_lower == kb) {
+                    lead = (unsigned)__ffs(~fail) - 1u;
+                    if (fail == 0xffffffffu) lead = 32;
+                    diag_lower += (int32_t)lead;
+                }
+                inv = lead >= 32 ? 0u : (fail & ~((1u << lead) - 1u));
+                if (succ) {
+                    const int top = 31 - __clz(succ);
+                    diag_upper = kb + top;
+                    if (e1) {
+                        end1_reached = true;
+                        if ((e1 >> top) & 1u) diag_upper = kb + top - 1;
+                    }
+                }
+            } else {
+                for (unsigned rem = act; rem; rem &= rem - 1) {    // the bookkeeping in ascending k
+                    const int b = __ffs(rem) - 1;
+                    const unsigned bit = 1u << b;
+                    const int32_t kk = kb + b;
+                    if (!(succ & bit)) {
+                        if (kk == diag_lower) diag_lower++;
+                        else inv |= bit;
+                    } else {
+                        diag_upper = kk;
+                        if (e2 & bit) { diag_lower = kk + 1; end2_reached = true; }
+                        if (e1 & bit) { diag_upper = kk - 1; end1_reached = true; }
+                    }
                 }
             }
             if (ok) cur[k] = seq2_index;
