@@ -93,7 +93,8 @@ class BnSetupOptions(C.Structure):
                 ("xdrop_gap_final", C.c_double), ("evalue", C.c_double),
                 ("low_score_perc", C.c_double),
                 ("db_length", C.c_int64), ("db_num_seqs", C.c_int32),
-                ("avg_subject_length", C.c_int32), ("device_lookup", C.c_int32)]
+                ("avg_subject_length", C.c_int32), ("device_lookup", C.c_int32),
+                ("hsp_num_max", C.c_int32)]
 
 
 HSP_DTYPE = np.dtype([("oid", "<i4"), ("context", "<i4"), ("q_off", "<i4"), ("q_end", "<i4"),

@@ -131,7 +131,7 @@ typedef struct BnQueryBatch {
     int32_t        gap_x_dropoff;    /* raw */
     int32_t        min_diag_separation;
     int32_t        round_down;       /* sbp->round_down (odd-score rounding) */
-    int32_t        hsp_num_max;      /* 0 => unlimited */
+    int32_t        hsp_num_max;      /* 0 => unlimited; no effect on gapped searches (BlastHspNumMax, core/blast_hits.c:169-191) */
     int32_t        hitlist_size;     /* for the low_score rule */
     double         evalue_cutoff;    /* hit_options->expect_value */
     double         low_score_perc;   /* 0 disables the rule */
@@ -364,6 +364,9 @@ typedef struct BnSetupOptions {
     int32_t avg_subject_length; /* BlastSeqSrcGetAvgSeqLen */
     int32_t device_lookup;      /* 1: leave the megablast table fill to bn_query_load (device); the batch
                                    then carries lookup_segments and NULL hashtable/next_pos */
+    int32_t hsp_num_max;        /* hit_options->hsp_num_max; carried into the batch, and — like the reference, whose
+                                   BlastHspNumMax returns INT4_MAX for gapped searches (core/blast_hits.c:169-191) —
+                                   without effect on this (always gapped) path */
 } BnSetupOptions;
 
 typedef struct BnSetup BnSetup;   /* opaque; owns the arrays a BnQueryBatch points to */

@@ -1307,6 +1307,90 @@ static void merge_chunks(Vec *comb, BnHSP *nw, int64_t n_new, int32_t split_offs
 }
 
 /* ------------------------------------------------------------------ whole preliminary stage */
+/* ------------------------------------------------------------------ hit lists behind hit_params->low_score
+ * The collector splits a subject's list per query (core/hspfilter_collector.c:104-150) and files each part with
+ * Blast_HitListUpdate (core/blast_hits.c:2924-2981) into a hit list of prelim_hitlist_size entries
+ * (BlastHSPCollectorParamsNew, core/hspfilter_collector.c:335-342); once a list is full and a better subject
+ * arrives it becomes a heap with the worst subject at the root (s_CreateHeap / s_Heapify :1470-1521 under
+ * s_EvalueCompareHSPLists :2759-2788).  The engine then raises low_score[query] to low_score_perc x the root's
+ * best score (core/blast_engine.c:1313-1320). */
+typedef struct HlKey { double best_evalue; int32_t best_score, oid; } HlKey;
+typedef struct HitList { HlKey *a; int32_t count, heapified, low_score; double worst_evalue; } HitList;
+
+static int hl_fuzzy(double e1, double e2)          /* s_FuzzyEvalueComp :2742-2753 */
+{
+    if (e1 < (1 - 1e-6) * e2) return -1;
+    if (e1 > (1 + 1e-6) * e2) return 1;
+    return 0;
+}
+static int hl_cmp(const HlKey *x, const HlKey *y)
+{
+    int r = hl_fuzzy(x->best_evalue, y->best_evalue);
+    if (r) return r;
+    if (x->best_score > y->best_score) return -1;
+    if (x->best_score < y->best_score) return 1;
+    return y->oid > x->oid ? 1 : (y->oid < x->oid ? -1 : 0);
+}
+static void hl_heapify(HlKey *a, int64_t base, int64_t lim, int64_t last)
+{
+    int64_t left = 2 * base + 1;
+    while (base <= lim) {
+        int64_t large = (left == last) ? left : (hl_cmp(&a[left], &a[left + 1]) >= 0 ? left : left + 1);
+        if (hl_cmp(&a[base], &a[large]) < 0) {
+            HlKey t = a[base]; a[base] = a[large]; a[large] = t;
+            base = large; left = 2 * base + 1;
+        } else break;
+    }
+}
+static void hl_update(HitList *L, int32_t max, HlKey k)
+{
+    if (L->count < max) {
+        if (!L->a) { L->a = (HlKey *)malloc((size_t)max * sizeof(HlKey)); L->low_score = INT_MAX; }
+        L->a[L->count++] = k;
+        if (k.best_evalue > L->worst_evalue) L->worst_evalue = k.best_evalue;
+        if (k.best_score < L->low_score) L->low_score = k.best_score;
+        return;
+    }
+    {
+        const int order = hl_fuzzy(k.best_evalue, L->worst_evalue);
+        if (order > 0 || (order == 0 && k.best_score < L->low_score)) return;
+    }
+    if (!L->heapified) {
+        const int64_t n = L->count;
+        if (n >= 2) {
+            int64_t i;
+            for (i = n / 2; i > 0; i--) hl_heapify(L->a, i - 1, (n - 2) / 2, n - 1);
+        }
+        L->heapified = 1;
+    }
+    L->a[0] = k;
+    if (L->count >= 2) hl_heapify(L->a, 0, L->count / 2 - 1, L->count - 1);
+    L->worst_evalue = L->a[0].best_evalue;
+    L->low_score = L->a[0].best_score;
+}
+/* one subject's final list (sorted by score) -> hit lists -> low_score[] */
+static void hl_subject_done(const BnQueryBatch *b, HitList *lists, int32_t max, const BnHSP *h, int64_t n,
+                            int32_t *low_score)
+{
+    int64_t i, j;
+    for (i = 0; i < n; i++) {
+        const int32_t qi = b->contexts[h[i].context].query_index;
+        HlKey k;
+        int seen = 0;
+        for (j = 0; j < i && !seen; j++) seen = b->contexts[h[j].context].query_index == qi;
+        if (seen) continue;
+        k.best_evalue = h[i].evalue; k.best_score = h[i].score; k.oid = h[i].oid;
+        for (j = i + 1; j < n; j++)
+            if (b->contexts[h[j].context].query_index == qi && h[j].evalue < k.best_evalue) k.best_evalue = h[j].evalue;
+        hl_update(&lists[qi], max, k);
+    }
+    for (i = 0; i < b->num_queries; i++)
+        if (lists[i].heapified) {
+            const double v = b->low_score_perc * (double)lists[i].low_score;
+            if ((double)low_score[i] < v) low_score[i] = (int32_t)v;
+        }
+}
+
 int port_prelim_search_masked(const BnQueryBatch *b, const uint8_t *packed, const int64_t *seq_byte_off,
                               const int32_t *seq_len, int32_t n_seq, int taps, int32_t smask_type,
                               const int32_t *smask_n, const int32_t *smask_iv, PortResults *out);
@@ -1330,7 +1414,7 @@ int port_prelim_search_masked(const BnQueryBatch *b, const uint8_t *packed, cons
     DpMem dm;
     int32_t oid, max_len = 0;
     int32_t *low_score = NULL;
-    int32_t *best_scores = NULL; int64_t *n_lists = NULL;   /* per query: hitlist model */
+    HitList *hitlists = NULL; int32_t hitlist_max = 0;       /* per query: hit-list model */
 
     memset(out, 0, sizeof *out);
     vec_init(&init, sizeof(BnInitHit)); vec_init(&gapped_tap, sizeof(BnHSP));
@@ -1343,8 +1427,13 @@ int port_prelim_search_masked(const BnQueryBatch *b, const uint8_t *packed, cons
     gm.max_score = (int32_t *)calloc((size_t)gm.max_d + 1 + 4096, 4);
     memset(&dm, 0, sizeof dm);
     diag_new(&diag, b);
-    if (b->low_score_perc > 0.00001) low_score = (int32_t *)calloc((size_t)b->num_queries, 4);
-    (void)best_scores; (void)n_lists;
+    if (b->low_score_perc > 0.00001) {
+        int32_t hs = b->hitlist_size > 0 ? b->hitlist_size : 500;
+        low_score = (int32_t *)calloc((size_t)b->num_queries, 4);
+        hitlists = (HitList *)calloc((size_t)b->num_queries, sizeof(HitList));
+        hs = PMIN(2 * hs, hs + 50);
+        hitlist_max = PMAX(hs, 10);
+    }
     if (smask_type && smask_n) {
         smask_first = (int64_t *)calloc((size_t)n_seq + 1, 8);
         for (oid = 0; oid < n_seq; oid++) smask_first[oid + 1] = smask_first[oid] + smask_n[oid];
@@ -1442,7 +1531,7 @@ int port_prelim_search_masked(const BnQueryBatch *b, const uint8_t *packed, cons
          * BLAST_KarlinStoE_simple core/blast_stat.c:4111-4125 */
         {
             int64_t k, kept = 0;
-            int32_t best_per_query_dummy = 0; (void)best_per_query_dummy;
+            const int64_t first_final = final_.n;
             for (k = 0; k < comb.n; k++) {
                 BnHSP *h = (BnHSP *)comb.p + k;
                 const BnContext *c = &b->contexts[h->context];
@@ -1452,6 +1541,8 @@ int port_prelim_search_masked(const BnQueryBatch *b, const uint8_t *packed, cons
                 kept++;
             }
             if (kept) out->stats.good_extensions += kept;
+            if (kept && hitlists)
+                hl_subject_done(b, hitlists, hitlist_max, (const BnHSP *)final_.p + first_final, kept, low_score);
         }
         free(comb.p);
         free(R); free(chunk_r);
@@ -1459,6 +1550,7 @@ int port_prelim_search_masked(const BnQueryBatch *b, const uint8_t *packed, cons
     diag_free(&diag);
     free(smask_first);
     free(gm.row[0]); free(gm.max_score); free(dm.best); free(dm.best_gap); free(low_score);
+    if (hitlists) { int32_t q; for (q = 0; q < b->num_queries; q++) free(hitlists[q].a); free(hitlists); }
     out->hsps = (BnHSP *)final_.p; out->n_hsps = final_.n;
     out->init = (BnInitHit *)init.p; out->n_init = init.n;
     out->gapped = (BnHSP *)gapped_tap.p; out->n_gapped = gapped_tap.n;

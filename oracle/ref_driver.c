@@ -491,6 +491,7 @@ static int build_setup(const RefConfig *cfg, int32_t nq, const uint8_t *qseq, co
         cfg->min_diag_separation >= 0 ? cfg->min_diag_separation : (mb ? 6 : 50);
     S->hit_options->mask_level = 101;
     S->hit_options->low_score_perc = cfg->low_score_perc >= 0 ? cfg->low_score_perc : 0.15;
+    S->hit_options->hsp_num_max = cfg->hsp_num_max;
     S->eff_len_options->db_length = cfg->db_length;
     S->eff_len_options->dbseq_num = cfg->db_num_seqs;
     S->query_options->strand_option = 3;
@@ -772,6 +773,20 @@ static void *worker_main(void *arg)
         Blast_HSPResultsFree(results);
     }
     g_tap = NULL;
+    if (w->status == 0 && !w->traceback && w->res->kept.ncol && stream->results) {
+        Int4 qi, li;
+        for (qi = 0; qi < stream->results->num_queries; qi++) {
+            const BlastHitList *hl = stream->results->hitlist_array[qi];
+            if (!hl) continue;
+            for (li = 0; li < hl->hsplist_count; li++) {
+                const BlastHSPList *l = hl->hsplist_array[li];
+                int32_t *r;
+                if (!l || l->hspcnt == 0) continue;
+                r = tab_row(&w->res->kept);
+                r[0] = qi; r[1] = l->oid; r[2] = l->hsp_array[0]->score; r[3] = l->hspcnt;
+            }
+        }
+    }
     BlastHSPStreamFree(stream);
     BlastSeqSrcFree(seq_src);
     return NULL;
@@ -797,6 +812,7 @@ int ref_search(const RefConfig *cfg,
     tab_init(&res->tb_calls, 15);
     tab_init(&res->tb_ops, 2);
     tab_init(&res->tb_final, 15);
+    tab_init(&res->kept, 4);
 
     st = build_setup(cfg, nq, qseq, qlens, qmask_n, qmask_iv, &S);
     if (st) { res->status = st; return st; }
@@ -968,7 +984,7 @@ int ref_traceback_calls(const RefConfig *cfg,
 void ref_free_result(RefResult *res)
 {
     free(res->scan.data); free(res->init.data); free(res->gapped.data); free(res->final_.data);
-    free(res->tb_calls.data); free(res->tb_ops.data); free(res->tb_final.data);
+    free(res->tb_calls.data); free(res->tb_ops.data); free(res->tb_final.data); free(res->kept.data);
     free(res->ctx_query_offset); free(res->ctx_query_length); free(res->ctx_length_adjustment);
     free(res->ctx_eff_searchsp); free(res->ctx_x_dropoff); free(res->ctx_cutoff_score);
     free(res->ctx_reduced_cutoff); free(res->ctx_gapped_cutoff);

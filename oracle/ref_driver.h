@@ -42,6 +42,9 @@ typedef struct RefConfig {
     int32_t smask_type;
     const int32_t *smask_n;
     const int32_t *smask_iv;
+    int32_t hsp_num_max;     /* hit_options->hsp_num_max (0 = unlimited); ignored by gapped searches (BlastHspNumMax,
+                              * core/blast_hits.c:169-191) */
+    int32_t reserved0;
 } RefConfig;
 
 /* Flat growable int32 table: rows x ncol */
@@ -99,6 +102,10 @@ typedef struct RefResult {
     RefTable tb_final;  /* query_index, oid, context, q_off, q_end, s_off, s_end, score, num_ident,
                          * evalue_lo, evalue_hi, bits_lo, bits_hi, esp_off, esp_n */
     double   seconds_traceback; /* wall time of Blast_RunTracebackSearch */
+    /* the per-query hit lists the HSP stream holds when the preliminary stage ends (single thread, prelim_only 1):
+     * what survives prelim_hitlist_size (core/hspfilter_collector.c:328-342, Blast_HitListUpdate) and reaches the
+     * traceback stage.  Array order (a heap once a list overflowed): compare as sets. */
+    RefTable kept;      /* query_index, oid, best score, number of HSPs */
 } RefResult;
 
 /* queries: blastna bytes (0..3 ACGT, 4..14 ambiguity) concatenated, lengths in qlens.

@@ -25,6 +25,7 @@ class RefConfig(C.Structure):
         ("db_length", C.c_int64), ("db_num_seqs", C.c_int32), ("num_threads", C.c_int32),
         ("taps", C.c_int32), ("prelim_only", C.c_int32),
         ("smask_type", C.c_int32), ("smask_n", C.c_void_p), ("smask_iv", C.c_void_p),
+        ("hsp_num_max", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -63,6 +64,7 @@ class RefResult(C.Structure):
         ("na_overflow_len", C.c_int64),
         ("tb_calls", RefTable), ("tb_ops", RefTable), ("tb_final", RefTable),
         ("seconds_traceback", C.c_double),
+        ("kept", RefTable),
     ]
 
 
@@ -191,6 +193,7 @@ def search(queries, volume, cfg: RefConfig | None = None, *, task="megablast", m
             "status": st,
             "scan": _tab(res.scan), "init": _tab(res.init), "gapped": _tab(res.gapped),
             "final": _tab(res.final_),
+            "kept": _tab(res.kept) if res.kept.ncol else np.zeros((0, 4), np.int32),
             "tb_calls": _tab(res.tb_calls), "tb_ops": _tab(res.tb_ops), "tb_final": _tab(res.tb_final),
             "num_contexts": n,
             "ctx_query_offset": _arr(res.ctx_query_offset, n, np.int32),

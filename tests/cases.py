@@ -125,6 +125,24 @@ CASES["blastn_bridged_segments"] = dict(task="blastn", cfg={}, seq_lens=[300_000
                                         nq=40, qlen=900, q_seed=64, sub=0.06, indel=0.0, planted=1.0, bridged=True)
 TRACEBACK_LIST_CASES = ["mb_bridged_segments", "blastn_bridged_segments"]
 
+# Repeat-family volumes: every query hits dozens of subjects, so the per-query hit lists of the HSP stream fill up
+# (prelim_hitlist_size = max(min(2 h, h + 50), 10), core/hspfilter_collector.c:335-342), turn into heaps
+# (Blast_HitListUpdate, core/blast_hits.c:2924-2981) and feed hit_params->low_score back into BLAST_GetGappedScore
+# (core/blast_engine.c:1313-1320, core/blast_gapalign.c:3340-3375): later subjects that only carry short fragments
+# of the family are skipped without a gapped extension.
+CASES["mb_repeat_family_hitlist5"] = dict(task="megablast", cfg={"hitlist_size": 5}, repeat_family=dict(
+    seed=71, n_subj=70, n_fam=6, elem_len=1200, frag_from=0.45), nq=18, q_seed=72, sub=0.01)
+CASES["mb_repeat_family_hitlist20"] = dict(task="megablast", cfg={"hitlist_size": 20}, repeat_family=dict(
+    seed=73, n_subj=90, n_fam=4, elem_len=900, frag_from=0.6), nq=12, q_seed=74, sub=0.015)
+CASES["blastn_repeat_family_hitlist5"] = dict(task="blastn", cfg={"hitlist_size": 5}, repeat_family=dict(
+    seed=75, n_subj=60, n_fam=4, elem_len=700, frag_from=0.5), nq=8, q_seed=76, sub=0.04)
+# hit_options->hsp_num_max is ignored by gapped searches (BlastHspNumMax, core/blast_hits.c:169-191): same lists
+CASES["mb_repeat_family_hsp_num_max2"] = dict(task="megablast", cfg={"hitlist_size": 5, "hsp_num_max": 2},
+                                              repeat_family=dict(seed=71, n_subj=70, n_fam=6, elem_len=1200,
+                                                                 frag_from=0.45), nq=18, q_seed=72, sub=0.01)
+HITLIST_CASES = ["mb_repeat_family_hitlist5", "mb_repeat_family_hitlist20", "blastn_repeat_family_hitlist5",
+                 "mb_repeat_family_hsp_num_max2"]
+
 FAST = ["c1_megablast_10kb_vs_1mb", "mb_lut11_hash_indels", "mb_smallna_diagarray", "blastn_mb11_dp",
         "blastn_smallna_dp", "mb_ws16", "blastn_ws11_greedy", "blastn_ws7_array", "mb_with_N", "mb_no_hits"]
 ALL = list(CASES.keys())
@@ -178,8 +196,47 @@ def _bridged_queries(vol, nq, qlen, seed, sub_rate):
     return out
 
 
+def _repeat_family(spec, nq, q_seed, sub):
+    """Subjects = random background with mutated copies of a small family of elements; the first `frag_from` of the
+    subjects carry whole copies at 1-9 % divergence (a later, better copy displaces the worst entry of a full hit
+    list), the rest mostly short fragments (40-160 bases: their ungapped scores stay below 15 % of the worst kept
+    score, so low_score skips them) with an occasional whole copy.  Queries = family members, lightly mutated."""
+    rng = np.random.default_rng(spec["seed"])
+    fam = [rng.integers(0, 4, size=spec["elem_len"], dtype=np.uint8) for _ in range(spec["n_fam"])]
+    seqs = []
+    for i in range(spec["n_subj"]):
+        L = int(rng.integers(2, 5)) * spec["elem_len"] * spec["n_fam"] // 2
+        s = rng.integers(0, 4, size=L, dtype=np.uint8)
+        pos = int(rng.integers(0, 200))
+        for f in rng.permutation(spec["n_fam"]):
+            if rng.random() < 0.15:
+                continue
+            whole = i < spec["frag_from"] * spec["n_subj"] or rng.random() < 0.12
+            e = synth.mutate(fam[f], rng, float(rng.uniform(0.01, 0.09)), 0.002)
+            if not whole:
+                a = int(rng.integers(0, e.shape[0] - 160))
+                e = e[a:a + int(rng.integers(40, 160))]
+            if rng.random() < 0.5:
+                e = synth.revcomp(e)
+            if pos + e.shape[0] >= L:
+                break
+            s[pos:pos + e.shape[0]] = e
+            pos += e.shape[0] + int(rng.integers(20, 400))
+        seqs.append(s)
+    vol = synth.make_volume_from_bases(seqs)
+    qrng = np.random.default_rng(q_seed)
+    qs = []
+    for k in range(nq):
+        q = synth.mutate(fam[k % spec["n_fam"]], qrng, sub, 0.0)
+        qs.append(np.ascontiguousarray(synth.revcomp(q) if k % 3 == 1 else q, dtype=np.uint8))
+    return vol, qs
+
+
 def make_case(name):
     c = CASES[name]
+    if c.get("repeat_family"):
+        vol, qs = _repeat_family(c["repeat_family"], c["nq"], c["q_seed"], c["sub"])
+        return c["task"], dict(c["cfg"]), vol, qs
     vol = synth.random_volume(_seq_lens(c["seq_lens"], c["vol_seed"]), seed=c["vol_seed"])
     if c.get("bridged"):
         return c["task"], dict(c["cfg"]), vol, _bridged_queries(vol, c["nq"], c["qlen"], c["q_seed"], c["sub"])

@@ -457,9 +457,12 @@ def test_gpu_with_database_masks(name, kw, mask_type):
 
 def test_batch_pipeline_equals_single_searches():
     """bn_prelim_search_batches: five different query batches (mixed table shapes, one empty result, one on
-    the general cub path) through the two-stage pipeline give byte-identical results to one search each."""
+    the general path) through the two-stage pipeline give byte-identical results to one search each, and each
+    equals the reference engine's result for that batch."""
     from gblastn_b200 import engine as E, setup as S, synth
+    from oracle import refdriver as R, portdriver as P
     vol = synth.random_volume([400_000, 150_000, 30_000, 777], seed=61)
+    all_qs = []
     specs = [dict(task="megablast", nq=120, qlen=900, seed=1, planted=0.7, sub=0.02),
              dict(task="megablast", nq=3, qlen=600, seed=2, planted=1.0, sub=0.04),          # small table, diag array
              dict(task="blastn", nq=8, qlen=700, seed=3, planted=0.8, sub=0.08),             # DP, many seed hits
@@ -469,6 +472,7 @@ def test_batch_pipeline_equals_single_searches():
     for sp in specs:
         qs = synth.planted_queries(vol, sp["nq"], sp["qlen"], seed=sp["seed"], planted_frac=sp["planted"],
                                    sub_rate=sp["sub"], indel_rate=0.003)
+        all_qs.append(qs)
         setups.append(S.Setup(qs, task=sp["task"], db_length=vol.total_bases, db_num_seqs=vol.n_seqs,
                               device_lookup=1 if sp["task"] == "megablast" else 0))
     V = E.Volume(vol)
@@ -483,6 +487,14 @@ def test_batch_pipeline_equals_single_searches():
             assert len(piped) == len(singles)
             for a, b in zip(singles, piped):
                 assert a["hsps"].tobytes() == b["hsps"].tobytes()
+            # ... and every batch equals the reference engine run on that batch alone
+            if R.available():
+                for sp, qs, b in zip(specs, all_qs, piped):
+                    r = R.search(qs, vol, R.default_config(sp["task"]))
+                    assert r["status"] == 0
+                    assert np.array_equal(P.final_table(b["hsps"]), r["final"]), f"pipelined batch differs from reference: {sp}"
+                    assert b["stats"]["lookup_hits"] == r["lookup_hits"]
+                    assert b["stats"]["gap_extensions"] == r["gap_extensions"]
                 for k in ("lookup_hits", "good_init_extends", "gap_extensions", "good_extensions"):
                     assert a["stats"][k] == b["stats"][k]
         assert sum(x["hsps"].size for x in singles) > 0 and singles[3]["hsps"].size == 0
@@ -651,5 +663,31 @@ def test_gpu_full_size_properties():
             if rec["q_end"] - rec["q_off"] >= 900:
                 covered.add(int(rec["context"]) // 2)
         assert len(covered) >= 0.95 * 0.8 * 1000 * 0.98
+    finally:
+        Q.free(); V.free(); s.free()
+
+
+def test_gpu_full_size_c2_equals_reference():
+    """BASELINE configs[1] at full size (1000 x 1 kb vs one 250 Mb sequence, two subject chunks): the final lists
+    with E-value bit patterns and the diagnostics counters equal the reference engine's, bit for bit."""
+    from gblastn_b200 import engine as E, setup as S, synth
+    from oracle import refdriver as R, portdriver as P
+    if not R.available():
+        pytest.skip("oracle/_ref/libblastref.so did not travel to this box")
+    vol = synth.random_volume([250_000_000], seed=2)
+    qs = synth.planted_queries(vol, 1000, 1000, seed=22, planted_frac=0.8, sub_rate=0.02)
+    r = R.search(qs, vol, R.default_config("megablast", taps=R.TAP_INIT))
+    assert r["status"] == 0 and r["final"].shape[0] > 700
+    s = S.Setup(qs, task="megablast", db_length=vol.total_bases, db_num_seqs=vol.n_seqs, device_lookup=1)
+    V, Q = E.Volume(vol), E.Query(s.batch)
+    try:
+        from gblastn_b200 import abi
+        g = E.prelim_search(V, Q, taps=abi.BN_TAP_INIT)
+        assert np.array_equal(P.init_table(g["init"]), r["init"]), "init-HSPs differ from reference"
+        assert np.array_equal(P.final_table(g["hsps"]), r["final"]), "final lists / E-value bits differ"
+        st = g["stats"]
+        assert (st["lookup_hits"], st["good_init_extends"], st["gap_extensions"], st["good_extensions"]) == \
+               (r["lookup_hits"], r["good_init_extends"], r["gap_extensions"], r["good_extensions"])
+        assert (r["final"][:, 4] > 200_000_000).any(), "no HSP in the second subject chunk"
     finally:
         Q.free(); V.free(); s.free()
