@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -121,17 +122,44 @@ struct Workspace {
     }
 };
 
-struct Device {
-    int id = -1;
+// One execution lane of a GPU: a stream pair and a workspace of its own.  A search (or a pipeline, or a table
+// build) holds one lane from start to end, so callers on several threads (blastn -num_threads, one thread per
+// volume in bn_prelim_search_volumes) run concurrently on the same device instead of queueing on a device lock:
+// the engine is re-entrant per GPU as api/prelim_search_runner.hpp:94-113 expects of the word finder.
+struct Lane {
+    int id = -1;                          // CUDA device ordinal
+    int index = 0;                        // lane number on its device
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // volume uploads of the host-buffer entry point (overlap with the table build)
     cudaEvent_t alloc_ev = nullptr;
-    // Two workspaces: the batch pipeline (bn_prelim_search_batches) lets a host thread finish batch k-1 out of
-    // one workspace's pinned result mirrors while batch k runs in the other.  Single searches use wss[cur].
-    Workspace wss[2];
-    int cur = 0;
-    Workspace &ws() { return wss[cur]; }
-    std::mutex mu;       // one search (or one pipeline) at a time per device
+    Workspace w;
+    Workspace &ws() { return w; }
+    std::mutex mu;                        // held by the thread that owns the lane
+};
+
+struct Gpu {
+    int id = -1;
+    std::vector<std::unique_ptr<Lane>> lanes;
+    std::atomic<unsigned> next{0};
+};
+
+// RAII ownership of a lane: the first free one, else wait for one picked round-robin
+struct LaneLock {
+    Lane *lane = nullptr;
+    LaneLock() = default;
+    explicit LaneLock(Gpu &g)
+    {
+        for (auto &l : g.lanes)
+            if (l->mu.try_lock()) { lane = l.get(); return; }
+        lane = g.lanes[g.next.fetch_add(1) % g.lanes.size()].get();
+        lane->mu.lock();
+    }
+    LaneLock(LaneLock &&o) noexcept : lane(o.lane) { o.lane = nullptr; }
+    LaneLock &operator=(LaneLock &&o) noexcept { release(); lane = o.lane; o.lane = nullptr; return *this; }
+    LaneLock(const LaneLock &) = delete;
+    LaneLock &operator=(const LaneLock &) = delete;
+    void release() { if (lane) lane->mu.unlock(); lane = nullptr; }
+    ~LaneLock() { release(); }
 };
 
 struct ChunkTable {
@@ -150,6 +178,21 @@ struct ChunkTable {
     int64_t total_pos = 0;
     int64_t total_bases = 0;
     int64_t n_blocks = 0;
+    int device_id = -1;
+    cudaEvent_t ready = nullptr;              // recorded behind the uploads: lanes other than the builder's wait on it
+    uint64_t last_use = 0;
+    ChunkTable() = default;
+    ChunkTable(const ChunkTable &) = delete;
+    ChunkTable &operator=(const ChunkTable &) = delete;
+    ~ChunkTable()
+    {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (device_id >= 0 && cur != device_id) cudaSetDevice(device_id);
+        if (ready) { cudaEventSynchronize(ready); cudaEventDestroy(ready); }      // the uploads read this object's vectors
+        dev.release(); units_dev.release(); ranges_dev.release(); block_chunk.release(); block_desc.release();
+        if (device_id >= 0 && cur >= 0 && cur != device_id) cudaSetDevice(cur);
+    }
 };
 
 struct Volume {
@@ -164,7 +207,18 @@ struct Volume {
     int32_t mask_type = 0, mask_version = 0;
     std::vector<int64_t> mask_first;
     std::vector<int32_t> mask_iv;
+    // whole-volume chunk tables per table shape (a handful at most: least recently used goes first); tables of
+    // partial oid ranges are temporaries of the call that needs them
+    std::mutex tmu;                // guards tables, the mask fields and use_clock
     std::map<std::string, std::shared_ptr<ChunkTable>> tables;
+    uint64_t use_clock = 0;
+    // ambiguity data of a BLAST DB volume (bn_db_load_files): per sequence amb_first[i]..amb_first[i+1] runs
+    // {start, length, blastna value} in amb_runs; empty for volumes without ambiguities
+    std::vector<int64_t> amb_first;
+    std::vector<int32_t> amb_runs;
+    int32_t *d_amb_runs = nullptr;
+    int64_t *d_amb_first = nullptr;
+    bool has_ambiguity() const { return !amb_runs.empty(); }
 };
 
 struct QueryDev {
@@ -192,11 +246,23 @@ struct Query {
     bool fast_path_refused = false;       // the device-grouped word finder did not apply to this batch last time
 };
 
+// Handle tables.  g_mu guards the three vectors; a call resolves its handles to shared_ptrs under it and
+// works on those, so a concurrent load / free on another thread can neither move nor destroy what it uses.
+// Freed slots are recycled.
 static std::mutex g_mu;
-static std::vector<std::unique_ptr<Device>> g_devices;
-static std::vector<std::unique_ptr<Volume>> g_volumes;
-static std::vector<std::unique_ptr<Query>> g_queries;
+static std::vector<std::unique_ptr<Gpu>> g_devices;
+static std::vector<std::shared_ptr<Volume>> g_volumes;
+static std::vector<std::shared_ptr<Query>> g_queries;
 static bool g_inited = false;
+
+template <typename T>
+static int put_handle(std::vector<std::shared_ptr<T>> &tab, std::shared_ptr<T> obj)      // g_mu held
+{
+    for (size_t i = 0; i < tab.size(); i++)
+        if (!tab[i]) { tab[i] = std::move(obj); return (int)i; }
+    tab.push_back(std::move(obj));
+    return (int)tab.size() - 1;
+}
 
 static int ensure_init()
 {
@@ -204,7 +270,7 @@ static int ensure_init()
     return bn_init(0, nullptr);
 }
 
-static Device *device_at(int d)
+static Gpu *device_at(int d)
 {
     if (d < 0 || d >= (int)g_devices.size()) return nullptr;
     return g_devices[d].get();
@@ -255,9 +321,8 @@ cudaError_t build_mb_lookup_device(const uint8_t *d_query, int32_t concat_len, i
 // `after_h2d` (optional) runs once every host->device copy of the batch has been queued and before the
 // derivation kernels are: the host-buffer entry point starts the volume upload there, so the small
 // query copies are not stuck behind it in the copy engine and the table build overlaps the upload.
-static int query_to_device(Query &Q, const BnQueryBatch &src, int d, const std::function<int()> *after_h2d = nullptr)
+static int query_to_device(Query &Q, const BnQueryBatch &src, int d, Lane *dev, const std::function<int()> *after_h2d = nullptr)
 {
-    Device *dev = device_at(d);
     QueryDev &qd = Q.dev[d];
     if (qd.ready) return BN_OK;
     CU_TRY(cudaSetDevice(dev->id));
@@ -371,21 +436,35 @@ static int query_to_device(Query &Q, const BnQueryBatch &src, int d, const std::
 // unmasked subjects) + scan-position prefix sums + the evolution of the diagonal container's
 // `offset` (Blast_ExtendWordExit core/blast_extend.c:164-186).
 // ------------------------------------------------------------------------------------------------
+static const size_t kMaxCachedTables = 4;
+
 static int build_chunk_table(Volume &V, const Query &Q, int32_t oid_begin, int32_t oid_end,
-                             cudaStream_t st, std::shared_ptr<ChunkTable> *out)
+                             Lane &L, std::shared_ptr<ChunkTable> *out)
 {
+    cudaStream_t st = L.stream;
     const BnQueryBatch &b = Q.batch;
+    const bool whole = oid_begin == 0 && oid_end == (int32_t)V.seq_len.size();
     char key[160];
-    snprintf(key, sizeof key, "%d/%d/%d/%d/%d/%d/%d", b.lut_word_length, b.scan_step, b.window_size,
-             oid_begin, oid_end, b.word_length, V.mask_version);
-    auto it = V.tables.find(key);
-    if (it != V.tables.end()) { *out = it->second; return BN_OK; }
+    std::unique_lock<std::mutex> tlk(V.tmu);
+    snprintf(key, sizeof key, "%d/%d/%d/%d/%d", b.lut_word_length, b.scan_step, b.window_size, b.word_length, V.mask_version);
+    if (whole) {
+        auto it = V.tables.find(key);
+        if (it != V.tables.end()) {
+            it->second->last_use = ++V.use_clock;
+            *out = it->second;
+            tlk.unlock();
+            // built on another lane's stream, perhaps a moment ago
+            if ((*out)->ready) CU_TRY(cudaStreamWaitEvent(st, (*out)->ready, 0));
+            return BN_OK;
+        }
+    }
 
     // s_GetNextSubjectChunk (core/blast_engine.c:220-301): 200 Mb chunks with a 100-base overlap inside every
     // hard range (the whole sequence without hard masks), chunk starts rounded down to a byte; soft ranges
     // clipped to the chunk.  BlastNaWordFinder (core/na_ungapped.c:1610-1645) then scans every unmasked range
     // of a masked subject from left + (word - lut).
     auto T = std::make_shared<ChunkTable>();
+    T->device_id = L.id;
     const int32_t lut = b.lut_word_length, step = b.scan_step, window = b.window_size;
     const int32_t ext_to = b.word_length - lut;
     const int32_t mt = V.mask_type;
@@ -529,9 +608,21 @@ static int build_chunk_table(Volume &V, const Query &Q, int32_t oid_begin, int32
         CU_TRY(T->block_desc.reserve(bd.size() + 1, st));
         CU_TRY(cudaMemcpyAsync(T->block_desc.p, bd.data(), bd.size() * sizeof(ScanBlockDesc),
                                cudaMemcpyHostToDevice, st));
-        // no synchronisation: the sources are members of the table and every consumer runs on `st`
+        // no synchronisation: the sources are members of the table; consumers on `st` are ordered behind the
+        // copies, consumers on other lanes (and the destructor) wait on `ready`
+        CU_TRY(cudaEventCreateWithFlags(&T->ready, cudaEventDisableTiming));
+        CU_TRY(cudaEventRecord(T->ready, st));
     }
-    V.tables[key] = T;
+    if (whole) {
+        if (V.tables.size() >= kMaxCachedTables) {
+            auto victim = V.tables.begin();
+            for (auto it = V.tables.begin(); it != V.tables.end(); ++it)
+                if (it->second->last_use < victim->second->last_use) victim = it;
+            V.tables.erase(victim);          // a search still using it holds its own reference
+        }
+        T->last_use = ++V.use_clock;
+        V.tables[key] = T;
+    }
     *out = T;
     return BN_OK;
 }
@@ -572,7 +663,7 @@ struct StageCounts { int64_t n_hits = 0, lookup_hits = 0, n_init = 0, n_extended
 
 // scan -> one stable radix sort on (diagonal group, global position) -> diagonal/ungapped kernel.
 // Leaves the sorted seed hits in ws.hits_b and the init hits (unsorted) in ws.init.
-static int run_word_finder(Device &D, Volume &V, Query &Q, ChunkTable &T, bool raw_pairs,
+static int run_word_finder(Lane &D, Volume &V, Query &Q, ChunkTable &T, bool raw_pairs,
                            StageCounts &cnt, BnStats *stats)
 {
     Workspace &ws = D.ws();
@@ -673,7 +764,7 @@ static int32_t greedy_xdrop_offset(const BnQueryBatch &b)
 
 // Tier-1 gapped launch over the init hits in ws.init; their number is read on the device
 // (counters[2], capped at max_init), so the call needs no host knowledge of it.
-static int enqueue_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t max_init, BnStats *stats)
+static int enqueue_gapped(Lane &D, Volume &V, Query &Q, ChunkTable &T, int64_t max_init, BnStats *stats)
 {
     Workspace &ws = D.ws();
     cudaStream_t st = D.stream;
@@ -718,7 +809,7 @@ static int enqueue_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t
 
 // D2H of the init hits and tier-1 results, then tier 2 (worst-case scratch) for the few extensions
 // that outgrew tier 1.
-static int finish_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t n_init,
+static int finish_gapped(Lane &D, Volume &V, Query &Q, ChunkTable &T, int64_t n_init,
                          DevInitHit *&h_init, DevGapResult *&h_gap, BnStats *stats, bool mirrored = false)
 {
     Workspace &ws = D.ws();
@@ -800,7 +891,7 @@ static int finish_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t 
     return BN_OK;
 }
 
-static int run_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t n_init,
+static int run_gapped(Lane &D, Volume &V, Query &Q, ChunkTable &T, int64_t n_init,
                       DevInitHit *&h_init, DevGapResult *&h_gap, BnStats *stats)
 {
     Workspace &ws = D.ws();
@@ -827,7 +918,7 @@ static int run_gapped(Device &D, Volume &V, Query &Q, ChunkTable &T, int64_t n_i
 // trusted) when the device refused the fast path or a buffer was too small: the caller then runs the
 // general path.
 // ------------------------------------------------------------------------------------------------
-static int run_fused(Device &D, Volume &V, Query &Q, ChunkTable &T, StageCounts &cnt, BnStats &stats,
+static int run_fused(Lane &D, Volume &V, Query &Q, ChunkTable &T, StageCounts &cnt, BnStats &stats,
                      DevInitHit *&h_init, DevGapResult *&h_gap, bool *redo)
 {
     *redo = false;
@@ -928,7 +1019,7 @@ struct GpuOut {
     double t0 = 0, t_table = 0, t_wf = 0, t_gap = 0;
 };
 
-static int search_gpu_phase(Device &D, Volume &V, Query &Q, int32_t oid_begin, int32_t oid_end, BnResults *out, GpuOut &G)
+static int search_gpu_phase(Lane &D, Volume &V, Query &Q, int32_t oid_begin, int32_t oid_end, BnResults *out, GpuOut &G)
 {
     memset(out, 0, sizeof *out);
     G.t0 = now_ms();
@@ -937,7 +1028,7 @@ static int search_gpu_phase(Device &D, Volume &V, Query &Q, int32_t oid_begin, i
     if (!Q.dev[V.device].ready) return fail(BN_ERR_INVALID, "query batch is not loaded on the volume's device");
     int rc;
     std::shared_ptr<ChunkTable> &T = G.T;
-    rc = build_chunk_table(V, Q, oid_begin, oid_end, D.stream, &T);
+    rc = build_chunk_table(V, Q, oid_begin, oid_end, D, &T);
     if (rc) return rc;
     BnStats &stats = out->stats;
     stats.subject_bases_scanned = T->total_bases;
@@ -972,7 +1063,15 @@ static int search_gpu_phase(Device &D, Volume &V, Query &Q, int32_t oid_begin, i
 
 // Host replay of one search (containment filter, per-chunk list post-processing, chunk merge, E-values,
 // low_score feedback).  Touches no device state: safe on a worker thread while the device runs the next batch.
-static int search_host_phase(const Query &Q, const GpuOut &G, int taps, BnResults *out)
+// One search's place in a larger one (bn_prelim_search_volumes): the hit lists behind low_score are shared by all
+// volumes, and the volume's sequences are numbered after those of the volumes before it.
+struct HostShared {
+    LowScoreTracker *tracker = nullptr;
+    bool bounds_fixed = false;
+    int32_t oid_base = 0;
+};
+
+static int search_host_phase(const Query &Q, const GpuOut &G, int taps, BnResults *out, const HostShared *sh = nullptr)
 {
     const std::shared_ptr<ChunkTable> &T = G.T;
     const StageCounts &cnt = G.cnt;
@@ -1049,7 +1148,9 @@ static int search_host_phase(const Query &Q, const GpuOut &G, int taps, BnResult
 
     std::vector<BnHSP> final_hsps, gapped_tap, comb;
     std::vector<BnInitHit> init_tap;
-    LowScoreTracker tracker(b);
+    LowScoreTracker own_tracker(b);
+    LowScoreTracker &tracker = sh ? *sh->tracker : own_tracker;
+    const int32_t oid_base = sh ? sh->oid_base : 0;
     struct GroupOut { std::vector<BnHSP> fresh, tap; BnStats stats{}; double t_sort = 0, t_replay = 0, t_finish = 0; };
     std::vector<GroupOut> gout(groups.size());
     // one group: sort, containment replay, per-chunk list post-processing
@@ -1068,7 +1169,7 @@ static int search_host_phase(const Query &Q, const GpuOut &G, int taps, BnResult
     // The per-chunk work only meets other chunks through hit_params->low_score.  When no bound can move
     // during this search (fewer subjects than a hit list holds) the chunks are independent and, for large
     // result sets (short-read batches), are replayed by a few host threads.
-    const bool bounds_fixed = tracker.bounds_stay_zero((int64_t)oid_end - oid_begin);
+    const bool bounds_fixed = sh ? sh->bounds_fixed : tracker.bounds_stay_zero((int64_t)oid_end - oid_begin);
     const bool parallel = cnt.n_init >= 16384 && groups.size() >= 2 && bounds_fixed;
     if (parallel) {
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
@@ -1090,6 +1191,7 @@ static int search_host_phase(const Query &Q, const GpuOut &G, int taps, BnResult
         t_eval += now_ms() - ta; ta = now_ms();
         if (!comb.empty()) {
             stats.good_extensions += (int64_t)comb.size();
+            if (oid_base) for (auto &h : comb) h.oid += oid_base;
             final_hsps.insert(final_hsps.end(), comb.begin(), comb.end());
             if (!bounds_fixed) tracker.subject_done(b, comb);      // the hit lists only matter when a bound can move
         }
@@ -1107,10 +1209,13 @@ static int search_host_phase(const Query &Q, const GpuOut &G, int taps, BnResult
         t_replay += now_ms() - ta; ta = now_ms();
         if (taps & BN_TAP_INIT)
             for (size_t k = lo; k < hi; k++)
-                init_tap.push_back(BnInitHit{ch.oid, ch.chunk_off, inits[k].q_off, inits[k].s_off,
+                init_tap.push_back(BnInitHit{ch.oid + oid_base, ch.chunk_off, inits[k].q_off, inits[k].s_off,
                                              inits[k].q_start, inits[k].s_start, inits[k].length,
                                              inits[k].score});
-        if (taps & BN_TAP_GAPPED) gapped_tap.insert(gapped_tap.end(), o.tap.begin(), o.tap.end());
+        if (taps & BN_TAP_GAPPED) {
+            if (oid_base) for (auto &h : o.tap) h.oid += oid_base;
+            gapped_tap.insert(gapped_tap.end(), o.tap.begin(), o.tap.end());
+        }
         for (auto &h : o.fresh) { h.s_off += ch.chunk_off; h.s_end += ch.chunk_off; h.s_gapped_start += ch.chunk_off; }
         merge_chunk_lists(comb, o.fresh, ch.chunk_off, ch.chunk_off == 0 ? 0 : BN_DBSEQ_CHUNK_OVERLAP);
         std::vector<BnHSP>().swap(o.fresh);
@@ -1135,7 +1240,7 @@ static int search_host_phase(const Query &Q, const GpuOut &G, int taps, BnResult
     return BN_OK;
 }
 
-static int prelim_search_locked(Device &D, Volume &V, Query &Q, int32_t oid_begin, int32_t oid_end,
+static int prelim_search_locked(Lane &D, Volume &V, Query &Q, int32_t oid_begin, int32_t oid_end,
                                 int taps, BnResults *out)
 {
     GpuOut G;
@@ -1153,7 +1258,7 @@ using namespace bn;
 // ================================================================================================
 // Greedy traceback batch (BLAST_GreedyGappedAlignment with do_traceback): one thread per alignment with a private
 // arena; alignments whose rows do not fit are retried with 16x larger arenas (fewer threads).
-static int traceback_greedy_host(Device &Dv, Volume &V, Query &Q, int32_t x_dropoff, const BnTracebackItem *items, int64_t n_items,
+static int traceback_greedy_host(Lane &Dv, Volume &V, Query &Q, int32_t x_dropoff, const BnTracebackItem *items, int64_t n_items,
                                  const std::vector<DevTracebackItem> &up, BnTracebackResult **results, BnEditOp **ops, int64_t *n_ops)
 {
     cudaStream_t st = Dv.stream;
@@ -1264,14 +1369,22 @@ int bn_init(int n_gpu, const int *device_ids)
     std::vector<int> ids;
     if (n_gpu <= 0 || !device_ids) { for (int i = 0; i < (n_gpu > 0 ? std::min(n_gpu, count) : count); i++) ids.push_back(i); }
     else for (int i = 0; i < n_gpu; i++) ids.push_back(device_ids[i]);
+    // lanes per device: concurrent callers beyond this number wait for a lane (BN_LANES, default 4)
+    int n_lanes = 4;
+    if (const char *e = getenv("BN_LANES")) n_lanes = std::max(2, std::min(16, atoi(e)));      // the batch pipeline needs two
     for (int id : ids) {
         if (id < 0 || id >= count) return fail(BN_ERR_INVALID, "device id out of range");
-        auto d = std::make_unique<Device>();
+        auto d = std::make_unique<Gpu>();
         d->id = id;
         CU_TRY(cudaSetDevice(id));
-        CU_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
-        CU_TRY(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
-        CU_TRY(cudaEventCreateWithFlags(&d->alloc_ev, cudaEventDisableTiming));
+        for (int k = 0; k < n_lanes; k++) {
+            auto l = std::make_unique<Lane>();
+            l->id = id; l->index = k;
+            CU_TRY(cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking));
+            CU_TRY(cudaStreamCreateWithFlags(&l->copy_stream, cudaStreamNonBlocking));
+            CU_TRY(cudaEventCreateWithFlags(&l->alloc_ev, cudaEventDisableTiming));
+            d->lanes.push_back(std::move(l));
+        }
         {   // keep freed blocks in the stream-ordered pool (volumes / query tables are re-loaded often)
             cudaMemPool_t pool;
             if (cudaDeviceGetDefaultMemPool(&pool, id) == cudaSuccess) {
@@ -1285,26 +1398,43 @@ int bn_init(int n_gpu, const int *device_ids)
     return BN_OK;
 }
 
+static void free_volume_dev(Volume &V)
+{
+    Gpu *g = g_devices[(size_t)V.device].get();
+    cudaSetDevice(g->id);
+    cudaStream_t st = g->lanes[0]->stream;
+    if (V.ready) { cudaEventSynchronize(V.ready); cudaEventDestroy(V.ready); V.ready = nullptr; }
+    if (V.d_raw) cudaFreeAsync(V.d_raw, st);
+    if (V.d_amb_runs) cudaFreeAsync(V.d_amb_runs, st);
+    if (V.d_amb_first) cudaFreeAsync(V.d_amb_first, st);
+    V.d_raw = nullptr; V.d_packed = nullptr; V.d_amb_runs = nullptr; V.d_amb_first = nullptr;
+    std::lock_guard<std::mutex> tlk(V.tmu);
+    V.tables.clear();
+}
+
+static void free_query_all(Query &Q)
+{
+    for (size_t d = 0; d < Q.dev.size() && d < g_devices.size(); d++)
+        if (Q.dev[d].ready) { cudaSetDevice(g_devices[d]->id); free_query_dev(Q.dev[d], g_devices[d]->lanes[0]->stream); }
+}
+
 void bn_release(void)
 {
     std::lock_guard<std::mutex> lk(g_mu);
-    for (auto &q : g_queries) if (q) for (size_t d = 0; d < q->dev.size(); d++) {
-        if (q->dev[d].ready) { cudaSetDevice(g_devices[d]->id); free_query_dev(q->dev[d], g_devices[d]->stream); }
-    }
+    for (auto &q : g_queries) if (q) free_query_all(*q);
     g_queries.clear();
-    for (auto &v : g_volumes) if (v) {
-        cudaSetDevice(g_devices[v->device]->id);
-        if (v->ready) { cudaEventSynchronize(v->ready); cudaEventDestroy(v->ready); }
-        cudaFreeAsync(v->d_raw, g_devices[v->device]->stream);
-        for (auto &kv : v->tables) { kv.second->dev.release(); kv.second->units_dev.release(); kv.second->ranges_dev.release(); kv.second->block_chunk.release(); kv.second->block_desc.release(); }
-    }
+    for (auto &v : g_volumes) if (v) free_volume_dev(*v);
     g_volumes.clear();
     for (auto &d : g_devices) {
         cudaSetDevice(d->id);
-        d->wss[0].release(); d->wss[1].release();
-        if (d->alloc_ev) cudaEventDestroy(d->alloc_ev);
-        if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
-        if (d->stream) cudaStreamDestroy(d->stream);
+        for (auto &l : d->lanes) {
+            std::lock_guard<std::mutex> ll(l->mu);          // wait for a search still running on the lane
+            cudaStreamSynchronize(l->stream);
+            l->w.release();
+            if (l->alloc_ev) cudaEventDestroy(l->alloc_ev);
+            if (l->copy_stream) cudaStreamDestroy(l->copy_stream);
+            if (l->stream) cudaStreamDestroy(l->stream);
+        }
     }
     g_devices.clear();
     g_inited = false;
@@ -1319,19 +1449,21 @@ int bn_device_count(void)
 // async: the upload runs on the device's copy stream and the call returns at once; searches on the
 // volume wait for it on the device (Volume::ready)
 static int db_load_impl(int device, const uint8_t *packed, int64_t packed_bytes, const int64_t *seq_byte_off,
-                        const int32_t *seq_len, int32_t n_seq, bool async, int *vol_handle)
+                        const int32_t *seq_len, int32_t n_seq, bool async, std::shared_ptr<Volume> *out, Lane *D = nullptr)
 {
     int rc = ensure_init();
     if (rc) return rc;
-    if (!packed || !seq_byte_off || !seq_len || n_seq < 0 || !vol_handle) return fail(BN_ERR_INVALID, "bn_db_load: bad argument");
-    Device *D = device_at(device);
-    if (!D) return fail(BN_ERR_INVALID, "bn_db_load: bad device");
+    if (!packed || !seq_byte_off || !seq_len || n_seq < 0 || !out) return fail(BN_ERR_INVALID, "bn_db_load: bad argument");
+    Gpu *G = device_at(device);
+    if (!G) return fail(BN_ERR_INVALID, "bn_db_load: bad device");
+    LaneLock own;
+    if (!D) { own = LaneLock(*G); D = own.lane; }
     for (int32_t i = 0; i < n_seq; i++) {
         const int64_t end = seq_byte_off[i] + (seq_len[i] + 3) / 4;
         if (seq_byte_off[i] < 0 || seq_len[i] < 0 || end + 16 > packed_bytes)
             return fail(BN_ERR_INVALID, "bn_db_load: sequence outside the packed buffer (16 pad bytes required)");
     }
-    auto V = std::make_unique<Volume>();
+    auto V = std::make_shared<Volume>();
     V->device = device; V->bytes = packed_bytes;
     V->byte_off.assign(seq_byte_off, seq_byte_off + n_seq);
     V->seq_len.assign(seq_len, seq_len + n_seq);
@@ -1351,16 +1483,20 @@ static int db_load_impl(int device, const uint8_t *packed, int64_t packed_bytes,
         CU_TRY(cudaEventCreateWithFlags(&V->ready, cudaEventDisableTiming));
         CU_TRY(cudaEventRecord(V->ready, cs));
     } else CU_TRY(cudaStreamSynchronize(cs));
-    std::lock_guard<std::mutex> lk(g_mu);
-    g_volumes.push_back(std::move(V));
-    *vol_handle = (int)g_volumes.size() - 1;
+    *out = std::move(V);
     return BN_OK;
 }
 
 int bn_db_load(int device, const uint8_t *packed, int64_t packed_bytes, const int64_t *seq_byte_off,
                const int32_t *seq_len, int32_t n_seq, int *vol_handle)
 {
-    return db_load_impl(device, packed, packed_bytes, seq_byte_off, seq_len, n_seq, false, vol_handle);
+    if (!vol_handle) return fail(BN_ERR_INVALID, "bn_db_load: bad argument");
+    std::shared_ptr<Volume> V;
+    int rc = db_load_impl(device, packed, packed_bytes, seq_byte_off, seq_len, n_seq, false, &V);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_mu);
+    *vol_handle = put_handle(g_volumes, std::move(V));
+    return BN_OK;
 }
 
 int bn_dbfile_index(const char *nin_path, const char *nsq_path, BnDbFileInfo *info, int64_t *seq_byte_off,
@@ -1400,14 +1536,16 @@ int bn_db_load_files(int device, const char *nin_path, const char *nsq_path, int
     int rc = ensure_init();
     if (rc) return rc;
     if (!nin_path || !nsq_path || !vol_handle) return fail(BN_ERR_INVALID, "bn_db_load_files: bad argument");
-    Device *D = device_at(device);
-    if (!D) return fail(BN_ERR_INVALID, "bn_db_load_files: bad device");
+    Gpu *G = device_at(device);
+    if (!G) return fail(BN_ERR_INVALID, "bn_db_load_files: bad device");
+    LaneLock own(*G);
+    Lane *D = own.lane;
     DbIndex idx;
     std::string err;
     if (!read_nin(nin_path, idx, err)) return fail(BN_ERR_INVALID, "bn_db_load_files: " + err);
     MappedFile nsq;
     if (!nsq.open(nsq_path, err)) return fail(BN_ERR_INVALID, "bn_db_load_files: " + err);
-    auto V = std::make_unique<Volume>();
+    auto V = std::make_shared<Volume>();
     V->device = device; V->bytes = nsq.size();
     if (!sequence_table(idx, nsq.data(), nsq.size(), V->byte_off, V->seq_len, err))
         return fail(BN_ERR_INVALID, "bn_db_load_files: " + err);
@@ -1421,17 +1559,20 @@ int bn_db_load_files(int device, const char *nin_path, const char *nsq_path, int
     CU_TRY(cudaMemsetAsync(V->d_packed + nsq.size(), 0, 128, D->stream));
     CU_TRY(cudaStreamSynchronize(D->stream));
     std::lock_guard<std::mutex> lk(g_mu);
-    g_volumes.push_back(std::move(V));
-    *vol_handle = (int)g_volumes.size() - 1;
+    *vol_handle = put_handle(g_volumes, std::move(V));
     return BN_OK;
 }
 
 int bn_db_set_masks(int vol_handle, int mask_type, const int32_t *mask_n, const int32_t *mask_iv)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (vol_handle < 0 || vol_handle >= (int)g_volumes.size() || !g_volumes[vol_handle])
-        return fail(BN_ERR_INVALID, "bn_db_set_masks: bad handle");
-    Volume &V = *g_volumes[vol_handle];
+    std::shared_ptr<Volume> Vp;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (vol_handle < 0 || vol_handle >= (int)g_volumes.size() || !g_volumes[vol_handle])
+            return fail(BN_ERR_INVALID, "bn_db_set_masks: bad handle");
+        Vp = g_volumes[vol_handle];
+    }
+    Volume &V = *Vp;
     if (mask_type != BN_MASK_NONE && mask_type != BN_MASK_SOFT && mask_type != BN_MASK_HARD)
         return fail(BN_ERR_INVALID, "bn_db_set_masks: bad mask type");
     const size_t n = V.seq_len.size();
@@ -1454,32 +1595,34 @@ int bn_db_set_masks(int vol_handle, int mask_type, const int32_t *mask_n, const 
             }
         }
     }
+    std::lock_guard<std::mutex> tlk(V.tmu);         // chunk-table builders read the masks under the same lock
     V.mask_type = mask_type;
     V.mask_first.swap(first);
     V.mask_iv.swap(iv);
     ++V.mask_version;                 // chunk tables are cached per mask version
+    V.tables.clear();                 // tables of the old masks are of no use any more
     return BN_OK;
 }
 
 int bn_db_free(int h)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (h < 0 || h >= (int)g_volumes.size() || !g_volumes[h]) return fail(BN_ERR_INVALID, "bn_db_free: bad handle");
-    Volume &V = *g_volumes[h];
-    cudaSetDevice(g_devices[V.device]->id);
-    if (V.ready) { cudaStreamWaitEvent(g_devices[V.device]->stream, V.ready, 0); cudaEventDestroy(V.ready); V.ready = nullptr; }
-    cudaFreeAsync(V.d_raw, g_devices[V.device]->stream);
-    for (auto &kv : V.tables) { kv.second->dev.release(); kv.second->units_dev.release(); kv.second->ranges_dev.release(); kv.second->block_chunk.release(); kv.second->block_desc.release(); }
-    g_volumes[h].reset();
+    std::shared_ptr<Volume> V;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (h < 0 || h >= (int)g_volumes.size() || !g_volumes[h]) return fail(BN_ERR_INVALID, "bn_db_free: bad handle");
+        V.swap(g_volumes[h]);
+    }
+    free_volume_dev(*V);
     return BN_OK;
 }
 
-static int query_load_impl(const BnQueryBatch *b, int *query_handle, int hook_device,
-                           const std::function<int()> *after_h2d)
+// `held`: a lane of device hook_device the caller already owns (its stream then carries the table build)
+static int query_load_impl(const BnQueryBatch *b, std::shared_ptr<Query> *out, int hook_device,
+                           const std::function<int()> *after_h2d, Lane *held = nullptr, bool hook_device_only = false)
 {
     int rc = ensure_init();
     if (rc) return rc;
-    if (!b || !query_handle || !b->query_start || !b->contexts || b->num_contexts <= 0)
+    if (!b || !out || !b->query_start || !b->contexts || b->num_contexts <= 0)
         return fail(BN_ERR_INVALID, "bn_query_load: bad argument");
     if (b->lut_type != BN_LUT_MB && b->lut_type != BN_LUT_SMALL_NA && b->lut_type != BN_LUT_NA)
         return fail(BN_ERR_UNSUPPORTED, "unknown lookup table type");
@@ -1492,7 +1635,7 @@ static int query_load_impl(const BnQueryBatch *b, int *query_handle, int hook_de
             if (b->lookup_segments[2 * i + 1] >= b->lookup_segments[2 * i + 2])
                 return fail(BN_ERR_INVALID, "bn_query_load: lookup_segments must be ascending and disjoint");
     if (b->lut_type == BN_LUT_SMALL_NA && !b->backbone) return fail(BN_ERR_INVALID, "bn_query_load: small table arrays missing");
-    auto Q = std::make_unique<Query>();
+    auto Q = std::make_shared<Query>();
     Q->batch = *b;
     Q->ctx.assign(b->contexts, b->contexts + b->num_contexts);
 
@@ -1510,58 +1653,89 @@ static int query_load_impl(const BnQueryBatch *b, int *query_handle, int hook_de
     Q->ctx_lite = make_ctx_lite(Q->batch);
     Q->dev.resize(g_devices.size());
     for (size_t d = 0; d < g_devices.size(); d++) {
-        rc = query_to_device(*Q, *b, (int)d, (int)d == hook_device ? after_h2d : nullptr);
-        if (rc) {
-            for (size_t k = 0; k < g_devices.size(); k++)
-                if (Q->dev[k].ready) { cudaSetDevice(g_devices[k]->id); free_query_dev(Q->dev[k], g_devices[k]->stream); }
-            return rc;
-        }
+        if (hook_device_only && (int)d != hook_device) continue;      // a batch of the host-buffer call lives on its device only
+        LaneLock own;
+        Lane *L = ((int)d == hook_device) ? held : nullptr;
+        if (!L) { own = LaneLock(*g_devices[d]); L = own.lane; }
+        rc = query_to_device(*Q, *b, (int)d, L, (int)d == hook_device ? after_h2d : nullptr);
+        if (rc) { free_query_all(*Q); return rc; }
     }
-    std::lock_guard<std::mutex> lk(g_mu);
-    g_queries.push_back(std::move(Q));
-    *query_handle = (int)g_queries.size() - 1;
+    *out = std::move(Q);
     return BN_OK;
 }
 
 int bn_query_load(const BnQueryBatch *b, int *query_handle)
 {
-    return query_load_impl(b, query_handle, -1, nullptr);
+    if (!query_handle) return fail(BN_ERR_INVALID, "bn_query_load: bad argument");
+    std::shared_ptr<Query> Q;
+    int rc = query_load_impl(b, &Q, -1, nullptr);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_mu);
+    *query_handle = put_handle(g_queries, std::move(Q));
+    return BN_OK;
 }
 
 int bn_query_free(int h)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (h < 0 || h >= (int)g_queries.size() || !g_queries[h]) return fail(BN_ERR_INVALID, "bn_query_free: bad handle");
-    Query &Q = *g_queries[h];
-    for (size_t d = 0; d < Q.dev.size(); d++)
-        if (Q.dev[d].ready) { cudaSetDevice(g_devices[d]->id); free_query_dev(Q.dev[d], g_devices[d]->stream); }
-    g_queries[h].reset();
+    std::shared_ptr<Query> Q;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (h < 0 || h >= (int)g_queries.size() || !g_queries[h]) return fail(BN_ERR_INVALID, "bn_query_free: bad handle");
+        Q.swap(g_queries[h]);
+    }
+    free_query_all(*Q);
     return BN_OK;
 }
 
-static int get_handles(int vol_handle, int query_handle, Volume **V, Query **Q, Device **D)
+// What a call works on: shared ownership of the volume and the query batch (a concurrent bn_*_free on another
+// thread only drops the table's reference) and one lane of the volume's device, held until the call returns.
+struct Handles {
+    std::shared_ptr<Volume> Vp;
+    std::shared_ptr<Query> Qp;
+    LaneLock lock;
+};
+
+static int get_volume(int vol_handle, std::shared_ptr<Volume> *V)
 {
+    std::lock_guard<std::mutex> lk(g_mu);
     if (vol_handle < 0 || vol_handle >= (int)g_volumes.size() || !g_volumes[vol_handle])
         return fail(BN_ERR_INVALID, "bad volume handle");
+    *V = g_volumes[vol_handle];
+    return BN_OK;
+}
+
+static int get_query(int query_handle, std::shared_ptr<Query> *Q)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
     if (query_handle < 0 || query_handle >= (int)g_queries.size() || !g_queries[query_handle])
         return fail(BN_ERR_INVALID, "bad query handle");
-    *V = g_volumes[vol_handle].get();
-    *Q = g_queries[query_handle].get();
-    *D = device_at((*V)->device);
+    *Q = g_queries[query_handle];
+    return BN_OK;
+}
+
+static int get_handles(int vol_handle, int query_handle, Handles &H, Volume **V, Query **Q, Lane **D)
+{
+    int rc = get_volume(vol_handle, &H.Vp);
+    if (rc) return rc;
+    rc = get_query(query_handle, &H.Qp);
+    if (rc) return rc;
+    Gpu *g = device_at(H.Vp->device);
+    if (!g) return fail(BN_ERR_INVALID, "volume on an unknown device");
+    H.lock = LaneLock(*g);
+    *V = H.Vp.get(); *Q = H.Qp.get(); *D = H.lock.lane;
     return BN_OK;
 }
 
 int bn_prelim_search(int vol_handle, int query_handle, int32_t oid_begin, int32_t oid_end, int taps,
                      BnResults *out)
 {
-    Volume *V; Query *Q; Device *D;
+    Volume *V; Query *Q; Lane *D; Handles H;
     if (!out) return fail(BN_ERR_INVALID, "bn_prelim_search: out is NULL");
-    int rc = get_handles(vol_handle, query_handle, &V, &Q, &D);
+    int rc = get_handles(vol_handle, query_handle, H, &V, &Q, &D);
     if (rc) return rc;
     const int32_t n = (int32_t)V->seq_len.size();
     if (oid_begin < 0) oid_begin = 0;
     if (oid_end < 0 || oid_end > n) oid_end = n;
-    std::lock_guard<std::mutex> lk(D->mu);
     return prelim_search_locked(*D, *V, *Q, oid_begin, oid_end, taps, out);
 }
 
@@ -1569,30 +1743,33 @@ int bn_prelim_search_host(int device, const BnQueryBatch *batch, const uint8_t *
                           int64_t packed_bytes, const int64_t *seq_byte_off, const int32_t *seq_len,
                           int32_t n_seq, int taps, BnResults *out)
 {
-    int vh = -1, qh = -1;
     static const bool trace = getenv("BN_TRACE") != nullptr;
     const double t0 = now_ms();
-    // the volume streams to the device on the copy stream while the query tables are built on the main
-    // one; its copy is queued right behind the (small) query copies
+    if (!out) return fail(BN_ERR_INVALID, "bn_prelim_search_host: out is NULL");
     int rc = ensure_init();
     if (rc) return rc;
+    Gpu *G = device_at(device);
+    if (!G) return fail(BN_ERR_INVALID, "bn_prelim_search_host: bad device");
+    // One lane for the whole call.  The volume streams to the device on the lane's copy stream while the query
+    // tables are built on its main stream; the copy is queued right behind the (small) query copies.  Volume and
+    // batch live for this call only and never enter the handle tables.
+    LaneLock lock(*G);
+    Lane *L = lock.lane;
+    std::shared_ptr<Volume> V;
+    std::shared_ptr<Query> Q;
     double t1 = t0;
-    int rc_load = BN_OK;
     const std::function<int()> start_volume = [&]() {
-        rc_load = db_load_impl(device, packed, packed_bytes, seq_byte_off, seq_len, n_seq, true, &vh);
+        const int r = db_load_impl(device, packed, packed_bytes, seq_byte_off, seq_len, n_seq, true, &V, L);
         t1 = now_ms();
-        return rc_load;
+        return r;
     };
-    rc = query_load_impl(batch, &qh, device, &start_volume);
-    if (vh < 0) {       // the hook did not run or failed
-        if (qh >= 0) bn_query_free(qh);
-        return rc ? rc : fail(BN_ERR_INVALID, "bn_prelim_search_host: bad device");
-    }
+    rc = query_load_impl(batch, &Q, device, &start_volume, L, true);
     const double t2 = now_ms();
-    if (rc == BN_OK) rc = bn_prelim_search(vh, qh, 0, n_seq, taps, out);
+    if (rc == BN_OK && !V) rc = fail(BN_ERR_INVALID, "bn_prelim_search_host: volume upload did not start");
+    if (rc == BN_OK) rc = prelim_search_locked(*L, *V, *Q, 0, n_seq, taps, out);
     const double t3 = now_ms();
-    if (qh >= 0) bn_query_free(qh);
-    bn_db_free(vh);
+    if (Q) free_query_all(*Q);
+    if (V) free_volume_dev(*V);
     if (trace)
         fprintf(stderr, "[bn] host-buffer call %.3f ms: query copies + volume enqueue %.3f table build %.3f search %.3f free %.3f\n",
                 now_ms() - t0, t1 - t0, t2 - t1, t3 - t2, now_ms() - t3);
@@ -1605,30 +1782,35 @@ int bn_prelim_search_batches(int vol_handle, int32_t n_batches, const BnQueryBat
     if (n_batches < 0 || (n_batches > 0 && (!batches || !results))) return fail(BN_ERR_INVALID, "bn_prelim_search_batches: bad argument");
     int rc = ensure_init();
     if (rc) return rc;
-    if (vol_handle < 0 || vol_handle >= (int)g_volumes.size() || !g_volumes[vol_handle])
-        return fail(BN_ERR_INVALID, "bad volume handle");
-    Volume *V = g_volumes[vol_handle].get();
-    Device *D = device_at(V->device);
+    std::shared_ptr<Volume> Vp;
+    rc = get_volume(vol_handle, &Vp);
+    if (rc) return rc;
+    Volume *V = Vp.get();
+    Gpu *g = device_at(V->device);
     for (int32_t k = 0; k < n_batches; k++) memset(&results[k], 0, sizeof results[k]);
-    std::lock_guard<std::mutex> lk(D->mu);
+    if (n_batches == 0) return BN_OK;
+    // two lanes: batch k runs on lane k & 1 while a host thread finishes batch k-1 out of the other lane's
+    // pinned result mirrors
+    LaneLock lanes[2];
+    lanes[0] = LaneLock(*g);
+    lanes[1] = LaneLock(*g);
     const int32_t n_seq = (int32_t)V->seq_len.size();
-    std::vector<int> qh((size_t)n_batches, -1);
+    std::vector<std::shared_ptr<Query>> Qs((size_t)n_batches);
     std::vector<GpuOut> G((size_t)n_batches);
     std::vector<int> host_rc((size_t)n_batches, BN_OK);
     std::vector<std::string> host_err((size_t)n_batches);
     std::thread pending[2];
     int first_error = BN_OK;
     std::string first_msg;
-    const int saved_cur = D->cur;
     for (int32_t k = 0; k < n_batches && first_error == BN_OK; k++) {
-        // tables of batch k (uploads + device-side derivation); the worker is finishing batch k-1 meanwhile
-        rc = bn_query_load(batches[k], &qh[(size_t)k]);
-        if (rc) { first_error = rc; first_msg = g_err; break; }
         const int slot = k & 1;
-        if (pending[slot].joinable()) pending[slot].join();      // batch k-2 has left this workspace's mirrors
-        D->cur = slot;
-        Query *Q = g_queries[(size_t)qh[(size_t)k]].get();
-        rc = search_gpu_phase(*D, *V, *Q, 0, n_seq, &results[k], G[(size_t)k]);
+        Lane *L = lanes[slot].lane;
+        if (pending[slot].joinable()) pending[slot].join();      // batch k-2 has left this lane's mirrors
+        // tables of batch k (uploads + device-side derivation); the worker is finishing batch k-1 meanwhile
+        rc = query_load_impl(batches[k], &Qs[(size_t)k], V->device, nullptr, L, true);
+        if (rc) { first_error = rc; first_msg = g_err; break; }
+        Query *Q = Qs[(size_t)k].get();
+        rc = search_gpu_phase(*L, *V, *Q, 0, n_seq, &results[k], G[(size_t)k]);
         if (rc) { first_error = rc; first_msg = g_err; break; }
         pending[slot] = std::thread([&, k, Q]() {
             host_rc[(size_t)k] = search_host_phase(*Q, G[(size_t)k], taps, &results[k]);
@@ -1636,15 +1818,136 @@ int bn_prelim_search_batches(int vol_handle, int32_t n_batches, const BnQueryBat
         });
     }
     for (auto &t : pending) if (t.joinable()) t.join();
-    D->cur = saved_cur;
     for (int32_t k = 0; k < n_batches; k++) {
-        if (qh[(size_t)k] >= 0) bn_query_free(qh[(size_t)k]);
+        if (Qs[(size_t)k]) free_query_all(*Qs[(size_t)k]);
         if (first_error == BN_OK && host_rc[(size_t)k]) { first_error = host_rc[(size_t)k]; first_msg = host_err[(size_t)k]; }
     }
     if (first_error) {
         for (int32_t k = 0; k < n_batches; k++) bn_results_free(&results[k]);
         return fail(first_error, first_msg);
     }
+    return BN_OK;
+}
+
+// database volumes shard over the GPUs, results meet on the host.  One worker thread per volume
+// runs the GPU phase on a lane of the volume's device (volumes on different devices — or on different lanes of
+// one device — overlap); the host replay then walks the volumes in order with ONE set of hit lists, so
+// hit_params->low_score evolves exactly as in a single pass over the concatenated database
+// (core/blast_engine.c:1313-1320) and prelim_hitlist_size (core/hspfilter_collector.c:328-342) is applied once,
+// after the gather, never per volume.
+int bn_prelim_search_volumes(int32_t n_volumes, const int *vol_handles, int query_handle, int taps,
+                             int prune_hitlists, BnResults *out)
+{
+    if (n_volumes < 0 || (n_volumes > 0 && !vol_handles) || !out)
+        return fail(BN_ERR_INVALID, "bn_prelim_search_volumes: bad argument");
+    int rc = ensure_init();
+    if (rc) return rc;
+    memset(out, 0, sizeof *out);
+    const double t0 = now_ms();
+    std::shared_ptr<Query> Qp;
+    rc = get_query(query_handle, &Qp);
+    if (rc) return rc;
+    Query &Q = *Qp;
+    const size_t nv = (size_t)n_volumes;
+    std::vector<std::shared_ptr<Volume>> Vs(nv);
+    std::vector<int32_t> oid_base(nv + 1, 0);
+    for (size_t v = 0; v < nv; v++) {
+        rc = get_volume(vol_handles[v], &Vs[v]);
+        if (rc) return rc;
+        if (!Q.dev[(size_t)Vs[v]->device].ready) return fail(BN_ERR_INVALID, "query batch is not loaded on a volume's device");
+        const int64_t next = (int64_t)oid_base[v] + (int64_t)Vs[v]->seq_len.size();
+        if (next > INT32_MAX) return fail(BN_ERR_OVERFLOW, "more than 2^31 sequences in the volumes");
+        oid_base[v + 1] = (int32_t)next;
+    }
+    struct Part {
+        GpuOut G;
+        BnResults res{};
+        std::vector<DevInitHit> init;         // copies of the lane's pinned mirrors (the lane moves on)
+        std::vector<DevGapResult> gap;
+        int rc = BN_OK;
+        std::string err;
+        bool done = false;
+    };
+    std::vector<Part> parts(nv);
+    std::mutex mu;
+    std::condition_variable cv;
+    std::atomic<size_t> next_vol{0};
+    auto worker = [&]() {
+        for (size_t v; (v = next_vol.fetch_add(1)) < nv;) {
+            Part &P = parts[v];
+            Volume &V = *Vs[v];
+            {
+                LaneLock lock(*device_at(V.device));
+                P.rc = search_gpu_phase(*lock.lane, V, Q, 0, (int32_t)V.seq_len.size(), &P.res, P.G);
+                if (P.rc) P.err = g_err;
+                else {
+                    P.init.assign(P.G.h_init, P.G.h_init + P.G.cnt.n_init);
+                    P.gap.assign(P.G.h_gap, P.G.h_gap + P.G.cnt.n_init);
+                    P.G.h_init = P.init.data(); P.G.h_gap = P.gap.data();
+                }
+            }
+            std::lock_guard<std::mutex> lk(mu);
+            P.done = true;
+            cv.notify_all();
+        }
+    };
+    size_t n_lanes_total = 0;
+    for (auto &g : g_devices) n_lanes_total += g->lanes.size();
+    const size_t n_workers = std::min(nv, std::max<size_t>(1, n_lanes_total));
+    std::vector<std::thread> pool;
+    for (size_t t = 0; t < n_workers; t++) pool.emplace_back(worker);
+
+    // host replay in volume order = OID order of the concatenated database
+    LowScoreTracker tracker(Q.batch, prune_hitlists != 0);
+    const bool bounds_fixed = (int64_t)oid_base[nv] <= (int64_t)tracker.hitlist_size();
+    std::vector<BnHSP> hsps, gapped;
+    std::vector<BnInitHit> init;
+    BnStats total{};
+    int first_error = BN_OK;
+    std::string first_msg;
+    for (size_t v = 0; v < nv; v++) {
+        Part &P = parts[v];
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&]() { return P.done; });
+        }
+        if (first_error) continue;
+        if (P.rc) { first_error = P.rc; first_msg = P.err; continue; }
+        HostShared sh;
+        sh.tracker = &tracker; sh.bounds_fixed = bounds_fixed; sh.oid_base = oid_base[v];
+        const int r = search_host_phase(Q, P.G, taps, &P.res, &sh);
+        if (r) { first_error = r; first_msg = g_err; continue; }
+        hsps.insert(hsps.end(), P.res.hsps, P.res.hsps + P.res.n_hsps);
+        init.insert(init.end(), P.res.init, P.res.init + P.res.n_init);
+        gapped.insert(gapped.end(), P.res.gapped, P.res.gapped + P.res.n_gapped);
+        const BnStats &s = P.res.stats;
+        total.lookup_hits += s.lookup_hits; total.init_extends += s.init_extends;
+        total.good_init_extends += s.good_init_extends; total.gap_extensions += s.gap_extensions;
+        total.good_extensions += s.good_extensions; total.subject_bases_scanned += s.subject_bases_scanned;
+        total.ms_scan += s.ms_scan; total.ms_extend += s.ms_extend; total.ms_gapped += s.ms_gapped;
+        total.ms_host += s.ms_host; total.kernel_launches += s.kernel_launches;
+        bn_results_free(&P.res);
+        P.init = std::vector<DevInitHit>(); P.gap = std::vector<DevGapResult>();
+    }
+    for (auto &t : pool) t.join();
+    for (auto &P : parts) bn_results_free(&P.res);
+    if (first_error) return fail(first_error, first_msg);
+    if (prune_hitlists && !bounds_fixed) {
+        // keep the lists the HSP stream still holds: per query the subjects of its hit list
+        std::vector<std::vector<int32_t>> kept((size_t)Q.batch.num_queries);
+        for (int32_t q = 0; q < Q.batch.num_queries; q++) kept[(size_t)q] = tracker.kept_oids(q);
+        size_t o = 0;
+        for (const BnHSP &h : hsps) {
+            const std::vector<int32_t> &k = kept[(size_t)Q.batch.contexts[h.context].query_index];
+            if (std::binary_search(k.begin(), k.end(), h.oid)) hsps[o++] = h;
+        }
+        hsps.resize(o);
+    }
+    out->n_hsps = (int64_t)hsps.size(); out->hsps = to_malloc(hsps);
+    out->n_init = (int64_t)init.size(); out->init = to_malloc(init);
+    out->n_gapped = (int64_t)gapped.size(); out->gapped = to_malloc(gapped);
+    total.ms_total = now_ms() - t0;
+    out->stats = total;
     return BN_OK;
 }
 
@@ -1668,16 +1971,15 @@ int bn_scan_subject(int vol_handle, int query_handle, int32_t oid, int32_t chunk
                     BnOffsetPair **pairs, int64_t *n_pairs)
 {
     (void)chunk_off; (void)chunk_len;
-    Volume *V; Query *Q; Device *D;
+    Volume *V; Query *Q; Lane *D; Handles H;
     if (!pairs || !n_pairs) return fail(BN_ERR_INVALID, "bn_scan_subject: NULL output");
-    int rc = get_handles(vol_handle, query_handle, &V, &Q, &D);
+    int rc = get_handles(vol_handle, query_handle, H, &V, &Q, &D);
     if (rc) return rc;
     if (oid < 0 || oid >= (int32_t)V->seq_len.size()) return fail(BN_ERR_INVALID, "bn_scan_subject: bad oid");
-    std::lock_guard<std::mutex> lk(D->mu);
     CU_TRY(cudaSetDevice(D->id));
     if (!Q->dev[V->device].ready) return fail(BN_ERR_INVALID, "query batch is not loaded on the volume's device");
     std::shared_ptr<ChunkTable> T;
-    rc = build_chunk_table(*V, *Q, oid, oid + 1, D->stream, &T);
+    rc = build_chunk_table(*V, *Q, oid, oid + 1, *D, &T);
     if (rc) return rc;
     if (V->ready) CU_TRY(cudaStreamWaitEvent(D->stream, V->ready, 0));
     StageCounts cnt;
@@ -1715,16 +2017,15 @@ int bn_get_gapped_score(int vol_handle, int query_handle, int32_t oid, int32_t c
                         const BnInitHit *init, int64_t n_init, const int32_t *low_score,
                         BnHSP **hsps, int64_t *n_hsps)
 {
-    Volume *V; Query *Q; Device *D;
+    Volume *V; Query *Q; Lane *D; Handles H;
     if (!hsps || !n_hsps || n_init < 0 || (n_init > 0 && !init)) return fail(BN_ERR_INVALID, "bn_get_gapped_score: bad argument");
-    int rc = get_handles(vol_handle, query_handle, &V, &Q, &D);
+    int rc = get_handles(vol_handle, query_handle, H, &V, &Q, &D);
     if (rc) return rc;
     if (oid < 0 || oid >= (int32_t)V->seq_len.size()) return fail(BN_ERR_INVALID, "bn_get_gapped_score: bad oid");
-    std::lock_guard<std::mutex> lk(D->mu);
     CU_TRY(cudaSetDevice(D->id));
     if (!Q->dev[V->device].ready) return fail(BN_ERR_INVALID, "query batch is not loaded on the volume's device");
     std::shared_ptr<ChunkTable> T;
-    rc = build_chunk_table(*V, *Q, oid, oid + 1, D->stream, &T);
+    rc = build_chunk_table(*V, *Q, oid, oid + 1, *D, &T);
     if (rc) return rc;
     int32_t chunk = -1;
     for (size_t c = 0; c < T->hchunks.size(); c++) if (T->hchunks[c].chunk_off == chunk_off) chunk = (int32_t)c;
@@ -1770,11 +2071,11 @@ int bn_get_gapped_score(int vol_handle, int query_handle, int32_t oid, int32_t c
 // BLAST_GappedAlignmentWithTraceback (core/blast_gapalign.c:3994-4155) for a batch of start points; the
 // alignments run on the device (traceback_kernel.cu), the two directions are joined here exactly like
 // Blast_PrelimEditBlockToGapEditScript (:2455-2517) and the leading / trailing gap pruning of :4115-4150.
-static int traceback_core(Device *D, Volume *V, Query *Q, int32_t gap_x_dropoff_final,
+static int traceback_core(Lane *D, Volume *V, Query *Q, int32_t gap_x_dropoff_final,
                           const BnTracebackItem *items, int64_t n_items,
                           BnTracebackResult **results, BnEditOp **ops, int64_t *n_ops)
 {
-    // the caller holds D->mu and has made the device current
+    // the caller holds the lane D and has made the device current
     *results = nullptr; *ops = nullptr; *n_ops = 0;
     const bool greedy = Q->batch.gap_algo == BN_GAP_GREEDY;
     if (!greedy && Q->batch.gap_extend <= 0)
@@ -1920,12 +2221,11 @@ int bn_gapped_traceback(int vol_handle, int query_handle, int32_t gap_x_dropoff_
                         const BnTracebackItem *items, int64_t n_items,
                         BnTracebackResult **results, BnEditOp **ops, int64_t *n_ops)
 {
-    Volume *V; Query *Q; Device *D;
+    Volume *V; Query *Q; Lane *D; Handles H;
     if (!results || !ops || !n_ops || n_items < 0 || (n_items > 0 && !items))
         return fail(BN_ERR_INVALID, "bn_gapped_traceback: bad argument");
-    int rc = get_handles(vol_handle, query_handle, &V, &Q, &D);
+    int rc = get_handles(vol_handle, query_handle, H, &V, &Q, &D);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(D->mu);
     CU_TRY(cudaSetDevice(D->id));
     return traceback_core(D, V, Q, gap_x_dropoff_final, items, n_items, results, ops, n_ops);
 }
@@ -1934,8 +2234,8 @@ int bn_gapped_traceback(int vol_handle, int query_handle, int32_t gap_x_dropoff_
 // start point (BLAST_CheckStartForGappedAlignment :97-153, BlastGetOffsetsForGappedAlignment
 // core/blast_gapalign.c:3059-3131, BlastGetStartForGappedAlignmentNucl :3134-3182) and AdjustSubjectRange (:3608-3636)
 // on the device, then the alignment with traceback.
-// start points + alignments for a list of preliminary HSPs; the caller holds D->mu and has made the device current
-static int traceback_hsps_core(Device *D, Volume *V, Query *Q, int32_t gap_x_dropoff_final, const BnHSP *hsps, int64_t n_hsps,
+// start points + alignments for a list of preliminary HSPs; the caller holds the lane D and has made the device current
+static int traceback_hsps_core(Lane *D, Volume *V, Query *Q, int32_t gap_x_dropoff_final, const BnHSP *hsps, int64_t n_hsps,
                                std::vector<BnTracebackItem> &all, std::vector<BnTracebackResult> &res,
                                BnEditOp **ops, int64_t *n_ops)
 {
@@ -1994,13 +2294,12 @@ int bn_traceback_hsps(int vol_handle, int query_handle, int32_t gap_x_dropoff_fi
                       const BnHSP *hsps, int64_t n_hsps, BnTracebackItem **items_out,
                       BnTracebackResult **results, BnEditOp **ops, int64_t *n_ops)
 {
-    Volume *V; Query *Q; Device *D;
+    Volume *V; Query *Q; Lane *D; Handles H;
     if (!items_out || !results || !ops || !n_ops || n_hsps < 0 || (n_hsps > 0 && !hsps))
         return fail(BN_ERR_INVALID, "bn_traceback_hsps: bad argument");
-    int rc = get_handles(vol_handle, query_handle, &V, &Q, &D);
+    int rc = get_handles(vol_handle, query_handle, H, &V, &Q, &D);
     if (rc) return rc;
     *items_out = nullptr; *results = nullptr; *ops = nullptr; *n_ops = 0;
-    std::lock_guard<std::mutex> lk(D->mu);
     CU_TRY(cudaSetDevice(D->id));
     std::vector<BnTracebackItem> all;
     std::vector<BnTracebackResult> res;
@@ -2020,13 +2319,12 @@ int bn_traceback_search(int vol_handle, int query_handle, int32_t gap_x_dropoff_
                         const BnHSP *hsps, int64_t n_hsps,
                         BnTracebackHSP **out, int64_t *n_out, BnEditOp **ops_out, int64_t *n_ops_out)
 {
-    Volume *V; Query *Q; Device *D;
+    Volume *V; Query *Q; Lane *D; Handles H;
     if (!out || !n_out || !ops_out || !n_ops_out || n_hsps < 0 || (n_hsps > 0 && !hsps))
         return fail(BN_ERR_INVALID, "bn_traceback_search: bad argument");
-    int rc = get_handles(vol_handle, query_handle, &V, &Q, &D);
+    int rc = get_handles(vol_handle, query_handle, H, &V, &Q, &D);
     if (rc) return rc;
     *out = nullptr; *n_out = 0; *ops_out = nullptr; *n_ops_out = 0;
-    std::lock_guard<std::mutex> lk(D->mu);
     CU_TRY(cudaSetDevice(D->id));
     const BnQueryBatch &b = Q->batch;
     const bool greedy = b.gap_algo == BN_GAP_GREEDY;
@@ -2161,13 +2459,15 @@ int bn_traceback_search(int vol_handle, int query_handle, int32_t gap_x_dropoff_
 
 int bn_query_download_lookup(int query_handle, int device, int32_t *hashtable, int32_t *next_pos)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (query_handle < 0 || query_handle >= (int)g_queries.size() || !g_queries[query_handle])
-        return fail(BN_ERR_INVALID, "bn_query_download_lookup: bad query handle");
-    Query &Q = *g_queries[query_handle];
-    Device *D = device_at(device);
-    if (!D || !Q.dev[device].ready || Q.batch.lut_type != BN_LUT_MB || !hashtable || !next_pos)
+    std::shared_ptr<Query> Qp;
+    int rc = get_query(query_handle, &Qp);
+    if (rc) return rc;
+    Query &Q = *Qp;
+    Gpu *G = device_at(device);
+    if (!G || !Q.dev[device].ready || Q.batch.lut_type != BN_LUT_MB || !hashtable || !next_pos)
         return fail(BN_ERR_INVALID, "bn_query_download_lookup: bad argument");
+    LaneLock lock(*G);
+    Lane *D = lock.lane;
     CU_TRY(cudaSetDevice(D->id));
     cudaStream_t st = D->stream;
     int32_t *tmp = nullptr;
@@ -2184,14 +2484,13 @@ int bn_query_download_lookup(int query_handle, int device, int32_t *hashtable, i
 int bn_bench_scan(int vol_handle, int query_handle, int iters, double *ms_per_launch,
                   int64_t *bases_per_launch, int64_t *hits)
 {
-    Volume *V; Query *Q; Device *D;
-    int rc = get_handles(vol_handle, query_handle, &V, &Q, &D);
+    Volume *V; Query *Q; Lane *D; Handles H;
+    int rc = get_handles(vol_handle, query_handle, H, &V, &Q, &D);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(D->mu);
     CU_TRY(cudaSetDevice(D->id));
     if (!Q->dev[V->device].ready) return fail(BN_ERR_INVALID, "query batch is not loaded on the volume's device");
     std::shared_ptr<ChunkTable> T;
-    rc = build_chunk_table(*V, *Q, 0, (int32_t)V->seq_len.size(), D->stream, &T);
+    rc = build_chunk_table(*V, *Q, 0, (int32_t)V->seq_len.size(), *D, &T);
     if (rc) return rc;
     if (V->ready) CU_TRY(cudaStreamWaitEvent(D->stream, V->ready, 0));
     Workspace &ws = D->ws();

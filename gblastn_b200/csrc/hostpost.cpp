@@ -709,9 +709,10 @@ void make_heap(std::vector<ListKey> &h)
 }
 }  // namespace
 
-LowScoreTracker::LowScoreTracker(const BnQueryBatch &b)
+LowScoreTracker::LowScoreTracker(const BnQueryBatch &b, bool track_lists)
 {
     enabled_ = b.low_score_perc > 0.00001;
+    track_ = track_lists;
     perc_ = b.low_score_perc;
     // BlastHSPCollectorParamsNew, core/hspfilter_collector.c:335-342 (gapped search)
     int32_t hs = b.hitlist_size > 0 ? b.hitlist_size : 500;
@@ -723,7 +724,7 @@ LowScoreTracker::LowScoreTracker(const BnQueryBatch &b)
 
 void LowScoreTracker::subject_done(const BnQueryBatch &b, const std::vector<BnHSP> &list)
 {
-    if (!enabled_ || list.empty()) return;
+    if (!(enabled_ || track_) || list.empty()) return;
     // the collector splits the subject's list per query (core/hspfilter_collector.c:104-150);
     // `list` is sorted by score, so the first HSP of a query is its hsp_array[0]
     touched_.clear();
@@ -771,12 +772,23 @@ void LowScoreTracker::subject_done(const BnQueryBatch &b, const std::vector<BnHS
             }
         }
         // core/blast_engine.c:1313-1320 (only a query whose hit list changed can change its bound)
-        if (S.heapified) {
+        if (S.heapified && enabled_) {
             const double v = perc_ * (double)S.low_score;
             if ((double)low_[qi] < v) low_[qi] = (int32_t)v;
         }
         slot_[qi] = -1;
     }
+}
+
+std::vector<int32_t> LowScoreTracker::kept_oids(int32_t qi) const
+{
+    std::vector<int32_t> out;
+    if (qi < 0 || (size_t)qi >= states_.size()) return out;
+    const HitListState &S = states_[(size_t)qi];
+    if (S.heapified) for (const HitListKey &k : full_[(size_t)S.full]) out.push_back(k.oid);
+    else for (int32_t at = S.head; at >= 0; at = arena_[(size_t)at].prev) out.push_back(arena_[(size_t)at].key.oid);
+    std::sort(out.begin(), out.end());
+    return out;
 }
 
 // ------------------------------------------------------------------------------------------------

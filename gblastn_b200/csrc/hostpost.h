@@ -105,14 +105,19 @@ struct HitListState {
 };
 class LowScoreTracker {
 public:
-    explicit LowScoreTracker(const BnQueryBatch &b);
+    // track_lists: keep the hit lists even when the low_score rule is off (low_score_perc == 0), for kept_oids()
+    explicit LowScoreTracker(const BnQueryBatch &b, bool track_lists = false);
     const int32_t *low_score() const { return enabled_ ? low_.data() : nullptr; }
     // true when a search over n_subjects subjects can never raise a bound: a hit list has to be full
     // (hitlist_size_ subjects) before a further subject can displace anything
     bool bounds_stay_zero(int64_t n_subjects) const { return !enabled_ || n_subjects <= (int64_t)hitlist_size_; }
     void subject_done(const BnQueryBatch &b, const std::vector<BnHSP> &list);
+    int32_t hitlist_size() const { return hitlist_size_; }
+    // the subjects a query's hit list holds now (what survives prelim_hitlist_size and reaches the traceback
+    // stage), ascending oids
+    std::vector<int32_t> kept_oids(int32_t query_index) const;
 private:
-    bool enabled_;
+    bool enabled_, track_;
     int32_t hitlist_size_;
     double perc_;
     std::vector<int32_t> low_;

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libgblastn_b200.so")
 EXPORTS = [
     "bn_init", "bn_release", "bn_device_count", "bn_last_error", "bn_version",
     "bn_db_load", "bn_db_free", "bn_query_load", "bn_query_free",
-    "bn_prelim_search", "bn_prelim_search_host", "bn_results_free",
+    "bn_prelim_search", "bn_prelim_search_host", "bn_prelim_search_volumes", "bn_results_free",
     "bn_scan_subject", "bn_word_finder", "bn_free", "bn_bench_scan", "bn_query_download_lookup", "bn_get_gapped_score", "bn_gapped_traceback", "bn_traceback_hsps", "bn_traceback_search",
     "bn_dbfile_index", "bn_db_load_files", "bn_dbfile_write", "bn_prelim_search_batches", "bn_db_set_masks", "bn_selftest_replay",
     "bn_setup_create", "bn_setup_batch", "bn_setup_kbp_std", "bn_setup_kbp_gap",
@@ -172,6 +172,17 @@ def prelim_search(volume: Volume, query: Query, oid_begin=0, oid_end=-1, taps=0)
     _check(lib().bn_prelim_search(C.c_int(volume.handle), C.c_int(query.handle),
                                   C.c_int32(oid_begin), C.c_int32(oid_end), C.c_int(taps),
                                   C.byref(res)))
+    return _results(res)
+
+
+def prelim_search_volumes(volumes, query: Query, taps=0, prune_hitlists=False) -> dict:
+    """One query batch against several resident volumes (any devices); OIDs are those of the concatenated database
+    and the hit-list rules (low_score, prelim_hitlist_size) are applied once, across the volumes."""
+    n = len(volumes)
+    hs = (C.c_int * n)(*[v.handle for v in volumes])
+    res = abi.BnResults()
+    _check(lib().bn_prelim_search_volumes(C.c_int32(n), hs, C.c_int(query.handle), C.c_int(taps),
+                                          C.c_int(1 if prune_hitlists else 0), C.byref(res)))
     return _results(res)
 
 

@@ -251,6 +251,16 @@ int  bn_prelim_search_host(int device, const BnQueryBatch *batch,
  * return for batches[k]; every batch sees the whole volume. */
 int  bn_prelim_search_batches(int vol_handle, int32_t n_batches, const BnQueryBatch *const *batches, int taps,
                               BnResults *results);
+/* Database volumes sharded over the GPUs: the preliminary stage for n_volumes resident volumes
+ * (any devices; one host thread per volume drives its device) and ONE query batch, gathered on the host.  OIDs of the
+ * result are those of the concatenated database: volume v's sequences follow those of volumes 0 .. v-1.  The host
+ * replay walks the volumes in that order with a single set of per-query hit lists, so hit_params->low_score
+ * (core/blast_engine.c:1313-1320) evolves as in one pass of the reference over the whole database, and with
+ * prune_hitlists != 0 only the subject lists that the HSP stream still holds at the end of the stage are returned:
+ * at most prelim_hitlist_size per query (BlastHSPCollectorParamsNew core/hspfilter_collector.c:328-342,
+ * Blast_HitListUpdate core/blast_hits.c:2924-2981) - the rule is applied once, after the gather, never per volume. */
+int  bn_prelim_search_volumes(int32_t n_volumes, const int *vol_handles, int query_handle, int taps,
+                              int prune_hitlists, BnResults *out);
 void bn_results_free(BnResults *r);
 
 /* Stage-level entry points (parity taps; same semantics as the reference callbacks). */

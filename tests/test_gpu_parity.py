@@ -691,3 +691,117 @@ def test_gpu_full_size_c2_equals_reference():
         assert (r["final"][:, 4] > 200_000_000).any(), "no HSP in the second subject chunk"
     finally:
         Q.free(); V.free(); s.free()
+
+
+def _split_volume(vol, n_vol):
+    """Contiguous OID ranges of a volume as volumes of their own (what a multi-volume database is)."""
+    from gblastn_b200 import synth
+    n = len(vol.seq_len)
+    cuts = [n * k // n_vol for k in range(n_vol + 1)]
+    out = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        lo = int(vol.byte_off[a])
+        hi = int(vol.byte_off[b - 1]) + int(vol.seq_len[b - 1]) // 4 + 1
+        packed = np.concatenate([vol.packed[lo:hi], np.zeros(synth.PAD_BYTES, np.uint8)])
+        out.append(synth.Volume(packed, (vol.byte_off[a:b] - lo).astype(np.int64), vol.seq_len[a:b].copy()))
+    return out
+
+
+@pytest.mark.parametrize("name", ["mb_repeat_family_hitlist5", "mb_repeat_family_hitlist20", "blastn_repeat_family_hitlist5",
+                                  "mb_ntlike_many_subjects", "blastn_ntlike_many_subjects"])
+@pytest.mark.parametrize("n_vol", [2, 4])
+def test_volumes_equal_one_reference_pass(name, n_vol):
+    """bn_prelim_search_volumes: the database split into n_vol volumes (spread over the visible devices) and gathered
+    on the host == ONE reference pass over the concatenated database, at every tap — the low_score feedback
+    (core/blast_engine.c:1313-1320) crosses volume boundaries — and with prune_hitlists the lists returned are the
+    ones the reference's HSP stream holds when the stage ends (prelim_hitlist_size applied once, after the gather)."""
+    from gblastn_b200 import engine as E, abi
+    from oracle import portdriver as P
+    r, h, vol = _setup(name)
+    parts = _split_volume(vol, n_vol)
+    n_dev = E.device_count()
+    Vs = [E.Volume(p, device=k % n_dev) for k, p in enumerate(parts)]
+    Q = E.Query(h)
+    try:
+        g = E.prelim_search_volumes(Vs, Q, taps=abi.BN_TAP_INIT | abi.BN_TAP_GAPPED)
+        assert np.array_equal(P.init_table(g["init"]), r["init"]), "init-HSPs differ from the single pass"
+        assert np.array_equal(P.gapped_table(g["gapped"]), r["gapped"]), "gapped lists differ from the single pass"
+        assert np.array_equal(P.final_table(g["hsps"]), r["final"]), "final lists differ from the single pass"
+        st = g["stats"]
+        assert (st["lookup_hits"], st["good_init_extends"], st["gap_extensions"], st["good_extensions"]) == \
+               (r["lookup_hits"], r["good_init_extends"], r["gap_extensions"], r["good_extensions"])
+        # the lists that reach the traceback stage
+        gp = E.prelim_search_volumes(Vs, Q, prune_hitlists=True)
+        ctx_q = np.arange(r["num_contexts"]) // 2
+        got = gp["hsps"]
+        kept = {(int(q), int(o)) for q, o in r["kept"][:, :2]}
+        assert {(int(ctx_q[c]), int(o)) for c, o in zip(got["context"], got["oid"])} == kept
+        fin = r["final"]
+        sel = np.array([(int(ctx_q[c]), int(o)) in kept for o, c in zip(fin[:, 0], fin[:, 1])], dtype=bool)
+        assert np.array_equal(P.final_table(got), fin[sel])
+        if name.startswith(("mb_repeat", "blastn_repeat")):
+            assert sel.sum() < fin.shape[0], "the case no longer overflows a hit list"
+    finally:
+        Q.free()
+        for V in Vs:
+            V.free()
+
+
+def test_concurrent_callers_one_device():
+    """Re-entrancy per GPU (SURVEY.md 8(b) threading; api/prelim_search_runner.hpp:94-113 runs the engine from
+    num_threads threads): four threads search one resident volume with four different query batches at the same time,
+    while a fifth keeps loading and freeing batches; every result equals the serial one."""
+    import threading
+    from gblastn_b200 import engine as E, setup as S, synth
+    vol = synth.random_volume([600_000, 250_000, 40_000, 999], seed=81)
+    specs = [dict(task="megablast", nq=150, qlen=800, seed=1), dict(task="blastn", nq=6, qlen=700, seed=2),
+             dict(task="megablast", nq=3, qlen=600, seed=3), dict(task="megablast", nq=400, qlen=1000, seed=4)]
+    setups = []
+    for sp in specs:
+        qs = synth.planted_queries(vol, sp["nq"], sp["qlen"], seed=sp["seed"], planted_frac=0.8, sub_rate=0.03, indel_rate=0.003)
+        setups.append(S.Setup(qs, task=sp["task"], db_length=vol.total_bases, db_num_seqs=vol.n_seqs,
+                              device_lookup=1 if sp["task"] == "megablast" else 0))
+    V = E.Volume(vol)
+    Qs = [E.Query(st.batch) for st in setups]
+    try:
+        serial = [E.prelim_search(V, Q) for Q in Qs]
+        assert sum(x["hsps"].size for x in serial) > 0
+        out = [[None] * 6 for _ in Qs]
+        errors = []
+        stop = threading.Event()
+
+        def run(k):
+            try:
+                for it in range(6):
+                    out[k][it] = E.prelim_search(V, Qs[k])
+            except Exception as e:      # noqa: BLE001
+                errors.append(e)
+
+        def churn():
+            try:
+                while not stop.is_set():
+                    q = E.Query(setups[0].batch)
+                    q.free()
+            except Exception as e:      # noqa: BLE001
+                errors.append(e)
+
+        ts = [threading.Thread(target=run, args=(k,)) for k in range(len(Qs))]
+        tc = threading.Thread(target=churn)
+        tc.start()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        stop.set()
+        tc.join()
+        assert not errors, errors
+        for k in range(len(Qs)):
+            for it in range(6):
+                assert out[k][it]["hsps"].tobytes() == serial[k]["hsps"].tobytes()
+                assert out[k][it]["stats"]["lookup_hits"] == serial[k]["stats"]["lookup_hits"]
+    finally:
+        for Q in Qs:
+            Q.free()
+        V.free()
+        for st in setups:
+            st.free()
