@@ -40,6 +40,8 @@ def build_oracles():
     subprocess.run(["make", "-s", "port"], check=True, cwd=odir)
     if os.path.isdir("/root/reference/c++/src/algo/blast/core"):
         subprocess.run(["make", "-s", "-j8", "ref"], check=True, cwd=odir)
+        if os.path.exists(LIB):
+            subprocess.run(["make", "-s", "-j8", "shim"], check=True, cwd=odir)
 
 
 if __name__ == "__main__":

@@ -1970,7 +1970,6 @@ int bn_selftest_replay(uint64_t seed, int32_t n_cases, int64_t *n_mismatch)
 int bn_scan_subject(int vol_handle, int query_handle, int32_t oid, int32_t chunk_off, int32_t chunk_len,
                     BnOffsetPair **pairs, int64_t *n_pairs)
 {
-    (void)chunk_off; (void)chunk_len;
     Volume *V; Query *Q; Lane *D; Handles H;
     if (!pairs || !n_pairs) return fail(BN_ERR_INVALID, "bn_scan_subject: NULL output");
     int rc = get_handles(vol_handle, query_handle, H, &V, &Q, &D);
@@ -1985,6 +1984,14 @@ int bn_scan_subject(int vol_handle, int query_handle, int32_t oid, int32_t chunk
     StageCounts cnt;
     rc = run_word_finder(*D, *V, *Q, *T, true, cnt, nullptr);
     if (rc) return rc;
+    // chunk_len > 0: the one subject chunk [chunk_off, chunk_off + chunk_len) (what one scansub call sequence of the
+    // reference covers); chunk_len == 0: every chunk of the subject, in order.  Offsets are chunk-relative.
+    int64_t want_chunk = -1;
+    if (chunk_len > 0) {
+        for (size_t c = 0; c < T->hchunks.size(); c++)
+            if (T->hchunks[c].chunk_off == chunk_off && T->hchunks[c].len == chunk_len) want_chunk = (int64_t)c;
+        if (want_chunk < 0) return fail(BN_ERR_INVALID, "bn_scan_subject: the subject has no chunk with this offset and length");
+    } else if (chunk_off != 0) return fail(BN_ERR_INVALID, "bn_scan_subject: chunk_off without chunk_len");
     std::vector<SeedHit> h((size_t)cnt.n_hits);
     if (cnt.n_hits) {
         CU_TRY(cudaMemcpyAsync(h.data(), D->ws().hits_b.p, h.size() * sizeof(SeedHit), cudaMemcpyDeviceToHost, D->stream));
@@ -1992,11 +1999,13 @@ int bn_scan_subject(int vol_handle, int query_handle, int32_t oid, int32_t chunk
     }
     BnOffsetPair *o = (BnOffsetPair *)malloc(std::max<size_t>(h.size(), 1) * sizeof(BnOffsetPair));
     if (!o) return fail(BN_ERR_MEMORY, "bn_scan_subject: out of memory");
+    size_t n_out = 0;
     for (size_t i = 0; i < h.size(); i++) {
-        // chunk-relative subject offsets, like the reference's per-chunk scansub calls
-        o[i].q_off = h[i].q_off; o[i].s_off = h[i].s_off;
+        if (want_chunk >= 0 && (int64_t)h[i].chunk != want_chunk) continue;
+        o[n_out].q_off = h[i].q_off; o[n_out].s_off = h[i].s_off;
+        ++n_out;
     }
-    *pairs = o; *n_pairs = (int64_t)h.size();
+    *pairs = o; *n_pairs = (int64_t)n_out;
     return BN_OK;
 }
 
@@ -2037,9 +2046,29 @@ int bn_get_gapped_score(int vol_handle, int query_handle, int32_t oid, int32_t c
     Workspace &ws = D->ws();
     cudaStream_t st = D->stream;
     std::vector<DevInitHit> up((size_t)n_init);
-    for (int64_t i = 0; i < n_init; i++) {
-        const BnInitHit &h = init[i];
-        up[(size_t)i] = DevInitHit{chunk, h.q_off, h.s_off, h.q_start, h.s_start, h.length, h.score, (uint32_t)i};
+    {
+        // caller-supplied records are read by the gapped kernels: the seed and the ungapped segment must lie
+        // inside one query context and inside the chunk
+        const int32_t clen = T->hchunks[(size_t)chunk].len;
+        const BnQueryBatch &b = Q->batch;
+        auto context_of = [&](int32_t q) {
+            int32_t lo = 0, hi = b.num_contexts;
+            while (lo < hi - 1) { const int32_t m = (lo + hi) / 2; if (b.contexts[m].query_offset > q) hi = m; else lo = m; }
+            return lo;
+        };
+        for (int64_t i = 0; i < n_init; i++) {
+            const BnInitHit &h = init[i];
+            bool ok = h.q_off >= 0 && h.q_off < b.concat_len && h.s_off >= 0 && h.s_off < clen && h.length >= 0 &&
+                      h.q_start >= 0 && (int64_t)h.q_start + h.length <= b.concat_len &&
+                      h.s_start >= 0 && (int64_t)h.s_start + h.length <= clen;
+            if (ok) {
+                const BnContext &c = b.contexts[context_of(h.q_off)];
+                ok = h.q_off >= c.query_offset && h.q_off < c.query_offset + c.query_length &&
+                     h.q_start >= c.query_offset && h.q_start + h.length <= c.query_offset + c.query_length;
+            }
+            if (!ok) return fail(BN_ERR_INVALID, "bn_get_gapped_score: init hit " + std::to_string(i) + " lies outside the query context or the subject chunk");
+            up[(size_t)i] = DevInitHit{chunk, h.q_off, h.s_off, h.q_start, h.s_start, h.length, h.score, (uint32_t)i};
+        }
     }
     CU_TRY(ws.counters.reserve(8));
     CU_TRY(ws.init.reserve((size_t)n_init));

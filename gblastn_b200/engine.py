@@ -210,11 +210,12 @@ def prelim_search_host(holder, vol, device=0, taps=0) -> dict:
     return _results(res)
 
 
-def scan_subject(volume: Volume, query: Query, oid: int) -> np.ndarray:
+def scan_subject(volume: Volume, query: Query, oid: int, chunk_off=0, chunk_len=0) -> np.ndarray:
+    """Scan tap of one subject: every chunk (chunk_len 0) or the chunk [chunk_off, chunk_off + chunk_len)."""
     p = C.POINTER(abi.BnOffsetPair)()
     n = C.c_int64(0)
     _check(lib().bn_scan_subject(C.c_int(volume.handle), C.c_int(query.handle), C.c_int32(oid),
-                                 C.c_int32(0), C.c_int32(0), C.byref(p), C.byref(n)))
+                                 C.c_int32(chunk_off), C.c_int32(chunk_len), C.byref(p), C.byref(n)))
     try:
         return abi.struct_array(p, n.value, abi.PAIR_DTYPE)
     finally:

@@ -263,7 +263,10 @@ int  bn_prelim_search_volumes(int32_t n_volumes, const int *vol_handles, int que
                               int prune_hitlists, BnResults *out);
 void bn_results_free(BnResults *r);
 
-/* Stage-level entry points (parity taps; same semantics as the reference callbacks). */
+/* Stage-level entry points (parity taps; same semantics as the reference callbacks).
+ * bn_scan_subject: chunk_len > 0 selects the subject chunk [chunk_off, chunk_off + chunk_len) of the reference's split
+ * (BN_ERR_INVALID if the subject has no such chunk); chunk_len == 0 (with chunk_off 0) returns every chunk of the
+ * subject in order.  Subject offsets are chunk-relative either way. */
 int  bn_scan_subject(int vol_handle, int query_handle, int32_t oid, int32_t chunk_off,
                      int32_t chunk_len, BnOffsetPair **pairs, int64_t *n_pairs);
 int  bn_word_finder(int vol_handle, int query_handle, int32_t oid_begin, int32_t oid_end,
@@ -273,7 +276,8 @@ int  bn_word_finder(int vol_handle, int query_handle, int32_t oid_begin, int32_t
  * finder produced for the chunk that starts at base chunk_off of sequence oid (any order; it is
  * sorted like Blast_InitHitListSortByScore, ties keep the given order), low_score is
  * hit_params->low_score (per query, may be NULL).  Returns the HSP list as it stands when the
- * reference function returns (before purge / sort / E-values), subject offsets chunk-relative. */
+ * reference function returns (before purge / sort / E-values), subject offsets chunk-relative.  Every init hit is
+ * checked (seed and ungapped segment inside one query context and inside the chunk): BN_ERR_INVALID otherwise. */
 int  bn_get_gapped_score(int vol_handle, int query_handle, int32_t oid, int32_t chunk_off,
                          const BnInitHit *init, int64_t n_init, const int32_t *low_score,
                          BnHSP **hsps, int64_t *n_hsps);

@@ -84,6 +84,19 @@ typedef struct TapCtx {
 } TapCtx;
 static __thread TapCtx *g_tap = NULL;
 
+/* Seam selection (RefConfig.seam): 0 = the reference's own BlastNaWordFinder / BLAST_GetGappedScore; 1 = the
+ * B200 engine through oracle/shim/gblastn_b200_shim.c.  The shim is only linked into oracle/_ref/libblastshim.so;
+ * in libblastref.so these weak symbols are NULL and seam 1 is refused. */
+#include "shim/gblastn_b200_shim.h"
+#pragma weak bnshim_word_finder
+#pragma weak bnshim_get_gapped_score
+#pragma weak bnshim_prelim_begin
+#pragma weak bnshim_prelim_end
+#pragma weak bnshim_attach_volume
+#pragma weak bnshim_detach_volume
+#pragma weak bnshim_last_error
+static __thread int g_seam = 0;
+
 static Int4 mdb_num_seqs(void *h, void *a) { (void)a; return ((MemDb *)h)->n; }
 static Int4 mdb_max_len(void *h, void *a) { (void)a; return ((MemDb *)h)->maxlen; }
 static Int4 mdb_min_len(void *h, void *a) { (void)a; (void)h; return 1; }
@@ -240,8 +253,13 @@ Int2 __wrap_BlastNaWordFinder(BLAST_SequenceBlk *subject, BLAST_SequenceBlk *que
             }
         }
     }
-    st = __real_BlastNaWordFinder(subject, query, query_info, lookup_wrap, matrix, word_params,
-                                  ewp, offset_pairs, max_hits, init_hitlist, ungapped_stats);
+    if (g_seam)
+        st = bnshim_word_finder(subject, query, query_info, lookup_wrap, matrix, word_params,
+                                ewp, offset_pairs, max_hits, init_hitlist, ungapped_stats);
+    else
+        st = __real_BlastNaWordFinder(subject, query, query_info, lookup_wrap, matrix, word_params,
+                                      ewp, offset_pairs, max_hits, init_hitlist, ungapped_stats);
+    if (st) return st;
     if (t && (t->taps & 2)) {
         Int4 i;
         for (i = 0; i < init_hitlist->total; i++) {
@@ -278,9 +296,14 @@ Int2 __wrap_BLAST_GetGappedScore(EBlastProgramType program_number, BLAST_Sequenc
                                  BlastGappedStats *gapped_stats, Boolean *fence_hit)
 {
     TapCtx *t = g_tap;
-    Int2 st = __real_BLAST_GetGappedScore(program_number, query, query_info, subject, gap_align,
-                                          score_params, ext_params, hit_params, init_hitlist,
-                                          hsp_list_ptr, gapped_stats, fence_hit);
+    Int2 st;
+    if (g_seam)
+        st = bnshim_get_gapped_score(program_number, query, query_info, subject, gap_align, score_params,
+                                     ext_params, hit_params, init_hitlist, hsp_list_ptr, gapped_stats, fence_hit);
+    else
+        st = __real_BLAST_GetGappedScore(program_number, query, query_info, subject, gap_align,
+                                         score_params, ext_params, hit_params, init_hitlist,
+                                         hsp_list_ptr, gapped_stats, fence_hit);
     if (t && (t->taps & 4) && hsp_list_ptr && *hsp_list_ptr) {
         BlastHSPList *l = *hsp_list_ptr;
         Int4 i;
@@ -293,6 +316,32 @@ Int2 __wrap_BLAST_GetGappedScore(EBlastProgramType program_number, BLAST_Sequenc
             r[8] = h->query.gapped_start; r[9] = h->subject.gapped_start;
         }
     }
+    return st;
+}
+
+Int4 __real_BLAST_PreliminarySearchEngine(EBlastProgramType, BLAST_SequenceBlk *, BlastQueryInfo *, const BlastSeqSrc *,
+                                          BlastGapAlignStruct *, BlastScoringParameters *, LookupTableWrap *,
+                                          const BlastInitialWordOptions *, BlastExtensionParameters *,
+                                          BlastHitSavingParameters *, BlastEffectiveLengthsParameters *,
+                                          const PSIBlastOptions *, const BlastDatabaseOptions *, BlastHSPStream *,
+                                          BlastDiagnostics *, TInterruptFnPtr, SBlastProgress *);
+Int4 __wrap_BLAST_PreliminarySearchEngine(EBlastProgramType program_number, BLAST_SequenceBlk *query,
+                                          BlastQueryInfo *query_info, const BlastSeqSrc *seq_src,
+                                          BlastGapAlignStruct *gap_align, BlastScoringParameters *score_params,
+                                          LookupTableWrap *lookup_wrap, const BlastInitialWordOptions *word_options,
+                                          BlastExtensionParameters *ext_params, BlastHitSavingParameters *hit_params,
+                                          BlastEffectiveLengthsParameters *eff_len_params,
+                                          const PSIBlastOptions *psi_options, const BlastDatabaseOptions *db_options,
+                                          BlastHSPStream *hsp_stream, BlastDiagnostics *diagnostics,
+                                          TInterruptFnPtr interrupt_search, SBlastProgress *progress_info)
+{
+    Int4 st;
+    if (g_seam) bnshim_prelim_begin(score_params, ext_params, hit_params, gap_align);
+    st = __real_BLAST_PreliminarySearchEngine(program_number, query, query_info, seq_src, gap_align, score_params,
+                                              lookup_wrap, word_options, ext_params, hit_params, eff_len_params,
+                                              psi_options, db_options, hsp_stream, diagnostics, interrupt_search,
+                                              progress_info);
+    if (g_seam) bnshim_prelim_end();
     return st;
 }
 
@@ -726,6 +775,7 @@ typedef struct Worker {
     RefResult *res;     /* thread-private result for final_ rows */
     int taps;
     int traceback;
+    int seam;
     int status;
     BlastDiagnostics *diag;
     pthread_t th;
@@ -756,6 +806,18 @@ static void *worker_main(void *arg)
     tap.res = w->res; tap.taps = w->taps; tap.db = &w->db; tap.cur_chunk_off = 0;
     tap.tb_seq = NULL; tap.tb_oid = -1; tap.q_base = S->query->sequence; tap.qinfo = S->query_info;
     g_tap = &tap;
+    g_seam = w->seam;
+    if (g_seam) {
+        /* the volume this thread's seqsrc hands out: last sequence's bytes + the 16 pad bytes every volume carries */
+        const int32_t last = w->db.n - 1;
+        const int64_t bytes = last >= 0 ? w->db.byteoff[last] + w->db.len[last] / 4 + 1 + 16 : 16;
+        if (bnshim_attach_volume(w->db.packed, bytes, w->db.byteoff, w->db.len, w->db.n, 0)) {
+            fprintf(stderr, "ref_driver: %s\n", bnshim_last_error());
+            w->status = 90; g_tap = NULL; g_seam = 0;
+            BlastHSPStreamFree(stream); BlastSeqSrcFree(seq_src);
+            return NULL;
+        }
+    }
     w->diag = Blast_DiagnosticsInit();
     w->status = Blast_RunPreliminarySearch(prog, S->query, S->query_info, seq_src,
                                            S->score_options, S->sbp, S->lookup_wrap,
@@ -773,6 +835,7 @@ static void *worker_main(void *arg)
         Blast_HSPResultsFree(results);
     }
     g_tap = NULL;
+    if (g_seam) { bnshim_detach_volume(); g_seam = 0; }
     if (w->status == 0 && !w->traceback && w->res->kept.ncol && stream->results) {
         Int4 qi, li;
         for (qi = 0; qi < stream->results->num_queries; qi++) {
@@ -814,6 +877,10 @@ int ref_search(const RefConfig *cfg,
     tab_init(&res->tb_final, 15);
     tab_init(&res->kept, 4);
 
+    if (cfg->seam && (!bnshim_word_finder || cfg->smask_n)) {
+        fprintf(stderr, "ref_driver: seam 1 needs libblastshim.so (and no database masks)\n");
+        res->status = 91; return 91;
+    }
     st = build_setup(cfg, nq, qseq, qlens, qmask_n, qmask_iv, &S);
     if (st) { res->status = st; return st; }
 
@@ -846,7 +913,7 @@ int ref_search(const RefConfig *cfg,
     if (nth > ns) nth = ns > 0 ? ns : 1;
     ws = (Worker *)calloc(nth, sizeof(Worker));
     for (i = 0; i < nth; i++) {
-        ws[i].S = &S; ws[i].db = db;
+        ws[i].S = &S; ws[i].db = db; ws[i].seam = cfg->seam;
         ws[i].db.oid_begin = (int32_t)((int64_t)ns * i / nth);
         ws[i].db.oid_end = (int32_t)((int64_t)ns * (i + 1) / nth);
         if (nth == 1) { ws[i].res = res; ws[i].taps = cfg->taps; ws[i].traceback = (cfg->prelim_only == 0); }

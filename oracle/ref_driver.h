@@ -44,7 +44,8 @@ typedef struct RefConfig {
     const int32_t *smask_iv;
     int32_t hsp_num_max;     /* hit_options->hsp_num_max (0 = unlimited); ignored by gapped searches (BlastHspNumMax,
                               * core/blast_hits.c:169-191) */
-    int32_t reserved0;
+    int32_t seam;            /* 0: the reference's own word finder and gapped stage; 1: the B200 engine behind the
+                              * same two seams through oracle/shim (only in oracle/_ref/libblastshim.so) */
 } RefConfig;
 
 /* Flat growable int32 table: rows x ncol */

@@ -11,6 +11,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libblastref.so")
+# the same reference engine + driver with oracle/shim linked in: cfg.seam = 1 routes the word finder and the gapped
+# stage through libgblastn_b200.so (needs a GPU); loaded only by tests/test_shim_hybrid.py
+SHIM_LIB_PATH = os.path.join(_HERE, "_ref", "libblastshim.so")
 
 
 class RefConfig(C.Structure):
@@ -25,7 +28,7 @@ class RefConfig(C.Structure):
         ("db_length", C.c_int64), ("db_num_seqs", C.c_int32), ("num_threads", C.c_int32),
         ("taps", C.c_int32), ("prelim_only", C.c_int32),
         ("smask_type", C.c_int32), ("smask_n", C.c_void_p), ("smask_iv", C.c_void_p),
-        ("hsp_num_max", C.c_int32), ("reserved0", C.c_int32),
+        ("hsp_num_max", C.c_int32), ("seam", C.c_int32),
     ]
 
 
@@ -69,19 +72,43 @@ class RefResult(C.Structure):
 
 
 _lib = None
+_shim_lib = None
+_use_shim = False
 
 
 def available() -> bool:
     return os.path.exists(LIB_PATH)
 
 
+def shim_available() -> bool:
+    return os.path.exists(SHIM_LIB_PATH)
+
+
 def lib():
-    global _lib
+    global _lib, _shim_lib
+    if _use_shim:
+        if _shim_lib is None:
+            _shim_lib = C.CDLL(SHIM_LIB_PATH)
+            _shim_lib.ref_search.restype = C.c_int
+            _shim_lib.ref_free_result.restype = None
+        return _shim_lib
     if _lib is None:
         _lib = C.CDLL(LIB_PATH)
         _lib.ref_search.restype = C.c_int
         _lib.ref_free_result.restype = None
     return _lib
+
+
+class use_shim_library:
+    """Context manager: calls inside go to libblastshim.so (reference engine + B200 seams)."""
+
+    def __enter__(self):
+        global _use_shim
+        _use_shim = True
+
+    def __exit__(self, *a):
+        global _use_shim
+        _use_shim = False
 
 
 TAP_SCAN, TAP_INIT, TAP_GAPPED, TAP_LUT, TAP_TRACEBACK = 1, 2, 4, 8, 16

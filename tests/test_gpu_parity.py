@@ -805,3 +805,33 @@ def test_concurrent_callers_one_device():
         V.free()
         for st in setups:
             st.free()
+
+
+def test_stage_entry_points_validate_their_input():
+    """bn_get_gapped_score rejects init hits outside the query context / subject chunk (they would be read by the
+    gapped kernels); bn_scan_subject selects one chunk of a split subject or rejects a chunk that does not exist."""
+    from gblastn_b200 import engine as E, abi
+    r, h, vol = _setup("mb_lut11_hash_indels")
+    V, Q = E.Volume(vol), E.Query(h)
+    try:
+        rows = r["init"][(r["init"][:, 0] == 0) & (r["init"][:, 1] == 0)]
+        arr = np.zeros(rows.shape[0], dtype=abi.INIT_DTYPE)
+        for k, col in enumerate(("oid", "chunk_off", "q_off", "s_off", "q_start", "s_start", "length", "score")):
+            arr[col] = rows[:, k]
+        assert E.get_gapped_score(V, Q, 0, 0, arr).size > 0
+        for field, value in (("s_off", int(vol.seq_len[0]) + 5), ("q_off", -1), ("q_off", 10 ** 9), ("length", 10 ** 7),
+                             ("s_start", -3), ("q_start", int(r["ctx_query_offset"][1]) - 2)):
+            bad = arr.copy()
+            bad[field][0] = value
+            with pytest.raises(E.BnError) as e:
+                E.get_gapped_score(V, Q, 0, 0, bad)
+            assert e.value.code == abi.BN_ERR_INVALID
+        whole = E.scan_subject(V, Q, 0)
+        one = E.scan_subject(V, Q, 0, 0, int(vol.seq_len[0]))
+        assert whole.tobytes() == one.tobytes() and whole.size > 0
+        with pytest.raises(E.BnError):
+            E.scan_subject(V, Q, 0, 0, int(vol.seq_len[0]) - 1)
+        with pytest.raises(E.BnError):
+            E.scan_subject(V, Q, 0, 4, 0)
+    finally:
+        Q.free(); V.free()
