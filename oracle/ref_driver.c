@@ -319,29 +319,28 @@ Int2 __wrap_BLAST_GetGappedScore(EBlastProgramType program_number, BLAST_Sequenc
     return st;
 }
 
-Int4 __real_BLAST_PreliminarySearchEngine(EBlastProgramType, BLAST_SequenceBlk *, BlastQueryInfo *, const BlastSeqSrc *,
-                                          BlastGapAlignStruct *, BlastScoringParameters *, LookupTableWrap *,
-                                          const BlastInitialWordOptions *, BlastExtensionParameters *,
-                                          BlastHitSavingParameters *, BlastEffectiveLengthsParameters *,
-                                          const PSIBlastOptions *, const BlastDatabaseOptions *, BlastHSPStream *,
-                                          BlastDiagnostics *, TInterruptFnPtr, SBlastProgress *);
-Int4 __wrap_BLAST_PreliminarySearchEngine(EBlastProgramType program_number, BLAST_SequenceBlk *query,
-                                          BlastQueryInfo *query_info, const BlastSeqSrc *seq_src,
-                                          BlastGapAlignStruct *gap_align, BlastScoringParameters *score_params,
-                                          LookupTableWrap *lookup_wrap, const BlastInitialWordOptions *word_options,
-                                          BlastExtensionParameters *ext_params, BlastHitSavingParameters *hit_params,
-                                          BlastEffectiveLengthsParameters *eff_len_params,
-                                          const PSIBlastOptions *psi_options, const BlastDatabaseOptions *db_options,
-                                          BlastHSPStream *hsp_stream, BlastDiagnostics *diagnostics,
-                                          TInterruptFnPtr interrupt_search, SBlastProgress *progress_info)
+/* BLAST_GapAlignSetUp (core/blast_setup.c) is what Blast_RunPreliminarySearchWithInterrupt calls to create the
+ * parameter blocks right before BLAST_PreliminarySearchEngine (core/blast_engine.c:1407-1420): the seams do not
+ * receive them all, so the binding picks them up here. */
+Int2 __real_BLAST_GapAlignSetUp(EBlastProgramType program_number, const BlastSeqSrc *seq_src,
+                                const BlastScoringOptions *scoring_options,
+                                const BlastEffectiveLengthsOptions *eff_len_options,
+                                const BlastExtensionOptions *ext_options, const BlastHitSavingOptions *hit_options,
+                                BlastQueryInfo *query_info, BlastScoreBlk *sbp, BlastScoringParameters **score_params,
+                                BlastExtensionParameters **ext_params, BlastHitSavingParameters **hit_params,
+                                BlastEffectiveLengthsParameters **eff_len_params, BlastGapAlignStruct **gap_align);
+Int2 __wrap_BLAST_GapAlignSetUp(EBlastProgramType program_number, const BlastSeqSrc *seq_src,
+                                const BlastScoringOptions *scoring_options,
+                                const BlastEffectiveLengthsOptions *eff_len_options,
+                                const BlastExtensionOptions *ext_options, const BlastHitSavingOptions *hit_options,
+                                BlastQueryInfo *query_info, BlastScoreBlk *sbp, BlastScoringParameters **score_params,
+                                BlastExtensionParameters **ext_params, BlastHitSavingParameters **hit_params,
+                                BlastEffectiveLengthsParameters **eff_len_params, BlastGapAlignStruct **gap_align)
 {
-    Int4 st;
-    if (g_seam) bnshim_prelim_begin(score_params, ext_params, hit_params, gap_align);
-    st = __real_BLAST_PreliminarySearchEngine(program_number, query, query_info, seq_src, gap_align, score_params,
-                                              lookup_wrap, word_options, ext_params, hit_params, eff_len_params,
-                                              psi_options, db_options, hsp_stream, diagnostics, interrupt_search,
-                                              progress_info);
-    if (g_seam) bnshim_prelim_end();
+    const Int2 st = __real_BLAST_GapAlignSetUp(program_number, seq_src, scoring_options, eff_len_options, ext_options,
+                                               hit_options, query_info, sbp, score_params, ext_params, hit_params,
+                                               eff_len_params, gap_align);
+    if (g_seam && st == 0) bnshim_prelim_begin(*score_params, *ext_params, *hit_params, *gap_align);
     return st;
 }
 
@@ -824,6 +823,13 @@ static void *worker_main(void *arg)
                                            S->word_options, S->ext_options, S->hit_options,
                                            S->eff_len_options, S->psi_options, S->db_options,
                                            stream, w->diag);
+    if (g_seam) {
+        bnshim_prelim_end();
+        if (w->status == 0 && bnshim_last_error()[0]) {      /* the engine ignores the word finder's status */
+            fprintf(stderr, "ref_driver: %s\n", bnshim_last_error());
+            w->status = 92;
+        }
+    }
     if (w->status == 0 && w->traceback) {
         BlastHSPResults *results = NULL;
         const double tb0 = now_s();

@@ -5,11 +5,16 @@
  *
  *   aux_struct->WordFinder     = BlastNaWordFinder     (core/blast_engine.c:926)  ->  bnshim_word_finder
  *   aux_struct->GetGappedScore = BLAST_GetGappedScore  (core/blast_engine.c:940)  ->  bnshim_get_gapped_score
- *   BLAST_PreliminarySearchEngine (core/blast_engine.c:1114)                      ->  bnshim_prelim_begin / _end
+ *   BLAST_GapAlignSetUp (core/blast_setup.c; called by Blast_RunPreliminarySearchWithInterrupt right before
+ *       BLAST_PreliminarySearchEngine, core/blast_engine.c:1407-1420)             ->  bnshim_prelim_begin
+ *   Blast_RunPreliminarySearchWithInterrupt (the call G-BLASTN itself replaces, api/prelim_search_runner.hpp:96,
+ *       inc-gpu/gpu_blastn.h:31-48)                            ->  bnshim_RunPreliminarySearchWithInterrupt
  *
  * Link recipe for a `blastn` built from the reference tree:
- *   -Wl,--wrap=BlastNaWordFinder -Wl,--wrap=BLAST_GetGappedScore -Wl,--wrap=BLAST_PreliminarySearchEngine
+ *   -Wl,--wrap=BlastNaWordFinder -Wl,--wrap=BLAST_GetGappedScore -Wl,--wrap=BLAST_GapAlignSetUp
  *   gblastn_b200_shim.o (compiled with -DBNSHIM_DEFINE_WRAPS) -lgblastn_b200
+ * (`ld --wrap` only redirects references between object files, which is why the seams are the three exported
+ * functions above and not BLAST_PreliminarySearchEngine, whose caller lives in the same object.)
  * With BNSHIM_DEFINE_WRAPS this file defines the three __wrap_ symbols itself.  In this repository the shim is
  * linked into oracle/_ref/libblastshim.so next to the test driver (oracle/ref_driver.c), whose own --wrap taps
  * call the bnshim_* functions when RefConfig.seam == 1, so the hybrid (reference engine + B200 seams) is
@@ -105,6 +110,8 @@ void bnshim_prelim_begin(const BlastScoringParameters *score_params, const Blast
                          const BlastHitSavingParameters *hit_params, const BlastGapAlignStruct *gap_align)
 {
     ShimState *S = &g_shim;
+    if (S->active) bnshim_prelim_end();          /* a search that never reached its end (error paths) */
+    S->err[0] = 0;
     S->score_params = score_params; S->ext_params = ext_params; S->hit_params = hit_params; S->gap_align = gap_align;
     S->active = 1; S->query_handle = -1; S->loaded_for = NULL; S->cached_oid = -1; S->init = NULL; S->n_init = 0;
 }
@@ -304,29 +311,46 @@ Int2 bnshim_get_gapped_score(EBlastProgramType program_number, BLAST_SequenceBlk
 
 #ifdef BNSHIM_DEFINE_WRAPS
 /* the symbols `ld --wrap` redirects the engine's references to */
-Int4 __real_BLAST_PreliminarySearchEngine(EBlastProgramType, BLAST_SequenceBlk *, BlastQueryInfo *, const BlastSeqSrc *,
-                                          BlastGapAlignStruct *, BlastScoringParameters *, LookupTableWrap *,
-                                          const BlastInitialWordOptions *, BlastExtensionParameters *,
-                                          BlastHitSavingParameters *, BlastEffectiveLengthsParameters *,
-                                          const PSIBlastOptions *, const BlastDatabaseOptions *, BlastHSPStream *,
-                                          BlastDiagnostics *, TInterruptFnPtr, SBlastProgress *);
-Int4 __wrap_BLAST_PreliminarySearchEngine(EBlastProgramType program_number, BLAST_SequenceBlk *query,
-                                          BlastQueryInfo *query_info, const BlastSeqSrc *seq_src,
-                                          BlastGapAlignStruct *gap_align, BlastScoringParameters *score_params,
-                                          LookupTableWrap *lookup_wrap, const BlastInitialWordOptions *word_options,
-                                          BlastExtensionParameters *ext_params, BlastHitSavingParameters *hit_params,
-                                          BlastEffectiveLengthsParameters *eff_len_params,
-                                          const PSIBlastOptions *psi_options, const BlastDatabaseOptions *db_options,
-                                          BlastHSPStream *hsp_stream, BlastDiagnostics *diagnostics,
-                                          TInterruptFnPtr interrupt_search, SBlastProgress *progress_info)
+Int2 __real_BLAST_GapAlignSetUp(EBlastProgramType, const BlastSeqSrc *, const BlastScoringOptions *,
+                                const BlastEffectiveLengthsOptions *, const BlastExtensionOptions *,
+                                const BlastHitSavingOptions *, BlastQueryInfo *, BlastScoreBlk *,
+                                BlastScoringParameters **, BlastExtensionParameters **, BlastHitSavingParameters **,
+                                BlastEffectiveLengthsParameters **, BlastGapAlignStruct **);
+static __thread int g_in_prelim = 0;
+Int2 __wrap_BLAST_GapAlignSetUp(EBlastProgramType program_number, const BlastSeqSrc *seq_src,
+                                const BlastScoringOptions *scoring_options,
+                                const BlastEffectiveLengthsOptions *eff_len_options,
+                                const BlastExtensionOptions *ext_options, const BlastHitSavingOptions *hit_options,
+                                BlastQueryInfo *query_info, BlastScoreBlk *sbp, BlastScoringParameters **score_params,
+                                BlastExtensionParameters **ext_params, BlastHitSavingParameters **hit_params,
+                                BlastEffectiveLengthsParameters **eff_len_params, BlastGapAlignStruct **gap_align)
+{
+    const Int2 st = __real_BLAST_GapAlignSetUp(program_number, seq_src, scoring_options, eff_len_options, ext_options,
+                                               hit_options, query_info, sbp, score_params, ext_params, hit_params,
+                                               eff_len_params, gap_align);
+    if (g_in_prelim && st == 0) bnshim_prelim_begin(*score_params, *ext_params, *hit_params, *gap_align);
+    return st;
+}
+/* drop-in for the call at api/prelim_search_runner.hpp:96 (where G-BLASTN calls Blast_gpu_RunPreliminarySearchWithInterrupt) */
+Int4 bnshim_RunPreliminarySearchWithInterrupt(EBlastProgramType program, BLAST_SequenceBlk *query,
+                                              BlastQueryInfo *query_info, const BlastSeqSrc *seq_src,
+                                              const BlastScoringOptions *score_options, BlastScoreBlk *sbp,
+                                              LookupTableWrap *lookup_wrap, const BlastInitialWordOptions *word_options,
+                                              const BlastExtensionOptions *ext_options,
+                                              const BlastHitSavingOptions *hit_options,
+                                              const BlastEffectiveLengthsOptions *eff_len_options,
+                                              const PSIBlastOptions *psi_options, const BlastDatabaseOptions *db_options,
+                                              BlastHSPStream *hsp_stream, BlastDiagnostics *diagnostics,
+                                              TInterruptFnPtr interrupt_search, SBlastProgress *progress_info)
 {
     Int4 st;
-    bnshim_prelim_begin(score_params, ext_params, hit_params, gap_align);
-    st = __real_BLAST_PreliminarySearchEngine(program_number, query, query_info, seq_src, gap_align, score_params,
-                                              lookup_wrap, word_options, ext_params, hit_params, eff_len_params,
-                                              psi_options, db_options, hsp_stream, diagnostics, interrupt_search,
-                                              progress_info);
+    g_in_prelim = 1;
+    st = Blast_RunPreliminarySearchWithInterrupt(program, query, query_info, seq_src, score_options, sbp, lookup_wrap,
+                                                 word_options, ext_options, hit_options, eff_len_options, psi_options,
+                                                 db_options, hsp_stream, diagnostics, interrupt_search, progress_info);
+    g_in_prelim = 0;
     bnshim_prelim_end();
+    if (st == 0 && g_shim.err[0]) st = -1;      /* the engine ignores the word finder's status (core/blast_engine.c:481) */
     return st;
 }
 Int2 __wrap_BlastNaWordFinder(BLAST_SequenceBlk *subject, BLAST_SequenceBlk *query, BlastQueryInfo *query_info,

@@ -18,7 +18,8 @@ int  bnshim_attach_volume(const uint8_t *packed, int64_t packed_bytes, const int
 int  bnshim_attach_resident_volume(int vol_handle, const uint8_t *host_base, const int64_t *seq_byte_off, int32_t n_seq);
 void bnshim_detach_volume(void);
 
-/* brackets of BLAST_PreliminarySearchEngine (core/blast_engine.c:1114): the parameter blocks the seams do not receive */
+/* brackets of one preliminary search: begin = right after BLAST_GapAlignSetUp created the parameter blocks the seams
+ * do not receive, end = after Blast_RunPreliminarySearchWithInterrupt returned */
 void bnshim_prelim_begin(const BlastScoringParameters *score_params, const BlastExtensionParameters *ext_params,
                          const BlastHitSavingParameters *hit_params, const BlastGapAlignStruct *gap_align);
 void bnshim_prelim_end(void);
