@@ -227,6 +227,10 @@ struct ScanLaunch {
     uint64_t *bucket_keys;        // with bucket_count: bucket_cap keys (position << 24 | emission slot) per bucket
     int32_t bucket_cap;
     int32_t one_group;            // 1: every survivor gets group 0 (serial replay, off-diagonal two-hit search)
+    // direct filter (lut == word, one-hit mode, unmasked volume): drop hits whose ungapped extension certainly
+    // stays below the cutoff; uni_*: the cutoffs when every context has the same ones (uni_ok), else per context
+    int32_t direct_filter;
+    int32_t uni_ok, uni_x, uni_cutoff, uni_reduced;
 };
 cudaError_t launch_scan(const DevQuery &q, const ScanLaunch &s, cudaStream_t st);
 int scan_positions_per_block();

@@ -244,6 +244,10 @@ struct Query {
     int32_t diag_array_length = 1;
     int32_t max_query_length = 0;
     bool fast_path_refused = false;       // the device-grouped word finder did not apply to this batch last time
+    // direct filter of the scan kernel (scan_kernel.cu): lut == word, one-hit mode, scoring tables of the plain
+    // match / mismatch form the filter evaluates in closed form
+    bool direct_ok = false;
+    int32_t uni_ok = 0, uni_x = 0, uni_cutoff = 0, uni_reduced = 0;
 };
 
 // Handle tables.  g_mu guards the three vectors; a call resolves its handles to shared_ptrs under it and
@@ -661,6 +665,12 @@ static int bits_for(uint64_t v) { int b = 1; while (b < 64 && (v >> b)) ++b; ret
 
 struct StageCounts { int64_t n_hits = 0, lookup_hits = 0, n_init = 0, n_extended = 0; };
 
+static void set_direct_filter(ScanLaunch &s, const Query &Q, const ChunkTable &T, bool raw_pairs)
+{
+    s.direct_filter = (Q.direct_ok && !raw_pairs && T.units.empty()) ? 1 : 0;      // unmasked volumes only
+    s.uni_ok = Q.uni_ok; s.uni_x = Q.uni_x; s.uni_cutoff = Q.uni_cutoff; s.uni_reduced = Q.uni_reduced;
+}
+
 // scan -> one stable radix sort on (diagonal group, global position) -> diagonal/ungapped kernel.
 // Leaves the sorted seed hits in ws.hits_b and the init hits (unsorted) in ws.init.
 static int run_word_finder(Lane &D, Volume &V, Query &Q, ChunkTable &T, bool raw_pairs,
@@ -691,6 +701,7 @@ static int run_word_finder(Lane &D, Volume &V, Query &Q, ChunkTable &T, bool raw
         s.raw_pairs = raw_pairs ? 1 : 0; s.gbits = gbits; s.diag_array_length = Q.diag_array_length;
         s.one_group = serial ? 1 : 0;
         s.tile_cap = scan_tile_cap(Q.batch.scan_step, Q.batch.word_length);
+        set_direct_filter(s, Q, T, raw_pairs);
         t_scan.start();
         CU_TRY(launch_scan(dq, s, st));
         t_scan.stop();
@@ -955,6 +966,7 @@ static int run_fused(Lane &D, Volume &V, Query &Q, ChunkTable &T, StageCounts &c
     s.raw_pairs = 0; s.gbits = gbits; s.diag_array_length = Q.diag_array_length;
     s.tile_cap = scan_tile_cap(Q.batch.scan_step, Q.batch.word_length);
     s.bucket_count = ws.buckets.p; s.bucket_keys = ws.keys_tmp.p; s.bucket_cap = group_sort_bucket_cap();
+    set_direct_filter(s, Q, T, false);
     t_scan.start();
     CU_TRY(launch_scan(dq, s, st));
     t_scan.stop();
@@ -1056,7 +1068,7 @@ static int search_gpu_phase(Lane &D, Volume &V, Query &Q, int32_t oid_begin, int
     const double tw2 = now_ms();
     G.t_table = tw0 - G.t0; G.t_wf = tw1 - tw0; G.t_gap = tw2 - tw1;
     stats.lookup_hits = cnt.lookup_hits;
-    stats.init_extends = cnt.n_extended;
+    stats.init_extends = cnt.n_init;        // the reference counts the extensions that were saved (hit_ready, core/na_ungapped.c:1000-1004)
     stats.good_init_extends = cnt.n_init;
     return BN_OK;
 }
@@ -1651,6 +1663,29 @@ static int query_load_impl(const BnQueryBatch *b, std::shared_ptr<Query> *out, i
     while (n < b->concat_len + b->window_size) n <<= 1;   // s_BlastDiagTableNew core/blast_extend.c:46-72
     Q->diag_array_length = n;
     Q->ctx_lite = make_ctx_lite(Q->batch);
+    {
+        // The direct filter applies to lookup word == full word (s_BlastNaExtendDirect), one-hit mode, the extension
+        // routine with the approximate pass (hash container or word >= 11, core/na_ungapped.c:720-721) and scoring
+        // tables that are what blastn builds from reward / penalty: nucl_score_table[x] = sum over the four base
+        // pairs of x of (pair == 0 ? reward : penalty) (core/blast_parameters.c:250-261), matrix[i][j] = reward on
+        // the diagonal and penalty off it for the four bases.
+        const BnQueryBatch &qb = Q->batch;
+        bool ok = qb.lut_type == BN_LUT_MB && qb.word_length == qb.lut_word_length && qb.window_size == 0 &&
+                  (qb.container_type == BN_DIAG_HASH || qb.word_length >= 11) && qb.reward > 0 && qb.penalty < 0;
+        for (int x = 0; ok && x < 256; x++) {
+            int32_t v = 0;
+            for (int k = 0; k < 4; k++) v += ((x >> (2 * k)) & 3) ? qb.penalty : qb.reward;
+            ok = qb.nucl_score_table[x] == v;
+        }
+        for (int i = 0; ok && i < 4; i++)
+            for (int j = 0; ok && j < 4; j++) ok = qb.matrix[16 * i + j] == (i == j ? qb.reward : qb.penalty);
+        if (getenv("BN_NO_DIRECT_FILTER")) ok = false;
+        Q->direct_ok = ok;
+        Q->uni_ok = 1;
+        Q->uni_x = Q->ctx[0].x_dropoff; Q->uni_cutoff = Q->ctx[0].cutoff_score; Q->uni_reduced = Q->ctx[0].reduced_cutoff;
+        for (const auto &c : Q->ctx)
+            if (c.x_dropoff != Q->uni_x || c.cutoff_score != Q->uni_cutoff || c.reduced_cutoff != Q->uni_reduced) Q->uni_ok = 0;
+    }
     Q->dev.resize(g_devices.size());
     for (size_t d = 0; d < g_devices.size(); d++) {
         if (hook_device_only && (int)d != hook_device) continue;      // a batch of the host-buffer call lives on its device only
@@ -2534,6 +2569,7 @@ int bn_bench_scan(int vol_handle, int query_handle, int iters, double *ms_per_la
     s.counters = ws.counters.p; s.capacity = cap; s.block_chunk = T->block_chunk.p; s.block_desc = T->block_desc.p; s.raw_pairs = 0;
     s.gbits = bits_for((uint64_t)std::max<int64_t>(T->total_pos, 1)); s.diag_array_length = Q->diag_array_length;
     s.tile_cap = scan_tile_cap(Q->batch.scan_step, Q->batch.word_length);
+    set_direct_filter(s, *Q, *T, false);
     const DevQuery &dq = Q->dev[V->device].view;
     Timer t(st);
     double total = 0;

@@ -333,6 +333,129 @@ __device__ __forceinline__ bool mini_extend_tile(const DevQuery &q, const uint32
     return true;
 }
 
+
+// ---- direct filter (blastn mode: lookup word == full word, one-hit) ---------------------------------
+// With lut == word every lookup hit goes straight to the diagonal logic and — unless an earlier extension on its
+// diagonal covers it — to s_NuclUngappedExtend (core/na_ungapped.c:263-350): at stride 1 that is one extension per
+// ~2 subject bases (C3: 4.8e8 for 1 Gb), of which ~1 % reach cutoff_score.  A hit whose extension scores below the
+// cutoff leaves nothing behind but last_hit = s_off + word on its diagonal (:888-915), which can only reject hits of
+// the same exact-match run, and those score the same; so hits that certainly fail are dropped right here, one
+// THREAD per hit on 16-base windows of the staged tile, and only the rest goes through sort + replay (where the
+// extension is recomputed bit-exactly).  The test below is the reference's own decision — approximate pass
+// (4 bases per step, nucl_score_table) >= reduced cutoff, then exact pass >= cutoff_score — evaluated exactly when
+// every base it reads is unambiguous; anything else (ambiguity codes, sentinels) is kept.
+struct DirectCtx {
+    const uint32_t *tile;      // staged slice
+    int32_t tile_bases;        // bases in the slice
+    int64_t tile_abs;          // absolute base index (4 * volume byte) of the slice's first base
+    const uint8_t *packed;
+};
+__device__ __forceinline__ uint32_t direct_swin(const DirectCtx &d, int32_t tb)
+{
+    if (tb >= 0 && tb + 32 <= d.tile_bases) return tile_win(d.tile, tb);
+    return swin(d.packed, d.tile_abs + tb);
+}
+
+// true = keep (may reach the cutoff); false = the reference's extension certainly stays below cutoff_score
+__device__ __noinline__ bool direct_keep(const DevQuery &q, const DirectCtx &d, int32_t tbase, int32_t slen,
+                                         int32_t q_off, int32_t s_off, int32_t x_dropoff, int32_t cutoff, int32_t reduced)
+{
+    const int32_t X = -x_dropoff;
+    const int32_t r = q.reward, pen = q.penalty, r4 = 4 * r, dd = r - pen;
+    const int32_t shift = (4 - (s_off & 3)) & 3;
+    const int32_t q_ext = q_off + shift, s_ext = s_off + shift;
+    int32_t score = 0;
+    {   // approximate pass, left: group k covers query [q_ext - 4k - 4, q_ext - 4k)
+        const int32_t n = min(q_ext, s_ext) >> 2;
+        int32_t sum = 0;
+        bool stop = false;
+        for (int32_t k = 0; k < n && !stop; k += 4) {
+            uint32_t qb, qa;
+            qwin(q, q_ext - 4 * k - 16, qb, qa);
+            const uint32_t m = mismatch_bits(qb, 0u, direct_swin(d, tbase + s_ext - 4 * k - 16));
+            const int cnt = min(4, n - k);
+            for (int j = 0; j < cnt; j++) {
+                if ((qa >> (8 * j)) & 0xFFu) return true;
+                sum += r4 - dd * __popc((m >> (8 * j)) & 0xFFu);
+                if (sum > 0) { score += sum; sum = 0; }
+                if (sum < X) { stop = true; break; }
+            }
+        }
+    }
+    {   // approximate pass, right: group k covers query [q_ext + 4k, q_ext + 4k + 4)
+        const int32_t n = min(q.concat_len - q_ext, slen - s_ext) >> 2;
+        int32_t sum = 0;
+        bool stop = false;
+        for (int32_t k = 0; k < n && !stop; k += 4) {
+            uint32_t qb, qa;
+            qwin(q, q_ext + 4 * k, qb, qa);
+            const uint32_t m = mismatch_bits(qb, 0u, direct_swin(d, tbase + s_ext + 4 * k));
+            const int cnt = min(4, n - k);
+            for (int j = 0; j < cnt; j++) {
+                if ((qa >> (24 - 8 * j)) & 0xFFu) return true;
+                sum += r4 - dd * __popc((m >> (24 - 8 * j)) & 0xFFu);
+                if (sum > 0) { score += sum; sum = 0; }
+                if (sum < X) { stop = true; break; }
+            }
+        }
+    }
+    if (score < reduced) return score >= cutoff;          // kept as computed by the approximate pass (:343-350)
+    // exact pass (s_NuclUngappedExtendExact :153-245), run by run of matching bases
+    score = 0;
+    {   // left of q_off
+        const int32_t n = min(q_off, s_off);
+        int32_t sum = 0, done = 0;
+        bool stop = false;
+        while (done < n && !stop) {
+            uint32_t qb, qa;
+            qwin(q, q_off - done - 16, qb, qa);
+            const int32_t rem = min(16, n - done);
+            // step t reads base 15 - t of the window: its flag sits at bit 2t
+            const uint32_t used = rem == 16 ? 0xFFFFFFFFu : ((1u << (2 * rem)) - 1u);
+            if (qa & used) return true;
+            const uint32_t m = mismatch_bits(qb, 0u, direct_swin(d, tbase + s_off - done - 16));
+            int32_t t = 0;
+            while (t < rem) {
+                const uint32_t mm = m >> (2 * t);
+                int32_t run = mm ? ((__ffs(mm) - 1) >> 1) : 16;
+                run = min(run, rem - t);
+                if (run > 0) { sum += run * r; if (sum > 0) { score += sum; sum = 0; } t += run; }
+                if (t >= rem) break;
+                sum += pen;
+                if (sum < X) { stop = true; break; }
+                ++t;
+            }
+            done += rem;
+        }
+    }
+    {   // right from q_off
+        const int32_t n = min(q.concat_len - q_off, slen - s_off);
+        int32_t sum = 0, done = 0;
+        bool stop = false;
+        while (done < n && !stop) {
+            uint32_t qb, qa;
+            qwin(q, q_off + done, qb, qa);
+            const int32_t rem = min(16, n - done);
+            const uint32_t used = rem == 16 ? 0xFFFFFFFFu : ~((1u << (32 - 2 * rem)) - 1u);
+            if (qa & used) return true;
+            const uint32_t m = mismatch_bits(qb, 0u, direct_swin(d, tbase + s_off + done));
+            int32_t t = 0;
+            while (t < rem) {
+                const uint32_t mm = m << (2 * t);
+                int32_t run = mm ? (__clz(mm) >> 1) : 16;
+                run = min(run, rem - t);
+                if (run > 0) { sum += run * r; if (sum > 0) { score += sum; sum = 0; } t += run; }
+                if (t >= rem) break;
+                sum += pen;
+                if (sum < X) { stop = true; break; }
+                ++t;
+            }
+            done += rem;
+        }
+    }
+    return score >= cutoff;
+}
+
 // ---- TMA (bulk async copy) + mbarrier helpers ------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
@@ -418,7 +541,8 @@ __device__ __noinline__ unsigned long long scan_block_direct(const DevQuery &q, 
     return my_lookup_hits;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS, 6)
+template <bool DIRECT>
+__global__ void __launch_bounds__(SCAN_THREADS, DIRECT ? 4 : 6)
 scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ ScanLaunch s)
 {
     extern __shared__ __align__(128) uint32_t smem_dyn[];
@@ -542,7 +666,18 @@ scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ S
             for (;;) {
                 ++my_lookup_hits;
                 int32_t qo, so;
-                if (s.raw_pairs) emit_hit(q, s, chunk, (uint32_t)p, g, qp - 1, p);
+                if (DIRECT) {
+                    // lut == word: no mini-extension; drop the hits whose ungapped extension cannot reach the cutoff
+                    int32_t xd = s.uni_x, co = s.uni_cutoff, rc = s.uni_reduced;
+                    if (!s.uni_ok) {
+                        const DevContext c = q.ctx[ctx_search(q, qp - 1)];
+                        xd = c.x_dropoff; co = c.cutoff_score; rc = c.reduced_cutoff;
+                    }
+                    DirectCtx dc{tile, bd.bytes * 4, bd.tile_lo * 4, s.packed};
+                    if (direct_keep(q, dc, tbase, len, qp - 1, p, xd, co, rc))
+                        emit_hit(q, s, chunk, (uint32_t)p, g, qp - 1, p);
+                }
+                else if (s.raw_pairs) emit_hit(q, s, chunk, (uint32_t)p, g, qp - 1, p);
                 else if (mini_extend_tile(q, tile, tbase, len, qp - 1, p, qi, qo, so))
                     emit_hit(q, s, chunk, (uint32_t)p, g, qo, so);
                 if (!more) break;
@@ -720,7 +855,10 @@ cudaError_t launch_scan(const DevQuery &q, const ScanLaunch &s, cudaStream_t st)
     int64_t blocks = (s.total_pos + POS_PER_BLOCK - 1) / POS_PER_BLOCK;
     if (q.lut_type == 0 && q.prk != nullptr && q.lut_word_length <= 13) {
         const size_t smem = (size_t)s.tile_cap + sizeof(uint2) * POS_PER_BLOCK;
-        scan_kernel_staged<<<(unsigned)blocks, SCAN_THREADS, smem, st>>>(q, s);
+        if (s.direct_filter && !s.raw_pairs)
+            scan_kernel_staged<true><<<(unsigned)blocks, SCAN_THREADS, smem, st>>>(q, s);
+        else
+            scan_kernel_staged<false><<<(unsigned)blocks, SCAN_THREADS, smem, st>>>(q, s);
     }
     else
         scan_kernel<<<(unsigned)blocks, SCAN_THREADS, 0, st>>>(q, s);

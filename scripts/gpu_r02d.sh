@@ -1,0 +1,7 @@
+#!/bin/bash
+TAG=r02d
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/tests_$TAG.log
+cat gpurun_out/tests_$TAG.log
+BN_TRACE=1 timeout 900 python scripts/exp_c3.py 100 10 100000000 > gpurun_out/exp_c3_full_$TAG.txt 2>&1
+tail -4 gpurun_out/exp_c3_full_$TAG.txt

@@ -140,6 +140,11 @@ CASES["blastn_repeat_family_hitlist5"] = dict(task="blastn", cfg={"hitlist_size"
 CASES["mb_repeat_family_hsp_num_max2"] = dict(task="megablast", cfg={"hitlist_size": 5, "hsp_num_max": 2},
                                               repeat_family=dict(seed=71, n_subj=70, n_fam=6, elem_len=1200,
                                                                  frag_from=0.45), nq=18, q_seed=72, sub=0.01)
+# blastn direct mode (lut == word) with queries of very different lengths (per-context cutoffs differ) and ambiguity
+# codes: the scan kernel's direct filter takes its per-context path and its keep-on-ambiguity path
+CASES["blastn_direct_mixed_lengths_N"] = dict(task="blastn", cfg={}, seq_lens=[400_000, 90_000, 5_000], vol_seed=77,
+                                              qlen_list=[(6, 120), (8, 700), (4, 4000), (2, 9000)], q_seed=78,
+                                              sub=0.07, indel=0.008, planted=0.85, n_frac=0.003)
 HITLIST_CASES = ["mb_repeat_family_hitlist5", "mb_repeat_family_hitlist20", "blastn_repeat_family_hitlist5",
                  "mb_repeat_family_hsp_num_max2"]
 
@@ -240,6 +245,12 @@ def make_case(name):
     vol = synth.random_volume(_seq_lens(c["seq_lens"], c["vol_seed"]), seed=c["vol_seed"])
     if c.get("bridged"):
         return c["task"], dict(c["cfg"]), vol, _bridged_queries(vol, c["nq"], c["qlen"], c["q_seed"], c["sub"])
+    if c.get("qlen_list"):
+        qs = []
+        for k, (n, ql) in enumerate(c["qlen_list"]):
+            qs += synth.planted_queries(vol, n, ql, seed=c["q_seed"] + k, planted_frac=c["planted"],
+                                        sub_rate=c["sub"], indel_rate=c["indel"], n_frac=c.get("n_frac", 0.0))
+        return c["task"], dict(c["cfg"]), vol, qs
     qs = synth.planted_queries(vol, c["nq"], c["qlen"], seed=c["q_seed"], planted_frac=c["planted"],
                                sub_rate=c["sub"], indel_rate=c["indel"], n_frac=c.get("n_frac", 0.0))
     return c["task"], dict(c["cfg"]), vol, qs

@@ -835,3 +835,36 @@ def test_stage_entry_points_validate_their_input():
             E.scan_subject(V, Q, 0, 4, 0)
     finally:
         Q.free(); V.free()
+
+
+@pytest.mark.parametrize("name", ["blastn_mb11_dp", "c3_scaled_blastn_10kb", "blastn_direct_mixed_lengths_N",
+                                  "blastn_bridged_segments", "blastn_ws11_greedy"])
+def test_direct_filter_changes_nothing(name, monkeypatch):
+    """blastn mode (lookup word == word): the scan kernel drops the lookup hits whose ungapped extension cannot reach
+    the cutoff before they are sorted and replayed.  With the filter switched off (BN_NO_DIRECT_FILTER, read when the
+    batch is loaded) every tap is the same, bit for bit — and equal to the reference."""
+    from gblastn_b200 import engine as E, abi
+    from oracle import portdriver as P
+    r, h, vol = _setup(name)
+    assert r["lut_word_length"] == r["word_length"], "the case must run in direct mode"
+    V = E.Volume(vol)
+    out = []
+    try:
+        for off in (False, True):
+            if off:
+                monkeypatch.setenv("BN_NO_DIRECT_FILTER", "1")
+            else:
+                monkeypatch.delenv("BN_NO_DIRECT_FILTER", raising=False)
+            Q = E.Query(h)
+            try:
+                out.append(E.prelim_search(V, Q, taps=abi.BN_TAP_INIT | abi.BN_TAP_GAPPED))
+            finally:
+                Q.free()
+        a, b = out
+        assert a["init"].tobytes() == b["init"].tobytes() and a["gapped"].tobytes() == b["gapped"].tobytes()
+        assert a["hsps"].tobytes() == b["hsps"].tobytes()
+        assert np.array_equal(P.init_table(a["init"]), r["init"])
+        assert np.array_equal(P.final_table(a["hsps"]), r["final"])
+        assert a["stats"]["lookup_hits"] == b["stats"]["lookup_hits"] == r["lookup_hits"]
+    finally:
+        V.free()
