@@ -356,6 +356,26 @@ int gapped_dp_smem_blocks();
 cudaError_t launch_gapped_warp(const DevQuery &q, const GappedLaunch &g, int blocks, cudaStream_t st);
 int gapped_warp_per_block();
 
+// ---- triage of the speculative gapped extensions (triage_kernel.cu) ----------------------------------
+struct TriageLaunch {
+    const DevInitHit *init;
+    const DevGapResult *gap;
+    const unsigned long long *n_init;   // device counter
+    int64_t max_init;
+    int32_t *ctx_of;                    // scratch: context per init-HSP, bit 31 = winner
+    DevInitHit *sel_init;               // winners, then the losers the host has to replay in order
+    DevGapResult *sel_gap;
+    int32_t *sel_ctx;
+    int64_t sel_cap;
+    unsigned long long *tcount;         // [0] winners, [1] undecided losers (zeroed by the caller)
+    uint2 *table;                       // per (chunk, context), zeroed by the caller: .x = counted losers | bit 31: has a
+                                        // winner, .y = highest ungapped score among the counted losers
+    int32_t n_ctx;
+};
+cudaError_t launch_triage(const DevQuery &q, const TriageLaunch &t, cudaStream_t st);
+cudaError_t launch_collect_status(const DevGapResult *gap, const unsigned long long *n_init, int64_t max_init, int32_t want,
+                                  int32_t *todo, unsigned long long *count, cudaStream_t st);
+
 // ---- gapped alignment with traceback (traceback_kernel.cu) -----------------------------------------
 struct DevTracebackItem {
     int64_t byte_off;            // byte offset of the subject sequence in the volume

@@ -104,6 +104,11 @@ struct Workspace {
     DevBuf<DevInitHit> init;
     DevBuf<DevGapResult> gap_out;
     DevBuf<int32_t> scratch, todo;
+    DevBuf<int32_t> tri_ctx, tri_sel_ctx;             // triage: context per init-HSP / per selected record
+    DevBuf<DevInitHit> tri_init;
+    DevBuf<DevGapResult> tri_gap;
+    DevBuf<uint2> tri_table;
+    PinnedBuf<uint2> h_table;
     DevBuf<unsigned long long> counters;
     DevBuf<uint8_t> cub_temp;
     unsigned long long *h_counters = nullptr;   // pinned
@@ -112,7 +117,8 @@ struct Workspace {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // stage timers, created once
     void release()
     {
-        h_init.release(); h_gap.release();
+        h_init.release(); h_gap.release(); h_table.release();
+        tri_ctx.release(); tri_sel_ctx.release(); tri_init.release(); tri_gap.release(); tri_table.release();
         for (auto &e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
         hits_a.release(); hits_b.release(); keys_a.release(); keys_b.release();
         cells.release(); heads.release(); leaders.release(); buckets.release(); keys_tmp.release(); spec.release(); init.release(); gap_out.release(); scratch.release(); todo.release();
@@ -665,6 +671,22 @@ static int bits_for(uint64_t v) { int b = 1; while (b < 64 && (v >> b)) ++b; ret
 
 struct StageCounts { int64_t n_hits = 0, lookup_hits = 0, n_init = 0, n_extended = 0; };
 
+// What the GPU side of one search leaves for the host: counts and the pinned mirrors of the init-HSPs and
+// their speculative gapped results (they belong to the workspace that was current during the search).
+struct GpuOut {
+    std::shared_ptr<ChunkTable> T;
+    StageCounts cnt;
+    DevInitHit *h_init = nullptr;
+    DevGapResult *h_gap = nullptr;
+    int32_t oid_begin = 0, oid_end = 0;
+    double t0 = 0, t_table = 0, t_wf = 0, t_gap = 0;
+    // triage (triage_kernel.cu): h_init / h_gap hold n_records selected init-HSPs (winners + undecided losers) instead
+    // of all cnt.n_init, and counted_losers extensions are known to have been made without being replayed
+    bool triaged = false;
+    int64_t n_records = 0, counted_losers = 0;
+};
+
+
 static void set_direct_filter(ScanLaunch &s, const Query &Q, const ChunkTable &T, bool raw_pairs)
 {
     s.direct_filter = (Q.direct_ok && !raw_pairs && T.units.empty()) ? 1 : 0;      // unmasked volumes only
@@ -679,8 +701,8 @@ static int run_word_finder(Lane &D, Volume &V, Query &Q, ChunkTable &T, bool raw
     Workspace &ws = D.ws();
     cudaStream_t st = D.stream;
     const DevQuery &dq = Q.dev[V.device].view;
-    CU_TRY(ws.counters.reserve(8));
-    if (!ws.h_counters) CU_TRY(cudaMallocHost(&ws.h_counters, 8 * sizeof(unsigned long long)));
+    CU_TRY(ws.counters.reserve(16));
+    if (!ws.h_counters) CU_TRY(cudaMallocHost(&ws.h_counters, 16 * sizeof(unsigned long long)));
     if (T.total_pos >= (int64_t)1 << 32) return fail(BN_ERR_OVERFLOW, "more than 2^32 scan positions in one search");
     const int gbits = bits_for((uint64_t)std::max<int64_t>(T.total_pos, 1));
     // off-diagonal two-hit search: neighbouring diagonals live in other buckets / cells -> one serial group
@@ -902,8 +924,126 @@ static int finish_gapped(Lane &D, Volume &V, Query &Q, ChunkTable &T, int64_t n_
     return BN_OK;
 }
 
+// The same tiers with hand-over lists built on the device, followed by the triage (triage_kernel.cu): only the
+// winners and the undecided losers cross PCIe, the other losers arrive as one count.  For the large general-path
+// searches of blastn mode (millions of init-HSPs, a few hundred HSPs).
+static int finish_gapped_triaged(Lane &D, Volume &V, Query &Q, ChunkTable &T, int64_t n_init, GpuOut &G, BnStats *stats)
+{
+    Workspace &ws = D.ws();
+    cudaStream_t st = D.stream;
+    const DevQuery &dq = Q.dev[V.device].view;
+    const BnQueryBatch &b = Q.batch;
+    const bool greedy = b.gap_algo == BN_GAP_GREEDY;
+    const bool affine = greedy && (b.gap_open != 0 || b.gap_extend != 0);
+    const int32_t xo = greedy_xdrop_offset(b);
+    const int wpb = 4;
+    CU_TRY(ws.todo.reserve((size_t)n_init));
+    unsigned long long *tc = ws.counters.p + 8;          // [8] status-2 count, [9] status-1 count, [10] winners, [11] undecided
+    auto collect = [&](int32_t want, int slot, int64_t &count) -> int {
+        CU_TRY(cudaMemsetAsync(tc + slot, 0, sizeof(unsigned long long), st));
+        CU_TRY(launch_collect_status(ws.gap_out.p, ws.counters.p + 2, n_init, want, ws.todo.p, tc + slot, st));
+        CU_TRY(cudaMemcpyAsync(ws.h_counters + 8 + slot, tc + slot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        count = (int64_t)ws.h_counters[8 + slot];
+        if (stats) stats->kernel_launches += 1;
+        return BN_OK;
+    };
+    int64_t n2 = 0, n1 = 0;
+    int rc;
+    if (!greedy) {
+        rc = collect(2, 0, n2);
+        if (rc) return rc;
+        if (n2) {       // long alignments: one warp each
+            GappedLaunch g{};
+            g.packed = V.d_packed; g.chunks = T.dev.p; g.init = ws.init.p; g.n_init = ws.counters.p + 2;
+            g.max_init = n_init; g.out = ws.gap_out.p;
+            g.todo = ws.todo.p; g.n_todo = (int32_t)n2;
+            const int wpb_dp = gapped_warp_per_block();
+            const int blocks = (int)std::min<int64_t>((n2 + wpb_dp - 1) / wpb_dp, 148 * 4);
+            CU_TRY(launch_gapped_warp(dq, g, blocks, st));
+            if (stats) stats->kernel_launches += 1;
+        }
+    }
+    rc = collect(1, 1, n1);
+    if (rc) return rc;
+    if (n1) {           // tier 2: worst-case scratch for the few that outgrew tier 1
+        int32_t max_len = 0;
+        for (const auto &c : T.host) max_len = std::max(max_len, c.len);
+        int32_t tier;
+        int64_t per_thread;
+        if (affine) {
+            tier = std::min(10000, max_len / 2 + 1);
+            per_thread = affine_scratch_ints(affine_costs(b.reward, b.penalty, b.gap_open, b.gap_extend, b.gap_x_dropoff), tier);
+        } else if (greedy) {
+            tier = std::min(10000, max_len / 2 + 1);
+            per_thread = 2 * (2 * (int64_t)tier + 6) + tier + 1 + xo + 8;
+        } else {
+            tier = 256;
+            while (tier < Q.max_query_length + 8) tier <<= 1;
+            per_thread = 2 * (int64_t)tier;
+        }
+        const bool warp_greedy = greedy && !affine;
+        const int tpb = warp_greedy ? wpb : gapped_threads_per_block();
+        const int hpb = warp_greedy ? wpb / 2 : tpb;
+        int64_t blocks = std::min<int64_t>((n1 + hpb - 1) / hpb, 64);
+        if (affine) blocks = std::max<int64_t>(1, std::min<int64_t>(blocks, ((int64_t)1 << 29) / (per_thread * tpb)));
+        CU_TRY(ws.scratch.reserve((size_t)(per_thread * blocks * tpb)));
+        GappedLaunch g{};
+        g.packed = V.d_packed; g.chunks = T.dev.p; g.init = ws.init.p; g.n_init = ws.counters.p + 2;
+        g.max_init = n_init; g.out = ws.gap_out.p;
+        g.scratch = ws.scratch.p; g.scratch_ints_per_thread = per_thread; g.tier_d = tier;
+        g.todo = ws.todo.p; g.n_todo = (int32_t)n1; g.grid_blocks = (int32_t)blocks;
+        if (warp_greedy) CU_TRY(launch_greedy_warp(dq, g, wpb, (int)blocks, false, st));
+        else CU_TRY(launch_gapped(dq, g, st));
+        if (stats) stats->kernel_launches += 1;
+        int64_t left = 0;
+        rc = collect(1, 1, left);
+        if (rc) return rc;
+        if (left) return fail(BN_ERR_OVERFLOW, "gapped extension scratch overflow in tier 2");
+    }
+    // ---- triage ---------------------------------------------------------------------------------------------
+    const size_t n_ctx = (size_t)b.num_contexts, n_cells = T.host.size() * n_ctx;
+    int64_t sel_cap = std::max<int64_t>((int64_t)ws.tri_init.cap, std::max<int64_t>(65536, n_init / 8));
+    for (int attempt = 0;; attempt++) {
+        CU_TRY(ws.tri_ctx.reserve((size_t)n_init));
+        CU_TRY(ws.tri_init.reserve((size_t)sel_cap)); CU_TRY(ws.tri_gap.reserve((size_t)sel_cap));
+        CU_TRY(ws.tri_sel_ctx.reserve((size_t)sel_cap));
+        sel_cap = (int64_t)std::min(std::min(ws.tri_init.cap, ws.tri_gap.cap), ws.tri_sel_ctx.cap);
+        CU_TRY(ws.tri_table.reserve(n_cells));
+        CU_TRY(cudaMemsetAsync(ws.tri_table.p, 0, n_cells * sizeof(uint2), st));
+        CU_TRY(cudaMemsetAsync(tc + 2, 0, 2 * sizeof(unsigned long long), st));
+        TriageLaunch t{};
+        t.init = ws.init.p; t.gap = ws.gap_out.p; t.n_init = ws.counters.p + 2; t.max_init = n_init;
+        t.ctx_of = ws.tri_ctx.p; t.sel_init = ws.tri_init.p; t.sel_gap = ws.tri_gap.p; t.sel_ctx = ws.tri_sel_ctx.p;
+        t.sel_cap = sel_cap; t.tcount = tc + 2; t.table = ws.tri_table.p; t.n_ctx = (int32_t)n_ctx;
+        CU_TRY(launch_triage(dq, t, st));
+        if (stats) stats->kernel_launches += 2;
+        CU_TRY(cudaMemcpyAsync(ws.h_counters + 10, tc + 2, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        const int64_t n_sel = (int64_t)(ws.h_counters[10] + ws.h_counters[11]);
+        if (n_sel <= sel_cap) { G.n_records = n_sel; break; }
+        if (attempt > 1) return fail(BN_ERR_OVERFLOW, "triage selection overflow");
+        sel_cap = n_sel + n_sel / 16 + 1024;
+    }
+    CU_TRY(ws.h_init.reserve((size_t)G.n_records + 1)); CU_TRY(ws.h_gap.reserve((size_t)G.n_records + 1));
+    CU_TRY(ws.h_table.reserve(n_cells + 1));
+    G.h_init = ws.h_init.p; G.h_gap = ws.h_gap.p;
+    if (G.n_records) {
+        CU_TRY(cudaMemcpyAsync(G.h_init, ws.tri_init.p, (size_t)G.n_records * sizeof(DevInitHit), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(G.h_gap, ws.tri_gap.p, (size_t)G.n_records * sizeof(DevGapResult), cudaMemcpyDeviceToHost, st));
+    }
+    CU_TRY(cudaMemcpyAsync(ws.h_table.p, ws.tri_table.p, n_cells * sizeof(uint2), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    int64_t counted = 0;
+    for (size_t i = 0; i < n_cells; i++) counted += (int64_t)(ws.h_table.p[i].x & 0x7fffffffu);
+    G.counted_losers = counted;
+    G.triaged = true;
+    if (G.n_records + counted != n_init) return fail(BN_ERR_CUDA, "triage lost init-HSPs");
+    return BN_OK;
+}
+
 static int run_gapped(Lane &D, Volume &V, Query &Q, ChunkTable &T, int64_t n_init,
-                      DevInitHit *&h_init, DevGapResult *&h_gap, BnStats *stats)
+                      DevInitHit *&h_init, DevGapResult *&h_gap, BnStats *stats, GpuOut *triage_into = nullptr)
 {
     Workspace &ws = D.ws();
     if (n_init == 0) {
@@ -915,7 +1055,8 @@ static int run_gapped(Lane &D, Volume &V, Query &Q, ChunkTable &T, int64_t n_ini
     t.start();
     int rc = enqueue_gapped(D, V, Q, T, n_init, stats);
     if (rc) return rc;
-    rc = finish_gapped(D, V, Q, T, n_init, h_init, h_gap, stats);
+    if (triage_into) rc = finish_gapped_triaged(D, V, Q, T, n_init, *triage_into, stats);
+    else rc = finish_gapped(D, V, Q, T, n_init, h_init, h_gap, stats);
     if (rc) return rc;
     t.stop();
     if (stats) stats->ms_gapped += t.ms();
@@ -936,8 +1077,8 @@ static int run_fused(Lane &D, Volume &V, Query &Q, ChunkTable &T, StageCounts &c
     Workspace &ws = D.ws();
     cudaStream_t st = D.stream;
     const DevQuery &dq = Q.dev[V.device].view;
-    CU_TRY(ws.counters.reserve(8));
-    if (!ws.h_counters) CU_TRY(cudaMallocHost(&ws.h_counters, 8 * sizeof(unsigned long long)));
+    CU_TRY(ws.counters.reserve(16));
+    if (!ws.h_counters) CU_TRY(cudaMallocHost(&ws.h_counters, 16 * sizeof(unsigned long long)));
     if (T.total_pos >= (int64_t)1 << 32) return fail(BN_ERR_OVERFLOW, "more than 2^32 scan positions in one search");
     const int gbits = bits_for((uint64_t)std::max<int64_t>(T.total_pos, 1));
     const int nb = group_sort_buckets();
@@ -1020,18 +1161,9 @@ static T *to_malloc(const std::vector<T> &v)
     return p;
 }
 
-// What the GPU side of one search leaves for the host: counts and the pinned mirrors of the init-HSPs and
-// their speculative gapped results (they belong to the workspace that was current during the search).
-struct GpuOut {
-    std::shared_ptr<ChunkTable> T;
-    StageCounts cnt;
-    DevInitHit *h_init = nullptr;
-    DevGapResult *h_gap = nullptr;
-    int32_t oid_begin = 0, oid_end = 0;
-    double t0 = 0, t_table = 0, t_wf = 0, t_gap = 0;
-};
-
-static int search_gpu_phase(Lane &D, Volume &V, Query &Q, int32_t oid_begin, int32_t oid_end, BnResults *out, GpuOut &G)
+// allow_triage: the caller's host phase takes no taps and its low_score bounds cannot move during the search
+static int search_gpu_phase(Lane &D, Volume &V, Query &Q, int32_t oid_begin, int32_t oid_end, BnResults *out, GpuOut &G,
+                            bool allow_triage = false)
 {
     memset(out, 0, sizeof *out);
     G.t0 = now_ms();
@@ -1050,7 +1182,7 @@ static int search_gpu_phase(Lane &D, Volume &V, Query &Q, int32_t oid_begin, int
     const double tw0 = now_ms();
     double tw1 = tw0;
     bool general = Q.batch.container_type != BN_DIAG_HASH || Q.fast_path_refused || T->total_pos <= 0 ||
-                   serial_replay(Q.batch);
+                   serial_replay(Q.batch) || getenv("BN_FORCE_GENERAL") != nullptr;
     if (!general) {
         bool redo = false;
         rc = run_fused(D, V, Q, *T, cnt, stats, G.h_init, G.h_gap, &redo);
@@ -1062,9 +1194,17 @@ static int search_gpu_phase(Lane &D, Volume &V, Query &Q, int32_t oid_begin, int
         rc = run_word_finder(D, V, Q, *T, false, cnt, &stats);
         if (rc) return rc;
         tw1 = now_ms();
-        rc = run_gapped(D, V, Q, *T, cnt.n_init, G.h_init, G.h_gap, &stats);
+        // triage on the device when the result set is large and a (chunk, context) table is affordable
+        const bool no_triage = getenv("BN_NO_TRIAGE") != nullptr;             // test switches, read per search
+        const int64_t triage_min = getenv("BN_TRIAGE_MIN") ? atoll(getenv("BN_TRIAGE_MIN")) : 100000;
+        bool strands_are_contexts = true;
+        for (int32_t c = 0; c < Q.batch.num_contexts && strands_are_contexts; c++) strands_are_contexts = Q.ctx_lite[(size_t)c].strand_ctx == c;
+        const bool triage = allow_triage && !no_triage && cnt.n_init >= triage_min && strands_are_contexts &&
+                            (int64_t)T->host.size() * Q.batch.num_contexts <= ((int64_t)1 << 22);
+        rc = run_gapped(D, V, Q, *T, cnt.n_init, G.h_init, G.h_gap, &stats, triage ? &G : nullptr);
         if (rc) return rc;
     }
+    if (!G.triaged) G.n_records = cnt.n_init;
     const double tw2 = now_ms();
     G.t_table = tw0 - G.t0; G.t_wf = tw1 - tw0; G.t_gap = tw2 - tw1;
     stats.lookup_hits = cnt.lookup_hits;
@@ -1101,7 +1241,7 @@ static int search_host_phase(const Query &Q, const GpuOut &G, int taps, BnResult
     // `inits`; a counting sort when the hits are many compared with the chunks, else a sort of the hits
     // (an nt-like volume has a million chunks and a few thousand init-HSPs).
     const size_t n_chunks = T->hchunks.size();
-    const size_t n_in = (size_t)cnt.n_init;
+    const size_t n_in = (size_t)G.n_records;        // all init-HSPs, or what the device-side triage selected
     std::vector<HostInit> inits(n_in);
     struct Group { size_t chunk, lo, hi; };
     std::vector<Group> groups;
@@ -1182,7 +1322,9 @@ static int search_host_phase(const Query &Q, const GpuOut &G, int taps, BnResult
     // during this search (fewer subjects than a hit list holds) the chunks are independent and, for large
     // result sets (short-read batches), are replayed by a few host threads.
     const bool bounds_fixed = sh ? sh->bounds_fixed : tracker.bounds_stay_zero((int64_t)oid_end - oid_begin);
-    const bool parallel = cnt.n_init >= 16384 && groups.size() >= 2 && bounds_fixed;
+    const bool parallel = n_in >= 16384 && groups.size() >= 2 && bounds_fixed;
+    // losers the device counted instead of shipping them: each is an extension the reference makes and drops
+    stats.gap_extensions += G.counted_losers;
     if (parallel) {
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
         const size_t n_threads = std::min<size_t>(std::min<size_t>(groups.size(), hw), 16);
@@ -1252,11 +1394,16 @@ static int search_host_phase(const Query &Q, const GpuOut &G, int taps, BnResult
     return BN_OK;
 }
 
+static bool triage_allowed(const Query &Q, int64_t n_subjects, int taps)
+{
+    return taps == 0 && LowScoreTracker(Q.batch).bounds_stay_zero(n_subjects);
+}
+
 static int prelim_search_locked(Lane &D, Volume &V, Query &Q, int32_t oid_begin, int32_t oid_end,
                                 int taps, BnResults *out)
 {
     GpuOut G;
-    int rc = search_gpu_phase(D, V, Q, oid_begin, oid_end, out, G);
+    int rc = search_gpu_phase(D, V, Q, oid_begin, oid_end, out, G, triage_allowed(Q, (int64_t)oid_end - oid_begin, taps));
     if (rc) return rc;
     return search_host_phase(Q, G, taps, out);
 }
@@ -1845,7 +1992,7 @@ int bn_prelim_search_batches(int vol_handle, int32_t n_batches, const BnQueryBat
         rc = query_load_impl(batches[k], &Qs[(size_t)k], V->device, nullptr, L, true);
         if (rc) { first_error = rc; first_msg = g_err; break; }
         Query *Q = Qs[(size_t)k].get();
-        rc = search_gpu_phase(*L, *V, *Q, 0, n_seq, &results[k], G[(size_t)k]);
+        rc = search_gpu_phase(*L, *V, *Q, 0, n_seq, &results[k], G[(size_t)k], triage_allowed(*Q, n_seq, taps));
         if (rc) { first_error = rc; first_msg = g_err; break; }
         pending[slot] = std::thread([&, k, Q]() {
             host_rc[(size_t)k] = search_host_phase(*Q, G[(size_t)k], taps, &results[k]);
@@ -1904,6 +2051,7 @@ int bn_prelim_search_volumes(int32_t n_volumes, const int *vol_handles, int quer
         bool done = false;
     };
     std::vector<Part> parts(nv);
+    const bool volumes_triage = taps == 0 && (int64_t)oid_base[nv] <= (int64_t)LowScoreTracker(Q.batch).hitlist_size();
     std::mutex mu;
     std::condition_variable cv;
     std::atomic<size_t> next_vol{0};
@@ -1913,11 +2061,11 @@ int bn_prelim_search_volumes(int32_t n_volumes, const int *vol_handles, int quer
             Volume &V = *Vs[v];
             {
                 LaneLock lock(*device_at(V.device));
-                P.rc = search_gpu_phase(*lock.lane, V, Q, 0, (int32_t)V.seq_len.size(), &P.res, P.G);
+                P.rc = search_gpu_phase(*lock.lane, V, Q, 0, (int32_t)V.seq_len.size(), &P.res, P.G, volumes_triage);
                 if (P.rc) P.err = g_err;
                 else {
-                    P.init.assign(P.G.h_init, P.G.h_init + P.G.cnt.n_init);
-                    P.gap.assign(P.G.h_gap, P.G.h_gap + P.G.cnt.n_init);
+                    P.init.assign(P.G.h_init, P.G.h_init + P.G.n_records);
+                    P.gap.assign(P.G.h_gap, P.G.h_gap + P.G.n_records);
                     P.G.h_init = P.init.data(); P.G.h_gap = P.gap.data();
                 }
             }
@@ -2105,7 +2253,7 @@ int bn_get_gapped_score(int vol_handle, int query_handle, int32_t oid, int32_t c
             up[(size_t)i] = DevInitHit{chunk, h.q_off, h.s_off, h.q_start, h.s_start, h.length, h.score, (uint32_t)i};
         }
     }
-    CU_TRY(ws.counters.reserve(8));
+    CU_TRY(ws.counters.reserve(16));
     CU_TRY(ws.init.reserve((size_t)n_init));
     const unsigned long long n_ull = (unsigned long long)n_init;
     CU_TRY(cudaMemsetAsync(ws.counters.p, 0, 8 * sizeof(unsigned long long), st));
@@ -2559,7 +2707,7 @@ int bn_bench_scan(int vol_handle, int query_handle, int iters, double *ms_per_la
     if (V->ready) CU_TRY(cudaStreamWaitEvent(D->stream, V->ready, 0));
     Workspace &ws = D->ws();
     cudaStream_t st = D->stream;
-    CU_TRY(ws.counters.reserve(8));
+    CU_TRY(ws.counters.reserve(16));
     int64_t cap = std::max<int64_t>((int64_t)ws.hits_a.cap, std::max<int64_t>(1 << 16, T->total_pos / 16));
     CU_TRY(ws.hits_a.reserve((size_t)cap)); CU_TRY(ws.keys_a.reserve((size_t)cap));
     cap = (int64_t)std::min(ws.hits_a.cap, ws.keys_a.cap);

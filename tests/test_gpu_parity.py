@@ -868,3 +868,32 @@ def test_direct_filter_changes_nothing(name, monkeypatch):
         assert a["stats"]["lookup_hits"] == b["stats"]["lookup_hits"] == r["lookup_hits"]
     finally:
         V.free()
+
+
+@pytest.mark.parametrize("name", ["blastn_mb11_dp", "c3_scaled_blastn_10kb", "blastn_direct_mixed_lengths_N",
+                                  "blastn_bridged_segments", "mb_lut12_stride17", "c4_scaled_short_reads",
+                                  "mb_bridged_segments", "blastn_smallna_dp", "mb_long_divergent_tier2"])
+def test_device_triage_changes_nothing(name, monkeypatch):
+    """Large result sets are triaged on the device after the gapped stage: winners (extension >= cutoff) and the losers
+    a winner's box could contain go to the host replay, every other loser arrives as a count.  Forced on here at small
+    size (BN_FORCE_GENERAL + BN_TRIAGE_MIN) and compared with the untriaged path and with the reference: lists,
+    E-value bits and the extension counters."""
+    from gblastn_b200 import engine as E
+    from oracle import portdriver as P
+    r, h, vol = _setup(name)
+    V, Q = E.Volume(vol), E.Query(h)
+    try:
+        monkeypatch.setenv("BN_FORCE_GENERAL", "1")
+        monkeypatch.setenv("BN_TRIAGE_MIN", "1")
+        monkeypatch.delenv("BN_NO_TRIAGE", raising=False)
+        a = E.prelim_search(V, Q)
+        monkeypatch.setenv("BN_NO_TRIAGE", "1")
+        b = E.prelim_search(V, Q)
+        assert a["hsps"].tobytes() == b["hsps"].tobytes()
+        assert np.array_equal(P.final_table(a["hsps"]), r["final"])
+        for st in (a["stats"], b["stats"]):
+            assert (st["lookup_hits"], st["good_init_extends"], st["gap_extensions"], st["good_extensions"]) == \
+                   (r["lookup_hits"], r["good_init_extends"], r["gap_extensions"], r["good_extensions"])
+        assert a["stats"]["kernel_launches"] > b["stats"]["kernel_launches"], "the triage kernels did not run"
+    finally:
+        Q.free(); V.free()
