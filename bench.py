@@ -38,6 +38,114 @@ METRIC = "Gbases/s subject scanned (megablast) at 1/2/4/8 B200; HSPs bit-exact v
 UNIT = "Gbases/s"
 N_QUERIES, QUERY_LEN, DB_BASES = 1000, 1000, 250_000_000
 WORKLOAD = "megablast: 1000x1kb synthetic queries vs 250Mb synthetic DB (BASELINE configs[1])"
+L2_NOTE = "GPU arm: L2 flushed between timed steps (256 MiB write)"
+
+
+def bench_config(n_vol):
+    """The `config` object of the JSON line: identical for the GPU arm and the reference arm."""
+    return {"workload": WORKLOAD, "volumes": n_vol, "l2": L2_NOTE}
+
+
+# ---- the other named configurations of BASELINE.json (configs[2..4]) at their stated sizes -------------------
+# C3 runs whole on one GPU; C4 and C5 are volume-sharded over 4 / 8 GPUs: a rank builds and searches ITS shard
+# (every rank sees the whole query batch).  At N=1 the line also carries one shard of C4 and of C5, labelled so.
+def named_config(name, shard=0):
+    if name == "C3":      # blastn ws 11: 100 x 10 kb vs 1 Gb (10 x 100 Mb), 8 % substitutions + 1 % indels
+        vol = synth.random_volume([100_000_000] * 10, seed=3)
+        qs = synth.planted_queries(vol, 100, 10_000, seed=33, planted_frac=0.8, sub_rate=0.08, indel_rate=0.01)
+        return dict(task="blastn", vol=vol, qs=qs, masks=None, db_length=1_000_000_000, db_num_seqs=10,
+                    workload="blastn word_size 11: 100x10kb queries vs 1Gb synthetic DB (10x100Mb), 1 GPU (BASELINE configs[2])",
+                    sample_oids=1)
+    if name == "C4":      # megablast: 100 k x 150 bp reads vs 3 Gb = 4 volumes x (7 x ~107 Mb)
+        vol = synth.random_volume([107_142_857] * 7, seed=40 + shard)
+        qs = synth.planted_queries(vol, 100_000, 150, seed=44, planted_frac=0.8, sub_rate=0.02)
+        return dict(task="megablast", vol=vol, qs=qs, masks=None, db_length=3_000_000_000, db_num_seqs=28,
+                    workload="megablast: 100kx150bp short reads vs 3Gb synthetic DB, volume-sharded 4 GPUs: "
+                             "one shard = 7x107Mb (BASELINE configs[3])", sample_oids=2)
+    if name == "C5":      # megablast + DUST: 1000 x 5 kb vs 20 Gb nt-like = 8 volumes x 2.5 Gb, log-normal lengths
+        rng = np.random.default_rng(50 + shard)
+        lens = np.clip(np.exp(rng.normal(np.log(2000.0), 1.2, size=625_000)).astype(np.int64), 30, 10_000_000)
+        lens = lens[: int(np.searchsorted(np.cumsum(lens), 2_500_000_000)) + 1]
+        vol = synth.random_volume(lens, seed=50 + shard)
+        qs = synth.planted_queries(vol, 1000, 5000, seed=55, planted_frac=0.8, sub_rate=0.02, indel_rate=0.002)
+        qs = synth.add_low_complexity(qs, seed=56, frac=0.3)
+        from gblastn_b200 import engine as _E
+        masks = [_E.dust_mask(q) for q in qs]          # blastn -dust yes (task default 20 64 1)
+        return dict(task="megablast", vol=vol, qs=qs, masks=masks, db_length=int(8 * vol.total_bases), db_num_seqs=int(8 * vol.n_seqs),
+                    workload="megablast + DUST: 1000x5kb queries (30 % with low-complexity inserts) vs 20Gb nt-like DB, "
+                             "volume-sharded 8 GPUs: one shard = 2.5Gb of log-normal length sequences (BASELINE configs[4])",
+                    sample_oids=60_000)
+    raise KeyError(name)
+
+
+def run_named_config(name, shard, engine, setup, torch, steps=3, with_reference=True):
+    """One named configuration (or one shard of it) on the current device: stage times, throughput, parity of a
+    bounded sample against the reference engine, the reference's own speed on that sample."""
+    t_gen = time.perf_counter()
+    w = named_config(name, shard)
+    vol, qs = w["vol"], w["qs"]
+    t_gen = time.perf_counter() - t_gen
+    kw = {}
+    if w["task"] == "megablast":
+        kw["device_lookup"] = 1
+    t0 = time.perf_counter()
+    s = setup.Setup(qs, task=w["task"], db_length=w["db_length"], db_num_seqs=w["db_num_seqs"], masks=w["masks"], **kw)
+    V = engine.Volume(vol, device=0)
+    Q = engine.Query(s.batch)
+    t_load = time.perf_counter() - t0
+    out = {"name": name, "workload": w["workload"], "shard": shard, "subject_bases": int(vol.total_bases),
+           "subjects": int(vol.n_seqs), "query_batches": 1,
+           "query_bases": int(sum(len(q) for q in qs)), "lut": f"lut {s.batch.lut_word_length} / stride {s.batch.scan_step}",
+           "seconds_generate": round(t_gen, 2), "seconds_setup_and_load": round(t_load, 2)}
+    try:
+        engine.prelim_search(V, Q)                     # warm-up: buffers, chunk table
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ms, stage = [], {"ms_scan": 0.0, "ms_extend": 0.0, "ms_gapped": 0.0, "ms_host": 0.0}
+        g = None
+        for _ in range(steps):
+            torch.cuda.synchronize()
+            ev0.record()
+            g = engine.prelim_search(V, Q)
+            ev1.record()
+            ev1.synchronize()
+            ms.append(ev0.elapsed_time(ev1))
+            for k in stage:
+                stage[k] += g["stats"][k] / steps
+        st = g["stats"]
+        out.update({"ms_per_pass": float(np.mean(ms)), "gbases_per_s": vol.total_bases / (np.mean(ms) * 1e-3) / 1e9,
+                    "stage_ms": {k: round(v, 3) for k, v in stage.items()}, "hsps": int(g["hsps"].size),
+                    "lookup_hits": int(st["lookup_hits"]), "init_hsps": int(st["good_init_extends"]),
+                    "gap_extensions": int(st["gap_extensions"]), "kernel_launches_per_pass": int(st["kernel_launches"])})
+        scan_ms, scan_bases, _ = engine.bench_scan(V, Q, 3)
+        peak, _ = peak_hbm()
+        out["scan_kernel"] = {"ms": scan_ms, "algorithmic_GBs": scan_bases * 0.25 / (scan_ms * 1e-3) / 1e9,
+                              "frac_of_hbm_peak": scan_bases * 0.25 / (scan_ms * 1e-3) / 1e9 / peak}
+        if with_reference:
+            from oracle import refdriver as R, portdriver as P
+            if R.available():
+                # bounded sample: the first k subjects of the shard, searched alone by the reference with the
+                # effective search space of the whole database (db_length / db_num_seqs), against the GPU lists
+                # of the same OID range
+                k = min(int(w["sample_oids"]), vol.n_seqs)
+                sub = synth.Volume(vol.packed, vol.byte_off[:k], vol.seq_len[:k])
+                cores = os.cpu_count() or 1
+                threads = max(1, min(cores, k))
+                cfg = R.default_config(w["task"], db_length=w["db_length"], db_num_seqs=w["db_num_seqs"], num_threads=threads)
+                t0 = time.perf_counter()
+                r = R.search(qs, sub, cfg, masks=w["masks"])
+                wall = time.perf_counter() - t0
+                gs = engine.prelim_search(V, Q, 0, k)
+                # with several reference threads the per-thread lists come back in OID order like ours
+                same = bool(r["status"] == 0 and np.array_equal(P.final_table(gs["hsps"]), r["final"]))
+                out["parity_vs_reference"] = {"identical": same, "sample": f"first {k} subject(s) of the shard = "
+                                              f"{int(sub.seq_len.astype(np.int64).sum())} bases, all queries",
+                                              "hsps": int(r["final"].shape[0])}
+                out["cpu_baseline"] = {"gbases_per_s": float(sub.seq_len.astype(np.int64).sum()) / r["seconds_prelim"] / 1e9,
+                                       "cores": threads, "kind": "reference", "seconds": round(r["seconds_prelim"], 2),
+                                       "wall_seconds": round(wall, 2)}
+    finally:
+        Q.free(); V.free(); s.free()
+    return out
 
 
 def make_workload(rank: int):
@@ -198,7 +306,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "volumes": n_vol},
+        "data": "synthetic", "config": bench_config(n_vol),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
                          "sample": f"full workload per step: {n_vol} volume(s) searched concurrently, one thread each "
                                    f"(the reference parallelises over subject sequences; a volume is one sequence), "
@@ -215,6 +323,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gblastn_b200", choices=["gblastn_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C3 / C4 / C5 blocks (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -342,8 +451,9 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "volumes": world, "l2": "flushed between timed steps (256 MiB write)",
-                   "lut": f"MB lut {b.lut_word_length} / stride {b.scan_step}, filled on the device", "hsps_per_step": int(g["hsps"].size)},
+        "config": bench_config(world),
+        "details": {"lut": f"MB lut {b.lut_word_length} / stride {b.scan_step}, filled on the device",
+                    "hsps_per_step": int(g["hsps"].size)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -22,7 +22,7 @@ EXPORTS = [
     "bn_scan_subject", "bn_word_finder", "bn_free", "bn_bench_scan", "bn_query_download_lookup", "bn_get_gapped_score", "bn_gapped_traceback", "bn_traceback_hsps", "bn_traceback_search",
     "bn_dbfile_index", "bn_db_load_files", "bn_dbfile_write", "bn_prelim_search_batches", "bn_db_set_masks", "bn_selftest_replay",
     "bn_setup_create", "bn_setup_batch", "bn_setup_kbp_std", "bn_setup_kbp_gap",
-    "bn_setup_gap_x_dropoff_final", "bn_setup_longest_chain", "bn_setup_free",
+    "bn_setup_gap_x_dropoff_final", "bn_setup_longest_chain", "bn_setup_free", "bn_dust_mask",
 ]
 
 
@@ -306,3 +306,16 @@ def bench_scan(volume: Volume, query: Query, iters: int):
     _check(lib().bn_bench_scan(C.c_int(volume.handle), C.c_int(query.handle), C.c_int(iters),
                                C.byref(ms), C.byref(bases), C.byref(hits)))
     return ms.value, bases.value, hits.value
+
+
+def dust_mask(query: np.ndarray, level=20, window=64, linker=1):
+    """Symmetric DUST of one query (blastna bytes): list of inclusive (from, to) intervals, as `masks` of setup.Setup."""
+    q = np.ascontiguousarray(query, dtype=np.uint8)
+    p = C.POINTER(C.c_int32)()
+    n = C.c_int32(0)
+    _check(lib().bn_dust_mask(q.ctypes.data_as(C.c_void_p), C.c_int32(q.shape[0]), C.c_int32(level), C.c_int32(window),
+                              C.c_int32(linker), C.byref(p), C.byref(n)))
+    try:
+        return [(int(p[2 * i]), int(p[2 * i + 1])) for i in range(n.value)]
+    finally:
+        lib().bn_free(p)

@@ -146,3 +146,22 @@ def planted_queries(vol: Volume, n_queries: int, qlen: int, seed: int, *, plante
             q[rng.random(qlen) < n_frac] = 14
         queries.append(np.ascontiguousarray(q, dtype=np.uint8))
     return queries
+
+
+def add_low_complexity(queries, seed: int, frac=0.3):
+    """low-complexity stretches — poly-A (30-80 bases), (CA)n, (GGA)n — written over random places
+    of `frac` of the queries (lengths unchanged), so that DUST has something to mask."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for q in queries:
+        q = q.copy()
+        if rng.random() < frac and q.shape[0] > 200:
+            for _ in range(int(rng.integers(1, 3))):
+                kind = int(rng.integers(0, 3))
+                n = int(rng.integers(30, 81))
+                unit = (np.array([0], np.uint8), np.array([1, 0], np.uint8), np.array([2, 2, 0], np.uint8))[kind]
+                rep = np.tile(unit, n // unit.shape[0] + 1)[:n]
+                a = int(rng.integers(0, q.shape[0] - n))
+                q[a:a + n] = rep
+        out.append(np.ascontiguousarray(q, dtype=np.uint8))
+    return out

@@ -397,6 +397,16 @@ int32_t bn_setup_gap_x_dropoff_final(const BnSetup *s);
 int32_t bn_setup_longest_chain(const BnSetup *s);
 void bn_setup_free(BnSetup *s);
 
+/* ---- query low-complexity masking ------------------------------------------------
+ * Symmetric DUST as blastn applies it to its queries (`-dust yes`, task default level 20 / window 64 / linker 1):
+ * CSymDustMasker (c++/src/algo/dustmask/symdust.cpp:213-319) called by Blast_FindDustFilterLoc
+ * (c++/src/algo/blast/api/dust_filter.cpp:65-151).  seq: blastna bytes of ONE query (codes >= 4 read as A, like every
+ * non-ACGT IUPAC letter does in the reference); out: n_intervals inclusive [from, to] pairs, ascending, already merged
+ * by `linker`; free with bn_free.  Host only (no device needed): the masks are the qmask_iv input of bn_setup_create,
+ * i.e. they only keep words out of the lookup table (mask-at-hash) and switch on s_TypeOfWord's re-probing. */
+int  bn_dust_mask(const uint8_t *seq, int32_t len, int32_t level, int32_t window, int32_t linker,
+                  int32_t **intervals, int32_t *n_intervals);
+
 #ifdef __cplusplus
 }
 #endif
