@@ -61,7 +61,7 @@ def named_config(name, shard=0):
         qs = synth.planted_queries(vol, 100_000, 150, seed=44, planted_frac=0.8, sub_rate=0.02)
         return dict(task="megablast", vol=vol, qs=qs, masks=None, db_length=3_000_000_000, db_num_seqs=28,
                     workload="megablast: 100kx150bp short reads vs 3Gb synthetic DB, volume-sharded 4 GPUs: "
-                             "one shard = 7x107Mb (BASELINE configs[3])", sample_oids=2)
+                             "one shard = 7x107Mb (BASELINE configs[3])", sample_oids=7, ref_threads=7)
     if name == "C5":      # megablast + DUST: 1000 x 5 kb vs 20 Gb nt-like = 8 volumes x 2.5 Gb, log-normal lengths
         rng = np.random.default_rng(50 + shard)
         lens = np.clip(np.exp(rng.normal(np.log(2000.0), 1.2, size=625_000)).astype(np.int64), 30, 10_000_000)
@@ -74,7 +74,7 @@ def named_config(name, shard=0):
         return dict(task="megablast", vol=vol, qs=qs, masks=masks, db_length=int(8 * vol.total_bases), db_num_seqs=int(8 * vol.n_seqs),
                     workload="megablast + DUST: 1000x5kb queries (30 % with low-complexity inserts) vs 20Gb nt-like DB, "
                              "volume-sharded 8 GPUs: one shard = 2.5Gb of log-normal length sequences (BASELINE configs[4])",
-                    sample_oids=60_000)
+                    sample_oids=10 ** 9, ref_threads=1)      # one thread: the hit lists overflow, low_score is order-dependent
     raise KeyError(name)
 
 
@@ -129,7 +129,7 @@ def run_named_config(name, shard, engine, setup, torch, steps=3, with_reference=
                 k = min(int(w["sample_oids"]), vol.n_seqs)
                 sub = synth.Volume(vol.packed, vol.byte_off[:k], vol.seq_len[:k])
                 cores = os.cpu_count() or 1
-                threads = max(1, min(cores, k))
+                threads = max(1, min(cores, k, int(w["ref_threads"])))
                 cfg = R.default_config(w["task"], db_length=w["db_length"], db_num_seqs=w["db_num_seqs"], num_threads=threads)
                 t0 = time.perf_counter()
                 r = R.search(qs, sub, cfg, masks=w["masks"])
@@ -137,7 +137,7 @@ def run_named_config(name, shard, engine, setup, torch, steps=3, with_reference=
                 gs = engine.prelim_search(V, Q, 0, k)
                 # with several reference threads the per-thread lists come back in OID order like ours
                 same = bool(r["status"] == 0 and np.array_equal(P.final_table(gs["hsps"]), r["final"]))
-                out["parity_vs_reference"] = {"identical": same, "sample": f"first {k} subject(s) of the shard = "
+                out["parity_vs_reference"] = {"identical": same, "sample": f"{'all' if k == vol.n_seqs else 'first'} {k} subject(s) of the shard = "
                                               f"{int(sub.seq_len.astype(np.int64).sum())} bases, all queries",
                                               "hsps": int(r["final"].shape[0])}
                 out["cpu_baseline"] = {"gbases_per_s": float(sub.seq_len.astype(np.int64).sum()) / r["seconds_prelim"] / 1e9,
@@ -514,11 +514,40 @@ def main():
         except Exception as e:  # the baseline must never take the bench down
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
                                     "sample": f"failed: {e}"}
-    if rank == 0:
-        print(json.dumps(line))
     Q.free()
     V.free()
     s.free()
+    del flush
+    torch.cuda.empty_cache()
+
+    # ---- the other named configurations at their stated sizes (not part of value / e2e) ---------------------------
+    # N = 1: C3 whole, plus ONE shard each of C4 and C5 measured on this GPU; N = 4: C4, N = 8: C5, one shard per rank.
+    if not args.no_configs:
+        blocks = []
+        plan = {1: [("C3", 0), ("C4", 0), ("C5", 0)], 4: [("C4", rank)], 8: [("C5", rank)]}.get(world, [])
+        for name, shard in plan:
+            try:
+                blk = run_named_config(name, shard, engine, setup, torch, steps=3,
+                                       with_reference=(rank == 0 and not args.no_cpu_baseline))
+            except Exception as e:      # a named block must never take the headline down
+                blk = {"name": name, "shard": shard, "error": f"{type(e).__name__}: {e}"}
+            if world > 1 and "ms_per_pass" in blk:
+                # the sharded configuration as a whole: all shards run concurrently, the job ends with the slowest
+                tt = torch.tensor([blk["ms_per_pass"], float(blk["subject_bases"]), float(blk["hsps"])],
+                                  dtype=torch.float64, device="cuda")
+                mx = tt.clone()
+                dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+                sm = tt.clone()
+                dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+                blk["all_shards"] = {"gpus": world, "ms_per_pass_max_over_ranks": float(mx[0]),
+                                     "subject_bases": int(sm[1]), "hsps": int(sm[2]),
+                                     "gbases_per_s": float(sm[1]) / (float(mx[0]) * 1e-3) / 1e9}
+            elif world > 1:
+                dist.barrier()
+            blocks.append(blk)
+        line["configs"] = blocks
+    if rank == 0:
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
