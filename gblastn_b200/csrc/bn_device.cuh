@@ -383,6 +383,8 @@ struct DevTracebackItem {
     int32_t s_shift, s_length;   // AdjustSubjectRange: subject = sequence + s_shift, s_length bases
     int32_t q_start, s_start;    // start point (s_start relative to s_shift)
     int32_t pad;
+    int32_t amb_first, amb_n;    // ambiguity runs of the subject sequence in the volume's run table (amb_n == 0: none)
+    int32_t pad2;
 };
 struct DevTracebackDir {         // one direction of one alignment
     int32_t score, a_off, b_off; // best score and the query / subject extents of ALIGN_EX
@@ -404,23 +406,26 @@ struct TracebackLaunch {
     long long ops_cap;
     unsigned long long *ops_used;
     DevTracebackDir *out;        // 2 n entries: left, right
+    const int4 *amb_runs;        // the volume's ambiguity runs {first base, end, blastna code, 0} (nullptr: none)
     const uint8_t *todo;         // greedy: optional per-item flags (retry of the items whose arena overflowed); nullptr = all
 };
 cudaError_t launch_traceback_dp(const DevQuery &q, const TracebackLaunch &L, int blocks, cudaStream_t st);
 struct DevTracebackHsp {         // a preliminary HSP (absolute subject coordinates) about to be traced back
     int64_t byte_off;            // of its subject sequence
     int32_t seq_len, context, q_off, q_end, s_off, s_end, q_gapped_start, s_gapped_start;
+    int32_t amb_first, amb_n;
 };
-cudaError_t launch_traceback_start(const DevQuery &q, const uint8_t *packed, const DevTracebackHsp *hsps, int64_t n,
-                                   DevTracebackItem *items, cudaStream_t st);
+cudaError_t launch_traceback_start(const DevQuery &q, const uint8_t *packed, const int4 *amb_runs, const DevTracebackHsp *hsps,
+                                   int64_t n, DevTracebackItem *items, cudaStream_t st);
 struct DevTracebackPost {        // an HSP after the list logic (absolute subject coordinates), edit script in ops[esp_off ..)
     int64_t byte_off, esp_off;
     int32_t seq_len, context, q_off, q_end, s_off, s_end, score, esp_n, reevaluate, pad;
+    int32_t amb_first, amb_n;
 };
 struct DevTracebackPostOut {
     int32_t deleted, q_off, q_end, s_off, s_end, score, first, last, num_ident, align_length;
 };
-cudaError_t launch_traceback_reevaluate(const DevQuery &q, const uint8_t *packed, const DevTracebackPost *items, int64_t n,
+cudaError_t launch_traceback_reevaluate(const DevQuery &q, const uint8_t *packed, const int4 *amb_runs, const DevTracebackPost *items, int64_t n,
                                         int2 *ops, DevTracebackPostOut *out, cudaStream_t st);
 cudaError_t launch_traceback_greedy_warp(const DevQuery &q, const TracebackLaunch &L, int blocks, cudaStream_t st);
 cudaError_t launch_traceback_greedy_affine(const DevQuery &q, const TracebackLaunch &L, int blocks, int threads_per_block, cudaStream_t st);

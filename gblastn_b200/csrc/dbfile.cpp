@@ -124,6 +124,45 @@ bool sequence_table(const DbIndex &idx, const uint8_t *nsq, int64_t nsq_bytes, s
     return true;
 }
 
+bool ambiguity_table(const DbIndex &idx, const uint8_t *nsq, int64_t nsq_bytes, std::vector<int64_t> &first,
+                     std::vector<int32_t> &runs, std::string &err)
+{
+    static const int32_t kNcbi4naToBlastna[16] = {15, 0, 1, 6, 2, 4, 9, 13, 3, 8, 5, 12, 7, 11, 10, 14};
+    first.assign((size_t)idx.n_seq + 1, 0);
+    runs.clear();
+    auto word = [&](int64_t at) -> uint32_t {
+        return ((uint32_t)nsq[at] << 24) | ((uint32_t)nsq[at + 1] << 16) | ((uint32_t)nsq[at + 2] << 8) | nsq[at + 3];
+    };
+    for (int32_t i = 0; i < idx.n_seq; i++) {
+        const int64_t a = idx.amb_off[(size_t)i], e = idx.seq_off[(size_t)i + 1];
+        first[(size_t)i] = (int64_t)(runs.size() / 3);
+        if (e <= a) continue;
+        if (e > nsq_bytes || (e - a) % 4 != 0 || e - a < 4) { err = "malformed ambiguity data"; return false; }
+        const int64_t n_words = (e - a) / 4;
+        uint32_t n = word(a);
+        const bool wide = (n & 0x80000000u) != 0;
+        n &= 0x7FFFFFFFu;
+        if ((int64_t)n > n_words - 1) { err = "ambiguity entry count exceeds the data"; return false; }
+        for (uint32_t k = 1; k < n + 1; k++) {
+            const uint32_t w = word(a + 4 * (int64_t)k);
+            const int32_t code = kNcbi4naToBlastna[(w >> 28) & 0xF];
+            int32_t len, pos;
+            if (wide) {
+                if ((int64_t)k + 1 > n_words - 1) { err = "truncated ambiguity entry"; return false; }
+                len = (int32_t)((w >> 16) & 0xFFF) + 1;
+                pos = (int32_t)word(a + 4 * (int64_t)(k + 1));
+                ++k;
+            } else {
+                len = (int32_t)((w >> 24) & 0xF) + 1;
+                pos = (int32_t)(w & 0xFFFFFF);
+            }
+            runs.push_back(pos); runs.push_back(len); runs.push_back(code);
+        }
+    }
+    first[(size_t)idx.n_seq] = (int64_t)(runs.size() / 3);
+    return true;
+}
+
 bool write_volume(const char *nin_path, const char *nsq_path, const char *title, const uint8_t *packed,
                   const int64_t *seq_byte_off, const int32_t *seq_len, int32_t n_seq, std::string &err)
 {

@@ -49,6 +49,15 @@ private:
 bool sequence_table(const DbIndex &idx, const uint8_t *nsq, int64_t nsq_bytes,
                     std::vector<int64_t> &byte_off, std::vector<int32_t> &seq_len, std::string &err);
 
+// Ambiguity data of a nucleotide volume: the words [amb[i], seq[i+1]) of the .nsq (big-endian Int4; the first is the
+// number of entries, its top bit selecting the 8-byte "new" entry form) decoded like s_SeqDBRebuildDNA_NA8
+// (objtools/blast/seqdb_reader/seqdbvol.cpp:832-870, accessors :640-745) into runs {first base, number of bases,
+// blastna code}: the ncbi4na residue of an entry mapped through SeqDB_ncbina8_to_blastna8 (:561-578).
+// first[i] .. first[i + 1] index the runs of sequence i (n_seq + 1 entries); runs are flat triples in file order
+// (the reference applies them in that order, later entries overwrite earlier ones).
+bool ambiguity_table(const DbIndex &idx, const uint8_t *nsq, int64_t nsq_bytes, std::vector<int64_t> &first,
+                     std::vector<int32_t> &runs, std::string &err);
+
 // Writes a volume (our in-memory layout: sequence i = (seq_len[i] + 3) / 4 bytes at seq_byte_off[i])
 // as .nin + .nsq without ambiguity data or deflines.
 bool write_volume(const char *nin_path, const char *nsq_path, const char *title, const uint8_t *packed,

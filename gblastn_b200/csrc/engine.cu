@@ -220,11 +220,15 @@ struct Volume {
     uint64_t use_clock = 0;
     // ambiguity data of a BLAST DB volume (bn_db_load_files): per sequence amb_first[i]..amb_first[i+1] runs
     // {start, length, blastna value} in amb_runs; empty for volumes without ambiguities
-    std::vector<int64_t> amb_first;
-    std::vector<int32_t> amb_runs;
-    int32_t *d_amb_runs = nullptr;
+    std::vector<int64_t> amb_first;      // n_seq + 1 (empty: the volume has no ambiguity data)
+    std::vector<int32_t> amb_runs;       // as given: flat {first base, bases, blastna code} in application order
+    std::vector<int64_t> amb_dev_first;  // per sequence: first entry of its runs in the device table
+    int4 *d_amb = nullptr;               // {first base, end, blastna code, 0}, sorted and disjoint per sequence
+    int32_t *d_amb_runs = nullptr;       // (unused, kept for free_volume_dev)
     int64_t *d_amb_first = nullptr;
-    bool has_ambiguity() const { return !amb_runs.empty(); }
+    bool has_ambiguity() const { return d_amb != nullptr; }
+    int32_t amb_first_of(int32_t oid) const { return amb_dev_first.empty() ? 0 : (int32_t)amb_dev_first[(size_t)oid]; }
+    int32_t amb_count_of(int32_t oid) const { return amb_dev_first.empty() ? 0 : (int32_t)(amb_dev_first[(size_t)oid + 1] - amb_dev_first[(size_t)oid]); }
 };
 
 struct QueryDev {
@@ -1469,7 +1473,7 @@ static int traceback_greedy_host(Lane &Dv, Volume &V, Query &Q, int32_t x_dropof
         CU_TRY(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), st));
         CU_TRY(cudaMemcpyAsync(d_todo, todo.data(), todo.size(), cudaMemcpyHostToDevice, st));
         TracebackLaunch L{};
-        L.packed = V.d_packed; L.items = d_items; L.n = n_items; L.x_dropoff = x_dropoff;
+        L.packed = V.d_packed; L.items = d_items; L.n = n_items; L.x_dropoff = x_dropoff; L.amb_runs = V.d_amb;
         L.arena = d_arena; L.arena_bytes = arena_bytes; L.arena_used = d_cnt;
         L.ops = d_ops; L.ops_cap = ops_cap; L.ops_used = d_cnt + 1; L.out = d_out; L.todo = d_todo;
         CU_TRY(affine ? launch_traceback_greedy_affine(dq, L, blocks, per_block, st) : launch_traceback_greedy_warp(dq, L, blocks, st));
@@ -1564,6 +1568,8 @@ static void free_volume_dev(Volume &V)
     cudaStream_t st = g->lanes[0]->stream;
     if (V.ready) { cudaEventSynchronize(V.ready); cudaEventDestroy(V.ready); V.ready = nullptr; }
     if (V.d_raw) cudaFreeAsync(V.d_raw, st);
+    if (V.d_amb) cudaFreeAsync(V.d_amb, st);
+    V.d_amb = nullptr;
     if (V.d_amb_runs) cudaFreeAsync(V.d_amb_runs, st);
     if (V.d_amb_first) cudaFreeAsync(V.d_amb_first, st);
     V.d_raw = nullptr; V.d_packed = nullptr; V.d_amb_runs = nullptr; V.d_amb_first = nullptr;
@@ -1679,6 +1685,95 @@ int bn_dbfile_index(const char *nin_path, const char *nsq_path, BnDbFileInfo *in
     return BN_OK;
 }
 
+static int get_volume(int vol_handle, std::shared_ptr<Volume> *V);
+
+// Ambiguity runs as the reference applies them (in order, later runs overwrite earlier ones) -> per sequence a
+// sorted list of disjoint {first base, end, code} on the device.
+static int install_ambiguity(Volume &V, Lane &L, const int64_t *first, const int32_t *runs)
+{
+    const size_t n_seq = V.seq_len.size();
+    std::vector<int4> table;
+    std::vector<int64_t> dev_first(n_seq + 1, 0);
+    struct Iv { int32_t a, e, code; };
+    std::vector<Iv> cur, next;
+    for (size_t i = 0; i < n_seq; i++) {
+        dev_first[i] = (int64_t)table.size();
+        cur.clear();
+        for (int64_t k = first[i]; k < first[i + 1]; k++) {
+            const int32_t a = runs[3 * k], e = a + runs[3 * k + 1], code = runs[3 * k + 2];
+            if (a < 0 || e <= a || e > V.seq_len[i] || code < 0 || code > 15)
+                return fail(BN_ERR_INVALID, "ambiguity run outside its sequence");
+            if (cur.empty() || cur.back().e <= a) { cur.push_back(Iv{a, e, code}); continue; }      // the usual, ascending case
+            next.clear();
+            bool placed = false;
+            for (const Iv &v : cur) {           // cut [a, e) out of what is there, then insert it in order
+                if (v.e <= a || v.a >= e) {
+                    if (!placed && v.a >= e) { next.push_back(Iv{a, e, code}); placed = true; }
+                    next.push_back(v);
+                    continue;
+                }
+                if (v.a < a) next.push_back(Iv{v.a, a, v.code});
+                if (!placed) { next.push_back(Iv{a, e, code}); placed = true; }
+                if (v.e > e) next.push_back(Iv{e, v.e, v.code});
+            }
+            if (!placed) next.push_back(Iv{a, e, code});
+            cur.swap(next);
+        }
+        for (const Iv &v : cur) table.push_back(make_int4(v.a, v.e, v.code, 0));
+    }
+    dev_first[n_seq] = (int64_t)table.size();
+    if ((int64_t)table.size() > INT32_MAX) return fail(BN_ERR_OVERFLOW, "more than 2^31 ambiguity runs in a volume");
+    CU_TRY(cudaSetDevice(L.id));
+    if (V.d_amb) { CU_TRY(cudaFreeAsync(V.d_amb, L.stream)); V.d_amb = nullptr; }
+    if (!table.empty()) {
+        CU_TRY(cudaMallocAsync((void **)&V.d_amb, table.size() * sizeof(int4), L.stream));
+        CU_TRY(cudaMemcpyAsync(V.d_amb, table.data(), table.size() * sizeof(int4), cudaMemcpyHostToDevice, L.stream));
+        CU_TRY(cudaStreamSynchronize(L.stream));
+    }
+    V.amb_dev_first.swap(dev_first);
+    if (table.empty()) V.amb_dev_first.clear();
+    return BN_OK;
+}
+
+int bn_db_set_ambiguity(int vol_handle, const int64_t *first, const int32_t *runs)
+{
+    std::shared_ptr<Volume> V;
+    int rc = get_volume(vol_handle, &V);
+    if (rc) return rc;
+    Gpu *g = device_at(V->device);
+    if (!g) return fail(BN_ERR_INVALID, "bn_db_set_ambiguity: volume on an unknown device");
+    LaneLock lock(*g);
+    if (!first) {                                   // remove
+        std::vector<int64_t> none(V->seq_len.size() + 1, 0);
+        return install_ambiguity(*V, *lock.lane, none.data(), nullptr);
+    }
+    if (first[V->seq_len.size()] > 0 && !runs) return fail(BN_ERR_INVALID, "bn_db_set_ambiguity: runs is NULL");
+    for (size_t i = 0; i < V->seq_len.size(); i++)
+        if (first[i + 1] < first[i] || first[i] < 0) return fail(BN_ERR_INVALID, "bn_db_set_ambiguity: first[] must ascend");
+    V->amb_first.assign(first, first + V->seq_len.size() + 1);
+    V->amb_runs.assign(runs, runs + 3 * first[V->seq_len.size()]);
+    return install_ambiguity(*V, *lock.lane, first, runs);
+}
+
+int bn_dbfile_ambiguity(const char *nin_path, const char *nsq_path, int64_t *first, int32_t **runs, int64_t *n_runs)
+{
+    if (!nin_path || !nsq_path || !first || !runs || !n_runs) return fail(BN_ERR_INVALID, "bn_dbfile_ambiguity: bad argument");
+    DbIndex idx;
+    std::string err;
+    if (!read_nin(nin_path, idx, err)) return fail(BN_ERR_INVALID, "bn_dbfile_ambiguity: " + err);
+    MappedFile nsq;
+    if (!nsq.open(nsq_path, err)) return fail(BN_ERR_INVALID, "bn_dbfile_ambiguity: " + err);
+    std::vector<int64_t> f;
+    std::vector<int32_t> r;
+    if (!ambiguity_table(idx, nsq.data(), nsq.size(), f, r, err)) return fail(BN_ERR_INVALID, "bn_dbfile_ambiguity: " + err);
+    memcpy(first, f.data(), f.size() * sizeof(int64_t));
+    *n_runs = (int64_t)(r.size() / 3);
+    *runs = (int32_t *)malloc(std::max<size_t>(r.size(), 3) * sizeof(int32_t));
+    if (!*runs) return fail(BN_ERR_MEMORY, "bn_dbfile_ambiguity: out of memory");
+    if (!r.empty()) memcpy(*runs, r.data(), r.size() * sizeof(int32_t));
+    return BN_OK;
+}
+
 int bn_dbfile_write(const char *nin_path, const char *nsq_path, const char *title, const uint8_t *packed,
                     const int64_t *seq_byte_off, const int32_t *seq_len, int32_t n_seq)
 {
@@ -1708,6 +1803,8 @@ int bn_db_load_files(int device, const char *nin_path, const char *nsq_path, int
     V->device = device; V->bytes = nsq.size();
     if (!sequence_table(idx, nsq.data(), nsq.size(), V->byte_off, V->seq_len, err))
         return fail(BN_ERR_INVALID, "bn_db_load_files: " + err);
+    if (!ambiguity_table(idx, nsq.data(), nsq.size(), V->amb_first, V->amb_runs, err))
+        return fail(BN_ERR_INVALID, "bn_db_load_files: " + err);
     CU_TRY(cudaSetDevice(D->id));
     // the file goes to the device as it is (the bytes between sequences are ambiguity data the
     // preliminary stage never reads); zeroed pads in front and behind as in bn_db_load
@@ -1717,6 +1814,9 @@ int bn_db_load_files(int device, const char *nin_path, const char *nsq_path, int
     CU_TRY(cudaMemcpyAsync(V->d_packed, nsq.data(), (size_t)nsq.size(), cudaMemcpyHostToDevice, D->stream));
     CU_TRY(cudaMemsetAsync(V->d_packed + nsq.size(), 0, 128, D->stream));
     CU_TRY(cudaStreamSynchronize(D->stream));
+    // the traceback stage lays the ambiguity runs over the packed bases (traceback_kernel.cu: SubjAmb)
+    rc = install_ambiguity(*V, *D, V->amb_first.data(), V->amb_runs.data());
+    if (rc) { free_volume_dev(*V); return rc; }
     std::lock_guard<std::mutex> lk(g_mu);
     *vol_handle = put_handle(g_volumes, std::move(V));
     return BN_OK;
@@ -2308,7 +2408,8 @@ static int traceback_core(Lane *D, Volume *V, Query *Q, int32_t gap_x_dropoff_fi
         if (t.s_shift < 0 || t.s_length < 0 || (int64_t)t.s_shift + t.s_length > V->seq_len[(size_t)t.oid] ||
             t.q_start < 0 || t.q_start >= qlen || t.s_start < 0 || t.s_start >= t.s_length)
             return fail(BN_ERR_INVALID, "bn_gapped_traceback: start point outside the sequences");
-        up[(size_t)i] = DevTracebackItem{V->byte_off[(size_t)t.oid], t.context, t.s_shift, t.s_length, t.q_start, t.s_start, 0};
+        up[(size_t)i] = DevTracebackItem{V->byte_off[(size_t)t.oid], t.context, t.s_shift, t.s_length, t.q_start, t.s_start, 0,
+                                         V->amb_first_of(t.oid), V->amb_count_of(t.oid), 0};
         rows += qlen + 2;
     }
     if (greedy) return traceback_greedy_host(*D, *V, *Q, gap_x_dropoff_final, items, n_items, up, results, ops, n_ops);
@@ -2346,7 +2447,7 @@ static int traceback_core(Lane *D, Volume *V, Query *Q, int32_t gap_x_dropoff_fi
         CU_TRY(cudaMallocAsync((void **)&d_ops, (size_t)ops_cap * sizeof(int2), st));
         CU_TRY(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), st));
         TracebackLaunch L{};
-        L.packed = V->d_packed; L.items = d_items; L.n = n_items; L.x_dropoff = gap_x_dropoff_final;
+        L.packed = V->d_packed; L.items = d_items; L.n = n_items; L.x_dropoff = gap_x_dropoff_final; L.amb_runs = V->d_amb;
         L.arena = d_arena; L.arena_bytes = arena_bytes; L.arena_used = d_cnt;
         L.ops = d_ops; L.ops_cap = ops_cap; L.ops_used = d_cnt + 1; L.out = d_out;
         const int wpb = traceback_warps_per_block();
@@ -2469,7 +2570,7 @@ static int traceback_hsps_core(Lane *D, Volume *V, Query *Q, int32_t gap_x_dropo
             (h.q_gapped_start < h.q_off || h.q_gapped_start >= h.q_end || h.s_gapped_start < h.s_off || h.s_gapped_start >= h.s_end))
             return fail(BN_ERR_INVALID, "bn_traceback_hsps: gapped start outside the HSP");
         up[(size_t)i] = DevTracebackHsp{V->byte_off[(size_t)h.oid], slen, h.context, h.q_off, h.q_end, h.s_off, h.s_end,
-                                        h.q_gapped_start, h.s_gapped_start};
+                                        h.q_gapped_start, h.s_gapped_start, V->amb_first_of(h.oid), V->amb_count_of(h.oid)};
     }
     DevTracebackHsp *d_h = nullptr;
     DevTracebackItem *d_it = nullptr;
@@ -2477,7 +2578,7 @@ static int traceback_hsps_core(Lane *D, Volume *V, Query *Q, int32_t gap_x_dropo
     CU_TRY(cudaMallocAsync((void **)&d_h, up.size() * sizeof(DevTracebackHsp), st));
     CU_TRY(cudaMallocAsync((void **)&d_it, its.size() * sizeof(DevTracebackItem), st));
     CU_TRY(cudaMemcpyAsync(d_h, up.data(), up.size() * sizeof(DevTracebackHsp), cudaMemcpyHostToDevice, st));
-    cudaError_t e = launch_traceback_start(Q->dev[V->device].view, V->d_packed, d_h, n_hsps, d_it, st);
+    cudaError_t e = launch_traceback_start(Q->dev[V->device].view, V->d_packed, V->d_amb, d_h, n_hsps, d_it, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(its.data(), d_it, its.size() * sizeof(DevTracebackItem), cudaMemcpyDeviceToHost, st);
     cudaFreeAsync(d_h, st); cudaFreeAsync(d_it, st);
     CU_TRY(e);
@@ -2597,6 +2698,7 @@ int bn_traceback_search(int vol_handle, int query_handle, int32_t gap_x_dropoff_
             p.q_off = h.q_off; p.q_end = h.q_end; p.s_off = h.s_off; p.s_end = h.s_end; p.score = h.score;
             p.esp_n = (int32_t)h.esp.size();
             p.reevaluate = (greedy || j >= L.extra_start) ? 1 : 0;
+            p.amb_first = V->amb_first_of(h.oid); p.amb_n = V->amb_count_of(h.oid);
             for (const BnEditOp &o : h.esp) pops.push_back(make_int2(o.op_type, o.num));
             post.push_back(p);
             who.emplace_back(li, j);
@@ -2611,7 +2713,7 @@ int bn_traceback_search(int vol_handle, int query_handle, int32_t gap_x_dropoff_
         CU_TRY(cudaMallocAsync((void **)&d_r, post.size() * sizeof(DevTracebackPostOut), st));
         cudaError_t e = cudaMemcpyAsync(d_p, post.data(), post.size() * sizeof(DevTracebackPost), cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess && !pops.empty()) e = cudaMemcpyAsync(d_o, pops.data(), pops.size() * sizeof(int2), cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) e = launch_traceback_reevaluate(Q->dev[V->device].view, V->d_packed, d_p, (int64_t)post.size(), d_o, d_r, st);
+        if (e == cudaSuccess) e = launch_traceback_reevaluate(Q->dev[V->device].view, V->d_packed, V->d_amb, d_p, (int64_t)post.size(), d_o, d_r, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(pout.data(), d_r, pout.size() * sizeof(DevTracebackPostOut), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess && !pops.empty()) e = cudaMemcpyAsync(pops.data(), d_o, pops.size() * sizeof(int2), cudaMemcpyDeviceToHost, st);
         cudaFreeAsync(d_p, st); cudaFreeAsync(d_o, st); cudaFreeAsync(d_r, st);

@@ -4,7 +4,7 @@
 // with score_only == FALSE (:711-745) -> ALIGN_EX (:350-709), as Blast_TracebackFromHSPList calls it for
 // blastn with eDynProgTbck (core/blast_traceback.c:565-571) on the blastna subject (one base per byte).
 //
-// Here the subject stays in its packed ncbi2na form in HBM (the volume has no ambiguity data, so the
+// Here the subject stays in its packed ncbi2na form in HBM (ambiguity runs of a BLAST DB volume are laid over it where a base is read: SubjAmb; otherwise the
 // blastna byte of base p is its 2-bit code) and one WARP computes one direction of one alignment with the
 // row-parallel formulation of gapped_kernel.cu (lane per band cell, prefix maxima for the horizontal gap
 // and the running best, prune flags by fixed-point iteration — exact).  On top of the score-only kernel
@@ -46,6 +46,73 @@ __device__ __forceinline__ int sbase64(const uint8_t *s, int64_t pos)      // NC
     return (__ldg(s + (pos >> 2)) >> (6 - 2 * (int)(pos & 3))) & 3;
 }
 
+// ---- subject ambiguity ------------------------------------------------------------------------------------
+// The traceback stage of the reference reads its subjects in blastna: the 2-bit bases with the volume's ambiguity
+// runs laid over them (CSeqDBVol::x_GetAmbigSeq, objtools/blast/seqdb_reader/seqdbvol.cpp:832-870, 1565-1640).  Here
+// the volume stays packed and the runs of the item's sequence ({first base, end, blastna code}, sorted, disjoint)
+// are consulted where a base is read; sequences without runs (nearly all) take the packed path untouched.
+struct SubjAmb {
+    const int4 *runs;
+    int32_t n;
+    int64_t origin;          // index (in the coordinates of the reads) of the sequence's base 0
+};
+__device__ __forceinline__ SubjAmb subj_amb(const int4 *all_runs, int32_t first, int32_t n, int64_t origin)
+{
+    SubjAmb a;
+    a.runs = (n > 0 && all_runs) ? all_runs + first : nullptr; a.n = a.runs ? n : 0; a.origin = origin;
+    return a;
+}
+// blastna code of an ambiguous base, -1 for an ordinary one
+__device__ int amb_code(const SubjAmb &A, int64_t at)
+{
+    const int32_t pos = (int32_t)(at - A.origin);
+    int32_t lo = 0, hi = A.n;                       // first run that ends behind pos
+    while (lo < hi) {
+        const int32_t m = (lo + hi) >> 1;
+        if (__ldg(&A.runs[m].y) > pos) hi = m; else lo = m + 1;
+    }
+    if (lo < A.n) {
+        const int4 r = __ldg(&A.runs[lo]);
+        if (r.x <= pos) return r.z;
+    }
+    return -1;
+}
+__device__ __forceinline__ int subj_code(const uint8_t *s, const SubjAmb &A, int64_t at)
+{
+    if (A.n) { const int c = amb_code(A, at); if (c >= 0) return c; }
+    return sbase64(s, at);
+}
+// Mismatch flags of a 16-base comparison (mismatch_bits) corrected for ambiguous subject bases: the reference compares
+// blastna bytes, so an ambiguous subject base differs from A/C/G/T and equals the same code in the query.
+__device__ uint32_t amb_fix16(const DevQuery &q, const SubjAmb &A, int32_t qpos, int64_t at, uint32_t m, bool equal_codes_match = true)
+{
+    const int32_t pos = (int32_t)(at - A.origin);
+    int32_t lo = 0, hi = A.n;
+    while (lo < hi) {
+        const int32_t mid = (lo + hi) >> 1;
+        if (__ldg(&A.runs[mid].y) > pos) hi = mid; else lo = mid + 1;
+    }
+    for (; lo < A.n; lo++) {
+        const int4 r = __ldg(&A.runs[lo]);
+        if (r.x >= pos + 16) break;
+        for (int32_t b = max(r.x, pos); b < min(r.y, pos + 16); b++) {
+            const int j = b - pos;
+            const int32_t qp = qpos + j;
+            const int qc = (qp >= -1 && qp <= q.concat_len) ? (int)__ldg(q.query + qp) : 15;
+            const uint32_t bit = 1u << (30 - 2 * j);
+            if (qc == r.z && equal_codes_match) m &= ~bit; else m |= bit;
+        }
+    }
+    return m;
+}
+__device__ __forceinline__ uint32_t subj_mismatch16(const DevQuery &q, const uint8_t *packed, const SubjAmb &A, int32_t qpos,
+                                                    int64_t at, uint32_t qb, uint32_t qa, bool equal_codes_match = true)
+{
+    uint32_t m = mismatch_bits(qb, qa, swin(packed, at));
+    if (A.n) m = amb_fix16(q, A, qpos, at, m, equal_codes_match);
+    return m;
+}
+
 // bump allocation from the launch's arena; returns -1 when it is exhausted
 __device__ __forceinline__ long long arena_alloc(const TracebackLaunch &L, long long bytes)
 {
@@ -64,7 +131,7 @@ constexpr long long ROW_CHUNK = 128 << 10;
 // ALIGN_EX for one direction.  M rows (query), N columns (subject).  qrow(a) = query byte of row a,
 // sub(b) = subject base that the diagonal step INTO column b consumes (b >= 1).
 // status: 0 ok, 1 band wider than the shared-memory ring, 3 arena exhausted.
-__device__ int32_t align_ex_warp(const TracebackLaunch &L, const uint8_t *qp, int q_inc, const uint8_t *S, int64_t s0, int s_inc,
+__device__ int32_t align_ex_warp(const TracebackLaunch &L, const uint8_t *qp, int q_inc, const uint8_t *S, const SubjAmb &amb, int64_t s0, int s_inc,
                                  int32_t M, int32_t N, const int32_t *matrix, int32_t gap_open, int32_t gap_extend,
                                  int32_t x_dropoff, int2 *ring, uint8_t *pf, RowStore &rs, int32_t &a_offset, int32_t &b_offset,
                                  int &status, int lane)
@@ -151,7 +218,7 @@ __device__ int32_t align_ex_warp(const TracebackLaunch &L, const uint8_t *qp, in
                 const int32_t up = j == 0 ? up0 : cell[j > 0 ? j - 1 : 0].x;
                 v[j] = NEGINF; dg[j] = MININT;
                 if (act[j]) {
-                    if (b != row_first) dg[j] = up + mrow[sbase64(S, s0 + (int64_t)b * s_inc)];
+                    if (b != row_first) dg[j] = up + mrow[subj_code(S, amb, s0 + (int64_t)b * s_inc)];
                     v[j] = max(dg[j], cell[j].y);
                 }
                 // first guess: what became of the cell's diagonal predecessor in the previous row (the band follows
@@ -337,7 +404,8 @@ traceback_dp_kernel(const DevQuery q, const TracebackLaunch L)
                 rs.row_off = reinterpret_cast<long long *>(L.arena + tab);
                 rs.row_first = reinterpret_cast<int32_t *>(L.arena + tab + (long long)(M + 1) * 8);
                 int32_t a_off, b_off;
-                out.score = align_ex_warp(L, qp, q_inc, S, s0, s_inc, M, N, s_matrix, q.gap_open, q.gap_extend,
+                const SubjAmb amb = subj_amb(L.amb_runs, it.amb_first, it.amb_n, 0);      // S-relative reads
+                out.score = align_ex_warp(L, qp, q_inc, S, amb, s0, s_inc, M, N, s_matrix, q.gap_open, q.gap_extend,
                                           L.x_dropoff, ring, s_pf[wib], rs, a_off, b_off, status, lane);
                 out.a_off = a_off; out.b_off = b_off;
                 __syncwarp();
@@ -445,11 +513,31 @@ struct GreedyTbSeq {
     int64_t sbase;      // absolute volume base of seq2[0]
     int32_t len1, len2;
     bool reverse;
+    SubjAmb amb;        // ambiguity runs of the subject sequence (origin = its absolute base index)
 };
 __device__ __forceinline__ int32_t tb_first_mismatch(const GreedyTbSeq &p, int32_t i1, int32_t i2)
 {
     const int32_t n = min(p.len1 - i1, p.len2 - i2);
     if (n <= 0) return 0;
+    if (p.amb.n) {          // s_FindFirstMismatch on blastna bytes (core/greedy_align.c:318-380), 16 bases at a time
+        int32_t cnt = 0;
+        while (cnt < n) {
+            uint32_t qb, qa;
+            if (p.reverse) {
+                const int32_t qpos = p.qbase + p.len1 - i1 - cnt - 16;
+                qwin(*p.q, qpos, qb, qa);
+                const uint32_t m = subj_mismatch16(*p.q, p.packed, p.amb, qpos, p.sbase + p.len2 - i2 - cnt - 16, qb, qa);
+                if (m) return min(cnt + ((__ffs(m) - 1) >> 1), n);
+            } else {
+                const int32_t qpos = p.qbase + i1 + cnt;
+                qwin(*p.q, qpos, qb, qa);
+                const uint32_t m = subj_mismatch16(*p.q, p.packed, p.amb, qpos, p.sbase + i2 + cnt, qb, qa);
+                if (m) return min(cnt + (__clz(m) >> 1), n);
+            }
+            cnt += 16;
+        }
+        return n;
+    }
     if (p.reverse) return match_run_rev(*p.q, p.packed, p.qbase + p.len1 - i1, p.sbase + p.len2 - i2, n);
     return match_run_fwd(*p.q, p.packed, p.qbase + i1, p.sbase + i2, n);
 }
@@ -468,11 +556,11 @@ struct OpList {                 // GapPrelimEditBlock: list grows DOWNWARD from 
 };
 
 // s_ReduceGaps (core/blast_gapalign.c:2545-2617) on {op[], num[]}; returns the new size
-__device__ int32_t reduce_gaps(const DevQuery &q, const uint8_t *packed, int32_t ctx_off, int32_t qi, int64_t si,
+__device__ int32_t reduce_gaps(const DevQuery &q, const uint8_t *packed, const SubjAmb &amb, int32_t ctx_off, int32_t qi, int64_t si,
                                int32_t *op, int32_t *num, int32_t size)
 {
     const uint8_t *Qb = q.query + ctx_off;
-    auto eq = [&](int32_t a, int64_t b) -> bool { return (int)__ldg(Qb + a) == sbase64(packed, b); };
+    auto eq = [&](int32_t a, int64_t b) -> bool { return (int)__ldg(Qb + a) == subj_code(packed, amb, b); };
     for (int32_t i = 0; i < size; i++) {
         if (op[i] == 3) { qi += num[i]; si += num[i]; continue; }
         if (i > 1 && op[i] != op[i - 2] && num[i - 2] > 0) {
@@ -525,11 +613,11 @@ __device__ int32_t tb_first_mismatch_warp(const GreedyTbSeq &p, int32_t i1, int3
             uint32_t qb, qa, m;
             if (p.reverse) {
                 qwin(*p.q, p.qbase + p.len1 - i1 - off - 16, qb, qa);
-                m = mismatch_bits(qb, qa, swin(p.packed, p.sbase + p.len2 - i2 - off - 16));
+                m = subj_mismatch16(*p.q, p.packed, p.amb, p.qbase + p.len1 - i1 - off - 16, p.sbase + p.len2 - i2 - off - 16, qb, qa);
                 if (m) c = (__ffs(m) - 1) >> 1;
             } else {
                 qwin(*p.q, p.qbase + i1 + off, qb, qa);
-                m = mismatch_bits(qb, qa, swin(p.packed, p.sbase + i2 + off));
+                m = subj_mismatch16(*p.q, p.packed, p.amb, p.qbase + i1 + off, p.sbase + i2 + off, qb, qa);
                 if (m) c = __clz(m) >> 1;
             }
         }
@@ -750,6 +838,7 @@ traceback_greedy_warp_kernel(const DevQuery q, const TracebackLaunch L)
         rev = fwd;
         GreedyTbSeq sp;
         sp.q = &q; sp.packed = L.packed;
+        sp.amb = subj_amb(L.amb_runs, it.amb_first, it.amb_n, it.byte_off * 4);
         sp.qbase = c.query_offset + q_off; sp.sbase = seq_base + s_off;
         sp.len1 = q_length - q_off; sp.len2 = s_length - s_off; sp.reverse = false;
         __syncwarp();
@@ -777,7 +866,7 @@ traceback_greedy_warp_kernel(const DevQuery q, const TracebackLaunch L)
                     if (merge) { num[idx - 1] += fwd.num(fwd.n - 1); i = fwd.n - 2; }
                     for (; i >= 0; i--) { op[idx] = fwd.op(i); num[idx] = fwd.num(i); idx++; }
                 }
-                size = reduce_gaps(q, L.packed, c.query_offset, q_off - q_ext_l, seq_base + s_off - s_ext_l, op, num, size);
+                size = reduce_gaps(q, L.packed, sp.amb, c.query_offset, q_off - q_ext_l, seq_base + s_off - s_ext_l, op, num, size);
                 const unsigned long long base = atomicAdd(L.ops_used, (unsigned long long)size);
                 if ((long long)(base + size) > L.ops_cap) status = 4;
                 else {
@@ -1000,6 +1089,7 @@ traceback_greedy_affine_kernel(const DevQuery q, const TracebackLaunch L)
         rev = fwd;
         GreedyTbSeq sp;
         sp.q = &q; sp.packed = L.packed;
+        sp.amb = subj_amb(L.amb_runs, it.amb_first, it.amb_n, it.byte_off * 4);
         sp.qbase = c.query_offset + q_off; sp.sbase = seq_base + s_off;
         sp.len1 = q_length - q_off; sp.len2 = s_length - s_off; sp.reverse = false;
         int32_t score = greedy_align_affine_tb(sp, ac, q_ext_r, s_ext_r, A, cap, fwd, status);
@@ -1023,7 +1113,7 @@ traceback_greedy_affine_kernel(const DevQuery q, const TracebackLaunch L)
                     if (merge) { num[idx - 1] += fwd.num(fwd.n - 1); i = fwd.n - 2; }
                     for (; i >= 0; i--) { op[idx] = fwd.op(i); num[idx] = fwd.num(i); idx++; }
                 }
-                size = reduce_gaps(q, L.packed, c.query_offset, q_off - q_ext_l, seq_base + s_off - s_ext_l, op, num, size);
+                size = reduce_gaps(q, L.packed, sp.amb, c.query_offset, q_off - q_ext_l, seq_base + s_off - s_ext_l, op, num, size);
                 const unsigned long long base = atomicAdd(L.ops_used, (unsigned long long)size);
                 if ((long long)(base + size) > L.ops_cap) status = 4;
                 else {
@@ -1061,8 +1151,8 @@ cudaError_t launch_traceback_greedy_warp(const DevQuery &q, const TracebackLaunc
 // BlastGetStartForGappedAlignmentNucl (:3134-3182) moves it into the longest run of identities; then
 // AdjustSubjectRange (:3608-3636).  items[i].pad = 1 when a start point exists (0: the reference drops the HSP).
 // ================================================================================================
-__global__ void traceback_start_kernel(const DevQuery q, const uint8_t *packed, const DevTracebackHsp *hsps, int64_t n,
-                                       DevTracebackItem *items)
+__global__ void traceback_start_kernel(const DevQuery q, const uint8_t *packed, const int4 *amb_runs, const DevTracebackHsp *hsps,
+                                       int64_t n, DevTracebackItem *items)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -1072,7 +1162,8 @@ __global__ void traceback_start_kernel(const DevQuery q, const uint8_t *packed, 
     const uint8_t *Q = q.query + c.query_offset;
     const int64_t sb = h.byte_off * 4;
     const int32_t *M = q.matrix;
-    auto sc = [&](int32_t qi, int32_t si) -> int32_t { return __ldg(M + 16 * (int)__ldg(Q + qi) + sbase64(packed, sb + si)); };
+    const SubjAmb amb = subj_amb(amb_runs, h.amb_first, h.amb_n, sb);
+    auto sc = [&](int32_t qi, int32_t si) -> int32_t { return __ldg(M + 16 * (int)__ldg(Q + qi) + subj_code(packed, amb, sb + si)); };
     int32_t qg = h.q_gapped_start, sg = h.s_gapped_start;
     int32_t q_start = 0, s_start = 0;
     bool found = true;
@@ -1116,7 +1207,7 @@ __global__ void traceback_start_kernel(const DevQuery q, const uint8_t *packed, 
         int32_t max_score = 0, max_offset = q0, score = 0, index;
         bool match = false, prev_match = false, done = false;
         for (index = q0; index < q0 + q_len; index++) {
-            match = ((int)__ldg(Q + index) == sbase64(packed, sb + s0 + (index - q0)));
+            match = ((int)__ldg(Q + index) == subj_code(packed, amb, sb + s0 + (index - q0)));
             if (match != prev_match) {
                 prev_match = match;
                 if (match) score = 1;
@@ -1148,14 +1239,15 @@ __global__ void traceback_start_kernel(const DevQuery q, const uint8_t *packed, 
     DevTracebackItem it;
     it.byte_off = h.byte_off; it.context = h.context; it.s_shift = shift; it.s_length = adj_len;
     it.q_start = q_start; it.s_start = s_start; it.pad = found ? 1 : 0;
+    it.amb_first = h.amb_first; it.amb_n = h.amb_n;
     items[i] = it;
 }
 
-cudaError_t launch_traceback_start(const DevQuery &q, const uint8_t *packed, const DevTracebackHsp *hsps, int64_t n,
-                                   DevTracebackItem *items, cudaStream_t st)
+cudaError_t launch_traceback_start(const DevQuery &q, const uint8_t *packed, const int4 *amb_runs, const DevTracebackHsp *hsps,
+                                   int64_t n, DevTracebackItem *items, cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;
-    traceback_start_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(q, packed, hsps, n, items);
+    traceback_start_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(q, packed, amb_runs, hsps, n, items);
     return cudaGetLastError();
 }
 
@@ -1167,8 +1259,8 @@ cudaError_t launch_traceback_start(const DevQuery &q, const uint8_t *packed, con
 // The edit script lives in ops[esp_off ..) and is modified in place exactly like the reference modifies esp->num[];
 // the surviving part is ops[esp_off + first .. esp_off + last].
 // ================================================================================================
-__global__ void traceback_reevaluate_kernel(const DevQuery q, const uint8_t *packed, const DevTracebackPost *items, int64_t n,
-                                            int2 *ops, DevTracebackPostOut *out)
+__global__ void traceback_reevaluate_kernel(const DevQuery q, const uint8_t *packed, const int4 *amb_runs,
+                                            const DevTracebackPost *items, int64_t n, int2 *ops, DevTracebackPostOut *out)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -1183,7 +1275,8 @@ __global__ void traceback_reevaluate_kernel(const DevQuery q, const uint8_t *pac
     o.deleted = 0; o.q_off = h.q_off; o.q_end = h.q_end; o.s_off = h.s_off; o.s_end = h.s_end; o.score = h.score;
     o.first = 0; o.last = size - 1; o.num_ident = 0; o.align_length = 0;
     auto qb = [&](int32_t p) -> int { return (int)__ldg(Q + p); };
-    auto sbs = [&](int32_t p) -> int { return sbase64(packed, sb + p); };
+    const SubjAmb amb = subj_amb(amb_runs, h.amb_first, h.amb_n, sb);
+    auto sbs = [&](int32_t p) -> int { return subj_code(packed, amb, sb + p); };
     if (h.reevaluate && size > 0) {
         int32_t factor = 1, gap_open, gap_extend;
         if (q.gap_open == 0 && q.gap_extend == 0) {
@@ -1211,7 +1304,8 @@ __global__ void traceback_reevaluate_kernel(const DevQuery q, const uint8_t *pac
                     if (uniform && num - op_index >= 16) {
                         uint32_t qw, qa;
                         qwin(q, c.query_offset + query, qw, qa);
-                        const uint32_t m = mismatch_bits(qw, qa, swin(packed, sb + subject));
+                        // an ambiguous subject base ends the run: it scores through the matrix, never `reward`
+                        const uint32_t m = subj_mismatch16(q, packed, amb, c.query_offset + query, sb + subject, qw, qa, false);
                         run = m ? (__clz(m) >> 1) : 16;
                     }
                     if (run > 0) { sum += run * factor * match_score; query += run; subject += run; op_index += run; }
@@ -1294,7 +1388,8 @@ __global__ void traceback_reevaluate_kernel(const DevQuery q, const uint8_t *pac
                     const int32_t nb = min(16, num - k);
                     uint32_t qw, qa;
                     qwin(q, c.query_offset + qp + k, qw, qa);
-                    const uint32_t m = mismatch_bits(qw, qa, swin(packed, sb + sp + k));
+                    // byte equality of blastna codes (core/blast_hits.c:640-660): the same ambiguity code on both sides counts
+                    const uint32_t m = subj_mismatch16(q, packed, amb, c.query_offset + qp + k, sb + sp + k, qw, qa, true);
                     ident += nb - __popc(m >> (32 - 2 * nb));
                 }
                 qp += num; sp += num;
@@ -1307,11 +1402,11 @@ __global__ void traceback_reevaluate_kernel(const DevQuery q, const uint8_t *pac
     out[i] = o;
 }
 
-cudaError_t launch_traceback_reevaluate(const DevQuery &q, const uint8_t *packed, const DevTracebackPost *items, int64_t n,
+cudaError_t launch_traceback_reevaluate(const DevQuery &q, const uint8_t *packed, const int4 *amb_runs, const DevTracebackPost *items, int64_t n,
                                         int2 *ops, DevTracebackPostOut *out, cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;
-    traceback_reevaluate_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(q, packed, items, n, ops, out);
+    traceback_reevaluate_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(q, packed, amb_runs, items, n, ops, out);
     return cudaGetLastError();
 }
 

@@ -20,7 +20,7 @@ EXPORTS = [
     "bn_db_load", "bn_db_free", "bn_query_load", "bn_query_free",
     "bn_prelim_search", "bn_prelim_search_host", "bn_prelim_search_volumes", "bn_results_free",
     "bn_scan_subject", "bn_word_finder", "bn_free", "bn_bench_scan", "bn_query_download_lookup", "bn_get_gapped_score", "bn_gapped_traceback", "bn_traceback_hsps", "bn_traceback_search",
-    "bn_dbfile_index", "bn_db_load_files", "bn_dbfile_write", "bn_prelim_search_batches", "bn_db_set_masks", "bn_selftest_replay",
+    "bn_dbfile_index", "bn_db_load_files", "bn_dbfile_write", "bn_dbfile_ambiguity", "bn_db_set_ambiguity", "bn_prelim_search_batches", "bn_db_set_masks", "bn_selftest_replay",
     "bn_setup_create", "bn_setup_batch", "bn_setup_kbp_std", "bn_setup_kbp_gap",
     "bn_setup_gap_x_dropoff_final", "bn_setup_longest_chain", "bn_setup_free", "bn_dust_mask",
 ]
@@ -91,6 +91,17 @@ class Volume:
             lib().bn_db_free(C.c_int(self.handle))
             self.handle = -1
 
+    def set_ambiguity(self, first, runs):
+        """Ambiguity runs (first: int64[n_seq + 1]; runs: int32[n, 3] = first base, bases, blastna code); None removes."""
+        if first is None:
+            _check(lib().bn_db_set_ambiguity(C.c_int(self.handle), None, None))
+            return
+        f = np.ascontiguousarray(first, dtype=np.int64)
+        r = np.ascontiguousarray(runs, dtype=np.int32).reshape(-1)
+        if r.size == 0:
+            r = np.zeros(3, np.int32)
+        _check(lib().bn_db_set_ambiguity(C.c_int(self.handle), f.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p)))
+
     def set_masks(self, masks, mask_type=abi.BN_MASK_SOFT):
         """Database masks: `masks` = per sequence a list of half-open (begin, end) masked intervals
         (ascending, disjoint); mask_type BN_MASK_SOFT / BN_MASK_HARD; None removes them."""
@@ -125,6 +136,20 @@ def dbfile_index(nin_path, nsq_path):
     d = {"n_seq": info.n_seq, "max_len": info.max_len, "total_bases": info.total_bases,
          "nsq_bytes": info.nsq_bytes, "title": info.title.decode(errors="replace")}
     return d, off, ln
+
+
+def dbfile_ambiguity(nin_path, nsq_path):
+    """Ambiguity runs of a volume: (first: int64[n_seq + 1], runs: int32[n, 3] = first base, bases, blastna code)."""
+    info, _, _ = dbfile_index(nin_path, nsq_path)
+    first = np.zeros(info["n_seq"] + 1, dtype=np.int64)
+    p, n = C.POINTER(C.c_int32)(), C.c_int64(0)
+    _check(lib().bn_dbfile_ambiguity(str(nin_path).encode(), str(nsq_path).encode(), first.ctypes.data_as(C.c_void_p),
+                                     C.byref(p), C.byref(n)))
+    try:
+        runs = np.ctypeslib.as_array(p, shape=(max(n.value, 1) * 3,)).copy()[: n.value * 3].reshape(-1, 3)
+    finally:
+        lib().bn_free(p)
+    return first, runs
 
 
 def dbfile_write(nin_path, nsq_path, vol, title="synthetic"):

@@ -227,6 +227,17 @@ typedef struct BnDbFileInfo {
 int  bn_dbfile_index(const char *nin_path, const char *nsq_path, BnDbFileInfo *info,
                      int64_t *seq_byte_off, int32_t *seq_len);
 int  bn_db_load_files(int device, const char *nin_path, const char *nsq_path, int *vol_handle);
+/* Ambiguity data of a volume's sequences (host only): what CSeqDBVol::x_GetAmbigSeq overlays on the 2-bit bases when the
+ * traceback stage fetches a subject in blastna (objtools/blast/seqdb_reader/seqdbvol.cpp:832-870, 1565-1640).
+ * first: n_seq + 1 entries, runs of sequence i are first[i] .. first[i+1]; *runs: malloc'ed flat triples
+ * {first base, number of bases, blastna code} in file order (later runs overwrite earlier ones); free with bn_free. */
+/* Ambiguity runs of a resident volume (bn_db_load_files installs the ones of its .nsq by itself; this is for volumes
+ * loaded from memory): same layout as bn_dbfile_ambiguity returns.  The preliminary stage reads the 2-bit bases as they
+ * are, exactly like the reference (api/seqsrc_seqdb.cpp:283-388 hands out ncbi2na there); the traceback stage
+ * (bn_gapped_traceback, bn_traceback_hsps, bn_traceback_search) lays the runs over them, as the reference's blastna
+ * subject fetch does.  first == NULL removes the runs. */
+int  bn_db_set_ambiguity(int vol_handle, const int64_t *first, const int32_t *runs);
+int  bn_dbfile_ambiguity(const char *nin_path, const char *nsq_path, int64_t *first, int32_t **runs, int64_t *n_runs);
 int  bn_dbfile_write(const char *nin_path, const char *nsq_path, const char *title, const uint8_t *packed,
                      const int64_t *seq_byte_off, const int32_t *seq_len, int32_t n_seq);
 
@@ -290,7 +301,7 @@ void bn_free(void *p);
  * sequence `oid` + s_shift with s_length bases (the window AdjustSubjectRange leaves, core/blast_traceback.c:513-520),
  * start point (q_start, s_start) relative to those, X-drop = gap_x_dropoff_final (gap_align->gap_x_dropoff is set to
  * it at core/blast_traceback.c:1403), costs and matrix from the query batch.  The subject is the resident packed
- * volume (no ambiguity data: the blastna byte of a base is its 2-bit code).
+ * volume with its ambiguity runs, if it has any, laid over the 2-bit bases (the blastna subject the reference fetches).
  * Results mirror BlastGapAlignStruct after the call: score, query_start/stop, subject_start/stop (relative to the
  * window) and gap_align->edit_script as ops[esp_off .. esp_off + esp_n) with op_type = EGapAlignOpType
  * (0 eGapAlignDel, 3 eGapAlignSub, 6 eGapAlignIns; inc-core/gapinfo.h:44-54).  When the batch's gap_algo is

@@ -68,7 +68,22 @@ typedef struct MemDb {
     const int32_t *smask_n;       /* masked intervals per subject */
     const int32_t *smask_iv;      /* flat [begin, end) pairs */
     const int64_t *smask_first;   /* index of each subject's first interval (prefix sum) */
+    const int64_t *amb_first;     /* ambiguity runs per subject (RefConfig), NULL = none */
+    const int32_t *amb_runs;
 } MemDb;
+
+/* s_SeqDBRebuildDNA_NA8 + s_SeqDBMapNcbiNA8ToBlastNA8 (objtools/blast/seqdb_reader/seqdbvol.cpp:832-870, 597-633):
+ * the runs, in order, written over the blastna bytes of subject oid (buf[0] = base 0) */
+static void mdb_overlay_ambiguity(const MemDb *d, Int4 oid, Uint1 *buf, Int4 len)
+{
+    int64_t k;
+    if (!d->amb_first || !d->amb_runs) return;
+    for (k = d->amb_first[oid]; k < d->amb_first[oid + 1]; k++) {
+        const int32_t a = d->amb_runs[3 * k], n = d->amb_runs[3 * k + 1], code = d->amb_runs[3 * k + 2];
+        int32_t j;
+        for (j = 0; j < n; j++) if (a + j >= 0 && a + j < len) buf[a + j] = (Uint1)code;
+    }
+}
 
 /* --------------------------------------------------------------- tap state */
 typedef struct TapCtx {
@@ -131,6 +146,7 @@ static Int2 mdb_get_seq(void *h, BlastSeqSrcGetSeqArg *args)
         if (!buf) return BLAST_SEQSRC_ERROR;
         buf[0] = buf[len + 1] = 15;
         for (k = 0; k < len; k++) buf[k + 1] = (pk[k >> 2] >> (6 - 2 * (k & 3))) & 3;
+        mdb_overlay_ambiguity(d, oid, buf + 1, len);
         BlastSetUp_SeqBlkNew(buf, len, &args->seq, TRUE);
         args->seq->oid = oid;
         if (g_tap) { g_tap->tb_seq = args->seq->sequence; g_tap->tb_oid = oid; }
@@ -895,6 +911,7 @@ int ref_search(const RefConfig *cfg,
     for (i = 0; i < ns; i++) { db.total += slen[i]; if (slen[i] > db.maxlen) db.maxlen = slen[i]; }
     db.smask_type = cfg->smask_n ? cfg->smask_type : 0;
     db.smask_n = cfg->smask_n; db.smask_iv = cfg->smask_iv; db.smask_first = NULL;
+    db.amb_first = cfg->amb_first; db.amb_runs = cfg->amb_runs;
     if (db.smask_type) {
         int64_t *first = (int64_t *)calloc((size_t)ns + 1, sizeof(int64_t));
         for (i = 0; i < ns; i++) first[i + 1] = first[i] + cfg->smask_n[i];
@@ -1000,6 +1017,7 @@ int ref_traceback_calls(const RefConfig *cfg,
     db.total = 0; db.maxlen = 0; db.oid_begin = 0; db.oid_end = ns;
     for (i = 0; i < ns; i++) { db.total += slen[i]; if (slen[i] > db.maxlen) db.maxlen = slen[i]; }
     db.smask_type = 0; db.smask_n = NULL; db.smask_iv = NULL; db.smask_first = NULL;
+    db.amb_first = cfg->amb_first; db.amb_runs = cfg->amb_runs;
     BlastChooseNucleotideScanSubject(S.lookup_wrap);
     BlastChooseNaExtend(S.lookup_wrap);
     info.constructor = &mdb_new; info.ctor_argument = &db;
@@ -1029,6 +1047,7 @@ int ref_traceback_calls(const RefConfig *cfg,
                 buf = (Uint1 *)malloc((size_t)len + 2);
                 buf[0] = buf[len + 1] = 15;
                 for (k = 0; k < len; k++) buf[k + 1] = (pk[k >> 2] >> (6 - 2 * (k & 3))) & 3;
+                mdb_overlay_ambiguity(&db, oid, buf + 1, len);
                 cur_oid = oid;
             }
             tap.tb_seq = buf + 1; tap.tb_oid = oid;

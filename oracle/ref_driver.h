@@ -44,6 +44,11 @@ typedef struct RefConfig {
     const int32_t *smask_iv;
     int32_t hsp_num_max;     /* hit_options->hsp_num_max (0 = unlimited); ignored by gapped searches (BlastHspNumMax,
                               * core/blast_hits.c:169-191) */
+    /* ambiguity data of the database (what CSeqDBVol::x_GetAmbigSeq lays over the 2-bit bases when a subject is
+     * fetched in blastna for the traceback stage): amb_first[n_subjects + 1] indexes flat triples
+     * {first base, bases, blastna code} in amb_runs, applied in order; NULL = none */
+    const int64_t *amb_first;
+    const int32_t *amb_runs;
     int32_t seam;            /* 0: the reference's own word finder and gapped stage; 1: the B200 engine behind the
                               * same two seams through oracle/shim (only in oracle/_ref/libblastshim.so) */
 } RefConfig;

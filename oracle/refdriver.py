@@ -28,7 +28,7 @@ class RefConfig(C.Structure):
         ("db_length", C.c_int64), ("db_num_seqs", C.c_int32), ("num_threads", C.c_int32),
         ("taps", C.c_int32), ("prelim_only", C.c_int32),
         ("smask_type", C.c_int32), ("smask_n", C.c_void_p), ("smask_iv", C.c_void_p),
-        ("hsp_num_max", C.c_int32), ("seam", C.c_int32),
+        ("hsp_num_max", C.c_int32), ("amb_first", C.c_void_p), ("amb_runs", C.c_void_p), ("seam", C.c_int32),
     ]
 
 
@@ -157,15 +157,16 @@ def default_config(task="megablast", **kw) -> RefConfig:
     return cfg
 
 
-def traceback_calls(queries, volume, items, cfg: RefConfig):
+def traceback_calls(queries, volume, items, cfg: RefConfig, ambiguity=None):
     """The reference's alignment-with-traceback routine on arbitrary start points.  `items`: int32 array (n, 6) of
     {oid, context, s_shift, s_length, q_start, s_start}.  Returns the same dict as search(); the calls are in
     tb_calls / tb_ops."""
-    return search(queries, volume, cfg, tb_items=np.ascontiguousarray(items, dtype=np.int32).reshape(-1, 6))
+    return search(queries, volume, cfg, tb_items=np.ascontiguousarray(items, dtype=np.int32).reshape(-1, 6),
+                  ambiguity=ambiguity)
 
 
 def search(queries, volume, cfg: RefConfig | None = None, *, task="megablast", masks=None,
-           subject_masks=None, subject_mask_type=1, tb_items=None, **kw):
+           subject_masks=None, subject_mask_type=1, tb_items=None, ambiguity=None, **kw):
     """Run the reference preliminary search. `queries`: list of uint8 blastna arrays;
     `volume`: gblastn_b200.synth.Volume (or any object with packed/byte_off/seq_len);
     `masks`: optional list (per query) of [(left, right)] inclusive plus-strand intervals;
@@ -174,6 +175,15 @@ def search(queries, volume, cfg: RefConfig | None = None, *, task="megablast", m
     if cfg is None:
         cfg = default_config(task, **kw)
     keep = []
+    if ambiguity is not None:       # (first: int64[n + 1], runs: int32[k, 3]) as gblastn_b200.engine.dbfile_ambiguity returns
+        af = np.ascontiguousarray(ambiguity[0], dtype=np.int64)
+        ar = np.ascontiguousarray(ambiguity[1], dtype=np.int32).reshape(-1)
+        if ar.size == 0:
+            ar = np.zeros(3, np.int32)
+        keep += [af, ar]
+        cfg.amb_first, cfg.amb_runs = af.ctypes.data, ar.ctypes.data
+    else:
+        cfg.amb_first, cfg.amb_runs = None, None
     if subject_masks is not None:
         sn = np.ascontiguousarray([len(m) for m in subject_masks], dtype=np.int32)
         sflat = [x for m in subject_masks for iv in m for x in iv]
