@@ -157,6 +157,11 @@ __device__ __forceinline__ int32_t match_run_rev(const DevQuery &q, const uint8_
     return n;
 }
 
+// cinfo / qinfo .x: bits 0-29 a 1-based query position (cinfo: the chain element itself; qinfo: the next one), bit 31
+// (cinfo) "the chain continues", bit 30 "the query position in front of this element is in the lookup table too"
+constexpr uint32_t QP_MASK = 0x3fffffffu;
+constexpr uint32_t PREV_INDEXED = 0x40000000u;
+
 // BSearchContextInfo (core/blast_query_info.c:220-236)
 __device__ __forceinline__ int32_t ctx_search(const DevQuery &q, int32_t n)
 {
@@ -193,7 +198,7 @@ __device__ __forceinline__ int32_t mb_cell(const DevQuery &q, uint32_t idx)
     const uint2 w = __ldg(&q.prk[idx >> 5]);
     const uint32_t bit = idx & 31u;
     if (!((w.x >> bit) & 1u)) return 0;
-    return (int32_t)(__ldg(&q.cinfo[2 * (size_t)(w.y + (uint32_t)__popc(w.x & ((1u << bit) - 1u)))].x) & 0x7fffffffu);
+    return (int32_t)(__ldg(&q.cinfo[2 * (size_t)(w.y + (uint32_t)__popc(w.x & ((1u << bit) - 1u)))].x) & QP_MASK);
 }
 
 // ---- launchers implemented in the .cu files ----------------------------------------------------
@@ -237,8 +242,8 @@ int scan_positions_per_block();
 int scan_tile_cap(int scan_step, int word_length);
 int scan_max_block_chunks();
 int scan_tile_margin();
-cudaError_t launch_build_qinfo(const DevQuery &q, const int32_t *next_pos, int32_t concat_len, uint4 *qinfo,
-                               cudaStream_t st);
+cudaError_t launch_build_qinfo(const DevQuery &q, const int32_t *next_pos, int32_t concat_len, const int32_t *heads,
+                               int64_t n_heads, uint32_t *indexed_scratch, uint4 *qinfo, cudaStream_t st);
 
 // Outcome of s_TypeOfWord + ungapped extension of one word hit (extend_kernel.cu), 32 bytes.
 struct SpecResult {
@@ -345,7 +350,9 @@ struct GappedLaunch {
     int32_t n_todo;
     int32_t grid_blocks;          // 0 = default persistent grid
     int32_t dp_max_rows;          // DP tier 1: rows (per direction) a single thread may walk before it reports status 2 (0 = no limit)
-    int32_t dp_smem_ring;         // DP: 1 = tier-1 rings in shared memory (no global scratch), 0 = global ring of tier_d cells (power of two)
+    int32_t dp_smem_ring;         // DP: 1 = tier-1 rings in shared memory (no global scratch), 2 = the same with 16-bit cells
+                                  // (needs dp_max_rows), 0 = global ring of tier_d cells (power of two)
+    unsigned long long *work_counter;   // optional, zeroed by the caller: extensions are handed out one by one
 };
 cudaError_t launch_gapped(const DevQuery &q, const GappedLaunch &g, cudaStream_t st);
 cudaError_t launch_greedy_warp(const DevQuery &q, const GappedLaunch &g, int warps_per_block, int blocks,
@@ -353,7 +360,10 @@ cudaError_t launch_greedy_warp(const DevQuery &q, const GappedLaunch &g, int war
 int gapped_threads();
 int gapped_threads_per_block();
 int gapped_dp_smem_blocks();
+int gapped_dp_ring16_blocks();
 cudaError_t launch_gapped_warp(const DevQuery &q, const GappedLaunch &g, int blocks, cudaStream_t st);
+// long alignments, one thread per (extension, direction): g.todo / g.n_todo list them; halves = 2 * n_todo int2 scratch
+cudaError_t launch_gapped_long(const DevQuery &q, const GappedLaunch &g, int2 *halves, cudaStream_t st);
 int gapped_warp_per_block();
 
 // ---- triage of the speculative gapped extensions (triage_kernel.cu) ----------------------------------
@@ -365,11 +375,11 @@ struct TriageLaunch {
     int32_t *ctx_of;                    // scratch: context per init-HSP, bit 31 = winner
     DevInitHit *sel_init;               // winners, then the losers the host has to replay in order
     DevGapResult *sel_gap;
-    int32_t *sel_ctx;
+    int32_t *sel_ctx;                   // per winner: the next winner (+1) of its (chunk, context), 0 = end of the chain
     int64_t sel_cap;
-    unsigned long long *tcount;         // [0] winners, [1] undecided losers (zeroed by the caller)
-    uint2 *table;                       // per (chunk, context), zeroed by the caller: .x = counted losers | bit 31: has a
-                                        // winner, .y = highest ungapped score among the counted losers
+    unsigned long long *tcount;         // [0] winners, [1] undecided losers, [2] counted losers (zeroed by the caller)
+    uint2 *table;                       // per (chunk, context), zeroed by the caller: .x bit 31 = has a winner, .y = newest
+                                        // winner + 1 (head of the chain through sel_ctx)
     int32_t n_ctx;
 };
 cudaError_t launch_triage(const DevQuery &q, const TriageLaunch &t, cudaStream_t st);

@@ -413,7 +413,13 @@ static int query_to_device(Query &Q, const BnQueryBatch &src, int d, Lane *dev, 
     v.gap_open = b.gap_open; v.gap_extend = b.gap_extend; v.gap_x_dropoff = b.gap_x_dropoff;
     if (b.lut_type == BN_LUT_MB) {
         CU_TRY(dev_alloc(&qd.qinfo, (size_t)b.concat_len + 2, st));
-        CU_TRY(launch_build_qinfo(v, qd.next_pos, b.concat_len, qd.qinfo, st));
+        // which query positions are in the table (chain heads + everything a link points to): the direct filter of the
+        // scan kernel asks it of a hit's predecessor on the diagonal
+        uint32_t *t_indexed = nullptr;
+        CU_TRY(dev_alloc(&t_indexed, (size_t)(b.concat_len + 1 + 32) / 32 + 2, st));
+        CU_TRY(launch_build_qinfo(v, qd.next_pos, b.concat_len, device_fill ? t_first_qp : t_hashtable,
+                                  device_fill ? (int64_t)b.concat_len + 1 : b.hashsize, t_indexed, qd.qinfo, st));
+        CU_TRY(cudaFreeAsync(t_indexed, st));
         v.qinfo = qd.qinfo;
         // compact table: {presence word, rank} per 32 cells (4^lut / 4 bytes, L2-resident) + the first
         // chain element of every occupied cell in cell order.  It stands in for hashtable[] everywhere
@@ -831,7 +837,15 @@ static int enqueue_gapped(Lane &D, Volume &V, Query &Q, ChunkTable &T, int64_t m
         const int64_t want = (max_init + gapped_threads_per_block() - 1) / gapped_threads_per_block();
         g.scratch = nullptr; g.dp_smem_ring = 1;
         g.dp_max_rows = 256;          // longer alignments go to the warp-parallel kernel (finish_gapped)
-        g.grid_blocks = (int32_t)std::max<int64_t>(1, std::min<int64_t>(gapped_dp_smem_blocks(), want));
+        // 16-bit ring cells when every live score of a 256-row extension fits them (gapped_kernel.cu: SmemRing16)
+        const int64_t hi = (int64_t)std::max(b.reward, 1) * (g.dp_max_rows + 80), lo = (int64_t)b.gap_x_dropoff + 2 * ((int64_t)b.gap_open + b.gap_extend);
+        const bool ring16 = hi < 30000 && lo < 30000 && !getenv("BN_NO_RING16");
+        if (ring16) {
+            g.dp_smem_ring = 2;
+            g.work_counter = ws.counters.p + 7;
+            CU_TRY(cudaMemsetAsync(g.work_counter, 0, sizeof(unsigned long long), st));
+        }
+        g.grid_blocks = (int32_t)std::max<int64_t>(1, std::min<int64_t>(ring16 ? gapped_dp_ring16_blocks() : gapped_dp_smem_blocks(), want));
         CU_TRY(launch_gapped(dq, g, st));
     } else {
         const int64_t threads = std::min<int64_t>(4096, ((max_init + 63) / 64) * 64);
@@ -876,10 +890,16 @@ static int finish_gapped(Lane &D, Volume &V, Query &Q, ChunkTable &T, int64_t n_
             g.packed = V.d_packed; g.chunks = T.dev.p; g.init = ws.init.p; g.n_init = ws.counters.p + 2;
             g.max_init = n_init; g.out = ws.gap_out.p;
             g.todo = ws.todo.p; g.n_todo = (int32_t)todo.size();
-            const int wpb_dp = gapped_warp_per_block();
-            const int blocks = (int)std::min<int64_t>(((int64_t)todo.size() + wpb_dp - 1) / wpb_dp, 148 * 4);
-            CU_TRY(launch_gapped_warp(dq, g, blocks, st));
-            if (stats) stats->kernel_launches += 1;
+            if (getenv("BN_WARP_DP")) {         // the lane-per-cell formulation, kept for comparison
+                const int wpb_dp = gapped_warp_per_block();
+                const int blocks = (int)std::min<int64_t>(((int64_t)todo.size() + wpb_dp - 1) / wpb_dp, 148 * 4);
+                CU_TRY(launch_gapped_warp(dq, g, blocks, st));
+                if (stats) stats->kernel_launches += 1;
+            } else {
+                CU_TRY(ws.scratch.reserve(4 * todo.size() + 16));
+                CU_TRY(launch_gapped_long(dq, g, reinterpret_cast<int2 *>(ws.scratch.p), st));
+                if (stats) stats->kernel_launches += 2;
+            }
             CU_TRY(cudaMemcpyAsync(h_gap, ws.gap_out.p, (size_t)n_init * sizeof(DevGapResult), cudaMemcpyDeviceToHost, st));
             CU_TRY(cudaStreamSynchronize(st));
             todo.clear();
@@ -942,7 +962,7 @@ static int finish_gapped_triaged(Lane &D, Volume &V, Query &Q, ChunkTable &T, in
     const int32_t xo = greedy_xdrop_offset(b);
     const int wpb = 4;
     CU_TRY(ws.todo.reserve((size_t)n_init));
-    unsigned long long *tc = ws.counters.p + 8;          // [8] status-2 count, [9] status-1 count, [10] winners, [11] undecided
+    unsigned long long *tc = ws.counters.p + 8;          // [8] status-2 count, [9] status-1 count, [10] winners, [11] undecided, [12] counted
     auto collect = [&](int32_t want, int slot, int64_t &count) -> int {
         CU_TRY(cudaMemsetAsync(tc + slot, 0, sizeof(unsigned long long), st));
         CU_TRY(launch_collect_status(ws.gap_out.p, ws.counters.p + 2, n_init, want, ws.todo.p, tc + slot, st));
@@ -962,10 +982,16 @@ static int finish_gapped_triaged(Lane &D, Volume &V, Query &Q, ChunkTable &T, in
             g.packed = V.d_packed; g.chunks = T.dev.p; g.init = ws.init.p; g.n_init = ws.counters.p + 2;
             g.max_init = n_init; g.out = ws.gap_out.p;
             g.todo = ws.todo.p; g.n_todo = (int32_t)n2;
-            const int wpb_dp = gapped_warp_per_block();
-            const int blocks = (int)std::min<int64_t>((n2 + wpb_dp - 1) / wpb_dp, 148 * 4);
-            CU_TRY(launch_gapped_warp(dq, g, blocks, st));
-            if (stats) stats->kernel_launches += 1;
+            if (getenv("BN_WARP_DP")) {
+                const int wpb_dp = gapped_warp_per_block();
+                const int blocks = (int)std::min<int64_t>((n2 + wpb_dp - 1) / wpb_dp, 148 * 4);
+                CU_TRY(launch_gapped_warp(dq, g, blocks, st));
+                if (stats) stats->kernel_launches += 1;
+            } else {
+                CU_TRY(ws.scratch.reserve((size_t)(4 * n2 + 16)));
+                CU_TRY(launch_gapped_long(dq, g, reinterpret_cast<int2 *>(ws.scratch.p), st));
+                if (stats) stats->kernel_launches += 2;
+            }
         }
     }
     rc = collect(1, 1, n1);
@@ -1015,14 +1041,14 @@ static int finish_gapped_triaged(Lane &D, Volume &V, Query &Q, ChunkTable &T, in
         sel_cap = (int64_t)std::min(std::min(ws.tri_init.cap, ws.tri_gap.cap), ws.tri_sel_ctx.cap);
         CU_TRY(ws.tri_table.reserve(n_cells));
         CU_TRY(cudaMemsetAsync(ws.tri_table.p, 0, n_cells * sizeof(uint2), st));
-        CU_TRY(cudaMemsetAsync(tc + 2, 0, 2 * sizeof(unsigned long long), st));
+        CU_TRY(cudaMemsetAsync(tc + 2, 0, 3 * sizeof(unsigned long long), st));
         TriageLaunch t{};
         t.init = ws.init.p; t.gap = ws.gap_out.p; t.n_init = ws.counters.p + 2; t.max_init = n_init;
         t.ctx_of = ws.tri_ctx.p; t.sel_init = ws.tri_init.p; t.sel_gap = ws.tri_gap.p; t.sel_ctx = ws.tri_sel_ctx.p;
         t.sel_cap = sel_cap; t.tcount = tc + 2; t.table = ws.tri_table.p; t.n_ctx = (int32_t)n_ctx;
         CU_TRY(launch_triage(dq, t, st));
         if (stats) stats->kernel_launches += 2;
-        CU_TRY(cudaMemcpyAsync(ws.h_counters + 10, tc + 2, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(ws.h_counters + 10, tc + 2, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
         const int64_t n_sel = (int64_t)(ws.h_counters[10] + ws.h_counters[11]);
         if (n_sel <= sel_cap) { G.n_records = n_sel; break; }
@@ -1030,16 +1056,13 @@ static int finish_gapped_triaged(Lane &D, Volume &V, Query &Q, ChunkTable &T, in
         sel_cap = n_sel + n_sel / 16 + 1024;
     }
     CU_TRY(ws.h_init.reserve((size_t)G.n_records + 1)); CU_TRY(ws.h_gap.reserve((size_t)G.n_records + 1));
-    CU_TRY(ws.h_table.reserve(n_cells + 1));
     G.h_init = ws.h_init.p; G.h_gap = ws.h_gap.p;
     if (G.n_records) {
         CU_TRY(cudaMemcpyAsync(G.h_init, ws.tri_init.p, (size_t)G.n_records * sizeof(DevInitHit), cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaMemcpyAsync(G.h_gap, ws.tri_gap.p, (size_t)G.n_records * sizeof(DevGapResult), cudaMemcpyDeviceToHost, st));
     }
-    CU_TRY(cudaMemcpyAsync(ws.h_table.p, ws.tri_table.p, n_cells * sizeof(uint2), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
-    int64_t counted = 0;
-    for (size_t i = 0; i < n_cells; i++) counted += (int64_t)(ws.h_table.p[i].x & 0x7fffffffu);
+    const int64_t counted = (int64_t)ws.h_counters[12];
     G.counted_losers = counted;
     G.triaged = true;
     if (G.n_records + counted != n_init) return fail(BN_ERR_CUDA, "triage lost init-HSPs");
@@ -1894,6 +1917,7 @@ static int query_load_impl(const BnQueryBatch *b, std::shared_ptr<Query> *out, i
             if (b->lookup_segments[2 * i + 1] >= b->lookup_segments[2 * i + 2])
                 return fail(BN_ERR_INVALID, "bn_query_load: lookup_segments must be ascending and disjoint");
     if (b->lut_type == BN_LUT_SMALL_NA && !b->backbone) return fail(BN_ERR_INVALID, "bn_query_load: small table arrays missing");
+    if (b->concat_len < 0 || b->concat_len >= (1 << 30)) return fail(BN_ERR_UNSUPPORTED, "bn_query_load: query batch of 2^30 bases or more");
     auto Q = std::make_shared<Query>();
     Q->batch = *b;
     Q->ctx.assign(b->contexts, b->contexts + b->num_contexts);

@@ -20,6 +20,7 @@
 // Scratch is tiered: tier 1 gives every thread a small window (greedy: distances <= tier_d,
 // DP: a ring of tier_d cells); an extension that outgrows it reports status 1 and is redone
 // in tier 2 with worst-case scratch (greedy max_dist 10000 rows, DP ring >= query length).
+#include <algorithm>
 #include "bn_device.cuh"
 
 namespace bn {
@@ -28,6 +29,7 @@ constexpr int GAP_THREADS = 64;
 constexpr int GAP_BLOCKS = 592;          // 4 x 148 SMs
 int gapped_threads() { return GAP_THREADS * GAP_BLOCKS; }
 int gapped_dp_smem_blocks() { return 148 * 3; }     // 64 KB of rings per block: three blocks per SM
+int gapped_dp_ring16_blocks() { return 148 * 10; }  // 16 KB of 16-bit rings per block: ten blocks (640 threads) per SM
 int gapped_threads_per_block() { return GAP_THREADS; }
 
 constexpr int32_t GREEDY_MAX_COST = 10000;
@@ -609,6 +611,27 @@ struct SmemRing {
     __device__ __forceinline__ void set(int32_t i, int2 v) const { base[(i & (DP_SMEM_CELLS - 1)) * GAP_THREADS] = v; }
     __device__ __forceinline__ int32_t capacity() const { return DP_SMEM_CELLS; }
 };
+// The same ring with 16-bit cells: a tier-1 extension walks at most dp_max_rows rows, so every live score lies in
+// (-(X + 2 (gap_open + gap_extend)), reward * rows]; the launcher picks this ring only when that interval fits 16 bits.
+// The reference's MININT is the one value outside it and travels as -32768.  (A stored score is either a live cell's
+// or exactly MININT: pruned cells are written as MININT and keep their old gap score, so no "MININT + small" value
+// is ever stored.)  Half the bytes per thread: 2.5 x the resident threads of the 32-bit ring, which is what this
+// latency-bound loop needs.
+constexpr int DP16_CELLS = 64;
+struct SmemRing16 {
+    short2 *base;               // &ring[0][thread]
+    __device__ __forceinline__ int2 get(int32_t i) const
+    {
+        const short2 v = base[(i & (DP16_CELLS - 1)) * GAP_THREADS];
+        return make_int2(v.x == -32768 ? MININT : (int32_t)v.x, v.y == -32768 ? MININT : (int32_t)v.y);
+    }
+    __device__ __forceinline__ void set(int32_t i, int2 v) const
+    {
+        base[(i & (DP16_CELLS - 1)) * GAP_THREADS] =
+            make_short2(v.x < -32000 ? (short)-32768 : (short)v.x, v.y < -32000 ? (short)-32768 : (short)v.y);
+    }
+    __device__ __forceinline__ int32_t capacity() const { return DP16_CELLS; }
+};
 struct GlobalRing {
     int2 *base;
     int32_t mask;               // capacity - 1
@@ -928,6 +951,174 @@ gapped_warp_kernel(const DevQuery q, const GappedLaunch L)
     }
 }
 
+// ================================================================================================
+// LONG alignments, latency first: one WARP per (extension, direction); the row's dependency chain runs in ONE lane.
+// A real 10 kb alignment is ~10^4 rows of a ~40-cell band, and a batch has a few hundred of them that run side by
+// side, so the stage ends when the longest DIRECTION ends: what counts is the time of one row.  Inside a row of
+// s_BlastAlignPackedNucl the cells form one chain (score -> horizontal gap / running best -> next score):
+//      s_b = max(v_b, r);  pruned_b = best - s_b > X;  unpruned: best = max(best, s_b), r = max(s_b - goe, r - ge)
+// with v_b = max(best_old[b-1] + matrix[a][B_b], best_gap_old[b]) free of it.  So per row
+//   1. all lanes compute v_b of the band into shared memory            (parallel, two rounds for a 40-cell band)
+//   2. lane 0 walks the chain: three dependent operations per cell     (~16 cycles a cell, loads run ahead)
+//   3. all lanes write the cells back (score, vertical gap; MININT for a pruned cell)
+// ~800 cycles for a 40-cell row.  The lane-per-cell kernel above resolves the same chain with two warp scans and a
+// fixed-point loop per 32-cell segment (~4500 cycles per row measured); one thread doing everything pays the
+// shared-memory and matrix look-ups inside the chain (~15000).  Values are those of dp_packed, cell for cell.
+// ================================================================================================
+constexpr int DPL_WARPS = 4;
+constexpr int DPL_CELLS = 512;
+
+__device__ int32_t dp_packed_chain(const uint8_t *B, const uint8_t *A, int32_t N, int32_t M, int32_t &b_offset, int32_t &a_offset,
+                                   const int32_t *matrix, int32_t gap_open, int32_t gap_extend, int32_t x_dropoff, bool reverse,
+                                   int2 *ring, int32_t *vbuf, int32_t *sbuf, bool &overflow, int lane)
+{
+    const int32_t goe = gap_open + gap_extend, ge = gap_extend;
+    constexpr int32_t C = DPL_CELLS, MASK = DPL_CELLS - 1;
+    a_offset = 0; b_offset = 0;
+    if (x_dropoff < goe) x_dropoff = goe;
+    if (N <= 0 || M <= 0) return 0;
+    // row 0: cell 0 = (0, -goe); cell i >= 1 = (-goe - (i-1) ge, that - goe) while that score is >= -X
+    int32_t b_size;
+    {
+        int32_t k = (ge == 0) ? N : (x_dropoff - goe) / ge + 1;
+        k = min(k, N);
+        if (k + 1 >= C) { overflow = true; return 0; }
+        for (int32_t i = lane; i <= k; i += 32) {
+            const int32_t sc = (i == 0) ? 0 : -goe - (i - 1) * ge;
+            ring[i & MASK] = make_int2(sc, sc - goe);
+        }
+        b_size = k + 1;
+        __syncwarp();
+    }
+    int32_t best = 0, first_b = 0, a_off = 0, b_off = 0;
+    for (int32_t a_index = 1; a_index <= M; a_index++) {
+        int a_bp;
+        if (reverse) a_bp = (__ldg(A + (M - a_index) / 4) >> (2 * ((a_index - 1) % 4))) & 3;
+        else a_bp = (__ldg(A + 1 + (a_index - 1) / 4) >> (2 * (3 - (a_index - 1) % 4))) & 3;
+        const int32_t *mrow = matrix + 16 * a_bp;
+        // 1. v_b for the whole band
+        for (int32_t b = first_b + lane; b < b_size; b += 32) {
+            const int2 cell = ring[b & MASK];
+            int32_t diag = MININT;
+            if (b > first_b) diag = ring[(b - 1) & MASK].x + mrow[(int)__ldg(reverse ? (B + N - b) : (B + b))];
+            vbuf[b & MASK] = max(diag, cell.y);
+        }
+        __syncwarp();
+        // 2. the chain
+        int32_t fb = first_b, last_b = first_b, r = MININT;
+        if (lane == 0) {
+#pragma unroll 4
+            for (int32_t b = first_b; b < b_size; b++) {
+                const int32_t score = max(vbuf[b & MASK], r);
+                if (best - score > x_dropoff) {
+                    if (b == fb) fb++;
+                    sbuf[b & MASK] = MININT;
+                } else {
+                    last_b = b;
+                    if (score > best) { best = score; a_off = a_index; b_off = b; }
+                    r = max(score - goe, r - ge);
+                    sbuf[b & MASK] = score;
+                }
+            }
+        }
+        __syncwarp();                        // lane 0's sbuf stores before everybody reads them
+        fb = __shfl_sync(FULLW, fb, 0); last_b = __shfl_sync(FULLW, last_b, 0); r = __shfl_sync(FULLW, r, 0);
+        best = __shfl_sync(FULLW, best, 0);
+        // 3. write back: an unpruned cell gets its score and vertical gap, a pruned one inside the band MININT
+        for (int32_t b = first_b + lane; b < b_size; b += 32) {
+            const int32_t sc = sbuf[b & MASK];
+            if (sc != MININT) {
+                const int32_t y = ring[b & MASK].y;
+                ring[b & MASK] = make_int2(sc, max(sc - goe, y - ge));
+            } else if (b >= fb) ring[b & MASK].x = MININT;
+        }
+        first_b = fb;
+        if (first_b == b_size) break;
+        if (last_b < b_size - 1) b_size = last_b + 1;
+        else {
+            while (r >= (best - x_dropoff) && b_size <= N) {
+                if (b_size - first_b + 2 >= C) { overflow = true; return 0; }
+                if (lane == 0) ring[b_size & MASK] = make_int2(r, r - goe);
+                r -= ge;
+                b_size++;
+            }
+        }
+        if (b_size <= N) {
+            if (b_size - first_b + 2 >= C) { overflow = true; return 0; }
+            if (lane == 0) ring[b_size & MASK] = make_int2(MININT, MININT);
+            b_size++;
+        }
+        __syncwarp();
+    }
+    a_offset = __shfl_sync(FULLW, a_off, 0); b_offset = __shfl_sync(FULLW, b_off, 0);
+    return best;
+}
+
+__global__ void __launch_bounds__(DPL_WARPS * 32)
+gapped_long_kernel(const DevQuery q, const GappedLaunch L, int2 *halves)
+{
+    __shared__ int2 rings[DPL_WARPS][DPL_CELLS];
+    __shared__ int32_t vbufs[DPL_WARPS][DPL_CELLS], sbufs[DPL_WARPS][DPL_CELLS];
+    __shared__ int32_t s_matrix[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_matrix[i] = q.matrix[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t warp0 = (int64_t)blockIdx.x * DPL_WARPS + wib, nwarps = (int64_t)gridDim.x * DPL_WARPS;
+    const int64_t n = (int64_t)L.n_todo;
+    for (int64_t w = warp0; w < 2 * n; w += nwarps) {
+        const int64_t i = (int64_t)L.todo[w >> 1];
+        const bool do_right = (w & 1) != 0;
+        const DevInitHit h = L.init[i];
+        const DevChunk ch = L.chunks[h.chunk];
+        const uint8_t *S = L.packed + ch.byte_off;
+        const DevContext c = q.ctx[ctx_search(q, h.q_off)];
+        const uint8_t *query = q.query + c.query_offset;
+        const int32_t qlen = c.query_length, slen = ch.len;
+        int32_t q_off = h.q_off - c.query_offset, s_off = h.s_off;
+        if (h.s_start + h.length >= s_off + 8) { s_off += 3; q_off += 3; }
+        const int32_t adj = 4 - (s_off % 4);                           // s_BlastDynProgNtGappedAlignment, as in dp_gapped
+        int32_t q_length = q_off + adj, s_length = s_off + adj;
+        if (q_length > qlen || s_length > slen) { q_length -= 4; s_length -= 4; }
+        bool overflow = false;
+        int32_t pq = 0, ps = 0, score = 0;
+        DevGapResult *g = &L.out[i];        // the two directions own different fields; score and status are joined afterwards
+        __syncwarp();
+        if (!do_right) {
+            score = dp_packed_chain(query, S, q_length, s_length, pq, ps, s_matrix, q.gap_open, q.gap_extend, q.gap_x_dropoff,
+                                    true, rings[wib], vbufs[wib], sbufs[wib], overflow, lane);
+            if (lane == 0) { g->q_start = q_length - pq; g->s_start = s_length - ps; g->q_seed = q_off; g->s_seed = s_off; }
+        } else if (q_length < qlen && s_length < slen) {
+            score = dp_packed_chain(query + q_length - 1, S + (s_length + 3) / 4 - 1, qlen - q_length, slen - s_length, pq, ps,
+                                    s_matrix, q.gap_open, q.gap_extend, q.gap_x_dropoff, false, rings[wib], vbufs[wib], sbufs[wib],
+                                    overflow, lane);
+            if (lane == 0) { g->q_stop = pq + q_length; g->s_stop = ps + s_length; }
+        } else if (lane == 0) { g->q_stop = q_length; g->s_stop = s_length; }
+        if (lane == 0) halves[w] = make_int2(score, overflow ? 1 : 0);
+        __syncwarp();
+    }
+}
+
+__global__ void gapped_long_combine_kernel(const GappedLaunch L, const int2 *halves)
+{
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= (int64_t)L.n_todo) return;
+    const int64_t i = (int64_t)L.todo[w];
+    const int2 l = halves[2 * w], r = halves[2 * w + 1];
+    L.out[i].score = l.x + r.x;
+    L.out[i].status = (l.y || r.y) ? 1 : 0;           // band wider than the ring: tier 2 takes it
+}
+
+// halves: 2 * n_todo int2 of scratch
+cudaError_t launch_gapped_long(const DevQuery &q, const GappedLaunch &g, int2 *halves, cudaStream_t st)
+{
+    if (g.n_todo <= 0) return cudaSuccess;
+    const int64_t items = 2 * (int64_t)g.n_todo;
+    const int blocks = (int)std::min<int64_t>((items + DPL_WARPS - 1) / DPL_WARPS, 148 * 16);
+    gapped_long_kernel<<<blocks, DPL_WARPS * 32, 0, st>>>(q, g, halves);
+    gapped_long_combine_kernel<<<(unsigned)((g.n_todo + 127) / 128), 128, 0, st>>>(g, halves);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_gapped_warp(const DevQuery &q, const GappedLaunch &g, int blocks, cudaStream_t st)
 {
     gapped_warp_kernel<<<blocks, DPW_WARPS * 32, 0, st>>>(q, g);
@@ -947,7 +1138,10 @@ gapped_kernel(const DevQuery q, const GappedLaunch L)
     int64_t n = L.todo ? (int64_t)L.n_todo : (int64_t)min((unsigned long long)L.max_init, *L.n_init);
     int32_t *scratch = L.scratch ? L.scratch + tid * L.scratch_ints_per_thread : nullptr;
 
-    for (int64_t w = tid; w < n; w += nthreads) {
+    // work is handed out one extension at a time when a counter is given (extensions differ in length by orders of
+    // magnitude: a fixed stride leaves most threads idle behind the slowest), else by a fixed stride
+    for (int64_t w = L.work_counter ? (int64_t)atomicAdd(L.work_counter, 1ull) : tid; w < n;
+         w = L.work_counter ? (int64_t)atomicAdd(L.work_counter, 1ull) : w + nthreads) {
         const int64_t i = L.todo ? (int64_t)L.todo[w] : w;
         const DevInitHit h = L.init[i];
         const DevChunk ch = L.chunks[h.chunk];
@@ -965,7 +1159,10 @@ gapped_kernel(const DevQuery q, const GappedLaunch L)
         } else {
             int32_t q_off = h.q_off - c.query_offset, s_off = h.s_off;
             if (h.s_start + h.length >= s_off + 8) { s_off += 3; q_off += 3; }
-            if (L.dp_smem_ring)
+            if (L.dp_smem_ring == 2)
+                dp_gapped(q, s_matrix, query, c.query_length, S, ch.len, q_off, s_off,
+                          SmemRing16{reinterpret_cast<short2 *>(dp_smem) + threadIdx.x}, L.dp_max_rows, g);
+            else if (L.dp_smem_ring)
                 dp_gapped(q, s_matrix, query, c.query_length, S, ch.len, q_off, s_off, SmemRing{dp_smem + threadIdx.x},
                           L.dp_max_rows > 0 ? L.dp_max_rows : INT32_MAX, g);
             else
@@ -978,7 +1175,8 @@ gapped_kernel(const DevQuery q, const GappedLaunch L)
 
 cudaError_t launch_gapped(const DevQuery &q, const GappedLaunch &g, cudaStream_t st)
 {
-    const size_t smem = g.dp_smem_ring ? (size_t)DP_SMEM_CELLS * GAP_THREADS * sizeof(int2) : 0;
+    const size_t smem = g.dp_smem_ring == 2 ? (size_t)DP16_CELLS * GAP_THREADS * sizeof(short2)
+                        : (g.dp_smem_ring ? (size_t)DP_SMEM_CELLS * GAP_THREADS * sizeof(int2) : 0);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(gapped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

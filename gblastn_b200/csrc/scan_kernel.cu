@@ -661,21 +661,30 @@ scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ S
             const int32_t tbase = ct_tbase[k], len = ct_len[k];
             const uint32_t chunk = (uint32_t)ct_parent[k];
             const int64_t g = block_pos0 + gl;
-            int32_t qp = (int32_t)(qi.x & 0x7fffffffu);
+            int32_t qp = (int32_t)(qi.x & QP_MASK);
             bool more = (qi.x >> 31) != 0, second = true;
+            // base in front of the scan position (direct filter: is this hit the continuation of a run of matches?)
+            const uint32_t s_prev = (DIRECT && p > 0) ? (tile_win(tile, tbase + p - 1) >> 30) : 4u;
             for (;;) {
                 ++my_lookup_hits;
                 int32_t qo, so;
                 if (DIRECT) {
-                    // lut == word: no mini-extension; drop the hits whose ungapped extension cannot reach the cutoff
-                    int32_t xd = s.uni_x, co = s.uni_cutoff, rc = s.uni_reduced;
-                    if (!s.uni_ok) {
-                        const DevContext c = q.ctx[ctx_search(q, qp - 1)];
-                        xd = c.x_dropoff; co = c.cutoff_score; rc = c.reduced_cutoff;
+                    // lut == word: no mini-extension.  A hit whose predecessor on the diagonal, (q_off - 1, s_off - 1),
+                    // is a lookup hit too belongs to the same run of matching bases as that hit and shares its fate:
+                    // rejected by the diagonal test when the run's first hit was extended successfully, below the
+                    // cutoff itself when that one was.  Only a run's first hit goes on, and only if its own
+                    // ungapped extension can reach the cutoff.
+                    const bool follower = (qi.x & PREV_INDEXED) && s_prev == (qi.y & 3u) && !(qi.w & 1u);
+                    if (!follower) {
+                        int32_t xd = s.uni_x, co = s.uni_cutoff, rc = s.uni_reduced;
+                        if (!s.uni_ok) {
+                            const DevContext c = q.ctx[ctx_search(q, qp - 1)];
+                            xd = c.x_dropoff; co = c.cutoff_score; rc = c.reduced_cutoff;
+                        }
+                        DirectCtx dc{tile, bd.bytes * 4, bd.tile_lo * 4, s.packed};
+                        if (direct_keep(q, dc, tbase, len, qp - 1, p, xd, co, rc))
+                            emit_hit(q, s, chunk, (uint32_t)p, g, qp - 1, p);
                     }
-                    DirectCtx dc{tile, bd.bytes * 4, bd.tile_lo * 4, s.packed};
-                    if (direct_keep(q, dc, tbase, len, qp - 1, p, xd, co, rc))
-                        emit_hit(q, s, chunk, (uint32_t)p, g, qp - 1, p);
                 }
                 else if (s.raw_pairs) emit_hit(q, s, chunk, (uint32_t)p, g, qp - 1, p);
                 else if (mini_extend_tile(q, tile, tbase, len, qp - 1, p, qi, qo, so))
@@ -684,12 +693,12 @@ scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ S
                 if (second) {                       // second element came with the first
                     second = false;
                     qi = qi1;
-                    qp = (int32_t)(qi.x & 0x7fffffffu);
+                    qp = (int32_t)(qi.x & QP_MASK);
                     more = (qi.x >> 31) != 0;
                 } else {                            // third and later (rare): pointer chase
                     qp = __ldg(&q.next_pos[qp]);
-                    qi = __ldg(&q.qinfo[qp]);       // {next, left 16 bases, right 16 bases, ambiguity}
-                    more = qi.x != 0;
+                    qi = __ldg(&q.qinfo[qp]);       // {next | PREV_INDEXED, left 16 bases, right 16 bases, ambiguity}
+                    more = (qi.x & QP_MASK) != 0;
                 }
             }
         }
@@ -701,7 +710,23 @@ scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ S
 
 // qinfo[qp] for every 1-based query position qp: {next_pos[qp], 16 bases left of the lookup word that
 // starts at qp-1, 16 bases right of it, ambiguity flags (left in the even bits, right in the odd bits)}
-__global__ void build_qinfo_kernel(const DevQuery q, const int32_t *next_pos, int32_t concat_len, uint4 *qinfo)
+// indexed[] bit qp <=> the 1-based query position qp is in the lookup table = it heads a chain or some position links to it
+__global__ void mark_linked_kernel(const int32_t *next_pos, int32_t concat_len, uint32_t *indexed)
+{
+    const int64_t qp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (qp < 1 || qp > concat_len) return;
+    const int32_t n = next_pos[qp];
+    if (n > 0) atomicOr(&indexed[n >> 5], 1u << (n & 31));
+}
+__global__ void mark_heads_kernel(const int32_t *heads, int64_t n, uint32_t *indexed)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t h = heads[i];
+    if (h > 0) atomicOr(&indexed[h >> 5], 1u << (h & 31));
+}
+__global__ void build_qinfo_kernel(const DevQuery q, const int32_t *next_pos, int32_t concat_len, const uint32_t *indexed,
+                                   uint4 *qinfo)
 {
     const int64_t qp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (qp > concat_len) return;
@@ -710,13 +735,22 @@ __global__ void build_qinfo_kernel(const DevQuery q, const int32_t *next_pos, in
         qwin(q, (int32_t)qp - 1 - 16, lb, la);
         qwin(q, (int32_t)qp - 1 + q.lut_word_length, rb, ra);
     }
-    qinfo[qp] = make_uint4((uint32_t)next_pos[qp], lb, rb, (la & 0x55555555u) | ((ra & 0x55555555u) << 1));
+    uint32_t x = (uint32_t)next_pos[qp];
+    if (indexed && qp >= 2 && ((indexed[(qp - 1) >> 5] >> ((qp - 1) & 31)) & 1u)) x |= PREV_INDEXED;
+    qinfo[qp] = make_uint4(x, lb, rb, (la & 0x55555555u) | ((ra & 0x55555555u) << 1));
 }
-cudaError_t launch_build_qinfo(const DevQuery &q, const int32_t *next_pos, int32_t concat_len, uint4 *qinfo,
-                               cudaStream_t st)
+// heads: the chain heads (hashtable[] of a host-built table, or the per-rank first positions of the device fill)
+cudaError_t launch_build_qinfo(const DevQuery &q, const int32_t *next_pos, int32_t concat_len, const int32_t *heads,
+                               int64_t n_heads, uint32_t *indexed_scratch, uint4 *qinfo, cudaStream_t st)
 {
     const int64_t n = (int64_t)concat_len + 1;
-    build_qinfo_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q, next_pos, concat_len, qinfo);
+    if (indexed_scratch) {
+        cudaError_t e = cudaMemsetAsync(indexed_scratch, 0, (size_t)((n + 32) / 32 + 1) * sizeof(uint32_t), st);
+        if (e != cudaSuccess) return e;
+        mark_linked_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(next_pos, concat_len, indexed_scratch);
+        if (n_heads > 0) mark_heads_kernel<<<(unsigned)((n_heads + 255) / 256), 256, 0, st>>>(heads, n_heads, indexed_scratch);
+    }
+    build_qinfo_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q, next_pos, concat_len, indexed_scratch, qinfo);
     return cudaGetLastError();
 }
 
@@ -767,11 +801,11 @@ __global__ void popc_kernel(const uint32_t *presence, int64_t nwords, uint32_t *
 __device__ __forceinline__ void store_cinfo_pair(uint4 *cinfo, uint32_t rank, uint32_t qp, const uint4 *qinfo)
 {
     uint4 v = qinfo[qp], w = make_uint4(0, 0, 0, 0);
-    const uint32_t nxt = v.x;
-    v.x = qp | (nxt ? 0x80000000u : 0u);
+    const uint32_t nxt = v.x & QP_MASK;
+    v.x = qp | (nxt ? 0x80000000u : 0u) | (v.x & PREV_INDEXED);
     if (nxt) {
         w = qinfo[nxt];
-        w.x = nxt | (w.x ? 0x80000000u : 0u);
+        w.x = nxt | ((w.x & QP_MASK) ? 0x80000000u : 0u) | (w.x & PREV_INDEXED);
     }
     cinfo[2 * (size_t)rank] = v;
     cinfo[2 * (size_t)rank + 1] = w;

@@ -519,19 +519,20 @@ __device__ __forceinline__ int32_t tb_first_mismatch(const GreedyTbSeq &p, int32
 {
     const int32_t n = min(p.len1 - i1, p.len2 - i2);
     if (n <= 0) return 0;
-    if (p.amb.n) {          // s_FindFirstMismatch on blastna bytes (core/greedy_align.c:318-380), 16 bases at a time
+    if (p.amb.n) {          // s_FindFirstMismatch on blastna bytes (core/greedy_align.c:318-380), 16 bases at a time; an
+                            // ambiguity code in the query never matches there, not even the same code in the subject
         int32_t cnt = 0;
         while (cnt < n) {
             uint32_t qb, qa;
             if (p.reverse) {
                 const int32_t qpos = p.qbase + p.len1 - i1 - cnt - 16;
                 qwin(*p.q, qpos, qb, qa);
-                const uint32_t m = subj_mismatch16(*p.q, p.packed, p.amb, qpos, p.sbase + p.len2 - i2 - cnt - 16, qb, qa);
+                const uint32_t m = subj_mismatch16(*p.q, p.packed, p.amb, qpos, p.sbase + p.len2 - i2 - cnt - 16, qb, qa, false);
                 if (m) return min(cnt + ((__ffs(m) - 1) >> 1), n);
             } else {
                 const int32_t qpos = p.qbase + i1 + cnt;
                 qwin(*p.q, qpos, qb, qa);
-                const uint32_t m = subj_mismatch16(*p.q, p.packed, p.amb, qpos, p.sbase + i2 + cnt, qb, qa);
+                const uint32_t m = subj_mismatch16(*p.q, p.packed, p.amb, qpos, p.sbase + i2 + cnt, qb, qa, false);
                 if (m) return min(cnt + (__clz(m) >> 1), n);
             }
             cnt += 16;
@@ -613,11 +614,11 @@ __device__ int32_t tb_first_mismatch_warp(const GreedyTbSeq &p, int32_t i1, int3
             uint32_t qb, qa, m;
             if (p.reverse) {
                 qwin(*p.q, p.qbase + p.len1 - i1 - off - 16, qb, qa);
-                m = subj_mismatch16(*p.q, p.packed, p.amb, p.qbase + p.len1 - i1 - off - 16, p.sbase + p.len2 - i2 - off - 16, qb, qa);
+                m = subj_mismatch16(*p.q, p.packed, p.amb, p.qbase + p.len1 - i1 - off - 16, p.sbase + p.len2 - i2 - off - 16, qb, qa, false);
                 if (m) c = (__ffs(m) - 1) >> 1;
             } else {
                 qwin(*p.q, p.qbase + i1 + off, qb, qa);
-                m = subj_mismatch16(*p.q, p.packed, p.amb, p.qbase + i1 + off, p.sbase + i2 + off, qb, qa);
+                m = subj_mismatch16(*p.q, p.packed, p.amb, p.qbase + i1 + off, p.sbase + i2 + off, qb, qa, false);
                 if (m) c = __clz(m) >> 1;
             }
         }

@@ -41,10 +41,13 @@ triage_classify_kernel(const DevQuery q, const TriageLaunch t)
         t.ctx_of[i] = winner ? (ctx | (int32_t)HAS_WINNER) : ctx;
         if (winner) {
             const uint64_t slot = warp_append(&t.tcount[0]);
+            uint2 *cell = &t.table[(size_t)h.chunk * (size_t)t.n_ctx + (size_t)ctx];
             if ((int64_t)slot < t.sel_cap) {
-                t.sel_init[slot] = h; t.sel_gap[slot] = g; t.sel_ctx[slot] = ctx;
+                // the winners of a (chunk, context) form a chain through sel_ctx: cell.y = newest winner + 1
+                t.sel_init[slot] = h; t.sel_gap[slot] = g;
+                t.sel_ctx[slot] = (int32_t)atomicExch(&cell->y, (uint32_t)slot + 1u);
             }
-            atomicOr(&t.table[(size_t)h.chunk * (size_t)t.n_ctx + (size_t)ctx].x, HAS_WINNER);
+            atomicOr(&cell->x, HAS_WINNER);
         }
     }
 }
@@ -53,31 +56,32 @@ __global__ void __launch_bounds__(256)
 triage_losers_kernel(const DevQuery q, const TriageLaunch t)
 {
     const int64_t n = min((int64_t)*t.n_init, t.max_init);
-    const int64_t n_w = min((int64_t)t.tcount[0], t.sel_cap);
+    const int64_t n_w = (int64_t)t.tcount[0];      // > sel_cap: the caller grows the buffers and runs the triage again
+    unsigned long long counted = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int32_t c = t.ctx_of[i];
         if (c < 0) continue;                                   // winner
         const DevInitHit h = t.init[i];
-        uint2 *cell = &t.table[(size_t)h.chunk * (size_t)t.n_ctx + (size_t)c];
+        const uint2 *cell = &t.table[(size_t)h.chunk * (size_t)t.n_ctx + (size_t)c];
         bool undecided = false;
-        if (cell->x & HAS_WINNER) {
+        if (__ldg(&cell->x) & HAS_WINNER) {
             const int32_t q0 = h.q_start - __ldg(&q.ctx[c].query_offset), q1 = q0 + h.length;
             const int32_t s0 = h.s_start, s1 = s0 + h.length;
-            for (int64_t k = 0; k < n_w && !undecided; k++) {
-                if (t.sel_ctx[k] != c || t.sel_init[k].chunk != h.chunk) continue;
-                const DevGapResult w = t.sel_gap[k];
+            for (uint32_t k1 = __ldg(&cell->y); k1 && !undecided; k1 = (uint32_t)t.sel_ctx[k1 - 1]) {
+                const DevGapResult w = t.sel_gap[k1 - 1];
                 undecided = h.score <= w.score && w.q_start <= q0 && q0 <= w.q_stop && w.s_start <= s0 && s0 <= w.s_stop &&
                             w.q_start <= q1 && q1 <= w.q_stop && w.s_start <= s1 && s1 <= w.s_stop;
             }
         }
         if (undecided) {
             const uint64_t slot = (uint64_t)n_w + warp_append(&t.tcount[1]);
-            if ((int64_t)slot < t.sel_cap) { t.sel_init[slot] = h; t.sel_gap[slot] = t.gap[i]; t.sel_ctx[slot] = c; }
-        } else {
-            atomicAdd(&cell->x, 1u);
-            atomicMax(&cell->y, (uint32_t)max(h.score, 0));
-        }
+            if ((int64_t)slot < t.sel_cap) { t.sel_init[slot] = h; t.sel_gap[slot] = t.gap[i]; t.sel_ctx[slot] = 0; }
+        } else ++counted;
     }
+    // one atomic per warp: the counted losers only matter as a total (the triage runs when no low_score bound can
+    // move, so every one of them is an extension the reference makes)
+    for (int o = 16; o > 0; o >>= 1) counted += __shfl_down_sync(0xffffffffu, counted, o);
+    if ((threadIdx.x & 31) == 0 && counted) atomicAdd(&t.tcount[2], counted);
 }
 
 cudaError_t launch_triage(const DevQuery &q, const TriageLaunch &t, cudaStream_t st)
