@@ -375,6 +375,7 @@ struct TriageLaunch {
     int32_t *ctx_of;                    // scratch: context per init-HSP, bit 31 = winner
     DevInitHit *sel_init;               // winners, then the losers the host has to replay in order
     DevGapResult *sel_gap;
+    int32_t *sel_idx;                   // index of the selected record among all init-HSPs
     int32_t *sel_ctx;                   // per winner: the next winner (+1) of its (chunk, context), 0 = end of the chain
     int64_t sel_cap;
     unsigned long long *tcount;         // [0] winners, [1] undecided losers, [2] counted losers (zeroed by the caller)
@@ -383,6 +384,24 @@ struct TriageLaunch {
     int32_t n_ctx;
 };
 cudaError_t launch_triage(const DevQuery &q, const TriageLaunch &t, cudaStream_t st);
+// Long gapped extensions made in rounds (triage_kernel.cu): per (chunk, context) the best pending one first, pending
+// ones inside a box made so far set aside (DevGapResult::status 3 = not computed).
+struct LongRounds {
+    const DevInitHit *init;
+    DevGapResult *gap;
+    const int32_t *todo;                // the long extensions (indices of init-HSPs); w = position in this list
+    int32_t n_todo;
+    int32_t *state, *ctx_w, *chain_next;        // per w: 0 pending / 1 made / 2 in this round / 3 set aside; context; chain link
+    unsigned long long *best;           // per (chunk, context): best pending key of the round (all ones = none)
+    uint32_t *chain_head;               // per (chunk, context): newest saved box (w + 1), zeroed by the caller
+    int32_t *round_list, *round_w;      // this round's extensions: init index, w
+    unsigned long long *round_count;
+    int32_t n_ctx, min_diag_separation;
+    int32_t set_aside_all;              // test switch: once a (chunk, context) has a box, set every other pending one aside
+};
+cudaError_t launch_long_prepare(const DevQuery &q, const LongRounds &r, cudaStream_t st);
+cudaError_t launch_long_select(const DevQuery &q, const LongRounds &r, cudaStream_t st);
+cudaError_t launch_long_commit(const DevQuery &q, const LongRounds &r, int32_t n_round, cudaStream_t st);
 cudaError_t launch_collect_status(const DevGapResult *gap, const unsigned long long *n_init, int64_t max_init, int32_t want,
                                   int32_t *todo, unsigned long long *count, cudaStream_t st);
 

@@ -104,7 +104,11 @@ struct Workspace {
     DevBuf<DevInitHit> init;
     DevBuf<DevGapResult> gap_out;
     DevBuf<int32_t> scratch, todo;
-    DevBuf<int32_t> tri_ctx, tri_sel_ctx;             // triage: context per init-HSP / per selected record
+    DevBuf<int32_t> tri_ctx, tri_sel_ctx, tri_sel_idx;   // triage: context per init-HSP / chain links / original index per selected record
+    DevBuf<int32_t> lr_state, lr_ctx, lr_next, lr_list, lr_w;      // long extensions in rounds (LongRounds)
+    DevBuf<unsigned long long> lr_best;
+    DevBuf<uint32_t> lr_head;
+    PinnedBuf<int32_t> h_sel_idx;
     DevBuf<DevInitHit> tri_init;
     DevBuf<DevGapResult> tri_gap;
     DevBuf<uint2> tri_table;
@@ -118,7 +122,9 @@ struct Workspace {
     void release()
     {
         h_init.release(); h_gap.release(); h_table.release();
-        tri_ctx.release(); tri_sel_ctx.release(); tri_init.release(); tri_gap.release(); tri_table.release();
+        tri_ctx.release(); tri_sel_ctx.release(); tri_sel_idx.release(); tri_init.release(); tri_gap.release(); tri_table.release();
+        lr_state.release(); lr_ctx.release(); lr_next.release(); lr_list.release(); lr_w.release(); lr_best.release(); lr_head.release();
+        h_sel_idx.release();
         for (auto &e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
         hits_a.release(); hits_b.release(); keys_a.release(); keys_b.release();
         cells.release(); heads.release(); leaders.release(); buckets.release(); keys_tmp.release(); spec.release(); init.release(); gap_out.release(); scratch.release(); todo.release();
@@ -977,26 +983,62 @@ static int finish_gapped_triaged(Lane &D, Volume &V, Query &Q, ChunkTable &T, in
     if (!greedy) {
         rc = collect(2, 0, n2);
         if (rc) return rc;
-        if (n2) {       // long alignments: one warp each
-            GappedLaunch g{};
-            g.packed = V.d_packed; g.chunks = T.dev.p; g.init = ws.init.p; g.n_init = ws.counters.p + 2;
-            g.max_init = n_init; g.out = ws.gap_out.p;
-            g.todo = ws.todo.p; g.n_todo = (int32_t)n2;
-            if (getenv("BN_WARP_DP")) {
-                const int wpb_dp = gapped_warp_per_block();
-                const int blocks = (int)std::min<int64_t>((n2 + wpb_dp - 1) / wpb_dp, 148 * 4);
-                CU_TRY(launch_gapped_warp(dq, g, blocks, st));
+        if (n2) {
+            // long alignments, in rounds (triage_kernel.cu: LongRounds): per (chunk, context) the best pending one,
+            // the ones inside a box made so far are set aside
+            const size_t n_cells_lr = T.host.size() * (size_t)b.num_contexts;
+            CU_TRY(ws.lr_state.reserve((size_t)n2)); CU_TRY(ws.lr_ctx.reserve((size_t)n2)); CU_TRY(ws.lr_next.reserve((size_t)n2));
+            CU_TRY(ws.lr_list.reserve((size_t)n2)); CU_TRY(ws.lr_w.reserve((size_t)n2));
+            CU_TRY(ws.lr_best.reserve(n_cells_lr)); CU_TRY(ws.lr_head.reserve(n_cells_lr));
+            CU_TRY(ws.scratch.reserve((size_t)(4 * n2 + 16)));
+            // the list of long extensions lives in ws.todo; the rounds need it while ws.todo is reused: keep a copy
+            CU_TRY(ws.lr_list.reserve((size_t)(2 * n2)));
+            int32_t *all_long = ws.lr_list.p + n2;
+            CU_TRY(cudaMemcpyAsync(all_long, ws.todo.p, (size_t)n2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+            CU_TRY(cudaMemsetAsync(ws.lr_head.p, 0, n_cells_lr * sizeof(uint32_t), st));
+            LongRounds r{};
+            r.init = ws.init.p; r.gap = ws.gap_out.p; r.todo = all_long; r.n_todo = (int32_t)n2;
+            r.state = ws.lr_state.p; r.ctx_w = ws.lr_ctx.p; r.chain_next = ws.lr_next.p;
+            r.best = ws.lr_best.p; r.chain_head = ws.lr_head.p; r.round_list = ws.lr_list.p; r.round_w = ws.lr_w.p;
+            r.round_count = tc + 5; r.n_ctx = b.num_contexts; r.min_diag_separation = b.min_diag_separation;
+            r.set_aside_all = getenv("BN_LONG_SET_ASIDE_ALL") ? 1 : 0;
+            CU_TRY(launch_long_prepare(dq, r, st));
+            const bool no_rounds = getenv("BN_NO_LONG_ROUNDS") != nullptr;      // test switch: extend all of them
+            for (int round = 0;; round++) {
+                int64_t n_round = n2;
+                if (no_rounds) {
+                    CU_TRY(cudaMemcpyAsync(ws.lr_list.p, all_long, (size_t)n2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+                } else {
+                    CU_TRY(cudaMemsetAsync(ws.lr_best.p, 0xFF, n_cells_lr * sizeof(unsigned long long), st));
+                    CU_TRY(cudaMemsetAsync(r.round_count, 0, sizeof(unsigned long long), st));
+                    CU_TRY(launch_long_select(dq, r, st));
+                    CU_TRY(cudaMemcpyAsync(ws.h_counters + 13, r.round_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+                    CU_TRY(cudaStreamSynchronize(st));
+                    n_round = (int64_t)ws.h_counters[13];
+                    if (stats) stats->kernel_launches += 2;
+                }
+                if (n_round == 0) break;
+                GappedLaunch g{};
+                g.packed = V.d_packed; g.chunks = T.dev.p; g.init = ws.init.p; g.n_init = ws.counters.p + 2;
+                g.max_init = n_init; g.out = ws.gap_out.p;
+                g.todo = ws.lr_list.p; g.n_todo = (int32_t)n_round;
+                if (getenv("BN_WARP_DP")) {         // the lane-per-cell formulation, kept for comparison
+                    const int wpb_dp = gapped_warp_per_block();
+                    const int blocks = (int)std::min<int64_t>((n_round + wpb_dp - 1) / wpb_dp, 148 * 4);
+                    CU_TRY(launch_gapped_warp(dq, g, blocks, st));
+                    if (stats) stats->kernel_launches += 1;
+                } else {
+                    CU_TRY(launch_gapped_long(dq, g, reinterpret_cast<int2 *>(ws.scratch.p), st));
+                    if (stats) stats->kernel_launches += 2;
+                }
+                if (no_rounds) break;
+                CU_TRY(launch_long_commit(dq, r, (int32_t)n_round, st));
                 if (stats) stats->kernel_launches += 1;
-            } else {
-                CU_TRY(ws.scratch.reserve((size_t)(4 * n2 + 16)));
-                CU_TRY(launch_gapped_long(dq, g, reinterpret_cast<int2 *>(ws.scratch.p), st));
-                if (stats) stats->kernel_launches += 2;
             }
         }
     }
-    rc = collect(1, 1, n1);
-    if (rc) return rc;
-    if (n1) {           // tier 2: worst-case scratch for the few that outgrew tier 1
+    // tier 2: worst-case scratch for the few that outgrew a shared-memory ring (their indices are in ws.todo)
+    auto run_tier2 = [&](int64_t count) -> int {
         int32_t max_len = 0;
         for (const auto &c : T.host) max_len = std::max(max_len, c.len);
         int32_t tier;
@@ -1015,36 +1057,41 @@ static int finish_gapped_triaged(Lane &D, Volume &V, Query &Q, ChunkTable &T, in
         const bool warp_greedy = greedy && !affine;
         const int tpb = warp_greedy ? wpb : gapped_threads_per_block();
         const int hpb = warp_greedy ? wpb / 2 : tpb;
-        int64_t blocks = std::min<int64_t>((n1 + hpb - 1) / hpb, 64);
+        int64_t blocks = std::min<int64_t>((count + hpb - 1) / hpb, 64);
         if (affine) blocks = std::max<int64_t>(1, std::min<int64_t>(blocks, ((int64_t)1 << 29) / (per_thread * tpb)));
         CU_TRY(ws.scratch.reserve((size_t)(per_thread * blocks * tpb)));
         GappedLaunch g{};
         g.packed = V.d_packed; g.chunks = T.dev.p; g.init = ws.init.p; g.n_init = ws.counters.p + 2;
         g.max_init = n_init; g.out = ws.gap_out.p;
         g.scratch = ws.scratch.p; g.scratch_ints_per_thread = per_thread; g.tier_d = tier;
-        g.todo = ws.todo.p; g.n_todo = (int32_t)n1; g.grid_blocks = (int32_t)blocks;
+        g.todo = ws.todo.p; g.n_todo = (int32_t)count; g.grid_blocks = (int32_t)blocks;
         if (warp_greedy) CU_TRY(launch_greedy_warp(dq, g, wpb, (int)blocks, false, st));
         else CU_TRY(launch_gapped(dq, g, st));
         if (stats) stats->kernel_launches += 1;
         int64_t left = 0;
-        rc = collect(1, 1, left);
-        if (rc) return rc;
+        const int r2 = collect(1, 1, left);
+        if (r2) return r2;
         if (left) return fail(BN_ERR_OVERFLOW, "gapped extension scratch overflow in tier 2");
-    }
+        return BN_OK;
+    };
+    rc = collect(1, 1, n1);
+    if (rc) return rc;
+    if (n1) { rc = run_tier2(n1); if (rc) return rc; }
     // ---- triage ---------------------------------------------------------------------------------------------
     const size_t n_ctx = (size_t)b.num_contexts, n_cells = T.host.size() * n_ctx;
     int64_t sel_cap = std::max<int64_t>((int64_t)ws.tri_init.cap, std::max<int64_t>(65536, n_init / 8));
     for (int attempt = 0;; attempt++) {
         CU_TRY(ws.tri_ctx.reserve((size_t)n_init));
         CU_TRY(ws.tri_init.reserve((size_t)sel_cap)); CU_TRY(ws.tri_gap.reserve((size_t)sel_cap));
-        CU_TRY(ws.tri_sel_ctx.reserve((size_t)sel_cap));
-        sel_cap = (int64_t)std::min(std::min(ws.tri_init.cap, ws.tri_gap.cap), ws.tri_sel_ctx.cap);
+        CU_TRY(ws.tri_sel_ctx.reserve((size_t)sel_cap)); CU_TRY(ws.tri_sel_idx.reserve((size_t)sel_cap));
+        sel_cap = (int64_t)std::min(std::min(ws.tri_init.cap, ws.tri_gap.cap), std::min(ws.tri_sel_ctx.cap, ws.tri_sel_idx.cap));
         CU_TRY(ws.tri_table.reserve(n_cells));
         CU_TRY(cudaMemsetAsync(ws.tri_table.p, 0, n_cells * sizeof(uint2), st));
         CU_TRY(cudaMemsetAsync(tc + 2, 0, 3 * sizeof(unsigned long long), st));
         TriageLaunch t{};
         t.init = ws.init.p; t.gap = ws.gap_out.p; t.n_init = ws.counters.p + 2; t.max_init = n_init;
         t.ctx_of = ws.tri_ctx.p; t.sel_init = ws.tri_init.p; t.sel_gap = ws.tri_gap.p; t.sel_ctx = ws.tri_sel_ctx.p;
+        t.sel_idx = ws.tri_sel_idx.p;
         t.sel_cap = sel_cap; t.tcount = tc + 2; t.table = ws.tri_table.p; t.n_ctx = (int32_t)n_ctx;
         CU_TRY(launch_triage(dq, t, st));
         if (stats) stats->kernel_launches += 2;
@@ -1061,11 +1108,80 @@ static int finish_gapped_triaged(Lane &D, Volume &V, Query &Q, ChunkTable &T, in
         CU_TRY(cudaMemcpyAsync(G.h_init, ws.tri_init.p, (size_t)G.n_records * sizeof(DevInitHit), cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaMemcpyAsync(G.h_gap, ws.tri_gap.p, (size_t)G.n_records * sizeof(DevGapResult), cudaMemcpyDeviceToHost, st));
     }
+    CU_TRY(ws.h_sel_idx.reserve((size_t)G.n_records + 1));
+    if (G.n_records)
+        CU_TRY(cudaMemcpyAsync(ws.h_sel_idx.p, ws.tri_sel_idx.p, (size_t)G.n_records * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
     const int64_t counted = (int64_t)ws.h_counters[12];
     G.counted_losers = counted;
     G.triaged = true;
     if (G.n_records + counted != n_init) return fail(BN_ERR_CUDA, "triage lost init-HSPs");
+
+    // ---- set-aside long extensions the replay needs after all -------------------------------------------------
+    // The rounds only PREDICT which long extensions the reference skips as contained.  The chunks that hold a
+    // set-aside record are replayed here, exactly as the host phase will replay them; wherever the replay reaches a
+    // set-aside record that is not contained, that extension is made now and the chunk is replayed again.
+    {
+        std::map<int32_t, std::vector<int64_t>> by_chunk;       // chunk -> records, only chunks with a set-aside record
+        for (int64_t k = 0; k < G.n_records; k++)
+            if (G.h_gap[k].status == 3) by_chunk[G.h_init[k].chunk];
+        if (!by_chunk.empty()) {
+            for (int64_t k = 0; k < G.n_records; k++) {
+                auto it = by_chunk.find(G.h_init[k].chunk);
+                if (it != by_chunk.end()) it->second.push_back(k);
+            }
+            struct Rec { HostInit h; int64_t rec; };
+            for (int iteration = 0;; iteration++) {
+                std::vector<int64_t> needs;                     // record positions
+                for (auto &kv : by_chunk) {
+                    std::vector<Rec> recs;
+                    recs.reserve(kv.second.size());
+                    for (int64_t k : kv.second) {
+                        const DevInitHit &h = G.h_init[k];
+                        const DevGapResult &g = G.h_gap[k];
+                        recs.push_back(Rec{HostInit{h.chunk, h.q_off, h.s_off, h.q_start, h.s_start, h.length, h.score, h.order,
+                                                    g.q_start, g.q_stop, g.s_start, g.s_stop, g.score, g.q_seed, g.s_seed, g.status}, k});
+                    }
+                    std::sort(recs.begin(), recs.end(), [](const Rec &x, const Rec &y) {      // Blast_InitHitListSortByScore + emission order
+                        const HostInit &a = x.h, &c = y.h;
+                        if (a.score != c.score) return a.score > c.score;
+                        if (a.s_start != c.s_start) return a.s_start < c.s_start;
+                        if (a.length != c.length) return a.length > c.length;
+                        if (a.q_start != c.q_start) return a.q_start < c.q_start;
+                        return a.order < c.order;
+                    });
+                    std::vector<HostInit> inits(recs.size());
+                    for (size_t j = 0; j < recs.size(); j++) inits[j] = recs[j].h;
+                    std::vector<BnHSP> scratch_out;
+                    BnStats scratch_stats{};
+                    int64_t needed = -1;
+                    replay_gapped(b, T.hchunks[(size_t)kv.first], inits.data(), inits.size(), nullptr, scratch_out, scratch_stats,
+                                  Q.ctx_lite.data(), &needed);
+                    if (needed >= 0) needs.push_back(recs[(size_t)needed].rec);
+                }
+                if (needs.empty()) break;
+                if (iteration > 10000) return fail(BN_ERR_OVERFLOW, "set-aside extensions do not converge");
+                std::vector<int32_t> idx(needs.size());
+                for (size_t j = 0; j < needs.size(); j++) idx[j] = ws.h_sel_idx.p[needs[j]];
+                CU_TRY(ws.todo.reserve(idx.size()));
+                CU_TRY(cudaMemcpyAsync(ws.todo.p, idx.data(), idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+                GappedLaunch g{};
+                g.packed = V.d_packed; g.chunks = T.dev.p; g.init = ws.init.p; g.n_init = ws.counters.p + 2;
+                g.max_init = n_init; g.out = ws.gap_out.p;
+                g.todo = ws.todo.p; g.n_todo = (int32_t)idx.size();
+                CU_TRY(ws.scratch.reserve(4 * idx.size() + 16));
+                CU_TRY(launch_gapped_long(dq, g, reinterpret_cast<int2 *>(ws.scratch.p), st));
+                if (stats) stats->kernel_launches += 2;
+                int64_t overflowed = 0;
+                rc = collect(1, 1, overflowed);                 // a band wider than the ring: tier 2 (its list is rebuilt in ws.todo)
+                if (rc) return rc;
+                if (overflowed) { rc = run_tier2(overflowed); if (rc) return rc; }
+                for (size_t j = 0; j < needs.size(); j++)
+                    CU_TRY(cudaMemcpyAsync(&G.h_gap[needs[j]], ws.gap_out.p + idx[j], sizeof(DevGapResult), cudaMemcpyDeviceToHost, st));
+                CU_TRY(cudaStreamSynchronize(st));
+            }
+        }
+    }
     return BN_OK;
 }
 
@@ -1276,7 +1392,7 @@ static int search_host_phase(const Query &Q, const GpuOut &G, int taps, BnResult
         const DevInitHit &h = h_init[i];
         const DevGapResult &g = h_gap[i];
         return HostInit{h.chunk, h.q_off, h.s_off, h.q_start, h.s_start, h.length, h.score, h.order,
-                        g.q_start, g.q_stop, g.s_start, g.s_stop, g.score, g.q_seed, g.s_seed};
+                        g.q_start, g.q_stop, g.s_start, g.s_stop, g.score, g.q_seed, g.s_seed, g.status};
     };
     // Small result sets (the usual case) take ONE sort of packed integer keys {chunk, score desc, s_start,
     // length desc, q_start, emission order} - grouping and the per-chunk Blast_InitHitListSortByScore order
@@ -2392,7 +2508,7 @@ int bn_get_gapped_score(int vol_handle, int query_handle, int32_t oid, int32_t c
         const DevInitHit &h = h_init[i];
         const DevGapResult &g = h_gap[i];
         inits[i] = HostInit{h.chunk, h.q_off, h.s_off, h.q_start, h.s_start, h.length, h.score, h.order,
-                            g.q_start, g.q_stop, g.s_start, g.s_stop, g.score, g.q_seed, g.s_seed};
+                            g.q_start, g.q_stop, g.s_start, g.s_stop, g.score, g.q_seed, g.s_seed, g.status};
     }
     sort_init_hits(inits);
     std::vector<BnHSP> out;

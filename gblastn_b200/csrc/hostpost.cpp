@@ -443,8 +443,9 @@ static int32_t ctx_search_lite(const CtxLite *L, int32_t n_ctx, int32_t n)
 }
 
 void replay_gapped(const BnQueryBatch &b, const HostChunk &ch, const HostInit *init, size_t n,
-                   const int32_t *low_score, std::vector<BnHSP> &out, BnStats &stats, const CtxLite *lite)
+                   const int32_t *low_score, std::vector<BnHSP> &out, BnStats &stats, const CtxLite *lite, int64_t *needed)
 {
+    if (needed) *needed = -1;
     if (n == 0) return;
     std::vector<CtxLite> local;
     if (!lite) { local = make_ctx_lite(b); lite = local.data(); }
@@ -484,6 +485,10 @@ void replay_gapped(const BnQueryBatch &b, const HostChunk &ch, const HostInit *i
             st = (int32_t)trees.size() - 1;
         }
         if (st >= 0 && trees[(size_t)st].contains(t, b.min_diag_separation)) continue;
+        if (h.g_status == 3) {               // the reference extends here, and the extension was set aside
+            if (needed) { *needed = (int64_t)i; return; }
+            continue;
+        }
         ++stats.gap_extensions;
         if (h.g_score >= c.gapped_cutoff) {
             BnHSP o;

@@ -19,6 +19,7 @@ struct HostInit {          // one init-HSP with its speculative gapped result
     uint32_t order;
     // gapped result
     int32_t g_q_start, g_q_stop, g_s_start, g_s_stop, g_score, g_q_seed, g_s_seed;
+    int32_t g_status = 0;  // 3: the extension was set aside (expected to be contained), there is no result
 };
 
 struct HostChunk { int32_t oid, chunk_off, len; };
@@ -68,9 +69,12 @@ struct CtxLite { int32_t query_offset, gapped_cutoff, query_index, strand_ctx; }
 std::vector<CtxLite> make_ctx_lite(const BnQueryBatch &b);
 
 // lite: optional compact context table from make_ctx_lite (built per call when NULL)
+// needed (optional): when the replay reaches an init-HSP that is NOT contained and whose extension was set aside
+// (g_status 3), its position in init[] is stored there and the replay of the chunk stops (what follows depends on
+// that extension); without `needed` such a record is an internal error and is skipped.
 void replay_gapped(const BnQueryBatch &b, const HostChunk &ch, const HostInit *init, size_t n,
                    const int32_t *low_score, std::vector<BnHSP> &out, BnStats &stats,
-                   const CtxLite *lite = nullptr);
+                   const CtxLite *lite = nullptr, int64_t *needed = nullptr);
 
 // the same with ONE tree for all strands, exactly as the reference lays it out (kept for bn_selftest_replay)
 void replay_gapped_single_tree(const BnQueryBatch &b, const HostChunk &ch, const HostInit *init, size_t n,

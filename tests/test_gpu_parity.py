@@ -897,3 +897,30 @@ def test_device_triage_changes_nothing(name, monkeypatch):
         assert a["stats"]["kernel_launches"] > b["stats"]["kernel_launches"], "the triage kernels did not run"
     finally:
         Q.free(); V.free()
+
+
+@pytest.mark.parametrize("name", ["c3_scaled_blastn_10kb", "blastn_bridged_segments", "blastn_mb11_dp"])
+@pytest.mark.parametrize("mode", ["rounds", "set_aside_all", "no_rounds"])
+def test_long_extensions_in_rounds(name, mode, monkeypatch):
+    """blastn mode: the long gapped extensions are made in rounds — per (chunk, context) the best pending one, the ones
+    inside a box made so far set aside — and the host replay asks for any set-aside extension it needs after all.
+    `set_aside_all` makes the prediction deliberately wrong (everything but the first box of a group is set aside) so the
+    replay has to ask; `no_rounds` extends them all.  Same lists and counters as the reference every time."""
+    from gblastn_b200 import engine as E
+    from oracle import portdriver as P
+    r, h, vol = _setup(name)
+    V, Q = E.Volume(vol), E.Query(h)
+    try:
+        monkeypatch.setenv("BN_FORCE_GENERAL", "1")
+        monkeypatch.setenv("BN_TRIAGE_MIN", "1")
+        if mode == "set_aside_all":
+            monkeypatch.setenv("BN_LONG_SET_ASIDE_ALL", "1")
+        if mode == "no_rounds":
+            monkeypatch.setenv("BN_NO_LONG_ROUNDS", "1")
+        a = E.prelim_search(V, Q)
+        assert np.array_equal(P.final_table(a["hsps"]), r["final"])
+        st = a["stats"]
+        assert (st["lookup_hits"], st["good_init_extends"], st["gap_extensions"], st["good_extensions"]) == \
+               (r["lookup_hits"], r["good_init_extends"], r["gap_extensions"], r["good_extensions"])
+    finally:
+        Q.free(); V.free()
