@@ -51,6 +51,8 @@ struct DevQuery {
     const uint4 *cinfo;                    // MB compact table: per occupied cell (in cell order) TWO entries = the qinfo
                                            // of its first and second chain element, .x = {qp, bit 31: chain continues}
     const uint4 *qinfo;                    // MB: per query position {next_pos, 16 bases left, 16 right, ambiguity}
+    const uint32_t *sig;                   // MB: per occupied cell (by rank) the 4 query bases on either side of its first chain
+                                           // element's lookup word: bits 0-7 left, 8-15 right, bit 16 = the chain has more elements
     const int16_t *backbone, *overflow;    // SmallNa
     const int4 *na_cells;                  // eNaLookupTable: thick backbone {num_used, entries[3] | overflow_cursor}
     const int32_t *na_overflow;
@@ -242,6 +244,7 @@ int scan_positions_per_block();
 int scan_tile_cap(int scan_step, int word_length);
 int scan_max_block_chunks();
 int scan_tile_margin();
+cudaError_t launch_build_sig(const uint4 *cinfo, int64_t n_ranks, uint32_t *sig, cudaStream_t st);
 cudaError_t launch_build_qinfo(const DevQuery &q, const int32_t *next_pos, int32_t concat_len, const int32_t *heads,
                                int64_t n_heads, uint32_t *indexed_scratch, uint4 *qinfo, cudaStream_t st);
 

@@ -248,6 +248,7 @@ struct QueryDev {
     uint2 *prk = nullptr;
     uint4 *cinfo = nullptr;
     uint4 *qinfo = nullptr;
+    uint32_t *sig = nullptr;
     DevQuery view{};
     bool ready = false;
 };
@@ -302,7 +303,7 @@ static Gpu *device_at(int d)
 static void free_query_dev(QueryDev &q, cudaStream_t st)
 {
     void *ptrs[] = {q.query, q.ctx, q.next_pos, q.backbone, q.overflow, q.na_cells, q.na_overflow,
-                    q.score_table, q.matrix, q.qpk, q.prk, q.cinfo, q.qinfo};
+                    q.score_table, q.matrix, q.qpk, q.prk, q.cinfo, q.qinfo, q.sig};
     for (void *p : ptrs) if (p) cudaFreeAsync(p, st);
     q = QueryDev{};
 }
@@ -447,6 +448,10 @@ static int query_to_device(Query &Q, const BnQueryBatch &src, int d, Lane *dev, 
             CU_TRY(launch_build_compact(t_hashtable, t_presence, t_prefix, nwords, qd.prk, qd.qinfo, qd.cinfo, st));
         v.prk = qd.prk;
         v.cinfo = qd.cinfo;
+        // flank signatures of the first chain elements (scan kernel pre-filter); unfilled ranks are never addressed
+        CU_TRY(dev_alloc(&qd.sig, (size_t)b.concat_len + 2, st));
+        CU_TRY(launch_build_sig(qd.cinfo, (int64_t)b.concat_len + 2, qd.sig, st));
+        v.sig = getenv("BN_NO_SIG") ? nullptr : qd.sig;
     }
     {
         void *tmp[] = {t_hashtable, t_first_qp, t_segs, t_presence, t_counts, t_prefix};

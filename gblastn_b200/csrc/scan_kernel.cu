@@ -651,9 +651,20 @@ scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ S
         __syncwarp();
 
         // ---- phase B: the warp's candidates, one per lane ----------------------------------------------
+        // mini-extension pre-filter: a hit reaches the full word only if the 4 bases right of the lookup word all match
+        // (when fewer than 4 match on the left, ext_to - 3 >= 4 are still owed on the right) or the 4 on the left do
+        const bool use_sig = !DIRECT && !s.raw_pairs && q.sig != nullptr && (q.word_length - lut) >= 7;
         for (int ci = lane; ci < ncand; ci += 32) {
             const uint2 cd = wcand[ci];
             const int32_t gl = (int32_t)(cd.y & 2047u), k = (int32_t)(cd.y >> 11);
+            if (use_sig) {
+                // 4 bytes per candidate from a table that stays in L2, instead of the 32-byte chain record from HBM:
+                // nine out of ten candidates of a megablast batch end here
+                const uint32_t sg = __ldg(&q.sig[cd.x]);
+                const int32_t p0 = ct_pfirst[k] + (gl - ct_start[k]) * step, tb0 = ct_tbase[k];
+                const uint32_t wl = tile_win(tile, tb0 + p0 - 4) >> 24, wr = tile_win(tile, tb0 + p0 + lut) >> 24;
+                if (!(sg & 0x10000u) && wl != (sg & 0xFFu) && wr != ((sg >> 8) & 0xFFu)) { ++my_lookup_hits; continue; }
+            }
             // first two chain elements of the cell in ONE 32-byte sector: {qp | more << 31, left 16, right 16, ambiguity} x 2
             uint4 qi, qi1;
             ld_cinfo_pair(q.cinfo + 2 * (size_t)cd.x, qi, qi1);
@@ -706,6 +717,21 @@ scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ S
     // one atomic per warp for the lookup-hit statistic (BlastUngappedStats.lookup_hits); REDUX.SUM
     const uint32_t warp_hits = __reduce_add_sync(0xffffffffu, my_lookup_hits);
     if (lane == 0 && warp_hits) atomicAdd(&s.counters[1], (unsigned long long)warp_hits);
+}
+
+// sig[rank]: see DevQuery::sig; from the cell's first chain record (cinfo[2 rank]: .y = 16 bases left of the word, the
+// nearest in the low bits; .z = 16 bases right of it, the nearest in the high bits; .x bit 31 = chain continues)
+__global__ void build_sig_kernel(const uint4 *cinfo, int64_t n_ranks, uint32_t *sig)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_ranks) return;
+    const uint4 c = cinfo[2 * r];
+    sig[r] = (c.y & 0xFFu) | ((c.z >> 24) << 8) | ((c.x >> 31) << 16);
+}
+cudaError_t launch_build_sig(const uint4 *cinfo, int64_t n_ranks, uint32_t *sig, cudaStream_t st)
+{
+    if (n_ranks > 0) build_sig_kernel<<<(unsigned)((n_ranks + 255) / 256), 256, 0, st>>>(cinfo, n_ranks, sig);
+    return cudaGetLastError();
 }
 
 // qinfo[qp] for every 1-based query position qp: {next_pos[qp], 16 bases left of the lookup word that
