@@ -1446,7 +1446,7 @@ static int search_host_phase(const Query &Q, const GpuOut &G, int taps, BnResult
         }
     }
 
-    std::vector<BnHSP> final_hsps, gapped_tap, comb;
+    std::vector<BnHSP> final_hsps, gapped_tap;
     std::vector<BnInitHit> init_tap;
     LowScoreTracker own_tracker(b);
     LowScoreTracker &tracker = sh ? *sh->tracker : own_tracker;
@@ -1473,57 +1473,78 @@ static int search_host_phase(const Query &Q, const GpuOut &G, int taps, BnResult
     const bool parallel = n_in >= 16384 && groups.size() >= 2 && bounds_fixed;
     // losers the device counted instead of shipping them: each is an extension the reference makes and drops
     stats.gap_extensions += G.counted_losers;
+    // runs of consecutive groups (chunks) of one subject: a subject's chunk lists are merged in order, subjects are
+    // independent of each other
+    struct Run { size_t lo, hi; };
+    std::vector<Run> runs;
+    for (size_t gi = 0; gi < groups.size(); gi++) {
+        if (!runs.empty() && T->hchunks[groups[gi].chunk].oid == T->hchunks[groups[runs.back().lo].chunk].oid) runs.back().hi = gi + 1;
+        else runs.push_back(Run{gi, gi + 1});
+    }
+    std::vector<std::vector<BnHSP>> run_out(parallel ? runs.size() : 0);
+    // the chunk lists of one subject -> its final list: absolute coordinates, chunk merge, E-values, reap
+    auto finish_run = [&](const Run &r, std::vector<BnHSP> &list) {
+        for (size_t gi = r.lo; gi < r.hi; gi++) {
+            const HostChunk &ch = T->hchunks[groups[gi].chunk];
+            GroupOut &o = gout[gi];
+            for (auto &h : o.fresh) { h.s_off += ch.chunk_off; h.s_end += ch.chunk_off; h.s_gapped_start += ch.chunk_off; }
+            merge_chunk_lists(list, o.fresh, ch.chunk_off, ch.chunk_off == 0 ? 0 : BN_DBSEQ_CHUNK_OVERLAP);
+            std::vector<BnHSP>().swap(o.fresh);
+        }
+        evalues_and_reap(b, list);
+        if (oid_base) for (auto &h : list) h.oid += oid_base;
+    };
     if (parallel) {
+        // whole subjects per worker: replay, list post-processing, merge and E-values all run in parallel
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        const size_t n_threads = std::min<size_t>(std::min<size_t>(groups.size(), hw), 16);
+        const size_t n_threads = std::min<size_t>(std::min<size_t>(runs.size(), hw), 16);
         std::atomic<size_t> next{0};
         std::vector<std::thread> pool;
-        auto worker = [&]() { for (size_t gi; (gi = next.fetch_add(1)) < groups.size();) do_group(gi); };
+        auto worker = [&]() {
+            for (size_t ri; (ri = next.fetch_add(1)) < runs.size();) {
+                for (size_t gi = runs[ri].lo; gi < runs[ri].hi; gi++) do_group(gi);
+                if (!(taps & (BN_TAP_INIT | BN_TAP_GAPPED))) finish_run(runs[ri], run_out[ri]);
+            }
+        };
         for (size_t t = 1; t < n_threads; t++) pool.emplace_back(worker);
         worker();
         for (auto &th : pool) th.join();
     }
     t_sort = now_ms() - th0;
 
-    int32_t cur_oid = -1;
-    auto finish_oid = [&]() {
-        if (cur_oid < 0) return;
-        double ta = now_ms();
-        evalues_and_reap(b, comb);
-        t_eval += now_ms() - ta; ta = now_ms();
-        if (!comb.empty()) {
-            stats.good_extensions += (int64_t)comb.size();
-            if (oid_base) for (auto &h : comb) h.oid += oid_base;
-            final_hsps.insert(final_hsps.end(), comb.begin(), comb.end());
-            if (!bounds_fixed) tracker.subject_done(b, comb);      // the hit lists only matter when a bound can move
+    for (size_t ri = 0; ri < runs.size(); ri++) {
+        std::vector<BnHSP> serial_list;
+        for (size_t gi = runs[ri].lo; gi < runs[ri].hi; gi++) {
+            const size_t c = groups[gi].chunk, lo = groups[gi].lo, hi = groups[gi].hi;
+            const HostChunk &ch = T->hchunks[c];
+            double ta = now_ms();
+            if (!parallel) do_group(gi);                  // in subject order: the bounds may move between subjects
+            GroupOut &o = gout[gi];
+            stats.gap_extensions += o.stats.gap_extensions;
+            t_replay += now_ms() - ta;
+            if (taps & BN_TAP_INIT)
+                for (size_t k = lo; k < hi; k++)
+                    init_tap.push_back(BnInitHit{ch.oid + oid_base, ch.chunk_off, inits[k].q_off, inits[k].s_off,
+                                                 inits[k].q_start, inits[k].s_start, inits[k].length,
+                                                 inits[k].score});
+            if (taps & BN_TAP_GAPPED) {
+                if (oid_base) for (auto &h : o.tap) h.oid += oid_base;
+                gapped_tap.insert(gapped_tap.end(), o.tap.begin(), o.tap.end());
+            }
         }
+        double ta = now_ms();
+        const bool done_by_worker = parallel && !(taps & (BN_TAP_INIT | BN_TAP_GAPPED));
+        std::vector<BnHSP> &list = done_by_worker ? run_out[ri] : serial_list;
+        if (!done_by_worker) finish_run(runs[ri], list);
+        t_merge += now_ms() - ta; ta = now_ms();
+        if (!list.empty()) {
+            stats.good_extensions += (int64_t)list.size();
+            final_hsps.insert(final_hsps.end(), list.begin(), list.end());
+            if (!bounds_fixed) tracker.subject_done(b, list);      // the hit lists only matter when a bound can move
+        }
+        std::vector<BnHSP>().swap(list);
         t_track += now_ms() - ta;
-        comb.clear();
-    };
-    for (size_t gi = 0; gi < groups.size(); gi++) {
-        const size_t c = groups[gi].chunk, lo = groups[gi].lo, hi = groups[gi].hi;
-        const HostChunk &ch = T->hchunks[c];
-        if (ch.oid != cur_oid) { finish_oid(); cur_oid = ch.oid; }
-        double ta = now_ms();
-        if (!parallel) do_group(gi);                  // in subject order: the bounds may move between subjects
-        GroupOut &o = gout[gi];
-        stats.gap_extensions += o.stats.gap_extensions;
-        t_replay += now_ms() - ta; ta = now_ms();
-        if (taps & BN_TAP_INIT)
-            for (size_t k = lo; k < hi; k++)
-                init_tap.push_back(BnInitHit{ch.oid + oid_base, ch.chunk_off, inits[k].q_off, inits[k].s_off,
-                                             inits[k].q_start, inits[k].s_start, inits[k].length,
-                                             inits[k].score});
-        if (taps & BN_TAP_GAPPED) {
-            if (oid_base) for (auto &h : o.tap) h.oid += oid_base;
-            gapped_tap.insert(gapped_tap.end(), o.tap.begin(), o.tap.end());
-        }
-        for (auto &h : o.fresh) { h.s_off += ch.chunk_off; h.s_end += ch.chunk_off; h.s_gapped_start += ch.chunk_off; }
-        merge_chunk_lists(comb, o.fresh, ch.chunk_off, ch.chunk_off == 0 ? 0 : BN_DBSEQ_CHUNK_OVERLAP);
-        std::vector<BnHSP>().swap(o.fresh);
-        t_merge += now_ms() - ta;
     }
-    finish_oid();
     stats.ms_host = now_ms() - th0;
     if (trace)
     {
