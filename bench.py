@@ -129,7 +129,7 @@ def run_named_config(name, shard, engine, setup, torch, steps=3, with_reference=
                 k = min(int(w["sample_oids"]), vol.n_seqs)
                 sub = synth.Volume(vol.packed, vol.byte_off[:k], vol.seq_len[:k])
                 cores = os.cpu_count() or 1
-                threads = max(1, min(cores, k, int(w["ref_threads"])))
+                threads = max(1, min(cores, k, int(w.get("ref_threads", 1))))
                 cfg = R.default_config(w["task"], db_length=w["db_length"], db_num_seqs=w["db_num_seqs"], num_threads=threads)
                 t0 = time.perf_counter()
                 r = R.search(qs, sub, cfg, masks=w["masks"])

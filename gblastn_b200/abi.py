@@ -43,7 +43,18 @@ class BnQueryBatch(C.Structure):
         ("evalue_cutoff", C.c_double), ("low_score_perc", C.c_double),
         ("lookup_segments", C.c_void_p), ("n_lookup_segments", C.c_int32),
         ("na_backbone", C.c_void_p), ("na_overflow", C.c_void_p), ("na_overflow_len", C.c_int64),
+        ("percent_identity", C.c_double), ("min_hit_length", C.c_int32), ("reserved0", C.c_int32),
     ]
+
+
+class BnJob(C.Structure):
+    _fields_ = [("vol_handle", C.c_int), ("query_handle", C.c_int), ("batch", C.POINTER(BnQueryBatch)),
+                ("packed", C.c_void_p), ("packed_bytes", C.c_int64), ("seq_byte_off", C.c_void_p),
+                ("seq_len", C.c_void_p), ("n_seq", C.c_int32), ("gap_x_dropoff_final", C.c_int32)]
+
+
+class BnTracebackOut(C.Structure):
+    _fields_ = [("hsps", C.c_void_p), ("n_hsps", C.c_int64), ("ops", C.c_void_p), ("n_ops", C.c_int64)]
 
 
 class BnOffsetPair(C.Structure):
@@ -94,7 +105,8 @@ class BnSetupOptions(C.Structure):
                 ("low_score_perc", C.c_double),
                 ("db_length", C.c_int64), ("db_num_seqs", C.c_int32),
                 ("avg_subject_length", C.c_int32), ("device_lookup", C.c_int32),
-                ("hsp_num_max", C.c_int32)]
+                ("hsp_num_max", C.c_int32),
+                ("percent_identity", C.c_double), ("min_hit_length", C.c_int32)]
 
 
 HSP_DTYPE = np.dtype([("oid", "<i4"), ("context", "<i4"), ("q_off", "<i4"), ("q_end", "<i4"),

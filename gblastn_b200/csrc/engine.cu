@@ -14,6 +14,7 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <deque>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -118,7 +119,7 @@ struct Workspace {
     unsigned long long *h_counters = nullptr;   // pinned
     PinnedBuf<DevInitHit> h_init;
     PinnedBuf<DevGapResult> h_gap;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // stage timers, created once
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // stage timers (0..5) + "search done" (6), created once
     void release()
     {
         h_init.release(); h_gap.release(); h_table.release();
@@ -342,7 +343,8 @@ cudaError_t build_mb_lookup_device(const uint8_t *d_query, int32_t concat_len, i
 // `after_h2d` (optional) runs once every host->device copy of the batch has been queued and before the
 // derivation kernels are: the host-buffer entry point starts the volume upload there, so the small
 // query copies are not stuck behind it in the copy engine and the table build overlaps the upload.
-static int query_to_device(Query &Q, const BnQueryBatch &src, int d, Lane *dev, const std::function<int()> *after_h2d = nullptr)
+static int query_to_device(Query &Q, const BnQueryBatch &src, int d, Lane *dev, const std::function<int()> *after_h2d = nullptr,
+                           bool keep_async = false)
 {
     QueryDev &qd = Q.dev[d];
     if (qd.ready) return BN_OK;
@@ -457,7 +459,8 @@ static int query_to_device(Query &Q, const BnQueryBatch &src, int d, Lane *dev, 
         void *tmp[] = {t_hashtable, t_first_qp, t_segs, t_presence, t_counts, t_prefix};
         for (void *p : tmp) if (p) CU_TRY(cudaFreeAsync(p, st));
     }
-    CU_TRY(cudaStreamSynchronize(st));     // caller's arrays may go away after bn_query_load returns
+    // caller's arrays may go away after bn_query_load returns (a pipeline's stay until its call does: keep_async)
+    if (!keep_async) CU_TRY(cudaStreamSynchronize(st));
     qd.ready = true;
     return BN_OK;
 }
@@ -1218,10 +1221,17 @@ static int run_gapped(Lane &D, Volume &V, Query &Q, ChunkTable &T, int64_t n_ini
 // trusted) when the device refused the fast path or a buffer was too small: the caller then runs the
 // general path.
 // ------------------------------------------------------------------------------------------------
-static int run_fused(Lane &D, Volume &V, Query &Q, ChunkTable &T, StageCounts &cnt, BnStats &stats,
-                     DevInitHit *&h_init, DevGapResult *&h_gap, bool *redo)
+// The fused pipeline of one search in two halves, so that a caller can queue the next search's kernels before it
+// waits for this one (bn_prelim_search_jobs): fused_enqueue launches scan ... gapped + the result mirror without any
+// host synchronisation and records `done`; fused_complete waits for that event and finishes on the host.
+struct FusedState {
+    int64_t cap = 0, n_limit = 0, init_cap = 0;
+    int spec_enabled = 0;
+    cudaEvent_t done = nullptr;        // ws.ev[6]: recorded behind the result mirror
+};
+
+static int fused_enqueue(Lane &D, Volume &V, Query &Q, ChunkTable &T, FusedState &F)
 {
-    *redo = false;
     Workspace &ws = D.ws();
     cudaStream_t st = D.stream;
     const DevQuery &dq = Q.dev[V.device].view;
@@ -1244,6 +1254,7 @@ static int run_fused(Lane &D, Volume &V, Query &Q, ChunkTable &T, StageCounts &c
     CU_TRY(ws.buckets.reserve((size_t)nb));
     CU_TRY(ws.init.reserve((size_t)std::max<int64_t>(4096, n_limit / 4)));
     const int64_t init_cap = (int64_t)ws.init.cap;
+    F.cap = cap; F.n_limit = n_limit; F.init_cap = init_cap;
 
     Timer t_scan(st, ws, 0), t_ext(st, ws, 1), t_gap(st, ws, 2);
     CU_TRY(cudaMemsetAsync(ws.counters.p, 0, 8 * sizeof(unsigned long long), st));
@@ -1266,6 +1277,7 @@ static int run_fused(Lane &D, Volume &V, Query &Q, ChunkTable &T, StageCounts &c
     L.keys_tmp = ws.keys_tmp.p; L.hits_out = ws.hits_b.p; L.keys_out = ws.keys_b.p;
     L.heads = ws.heads.p; L.leaders = ws.leaders.p; L.spec = ws.spec.p; L.counters = ws.counters.p;
     L.n_limit = n_limit; L.gbits = gbits; L.spec_enabled = Q.batch.window_size > 0 ? 0 : 1;
+    F.spec_enabled = L.spec_enabled;
     CU_TRY(launch_bucket_group(L, st));
     ExtendLaunch e{};
     e.packed = V.d_packed; e.chunks = T.dev.p; e.ranges = T.ranges_dev.p; e.hits = ws.hits_b.p;
@@ -1282,22 +1294,44 @@ static int run_fused(Lane &D, Volume &V, Query &Q, ChunkTable &T, StageCounts &c
     // counters + results into the pinned mirrors by one kernel, then the only synchronisation of the step
     CU_TRY(launch_mirror_results(ws.init.p, ws.gap_out.p, ws.counters.p, init_cap, ws.h_init.p, ws.h_gap.p,
                                  ws.h_counters, st));
-    CU_TRY(cudaStreamSynchronize(st));
+    t_gap.stop();
+    if (!ws.ev[6]) CU_TRY(cudaEventCreateWithFlags(&ws.ev[6], cudaEventDisableTiming));
+    F.done = ws.ev[6];
+    CU_TRY(cudaEventRecord(F.done, st));
+    return BN_OK;
+}
+
+static int fused_complete(Lane &D, Volume &V, Query &Q, ChunkTable &T, const FusedState &F, StageCounts &cnt, BnStats &stats,
+                          DevInitHit *&h_init, DevGapResult *&h_gap, bool *redo)
+{
+    *redo = false;
+    Workspace &ws = D.ws();
+    CU_TRY(cudaEventSynchronize(F.done));
     cnt.n_hits = (int64_t)ws.h_counters[0];
     cnt.lookup_hits = (int64_t)ws.h_counters[1];
     cnt.n_init = (int64_t)ws.h_counters[2];
     cnt.n_extended = (int64_t)ws.h_counters[3];
-    if (cnt.n_hits > cap) {                    // scan output overflowed: grow for the general path's retry
+    if (cnt.n_hits > F.cap) {                    // scan output overflowed: grow for the general path's retry
         CU_TRY(ws.hits_a.reserve((size_t)(cnt.n_hits + cnt.n_hits / 16 + 1024)));
         CU_TRY(ws.keys_a.reserve((size_t)(cnt.n_hits + cnt.n_hits / 16 + 1024)));
     }
-    if (cnt.n_hits > cap || ws.h_counters[6] || cnt.n_init > init_cap) { *redo = true; return BN_OK; }
-    rc = finish_gapped(D, V, Q, T, cnt.n_init, h_init, h_gap, &stats, true);
+    if (cnt.n_hits > F.cap || ws.h_counters[6] || cnt.n_init > F.init_cap) { *redo = true; return BN_OK; }
+    Timer t_scan(D.stream, ws, 0), t_ext(D.stream, ws, 1), t_gap(D.stream, ws, 2);
+    const double ms_scan = t_scan.ms(), ms_ext = t_ext.ms(), ms_gap = t_gap.ms();      // before tier 2 re-uses the stream
+    int rc = finish_gapped(D, V, Q, T, cnt.n_init, h_init, h_gap, &stats, true);
     if (rc) return rc;
-    t_gap.stop();
-    stats.kernel_launches += 1 + 1 + (L.spec_enabled ? 2 : 1) + 1 + 1;      // scan, grouping, extension, gapped, result mirror
-    stats.ms_scan += t_scan.ms(); stats.ms_extend += t_ext.ms(); stats.ms_gapped += t_gap.ms();
+    stats.kernel_launches += 1 + 1 + (F.spec_enabled ? 2 : 1) + 1 + 1;      // scan, grouping, extension, gapped, result mirror
+    stats.ms_scan += ms_scan; stats.ms_extend += ms_ext; stats.ms_gapped += ms_gap;
     return BN_OK;
+}
+
+static int run_fused(Lane &D, Volume &V, Query &Q, ChunkTable &T, StageCounts &cnt, BnStats &stats,
+                     DevInitHit *&h_init, DevGapResult *&h_gap, bool *redo)
+{
+    FusedState F;
+    int rc = fused_enqueue(D, V, Q, T, F);
+    if (rc) return rc;
+    return fused_complete(D, V, Q, T, F, cnt, stats, h_init, h_gap, redo);
 }
 
 template <typename T>
@@ -1309,31 +1343,52 @@ static T *to_malloc(const std::vector<T> &v)
     return p;
 }
 
+// The GPU side of one search in two halves (see FusedState): search_gpu_begin builds / finds the chunk table and, for
+// the searches the fused pipeline serves, queues all of its kernels; search_gpu_end waits for them and runs whatever
+// is left (the general path from the start when the fused one did not apply or overflowed).
+struct SearchPending {
+    bool fused = false;
+    bool allow_triage = false;
+    FusedState F;
+    double tw0 = 0;
+};
+
 // allow_triage: the caller's host phase takes no taps and its low_score bounds cannot move during the search
-static int search_gpu_phase(Lane &D, Volume &V, Query &Q, int32_t oid_begin, int32_t oid_end, BnResults *out, GpuOut &G,
-                            bool allow_triage = false)
+static int search_gpu_begin(Lane &D, Volume &V, Query &Q, int32_t oid_begin, int32_t oid_end, BnResults *out, GpuOut &G,
+                            bool allow_triage, SearchPending &P)
 {
     memset(out, 0, sizeof *out);
     G.t0 = now_ms();
     G.oid_begin = oid_begin; G.oid_end = oid_end;
+    P.allow_triage = allow_triage;
     CU_TRY(cudaSetDevice(D.id));
     if (!Q.dev[V.device].ready) return fail(BN_ERR_INVALID, "query batch is not loaded on the volume's device");
-    int rc;
     std::shared_ptr<ChunkTable> &T = G.T;
-    rc = build_chunk_table(V, Q, oid_begin, oid_end, D, &T);
+    int rc = build_chunk_table(V, Q, oid_begin, oid_end, D, &T);
     if (rc) return rc;
-    BnStats &stats = out->stats;
-    stats.subject_bases_scanned = T->total_bases;
+    out->stats.subject_bases_scanned = T->total_bases;
     if (V.ready) CU_TRY(cudaStreamWaitEvent(D.stream, V.ready, 0));
+    P.tw0 = now_ms();
+    const bool general = Q.batch.container_type != BN_DIAG_HASH || Q.fast_path_refused || T->total_pos <= 0 ||
+                         serial_replay(Q.batch) || getenv("BN_FORCE_GENERAL") != nullptr;
+    P.fused = !general;
+    if (P.fused) return fused_enqueue(D, V, Q, *T, P.F);
+    return BN_OK;
+}
 
+static int search_gpu_end(Lane &D, Volume &V, Query &Q, BnResults *out, GpuOut &G, SearchPending &P)
+{
+    CU_TRY(cudaSetDevice(D.id));
+    std::shared_ptr<ChunkTable> &T = G.T;
+    BnStats &stats = out->stats;
     StageCounts &cnt = G.cnt;
-    const double tw0 = now_ms();
+    const double tw0 = P.tw0;
     double tw1 = tw0;
-    bool general = Q.batch.container_type != BN_DIAG_HASH || Q.fast_path_refused || T->total_pos <= 0 ||
-                   serial_replay(Q.batch) || getenv("BN_FORCE_GENERAL") != nullptr;
-    if (!general) {
+    int rc;
+    bool general = !P.fused;
+    if (P.fused) {
         bool redo = false;
-        rc = run_fused(D, V, Q, *T, cnt, stats, G.h_init, G.h_gap, &redo);
+        rc = fused_complete(D, V, Q, *T, P.F, cnt, stats, G.h_init, G.h_gap, &redo);
         if (rc) return rc;
         if (redo) { general = true; Q.fast_path_refused = true; cnt = StageCounts{}; }
         tw1 = now_ms();
@@ -1347,7 +1402,7 @@ static int search_gpu_phase(Lane &D, Volume &V, Query &Q, int32_t oid_begin, int
         const int64_t triage_min = getenv("BN_TRIAGE_MIN") ? atoll(getenv("BN_TRIAGE_MIN")) : 100000;
         bool strands_are_contexts = true;
         for (int32_t c = 0; c < Q.batch.num_contexts && strands_are_contexts; c++) strands_are_contexts = Q.ctx_lite[(size_t)c].strand_ctx == c;
-        const bool triage = allow_triage && !no_triage && cnt.n_init >= triage_min && strands_are_contexts &&
+        const bool triage = P.allow_triage && !no_triage && cnt.n_init >= triage_min && strands_are_contexts &&
                             (int64_t)T->host.size() * Q.batch.num_contexts <= ((int64_t)1 << 22);
         rc = run_gapped(D, V, Q, *T, cnt.n_init, G.h_init, G.h_gap, &stats, triage ? &G : nullptr);
         if (rc) return rc;
@@ -1359,6 +1414,15 @@ static int search_gpu_phase(Lane &D, Volume &V, Query &Q, int32_t oid_begin, int
     stats.init_extends = cnt.n_init;        // the reference counts the extensions that were saved (hit_ready, core/na_ungapped.c:1000-1004)
     stats.good_init_extends = cnt.n_init;
     return BN_OK;
+}
+
+static int search_gpu_phase(Lane &D, Volume &V, Query &Q, int32_t oid_begin, int32_t oid_end, BnResults *out, GpuOut &G,
+                            bool allow_triage = false)
+{
+    SearchPending P;
+    int rc = search_gpu_begin(D, V, Q, oid_begin, oid_end, out, G, allow_triage, P);
+    if (rc) return rc;
+    return search_gpu_end(D, V, Q, out, G, P);
 }
 
 // Host replay of one search (containment filter, per-chunk list post-processing, chunk merge, E-values,
@@ -1699,7 +1763,7 @@ int bn_init(int n_gpu, const int *device_ids)
     else for (int i = 0; i < n_gpu; i++) ids.push_back(device_ids[i]);
     // lanes per device: concurrent callers beyond this number wait for a lane (BN_LANES, default 4)
     int n_lanes = 4;
-    if (const char *e = getenv("BN_LANES")) n_lanes = std::max(2, std::min(16, atoi(e)));      // the batch pipeline needs two
+    if (const char *e = getenv("BN_LANES")) n_lanes = std::max(3, std::min(16, atoi(e)));      // the job pipeline needs two + one for its traceback stage
     for (int id : ids) {
         if (id < 0 || id >= count) return fail(BN_ERR_INVALID, "device id out of range");
         auto d = std::make_unique<Gpu>();
@@ -2042,7 +2106,8 @@ int bn_db_free(int h)
 
 // `held`: a lane of device hook_device the caller already owns (its stream then carries the table build)
 static int query_load_impl(const BnQueryBatch *b, std::shared_ptr<Query> *out, int hook_device,
-                           const std::function<int()> *after_h2d, Lane *held = nullptr, bool hook_device_only = false)
+                           const std::function<int()> *after_h2d, Lane *held = nullptr, bool hook_device_only = false,
+                           bool keep_async = false)
 {
     int rc = ensure_init();
     if (rc) return rc;
@@ -2105,7 +2170,7 @@ static int query_load_impl(const BnQueryBatch *b, std::shared_ptr<Query> *out, i
         LaneLock own;
         Lane *L = ((int)d == hook_device) ? held : nullptr;
         if (!L) { own = LaneLock(*g_devices[d]); L = own.lane; }
-        rc = query_to_device(*Q, *b, (int)d, L, (int)d == hook_device ? after_h2d : nullptr);
+        rc = query_to_device(*Q, *b, (int)d, L, (int)d == hook_device ? after_h2d : nullptr, keep_async && (int)d == hook_device);
         if (rc) { free_query_all(*Q); return rc; }
     }
     *out = std::move(Q);
@@ -2233,45 +2298,194 @@ int bn_prelim_search_batches(int vol_handle, int32_t n_batches, const BnQueryBat
     std::shared_ptr<Volume> Vp;
     rc = get_volume(vol_handle, &Vp);
     if (rc) return rc;
-    Volume *V = Vp.get();
-    Gpu *g = device_at(V->device);
-    for (int32_t k = 0; k < n_batches; k++) memset(&results[k], 0, sizeof results[k]);
-    if (n_batches == 0) return BN_OK;
-    // two lanes: batch k runs on lane k & 1 while a host thread finishes batch k-1 out of the other lane's
-    // pinned result mirrors
+    // the job pipeline with one resident volume and host-side batches
+    std::vector<BnJob> jobs((size_t)n_batches);
+    for (int32_t k = 0; k < n_batches; k++) {
+        BnJob j{};
+        j.vol_handle = vol_handle; j.query_handle = -1; j.batch = batches[k];
+        jobs[(size_t)k] = j;
+    }
+    return bn_prelim_search_jobs(Vp->device, n_batches, jobs.data(), taps, results, nullptr);
+}
+
+static int traceback_search_impl(Lane *D, Volume *V, Query *Q, int32_t gap_x_dropoff_final, const BnHSP *hsps, int64_t n_hsps,
+                                 BnTracebackHSP **out, int64_t *n_out, BnEditOp **ops_out, int64_t *n_ops_out);
+
+// Prepare -> (device) -> complete -> host replay -> traceback, as a software pipeline over two lanes of one device
+// (header: BnJob).  The caller's thread prepares job k+1 (uploads, chunk table, every kernel of the preliminary stage
+// queued on the lane's stream) BEFORE it waits for job k, so the device always has the next search queued and a
+// host-side volume crosses PCIe while the previous job's kernels run; one worker thread replays finished jobs on
+// the host, a second one runs their traceback stage on a lane of its own.
+int bn_prelim_search_jobs(int device, int32_t n_jobs, const BnJob *jobs, int taps, BnResults *results, BnTracebackOut *tb)
+{
+    if (n_jobs < 0 || (n_jobs > 0 && (!jobs || !results))) return fail(BN_ERR_INVALID, "bn_prelim_search_jobs: bad argument");
+    int rc = ensure_init();
+    if (rc) return rc;
+    Gpu *g = device_at(device);
+    if (!g) return fail(BN_ERR_INVALID, "bn_prelim_search_jobs: bad device");
+    for (int32_t k = 0; k < n_jobs; k++) {
+        memset(&results[k], 0, sizeof results[k]);
+        if (tb) memset(&tb[k], 0, sizeof tb[k]);
+        if (jobs[k].query_handle < 0 && !jobs[k].batch) return fail(BN_ERR_INVALID, "bn_prelim_search_jobs: job without a query batch");
+        if (jobs[k].vol_handle < 0 && !jobs[k].packed) return fail(BN_ERR_INVALID, "bn_prelim_search_jobs: job without a volume");
+    }
+    if (n_jobs == 0) return BN_OK;
+    CU_TRY(cudaSetDevice(g->id));
     LaneLock lanes[2];
     lanes[0] = LaneLock(*g);
     lanes[1] = LaneLock(*g);
-    const int32_t n_seq = (int32_t)V->seq_len.size();
-    std::vector<std::shared_ptr<Query>> Qs((size_t)n_batches);
-    std::vector<GpuOut> G((size_t)n_batches);
-    std::vector<int> host_rc((size_t)n_batches, BN_OK);
-    std::vector<std::string> host_err((size_t)n_batches);
-    std::thread pending[2];
+
+    struct JobState {
+        std::shared_ptr<Volume> V;
+        std::shared_ptr<Query> Q;
+        bool own_v = false, own_q = false, freed = false;
+        GpuOut G;
+        SearchPending P;
+        int rc = BN_OK;
+        std::string err;
+        bool host_done = false, all_done = false;
+    };
+    std::vector<JobState> J((size_t)n_jobs);
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<int32_t> host_q, tb_q;
+    bool host_closed = false, tb_closed = false;
+
+    std::thread host_worker([&]() {
+        for (;;) {
+            int32_t k;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&]() { return !host_q.empty() || host_closed; });
+                if (host_q.empty()) break;
+                k = host_q.front(); host_q.pop_front();
+            }
+            JobState &S = J[(size_t)k];
+            const int r = search_host_phase(*S.Q, S.G, taps, &results[k]);
+            std::lock_guard<std::mutex> lk(mu);
+            if (r) { S.rc = r; S.err = g_err; }
+            S.host_done = true;
+            if (tb && !r) tb_q.push_back(k); else S.all_done = true;
+            cv.notify_all();
+        }
+        std::lock_guard<std::mutex> lk(mu);
+        tb_closed = true;
+        cv.notify_all();
+    });
+    std::thread tb_worker;
+    if (tb) tb_worker = std::thread([&]() {
+        for (;;) {
+            int32_t k;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&]() { return !tb_q.empty() || tb_closed; });
+                if (tb_q.empty()) break;
+                k = tb_q.front(); tb_q.pop_front();
+            }
+            JobState &S = J[(size_t)k];
+            int r;
+            {
+                LaneLock own(*g);          // a third lane: the traceback kernels run beside the next jobs' searches
+                r = traceback_search_impl(own.lane, S.V.get(), S.Q.get(), jobs[k].gap_x_dropoff_final, results[k].hsps,
+                                          results[k].n_hsps, &tb[k].hsps, &tb[k].n_hsps, &tb[k].ops, &tb[k].n_ops);
+            }
+            std::lock_guard<std::mutex> lk(mu);
+            if (r) { S.rc = r; S.err = g_err; }
+            S.all_done = true;
+            cv.notify_all();
+        }
+    });
+
     int first_error = BN_OK;
     std::string first_msg;
-    for (int32_t k = 0; k < n_batches && first_error == BN_OK; k++) {
-        const int slot = k & 1;
-        Lane *L = lanes[slot].lane;
-        if (pending[slot].joinable()) pending[slot].join();      // batch k-2 has left this lane's mirrors
-        // tables of batch k (uploads + device-side derivation); the worker is finishing batch k-1 meanwhile
-        rc = query_load_impl(batches[k], &Qs[(size_t)k], V->device, nullptr, L, true);
-        if (rc) { first_error = rc; first_msg = g_err; break; }
-        Query *Q = Qs[(size_t)k].get();
-        rc = search_gpu_phase(*L, *V, *Q, 0, n_seq, &results[k], G[(size_t)k], triage_allowed(*Q, n_seq, taps));
-        if (rc) { first_error = rc; first_msg = g_err; break; }
-        pending[slot] = std::thread([&, k, Q]() {
-            host_rc[(size_t)k] = search_host_phase(*Q, G[(size_t)k], taps, &results[k]);
-            if (host_rc[(size_t)k]) host_err[(size_t)k] = g_err;      // thread-local message of the worker
-        });
+    int32_t free_cursor = 0;
+    // device memory of the jobs' own volumes / batches goes back to the pool as soon as every stage of the job is through
+    auto release_finished = [&](bool wait_all) {
+        for (; free_cursor < n_jobs; free_cursor++) {
+            JobState &S = J[(size_t)free_cursor];
+            if (!S.Q && !S.V) { if (!wait_all) break; continue; }     // not prepared (yet)
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                if (wait_all) cv.wait(lk, [&]() { return S.all_done; });
+                else if (!S.all_done) break;
+            }
+            S.G.T.reset();
+            if (S.own_q && S.Q) free_query_all(*S.Q);
+            if (S.own_v && S.V) free_volume_dev(*S.V);
+            S.freed = true;
+        }
+    };
+    auto prepare = [&](int32_t k) -> int {
+        JobState &S = J[(size_t)k];
+        const BnJob &jb = jobs[k];
+        Lane *L = lanes[k & 1].lane;
+        if (k >= 2) {           // the lane's pinned result mirrors are being read by the host replay of job k-2
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&]() { return J[(size_t)k - 2].host_done; });
+        }
+        release_finished(false);
+        int r = BN_OK;
+        const std::function<int()> start_volume = [&]() {
+            if (jb.vol_handle >= 0) return BN_OK;
+            S.own_v = true;
+            return db_load_impl(device, jb.packed, jb.packed_bytes, jb.seq_byte_off, jb.seq_len, jb.n_seq, true, &S.V, L);
+        };
+        if (jb.query_handle >= 0) {
+            r = get_query(jb.query_handle, &S.Q);
+            if (r == BN_OK) r = start_volume();
+        } else {
+            S.own_q = true;
+            r = query_load_impl(jb.batch, &S.Q, device, &start_volume, L, true, true);
+        }
+        if (r) return r;
+        if (jb.vol_handle >= 0) {
+            r = get_volume(jb.vol_handle, &S.V);
+            if (r) return r;
+            if (S.V->device != device) return fail(BN_ERR_INVALID, "bn_prelim_search_jobs: volume lives on another device");
+        } else if (!S.V) return fail(BN_ERR_INVALID, "bn_prelim_search_jobs: volume upload did not start");
+        const int32_t n_seq = (int32_t)S.V->seq_len.size();
+        return search_gpu_begin(*L, *S.V, *S.Q, 0, n_seq, &results[k], S.G, triage_allowed(*S.Q, n_seq, taps), S.P);
+    };
+
+    int32_t dispatched = 0;
+    rc = prepare(0);
+    if (rc) { first_error = rc; first_msg = g_err; }
+    for (int32_t k = 0; k < n_jobs && first_error == BN_OK; k++) {
+        if (k + 1 < n_jobs) {
+            rc = prepare(k + 1);
+            if (rc) { first_error = rc; first_msg = g_err; }
+        }
+        JobState &S = J[(size_t)k];
+        rc = search_gpu_end(*lanes[k & 1].lane, *S.V, *S.Q, &results[k], S.G, S.P);
+        if (rc) { if (first_error == BN_OK) { first_error = rc; first_msg = g_err; } break; }
+        if (first_error) break;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            host_q.push_back(k);
+            dispatched = k + 1;
+            cv.notify_all();
+        }
     }
-    for (auto &t : pending) if (t.joinable()) t.join();
-    for (int32_t k = 0; k < n_batches; k++) {
-        if (Qs[(size_t)k]) free_query_all(*Qs[(size_t)k]);
-        if (first_error == BN_OK && host_rc[(size_t)k]) { first_error = host_rc[(size_t)k]; first_msg = host_err[(size_t)k]; }
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        host_closed = true;
+        cv.notify_all();
     }
+    host_worker.join();
+    if (tb_worker.joinable()) tb_worker.join();
+    // jobs that were prepared but never completed still own queued device work
+    for (auto &l : lanes) cudaStreamSynchronize(l.lane->stream);
+    for (int32_t k = 0; k < n_jobs; k++) {
+        JobState &S = J[(size_t)k];
+        if (k >= dispatched) S.all_done = true;
+        if (first_error == BN_OK && S.rc) { first_error = S.rc; first_msg = S.err; }
+    }
+    release_finished(true);
     if (first_error) {
-        for (int32_t k = 0; k < n_batches; k++) bn_results_free(&results[k]);
+        for (int32_t k = 0; k < n_jobs; k++) {
+            bn_results_free(&results[k]);
+            if (tb) { free(tb[k].hsps); free(tb[k].ops); memset(&tb[k], 0, sizeof tb[k]); }
+        }
         return fail(first_error, first_msg);
     }
     return BN_OK;
@@ -2794,6 +3008,8 @@ int bn_traceback_hsps(int vol_handle, int query_handle, int32_t gap_x_dropoff_fi
 // BLAST_ComputeTraceback (core/blast_traceback.c:1375-1640) for blastn / megablast database searches: every
 // preliminary HSP is aligned with traceback on the device, the list logic of Blast_TracebackFromHSPList (:336-790)
 // is replayed on the host (hostpost.cpp), the re-evaluation and identity counts run on the device again.
+static int traceback_search_impl(Lane *D, Volume *V, Query *Q, int32_t gap_x_dropoff_final, const BnHSP *hsps, int64_t n_hsps,
+                                 BnTracebackHSP **out, int64_t *n_out, BnEditOp **ops_out, int64_t *n_ops_out);
 int bn_traceback_search(int vol_handle, int query_handle, int32_t gap_x_dropoff_final,
                         const BnHSP *hsps, int64_t n_hsps,
                         BnTracebackHSP **out, int64_t *n_out, BnEditOp **ops_out, int64_t *n_ops_out)
@@ -2803,6 +3019,13 @@ int bn_traceback_search(int vol_handle, int query_handle, int32_t gap_x_dropoff_
         return fail(BN_ERR_INVALID, "bn_traceback_search: bad argument");
     int rc = get_handles(vol_handle, query_handle, H, &V, &Q, &D);
     if (rc) return rc;
+    return traceback_search_impl(D, V, Q, gap_x_dropoff_final, hsps, n_hsps, out, n_out, ops_out, n_ops_out);
+}
+
+static int traceback_search_impl(Lane *D, Volume *V, Query *Q, int32_t gap_x_dropoff_final, const BnHSP *hsps, int64_t n_hsps,
+                                 BnTracebackHSP **out, int64_t *n_out, BnEditOp **ops_out, int64_t *n_ops_out)
+{
+    int rc;
     *out = nullptr; *n_out = 0; *ops_out = nullptr; *n_ops_out = 0;
     CU_TRY(cudaSetDevice(D->id));
     const BnQueryBatch &b = Q->batch;
@@ -2818,6 +3041,55 @@ int bn_traceback_search(int vol_handle, int query_handle, int32_t gap_x_dropoff_
     struct FreeOps { BnEditOp *&p; ~FreeOps() { free(p); } } free_ops{ops};
     if (n_hsps == 0) return BN_OK;
     const double t1 = now();
+
+    // device pass over a set of HSPs with their edit scripts: re-evaluation where asked for, then the identity count
+    auto run_post = [&](const std::vector<DevTracebackPost> &post, std::vector<int2> &pops, std::vector<DevTracebackPostOut> &pout) -> int {
+        pout.resize(post.size());
+        if (post.empty()) return BN_OK;
+        cudaStream_t st = D->stream;
+        DevTracebackPost *d_p = nullptr; int2 *d_o = nullptr; DevTracebackPostOut *d_r = nullptr;
+        CU_TRY(cudaMallocAsync((void **)&d_p, post.size() * sizeof(DevTracebackPost), st));
+        CU_TRY(cudaMallocAsync((void **)&d_o, std::max<size_t>(pops.size(), 1) * sizeof(int2), st));
+        CU_TRY(cudaMallocAsync((void **)&d_r, post.size() * sizeof(DevTracebackPostOut), st));
+        cudaError_t e = cudaMemcpyAsync(d_p, post.data(), post.size() * sizeof(DevTracebackPost), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess && !pops.empty()) e = cudaMemcpyAsync(d_o, pops.data(), pops.size() * sizeof(int2), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = launch_traceback_reevaluate(Q->dev[V->device].view, V->d_packed, V->d_amb, d_p, (int64_t)post.size(), d_o, d_r, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(pout.data(), d_r, pout.size() * sizeof(DevTracebackPostOut), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && !pops.empty()) e = cudaMemcpyAsync(pops.data(), d_o, pops.size() * sizeof(int2), cudaMemcpyDeviceToHost, st);
+        cudaFreeAsync(d_p, st); cudaFreeAsync(d_o, st); cudaFreeAsync(d_r, st);
+        CU_TRY(e);
+        CU_TRY(cudaStreamSynchronize(st));
+        return BN_OK;
+    };
+    // hit_options->percent_identity / min_hit_length with DP tracebacks: the reference counts the identities of every
+    // alignment it makes and tests it before the HSP enters the containment tree (core/blast_traceback.c:658-669), so
+    // the counts of ALL speculative alignments are needed before the list replay
+    const bool filter_on = identity_filter_on(b);
+    std::vector<DevTracebackPostOut> raw_ident;
+    if (filter_on && !greedy) {
+        std::vector<DevTracebackPost> post;
+        std::vector<int2> pops;
+        std::vector<int64_t> who((size_t)n_hsps, -1);
+        for (int64_t i = 0; i < n_hsps; i++) {
+            if (items[(size_t)i].oid < 0) continue;
+            const BnTracebackResult &r = res[(size_t)i];
+            const int32_t oid = hsps[i].oid, sh = items[(size_t)i].s_shift;
+            DevTracebackPost p{};
+            p.byte_off = V->byte_off[(size_t)oid]; p.esp_off = (int64_t)pops.size();
+            p.seq_len = V->seq_len[(size_t)oid]; p.context = hsps[i].context;
+            p.q_off = r.query_start; p.q_end = r.query_stop; p.s_off = r.subject_start + sh; p.s_end = r.subject_stop + sh;
+            p.score = r.score; p.esp_n = r.esp_n; p.reevaluate = 0;
+            p.amb_first = V->amb_first_of(oid); p.amb_n = V->amb_count_of(oid);
+            for (int32_t x = 0; x < r.esp_n; x++) pops.push_back(make_int2(ops[r.esp_off + x].op_type, ops[r.esp_off + x].num));
+            who[(size_t)i] = (int64_t)post.size();
+            post.push_back(p);
+        }
+        std::vector<DevTracebackPostOut> pout;
+        rc = run_post(post, pops, pout);
+        if (rc) return rc;
+        raw_ident.assign((size_t)n_hsps, DevTracebackPostOut{});
+        for (int64_t i = 0; i < n_hsps; i++) if (who[(size_t)i] >= 0) raw_ident[(size_t)i] = pout[(size_t)who[(size_t)i]];
+    }
 
     // lists = HSPs of one (subject, query) pair in the order given (the preliminary lists are sorted by score)
     std::vector<int64_t> order((size_t)n_hsps);
@@ -2841,6 +3113,8 @@ int bn_traceback_search(int vol_handle, int query_handle, int32_t gap_x_dropoff_
             c.s_shift = items[(size_t)i].s_shift; c.q_start = items[(size_t)i].q_start; c.s_start = items[(size_t)i].s_start;
             c.res = res[(size_t)i];
             c.ops = c.has_start ? ops + res[(size_t)i].esp_off : nullptr;
+            c.num_ident = raw_ident.empty() ? 0 : raw_ident[(size_t)i].num_ident;
+            c.align_length = raw_ident.empty() ? 0 : raw_ident[(size_t)i].align_length;
             cand.push_back(c);
         }
         List L; L.oid = oid; L.query_index = qi; L.extra_start = 0;
@@ -2870,26 +3144,15 @@ int bn_traceback_search(int vol_handle, int query_handle, int32_t gap_x_dropoff_
             who.emplace_back(li, j);
         }
     }
-    std::vector<DevTracebackPostOut> pout(post.size());
-    if (!post.empty()) {
-        cudaStream_t st = D->stream;
-        DevTracebackPost *d_p = nullptr; int2 *d_o = nullptr; DevTracebackPostOut *d_r = nullptr;
-        CU_TRY(cudaMallocAsync((void **)&d_p, post.size() * sizeof(DevTracebackPost), st));
-        CU_TRY(cudaMallocAsync((void **)&d_o, std::max<size_t>(pops.size(), 1) * sizeof(int2), st));
-        CU_TRY(cudaMallocAsync((void **)&d_r, post.size() * sizeof(DevTracebackPostOut), st));
-        cudaError_t e = cudaMemcpyAsync(d_p, post.data(), post.size() * sizeof(DevTracebackPost), cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess && !pops.empty()) e = cudaMemcpyAsync(d_o, pops.data(), pops.size() * sizeof(int2), cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) e = launch_traceback_reevaluate(Q->dev[V->device].view, V->d_packed, V->d_amb, d_p, (int64_t)post.size(), d_o, d_r, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(pout.data(), d_r, pout.size() * sizeof(DevTracebackPostOut), cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess && !pops.empty()) e = cudaMemcpyAsync(pops.data(), d_o, pops.size() * sizeof(int2), cudaMemcpyDeviceToHost, st);
-        cudaFreeAsync(d_p, st); cudaFreeAsync(d_o, st); cudaFreeAsync(d_r, st);
-        CU_TRY(e);
-        CU_TRY(cudaStreamSynchronize(st));
-    }
+    std::vector<DevTracebackPostOut> pout;
+    rc = run_post(post, pops, pout);
+    if (rc) return rc;
     for (size_t k = 0; k < post.size(); k++) {
         TbHsp &h = lists[who[k].first].arr[who[k].second];
         const DevTracebackPostOut &o = pout[k];
         if (o.deleted) { h.alive = false; continue; }
+        // Blast_HSPTestIdentityAndLength after the re-evaluation (core/blast_traceback.c:733-735)
+        if (filter_on && post[k].reevaluate && hsp_fails_identity_or_length(b, o.num_ident, o.align_length)) { h.alive = false; continue; }
         h.q_off = o.q_off; h.q_end = o.q_end; h.s_off = o.s_off; h.s_end = o.s_end; h.score = o.score;
         h.num_ident = o.num_ident;
         h.esp.clear();

@@ -941,9 +941,13 @@ void traceback_list_stage1(const BnQueryBatch &b, int32_t subject_length, const 
     arr.clear();
     extra_start = 0;
     if (n == 0) return;
+    // DP tracebacks are tested for identity / length right after the alignment and a failing HSP never enters the tree
+    // (core/blast_traceback.c:658-676); greedy ones are tested after the re-evaluation (:727-735, the caller)
+    const bool dp_filter = b.gap_algo != BN_GAP_GREEDY && identity_filter_on(b);
     if (n == 1) {       // a list of one HSP (the usual case for short reads): nothing to be contained in, nothing to purge
         const TbCand &c = cand[0];
         if (!c.has_start) return;
+        if (dp_filter && hsp_fails_identity_or_length(b, c.num_ident, c.align_length)) return;
         TbHsp h{};
         h.alive = true; h.was_cut = false;
         h.oid = c.pre.oid; h.context = c.pre.context;
@@ -965,7 +969,8 @@ void traceback_list_stage1(const BnQueryBatch &b, int32_t subject_length, const 
         IntervalTree::Item t;
         t.q_strand_start = strand_offset(b, c.pre.context);
         t.q_off = c.pre.q_off; t.q_end = c.pre.q_end; t.s_off = c.pre.s_off; t.s_end = c.pre.s_end; t.score = c.pre.score;
-        if (!tree.contains(t, b.min_diag_separation) && c.has_start) {
+        if (!tree.contains(t, b.min_diag_separation) && c.has_start &&
+            !(dp_filter && hsp_fails_identity_or_length(b, c.num_ident, c.align_length))) {
             // Blast_HSPUpdateWithTraceback (:156-175) + Blast_HSPAdjustSubjectOffset (core/blast_hits.c:1168-1179)
             h.alive = true;
             h.score = c.res.score;

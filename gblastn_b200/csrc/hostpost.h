@@ -145,7 +145,14 @@ struct TbCand {                 // one preliminary HSP with its speculative trac
     int32_t s_shift, q_start, s_start;      // AdjustSubjectRange shift, start point (subject: window-relative)
     BnTracebackResult res;      // alignment (subject coordinates window-relative)
     const BnEditOp *ops;        // res.esp_n operations
+    int32_t num_ident, align_length;    // of the alignment as it stands (DP tracebacks with an identity / length filter)
 };
+// Blast_HSPTest (core/blast_hits.c:864-871): true = the HSP fails percent_identity / min_hit_length
+inline bool hsp_fails_identity_or_length(const BnQueryBatch &b, int32_t num_ident, int32_t align_length)
+{
+    return (num_ident * 100.0 < align_length * b.percent_identity) || align_length < b.min_hit_length;
+}
+inline bool identity_filter_on(const BnQueryBatch &b) { return b.percent_identity > 0 || b.min_hit_length > 0; }
 
 struct TbHsp {                  // an HSP of the traceback stage
     int32_t oid, context, q_off, q_end, s_off, s_end, score, q_gapped_start, s_gapped_start;

@@ -861,6 +861,7 @@ int bn_setup_create(const BnSetupOptions *opt, int32_t nq, const uint8_t *qseq, 
     b.min_diag_separation = opt->min_diag_separation >= 0 ? opt->min_diag_separation : (mb ? 6 : 50);
     b.round_down = round_down ? 1 : 0;
     b.hsp_num_max = opt->hsp_num_max;
+    b.percent_identity = opt->percent_identity; b.min_hit_length = opt->min_hit_length;
     b.hitlist_size = opt->hitlist_size ? opt->hitlist_size : 500;
     b.evalue_cutoff = evalue;
     b.low_score_perc = opt->low_score_perc >= 0 ? opt->low_score_perc : 0.15;

@@ -20,7 +20,7 @@ EXPORTS = [
     "bn_db_load", "bn_db_free", "bn_query_load", "bn_query_free",
     "bn_prelim_search", "bn_prelim_search_host", "bn_prelim_search_volumes", "bn_results_free",
     "bn_scan_subject", "bn_word_finder", "bn_free", "bn_bench_scan", "bn_query_download_lookup", "bn_get_gapped_score", "bn_gapped_traceback", "bn_traceback_hsps", "bn_traceback_search",
-    "bn_dbfile_index", "bn_db_load_files", "bn_dbfile_write", "bn_dbfile_ambiguity", "bn_db_set_ambiguity", "bn_prelim_search_batches", "bn_db_set_masks", "bn_selftest_replay",
+    "bn_dbfile_index", "bn_db_load_files", "bn_dbfile_write", "bn_dbfile_ambiguity", "bn_db_set_ambiguity", "bn_prelim_search_batches", "bn_prelim_search_jobs", "bn_db_set_masks", "bn_selftest_replay",
     "bn_setup_create", "bn_setup_batch", "bn_setup_kbp_std", "bn_setup_kbp_gap",
     "bn_setup_gap_x_dropoff_final", "bn_setup_longest_chain", "bn_setup_free", "bn_dust_mask",
 ]
@@ -219,6 +219,61 @@ def prelim_search_batches(volume: Volume, holders, taps=0) -> list:
     res = (abi.BnResults * n)()
     _check(lib().bn_prelim_search_batches(C.c_int(volume.handle), C.c_int32(n), ptrs, C.c_int(taps), res))
     return [_results(res[k]) for k in range(n)]
+
+
+def prelim_search_jobs(jobs, device=0, taps=0, traceback=False) -> list:
+    """The job pipeline (bn_prelim_search_jobs).  jobs: list of dicts with
+         volume = engine.Volume (resident)  |  host_volume = synth.Volume (uploaded as part of the job)
+         query  = engine.Query (resident)   |  batch = BnQueryBatch / holder (loaded as part of the job)
+         gap_x_dropoff_final (with traceback=True)
+    Returns one result dict per job; with traceback=True each also carries "tb" = (final HSPs, ops)."""
+    n = len(jobs)
+    arr = (abi.BnJob * n)()
+    keep = []
+    for k, j in enumerate(jobs):
+        a = arr[k]
+        if j.get("volume") is not None:
+            a.vol_handle = j["volume"].handle
+        else:
+            v = j["host_volume"]
+            packed = v.packed if (isinstance(v.packed, np.ndarray) and v.packed.dtype == np.uint8 and v.packed.flags.c_contiguous) \
+                else np.ascontiguousarray(v.packed, dtype=np.uint8)
+            boff = np.ascontiguousarray(v.byte_off, dtype=np.int64)
+            slen = np.ascontiguousarray(v.seq_len, dtype=np.int32)
+            keep += [packed, boff, slen]
+            a.vol_handle = -1
+            a.packed = packed.ctypes.data
+            a.packed_bytes = packed.shape[0]
+            a.seq_byte_off = boff.ctypes.data
+            a.seq_len = slen.ctypes.data
+            a.n_seq = slen.shape[0]
+        if j.get("query") is not None:
+            a.query_handle = j["query"].handle
+        else:
+            b = j["batch"]
+            b = b.batch if hasattr(b, "batch") else b
+            keep.append(b)
+            a.query_handle = -1
+            a.batch = C.pointer(b)
+        a.gap_x_dropoff_final = int(j.get("gap_x_dropoff_final", 0))
+    res = (abi.BnResults * n)()
+    tb = (abi.BnTracebackOut * n)() if traceback else None
+    _check(lib().bn_prelim_search_jobs(C.c_int(device), C.c_int32(n), arr, C.c_int(taps), res, tb))
+    out = []
+    for k in range(n):
+        if traceback:
+            t = tb[k]
+            try:
+                pair = (abi.struct_array(C.c_void_p(t.hsps), t.n_hsps, abi.TB_HSP_DTYPE),
+                        abi.struct_array(C.c_void_p(t.ops), t.n_ops, abi.EDIT_OP_DTYPE))
+            finally:
+                lib().bn_free(C.c_void_p(t.hsps))
+                lib().bn_free(C.c_void_p(t.ops))
+        d = _results(res[k])
+        if traceback:
+            d["tb"] = pair
+        out.append(d)
+    return out
 
 
 def prelim_search_host(holder, vol, device=0, taps=0) -> dict:

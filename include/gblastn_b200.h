@@ -149,6 +149,13 @@ typedef struct BnQueryBatch {
     const int32_t *na_backbone;
     const int32_t *na_overflow;
     int64_t        na_overflow_len;
+
+    /* BlastHitSavingOptions of the traceback stage (Blast_HSPTest, core/blast_hits.c:864-871): an HSP whose
+     * num_ident * 100 < align_length * percent_identity, or whose align_length < min_hit_length, is dropped
+     * (blastn -perc_identity; 0 / 0 = off).  The preliminary gapped stage does not look at them. */
+    double         percent_identity;
+    int32_t        min_hit_length;
+    int32_t        reserved0;
 } BnQueryBatch;
 
 /* BlastOffsetPair (inc-core/blast_def.h:141) tagged with its subject. */
@@ -343,9 +350,11 @@ int  bn_traceback_hsps(int vol_handle, int query_handle, int32_t gap_x_dropoff_f
  * second containment pass, odd-score rounding, E-values (BLAST_KarlinStoE_simple), reap, bit scores — are replayed on
  * the host over those results, and Blast_HSPReevaluateWithAmbiguitiesGapped + the identity count run on the device
  * in between.  Output: per query (ascending), the subject lists in s_EvalueCompareHSPLists order, at most hitlist_size
- * of them, HSPs in list order; edit scripts in ops.  Limits: hit_options->percent_identity / min_hit_length are taken
- * as 0 (the batch does not carry them); the identity count reads the query block the batch carries (`sequence`), which
- * equals `sequence_nomask` unless the query was hard-masked; the per-query pruning of the preliminary hit lists
+ * of them, HSPs in list order; edit scripts in ops.  hit_options->percent_identity / min_hit_length (Blast_HSPTest,
+ * core/blast_hits.c:864-871) come with the batch: DP tracebacks are tested right after the alignment, before the HSP
+ * enters the containment tree (core/blast_traceback.c:658-669), greedy ones and trimmed HSPs after the re-evaluation
+ * (:727-735).  Limits: the identity count reads the query block the batch carries (`sequence`), which equals
+ * `sequence_nomask` unless the query was hard-masked; the per-query pruning of the preliminary hit lists
  * (prelim_hitlist_size) is the caller's. */
 typedef struct BnTracebackHSP {
     int32_t query_index, oid, context;
@@ -357,6 +366,37 @@ typedef struct BnTracebackHSP {
 int  bn_traceback_search(int vol_handle, int query_handle, int32_t gap_x_dropoff_final,
                          const BnHSP *hsps, int64_t n_hsps,
                          BnTracebackHSP **out, int64_t *n_out, BnEditOp **ops, int64_t *n_ops);
+
+/* A stream of searches on one device as a software pipeline — G-BLASTN's Prepare -> Prelim -> Traceback -> Print worker
+ * threads (gpu/work_thread.cpp:16-438, app/blast/blastn_app.cpp:886-989) without the Print stage.  A job is one
+ * (volume, query batch) pair; either side may be resident (a handle) or come from the caller's HOST buffers for this
+ * job only (handle -1: the upload is part of the job).  Per job:
+ *   prepare    on the caller's thread: uploads + device-side table fill of a host-side batch, upload of a host-side
+ *              volume (copy stream), chunk table, and ALL kernels of the preliminary stage queued on the lane's stream;
+ *              job k+1 is prepared before the call waits for job k, so the device never idles between jobs and the
+ *              upload of job k+1's volume overlaps the kernels of job k
+ *   complete   wait for the job's kernels, second-tier gapped extensions if any were needed
+ *   host       on a worker thread: containment replay, list post-processing, E-values (results[k])
+ *   traceback  (tb != NULL) on a second worker with a lane of its own: bn_traceback_search on results[k].hsps
+ * results[k] (and tb[k]) are exactly what bn_prelim_search (bn_traceback_search) returns for the pair; free them with
+ * bn_results_free / bn_free.  All host arrays the jobs point to must stay valid until the call returns. */
+typedef struct BnJob {
+    int vol_handle;                 /* resident volume, or -1 */
+    int query_handle;               /* resident batch, or -1 */
+    const BnQueryBatch *batch;      /* query_handle == -1 */
+    const uint8_t *packed;          /* vol_handle == -1: as for bn_db_load */
+    int64_t        packed_bytes;
+    const int64_t *seq_byte_off;
+    const int32_t *seq_len;
+    int32_t        n_seq;
+    int32_t        gap_x_dropoff_final;   /* traceback stage (tb != NULL) */
+} BnJob;
+typedef struct BnTracebackOut {
+    BnTracebackHSP *hsps; int64_t n_hsps;
+    BnEditOp *ops;        int64_t n_ops;
+} BnTracebackOut;
+int  bn_prelim_search_jobs(int device, int32_t n_jobs, const BnJob *jobs, int taps, BnResults *results,
+                           BnTracebackOut *tb);
 
 /* Host-only self-test: the containment replay (BLAST_GetGappedScore's interval-tree filter, core/blast_itree.c)
  * runs with one tree per query strand; this compares it with the reference's one-tree-per-subject layout on
@@ -392,6 +432,8 @@ typedef struct BnSetupOptions {
     int32_t hsp_num_max;        /* hit_options->hsp_num_max; carried into the batch, and — like the reference, whose
                                    BlastHspNumMax returns INT4_MAX for gapped searches (core/blast_hits.c:169-191) —
                                    without effect on this (always gapped) path */
+    double  percent_identity;   /* hit_options->percent_identity (blastn -perc_identity), 0 = off */
+    int32_t min_hit_length;     /* hit_options->min_hit_length, 0 = off */
 } BnSetupOptions;
 
 typedef struct BnSetup BnSetup;   /* opaque; owns the arrays a BnQueryBatch points to */

@@ -116,6 +116,8 @@ def batch_from_reference(r: dict, *, task: str, cfg=None, use_pv=True) -> abi.Ba
     # sbp->round_down as the reference computed it (s_GetNuclValuesArray, core/blast_stat.c:3207-3345)
     b.round_down = int(r["round_down"])
     b.hsp_num_max = 0
+    b.percent_identity = float(cfg.percent_identity) if cfg is not None else 0.0
+    b.min_hit_length = int(cfg.min_hit_length) if cfg is not None else 0
     b.hitlist_size = (cfg.hitlist_size if cfg is not None and cfg.hitlist_size else 500)
     b.evalue_cutoff = (cfg.evalue if cfg is not None and cfg.evalue > 0 else 10.0)
     lsp = cfg.low_score_perc if cfg is not None else -1.0

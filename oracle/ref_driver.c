@@ -556,6 +556,8 @@ static int build_setup(const RefConfig *cfg, int32_t nq, const uint8_t *qseq, co
     S->hit_options->mask_level = 101;
     S->hit_options->low_score_perc = cfg->low_score_perc >= 0 ? cfg->low_score_perc : 0.15;
     S->hit_options->hsp_num_max = cfg->hsp_num_max;
+    S->hit_options->percent_identity = cfg->percent_identity;
+    S->hit_options->min_hit_length = cfg->min_hit_length;
     S->eff_len_options->db_length = cfg->db_length;
     S->eff_len_options->dbseq_num = cfg->db_num_seqs;
     S->query_options->strand_option = 3;

@@ -51,6 +51,8 @@ typedef struct RefConfig {
     const int32_t *amb_runs;
     int32_t seam;            /* 0: the reference's own word finder and gapped stage; 1: the B200 engine behind the
                               * same two seams through oracle/shim (only in oracle/_ref/libblastshim.so) */
+    double  percent_identity; /* hit_options->percent_identity (blastn -perc_identity), 0 = off */
+    int32_t min_hit_length;  /* hit_options->min_hit_length, 0 = off */
 } RefConfig;
 
 /* Flat growable int32 table: rows x ncol */

@@ -29,6 +29,7 @@ class RefConfig(C.Structure):
         ("taps", C.c_int32), ("prelim_only", C.c_int32),
         ("smask_type", C.c_int32), ("smask_n", C.c_void_p), ("smask_iv", C.c_void_p),
         ("hsp_num_max", C.c_int32), ("amb_first", C.c_void_p), ("amb_runs", C.c_void_p), ("seam", C.c_int32),
+        ("percent_identity", C.c_double), ("min_hit_length", C.c_int32),
     ]
 
 

@@ -211,6 +211,7 @@ static int load_query(BLAST_SequenceBlk *query, BlastQueryInfo *query_info, Look
     b.min_diag_separation = hopt->min_diag_separation; b.round_down = sbp->round_down ? 1 : 0;
     b.hsp_num_max = hopt->hsp_num_max; b.hitlist_size = hopt->hitlist_size;
     b.evalue_cutoff = hopt->expect_value; b.low_score_perc = hopt->low_score_perc;
+    b.percent_identity = hopt->percent_identity; b.min_hit_length = hopt->min_hit_length;
     rc = bn_query_load(&b, &S->query_handle);
     free(ctx); free(masked);
     if (rc != BN_OK) { S->query_handle = -1; return shim_fail("bn_query_load"); }

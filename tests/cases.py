@@ -145,6 +145,18 @@ CASES["mb_repeat_family_hsp_num_max2"] = dict(task="megablast", cfg={"hitlist_si
 CASES["blastn_direct_mixed_lengths_N"] = dict(task="blastn", cfg={}, seq_lens=[400_000, 90_000, 5_000], vol_seed=77,
                                               qlen_list=[(6, 120), (8, 700), (4, 4000), (2, 9000)], q_seed=78,
                                               sub=0.07, indel=0.008, planted=0.85, n_frac=0.003)
+# hit_options->percent_identity / min_hit_length (blastn -perc_identity): Blast_HSPTest in the traceback stage
+# (core/blast_traceback.c:658-669 for DP tracebacks, :727-735 after the re-evaluation); thresholds chosen inside the
+# spread of the planted alignments' identities so that part of the HSPs goes and part stays
+CASES["blastn_bridged_perc_identity"] = dict(task="blastn", cfg={"percent_identity": 92.0, "min_hit_length": 120},
+                                             seq_lens=[300_000, 120_000, 40_000], vol_seed=63, nq=40, qlen=900,
+                                             q_seed=64, sub=0.06, indel=0.0, planted=1.0, bridged=True)
+CASES["mb_bridged_perc_identity"] = dict(task="megablast", cfg={"percent_identity": 96.5, "min_hit_length": 150},
+                                         seq_lens=[300_000, 120_000, 40_000], vol_seed=61, nq=60, qlen=900,
+                                         q_seed=62, sub=0.02, indel=0.0, planted=1.0, bridged=True)
+CASES["blastn_dp_perc_identity"] = dict(task="blastn", cfg={"percent_identity": 91.0}, seq_lens=[300_000, 50_000, 777, 120_001, 13],
+                                        vol_seed=2, nq=30, qlen=800, q_seed=14, sub=0.08, indel=0.01, planted=0.8)
+IDENTITY_FILTER_CASES = ["blastn_bridged_perc_identity", "mb_bridged_perc_identity", "blastn_dp_perc_identity"]
 HITLIST_CASES = ["mb_repeat_family_hitlist5", "mb_repeat_family_hitlist20", "blastn_repeat_family_hitlist5",
                  "mb_repeat_family_hsp_num_max2"]
 

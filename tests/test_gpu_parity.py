@@ -218,7 +218,23 @@ def test_traceback_search_matches_reference(name):
         Q.free(); V.free()
 
 
+@pytest.mark.parametrize("name", cases.IDENTITY_FILTER_CASES)
+def test_traceback_identity_and_length_filter(name):
+    """hit_options->percent_identity / min_hit_length: the traceback stage drops the same HSPs as the reference
+    (Blast_HSPTest) and the filter is not vacuous in these cases (the unfiltered run keeps more)."""
+    from oracle import refdriver as R
+    task, cfgkw, vol, qs = cases.make_case(name)
+    if not R.available():
+        pytest.skip("oracle/_ref/libblastref.so did not travel to this box")
+    test_traceback_search_matches_reference(name)
+    with_filter = R.search(qs, vol, R.default_config(task, taps=R.TAP_TRACEBACK, prelim_only=0, **cfgkw))
+    plain = {k: v for k, v in cfgkw.items() if k not in ("percent_identity", "min_hit_length")}
+    without = R.search(qs, vol, R.default_config(task, taps=R.TAP_TRACEBACK, prelim_only=0, **plain))
+    assert 0 < with_filter["tb_final"].shape[0] < without["tb_final"].shape[0]
+
+
 @pytest.mark.parametrize("name", ["mb_bridged_segments", "blastn_bridged_segments", "c4_scaled_short_reads",
+                                  "blastn_bridged_perc_identity", "mb_bridged_perc_identity",
                                   "c5_scaled_ntlike_5kb", "c3_scaled_blastn_10kb", "mb_with_N"])
 def test_full_search_product_path(name):
     """Preliminary stage + traceback stage, both on the GPU path with the product's own set-up (no reference data in
@@ -502,6 +518,80 @@ def test_batch_pipeline_equals_single_searches():
         V.free()
         for st in setups:
             st.free()
+
+
+def _assert_tb_equals_reference(got, ops, r):
+    want, ref_ops = r["tb_final"], r["tb_ops"]
+    assert got.shape[0] == want.shape[0]
+    for k, col in enumerate(("query_index", "oid", "context", "q_off", "q_end", "s_off", "s_end", "score", "num_ident")):
+        assert np.array_equal(got[col], want[:, k]), col
+    ev = want[:, 9].astype(np.uint32).astype(np.uint64) | (want[:, 10].astype(np.uint32).astype(np.uint64) << np.uint64(32))
+    bs = want[:, 11].astype(np.uint32).astype(np.uint64) | (want[:, 12].astype(np.uint32).astype(np.uint64) << np.uint64(32))
+    assert np.array_equal(got["evalue"].view(np.uint64), ev) and np.array_equal(got["bit_score"].view(np.uint64), bs)
+    if want.shape[0]:
+        flat = np.concatenate([ref_ops[want[i, 13]:want[i, 13] + want[i, 14]] for i in range(want.shape[0])])
+        mine = np.concatenate([np.stack([ops["op_type"][a:a + n], ops["num"][a:a + n]], axis=1)
+                               for a, n in zip(got["esp_off"], got["esp_n"])])
+        assert np.array_equal(flat, mine), "edit scripts differ"
+
+
+def test_job_pipeline_equals_reference():
+    """bn_prelim_search_jobs (prepare -> device -> host replay -> traceback, software-pipelined over two lanes): a mixed
+    stream of jobs — resident and host-side volumes, resident and host-side batches, megablast and blastn, fused and
+    general path, an empty result — returns per job exactly what the reference's preliminary + traceback stages return
+    for that (volume, batch) pair alone; run twice (steady state re-uses the lanes' buffers)."""
+    from gblastn_b200 import engine as E, setup as S
+    from oracle import refdriver as R, portdriver as P
+    if not R.available():
+        pytest.skip("oracle/_ref/libblastref.so did not travel to this box")
+    names = ["mb_lut12_stride17", "blastn_mb11_dp", "mb_smallna_diagarray", "mb_no_hits", "c4_scaled_short_reads",
+             "mb_bridged_segments", "blastn_bridged_perc_identity", "mb_lut11_hash_indels"]
+    jobs, refs, keep = [], [], []
+    try:
+        for k, name in enumerate(names):
+            task, cfgkw, vol, qs = cases.make_case(name)
+            r = R.search(qs, vol, R.default_config(task, taps=R.TAP_TRACEBACK, prelim_only=0, **cfgkw))
+            assert r["status"] == 0
+            st = S.Setup(qs, task=task, db_length=vol.total_bases, db_num_seqs=vol.n_seqs,
+                         device_lookup=1 if task == "megablast" else 0, **cfgkw)
+            keep.append(st)
+            j = {"gap_x_dropoff_final": st.gap_x_dropoff_final()}
+            if k % 2 == 0:
+                j["host_volume"] = vol
+            else:
+                V = E.Volume(vol); keep.append(V); j["volume"] = V
+            if k % 3 == 0:
+                Q = E.Query(st.batch); keep.append(Q); j["query"] = Q
+            else:
+                j["batch"] = st.batch
+            jobs.append(j); refs.append(r)
+        for _ in range(2):
+            out = E.prelim_search_jobs(jobs, traceback=True)
+            assert len(out) == len(jobs)
+            for name, o, r in zip(names, out, refs):
+                assert np.array_equal(P.final_table(o["hsps"]), r["final"]), f"preliminary lists of {name}"
+                assert o["stats"]["lookup_hits"] == r["lookup_hits"] and o["stats"]["gap_extensions"] == r["gap_extensions"]
+                _assert_tb_equals_reference(o["tb"][0], o["tb"][1], r)
+        plain = E.prelim_search_jobs(jobs)              # without the traceback stage
+        for a, b in zip(out, plain):
+            assert a["hsps"].tobytes() == b["hsps"].tobytes() and "tb" not in b
+        assert sum(o["hsps"].size for o in out) > 0 and out[3]["hsps"].size == 0
+    finally:
+        for x in keep:
+            x.free()
+
+
+def test_job_pipeline_reports_errors():
+    from gblastn_b200 import engine as E, abi
+    r, h, vol = _setup("mb_lut11_hash_indels")
+    V = E.Volume(vol)
+    try:
+        with pytest.raises(E.BnError):
+            E.prelim_search_jobs([{"volume": V, "batch": h}, {"volume": V, "query": type("Q", (), {"handle": 9999})()}])
+        ok = E.prelim_search_jobs([{"volume": V, "batch": h}])          # the device is usable afterwards
+        assert ok[0]["hsps"].size == r["final"].shape[0]
+    finally:
+        V.free()
 
 
 def test_host_buffer_entry_point():
