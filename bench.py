@@ -38,7 +38,9 @@ METRIC = "Gbases/s subject scanned (megablast) at 1/2/4/8 B200; HSPs bit-exact v
 UNIT = "Gbases/s"
 N_QUERIES, QUERY_LEN, DB_BASES = 1000, 1000, 250_000_000
 WORKLOAD = "megablast: 1000x1kb synthetic queries vs 250Mb synthetic DB (BASELINE configs[1])"
-L2_NOTE = "GPU arm: L2 flushed between timed steps (256 MiB write)"
+N_SETS = 4          # (volume, query batch) sets a rank cycles through: step i searches set i % N_SETS
+L2_NOTE = ("inputs larger than L2: consecutive steps search different (volume, query batch) sets, 4 sets of 62.5 MB packed "
+           "subject + ~20 MB of touched table data per GPU, cycled; no flush inside the timed region")
 
 
 def bench_config(n_vol):
@@ -148,9 +150,10 @@ def run_named_config(name, shard, engine, setup, torch, steps=3, with_reference=
     return out
 
 
-def make_workload(rank: int):
-    vol = synth.random_volume([DB_BASES], seed=2 + 1000 * rank)
-    qs = synth.planted_queries(vol, N_QUERIES, QUERY_LEN, seed=22 + 1000 * rank, planted_frac=0.8,
+def make_workload(rank: int, k: int = 0):
+    """Set k of rank `rank`: a 250 Mb volume and the 1000 x 1 kb queries planted in it (80 % planted, 2 % substitutions)."""
+    vol = synth.random_volume([DB_BASES], seed=2 + 1000 * rank + 100 * k)
+    qs = synth.planted_queries(vol, N_QUERIES, QUERY_LEN, seed=22 + 1000 * rank + 100 * k, planted_frac=0.8,
                                sub_rate=0.02, rc_frac=0.5)
     return vol, qs
 
@@ -262,13 +265,14 @@ def bind_near_gpu(bus_id: str):
 
 
 def _reference_worker(job):
-    """One volume of the reference arm: `steps` timed preliminary searches of query set r vs volume r."""
+    """One rank's share of the reference arm: `steps` timed preliminary searches, step i on set i % N_SETS."""
     r, warmup, steps = job
     from oracle import refdriver as R
-    vol, qs = make_workload(r)
+    sets = [make_workload(r, k) for k in range(min(N_SETS, max(1, steps)))]
     cfg = R.default_config("megablast", num_threads=1)
     times = []
     for i in range(warmup + steps):
+        vol, qs = sets[i % len(sets)]
         res = R.search(qs, vol, cfg)
         assert res["status"] == 0
         if i >= warmup:
@@ -359,6 +363,16 @@ def main():
                     break
         except Exception:
             numa = None
+        if numa is None:
+            # no NUMA information for the GPU (single-node hosts report -1): give every rank its own slice of the
+            # cores instead, so that the ranks' launch / replay / traceback threads never share a core
+            try:
+                cpus = sorted(os.sched_getaffinity(0))
+                per = len(cpus) // world
+                if per >= 2:
+                    os.sched_setaffinity(0, set(cpus[local_rank * per:(local_rank + 1) * per]))
+            except Exception:
+                pass
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -368,69 +382,92 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    vol, qs = make_workload(rank)
-    # packed volume in pinned host memory (source of the e2e H2D copies)
-    pinned = torch.empty(vol.packed.shape[0], dtype=torch.uint8).pin_memory()
-    pinned.numpy()[:] = vol.packed
-    vol.packed = pinned.numpy()
+    # N_SETS (volume, query batch) sets per rank; the packed volumes live in pinned host memory (source of the e2e H2D copies)
+    sets = [make_workload(rank, k) for k in range(N_SETS)]
+    for vol_k, _ in sets:
+        pinned = torch.empty(vol_k.packed.shape[0], dtype=torch.uint8).pin_memory()
+        pinned.numpy()[:] = vol_k.packed
+        vol_k.packed = pinned.numpy()
+    vol, qs = sets[0]
 
     engine.init(0, [local_rank])
     # device_lookup: the megablast table is filled on the GPU at bn_query_load (s_FillContigMBTable
     # semantics), so a step's H2D is the packed volume + the query bytes, not the 4^lut-entry hashtable
-    s = setup.Setup(qs, task="megablast", db_length=vol.total_bases, db_num_seqs=vol.n_seqs, device_lookup=1)
-    V = engine.Volume(vol, device=0)
-    Q = engine.Query(s.batch)
+    setups = [setup.Setup(q_k, task="megablast", db_length=v_k.total_bases, db_num_seqs=v_k.n_seqs, device_lookup=1)
+              for v_k, q_k in sets]
+    s = setups[0]
+    Vs = [engine.Volume(v_k, device=0) for v_k, _ in sets]
+    Qs = [engine.Query(st.batch) for st in setups]
+    V, Q = Vs[0], Qs[0]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     def l2_flush():
         flush.fill_(1)
         torch.cuda.synchronize()
 
-    # ---- resident-input throughput -----------------------------------------------------------------
-    for _ in range(args.warmup):
-        g = engine.prelim_search(V, Q)
-    launches = 0
-    step_ms, step_ms_wall = [], []
-    stage = {"ms_scan": 0.0, "ms_extend": 0.0, "ms_gapped": 0.0, "ms_host": 0.0}
-    # A step ends on the host (the replay of the precomputed extensions), so it is bracketed by two CUDA events
-    # recorded around the call: device timestamps of "call issued" and "results in host memory"; the wall clock
-    # is kept beside them as a cross-check.
+    def resident_jobs(n):
+        return [{"volume": Vs[i % N_SETS], "query": Qs[i % N_SETS]} for i in range(n)]
+
+    def host_jobs(n):
+        return [{"host_volume": sets[i % N_SETS][0], "batch": setups[i % N_SETS].batch} for i in range(n)]
+
+    # ---- resident-input throughput: K steps = K jobs through the job pipeline (bn_prelim_search_jobs) ----------
+    # Every job is a complete preliminary search (scan ... gapped on the device, replay / E-values on the host); the
+    # pipeline queues job k+1's kernels before it waits for job k and replays finished jobs on a worker thread.
+    results = engine.prelim_search_jobs(resident_jobs(max(args.warmup, N_SETS)))
+    per_set = results[:N_SETS]                       # one result per set, for the parity check below
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage = {"ms_scan": 0.0, "ms_extend": 0.0, "ms_gapped": 0.0, "ms_host": 0.0}
     barrier()
     with ClockSampler(local_rank) as clk:
-        for _ in range(args.steps):
-            l2_flush()
-            barrier()
-            t0 = time.perf_counter()
-            ev0.record()
-            g = engine.prelim_search(V, Q)
-            ev1.record()
-            ev1.synchronize()
-            step_ms_wall.append(1e3 * (time.perf_counter() - t0))
-            step_ms.append(ev0.elapsed_time(ev1))
-            launches += g["stats"]["kernel_launches"]
+        t0 = time.perf_counter()
+        ev0.record()
+        results = engine.prelim_search_jobs(resident_jobs(args.steps))
+        ev1.record()
+        ev1.synchronize()
+        total_ms_wall = 1e3 * (time.perf_counter() - t0)
+        total_ms = float(ev0.elapsed_time(ev1))
+        launches = sum(r["stats"]["kernel_launches"] for r in results)
+        for r in results:
             for k in stage:
-                stage[k] += g["stats"][k]
-        # ---- end to end through the host-buffer entry point --------------------------------------
-        e2e_ms = []
-        for i in range(3 + args.steps):
+                stage[k] += r["stats"][k]
+        g = results[0]
+        # ---- end to end: the same K steps with every input in HOST memory — per job the packed volume (pinned) and
+        # the query batch cross PCIe, the lookup table is filled on the device, the results come back ----------------
+        engine.prelim_search_jobs(host_jobs(max(args.warmup, 3)))
+        barrier()
+        ev0.record()
+        e2e_results = engine.prelim_search_jobs(host_jobs(args.steps))
+        ev1.record()
+        ev1.synchronize()
+        total_e2e_ms = float(ev0.elapsed_time(ev1))
+        ge = e2e_results[0]
+        e2e_same = all(a["hsps"].tobytes() == b["hsps"].tobytes() for a, b in zip(results, e2e_results))
+        # ---- one blocking call per step (bn_prelim_search / bn_prelim_search_host), L2 flushed in between: what a
+        # caller without a job stream sees -------------------------------------------------------------------------
+        single_ms, single_e2e_ms = [], []
+        for i in range(min(args.steps, 10)):
             l2_flush()
-            barrier()
             ev0.record()
-            ge = engine.prelim_search_host(s.batch, vol, device=0)
+            engine.prelim_search(V, Q)
             ev1.record()
             ev1.synchronize()
-            if i >= 3:
-                e2e_ms.append(ev0.elapsed_time(ev1))
+            single_ms.append(ev0.elapsed_time(ev1))
+        for i in range(min(args.steps, 5)):
+            l2_flush()
+            ev0.record()
+            engine.prelim_search_host(s.batch, vol, device=0)
+            ev1.record()
+            ev1.synchronize()
+            single_e2e_ms.append(ev0.elapsed_time(ev1))
         # ---- scan kernel alone (roofline) -----------------------------------------------------------
         engine.bench_scan(V, Q, 3)
         scan_ms, scan_bases, survivors = engine.bench_scan(V, Q, max(args.steps, 10))
-    total_ms = float(sum(step_ms))
-    total_e2e_ms = float(sum(e2e_ms))
+    n_e2e = args.steps
     t = torch.tensor([total_ms, total_e2e_ms, scan_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    mine = torch.tensor([total_ms / args.steps, total_e2e_ms / max(1, len(e2e_ms)), stage["ms_scan"] / args.steps,
+    mine = torch.tensor([total_ms / args.steps, total_e2e_ms / n_e2e, stage["ms_scan"] / args.steps,
                          stage["ms_extend"] / args.steps, stage["ms_gapped"] / args.steps, stage["ms_host"] / args.steps,
                          -1.0 if numa is None else float(numa)], dtype=torch.float64, device="cuda")
     per_rank = [mine.clone() for _ in range(world)]
@@ -439,7 +476,7 @@ def main():
     total_ms, total_e2e_ms, scan_ms_max = [float(x) for x in t.tolist()]
     bases_per_step = int(g["stats"]["subject_bases_scanned"])
     value = world * bases_per_step * args.steps / (total_ms * 1e-3) / 1e9
-    e2e_value = world * bases_per_step * len(e2e_ms) / (total_e2e_ms * 1e-3) / 1e9
+    e2e_value = world * bases_per_step * n_e2e / (total_e2e_ms * 1e-3) / 1e9
 
     b = s.batch
     h2d = int(vol.packed.shape[0] + (b.concat_len + 2) + 32 * b.num_contexts + 8 * b.n_lookup_segments + 2048)
@@ -461,8 +498,14 @@ def main():
                      "peak_kind": peak_kind, "ms_per_launch": scan_ms,
                      "algorithmic_bytes_per_launch": scan_bases * 0.25},
         "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
-        "ms_per_step_wall": float(sum(step_ms_wall)) / args.steps,
-        "timing": "CUDA events around each step (the step ends with the host replay); max over ranks",
+        "ms_per_step_wall": total_ms_wall / args.steps,
+        "timing": "CUDA events around the K steps (K complete searches through the job pipeline, the last host replay "
+                  "included); max over ranks.  stage_ms_per_step are per-search device spans; consecutive searches overlap",
+        "single_call": {"ms_per_step": float(np.mean(single_ms)), "gbases_per_s": bases_per_step / (np.mean(single_ms) * 1e-3) / 1e9,
+                        "e2e_ms_per_step": float(np.mean(single_e2e_ms)),
+                        "e2e_gbases_per_s": bases_per_step / (np.mean(single_e2e_ms) * 1e-3) / 1e9,
+                        "note": "one blocking bn_prelim_search / bn_prelim_search_host call per step, L2 flushed between steps (this rank)"},
+        "e2e_equals_resident": bool(e2e_same),
         "clocks": clk.summary(),
         "ranks": [dict(zip(("ms_per_step", "e2e_ms_per_step", "ms_scan", "ms_extend", "ms_gapped", "ms_host", "numa"),
                            [round(float(x), 4) for x in r.tolist()])) for r in per_rank],
@@ -486,7 +529,11 @@ def main():
                     "value": DB_BASES * reps / secs / 1e9, "unit": UNIT, "cores": threads, "kind": "reference",
                     "sample": f"{reps} repeats of the full workload (prelim stage only); the reference "
                               f"parallelises over subject sequences, DB has {vol.n_seqs} -> {threads} thread"}
-                line["parity_vs_reference"] = bool(np.array_equal(P.final_table(g["hsps"]), r["final"]))
+                same_all = bool(np.array_equal(P.final_table(per_set[0]["hsps"]), r["final"]))
+                for k in range(1, N_SETS):
+                    rk = R.search(sets[k][1], sets[k][0], cfg)
+                    same_all = same_all and bool(np.array_equal(P.final_table(per_set[k]["hsps"]), rk["final"]))
+                line["parity_vs_reference"] = same_all
                 # ---- the stage after the path, outside every timed region above: the same
                 # step's preliminary lists through bn_traceback_search, next to the reference's traceback stage
                 try:
@@ -514,9 +561,8 @@ def main():
         except Exception as e:  # the baseline must never take the bench down
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
                                     "sample": f"failed: {e}"}
-    Q.free()
-    V.free()
-    s.free()
+    for x in Qs + Vs + setups:
+        x.free()
     del flush
     torch.cuda.empty_cache()
 

@@ -143,8 +143,13 @@ struct Lane {
     int id = -1;                          // CUDA device ordinal
     int index = 0;                        // lane number on its device
     cudaStream_t stream = nullptr;
-    cudaStream_t copy_stream = nullptr;   // volume uploads of the host-buffer entry point (overlap with the table build)
+    // high-priority stream for what follows the scan kernel in the fused pipeline: when several searches are in flight
+    // on the device (job pipeline, concurrent callers) the small latency-bound kernels of the search that is ahead
+    // get their blocks scheduled in front of the thousands of pending scan blocks of the searches behind it
+    cudaStream_t tail_stream = nullptr;
+    cudaEvent_t scan_ev = nullptr;
     cudaEvent_t alloc_ev = nullptr;
+    PinnedBuf<uint8_t> stage;             // pinned staging of a pipeline job's small uploads (Stager)
     Workspace w;
     Workspace &ws() { return w; }
     std::mutex mu;                        // held by the thread that owns the lane
@@ -152,6 +157,12 @@ struct Lane {
 
 struct Gpu {
     int id = -1;
+    // volume uploads of the host-buffer entry points, ONE queue per device: uploads of consecutive jobs cross PCIe one
+    // after the other (each at full bandwidth, the first one done first) instead of sharing the link and all
+    // finishing together; they overlap the table builds and searches on the lanes' streams
+    cudaStream_t copy_stream = nullptr;
+    cudaStream_t free_stream = nullptr;   // never carries work: a cudaFreeAsync on it completes at once, so the block is
+                                          // reusable by the next allocation on any lane (the callers free after a host sync)
     std::vector<std::unique_ptr<Lane>> lanes;
     std::atomic<unsigned> next{0};
 };
@@ -317,12 +328,31 @@ static cudaError_t dev_alloc(T **dst, size_t n, cudaStream_t st)
     return cudaMallocAsync((void **)dst, n * sizeof(T), st);
 }
 
+// Pinned staging of small host->device copies (job pipeline): a cudaMemcpyAsync from pageable memory blocks the
+// calling thread until the copy engine has taken the data, i.e. behind whatever volume upload is in flight; staged
+// through a pinned buffer of the lane the copy is queued and the thread moves on.  The buffer belongs to one job at
+// a time (the lane's previous job is complete when the next one is prepared).
+struct Stager {
+    uint8_t *base = nullptr;
+    size_t cap = 0, used = 0;
+    const void *stage(const void *src, size_t bytes)
+    {
+        const size_t at = (used + 255) & ~size_t(255);
+        if (!base || at + bytes > cap) return src;          // does not fit: plain (blocking) copy
+        memcpy(base + at, src, bytes);
+        used = at + bytes;
+        return base + at;
+    }
+};
+static thread_local Stager *g_stager = nullptr;
+static inline const void *staged(const void *src, size_t bytes) { return g_stager ? g_stager->stage(src, bytes) : src; }
+
 template <typename T>
 static cudaError_t upload(T **dst, const T *src, size_t n, cudaStream_t st)
 {
     cudaError_t e = dev_alloc(dst, n, st);
     if (e != cudaSuccess || n == 0) return e;
-    return cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, st);
+    return cudaMemcpyAsync(*dst, staged(src, n * sizeof(T)), n * sizeof(T), cudaMemcpyHostToDevice, st);
 }
 
 cudaError_t launch_build_presence(const int32_t *hashtable, int64_t hashsize, uint32_t *presence, cudaStream_t st);
@@ -626,21 +656,21 @@ static int build_chunk_table(Volume &V, const Query &Q, int32_t oid_begin, int32
     }
     if (!T->host.empty()) {
         CU_TRY(T->dev.reserve(T->host.size(), st));
-        CU_TRY(cudaMemcpyAsync(T->dev.p, T->host.data(), T->host.size() * sizeof(DevChunk),
+        CU_TRY(cudaMemcpyAsync(T->dev.p, staged(T->host.data(), T->host.size() * sizeof(DevChunk)), T->host.size() * sizeof(DevChunk),
                                cudaMemcpyHostToDevice, st));
         if (!T->units.empty()) {
             CU_TRY(T->units_dev.reserve(T->units.size(), st));
-            CU_TRY(cudaMemcpyAsync(T->units_dev.p, T->units.data(), T->units.size() * sizeof(DevChunk),
+            CU_TRY(cudaMemcpyAsync(T->units_dev.p, staged(T->units.data(), T->units.size() * sizeof(DevChunk)), T->units.size() * sizeof(DevChunk),
                                    cudaMemcpyHostToDevice, st));
             CU_TRY(T->ranges_dev.reserve(T->ranges.size() + 1, st));
-            CU_TRY(cudaMemcpyAsync(T->ranges_dev.p, T->ranges.data(), T->ranges.size() * sizeof(int2),
+            CU_TRY(cudaMemcpyAsync(T->ranges_dev.p, staged(T->ranges.data(), T->ranges.size() * sizeof(int2)), T->ranges.size() * sizeof(int2),
                                    cudaMemcpyHostToDevice, st));
         }
         CU_TRY(T->block_chunk.reserve(bc.size(), st));
-        CU_TRY(cudaMemcpyAsync(T->block_chunk.p, bc.data(), bc.size() * sizeof(int32_t),
+        CU_TRY(cudaMemcpyAsync(T->block_chunk.p, staged(bc.data(), bc.size() * sizeof(int32_t)), bc.size() * sizeof(int32_t),
                                cudaMemcpyHostToDevice, st));
         CU_TRY(T->block_desc.reserve(bd.size() + 1, st));
-        CU_TRY(cudaMemcpyAsync(T->block_desc.p, bd.data(), bd.size() * sizeof(ScanBlockDesc),
+        CU_TRY(cudaMemcpyAsync(T->block_desc.p, staged(bd.data(), bd.size() * sizeof(ScanBlockDesc)), bd.size() * sizeof(ScanBlockDesc),
                                cudaMemcpyHostToDevice, st));
         // no synchronisation: the sources are members of the table; consumers on `st` are ordered behind the
         // copies, consumers on other lanes (and the destructor) wait on `ready`
@@ -821,10 +851,11 @@ static int32_t greedy_xdrop_offset(const BnQueryBatch &b)
 
 // Tier-1 gapped launch over the init hits in ws.init; their number is read on the device
 // (counters[2], capped at max_init), so the call needs no host knowledge of it.
-static int enqueue_gapped(Lane &D, Volume &V, Query &Q, ChunkTable &T, int64_t max_init, BnStats *stats)
+static int enqueue_gapped(Lane &D, Volume &V, Query &Q, ChunkTable &T, int64_t max_init, BnStats *stats,
+                          cudaStream_t on_stream = nullptr)
 {
     Workspace &ws = D.ws();
-    cudaStream_t st = D.stream;
+    cudaStream_t st = on_stream ? on_stream : D.stream;
     const DevQuery &dq = Q.dev[V.device].view;
     const BnQueryBatch &b = Q.batch;
     CU_TRY(ws.gap_out.reserve((size_t)max_init));
@@ -1270,6 +1301,11 @@ static int fused_enqueue(Lane &D, Volume &V, Query &Q, ChunkTable &T, FusedState
     t_scan.start();
     CU_TRY(launch_scan(dq, s, st));
     t_scan.stop();
+    // everything behind the scan runs on the lane's high-priority stream
+    CU_TRY(cudaEventRecord(D.scan_ev, st));
+    st = D.tail_stream;
+    CU_TRY(cudaStreamWaitEvent(st, D.scan_ev, 0));
+    t_ext.st = st; t_gap.st = st;
 
     t_ext.start();
     BucketLaunch L{};
@@ -1289,7 +1325,7 @@ static int fused_enqueue(Lane &D, Volume &V, Query &Q, ChunkTable &T, FusedState
 
     t_gap.start();
     CU_TRY(ws.h_init.reserve((size_t)init_cap + 1)); CU_TRY(ws.h_gap.reserve((size_t)init_cap + 1));
-    int rc = enqueue_gapped(D, V, Q, T, init_cap, nullptr);
+    int rc = enqueue_gapped(D, V, Q, T, init_cap, nullptr, st);
     if (rc) return rc;
     // counters + results into the pinned mirrors by one kernel, then the only synchronisation of the step
     CU_TRY(launch_mirror_results(ws.init.p, ws.gap_out.p, ws.counters.p, init_cap, ws.h_init.p, ws.h_gap.p,
@@ -1761,9 +1797,9 @@ int bn_init(int n_gpu, const int *device_ids)
     std::vector<int> ids;
     if (n_gpu <= 0 || !device_ids) { for (int i = 0; i < (n_gpu > 0 ? std::min(n_gpu, count) : count); i++) ids.push_back(i); }
     else for (int i = 0; i < n_gpu; i++) ids.push_back(device_ids[i]);
-    // lanes per device: concurrent callers beyond this number wait for a lane (BN_LANES, default 4)
-    int n_lanes = 4;
-    if (const char *e = getenv("BN_LANES")) n_lanes = std::max(3, std::min(16, atoi(e)));      // the job pipeline needs two + one for its traceback stage
+    // lanes per device: concurrent callers beyond this number wait for a lane (BN_LANES, default 6)
+    int n_lanes = 6;
+    if (const char *e = getenv("BN_LANES")) n_lanes = std::max(4, std::min(16, atoi(e)));      // the job pipeline needs three + one for its traceback stage
     for (int id : ids) {
         if (id < 0 || id >= count) return fail(BN_ERR_INVALID, "device id out of range");
         auto d = std::make_unique<Gpu>();
@@ -1773,10 +1809,17 @@ int bn_init(int n_gpu, const int *device_ids)
             auto l = std::make_unique<Lane>();
             l->id = id; l->index = k;
             CU_TRY(cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking));
-            CU_TRY(cudaStreamCreateWithFlags(&l->copy_stream, cudaStreamNonBlocking));
+            {
+                int lo = 0, hi = 0;
+                CU_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                CU_TRY(cudaStreamCreateWithPriority(&l->tail_stream, cudaStreamNonBlocking, hi));
+                CU_TRY(cudaEventCreateWithFlags(&l->scan_ev, cudaEventDisableTiming));
+            }
             CU_TRY(cudaEventCreateWithFlags(&l->alloc_ev, cudaEventDisableTiming));
             d->lanes.push_back(std::move(l));
         }
+        CU_TRY(cudaStreamCreateWithFlags(&d->free_stream, cudaStreamNonBlocking));
+        CU_TRY(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
         {   // keep freed blocks in the stream-ordered pool (volumes / query tables are re-loaded often)
             cudaMemPool_t pool;
             if (cudaDeviceGetDefaultMemPool(&pool, id) == cudaSuccess) {
@@ -1794,7 +1837,7 @@ static void free_volume_dev(Volume &V)
 {
     Gpu *g = g_devices[(size_t)V.device].get();
     cudaSetDevice(g->id);
-    cudaStream_t st = g->lanes[0]->stream;
+    cudaStream_t st = g->free_stream;
     if (V.ready) { cudaEventSynchronize(V.ready); cudaEventDestroy(V.ready); V.ready = nullptr; }
     if (V.d_raw) cudaFreeAsync(V.d_raw, st);
     if (V.d_amb) cudaFreeAsync(V.d_amb, st);
@@ -1809,7 +1852,7 @@ static void free_volume_dev(Volume &V)
 static void free_query_all(Query &Q)
 {
     for (size_t d = 0; d < Q.dev.size() && d < g_devices.size(); d++)
-        if (Q.dev[d].ready) { cudaSetDevice(g_devices[d]->id); free_query_dev(Q.dev[d], g_devices[d]->lanes[0]->stream); }
+        if (Q.dev[d].ready) { cudaSetDevice(g_devices[d]->id); free_query_dev(Q.dev[d], g_devices[d]->free_stream); }
 }
 
 void bn_release(void)
@@ -1825,11 +1868,14 @@ void bn_release(void)
             std::lock_guard<std::mutex> ll(l->mu);          // wait for a search still running on the lane
             cudaStreamSynchronize(l->stream);
             l->w.release();
+            l->stage.release();
             if (l->alloc_ev) cudaEventDestroy(l->alloc_ev);
-            if (l->copy_stream) cudaStreamDestroy(l->copy_stream);
+            if (l->tail_stream) cudaStreamDestroy(l->tail_stream);
+            if (l->scan_ev) cudaEventDestroy(l->scan_ev);
             if (l->stream) cudaStreamDestroy(l->stream);
         }
     }
+    for (auto &d : g_devices) if (d->free_stream) { cudaSetDevice(d->id); cudaStreamDestroy(d->free_stream); cudaStreamDestroy(d->copy_stream); }
     g_devices.clear();
     g_inited = false;
 }
@@ -1865,7 +1911,7 @@ static int db_load_impl(int device, const uint8_t *packed, int64_t packed_bytes,
     // 64 readable bytes in front (reverse 16-base windows may start before the first base) and behind
     CU_TRY(cudaMallocAsync((void **)&V->d_raw, (size_t)packed_bytes + 192, D->stream));
     V->d_packed = V->d_raw + 64;
-    cudaStream_t cs = async ? D->copy_stream : D->stream;
+    cudaStream_t cs = async ? G->copy_stream : D->stream;
     if (async) {
         CU_TRY(cudaEventRecord(D->alloc_ev, D->stream));
         CU_TRY(cudaStreamWaitEvent(cs, D->alloc_ev, 0));
@@ -2331,9 +2377,14 @@ int bn_prelim_search_jobs(int device, int32_t n_jobs, const BnJob *jobs, int tap
     }
     if (n_jobs == 0) return BN_OK;
     CU_TRY(cudaSetDevice(g->id));
-    LaneLock lanes[2];
-    lanes[0] = LaneLock(*g);
-    lanes[1] = LaneLock(*g);
+    // three lanes: while the call waits for job k, jobs k+1 and k+2 are queued on the device
+    constexpr int NL = 3;
+    LaneLock lanes[NL];
+    Stager stagers[NL];
+    for (int i = 0; i < NL; i++) {
+        lanes[i] = LaneLock(*g);
+        if (lanes[i].lane->stage.reserve((size_t)6 << 20) == cudaSuccess) { stagers[i].base = lanes[i].lane->stage.p; stagers[i].cap = (size_t)6 << 20; }
+    }
 
     struct JobState {
         std::shared_ptr<Volume> V;
@@ -2344,14 +2395,23 @@ int bn_prelim_search_jobs(int device, int32_t n_jobs, const BnJob *jobs, int tap
         int rc = BN_OK;
         std::string err;
         bool host_done = false, all_done = false;
+        double t_prep0 = 0, t_prep1 = 0, t_end0 = 0, t_end1 = 0, t_host0 = 0, t_host1 = 0;     // BN_TRACE timeline
+        double t_prep_q = 0, t_prep_v = 0;
+        // small result sets leave the lane's pinned mirrors right after the search, so the lane's next job need not
+        // wait for this one's host replay
+        std::vector<DevInitHit> init_copy;
+        std::vector<DevGapResult> gap_copy;
+        bool mirrors_free = false;
     };
     std::vector<JobState> J((size_t)n_jobs);
+    const double t_call = now_ms();
     std::mutex mu;
     std::condition_variable cv;
     std::deque<int32_t> host_q, tb_q;
     bool host_closed = false, tb_closed = false;
 
-    std::thread host_worker([&]() {
+    std::atomic<int> host_workers_live{2};
+    auto host_loop = [&]() {
         for (;;) {
             int32_t k;
             {
@@ -2361,17 +2421,22 @@ int bn_prelim_search_jobs(int device, int32_t n_jobs, const BnJob *jobs, int tap
                 k = host_q.front(); host_q.pop_front();
             }
             JobState &S = J[(size_t)k];
+            S.t_host0 = now_ms();
             const int r = search_host_phase(*S.Q, S.G, taps, &results[k]);
+            S.t_host1 = now_ms();
             std::lock_guard<std::mutex> lk(mu);
             if (r) { S.rc = r; S.err = g_err; }
             S.host_done = true;
             if (tb && !r) tb_q.push_back(k); else S.all_done = true;
             cv.notify_all();
         }
-        std::lock_guard<std::mutex> lk(mu);
-        tb_closed = true;
-        cv.notify_all();
-    });
+        if (host_workers_live.fetch_sub(1) == 1) {
+            std::lock_guard<std::mutex> lk(mu);
+            tb_closed = true;
+            cv.notify_all();
+        }
+    };
+    std::thread host_worker(host_loop), host_worker2(host_loop);
     std::thread tb_worker;
     if (tb) tb_worker = std::thread([&]() {
         for (;;) {
@@ -2418,11 +2483,14 @@ int bn_prelim_search_jobs(int device, int32_t n_jobs, const BnJob *jobs, int tap
     auto prepare = [&](int32_t k) -> int {
         JobState &S = J[(size_t)k];
         const BnJob &jb = jobs[k];
-        Lane *L = lanes[k & 1].lane;
-        if (k >= 2) {           // the lane's pinned result mirrors are being read by the host replay of job k-2
+        Lane *L = lanes[k % NL].lane;
+        S.t_prep0 = now_ms();
+        if (k >= NL && !J[(size_t)k - NL].mirrors_free) {   // the lane's pinned result mirrors are being read by the host replay of job k-NL
             std::unique_lock<std::mutex> lk(mu);
-            cv.wait(lk, [&]() { return J[(size_t)k - 2].host_done; });
+            cv.wait(lk, [&]() { return J[(size_t)k - NL].host_done; });
         }
+        stagers[k % NL].used = 0;
+        struct UseStager { UseStager(Stager *s) { g_stager = s; } ~UseStager() { g_stager = nullptr; } } use_stager(&stagers[k % NL]);
         release_finished(false);
         int r = BN_OK;
         const std::function<int()> start_volume = [&]() {
@@ -2437,6 +2505,7 @@ int bn_prelim_search_jobs(int device, int32_t n_jobs, const BnJob *jobs, int tap
             S.own_q = true;
             r = query_load_impl(jb.batch, &S.Q, device, &start_volume, L, true, true);
         }
+        S.t_prep_q = now_ms();
         if (r) return r;
         if (jb.vol_handle >= 0) {
             r = get_volume(jb.vol_handle, &S.V);
@@ -2444,21 +2513,34 @@ int bn_prelim_search_jobs(int device, int32_t n_jobs, const BnJob *jobs, int tap
             if (S.V->device != device) return fail(BN_ERR_INVALID, "bn_prelim_search_jobs: volume lives on another device");
         } else if (!S.V) return fail(BN_ERR_INVALID, "bn_prelim_search_jobs: volume upload did not start");
         const int32_t n_seq = (int32_t)S.V->seq_len.size();
-        return search_gpu_begin(*L, *S.V, *S.Q, 0, n_seq, &results[k], S.G, triage_allowed(*S.Q, n_seq, taps), S.P);
+        r = search_gpu_begin(*L, *S.V, *S.Q, 0, n_seq, &results[k], S.G, triage_allowed(*S.Q, n_seq, taps), S.P);
+        S.t_prep1 = now_ms();
+        return r;
     };
 
-    int32_t dispatched = 0;
-    rc = prepare(0);
-    if (rc) { first_error = rc; first_msg = g_err; }
-    for (int32_t k = 0; k < n_jobs && first_error == BN_OK; k++) {
-        if (k + 1 < n_jobs) {
-            rc = prepare(k + 1);
-            if (rc) { first_error = rc; first_msg = g_err; }
+    int32_t dispatched = 0, prepared = 0;
+    while (prepared < std::min<int32_t>(NL - 1, n_jobs)) {
+        rc = prepare(prepared);
+        if (rc) { first_error = rc; first_msg = g_err; break; }
+        prepared++;
+    }
+    for (int32_t k = 0; k < n_jobs && k < prepared; k++) {
+        if (prepared < n_jobs && first_error == BN_OK) {
+            rc = prepare(prepared);
+            if (rc) { first_error = rc; first_msg = g_err; } else prepared++;
         }
         JobState &S = J[(size_t)k];
-        rc = search_gpu_end(*lanes[k & 1].lane, *S.V, *S.Q, &results[k], S.G, S.P);
+        S.t_end0 = now_ms();
+        rc = search_gpu_end(*lanes[k % NL].lane, *S.V, *S.Q, &results[k], S.G, S.P);
+        S.t_end1 = now_ms();
         if (rc) { if (first_error == BN_OK) { first_error = rc; first_msg = g_err; } break; }
         if (first_error) break;
+        if (!S.G.triaged && S.G.n_records <= (int64_t)1 << 16 && S.G.h_init && S.G.h_gap) {
+            S.init_copy.assign(S.G.h_init, S.G.h_init + S.G.n_records);
+            S.gap_copy.assign(S.G.h_gap, S.G.h_gap + S.G.n_records);
+            S.G.h_init = S.init_copy.data(); S.G.h_gap = S.gap_copy.data();
+            S.mirrors_free = true;
+        } else if (!S.G.triaged && S.G.n_records == 0) S.mirrors_free = true;
         {
             std::lock_guard<std::mutex> lk(mu);
             host_q.push_back(k);
@@ -2472,6 +2554,7 @@ int bn_prelim_search_jobs(int device, int32_t n_jobs, const BnJob *jobs, int tap
         cv.notify_all();
     }
     host_worker.join();
+    host_worker2.join();
     if (tb_worker.joinable()) tb_worker.join();
     // jobs that were prepared but never completed still own queued device work
     for (auto &l : lanes) cudaStreamSynchronize(l.lane->stream);
@@ -2481,6 +2564,13 @@ int bn_prelim_search_jobs(int device, int32_t n_jobs, const BnJob *jobs, int tap
         if (first_error == BN_OK && S.rc) { first_error = S.rc; first_msg = S.err; }
     }
     release_finished(true);
+    if (getenv("BN_TRACE") && atoi(getenv("BN_TRACE")) >= 2)
+        for (int32_t k = 0; k < n_jobs; k++) {
+            const JobState &S = J[(size_t)k];
+            fprintf(stderr, "[bn] job %3d: prepare %.3f (tables %.3f)..%.3f  complete %.3f..%.3f  host %.3f..%.3f | device spans scan %.3f ext %.3f gap %.3f\n",
+                    k, S.t_prep0 - t_call, S.t_prep_q - t_call, S.t_prep1 - t_call, S.t_end0 - t_call, S.t_end1 - t_call, S.t_host0 - t_call,
+                    S.t_host1 - t_call, results[k].stats.ms_scan, results[k].stats.ms_extend, results[k].stats.ms_gapped);
+        }
     if (first_error) {
         for (int32_t k = 0; k < n_jobs; k++) {
             bn_results_free(&results[k]);

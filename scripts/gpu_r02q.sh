@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+BN_TRACE=2 python scripts/exp_jobs.py resident 12 2> gpurun_out/jobs_resident.txt
+tail -14 gpurun_out/jobs_resident.txt
+BN_TRACE=2 python scripts/exp_jobs.py host 12 2> gpurun_out/jobs_host.txt
+tail -14 gpurun_out/jobs_host.txt
