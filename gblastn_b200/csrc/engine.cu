@@ -24,10 +24,50 @@
 #include <cub/cub.cuh>
 
 #include "bn_device.cuh"
+#include "devmem.h"
 #include "dbfile.h"
 #include "hostpost.h"
 
 namespace bn {
+
+// ---- devmem.h ------------------------------------------------------------------------------------
+static thread_local DevArena *g_arena_tls = nullptr;
+DevArena *&current_arena() { return g_arena_tls; }
+static std::mutex g_arena_mu;
+static std::vector<std::pair<uintptr_t, uintptr_t>> g_arena_ranges;
+void arena_register(const DevArena &a)
+{
+    if (!a.base) return;
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    g_arena_ranges.emplace_back((uintptr_t)a.base, (uintptr_t)a.base + a.cap);
+}
+void arena_unregister(const DevArena &a)
+{
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    for (size_t i = 0; i < g_arena_ranges.size(); i++)
+        if (g_arena_ranges[i].first == (uintptr_t)a.base) { g_arena_ranges.erase(g_arena_ranges.begin() + (long)i); break; }
+}
+static bool in_arena(const void *p)
+{
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    for (const auto &r : g_arena_ranges) if ((uintptr_t)p >= r.first && (uintptr_t)p < r.second) return true;
+    return false;
+}
+cudaError_t dev_malloc(void **p, size_t bytes, cudaStream_t st)
+{
+    DevArena *a = g_arena_tls;
+    if (a) {
+        const size_t at = (a->used + 255) & ~size_t(255);
+        a->used = at + bytes;
+        if (a->base && at + bytes <= a->cap) { *p = a->base + at; return cudaSuccess; }
+    }
+    return cudaMallocAsync(p, bytes, st);
+}
+cudaError_t dev_free(void *p, cudaStream_t st)
+{
+    if (!p || in_arena(p)) return cudaSuccess;
+    return cudaFreeAsync(p, st);
+}
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
@@ -39,6 +79,12 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
             return fail(e__ == cudaErrorMemoryAllocation ? BN_ERR_MEMORY : BN_ERR_CUDA,      \
                         std::string(#expr) + ": " + cudaGetErrorString(e__));                \
     } while (0)
+
+// BN_TRACE >= 3: report host-side steps of a table / volume load that take longer than 1 ms
+static double now_ms();
+static thread_local double g_tlast = 0;
+static const bool g_t3 = getenv("BN_TRACE") && atoi(getenv("BN_TRACE")) >= 3;
+#define TSTEP(label) do { if (g_t3) { const double n__ = now_ms(); if (n__ - g_tlast > 1.0) fprintf(stderr, "[bn] slow step %s: %.3f ms\n", label, n__ - g_tlast); g_tlast = n__; } } while (0)
 
 template <typename T>
 struct DevBuf {
@@ -69,11 +115,11 @@ struct PoolBuf {
         if (n <= cap) return cudaSuccess;
         release();
         st = stream;
-        cudaError_t e = cudaMallocAsync((void **)&p, n * sizeof(T), st);
+        cudaError_t e = dev_malloc((void **)&p, n * sizeof(T), st);
         if (e == cudaSuccess) cap = n; else p = nullptr;
         return e;
     }
-    void release() { if (p) cudaFreeAsync(p, st); p = nullptr; cap = 0; }
+    void release() { if (p) dev_free(p, st); p = nullptr; cap = 0; }
 };
 
 // grow-only pinned host buffer (target of the D2H result copies: pageable targets go through a
@@ -150,6 +196,7 @@ struct Lane {
     cudaEvent_t scan_ev = nullptr;
     cudaEvent_t alloc_ev = nullptr;
     PinnedBuf<uint8_t> stage;             // pinned staging of a pipeline job's small uploads (Stager)
+    DevArena arena;                       // device memory of a pipeline job's own batch / volume (devmem.h)
     Workspace w;
     Workspace &ws() { return w; }
     std::mutex mu;                        // held by the thread that owns the lane
@@ -316,7 +363,7 @@ static void free_query_dev(QueryDev &q, cudaStream_t st)
 {
     void *ptrs[] = {q.query, q.ctx, q.next_pos, q.backbone, q.overflow, q.na_cells, q.na_overflow,
                     q.score_table, q.matrix, q.qpk, q.prk, q.cinfo, q.qinfo, q.sig};
-    for (void *p : ptrs) if (p) cudaFreeAsync(p, st);
+    for (void *p : ptrs) if (p) dev_free(p, st);
     q = QueryDev{};
 }
 
@@ -325,7 +372,7 @@ static cudaError_t dev_alloc(T **dst, size_t n, cudaStream_t st)
 {
     *dst = nullptr;
     if (n == 0) return cudaSuccess;
-    return cudaMallocAsync((void **)dst, n * sizeof(T), st);
+    return dev_malloc((void **)dst, n * sizeof(T), st);
 }
 
 // Pinned staging of small host->device copies (job pipeline): a cudaMemcpyAsync from pageable memory blocks the
@@ -388,7 +435,9 @@ static int query_to_device(Query &Q, const BnQueryBatch &src, int d, Lane *dev, 
                              c.x_dropoff, c.cutoff_score, c.reduced_cutoff, c.gapped_cutoff};
     }
     // ---- host -> device copies first ------------------------------------------------------------------
+    TSTEP("query: begin");
     CU_TRY(upload(&qd.query, src.query_start, (size_t)b.concat_len + 2, st));
+    TSTEP("query: first upload");
     CU_TRY(upload(&qd.ctx, dctx.data(), dctx.size(), st));
     CU_TRY(upload(&qd.score_table, b.nucl_score_table, (size_t)256, st));
     CU_TRY(upload(&qd.matrix, b.matrix, (size_t)256, st));
@@ -415,7 +464,9 @@ static int query_to_device(Query &Q, const BnQueryBatch &src, int d, Lane *dev, 
         if (src.overflow && b.overflow_len > 0) CU_TRY(upload(&qd.overflow, src.overflow, (size_t)b.overflow_len, st));
         else CU_TRY(upload(&qd.overflow, kEmptyOverflow, (size_t)2, st));
     }
+    TSTEP("query: uploads");
     if (after_h2d) { const int rc = (*after_h2d)(); if (rc) return rc; }
+    TSTEP("query: volume hook");
 
     // ---- derived arrays (device only) --------------------------------------------------------------------
     if (b.lut_type == BN_LUT_MB) {
@@ -433,6 +484,7 @@ static int query_to_device(Query &Q, const BnQueryBatch &src, int d, Lane *dev, 
             CU_TRY(launch_build_presence(t_hashtable, b.hashsize, t_presence, st));
         }
     }
+    TSTEP("query: lookup fill");
     const int64_t nw = (int64_t)((b.concat_len + 2 + 16) >> 4) + 3;
     CU_TRY(dev_alloc(&qd.qpk, (size_t)nw, st));
     CU_TRY(launch_build_qpk(qd.query, b.concat_len, qd.qpk, nw, st));
@@ -458,7 +510,7 @@ static int query_to_device(Query &Q, const BnQueryBatch &src, int d, Lane *dev, 
         CU_TRY(dev_alloc(&t_indexed, (size_t)(b.concat_len + 1 + 32) / 32 + 2, st));
         CU_TRY(launch_build_qinfo(v, qd.next_pos, b.concat_len, device_fill ? t_first_qp : t_hashtable,
                                   device_fill ? (int64_t)b.concat_len + 1 : b.hashsize, t_indexed, qd.qinfo, st));
-        CU_TRY(cudaFreeAsync(t_indexed, st));
+        CU_TRY(dev_free(t_indexed, st));
         v.qinfo = qd.qinfo;
         // compact table: {presence word, rank} per 32 cells (4^lut / 4 bytes, L2-resident) + the first
         // chain element of every occupied cell in cell order.  It stands in for hashtable[] everywhere
@@ -485,10 +537,12 @@ static int query_to_device(Query &Q, const BnQueryBatch &src, int d, Lane *dev, 
         CU_TRY(launch_build_sig(qd.cinfo, (int64_t)b.concat_len + 2, qd.sig, st));
         v.sig = getenv("BN_NO_SIG") ? nullptr : qd.sig;
     }
+    TSTEP("query: derived tables");
     {
         void *tmp[] = {t_hashtable, t_first_qp, t_segs, t_presence, t_counts, t_prefix};
-        for (void *p : tmp) if (p) CU_TRY(cudaFreeAsync(p, st));
+        for (void *p : tmp) if (p) CU_TRY(dev_free(p, st));
     }
+    TSTEP("query: frees");
     // caller's arrays may go away after bn_query_load returns (a pipeline's stay until its call does: keep_async)
     if (!keep_async) CU_TRY(cudaStreamSynchronize(st));
     qd.ready = true;
@@ -1839,7 +1893,7 @@ static void free_volume_dev(Volume &V)
     cudaSetDevice(g->id);
     cudaStream_t st = g->free_stream;
     if (V.ready) { cudaEventSynchronize(V.ready); cudaEventDestroy(V.ready); V.ready = nullptr; }
-    if (V.d_raw) cudaFreeAsync(V.d_raw, st);
+    if (V.d_raw) dev_free(V.d_raw, st);
     if (V.d_amb) cudaFreeAsync(V.d_amb, st);
     V.d_amb = nullptr;
     if (V.d_amb_runs) cudaFreeAsync(V.d_amb_runs, st);
@@ -1869,6 +1923,7 @@ void bn_release(void)
             cudaStreamSynchronize(l->stream);
             l->w.release();
             l->stage.release();
+            if (l->arena.base) { arena_unregister(l->arena); cudaFree(l->arena.base); l->arena = DevArena{}; }
             if (l->alloc_ev) cudaEventDestroy(l->alloc_ev);
             if (l->tail_stream) cudaStreamDestroy(l->tail_stream);
             if (l->scan_ev) cudaEventDestroy(l->scan_ev);
@@ -1909,7 +1964,9 @@ static int db_load_impl(int device, const uint8_t *packed, int64_t packed_bytes,
     V->seq_len.assign(seq_len, seq_len + n_seq);
     CU_TRY(cudaSetDevice(D->id));
     // 64 readable bytes in front (reverse 16-base windows may start before the first base) and behind
-    CU_TRY(cudaMallocAsync((void **)&V->d_raw, (size_t)packed_bytes + 192, D->stream));
+    TSTEP("volume: begin");
+    CU_TRY(dev_malloc((void **)&V->d_raw, (size_t)packed_bytes + 192, D->stream));
+    TSTEP("volume: malloc");
     V->d_packed = V->d_raw + 64;
     cudaStream_t cs = async ? G->copy_stream : D->stream;
     if (async) {
@@ -1919,6 +1976,7 @@ static int db_load_impl(int device, const uint8_t *packed, int64_t packed_bytes,
     CU_TRY(cudaMemsetAsync(V->d_raw, 0, 64, cs));
     CU_TRY(cudaMemcpyAsync(V->d_packed, packed, (size_t)packed_bytes, cudaMemcpyHostToDevice, cs));
     CU_TRY(cudaMemsetAsync(V->d_packed + packed_bytes, 0, 128, cs));
+    TSTEP("volume: copies queued");
     if (async) {
         CU_TRY(cudaEventCreateWithFlags(&V->ready, cudaEventDisableTiming));
         CU_TRY(cudaEventRecord(V->ready, cs));
@@ -2465,6 +2523,13 @@ int bn_prelim_search_jobs(int device, int32_t n_jobs, const BnJob *jobs, int tap
     std::string first_msg;
     int32_t free_cursor = 0;
     // device memory of the jobs' own volumes / batches goes back to the pool as soon as every stage of the job is through
+    auto release_job = [&](JobState &S) {          // every stage of the job is through
+        if (S.freed) return;
+        S.G.T.reset();
+        if (S.own_q && S.Q) free_query_all(*S.Q);
+        if (S.own_v && S.V) free_volume_dev(*S.V);
+        S.freed = true;
+    };
     auto release_finished = [&](bool wait_all) {
         for (; free_cursor < n_jobs; free_cursor++) {
             JobState &S = J[(size_t)free_cursor];
@@ -2474,10 +2539,7 @@ int bn_prelim_search_jobs(int device, int32_t n_jobs, const BnJob *jobs, int tap
                 if (wait_all) cv.wait(lk, [&]() { return S.all_done; });
                 else if (!S.all_done) break;
             }
-            S.G.T.reset();
-            if (S.own_q && S.Q) free_query_all(*S.Q);
-            if (S.own_v && S.V) free_volume_dev(*S.V);
-            S.freed = true;
+            release_job(S);
         }
     };
     auto prepare = [&](int32_t k) -> int {
@@ -2485,13 +2547,41 @@ int bn_prelim_search_jobs(int device, int32_t n_jobs, const BnJob *jobs, int tap
         const BnJob &jb = jobs[k];
         Lane *L = lanes[k % NL].lane;
         S.t_prep0 = now_ms();
-        if (k >= NL && !J[(size_t)k - NL].mirrors_free) {   // the lane's pinned result mirrors are being read by the host replay of job k-NL
+        const bool own_data = jb.query_handle < 0 || jb.vol_handle < 0;
+        if (k >= NL) {
+            JobState &prev = J[(size_t)k - NL];          // the lane's previous job
             std::unique_lock<std::mutex> lk(mu);
-            cv.wait(lk, [&]() { return J[(size_t)k - NL].host_done; });
+            if (prev.own_q || prev.own_v) {              // its batch / volume live in the lane's arena: every stage must be through
+                cv.wait(lk, [&]() { return prev.all_done; });
+                lk.unlock();
+                release_job(prev);
+            } else if (!prev.mirrors_free)               // the lane's pinned result mirrors are being read by its host replay
+                cv.wait(lk, [&]() { return prev.host_done; });
         }
         stagers[k % NL].used = 0;
         struct UseStager { UseStager(Stager *s) { g_stager = s; } ~UseStager() { g_stager = nullptr; } } use_stager(&stagers[k % NL]);
         release_finished(false);
+        // the job's own batch / volume / chunk table come from the lane's arena (devmem.h); the arena grows to what the
+        // lane's previous job asked for (the first jobs of a call fall back to the pool)
+        struct UseArena {
+            bool on = false;
+            void set(DevArena *a) { current_arena() = a; on = true; }
+            void off() { if (on) current_arena() = nullptr; on = false; }
+            ~UseArena() { off(); }
+        } use_arena;
+        if (own_data) {
+            DevArena &A = L->arena;
+            if (A.used > A.cap) {
+                cudaStreamSynchronize(L->stream);
+                cudaStreamSynchronize(L->tail_stream);
+                if (A.base) { arena_unregister(A); cudaFree(A.base); A.base = nullptr; A.cap = 0; }
+                const size_t want = A.used + A.used / 8 + ((size_t)1 << 20);
+                if (cudaMalloc((void **)&A.base, want) == cudaSuccess) { A.cap = want; arena_register(A); }
+                else { A.base = nullptr; cudaGetLastError(); }
+            }
+            A.used = 0;
+            use_arena.set(&A);
+        }
         int r = BN_OK;
         const std::function<int()> start_volume = [&]() {
             if (jb.vol_handle >= 0) return BN_OK;
@@ -2512,6 +2602,7 @@ int bn_prelim_search_jobs(int device, int32_t n_jobs, const BnJob *jobs, int tap
             if (r) return r;
             if (S.V->device != device) return fail(BN_ERR_INVALID, "bn_prelim_search_jobs: volume lives on another device");
         } else if (!S.V) return fail(BN_ERR_INVALID, "bn_prelim_search_jobs: volume upload did not start");
+        if (!S.own_v) use_arena.off();          // the chunk table of a resident volume is cached with the volume
         const int32_t n_seq = (int32_t)S.V->seq_len.size();
         r = search_gpu_begin(*L, *S.V, *S.Q, 0, n_seq, &results[k], S.G, triage_allowed(*S.Q, n_seq, taps), S.P);
         S.t_prep1 = now_ms();

@@ -22,6 +22,7 @@
 #include <cub/cub.cuh>
 
 #include "bn_device.cuh"
+#include "devmem.h"
 
 namespace bn {
 
@@ -99,12 +100,12 @@ cudaError_t build_mb_lookup_device(const uint8_t *d_query /* base 0 */, int32_t 
     LookupBuildTemp t{};
     void *cub_tmp = nullptr;
 #define LB_TRY(x) do { e = (x); if (e != cudaSuccess) goto done; } while (0)
-    LB_TRY(cudaMallocAsync((void **)&t.segmark, (size_t)n, st));
-    LB_TRY(cudaMallocAsync((void **)&t.keys_a, (size_t)n * 4, st));
-    LB_TRY(cudaMallocAsync((void **)&t.keys_b, (size_t)n * 4, st));
-    LB_TRY(cudaMallocAsync((void **)&t.vals_a, (size_t)n * 4, st));
-    LB_TRY(cudaMallocAsync((void **)&t.vals_b, (size_t)n * 4, st));
-    LB_TRY(cudaMallocAsync((void **)&t.flags, (size_t)n * 4, st));
+    LB_TRY(dev_malloc((void **)&t.segmark, (size_t)n, st));
+    LB_TRY(dev_malloc((void **)&t.keys_a, (size_t)n * 4, st));
+    LB_TRY(dev_malloc((void **)&t.keys_b, (size_t)n * 4, st));
+    LB_TRY(dev_malloc((void **)&t.vals_a, (size_t)n * 4, st));
+    LB_TRY(dev_malloc((void **)&t.vals_b, (size_t)n * 4, st));
+    LB_TRY(dev_malloc((void **)&t.flags, (size_t)n * 4, st));
     LB_TRY(cudaMemsetAsync(t.segmark, 0, (size_t)n, st));
     LB_TRY(cudaMemsetAsync(d_next_pos, 0, ((size_t)concat_len + 1) * 4, st));
     LB_TRY(cudaMemsetAsync(d_presence, 0, (size_t)((hashsize + 31) / 32) * 4, st));
@@ -121,7 +122,7 @@ cudaError_t build_mb_lookup_device(const uint8_t *d_query /* base 0 */, int32_t 
         LB_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, t.keys_a, t.keys_b, t.vals_a, t.vals_b, n, 0, 2 * lut + 1, st));
         LB_TRY(cub::DeviceScan::InclusiveSum(nullptr, bytes2, t.flags, t.flags, n, st));
         bytes = std::max(bytes, bytes2);
-        LB_TRY(cudaMallocAsync(&cub_tmp, bytes, st));
+        LB_TRY(dev_malloc(&cub_tmp, bytes, st));
         LB_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, bytes, t.keys_a, t.keys_b, t.vals_a, t.vals_b, n, 0, 2 * lut + 1, st));
         mb_heads_kernel<<<blocks, 256, 0, st>>>(t.keys_b, n, invalid, t.flags);
         LB_TRY(cudaGetLastError());
@@ -134,7 +135,7 @@ cudaError_t build_mb_lookup_device(const uint8_t *d_query /* base 0 */, int32_t 
 done:
     {
         void *ptrs[] = {t.segmark, t.keys_a, t.keys_b, t.vals_a, t.vals_b, t.flags, cub_tmp};
-        for (void *p : ptrs) if (p) cudaFreeAsync(p, st);
+        for (void *p : ptrs) if (p) dev_free(p, st);
     }
     return e;
 }

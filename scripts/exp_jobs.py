@@ -24,7 +24,12 @@ tr = os.environ.pop("BN_TRACE", None)
 engine.prelim_search_jobs(jobs[:4])
 if tr:
     os.environ["BN_TRACE"] = tr
-for rep in range(2):
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+for rep in range(reps):
+    if tr and rep < reps - 1:
+        os.environ.pop("BN_TRACE", None)
+    elif tr:
+        os.environ["BN_TRACE"] = tr
     t0 = time.perf_counter()
     engine.prelim_search_jobs(jobs)
     print(f"{mode}: {1e3 * (time.perf_counter() - t0) / n:.3f} ms per job", file=sys.stderr)
