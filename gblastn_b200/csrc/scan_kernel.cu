@@ -37,8 +37,17 @@
 
 namespace bn {
 
-constexpr int SCAN_THREADS = 256;
-constexpr int POS_PER_THREAD = 8;
+#ifndef BN_SCAN_THREADS
+#define BN_SCAN_THREADS 256
+#endif
+#ifndef BN_POS_PER_THREAD
+#define BN_POS_PER_THREAD 8
+#endif
+#ifndef BN_SCAN_MIN_BLOCKS
+#define BN_SCAN_MIN_BLOCKS 6
+#endif
+constexpr int SCAN_THREADS = BN_SCAN_THREADS;
+constexpr int POS_PER_THREAD = BN_POS_PER_THREAD;
 constexpr int POS_PER_BLOCK = SCAN_THREADS * POS_PER_THREAD;
 constexpr int TILE_BYTES = 20 * 1024;      // staged subject slice (incl. 64-byte margins)
 constexpr int TILE_MARGIN = 64;
@@ -468,10 +477,14 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 // global -> shared bulk copy executed by the TMA unit (SASS UBLKCP); src/dst 16-byte aligned, bytes % 16 == 0
+// The subject streams through once per search: its sectors are marked evict-first in L2, so that they do not push
+// out the lookup data (prk / sig / cinfo) every probe of the next tiles — and of the next search — gathers from there.
 __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+    unsigned long long policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
 {
@@ -542,7 +555,7 @@ __device__ __noinline__ unsigned long long scan_block_direct(const DevQuery &q, 
 }
 
 template <bool DIRECT>
-__global__ void __launch_bounds__(SCAN_THREADS, DIRECT ? 4 : 6)
+__global__ void __launch_bounds__(SCAN_THREADS, DIRECT ? 4 : BN_SCAN_MIN_BLOCKS)
 scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ ScanLaunch s)
 {
     extern __shared__ __align__(128) uint32_t smem_dyn[];
@@ -604,7 +617,7 @@ scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ S
                 if ((it & 3) == 0) bitpack[it >> 2] = 0;
                 bitpack[it >> 2] |= (idx & 31u) << (8 * (it & 3));
             }
-            cpack[0] = cpack[1] = 0;
+            for (int i = 0; i < POS_PER_THREAD / 4; i++) cpack[i] = 0;
         } else {
             {   // chunk of each of the thread's positions: monotone cursor over the block's chunk table
                 int32_t c = 0, cnext = ct_start[1];

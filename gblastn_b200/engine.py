@@ -13,7 +13,7 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgblastn_b200.so")
+LIB_PATH = os.environ.get("GBLASTN_B200_LIB") or os.path.join(_HERE, "libgblastn_b200.so")      # override: kernel experiments
 
 EXPORTS = [
     "bn_init", "bn_release", "bn_device_count", "bn_last_error", "bn_version",
@@ -221,59 +221,81 @@ def prelim_search_batches(volume: Volume, holders, taps=0) -> list:
     return [_results(res[k]) for k in range(n)]
 
 
-def prelim_search_jobs(jobs, device=0, taps=0, traceback=False) -> list:
-    """The job pipeline (bn_prelim_search_jobs).  jobs: list of dicts with
+class JobBatch:
+    """A prepared call of bn_prelim_search_jobs: the ctypes job array is built once, `run()` is the C call alone (what
+    bench.py times), `results()` converts and frees what it returned.  jobs: list of dicts with
          volume = engine.Volume (resident)  |  host_volume = synth.Volume (uploaded as part of the job)
          query  = engine.Query (resident)   |  batch = BnQueryBatch / holder (loaded as part of the job)
-         gap_x_dropoff_final (with traceback=True)
-    Returns one result dict per job; with traceback=True each also carries "tb" = (final HSPs, ops)."""
-    n = len(jobs)
-    arr = (abi.BnJob * n)()
-    keep = []
-    for k, j in enumerate(jobs):
-        a = arr[k]
-        if j.get("volume") is not None:
-            a.vol_handle = j["volume"].handle
-        else:
-            v = j["host_volume"]
-            packed = v.packed if (isinstance(v.packed, np.ndarray) and v.packed.dtype == np.uint8 and v.packed.flags.c_contiguous) \
-                else np.ascontiguousarray(v.packed, dtype=np.uint8)
-            boff = np.ascontiguousarray(v.byte_off, dtype=np.int64)
-            slen = np.ascontiguousarray(v.seq_len, dtype=np.int32)
-            keep += [packed, boff, slen]
-            a.vol_handle = -1
-            a.packed = packed.ctypes.data
-            a.packed_bytes = packed.shape[0]
-            a.seq_byte_off = boff.ctypes.data
-            a.seq_len = slen.ctypes.data
-            a.n_seq = slen.shape[0]
-        if j.get("query") is not None:
-            a.query_handle = j["query"].handle
-        else:
-            b = j["batch"]
-            b = b.batch if hasattr(b, "batch") else b
-            keep.append(b)
-            a.query_handle = -1
-            a.batch = C.pointer(b)
-        a.gap_x_dropoff_final = int(j.get("gap_x_dropoff_final", 0))
-    res = (abi.BnResults * n)()
-    tb = (abi.BnTracebackOut * n)() if traceback else None
-    _check(lib().bn_prelim_search_jobs(C.c_int(device), C.c_int32(n), arr, C.c_int(taps), res, tb))
-    out = []
-    for k in range(n):
-        if traceback:
-            t = tb[k]
-            try:
-                pair = (abi.struct_array(C.c_void_p(t.hsps), t.n_hsps, abi.TB_HSP_DTYPE),
-                        abi.struct_array(C.c_void_p(t.ops), t.n_ops, abi.EDIT_OP_DTYPE))
-            finally:
-                lib().bn_free(C.c_void_p(t.hsps))
-                lib().bn_free(C.c_void_p(t.ops))
-        d = _results(res[k])
-        if traceback:
-            d["tb"] = pair
-        out.append(d)
-    return out
+         gap_x_dropoff_final (with traceback=True)"""
+
+    def __init__(self, jobs, device=0, taps=0, traceback=False):
+        n = len(jobs)
+        self.n, self.device, self.taps, self.traceback = n, device, taps, traceback
+        self.arr = (abi.BnJob * n)()
+        self.keep = []
+        for k, j in enumerate(jobs):
+            a = self.arr[k]
+            if j.get("volume") is not None:
+                a.vol_handle = j["volume"].handle
+            else:
+                v = j["host_volume"]
+                packed = v.packed if (isinstance(v.packed, np.ndarray) and v.packed.dtype == np.uint8 and v.packed.flags.c_contiguous) \
+                    else np.ascontiguousarray(v.packed, dtype=np.uint8)
+                boff = np.ascontiguousarray(v.byte_off, dtype=np.int64)
+                slen = np.ascontiguousarray(v.seq_len, dtype=np.int32)
+                self.keep += [packed, boff, slen]
+                a.vol_handle = -1
+                a.packed = packed.ctypes.data
+                a.packed_bytes = packed.shape[0]
+                a.seq_byte_off = boff.ctypes.data
+                a.seq_len = slen.ctypes.data
+                a.n_seq = slen.shape[0]
+            if j.get("query") is not None:
+                a.query_handle = j["query"].handle
+            else:
+                b = j["batch"]
+                b = b.batch if hasattr(b, "batch") else b
+                self.keep.append(b)
+                a.query_handle = -1
+                a.batch = C.pointer(b)
+            a.gap_x_dropoff_final = int(j.get("gap_x_dropoff_final", 0))
+        self.res = (abi.BnResults * n)()
+        self.tb = (abi.BnTracebackOut * n)() if traceback else None
+        self._fn = lib().bn_prelim_search_jobs
+        self._pending = False
+
+    def run(self):
+        if self._pending:
+            self.results()
+        _check(self._fn(C.c_int(self.device), C.c_int32(self.n), self.arr, C.c_int(self.taps), self.res, self.tb))
+        self._pending = True
+
+    def results(self) -> list:
+        assert self._pending, "run() first"
+        self._pending = False
+        out = []
+        for k in range(self.n):
+            if self.traceback:
+                t = self.tb[k]
+                try:
+                    pair = (abi.struct_array(C.c_void_p(t.hsps), t.n_hsps, abi.TB_HSP_DTYPE),
+                            abi.struct_array(C.c_void_p(t.ops), t.n_ops, abi.EDIT_OP_DTYPE))
+                finally:
+                    lib().bn_free(C.c_void_p(t.hsps))
+                    lib().bn_free(C.c_void_p(t.ops))
+            d = _results(self.res[k])
+            if self.traceback:
+                d["tb"] = pair
+            out.append(d)
+        return out
+
+
+def prelim_search_jobs(jobs, device=0, taps=0, traceback=False) -> list:
+    """The job pipeline (bn_prelim_search_jobs), one call: one result dict per job; with traceback=True each also
+    carries "tb" = (final HSPs, ops)."""
+    jb = JobBatch(jobs, device=device, taps=taps, traceback=traceback)
+    jb.run()
+    return jb.results()
 
 
 def prelim_search_host(holder, vol, device=0, taps=0) -> dict:
