@@ -402,6 +402,9 @@ static cudaError_t upload(T **dst, const T *src, size_t n, cudaStream_t st)
     return cudaMemcpyAsync(*dst, staged(src, n * sizeof(T)), n * sizeof(T), cudaMemcpyHostToDevice, st);
 }
 
+cudaError_t launch_dust(const uint8_t *seqs, const int64_t *seq_off, const int32_t *lens, int32_t n_seq, uint32_t level,
+                        uint32_t window, uint32_t linker, const int64_t *out_off, int32_t *out, int32_t *out_n,
+                        int32_t *compact, int64_t *compact_off, unsigned long long *cursor, cudaStream_t st);
 cudaError_t launch_build_presence(const int32_t *hashtable, int64_t hashsize, uint32_t *presence, cudaStream_t st);
 cudaError_t launch_build_qpk(const uint8_t *query_start, int32_t concat_len, uint2 *qpk, int64_t nwords, cudaStream_t st);
 cudaError_t launch_popc(const uint32_t *presence, int64_t nwords, uint32_t *counts, cudaStream_t st);
@@ -3378,6 +3381,99 @@ static int traceback_search_impl(Lane *D, Volume *V, Query *Q, int32_t gap_x_dro
     *out = to_malloc(result); *n_out = (int64_t)result.size();
     *ops_out = to_malloc(result_ops); *n_ops_out = (int64_t)result_ops.size();
     if ((!result.empty() && !*out) || (!result_ops.empty() && !*ops_out)) return fail(BN_ERR_MEMORY, "bn_traceback_search: out of memory");
+    return BN_OK;
+}
+
+int bn_dust_mask_batch(int device, const uint8_t *seqs, const int32_t *lens, int32_t n_queries, int32_t level, int32_t window,
+                       int32_t linker, int32_t **mask_n, int32_t **mask_iv, int64_t *n_intervals)
+{
+    if (!mask_n || !mask_iv || !n_intervals || n_queries < 0 || (n_queries > 0 && (!seqs || !lens)))
+        return fail(BN_ERR_INVALID, "bn_dust_mask_batch: bad argument");
+    *mask_n = nullptr; *mask_iv = nullptr; *n_intervals = 0;
+    int rc = ensure_init();
+    if (rc) return rc;
+    Gpu *G = device_at(device);
+    if (!G) return fail(BN_ERR_INVALID, "bn_dust_mask_batch: bad device");
+    // the parameter ranges of CSymDustMasker's constructor (symdust.cpp:213-226)
+    const uint32_t lv = (level >= 2 && level <= 64) ? (uint32_t)level : 20u;
+    const uint32_t w = (window >= 8 && window <= 64) ? (uint32_t)window : 64u;
+    const uint32_t lk = (linker >= 1 && linker <= 32) ? (uint32_t)linker : 1u;
+    const size_t n = (size_t)n_queries;
+    std::vector<int64_t> seq_off(n + 1, 0), out_off(n + 1, 0);
+    for (size_t i = 0; i < n; i++) {
+        if (lens[i] < 0) return fail(BN_ERR_INVALID, "bn_dust_mask_batch: negative length");
+        seq_off[i + 1] = seq_off[i] + lens[i];
+        out_off[i + 1] = out_off[i] + 2 * ((int64_t)lens[i] / 2 + 1);
+    }
+    const double t0 = now_ms();
+    double t_dev0 = t0, t_dev1 = t0;
+    std::vector<int32_t> counts(n, 0), flat;
+    std::vector<int64_t> coff(n, 0);
+    if (n > 0) {
+        LaneLock lock(*G);
+        Lane *L = lock.lane;
+        CU_TRY(cudaSetDevice(L->id));
+        cudaStream_t st = L->stream;
+        uint8_t *d_seq = nullptr; int64_t *d_soff = nullptr, *d_ooff = nullptr, *d_coff = nullptr;
+        int32_t *d_len = nullptr, *d_out = nullptr, *d_n = nullptr, *d_compact = nullptr;
+        unsigned long long *d_cursor = nullptr, total = 0;
+        cudaError_t e = cudaMallocAsync((void **)&d_seq, (size_t)std::max<int64_t>(seq_off[n], 1), st);
+        if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_soff, (n + 1) * sizeof(int64_t), st);
+        if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_ooff, (n + 1) * sizeof(int64_t), st);
+        if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_coff, n * sizeof(int64_t), st);
+        if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_len, n * sizeof(int32_t), st);
+        if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_out, (size_t)out_off[n] * sizeof(int32_t), st);
+        if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_compact, (size_t)out_off[n] * sizeof(int32_t), st);
+        if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_n, n * sizeof(int32_t), st);
+        if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_cursor, sizeof(unsigned long long), st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), st);
+        if (e == cudaSuccess && seq_off[n] > 0) e = cudaMemcpyAsync(d_seq, seqs, (size_t)seq_off[n], cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_soff, seq_off.data(), (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_ooff, out_off.data(), (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_len, lens, n * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+        if (getenv("BN_TRACE")) { cudaStreamSynchronize(st); t_dev0 = now_ms(); }
+        if (e == cudaSuccess) e = launch_dust(d_seq, d_soff, d_len, n_queries, lv, w, lk, d_ooff, d_out, d_n, d_compact, d_coff, d_cursor, st);
+        if (getenv("BN_TRACE")) { cudaStreamSynchronize(st); t_dev1 = now_ms(); }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(counts.data(), d_n, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(coff.data(), d_coff, n * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&total, d_cursor, sizeof total, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess && total > 0) {
+            flat.resize((size_t)total);
+            e = cudaMemcpyAsync(flat.data(), d_compact, (size_t)total * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+        }
+        void *ptrs[] = {d_seq, d_soff, d_ooff, d_coff, d_len, d_out, d_compact, d_n, d_cursor};
+        for (void *p : ptrs) if (p) cudaFreeAsync(p, st);
+        CU_TRY(e);
+        CU_TRY(cudaStreamSynchronize(st));
+    }
+    std::vector<int32_t> iv;
+    int64_t n_redone = 0;
+    const double t_host0 = now_ms();
+    int32_t *mn = (int32_t *)malloc(sizeof(int32_t) * std::max<size_t>(n, 1));
+    if (!mn) return fail(BN_ERR_MEMORY, "bn_dust_mask_batch: out of memory");
+    for (size_t i = 0; i < n; i++) {
+        if (counts[i] >= 0) {
+            mn[i] = counts[i];
+            iv.insert(iv.end(), flat.begin() + coff[i], flat.begin() + coff[i] + 2 * (int64_t)counts[i]);
+        } else {            // the kernel's list of perfect intervals overflowed: the host routine redoes this query
+            ++n_redone;
+            int32_t *one = nullptr, cnt = 0;
+            rc = bn_dust_mask(seqs + seq_off[i], lens[i], level, window, linker, &one, &cnt);
+            if (rc) { free(mn); return fail(rc, "bn_dust_mask_batch: host pass failed"); }
+            mn[i] = cnt;
+            iv.insert(iv.end(), one, one + 2 * (size_t)cnt);
+            free(one);
+        }
+    }
+    int32_t *out = (int32_t *)malloc(sizeof(int32_t) * std::max<size_t>(iv.size(), 2));
+    if (!out) { free(mn); return fail(BN_ERR_MEMORY, "bn_dust_mask_batch: out of memory"); }
+    if (!iv.empty()) memcpy(out, iv.data(), iv.size() * sizeof(int32_t));
+    *mask_n = mn; *mask_iv = out; *n_intervals = (int64_t)(iv.size() / 2);
+    if (getenv("BN_TRACE"))
+        fprintf(stderr, "[bn] dust batch %.3f ms: uploads %.3f kernel %.3f results %.3f + host %.3f (%d queries, %lld bases, %zu intervals, %lld redone on the host)\n",
+                now_ms() - t0, t_dev0 - t0, t_dev1 - t_dev0, t_host0 - t_dev1, now_ms() - t_host0, n_queries, (long long)seq_off[n], iv.size() / 2,
+                (long long)n_redone);
     return BN_OK;
 }
 

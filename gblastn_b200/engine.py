@@ -22,7 +22,7 @@ EXPORTS = [
     "bn_scan_subject", "bn_word_finder", "bn_free", "bn_bench_scan", "bn_query_download_lookup", "bn_get_gapped_score", "bn_gapped_traceback", "bn_traceback_hsps", "bn_traceback_search",
     "bn_dbfile_index", "bn_db_load_files", "bn_dbfile_write", "bn_dbfile_ambiguity", "bn_db_set_ambiguity", "bn_prelim_search_batches", "bn_prelim_search_jobs", "bn_db_set_masks", "bn_selftest_replay",
     "bn_setup_create", "bn_setup_batch", "bn_setup_kbp_std", "bn_setup_kbp_gap",
-    "bn_setup_gap_x_dropoff_final", "bn_setup_longest_chain", "bn_setup_free", "bn_dust_mask",
+    "bn_setup_gap_x_dropoff_final", "bn_setup_longest_chain", "bn_setup_free", "bn_dust_mask", "bn_dust_mask_batch",
 ]
 
 
@@ -421,3 +421,24 @@ def dust_mask(query: np.ndarray, level=20, window=64, linker=1):
         return [(int(p[2 * i]), int(p[2 * i + 1])) for i in range(n.value)]
     finally:
         lib().bn_free(p)
+
+
+def dust_mask_batch(queries, level=20, window=64, linker=1, device=0):
+    """Symmetric DUST of a whole query batch on the device (bn_dust_mask_batch): one list of (from, to) per query."""
+    lens = np.ascontiguousarray([len(q) for q in queries], dtype=np.int32)
+    cat = np.ascontiguousarray(np.concatenate(queries) if len(queries) else np.zeros(0, np.uint8), dtype=np.uint8)
+    pn, pv, total = C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)(), C.c_int64(0)
+    _check(lib().bn_dust_mask_batch(C.c_int(device), cat.ctypes.data_as(C.c_void_p), lens.ctypes.data_as(C.c_void_p),
+                                    C.c_int32(len(queries)), C.c_int32(level), C.c_int32(window), C.c_int32(linker),
+                                    C.byref(pn), C.byref(pv), C.byref(total)))
+    try:
+        counts = np.ctypeslib.as_array(pn, shape=(max(len(queries), 1),))[:len(queries)].copy()
+        flat = np.ctypeslib.as_array(pv, shape=(max(2 * total.value, 2),))[:2 * total.value].copy()
+    finally:
+        lib().bn_free(pn)
+        lib().bn_free(pv)
+    out, at = [], 0
+    for c in counts:
+        out.append([(int(flat[2 * (at + i)]), int(flat[2 * (at + i) + 1])) for i in range(int(c))])
+        at += int(c)
+    return out

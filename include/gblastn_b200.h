@@ -459,6 +459,14 @@ void bn_setup_free(BnSetup *s);
  * i.e. they only keep words out of the lookup table (mask-at-hash) and switch on s_TypeOfWord's re-probing. */
 int  bn_dust_mask(const uint8_t *seq, int32_t len, int32_t level, int32_t window, int32_t linker,
                   int32_t **intervals, int32_t *n_intervals);
+/* The same for a whole query batch ON THE DEVICE (csrc/dust_kernel.cu: one thread per query runs the window scan with
+ * its state in local memory; identical intervals).  seqs: the queries' blastna bytes back to back, lens[n_queries].
+ * Output in the form bn_setup_create takes: mask_n[i] intervals for query i, flat inclusive [from, to] pairs in
+ * mask_iv (query coordinates); free both with bn_free.  A query whose window ever holds more perfect intervals than the
+ * kernel's list (2048) is redone by bn_dust_mask. */
+int  bn_dust_mask_batch(int device, const uint8_t *seqs, const int32_t *lens, int32_t n_queries,
+                        int32_t level, int32_t window, int32_t linker, int32_t **mask_n, int32_t **mask_iv,
+                        int64_t *n_intervals);
 
 #ifdef __cplusplus
 }

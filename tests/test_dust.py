@@ -72,6 +72,30 @@ def test_dust_matches_golden(built):
         assert E.dust_mask(q) == [tuple(x) for x in want]
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("params", [(20, 64, 1), (10, 32, 5), (40, 64, 1), (20, 16, 32)])
+def test_dust_kernel_equals_host_routine(params):
+    """bn_dust_mask_batch (one thread per query on the device) == bn_dust_mask per query — which the CPU tests pin to
+    the reference's symdust.cpp and to the golden intervals — on the seeded cases, a C5-style batch of 5 kb queries with
+    low-complexity inserts, and empty / tiny sequences."""
+    from gblastn_b200 import engine as E, synth
+    qs = dust_cases()
+    vol = synth.random_volume([300_000], seed=5)
+    big = synth.add_low_complexity(synth.planted_queries(vol, 60, 5000, seed=6, planted_frac=0.5, sub_rate=0.02), seed=7, frac=0.5)
+    qs = qs + big + [np.zeros(0, np.uint8), np.zeros(2, np.uint8), np.array([0, 1, 2], np.uint8)]
+    got = E.dust_mask_batch(qs, *params)
+    assert len(got) == len(qs)
+    masked = 0
+    for q, g in zip(qs, got):
+        want = E.dust_mask(q, *params)
+        assert g == want, f"len {len(q)} params {params}: {g[:4]} vs {want[:4]}"
+        masked += len(want)
+    assert masked > 100
+    if os.path.exists(REF):
+        for q, g in list(zip(qs, got))[::7]:
+            assert g == ref_dust(q, *params)
+
+
 def test_dust_masks_reach_the_lookup_table(built):
     """DUST intervals as query masks of the product set-up == the reference's set-up given the same intervals:
     words inside the masked stretches stay out of the lookup table (mask-at-hash)."""
