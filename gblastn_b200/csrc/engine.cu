@@ -211,27 +211,64 @@ struct Gpu {
     cudaStream_t free_stream = nullptr;   // never carries work: a cudaFreeAsync on it completes at once, so the block is
                                           // reusable by the next allocation on any lane (the callers free after a host sync)
     std::vector<std::unique_ptr<Lane>> lanes;
-    std::atomic<unsigned> next{0};
+    // lane hand-out: a caller takes all the lanes it needs in one step (a job pipeline: three + one for its traceback
+    // stage) or waits holding none, so callers that need several lanes cannot deadlock on each other's partial sets
+    std::mutex pool_mu;
+    std::condition_variable pool_cv;
 };
 
-// RAII ownership of a lane: the first free one, else wait for one picked round-robin
+// RAII ownership of one lane (LaneLock) or several (acquire_lanes): free lanes are taken under the device's pool
+// mutex; when there are not enough the caller waits for a release
 struct LaneLock {
     Lane *lane = nullptr;
+    Gpu *gpu = nullptr;
     LaneLock() = default;
-    explicit LaneLock(Gpu &g)
+    explicit LaneLock(Gpu &g) : gpu(&g)
     {
-        for (auto &l : g.lanes)
-            if (l->mu.try_lock()) { lane = l.get(); return; }
-        lane = g.lanes[g.next.fetch_add(1) % g.lanes.size()].get();
-        lane->mu.lock();
+        std::unique_lock<std::mutex> lk(g.pool_mu);
+        for (;;) {
+            for (auto &l : g.lanes)
+                if (l->mu.try_lock()) { lane = l.get(); return; }
+            g.pool_cv.wait(lk);
+        }
     }
-    LaneLock(LaneLock &&o) noexcept : lane(o.lane) { o.lane = nullptr; }
-    LaneLock &operator=(LaneLock &&o) noexcept { release(); lane = o.lane; o.lane = nullptr; return *this; }
+    LaneLock(LaneLock &&o) noexcept : lane(o.lane), gpu(o.gpu) { o.lane = nullptr; }
+    LaneLock &operator=(LaneLock &&o) noexcept { release(); lane = o.lane; gpu = o.gpu; o.lane = nullptr; return *this; }
     LaneLock(const LaneLock &) = delete;
     LaneLock &operator=(const LaneLock &) = delete;
-    void release() { if (lane) lane->mu.unlock(); lane = nullptr; }
+    void release()
+    {
+        if (!lane) return;
+        {
+            std::lock_guard<std::mutex> lk(gpu->pool_mu);
+            lane->mu.unlock();
+        }
+        gpu->pool_cv.notify_all();
+        lane = nullptr;
+    }
     ~LaneLock() { release(); }
+    // adopt a lane whose mutex the caller already holds (acquire_lanes)
+    static LaneLock adopt(Gpu &g, Lane *l) { LaneLock k; k.gpu = &g; k.lane = l; return k; }
 };
+
+// k lanes at once (k <= lanes of the device), or none while waiting
+static void acquire_lanes(Gpu &g, int k, LaneLock *out)
+{
+    std::unique_lock<std::mutex> lk(g.pool_mu);
+    for (;;) {
+        std::vector<Lane *> got;
+        for (auto &l : g.lanes) {
+            if ((int)got.size() == k) break;
+            if (l->mu.try_lock()) got.push_back(l.get());
+        }
+        if ((int)got.size() == k) {
+            for (int i = 0; i < k; i++) out[i] = LaneLock::adopt(g, got[(size_t)i]);
+            return;
+        }
+        for (Lane *l : got) l->mu.unlock();
+        g.pool_cv.wait(lk);
+    }
+}
 
 struct ChunkTable {
     std::vector<DevChunk> host;               // chunks (what seed hits, init-HSPs and the host replay refer to)
@@ -2440,10 +2477,10 @@ int bn_prelim_search_jobs(int device, int32_t n_jobs, const BnJob *jobs, int tap
     CU_TRY(cudaSetDevice(g->id));
     // three lanes: while the call waits for job k, jobs k+1 and k+2 are queued on the device
     constexpr int NL = 3;
-    LaneLock lanes[NL];
+    LaneLock lanes[NL + 1];               // [NL]: the traceback stage's lane (tb != NULL)
     Stager stagers[NL];
+    acquire_lanes(*g, tb ? NL + 1 : NL, lanes);
     for (int i = 0; i < NL; i++) {
-        lanes[i] = LaneLock(*g);
         if (lanes[i].lane->stage.reserve((size_t)6 << 20) == cudaSuccess) { stagers[i].base = lanes[i].lane->stage.p; stagers[i].cap = (size_t)6 << 20; }
     }
 
@@ -2509,12 +2546,9 @@ int bn_prelim_search_jobs(int device, int32_t n_jobs, const BnJob *jobs, int tap
                 k = tb_q.front(); tb_q.pop_front();
             }
             JobState &S = J[(size_t)k];
-            int r;
-            {
-                LaneLock own(*g);          // a third lane: the traceback kernels run beside the next jobs' searches
-                r = traceback_search_impl(own.lane, S.V.get(), S.Q.get(), jobs[k].gap_x_dropoff_final, results[k].hsps,
-                                          results[k].n_hsps, &tb[k].hsps, &tb[k].n_hsps, &tb[k].ops, &tb[k].n_ops);
-            }
+            // a lane of its own: the traceback kernels run beside the next jobs' searches
+            const int r = traceback_search_impl(lanes[NL].lane, S.V.get(), S.Q.get(), jobs[k].gap_x_dropoff_final, results[k].hsps,
+                                                results[k].n_hsps, &tb[k].hsps, &tb[k].n_hsps, &tb[k].ops, &tb[k].n_ops);
             std::lock_guard<std::mutex> lk(mu);
             if (r) { S.rc = r; S.err = g_err; }
             S.all_done = true;
@@ -2651,7 +2685,7 @@ int bn_prelim_search_jobs(int device, int32_t n_jobs, const BnJob *jobs, int tap
     host_worker2.join();
     if (tb_worker.joinable()) tb_worker.join();
     // jobs that were prepared but never completed still own queued device work
-    for (auto &l : lanes) cudaStreamSynchronize(l.lane->stream);
+    for (auto &l : lanes) if (l.lane) { cudaStreamSynchronize(l.lane->stream); cudaStreamSynchronize(l.lane->tail_stream); }
     for (int32_t k = 0; k < n_jobs; k++) {
         JobState &S = J[(size_t)k];
         if (k >= dispatched) S.all_done = true;

@@ -581,6 +581,42 @@ def test_job_pipeline_equals_reference():
             x.free()
 
 
+def test_job_pipelines_on_concurrent_threads():
+    """Three caller threads each run a job pipeline WITH its traceback stage on the same device (4 lanes each, 6 on the
+    device): lanes are handed out all-or-nothing, so the calls queue instead of deadlocking on partial sets, and every
+    job still equals the single calls."""
+    import threading
+    from gblastn_b200 import engine as E, setup as S
+    task, cfgkw, vol, qs = cases.make_case("mb_lut11_hash_indels")
+    st = S.Setup(qs, task=task, db_length=vol.total_bases, db_num_seqs=vol.n_seqs, device_lookup=1, **cfgkw)
+    V, Q = E.Volume(vol), E.Query(st.batch)
+    try:
+        want = E.prelim_search(V, Q)
+        want_tb, want_ops = E.traceback_search(V, Q, st.gap_x_dropoff_final(), want["hsps"])
+        jobs = [{"volume": V, "query": Q, "gap_x_dropoff_final": st.gap_x_dropoff_final()},
+                {"host_volume": vol, "batch": st.batch, "gap_x_dropoff_final": st.gap_x_dropoff_final()}] * 4
+        out, errs = {}, []
+
+        def run(i):
+            try:
+                out[i] = E.prelim_search_jobs(jobs, traceback=True)
+            except Exception as e:          # noqa: BLE001
+                errs.append(e)
+        threads = [threading.Thread(target=run, args=(i,)) for i in range(3)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(timeout=120)
+        assert not any(t.is_alive() for t in threads), "job pipelines deadlocked"
+        assert not errs, errs
+        for i in range(3):
+            for o in out[i]:
+                assert o["hsps"].tobytes() == want["hsps"].tobytes()
+                assert o["tb"][0].tobytes() == want_tb.tobytes() and o["tb"][1].tobytes() == want_ops.tobytes()
+    finally:
+        Q.free(); V.free(); st.free()
+
+
 def test_job_pipeline_reports_errors():
     from gblastn_b200 import engine as E, abi
     r, h, vol = _setup("mb_lut11_hash_indels")
