@@ -53,6 +53,8 @@ struct DevQuery {
     const uint4 *qinfo;                    // MB: per query position {next_pos, 16 bases left, 16 right, ambiguity}
     const uint32_t *sig;                   // MB: per occupied cell (by rank) the 4 query bases on either side of its first chain
                                            // element's lookup word: bits 0-7 left, 8-15 right, bit 16 = the chain has more elements
+    const uint32_t *filt;                  // MB, small batches only: FILT_BITS-bit hashed presence filter (filt_hash of every occupied
+                                           // cell), kept in shared memory by scan_kernel_filtered; NULL otherwise
     const int16_t *backbone, *overflow;    // SmallNa
     const int4 *na_cells;                  // eNaLookupTable: thick backbone {num_used, entries[3] | overflow_cursor}
     const int32_t *na_overflow;
@@ -159,6 +161,12 @@ __device__ __forceinline__ int32_t match_run_rev(const DevQuery &q, const uint8_
     return n;
 }
 
+// Hashed presence filter of a small MB table (scan_kernel_filtered): cell idx -> bit filt_hash(idx) of a 2^20-bit map;
+// exact for lut <= 10.  A 2^19-bit map is the OR of the two halves (hash & (2^19 - 1)).
+constexpr int FILT_LOG2 = 20;
+constexpr uint32_t FILT_BITS = 1u << FILT_LOG2;
+__host__ __device__ __forceinline__ uint32_t filt_hash(uint32_t idx) { return (idx ^ (idx >> FILT_LOG2)) & (FILT_BITS - 1u); }
+
 // cinfo / qinfo .x: bits 0-29 a 1-based query position (cinfo: the chain element itself; qinfo: the next one), bit 31
 // (cinfo) "the chain continues", bit 30 "the query position in front of this element is in the lookup table too"
 constexpr uint32_t QP_MASK = 0x3fffffffu;
@@ -244,6 +252,7 @@ int scan_positions_per_block();
 int scan_tile_cap(int scan_step, int word_length);
 int scan_max_block_chunks();
 int scan_tile_margin();
+cudaError_t launch_build_filter(const uint32_t *presence, int64_t nwords, uint32_t *filt, cudaStream_t st);
 cudaError_t launch_build_sig(const uint4 *cinfo, int64_t n_ranks, uint32_t *sig, cudaStream_t st);
 cudaError_t launch_build_qinfo(const DevQuery &q, const int32_t *next_pos, int32_t concat_len, const int32_t *heads,
                                int64_t n_heads, uint32_t *indexed_scratch, uint4 *qinfo, cudaStream_t st);

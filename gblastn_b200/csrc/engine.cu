@@ -345,6 +345,7 @@ struct QueryDev {
     uint4 *cinfo = nullptr;
     uint4 *qinfo = nullptr;
     uint32_t *sig = nullptr;
+    uint32_t *filt = nullptr;
     DevQuery view{};
     bool ready = false;
 };
@@ -399,7 +400,7 @@ static Gpu *device_at(int d)
 static void free_query_dev(QueryDev &q, cudaStream_t st)
 {
     void *ptrs[] = {q.query, q.ctx, q.next_pos, q.backbone, q.overflow, q.na_cells, q.na_overflow,
-                    q.score_table, q.matrix, q.qpk, q.prk, q.cinfo, q.qinfo, q.sig};
+                    q.score_table, q.matrix, q.qpk, q.prk, q.cinfo, q.qinfo, q.sig, q.filt};
     for (void *p : ptrs) if (p) dev_free(p, st);
     q = QueryDev{};
 }
@@ -576,6 +577,17 @@ static int query_to_device(Query &Q, const BnQueryBatch &src, int d, Lane *dev, 
         CU_TRY(dev_alloc(&qd.sig, (size_t)b.concat_len + 2, st));
         CU_TRY(launch_build_sig(qd.cinfo, (int64_t)b.concat_len + 2, qd.sig, st));
         v.sig = getenv("BN_NO_SIG") ? nullptr : qd.sig;
+        // small batch: hashed presence filter for the shared-memory scan (scan_kernel_filtered).  The number of occupied
+        // cells is only known on the device; concat_len bounds it, and a filter with more than a quarter of its
+        // bits set is not worth a CTA per SM
+        {
+            const long filt_max = getenv("BN_FILT_MAX") ? atol(getenv("BN_FILT_MAX")) : (long)(FILT_BITS / 4);   // test switch, read per load
+            if ((long)b.concat_len <= filt_max) {
+                CU_TRY(dev_alloc(&qd.filt, (size_t)(FILT_BITS / 32), st));
+                CU_TRY(launch_build_filter(t_presence, nwords, qd.filt, st));
+                v.filt = qd.filt;
+            }
+        }
     }
     TSTEP("query: derived tables");
     {

@@ -34,6 +34,7 @@
 // The generic kernel (direct global loads, full hashtable) is kept for small tables and for blocks
 // whose byte span does not fit the tile.
 #include "bn_device.cuh"
+#include <cstdlib>
 
 namespace bn {
 
@@ -524,12 +525,12 @@ __device__ __forceinline__ void ld_cinfo_pair(const uint4 *p, uint4 &e0, uint4 &
 // Direct-load path for the rare block whose byte span does not fit the tile (runs of sequences
 // shorter than a word) : same semantics, per-position global loads.
 __device__ __noinline__ unsigned long long scan_block_direct(const DevQuery &q, const ScanLaunch &s, int64_t block_pos0,
-                                                             int32_t c_lo, int32_t c_hi)
+                                                             int32_t c_lo, int32_t c_hi, int tid)
 {
     unsigned long long my_lookup_hits = 0;
     const int32_t lut = q.lut_word_length, step = q.scan_step;
     for (int it = 0; it < POS_PER_THREAD; it++) {
-        const int64_t g = block_pos0 + (int64_t)it * SCAN_THREADS + threadIdx.x;
+        const int64_t g = block_pos0 + (int64_t)it * SCAN_THREADS + tid;
         if (g >= s.total_pos) break;
         int32_t lo = c_lo, hi = c_hi;
         while (lo < hi) {
@@ -552,6 +553,81 @@ __device__ __noinline__ unsigned long long scan_block_direct(const DevQuery &q, 
         }
     }
     return my_lookup_hits;
+}
+
+
+// One occupied table cell met at a scan position (rank = its index among the occupied cells; gl = block-relative
+// position; k = index in the block's chunk table): flank-signature pre-filter, chain walk, mini-extension (or
+// direct filter), emission.  Shared by the queue-driven kernel and the filtered one.
+struct BlockView {
+    const uint32_t *tile;
+    const int32_t *ct_start, *ct_tbase, *ct_len, *ct_pfirst, *ct_parent;
+    int64_t block_pos0, tile_lo;
+    int32_t tile_bytes;
+};
+template <bool DIRECT>
+__device__ __forceinline__ void scan_candidate(const DevQuery &q, const ScanLaunch &s, const BlockView &b, uint32_t rank,
+                                               int32_t gl, int32_t k, bool use_sig, uint32_t &my_lookup_hits)
+{
+    const int32_t lut = q.lut_word_length, step = q.scan_step;
+    const uint32_t *tile = b.tile;
+    // mini-extension pre-filter: a hit reaches the full word only if the 4 bases right of the lookup word all match
+    // (when fewer than 4 match on the left, ext_to - 3 >= 4 are still owed on the right) or the 4 on the left do
+    if (use_sig) {
+        // 4 bytes per candidate from a table that stays in L2, instead of the 32-byte chain record from HBM:
+        // nine out of ten candidates of a megablast batch end here
+        const uint32_t sg = __ldg(&q.sig[rank]);
+        const int32_t p0 = b.ct_pfirst[k] + (gl - b.ct_start[k]) * step, tb0 = b.ct_tbase[k];
+        const uint32_t wl = tile_win(tile, tb0 + p0 - 4) >> 24, wr = tile_win(tile, tb0 + p0 + lut) >> 24;
+        if (!(sg & 0x10000u) && wl != (sg & 0xFFu) && wr != ((sg >> 8) & 0xFFu)) { ++my_lookup_hits; return; }
+    }
+    // first two chain elements of the cell in ONE 32-byte sector: {qp | more << 31, left 16, right 16, ambiguity} x 2
+    uint4 qi, qi1;
+    ld_cinfo_pair(q.cinfo + 2 * (size_t)rank, qi, qi1);
+    const int32_t p = b.ct_pfirst[k] + (gl - b.ct_start[k]) * step;
+    const int32_t tbase = b.ct_tbase[k], len = b.ct_len[k];
+    const uint32_t chunk = (uint32_t)b.ct_parent[k];
+    const int64_t g = b.block_pos0 + gl;
+    int32_t qp = (int32_t)(qi.x & QP_MASK);
+    bool more = (qi.x >> 31) != 0, second = true;
+    // base in front of the scan position (direct filter: is this hit the continuation of a run of matches?)
+    const uint32_t s_prev = (DIRECT && p > 0) ? (tile_win(tile, tbase + p - 1) >> 30) : 4u;
+    for (;;) {
+        ++my_lookup_hits;
+        int32_t qo, so;
+        if (DIRECT) {
+            // lut == word: no mini-extension.  A hit whose predecessor on the diagonal, (q_off - 1, s_off - 1),
+            // is a lookup hit too belongs to the same run of matching bases as that hit and shares its fate:
+            // rejected by the diagonal test when the run's first hit was extended successfully, below the
+            // cutoff itself when that one was.  Only a run's first hit goes on, and only if its own
+            // ungapped extension can reach the cutoff.
+            const bool follower = (qi.x & PREV_INDEXED) && s_prev == (qi.y & 3u) && !(qi.w & 1u);
+            if (!follower) {
+                int32_t xd = s.uni_x, co = s.uni_cutoff, rc = s.uni_reduced;
+                if (!s.uni_ok) {
+                    const DevContext c = q.ctx[ctx_search(q, qp - 1)];
+                    xd = c.x_dropoff; co = c.cutoff_score; rc = c.reduced_cutoff;
+                }
+                DirectCtx dc{tile, b.tile_bytes * 4, b.tile_lo * 4, s.packed};
+                if (direct_keep(q, dc, tbase, len, qp - 1, p, xd, co, rc))
+                    emit_hit(q, s, chunk, (uint32_t)p, g, qp - 1, p);
+            }
+        }
+        else if (s.raw_pairs) emit_hit(q, s, chunk, (uint32_t)p, g, qp - 1, p);
+        else if (mini_extend_tile(q, tile, tbase, len, qp - 1, p, qi, qo, so))
+            emit_hit(q, s, chunk, (uint32_t)p, g, qo, so);
+        if (!more) break;
+        if (second) {                       // second element came with the first
+            second = false;
+            qi = qi1;
+            qp = (int32_t)(qi.x & QP_MASK);
+            more = (qi.x >> 31) != 0;
+        } else {                            // third and later (rare): pointer chase
+            qp = __ldg(&q.next_pos[qp]);
+            qi = __ldg(&q.qinfo[qp]);       // {next | PREV_INDEXED, left 16 bases, right 16 bases, ambiguity}
+            more = (qi.x & QP_MASK) != 0;
+        }
+    }
 }
 
 template <bool DIRECT>
@@ -581,7 +657,7 @@ scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ S
     const int32_t nch = bd.c_hi - c_lo + 1;
     uint32_t my_lookup_hits = 0;
     if (!bd.staged) {
-        my_lookup_hits = (uint32_t)scan_block_direct(q, s, block_pos0, c_lo, bd.c_hi);
+        my_lookup_hits = (uint32_t)scan_block_direct(q, s, block_pos0, c_lo, bd.c_hi, tid);
     } else {
         const int64_t tile_lo = bd.tile_lo;
         for (int i = tid; i < nch; i += SCAN_THREADS) {
@@ -664,72 +740,193 @@ scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ S
         __syncwarp();
 
         // ---- phase B: the warp's candidates, one per lane ----------------------------------------------
-        // mini-extension pre-filter: a hit reaches the full word only if the 4 bases right of the lookup word all match
-        // (when fewer than 4 match on the left, ext_to - 3 >= 4 are still owed on the right) or the 4 on the left do
         const bool use_sig = !DIRECT && !s.raw_pairs && q.sig != nullptr && (q.word_length - lut) >= 7;
+        const BlockView bv{tile, ct_start, ct_tbase, ct_len, ct_pfirst, ct_parent, block_pos0, bd.tile_lo, bd.bytes};
         for (int ci = lane; ci < ncand; ci += 32) {
             const uint2 cd = wcand[ci];
-            const int32_t gl = (int32_t)(cd.y & 2047u), k = (int32_t)(cd.y >> 11);
-            if (use_sig) {
-                // 4 bytes per candidate from a table that stays in L2, instead of the 32-byte chain record from HBM:
-                // nine out of ten candidates of a megablast batch end here
-                const uint32_t sg = __ldg(&q.sig[cd.x]);
-                const int32_t p0 = ct_pfirst[k] + (gl - ct_start[k]) * step, tb0 = ct_tbase[k];
-                const uint32_t wl = tile_win(tile, tb0 + p0 - 4) >> 24, wr = tile_win(tile, tb0 + p0 + lut) >> 24;
-                if (!(sg & 0x10000u) && wl != (sg & 0xFFu) && wr != ((sg >> 8) & 0xFFu)) { ++my_lookup_hits; continue; }
-            }
-            // first two chain elements of the cell in ONE 32-byte sector: {qp | more << 31, left 16, right 16, ambiguity} x 2
-            uint4 qi, qi1;
-            ld_cinfo_pair(q.cinfo + 2 * (size_t)cd.x, qi, qi1);
-            const int32_t p = ct_pfirst[k] + (gl - ct_start[k]) * step;
-            const int32_t tbase = ct_tbase[k], len = ct_len[k];
-            const uint32_t chunk = (uint32_t)ct_parent[k];
-            const int64_t g = block_pos0 + gl;
-            int32_t qp = (int32_t)(qi.x & QP_MASK);
-            bool more = (qi.x >> 31) != 0, second = true;
-            // base in front of the scan position (direct filter: is this hit the continuation of a run of matches?)
-            const uint32_t s_prev = (DIRECT && p > 0) ? (tile_win(tile, tbase + p - 1) >> 30) : 4u;
-            for (;;) {
-                ++my_lookup_hits;
-                int32_t qo, so;
-                if (DIRECT) {
-                    // lut == word: no mini-extension.  A hit whose predecessor on the diagonal, (q_off - 1, s_off - 1),
-                    // is a lookup hit too belongs to the same run of matching bases as that hit and shares its fate:
-                    // rejected by the diagonal test when the run's first hit was extended successfully, below the
-                    // cutoff itself when that one was.  Only a run's first hit goes on, and only if its own
-                    // ungapped extension can reach the cutoff.
-                    const bool follower = (qi.x & PREV_INDEXED) && s_prev == (qi.y & 3u) && !(qi.w & 1u);
-                    if (!follower) {
-                        int32_t xd = s.uni_x, co = s.uni_cutoff, rc = s.uni_reduced;
-                        if (!s.uni_ok) {
-                            const DevContext c = q.ctx[ctx_search(q, qp - 1)];
-                            xd = c.x_dropoff; co = c.cutoff_score; rc = c.reduced_cutoff;
-                        }
-                        DirectCtx dc{tile, bd.bytes * 4, bd.tile_lo * 4, s.packed};
-                        if (direct_keep(q, dc, tbase, len, qp - 1, p, xd, co, rc))
-                            emit_hit(q, s, chunk, (uint32_t)p, g, qp - 1, p);
-                    }
-                }
-                else if (s.raw_pairs) emit_hit(q, s, chunk, (uint32_t)p, g, qp - 1, p);
-                else if (mini_extend_tile(q, tile, tbase, len, qp - 1, p, qi, qo, so))
-                    emit_hit(q, s, chunk, (uint32_t)p, g, qo, so);
-                if (!more) break;
-                if (second) {                       // second element came with the first
-                    second = false;
-                    qi = qi1;
-                    qp = (int32_t)(qi.x & QP_MASK);
-                    more = (qi.x >> 31) != 0;
-                } else {                            // third and later (rare): pointer chase
-                    qp = __ldg(&q.next_pos[qp]);
-                    qi = __ldg(&q.qinfo[qp]);       // {next | PREV_INDEXED, left 16 bases, right 16 bases, ambiguity}
-                    more = (qi.x & QP_MASK) != 0;
-                }
-            }
+            scan_candidate<DIRECT>(q, s, bv, cd.x, (int32_t)(cd.y & 2047u), (int32_t)(cd.y >> 11), use_sig, my_lookup_hits);
         }
     }
     // one atomic per warp for the lookup-hit statistic (BlastUngappedStats.lookup_hits); REDUX.SUM
     const uint32_t warp_hits = __reduce_add_sync(0xffffffffu, my_lookup_hits);
     if (lane == 0 && warp_hits) atomicAdd(&s.counters[1], (unsigned long long)warp_hits);
+}
+
+
+// ---- filtered kernel (small megablast tables) ---------------------------------------------------------
+// A small query batch (one 10 kb query = 20 k table entries in 4^11 cells) leaves almost every cell empty, yet in the
+// queue-driven kernel above every scan position still costs one random L2 sector.  Here a hashed presence filter of
+// the table (2^20 or 2^19 bits, DevQuery::filt) lives in SHARED memory: a probe is one LDS with a few-way bank
+// conflict instead of 32 L1 wavefronts per warp, and only the positions it passes (table density) go on to the exact
+// {presence, rank} word in L2.  One persistent 1024-thread CTA per SM holds the filter; its four 256-thread groups
+// each walk their own sequence of 2048-position blocks (same block descriptors, same staged slice by TMA, same
+// candidate routine as above), synchronised by a named barrier per group.  Candidates are rare by construction, so
+// they are handled right where they are met, without a queue.
+constexpr int FILT_GROUPS = 4;
+__host__ __device__ constexpr int filt_ct_ints(int maxc) { return 5 * maxc + 4; }     // ct_start[maxc + 1] + 4 arrays, 16-byte multiple
+__device__ __forceinline__ void group_sync(int group)
+{
+    asm volatile("bar.sync %0, %1;" :: "r"(group + 1), "r"(SCAN_THREADS) : "memory");
+}
+
+// Each group double-buffers: while it works on block r, the slice of block r + 1 is in flight (TMA) and its chunk
+// table is already written; the descriptor of block r + 2 is loaded a round ahead.  maxc = chunks a block may span
+// and still be staged here (a block with more takes the direct-load path).
+template <bool DIRECT>
+__global__ void __launch_bounds__(FILT_GROUPS * SCAN_THREADS, 1)
+scan_kernel_filtered(const __grid_constant__ DevQuery q, const __grid_constant__ ScanLaunch s, const int32_t filt_log2,
+                     const int32_t maxc)
+{
+    extern __shared__ __align__(128) uint32_t smem_dyn[];
+    __shared__ __align__(8) unsigned long long bars[FILT_GROUPS][2];
+    const uint32_t fwords = 1u << (filt_log2 - 5), fmask = (1u << filt_log2) - 1u;
+    uint32_t *filt = smem_dyn;
+    const int group = threadIdx.x / SCAN_THREADS, tid = threadIdx.x % SCAN_THREADS, lane = tid & 31;
+    const int32_t stage_words = s.tile_cap / 4 + filt_ct_ints(maxc);
+    uint32_t *gmem = smem_dyn + fwords + (size_t)group * 2 * stage_words;
+
+    {   // the filter: 128 KB (or the OR of its two halves) from L2, once per CTA
+        const uint4 *src = reinterpret_cast<const uint4 *>(q.filt);
+        uint4 *dst = reinterpret_cast<uint4 *>(filt);
+        const uint32_t n4 = fwords / 4;
+        if (filt_log2 == FILT_LOG2)
+            for (uint32_t i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = __ldg(src + i);
+        else
+            for (uint32_t i = threadIdx.x; i < n4; i += blockDim.x) {
+                const uint4 a = __ldg(src + i), b = __ldg(src + i + n4);
+                dst[i] = make_uint4(a.x | b.x, a.y | b.y, a.z | b.z, a.w | b.w);
+            }
+    }
+    if (tid == 0) { mbar_init(&bars[group][0], 1); mbar_init(&bars[group][1], 1); }
+    __syncthreads();
+
+    const int32_t lut = q.lut_word_length, step = q.scan_step;
+    const uint32_t shr = 32u - 2u * (uint32_t)lut;
+    const bool use_sig = !DIRECT && !s.raw_pairs && q.sig != nullptr && (q.word_length - lut) >= 7;
+    const int64_t n_blocks = (s.total_pos + POS_PER_BLOCK - 1) / POS_PER_BLOCK;
+    const int64_t stride = (int64_t)gridDim.x * FILT_GROUPS;
+    uint32_t my_lookup_hits = 0, parity = 0;        // parity: bit st = phase of stage st's barrier
+
+    // stage a block: TMA of its slice + its chunk table (block-relative first positions, tile-relative bases)
+    auto prefetch = [&](const ScanBlockDesc &d, int64_t vb, int st) {
+        const int32_t nch = d.c_hi - d.c_lo + 1;
+        if (!d.staged || nch > maxc) return;
+        uint32_t *tile = gmem + (size_t)st * stage_words;
+        if (tid == 0) {
+            mbar_expect_tx(&bars[group][st], (uint32_t)d.bytes);
+            tma_bulk_g2s(tile, s.packed + d.tile_lo, (uint32_t)d.bytes, &bars[group][st]);
+        }
+        int32_t *ct_start = reinterpret_cast<int32_t *>(tile + s.tile_cap / 4);
+        int32_t *ct_tbase = ct_start + maxc + 4, *ct_len = ct_tbase + maxc, *ct_pfirst = ct_len + maxc, *ct_parent = ct_pfirst + maxc;
+        const int64_t block_pos0 = vb * POS_PER_BLOCK;
+        for (int i = tid; i < nch; i += SCAN_THREADS) {
+            const DevChunk c = s.chunks[d.c_lo + i];
+            ct_start[i] = (int32_t)(c.pos_prefix - block_pos0);
+            ct_tbase[i] = (int32_t)((c.byte_off - d.tile_lo) * 4);
+            ct_len[i] = c.s_range;
+            ct_pfirst[i] = c.p_first;
+            ct_parent[i] = c.parent;
+        }
+        if (tid == 0) ct_start[nch] = INT32_MAX;
+    };
+
+    int64_t vb = (int64_t)blockIdx.x * FILT_GROUPS + group;
+    ScanBlockDesc bd{}, bd1{};
+    if (vb < n_blocks) { bd = ld_block_desc(s.block_desc + vb); prefetch(bd, vb, 0); }
+    if (vb + stride < n_blocks) bd1 = ld_block_desc(s.block_desc + vb + stride);
+    group_sync(group);
+    for (int st = 0; vb < n_blocks; vb += stride, st ^= 1) {
+        ScanBlockDesc bd2{};
+        if (vb + stride < n_blocks) prefetch(bd1, vb + stride, st ^ 1);
+        if (vb + 2 * stride < n_blocks) bd2 = ld_block_desc(s.block_desc + vb + 2 * stride);
+
+        const int64_t block_pos0 = vb * POS_PER_BLOCK;
+        const int32_t npos = (int32_t)min((int64_t)POS_PER_BLOCK, s.total_pos - block_pos0);
+        const int32_t nch = bd.c_hi - bd.c_lo + 1;
+        if (!bd.staged || nch > maxc) {
+            my_lookup_hits += (uint32_t)scan_block_direct(q, s, block_pos0, bd.c_lo, bd.c_hi, tid);
+        } else {
+            const uint32_t *tile = gmem + (size_t)st * stage_words;
+            const int32_t *ct_start = reinterpret_cast<const int32_t *>(tile + s.tile_cap / 4);
+            const int32_t *ct_tbase = ct_start + maxc + 4, *ct_len = ct_tbase + maxc, *ct_pfirst = ct_len + maxc,
+                          *ct_parent = ct_pfirst + maxc;
+            mbar_wait(&bars[group][st], (parity >> st) & 1u);
+            parity ^= 1u << st;
+            const BlockView bv{tile, ct_start, ct_tbase, ct_len, ct_pfirst, ct_parent, block_pos0, bd.tile_lo, bd.bytes};
+            // lookup words of the thread's 8 positions, filter bits gathered first (8 independent LDS), then the few that pass
+            uint32_t idxs[POS_PER_THREAD];
+            uint32_t cpack[POS_PER_THREAD / 4];
+            uint32_t pass = 0;
+            if (nch == 1) {
+                const int32_t tb0 = ct_tbase[0] + ct_pfirst[0] - ct_start[0] * step;
+#pragma unroll
+                for (int it = 0; it < POS_PER_THREAD; it++) {
+                    const int32_t gl = min(it * SCAN_THREADS + tid, npos - 1);
+                    const int32_t tb = tb0 + gl * step;
+                    const uint32_t w0 = tile[tb >> 4], w1 = tile[(tb >> 4) + 1];
+                    const uint32_t W = __byte_perm(w0, w1, 0x0123u + 0x1111u * ((uint32_t)(tb >> 2) & 3u));
+                    idxs[it] = (W << (2u * ((uint32_t)tb & 3u))) >> shr;
+                }
+                for (int i = 0; i < POS_PER_THREAD / 4; i++) cpack[i] = 0;
+            } else {
+                int32_t c = 0, cnext = ct_start[1];
+#pragma unroll
+                for (int it = 0; it < POS_PER_THREAD; it++) {
+                    const int32_t gl = min(it * SCAN_THREADS + tid, npos - 1);
+                    while (gl >= cnext) { ++c; cnext = ct_start[c + 1]; }
+                    if ((it & 3) == 0) cpack[it >> 2] = 0;
+                    cpack[it >> 2] |= (uint32_t)c << (8 * (it & 3));
+                    const int32_t tb = ct_tbase[c] + ct_pfirst[c] + (gl - ct_start[c]) * step;
+                    const uint32_t w0 = tile[tb >> 4], w1 = tile[(tb >> 4) + 1];
+                    const uint32_t W = __byte_perm(w0, w1, 0x0123u + 0x1111u * ((uint32_t)(tb >> 2) & 3u));
+                    idxs[it] = (W << (2u * ((uint32_t)tb & 3u))) >> shr;
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < POS_PER_THREAD; it++) {
+                const uint32_t h = (idxs[it] ^ (idxs[it] >> FILT_LOG2)) & fmask;
+                const uint32_t f = filt[h >> 5];
+                if (((f >> (h & 31u)) & 1u) && it * SCAN_THREADS + tid < npos) pass |= 1u << it;
+            }
+            while (pass) {
+                const int it = __ffs(pass) - 1;
+                pass &= pass - 1u;
+                uint32_t idx = idxs[0], cp = cpack[0];
+#pragma unroll
+                for (int j = 1; j < POS_PER_THREAD; j++) if (j == it) idx = idxs[j];
+#pragma unroll
+                for (int j = 1; j < POS_PER_THREAD / 4; j++) if (j == (it >> 2)) cp = cpack[j];
+                const uint2 w = __ldg(&q.prk[idx >> 5]);
+                const uint32_t bit = idx & 31u;
+                if ((w.x >> bit) & 1u)
+                    scan_candidate<DIRECT>(q, s, bv, w.y + (uint32_t)__popc(w.x & ((1u << bit) - 1u)), it * SCAN_THREADS + tid,
+                                           (int32_t)((cp >> (8 * (it & 3))) & 255u), use_sig, my_lookup_hits);
+            }
+        }
+        group_sync(group);          // stage st is free for block r + 2; block r + 1's chunk table is complete
+        bd = bd1; bd1 = bd2;
+    }
+    const uint32_t warp_hits = __reduce_add_sync(0xffffffffu, my_lookup_hits);
+    if (lane == 0 && warp_hits) atomicAdd(&s.counters[1], (unsigned long long)warp_hits);
+}
+
+__global__ void build_filter_kernel(const uint32_t *presence, int64_t nwords, uint32_t *filt)
+{
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwords) return;
+    uint32_t m = presence[w];
+    while (m) {
+        const uint32_t h = filt_hash((uint32_t)(w * 32) + (uint32_t)(__ffs(m) - 1));
+        m &= m - 1u;
+        atomicOr(&filt[h >> 5], 1u << (h & 31u));
+    }
+}
+cudaError_t launch_build_filter(const uint32_t *presence, int64_t nwords, uint32_t *filt, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(filt, 0, FILT_BITS / 8, st);
+    if (e != cudaSuccess) return e;
+    build_filter_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, st>>>(presence, nwords, filt);
+    return cudaGetLastError();
 }
 
 // sig[rank]: see DevQuery::sig; from the cell's first chain record (cinfo[2 rank]: .y = 16 bases left of the word, the
@@ -926,6 +1123,36 @@ cudaError_t launch_scan(const DevQuery &q, const ScanLaunch &s, cudaStream_t st)
 {
     if (s.total_pos <= 0) return cudaSuccess;
     int64_t blocks = (s.total_pos + POS_PER_BLOCK - 1) / POS_PER_BLOCK;
+    if (q.lut_type == 0 && q.prk != nullptr && q.lut_word_length <= 13 && q.filt != nullptr) {
+        // small table: shared-memory filter, one persistent CTA per SM
+        static int n_sm = 0, smem_max = 0;
+        if (!n_sm) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+            cudaFuncSetAttribute(scan_kernel_filtered<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - 1024);
+            cudaFuncSetAttribute(scan_kernel_filtered<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - 1024);
+        }
+        const bool half = getenv("BN_FILT_HALF") != nullptr;        // test switch: the folded 2^19-bit map
+        int flog = 0, maxc = 0;
+        size_t smem = 0;
+        for (int fl = half ? FILT_LOG2 - 1 : FILT_LOG2; fl >= FILT_LOG2 - 1 && !flog; fl--)
+            for (int mc = 128; mc >= 64 && !flog; mc >>= 1) {
+                const size_t need = ((size_t)1 << (fl - 3)) +
+                                    (size_t)FILT_GROUPS * 2 * ((size_t)s.tile_cap + sizeof(int32_t) * filt_ct_ints(mc));
+                if (need <= (size_t)smem_max - 1024) { flog = fl; maxc = mc; smem = need; }
+            }
+        if (flog) {
+            const int64_t ctas = (blocks + FILT_GROUPS - 1) / FILT_GROUPS;
+            const unsigned grid = (unsigned)(ctas < n_sm ? ctas : n_sm);
+            if (s.direct_filter && !s.raw_pairs)
+                scan_kernel_filtered<true><<<grid, FILT_GROUPS * SCAN_THREADS, smem, st>>>(q, s, flog, maxc);
+            else
+                scan_kernel_filtered<false><<<grid, FILT_GROUPS * SCAN_THREADS, smem, st>>>(q, s, flog, maxc);
+            return cudaGetLastError();
+        }
+    }
     if (q.lut_type == 0 && q.prk != nullptr && q.lut_word_length <= 13) {
         const size_t smem = (size_t)s.tile_cap + sizeof(uint2) * POS_PER_BLOCK;
         if (s.direct_filter && !s.raw_pairs)

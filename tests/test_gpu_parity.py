@@ -1050,3 +1050,51 @@ def test_long_extensions_in_rounds(name, mode, monkeypatch):
                (r["lookup_hits"], r["good_init_extends"], r["gap_extensions"], r["good_extensions"])
     finally:
         Q.free(); V.free()
+
+
+@pytest.mark.parametrize("name", ["c1_megablast_10kb_vs_1mb", "mb_lut11_hash_indels", "mb_lut12_stride17", "blastn_mb11_dp",
+                                  "c3_scaled_blastn_10kb", "c4_scaled_short_reads", "c5_scaled_ntlike_5kb", "mb_bridged_segments",
+                                  "blastn_direct_mixed_lengths_N", "mb_ntlike_many_subjects", "mb_with_N", "mb_ws16",
+                                  "mb_repeat_family_hitlist5", "mb_two_hit_w40_hash"])
+def test_filtered_scan_changes_nothing(name, monkeypatch):
+    """Small megablast tables are scanned by scan_kernel_filtered (hashed presence filter in shared memory, one
+    persistent CTA per SM).  Same seed hits as the queue-driven kernel (filter off: BN_FILT_MAX=0, read when the batch
+    is loaded) and as the folded 2^19-bit map (BN_FILT_HALF): every tap bit for bit, the scan tap included, and equal
+    to the reference."""
+    from gblastn_b200 import engine as E, abi
+    from oracle import portdriver as P
+    r, h, vol = _setup(name)
+    assert h.batch.lut_type == abi.BN_LUT_MB
+    if h.batch.concat_len > (1 << 18):
+        monkeypatch.setenv("BN_FILT_MAX", str(1 << 30))     # larger batches: forced, the filter is merely denser
+    V = E.Volume(vol)
+    out = []
+    try:
+        forced = h.batch.concat_len > (1 << 18)
+        for mode in ("filtered", "half", "queue"):
+            if not forced:
+                monkeypatch.delenv("BN_FILT_MAX", raising=False)
+            monkeypatch.delenv("BN_FILT_HALF", raising=False)
+            if mode == "queue":
+                monkeypatch.setenv("BN_FILT_MAX", "0")
+            if mode == "half":
+                monkeypatch.setenv("BN_FILT_HALF", "1")
+            Q = E.Query(h)
+            try:
+                g = E.prelim_search(V, Q, taps=abi.BN_TAP_INIT | abi.BN_TAP_GAPPED)
+                oid = int(np.argmax(vol.seq_len))
+                g["pairs"] = E.scan_subject(V, Q, oid) if vol.seq_len[oid] <= 200_000_000 else None
+                out.append(g)
+            finally:
+                Q.free()
+        a = out[0]
+        for b in out[1:]:
+            assert a["init"].tobytes() == b["init"].tobytes() and a["gapped"].tobytes() == b["gapped"].tobytes()
+            assert a["hsps"].tobytes() == b["hsps"].tobytes()
+            assert a["stats"]["lookup_hits"] == b["stats"]["lookup_hits"] == r["lookup_hits"]
+            if a["pairs"] is not None:
+                assert a["pairs"].tobytes() == b["pairs"].tobytes()
+        assert np.array_equal(P.init_table(a["init"]), r["init"])
+        assert np.array_equal(P.final_table(a["hsps"]), r["final"])
+    finally:
+        V.free()
