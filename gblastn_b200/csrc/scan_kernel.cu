@@ -294,6 +294,31 @@ __device__ __forceinline__ uint32_t tile_win(const uint32_t *tile, int32_t tb)
     return __funnelshift_l(b, a, (uint32_t)(tb & 15) * 2);
 }
 
+
+// Lookup words of 8 CONSECUTIVE scan positions of one chunk (compile-time stride STEP bases), first position at
+// tile-relative base tb_first: the 10 words that hold them are loaded once (lanes 8 * STEP bases apart: for STEP 17
+// and 18 an odd number of words, no bank conflict), aligned to the first position with 9 funnel shifts, and every
+// word is then one more shift by a compile-time amount — ~6 instructions per position where the per-position
+// form (two LDS, selector arithmetic, PRMT, two shifts on run-time amounts) takes ~25.
+template <int STEP>
+__device__ __forceinline__ void words8(const uint32_t *tile, int32_t tb_first, uint32_t shr, uint32_t (&idx)[8])
+{
+    static_assert(STEP >= 16 && 14 * STEP + 26 + 30 <= 320 && (14 * STEP) / 32 + 1 <= 8, "ten raw words cover the span");
+    const uint32_t *w = tile + (tb_first >> 4);
+    uint32_t R[10], N[9];
+#pragma unroll
+    for (int i = 0; i < 10; i++) R[i] = __byte_perm(w[i], 0, 0x0123);
+    const uint32_t off0 = ((uint32_t)tb_first & 15u) * 2u;
+#pragma unroll
+    for (int i = 0; i < 9; i++) N[i] = __funnelshift_l(R[i + 1], R[i], off0);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int bit = j * 2 * STEP, a = bit >> 5, sh = bit & 31;
+        const uint32_t v = sh ? __funnelshift_l(N[a + 1 < 9 ? a + 1 : 8], N[a], (uint32_t)sh) : N[a];
+        idx[j] = v >> shr;
+    }
+}
+
 // s_BlastNaExtend on 16-base windows.  The query's 16 bases on either side of the lookup word come
 // with the chain element (qinfo), so the common case needs no further query access; tbase =
 // tile-relative base index of the chunk's base 0.
@@ -630,7 +655,8 @@ __device__ __forceinline__ void scan_candidate(const DevQuery &q, const ScanLaun
     }
 }
 
-template <bool DIRECT>
+// STEP: compile-time scan stride for the consecutive-position word loader (blocks inside one chunk), 0 = run-time stride
+template <bool DIRECT, int STEP>
 __global__ void __launch_bounds__(SCAN_THREADS, DIRECT ? 4 : BN_SCAN_MIN_BLOCKS)
 scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ ScanLaunch s)
 {
@@ -678,7 +704,25 @@ scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ S
         uint2 words[POS_PER_THREAD];
         uint32_t bitpack[POS_PER_THREAD / 4], cpack[POS_PER_THREAD / 4];
         const uint32_t shr = 32u - 2u * (uint32_t)lut;
-        if (nch == 1) {
+        // thread -> position map: round it of thread tid handles block-relative position it * 256 + tid, or — blocks
+        // inside one chunk with a compile-time stride — tid * 8 + it (consecutive positions, words8)
+        const bool consec = STEP > 0 && POS_PER_THREAD == 8 && nch == 1;
+        if constexpr (STEP > 0 && POS_PER_THREAD == 8) {
+            if (consec) {
+                const int32_t tb0 = ct_tbase[0] + ct_pfirst[0] - ct_start[0] * STEP;
+                uint32_t idxs[8];
+                words8<STEP>(tile, tb0 + tid * 8 * STEP, shr, idxs);
+#pragma unroll
+                for (int it = 0; it < 8; it++) {
+                    words[it] = __ldg(&q.prk[idxs[it] >> 5]);
+                    if ((it & 3) == 0) bitpack[it >> 2] = 0;
+                    bitpack[it >> 2] |= (idxs[it] & 31u) << (8 * (it & 3));
+                }
+                for (int i = 0; i < POS_PER_THREAD / 4; i++) cpack[i] = 0;
+            }
+        }
+        if (consec) {
+        } else if (nch == 1) {
             // the whole block lies in one chunk: tile offsets are an arithmetic progression
             const int32_t tb0 = ct_tbase[0] + ct_pfirst[0] - ct_start[0] * step;
 #pragma unroll
@@ -726,13 +770,14 @@ scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ S
 #pragma unroll
             for (int it = 0; it < POS_PER_THREAD; it++) {
                 const uint32_t bit = (bitpack[it >> 2] >> (8 * (it & 3))) & 31u;
-                const bool hit = (it * SCAN_THREADS + tid < npos) && ((words[it].x >> bit) & 1u);
+                const int32_t gl = consec ? tid * POS_PER_THREAD + it : it * SCAN_THREADS + tid;
+                const bool hit = (gl < npos) && ((words[it].x >> bit) & 1u);
                 const uint32_t m = __ballot_sync(0xffffffffu, hit);
                 if (hit) {
                     const uint32_t c = (cpack[it >> 2] >> (8 * (it & 3))) & 255u;
                     wcand[ncand + __popc(m & lt)] =
                         make_uint2(words[it].y + (uint32_t)__popc(words[it].x & ((1u << bit) - 1u)),
-                                   (c << 11) | (uint32_t)(it * SCAN_THREADS + tid));
+                                   (c << 11) | (uint32_t)gl);
                 }
                 ncand += __popc(m);
             }
@@ -772,7 +817,7 @@ __device__ __forceinline__ void group_sync(int group)
 // Each group double-buffers: while it works on block r, the slice of block r + 1 is in flight (TMA) and its chunk
 // table is already written; the descriptor of block r + 2 is loaded a round ahead.  maxc = chunks a block may span
 // and still be staged here (a block with more takes the direct-load path).
-template <bool DIRECT>
+template <bool DIRECT, int STEP>
 __global__ void __launch_bounds__(FILT_GROUPS * SCAN_THREADS, 1)
 scan_kernel_filtered(const __grid_constant__ DevQuery q, const __grid_constant__ ScanLaunch s, const int32_t filt_log2,
                      const int32_t maxc)
@@ -811,6 +856,7 @@ scan_kernel_filtered(const __grid_constant__ DevQuery q, const __grid_constant__
     auto prefetch = [&](const ScanBlockDesc &d, int64_t vb, int st) {
         const int32_t nch = d.c_hi - d.c_lo + 1;
         if (!d.staged || nch > maxc) return;
+        if (tid >= 32 && tid >= nch) return;                // warps with nothing to write (the usual block spans a few chunks)
         uint32_t *tile = gmem + (size_t)st * stage_words;
         if (tid == 0) {
             mbar_expect_tx(&bars[group][st], (uint32_t)d.bytes);
@@ -857,7 +903,16 @@ scan_kernel_filtered(const __grid_constant__ DevQuery q, const __grid_constant__
             uint32_t idxs[POS_PER_THREAD];
             uint32_t cpack[POS_PER_THREAD / 4];
             uint32_t pass = 0;
-            if (nch == 1) {
+            const bool consec = STEP > 0 && POS_PER_THREAD == 8 && nch == 1;      // thread -> position map, see scan_kernel_staged
+            if constexpr (STEP > 0 && POS_PER_THREAD == 8) {
+                if (consec) {
+                    const int32_t tb0 = ct_tbase[0] + ct_pfirst[0] - ct_start[0] * STEP;
+                    words8<STEP>(tile, tb0 + tid * 8 * STEP, shr, idxs);
+                    for (int i = 0; i < POS_PER_THREAD / 4; i++) cpack[i] = 0;
+                }
+            }
+            if (consec) {
+            } else if (nch == 1) {
                 const int32_t tb0 = ct_tbase[0] + ct_pfirst[0] - ct_start[0] * step;
 #pragma unroll
                 for (int it = 0; it < POS_PER_THREAD; it++) {
@@ -886,7 +941,11 @@ scan_kernel_filtered(const __grid_constant__ DevQuery q, const __grid_constant__
             for (int it = 0; it < POS_PER_THREAD; it++) {
                 const uint32_t h = (idxs[it] ^ (idxs[it] >> FILT_LOG2)) & fmask;
                 const uint32_t f = filt[h >> 5];
-                if (((f >> (h & 31u)) & 1u) && it * SCAN_THREADS + tid < npos) pass |= 1u << it;
+                pass |= (__funnelshift_r(f, 0u, h) & 1u) << it;           // shift amount taken mod 32
+            }
+            {   // positions behind the end of the volume (last block only)
+                const int32_t left = consec ? npos - tid * POS_PER_THREAD : (npos - tid + SCAN_THREADS - 1) / SCAN_THREADS;
+                if (left < POS_PER_THREAD) pass &= left <= 0 ? 0u : (1u << left) - 1u;
             }
             while (pass) {
                 const int it = __ffs(pass) - 1;
@@ -899,7 +958,8 @@ scan_kernel_filtered(const __grid_constant__ DevQuery q, const __grid_constant__
                 const uint2 w = __ldg(&q.prk[idx >> 5]);
                 const uint32_t bit = idx & 31u;
                 if ((w.x >> bit) & 1u)
-                    scan_candidate<DIRECT>(q, s, bv, w.y + (uint32_t)__popc(w.x & ((1u << bit) - 1u)), it * SCAN_THREADS + tid,
+                    scan_candidate<DIRECT>(q, s, bv, w.y + (uint32_t)__popc(w.x & ((1u << bit) - 1u)),
+                                           consec ? tid * POS_PER_THREAD + it : it * SCAN_THREADS + tid,
                                            (int32_t)((cp >> (8 * (it & 3))) & 255u), use_sig, my_lookup_hits);
             }
         }
@@ -1123,6 +1183,8 @@ cudaError_t launch_scan(const DevQuery &q, const ScanLaunch &s, cudaStream_t st)
 {
     if (s.total_pos <= 0) return cudaSuccess;
     int64_t blocks = (s.total_pos + POS_PER_BLOCK - 1) / POS_PER_BLOCK;
+    // compile-time stride of the consecutive-position loader (the megablast defaults); BN_NO_CONSEC: test switch
+    const int cstep = (!getenv("BN_NO_CONSEC") && (q.scan_step == 17 || q.scan_step == 18)) ? q.scan_step : 0;
     if (q.lut_type == 0 && q.prk != nullptr && q.lut_word_length <= 13 && q.filt != nullptr) {
         // small table: shared-memory filter, one persistent CTA per SM
         static int n_sm = 0, smem_max = 0;
@@ -1131,8 +1193,11 @@ cudaError_t launch_scan(const DevQuery &q, const ScanLaunch &s, cudaStream_t st)
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
             cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-            cudaFuncSetAttribute(scan_kernel_filtered<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - 1024);
-            cudaFuncSetAttribute(scan_kernel_filtered<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - 1024);
+            const int lim = smem_max - 1024;
+            cudaFuncSetAttribute(scan_kernel_filtered<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+            cudaFuncSetAttribute(scan_kernel_filtered<false, 17>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+            cudaFuncSetAttribute(scan_kernel_filtered<false, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+            cudaFuncSetAttribute(scan_kernel_filtered<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
         }
         const bool half = getenv("BN_FILT_HALF") != nullptr;        // test switch: the folded 2^19-bit map
         int flog = 0, maxc = 0;
@@ -1146,19 +1211,20 @@ cudaError_t launch_scan(const DevQuery &q, const ScanLaunch &s, cudaStream_t st)
         if (flog) {
             const int64_t ctas = (blocks + FILT_GROUPS - 1) / FILT_GROUPS;
             const unsigned grid = (unsigned)(ctas < n_sm ? ctas : n_sm);
-            if (s.direct_filter && !s.raw_pairs)
-                scan_kernel_filtered<true><<<grid, FILT_GROUPS * SCAN_THREADS, smem, st>>>(q, s, flog, maxc);
-            else
-                scan_kernel_filtered<false><<<grid, FILT_GROUPS * SCAN_THREADS, smem, st>>>(q, s, flog, maxc);
+            const unsigned nt = FILT_GROUPS * SCAN_THREADS;
+            if (s.direct_filter && !s.raw_pairs) scan_kernel_filtered<true, 0><<<grid, nt, smem, st>>>(q, s, flog, maxc);
+            else if (cstep == 17) scan_kernel_filtered<false, 17><<<grid, nt, smem, st>>>(q, s, flog, maxc);
+            else if (cstep == 18) scan_kernel_filtered<false, 18><<<grid, nt, smem, st>>>(q, s, flog, maxc);
+            else scan_kernel_filtered<false, 0><<<grid, nt, smem, st>>>(q, s, flog, maxc);
             return cudaGetLastError();
         }
     }
     if (q.lut_type == 0 && q.prk != nullptr && q.lut_word_length <= 13) {
         const size_t smem = (size_t)s.tile_cap + sizeof(uint2) * POS_PER_BLOCK;
-        if (s.direct_filter && !s.raw_pairs)
-            scan_kernel_staged<true><<<(unsigned)blocks, SCAN_THREADS, smem, st>>>(q, s);
-        else
-            scan_kernel_staged<false><<<(unsigned)blocks, SCAN_THREADS, smem, st>>>(q, s);
+        if (s.direct_filter && !s.raw_pairs) scan_kernel_staged<true, 0><<<(unsigned)blocks, SCAN_THREADS, smem, st>>>(q, s);
+        else if (cstep == 17) scan_kernel_staged<false, 17><<<(unsigned)blocks, SCAN_THREADS, smem, st>>>(q, s);
+        else if (cstep == 18) scan_kernel_staged<false, 18><<<(unsigned)blocks, SCAN_THREADS, smem, st>>>(q, s);
+        else scan_kernel_staged<false, 0><<<(unsigned)blocks, SCAN_THREADS, smem, st>>>(q, s);
     }
     else
         scan_kernel<<<(unsigned)blocks, SCAN_THREADS, 0, st>>>(q, s);

@@ -1065,17 +1065,20 @@ def test_filtered_scan_changes_nothing(name, monkeypatch):
     from oracle import portdriver as P
     r, h, vol = _setup(name)
     assert h.batch.lut_type == abi.BN_LUT_MB
-    if h.batch.concat_len > (1 << 18):
+    if h.batch.concat_len > (1 << 16):
         monkeypatch.setenv("BN_FILT_MAX", str(1 << 30))     # larger batches: forced, the filter is merely denser
     V = E.Volume(vol)
     out = []
     try:
-        forced = h.batch.concat_len > (1 << 18)
-        for mode in ("filtered", "half", "queue"):
+        forced = h.batch.concat_len > (1 << 16)
+        for mode in ("filtered", "half", "queue", "filtered_strided", "queue_strided"):
             if not forced:
                 monkeypatch.delenv("BN_FILT_MAX", raising=False)
             monkeypatch.delenv("BN_FILT_HALF", raising=False)
-            if mode == "queue":
+            monkeypatch.delenv("BN_NO_CONSEC", raising=False)
+            if mode.endswith("strided"):        # words formed position by position instead of 8 consecutive ones per thread
+                monkeypatch.setenv("BN_NO_CONSEC", "1")
+            if mode.startswith("queue"):
                 monkeypatch.setenv("BN_FILT_MAX", "0")
             if mode == "half":
                 monkeypatch.setenv("BN_FILT_HALF", "1")
