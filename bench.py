@@ -425,7 +425,7 @@ def main():
     # ---- resident-input throughput: K steps = K jobs through the job pipeline (bn_prelim_search_jobs) ----------
     # Every job is a complete preliminary search (scan ... gapped on the device, replay / E-values on the host); the
     # pipeline queues job k+1's kernels before it waits for job k and replays finished jobs on a worker thread.
-    results = engine.prelim_search_jobs(resident_jobs(max(args.warmup, N_SETS)))
+    results = engine.prelim_search_jobs(resident_jobs(max(args.warmup, N_SETS, 12)))      # every lane of the pipeline has run twice
     per_set = results[:N_SETS]                       # one result per set, for the parity check below
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage = {"ms_scan": 0.0, "ms_extend": 0.0, "ms_gapped": 0.0, "ms_host": 0.0}
@@ -449,7 +449,7 @@ def main():
         g = results[0]
         # ---- end to end: the same K steps with every input in HOST memory — per job the packed volume (pinned) and
         # the query batch cross PCIe, the lookup table is filled on the device, the results come back ----------------
-        engine.prelim_search_jobs(host_jobs(max(args.warmup, 8)))      # every lane of the pipeline has sized its arena
+        engine.prelim_search_jobs(host_jobs(max(args.warmup, 12)))      # every lane of the pipeline has sized its arena
         timed = engine.JobBatch(host_jobs(args.steps))
         barrier()
         ev0.record()
@@ -527,6 +527,51 @@ def main():
         "ranks": [dict(zip(("ms_per_step", "e2e_ms_per_step", "ms_scan", "ms_extend", "ms_gapped", "ms_host", "numa"),
                            [round(float(x), 4) for x in r.tolist()])) for r in per_rank],
     }
+
+    # ---- small query batch on the same volume (BASELINE configs[0]'s query shape: ONE 10 kb query; N=1 only): the scan
+    # goes through scan_kernel_filtered (presence filter of the table in shared memory), timed beside the queue-driven
+    # kernel on the same batch; its fraction of the HBM peak is reported here, separately from `roofline` ------------------
+    if rank == 0 and world == 1:
+        try:
+            qs1 = synth.planted_queries(vol, 1, 10_000, seed=5, planted_frac=1.0, sub_rate=0.02, rc_frac=0.5)
+            s1 = setup.Setup(qs1, task="megablast", db_length=vol.total_bases, db_num_seqs=vol.n_seqs, device_lookup=1)
+            sb = {"workload": "megablast: 1x10kb synthetic query (BASELINE configs[0] query shape) vs the 250Mb volume of configs[1]",
+                  "lut": f"MB lut {s1.batch.lut_word_length} / stride {s1.batch.scan_step}"}
+            outs = {}
+            for mode in ("filtered", "queue"):
+                if mode == "queue":
+                    os.environ["BN_FILT_MAX"] = "0"
+                else:
+                    os.environ.pop("BN_FILT_MAX", None)
+                Q1 = engine.Query(s1.batch)
+                engine.bench_scan(V, Q1, 3)
+                ms1, bases1, _ = engine.bench_scan(V, Q1, max(args.steps, 10))
+                engine.prelim_search(V, Q1)
+                l2_flush()
+                ev0.record()
+                outs[mode] = engine.prelim_search(V, Q1)
+                ev1.record()
+                ev1.synchronize()
+                sb[mode] = {"scan_ms": ms1, "algorithmic_GBs": bases1 * 0.25 / (ms1 * 1e-3) / 1e9,
+                            "frac_of_hbm_peak": bases1 * 0.25 / (ms1 * 1e-3) / 1e9 / peak,
+                            "search_ms": float(ev0.elapsed_time(ev1)),
+                            "kernel": "bn::scan_kernel_filtered" if mode == "filtered" else "bn::scan_kernel_staged"}
+                Q1.free()
+            os.environ.pop("BN_FILT_MAX", None)
+            sb["identical"] = bool(outs["filtered"]["hsps"].tobytes() == outs["queue"]["hsps"].tobytes() and
+                                   outs["filtered"]["stats"]["lookup_hits"] == outs["queue"]["stats"]["lookup_hits"])
+            sb["hsps"] = int(outs["filtered"]["hsps"].size)
+            sb["lookup_hits"] = int(outs["filtered"]["stats"]["lookup_hits"])
+            if not args.no_cpu_baseline:
+                from oracle import refdriver as R, portdriver as P
+                if R.available():
+                    r1 = R.search(qs1, vol, R.default_config("megablast", num_threads=1))
+                    sb["parity_vs_reference"] = bool(np.array_equal(P.final_table(outs["filtered"]["hsps"]), r1["final"]))
+                    sb["reference_ms_1core"] = 1e3 * r1["seconds_prelim"]
+            s1.free()
+            line["small_batch"] = sb
+        except Exception as e:
+            line["small_batch"] = {"error": f"{type(e).__name__}: {e}"}
 
     # ---- CPU baseline (reference engine on the host cores), rank 0 at N=1 only --------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -2487,11 +2487,15 @@ int bn_prelim_search_jobs(int device, int32_t n_jobs, const BnJob *jobs, int tap
     }
     if (n_jobs == 0) return BN_OK;
     CU_TRY(cudaSetDevice(g->id));
-    // three lanes: while the call waits for job k, jobs k+1 and k+2 are queued on the device
-    constexpr int NL = 3;
-    LaneLock lanes[NL + 1];               // [NL]: the traceback stage's lane (tb != NULL)
-    Stager stagers[NL];
-    acquire_lanes(*g, tb ? NL + 1 : NL, lanes);
+    // NL lanes (default five, BN_JOB_DEPTH): while the call waits for job k, jobs k+1 .. k+NL-1 are queued on the device.
+    // A job's latency (scan -> grouping -> ungapped -> gapped -> mirror, ~0.4 ms for a C2 search) over the number in
+    // flight bounds the rate: three lanes gave 0.135 ms per C2 search, four 0.123, five 0.121 (scan kernel alone 0.100)
+    int NL = 5;
+    if (const char *e = getenv("BN_JOB_DEPTH")) NL = atoi(e);
+    NL = std::max(2, std::min(NL, (int)g->lanes.size() - 1));
+    std::vector<LaneLock> lanes((size_t)NL + 1);               // [NL]: the traceback stage's lane (tb != NULL)
+    std::vector<Stager> stagers((size_t)NL);
+    acquire_lanes(*g, tb ? NL + 1 : NL, lanes.data());
     for (int i = 0; i < NL; i++) {
         if (lanes[i].lane->stage.reserve((size_t)6 << 20) == cudaSuccess) { stagers[i].base = lanes[i].lane->stage.p; stagers[i].cap = (size_t)6 << 20; }
     }
