@@ -380,7 +380,7 @@ def main():
             try:
                 cpus = sorted(os.sched_getaffinity(0))
                 per = len(cpus) // world
-                if per >= 2:
+                if per >= 2 and not os.environ.get("BN_BENCH_NO_BIND"):
                     os.sched_setaffinity(0, set(cpus[local_rank * per:(local_rank + 1) * per]))
             except Exception:
                 pass

@@ -245,6 +245,7 @@ struct ScanLaunch {
     // direct filter (lut == word, one-hit mode, unmasked volume): drop hits whose ungapped extension certainly
     // stays below the cutoff; uni_*: the cutoffs when every context has the same ones (uni_ok), else per context
     int32_t direct_filter;
+    int32_t direct_dense;         // queue the filter evaluations and run them 32 at a time (test switch BN_NO_DIRECT_DENSE: inline)
     int32_t uni_ok, uni_x, uni_cutoff, uni_reduced;
 };
 cudaError_t launch_scan(const DevQuery &q, const ScanLaunch &s, cudaStream_t st);

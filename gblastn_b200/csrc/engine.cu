@@ -850,6 +850,7 @@ struct GpuOut {
 static void set_direct_filter(ScanLaunch &s, const Query &Q, const ChunkTable &T, bool raw_pairs)
 {
     s.direct_filter = (Q.direct_ok && !raw_pairs && T.units.empty()) ? 1 : 0;      // unmasked volumes only
+    s.direct_dense = getenv("BN_NO_DIRECT_DENSE") ? 0 : 1;
     s.uni_ok = Q.uni_ok; s.uni_x = Q.uni_x; s.uni_cutoff = Q.uni_cutoff; s.uni_reduced = Q.uni_reduced;
 }
 

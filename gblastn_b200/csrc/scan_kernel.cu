@@ -397,6 +397,10 @@ __device__ __noinline__ bool direct_keep(const DevQuery &q, const DirectCtx &d, 
 {
     const int32_t X = -x_dropoff;
     const int32_t r = q.reward, pen = q.penalty, r4 = 4 * r, dd = r - pen;
+    // Keeping a hit is always allowed (the extension is recomputed behind the filter), so an evaluation stops as soon as
+    // the running score says "keep": inside a true alignment that is after a few dozen bases instead of the whole
+    // alignment, which a lone lane would otherwise walk while the other 31 of its warp wait
+    const int32_t keep_at = max(cutoff, reduced);
     const int32_t shift = (4 - (s_off & 3)) & 3;
     const int32_t q_ext = q_off + shift, s_ext = s_off + shift;
     int32_t score = 0;
@@ -412,7 +416,7 @@ __device__ __noinline__ bool direct_keep(const DevQuery &q, const DirectCtx &d, 
             for (int j = 0; j < cnt; j++) {
                 if ((qa >> (8 * j)) & 0xFFu) return true;
                 sum += r4 - dd * __popc((m >> (8 * j)) & 0xFFu);
-                if (sum > 0) { score += sum; sum = 0; }
+                if (sum > 0) { score += sum; sum = 0; if (score >= keep_at) return true; }
                 if (sum < X) { stop = true; break; }
             }
         }
@@ -429,7 +433,7 @@ __device__ __noinline__ bool direct_keep(const DevQuery &q, const DirectCtx &d, 
             for (int j = 0; j < cnt; j++) {
                 if ((qa >> (24 - 8 * j)) & 0xFFu) return true;
                 sum += r4 - dd * __popc((m >> (24 - 8 * j)) & 0xFFu);
-                if (sum > 0) { score += sum; sum = 0; }
+                if (sum > 0) { score += sum; sum = 0; if (score >= keep_at) return true; }
                 if (sum < X) { stop = true; break; }
             }
         }
@@ -454,7 +458,7 @@ __device__ __noinline__ bool direct_keep(const DevQuery &q, const DirectCtx &d, 
                 const uint32_t mm = m >> (2 * t);
                 int32_t run = mm ? ((__ffs(mm) - 1) >> 1) : 16;
                 run = min(run, rem - t);
-                if (run > 0) { sum += run * r; if (sum > 0) { score += sum; sum = 0; } t += run; }
+                if (run > 0) { sum += run * r; if (sum > 0) { score += sum; sum = 0; if (score >= cutoff) return true; } t += run; }
                 if (t >= rem) break;
                 sum += pen;
                 if (sum < X) { stop = true; break; }
@@ -479,7 +483,7 @@ __device__ __noinline__ bool direct_keep(const DevQuery &q, const DirectCtx &d, 
                 const uint32_t mm = m << (2 * t);
                 int32_t run = mm ? (__clz(mm) >> 1) : 16;
                 run = min(run, rem - t);
-                if (run > 0) { sum += run * r; if (sum > 0) { score += sum; sum = 0; } t += run; }
+                if (run > 0) { sum += run * r; if (sum > 0) { score += sum; sum = 0; if (score >= cutoff) return true; } t += run; }
                 if (t >= rem) break;
                 sum += pen;
                 if (sum < X) { stop = true; break; }
@@ -590,9 +594,20 @@ struct BlockView {
     int64_t block_pos0, tile_lo;
     int32_t tile_bytes;
 };
+// Direct filter, dense: the lanes of a warp meet their non-follower hits at different steps of different chains, and
+// a filter evaluation entered by 10 lanes out of 32 that then leave it one by one costs the warp ~700 instructions
+// per call (C3: 3.7 G warp instructions for 100 Mb).  With a queue the chain walk only records {query position, block
+// position | chunk << 11}; full sets of 32 records are then evaluated together.
+constexpr int DQ_CAP = 128;
+struct DirectQueue {
+    uint2 rec[DQ_CAP];
+    uint32_t count;
+    uint32_t pad[3];
+};
 template <bool DIRECT>
 __device__ __forceinline__ void scan_candidate(const DevQuery &q, const ScanLaunch &s, const BlockView &b, uint32_t rank,
-                                               int32_t gl, int32_t k, bool use_sig, uint32_t &my_lookup_hits)
+                                               int32_t gl, int32_t k, bool use_sig, uint32_t &my_lookup_hits,
+                                               DirectQueue *dq = nullptr)
 {
     const int32_t lut = q.lut_word_length, step = q.scan_step;
     const uint32_t *tile = b.tile;
@@ -627,7 +642,10 @@ __device__ __forceinline__ void scan_candidate(const DevQuery &q, const ScanLaun
             // cutoff itself when that one was.  Only a run's first hit goes on, and only if its own
             // ungapped extension can reach the cutoff.
             const bool follower = (qi.x & PREV_INDEXED) && s_prev == (qi.y & 3u) && !(qi.w & 1u);
-            if (!follower) {
+            uint32_t slot = DQ_CAP;
+            if (!follower && dq) slot = atomicAdd(&dq->count, 1u);
+            if (slot < (uint32_t)DQ_CAP) dq->rec[slot] = make_uint2((uint32_t)qp, (uint32_t)gl | ((uint32_t)k << 11));
+            else if (!follower) {
                 int32_t xd = s.uni_x, co = s.uni_cutoff, rc = s.uni_reduced;
                 if (!s.uni_ok) {
                     const DevContext c = q.ctx[ctx_search(q, qp - 1)];
@@ -653,6 +671,42 @@ __device__ __forceinline__ void scan_candidate(const DevQuery &q, const ScanLaun
             more = (qi.x & QP_MASK) != 0;
         }
     }
+}
+
+// Evaluates queued hits of the direct filter, 32 at a time (only full sets unless `all`); what is left moves to the front.
+__device__ __forceinline__ void direct_drain(const DevQuery &q, const ScanLaunch &s, const BlockView &b, DirectQueue *dq, bool all,
+                                             int lane)
+{
+    __syncwarp();
+    const int32_t n = (int32_t)min(dq->count, (uint32_t)DQ_CAP);
+    int32_t done = 0;
+    const int32_t step = q.scan_step;
+    while (n - done >= 32 || (all && done < n)) {
+        const int32_t i = done + lane;
+        if (i < n) {
+            const uint2 r = dq->rec[i];
+            const int32_t qp = (int32_t)r.x, gl = (int32_t)(r.y & 2047u), k = (int32_t)(r.y >> 11);
+            const int32_t p = b.ct_pfirst[k] + (gl - b.ct_start[k]) * step;
+            int32_t xd = s.uni_x, co = s.uni_cutoff, rc = s.uni_reduced;
+            if (!s.uni_ok) {
+                const DevContext c = q.ctx[ctx_search(q, qp - 1)];
+                xd = c.x_dropoff; co = c.cutoff_score; rc = c.reduced_cutoff;
+            }
+            DirectCtx dc{b.tile, b.tile_bytes * 4, b.tile_lo * 4, s.packed};
+            if (direct_keep(q, dc, b.ct_tbase[k], b.ct_len[k], qp - 1, p, xd, co, rc))
+                emit_hit(q, s, (uint32_t)b.ct_parent[k], (uint32_t)p, b.block_pos0 + gl, qp - 1, p);
+        }
+        done += 32;
+        __syncwarp();
+    }
+    done = min(done, n);
+    const int32_t left = n - done;
+    uint2 r = make_uint2(0u, 0u);
+    if (lane < left) r = dq->rec[done + lane];
+    __syncwarp();
+    if (lane < left) dq->rec[lane] = r;
+    if (lane == 0) dq->count = (uint32_t)left;
+    __syncwarp();
 }
 
 // STEP: compile-time scan stride for the consecutive-position word loader (blocks inside one chunk), 0 = run-time stride
@@ -787,9 +841,24 @@ scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ S
         // ---- phase B: the warp's candidates, one per lane ----------------------------------------------
         const bool use_sig = !DIRECT && !s.raw_pairs && q.sig != nullptr && (q.word_length - lut) >= 7;
         const BlockView bv{tile, ct_start, ct_tbase, ct_len, ct_pfirst, ct_parent, block_pos0, bd.tile_lo, bd.bytes};
-        for (int ci = lane; ci < ncand; ci += 32) {
-            const uint2 cd = wcand[ci];
-            scan_candidate<DIRECT>(q, s, bv, cd.x, (int32_t)(cd.y & 2047u), (int32_t)(cd.y >> 11), use_sig, my_lookup_hits);
+        if constexpr (DIRECT) {
+            DirectQueue *dq = reinterpret_cast<DirectQueue *>(cand + POS_PER_BLOCK) + (tid >> 5);
+            if (lane == 0) dq->count = 0;
+            __syncwarp();
+            for (int c0 = 0; c0 < ncand; c0 += 32) {
+                const int ci = c0 + lane;
+                if (ci < ncand) {
+                    const uint2 cd = wcand[ci];
+                    scan_candidate<DIRECT>(q, s, bv, cd.x, (int32_t)(cd.y & 2047u), (int32_t)(cd.y >> 11), use_sig, my_lookup_hits,
+                                           s.direct_dense ? dq : nullptr);
+                }
+                direct_drain(q, s, bv, dq, c0 + 32 >= ncand, lane);
+            }
+        } else {
+            for (int ci = lane; ci < ncand; ci += 32) {
+                const uint2 cd = wcand[ci];
+                scan_candidate<DIRECT>(q, s, bv, cd.x, (int32_t)(cd.y & 2047u), (int32_t)(cd.y >> 11), use_sig, my_lookup_hits);
+            }
         }
     }
     // one atomic per warp for the lookup-hit statistic (BlastUngappedStats.lookup_hits); REDUX.SUM
@@ -1221,7 +1290,8 @@ cudaError_t launch_scan(const DevQuery &q, const ScanLaunch &s, cudaStream_t st)
     }
     if (q.lut_type == 0 && q.prk != nullptr && q.lut_word_length <= 13) {
         const size_t smem = (size_t)s.tile_cap + sizeof(uint2) * POS_PER_BLOCK;
-        if (s.direct_filter && !s.raw_pairs) scan_kernel_staged<true, 0><<<(unsigned)blocks, SCAN_THREADS, smem, st>>>(q, s);
+        if (s.direct_filter && !s.raw_pairs)
+            scan_kernel_staged<true, 0><<<(unsigned)blocks, SCAN_THREADS, smem + sizeof(DirectQueue) * (SCAN_THREADS / 32), st>>>(q, s);
         else if (cstep == 17) scan_kernel_staged<false, 17><<<(unsigned)blocks, SCAN_THREADS, smem, st>>>(q, s);
         else if (cstep == 18) scan_kernel_staged<false, 18><<<(unsigned)blocks, SCAN_THREADS, smem, st>>>(q, s);
         else scan_kernel_staged<false, 0><<<(unsigned)blocks, SCAN_THREADS, smem, st>>>(q, s);

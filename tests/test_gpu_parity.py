@@ -976,19 +976,24 @@ def test_direct_filter_changes_nothing(name, monkeypatch):
     V = E.Volume(vol)
     out = []
     try:
-        for off in (False, True):
-            if off:
+        for mode in ("dense", "off", "inline"):
+            monkeypatch.delenv("BN_NO_DIRECT_FILTER", raising=False)
+            monkeypatch.delenv("BN_NO_DIRECT_DENSE", raising=False)
+            monkeypatch.setenv("BN_FILT_MAX", "0")              # the queue-driven kernel: the one with the dense evaluation
+            if mode == "off":
                 monkeypatch.setenv("BN_NO_DIRECT_FILTER", "1")
-            else:
-                monkeypatch.delenv("BN_NO_DIRECT_FILTER", raising=False)
+            if mode == "inline":                                # evaluations where the chain walk meets the hits (read per search)
+                monkeypatch.setenv("BN_NO_DIRECT_DENSE", "1")
             Q = E.Query(h)
             try:
                 out.append(E.prelim_search(V, Q, taps=abi.BN_TAP_INIT | abi.BN_TAP_GAPPED))
             finally:
                 Q.free()
-        a, b = out
+        a, b, c = out
         assert a["init"].tobytes() == b["init"].tobytes() and a["gapped"].tobytes() == b["gapped"].tobytes()
         assert a["hsps"].tobytes() == b["hsps"].tobytes()
+        assert a["init"].tobytes() == c["init"].tobytes() and a["hsps"].tobytes() == c["hsps"].tobytes()
+        assert a["stats"]["lookup_hits"] == c["stats"]["lookup_hits"]
         assert np.array_equal(P.init_table(a["init"]), r["init"])
         assert np.array_equal(P.final_table(a["hsps"]), r["final"])
         assert a["stats"]["lookup_hits"] == b["stats"]["lookup_hits"] == r["lookup_hits"]
