@@ -1,4 +1,6 @@
 #!/bin/bash
-timeout 120 python scripts/exp_c3.py 100 2 50000000 2>&1 | tail -1
-BN_NO_DIRECT_DENSE=1 timeout 120 python scripts/exp_c3.py 100 2 50000000 2>&1 | tail -1
-timeout 300 python -m pytest tests -m gpu -x -q -k "direct or c3 or blastn" 2>&1 | tail -3
+for v in mb4 mb5 mb6; do
+GBLASTN_B200_LIB=$PWD/gblastn_b200/libvar_$v.so timeout 200 python bench.py --steps 60 --warmup 3 --no-configs --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$v value', round(d['value'],1), round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value'],1), 'scan', round(d['roofline']['ms_per_launch'],4))"
+done
