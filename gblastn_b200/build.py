@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgblastn_b200.so")
-SOURCES = ["scan_kernel.cu", "extend_kernel.cu", "gapped_kernel.cu", "traceback_kernel.cu", "lookup_build.cu", "group_sort.cu", "triage_kernel.cu", "dust_kernel.cu", "engine.cu", "hostpost.cpp", "setup.cpp", "dbfile.cpp", "dust.cpp"]
+SOURCES = ["scan_kernel.cu", "radix_sort.cu", "extend_kernel.cu", "gapped_kernel.cu", "traceback_kernel.cu", "lookup_build.cu", "group_sort.cu", "triage_kernel.cu", "dust_kernel.cu", "engine.cu", "hostpost.cpp", "setup.cpp", "dbfile.cpp", "dust.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

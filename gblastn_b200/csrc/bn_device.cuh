@@ -253,6 +253,14 @@ int scan_positions_per_block();
 int scan_tile_cap(int scan_step, int word_length);
 int scan_max_block_chunks();
 int scan_tile_margin();
+// radix_sort.cu: the device-wide sort and prefix sums of the path (no library kernels)
+size_t prefix_sum_temp_bytes(int64_t n);
+cudaError_t prefix_sum_u32(const uint32_t *in, uint32_t *out, int64_t n, bool inclusive, void *temp, cudaStream_t st);
+size_t radix_sort_temp_bytes(int64_t n);
+cudaError_t radix_sort_hits(uint64_t *ka, uint64_t *kb, SeedHit *va, SeedHit *vb, int64_t n, int end_bit, void *temp, bool *in_b,
+                            int64_t *n_launches, cudaStream_t st);
+cudaError_t radix_sort_u32(uint32_t *ka, uint32_t *kb, uint32_t *va, uint32_t *vb, int64_t n, int end_bit, void *temp, bool *in_b,
+                           int64_t *n_launches, cudaStream_t st);
 cudaError_t launch_build_filter(const uint32_t *presence, int64_t nwords, uint32_t *filt, cudaStream_t st);
 cudaError_t launch_build_sig(const uint4 *cinfo, int64_t n_ranks, uint32_t *sig, cudaStream_t st);
 cudaError_t launch_build_qinfo(const DevQuery &q, const int32_t *next_pos, int32_t concat_len, const int32_t *heads,

@@ -21,7 +21,6 @@
 #include <thread>
 #include <vector>
 
-#include <cub/cub.cuh>
 
 #include "bn_device.cuh"
 #include "devmem.h"
@@ -562,10 +561,8 @@ static int query_to_device(Query &Q, const BnQueryBatch &src, int d, Lane *dev, 
         CU_TRY(dev_alloc(&qd.prk, (size_t)nwords, st));
         CU_TRY(dev_alloc(&qd.cinfo, 2 * ((size_t)b.concat_len + 2), st));
         CU_TRY(launch_popc(t_presence, nwords, t_counts, st));
-        size_t tmp_bytes = 0;
-        CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, t_counts, t_prefix, (int)nwords, st));
-        CU_TRY(dev->ws().cub_temp.reserve(tmp_bytes));
-        CU_TRY(cub::DeviceScan::ExclusiveSum(dev->ws().cub_temp.p, tmp_bytes, t_counts, t_prefix, (int)nwords, st));
+        CU_TRY(dev->ws().cub_temp.reserve(prefix_sum_temp_bytes(nwords)));
+        CU_TRY(prefix_sum_u32(t_counts, t_prefix, nwords, false, dev->ws().cub_temp.p, st));
         if (device_fill)
             CU_TRY(launch_build_prk_cinfo(t_presence, t_prefix, nwords, qd.prk, t_first_qp, (int64_t)b.concat_len + 1,
                                           qd.qinfo, qd.cinfo, st));
@@ -907,14 +904,14 @@ static int run_word_finder(Lane &D, Volume &V, Query &Q, ChunkTable &T, bool raw
     CU_TRY(ws.keys_b.reserve((size_t)n));
     CU_TRY(ws.hits_b.reserve((size_t)n));
     {
-        size_t bytes = 0;
+        // stable radix sort on (diagonal group, global position): radix_sort.cu
         const int end_bit = std::min(64, gbits + grp_bits);
-        CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, ws.keys_a.p, ws.keys_b.p, ws.hits_a.p, ws.hits_b.p,
-                                               (int)n, 0, end_bit, st));
-        CU_TRY(ws.cub_temp.reserve(bytes));
-        CU_TRY(cub::DeviceRadixSort::SortPairs(ws.cub_temp.p, bytes, ws.keys_a.p, ws.keys_b.p, ws.hits_a.p,
-                                               ws.hits_b.p, (int)n, 0, end_bit, st));
-        if (stats) stats->kernel_launches += 2 + (end_bit + 7) / 8;
+        CU_TRY(ws.cub_temp.reserve(radix_sort_temp_bytes(n)));
+        bool in_b = false;
+        int64_t launches = 0;
+        CU_TRY(radix_sort_hits(ws.keys_a.p, ws.keys_b.p, ws.hits_a.p, ws.hits_b.p, n, end_bit, ws.cub_temp.p, &in_b, &launches, st));
+        if (!in_b) { std::swap(ws.keys_a, ws.keys_b); std::swap(ws.hits_a, ws.hits_b); }     // the sorted pairs are the "b" buffers
+        if (stats) stats->kernel_launches += launches;
     }
     if (raw_pairs) { t_ext.stop(); if (stats) stats->ms_extend += t_ext.ms(); return BN_OK; }
 
@@ -2862,6 +2859,69 @@ int bn_selftest_replay(uint64_t seed, int32_t n_cases, int64_t *n_mismatch)
 {
     if (!n_mismatch || n_cases < 0) return fail(BN_ERR_INVALID, "bn_selftest_replay: bad argument");
     *n_mismatch = selftest_replay(seed, n_cases);
+    return BN_OK;
+}
+
+int bn_selftest_sort(int device, int64_t n, int key_bits, uint64_t seed, int64_t *n_mismatch)
+{
+    if (!n_mismatch || n < 0 || n >= ((int64_t)1 << 31) || key_bits < 1 || key_bits > 64)
+        return fail(BN_ERR_INVALID, "bn_selftest_sort: bad argument");
+    int rc = ensure_init();
+    if (rc) return rc;
+    Gpu *g = device_at(device);
+    if (!g) return fail(BN_ERR_INVALID, "bn_selftest_sort: bad device");
+    CU_TRY(cudaSetDevice(g->id));
+    *n_mismatch = 0;
+    if (n == 0) return BN_OK;
+    LaneLock lk(*g);
+    cudaStream_t st = lk.lane->stream;
+    // few distinct keys in the low digit, so that equal keys are common and stability is exercised
+    std::vector<uint64_t> keys((size_t)n);
+    std::vector<SeedHit> vals((size_t)n);
+    std::vector<uint32_t> counts((size_t)n);
+    uint64_t x = seed * 0x9E3779B97F4A7C15ull + 1;
+    const uint64_t mask = key_bits == 64 ? ~0ull : (((uint64_t)1 << key_bits) - 1);
+    for (int64_t i = 0; i < n; i++) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        keys[(size_t)i] = ((x >> 11) & mask) & ~(uint64_t)((x & 3) ? 0 : 0xF0);
+        vals[(size_t)i] = SeedHit{(uint32_t)i, (uint32_t)(x >> 40), (uint32_t)(x >> 20), (uint32_t)x};
+        counts[(size_t)i] = (uint32_t)(x >> 58);
+    }
+    uint64_t *ka = nullptr, *kb = nullptr;
+    SeedHit *va = nullptr, *vb = nullptr;
+    uint32_t *c = nullptr;
+    void *tmp = nullptr;
+    auto release = [&]() { for (void *p : {(void *)ka, (void *)kb, (void *)va, (void *)vb, (void *)c, tmp}) if (p) cudaFree(p); };
+    struct Guard { decltype(release) &f; ~Guard() { f(); } } guard{release};
+    CU_TRY(cudaMalloc((void **)&ka, (size_t)n * 8)); CU_TRY(cudaMalloc((void **)&kb, (size_t)n * 8));
+    CU_TRY(cudaMalloc((void **)&va, (size_t)n * 16)); CU_TRY(cudaMalloc((void **)&vb, (size_t)n * 16));
+    CU_TRY(cudaMalloc((void **)&c, (size_t)n * 4));
+    CU_TRY(cudaMalloc(&tmp, std::max(radix_sort_temp_bytes(n), prefix_sum_temp_bytes(n))));
+    CU_TRY(cudaMemcpyAsync(ka, keys.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(va, vals.data(), (size_t)n * 16, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(c, counts.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    bool in_b = false;
+    CU_TRY(radix_sort_hits(ka, kb, va, vb, n, key_bits, tmp, &in_b, nullptr, st));
+    CU_TRY(prefix_sum_u32(c, c, n, true, tmp, st));
+    std::vector<uint64_t> gk((size_t)n);
+    std::vector<SeedHit> gv((size_t)n);
+    std::vector<uint32_t> gc((size_t)n);
+    CU_TRY(cudaMemcpyAsync(gk.data(), in_b ? kb : ka, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(gv.data(), in_b ? vb : va, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(gc.data(), c, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    std::vector<uint32_t> order((size_t)n);
+    for (int64_t i = 0; i < n; i++) order[(size_t)i] = (uint32_t)i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+    uint32_t run = 0;
+    int64_t bad = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const uint32_t o = order[(size_t)i];
+        if (gk[(size_t)i] != keys[o] || memcmp(&gv[(size_t)i], &vals[o], sizeof(SeedHit)) != 0) ++bad;
+        run += counts[(size_t)i];
+        if (gc[(size_t)i] != run) ++bad;
+    }
+    *n_mismatch = bad;
     return BN_OK;
 }
 

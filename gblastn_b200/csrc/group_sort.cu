@@ -5,7 +5,7 @@
 // emission order (subject offset ascending, lookup chain order: core/blast_nascan.c:1413-1427 emits a
 // cell's chain in chain order and the scanners walk the subject left to right).
 //
-// The general path is one cub radix sort on (bucket, global scan position), which needs the number
+// The general path is one radix sort (radix_sort.cu) on (bucket, global scan position), which needs the number
 // of survivors on the host (a stream synchronisation) and 7 launches.  For the usual case - at most
 // a few hundred thousand survivors, no bucket larger than BUCKET_MAX - the same ordering comes out of
 // a counting sort whose sizes never leave the device, in ONE launch after the scan:

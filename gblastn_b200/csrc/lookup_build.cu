@@ -11,15 +11,13 @@
 // unambiguous, does   next_pos[index] = hashtable[word]; hashtable[word] = index;
 // so a cell's chain lists its positions in DESCENDING order.  Equivalent parallel formulation:
 //   1. every position computes (word | invalid marker)                       mb_words_kernel
-//   2. one stable radix sort of (word, position)                            cub
+//   2. one stable radix sort of (word, position)                            radix_sort.cu
 //   3. inside a run of equal words the predecessor is next_pos, the last element is the cell's
 //      hashtable value; runs in ascending word order ARE the occupied cells in cell order, i.e.
 //      the rank space of the scan kernel's compact table                     mb_link_kernel
 // The 4^lut-entry hashtable itself is never materialised on this path: the scan kernel works from
 // {presence word, rank} + the per-rank first chain element (scan_kernel.cu).
 #include <algorithm>
-
-#include <cub/cub.cuh>
 
 #include "bn_device.cuh"
 #include "devmem.h"
@@ -118,18 +116,18 @@ cudaError_t build_mb_lookup_device(const uint8_t *d_query /* base 0 */, int32_t 
         const uint32_t invalid = 1u << (2 * lut);
         mb_words_kernel<<<blocks, 256, 0, st>>>(d_query, concat_len, lut, t.segmark, t.keys_a, t.vals_a);
         LB_TRY(cudaGetLastError());
-        size_t bytes = 0, bytes2 = 0;
-        LB_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, t.keys_a, t.keys_b, t.vals_a, t.vals_b, n, 0, 2 * lut + 1, st));
-        LB_TRY(cub::DeviceScan::InclusiveSum(nullptr, bytes2, t.flags, t.flags, n, st));
-        bytes = std::max(bytes, bytes2);
-        LB_TRY(dev_malloc(&cub_tmp, bytes, st));
-        LB_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, bytes, t.keys_a, t.keys_b, t.vals_a, t.vals_b, n, 0, 2 * lut + 1, st));
+        // one stable sort of (word, position) = every chain in position order (radix_sort.cu), run numbers by a prefix sum
+        LB_TRY(dev_malloc(&cub_tmp, std::max(radix_sort_temp_bytes(n), prefix_sum_temp_bytes(n)), st));
+        bool in_b = false;
+        int64_t launches = 0;
+        LB_TRY(radix_sort_u32(t.keys_a, t.keys_b, t.vals_a, t.vals_b, n, 2 * lut + 1, cub_tmp, &in_b, &launches, st));
+        if (!in_b) { std::swap(t.keys_a, t.keys_b); std::swap(t.vals_a, t.vals_b); }
         mb_heads_kernel<<<blocks, 256, 0, st>>>(t.keys_b, n, invalid, t.flags);
         LB_TRY(cudaGetLastError());
-        LB_TRY(cub::DeviceScan::InclusiveSum(cub_tmp, bytes, t.flags, t.flags, n, st));
+        LB_TRY(prefix_sum_u32(t.flags, t.flags, n, true, cub_tmp, st));
         mb_link_kernel<<<blocks, 256, 0, st>>>(t.keys_b, t.vals_b, t.flags, n, invalid, d_next_pos, d_presence, d_first_qp);
         LB_TRY(cudaGetLastError());
-        if (n_launches) *n_launches += 4 + 2 + (2 * lut + 1 + 7) / 8 + 2;
+        if (n_launches) *n_launches += 4 + launches + 3;
     }
 #undef LB_TRY
 done:

@@ -1155,7 +1155,7 @@ __global__ void build_qpk_kernel(const uint8_t *query_start, int32_t concat_len,
 }
 
 // prk[w] = {presence word, number of occupied cells before word w}; dense[rank] = hashtable value of
-// the rank-th occupied cell.  `prefix` = exclusive scan of popcounts (done by the caller with cub).
+// the rank-th occupied cell.  `prefix` = exclusive scan of popcounts (prefix_sum_u32, radix_sort.cu).
 __global__ void popc_kernel(const uint32_t *presence, int64_t nwords, uint32_t *counts)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

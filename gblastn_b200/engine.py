@@ -20,7 +20,7 @@ EXPORTS = [
     "bn_db_load", "bn_db_free", "bn_query_load", "bn_query_free",
     "bn_prelim_search", "bn_prelim_search_host", "bn_prelim_search_volumes", "bn_results_free",
     "bn_scan_subject", "bn_word_finder", "bn_free", "bn_bench_scan", "bn_query_download_lookup", "bn_get_gapped_score", "bn_gapped_traceback", "bn_traceback_hsps", "bn_traceback_search",
-    "bn_dbfile_index", "bn_db_load_files", "bn_dbfile_write", "bn_dbfile_ambiguity", "bn_db_set_ambiguity", "bn_prelim_search_batches", "bn_prelim_search_jobs", "bn_db_set_masks", "bn_selftest_replay",
+    "bn_dbfile_index", "bn_db_load_files", "bn_dbfile_write", "bn_dbfile_ambiguity", "bn_db_set_ambiguity", "bn_prelim_search_batches", "bn_prelim_search_jobs", "bn_db_set_masks", "bn_selftest_replay", "bn_selftest_sort",
     "bn_setup_create", "bn_setup_batch", "bn_setup_kbp_std", "bn_setup_kbp_gap",
     "bn_setup_gap_x_dropoff_final", "bn_setup_longest_chain", "bn_setup_free", "bn_dust_mask", "bn_dust_mask_batch",
 ]

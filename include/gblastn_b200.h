@@ -403,6 +403,12 @@ int  bn_prelim_search_jobs(int device, int32_t n_jobs, const BnJob *jobs, int ta
  * n_cases seeded random init-HSP sets and reports how many differ (0 expected).  Needs no device. */
 int  bn_selftest_replay(uint64_t seed, int32_t n_cases, int64_t *n_mismatch);
 
+/* Device self-test of the path's own sort and prefix sum (csrc/radix_sort.cu: the seed hits of the general word-finder
+ * path, the (word, position) pairs of the device-side table fill): n seeded random pairs with key_bits-bit keys are
+ * sorted on `device` and compared with a stable host sort, the inclusive prefix sum of n counts with a host loop;
+ * *n_mismatch = positions that differ (0 expected). */
+int  bn_selftest_sort(int device, int64_t n, int key_bits, uint64_t seed, int64_t *n_mismatch);
+
 /* Parity tap for the device-side table fill: reconstructs hashtable[hashsize] and
  * next_pos[concat_len + 1] of an MB batch from the arrays resident on `device`. */
 int  bn_query_download_lookup(int query_handle, int device, int32_t *hashtable, int32_t *next_pos);

@@ -1106,3 +1106,17 @@ def test_filtered_scan_changes_nothing(name, monkeypatch):
         assert np.array_equal(P.final_table(a["hsps"]), r["final"])
     finally:
         V.free()
+
+
+@pytest.mark.parametrize("n,bits", [(1, 8), (31, 9), (2047, 17), (2048, 24), (2049, 25), (65_537, 33), (1_000_003, 41),
+                                    (6_000_000, 39), (300_000, 64)])
+def test_own_radix_sort_and_prefix_sum(n, bits):
+    """csrc/radix_sort.cu (the path's own device-wide sort and scans, no library kernels): seeded random pairs with many
+    equal keys against a stable host sort, inclusive prefix sum against a host loop; sizes around the warp-tile and
+    scan-tile boundaries and C3's seed-hit count."""
+    import ctypes as C
+    from gblastn_b200 import engine as E
+    E.init(1)
+    bad = C.c_int64(-1)
+    rc = E.lib().bn_selftest_sort(C.c_int(0), C.c_int64(n), C.c_int(bits), C.c_uint64(7 + n), C.byref(bad))
+    assert rc == 0 and bad.value == 0
