@@ -458,7 +458,10 @@ struct TracebackLaunch {
     DevTracebackDir *out;        // 2 n entries: left, right
     const int4 *amb_runs;        // the volume's ambiguity runs {first base, end, blastna code, 0} (nullptr: none)
     const uint8_t *todo;         // greedy: optional per-item flags (retry of the items whose arena overflowed); nullptr = all
+    int2 *wide_ring;             // DP, wide variant: traceback_wide_cells() band cells per warp of the grid in global memory
+    uint8_t *wide_pf;            // (nullptr: the shared-memory ring)
 };
+int traceback_wide_cells();
 cudaError_t launch_traceback_dp(const DevQuery &q, const TracebackLaunch &L, int blocks, cudaStream_t st);
 struct DevTracebackHsp {         // a preliminary HSP (absolute subject coordinates) about to be traced back
     int64_t byte_off;            // of its subject sequence

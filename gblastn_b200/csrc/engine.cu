@@ -3115,6 +3115,9 @@ static int traceback_core(Lane *D, Volume *V, Query *Q, int32_t gap_x_dropoff_fi
     CU_TRY(cudaMallocAsync((void **)&d_cnt, 2 * sizeof(unsigned long long), st));
     CU_TRY(cudaMemcpyAsync(d_items, up.data(), up.size() * sizeof(DevTracebackItem), cudaMemcpyHostToDevice, st));
     unsigned long long used[2] = {0, 0};
+    int2 *d_wide_ring = nullptr;
+    uint8_t *d_wide_pf = nullptr;
+    struct WideGuard { int2 *&r; uint8_t *&p; cudaStream_t st; ~WideGuard() { if (r) cudaFreeAsync(r, st); if (p) cudaFreeAsync(p, st); } } wide_guard{d_wide_ring, d_wide_pf, st};
     for (int attempt = 0; attempt < 4; attempt++) {
         if (d_arena) { cudaFreeAsync(d_arena, st); d_arena = nullptr; }
         if (d_ops) { cudaFreeAsync(d_ops, st); d_ops = nullptr; }
@@ -3126,16 +3129,27 @@ static int traceback_core(Lane *D, Volume *V, Query *Q, int32_t gap_x_dropoff_fi
         L.arena = d_arena; L.arena_bytes = arena_bytes; L.arena_used = d_cnt;
         L.ops = d_ops; L.ops_cap = ops_cap; L.ops_used = d_cnt + 1; L.out = d_out;
         const int wpb = traceback_warps_per_block();
-        const int blocks = (int)std::min<int64_t>((2 * n_items + wpb - 1) / wpb, 148 * 8);
+        const int blocks = (int)std::min<int64_t>((2 * n_items + wpb - 1) / wpb, d_wide_ring ? 148 : 148 * 8);
+        L.wide_ring = d_wide_ring; L.wide_pf = d_wide_pf;
         CU_TRY(launch_traceback_dp(dq, L, blocks, st));
         CU_TRY(cudaMemcpyAsync(dirs.data(), d_out, dirs.size() * sizeof(DevTracebackDir), cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaMemcpyAsync(used, d_cnt, sizeof used, cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
-        bool grow_arena = false, grow_ops = false;
+        bool grow_arena = false, grow_ops = false, too_wide = false;
         for (const DevTracebackDir &d : dirs) {
-            if (d.status == 1) return fail(BN_ERR_OVERFLOW, "bn_gapped_traceback: alignment band wider than the device ring");
+            too_wide |= d.status == 1;
             grow_arena |= d.status == 3;
             grow_ops |= d.status == 4;
+        }
+        if (too_wide) {
+            // a band beyond the shared-memory ring (2 X_final / gap_extend above ~1000): the batch runs again with the
+            // rings in global memory, one grid's worth of them
+            if (d_wide_ring) return fail(BN_ERR_OVERFLOW, "bn_gapped_traceback: alignment band wider than the device ring");
+            const size_t cells = (size_t)148 * (size_t)wpb * (size_t)traceback_wide_cells();
+            CU_TRY(cudaMallocAsync((void **)&d_wide_ring, cells * sizeof(int2), st));
+            CU_TRY(cudaMallocAsync((void **)&d_wide_pf, cells, st));
+            --attempt;
+            continue;
         }
         if (!grow_arena && !grow_ops) break;
         if (attempt == 3) return fail(BN_ERR_OVERFLOW, "bn_gapped_traceback: traceback scratch exhausted");

@@ -130,14 +130,15 @@ constexpr long long ROW_CHUNK = 128 << 10;
 
 // ALIGN_EX for one direction.  M rows (query), N columns (subject).  qrow(a) = query byte of row a,
 // sub(b) = subject base that the diagonal step INTO column b consumes (b >= 1).
-// status: 0 ok, 1 band wider than the shared-memory ring, 3 arena exhausted.
+// status: 0 ok, 1 band wider than the ring of C cells (shared memory; the wide variant's is in global memory), 3 arena exhausted.
+template <int C>
 __device__ int32_t align_ex_warp(const TracebackLaunch &L, const uint8_t *qp, int q_inc, const uint8_t *S, const SubjAmb &amb, int64_t s0, int s_inc,
                                  int32_t M, int32_t N, const int32_t *matrix, int32_t gap_open, int32_t gap_extend,
                                  int32_t x_dropoff, int2 *ring, uint8_t *pf, RowStore &rs, int32_t &a_offset, int32_t &b_offset,
                                  int &status, int lane)
 {
     const int32_t goe = gap_open + gap_extend, ge = gap_extend;
-    constexpr int32_t C = TB_CELLS, MASK = TB_CELLS - 1;
+    constexpr int32_t MASK = C - 1;
     a_offset = 0; b_offset = 0;
     if (x_dropoff < goe) x_dropoff = goe;
     if (N <= 0 || M <= 0) return 0;
@@ -358,17 +359,22 @@ __device__ int32_t align_ex_warp(const TracebackLaunch &L, const uint8_t *qp, in
 }  // namespace
 
 // One warp per (item, direction): warp 2 i = left extension of item i, warp 2 i + 1 = right extension.
+// CELLS = band cells a warp can hold: TB_CELLS in shared memory, or (WIDE) TB_WIDE_CELLS in global memory for the rare
+// batch with a band beyond that (2 X_final / gap_extend above ~1000: gap_extend 1 with a large final X-drop).
+constexpr int TB_WIDE_CELLS = 32768;
+template <int CELLS, bool WIDE>
 __global__ void __launch_bounds__(TB_WARPS * 32)
 traceback_dp_kernel(const DevQuery q, const TracebackLaunch L)
 {
-    __shared__ int2 rings[TB_WARPS][TB_CELLS];
-    __shared__ uint8_t s_pf[TB_WARPS][TB_CELLS];
+    __shared__ int2 rings[WIDE ? 1 : TB_WARPS][WIDE ? 1 : CELLS];
+    __shared__ uint8_t s_pf[WIDE ? 1 : TB_WARPS][WIDE ? 1 : CELLS];
     __shared__ int32_t s_matrix[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_matrix[i] = q.matrix[i];
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t warp0 = (int64_t)blockIdx.x * TB_WARPS + wib, nwarps = (int64_t)gridDim.x * TB_WARPS;
-    int2 *ring = rings[wib];
+    int2 *ring = WIDE ? L.wide_ring + warp0 * CELLS : rings[wib];
+    uint8_t *pf = WIDE ? L.wide_pf + warp0 * CELLS : s_pf[wib];
     for (int64_t w = warp0; w < 2 * L.n; w += nwarps) {
         const DevTracebackItem it = L.items[w >> 1];
         const bool right = (w & 1) != 0;
@@ -405,8 +411,8 @@ traceback_dp_kernel(const DevQuery q, const TracebackLaunch L)
                 rs.row_first = reinterpret_cast<int32_t *>(L.arena + tab + (long long)(M + 1) * 8);
                 int32_t a_off, b_off;
                 const SubjAmb amb = subj_amb(L.amb_runs, it.amb_first, it.amb_n, 0);      // S-relative reads
-                out.score = align_ex_warp(L, qp, q_inc, S, amb, s0, s_inc, M, N, s_matrix, q.gap_open, q.gap_extend,
-                                          L.x_dropoff, ring, s_pf[wib], rs, a_off, b_off, status, lane);
+                out.score = align_ex_warp<CELLS>(L, qp, q_inc, S, amb, s0, s_inc, M, N, s_matrix, q.gap_open, q.gap_extend,
+                                                 L.x_dropoff, ring, pf, rs, a_off, b_off, status, lane);
                 out.a_off = a_off; out.b_off = b_off;
                 __syncwarp();
                 __threadfence_block();
@@ -435,7 +441,7 @@ traceback_dp_kernel(const DevQuery q, const TracebackLaunch L)
                                 if (aj >= 0 && bj >= 0) {
                                     const long long off = rs.row_off[aj];
                                     const int32_t first = rs.row_first[aj];
-                                    if (bj >= first && bj - first < TB_CELLS + 64 && off + (bj - first) < L.arena_bytes)
+                                    if (bj >= first && bj - first < CELLS + 64 && off + (bj - first) < L.arena_bytes)
                                         pre = ar[off + (bj - first)];
                                 }
                                 for (;;) {
@@ -1413,9 +1419,11 @@ cudaError_t launch_traceback_reevaluate(const DevQuery &q, const uint8_t *packed
 
 cudaError_t launch_traceback_dp(const DevQuery &q, const TracebackLaunch &L, int blocks, cudaStream_t st)
 {
-    traceback_dp_kernel<<<blocks, TB_WARPS * 32, 0, st>>>(q, L);
+    if (L.wide_ring) traceback_dp_kernel<TB_WIDE_CELLS, true><<<blocks, TB_WARPS * 32, 0, st>>>(q, L);
+    else traceback_dp_kernel<TB_CELLS, false><<<blocks, TB_WARPS * 32, 0, st>>>(q, L);
     return cudaGetLastError();
 }
+int traceback_wide_cells() { return TB_WIDE_CELLS; }
 int traceback_warps_per_block() { return TB_WARPS; }
 
 }  // namespace bn

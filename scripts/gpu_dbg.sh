@@ -1,2 +1,2 @@
 #!/bin/bash
-timeout 300 python -m pytest tests -m gpu -x -q -k "radix or device_lookup" 2>&1 | tail -5
+timeout 400 python -m pytest tests -m gpu -x -q -k "band_wider" 2>&1 | tail -12

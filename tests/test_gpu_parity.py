@@ -1120,3 +1120,41 @@ def test_own_radix_sort_and_prefix_sum(n, bits):
     bad = C.c_int64(-1)
     rc = E.lib().bn_selftest_sort(C.c_int(0), C.c_int64(n), C.c_int(bits), C.c_uint64(7 + n), C.byref(bad))
     assert rc == 0 and bad.value == 0
+
+
+def test_gapped_traceback_band_wider_than_shared_ring():
+    """ALIGN_EX with a final X-drop whose band (2 X / gap_extend cells) exceeds the DP kernel's shared-memory ring of
+    1024 cells: the batch is re-run with the rings in global memory (traceback_dp_kernel<32768, true>); same scores, end
+    points and edit scripts as the reference's BLAST_GappedAlignmentWithTraceback, which has no such limit."""
+    from gblastn_b200 import engine as E, abi
+    from oracle import refdriver as R, portdriver as P
+    task, cfgkw, vol, qs = cases.make_case("blastn_mb11_dp")
+    if not R.available():
+        pytest.skip("oracle/_ref/libblastref.so did not travel to this box")
+    cfgkw = dict(cfgkw, gap_open=2, gap_extend=2, xdrop_gap_final=1300.0)
+    cfg = R.default_config(task, taps=R.TAP_LUT, **cfgkw)
+    r = R.search(qs, vol, cfg)
+    assert r["status"] == 0 and r["final"].shape[0] > 0
+    x_final = int(r["gap_x_dropoff_final"])
+    assert 2 * x_final // 2 > 1100, f"X_final {x_final}: the band would fit the shared ring"
+    it = _random_start_items(r, vol, np.random.default_rng(9), per_hsp=1, max_hsps=12)
+    rc = R.traceback_calls(qs, vol, it, cfg)
+    assert rc["status"] == 0
+    calls = rc["tb_calls"]
+    h = P.batch_from_reference(r, task=task, cfg=cfg)
+    V, Q = E.Volume(vol), E.Query(h)
+    try:
+        items = np.zeros(it.shape[0], dtype=abi.TB_ITEM_DTYPE)
+        for k, col in enumerate(("oid", "context", "s_shift", "s_length", "q_start", "s_start")):
+            items[col] = it[:, k]
+        res, ops = E.gapped_traceback(V, Q, x_final, items)
+        for k, col in ((8, "score"), (9, "query_start"), (10, "query_stop"), (11, "subject_start"), (12, "subject_stop"),
+                       (14, "esp_n")):
+            assert np.array_equal(res[col], calls[:, k]), col
+        ref_ops = rc["tb_ops"]
+        for i in range(calls.shape[0]):
+            want = ref_ops[calls[i, 13]:calls[i, 13] + calls[i, 14]]
+            got = ops[res["esp_off"][i]:res["esp_off"][i] + res["esp_n"][i]]
+            assert np.array_equal(got["op_type"], want[:, 0]) and np.array_equal(got["num"], want[:, 1])
+    finally:
+        Q.free(); V.free()
