@@ -286,6 +286,9 @@ struct ExtendLaunch {
     unsigned long long *counters; // [2] = #init hits, [3] = #extended, [4] = #groups, [5] = #leaders, [6] = fast path refused
     int64_t init_capacity;
     int32_t n_from_device;        // 1: the number of hits is counters[0] (no host round trip), kernels idle if counters[6]
+    // blastn mode with plain reward / penalty tables (Query::direct_ok): the speculative pass extends one leader per LANE
+    // with the closed-form scores (extend_leaders_kernel); uni_*: the cutoffs when every context has the same ones
+    int32_t scalar_ok, uni_ok, uni_x, uni_cutoff, uni_reduced;
 };
 cudaError_t launch_extend_groups(const DevQuery &q, const ExtendLaunch &e, const uint64_t *keys,
                                  uint32_t *heads, int64_t n_hits, int gbits, cudaStream_t st);

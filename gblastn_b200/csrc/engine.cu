@@ -929,6 +929,8 @@ static int run_word_finder(Lane &D, Volume &V, Query &Q, ChunkTable &T, bool raw
         e.cells = reinterpret_cast<int32_t *>(ws.cells.p); e.init = ws.init.p;
         e.counters = ws.counters.p; e.init_capacity = init_cap;
         e.spec = ws.spec.p; e.leaders = ws.leaders.p;
+        e.scalar_ok = (Q.direct_ok && !getenv("BN_NO_SCALAR_LEADERS")) ? 1 : 0;
+        e.uni_ok = Q.uni_ok; e.uni_x = Q.uni_x; e.uni_cutoff = Q.uni_cutoff; e.uni_reduced = Q.uni_reduced;
         if (serial) CU_TRY(launch_extend_serial(dq, e, ws.keys_b.p, n, gbits, Q.diag_array_length, st));
         else CU_TRY(launch_extend_groups(dq, e, ws.keys_b.p, ws.heads.p, n, gbits, st));
         if (stats) stats->kernel_launches += serial ? 1 : 3;
@@ -1424,6 +1426,8 @@ static int fused_enqueue(Lane &D, Volume &V, Query &Q, ChunkTable &T, FusedState
     e.cells = reinterpret_cast<int32_t *>(ws.cells.p); e.init = ws.init.p;
     e.counters = ws.counters.p; e.init_capacity = init_cap;
     e.spec = ws.spec.p; e.leaders = ws.leaders.p; e.n_from_device = 1;
+    e.scalar_ok = (Q.direct_ok && !getenv("BN_NO_SCALAR_LEADERS")) ? 1 : 0;
+    e.uni_ok = Q.uni_ok; e.uni_x = Q.uni_x; e.uni_cutoff = Q.uni_cutoff; e.uni_reduced = Q.uni_reduced;
     CU_TRY(launch_extend_grouped(dq, e, ws.keys_b.p, ws.heads.p, gbits, st));
     t_ext.stop();
 

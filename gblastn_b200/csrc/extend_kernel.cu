@@ -476,6 +476,118 @@ __global__ void group_heads_kernel(const uint64_t *keys, const SeedHit *hits, in
     }
 }
 
+
+// ---- one leader per LANE (blastn mode, plain reward / penalty scoring) -----------------------------------------------
+// The warp-wide walks above take 128 (approximate) or 512 (exact) bases per step: right for the long extensions of a
+// megablast batch, ~3000 warp instructions too many for the hit of a blastn-mode batch whose extension dies after a
+// dozen bases — and those are 5.6 M per pass of C3.  Here a lane runs the same two recurrences alone, 16-base windows,
+// group scores in closed form (4 r - (r - p) * mismatches, what nucl_score_table holds for such a batch: Query::direct_ok).
+// Returns false = undecided (an ambiguity code or sentinel in a window it needs, or an extension beyond SC_LIMIT bases):
+// the warp then extends that hit together, as before.
+constexpr int32_t SC_LIMIT = 128;
+__device__ bool scalar_extend_direct(const DevQuery &q, const uint8_t *packed, int64_t chunk_base, int32_t slen, int32_t q_off,
+                                     int32_t s_off, int32_t s_match_end, int32_t X, int32_t reduced, Ungapped &u)
+{
+    const int32_t r = q.reward, pen = q.penalty, r4 = 4 * r, dd = r - pen;
+    const int32_t shift = (4 - (s_off % 4)) % 4;
+    const int32_t q_ext = q_off + shift, s_ext = s_off + shift;
+    int32_t score, new_q_r;
+    {   // approximate pass, left: step k covers query [q_ext - 4k - 4, q_ext - 4k)
+        const int32_t n = min(q_ext, s_ext) >> 2;
+        int32_t M = 0, sum = 0, best = -1;
+        bool stop = false;
+        for (int32_t k = 0; k < n && !stop; k += 4) {
+            if (4 * k >= SC_LIMIT) return false;
+            uint32_t qb, qa;
+            qwin(q, q_ext - 4 * k - 16, qb, qa);
+            const int cnt = min(4, n - k);
+            if (qa & (cnt == 4 ? 0xFFFFFFFFu : ((1u << (8 * cnt)) - 1u))) return false;
+            const uint32_t m = mismatch_bits(qb, 0u, swin(packed, chunk_base + s_ext - 4 * k - 16));
+            for (int j = 0; j < cnt; j++) {
+                sum += r4 - dd * __popc((m >> (8 * j)) & 0xFFu);
+                if (sum > 0) { M += sum; sum = 0; best = k + j; }
+                if (sum < X) { stop = true; break; }
+            }
+        }
+        score = M;
+        const int32_t new_q = best >= 0 ? q_ext - 4 * (best + 1) : q_ext;
+        u.q_start = new_q;
+        u.s_start = s_ext - (q_ext - new_q);
+    }
+    {   // approximate pass, right: step k covers query [q_ext + 4k, q_ext + 4k + 4)
+        const int32_t n = min(q.concat_len - q_ext, slen - s_ext) >> 2;
+        int32_t M = 0, sum = 0, best = -1;
+        bool stop = false;
+        for (int32_t k = 0; k < n && !stop; k += 4) {
+            if (4 * k >= SC_LIMIT) return false;
+            uint32_t qb, qa;
+            qwin(q, q_ext + 4 * k, qb, qa);
+            const int cnt = min(4, n - k);
+            if (qa & (cnt == 4 ? 0xFFFFFFFFu : ~((1u << (32 - 8 * cnt)) - 1u))) return false;
+            const uint32_t m = mismatch_bits(qb, 0u, swin(packed, chunk_base + s_ext + 4 * k));
+            for (int j = 0; j < cnt; j++) {
+                sum += r4 - dd * __popc((m >> (24 - 8 * j)) & 0xFFu);
+                if (sum > 0) { M += sum; sum = 0; best = k + j; }
+                if (sum < X) { stop = true; break; }
+            }
+        }
+        score += M;
+        new_q_r = best >= 0 ? q_ext + 4 * best + 3 : q_ext;
+    }
+    if (score < reduced) {
+        u.score = score;
+        u.length = max(s_match_end - u.s_start, new_q_r - u.q_start + 1);
+        return true;
+    }
+    // exact pass (s_NuclUngappedExtendExact), one base per step
+    int32_t q_beg;
+    {
+        const int32_t n = min(q_off, s_off);
+        int32_t M = 0, sum = 0, best = -1;
+        bool stop = false;
+        for (int32_t done = 0; done < n && !stop; done += 16) {
+            if (done >= SC_LIMIT) return false;
+            uint32_t qb, qa;
+            qwin(q, q_off - done - 16, qb, qa);
+            const int rem = min(16, n - done);
+            if (qa & (rem == 16 ? 0xFFFFFFFFu : ((1u << (2 * rem)) - 1u))) return false;     // step t = base 15 - t, flag at bit 2t
+            const uint32_t m = mismatch_bits(qb, 0u, swin(packed, chunk_base + s_off - done - 16));
+            for (int t = 0; t < rem; t++) {
+                sum += ((m >> (2 * t)) & 1u) ? pen : r;
+                if (sum > 0) { M += sum; sum = 0; best = done + t; }
+                if (sum < X) { stop = true; break; }
+            }
+        }
+        score = M;
+        q_beg = best >= 0 ? q_off - 1 - best : q_off;
+        u.q_start = q_beg;
+        u.s_start = s_off - (q_off - q_beg);
+    }
+    {
+        const int32_t n = min(q.concat_len - q_off, slen - s_off);
+        int32_t M = 0, sum = 0, best = -1;
+        bool stop = false;
+        for (int32_t done = 0; done < n && !stop; done += 16) {
+            if (done >= SC_LIMIT) return false;
+            uint32_t qb, qa;
+            qwin(q, q_off + done, qb, qa);
+            const int rem = min(16, n - done);
+            if (qa & (rem == 16 ? 0xFFFFFFFFu : ~((1u << (32 - 2 * rem)) - 1u))) return false;   // step t = base t, flag at bit 30 - 2t
+            const uint32_t m = mismatch_bits(qb, 0u, swin(packed, chunk_base + s_off + done));
+            for (int t = 0; t < rem; t++) {
+                sum += ((m >> (30 - 2 * t)) & 1u) ? pen : r;
+                if (sum > 0) { M += sum; sum = 0; best = done + t; }
+                if (sum < X) { stop = true; break; }
+            }
+        }
+        score += M;
+        const int32_t q_end = best >= 0 ? q_off + best + 1 : q_off;
+        u.length = q_end - q_beg;
+        u.score = score;
+    }
+    return true;
+}
+
 // Speculative pass: one warp per leader runs s_TypeOfWord + the ungapped extension and parks the
 // outcome next to the hit; the replay consumes it if (and only if) the diagonal test lets the hit
 // through, exactly where the reference would have extended.
@@ -495,6 +607,47 @@ extend_leaders_kernel(const DevQuery q, const ExtendLaunch e)
     const bool direct = (word == lut);
     const bool has_loc = q.has_locations && !direct;
     CtxCache cc{0, -1, 0, 0, 0};
+    if (e.scalar_ok && direct) {
+        // one leader per lane; what a lane cannot decide alone is extended by the warp afterwards
+        for (int64_t w0 = warp0 * 32; w0 < n; w0 += nwarps * 32) {
+            const int64_t w = w0 + lane;
+            uint32_t j = 0;
+            bool pending = false;
+            if (w < n) {
+                j = e.leaders[w];
+                const SeedHit h = e.hits[j];
+                const DevChunk ch = e.chunks[h.chunk];
+                int32_t xd = e.uni_x, co = e.uni_cutoff, rc = e.uni_reduced;
+                if (!e.uni_ok) {
+                    const DevContext c = q.ctx[ctx_search(q, (int32_t)h.q_off)];
+                    xd = c.x_dropoff; co = c.cutoff_score; rc = c.reduced_cutoff;
+                }
+                Ungapped u;
+                if (scalar_extend_direct(q, e.packed, ch.byte_off * 4, ch.len, (int32_t)h.q_off, (int32_t)h.s_off,
+                                         (int32_t)h.s_off + word, -xd, rc, u)) {
+                    SpecResult r;
+                    r.status = (u.score >= co) ? SPEC_READY : SPEC_LOW;
+                    r.q_off = (int32_t)h.q_off; r.s_off = (int32_t)h.s_off; r.extended = 0;
+                    r.q_start = u.q_start; r.s_start = u.s_start; r.length = u.length; r.score = u.score;
+                    e.spec[j] = r;
+                } else pending = true;
+            }
+            unsigned m = __ballot_sync(0xffffffffu, pending);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1u;
+                const uint32_t jj = __shfl_sync(0xffffffffu, j, src);
+                const SeedHit h = e.hits[jj];
+                const DevChunk ch = e.chunks[h.chunk];
+                SpecResult r;
+                r.status = SPEC_NONE; r.q_off = r.s_off = r.extended = r.q_start = r.s_start = r.length = r.score = 0;
+                extend_one(q, e.packed, ch, hit_s_range(e.ranges, ch, (int32_t)h.scan_pos), s_tab, is_hash, has_loc, word, lut,
+                           direct, false, (int32_t)h.q_off, (int32_t)h.s_off, lane, cc, r);
+                if (lane == 0) e.spec[jj] = r;
+            }
+        }
+        return;
+    }
     for (int64_t w = warp0; w < n; w += nwarps) {
         const uint32_t j = e.leaders[w];
         const SeedHit h = e.hits[j];

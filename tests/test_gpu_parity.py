@@ -976,9 +976,12 @@ def test_direct_filter_changes_nothing(name, monkeypatch):
     V = E.Volume(vol)
     out = []
     try:
-        for mode in ("dense", "off", "inline"):
+        for mode in ("dense", "off", "inline", "warp_leaders"):
             monkeypatch.delenv("BN_NO_DIRECT_FILTER", raising=False)
             monkeypatch.delenv("BN_NO_DIRECT_DENSE", raising=False)
+            monkeypatch.delenv("BN_NO_SCALAR_LEADERS", raising=False)
+            if mode == "warp_leaders":                          # speculative ungapped extensions by whole warps (read per search)
+                monkeypatch.setenv("BN_NO_SCALAR_LEADERS", "1")
             monkeypatch.setenv("BN_FILT_MAX", "0")              # the queue-driven kernel: the one with the dense evaluation
             if mode == "off":
                 monkeypatch.setenv("BN_NO_DIRECT_FILTER", "1")
@@ -989,10 +992,11 @@ def test_direct_filter_changes_nothing(name, monkeypatch):
                 out.append(E.prelim_search(V, Q, taps=abi.BN_TAP_INIT | abi.BN_TAP_GAPPED))
             finally:
                 Q.free()
-        a, b, c = out
+        a, b, c, d = out
         assert a["init"].tobytes() == b["init"].tobytes() and a["gapped"].tobytes() == b["gapped"].tobytes()
         assert a["hsps"].tobytes() == b["hsps"].tobytes()
         assert a["init"].tobytes() == c["init"].tobytes() and a["hsps"].tobytes() == c["hsps"].tobytes()
+        assert a["init"].tobytes() == d["init"].tobytes() and a["hsps"].tobytes() == d["hsps"].tobytes()
         assert a["stats"]["lookup_hits"] == c["stats"]["lookup_hits"]
         assert np.array_equal(P.init_table(a["init"]), r["init"])
         assert np.array_equal(P.final_table(a["hsps"]), r["final"])
