@@ -91,6 +91,26 @@ __global__ void __launch_bounds__(1024) k_dsmem(const uint32_t *__restrict__ t4,
     cluster.sync();
 }
 
+// texture path: the same probes through tex1Dfetch on a linear texture object (TEX pipe instead of the LSU pipe)
+template <int PER, int WIDE>
+__global__ void __launch_bounds__(256) k_tex(cudaTextureObject_t tex, uint32_t mask, int64_t n, unsigned long long *out)
+{
+    unsigned long long acc = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * PER;
+    for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * PER; base < n; base += stride) {
+        uint32_t v[PER];
+#pragma unroll
+        for (int i = 0; i < PER; i++) {
+            const uint32_t idx = mix((uint32_t)(base + i) * 2654435761u + 12345u);
+            if (WIDE) { const uint2 w = tex1Dfetch<uint2>(tex, (int)(idx & mask)); v[i] = w.x ^ w.y; }
+            else v[i] = tex1Dfetch<uint32_t>(tex, (int)(idx & mask));
+        }
+#pragma unroll
+        for (int i = 0; i < PER; i++) acc += v[i] & 1u;
+    }
+    if (acc == 0xFFFFFFFFFFFFull) *out = acc;
+}
+
 template <typename F>
 static float timeit(F f, int iters = 5)
 {
@@ -139,6 +159,29 @@ int main()
         report(nm, timeit([&] { k_cpasync<8><<<grid, 256>>>(t4, W4 - 1, N, out); }));
         snprintf(nm, sizeof nm, "LDGSTS 4B per=16 blocks/SM=%d", bps);
         report(nm, timeit([&] { k_cpasync<16><<<grid, 256>>>(t4, W4 - 1, N, out); }));
+    }
+    {   // texture objects over the same tables
+        cudaTextureObject_t tex4 = 0, tex8 = 0;
+        cudaResourceDesc rd = {};
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = t4; rd.res.linear.sizeInBytes = (size_t)W4 * 4;
+        rd.res.linear.desc = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindUnsigned);
+        cudaTextureDesc td = {};
+        td.readMode = cudaReadModeElementType;
+        CK(cudaCreateTextureObject(&tex4, &rd, &td, nullptr));
+        rd.res.linear.devPtr = t8; rd.res.linear.sizeInBytes = (size_t)W8 * 8;
+        rd.res.linear.desc = cudaCreateChannelDesc(32, 32, 0, 0, cudaChannelFormatKindUnsigned);
+        CK(cudaCreateTextureObject(&tex8, &rd, &td, nullptr));
+        for (int bps : {2, 4, 8}) {
+            const int grid = 148 * bps;
+            char nm[96];
+            snprintf(nm, sizeof nm, "TEX.32 2MB per=8 blocks/SM=%d", bps);
+            report(nm, timeit([&] { k_tex<8, 0><<<grid, 256>>>(tex4, W4 - 1, N, out); }));
+            snprintf(nm, sizeof nm, "TEX.32 2MB per=16 blocks/SM=%d", bps);
+            report(nm, timeit([&] { k_tex<16, 0><<<grid, 256>>>(tex4, W4 - 1, N, out); }));
+            snprintf(nm, sizeof nm, "TEX.64 4MB per=8 blocks/SM=%d", bps);
+            report(nm, timeit([&] { k_tex<8, 1><<<grid, 256>>>(tex8, W8 - 1, N, out); }));
+        }
     }
     {   // DSMEM, cluster of 16 x 128 KB
         constexpr int CS = 16;

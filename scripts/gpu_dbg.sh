@@ -1,4 +1,3 @@
 #!/bin/bash
-timeout 120 python scripts/exp_c3.py 100 2 50000000 2>&1 | tail -1
-BN_NO_SCALAR_LEADERS=1 timeout 120 python scripts/exp_c3.py 100 2 50000000 2>&1 | tail -1
-timeout 400 python -m pytest tests -m gpu -x -q -k "direct or c3 or blastn" 2>&1 | tail -4
+mkdir -p gpurun_out
+timeout 120 ./scripts/gather_probe 2>&1 | grep -E "TEX|LDG.64 4MB per=8 blocks/SM=4|LDG.32 2MB per=8 blocks/SM=4" | tee gpurun_out/gather_probe_r03n.txt
