@@ -53,6 +53,10 @@ struct DevQuery {
     const uint4 *qinfo;                    // MB: per query position {next_pos, 16 bases left, 16 right, ambiguity}
     const uint32_t *sig;                   // MB: per occupied cell (by rank) the 4 query bases on either side of its first chain
                                            // element's lookup word: bits 0-7 left, 8-15 right, bit 16 = the chain has more elements
+    const uint16_t *psig;                  // MB: the same signature per table CELL (4^lut entries, dense): bit 15 = cell occupied, bit 14 =
+                                           // its chain has more elements, bits 8-13 = the 3 query bases left of the first element's lookup
+                                           // word, bits 0-7 = the 4 right of it.  ONE gather per scan position answers "occupied?" and
+                                           // "can the mini-extension succeed?" (scan_kernel_staged<.., DENSE>); NULL: prk + sig are used
     const uint32_t *filt;                  // MB, small batches only: FILT_BITS-bit hashed presence filter (filt_hash of every occupied
                                            // cell), kept in shared memory by scan_kernel_filtered; NULL otherwise
     const int16_t *backbone, *overflow;    // SmallNa
@@ -263,6 +267,7 @@ cudaError_t radix_sort_u32(uint32_t *ka, uint32_t *kb, uint32_t *va, uint32_t *v
                            int64_t *n_launches, cudaStream_t st);
 cudaError_t launch_build_filter(const uint32_t *presence, int64_t nwords, uint32_t *filt, cudaStream_t st);
 cudaError_t launch_build_sig(const uint4 *cinfo, int64_t n_ranks, uint32_t *sig, cudaStream_t st);
+cudaError_t launch_build_psig(const uint2 *prk, const uint32_t *sig, int64_t n_cells, uint16_t *psig, cudaStream_t st);
 cudaError_t launch_build_qinfo(const DevQuery &q, const int32_t *next_pos, int32_t concat_len, const int32_t *heads,
                                int64_t n_heads, uint32_t *indexed_scratch, uint4 *qinfo, cudaStream_t st);
 

@@ -344,6 +344,7 @@ struct QueryDev {
     uint4 *cinfo = nullptr;
     uint4 *qinfo = nullptr;
     uint32_t *sig = nullptr;
+    uint16_t *psig = nullptr;
     uint32_t *filt = nullptr;
     DevQuery view{};
     bool ready = false;
@@ -399,7 +400,7 @@ static Gpu *device_at(int d)
 static void free_query_dev(QueryDev &q, cudaStream_t st)
 {
     void *ptrs[] = {q.query, q.ctx, q.next_pos, q.backbone, q.overflow, q.na_cells, q.na_overflow,
-                    q.score_table, q.matrix, q.qpk, q.prk, q.cinfo, q.qinfo, q.sig, q.filt};
+                    q.score_table, q.matrix, q.qpk, q.prk, q.cinfo, q.qinfo, q.sig, q.psig, q.filt};
     for (void *p : ptrs) if (p) dev_free(p, st);
     q = QueryDev{};
 }
@@ -574,6 +575,14 @@ static int query_to_device(Query &Q, const BnQueryBatch &src, int d, Lane *dev, 
         CU_TRY(dev_alloc(&qd.sig, (size_t)b.concat_len + 2, st));
         CU_TRY(launch_build_sig(qd.cinfo, (int64_t)b.concat_len + 2, qd.sig, st));
         v.sig = getenv("BN_NO_SIG") ? nullptr : qd.sig;
+        // the same signatures per table cell: one 2-byte gather per scan position instead of {presence, rank} first and the
+        // signature of an occupied cell after it (hashsize even: a power of 4).  32 MB at lut 12: stays in L2
+        // (`profiles/r04c_gather_table_size_and_serial_trips.txt`: the gather rate does not depend on the table size up to 64 MB)
+        if (v.sig && b.word_length - b.lut_word_length >= 7 && b.lut_word_length <= 12 && !getenv("BN_NO_PSIG")) {
+            CU_TRY(dev_alloc(&qd.psig, (size_t)b.hashsize, st));
+            CU_TRY(launch_build_psig(qd.prk, qd.sig, b.hashsize, qd.psig, st));
+            v.psig = qd.psig;
+        }
         // small batch: hashed presence filter for the shared-memory scan (scan_kernel_filtered).  The number of occupied
         // cells is only known on the device; concat_len bounds it.  Measured against the queue-driven kernel on a
         // 250 Mb volume: 1.75x faster at 1 % - 2 % of the filter's bits set, even at ~15 %, so the path is taken up to 1/16

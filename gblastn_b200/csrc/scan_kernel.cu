@@ -319,6 +319,44 @@ __device__ __forceinline__ void words8(const uint32_t *tile, int32_t tb_first, u
     }
 }
 
+// Dense-signature probe (DevQuery::psig): what a scan position contributes is its table cell and the 14 bits its psig
+// entry is compared with.  v0 = 16 bases from 4 bases in front of the position, v1 = the 16 after them.
+__device__ __forceinline__ void probe_key(uint32_t v0, uint32_t v1, uint32_t shr, uint32_t &idx, uint32_t &want)
+{
+    const uint32_t v = __funnelshift_l(v1, v0, 8);           // 16 bases from the position on
+    idx = v >> shr;
+    want = ((v0 >> 16) & 0x3F00u) | ((v >> (shr - 8u)) & 0xFFu);     // 3 bases left of the word | 4 bases right of it (lut <= 12)
+}
+// occupied cell whose first chain element cannot reach the full word: fewer than 3 matching bases on its left and fewer
+// than 4 on its right, no further chain elements (see scan_candidate)
+__device__ __forceinline__ bool psig_pass(uint32_t ps, uint32_t want)
+{
+    const uint32_t x = ps ^ want;
+    return (ps & 0x4000u) || !(x & 0x3F00u) || !(x & 0xFFu);
+}
+// words8 for the dense-signature probe: the stream is aligned 4 bases in front of the first position and one raw word
+// longer (11 words: position 7 of stride 18 ends at bit 252 + 64)
+template <int STEP>
+__device__ __forceinline__ void words8f(const uint32_t *tile, int32_t tb_first, uint32_t shr, uint32_t (&idx)[8], uint32_t (&want)[8])
+{
+    static_assert(STEP >= 16 && 14 * STEP + 64 <= 320, "eleven raw words cover the span");
+    const int32_t t0 = tb_first - 4;
+    const uint32_t *w = tile + (t0 >> 4);
+    uint32_t R[11], N[10];
+#pragma unroll
+    for (int i = 0; i < 11; i++) R[i] = __byte_perm(w[i], 0, 0x0123);
+    const uint32_t off0 = ((uint32_t)t0 & 15u) * 2u;
+#pragma unroll
+    for (int i = 0; i < 10; i++) N[i] = __funnelshift_l(R[i + 1], R[i], off0);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int bit = j * 2 * STEP, a = bit >> 5, sh = bit & 31;
+        const uint32_t v0 = sh ? __funnelshift_l(N[a + 1], N[a], (uint32_t)sh) : N[a];
+        const uint32_t v1 = sh ? __funnelshift_l(N[a + 2 < 10 ? a + 2 : 9], N[a + 1], (uint32_t)sh) : N[a + 1];
+        probe_key(v0, v1, shr, idx[j], want[j]);
+    }
+}
+
 // s_BlastNaExtend on 16-base windows.  The query's 16 bases on either side of the lookup word come
 // with the chain element (qinfo), so the common case needs no further query access; tbase =
 // tile-relative base index of the chunk's base 0.
@@ -710,7 +748,10 @@ __device__ __forceinline__ void direct_drain(const DevQuery &q, const ScanLaunch
 }
 
 // STEP: compile-time scan stride for the consecutive-position word loader (blocks inside one chunk), 0 = run-time stride
-template <bool DIRECT, int STEP>
+// DENSE: the probe is the per-cell signature table (DevQuery::psig) instead of {presence, rank}: a position becomes a
+// candidate only if its cell is occupied AND the signature lets the mini-extension succeed (1 % of the positions of a
+// megablast batch instead of 12 %); the rank is looked up for those alone
+template <bool DIRECT, int STEP, bool DENSE = false>
 __global__ void __launch_bounds__(SCAN_THREADS, DIRECT ? 4 : BN_SCAN_MIN_BLOCKS)
 scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ ScanLaunch s)
 {
@@ -755,13 +796,39 @@ scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ S
         // From here on every warp works alone on its 256 positions (block-relative position of lane l,
         // round it: it * 256 + warp * 32 + l): no block barrier between the probe and the candidate phase.
         // ---- phase A: lookup words from the tile, all 8 presence probes of the thread in flight ------
-        uint2 words[POS_PER_THREAD];
+        uint2 words[DENSE ? 1 : POS_PER_THREAD];
         uint32_t bitpack[POS_PER_THREAD / 4], cpack[POS_PER_THREAD / 4];
+        // DENSE: psig entry, table cell and the bits the entry is compared with, per position
+        uint32_t pw[DENSE ? POS_PER_THREAD : 1], cell[DENSE ? POS_PER_THREAD : 1], want[DENSE ? POS_PER_THREAD : 1];
         const uint32_t shr = 32u - 2u * (uint32_t)lut;
         // thread -> position map: round it of thread tid handles block-relative position it * 256 + tid, or — blocks
         // inside one chunk with a compile-time stride — tid * 8 + it (consecutive positions, words8)
         const bool consec = STEP > 0 && POS_PER_THREAD == 8 && nch == 1;
-        if constexpr (STEP > 0 && POS_PER_THREAD == 8) {
+        if constexpr (DENSE) {
+            if constexpr (STEP > 0 && POS_PER_THREAD == 8) {
+                if (consec) {
+                    const int32_t tb0 = ct_tbase[0] + ct_pfirst[0] - ct_start[0] * STEP;
+                    words8f<STEP>(tile, tb0 + tid * 8 * STEP, shr, cell, want);
+#pragma unroll
+                    for (int it = 0; it < 8; it++) pw[it] = __ldg(&q.psig[cell[it]]);
+                    for (int i = 0; i < POS_PER_THREAD / 4; i++) cpack[i] = 0;
+                }
+            }
+            if (!consec) {
+                int32_t c = 0, cnext = ct_start[1];
+#pragma unroll
+                for (int it = 0; it < POS_PER_THREAD; it++) {
+                    const int32_t gl = min(it * SCAN_THREADS + tid, npos - 1);
+                    while (gl >= cnext) { ++c; cnext = ct_start[c + 1]; }          // monotone cursor over the block's chunk table
+                    if ((it & 3) == 0) cpack[it >> 2] = 0;
+                    cpack[it >> 2] |= (uint32_t)c << (8 * (it & 3));
+                    const int32_t tb = ct_tbase[c] + ct_pfirst[c] + (gl - ct_start[c]) * step;
+                    probe_key(tile_win(tile, tb - 4), tile_win(tile, tb + 12), shr, cell[it], want[it]);
+                    pw[it] = __ldg(&q.psig[cell[it]]);
+                }
+            }
+        }
+        if constexpr (!DENSE && STEP > 0 && POS_PER_THREAD == 8) {
             if (consec) {
                 const int32_t tb0 = ct_tbase[0] + ct_pfirst[0] - ct_start[0] * STEP;
                 uint32_t idxs[8];
@@ -775,6 +842,7 @@ scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ S
                 for (int i = 0; i < POS_PER_THREAD / 4; i++) cpack[i] = 0;
             }
         }
+        if constexpr (!DENSE) {
         if (consec) {
         } else if (nch == 1) {
             // the whole block lies in one chunk: tile offsets are an arithmetic progression
@@ -816,6 +884,7 @@ scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ S
                 bitpack[it >> 2] |= (idx & 31u) << (8 * (it & 3));
             }
         }
+        }
         // ---- warp-local compaction of the occupied cells (ballots, no atomics) ----------------------
         uint2 *wcand = cand + (tid >> 5) * (32 * POS_PER_THREAD);
         int ncand = 0;
@@ -823,15 +892,24 @@ scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ S
             const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
             for (int it = 0; it < POS_PER_THREAD; it++) {
-                const uint32_t bit = (bitpack[it >> 2] >> (8 * (it & 3))) & 31u;
                 const int32_t gl = consec ? tid * POS_PER_THREAD + it : it * SCAN_THREADS + tid;
-                const bool hit = (gl < npos) && ((words[it].x >> bit) & 1u);
+                bool hit;
+                uint32_t rec;                   // DENSE: the table cell (its rank is looked up in phase B), else the rank
+                if constexpr (DENSE) {
+                    const bool occupied = (gl < npos) && (pw[it] & 0x8000u);
+                    hit = occupied && psig_pass(pw[it], want[it]);
+                    my_lookup_hits += (occupied && !hit) ? 1u : 0u;         // the one chain element that cannot reach the word
+                    rec = cell[it];
+                } else {
+                    const uint32_t bit = (bitpack[it >> 2] >> (8 * (it & 3))) & 31u;
+                    const uint2 wd = words[it];
+                    hit = (gl < npos) && ((wd.x >> bit) & 1u);
+                    rec = wd.y + (uint32_t)__popc(wd.x & ((1u << bit) - 1u));
+                }
                 const uint32_t m = __ballot_sync(0xffffffffu, hit);
                 if (hit) {
                     const uint32_t c = (cpack[it >> 2] >> (8 * (it & 3))) & 255u;
-                    wcand[ncand + __popc(m & lt)] =
-                        make_uint2(words[it].y + (uint32_t)__popc(words[it].x & ((1u << bit) - 1u)),
-                                   (c << 11) | (uint32_t)gl);
+                    wcand[ncand + __popc(m & lt)] = make_uint2(rec, (c << 11) | (uint32_t)gl);
                 }
                 ncand += __popc(m);
             }
@@ -857,7 +935,12 @@ scan_kernel_staged(const __grid_constant__ DevQuery q, const __grid_constant__ S
         } else {
             for (int ci = lane; ci < ncand; ci += 32) {
                 const uint2 cd = wcand[ci];
-                scan_candidate<DIRECT>(q, s, bv, cd.x, (int32_t)(cd.y & 2047u), (int32_t)(cd.y >> 11), use_sig, my_lookup_hits);
+                uint32_t rank = cd.x;
+                if constexpr (DENSE) {
+                    const uint2 wd = __ldg(&q.prk[cd.x >> 5]);
+                    rank = wd.y + (uint32_t)__popc(wd.x & ((1u << (cd.x & 31u)) - 1u));
+                }
+                scan_candidate<DIRECT>(q, s, bv, rank, (int32_t)(cd.y & 2047u), (int32_t)(cd.y >> 11), use_sig && !DENSE, my_lookup_hits);
             }
         }
     }
@@ -1070,6 +1153,30 @@ __global__ void build_sig_kernel(const uint4 *cinfo, int64_t n_ranks, uint32_t *
 cudaError_t launch_build_sig(const uint4 *cinfo, int64_t n_ranks, uint32_t *sig, cudaStream_t st)
 {
     if (n_ranks > 0) build_sig_kernel<<<(unsigned)((n_ranks + 255) / 256), 256, 0, st>>>(cinfo, n_ranks, sig);
+    return cudaGetLastError();
+}
+// psig[cell]: see DevQuery::psig; the cell's sig entry spread over the 4^lut cells (two cells per thread, one 4-byte store)
+__global__ void build_psig_kernel(const uint2 *prk, const uint32_t *sig, int64_t n_cells, uint16_t *psig)
+{
+    const int64_t c0 = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    if (c0 >= n_cells) return;
+    const uint2 w = prk[c0 >> 5];
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const uint32_t bit = (uint32_t)(c0 & 31) + k;
+        if ((w.x >> bit) & 1u) {
+            const uint32_t sg = sig[w.y + (uint32_t)__popc(w.x & ((1u << bit) - 1u))];
+            out |= (0x8000u | ((sg >> 16) & 1u) << 14 | (sg & 0x3Fu) << 8 | ((sg >> 8) & 0xFFu)) << (16 * k);
+        }
+    }
+    if (c0 + 1 < n_cells) *reinterpret_cast<uint32_t *>(psig + c0) = out;
+    else psig[c0] = (uint16_t)out;
+}
+cudaError_t launch_build_psig(const uint2 *prk, const uint32_t *sig, int64_t n_cells, uint16_t *psig, cudaStream_t st)
+{
+    const int64_t threads = (n_cells + 1) / 2;
+    if (threads > 0) build_psig_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(prk, sig, n_cells, psig);
     return cudaGetLastError();
 }
 
@@ -1292,6 +1399,11 @@ cudaError_t launch_scan(const DevQuery &q, const ScanLaunch &s, cudaStream_t st)
         const size_t smem = (size_t)s.tile_cap + sizeof(uint2) * POS_PER_BLOCK;
         if (s.direct_filter && !s.raw_pairs)
             scan_kernel_staged<true, 0><<<(unsigned)blocks, SCAN_THREADS, smem + sizeof(DirectQueue) * (SCAN_THREADS / 32), st>>>(q, s);
+        else if (q.psig != nullptr && !s.raw_pairs) {           // dense-signature probe
+            if (cstep == 17) scan_kernel_staged<false, 17, true><<<(unsigned)blocks, SCAN_THREADS, smem, st>>>(q, s);
+            else if (cstep == 18) scan_kernel_staged<false, 18, true><<<(unsigned)blocks, SCAN_THREADS, smem, st>>>(q, s);
+            else scan_kernel_staged<false, 0, true><<<(unsigned)blocks, SCAN_THREADS, smem, st>>>(q, s);
+        }
         else if (cstep == 17) scan_kernel_staged<false, 17><<<(unsigned)blocks, SCAN_THREADS, smem, st>>>(q, s);
         else if (cstep == 18) scan_kernel_staged<false, 18><<<(unsigned)blocks, SCAN_THREADS, smem, st>>>(q, s);
         else scan_kernel_staged<false, 0><<<(unsigned)blocks, SCAN_THREADS, smem, st>>>(q, s);

@@ -471,6 +471,57 @@ def test_gpu_with_database_masks(name, kw, mask_type):
         Q.free(); V.free()
 
 
+@pytest.mark.parametrize("name", ["c1_megablast_10kb_vs_1mb", "mb_lut11_hash_indels", "mb_lut12_stride17",
+                                  "c4_scaled_short_reads", "c5_scaled_ntlike_5kb", "mb_bridged_segments",
+                                  "mb_ntlike_many_subjects", "mb_with_N", "mb_repeat_family_hitlist5"])
+@pytest.mark.parametrize("mask_type", [0, 1, 2])
+def test_dense_signature_scan_changes_nothing(name, mask_type, monkeypatch):
+    """Megablast tables with word - lut >= 7 carry the dense signature table (DevQuery::psig: one 2-byte gather per scan
+    position answers "cell occupied?" and "can its mini-extension reach the word?").  The queue-driven kernel with the
+    dense probe (words formed 8 consecutive positions per thread, or position by position: BN_NO_CONSEC) and with the
+    {presence, rank} + signature-by-rank probe (BN_NO_PSIG, read when the batch is loaded) give the same seed hits and
+    counters, bit for bit at every tap, with and without database masks (soft: scan units with p_first > 0; hard: chunks
+    split at the masks), and equal the reference."""
+    from gblastn_b200 import engine as E, abi
+    from oracle import refdriver as R, portdriver as P
+    if not R.available():
+        pytest.skip("reference library not present")
+    task, cfgkw, vol, qs = cases.make_case(name)
+    sm = _db_masks(vol, np.random.default_rng(7 * mask_type + len(name)), 5) if mask_type else None
+    cfg = R.default_config(task, taps=R.TAP_INIT | R.TAP_GAPPED | R.TAP_LUT, **cfgkw)
+    r = R.search(qs, vol, cfg, subject_masks=sm, subject_mask_type=mask_type) if mask_type else R.search(qs, vol, cfg)
+    assert r["status"] == 0
+    h = P.batch_from_reference(r, task=task, cfg=cfg)
+    assert h.batch.lut_type == abi.BN_LUT_MB and h.batch.word_length - h.batch.lut_word_length >= 7
+    monkeypatch.setenv("BN_FILT_MAX", "0")          # small batches: not the shared-memory filter kernel
+    V = E.Volume(vol)
+    out = []
+    try:
+        if mask_type:
+            V.set_masks(sm, mask_type)
+        for mode in ("dense", "rank_probe", "dense_strided"):
+            for k in ("BN_NO_PSIG", "BN_NO_CONSEC"):
+                monkeypatch.delenv(k, raising=False)
+            if mode == "rank_probe":
+                monkeypatch.setenv("BN_NO_PSIG", "1")
+            if mode == "dense_strided":
+                monkeypatch.setenv("BN_NO_CONSEC", "1")
+            Q = E.Query(h)
+            try:
+                out.append(E.prelim_search(V, Q, taps=abi.BN_TAP_INIT | abi.BN_TAP_GAPPED))
+            finally:
+                Q.free()
+        a = out[0]
+        for b in out[1:]:
+            assert a["init"].tobytes() == b["init"].tobytes() and a["gapped"].tobytes() == b["gapped"].tobytes()
+            assert a["hsps"].tobytes() == b["hsps"].tobytes()
+            assert a["stats"]["lookup_hits"] == b["stats"]["lookup_hits"] == r["lookup_hits"]
+        assert np.array_equal(P.init_table(a["init"]), r["init"])
+        assert np.array_equal(P.final_table(a["hsps"]), r["final"])
+    finally:
+        V.free()
+
+
 def test_batch_pipeline_equals_single_searches():
     """bn_prelim_search_batches: five different query batches (mixed table shapes, one empty result, one on
     the general path) through the two-stage pipeline give byte-identical results to one search each, and each
