@@ -1663,6 +1663,7 @@ static int search_host_phase(const Query &Q, const GpuOut &G, int taps, BnResult
         }
     }
 
+    const double t_grouped = now_ms();
     std::vector<BnHSP> final_hsps, gapped_tap;
     std::vector<BnInitHit> init_tap;
     LowScoreTracker own_tracker(b);
@@ -1712,15 +1713,30 @@ static int search_host_phase(const Query &Q, const GpuOut &G, int taps, BnResult
         if (oid_base) for (auto &h : list) h.oid += oid_base;
     };
     if (parallel) {
-        // whole subjects per worker: replay, list post-processing, merge and E-values all run in parallel
+        // Chunks are replayed independently of each other (a 107 Mb subject is 22 of them), then every subject's chunk lists
+        // are merged and evaluated: workers take chunks first, largest first, and a subject's merge goes to the worker that
+        // finishes its last chunk — replay, list post-processing, merge and E-values all run in parallel, and the
+        // parallelism is the number of chunks, not of subjects (C4: 150 against 7).
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        const size_t n_threads = std::min<size_t>(std::min<size_t>(runs.size(), hw), 16);
+        const size_t n_threads = std::min<size_t>(std::min<size_t>(groups.size(), hw), 16);
+        std::vector<uint32_t> order(groups.size()), run_of(groups.size());
+        for (size_t ri = 0; ri < runs.size(); ri++)
+            for (size_t gi = runs[ri].lo; gi < runs[ri].hi; gi++) run_of[gi] = (uint32_t)ri;
+        for (size_t gi = 0; gi < groups.size(); gi++) order[gi] = (uint32_t)gi;
+        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+            const size_t na = groups[a].hi - groups[a].lo, nb = groups[b].hi - groups[b].lo;
+            return na != nb ? na > nb : a < b;
+        });
+        std::vector<std::atomic<uint32_t>> left(runs.size());
+        for (size_t ri = 0; ri < runs.size(); ri++) left[ri].store((uint32_t)(runs[ri].hi - runs[ri].lo));
+        const bool finish_here = !(taps & (BN_TAP_INIT | BN_TAP_GAPPED));
         std::atomic<size_t> next{0};
         std::vector<std::thread> pool;
         auto worker = [&]() {
-            for (size_t ri; (ri = next.fetch_add(1)) < runs.size();) {
-                for (size_t gi = runs[ri].lo; gi < runs[ri].hi; gi++) do_group(gi);
-                if (!(taps & (BN_TAP_INIT | BN_TAP_GAPPED))) finish_run(runs[ri], run_out[ri]);
+            for (size_t k; (k = next.fetch_add(1)) < order.size();) {
+                const size_t gi = order[k], ri = run_of[gi];
+                do_group(gi);
+                if (left[ri].fetch_sub(1, std::memory_order_acq_rel) == 1 && finish_here) finish_run(runs[ri], run_out[ri]);
             }
         };
         for (size_t t = 1; t < n_threads; t++) pool.emplace_back(worker);
@@ -1729,6 +1745,11 @@ static int search_host_phase(const Query &Q, const GpuOut &G, int taps, BnResult
     }
     t_sort = now_ms() - th0;
 
+    if (parallel) {
+        size_t total = 0;
+        for (const auto &l : run_out) total += l.size();
+        final_hsps.reserve(total);
+    }
     for (size_t ri = 0; ri < runs.size(); ri++) {
         std::vector<BnHSP> serial_list;
         for (size_t gi = runs[ri].lo; gi < runs[ri].hi; gi++) {
@@ -1767,6 +1788,7 @@ static int search_host_phase(const Query &Q, const GpuOut &G, int taps, BnResult
     {
         double gs = 0, gr = 0, gf = 0;
         for (const auto &o : gout) { gs += o.t_sort; gr += o.t_replay; gf += o.t_finish; }
+        fprintf(stderr, "[bn] host: grouping %.3f ms, %u hardware threads\n", t_grouped - th0, std::thread::hardware_concurrency());
         fprintf(stderr, "[bn] wall: table %.3f word-finder %.3f gapped %.3f | host %.3f ms: group(+parallel) %.3f [sum over chunks: sort %.3f replay %.3f finish %.3f] serial-groups %.3f merge %.3f eval %.3f track %.3f tail %.3f (n_hits %lld n_init %lld)\n",
                 tw0 - t0, tw1 - tw0, tw2 - tw1, stats.ms_host, t_sort, gs, gr, gf, t_replay, t_merge, t_eval, t_track,
                 stats.ms_host - (t_sort + t_replay + t_merge + t_eval + t_track),

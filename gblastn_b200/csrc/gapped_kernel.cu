@@ -996,29 +996,38 @@ __device__ int32_t dp_packed_chain(const uint8_t *B, const uint8_t *A, int32_t N
         if (reverse) a_bp = (__ldg(A + (M - a_index) / 4) >> (2 * ((a_index - 1) % 4))) & 3;
         else a_bp = (__ldg(A + 1 + (a_index - 1) / 4) >> (2 * (3 - (a_index - 1) % 4))) & 3;
         const int32_t *mrow = matrix + 16 * a_bp;
-        // 1. v_b for the whole band
+        // 1. v_b for the whole band (the lane keeps its first cell's vertical gap score for step 3)
+        int32_t my_y = MININT;
         for (int32_t b = first_b + lane; b < b_size; b += 32) {
             const int2 cell = ring[b & MASK];
+            if (b < first_b + 32) my_y = cell.y;
             int32_t diag = MININT;
             if (b > first_b) diag = ring[(b - 1) & MASK].x + mrow[(int)__ldg(reverse ? (B + N - b) : (B + b))];
             vbuf[b & MASK] = max(diag, cell.y);
         }
         __syncwarp();
-        // 2. the chain
+        // 2. the chain, without branches: per cell  s = max(v, r);  keep = s >= best - X;  r = keep ? max(v - goe, r - ge) : r
+        // (= max(s - goe, r - ge): when r > v, s - goe = r - goe <= r - ge as gap_open >= 0);  best = max(best, s).  Three
+        // dependent operations from r to r; the loads of v run ahead (unrolled), the stores trail.
         int32_t fb = first_b, last_b = first_b, r = MININT;
         if (lane == 0) {
-#pragma unroll 4
+            int32_t thr = best - x_dropoff;             // prune a cell if s < thr
+            bool lead = true;
+#pragma unroll 8
             for (int32_t b = first_b; b < b_size; b++) {
-                const int32_t score = max(vbuf[b & MASK], r);
-                if (best - score > x_dropoff) {
-                    if (b == fb) fb++;
-                    sbuf[b & MASK] = MININT;
-                } else {
-                    last_b = b;
-                    if (score > best) { best = score; a_off = a_index; b_off = b; }
-                    r = max(score - goe, r - ge);
-                    sbuf[b & MASK] = score;
-                }
+                const int32_t v = vbuf[b & MASK];
+                const int32_t s = max(v, r);
+                const bool keep = s >= thr;
+                const bool improved = s > best;          // implies keep
+                r = keep ? max(v - goe, r - ge) : r;
+                sbuf[b & MASK] = keep ? s : MININT;
+                b_off = improved ? b : b_off;
+                a_off = improved ? a_index : a_off;
+                best = max(best, s);
+                thr = max(thr, s - x_dropoff);
+                last_b = keep ? b : last_b;
+                lead = lead && !keep;
+                fb += lead ? 1 : 0;
             }
         }
         __syncwarp();                        // lane 0's sbuf stores before everybody reads them
@@ -1028,7 +1037,7 @@ __device__ int32_t dp_packed_chain(const uint8_t *B, const uint8_t *A, int32_t N
         for (int32_t b = first_b + lane; b < b_size; b += 32) {
             const int32_t sc = sbuf[b & MASK];
             if (sc != MININT) {
-                const int32_t y = ring[b & MASK].y;
+                const int32_t y = (b < first_b + 32) ? my_y : ring[b & MASK].y;
                 ring[b & MASK] = make_int2(sc, max(sc - goe, y - ge));
             } else if (b >= fb) ring[b & MASK].x = MININT;
         }
