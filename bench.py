@@ -511,7 +511,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": scan_traffic(), "kernel": "bn::scan_kernel_staged<0,17>",
+                     "frac": achieved / peak, "traffic": scan_traffic(), "kernel": "bn::scan_kernel_staged<0,17,1>",
                      "peak_kind": peak_kind, "ms_per_launch": scan_ms,
                      "algorithmic_bytes_per_launch": scan_bases * 0.25},
         "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},

@@ -1,4 +1,3 @@
 #!/bin/bash
-mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 300 python scripts/exp_c3.py 100 2 50000000 2>&1 | tail -1
+echo "--- dense + lane-private, 6 blocks/SM"
+timeout 120 python scripts/exp_scan.py 2>&1 | tail -1
