@@ -1478,15 +1478,6 @@ static int fused_complete(Lane &D, Volume &V, Query &Q, ChunkTable &T, const Fus
     return BN_OK;
 }
 
-static int run_fused(Lane &D, Volume &V, Query &Q, ChunkTable &T, StageCounts &cnt, BnStats &stats,
-                     DevInitHit *&h_init, DevGapResult *&h_gap, bool *redo)
-{
-    FusedState F;
-    int rc = fused_enqueue(D, V, Q, T, F);
-    if (rc) return rc;
-    return fused_complete(D, V, Q, T, F, cnt, stats, h_init, h_gap, redo);
-}
-
 template <typename T>
 static T *to_malloc(const std::vector<T> &v)
 {
@@ -1600,7 +1591,7 @@ static int search_host_phase(const Query &Q, const GpuOut &G, int taps, BnResult
     // ---- host replay -------------------------------------------------------------------------
     const double th0 = now_ms();
     static const bool trace = getenv("BN_TRACE") != nullptr;
-    double t_sort = 0, t_replay = 0, t_finish = 0, t_merge = 0, t_eval = 0, t_track = 0;
+    double t_sort = 0, t_replay = 0, t_merge = 0, t_eval = 0, t_track = 0;
     const BnQueryBatch &b = Q.batch;
     // init hits grouped by chunk, each group in the reference's order.  groups[k] = {chunk, begin, end} into
     // `inits`; a counting sort when the hits are many compared with the chunks, else a sort of the hits

@@ -580,7 +580,7 @@ __device__ __forceinline__ ScanBlockDesc ld_block_desc(const ScanBlockDesc *p)
     ScanBlockDesc d;
     d.tile_lo = (int64_t)(((uint64_t)a1 << 32) | a0);
     d.bytes = (int32_t)a2; d.c_lo = (int32_t)a3; d.c_hi = (int32_t)a4; d.staged = (int32_t)a5;
-    d.pad0 = d.pad1 = 0;
+    d.pad0 = (int32_t)a6; d.pad1 = (int32_t)a7;
     return d;
 }
 __device__ __forceinline__ void ld_cinfo_pair(const uint4 *p, uint4 &e0, uint4 &e1)
