@@ -1,5 +1,7 @@
 #!/bin/bash
-echo "--- dense, mask-first compaction"; timeout 120 python scripts/exp_scan.py 2>&1 | tail -1
-timeout 300 python scripts/exp_c5.py c5 1.0 2>&1 | grep -E "^search" | tail -1 | cut -c1-120
-timeout 300 python scripts/exp_c5.py c4 1.0 2>&1 | grep -E "^search" | tail -1 | cut -c1-120
-timeout 600 python -m pytest tests -m gpu -x -q -k "dense_signature or filtered_scan or full_size or masks" 2>&1 | tail -2
+mkdir -p gpurun_out
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_c4_r04z.csv \
+    python scripts/exp_c5.py c4 1.0 > gpurun_out/c4_ncu_r04z.log 2>&1
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_c5_r04z.csv \
+    python scripts/exp_c5.py c5 1.0 > gpurun_out/c5_ncu_r04z.log 2>&1
+wc -l gpurun_out/launches_c4_r04z.csv gpurun_out/launches_c5_r04z.csv
