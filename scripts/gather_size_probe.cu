@@ -62,6 +62,54 @@ __global__ void __launch_bounds__(256) k_trips(const uint16_t *__restrict__ t, u
     if (acc == 0xFFFFFFFFFFFFull) *out = acc;
 }
 
+// Does the instruction stream AROUND the gathers cost throughput?  PRE dependent integer operations in front of a round's
+// eight gathers (their addresses depend on the result, like the lookup words formed from the staged slice), POST
+// dependent operations behind them (like the votes / queue / bookkeeping), per thread and round.
+template <int PRE, int POST>
+__global__ void __launch_bounds__(256) k_pad(const uint16_t *__restrict__ t, uint32_t mask, int64_t n, unsigned long long *out)
+{
+    unsigned long long acc = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 8;
+    for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8; base < n; base += stride) {
+        uint32_t x = (uint32_t)base;
+#pragma unroll 16
+        for (int i = 0; i < PRE; i++) x = x * 1664525u + 1013904223u;
+        uint32_t v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = __ldg(&t[(mix((uint32_t)(base + i) * 2654435761u + 12345u) ^ (PRE ? (x & 0xFFu) : 0u)) & mask]);
+        uint32_t y = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) y += v[i];
+#pragma unroll 16
+        for (int i = 0; i < POST; i++) y = y * 1664525u + 1013904223u;
+        acc += y & 1u;
+    }
+    if (acc == 0xFFFFFFFFFFFFull) *out = acc;
+}
+
+// How much do DEPENDENT shared-memory round trips per round cost (each read's address comes from the previous read)?
+// The load/store pipe they go through is the one the gathers' 32 wavefronts per instruction occupy.
+template <int K>
+__global__ void __launch_bounds__(256) k_lds(const uint16_t *__restrict__ t, uint32_t mask, int64_t n, unsigned long long *out)
+{
+    __shared__ uint32_t sm[2048];
+    for (int i = threadIdx.x; i < 2048; i += 256) sm[i] = (i * 2654435761u) >> 21;       // values in 0 .. 2047
+    __syncthreads();
+    unsigned long long acc = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 8;
+    for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8; base < n; base += stride) {
+        uint32_t x = (uint32_t)(base >> 3) & 2047u;
+#pragma unroll
+        for (int i = 0; i < K; i++) x = sm[x];
+        uint32_t v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = __ldg(&t[(mix((uint32_t)(base + i) * 2654435761u + 12345u) ^ (x & 0xFFu)) & mask]);
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc += v[i] & 1u;
+    }
+    if (acc == 0xFFFFFFFFFFFFull) *out = acc;
+}
+
 int main()
 {
     const int64_t N = 14705888;
@@ -106,6 +154,29 @@ int main()
             }
             printf("%-60s %7.1f us (%.3f probes/clk/SM)\n", name, best * 1e3, N / (best * 1e-3) / clk / p.multiProcessorCount);
         };
+        {   // the same table from the stream-ordered pool (cudaMallocAsync), as the engine allocates its query tables
+            uint16_t *ta = nullptr;
+            CK(cudaMallocAsync((void **)&ta, bytes, 0)); CK(cudaMemsetAsync(ta, 0x5a, bytes, 0)); CK(cudaDeviceSynchronize());
+            run("plain gather loop, table from cudaMallocAsync, 4 blocks/SM", [&] { k_pad<0, 0><<<148 * 4, 256>>>(ta, mask, N, out); });
+            // and with 200 MB of other pool allocations made first (fragmented pool, like a lane that holds several tables)
+            void *other[8];
+            for (int i = 0; i < 8; i++) CK(cudaMallocAsync(&other[i], (size_t)25 << 20, 0));
+            uint16_t *tb = nullptr;
+            CK(cudaMallocAsync((void **)&tb, bytes, 0)); CK(cudaMemsetAsync(tb, 0x5a, bytes, 0)); CK(cudaDeviceSynchronize());
+            run("plain gather loop, pool table allocated behind 200 MB of others", [&] { k_pad<0, 0><<<148 * 4, 256>>>(tb, mask, N, out); });
+        }
+        run("dependent shared-memory reads per round:  0, 6 blocks/SM", [&] { k_lds<0><<<148 * 6, 256>>>(t, mask, N, out); });
+        run("dependent shared-memory reads per round:  2", [&] { k_lds<2><<<148 * 6, 256>>>(t, mask, N, out); });
+        run("dependent shared-memory reads per round:  4", [&] { k_lds<4><<<148 * 6, 256>>>(t, mask, N, out); });
+        run("dependent shared-memory reads per round:  8", [&] { k_lds<8><<<148 * 6, 256>>>(t, mask, N, out); });
+        run("dependent shared-memory reads per round: 16", [&] { k_lds<16><<<148 * 6, 256>>>(t, mask, N, out); });
+        run("dependent shared-memory reads per round: 32", [&] { k_lds<32><<<148 * 6, 256>>>(t, mask, N, out); });
+        run("pad   0 /   0 dependent ops around a round, 4 blocks/SM", [&] { k_pad<0, 0><<<148 * 4, 256>>>(t, mask, N, out); });
+        run("pad 150 /   0", [&] { k_pad<150, 0><<<148 * 4, 256>>>(t, mask, N, out); });
+        run("pad 150 / 400", [&] { k_pad<150, 400><<<148 * 4, 256>>>(t, mask, N, out); });
+        run("pad 150 / 400, 6 blocks/SM", [&] { k_pad<150, 400><<<148 * 6, 256>>>(t, mask, N, out); });
+        run("pad 300 / 800, 6 blocks/SM", [&] { k_pad<300, 800><<<148 * 6, 256>>>(t, mask, N, out); });
+        run("pad 150 / 400, 2 blocks/SM", [&] { k_pad<150, 400><<<148 * 2, 256>>>(t, mask, N, out); });
         run("serial trips 0 (plain gather loop), 4 blocks/SM", [&] { k_trips<0, 0><<<148 * 4, 256>>>(t, mask, small, N, out); });
         run("serial trips 1 (LDS in front of each burst)", [&] { k_trips<1, 0><<<148 * 4, 256>>>(t, mask, small, N, out); });
         run("serial trips 2 (LDG L1-hit -> LDS -> burst)", [&] { k_trips<2, 0><<<148 * 4, 256>>>(t, mask, small, N, out); });
